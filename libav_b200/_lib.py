@@ -1,0 +1,93 @@
+"""ctypes binding of libavdsp_b200.so (the C-ABI in include/avdsp_b200.h).
+
+Loading fails loudly when the shared library has not been built: there is no Python / CPU fallback for
+any op.  Importing this module does not need a GPU (the CPU test suite checks the exported symbols);
+calling a compute entry point without a B200 returns -1 and raises AVB200Error.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavdsp_b200.so")
+
+
+class AVB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise AVB200Error("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no fallback path." % LIB_PATH)
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+vp, sz, i32, i64 = C.c_void_p, C.c_size_t, C.c_int, C.c_int64
+pd = C.c_ssize_t  # ptrdiff_t
+
+# name -> (restype, argtypes); mirrors include/avdsp_b200.h one to one (tests/test_abi_cpu.py parses the
+# header and checks that every declared symbol is exported and listed here)
+PROTOTYPES = {
+    "avb200_device_count": (i32, []),
+    "avb200_init": (i32, [i32]),
+    "avb200_last_error": (C.c_char_p, []),
+    "avb200_clear_error": (None, []),
+    "avb200_set_log_callback": (None, [vp]),
+    "avb200_malloc": (vp, [sz]),
+    "avb200_free": (None, [vp]),
+    "avb200_host_alloc": (vp, [sz]),
+    "avb200_host_free": (None, [vp]),
+    "avb200_host_register": (i32, [vp, sz]),
+    "avb200_host_unregister": (i32, [vp]),
+    "avb200_memcpy_h2d": (i32, [vp, vp, sz, vp]),
+    "avb200_memcpy_d2h": (i32, [vp, vp, sz, vp]),
+    "avb200_memcpy2d_h2d": (i32, [vp, sz, vp, sz, sz, sz, vp]),
+    "avb200_memcpy2d_d2h": (i32, [vp, sz, vp, sz, sz, sz, vp]),
+    "avb200_memset": (i32, [vp, i32, sz, vp]),
+    "avb200_stream_create": (vp, []),
+    "avb200_stream_destroy": (None, [vp]),
+    "avb200_stream_sync": (i32, [vp]),
+    "avb200_device_sync": (i32, []),
+    "avb200_event_create": (vp, []),
+    "avb200_event_destroy": (None, [vp]),
+    "avb200_event_record": (i32, [vp, vp]),
+    "avb200_event_sync": (i32, [vp]),
+    "avb200_event_elapsed_ms": (C.c_float, [vp, vp]),
+    "ff_simple_idct_batch_cuda": (i32, [i32, vp, vp, vp, pd, sz, i32, i32, vp]),
+    "ff_pixels_clamped_batch_cuda": (i32, [i32, vp, vp, vp, pd, sz, i32, vp]),
+    "ff_clear_blocks_batch_cuda": (i32, [vp, sz, vp]),
+    "ff_fill_blocks_batch_cuda": (i32, [vp, vp, vp, pd, i32, i32, sz, vp]),
+    "ff_simple_idct_batch_host_cuda": (i32, [i32, vp, vp, sz, vp, pd, sz, i32]),
+    "ff_idctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
+    "ff_blockdsp_init_cuda": (None, [vp]),
+}
+
+for _name, (_res, _args) in PROTOTYPES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def last_error():
+    return lib.avb200_last_error().decode()
+
+
+def check(rc, what=""):
+    """Raise on a failed call or on a pending sticky error."""
+    if rc != 0:
+        msg = last_error()
+        lib.avb200_clear_error()
+        raise AVB200Error("%s failed: %s" % (what or "libavdsp_b200 call", msg or "unknown error"))
+    return rc
+
+
+_initialised = {}
+
+
+def init(device=0):
+    if device not in _initialised:
+        check(lib.avb200_init(device), "avb200_init(%d)" % device)
+        _initialised[device] = True
+    return True

@@ -1,0 +1,298 @@
+// libav_b200/csrc/idctdsp.cu -- batched 8x8 "simple" IDCT family + clamped pixel ops + block clear
+// for sm_100a.  Replaces, bit-exactly, the C slots of IDCTDSPContext / BlockDSPContext:
+//   ff_simple_idct_put_8 / _add_8 / ff_simple_idct_8   libavcodec/simple_idct_template.c:289-326
+//   put/put_signed/add_pixels_clamped_c                libavcodec/idctdsp.c:85-145
+//   clear_block(s)                                     libavcodec/blockdsp.c:29-37
+//
+// Work mapping: ONE THREAD PER 8x8 BLOCK, 32 blocks (4 KB of coefficients) per warp.
+//   * the warp's 4 KB is brought in with 8 fully coalesced 512-byte cp.async (LDGSTS) requests into
+//     a 128-byte-row XOR-swizzled shared tile (chunk c of block b lands at chunk c ^ (b & 7)), so
+//     the per-thread row reads (LDS.128, thread = block) are bank-conflict free;
+//   * both passes run in registers: no shuffles, no second transpose.  Integer semantics follow
+//     the reference exactly: W4 = 16383, the DC-only row shortcut (x0 << 3), int16 truncation of the
+//     row pass, rounding folded in the column DC term, 32-bit wrap-around arithmetic;
+//   * results leave as one 8-byte row store per (thread,row): with raster-ordered blocks a warp
+//     writes 256 contiguous bytes per picture row.
+// Two tiles per warp are double-buffered so the next group's loads fly during the math.
+// Algorithmic traffic: put 128 B in + 64 B out (+4 B offset) per block; add 256 B; idct 256 B.
+#include "common.cuh"
+
+namespace avb {
+
+enum { C1 = 22725, C2 = 21407, C3 = 19266, C4 = 16383, C5 = 12873, C6 = 8867, C7 = 4520 };
+
+struct Idct1D { int v[8]; };
+
+// even/odd butterflies shared by both passes; `base` already holds the DC term + rounding.
+__device__ __forceinline__ void butterfly(int base, int x1, int x2, int x3, int x4, int x5, int x6, int x7,
+                                          int (&s)[4], int (&d)[4])
+{
+    int b0 = base + C4 * x4, b1 = base - C4 * x4;
+    int p  = C2 * x2 + C6 * x6;
+    int q  = C6 * x2 - C2 * x6;
+    int e0 = b0 + p, e3 = b0 - p, e1 = b1 + q, e2 = b1 - q;
+    int o0 = C1 * x1 + C3 * x3 + C5 * x5 + C7 * x7;
+    int o1 = C3 * x1 - C7 * x3 - C1 * x5 - C5 * x7;
+    int o2 = C5 * x1 - C1 * x3 + C7 * x5 + C3 * x7;
+    int o3 = C7 * x1 - C5 * x3 + C3 * x5 - C1 * x7;
+    s[0] = e0 + o0; d[0] = e0 - o0;
+    s[1] = e1 + o1; d[1] = e1 - o1;
+    s[2] = e2 + o2; d[2] = e2 - o2;
+    s[3] = e3 + o3; d[3] = e3 - o3;
+}
+
+// Row pass on one packed row (4 words = 8 int16); result is the int16-truncated row, packed.
+// (x << 5) >> 16 keeps bits [26:11] sign-extended from bit 26 == (int16_t)(x >> 11).
+__device__ __forceinline__ uint4 row_pass(uint4 r)
+{
+    int x0 = lo16s(r.x), x1 = hi16s(r.x), x2 = lo16s(r.y), x3 = hi16s(r.y);
+    int x4 = lo16s(r.z), x5 = hi16s(r.z), x6 = lo16s(r.w), x7 = hi16s(r.w);
+    // all seven AC terms zero -> every output is (x0 << 3): feed base = x0 << 14 through the same
+    // datapath (the butterflies add zero), simple_idct_template.c:94-106
+    bool dc_only = ((r.x & 0xffff0000u) | r.y | r.z | r.w) == 0;
+    int base = dc_only ? (x0 << 14) : (C4 * x0 + (1 << 10));
+    int s[4], d[4];
+    butterfly(base, x1, x2, x3, x4, x5, x6, x7, s, d);
+    uint4 o;
+    o.x = __byte_perm((uint32_t)(s[0] << 5), (uint32_t)(s[1] << 5), 0x7632);
+    o.y = __byte_perm((uint32_t)(s[2] << 5), (uint32_t)(s[3] << 5), 0x7632);
+    o.z = __byte_perm((uint32_t)(d[3] << 5), (uint32_t)(d[2] << 5), 0x7632);
+    o.w = __byte_perm((uint32_t)(d[1] << 5), (uint32_t)(d[0] << 5), 0x7632);
+    return o;
+}
+
+// Column pass for column x given the eight row words that contain it; out[y] = value >> 20.
+template <int HI>
+__device__ __forceinline__ void col_pass(const uint32_t (&w)[8], int (&out)[8])
+{
+    int x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = HI ? hi16s(w[k]) : lo16s(w[k]);
+    int base = C4 * (x[0] + 32);            // (1 << 19) / 16383 == 32
+    int s[4], d[4];
+    butterfly(base, x[1], x[2], x[3], x[4], x[5], x[6], x[7], s, d);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { out[k] = s[k] >> 20; out[7 - k] = d[k] >> 20; }
+}
+
+__device__ __forceinline__ size_t block_dst(const uint32_t *__restrict__ dst_off, size_t i,
+                                            int tiles_per_row, ptrdiff_t stride)
+{
+    if (dst_off) return dst_off[i];
+    size_t ty = i / (unsigned)tiles_per_row, tx = i - ty * (unsigned)tiles_per_row;
+    return ty * 8 * (size_t)stride + tx * 8;
+}
+
+constexpr int IDCT_WARPS = 4;   // warps per CTA; each owns 2 x 4 KB of shared memory
+
+// MODE 0: put, 1: add, 2: plain (in place int16).  CLEAR: also zero the coefficient block
+// afterwards (fused BlockDSPContext.clear_block, what every caller does next).
+template <int MODE, bool CLEAR>
+__global__ void __launch_bounds__(IDCT_WARPS * 32)
+simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
+                   const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
+{
+    __shared__ __align__(128) uint4 tile[IDCT_WARPS][2][256];   // 32 blocks x 8 chunks of 16 B
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t groups = (n + 31) / 32;
+    const size_t gstride = (size_t)gridDim.x * IDCT_WARPS;
+    size_t g = (size_t)blockIdx.x * IDCT_WARPS + warp;
+
+    auto issue = [&](size_t grp, int buf) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blocks) + grp * 256;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int u = j * 32 + lane, b = u >> 3, c = u & 7;
+            bool ok = grp * 32 + b < n;
+            cp_async16(&tile[warp][buf][b * 8 + (c ^ (b & 7))], ok ? src + u : src, ok);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    if (g < groups) issue(g, 0);
+    for (; g < groups; g += gstride, buf ^= 1) {
+        size_t gn = g + gstride;
+        if (gn < groups) { issue(gn, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncwarp();
+
+        uint4 row[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) row[r] = row_pass(tile[warp][buf][lane * 8 + (r ^ (lane & 7))]);
+        __syncwarp();     // tile[buf] is free for the load issued two iterations from now
+
+        const size_t i = g * 32 + lane;
+        const bool live = i < n;
+        if (MODE == 2) {
+            // plain idct: results go back in place as int16, column by column pair
+            uint32_t o[8][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t w[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) w[r] = c == 0 ? row[r].x : c == 1 ? row[r].y : c == 2 ? row[r].z : row[r].w;
+                int lo[8], hi[8];
+                col_pass<0>(w, lo);
+                col_pass<1>(w, hi);
+#pragma unroll
+                for (int y = 0; y < 8; y++) o[y][c] = pack16(lo[y], hi[y]);
+            }
+            if (live) {
+                uint4 *dst = reinterpret_cast<uint4 *>(blocks) + i * 8;
+#pragma unroll
+                for (int y = 0; y < 8; y++) dst[y] = make_uint4(o[y][0], o[y][1], o[y][2], o[y][3]);
+            }
+        } else {
+            uint8_t *dst = frame + (live ? block_dst(dst_off, i, tiles_per_row, stride) : 0);
+            uint2 px[8];
+            if (MODE == 1 && live) {
+#pragma unroll
+                for (int y = 0; y < 8; y++) px[y] = *reinterpret_cast<const uint2 *>(dst + y * stride);
+            }
+            uint32_t o[8][2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int v[4][8];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        w[r] = h == 0 ? (c == 0 ? row[r].x : row[r].y) : (c == 0 ? row[r].z : row[r].w);
+                    col_pass<0>(w, v[2 * c]);
+                    col_pass<1>(w, v[2 * c + 1]);
+                }
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    if (MODE == 1) {
+                        uint32_t p = h == 0 ? px[y].x : px[y].y;
+                        o[y][h] = pack4_sat_u8(v[0][y] + byte_of(p, 0), v[1][y] + byte_of(p, 1),
+                                               v[2][y] + byte_of(p, 2), v[3][y] + byte_of(p, 3));
+                    } else {
+                        o[y][h] = pack4_sat_u8(v[0][y], v[1][y], v[2][y], v[3][y]);
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int y = 0; y < 8; y++)
+                    *reinterpret_cast<uint2 *>(dst + y * stride) = make_uint2(o[y][0], o[y][1]);
+            }
+            if (CLEAR && live) {
+                uint4 *b = reinterpret_cast<uint4 *>(blocks) + i * 8;
+#pragma unroll
+                for (int y = 0; y < 8; y++) b[y] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+}
+
+// put / put_signed / add pixels clamped (idctdsp.c:85-145): 16-byte row in, 8-byte row out.
+// One thread per block row; a warp covers 4 blocks.  Purely HBM bound.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pixels_clamped_kernel(const int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
+                      const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = n * 8;
+    for (; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        size_t i = t >> 3; int y = (int)(t & 7);
+        uint4 r = ldg_stream(reinterpret_cast<const uint4 *>(blocks) + t);
+        uint8_t *dst = frame + block_dst(dst_off, i, tiles_per_row, stride) + y * stride;
+        int x[8] = { lo16s(r.x), hi16s(r.x), lo16s(r.y), hi16s(r.y), lo16s(r.z), hi16s(r.z), lo16s(r.w), hi16s(r.w) };
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] += 128;
+        } else if (MODE == 2) {
+            uint2 p = *reinterpret_cast<const uint2 *>(dst);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { x[k] += byte_of(p.x, k); x[4 + k] += byte_of(p.y, k); }
+        }
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(pack4_sat_u8(x[0], x[1], x[2], x[3]), pack4_sat_u8(x[4], x[5], x[6], x[7]));
+    }
+}
+
+__global__ void __launch_bounds__(256) clear_blocks_kernel(uint4 *__restrict__ p, size_t n16)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t < n16; t += (size_t)gridDim.x * blockDim.x) p[t] = make_uint4(0, 0, 0, 0);
+}
+
+// fill_block_tab (blockdsp.c:39-58): rows of 16 or 8 identical bytes; records = (offset, value, h)
+__global__ void __launch_bounds__(256)
+fill_blocks_kernel(uint8_t *__restrict__ frame, const uint32_t *__restrict__ dst_off,
+                   const uint8_t *__restrict__ value, ptrdiff_t stride, int h, int w16, size_t n)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = n * (size_t)h;
+    for (; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        size_t i = t / (unsigned)h; int y = (int)(t - i * (unsigned)h);
+        uint32_t v = value[i] * 0x01010101u;
+        uint8_t *d = frame + dst_off[i] + y * stride;
+        if (w16) *reinterpret_cast<uint4 *>(d) = make_uint4(v, v, v, v);
+        else     *reinterpret_cast<uint2 *>(d) = make_uint2(v, v);
+    }
+}
+
+static int grid_for(size_t work_items, int per_cta, int ctas_per_sm)
+{
+    size_t need = (work_items + per_cta - 1) / per_cta;
+    size_t cap = (size_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride,
+                       size_t n, int tiles_per_row, int clear, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    if (mode < 0 || mode > 2) { set_error_msg("simple_idct_batch", "bad mode"); return -1; }
+    if (mode != 2 && !dst_off && tiles_per_row <= 0) { set_error_msg("simple_idct_batch", "need dst_off or tiles_per_row"); return -1; }
+    size_t groups = (n + 31) / 32;
+    int grid = grid_for(groups, IDCT_WARPS, 8);
+    dim3 b(IDCT_WARPS * 32);
+    if (mode == 0) {
+        if (clear) simple_idct_kernel<0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else       simple_idct_kernel<0, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+    } else if (mode == 1) {
+        if (clear) simple_idct_kernel<1, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else       simple_idct_kernel<1, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+    } else {
+        simple_idct_kernel<2, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+    }
+    return check_launch("simple_idct_batch");
+}
+
+int launch_pixels_clamped(int mode, const int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,
+                          ptrdiff_t stride, size_t n, int tiles_per_row, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    if (!dst_off && tiles_per_row <= 0) { set_error_msg("pixels_clamped_batch", "need dst_off or tiles_per_row"); return -1; }
+    int grid = grid_for(n * 8, 256, 8);
+    switch (mode) {
+    case 0: pixels_clamped_kernel<0><<<grid, 256, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row); break;
+    case 1: pixels_clamped_kernel<1><<<grid, 256, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row); break;
+    case 2: pixels_clamped_kernel<2><<<grid, 256, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row); break;
+    default: set_error_msg("pixels_clamped_batch", "bad mode"); return -1;
+    }
+    return check_launch("pixels_clamped_batch");
+}
+
+int launch_clear_blocks(int16_t *blocks, size_t n_blocks, cudaStream_t st)
+{
+    if (n_blocks == 0) return 0;
+    size_t n16 = n_blocks * 8;
+    clear_blocks_kernel<<<grid_for(n16, 256, 8), 256, 0, st>>>(reinterpret_cast<uint4 *>(blocks), n16);
+    return check_launch("clear_blocks_batch");
+}
+
+int launch_fill_blocks(uint8_t *frame, const uint32_t *dst_off, const uint8_t *value, ptrdiff_t stride, int h,
+                       int w16, size_t n, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    fill_blocks_kernel<<<grid_for(n * h, 256, 8), 256, 0, st>>>(frame, dst_off, value, stride, h, w16, n);
+    return check_launch("fill_blocks_batch");
+}
+
+}  // namespace avb

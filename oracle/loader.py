@@ -1,0 +1,92 @@
+"""ctypes loaders for the two CPU oracles.  TEST INFRASTRUCTURE: import only from tests/,
+__graft_entry__.smoke() and bench.py's CPU legs.
+
+  port()  oracle/liboracle_port.so   orc_*  plain-C restatement (always buildable with gcc)
+  ref()   oracle/_ref/libavref.so    ref_*  the unmodified reference (built where /root/reference exists;
+                                            the prebuilt .so travels to the GPU box)
+Both expose the prototypes of oracle/oracle_api.h through the same attribute names without prefix.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_PATH = os.path.join(_HERE, "liboracle_port.so")
+REF_PATH = os.path.join(_HERE, "_ref", "libavref.so")
+
+vp, sz, i32, pd, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_ssize_t, C.c_double
+
+API = {
+    "simple_idct_put": (None, [vp, pd, vp]),
+    "simple_idct_add": (None, [vp, pd, vp]),
+    "simple_idct": (None, [vp]),
+    "put_pixels_clamped": (None, [vp, vp, pd]),
+    "put_signed_pixels_clamped": (None, [vp, vp, pd]),
+    "add_pixels_clamped": (None, [vp, vp, pd]),
+    "clear_block": (None, [vp]),
+    "clear_blocks": (None, [vp]),
+    "fill_block": (None, [i32, vp, C.c_uint8, pd, i32]),
+    "idct_batch": (None, [i32, vp, vp, vp, pd, sz, i32]),
+    "fdct": (None, [i32, vp]),
+    "h264_idct": (None, [i32, vp, vp, i32]),
+    "h264_idct_mb": (None, [i32, vp, vp, vp, vp, i32, vp]),
+    "h264_luma_dc_dequant_idct": (None, [vp, vp, i32]),
+    "h264_chroma_dc_dequant_idct": (None, [vp, i32]),
+    "h264_loop_filter": (None, [i32, vp, i32, i32, i32, vp]),
+    "h264_weight": (None, [i32, vp, i32, i32, i32, i32, i32]),
+    "h264_biweight": (None, [i32, vp, vp, i32, i32, i32, i32, i32, i32]),
+    "h264_add_pixels_clear": (None, [i32, vp, vp, i32]),
+    "h264_qpel": (None, [i32, i32, i32, vp, vp, pd]),
+    "h264_chroma": (None, [i32, i32, vp, vp, pd, i32, i32, i32]),
+    "hpel": (i32, [i32, i32, i32, vp, vp, pd, i32]),
+    "me_cmp": (i32, [i32, i32, i32, vp, vp, pd, i32]),
+    "full_search": (None, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32]),
+    "sws_yuv420p_to_rgb24": (i32, [vp, vp, i32, i32, vp, i32, i32, i32, i32]),
+    "sws_yuv420p_to_yuv420p": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32]),
+    "sws_get_filter": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "sws_rgb24_tables": (None, [vp, vp, vp, vp, vp]),
+    "fft": (None, [i32, i32, vp]),
+    "imdct_half": (None, [i32, dbl, vp, vp]),
+    "imdct_calc": (None, [i32, dbl, vp, vp]),
+    "mdct_calc": (None, [i32, dbl, vp, vp]),
+}
+
+
+class Oracle:
+    def __init__(self, path, prefix):
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        self.missing = []
+        for name, (res, args) in API.items():
+            try:
+                f = getattr(self.lib, prefix + name)
+            except AttributeError:
+                self.missing.append(name)
+                continue
+            f.restype, f.argtypes = res, args
+            setattr(self, name, f)
+
+    def has(self, name):
+        return hasattr(self, name)
+
+
+_cache = {}
+
+
+def port():
+    if "port" not in _cache:
+        if not os.path.exists(PORT_PATH):
+            raise RuntimeError("oracle port not built: run __graft_entry__.build()")
+        _cache["port"] = Oracle(PORT_PATH, "orc_")
+    return _cache["port"]
+
+
+def ref():
+    """The compiled reference, or None when oracle/_ref has not been built (no /root/reference)."""
+    if "ref" not in _cache:
+        _cache["ref"] = Oracle(REF_PATH, "ref_") if os.path.exists(REF_PATH) else None
+    return _cache["ref"]
+
+
+def ptr(a):
+    """numpy array -> void* (array must stay alive)."""
+    return a.ctypes.data_as(vp)

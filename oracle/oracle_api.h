@@ -1,0 +1,130 @@
+/*
+ * oracle/oracle_api.h -- TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * One flat C API, implemented twice:
+ *   orc_*  oracle/port/*.c          plain-C restatement of the reference algorithms
+ *   ref_*  oracle/refbuild/refapi.c thin calls into the UNMODIFIED reference, compiled
+ *                                   from /root/reference into oracle/_ref/libavref.so
+ * tests/ drive both with the same ctypes prototypes, so every restated function is
+ * byte-compared with the real reference in this container; the port (and the prebuilt
+ * _ref .so) then travel to the GPU box as the checker for the CUDA path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use this API.
+ */
+#ifndef ORACLE_API_H
+#define ORACLE_API_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifndef ORC_PREFIX
+#define ORC_PREFIX orc_
+#endif
+#define ORC_CAT2(a, b) a##b
+#define ORC_CAT(a, b) ORC_CAT2(a, b)
+#define ORC(n) ORC_CAT(ORC_PREFIX, n)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- IDCTDSPContext / BlockDSPContext (libavcodec/idctdsp.h:53-98, blockdsp.h:32-37) */
+void ORC(simple_idct_put)(uint8_t *dst, ptrdiff_t stride, int16_t *block);
+void ORC(simple_idct_add)(uint8_t *dst, ptrdiff_t stride, int16_t *block);
+void ORC(simple_idct)(int16_t *block);
+void ORC(put_pixels_clamped)(const int16_t *block, uint8_t *pixels, ptrdiff_t stride);
+void ORC(put_signed_pixels_clamped)(const int16_t *block, uint8_t *pixels, ptrdiff_t stride);
+void ORC(add_pixels_clamped)(const int16_t *block, uint8_t *pixels, ptrdiff_t stride);
+void ORC(clear_block)(int16_t *block);
+void ORC(clear_blocks)(int16_t *blocks);
+void ORC(fill_block)(int w16, uint8_t *block, uint8_t value, ptrdiff_t stride, int h);
+
+/* batch driver used for parity at scale and for CPU timing: block i -> frame + dst_off[i].
+ * mode 0 = idct_put, 1 = idct_add, 2 = idct (in place, frame ignored).
+ * nthreads > 1 splits the block range over pthreads. The blocks array is clobbered exactly
+ * as the per-block functions clobber it. */
+void ORC(idct_batch)(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,
+                     ptrdiff_t stride, size_t n, int nthreads);
+
+/* ---- FDCTDSPContext (libavcodec/fdctdsp.h:26-29): 0 = jpeg_fdct_islow_8, 1 = fdct248_islow_8,
+ *      2 = fdct_ifast, 3 = fdct_ifast248 */
+void ORC(fdct)(int which, int16_t *block);
+
+/* ---- H264DSPContext (libavcodec/h264dsp.h:41-117), 8-bit ---- */
+/* which: 0 idct_add, 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add */
+void ORC(h264_idct)(int which, uint8_t *dst, int16_t *block, int stride);
+/* which: 0 idct_add16, 1 idct_add16intra, 2 idct8_add4, 3 idct_add8 (dst2 = {cb, cr}) */
+void ORC(h264_idct_mb)(int which, uint8_t *dst, uint8_t **dst2, const int *block_offset,
+                       int16_t *block, int stride, const uint8_t *nnzc);
+void ORC(h264_luma_dc_dequant_idct)(int16_t *output, int16_t *input, int qmul);
+void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
+/* which: 0 v_luma 1 h_luma 2 v_luma_intra 3 h_luma_intra 4 v_chroma 5 h_chroma
+ *        6 v_chroma_intra 7 h_chroma_intra ; tc0 ignored for intra */
+void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
+                           const int8_t *tc0);
+/* widx: 0..3 = width 16,8,4,2 */
+void ORC(h264_weight)(int widx, uint8_t *block, int stride, int height, int log2_denom,
+                      int weight, int offset);
+void ORC(h264_biweight)(int widx, uint8_t *dst, uint8_t *src, int stride, int height,
+                        int log2_denom, int weightd, int weights, int offset);
+void ORC(h264_add_pixels_clear)(int w8, uint8_t *dst, int16_t *block, int stride);
+
+/* ---- H264QpelContext / H264ChromaContext (h264qpel.h:27-30, h264chroma.h:25-30) ---- */
+/* sidx 0..3 = 16,8,4,2 ; mc = (mx&3) + 4*(my&3) */
+void ORC(h264_qpel)(int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+/* widx 0..2 = 8,4,2 */
+void ORC(h264_chroma)(int avg, int widx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int h,
+                      int x, int y);
+
+/* ---- HpelDSPContext (hpeldsp.h:45-93) ----
+ * tab 0 put, 1 avg, 2 put_no_rnd, 3 avg_no_rnd ; sidx 0..3 = 16,8,4,2 ; dxy 0..3 */
+int ORC(hpel)(int tab, int sidx, int dxy, uint8_t *block, const uint8_t *pixels,
+              ptrdiff_t line_size, int h);
+
+/* ---- MECmpContext (me_cmp.h:39-63) ----
+ * kind: 0 pix_abs[sidx][dxy] (sidx 0 = 16 wide, 1 = 8 wide)
+ *       1 sad[sidx] 2 sse[sidx] (sidx 2 = 4 wide) 3 hadamard8_diff[sidx]
+ *       4 vsad[sidx] 5 vsse[sidx] 6 nsse[sidx] (weight 8, NULL ctx)
+ *       7 hadamard8 intra (me_cmp[4..5]) 8 vsad_intra 9 vsse_intra
+ *      10 sum_abs_dctelem(blk1 as int16[64]) */
+int ORC(me_cmp)(int kind, int sidx, int dxy, const uint8_t *blk1, const uint8_t *blk2,
+                ptrdiff_t stride, int h);
+/* exhaustive search restating motion_est_template.c:620-655 for config 4: for each 16x16 MB
+ * of cur, search ref within +-range clipped so the block stays inside the picture, SAD16,
+ * lambda 0, strict-< argmin in raster order.  out[3*mb] = mx, my, sad.  MB rows
+ * [mb_y0, mb_y1). */
+void ORC(full_search)(const uint8_t *cur, const uint8_t *ref, int stride, int w, int h,
+                      int range, int mb_y0, int mb_y1, int32_t *out, int nthreads);
+
+/* ---- libswscale (boundary B) ---- */
+/* whole-frame yuv420p -> rgb24 through sws_getContext/sws_scale semantics
+ * (swscale.h:159-207). flags are the reference's SWS_* bit values. Returns number of output
+ * lines, <0 on error. */
+int ORC(sws_yuv420p_to_rgb24)(const uint8_t *const src[3], const int src_stride[3], int src_w,
+                              int src_h, uint8_t *dst, int dst_stride, int dst_w, int dst_h,
+                              int flags);
+/* whole-frame yuv420p -> yuv420p scaling (hscale + yuv2planeX vertical path) */
+int ORC(sws_yuv420p_to_yuv420p)(const uint8_t *const src[3], const int src_stride[3], int src_w,
+                                int src_h, uint8_t *const dst[3], const int dst_stride[3],
+                                int dst_w, int dst_h, int flags);
+/* filter bank as designed by initFilter (utils.c:249-632) with the geometry sws_init_context
+ * (utils.c:887-1340) derives for yuv420p -> (to_rgb ? rgb24 : yuv420p).
+ * which: 0 hLum, 1 hChr, 2 vLum, 3 vChr.  Fills filter (int16, n*fsize) and pos (int32, n), where
+ * n = number of output samples of that axis (returned in *n_out); returns fsize (<0 on error).
+ * filter_align is forced to 1 (the padding taps are zero under SWS_BITEXACT). */
+int ORC(sws_get_filter)(int which, int to_rgb, int src_w, int src_h, int dst_w, int dst_h, int flags,
+                        int16_t *filter, int32_t *pos, int cap, int *n_out);
+/* yuv->rgb 24 bpp LUTs (yuv2rgb.c:671-863) with the default colourspace (ITU601, limited range):
+ * ytab[1024]; rv, gu, gv, bu int32[256]: byte offsets into ytab (gv: plain int added to gu). */
+void ORC(sws_rgb24_tables)(uint8_t *ytab, int32_t *rv, int32_t *gu, int32_t *gv, int32_t *bu);
+
+/* ---- float FFT / MDCT (fft.h:73-99) : in-place complex FFT of 2^nbits points (permute +
+ *      calc), inverse != 0 for the inverse transform; imdct/mdct with scale ---- */
+void ORC(fft)(int nbits, int inverse, float *z /* 2 << nbits floats */);
+void ORC(imdct_half)(int nbits, double scale, float *out, const float *in);
+void ORC(imdct_calc)(int nbits, double scale, float *out, const float *in);
+void ORC(mdct_calc)(int nbits, double scale, float *out, const float *in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

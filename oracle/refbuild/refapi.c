@@ -1,0 +1,328 @@
+/*
+ * oracle/refbuild/refapi.c -- TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * Implements oracle/oracle_api.h with the prefix ref_ by calling the UNMODIFIED reference
+ * (compiled from /root/reference by build_ref.sh into oracle/_ref/libavref.so) through
+ * the reference's own init functions and function-pointer tables: every call goes
+ * ff_*_init() -> table slot, exactly what a codec does.  No arithmetic of its own.
+ */
+#define ORC_PREFIX ref_
+#include "../oracle_api.h"
+
+#include <pthread.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include "libavutil/mem.h"
+#include "libavutil/cpu.h"
+#include "libavutil/pixfmt.h"
+#include "libavcodec/avcodec.h"
+#include "libavcodec/idctdsp.h"
+#include "libavcodec/fdctdsp.h"
+#include "libavcodec/blockdsp.h"
+#include "libavcodec/me_cmp.h"
+#include "libavcodec/h264dsp.h"
+#include "libavcodec/h264qpel.h"
+#include "libavcodec/h264chroma.h"
+#include "libavcodec/hpeldsp.h"
+#include "libavcodec/fft.h"
+#include "libavcodec/dct.h"
+#include "libswscale/swscale.h"
+#include "libswscale/swscale_internal.h"
+
+static pthread_once_t once = PTHREAD_ONCE_INIT;
+static IDCTDSPContext idsp;
+static FDCTDSPContext fdsp_islow, fdsp_ifast;
+static BlockDSPContext bdsp;
+static MECmpContext mecc;
+static H264DSPContext h264;
+static H264QpelContext qpel;
+static H264ChromaContext chroma;
+static HpelDSPContext hpel;
+
+static void init_all(void)
+{
+    AVCodecContext *avctx = calloc(1, sizeof(*avctx));
+    av_set_cpu_flags_mask(0);             /* what FATE's -cpuflags 0 does: portable C only */
+    avctx->idct_algo           = FF_IDCT_SIMPLE;
+    avctx->bits_per_raw_sample = 8;
+    avctx->flags               = AV_CODEC_FLAG_BITEXACT;
+    avctx->dct_algo            = FF_DCT_INT;
+    ff_idctdsp_init(&idsp, avctx);
+    ff_fdctdsp_init(&fdsp_islow, avctx);
+    avctx->dct_algo = FF_DCT_FASTINT;
+    ff_fdctdsp_init(&fdsp_ifast, avctx);
+    ff_blockdsp_init(&bdsp);
+    ff_me_cmp_init_static();
+    ff_me_cmp_init(&mecc, avctx);
+    ff_h264dsp_init(&h264, 8, 1);
+    ff_h264qpel_init(&qpel, 8);
+    ff_h264chroma_init(&chroma, 8);
+    ff_hpeldsp_init(&hpel, AV_CODEC_FLAG_BITEXACT);
+    free(avctx);
+}
+#define INIT() pthread_once(&once, init_all)
+
+void ref_simple_idct_put(uint8_t *d, ptrdiff_t s, int16_t *b) { INIT(); idsp.idct_put(d, s, b); }
+void ref_simple_idct_add(uint8_t *d, ptrdiff_t s, int16_t *b) { INIT(); idsp.idct_add(d, s, b); }
+void ref_simple_idct(int16_t *b) { INIT(); idsp.idct(b); }
+void ref_put_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.put_pixels_clamped(b, p, s); }
+void ref_put_signed_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.put_signed_pixels_clamped(b, p, s); }
+void ref_add_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.add_pixels_clamped(b, p, s); }
+void ref_clear_block(int16_t *b) { INIT(); bdsp.clear_block(b); }
+void ref_clear_blocks(int16_t *b) { INIT(); bdsp.clear_blocks(b); }
+void ref_fill_block(int w16, uint8_t *b, uint8_t v, ptrdiff_t s, int h) { INIT(); bdsp.fill_block_tab[w16 ? 0 : 1](b, v, s, h); }
+
+struct idct_job { int mode; int16_t *blocks; uint8_t *frame; const uint32_t *off; ptrdiff_t stride; size_t lo, hi; };
+static void *idct_worker(void *p)
+{
+    struct idct_job *j = p;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        int16_t *b = j->blocks + 64 * i;
+        if (j->mode == 0)      idsp.idct_put(j->frame + j->off[i], j->stride, b);
+        else if (j->mode == 1) idsp.idct_add(j->frame + j->off[i], j->stride, b);
+        else                   idsp.idct(b);
+    }
+    return NULL;
+}
+void ref_idct_batch(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *off, ptrdiff_t stride,
+                    size_t n, int nthreads)
+{
+    INIT();
+    if (nthreads < 1) nthreads = 1;
+    pthread_t th[256]; struct idct_job jobs[256];
+    if (nthreads > 256) nthreads = 256;
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (struct idct_job){ mode, blocks, frame, off, stride, n * t / nthreads, n * (t + 1) / nthreads };
+        if (nthreads == 1) idct_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, idct_worker, &jobs[t]);
+    }
+    if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+
+void ref_fdct(int which, int16_t *block)
+{
+    INIT();
+    switch (which) {
+    case 0: fdsp_islow.fdct(block); break;
+    case 1: fdsp_islow.fdct248(block); break;
+    case 2: fdsp_ifast.fdct(block); break;
+    default: fdsp_ifast.fdct248(block); break;
+    }
+}
+
+void ref_h264_idct(int which, uint8_t *dst, int16_t *block, int stride)
+{
+    INIT();
+    switch (which) {
+    case 0: h264.h264_idct_add(dst, block, stride); break;
+    case 1: h264.h264_idct8_add(dst, block, stride); break;
+    case 2: h264.h264_idct_dc_add(dst, block, stride); break;
+    default: h264.h264_idct8_dc_add(dst, block, stride); break;
+    }
+}
+void ref_h264_idct_mb(int which, uint8_t *dst, uint8_t **dst2, const int *bo, int16_t *block, int stride,
+                      const uint8_t *nnzc)
+{
+    INIT();
+    switch (which) {
+    case 0: h264.h264_idct_add16(dst, bo, block, stride, nnzc); break;
+    case 1: h264.h264_idct_add16intra(dst, bo, block, stride, nnzc); break;
+    case 2: h264.h264_idct8_add4(dst, bo, block, stride, nnzc); break;
+    default: h264.h264_idct_add8(dst2, bo, block, stride, nnzc); break;
+    }
+}
+void ref_h264_luma_dc_dequant_idct(int16_t *o, int16_t *i, int q) { INIT(); h264.h264_luma_dc_dequant_idct(o, i, q); }
+void ref_h264_chroma_dc_dequant_idct(int16_t *b, int q) { INIT(); h264.h264_chroma_dc_dequant_idct(b, q); }
+void ref_h264_loop_filter(int which, uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0)
+{
+    INIT();
+    int8_t *t = (int8_t *)tc0;
+    switch (which) {
+    case 0: h264.h264_v_loop_filter_luma(pix, stride, alpha, beta, t); break;
+    case 1: h264.h264_h_loop_filter_luma(pix, stride, alpha, beta, t); break;
+    case 2: h264.h264_v_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 3: h264.h264_h_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 4: h264.h264_v_loop_filter_chroma(pix, stride, alpha, beta, t); break;
+    case 5: h264.h264_h_loop_filter_chroma(pix, stride, alpha, beta, t); break;
+    case 6: h264.h264_v_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    default: h264.h264_h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    }
+}
+void ref_h264_weight(int widx, uint8_t *b, int stride, int h, int ld, int w, int off)
+{ INIT(); h264.weight_h264_pixels_tab[widx](b, stride, h, ld, w, off); }
+void ref_h264_biweight(int widx, uint8_t *d, uint8_t *s, int stride, int h, int ld, int wd, int ws, int off)
+{ INIT(); h264.biweight_h264_pixels_tab[widx](d, s, stride, h, ld, wd, ws, off); }
+void ref_h264_add_pixels_clear(int w8, uint8_t *dst, int16_t *block, int stride)
+{ INIT(); if (w8) h264.h264_add_pixels8_clear(dst, block, stride); else h264.h264_add_pixels4_clear(dst, block, stride); }
+
+void ref_h264_qpel(int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    INIT();
+    (avg ? qpel.avg_h264_qpel_pixels_tab : qpel.put_h264_qpel_pixels_tab)[sidx][mc](dst, src, stride);
+}
+void ref_h264_chroma(int avg, int widx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int h, int x, int y)
+{
+    INIT();
+    (avg ? chroma.avg_h264_chroma_pixels_tab : chroma.put_h264_chroma_pixels_tab)[widx](dst, src, stride, h, x, y);
+}
+
+int ref_hpel(int tab, int sidx, int dxy, uint8_t *block, const uint8_t *pixels, ptrdiff_t ls, int h)
+{
+    INIT();
+    op_pixels_func f = NULL;
+    switch (tab) {
+    case 0: f = hpel.put_pixels_tab[sidx][dxy]; break;
+    case 1: f = hpel.avg_pixels_tab[sidx][dxy]; break;
+    case 2: f = hpel.put_no_rnd_pixels_tab[sidx][dxy]; break;
+    default: f = sidx == 0 ? hpel.avg_no_rnd_pixels_tab[dxy] : NULL; break;
+    }
+    if (!f) return -1;
+    f(block, pixels, ls, h);
+    return 0;
+}
+
+int ref_me_cmp(int kind, int sidx, int dxy, const uint8_t *b1, const uint8_t *b2, ptrdiff_t stride, int h)
+{
+    INIT();
+    me_cmp_func f = NULL;
+    uint8_t *p1 = (uint8_t *)b1, *p2 = (uint8_t *)b2;
+    switch (kind) {
+    case 0: f = mecc.pix_abs[sidx][dxy]; break;
+    case 1: f = mecc.sad[sidx]; break;
+    case 2: f = mecc.sse[sidx]; break;
+    case 3: f = mecc.hadamard8_diff[sidx]; break;
+    case 4: f = mecc.vsad[sidx]; break;
+    case 5: f = mecc.vsse[sidx]; break;
+    case 6: f = mecc.nsse[sidx]; break;
+    case 7: f = mecc.hadamard8_diff[4 + sidx]; break;
+    case 8: f = mecc.vsad[4 + sidx]; break;
+    case 9: f = mecc.vsse[4 + sidx]; break;
+    case 10: return mecc.sum_abs_dctelem((int16_t *)p1);
+    }
+    if (!f) return -1;
+    return f(NULL, p1, p2, stride, h);
+}
+
+struct fs_job { const uint8_t *cur, *ref; int stride, w, h, range, y0, y1; int32_t *out; };
+static void *fs_worker(void *p)
+{
+    struct fs_job *j = p;
+    int mbw = j->w / 16;
+    for (int mby = j->y0; mby < j->y1; mby++)
+        for (int mbx = 0; mbx < mbw; mbx++) {
+            int px = mbx * 16, py = mby * 16;
+            int xmin = -px, xmax = j->w - 16 - px, ymin = -py, ymax = j->h - 16 - py;
+            if (xmin < -j->range) xmin = -j->range;
+            if (ymin < -j->range) ymin = -j->range;
+            if (xmax > j->range) xmax = j->range;
+            if (ymax > j->range) ymax = j->range;
+            uint8_t *c = (uint8_t *)j->cur + py * j->stride + px;
+            int best = 1 << 30, bx = 0, by = 0;
+            for (int y = ymin; y <= ymax; y++)
+                for (int x = xmin; x <= xmax; x++) {
+                    int d = mecc.pix_abs[0][0](NULL, c, (uint8_t *)j->ref + (py + y) * j->stride + px + x, j->stride, 16);
+                    if (d < best) { best = d; bx = x; by = y; }
+                }
+            int32_t *o = j->out + 3 * (mby * mbw + mbx);
+            o[0] = bx; o[1] = by; o[2] = best;
+        }
+    return NULL;
+}
+void ref_full_search(const uint8_t *cur, const uint8_t *ref, int stride, int w, int h, int range,
+                     int y0, int y1, int32_t *out, int nthreads)
+{
+    INIT();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256]; struct fs_job jobs[256];
+    int rows = y1 - y0;
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (struct fs_job){ cur, ref, stride, w, h, range, y0 + rows * t / nthreads, y0 + rows * (t + 1) / nthreads, out };
+        if (nthreads == 1) fs_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, fs_worker, &jobs[t]);
+    }
+    if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+
+/* ---- swscale ---- */
+static struct SwsContext *mk_sws(int sw, int sh, int dw, int dh, enum AVPixelFormat df, int flags)
+{
+    INIT();
+    return sws_getContext(sw, sh, AV_PIX_FMT_YUV420P, dw, dh, df, flags, NULL, NULL, NULL);
+}
+int ref_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst,
+                             int dstride, int dw, int dh, int flags)
+{
+    struct SwsContext *c = mk_sws(sw, sh, dw, dh, AV_PIX_FMT_RGB24, flags);
+    if (!c) return -1;
+    uint8_t *d[4] = { dst, NULL, NULL, NULL };
+    int ds[4] = { dstride, 0, 0, 0 };
+    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
+    int sst[4] = { ss[0], ss[1], ss[2], 0 };
+    int r = sws_scale(c, s, sst, 0, sh, d, ds);
+    sws_freeContext(c);
+    return r;
+}
+int ref_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int sw, int sh,
+                               uint8_t *const dst[3], const int dstr[3], int dw, int dh, int flags)
+{
+    struct SwsContext *c = mk_sws(sw, sh, dw, dh, AV_PIX_FMT_YUV420P, flags);
+    if (!c) return -1;
+    uint8_t *d[4] = { dst[0], dst[1], dst[2], NULL };
+    int ds[4] = { dstr[0], dstr[1], dstr[2], 0 };
+    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
+    int sst[4] = { ss[0], ss[1], ss[2], 0 };
+    int r = sws_scale(c, s, sst, 0, sh, d, ds);
+    sws_freeContext(c);
+    return r;
+}
+int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,
+                       int32_t *pos, int cap, int *n_out)
+{
+    struct SwsContext *c = mk_sws(sw, sh, dw, dh, to_rgb ? AV_PIX_FMT_RGB24 : AV_PIX_FMT_YUV420P, flags);
+    if (!c) return -1;
+    int16_t *f; int32_t *p; int fs, n;
+    switch (which) {
+    case 0: f = c->hLumFilter; p = c->hLumFilterPos; fs = c->hLumFilterSize; n = c->dstW; break;
+    case 1: f = c->hChrFilter; p = c->hChrFilterPos; fs = c->hChrFilterSize; n = c->chrDstW; break;
+    case 2: f = c->vLumFilter; p = c->vLumFilterPos; fs = c->vLumFilterSize; n = c->dstH; break;
+    default: f = c->vChrFilter; p = c->vChrFilterPos; fs = c->vChrFilterSize; n = c->chrDstH; break;
+    }
+    *n_out = n;
+    if (n > cap || n * fs > cap) { sws_freeContext(c); return -2; }
+    memcpy(filter, f, sizeof(int16_t) * n * fs);
+    memcpy(pos, p, sizeof(int32_t) * n);
+    sws_freeContext(c);
+    return fs;
+}
+void ref_sws_rgb24_tables(uint8_t *ytab, int32_t *rv, int32_t *gu, int32_t *gv, int32_t *bu)
+{
+    struct SwsContext *c = mk_sws(16, 16, 16, 16, AV_PIX_FMT_RGB24, SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT);
+    uint8_t *base = c->yuvTable;
+    memcpy(ytab, base, 1024);
+    for (int i = 0; i < 256; i++) {
+        rv[i] = (int32_t)(c->table_rV[i] - base);
+        gu[i] = (int32_t)(c->table_gU[i] - base);
+        gv[i] = c->table_gV[i];
+        bu[i] = (int32_t)(c->table_bU[i] - base);
+    }
+    sws_freeContext(c);
+}
+
+/* ---- FFT / MDCT ---- */
+void ref_fft(int nbits, int inverse, float *z)
+{
+    FFTContext s;
+    INIT();
+    ff_fft_init(&s, nbits, inverse);
+    s.fft_permute(&s, (FFTComplex *)z);
+    s.fft_calc(&s, (FFTComplex *)z);
+    ff_fft_end(&s);
+}
+void ref_imdct_half(int nbits, double scale, float *out, const float *in)
+{ FFTContext s; INIT(); ff_mdct_init(&s, nbits, 1, scale); s.imdct_half(&s, out, in); ff_mdct_end(&s); }
+void ref_imdct_calc(int nbits, double scale, float *out, const float *in)
+{ FFTContext s; INIT(); ff_mdct_init(&s, nbits, 1, scale); s.imdct_calc(&s, out, in); ff_mdct_end(&s); }
+void ref_mdct_calc(int nbits, double scale, float *out, const float *in)
+{ FFTContext s; INIT(); ff_mdct_init(&s, nbits, 0, scale); s.mdct_calc(&s, out, in); ff_mdct_end(&s); }

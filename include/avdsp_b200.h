@@ -92,6 +92,37 @@ int ff_fill_blocks_batch_cuda(uint8_t *frame, const uint32_t *dst_off, const uin
 int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, size_t frame_bytes,
                                    const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row);
 
+/* ---- libswscale boundary (libswscale/swscale.h:159-207) ------------------------------------------------
+ * Same argument lists as sws_getContext / sws_scale / sws_freeContext; pixel formats are the reference's
+ * AVPixelFormat values (AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_RGB24 = 2, AV_PIX_FMT_BGR24 = 3), flags the
+ * reference's SWS_* bits.  Taken over: yuv420p -> rgb24 / bgr24 / yuv420p, any size, every scaler
+ * algorithm of initFilter (libswscale/utils.c:249-632), results identical to the reference's C path under
+ * SWS_ACCURATE_RND | SWS_BITEXACT.  Anything else returns NULL with an error (no fallback).
+ *   sws_scale_cuda         HOST pointers, whole frames (srcSliceY = 0, srcSliceH = srcH); uploads, runs,
+ *                          downloads, synchronises; returns output lines like sws_scale(), 0 on bad arguments.
+ *   sws_scale_frames_cuda  DEVICE pointers, asynchronous on `stream`: nframes frames whose planes lie
+ *                          *_frame_stride[] bytes apart (NULL = a single frame); returns lines written or -1.
+ *                          For odd dstW the reference writes whole pixel pairs (libswscale/output.c:947); that
+ *                          extra pixel is written only when dst_stride >= 3 * (dstW + 1). */
+#define AVB_PIX_FMT_YUV420P 0
+#define AVB_PIX_FMT_RGB24   2
+#define AVB_PIX_FMT_BGR24   3
+typedef struct SwsContextCUDA SwsContextCUDA;
+SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
+                                    void *srcFilter, void *dstFilter, const double *param);
+void sws_freeContext_cuda(SwsContextCUDA *ctx);
+int  sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY,
+                    int srcSliceH, uint8_t *const dst[], const int dstStride[]);
+int  sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], const int srcStride[3],
+                           const size_t srcFrameStride[3], uint8_t *const dst[3], const int dstStride[3],
+                           const size_t dstFrameStride[3], int nframes, void *stream);
+int  sws_is_fused_cuda(SwsContextCUDA *ctx);   /* 1 when the single-kernel same-size path is selected */
+/* host-only introspection of the set-up stage (filter banks / colour constants), used to pin it against the
+ * reference without a GPU: which = 0 hLum, 1 hChr, 2 vLum, 3 vChr; returns taps per output sample */
+int  sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags,
+                           int16_t *filter, int32_t *pos, int cap, int *n_out);
+void sws_debug_rgb_constants_cuda(int32_t out[10]);
+
 /* ------------------------------------------------------------------ 3. table hooks --------------- */
 /* One more arch behind ff_idctdsp_init()'s dispatch (libavcodec/idctdsp.c:183-188; same shape as
  * ff_idctdsp_init_x86, libavcodec/idctdsp.h:109-110).  AVCodecContext is opaque to this library, so the

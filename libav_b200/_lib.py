@@ -60,6 +60,13 @@ PROTOTYPES = {
     "ff_clear_blocks_batch_cuda": (i32, [vp, sz, vp]),
     "ff_fill_blocks_batch_cuda": (i32, [vp, vp, vp, pd, i32, i32, sz, vp]),
     "ff_simple_idct_batch_host_cuda": (i32, [i32, vp, vp, sz, vp, pd, sz, i32]),
+    "sws_getContext_cuda": (vp, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "sws_freeContext_cuda": (None, [vp]),
+    "sws_scale_cuda": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    "sws_scale_frames_cuda": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "sws_is_fused_cuda": (i32, [vp]),
+    "sws_debug_filter_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "sws_debug_rgb_constants_cuda": (None, [vp]),
     "ff_idctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
     "ff_blockdsp_init_cuda": (None, [vp]),
 }

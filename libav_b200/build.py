@@ -70,7 +70,7 @@ def build_oracle_port(force=False):
     deps = srcs + [os.path.join(ROOT, "oracle", "oracle_api.h")]
     if not force and not _newer(ORACLE_PORT, deps):
         return ORACLE_PORT
-    _run(["gcc", "-O2", "-fPIC", "-shared", "-std=c99", "-Wall", "-fwrapv", "-o", ORACLE_PORT] + srcs + ["-lm", "-lpthread"])
+    _run(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu99", "-Wall", "-Wno-comment", "-fwrapv", "-o", ORACLE_PORT] + srcs + ["-lm", "-lpthread"])
     return ORACLE_PORT
 
 

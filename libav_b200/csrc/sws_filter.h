@@ -1,0 +1,48 @@
+// libav_b200/csrc/sws_filter.h -- host-side scaler set-up for the CUDA swscale path: integer filter banks
+// and yuv->rgb constants.  This is the part of libswscale that stays on the host (once per context); it
+// has to reproduce the reference's numbers exactly because they are the kernels' constant inputs:
+//   filter design      libswscale/utils.c:249-632 (initFilter)
+//   geometry           libswscale/utils.c:887-1198 (sws_init_context)
+//   colour constants   libswscale/yuv2rgb.c:671-863 (ff_yuv2rgb_c_init_tables, 24 bpp case)
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace avb {
+
+enum {   // libswscale/swscale.h:57-83
+    SWS_FAST_BILINEAR = 1, SWS_BILINEAR = 2, SWS_BICUBIC = 4, SWS_X = 8, SWS_POINT = 0x10, SWS_AREA = 0x20,
+    SWS_BICUBLIN = 0x40, SWS_GAUSS = 0x80, SWS_SINC = 0x100, SWS_LANCZOS = 0x200, SWS_SPLINE = 0x400,
+    SWS_FULL_CHR_H_INT = 0x2000, SWS_ACCURATE_RND = 0x40000, SWS_BITEXACT = 0x80000,
+};
+constexpr double SWS_PARAM_DEFAULT = 123456;
+
+struct FilterBank {
+    int size = 0;                 // taps per output sample
+    int n = 0;                    // output samples
+    std::vector<int16_t> coef;    // n * size
+    std::vector<int32_t> pos;     // n
+};
+
+// returns 0, or -1 with *err set
+int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, int flags,
+                  const double param[2], bool horizontal, const char **err);
+
+struct SwsGeometry {
+    int srcW, srcH, dstW, dstH;
+    int chrSrcW, chrSrcH, chrDstW, chrDstH;
+    int chrSrcHSub, chrSrcVSub, chrDstHSub, chrDstVSub;
+    int lumXInc, lumYInc, chrXInc, chrYInc;
+    int flags;
+};
+// yuv420p source; dst_is_rgb selects packed 24-bit RGB (chroma shared by pixel pairs) or planar yuv420p
+int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool dst_is_rgb, int flags, const char **err);
+
+struct RgbConstants {      // r = clip_u8((cy * (Y + ar + ((V * crv) >> 16)) + k1) >> 16), etc.
+    int cy, k1;
+    int crv, cgu, cgv, cbu;
+    int ar, agu, agv, ab;  // yoffs - (crv >> 9), yoffs - (cgu >> 9), -(cgv >> 9), yoffs - (cbu >> 9)
+};
+void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int brightness, int contrast, int saturation);
+
+}  // namespace avb

@@ -1,0 +1,554 @@
+// libav_b200/csrc/swscale.cu -- libswscale's scaler for yuv420p sources on sm_100a.
+//
+// Replaces, bit-exactly (SWS_ACCURATE_RND | SWS_BITEXACT semantics), the C slots that swscale() drives
+// (libswscale/swscale.c:343-721):
+//   hyScale / hcScale = hScale8To15_c                       libswscale/swscale.c:133-147
+//   yuv2packedX/2/1   = yuv2rgb24_{X,2,1}_c                 libswscale/output.c:936-1110 (+ write :853-866)
+//   yuv2planeX / yuv2plane1 (8 bit)                         libswscale/output.c:242-265
+//   line scheduling + vertical edge replication             libswscale/swscale.c:450-616
+// The yuv->rgb look-up tables (libswscale/yuv2rgb.c:633-658, :850-863) are never materialised: the table
+// entry ytab[Y + off(U,V)] == clip_u8((cy * (Y + off) + k1) >> 16) is evaluated arithmetically, which is
+// exact for every in-range index and removes 5 scattered byte/word gathers per pixel.
+//
+// Two execution shapes:
+//   FUSED (the 4K benchmark geometry: same-size yuv420p -> rgb24/bgr24, bicubic): the horizontal filters are
+//     the identity and vLum is {4096}, so one kernel reads Y,U,V bytes and writes RGB: 1.5 B in + 3 B out per
+//     pixel, nothing else touches HBM.  A thread owns 8 pixels x 2 rows (one chroma window, two phases).
+//   GENERAL (any other geometry): hscale pass into 15-bit int16 planes, then a vertical+output pass that
+//     follows the reference's X / 2 / 1 function selection (swscale.c:659-682) line for line.
+#include "common.cuh"
+#include "scratch.h"
+#include "sws_filter.h"
+#include "../../include/avdsp_b200.h"
+#include <new>
+#include <limits.h>
+#include <string.h>
+
+namespace avb {
+
+struct SwsDev {                       // kernel-side view of a context (passed by value)
+    int srcW, srcH, dstW, dstH, chrSrcW, chrSrcH, chrDstW, chrDstH;
+    int hLumSize, hChrSize, vLumSize, vChrSize;
+    const int16_t *hLumF, *hChrF, *vLumF, *vChrF;
+    const int32_t *hLumP, *hChrP, *vLumP, *vChrP;
+    RgbConstants k;
+    int bgr;
+};
+
+struct ChromaTerms { int tr, tg, tb; };
+
+// per (U,V): the additive term of each channel, so a pixel costs one IMAD + shift per channel
+__device__ __forceinline__ ChromaTerms chroma_terms(int U, int V, const RgbConstants &k)
+{
+    int ro = k.ar + ((V * k.crv) >> 16);
+    int go = k.agu + ((U * k.cgu) >> 16) + k.agv + ((V * k.cgv) >> 16);
+    int bo = k.ab + ((U * k.cbu) >> 16);
+    ChromaTerms t;
+    t.tr = k.cy * ro + k.k1;
+    t.tg = k.cy * go + k.k1;
+    t.tb = k.cy * bo + k.k1;
+    return t;
+}
+
+// the "clip only when bit 8 is set somewhere" rule of yuv2rgb_X_c_template (output.c:966-971)
+__device__ __forceinline__ void clip_if_flagged(int &y1, int &y2, int &u, int &v)
+{
+    if ((y1 | y2 | u | v) & 0x100) { y1 = clip_u8(y1); y2 = clip_u8(y2); u = clip_u8(u); v = clip_u8(v); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FUSED kernel: horizontal identity, vLum identity, 4-tap vertical chroma.
+// ---------------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const uint8_t *y, *u, *v; uint8_t *dst;
+    int yStride, uStride, vStride, dstStride;
+    size_t yFrame, uFrame, vFrame, dstFrame;      // byte distance between consecutive frames of a batch
+};
+
+// one output row of 8 pixels from 8 luma bytes and 4 already filtered (U,V) pairs -> 6 packed words
+__device__ __forceinline__ void rgb_row8(uint2 yy, const int (&U)[4], const int (&V)[4], const RgbConstants &k, int bgr,
+                                         uint32_t (&out)[6])
+{
+    int r[8], g[8], b[8];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int u = U[c], v = V[c];
+        if ((u | v) & 0x100) { u = clip_u8(u); v = clip_u8(v); }     // luma is a byte: only chroma can flag
+        ChromaTerms t = chroma_terms(u, v, k);
+        int tr = bgr ? t.tb : t.tr, tb = bgr ? t.tr : t.tb;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            int p = 2 * c + s;
+            int Y = byte_of(p < 4 ? yy.x : yy.y, p & 3);
+            r[p] = (k.cy * Y + tr) >> 16;
+            g[p] = (k.cy * Y + t.tg) >> 16;
+            b[p] = (k.cy * Y + tb) >> 16;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int o = 4 * h;
+        out[3 * h + 0] = pack4_sat_u8(r[o], g[o], b[o], r[o + 1]);
+        out[3 * h + 1] = pack4_sat_u8(g[o + 1], b[o + 1], r[o + 2], g[o + 2]);
+        out[3 * h + 2] = pack4_sat_u8(b[o + 2], r[o + 3], g[o + 3], b[o + 3]);
+    }
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+sws_fused_rgb24_kernel(SwsDev p, FusedArgs a)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x;            // group of 8 pixels
+    const int rp = blockIdx.y * 8 + threadIdx.y;             // row pair
+    const int x0 = gx * 8, y0 = rp * 2;
+    if (x0 >= p.dstW || y0 >= p.dstH) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *Y = a.y + f * a.yFrame, *Uc = a.u + f * a.uFrame, *Vc = a.v + f * a.vFrame;
+    uint8_t *D = a.dst + f * a.dstFrame;
+    const bool full = ALIGNED && x0 + 8 <= p.dstW;     // vector path; otherwise byte accesses (tails, odd pitches)
+    // whole pixel pairs are written like the reference (one pixel past an odd dstW, output.c:947) only when the
+    // row pitch has room for it -- rows are concurrent here, the spill must never land in the next row
+    const int writeW = ((p.dstW & 1) && a.dstStride >= 3 * (p.dstW + 1)) ? p.dstW + 1 : p.dstW;
+
+    uint32_t uw[4], vw[4];
+    int loaded_first = INT_MIN;
+#pragma unroll
+    for (int ry = 0; ry < 2; ry++) {
+        const int y = y0 + ry;
+        if (y >= p.dstH) break;
+        const int first = max(1 - 4, p.vChrP[y]);            // swscale.c:463
+        if (first != loaded_first) {                         // both rows of a pair normally share the window
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int row = clampi(first + j, 0, p.chrSrcH - 1);   // vertical edge replication, swscale.c:592-616
+                if (full) {
+                    uw[j] = *reinterpret_cast<const uint32_t *>(Uc + (size_t)row * a.uStride + x0 / 2);
+                    vw[j] = *reinterpret_cast<const uint32_t *>(Vc + (size_t)row * a.vStride + x0 / 2);
+                } else {
+                    uint32_t uu = 0, vv = 0;
+                    for (int c = 0; c < 4; c++) {
+                        int cx = min(x0 / 2 + c, p.chrSrcW - 1);
+                        uu |= (uint32_t)Uc[(size_t)row * a.uStride + cx] << (8 * c);
+                        vv |= (uint32_t)Vc[(size_t)row * a.vStride + cx] << (8 * c);
+                    }
+                    uw[j] = uu; vw[j] = vv;
+                }
+            }
+            loaded_first = first;
+        }
+        const int16_t *cf = p.vChrF + (size_t)y * 4;
+        const int c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3];
+        int U[4], V[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // (2^18 + sum (u << 7) * coef) >> 19  ==  (2^11 + sum u * coef) >> 12
+            U[c] = (2048 + byte_of(uw[0], c) * c0 + byte_of(uw[1], c) * c1 + byte_of(uw[2], c) * c2 + byte_of(uw[3], c) * c3) >> 12;
+            V[c] = (2048 + byte_of(vw[0], c) * c0 + byte_of(vw[1], c) * c1 + byte_of(vw[2], c) * c2 + byte_of(vw[3], c) * c3) >> 12;
+        }
+        uint2 yy;
+        const uint8_t *yrow = Y + (size_t)y * a.yStride + x0;
+        if (full) yy = *reinterpret_cast<const uint2 *>(yrow);
+        else {
+            yy = make_uint2(0, 0);               // pixels beyond dstW read as 0, like the zeroed line buffer
+            for (int c = 0; c < 8 && x0 + c < p.dstW; c++) {
+                if (c < 4) yy.x |= (uint32_t)yrow[c] << (8 * c); else yy.y |= (uint32_t)yrow[c] << (8 * (c - 4));
+            }
+        }
+        uint32_t o[6];
+        rgb_row8(yy, U, V, p.k, p.bgr, o);
+        uint8_t *drow = D + (size_t)y * a.dstStride + (size_t)x0 * 3;
+        if (full) {
+            uint2 *d2 = reinterpret_cast<uint2 *>(drow);
+            d2[0] = make_uint2(o[0], o[1]); d2[1] = make_uint2(o[2], o[3]); d2[2] = make_uint2(o[4], o[5]);
+        } else {
+            int npx = min(8, writeW - x0);
+            for (int c = 0; c < npx * 3; c++) drow[c] = (uint8_t)(o[c >> 2] >> (8 * (c & 3)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GENERAL path, pass 1: hScale8To15 (swscale.c:133-147) for one plane; thread = (column, row)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sws_hscale8to15_kernel(const uint8_t *__restrict__ src, int srcStride, int16_t *__restrict__ dst, int dstStridePx,
+                       const int16_t *__restrict__ filter, const int32_t *__restrict__ pos, int fs, int dstW, int rows)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= dstW || y >= rows) return;
+    const uint8_t *s = src + (size_t)y * srcStride + pos[i];
+    const int16_t *f = filter + (size_t)i * fs;
+    int val = 0;
+    for (int j = 0; j < fs; j++) val += (int)s[j] * f[j];
+    dst[(size_t)y * dstStridePx + i] = (int16_t)min(val >> 7, (1 << 15) - 1);
+}
+
+// hyscale_fast_c / hcscale_fast_c (swscale.c:238-250, :286-299), selected by SWS_FAST_BILINEAR instead of the filter
+// bank.  The reference reads src[xx + 1] one byte past the last source pixel; that byte is defined here as a copy
+// of the last pixel (documented deviation: the reference's value is whatever follows the row in memory).
+__global__ void __launch_bounds__(256)
+sws_hscale_fast_kernel(const uint8_t *__restrict__ src, int srcStride, int16_t *__restrict__ dst, int dstStridePx,
+                       int srcW, int dstW, int rows, unsigned xInc, int chroma)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= dstW || y >= rows) return;
+    unsigned xpos = (unsigned)i * xInc, xx = xpos >> 16, xa = (xpos & 0xFFFF) >> 9;
+    const uint8_t *s = src + (size_t)y * srcStride;
+    int a = s[xx], b = s[min(xx + 1, (unsigned)srcW - 1)];
+    dst[(size_t)y * dstStridePx + i] = (int16_t)(chroma ? a * (int)(xa ^ 127) + b * (int)xa : (a << 7) + (b - a) * (int)xa);
+}
+
+__device__ __forceinline__ int line_index(int first, int j, int srcH) { return clampi(first + j, 0, srcH - 1); }
+
+// pass 2 for packed RGB: thread = (pixel pair, output row); X / 2 / 1 selection as swscale.c:659-682
+__global__ void __launch_bounds__(256)
+sws_vscale_rgb24_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t *__restrict__ chrU,
+                        const int16_t *__restrict__ chrV, int lumStride, int chrStride, uint8_t *__restrict__ dst,
+                        int dstStride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= ((p.dstW + 1) >> 1) || y >= p.dstH) return;
+    const int fl = p.vLumSize, fc = p.vChrSize;
+    const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
+    const bool has2 = 2 * i + 1 < p.dstW;     // odd width: the second pixel of the last pair reads the zeroed tail
+    int Y1, Y2, U, V;
+    auto L = [&](int j, int x) -> int { return x < p.dstW ? lum[(size_t)line_index(firstL, j, p.srcH) * lumStride + x] : 0; };
+    auto CU = [&](int j) -> int { return chrU[(size_t)line_index(firstC, j, p.chrSrcH) * chrStride + i]; };
+    auto CV = [&](int j) -> int { return chrV[(size_t)line_index(firstC, j, p.chrSrcH) * chrStride + i]; };
+    if (fl == 1 && fc <= 2) {                                  // yuv2rgb24_1_c, output.c:1042-1110
+        int uvalpha = fc == 1 ? 0 : p.vChrF[2 * y + 1];
+        Y1 = L(0, 2 * i) >> 7; Y2 = L(0, 2 * i + 1) >> 7;
+        if (uvalpha < 2048) { U = CU(0) >> 7; V = CV(0) >> 7; }
+        else                { U = (CU(0) + CU(1)) >> 8; V = (CV(0) + CV(1)) >> 8; }
+        Y1 = clip_u8(Y1); Y2 = clip_u8(Y2); U = clip_u8(U); V = clip_u8(V);
+    } else if (fl == 2 && fc == 2) {                           // yuv2rgb24_2_c, output.c:997-1040
+        int ya = p.vLumF[2 * y + 1], ua = p.vChrF[2 * y + 1], ya1 = 4096 - ya, ua1 = 4096 - ua;
+        Y1 = (L(0, 2 * i) * ya1 + L(1, 2 * i) * ya) >> 19;
+        Y2 = (L(0, 2 * i + 1) * ya1 + L(1, 2 * i + 1) * ya) >> 19;
+        U = (CU(0) * ua1 + CU(1) * ua) >> 19;
+        V = (CV(0) * ua1 + CV(1) * ua) >> 19;
+        Y1 = clip_u8(Y1); Y2 = clip_u8(Y2); U = clip_u8(U); V = clip_u8(V);
+    } else {                                                   // yuv2rgb24_X_c, output.c:936-995
+        const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+        Y1 = Y2 = U = V = 1 << 18;
+        for (int j = 0; j < fl; j++) { Y1 += L(j, 2 * i) * lf[j]; Y2 += L(j, 2 * i + 1) * lf[j]; }
+        for (int j = 0; j < fc; j++) { U += CU(j) * cf[j]; V += CV(j) * cf[j]; }
+        Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
+        clip_if_flagged(Y1, Y2, U, V);
+    }
+    ChromaTerms t = chroma_terms(U, V, p.k);
+    int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
+    uint8_t *d = dst + (size_t)y * dstStride + (size_t)i * 6;
+    d[0] = (uint8_t)clip_u8((p.k.cy * Y1 + tr) >> 16);
+    d[1] = (uint8_t)clip_u8((p.k.cy * Y1 + t.tg) >> 16);
+    d[2] = (uint8_t)clip_u8((p.k.cy * Y1 + tb) >> 16);
+    if (!has2 && dstStride < 3 * (p.dstW + 1)) return;         // odd width, no room for the pair's second pixel
+    d[3] = (uint8_t)clip_u8((p.k.cy * Y2 + tr) >> 16);
+    d[4] = (uint8_t)clip_u8((p.k.cy * Y2 + t.tg) >> 16);
+    d[5] = (uint8_t)clip_u8((p.k.cy * Y2 + tb) >> 16);
+}
+
+// pass 2 for planar 8-bit output: yuv2planeX_8_c / yuv2plane1_8_c (output.c:242-265), dither = 64 everywhere
+__global__ void __launch_bounds__(256)
+sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
+                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= dstW || y >= dstH) return;
+    const int first = max(1 - fs, pos[y]);
+    int val;
+    if (fs == 1) {
+        val = (src[(size_t)line_index(first, 0, srcH) * srcStride + i] + 64) >> 7;
+    } else {
+        const int16_t *f = filter + (size_t)y * fs;
+        val = 64 << 12;
+        for (int j = 0; j < fs; j++) val += src[(size_t)line_index(first, j, srcH) * srcStride + i] * f[j];
+        val >>= 19;
+    }
+    dst[(size_t)y * dstStride + i] = (uint8_t)clip_u8(val);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3 };       // libavutil/pixfmt.h enum values
+
+struct SwsCudaContext {
+    SwsGeometry g;
+    FilterBank hLum, hChr, vLum, vChr;
+    RgbConstants k;
+    int dstFormat;
+    bool copy = false;          // unscaled yuv420p -> yuv420p: the reference installs a plain plane copy
+                                // (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper), whatever the flags
+    bool fused;                 // horizontal identity + vLum identity + 4-tap vChr -> one kernel
+    void *d_tables = nullptr;   // all filter banks in one device allocation
+    SwsDev dev;
+    int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
+    int lumStridePx = 0, chrStridePx = 0;
+    // staging for the host-pointer sws_scale_cuda()
+    uint8_t *d_src = nullptr, *d_dst = nullptr; size_t src_bytes = 0, dst_bytes = 0;
+};
+
+static bool is_identity(const FilterBank &b, int one)
+{
+    if (b.size != 1) return false;
+    for (int i = 0; i < b.n; i++) if (b.coef[i] != one || b.pos[i] != i) return false;
+    return true;
+}
+
+static int upload_tables(SwsCudaContext *c)
+{
+    const FilterBank *banks[4] = { &c->hLum, &c->hChr, &c->vLum, &c->vChr };
+    size_t off[8], total = 0;
+    for (int b = 0; b < 4; b++) {
+        off[2 * b] = total;     total += (banks[b]->coef.size() * 2 + 255) & ~(size_t)255;
+        off[2 * b + 1] = total; total += (banks[b]->pos.size() * 4 + 255) & ~(size_t)255;
+    }
+    AVB_CUDA(cudaMalloc(&c->d_tables, total), "sws:tables");
+    uint8_t *base = (uint8_t *)c->d_tables;
+    for (int b = 0; b < 4; b++) {
+        AVB_CUDA(cudaMemcpy(base + off[2 * b], banks[b]->coef.data(), banks[b]->coef.size() * 2, cudaMemcpyHostToDevice), "sws:tables");
+        AVB_CUDA(cudaMemcpy(base + off[2 * b + 1], banks[b]->pos.data(), banks[b]->pos.size() * 4, cudaMemcpyHostToDevice), "sws:tables");
+    }
+    SwsDev &d = c->dev;
+    d.srcW = c->g.srcW; d.srcH = c->g.srcH; d.dstW = c->g.dstW; d.dstH = c->g.dstH;
+    d.chrSrcW = c->g.chrSrcW; d.chrSrcH = c->g.chrSrcH; d.chrDstW = c->g.chrDstW; d.chrDstH = c->g.chrDstH;
+    d.hLumSize = c->hLum.size; d.hChrSize = c->hChr.size; d.vLumSize = c->vLum.size; d.vChrSize = c->vChr.size;
+    d.hLumF = (const int16_t *)(base + off[0]); d.hLumP = (const int32_t *)(base + off[1]);
+    d.hChrF = (const int16_t *)(base + off[2]); d.hChrP = (const int32_t *)(base + off[3]);
+    d.vLumF = (const int16_t *)(base + off[4]); d.vLumP = (const int32_t *)(base + off[5]);
+    d.vChrF = (const int16_t *)(base + off[6]); d.vChrP = (const int32_t *)(base + off[7]);
+    d.k = c->k;
+    d.bgr = c->dstFormat == FMT_BGR24;
+    return 0;
+}
+
+static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
+                                    const double *param, bool device_side)
+{
+    const char *err = nullptr;
+    if (srcFormat != FMT_YUV420P) { set_error_msg("sws_getContext_cuda", "only AV_PIX_FMT_YUV420P sources are taken over"); return nullptr; }
+    if (dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && dstFormat != FMT_YUV420P) {
+        set_error_msg("sws_getContext_cuda", "destination must be RGB24, BGR24 or YUV420P"); return nullptr;
+    }
+    const bool rgb = dstFormat != FMT_YUV420P;
+    if (flags & SWS_FULL_CHR_H_INT) { set_error_msg("sws_getContext_cuda", "SWS_FULL_CHR_H_INT is not taken over"); return nullptr; }
+    if (rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1)) {
+        // the reference would pick its table-driven unscaled converter here (swscale_unscaled.c:1051-1055),
+        // whose output differs from the scaler path; that SwsFunc is not part of this back-end yet
+        set_error_msg("sws_getContext_cuda", "unscaled yuv2rgb without SWS_ACCURATE_RND is not taken over");
+        return nullptr;
+    }
+    SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
+    if (!c) return nullptr;
+    c->dstFormat = dstFormat;
+    double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
+    if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err)) goto fail;
+    {
+        const int fl = c->g.flags;
+        const int lumFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BICUBIC) : fl;
+        const int chrFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BILINEAR) : fl;
+        if (design_filter(c->hLum, c->g.lumXInc, srcW, dstW, 1 << 14, lumFlags, prm, true, &err)) goto fail;
+        if (design_filter(c->hChr, c->g.chrXInc, c->g.chrSrcW, c->g.chrDstW, 1 << 14, chrFlags, prm, true, &err)) goto fail;
+        if (design_filter(c->vLum, c->g.lumYInc, srcH, dstH, 1 << 12, lumFlags, prm, false, &err)) goto fail;
+        if (design_filter(c->vChr, c->g.chrYInc, c->g.chrSrcH, c->g.chrDstH, 1 << 12, chrFlags, prm, false, &err)) goto fail;
+    }
+    {
+        static const int itu601[4] = { 104597, 132201, 25675, 53279 };     // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT]
+        rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
+    }
+    c->fused = rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+               c->vChr.size == 4;
+    c->copy = !rgb && srcW == dstW && srcH == dstH;
+    if (!device_side) return c;
+    if (upload_tables(c)) { delete c; return nullptr; }
+    if (!c->fused && !c->copy) {
+        c->lumStridePx = (dstW + 1 + 7) & ~7;
+        c->chrStridePx = (c->g.chrDstW + 7) & ~7;
+        if (cudaMalloc(&c->d_lum, (size_t)c->lumStridePx * srcH * 2) != cudaSuccess ||
+            cudaMalloc(&c->d_chrU, (size_t)c->chrStridePx * c->g.chrSrcH * 2) != cudaSuccess ||
+            cudaMalloc(&c->d_chrV, (size_t)c->chrStridePx * c->g.chrSrcH * 2) != cudaSuccess) {
+            set_error("sws_getContext_cuda", cudaGetLastError());
+            cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_tables);
+            delete c; return nullptr;
+        }
+    }
+    return c;
+fail:
+    set_error_msg("sws_getContext_cuda", err ? err : "init failed");
+    delete c;
+    return nullptr;
+}
+
+static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                      uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
+{
+    const SwsDev &p = c->dev;
+    if (nframes <= 0) return 0;
+    if (c->copy) {
+        for (int f = 0; f < nframes; f++)
+            for (int pl = 0; pl < 3; pl++) {
+                int w = pl ? p.chrSrcW : p.srcW, h = pl ? p.chrSrcH : p.srcH;
+                AVB_CUDA(cudaMemcpy2DAsync(dst[pl] + f * dstFrame[pl], dstStride[pl], src[pl] + f * srcFrame[pl], srcStride[pl], w, h,
+                                           cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
+            }
+        return 0;
+    }
+    if (c->fused) {
+        FusedArgs a;
+        a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst = dst[0];
+        a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2]; a.dstStride = dstStride[0];
+        a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2]; a.dstFrame = dstFrame[0];
+        // vector accesses need 8-byte aligned luma / output rows and 4-byte aligned chroma rows
+        bool aligned = !((uintptr_t)a.y & 7) && !(a.yStride & 7) && !((uintptr_t)a.dst & 7) && !(a.dstStride & 7) && !(a.yFrame & 7) &&
+                       !(a.dstFrame & 7) && !((uintptr_t)a.u & 3) && !((uintptr_t)a.v & 3) && !(a.uStride & 3) && !(a.vStride & 3) &&
+                       !(a.uFrame & 3) && !(a.vFrame & 3);
+        dim3 b(32, 8), g((p.dstW + 255) / 256, (p.dstH + 15) / 16, nframes);
+        if (aligned) sws_fused_rgb24_kernel<true><<<g, b, 0, st>>>(p, a);
+        else         sws_fused_rgb24_kernel<false><<<g, b, 0, st>>>(p, a);    // same arithmetic, byte accesses
+        return check_launch("sws_scale:fused");
+    }
+    for (int f = 0; f < nframes; f++) {      // general path: frames are serialised on the stream (shared line planes)
+        const uint8_t *y = src[0] + f * srcFrame[0], *u = src[1] + f * srcFrame[1], *v = src[2] + f * srcFrame[2];
+        dim3 b(256);
+        if (c->g.flags & SWS_FAST_BILINEAR) {
+            sws_hscale_fast_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.srcW, p.dstW, p.srcH, c->g.lumXInc, 0);
+            sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
+            sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
+        } else {
+            sws_hscale8to15_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH);
+            sws_hscale8to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
+            sws_hscale8to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
+        }
+        if (c->dstFormat == FMT_YUV420P) {
+            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH);
+        } else {
+            int pairs = (p.dstW + 1) >> 1;
+            sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, dst[0] + f * dstFrame[0], dstStride[0]);
+        }
+        if (check_launch("sws_scale:general")) return -1;
+    }
+    return 0;
+}
+
+static void destroy(SwsCudaContext *c)
+{
+    if (!c) return;
+    cudaFree(c->d_tables); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    delete c;
+}
+
+}  // namespace avb
+
+using namespace avb;
+
+extern "C" {
+
+SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
+                                    void *srcFilter, void *dstFilter, const double *param)
+{
+    if (srcFilter || dstFilter) { set_error_msg("sws_getContext_cuda", "SwsFilter pre/post filters are not taken over"); return nullptr; }
+    return (SwsContextCUDA *)make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, param, true);
+}
+
+void sws_freeContext_cuda(SwsContextCUDA *ctx) { destroy((SwsCudaContext *)ctx); }
+
+int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrameStride[3],
+                          uint8_t *const dst[3], const int dstStride[3], const size_t dstFrameStride[3], int nframes, void *stream)
+{
+    SwsCudaContext *c = (SwsCudaContext *)ctx;
+    if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
+    if (!src || !dst || !src[0] || !src[1] || !src[2] || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
+    static const size_t zero3[3] = { 0, 0, 0 };
+    if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
+                   nframes, (cudaStream_t)stream)) return -1;
+    return c->g.dstH * nframes;
+}
+
+// Host-pointer drop-in for sws_scale() (libswscale/swscale_unscaled.c:1212-1340): whole frames only.
+// Returns the number of output lines like the reference, 0 on bad arguments.
+int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY, int srcSliceH,
+                   uint8_t *const dst[], const int dstStride[])
+{
+    SwsCudaContext *c = (SwsCudaContext *)ctx;
+    if (!c || srcSliceH == 0) return 0;
+    const bool rgb = c->dstFormat != FMT_YUV420P;
+    if (!srcSlice || !dst || !srcSlice[0] || !srcSlice[1] || !srcSlice[2] || !srcStride[0] || !srcStride[1] || !srcStride[2] ||
+        !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dst[2] || !dstStride[1] || !dstStride[2]))) {
+        set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
+    }
+    if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
+    if (srcStride[0] < 0 || srcStride[1] < 0 || srcStride[2] < 0 || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
+    ScratchLock lk;
+    cudaStream_t *st = scratch().streams();
+    if (!st) return 0;
+    cudaStream_t s = st[0];
+    const SwsGeometry &g = c->g;
+    // device staging: tight, aligned pitches
+    const int yP = (g.srcW + 15) & ~15, cP = (g.chrSrcW + 15) & ~15;
+    const size_t yB = (size_t)yP * g.srcH, cB = (size_t)cP * g.chrSrcH;
+    const size_t needS = yB + 2 * cB;
+    const int odd = g.dstW & 1;
+    const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW + 15) & ~15, dcP = (g.chrDstW + 15) & ~15;
+    const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
+    const size_t needD = dB + 2 * dcB;
+    if (c->src_bytes < needS) { cudaFree(c->d_src); c->d_src = nullptr; if (cudaMalloc(&c->d_src, needS) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->src_bytes = needS; }
+    if (c->dst_bytes < needD) { cudaFree(c->d_dst); c->d_dst = nullptr; if (cudaMalloc(&c->d_dst, needD) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->dst_bytes = needD; }
+    const uint8_t *ds[3] = { c->d_src, c->d_src + yB, c->d_src + yB + cB };
+    uint8_t *dd[3] = { c->d_dst, c->d_dst + dB, c->d_dst + dB + dcB };
+    const int dsS[3] = { yP, cP, cP }, ddS[3] = { dP, dcP, dcP };
+    if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
+    }
+    static const size_t zero3[3] = { 0, 0, 0 };
+    if (run_frames(c, ds, dsS, zero3, dd, ddS, zero3, 1, s)) return 0;
+    cudaError_t e;
+    if (rgb) {
+        // whole pixel pairs are written (one pixel past an odd width) when the caller's stride has room
+        size_t wbytes = (size_t)g.dstW * 3;
+        if (odd && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;
+        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
+    } else {
+        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, g.chrDstW, g.chrDstH, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, g.chrDstW, g.chrDstH, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("sws_scale_cuda:d2h", e); return 0; }
+    return g.dstH;
+}
+
+int sws_is_fused_cuda(SwsContextCUDA *ctx) { return ctx ? ((SwsCudaContext *)ctx)->fused : 0; }
+
+// Host-only introspection used by the CPU test-suite to pin the set-up stage against the reference
+// (no device is touched): filter bank `which` (0 hLum, 1 hChr, 2 vLum, 3 vChr) of the context that
+// sws_getContext_cuda() would build.  Returns the tap count, <0 on error.
+int sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, int16_t *filter,
+                          int32_t *pos, int cap, int *n_out)
+{
+    SwsCudaContext *c = make_context(srcW, srcH, FMT_YUV420P, dstW, dstH, dstFormat, flags, nullptr, false);
+    if (!c) return -1;
+    const FilterBank &b = which == 0 ? c->hLum : which == 1 ? c->hChr : which == 2 ? c->vLum : c->vChr;
+    int fs = b.size;
+    *n_out = b.n;
+    if (b.n > cap || (int)b.coef.size() > cap) fs = -2;
+    else { memcpy(filter, b.coef.data(), b.coef.size() * 2); memcpy(pos, b.pos.data(), b.pos.size() * 4); }
+    delete c;
+    return fs;
+}
+void sws_debug_rgb_constants_cuda(int32_t out[10])
+{
+    static const int itu601[4] = { 104597, 132201, 25675, 53279 };
+    RgbConstants k;
+    rgb_constants(k, itu601, 0, 0, 1 << 16, 1 << 16);
+    int v[10] = { k.cy, k.k1, k.crv, k.cgu, k.cgv, k.cbu, k.ar, k.agu, k.agv, k.ab };
+    for (int i = 0; i < 10; i++) out[i] = v[i];
+}
+
+}  // extern "C"

@@ -130,15 +130,41 @@ def yuv420p_frame(w, h, seed=1):
     return y, u, v
 
 
-def crc32_ieee_be(data, crc=0):
-    """av_crc(av_crc_get_table(AV_CRC_32_IEEE), 0, ...) -- MSB-first CRC-32, poly 0x04C11DB7, init 0, no
-    final xor (libavutil/crc.c).  Table driven, numpy-chunked."""
+def pad_rows(plane, pad=8):
+    """Copy a plane into rows of width+pad bytes whose padding repeats the last pixel (the byte the reference's
+    fast-bilinear scaler reads past the end of each row); returns the strided view of the valid region."""
+    h, w = plane.shape
+    buf = np.empty((h, w + pad), dtype=plane.dtype)
+    buf[:, :w] = plane
+    buf[:, w:] = plane[:, -1:]
+    return buf[:, :w]
+
+
+def crc32_ieee_be(data):
+    """av_crc(av_crc_get_table(AV_CRC_32_IEEE), 0, buf, len) (libavutil/crc.c): MSB-first CRC-32, polynomial
+    0x04C11DB7, init 0, no final xor; av_crc keeps its state byte-swapped, so the value it returns is the
+    byte-swapped register.  Chunk-parallel numpy evaluation (CRC with zero init is linear in the message)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
     tab = _crc_table()
-    crc &= 0xFFFFFFFF
-    mv = memoryview(bytes(data))
-    for b in mv:
-        crc = ((crc << 8) & 0xFFFFFFFF) ^ tab[((crc >> 24) ^ b) & 0xFF]
-    return crc
+    n = buf.size
+    if n == 0:
+        return 0
+    chunks = max(1, min(4096, n // 64))
+    clen = -(-n // chunks)
+    pad = chunks * clen - n
+    m = np.concatenate([np.zeros(pad, np.uint8), buf]).reshape(chunks, clen)   # leading zeros are neutral
+    crc = np.zeros(chunks, dtype=np.uint32)
+    for k in range(clen):
+        crc = ((crc << np.uint32(8)) ^ tab[((crc >> np.uint32(24)) ^ m[:, k]) & 0xFF]).astype(np.uint32)
+    # operator "append clen zero bytes" as four byte tables
+    basis = (np.arange(256, dtype=np.uint32)[None, :] << (np.arange(4, dtype=np.uint32)[:, None] * 8)).astype(np.uint32).reshape(-1)
+    for _ in range(clen):
+        basis = ((basis << np.uint32(8)) ^ tab[(basis >> np.uint32(24)) & 0xFF]).astype(np.uint32)
+    basis = basis.reshape(4, 256)
+    acc = 0
+    for c in crc.tolist():
+        acc = int(basis[0][acc & 0xFF] ^ basis[1][(acc >> 8) & 0xFF] ^ basis[2][(acc >> 16) & 0xFF] ^ basis[3][acc >> 24]) ^ c
+    return int.from_bytes(acc.to_bytes(4, "big"), "little")
 
 
 _CRC_TAB = None
@@ -153,5 +179,5 @@ def _crc_table():
             for _ in range(8):
                 c = ((c << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if c & 0x80000000 else (c << 1) & 0xFFFFFFFF
             t.append(c)
-        _CRC_TAB = t
+        _CRC_TAB = np.array(t, dtype=np.uint32)
     return _CRC_TAB

@@ -1,0 +1,408 @@
+/*
+ * oracle/port/orc_sws.c -- TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * CPU restatement of libswscale's scaler for yuv420p sources, 8-bit, as selected by
+ * SWS_ACCURATE_RND | SWS_BITEXACT:
+ *   filter design           libswscale/utils.c:249-632   (initFilter)
+ *   geometry                libswscale/utils.c:887-1198  (sws_init_context)
+ *   line scheduling, edges  libswscale/swscale.c:450-682 (swscale)
+ *   horizontal pass         libswscale/swscale.c:133-147 (hScale8To15_c)
+ *   packed RGB output       libswscale/output.c:936-1110 (yuv2rgb_{X,2,1}_c_template) + :853-866
+ *   planar output           libswscale/output.c:242-265  (yuv2planeX_8_c, yuv2plane1_8_c)
+ *   yuv->rgb tables         libswscale/yuv2rgb.c:633-658, :671-863 (24 bpp)
+ * Unlike the product (which evaluates the table arithmetically) this restatement builds the
+ * 1024-entry table and the four 256-entry offset tables and indexes them like the reference.
+ * Pinned against oracle/_ref (tests/test_oracle_sws_cpu.py) and the CRC known answers in tests/golden.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../oracle_api.h"
+
+#define F_FAST_BILINEAR 1
+#define F_BILINEAR 2
+#define F_BICUBIC 4
+#define F_X 8
+#define F_POINT 0x10
+#define F_AREA 0x20
+#define F_BICUBLIN 0x40
+#define F_GAUSS 0x80
+#define F_SINC 0x100
+#define F_LANCZOS 0x200
+#define F_SPLINE 0x400
+#define F_FULL_CHR_H_INT 0x2000
+#define F_ACCURATE_RND 0x40000
+#define PARAM_DEFAULT 123456.0
+
+typedef struct { int taps, n; int16_t *coef; int32_t *pos; } bank_t;
+typedef struct {
+    int srcW, srcH, dstW, dstH, chrSrcW, chrSrcH, chrDstW, chrDstH, flags, rgb, lumXInc, chrXInc;
+    bank_t hl, hc, vl, vc;
+} sws_t;
+
+static const int64_t ONE = 1LL << 54;
+static int64_t ll_abs(int64_t v) { return v < 0 ? -v : v; }
+
+static double spline(double a, double b, double c, double d, double x)
+{
+    if (x <= 1.0) return ((d * x + c) * x + b) * x + a;
+    return spline(0.0, b + 2.0 * c + 3.0 * d, c + 3.0 * d, -b - 3.0 * c - 6.0 * d, x - 1.0);
+}
+
+static int64_t tap_weight(int flags, int64_t d, int xinc)
+{
+    double fd = d * (1.0 / (1 << 30));
+    int64_t c;
+    if (flags & F_BICUBIC) {
+        int64_t B = 0, C = (int64_t)(0.6 * (1 << 24));
+        if (d >= 1LL << 31) c = 0;
+        else {
+            int64_t dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+            if (d < 1LL << 30)
+                c = (12 * (1 << 24) - 9 * B - 6 * C) * ddd + (-18 * (1 << 24) + 12 * B + 6 * C) * dd + (6 * (1 << 24) - 2 * B) * (1LL << 30);
+            else
+                c = (-B - 6 * C) * ddd + (6 * B + 30 * C) * dd + (-12 * B - 48 * C) * d + (8 * B + 24 * C) * (1LL << 30);
+        }
+        return c * (ONE >> 54);
+    } else if (flags & F_X) {
+        double v = fd < 1.0 ? cos(fd * M_PI) : -1.0;
+        v = v < 0.0 ? -pow(-v, 1.0) : pow(v, 1.0);
+        return (int64_t)((v * 0.5 + 0.5) * ONE);
+    } else if (flags & F_AREA) {
+        int64_t d2 = d - (1 << 29);
+        if (d2 * xinc < -(1LL << 45)) c = 1LL << 46;
+        else if (d2 * xinc < (1LL << 45)) c = -d2 * xinc + (1LL << 45);
+        else c = 0;
+        return c * (ONE >> 46);
+    } else if (flags & F_GAUSS) {
+        return (int64_t)(pow(2.0, -3.0 * fd * fd) * ONE);
+    } else if (flags & F_SINC) {
+        return (int64_t)((d ? sin(fd * M_PI) / (fd * M_PI) : 1.0) * ONE);
+    } else if (flags & F_LANCZOS) {
+        c = (int64_t)((d ? sin(fd * M_PI) * sin(fd * M_PI / 3.0) / (fd * fd * M_PI * M_PI / 3.0) : 1.0) * ONE);
+        return fd > 3.0 ? 0 : c;
+    } else if (flags & F_BILINEAR) {
+        c = (1 << 30) - d;
+        return (c < 0 ? 0 : c) * (ONE >> 30);
+    } else if (flags & F_SPLINE) {
+        double p = -2.196152422706632;
+        return (int64_t)(spline(1.0, 0.0, p, -p - 1.0, fd) * ONE);
+    }
+    return 0;
+}
+
+static int make_bank(bank_t *b, int xinc, int slen, int dlen, int one, int flags, int horiz)
+{
+    int taps, i, j, k;
+    int64_t *w;
+    int32_t *pos = calloc(dlen + 1, sizeof(*pos));
+    if (abs(xinc - 0x10000) < 10) {
+        taps = 1; w = calloc(dlen, sizeof(*w));
+        for (i = 0; i < dlen; i++) { w[i] = ONE; pos[i] = i; }
+    } else if (flags & F_POINT) {
+        int x = xinc / 2 - 0x8000;
+        taps = 1; w = calloc(dlen, sizeof(*w));
+        for (i = 0; i < dlen; i++) { pos[i] = (x + 0x8000) >> 16; w[i] = ONE; x += xinc; }
+    } else if ((xinc <= 65536 && (flags & F_AREA)) || (flags & F_FAST_BILINEAR)) {
+        int x = xinc / 2 - 0x8000;
+        taps = 2; w = calloc(2 * dlen, sizeof(*w));
+        for (i = 0; i < dlen; i++) {
+            int xx = x >> 16;
+            pos[i] = xx;
+            for (j = 0; j < 2; j++) {
+                int dist = (int)(((unsigned)xx << 16) - (unsigned)x);
+                int64_t c = ONE - (int64_t)abs(dist) * (ONE >> 16);
+                w[2 * i + j] = c < 0 ? 0 : c;
+                xx++;
+            }
+            x += xinc;
+        }
+    } else {
+        int sf = (flags & F_BICUBIC) ? 4 : (flags & F_X) ? 8 : (flags & F_AREA) ? 1 : (flags & F_GAUSS) ? 8 :
+                 (flags & F_LANCZOS) ? 6 : (flags & F_SINC) ? 20 : (flags & F_SPLINE) ? 20 : (flags & F_BILINEAR) ? 2 : 0;
+        int64_t x = xinc - 0x10000;
+        if (!sf) { free(pos); return -1; }
+        taps = xinc <= 65536 ? 1 + sf : 1 + (sf * slen + dlen - 1) / dlen;
+        if (taps > slen - 2) taps = slen - 2;
+        if (taps < 1) taps = 1;
+        w = calloc((size_t)taps * dlen, sizeof(*w));
+        for (i = 0; i < dlen; i++) {
+            int xx = (int)((x - ((int64_t)(taps - 2) << 16)) / (1 << 17));
+            pos[i] = xx;
+            for (j = 0; j < taps; j++) {
+                int64_t d = ll_abs(((int64_t)xx << 17) - x) << 13;
+                if (xinc > 65536) d = d * dlen / slen;
+                w[(size_t)i * taps + j] = tap_weight(flags, d, xinc);
+                xx++;
+            }
+            x += 2 * (int64_t)xinc;
+        }
+    }
+    /* shrink (utils.c:476-520) */
+    int minsize = 0;
+    for (i = dlen - 1; i >= 0; i--) {
+        int64_t *r = w + (size_t)i * taps, cut = 0;
+        int m = taps;
+        for (j = 0; j < taps; j++) {
+            cut += ll_abs(r[0]);
+            if (cut > 0.002 * ONE) break;
+            if (i < dlen - 1 && pos[i] >= pos[i + 1]) break;
+            for (k = 1; k < taps; k++) r[k - 1] = r[k];
+            r[k - 1] = 0;
+            pos[i]++;
+        }
+        cut = 0;
+        for (j = taps - 1; j > 0; j--) {
+            cut += ll_abs(r[j]);
+            if (cut > 0.002 * ONE) break;
+            m--;
+        }
+        if (m > minsize) minsize = m;
+    }
+    if (minsize < 1 || minsize >= 256) { free(w); free(pos); return -1; }
+    int64_t *f = calloc((size_t)minsize * dlen, sizeof(*f));
+    for (i = 0; i < dlen; i++)
+        for (j = 0; j < minsize; j++) f[(size_t)i * minsize + j] = j < taps ? w[(size_t)i * taps + j] : 0;
+    free(w);
+    if (horiz) {
+        for (i = 0; i < dlen; i++) {
+            int64_t *r = f + (size_t)i * minsize;
+            if (pos[i] < 0) {
+                for (j = 1; j < minsize; j++) {
+                    int left = j + pos[i] > 0 ? j + pos[i] : 0;
+                    r[left] += r[j]; r[j] = 0;
+                }
+                pos[i] = 0;
+            }
+            if (pos[i] + minsize > slen) {
+                int sh = pos[i] + minsize - slen;
+                for (j = minsize - 2; j >= 0; j--) {
+                    int right = j + sh < minsize - 1 ? j + sh : minsize - 1;
+                    r[right] += r[j]; r[j] = 0;
+                }
+                pos[i] = slen - minsize;
+            }
+        }
+    }
+    b->taps = minsize; b->n = dlen; b->pos = pos;
+    b->coef = calloc((size_t)minsize * dlen, sizeof(int16_t));
+    for (i = 0; i < dlen; i++) {
+        int64_t err = 0, sum = 0;
+        for (j = 0; j < minsize; j++) sum += f[(size_t)i * minsize + j];
+        sum = (sum + one / 2) / one;
+        for (j = 0; j < minsize; j++) {
+            int64_t v = f[(size_t)i * minsize + j] + err;
+            int q = (int)((v > 0 ? v + (sum >> 1) : v - (sum >> 1)) / sum);
+            b->coef[(size_t)i * minsize + j] = (int16_t)q;
+            err = v - q * sum;
+        }
+    }
+    free(f);
+    return 0;
+}
+
+static void free_bank(bank_t *b) { free(b->coef); free(b->pos); memset(b, 0, sizeof(*b)); }
+static void sws_close(sws_t *c) { free_bank(&c->hl); free_bank(&c->hc); free_bank(&c->vl); free_bank(&c->vc); }
+
+static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags)
+{
+    memset(c, 0, sizeof(*c));
+    int algo = flags & (F_POINT | F_AREA | F_BILINEAR | F_FAST_BILINEAR | F_BICUBIC | F_X | F_GAUSS | F_LANCZOS | F_SINC | F_SPLINE | F_BICUBLIN);
+    if (!algo) flags |= (dw < sw && dh < sh) ? F_GAUSS : (dw > sw && dh > sh) ? F_SINC : F_LANCZOS;
+    else if (algo & (algo - 1)) return -1;
+    if (sw < 4 || sh < 1 || dw < 8 || dh < 1 || (flags & F_FULL_CHR_H_INT)) return -1;
+    c->srcW = sw; c->srcH = sh; c->dstW = dw; c->dstH = dh; c->flags = flags; c->rgb = rgb;
+    c->chrSrcW = (sw + 1) >> 1; c->chrSrcH = (sh + 1) >> 1;
+    c->chrDstW = (dw + 1) >> 1; c->chrDstH = rgb ? dh : (dh + 1) >> 1;
+    int lx = (int)((((int64_t)sw << 16) + (dw >> 1)) / dw), ly = (int)((((int64_t)sh << 16) + (dh >> 1)) / dh);
+    int cx = (int)((((int64_t)c->chrSrcW << 16) + (c->chrDstW >> 1)) / c->chrDstW);
+    int cyi = (int)((((int64_t)c->chrSrcH << 16) + (c->chrDstH >> 1)) / c->chrDstH);
+    c->lumXInc = lx; c->chrXInc = cx;
+    int lf = (flags & F_BICUBLIN) ? (flags | F_BICUBIC) : flags, cf = (flags & F_BICUBLIN) ? (flags | F_BILINEAR) : flags;
+    if (make_bank(&c->hl, lx, sw, dw, 1 << 14, lf, 1) || make_bank(&c->hc, cx, c->chrSrcW, c->chrDstW, 1 << 14, cf, 1) ||
+        make_bank(&c->vl, ly, sh, dh, 1 << 12, lf, 0) || make_bank(&c->vc, cyi, c->chrSrcH, c->chrDstH, 1 << 12, cf, 0)) {
+        sws_close(c);
+        return -1;
+    }
+    return 0;
+}
+
+int orc_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,
+                       int32_t *pos, int cap, int *n_out)
+{
+    sws_t c;
+    if (sws_open(&c, sw, sh, dw, dh, to_rgb, flags)) return -1;
+    bank_t *b = which == 0 ? &c.hl : which == 1 ? &c.hc : which == 2 ? &c.vl : &c.vc;
+    int taps = b->taps;
+    *n_out = b->n;
+    if (b->n > cap || b->n * taps > cap) taps = -2;
+    else { memcpy(filter, b->coef, sizeof(int16_t) * b->n * taps); memcpy(pos, b->pos, sizeof(int32_t) * b->n); }
+    sws_close(&c);
+    return taps;
+}
+
+/* yuv2rgb.c:633-658, :671-863 with inv_table = ITU601, limited range, neutral brightness/contrast/saturation */
+void orc_sws_rgb24_tables(uint8_t *ytab, int32_t *rv, int32_t *gu, int32_t *gv, int32_t *bu)
+{
+    const int yoffs = 326;
+    int64_t crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279;
+    int64_t cy = ((1LL << 16) * 255) / 219, oy = 16 << 16, yb;
+    cy = (cy * 65536) >> 16;
+    crv = (crv * 65536 * 65536) >> 32; cbu = (cbu * 65536 * 65536) >> 32;
+    cgu = (cgu * 65536 * 65536) >> 32; cgv = (cgv * 65536 * 65536) >> 32;
+    crv = ((crv << 16) + 0x8000) / cy; cbu = ((cbu << 16) + 0x8000) / cy;
+    cgu = ((cgu * 65536) + 0x8000) / cy; cgv = ((cgv * 65536) + 0x8000) / cy;
+    yb = -(384 << 16) - oy;
+    for (int i = 0; i < 1024; i++) {
+        int64_t v = (yb + 0x8000) >> 16;
+        ytab[i] = v < 0 ? 0 : v > 255 ? 255 : (uint8_t)v;
+        yb += cy;
+    }
+    int64_t a = 0, b = 0, c = 0, d = 0;
+    for (int i = 0; i < 256; i++) {
+        rv[i] = yoffs - (int)(crv >> 9) + (int)(a >> 16);
+        gu[i] = yoffs - (int)(cgu >> 9) + (int)(b >> 16);
+        bu[i] = yoffs - (int)(cbu >> 9) + (int)(c >> 16);
+        gv[i] = -(int)(cgv >> 9) + (int)(d >> 16);
+        a += crv; b += cgu; c += cbu; d += cgv;
+    }
+}
+
+static uint8_t u8clip(int v) { return v < 0 ? 0 : v > 255 ? 255 : (uint8_t)v; }
+
+/* hyscale_fast_c / hcscale_fast_c (swscale.c:238-250, :286-299), used instead of the filter bank when
+ * SWS_FAST_BILINEAR is set.  The reference reads src[xx + 1] even for the last source pixel, i.e. one byte
+ * past the row; here that byte is defined as a copy of the last pixel (tests pad their rows the same way). */
+static int16_t *hfast(const uint8_t *src, int stride, int rows, int sw, int dw, int xinc, int chroma, int *pitch)
+{
+    int p = dw + 2;
+    int16_t *out = calloc((size_t)p * rows, sizeof(*out));
+    for (int y = 0; y < rows; y++) {
+        const uint8_t *s = src + (size_t)y * stride;
+        unsigned xpos = 0;
+        for (int i = 0; i < dw; i++) {
+            unsigned xx = xpos >> 16, xa = (xpos & 0xFFFF) >> 9;
+            int a = s[xx], b = s[xx + 1 < (unsigned)sw ? xx + 1 : (unsigned)sw - 1];
+            out[(size_t)y * p + i] = (int16_t)(chroma ? a * (int)(xa ^ 127) + b * (int)xa : (a << 7) + (b - a) * (int)xa);
+            xpos += xinc;
+        }
+    }
+    *pitch = p;
+    return out;
+}
+
+/* hScale8To15_c over a whole plane into (rows x (n + 2)) int16, trailing columns zero like the zeroed line buffers */
+static int16_t *hpass(const uint8_t *src, int stride, int rows, const bank_t *b, int *pitch)
+{
+    int p = b->n + 2;
+    int16_t *out = calloc((size_t)p * rows, sizeof(*out));
+    for (int y = 0; y < rows; y++)
+        for (int i = 0; i < b->n; i++) {
+            int v = 0;
+            for (int j = 0; j < b->taps; j++) v += src[(size_t)y * stride + b->pos[i] + j] * b->coef[(size_t)i * b->taps + j];
+            v >>= 7;
+            out[(size_t)y * p + i] = (int16_t)(v > 32767 ? 32767 : v);
+        }
+    *pitch = p;
+    return out;
+}
+
+static int rowsel(int first, int j, int h) { int r = first + j; return r < 0 ? 0 : r > h - 1 ? h - 1 : r; }
+
+int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst, int dstride,
+                             int dw, int dh, int flags)
+{
+    sws_t c;
+    if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
+    uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
+    orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
+    int lp, cp;
+    const int fast = c.flags & F_FAST_BILINEAR;
+    int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
+    int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
+    int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    const int fl = c.vl.taps, fc = c.vc.taps;
+    for (int y = 0; y < dh; y++) {
+        int firstL = c.vl.pos[y] > 1 - fl ? c.vl.pos[y] : 1 - fl;
+        int firstC = c.vc.pos[y] > 1 - fc ? c.vc.pos[y] : 1 - fc;
+        const int16_t *lf = c.vl.coef + (size_t)y * fl, *cf = c.vc.coef + (size_t)y * fc;
+        uint8_t *d = dst + (size_t)y * dstride;
+        for (int i = 0; i < (dw + 1) >> 1; i++) {
+            int Y1, Y2, Uv, Vv, j;
+#define LUM(j, x) L[(size_t)rowsel(firstL, j, sh) * lp + (x)]
+#define CHU(j) U[(size_t)rowsel(firstC, j, c.chrSrcH) * cp + i]
+#define CHV(j) V[(size_t)rowsel(firstC, j, c.chrSrcH) * cp + i]
+            if (fl == 1 && fc <= 2) {
+                int ua = fc == 1 ? 0 : cf[1];
+                Y1 = LUM(0, 2 * i) >> 7; Y2 = LUM(0, 2 * i + 1) >> 7;
+                if (ua < 2048) { Uv = CHU(0) >> 7; Vv = CHV(0) >> 7; }
+                else { Uv = (CHU(0) + CHU(1)) >> 8; Vv = (CHV(0) + CHV(1)) >> 8; }
+                Y1 = u8clip(Y1); Y2 = u8clip(Y2); Uv = u8clip(Uv); Vv = u8clip(Vv);
+            } else if (fl == 2 && fc == 2) {
+                int ya = lf[1], ua = cf[1];
+                Y1 = (LUM(0, 2 * i) * (4096 - ya) + LUM(1, 2 * i) * ya) >> 19;
+                Y2 = (LUM(0, 2 * i + 1) * (4096 - ya) + LUM(1, 2 * i + 1) * ya) >> 19;
+                Uv = (CHU(0) * (4096 - ua) + CHU(1) * ua) >> 19;
+                Vv = (CHV(0) * (4096 - ua) + CHV(1) * ua) >> 19;
+                Y1 = u8clip(Y1); Y2 = u8clip(Y2); Uv = u8clip(Uv); Vv = u8clip(Vv);
+            } else {
+                Y1 = Y2 = Uv = Vv = 1 << 18;
+                for (j = 0; j < fl; j++) { Y1 += LUM(j, 2 * i) * lf[j]; Y2 += LUM(j, 2 * i + 1) * lf[j]; }
+                for (j = 0; j < fc; j++) { Uv += CHU(j) * cf[j]; Vv += CHV(j) * cf[j]; }
+                Y1 >>= 19; Y2 >>= 19; Uv >>= 19; Vv >>= 19;
+                if ((Y1 | Y2 | Uv | Vv) & 0x100) { Y1 = u8clip(Y1); Y2 = u8clip(Y2); Uv = u8clip(Uv); Vv = u8clip(Vv); }
+            }
+            const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
+            d[6 * i + 0] = r[Y1]; d[6 * i + 1] = g[Y1]; d[6 * i + 2] = b[Y1];
+            if (2 * i + 1 < dw || dstride >= 3 * (dw + 1)) { d[6 * i + 3] = r[Y2]; d[6 * i + 4] = g[Y2]; d[6 * i + 5] = b[Y2]; }
+        }
+    }
+    free(L); free(U); free(V);
+    sws_close(&c);
+    return dh;
+}
+
+static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t *dst, int dstride, int w, int h)
+{
+    for (int y = 0; y < h; y++) {
+        int fs = b->taps, first = b->pos[y] > 1 - fs ? b->pos[y] : 1 - fs;
+        for (int i = 0; i < w; i++) {
+            int v;
+            if (fs == 1) v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + 64) >> 7;
+            else {
+                v = 64 << 12;
+                for (int j = 0; j < fs; j++) v += s[(size_t)rowsel(first, j, sh) * pitch + i] * b->coef[(size_t)y * fs + j];
+                v >>= 19;
+            }
+            dst[(size_t)y * dstride + i] = u8clip(v);
+        }
+    }
+}
+
+int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *const dst[3],
+                               const int ds[3], int dw, int dh, int flags)
+{
+    sws_t c;
+    if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
+    if (sw == dw && sh == dh) {       /* unscaled same-format special converter: plain plane copy
+                                         (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper) */
+        for (int p = 0; p < 3; p++) {
+            int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
+            for (int y = 0; y < h; y++) memcpy(dst[p] + (size_t)y * ds[p], src[p] + (size_t)y * ss[p], w);
+        }
+        sws_close(&c);
+        return dh;
+    }
+    int lp, cp;
+    const int fast = c.flags & F_FAST_BILINEAR;
+    int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
+    int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
+    int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    vplane(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
+    vplane(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
+    vplane(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH);
+    free(L); free(U); free(V);
+    sws_close(&c);
+    return dh;
+}

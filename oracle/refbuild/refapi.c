@@ -290,6 +290,7 @@ int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, in
     default: f = c->vChrFilter; p = c->vChrFilterPos; fs = c->vChrFilterSize; n = c->chrDstH; break;
     }
     *n_out = n;
+    if (!f || !p) { sws_freeContext(c); return -3; }   /* unscaled special converter: no filter banks exist */
     if (n > cap || n * fs > cap) { sws_freeContext(c); return -2; }
     memcpy(filter, f, sizeof(int16_t) * n * fs);
     memcpy(pos, p, sizeof(int32_t) * n);

@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 DSP/scaler hot path (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload idct_put|sws4k] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input that is already resident in HBM:
+  idct_put (default, BASELINE.json configs[1]): IDCTDSPContext.idct_put (FF_IDCT_SIMPLE) over 2^20 dense
+            int16 blocks per GPU into an 8192x8192 frame                       -> 64 output pixels per block
+  sws4k    (configs[4] shape, one GPU's share): sws_scale 3840x2160 yuv420p->rgb24, bicubic|accurate_rnd|
+            bitexact, 16 frames per launch                                     -> 8.29 Mpixel per frame
+Every rank (one per GPU, torchrun) runs the same per-GPU batch: weak scaling, no data-path collective.
+`value` is device time (CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
+the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region).  The secondary workload is
+reported under "workloads".  --impl reference times the reference's CPU path (oracle/_ref, else the oracle
+port) on all host cores for the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_BLOCKS = 1 << 20
+TILES_PER_ROW = 1024            # 8192-pixel wide frame
+SWS_W, SWS_H, SWS_FRAMES = 3840, 2160, 16
+SWS_FLAGS = 4 | 0x40000 | 0x80000
+IDCT_BYTES_PER_BLOCK = 128 + 64           # algorithmic traffic: coefficients in, pixels out
+SWS_BYTES_PER_PIXEL = 1.5 + 3.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(kernel):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop:
+            self._poll()
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._stop = False
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self.nv and self._t:
+            self._poll()
+            self._stop = True
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# workloads (GPU arm).  Each returns a dict with run(step_index) launching on `stream`, pixel counts etc.
+# ----------------------------------------------------------------------------------------------------
+def make_idct_workload(torch, L, stream, rank):
+    from libav_b200 import synth
+    lib = L.lib
+    base = synth.dense_blocks(1 << 14, seed=1 + rank)
+    blocks_h = synth.tile_large(base, N_BLOCKS)
+    nbuf = 3                                               # rotate buffer sets: 3 x 192 MiB never fits the 126 MB L2
+    d_blocks = [torch.from_numpy(blocks_h).cuda() for _ in range(nbuf)]
+    stride = TILES_PER_ROW * 8
+    rows = (N_BLOCKS // TILES_PER_ROW) * 8
+    d_frame = [torch.zeros((rows, stride), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    # pinned host buffers for the end-to-end arm
+    h_blocks = torch.from_numpy(blocks_h).pin_memory()
+    h_frame = torch.zeros((rows, stride), dtype=torch.uint8).pin_memory()
+
+    def run(i):
+        k = i % nbuf
+        L.check(lib.ff_simple_idct_batch_cuda(0, d_blocks[k].data_ptr(), d_frame[k].data_ptr(), None, stride, N_BLOCKS,
+                                              TILES_PER_ROW, 0, stream), "ff_simple_idct_batch_cuda")
+
+    def run_e2e(i):
+        L.check(lib.ff_simple_idct_batch_host_cuda(0, h_blocks.data_ptr(), h_frame.data_ptr(), h_frame.numel(), None, stride,
+                                                   N_BLOCKS, TILES_PER_ROW), "ff_simple_idct_batch_host_cuda")
+        return int(h_frame[0, 0])                          # the step's result is read on the host
+
+    return {
+        "name": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
+        "run": run, "run_e2e": run_e2e, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * IDCT_BYTES_PER_BLOCK,
+        "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false>", "dtype": "int32 (int16 in, u8 out)",
+        "h2d": N_BLOCKS * 128, "d2h": rows * stride,
+        "l2": "3 rotating 192 MiB buffer sets (inputs larger than the 126 MB L2)",
+        "keep": (d_blocks, d_frame, h_blocks, h_frame),
+    }
+
+
+def make_sws_workload(torch, L, stream, rank):
+    from libav_b200 import synth, device
+    w, h, K = SWS_W, SWS_H, SWS_FRAMES
+    ysz, csz, osz = w * h, (w // 2) * (h // 2), w * h * 3
+    frames = [synth.yuv420p_frame(w, h, 1 + rank * 64 + k) for k in range(2)]
+    y = np.concatenate([frames[k % 2][0].reshape(-1) for k in range(K)])
+    u = np.concatenate([frames[k % 2][1].reshape(-1) for k in range(K)])
+    v = np.concatenate([frames[k % 2][2].reshape(-1) for k in range(K)])
+    nbuf = 2
+    d_y = [torch.from_numpy(y).cuda() for _ in range(nbuf)]
+    d_u = [torch.from_numpy(u).cuda() for _ in range(nbuf)]
+    d_v = [torch.from_numpy(v).cuda() for _ in range(nbuf)]
+    d_o = [torch.empty(osz * K, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, SWS_FLAGS)
+    assert ctx.fused
+    # end-to-end arm: one frame per call through the host-pointer sws_scale_cuda (the reference's own call shape)
+    hy, hu, hv = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in frames[0]]
+    ho = torch.empty((h, w * 3), dtype=torch.uint8).pin_memory()
+    src = (C.c_void_p * 4)(hy.data_ptr(), hu.data_ptr(), hv.data_ptr(), None)
+    sst = (C.c_int * 4)(w, w // 2, w // 2, 0)
+    dst = (C.c_void_p * 4)(ho.data_ptr(), None, None, None)
+    dstr = (C.c_int * 4)(w * 3, 0, 0, 0)
+
+    def run(i):
+        k = i % nbuf
+        ctx.scale_device([d_y[k].data_ptr(), d_u[k].data_ptr(), d_v[k].data_ptr()], [w, w // 2, w // 2], [d_o[k].data_ptr()],
+                         [w * 3], nframes=K, src_frame=[ysz, csz, csz], dst_frame=[osz], stream=stream)
+
+    def run_e2e(i):
+        for _ in range(K):
+            if L.lib.sws_scale_cuda(ctx.ctx, src, sst, 0, h, dst, dstr) != h:
+                L.check(-1, "sws_scale_cuda")
+        return int(ho[0, 0])
+
+    return {
+        "name": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % K,
+        "run": run, "run_e2e": run_e2e, "pixels": w * h * K, "alg_bytes": int(w * h * K * SWS_BYTES_PER_PIXEL),
+        "launches_per_step": 1, "kernel": "sws_fused_rgb24_kernel<true>", "dtype": "int32 (u8 in, u8 out)",
+        "h2d": int(w * h * 1.5) * K, "d2h": osz * K,
+        "l2": "2 rotating %d MiB buffer sets (inputs+outputs larger than the 126 MB L2)" % ((ysz + 2 * csz + osz) * K >> 20),
+        "keep": (d_y, d_u, d_v, d_o, ctx, hy, hu, hv, ho),
+    }
+
+
+def time_gpu(torch, dist, wl, steps, warmup, world, sampler=None):
+    for i in range(warmup):
+        wl["run"](i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    e0.record()
+    for i in range(steps):
+        wl["run"](warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def time_e2e(torch, dist, wl, steps, warmup, world):
+    for i in range(min(warmup, 2)):
+        wl["run_e2e"](i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        wl["run_e2e"](i)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------------
+def cpu_oracle():
+    from oracle import loader
+    r = loader.ref()
+    if r is not None:
+        return r, "reference"
+    return loader.port(), "port"
+
+
+def cpu_idct(nthreads, seconds=3.0, reps=None):
+    """reference C ff_simple_idct_put_8 over the full 2^20-block workload, all host threads; median of reps."""
+    from libav_b200 import synth
+    from oracle.loader import ptr
+    o, kind = cpu_oracle()
+    base = synth.tile_large(synth.dense_blocks(1 << 14, seed=1), N_BLOCKS)
+    stride = TILES_PER_ROW * 8
+    frame = np.zeros((N_BLOCKS // TILES_PER_ROW * 8, stride), dtype=np.uint8)
+    i = np.arange(N_BLOCKS, dtype=np.uint64)
+    off = ((i // TILES_PER_ROW) * 8 * stride + (i % TILES_PER_ROW) * 8).astype(np.uint32)
+    times = []
+    t_all = time.perf_counter()
+    while (len(times) < reps) if reps else (time.perf_counter() - t_all < seconds or len(times) < 3):
+        b = base.copy()                                   # the reference clobbers its input block
+        t0 = time.perf_counter()
+        o.idct_batch(0, ptr(b), ptr(frame), ptr(off), stride, N_BLOCKS, nthreads)
+        times.append(time.perf_counter() - t0)
+    return {"sec_per_step": float(np.median(times)), "kind": kind, "cores": nthreads, "reps": len(times),
+            "sample": "full step: 2^20 dense blocks, %d pthreads, median of %d passes" % (nthreads, len(times)),
+            "pixels": N_BLOCKS * 64}
+
+
+def cpu_sws(nthreads, seconds=3.0, reps=None, frames_per_thread=1):
+    """reference sws_scale 4K yuv420p->rgb24 on all host threads (one context per thread, one frame each)."""
+    from libav_b200 import synth
+    from oracle.loader import ptr
+    o, kind = cpu_oracle()
+    w, h = SWS_W, SWS_H
+    yuv = synth.yuv420p_frame(w, h, 1)
+    src = (C.c_void_p * 3)(*[a.ctypes.data for a in yuv])
+    sst = (C.c_int * 3)(w, w // 2, w // 2)
+    outs = [np.zeros((h, w * 3), np.uint8) for _ in range(nthreads)]
+
+    def work(t):
+        for _ in range(frames_per_thread):
+            o.sws_yuv420p_to_rgb24(src, sst, w, h, ptr(outs[t]), w * 3, w, h, SWS_FLAGS)
+
+    times = []
+    t_all = time.perf_counter()
+    while (len(times) < reps) if reps else (time.perf_counter() - t_all < seconds or len(times) < 2):
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        times.append(time.perf_counter() - t0)
+    sec = float(np.median(times))
+    return {"sec_per_step": sec, "kind": kind, "cores": nthreads, "reps": len(times),
+            "sample": "%d concurrent 4K frames (one SwsContext per thread, context set-up included), median of %d rounds"
+                      % (nthreads * frames_per_thread, len(times)),
+            "pixels": w * h * nthreads * frames_per_thread}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    hbm_peak, peak_src = peaks()
+    ncores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(steps, 20)
+        fn = cpu_idct if args.workload == "idct_put" else cpu_sws
+        fn(ncores, reps=1)                                    # warm-up pass (page in, spin up threads)
+        r = fn(ncores, reps=steps)
+        mpix = r["pixels"] / r["sec_per_step"] / 1e6
+        name = ("batched simple_idct_put 8x8, 2^20 dense int16 blocks -> 8192x8192 u8 frame" if args.workload == "idct_put"
+                else "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact")
+        print(json.dumps({
+            "impl": "reference", "metric": "Mpixels/s", "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": {"workload": name, "host_threads": ncores},
+            "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import libav_b200._lib as L
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    L.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload}
+    order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
+    results = {}
+    for idx, wname in enumerate(order):
+        wl = makers[wname](torch, L, stream, rank)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ms = time_gpu(torch, dist, wl, steps, warmup, world, sampler)
+        e2e_steps = max(1, min(steps, 5))
+        e2e_sec = time_e2e(torch, dist, wl, e2e_steps, warmup, world)
+        ms_step = ms / steps
+        mpix = wl["pixels"] * world / (ms_step * 1e-3) / 1e6
+        gbs = wl["alg_bytes"] / (ms_step * 1e-3) / 1e9
+        results[wname] = {
+            "workload": wl["name"], "value": mpix, "ms_per_step": ms_step,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "traffic": traffic_for(wl["kernel"]), "kernel": wl["kernel"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": wl["alg_bytes"]},
+            "e2e": {"value": wl["pixels"] * world / (e2e_sec / e2e_steps) / 1e6, "unit": "Mpixels/s",
+                    "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps},
+            "gpu_launches": wl["launches_per_step"] * steps * world,
+            "clocks": sampler.summary() if sampler else None, "dtype": wl["dtype"], "l2": wl["l2"],
+        }
+        del wl
+        torch.cuda.empty_cache()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        r = cpu_idct(ncores) if args.workload == "idct_put" else cpu_sws(ncores)
+        cpu = {"value": r["pixels"] / r["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        m = results[args.workload]
+        line = {
+            "metric": "Mpixels/s", "value": m["value"], "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": m["dtype"], "data": "synthetic",
+            "config": {"workload": m["workload"], "per_gpu_batch": "identical on every rank (weak scaling, no collective on the data path)",
+                       "l2": m["l2"], "idct_algo": "FF_IDCT_SIMPLE", "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
+            "roofline": m["roofline"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+            "cpu_baseline": cpu,
+            "workloads": {k: {kk: vv for kk, vv in v.items()} for k, v in results.items() if k != args.workload},
+        }
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

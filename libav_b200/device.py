@@ -88,3 +88,67 @@ def idct_put_tiles(blocks, tiles_per_row, mode=0, frame=None, use_offsets=False,
     if clear:
         return out, d_blocks.download(np.int16, (n, 64))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# libswscale boundary
+# ---------------------------------------------------------------------------------------------------
+PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24 = 0, 2, 3
+SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
+SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400
+SWS_ACCURATE_RND, SWS_BITEXACT = 0x40000, 0x80000
+
+
+class SwsContext:
+    """sws_getContext_cuda / sws_scale_cuda / sws_freeContext_cuda with numpy planes (HOST pointers), plus the
+    device-pointer batch call."""
+
+    def __init__(self, src_w, src_h, dst_w, dst_h, dst_fmt=PIX_FMT_RGB24, flags=SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT):
+        self.src_w, self.src_h, self.dst_w, self.dst_h, self.dst_fmt = src_w, src_h, dst_w, dst_h, dst_fmt
+        self.ctx = lib.sws_getContext_cuda(src_w, src_h, PIX_FMT_YUV420P, dst_w, dst_h, dst_fmt, flags, None, None, None)
+        if not self.ctx:
+            L.check(-1, "sws_getContext_cuda")
+
+    @property
+    def fused(self):
+        return bool(lib.sws_is_fused_cuda(self.ctx))
+
+    def scale(self, yuv, dst_pad=0):
+        """Host-pointer drop-in call: (Y, U, V) uint8 arrays (any row stride) -> rgb (h, 3w [+pad]) or 3 planes."""
+        src = (C.c_void_p * 4)(*[a.ctypes.data for a in yuv], None)
+        sst = (C.c_int * 4)(*[a.strides[0] for a in yuv], 0)
+        if self.dst_fmt == PIX_FMT_YUV420P:
+            out = [np.zeros((self.dst_h, self.dst_w), np.uint8),
+                   np.zeros(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), np.uint8),
+                   np.zeros(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), np.uint8)]
+        else:
+            out = [np.zeros((self.dst_h, self.dst_w * 3 + dst_pad), np.uint8)]
+        dst = (C.c_void_p * 4)(*([a.ctypes.data for a in out] + [None] * (4 - len(out))))
+        dstr = (C.c_int * 4)(*([a.strides[0] for a in out] + [0] * (4 - len(out))))
+        r = lib.sws_scale_cuda(self.ctx, src, sst, 0, self.src_h, dst, dstr)
+        if r != self.dst_h:
+            L.check(-1, "sws_scale_cuda")
+        return out[0] if len(out) == 1 else out
+
+    def scale_device(self, d_src, src_strides, d_dst, dst_strides, nframes=1, src_frame=None, dst_frame=None, stream=None):
+        src = (C.c_void_p * 3)(*d_src)
+        sst = (C.c_int * 3)(*src_strides)
+        dst = (C.c_void_p * 3)(*(list(d_dst) + [None] * (3 - len(d_dst))))
+        dstr = (C.c_int * 3)(*(list(dst_strides) + [0] * (3 - len(dst_strides))))
+        sf = (C.c_size_t * 3)(*src_frame) if src_frame else None
+        df = (C.c_size_t * 3)(*(list(dst_frame) + [0] * (3 - len(dst_frame)))) if dst_frame else None
+        r = lib.sws_scale_frames_cuda(self.ctx, src, sst, sf, dst, dstr, df, nframes, stream)
+        if r < 0:
+            L.check(-1, "sws_scale_frames_cuda")
+        return r
+
+    def close(self):
+        if self.ctx:
+            lib.sws_freeContext_cuda(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,84 @@
+"""ctypes mirrors of the reference's DSP function-pointer tables (include/avdsp_b200_tables.h), so the harness
+can call the slots that ff_*_init_cuda() installs exactly the way a codec calls them."""
+import ctypes as C
+
+u8p, i16p, i8p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_int8)
+pd = C.c_ssize_t
+FF_IDCT_AUTO, FF_IDCT_SIMPLE = 0, 2
+
+_clamped = C.CFUNCTYPE(None, i16p, u8p, pd)
+_idct = C.CFUNCTYPE(None, i16p)
+_idct_px = C.CFUNCTYPE(None, u8p, pd, i16p)
+
+
+class IDCTDSPContext(C.Structure):          # libavcodec/idctdsp.h:53-98
+    _fields_ = [("put_pixels_clamped", _clamped), ("put_signed_pixels_clamped", _clamped), ("add_pixels_clamped", _clamped),
+                ("idct", _idct), ("idct_put", _idct_px), ("idct_add", _idct_px),
+                ("idct_permutation", C.c_uint8 * 64), ("perm_type", C.c_int)]
+
+
+class FDCTDSPContext(C.Structure):          # libavcodec/fdctdsp.h:26-29
+    _fields_ = [("fdct", _idct), ("fdct248", _idct)]
+
+
+_fill = C.CFUNCTYPE(None, u8p, C.c_uint8, pd, C.c_int)
+
+
+class BlockDSPContext(C.Structure):         # libavcodec/blockdsp.h:32-37
+    _fields_ = [("clear_block", _idct), ("clear_blocks", _idct), ("fill_block_tab", _fill * 2)]
+
+
+me_cmp_func = C.CFUNCTYPE(C.c_int, C.c_void_p, u8p, u8p, pd, C.c_int)
+
+
+class MECmpContext(C.Structure):            # libavcodec/me_cmp.h:39-63
+    _fields_ = [("sum_abs_dctelem", C.CFUNCTYPE(C.c_int, i16p))] + \
+        [(n, me_cmp_func * 6) for n in ("sad", "sse", "hadamard8_diff", "dct_sad", "quant_psnr", "bit", "rd", "vsad", "vsse", "nsse",
+                                         "dct_max", "dct264_sad", "me_pre_cmp", "me_cmp", "me_sub_cmp", "mb_cmp", "ildct_cmp",
+                                         "frame_skip_cmp")] + [("pix_abs", (me_cmp_func * 4) * 2)]
+
+
+_weight = C.CFUNCTYPE(None, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+_biweight = C.CFUNCTYPE(None, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+_lf = C.CFUNCTYPE(None, u8p, C.c_int, C.c_int, C.c_int, i8p)
+_lfi = C.CFUNCTYPE(None, u8p, C.c_int, C.c_int, C.c_int)
+_hidct = C.CFUNCTYPE(None, u8p, i16p, C.c_int)
+_hidct_mb = C.CFUNCTYPE(None, u8p, C.POINTER(C.c_int), i16p, C.c_int, u8p)
+_hidct_mb8 = C.CFUNCTYPE(None, C.POINTER(u8p), C.POINTER(C.c_int), i16p, C.c_int, u8p)
+
+
+class H264DSPContext(C.Structure):          # libavcodec/h264dsp.h:41-117
+    _fields_ = [("weight_h264_pixels_tab", _weight * 4), ("biweight_h264_pixels_tab", _biweight * 4),
+                ("h264_v_loop_filter_luma", _lf), ("h264_h_loop_filter_luma", _lf), ("h264_h_loop_filter_luma_mbaff", _lf),
+                ("h264_v_loop_filter_luma_intra", _lfi), ("h264_h_loop_filter_luma_intra", _lfi), ("h264_h_loop_filter_luma_mbaff_intra", _lfi),
+                ("h264_v_loop_filter_chroma", _lf), ("h264_h_loop_filter_chroma", _lf), ("h264_h_loop_filter_chroma_mbaff", _lf),
+                ("h264_v_loop_filter_chroma_intra", _lfi), ("h264_h_loop_filter_chroma_intra", _lfi), ("h264_h_loop_filter_chroma_mbaff_intra", _lfi),
+                ("h264_loop_filter_strength", C.c_void_p),
+                ("h264_idct_add", _hidct), ("h264_idct8_add", _hidct), ("h264_idct_dc_add", _hidct), ("h264_idct8_dc_add", _hidct),
+                ("h264_idct_add16", _hidct_mb), ("h264_idct8_add4", _hidct_mb), ("h264_idct_add8", _hidct_mb8), ("h264_idct_add16intra", _hidct_mb),
+                ("h264_luma_dc_dequant_idct", C.CFUNCTYPE(None, i16p, i16p, C.c_int)),
+                ("h264_chroma_dc_dequant_idct", C.CFUNCTYPE(None, i16p, C.c_int)),
+                ("h264_add_pixels8_clear", _hidct), ("h264_add_pixels4_clear", _hidct),
+                ("startcode_find_candidate", C.CFUNCTYPE(C.c_int, u8p, C.c_int))]
+
+
+qpel_mc_func = C.CFUNCTYPE(None, u8p, u8p, pd)
+
+
+class H264QpelContext(C.Structure):         # libavcodec/h264qpel.h:27-30
+    _fields_ = [("put_h264_qpel_pixels_tab", (qpel_mc_func * 16) * 4), ("avg_h264_qpel_pixels_tab", (qpel_mc_func * 16) * 4)]
+
+
+h264_chroma_mc_func = C.CFUNCTYPE(None, u8p, u8p, pd, C.c_int, C.c_int, C.c_int)
+
+
+class H264ChromaContext(C.Structure):       # libavcodec/h264chroma.h:25-30
+    _fields_ = [("put_h264_chroma_pixels_tab", h264_chroma_mc_func * 3), ("avg_h264_chroma_pixels_tab", h264_chroma_mc_func * 3)]
+
+
+op_pixels_func = C.CFUNCTYPE(None, u8p, u8p, pd, C.c_int)
+
+
+class HpelDSPContext(C.Structure):          # libavcodec/hpeldsp.h:45-93
+    _fields_ = [("put_pixels_tab", (op_pixels_func * 4) * 4), ("avg_pixels_tab", (op_pixels_func * 4) * 4),
+                ("put_no_rnd_pixels_tab", (op_pixels_func * 4) * 4), ("avg_no_rnd_pixels_tab", op_pixels_func * 4)]

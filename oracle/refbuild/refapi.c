@@ -327,3 +327,21 @@ void ref_imdct_calc(int nbits, double scale, float *out, const float *in)
 { FFTContext s; INIT(); ff_mdct_init(&s, nbits, 1, scale); s.imdct_calc(&s, out, in); ff_mdct_end(&s); }
 void ref_mdct_calc(int nbits, double scale, float *out, const float *in)
 { FFTContext s; INIT(); ff_mdct_init(&s, nbits, 0, scale); s.mdct_calc(&s, out, in); ff_mdct_end(&s); }
+
+/* ---- ABI facts of the reference's tables (sizes and a few offsets), for tests/test_abi_cpu.py ---- */
+#include <stddef.h>
+int ref_abi_info(int32_t *out, int cap)
+{
+    int32_t v[] = {
+        sizeof(IDCTDSPContext), offsetof(IDCTDSPContext, idct), offsetof(IDCTDSPContext, idct_permutation), offsetof(IDCTDSPContext, perm_type),
+        sizeof(FDCTDSPContext), sizeof(BlockDSPContext), offsetof(BlockDSPContext, fill_block_tab),
+        sizeof(MECmpContext), offsetof(MECmpContext, sad), offsetof(MECmpContext, nsse), offsetof(MECmpContext, pix_abs),
+        sizeof(H264DSPContext), offsetof(H264DSPContext, h264_v_loop_filter_luma), offsetof(H264DSPContext, h264_idct_add),
+        offsetof(H264DSPContext, h264_idct_add16), offsetof(H264DSPContext, h264_add_pixels8_clear), offsetof(H264DSPContext, startcode_find_candidate),
+        sizeof(H264QpelContext), offsetof(H264QpelContext, avg_h264_qpel_pixels_tab),
+        sizeof(H264ChromaContext), sizeof(HpelDSPContext), offsetof(HpelDSPContext, put_no_rnd_pixels_tab), offsetof(HpelDSPContext, avg_no_rnd_pixels_tab),
+    };
+    int n = sizeof(v) / sizeof(v[0]);
+    for (int i = 0; i < n && i < cap; i++) out[i] = v[i];
+    return n;
+}

@@ -92,6 +92,74 @@ int ff_fill_blocks_batch_cuda(uint8_t *frame, const uint32_t *dst_off, const uin
 int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, size_t frame_bytes,
                                    const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row);
 
+/* ---- H.264 (8 bit, 4:2:0, frame macroblocks) ------------------------------------------------------------
+ * The reference calls these slots once per block / partition / edge from its macroblock loop
+ * (libavcodec/h264_mb_template.c:40-, h264_mb.c:204-320, h264_loopfilter.c:238-418).  The batched entry points take
+ * the same information as arrays of per-macroblock records plus the picture planes, all DEVICE memory. */
+
+/* Residual: H264DSPContext.h264_idct_add16 / _add16intra / idct8_add4 (+ h264_idct_add8 for chroma)
+ * (libavcodec/h264idct_template.c:174-214).  Record i consumes coeffs + i * coeff_stride (int16; block k of the MB at
+ * + 16 * k, luma k = 0..15, cb 16..19, cr 32..35 -- the reference's sl->mb layout) and nnzc + i * 120
+ * (non_zero_count_cache, scan8 addressing, libavcodec/h264dec.h:631-645).  Block offsets are the frame-MB defaults
+ * (libavcodec/h264_slice.c:486-493).  Consumed coefficients are zeroed exactly as the C functions zero them. */
+typedef struct FFH264ResidualMB {
+    uint32_t luma_off;     /* byte offset of the MB origin in the luma plane */
+    uint32_t chroma_off;   /* byte offset of the MB origin in the cb / cr planes */
+    uint8_t  luma_mode;    /* 0 idct_add16, 1 idct_add16intra, 2 idct8_add4, 3 no luma residual */
+    uint8_t  chroma;       /* != 0: run h264_idct_add8 on cb and cr */
+    uint8_t  pad[2];
+} FFH264ResidualMB;
+int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride,
+                                   const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
+                                   int uvlinesize, void *stream);
+
+/* Motion compensation: H264QpelContext put/avg tabs + H264ChromaContext put/avg tabs driven like mc_dir_part()
+ * (libavcodec/h264_mb.c:204-320): one record = one luma partition and its two chroma partitions.  (x, y) is the
+ * partition's luma position, (mvx, mvy) the quarter-pel vector; luma_xy = (mvx & 3) + 4 * (mvy & 3), chroma phase
+ * (mvx & 7, mvy & 7).  Reference samples outside the picture are edge-replicated by clamped addressing, which is what
+ * emulated_edge_mc (libavcodec/videodsp_template.c:27-94) / the decoder's padded edges provide. */
+typedef struct FFH264MCRecord {
+    int16_t x, y;          /* luma position of the partition */
+    int16_t mvx, mvy;      /* quarter-pel motion vector */
+    uint8_t w, h;          /* luma partition size: 16, 8 or 4 each */
+    uint8_t avg;           /* 0 put, 1 avg (second prediction direction) */
+    uint8_t ref;           /* index into refs[] */
+} FFH264MCRecord;
+typedef struct FFH264RefPlanes { const uint8_t *y, *cb, *cr; } FFH264RefPlanes;
+int ff_h264_mc_batch_cuda(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y, uint8_t *dst_cb,
+                          uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h, void *stream);
+
+/* Weighted prediction: H264DSPContext.weight_h264_pixels_tab / biweight_h264_pixels_tab
+ * (libavcodec/h264dsp_template.c:30-98) over n rectangles of one plane. */
+typedef struct FFH264WeightRecord {
+    uint32_t off;          /* byte offset of the block in the plane (dst; src uses the same offset in `src`) */
+    uint8_t  w, h;         /* width 16 / 8 / 4 / 2, height */
+    uint8_t  log2_denom, pad;
+    int16_t  weight, weight_src;   /* weight (uni) or weightd / weights (bi) */
+    int16_t  offset, pad2;
+} FFH264WeightRecord;
+int ff_h264_weight_batch_cuda(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src /* NULL = uni */,
+                              int stride, void *stream);
+
+/* Deblocking: the 12 loop-filter slots of H264DSPContext (libavcodec/h264dsp_template.c:104-328) applied in the
+ * reference's order (macroblocks in raster order; inside one: vertical edges 0..3 then horizontal edges 0..3,
+ * libavcodec/h264_loopfilter.c:397-415) to a whole picture.  One record per macroblock, raster order, carrying what
+ * filter_mb_edge{v,h,cv,ch} (h264_loopfilter.c:104-236) pass to the slots.  Macroblock rows run as a wavefront that
+ * stays two macroblocks behind the row above, so the result is bit-identical to the serial order.
+ * dir 0 = vertical edges (h264_h_loop_filter_*), dir 1 = horizontal edges (h264_v_loop_filter_*).
+ * An edge with alpha == 0 or beta == 0 is skipped (h264_loopfilter.c:112). */
+typedef struct FFH264DeblockMB {
+    uint8_t alpha[2][4], beta[2][4];
+    int8_t  tc0[2][4][4];          /* per 4-line group, < 0 = group not filtered; ignored on intra edges */
+    uint8_t intra[2];              /* bit e set: edge e uses the *_intra (bS = 4) filter */
+    uint8_t calpha[2][2][2], cbeta[2][2][2];   /* [plane cb/cr][dir][chroma edge 0/1 = luma edge 0/2] */
+    int8_t  ctc0[2][2][2][4];      /* as passed to the chroma slots (already +1), <= 0 = group not filtered */
+    uint8_t cintra[2][2];          /* [plane][dir], bit e */
+    uint8_t pad[2];
+} FFH264DeblockMB;
+int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                                 int linesize, int uvlinesize, uint32_t *progress /* mb_h uint32, scratch */, void *stream);
+
 /* ---- libswscale boundary (libswscale/swscale.h:159-207) ------------------------------------------------
  * Same argument lists as sws_getContext / sws_scale / sws_freeContext; pixel formats are the reference's
  * AVPixelFormat values (AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_RGB24 = 2, AV_PIX_FMT_BGR24 = 3), flags the

@@ -60,6 +60,10 @@ PROTOTYPES = {
     "ff_clear_blocks_batch_cuda": (i32, [vp, sz, vp]),
     "ff_fill_blocks_batch_cuda": (i32, [vp, vp, vp, pd, i32, i32, sz, vp]),
     "ff_simple_idct_batch_host_cuda": (i32, [i32, vp, vp, sz, vp, pd, sz, i32]),
+    "ff_h264_idct_add_mb_batch_cuda": (i32, [vp, sz, vp, sz, vp, vp, vp, vp, i32, i32, vp]),
+    "ff_h264_mc_batch_cuda": (i32, [vp, sz, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ff_h264_weight_batch_cuda": (i32, [vp, sz, vp, vp, i32, vp]),
+    "ff_h264_deblock_picture_cuda": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
     "sws_getContext_cuda": (vp, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "sws_freeContext_cuda": (None, [vp]),
     "sws_scale_cuda": (i32, [vp, vp, vp, i32, i32, vp, vp]),

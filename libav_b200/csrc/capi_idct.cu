@@ -53,13 +53,16 @@ int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, si
     cudaStream_t *st = S.streams();
     if (!st) return -1;
 
-    const bool banded = mode != 2 && !dst_off && tiles_per_row > 0 && stride > 0;
-    // chunk = whole tile rows when banded so each chunk owns a contiguous band of the frame
+    // Only the pixels that blocks address may change in the caller's frame.  Banded (raster-of-tiles) addressing
+    // lets each chunk own whole tile rows: its band is downloaded with a 2-D copy limited to the tile columns (and,
+    // for a ragged last tile row, to the tiles that exist).  With explicit offsets the touched set is arbitrary, so
+    // the frame is uploaded first and downloaded whole.
+    const bool banded = mode != 2 && !dst_off && tiles_per_row > 0 && stride >= (ptrdiff_t)tiles_per_row * 8;
     size_t chunk = 1 << 16;
     if (banded) { size_t rows = chunk / tiles_per_row; if (rows < 1) rows = 1; chunk = rows * tiles_per_row; }
-    if (mode == 1 && !banded) AVB_CUDA(cudaMemcpyAsync(d_frame, frame, frame_bytes, cudaMemcpyHostToDevice, st[0]), "idct_host:h2d frame");
+    if (mode != 2 && !banded) AVB_CUDA(cudaMemcpyAsync(d_frame, frame, frame_bytes, cudaMemcpyHostToDevice, st[0]), "idct_host:h2d frame");
     if (d_off) AVB_CUDA(cudaMemcpyAsync(d_off, dst_off, n * 4, cudaMemcpyHostToDevice, st[0]), "idct_host:h2d off");
-    if ((mode == 1 && !banded) || d_off) {
+    if ((mode != 2 && !banded) || d_off) {
         AVB_CUDA(cudaEventRecord(S.event(0), st[0]), "idct_host");
         for (int k = 1; k < 3; k++) AVB_CUDA(cudaStreamWaitEvent(st[k], S.event(0), 0), "idct_host");
     }
@@ -68,17 +71,17 @@ int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, si
         size_t cnt = n - lo < chunk ? n - lo : chunk;
         cudaStream_t s = st[k];
         AVB_CUDA(cudaMemcpyAsync(d_blocks + lo * 64, blocks + lo * 64, cnt * 128, cudaMemcpyHostToDevice, s), "idct_host:h2d blocks");
-        size_t band_off = 0, band_bytes = 0;
         if (banded) {
-            size_t row0 = lo / tiles_per_row, rows = (cnt + tiles_per_row - 1) / tiles_per_row;
-            band_off = row0 * 8 * (size_t)stride;
-            band_bytes = rows * 8 * (size_t)stride;
-            if (band_off + band_bytes > frame_bytes) band_bytes = frame_bytes - band_off;
-            if (mode == 1) AVB_CUDA(cudaMemcpyAsync(d_frame + band_off, frame + band_off, band_bytes, cudaMemcpyHostToDevice, s), "idct_host:h2d band");
-        }
-        if (banded) {
-            if (launch_simple_idct(mode, d_blocks + lo * 64, d_frame + band_off, nullptr, stride, cnt, tiles_per_row, 0, s)) return -1;
-            AVB_CUDA(cudaMemcpyAsync(frame + band_off, d_frame + band_off, band_bytes, cudaMemcpyDeviceToHost, s), "idct_host:d2h band");
+            const size_t row0 = lo / tiles_per_row, full = cnt / tiles_per_row, rem = cnt % tiles_per_row;
+            const size_t band_off = row0 * 8 * (size_t)stride, wfull = (size_t)tiles_per_row * 8;
+            uint8_t *hb = frame + band_off, *db = d_frame + band_off;
+            if (mode == 1) {
+                if (full) AVB_CUDA(cudaMemcpy2DAsync(db, stride, hb, stride, wfull, full * 8, cudaMemcpyHostToDevice, s), "idct_host:h2d band");
+                if (rem) AVB_CUDA(cudaMemcpy2DAsync(db + full * 8 * stride, stride, hb + full * 8 * stride, stride, rem * 8, 8, cudaMemcpyHostToDevice, s), "idct_host:h2d band");
+            }
+            if (launch_simple_idct(mode, d_blocks + lo * 64, db, nullptr, stride, cnt, tiles_per_row, 0, s)) return -1;
+            if (full) AVB_CUDA(cudaMemcpy2DAsync(hb, stride, db, stride, wfull, full * 8, cudaMemcpyDeviceToHost, s), "idct_host:d2h band");
+            if (rem) AVB_CUDA(cudaMemcpy2DAsync(hb + full * 8 * stride, stride, db + full * 8 * stride, stride, rem * 8, 8, cudaMemcpyDeviceToHost, s), "idct_host:d2h band");
         } else {
             if (launch_simple_idct(mode, d_blocks + lo * 64, d_frame, d_off ? d_off + lo : nullptr, stride, cnt, tiles_per_row, 0, s)) return -1;
             if (mode == 2) AVB_CUDA(cudaMemcpyAsync(blocks + lo * 64, d_blocks + lo * 64, cnt * 128, cudaMemcpyDeviceToHost, s), "idct_host:d2h blocks");

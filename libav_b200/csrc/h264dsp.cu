@@ -1,0 +1,259 @@
+// libav_b200/csrc/h264dsp.cu -- batched H.264 DSP for sm_100a: residual add, motion compensation, weighted
+// prediction and in-loop deblocking, driven by per-macroblock records (include/avdsp_b200.h).
+//
+//   residual   one warp per macroblock, one lane per 4x4 (or 8x8) block: 32-byte coefficient rows in, 4-byte pixel
+//              rows read-modify-written, consumed coefficients zeroed (parity also holds on the coefficient buffer).
+//   MC         one warp per partition record, lanes stride over the partition's luma + 2 x chroma samples; reference
+//              samples come through a clamped fetch (replaces emulated_edge_mc), read-only path, L1-resident window.
+//   deblock    one warp per macroblock ROW, rows run as a wavefront two macroblocks behind the row above (progress
+//              counters in global memory), so the serial raster order of the reference is reproduced exactly.
+//              A macroblock lives in shared memory while its 8 luma + 4 chroma edge passes run: lanes 0-15 own the 16
+//              luma lines of an edge, lanes 16-23 / 24-31 the 8 cb / cr lines.
+// All arithmetic is in h264dsp.cuh.
+#include "h264dsp.cuh"
+#include "../../include/avdsp_b200.h"
+
+namespace avb {
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
+                     const uint8_t *__restrict__ nnzc, uint8_t *__restrict__ luma, uint8_t *__restrict__ cb,
+                     uint8_t *__restrict__ cr, int ls, int uvls)
+{
+    const int lane = threadIdx.x & 31;
+    size_t mb = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (mb >= n) return;
+    const FFH264ResidualMB r = mbs[mb];
+    int16_t *c = coeffs + mb * coeff_stride;
+    const uint8_t *nz = nnzc + mb * 120;
+    if (lane < 16) {
+        const int i = lane;
+        uint8_t *d = luma + r.luma_off + blk_x(i) + blk_y(i) * ls;
+        int16_t *b = c + 16 * i;
+        const int nnz = nz[scan8_of(i)];
+        if (r.luma_mode == 0) {                                   // h264_idct_add16, h264idct_template.c:174-183
+            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, ls, 4); else h264_idct4_add(d, b, ls); }
+        } else if (r.luma_mode == 1) {                            // h264_idct_add16intra, :185-191
+            if (nnz) h264_idct4_add(d, b, ls); else if (b[0]) h264_dc_add(d, b, ls, 4);
+        } else if (r.luma_mode == 2 && (i & 3) == 0) {            // h264_idct8_add4, :193-202
+            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, ls, 8); else h264_idct8_add(d, b, ls); }
+        }
+    } else if (lane < 24 && r.chroma) {                           // h264_idct_add8, :204-214
+        const int plane = (lane - 16) >> 2, k = (lane - 16) & 3, i = 16 + 16 * plane + k;
+        uint8_t *d = (plane ? cr : cb) + r.chroma_off + blk_x(k) + blk_y(k) * uvls;
+        int16_t *b = c + 16 * i;
+        if (nz[scan8_of(i)]) h264_idct4_add(d, b, uvls); else if (b[0]) h264_dc_add(d, b, uvls, 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct ClampFetch {
+    const uint8_t *p; int stride, w, h;
+    __device__ __forceinline__ int operator()(int x, int y) const
+    { return __ldg(p + (size_t)min(max(y, 0), h - 1) * stride + min(max(x, 0), w - 1)); }
+};
+
+__global__ void __launch_bounds__(128)
+h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
+               uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph)
+{
+    const int lane = threadIdx.x & 31;
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFH264MCRecord r = recs[ri];
+    const FFH264RefPlanes ref = refs[r.ref];
+    const int mx = r.mvx + r.x * 4, my = r.mvy + r.y * 4;          // quarter-pel position, h264_mb.c:216-217
+    const int nl = r.w * r.h, cw = r.w >> 1, chh = r.h >> 1, nc = cw * chh;
+    const ClampFetch Y = { ref.y, ls, pw, ph }, CB = { ref.cb, uvls, pw >> 1, ph >> 1 }, CR = { ref.cr, uvls, pw >> 1, ph >> 1 };
+    for (int it = lane; it < nl + 2 * nc; it += 32) {
+        if (it < nl) {
+            int px = it % r.w, py = it / r.w;
+            int v = qpel_sample(Y, (mx >> 2) + px, (my >> 2) + py, mx & 3, my & 3);
+            uint8_t *d = dy + (size_t)(r.y + py) * ls + r.x + px;
+            *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
+        } else {
+            int k = it - nl, plane = k >= nc;
+            k -= plane * nc;
+            int px = k % cw, py = k / cw;
+            int v = chroma_sample(plane ? CR : CB, (mx >> 3) + px, (my >> 3) + py, mx & 7, my & 7);
+            uint8_t *d = (plane ? dcr : dcb) + (size_t)((r.y >> 1) + py) * uvls + (r.x >> 1) + px;
+            *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+h264_weight_kernel(const FFH264WeightRecord *__restrict__ recs, size_t n, uint8_t *__restrict__ plane,
+                   const uint8_t *__restrict__ src, int stride)
+{
+    const int lane = threadIdx.x & 31;
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFH264WeightRecord r = recs[ri];
+    const int ld = r.log2_denom;
+    int off = r.offset;
+    if (!src) { off <<= ld; if (ld) off += 1 << (ld - 1); }       // h264dsp_template.c:39-40
+    else off = ((off + 1) | 1) << ld;                             // :70-71
+    for (int it = lane; it < r.w * r.h; it += 32) {
+        size_t o = r.off + (size_t)(it / r.w) * stride + it % r.w;
+        int v = src ? (src[o] * r.weight_src + plane[o] * r.weight + off) >> (ld + 1) : (plane[o] * r.weight + off) >> ld;
+        plane[o] = (uint8_t)clip_u8(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Deblocking wavefront.
+constexpr int LT = 24;      // luma tile pitch   (20 columns used: -4 .. 15)
+constexpr int CT = 16;      // chroma tile pitch (12 columns used: -4 .. 7)
+
+__device__ __forceinline__ uint32_t ld_cg32(const uint8_t *p) { return __ldcg(reinterpret_cast<const uint32_t *>(p)); }
+
+__global__ void __launch_bounds__(32)
+h264_deblock_kernel(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                    int ls, int uvls, uint32_t *progress)
+{
+    __shared__ __align__(16) uint8_t Y[20 * LT];
+    __shared__ __align__(16) uint8_t C[2][10 * CT];
+    __shared__ FFH264DeblockMB P;
+    const int lane = threadIdx.x, row = blockIdx.x;
+    volatile uint32_t *prog = progress;
+    uint8_t *const chroma_plane[2] = { cb, cr };
+
+    for (int x = 0; x < mb_w; x++) {
+        // wait until the row above has finished macroblock x + 1 (its left edge touches MB x's right columns)
+        if (row > 0) {
+            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
+            __syncwarp();
+        }
+        // left context: the previous macroblock's last 4 columns (luma 12..15, chroma 4..7) become columns -4..-1
+        if (x > 0 && lane < 20) {
+            *reinterpret_cast<uint32_t *>(&Y[lane * LT]) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
+            const int p = lane / 10, r = lane % 10;
+            *reinterpret_cast<uint32_t *>(&C[p][r * CT]) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
+        }
+        __syncwarp();
+        // load columns 0..15 (luma) / 0..7 (chroma); rows above the picture do not exist
+        if (lane < 20) {
+            const int ry = lane - 4, gy = row * 16 + ry;
+            if (gy >= 0) {
+                const uint8_t *g = luma + (size_t)gy * ls + x * 16;
+#pragma unroll
+                for (int k = 0; k < 4; k++) *reinterpret_cast<uint32_t *>(&Y[lane * LT + 4 + 4 * k]) = ld_cg32(g + 4 * k);
+            }
+            const int p = lane / 10, r = lane % 10, cy = row * 8 + r - 2;
+            if (cy >= 0) {
+                const uint8_t *g = chroma_plane[p] + (size_t)cy * uvls + x * 8;
+                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 4]) = ld_cg32(g);
+                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 8]) = ld_cg32(g + 4);
+            }
+        }
+        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
+            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
+        __syncwarp();
+
+        // vertical edges (filter across x), then horizontal edges (filter across y): h264_loopfilter.c:397-415
+#pragma unroll 1
+        for (int dir = 0; dir < 2; dir++) {
+#pragma unroll 1
+            for (int e = 0; e < 4; e++) {
+                if (lane < 16) {
+                    const int a = P.alpha[dir][e], b = P.beta[dir][e];
+                    if (a && b) {
+                        uint8_t *q = dir == 0 ? &Y[(4 + lane) * LT + 4 + 4 * e] : &Y[(4 + 4 * e) * LT + 4 + lane];
+                        const int px = dir == 0 ? 1 : LT;
+                        if (P.intra[dir] >> e & 1) h264_luma_intra_line(q, px, a, b);
+                        else { const int tc = P.tc0[dir][e][lane >> 2]; if (tc >= 0) h264_luma_line(q, px, a, b, tc); }
+                    }
+                } else if (!(e & 1)) {
+                    const int p = (lane - 16) >> 3, l = (lane - 16) & 7, ce = e >> 1;
+                    const int a = P.calpha[p][dir][ce], b = P.cbeta[p][dir][ce];
+                    if (a && b) {
+                        uint8_t *q = dir == 0 ? &C[p][(2 + l) * CT + 4 + 4 * ce] : &C[p][(2 + 4 * ce) * CT + 4 + l];
+                        const int px = dir == 0 ? 1 : CT;
+                        const int in = P.cintra[p][dir] >> ce & 1, tc = P.ctc0[p][dir][ce][l >> 1];
+                        if (in || tc > 0) h264_chroma_line(q, px, a, b, tc, in);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // write back what is final for this row: columns -4..11 (all 20 at the end of the row), rows -3..15
+        const int last = x == mb_w - 1;
+        if (lane < 20) {
+            const int ry = lane - 4, gy = row * 16 + ry;
+            if (ry >= -3 && gy >= 0) {
+                uint8_t *g = luma + (size_t)gy * ls + x * 16;
+                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT]);
+#pragma unroll
+                for (int k = 0; k < 3; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 4 + 4 * k]);
+                if (last) *reinterpret_cast<uint32_t *>(g + 12) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
+            }
+            const int p = lane / 10, r = lane % 10, cy = row * 8 + r - 2;
+            if (cy >= 0) {
+                uint8_t *g = chroma_plane[p] + (size_t)cy * uvls + x * 8;
+                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT]);
+                *reinterpret_cast<uint32_t *>(g) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 4]);
+                if (last) *reinterpret_cast<uint32_t *>(g + 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) prog[row] = x + 1;
+    }
+}
+
+static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
+
+int launch_h264_residual(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
+                         uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, cudaStream_t st)
+{
+    if (!n) return 0;
+    if (coeff_stride < 16 * 36) { set_error_msg("h264_idct_add_mb_batch", "coeff_stride must cover blocks 0..35 (>= 576)"); return -1; }
+    h264_residual_kernel<<<warps_grid(n, 4), 128, 0, st>>>(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, ls, uvls);
+    return check_launch("h264_idct_add_mb_batch");
+}
+int launch_h264_mc(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dy, uint8_t *dcb, uint8_t *dcr,
+                   int ls, int uvls, int pw, int ph, cudaStream_t st)
+{
+    if (!n) return 0;
+    h264_mc_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph);
+    return check_launch("h264_mc_batch");
+}
+int launch_h264_weight(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, cudaStream_t st)
+{
+    if (!n) return 0;
+    h264_weight_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, plane, src, stride);
+    return check_launch("h264_weight_batch");
+}
+int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls,
+                        uint32_t *progress, cudaStream_t st)
+{
+    if (mb_w <= 0 || mb_h <= 0) return 0;
+    if ((ls & 3) || (uvls & 3) || ((uintptr_t)luma & 3) || ((uintptr_t)cb & 3) || ((uintptr_t)cr & 3)) {
+        set_error_msg("h264_deblock_picture", "planes and line sizes must be 4-byte aligned"); return -1;
+    }
+    if (mb_h > 148 * 16) { set_error_msg("h264_deblock_picture", "picture too tall for one wavefront launch"); return -1; }
+    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * mb_h, st), "h264_deblock_picture");
+    h264_deblock_kernel<<<mb_h, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
+    return check_launch("h264_deblock_picture");
+}
+
+}  // namespace avb
+
+using namespace avb;
+extern "C" {
+int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
+                                   uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
+{ return launch_h264_residual(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream); }
+int ff_h264_mc_batch_cuda(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y, uint8_t *dst_cb,
+                          uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h, void *stream)
+{ return launch_h264_mc(recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream); }
+int ff_h264_weight_batch_cuda(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, void *stream)
+{ return launch_h264_weight(recs, n, plane, src, stride, (cudaStream_t)stream); }
+int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                                 int linesize, int uvlinesize, uint32_t *progress, void *stream)
+{ return launch_h264_deblock(mbs, mb_w, mb_h, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
+}

@@ -181,3 +181,116 @@ def _crc_table():
             t.append(c)
         _CRC_TAB = np.array(t, dtype=np.uint32)
     return _CRC_TAB
+
+
+# ---------------------------------------------------------------------------------------------------
+# H.264 synthetic macroblock work (SURVEY 8d config 3 shape): numpy structured arrays that match the record
+# structs of include/avdsp_b200.h byte for byte.
+# ---------------------------------------------------------------------------------------------------
+RESIDUAL_DT = np.dtype([("luma_off", "<u4"), ("chroma_off", "<u4"), ("luma_mode", "u1"), ("chroma", "u1"), ("pad", "u1", (2,))])
+MC_DT = np.dtype([("x", "<i2"), ("y", "<i2"), ("mvx", "<i2"), ("mvy", "<i2"), ("w", "u1"), ("h", "u1"), ("avg", "u1"), ("ref", "u1")])
+WEIGHT_DT = np.dtype([("off", "<u4"), ("w", "u1"), ("h", "u1"), ("log2_denom", "u1"), ("pad", "u1"), ("weight", "<i2"),
+                      ("weight_src", "<i2"), ("offset", "<i2"), ("pad2", "<i2")])
+DEBLOCK_DT = np.dtype([("alpha", "u1", (2, 4)), ("beta", "u1", (2, 4)), ("tc0", "i1", (2, 4, 4)), ("intra", "u1", (2,)),
+                       ("calpha", "u1", (2, 2, 2)), ("cbeta", "u1", (2, 2, 2)), ("ctc0", "i1", (2, 2, 2, 4)),
+                       ("cintra", "u1", (2, 2)), ("pad", "u1", (2,))])
+assert RESIDUAL_DT.itemsize == 12 and MC_DT.itemsize == 12 and WEIGHT_DT.itemsize == 16 and DEBLOCK_DT.itemsize == 104
+
+
+def scan8(i):
+    """libavcodec/h264dec.h:631-645"""
+    plane, k = i >> 4, i & 15
+    return 4 + (k & 1) + 2 * ((k >> 2) & 1) + 8 * (1 + ((k >> 1) & 1) + 2 * (k >> 3) + 5 * plane)
+
+
+def h264_picture(mb_w, mb_h, seed=1):
+    """Random 4:2:0 picture planes (tight strides, 16*mb_w x 16*mb_h)."""
+    w, h = 16 * mb_w, 16 * mb_h
+    r = lfg(seed, w * h * 3 // 2)
+    y = (r[:w * h] & 0xFF).astype(np.uint8).reshape(h, w)
+    cb = (r[w * h:w * h + w * h // 4] & 0xFF).astype(np.uint8).reshape(h // 2, w // 2)
+    cr = (r[w * h + w * h // 4:] & 0xFF).astype(np.uint8).reshape(h // 2, w // 2)
+    return y, cb, cr
+
+
+def h264_residual_work(mb_w, mb_h, seed=2, p_coded=0.5, modes=(0, 1, 2)):
+    """Per-MB residual records, the reference-layout coefficient buffer (n, 768) int16 and nnzc (n, 120) u8."""
+    rng = np.random.default_rng(seed)
+    n = mb_w * mb_h
+    rec = np.zeros(n, dtype=RESIDUAL_DT)
+    mbx, mby = np.arange(n) % mb_w, np.arange(n) // mb_w
+    rec["luma_off"] = mby * 16 * (16 * mb_w) + mbx * 16
+    rec["chroma_off"] = mby * 8 * (8 * mb_w) + mbx * 8
+    rec["luma_mode"] = rng.choice(np.array(modes, dtype=np.uint8), size=n)
+    rec["chroma"] = rng.integers(0, 2, size=n)
+    coeffs = np.zeros((n, 768), dtype=np.int16)
+    nnzc = np.zeros((n, 120), dtype=np.uint8)
+    for m in range(n):
+        mode = int(rec["luma_mode"][m])
+        blocks = list(range(0, 16, 4)) if mode == 2 else list(range(16))
+        size = 64 if mode == 2 else 16
+        for i in blocks + [16, 17, 18, 19, 32, 33, 34, 35]:
+            sz = size if i < 16 else 16
+            kind = rng.integers(0, 4) if rng.random() < p_coded * 1.5 else 0      # 0 none, 1 dc only (nnz 0), 2 dc (nnz 1), 3 full
+            if kind == 0:
+                continue
+            if kind in (1, 2):
+                coeffs[m, 16 * i] = rng.integers(-2000, 2000)
+                nnzc[m, scan8(i)] = 0 if kind == 1 else 1
+            else:
+                coeffs[m, 16 * i:16 * i + sz] = rng.integers(-300, 300, size=sz)
+                nnzc[m, scan8(i)] = rng.integers(2, 17)
+    return rec, coeffs, nnzc
+
+
+def h264_mc_work(mb_w, mb_h, seed=3, max_mv=64, nrefs=2, avg_second=True):
+    """One record per 8x8 / 16x8 / 8x16 / 16x16 / 4x4 partition, covering every MB exactly once with `put`, plus an
+    `avg` second direction on some partitions.  Vectors may leave the picture (edge replication is exercised)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for mby in range(mb_h):
+        for mbx in range(mb_w):
+            shape = rng.integers(0, 5)
+            parts = {0: [(0, 0, 16, 16)], 1: [(0, 0, 16, 8), (0, 8, 16, 8)], 2: [(0, 0, 8, 16), (8, 0, 8, 16)],
+                     3: [(x, y, 8, 8) for y in (0, 8) for x in (0, 8)],
+                     4: [(x, y, 4, 4) for y in range(0, 16, 4) for x in range(0, 16, 4)]}[int(shape)]
+            for (px, py, w, h) in parts:
+                mv = rng.integers(-max_mv, max_mv + 1, size=2)
+                out.append((16 * mbx + px, 16 * mby + py, mv[0], mv[1], w, h, 0, rng.integers(0, nrefs)))
+                if avg_second and rng.random() < 0.3:
+                    mv = rng.integers(-max_mv, max_mv + 1, size=2)
+                    out.append((16 * mbx + px, 16 * mby + py, mv[0], mv[1], w, h, 1, rng.integers(0, nrefs)))
+    rec = np.zeros(len(out), dtype=MC_DT)
+    for k, name in enumerate(("x", "y", "mvx", "mvy", "w", "h", "avg", "ref")):
+        rec[name] = [o[k] for o in out]
+    return rec
+
+
+def h264_deblock_work(mb_w, mb_h, seed=4, slices=1):
+    """Random per-edge parameters in the ranges of the reference's alpha/beta/tc0 tables
+    (libavcodec/h264_loopfilter.c:40-101).  Picture-boundary edges (and slice-boundary edges when slices > 1,
+    disable_deblocking_filter_idc = 2) carry alpha = 0."""
+    rng = np.random.default_rng(seed)
+    n = mb_w * mb_h
+    rec = np.zeros(n, dtype=DEBLOCK_DT)
+    rec["alpha"] = rng.integers(0, 120, size=(n, 2, 4))
+    rec["beta"] = rng.integers(0, 19, size=(n, 2, 4))
+    rec["tc0"] = rng.integers(-1, 10, size=(n, 2, 4, 4))
+    rec["intra"] = rng.integers(0, 2, size=(n, 2))                   # only edge 0 may be intra
+    rec["calpha"] = rng.integers(0, 120, size=(n, 2, 2, 2))
+    rec["cbeta"] = rng.integers(0, 19, size=(n, 2, 2, 2))
+    rec["ctc0"] = rng.integers(0, 11, size=(n, 2, 2, 2, 4))
+    rec["cintra"] = rng.integers(0, 2, size=(n, 2, 2))
+    per = -(-n // slices)
+    for m in range(n):
+        mbx, mby = m % mb_w, m // mb_w
+        first_in_slice = (m % per) == 0
+        left_other = mbx == 0 or (slices > 1 and first_in_slice)
+        top_other = mby == 0 or (slices > 1 and (m - mb_w) // per != m // per)
+        if left_other:
+            rec["alpha"][m, 0, 0] = 0
+            rec["calpha"][m, :, 0, 0] = 0
+        if top_other:
+            rec["alpha"][m, 1, 0] = 0
+            rec["calpha"][m, :, 1, 0] = 0
+    return rec

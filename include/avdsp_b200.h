@@ -117,7 +117,9 @@ int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_
  * (libavcodec/h264_mb.c:204-320): one record = one luma partition and its two chroma partitions.  (x, y) is the
  * partition's luma position, (mvx, mvy) the quarter-pel vector; luma_xy = (mvx & 3) + 4 * (mvy & 3), chroma phase
  * (mvx & 7, mvy & 7).  Reference samples outside the picture are edge-replicated by clamped addressing, which is what
- * emulated_edge_mc (libavcodec/videodsp_template.c:27-94) / the decoder's padded edges provide. */
+ * emulated_edge_mc (libavcodec/videodsp_template.c:27-94) / the decoder's padded edges provide.
+ * All `put` records run before all `avg` records (list 0 then list 1, h264_mb.c:322-366); records of the same kind
+ * must address disjoint destination pixels. */
 typedef struct FFH264MCRecord {
     int16_t x, y;          /* luma position of the partition */
     int16_t mvx, mvy;      /* quarter-pel motion vector */
@@ -159,6 +161,35 @@ typedef struct FFH264DeblockMB {
 } FFH264DeblockMB;
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress /* mb_h uint32, scratch */, void *stream);
+
+/* ---- MECmpContext, motion search, HpelDSPContext, FDCTDSPContext -----------------------------------------
+ * me_cmp: n block pairs (cur + cur_off vs ref + ref_off, common stride, height h) through one metric; out[i] is
+ * what the C slot returns.  kind / sidx / dxy select the slot like the reference's tables (libavcodec/me_cmp.h:39-63):
+ *   kind 0 pix_abs[sidx][dxy] (sidx 0 = 16 wide, 1 = 8 wide; dxy = x2 + 2*y2 half-pel flag)   me_cmp.c:109-307
+ *        1 sad[sidx]   2 sse[sidx] (sidx 2 = 4 wide)   3 hadamard8_diff[sidx]   4 vsad[0]   5 vsse[0]
+ *        6 nsse[sidx] (weight 8: the NULL-context default, me_cmp.c:331)   7 hadamard8_diff[4 + sidx] (intra)
+ *        8 vsad[4 + sidx] (intra)   9 vsse[4 + sidx] (intra)   10 sum_abs_dctelem (cur_off in bytes into int16 blocks)
+ * The encoder-state metrics (dct_sad, quant_psnr, bit, rd, dct_max, dct264_sad: me_cmp.c:538-782) need a live
+ * MpegEncContext and are not taken over. */
+typedef struct FFMECmpRecord { uint32_t cur_off, ref_off; } FFMECmpRecord;
+int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
+                         const FFMECmpRecord *recs, size_t n, int32_t *out, void *stream);
+
+/* Exhaustive search (libavcodec/motion_est_template.c:620-655) for every 16x16 macroblock of rows [mb_y0, mb_y1):
+ * candidates within +-range (16) clipped so the block stays inside the picture (get_limits, motion_est.c:517-548),
+ * score = pix_abs[0][0] (h = 16), penalty_factor 0, strict-< minimum in raster order (mathops.h:133-140).
+ * out[3 * (mb_y * (w / 16) + mb_x)] = { mx, my, sad }.  Sharding over GPUs = disjoint row ranges. */
+int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int w, int h, int range, int mb_y0, int mb_y1,
+                        int32_t *out, void *stream);
+
+/* HpelDSPContext (libavcodec/hpeldsp.h:45-93): tab 0 put, 1 avg, 2 put_no_rnd, 3 avg_no_rnd; sidx 0..3 = width
+ * 16 / 8 / 4 / 2; dxy = x_halfpel + 2 * y_halfpel; h rows.  dst and src share `stride` like the C slots. */
+typedef struct FFHpelRecord { uint32_t dst_off, src_off; uint8_t tab, sidx, dxy, h; } FFHpelRecord;
+int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream);
+
+/* FDCTDSPContext (libavcodec/fdctdsp.h:26-29), in place over n blocks: which 0 = ff_jpeg_fdct_islow_8, 1 =
+ * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332). */
+int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream);
 
 /* ---- libswscale boundary (libswscale/swscale.h:159-207) ------------------------------------------------
  * Same argument lists as sws_getContext / sws_scale / sws_freeContext; pixel formats are the reference's

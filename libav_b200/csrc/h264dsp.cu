@@ -56,12 +56,14 @@ struct ClampFetch {
 
 __global__ void __launch_bounds__(128)
 h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
-               uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph)
+               uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph,
+               int pass)
 {
     const int lane = threadIdx.x & 31;
     size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ri >= n) return;
     const FFH264MCRecord r = recs[ri];
+    if ((r.avg != 0) != (pass != 0)) return;          // pass 0: every `put`; pass 1: the `avg` second directions
     const FFH264RefPlanes ref = refs[r.ref];
     const int mx = r.mvx + r.x * 4, my = r.mvy + r.y * 4;          // quarter-pel position, h264_mb.c:216-217
     const int nl = r.w * r.h, cw = r.w >> 1, chh = r.h >> 1, nc = cw * chh;
@@ -219,7 +221,10 @@ int launch_h264_mc(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *
                    int ls, int uvls, int pw, int ph, cudaStream_t st)
 {
     if (!n) return 0;
-    h264_mc_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph);
+    // bi-prediction is put (list 0) then avg (list 1) on the same pixels (h264_mb.c:322-366): two ordered passes
+    // over the record array keep that order without any ordering requirement on the records themselves
+    h264_mc_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, 0);
+    h264_mc_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, 1);
     return check_launch("h264_mc_batch");
 }
 int launch_h264_weight(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, cudaStream_t st)

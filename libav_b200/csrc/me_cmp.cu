@@ -1,0 +1,327 @@
+// libav_b200/csrc/me_cmp.cu -- MECmpContext metrics, exhaustive motion search, HpelDSPContext and FDCTDSPContext
+// batches for sm_100a.  Bit-exact replacements of
+//   pix_abs / sad / sse / hadamard8_diff / hadamard8_intra / vsad / vsse / nsse / sum_abs_dctelem
+//                                                      libavcodec/me_cmp.c:29-357, :434-536, :784-885
+//   full_search + get_limits (restricted MVs, lambda 0) libavcodec/motion_est_template.c:620-655, motion_est.c:517-548
+//   put / avg / no_rnd half-pel MC                      libavcodec/hpeldsp.c:38-366
+//   jpeg_fdct_islow_8, fdct248_islow_8, fdct_ifast(248) libavcodec/jfdctint_template.c:182-398, jfdctfst.c:141-332
+// Compare metrics: one warp per (block pair) record, lanes stride over samples, warp-shuffle reduction tree;
+// the 8x8 Hadamard runs 8 lanes per block (lane = row) with the column butterflies done by __shfl_xor.
+// Full search: one CTA per macroblock, 48x48 reference window staged in shared memory, current block in
+// registers, 4-byte SAD (vabsdiff4) per word, candidates flattened in raster order so that the packed key
+// (sad << 11 | raster index) reproduces the reference's strict-< first-wins tie break.
+#include "common.cuh"
+#include "../../include/avdsp_b200.h"
+
+namespace avb {
+
+__device__ __forceinline__ int iabs_m(int v) { return v < 0 ? -v : v; }
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- 8x8 Hadamard on 8 consecutive lanes (lane & 7 = row); returns the block's sum of |coeff| in every lane ----
+__device__ __forceinline__ int hadamard8_lanes(const uint8_t *a, const uint8_t *b, ptrdiff_t st, int intra, int lane)
+{
+    const int row = lane & 7;
+    int v[8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) v[x] = intra ? a[row * st + x] : (int)b[row * st + x] - (int)a[row * st + x];
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)                    // row transform in registers
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (!(i & len)) { int p = v[i], q = v[i + len]; v[i] = p + q; v[i + len] = p - q; }
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)                    // column transform across the 8 lanes
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            int o = __shfl_xor_sync(0xffffffffu, v[x], len);
+            v[x] = (row & len) ? o - v[x] : v[x] + o;
+        }
+    int s = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) s += iabs_m(v[x]);
+    if (intra && row == 0) s -= iabs_m(v[0]);                // minus the mean (me_cmp.c:533)
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+}
+
+__global__ void __launch_bounds__(128)
+me_cmp_kernel(int kind, int sidx, int dxy, const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, ptrdiff_t st, int h,
+              const FFMECmpRecord *__restrict__ recs, size_t n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const uint8_t *a = cur + recs[ri].cur_off, *b = ref + recs[ri].ref_off;
+    const int w = sidx == 0 ? 16 : sidx == 1 ? 8 : 4;
+    int s = 0;
+    if (kind == 3 || kind == 7) {                            // hadamard8_diff / hadamard8_intra (+ 16-wide wrappers :859-874)
+        const int intra = kind == 7, nblk = sidx == 0 ? (h == 16 ? 4 : 2) : 1, blk = lane >> 3;
+        const int eb = blk < nblk ? blk : 0;                 // idle lanes recompute block 0 (they still take part in the shuffles)
+        const int bx = (eb & 1) * 8, by = (eb >> 1) * 8;
+        int v = hadamard8_lanes(a + by * st + bx, b + by * st + bx, st, intra, lane);   // all lanes participate in the shuffles
+        s = (blk < nblk && (lane & 7) == 0) ? v : 0;
+        s = warp_sum(s);
+    } else if (kind == 10) {                                 // sum_abs_dctelem
+        const int16_t *c = reinterpret_cast<const int16_t *>(a);
+        s = warp_sum(iabs_m(c[lane]) + iabs_m(c[lane + 32]));
+    } else {
+        int s2 = 0;
+        for (int it = lane; it < w * h; it += 32) {
+            const int x = it % w, y = it / w;
+            const uint8_t *p = a + y * st + x, *q = b + y * st + x;
+            switch (kind) {
+            case 0: case 1: {
+                int d = kind == 1 ? 0 : dxy;
+                int r = d == 0 ? q[0] : d == 1 ? (q[0] + q[1] + 1) >> 1 : d == 2 ? (q[0] + q[st] + 1) >> 1 : (q[0] + q[1] + q[st] + q[st + 1] + 2) >> 2;
+                s += iabs_m(p[0] - r);
+            } break;
+            case 2: { int d = p[0] - q[0]; s += d * d; } break;
+            case 4: case 5: if (y > 0) { int d = p[-st] - q[-st] - p[0] + q[0]; s += kind == 4 ? iabs_m(d) : d * d; } break;
+            case 8: case 9: if (y > 0) { int d = p[-st] - p[0]; s += kind == 8 ? iabs_m(d) : d * d; } break;
+            case 6: {
+                int d = p[0] - q[0]; s += d * d;
+                if (y + 1 < h && x + 1 < w) s2 += iabs_m(p[0] - p[st] - p[1] + p[st + 1]) - iabs_m(q[0] - q[st] - q[1] + q[st + 1]);
+            } break;
+            }
+        }
+        s = warp_sum(s);
+        if (kind == 6) s += iabs_m(warp_sum(s2)) * 8;        // nsse weight 8 = the NULL-context default (me_cmp.c:331)
+    }
+    if (lane == 0) out[ri] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int FS_R = 16, FS_WIN = 48, FS_PITCH = 52;          // search range, window edge, smem pitch (words: 13)
+
+__global__ void __launch_bounds__(256)
+full_search_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int stride, int w, int h, int mb_y0,
+                   int32_t *__restrict__ out)
+{
+    __shared__ __align__(16) uint8_t win[FS_WIN * FS_PITCH];
+    __shared__ unsigned long long best_s[8];
+    const int mbw = w >> 4, mbx = blockIdx.x, mby = mb_y0 + blockIdx.y, t = threadIdx.x;
+    const int px = mbx * 16, py = mby * 16;
+    // 48x48 window around the block, addresses clamped into the picture (clipped candidates never read the clamped part)
+    for (int i = t; i < FS_WIN * (FS_WIN / 4); i += 256) {
+        int r = i / (FS_WIN / 4), c4 = i % (FS_WIN / 4);
+        int gy = min(max(py - FS_R + r, 0), h - 1);
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int gx = min(max(px - FS_R + 4 * c4 + k, 0), w - 1);
+            v |= (uint32_t)__ldg(ref + (size_t)gy * stride + gx) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(&win[r * FS_PITCH + 4 * c4]) = v;
+    }
+    uint32_t c[16][4];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(cur + (size_t)(py + r) * stride + px);
+        c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
+    }
+    __syncthreads();
+    // get_limits(): the block must stay inside the picture (motion_est.c:537-540), then +-range
+    const int xmin = max(-px, -FS_R), xmax = min(w - 16 - px, FS_R), ymin = max(-py, -FS_R), ymax = min(h - 16 - py, FS_R);
+    unsigned long long best = ~0ull;
+    for (int idx = t; idx < 33 * 33; idx += 256) {
+        const int dy = idx / 33 - FS_R, dx = idx % 33 - FS_R;
+        if (dx < xmin || dx > xmax || dy < ymin || dy > ymax) continue;
+        const uint8_t *wp = &win[(dy + FS_R) * FS_PITCH + ((dx + FS_R) & ~3)];
+        const int sh = ((dx + FS_R) & 3) * 8;
+        unsigned sad = 0;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(wp + r * FS_PITCH);
+            uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
+            sad = __vsadu4(c[r][0], __funnelshift_r(w0, w1, sh)) + sad;
+            sad = __vsadu4(c[r][1], __funnelshift_r(w1, w2, sh)) + sad;
+            sad = __vsadu4(c[r][2], __funnelshift_r(w2, w3, sh)) + sad;
+            sad = __vsadu4(c[r][3], __funnelshift_r(w3, w4, sh)) + sad;
+        }
+        unsigned long long key = ((unsigned long long)sad << 11) | (unsigned)idx;   // strict <, first in raster order wins
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v < best ? v : best; }
+    if ((t & 31) == 0) best_s[t >> 5] = best;
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; k++) best = best_s[k] < best ? best_s[k] : best;
+        const int idx = (int)(best & 2047);
+        int32_t *o = out + 3 * ((size_t)mby * mbw + mbx);
+        o[0] = idx % 33 - FS_R; o[1] = idx / 33 - FS_R; o[2] = (int32_t)(best >> 11);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+hpel_kernel(const FFHpelRecord *__restrict__ recs, size_t n, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, ptrdiff_t st)
+{
+    const int lane = threadIdx.x & 31;
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFHpelRecord r = recs[ri];
+    const int w = 16 >> r.sidx, no_rnd = r.tab >= 2;
+    // avg_pixels2_xy2 stores without averaging in the reference ("FIXME non put", hpeldsp.c:151): keep the quirk
+    const int avg = (r.tab & 1) && !(r.sidx == 3 && r.dxy == 3);
+    for (int it = lane; it < w * r.h; it += 32) {
+        const int x = it % w, y = it / w;
+        const uint8_t *p = src + r.src_off + y * st + x;
+        int v;
+        switch (r.dxy) {
+        case 0: v = p[0]; break;
+        case 1: v = (p[0] + p[1] + 1 - no_rnd) >> 1; break;
+        case 2: v = (p[0] + p[st] + 1 - no_rnd) >> 1; break;
+        default: v = (p[0] + p[1] + p[st] + p[st + 1] + 2 - no_rnd) >> 2; break;
+        }
+        uint8_t *d = dst + r.dst_off + y * st + x;
+        *d = (uint8_t)(avg ? (*d + v + 1) >> 1 : v);          // the fold into dst always rounds (op_avg = rnd_avg32, :330)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+enum { K0298 = 2446, K0390 = 3196, K0541 = 4433, K0765 = 6270, K0899 = 7373, K1175 = 9633, K1501 = 12299,
+       K1847 = 15137, K1961 = 16069, K2053 = 16819, K2562 = 20995, K3072 = 25172 };
+__device__ __forceinline__ int rsr(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ int fmul8(int v, int k) { return (int)(int16_t)((v * k) >> 8); }
+
+template <int UP, int DN> __device__ __forceinline__ void islow_1d(const int (&in)[8], int (&out)[8])
+{
+    int s0 = in[0] + in[7], d0 = in[0] - in[7], s1 = in[1] + in[6], d1 = in[1] - in[6];
+    int s2 = in[2] + in[5], d2 = in[2] - in[5], s3 = in[3] + in[4], d3 = in[3] - in[4];
+    int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
+    out[0] = UP >= 0 ? (e0 + e1) * (1 << (UP >= 0 ? UP : 0)) : rsr(e0 + e1, UP < 0 ? -UP : 1);
+    out[4] = UP >= 0 ? (e0 - e1) * (1 << (UP >= 0 ? UP : 0)) : rsr(e0 - e1, UP < 0 ? -UP : 1);
+    int z = (e2 + e3) * K0541;
+    out[2] = rsr(z + e3 * K0765, DN);
+    out[6] = rsr(z - e2 * K1847, DN);
+    int z1 = d3 + d0, z2 = d2 + d1, z3 = d3 + d1, z4 = d2 + d0, z5 = (z3 + z4) * K1175;
+    int t4 = d3 * K0298, t5 = d2 * K2053, t6 = d1 * K3072, t7 = d0 * K1501;
+    z1 *= -K0899; z2 *= -K2562; z3 = z3 * -K1961 + z5; z4 = z4 * -K0390 + z5;
+    out[7] = rsr(t4 + z1 + z3, DN); out[5] = rsr(t5 + z2 + z4, DN); out[3] = rsr(t6 + z2 + z3, DN); out[1] = rsr(t7 + z1 + z4, DN);
+}
+template <bool FAST> __device__ __forceinline__ void col_248(const int (&in)[8], int (&out)[8])
+{
+    int a0 = in[0] + in[1], a1 = in[2] + in[3], a2 = in[4] + in[5], a3 = in[6] + in[7];
+    int b0 = in[0] - in[1], b1 = in[2] - in[3], b2 = in[4] - in[5], b3 = in[6] - in[7];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        int e0 = half ? b0 + b3 : a0 + a3, e1 = half ? b1 + b2 : a1 + a2, e2 = half ? b1 - b2 : a1 - a2, e3 = half ? b0 - b3 : a0 - a3;
+        if (FAST) {
+            int z = fmul8(e2 + e3, 181);
+            out[half] = e0 + e1; out[4 + half] = e0 - e1; out[2 + half] = e3 + z; out[6 + half] = e3 - z;
+        } else {
+            int z = (e2 + e3) * K0541;
+            out[half] = rsr(e0 + e1, 4); out[4 + half] = rsr(e0 - e1, 4);
+            out[2 + half] = rsr(z + e3 * K0765, 17); out[6 + half] = rsr(z - e2 * K1847, 17);
+        }
+    }
+}
+__device__ __forceinline__ void ifast_1d(const int (&in)[8], int (&out)[8])
+{
+    int s0 = in[0] + in[7], d0 = in[0] - in[7], s1 = in[1] + in[6], d1 = in[1] - in[6];
+    int s2 = in[2] + in[5], d2 = in[2] - in[5], s3 = in[3] + in[4], d3 = in[3] - in[4];
+    int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
+    out[0] = e0 + e1; out[4] = e0 - e1;
+    int z1 = fmul8(e2 + e3, 181);
+    out[2] = e3 + z1; out[6] = e3 - z1;
+    int p0 = d3 + d2, p1 = d2 + d1, p2 = d1 + d0;
+    int z5 = fmul8(p0 - p2, 98), z2 = fmul8(p0, 139) + z5, z4 = fmul8(p2, 334) + z5, z3 = fmul8(p1, 181);
+    int z11 = d0 + z3, z13 = d0 - z3;
+    out[5] = z13 + z2; out[3] = z13 - z2; out[1] = z11 + z4; out[7] = z11 - z4;
+}
+
+// one thread per block, int16 write-back between the passes kept
+template <int WHICH>
+__global__ void __launch_bounds__(128) fdct_kernel(int16_t *__restrict__ blocks, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int16_t *b = blocks + 64 * i;
+    int m[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint4 v = reinterpret_cast<const uint4 *>(b)[r];
+        int in[8] = { lo16s(v.x), hi16s(v.x), lo16s(v.y), hi16s(v.y), lo16s(v.z), hi16s(v.z), lo16s(v.w), hi16s(v.w) }, o[8];
+        if (WHICH < 2) islow_1d<4, 9>(in, o); else ifast_1d(in, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[r][k] = (int)(int16_t)o[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int in[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) in[k] = m[k][c];
+        if (WHICH == 0) islow_1d<-4, 17>(in, o);
+        else if (WHICH == 1) col_248<false>(in, o);
+        else if (WHICH == 2) ifast_1d(in, o);
+        else col_248<true>(in, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[k][c] = o[k];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        reinterpret_cast<uint4 *>(b)[r] = make_uint4(pack16(m[r][0], m[r][1]), pack16(m[r][2], m[r][3]), pack16(m[r][4], m[r][5]), pack16(m[r][6], m[r][7]));
+}
+
+static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
+
+}  // namespace avb
+
+using namespace avb;
+extern "C" {
+
+int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
+                         const FFMECmpRecord *recs, size_t n, int32_t *out, void *stream)
+{
+    if (!n) return 0;
+    const bool ok = (kind == 0 && sidx <= 1 && dxy >= 0 && dxy <= 3) || (kind == 1 && sidx <= 1) || (kind == 2 && sidx <= 2) ||
+                    ((kind == 3 || kind == 7) && sidx <= 1) || ((kind == 4 || kind == 5) && sidx == 0) || (kind == 6 && sidx <= 1) ||
+                    ((kind == 8 || kind == 9) && sidx <= 1) || kind == 10;
+    if (!ok || sidx < 0) { set_error_msg("me_cmp_batch", "this (kind, size) slot is NULL in the reference table as well"); return -1; }
+    me_cmp_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(kind, sidx, dxy, cur, ref, stride, h, recs, n, out);
+    return check_launch("me_cmp_batch");
+}
+
+int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int w, int h, int range, int mb_y0, int mb_y1,
+                        int32_t *out, void *stream)
+{
+    if (mb_y1 <= mb_y0) return 0;
+    if (range != FS_R) { set_error_msg("full_search", "only me_range 16 is built"); return -1; }
+    if ((w & 15) || (h & 15) || (stride & 15) || ((uintptr_t)cur & 15)) { set_error_msg("full_search", "picture must be MB aligned, cur 16-byte aligned"); return -1; }
+    full_search_kernel<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
+    return check_launch("full_search");
+}
+
+int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream)
+{
+    if (!n) return 0;
+    hpel_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(recs, n, dst, src, stride);
+    return check_launch("hpel_batch");
+}
+
+int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
+{
+    if (!n) return 0;
+    const int grid = (int)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (which) {
+    case 0: fdct_kernel<0><<<grid, 128, 0, st>>>(blocks, n); break;
+    case 1: fdct_kernel<1><<<grid, 128, 0, st>>>(blocks, n); break;
+    case 2: fdct_kernel<2><<<grid, 128, 0, st>>>(blocks, n); break;
+    case 3: fdct_kernel<3><<<grid, 128, 0, st>>>(blocks, n); break;
+    default: set_error_msg("fdct_batch", "bad transform selector"); return -1;
+    }
+    return check_launch("fdct_batch");
+}
+
+}  // extern "C"

@@ -294,3 +294,17 @@ def h264_deblock_work(mb_w, mb_h, seed=4, slices=1):
             rec["alpha"][m, 1, 0] = 0
             rec["calpha"][m, :, 1, 0] = 0
     return rec
+
+
+MECMP_DT = np.dtype([("cur_off", "<u4"), ("ref_off", "<u4")])
+HPEL_DT = np.dtype([("dst_off", "<u4"), ("src_off", "<u4"), ("tab", "u1"), ("sidx", "u1"), ("dxy", "u1"), ("h", "u1")])
+assert MECMP_DT.itemsize == 8 and HPEL_DT.itemsize == 12
+
+
+def me_frames(w, h, seed=1, shift=(3, -5), noise=3):
+    """cur / ref luma planes for the motion-search workload: ref from the LFG, cur = ref shifted by `shift` plus small
+    noise (so the arg-min is meaningful), as SURVEY 8d config 4 asks."""
+    ref = (lfg(seed, w * h) & 0xFF).astype(np.uint8).reshape(h, w)
+    rng = np.random.default_rng(seed)
+    cur = np.roll(ref, shift, axis=(0, 1)).astype(np.int64) + rng.integers(-noise, noise + 1, size=(h, w))
+    return np.clip(cur, 0, 255).astype(np.uint8), ref

@@ -33,11 +33,12 @@ def test_residual_batch(gpu, checker, mb_w, mb_h):
     assert np.array_equal(d[1].download(np.int16, coeffs.shape), wco)      # consumed coefficients are zeroed identically
 
 
+@pytest.mark.parametrize("bipred", [False, True])
 @pytest.mark.parametrize("mb_w,mb_h", SIZES + [(120, 68)])
-def test_mc_batch(gpu, checker, mb_w, mb_h):
+def test_mc_batch(gpu, checker, mb_w, mb_h, bipred):
     from libav_b200 import device
     refs = [synth.h264_picture(mb_w, mb_h, seed=11), synth.h264_picture(mb_w, mb_h, seed=12)]
-    rec = synth.h264_mc_work(mb_w, mb_h, seed=mb_h, max_mv=64 if mb_w > 4 else 24)
+    rec = synth.h264_mc_work(mb_w, mb_h, seed=mb_h, max_mv=64 if mb_w > 4 else 24, avg_second=bipred)
     y, cb, cr = synth.h264_picture(mb_w, mb_h, seed=13)
     wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
     hu.oracle_mc(checker, rec, refs, wy, wcb, wcr)

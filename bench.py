@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
+    ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -334,6 +335,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream().cuda_stream
+    for kv in args.tune:
+        k, v = kv.split("=")
+        L.lib.avb200_set_tuning(k.encode(), int(v))
 
     makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
@@ -376,7 +380,7 @@ def main():
             "dtype": m["dtype"], "data": "synthetic",
             "config": {"workload": m["workload"], "per_gpu_batch": "identical on every rank (weak scaling, no collective on the data path)",
                        "l2": m["l2"], "idct_algo": "FF_IDCT_SIMPLE", "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
-            "roofline": m["roofline"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+            "tuning": args.tune, "roofline": m["roofline"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
             "cpu_baseline": cpu,
             "workloads": {k: {kk: vv for kk, vv in v.items()} for k, v in results.items() if k != args.workload},
         }

@@ -35,6 +35,7 @@ int         avb200_init(int device);              /* cudaSetDevice + context war
 const char *avb200_last_error(void);              /* "" when no error is pending */
 void        avb200_clear_error(void);
 void        avb200_set_log_callback(void (*cb)(int av_log_level, const char *msg)); /* av_log-style sink */
+void        avb200_set_tuning(const char *key, int value);   /* kernel-variant knobs for profiling; see DESIGN.md */
 void       *avb200_malloc(size_t bytes);          /* device memory */
 void        avb200_free(void *dptr);
 void       *avb200_host_alloc(size_t bytes);      /* pinned host memory */
@@ -229,6 +230,16 @@ void sws_debug_rgb_constants_cuda(int32_t out[10]);
  * Only idct_algo FF_IDCT_SIMPLE/FF_IDCT_AUTO at 8 bit is taken over; anything else leaves `c` untouched. */
 void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
 void ff_blockdsp_init_cuda(BlockDSPContext *c);   /* libavcodec/blockdsp.c:60-74 */
+/* libavcodec/fdctdsp.c:27-50 (same shape as ff_fdctdsp_init_x86): dct_algo FF_DCT_AUTO / FF_DCT_INT -> islow,
+ * FF_DCT_FASTINT -> ifast; FF_DCT_FAAN and 10-bit are left to the C path */
+void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
+/* libavcodec/me_cmp.c:895-944: every slot ff_me_cmp_init fills except the encoder-state metrics */
+void ff_me_cmp_init_cuda(MECmpContext *c);
+/* libavcodec/h264dsp.c:57-143, h264qpel.c:36-89, h264chroma.c:32-55, hpeldsp.c:338-366: 8-bit 4:2:0 slots */
+void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc);
+void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth);
+void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth);
+void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "avb200_last_error": (C.c_char_p, []),
     "avb200_clear_error": (None, []),
     "avb200_set_log_callback": (None, [vp]),
+    "avb200_set_tuning": (None, [C.c_char_p, i32]),
     "avb200_malloc": (vp, [sz]),
     "avb200_free": (None, [vp]),
     "avb200_host_alloc": (vp, [sz]),
@@ -77,6 +78,12 @@ PROTOTYPES = {
     "sws_debug_rgb_constants_cuda": (None, [vp]),
     "ff_idctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
     "ff_blockdsp_init_cuda": (None, [vp]),
+    "ff_fdctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
+    "ff_me_cmp_init_cuda": (None, [vp]),
+    "ff_h264dsp_init_cuda": (None, [vp, i32, i32]),
+    "ff_h264qpel_init_cuda": (None, [vp, i32]),
+    "ff_h264chroma_init_cuda": (None, [vp, i32]),
+    "ff_hpeldsp_init_cuda": (None, [vp, i32]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -18,7 +18,8 @@ int  check_launch(const char *where);   // cudaGetLastError() -> sticky error, r
         if (e__ != cudaSuccess) { avb::set_error(where, e__); return -1; } \
     } while (0)
 
-int sm_count();   // multiprocessor count of the current device (cached)
+int sm_count();                 // multiprocessor count of the current device (cached)
+int tuning(const char *key);    // experiment knob set through avb200_set_tuning(); 0 when unset
 
 // ---- device helpers ------------------------------------------------------------------------
 // streaming 128-bit global accesses (data touched exactly once: keep it out of L1)

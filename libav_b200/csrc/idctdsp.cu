@@ -21,43 +21,46 @@ namespace avb {
 
 enum { C1 = 22725, C2 = 21407, C3 = 19266, C4 = 16383, C5 = 12873, C6 = 8867, C7 = 4520 };
 
-struct Idct1D { int v[8]; };
-
-// even/odd butterflies shared by both passes; `base` already holds the DC term + rounding.
+// Shared butterflies.  K = 1 for the column pass, 32 for the row pass: the row pass needs bits [26:11] of each sum
+// (the int16 the reference stores back), and with every constant pre-multiplied by 32 those bits land in the upper
+// half-word of the 32-bit wrap-around result, ready for a byte-permute -- no shift per output.  Multiplying all terms
+// by 32 commutes with the mod-2^32 arithmetic, so the selected bits are identical.
+// s[k] = e[k] + o[k] is accumulated as one IMAD chain that starts from e[k]; d[k] = e[k] - o[k] = 2 e[k] - s[k] then
+// costs a single 3-input add.
+template <int K>
 __device__ __forceinline__ void butterfly(int base, int x1, int x2, int x3, int x4, int x5, int x6, int x7,
                                           int (&s)[4], int (&d)[4])
 {
-    int b0 = base + C4 * x4, b1 = base - C4 * x4;
-    int p  = C2 * x2 + C6 * x6;
-    int q  = C6 * x2 - C2 * x6;
-    int e0 = b0 + p, e3 = b0 - p, e1 = b1 + q, e2 = b1 - q;
-    int o0 = C1 * x1 + C3 * x3 + C5 * x5 + C7 * x7;
-    int o1 = C3 * x1 - C7 * x3 - C1 * x5 - C5 * x7;
-    int o2 = C5 * x1 - C1 * x3 + C7 * x5 + C3 * x7;
-    int o3 = C7 * x1 - C5 * x3 + C3 * x5 - C1 * x7;
-    s[0] = e0 + o0; d[0] = e0 - o0;
-    s[1] = e1 + o1; d[1] = e1 - o1;
-    s[2] = e2 + o2; d[2] = e2 - o2;
-    s[3] = e3 + o3; d[3] = e3 - o3;
+    const int b0 = base + (K * C4) * x4, b1 = base - (K * C4) * x4;
+    const int p  = (K * C2) * x2 + (K * C6) * x6;
+    const int q  = (K * C6) * x2 - (K * C2) * x6;
+    const int e0 = b0 + p, e3 = b0 - p, e1 = b1 + q, e2 = b1 - q;
+    s[0] = e0 + (K * C1) * x1 + (K * C3) * x3 + (K * C5) * x5 + (K * C7) * x7;
+    s[1] = e1 + (K * C3) * x1 - (K * C7) * x3 - (K * C1) * x5 - (K * C5) * x7;
+    s[2] = e2 + (K * C5) * x1 - (K * C1) * x3 + (K * C7) * x5 + (K * C3) * x7;
+    s[3] = e3 + (K * C7) * x1 - (K * C5) * x3 + (K * C3) * x5 - (K * C1) * x7;
+    d[0] = e0 + e0 - s[0];
+    d[1] = e1 + e1 - s[1];
+    d[2] = e2 + e2 - s[2];
+    d[3] = e3 + e3 - s[3];
 }
 
 // Row pass on one packed row (4 words = 8 int16); result is the int16-truncated row, packed.
-// (x << 5) >> 16 keeps bits [26:11] sign-extended from bit 26 == (int16_t)(x >> 11).
 __device__ __forceinline__ uint4 row_pass(uint4 r)
 {
     int x0 = lo16s(r.x), x1 = hi16s(r.x), x2 = lo16s(r.y), x3 = hi16s(r.y);
     int x4 = lo16s(r.z), x5 = hi16s(r.z), x6 = lo16s(r.w), x7 = hi16s(r.w);
-    // all seven AC terms zero -> every output is (x0 << 3): feed base = x0 << 14 through the same
-    // datapath (the butterflies add zero), simple_idct_template.c:94-106
+    // all seven AC terms zero -> every output is (x0 << 3): feed base = (x0 << 14) * 32 through the same datapath
+    // (the butterflies add zero), simple_idct_template.c:94-106
     bool dc_only = ((r.x & 0xffff0000u) | r.y | r.z | r.w) == 0;
-    int base = dc_only ? (x0 << 14) : (C4 * x0 + (1 << 10));
+    int base = dc_only ? (x0 << 19) : ((32 * C4) * x0 + (1 << 15));
     int s[4], d[4];
-    butterfly(base, x1, x2, x3, x4, x5, x6, x7, s, d);
-    uint4 o;
-    o.x = __byte_perm((uint32_t)(s[0] << 5), (uint32_t)(s[1] << 5), 0x7632);
-    o.y = __byte_perm((uint32_t)(s[2] << 5), (uint32_t)(s[3] << 5), 0x7632);
-    o.z = __byte_perm((uint32_t)(d[3] << 5), (uint32_t)(d[2] << 5), 0x7632);
-    o.w = __byte_perm((uint32_t)(d[1] << 5), (uint32_t)(d[0] << 5), 0x7632);
+    butterfly<32>(base, x1, x2, x3, x4, x5, x6, x7, s, d);
+    uint4 o;                                   // upper half-words = (int16_t)(sum >> 11)
+    o.x = __byte_perm((uint32_t)s[0], (uint32_t)s[1], 0x7632);
+    o.y = __byte_perm((uint32_t)s[2], (uint32_t)s[3], 0x7632);
+    o.z = __byte_perm((uint32_t)d[3], (uint32_t)d[2], 0x7632);
+    o.w = __byte_perm((uint32_t)d[1], (uint32_t)d[0], 0x7632);
     return o;
 }
 
@@ -70,7 +73,7 @@ __device__ __forceinline__ void col_pass(const uint32_t (&w)[8], int (&out)[8])
     for (int k = 0; k < 8; k++) x[k] = HI ? hi16s(w[k]) : lo16s(w[k]);
     int base = C4 * (x[0] + 32);            // (1 << 19) / 16383 == 32
     int s[4], d[4];
-    butterfly(base, x[1], x[2], x[3], x[4], x[5], x[6], x[7], s, d);
+    butterfly<1>(base, x[1], x[2], x[3], x[4], x[5], x[6], x[7], s, d);
 #pragma unroll
     for (int k = 0; k < 4; k++) { out[k] = s[k] >> 20; out[7 - k] = d[k] >> 20; }
 }
@@ -87,8 +90,8 @@ constexpr int IDCT_WARPS = 4;   // warps per CTA; each owns 2 x 4 KB of shared m
 
 // MODE 0: put, 1: add, 2: plain (in place int16).  CLEAR: also zero the coefficient block
 // afterwards (fused BlockDSPContext.clear_block, what every caller does next).
-template <int MODE, bool CLEAR>
-__global__ void __launch_bounds__(IDCT_WARPS * 32)
+template <int MODE, bool CLEAR, int MINB = 5>
+__global__ void __launch_bounds__(IDCT_WARPS * 32, MINB)
 simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
                    const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
 {
@@ -250,10 +253,14 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
     if (mode < 0 || mode > 2) { set_error_msg("simple_idct_batch", "bad mode"); return -1; }
     if (mode != 2 && !dst_off && tiles_per_row <= 0) { set_error_msg("simple_idct_batch", "need dst_off or tiles_per_row"); return -1; }
     size_t groups = (n + 31) / 32;
-    int grid = grid_for(groups, IDCT_WARPS, 8);
+    const int minb = tuning("idct_min_blocks");            // profiling knob: resident CTAs per SM the kernel is compiled for
+    int grid = grid_for(groups, IDCT_WARPS, minb == 4 ? 4 : minb == 6 ? 6 : 5);
+    if (tuning("idct_grid_mult") > 0) grid = grid_for(groups, IDCT_WARPS, tuning("idct_grid_mult"));
     dim3 b(IDCT_WARPS * 32);
     if (mode == 0) {
         if (clear) simple_idct_kernel<0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else if (minb == 4) simple_idct_kernel<0, false, 4><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else if (minb == 6) simple_idct_kernel<0, false, 6><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else       simple_idct_kernel<0, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
     } else if (mode == 1) {
         if (clear) simple_idct_kernel<1, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);

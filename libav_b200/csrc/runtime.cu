@@ -5,6 +5,8 @@
 #include "../../include/avdsp_b200.h"
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 #include <string.h>
 
 namespace avb {
@@ -27,6 +29,15 @@ int check_launch(const char *where)
     if (e != cudaSuccess) { set_error(where, e); return -1; }
     return 0;
 }
+// experiment knobs (bench / profiling only): small string-keyed integer table
+static std::mutex g_tune_mu;
+static std::vector<std::pair<std::string, int>> g_tune;
+int tuning(const char *key)
+{
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    for (auto &kv : g_tune) if (kv.first == key) return kv.second;
+    return 0;
+}
 int sm_count()
 {
     if (g_sms) return g_sms;
@@ -42,6 +53,13 @@ int sm_count()
 using namespace avb;
 
 extern "C" {
+
+void avb200_set_tuning(const char *key, int value)
+{
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    for (auto &kv : g_tune) if (kv.first == key) { kv.second = value; return; }
+    g_tune.emplace_back(key, value);
+}
 
 int avb200_device_count(void)
 {

@@ -267,6 +267,9 @@ void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int 
     k.agu = yoffs - (int)(cgu >> 9);
     k.agv = -(int)(cgv >> 9);
     k.ab  = yoffs - (int)(cbu >> 9);
+    k.kr = k.cy * k.ar + k.k1;
+    k.kg = k.cy * (k.agu + k.agv) + k.k1;
+    k.kb = k.cy * k.ab + k.k1;
 }
 
 }  // namespace avb

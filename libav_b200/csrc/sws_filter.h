@@ -42,6 +42,7 @@ struct RgbConstants {      // r = clip_u8((cy * (Y + ar + ((V * crv) >> 16)) + k
     int cy, k1;
     int crv, cgu, cgv, cbu;
     int ar, agu, agv, ab;  // yoffs - (crv >> 9), yoffs - (cgu >> 9), -(cgv >> 9), yoffs - (cbu >> 9)
+    int kr, kg, kb;        // cy * ar + k1, cy * (agu + agv) + k1, cy * ab + k1: the additive terms with the offsets folded in
 };
 void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int brightness, int contrast, int saturation);
 

@@ -170,6 +170,85 @@ sws_fused_rgb24_kernel(SwsDev p, FusedArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FUSED kernel, interior fast path: a thread owns 16 pixels x 2 rows (one LDG.128 of luma per row, one LDG.64 per
+// chroma line) and walks its 8 chroma columns once, producing both rows from the same extracted bytes.
+// Preconditions checked on the host (else the kernel above runs): 16-byte aligned planes / pitches, dstW % 16 == 0,
+// dstH even, both rows of every pair share their chroma window, and the filter bank cannot push U,V outside
+// (-256, 512) -- then clipping each value on its own is identical to the reference's "clip all four if any has bit 8
+// set" (output.c:966-971) because an in-range value is unchanged by av_clip_uint8.
+// Per pixel pair and row: 8 IMAD + 2 shifts + 2 clamps for the FIR, 12 for the colour terms, 17 for the two pixels.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sat255(int v) { return __vimin_s32_relu(v, 255); }       // max(min(v, 255), 0), one VIMNMX
+
+template <bool BGR>
+__global__ void __launch_bounds__(128)
+sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x;            // group of 16 pixels
+    const int rp = blockIdx.y * 4 + threadIdx.y;             // row pair
+    if (gx * 16 >= p.dstW || rp * 2 >= p.dstH) return;
+    const size_t f = blockIdx.z;
+    const int y0 = rp * 2;
+    const uint8_t *Yp = a.y + f * a.yFrame + (size_t)y0 * a.yStride + gx * 16;
+    const uint8_t *Up = a.u + f * a.uFrame + gx * 8, *Vp = a.v + f * a.vFrame + gx * 8;
+    uint8_t *D = a.dst + f * a.dstFrame + (size_t)y0 * a.dstStride + gx * 48;
+
+    const int first = max(-3, p.vChrP[y0]);
+    uint2 u[4], v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int row = min(max(first + j, 0), p.chrSrcH - 1);
+        u[j] = __ldg(reinterpret_cast<const uint2 *>(Up + (size_t)row * a.uStride));
+        v[j] = __ldg(reinterpret_cast<const uint2 *>(Vp + (size_t)row * a.vStride));
+    }
+    const uint4 yy0 = ldg_stream(Yp), yy1 = ldg_stream(Yp + a.yStride);
+    const uint4 cf = __ldg(reinterpret_cast<const uint4 *>(p.vChrF + (size_t)y0 * 4));   // 2 rows x 4 int16 taps
+    const int c00 = lo16s(cf.x), c01 = hi16s(cf.x), c02 = lo16s(cf.y), c03 = hi16s(cf.y);
+    const int c10 = lo16s(cf.z), c11 = hi16s(cf.z), c12 = lo16s(cf.w), c13 = hi16s(cf.w);
+    const int cy = p.k.cy, crv = p.k.crv, cgu = p.k.cgu, cgv = p.k.cgv, cbu = p.k.cbu, kr = p.k.kr, kg = p.k.kg, kb = p.k.kb;
+
+    uint32_t o0[12], o1[12];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {                            // 4 pixels = 2 chroma columns per step
+        int r0[4], g0[4], b0[4], r1[4], g1[4], b1[4];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c = 2 * q + e;                         // chroma column 0..7
+            const int u0 = byte_of(c < 4 ? u[0].x : u[0].y, c & 3), u1 = byte_of(c < 4 ? u[1].x : u[1].y, c & 3);
+            const int u2 = byte_of(c < 4 ? u[2].x : u[2].y, c & 3), u3 = byte_of(c < 4 ? u[3].x : u[3].y, c & 3);
+            const int v0 = byte_of(c < 4 ? v[0].x : v[0].y, c & 3), v1 = byte_of(c < 4 ? v[1].x : v[1].y, c & 3);
+            const int v2 = byte_of(c < 4 ? v[2].x : v[2].y, c & 3), v3 = byte_of(c < 4 ? v[3].x : v[3].y, c & 3);
+#pragma unroll
+            for (int ry = 0; ry < 2; ry++) {
+                const int k0 = ry ? c10 : c00, k1 = ry ? c11 : c01, k2 = ry ? c12 : c02, k3 = ry ? c13 : c03;
+                const int U = sat255((2048 + u0 * k0 + u1 * k1 + u2 * k2 + u3 * k3) >> 12);
+                const int V = sat255((2048 + v0 * k0 + v1 * k1 + v2 * k2 + v3 * k3) >> 12);
+                const int tr = cy * ((V * crv) >> 16) + kr;
+                const int tg = cy * (((U * cgu) >> 16) + ((V * cgv) >> 16)) + kg;
+                const int tb = cy * ((U * cbu) >> 16) + kb;
+                const uint4 yy = ry ? yy1 : yy0;
+                const uint32_t yw = q == 0 ? yy.x : q == 1 ? yy.y : q == 2 ? yy.z : yy.w;
+                const int Ya = cy * byte_of(yw, 2 * e), Yb = cy * byte_of(yw, 2 * e + 1);
+                int *r = ry ? r1 : r0, *g = ry ? g1 : g0, *b = ry ? b1 : b0;
+                r[2 * e] = (Ya + (BGR ? tb : tr)) >> 16; g[2 * e] = (Ya + tg) >> 16; b[2 * e] = (Ya + (BGR ? tr : tb)) >> 16;
+                r[2 * e + 1] = (Yb + (BGR ? tb : tr)) >> 16; g[2 * e + 1] = (Yb + tg) >> 16; b[2 * e + 1] = (Yb + (BGR ? tr : tb)) >> 16;
+            }
+        }
+        o0[3 * q + 0] = pack4_sat_u8(r0[0], g0[0], b0[0], r0[1]);
+        o0[3 * q + 1] = pack4_sat_u8(g0[1], b0[1], r0[2], g0[2]);
+        o0[3 * q + 2] = pack4_sat_u8(b0[2], r0[3], g0[3], b0[3]);
+        o1[3 * q + 0] = pack4_sat_u8(r1[0], g1[0], b1[0], r1[1]);
+        o1[3 * q + 1] = pack4_sat_u8(g1[1], b1[1], r1[2], g1[2]);
+        o1[3 * q + 2] = pack4_sat_u8(b1[2], r1[3], g1[3], b1[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        stg_stream(D + 16 * k, make_uint4(o0[4 * k], o0[4 * k + 1], o0[4 * k + 2], o0[4 * k + 3]));
+        stg_stream(D + a.dstStride + 16 * k, make_uint4(o1[4 * k], o1[4 * k + 1], o1[4 * k + 2], o1[4 * k + 3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // GENERAL path, pass 1: hScale8To15 (swscale.c:133-147) for one plane; thread = (column, row)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -282,6 +361,7 @@ struct SwsCudaContext {
     int dstFormat;
     bool copy = false;          // unscaled yuv420p -> yuv420p: the reference installs a plain plane copy
                                 // (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper), whatever the flags
+    bool fast_ok = false;       // the fused interior kernel's host-side preconditions on the filter bank hold
     bool fused;                 // horizontal identity + vLum identity + 4-tap vChr -> one kernel
     void *d_tables = nullptr;   // all filter banks in one device allocation
     SwsDev dev;
@@ -361,6 +441,18 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     c->fused = rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
+    if (c->fused && !(dstW & 15) && !(dstH & 1)) {
+        bool ok = true;
+        for (int y = 0; y < dstH && ok; y += 2) {
+            if (c->vChr.pos[y] != c->vChr.pos[y + 1]) ok = false;
+            for (int r = 0; r < 2 && ok; r++) {
+                int lo = 2048, hi = 2048;
+                for (int j = 0; j < 4; j++) { int k = c->vChr.coef[(size_t)(y + r) * 4 + j]; if (k < 0) lo += 255 * k; else hi += 255 * k; }
+                if ((lo >> 12) <= -256 || (hi >> 12) >= 512) ok = false;
+            }
+        }
+        c->fast_ok = ok;
+    }
     c->copy = !rgb && srcW == dstW && srcH == dstH;
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
@@ -405,6 +497,15 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
         bool aligned = !((uintptr_t)a.y & 7) && !(a.yStride & 7) && !((uintptr_t)a.dst & 7) && !(a.dstStride & 7) && !(a.yFrame & 7) &&
                        !(a.dstFrame & 7) && !((uintptr_t)a.u & 3) && !((uintptr_t)a.v & 3) && !(a.uStride & 3) && !(a.vStride & 3) &&
                        !(a.uFrame & 3) && !(a.vFrame & 3);
+        const bool a16 = aligned && !((uintptr_t)a.y & 15) && !(a.yStride & 15) && !((uintptr_t)a.dst & 15) && !(a.dstStride & 15) &&
+                         !(a.yFrame & 15) && !(a.dstFrame & 15) && !((uintptr_t)a.u & 7) && !((uintptr_t)a.v & 7) && !(a.uStride & 7) &&
+                         !(a.vStride & 7) && !(a.uFrame & 7) && !(a.vFrame & 7) && !((uintptr_t)p.vChrF & 15);
+        if (c->fast_ok && a16 && tuning("sws_fused_variant") != 1) {
+            dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (p.dstH / 2 + 3) / 4, nframes);
+            if (p.bgr) sws_fused_rgb24_v2_kernel<true><<<g2, b2, 0, st>>>(p, a);
+            else       sws_fused_rgb24_v2_kernel<false><<<g2, b2, 0, st>>>(p, a);
+            return check_launch("sws_scale:fused");
+        }
         dim3 b(32, 8), g((p.dstW + 255) / 256, (p.dstH + 15) / 16, nframes);
         if (aligned) sws_fused_rgb24_kernel<true><<<g, b, 0, st>>>(p, a);
         else         sws_fused_rgb24_kernel<false><<<g, b, 0, st>>>(p, a);    // same arithmetic, byte accesses

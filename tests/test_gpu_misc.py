@@ -36,8 +36,8 @@ def test_me_cmp_batch(gpu, checker, kind, sidx, dxy):
         rec["ref_off"] = rng.integers(0, H - 18, size=n) * W + rng.integers(0, W - 20, size=n)
         want = np.array([checker.me_cmp(kind, sidx, dxy, at(cur, r["cur_off"]), at(ref, r["ref_off"]), W, h) for r in rec], dtype=np.int32)
         assert (want >= 0).all()
-        d_out = device.DevBuf(4 * n)
-        gpu.check(gpu.lib.ff_me_cmp_batch_cuda(kind, sidx, dxy, _dev(cur).ptr, _dev(ref).ptr, W, h, _dev(rec).ptr, n, d_out.ptr, None))
+        d_out, d_cur, d_ref, d_rec = device.DevBuf(4 * n), _dev(cur), _dev(ref), _dev(rec)      # keep the buffers alive
+        gpu.check(gpu.lib.ff_me_cmp_batch_cuda(kind, sidx, dxy, d_cur.ptr, d_ref.ptr, W, h, d_rec.ptr, n, d_out.ptr, None))
         device.sync()
         assert np.array_equal(d_out.download(np.int32, (n,)), want), (kind, sidx, dxy, h)
 
@@ -50,11 +50,11 @@ def test_sum_abs_dctelem_and_null_slots(gpu, checker):
     rec["cur_off"] = np.arange(300) * 128
     want = np.array([checker.me_cmp(10, 0, 0, ptr(b), None, 0, 0) for b in blocks], dtype=np.int32)
     d_out = device.DevBuf(1200)
-    db = _dev(blocks)
-    gpu.check(gpu.lib.ff_me_cmp_batch_cuda(10, 0, 0, db.ptr, db.ptr, 0, 0, _dev(rec).ptr, 300, d_out.ptr, None))
+    db, d_rec = _dev(blocks), _dev(rec)
+    gpu.check(gpu.lib.ff_me_cmp_batch_cuda(10, 0, 0, db.ptr, db.ptr, 0, 0, d_rec.ptr, 300, d_out.ptr, None))
     device.sync()
     assert np.array_equal(d_out.download(np.int32, (300,)), want)
-    assert gpu.lib.ff_me_cmp_batch_cuda(4, 1, 0, db.ptr, db.ptr, 16, 8, _dev(rec).ptr, 1, d_out.ptr, None) == -1   # vsad[1] is NULL in C too
+    assert gpu.lib.ff_me_cmp_batch_cuda(4, 1, 0, db.ptr, db.ptr, 16, 8, d_rec.ptr, 1, d_out.ptr, None) == -1   # vsad[1] is NULL in C too
     gpu.lib.avb200_clear_error()
 
 
@@ -82,7 +82,7 @@ def test_full_search(gpu, checker, w, h):
 def test_hpel_batch(gpu, checker):
     from libav_b200 import device
     rng = np.random.default_rng(3)
-    W, H = 512, 128
+    W, H = 512, 256
     src = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
     dst = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
     recs = []
@@ -103,8 +103,8 @@ def test_hpel_batch(gpu, checker):
     want = dst.copy()
     for r in rec:
         assert checker.hpel(int(r["tab"]), int(r["sidx"]), int(r["dxy"]), at(want, r["dst_off"]), at(src, r["src_off"]), W, int(r["h"])) == 0
-    d_dst = _dev(dst)
-    gpu.check(gpu.lib.ff_hpel_batch_cuda(_dev(rec).ptr, rec.shape[0], d_dst.ptr, _dev(src).ptr, W, None))
+    d_dst, d_rec, d_src = _dev(dst), _dev(rec), _dev(src)
+    gpu.check(gpu.lib.ff_hpel_batch_cuda(d_rec.ptr, rec.shape[0], d_dst.ptr, d_src.ptr, W, None))
     device.sync()
     assert np.array_equal(d_dst.download(np.uint8, dst.shape), want)
 

@@ -173,7 +173,7 @@ def make_sws_workload(torch, L, stream, rank):
     return {
         "name": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % K,
         "run": run, "run_e2e": run_e2e, "pixels": w * h * K, "alg_bytes": int(w * h * K * SWS_BYTES_PER_PIXEL),
-        "launches_per_step": 1, "kernel": "sws_fused_rgb24_kernel<true>", "dtype": "int32 (u8 in, u8 out)",
+        "launches_per_step": 1, "kernel": "sws_fused_rgb24_v3_kernel", "dtype": "int32 (u8 in, u8 out)",
         "h2d": int(w * h * 1.5) * K, "d2h": osz * K,
         "l2": "2 rotating %d MiB buffer sets (inputs+outputs larger than the 126 MB L2)" % ((ysz + 2 * csz + osz) * K >> 20),
         "keep": (d_y, d_u, d_v, d_o, ctx, hy, hu, hv, ho),

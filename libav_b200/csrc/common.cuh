@@ -74,5 +74,8 @@ __device__ __forceinline__ int lo16s(uint32_t w) { return (int)(int16_t)(w & 0xf
 __device__ __forceinline__ int hi16s(uint32_t w) { return (int)w >> 16; }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
 __device__ __forceinline__ int clip_u8(int v) { return min(max(v, 0), 255); }
+// arithmetic shift right by a constant.  MULHI = true issues it as IMAD.HI (x * 2^(32-N) >> 32 == x >> N for signed x) on the
+// FMA pipe instead of SHF on the ALU pipe -- these kernels are bound by the 16-lane integer ALU pipe, the FMA pipe has slack.
+template <int N, bool MULHI> __device__ __forceinline__ int sra(int x) { return MULHI ? __mulhi(x, 1 << (32 - N)) : (x >> N); }
 
 }  // namespace avb

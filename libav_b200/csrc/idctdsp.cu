@@ -45,11 +45,14 @@ __device__ __forceinline__ void butterfly(int base, int x1, int x2, int x3, int 
     d[3] = e3 + e3 - s[3];
 }
 
+template <bool MH> __device__ __forceinline__ int hi16x(uint32_t w) { return sra<16, MH>((int)w); }
+
 // Row pass on one packed row (4 words = 8 int16); result is the int16-truncated row, packed.
+template <bool MH>
 __device__ __forceinline__ uint4 row_pass(uint4 r)
 {
-    int x0 = lo16s(r.x), x1 = hi16s(r.x), x2 = lo16s(r.y), x3 = hi16s(r.y);
-    int x4 = lo16s(r.z), x5 = hi16s(r.z), x6 = lo16s(r.w), x7 = hi16s(r.w);
+    int x0 = lo16s(r.x), x1 = hi16x<MH>(r.x), x2 = lo16s(r.y), x3 = hi16x<MH>(r.y);
+    int x4 = lo16s(r.z), x5 = hi16x<MH>(r.z), x6 = lo16s(r.w), x7 = hi16x<MH>(r.w);
     // all seven AC terms zero -> every output is (x0 << 3): feed base = (x0 << 14) * 32 through the same datapath
     // (the butterflies add zero), simple_idct_template.c:94-106
     bool dc_only = ((r.x & 0xffff0000u) | r.y | r.z | r.w) == 0;
@@ -65,17 +68,17 @@ __device__ __forceinline__ uint4 row_pass(uint4 r)
 }
 
 // Column pass for column x given the eight row words that contain it; out[y] = value >> 20.
-template <int HI>
+template <int HI, bool MH>
 __device__ __forceinline__ void col_pass(const uint32_t (&w)[8], int (&out)[8])
 {
     int x[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = HI ? hi16s(w[k]) : lo16s(w[k]);
+    for (int k = 0; k < 8; k++) x[k] = HI ? hi16x<MH>(w[k]) : lo16s(w[k]);
     int base = C4 * (x[0] + 32);            // (1 << 19) / 16383 == 32
     int s[4], d[4];
     butterfly<1>(base, x[1], x[2], x[3], x[4], x[5], x[6], x[7], s, d);
 #pragma unroll
-    for (int k = 0; k < 4; k++) { out[k] = s[k] >> 20; out[7 - k] = d[k] >> 20; }
+    for (int k = 0; k < 4; k++) { out[k] = sra<20, MH>(s[k]); out[7 - k] = sra<20, MH>(d[k]); }
 }
 
 __device__ __forceinline__ size_t block_dst(const uint32_t *__restrict__ dst_off, size_t i,
@@ -90,7 +93,22 @@ constexpr int IDCT_WARPS = 4;   // warps per CTA; each owns 2 x 4 KB of shared m
 
 // MODE 0: put, 1: add, 2: plain (in place int16).  CLEAR: also zero the coefficient block
 // afterwards (fused BlockDSPContext.clear_block, what every caller does next).
-template <int MODE, bool CLEAR, int MINB = 5>
+// cp.async / ld.shared on raw 32-bit shared addresses: every per-lane offset below is loop invariant, so the steady
+// state of the loop issues no address arithmetic beyond one add per buffer flip.
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void *gmem)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(gmem) : "memory"); }
+__device__ __forceinline__ void cp_async16_sz(unsigned saddr, const void *gmem, int bytes)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(gmem), "r"(bytes) : "memory"); }
+__device__ __forceinline__ uint4 lds128(unsigned saddr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+
+// MODE 0: put, 1: add, 2: plain (in place int16).  CLEAR: also zero the coefficient block
+// afterwards (fused BlockDSPContext.clear_block, what every caller does next).
+template <int MODE, bool CLEAR, int MINB = 5, bool MH = false>
 __global__ void __launch_bounds__(IDCT_WARPS * 32, MINB)
 simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
                    const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
@@ -101,28 +119,48 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
     const size_t gstride = (size_t)gridDim.x * IDCT_WARPS;
     size_t g = (size_t)blockIdx.x * IDCT_WARPS + warp;
 
-    auto issue = [&](size_t grp, int buf) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(blocks) + grp * 256;
+    // loop-invariant shared-memory byte offsets.  A 512-byte slab j of the group holds blocks 4j..4j+3; lane writes chunk
+    // c = lane & 7 of block 4j + (lane >> 3) to chunk position c ^ (block & 7), and (block & 7) = 4 (j & 1) + (lane >> 3).
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(&tile[warp][0][0]);
+    const int l3 = lane >> 3, lc = lane & 7;
+    const unsigned wr_even = (unsigned)(l3 * 8 + (lc ^ l3)) * 16, wr_odd = (unsigned)(l3 * 8 + (lc ^ (4 + l3))) * 16;
+    const unsigned rd_base = (unsigned)lane * 128, rd_key = (unsigned)lc << 4;
+
+    auto issue = [&](size_t grp, unsigned tb) {
+        const char *src = reinterpret_cast<const char *>(blocks) + grp * 4096 + lane * 16;
+        if (grp * 32 + 32 <= n) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int u = j * 32 + lane, b = u >> 3, c = u & 7;
-            bool ok = grp * 32 + b < n;
-            cp_async16(&tile[warp][buf][b * 8 + (c ^ (b & 7))], ok ? src + u : src, ok);
+            for (int j = 0; j < 8; j++) cp_async16_s(tb + j * 512 + ((j & 1) ? wr_odd : wr_even), src + j * 512);
+        } else {                                              // ragged last group: zero-fill the missing blocks
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ok = grp * 32 + j * 4 + l3 < n;
+                cp_async16_sz(tb + j * 512 + ((j & 1) ? wr_odd : wr_even), ok ? src + j * 512 : reinterpret_cast<const char *>(blocks), ok ? 16 : 0);
+            }
         }
         cp_async_commit();
     };
 
-    int buf = 0;
-    if (g < groups) issue(g, 0);
-    for (; g < groups; g += gstride, buf ^= 1) {
-        size_t gn = g + gstride;
-        if (gn < groups) { issue(gn, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    // raster-of-tiles destination: (ty, tx) of this lane's block advances by a constant step per iteration (no division)
+    size_t ty = 0; unsigned tx = 0, step_q = 0, step_r = 0;
+    if (MODE != 2 && !dst_off) {
+        const size_t i0 = g * 32 + lane, st = gstride * 32;
+        ty = i0 / (unsigned)tiles_per_row; tx = (unsigned)(i0 - ty * (unsigned)tiles_per_row);
+        step_q = (unsigned)(st / (unsigned)tiles_per_row); step_r = (unsigned)(st - (size_t)step_q * (unsigned)tiles_per_row);
+    }
+
+    unsigned buf = 0;
+    if (g < groups) issue(g, tile_s);
+    for (; g < groups; g += gstride, buf ^= 4096u) {
+        const size_t gn = g + gstride;
+        const unsigned tb = tile_s + buf;
+        if (gn < groups) { issue(gn, tile_s + (buf ^ 4096u)); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncwarp();
 
         uint4 row[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) row[r] = row_pass(tile[warp][buf][lane * 8 + (r ^ (lane & 7))]);
-        __syncwarp();     // tile[buf] is free for the load issued two iterations from now
+        for (int r = 0; r < 8; r++) row[r] = row_pass<MH>(lds128(tb + rd_base + (((unsigned)r << 4) ^ rd_key)));
+        __syncwarp();     // this buffer is free for the load issued two iterations from now
 
         const size_t i = g * 32 + lane;
         const bool live = i < n;
@@ -135,8 +173,8 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
 #pragma unroll
                 for (int r = 0; r < 8; r++) w[r] = c == 0 ? row[r].x : c == 1 ? row[r].y : c == 2 ? row[r].z : row[r].w;
                 int lo[8], hi[8];
-                col_pass<0>(w, lo);
-                col_pass<1>(w, hi);
+                col_pass<0, MH>(w, lo);
+                col_pass<1, MH>(w, hi);
 #pragma unroll
                 for (int y = 0; y < 8; y++) o[y][c] = pack16(lo[y], hi[y]);
             }
@@ -146,7 +184,13 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
                 for (int y = 0; y < 8; y++) dst[y] = make_uint4(o[y][0], o[y][1], o[y][2], o[y][3]);
             }
         } else {
-            uint8_t *dst = frame + (live ? block_dst(dst_off, i, tiles_per_row, stride) : 0);
+            uint8_t *dst = frame;
+            if (dst_off) dst += live ? dst_off[i] : 0;
+            else {
+                dst += ty * 8 * (size_t)stride + (size_t)tx * 8;
+                tx += step_r; ty += step_q;
+                if (tx >= (unsigned)tiles_per_row) { tx -= (unsigned)tiles_per_row; ty++; }
+            }
             uint2 px[8];
             if (MODE == 1 && live) {
 #pragma unroll
@@ -162,8 +206,8 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
 #pragma unroll
                     for (int r = 0; r < 8; r++)
                         w[r] = h == 0 ? (c == 0 ? row[r].x : row[r].y) : (c == 0 ? row[r].z : row[r].w);
-                    col_pass<0>(w, v[2 * c]);
-                    col_pass<1>(w, v[2 * c + 1]);
+                    col_pass<0, MH>(w, v[2 * c]);
+                    col_pass<1, MH>(w, v[2 * c + 1]);
                 }
 #pragma unroll
                 for (int y = 0; y < 8; y++) {
@@ -254,13 +298,16 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
     if (mode != 2 && !dst_off && tiles_per_row <= 0) { set_error_msg("simple_idct_batch", "need dst_off or tiles_per_row"); return -1; }
     size_t groups = (n + 31) / 32;
     const int minb = tuning("idct_min_blocks");            // profiling knob: resident CTAs per SM the kernel is compiled for
-    int grid = grid_for(groups, IDCT_WARPS, minb == 4 ? 4 : minb == 6 ? 6 : 5);
-    if (tuning("idct_grid_mult") > 0) grid = grid_for(groups, IDCT_WARPS, tuning("idct_grid_mult"));
+    // 16 CTAs per SM in the grid (about 3 waves of the 5 resident ones): measured +4 % over exactly one persistent wave,
+    // the shorter per-CTA loops even out the tail
+    int grid = grid_for(groups, IDCT_WARPS, tuning("idct_grid_mult") > 0 ? tuning("idct_grid_mult") : 16);
     dim3 b(IDCT_WARPS * 32);
     if (mode == 0) {
         if (clear) simple_idct_kernel<0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else if (minb == 4) simple_idct_kernel<0, false, 4><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else if (minb == 6) simple_idct_kernel<0, false, 6><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else if (tuning("idct_mulhi") == 1) simple_idct_kernel<0, false, 5, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
+        else if (tuning("idct_mulhi") == 2) simple_idct_kernel<0, false, 4, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else       simple_idct_kernel<0, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
     } else if (mode == 1) {
         if (clear) simple_idct_kernel<1, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);

@@ -21,6 +21,7 @@
 #include "sws_filter.h"
 #include "../../include/avdsp_b200.h"
 #include <new>
+#include <vector>
 #include <limits.h>
 #include <string.h>
 
@@ -173,14 +174,15 @@ sws_fused_rgb24_kernel(SwsDev p, FusedArgs a)
 // FUSED kernel, interior fast path: a thread owns 16 pixels x 2 rows (one LDG.128 of luma per row, one LDG.64 per
 // chroma line) and walks its 8 chroma columns once, producing both rows from the same extracted bytes.
 // Preconditions checked on the host (else the kernel above runs): 16-byte aligned planes / pitches, dstW % 16 == 0,
-// dstH even, both rows of every pair share their chroma window, and the filter bank cannot push U,V outside
+// dstH even, the chroma windows of the two rows of every pair start at most one line apart, and the filter bank cannot
+// push U,V outside
 // (-256, 512) -- then clipping each value on its own is identical to the reference's "clip all four if any has bit 8
 // set" (output.c:966-971) because an in-range value is unchanged by av_clip_uint8.
 // Per pixel pair and row: 8 IMAD + 2 shifts + 2 clamps for the FIR, 12 for the colour terms, 17 for the two pixels.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int sat255(int v) { return __vimin_s32_relu(v, 255); }       // max(min(v, 255), 0), one VIMNMX
 
-template <bool BGR>
+template <bool BGR, bool MH>
 __global__ void __launch_bounds__(128)
 sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
 {
@@ -193,10 +195,13 @@ sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
     const uint8_t *Up = a.u + f * a.uFrame + gx * 8, *Vp = a.v + f * a.vFrame + gx * 8;
     uint8_t *D = a.dst + f * a.dstFrame + (size_t)y0 * a.dstStride + gx * 48;
 
+    // The two rows of a pair use chroma windows that start at the same line or one line apart (host-checked): five
+    // lines are loaded and row 1 runs a 5-tap filter whose first or last tap is zero.
     const int first = max(-3, p.vChrP[y0]);
-    uint2 u[4], v[4];
+    const int d1 = max(-3, p.vChrP[y0 + 1]) - first;         // 0 or 1
+    uint2 u[5], v[5];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 5; j++) {
         const int row = min(max(first + j, 0), p.chrSrcH - 1);
         u[j] = __ldg(reinterpret_cast<const uint2 *>(Up + (size_t)row * a.uStride));
         v[j] = __ldg(reinterpret_cast<const uint2 *>(Vp + (size_t)row * a.vStride));
@@ -204,7 +209,8 @@ sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
     const uint4 yy0 = ldg_stream(Yp), yy1 = ldg_stream(Yp + a.yStride);
     const uint4 cf = __ldg(reinterpret_cast<const uint4 *>(p.vChrF + (size_t)y0 * 4));   // 2 rows x 4 int16 taps
     const int c00 = lo16s(cf.x), c01 = hi16s(cf.x), c02 = lo16s(cf.y), c03 = hi16s(cf.y);
-    const int c10 = lo16s(cf.z), c11 = hi16s(cf.z), c12 = lo16s(cf.w), c13 = hi16s(cf.w);
+    const int t0 = lo16s(cf.z), t1 = hi16s(cf.z), t2 = lo16s(cf.w), t3 = hi16s(cf.w);
+    const int c10 = d1 ? 0 : t0, c11 = d1 ? t0 : t1, c12 = d1 ? t1 : t2, c13 = d1 ? t2 : t3, c14 = d1 ? t3 : 0;
     const int cy = p.k.cy, crv = p.k.crv, cgu = p.k.cgu, cgv = p.k.cgv, cbu = p.k.cbu, kr = p.k.kr, kg = p.k.kg, kb = p.k.kb;
 
     uint32_t o0[12], o1[12];
@@ -218,20 +224,23 @@ sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
             const int u2 = byte_of(c < 4 ? u[2].x : u[2].y, c & 3), u3 = byte_of(c < 4 ? u[3].x : u[3].y, c & 3);
             const int v0 = byte_of(c < 4 ? v[0].x : v[0].y, c & 3), v1 = byte_of(c < 4 ? v[1].x : v[1].y, c & 3);
             const int v2 = byte_of(c < 4 ? v[2].x : v[2].y, c & 3), v3 = byte_of(c < 4 ? v[3].x : v[3].y, c & 3);
+            const int u4 = byte_of(c < 4 ? u[4].x : u[4].y, c & 3), v4 = byte_of(c < 4 ? v[4].x : v[4].y, c & 3);
 #pragma unroll
             for (int ry = 0; ry < 2; ry++) {
                 const int k0 = ry ? c10 : c00, k1 = ry ? c11 : c01, k2 = ry ? c12 : c02, k3 = ry ? c13 : c03;
-                const int U = sat255((2048 + u0 * k0 + u1 * k1 + u2 * k2 + u3 * k3) >> 12);
-                const int V = sat255((2048 + v0 * k0 + v1 * k1 + v2 * k2 + v3 * k3) >> 12);
-                const int tr = cy * ((V * crv) >> 16) + kr;
-                const int tg = cy * (((U * cgu) >> 16) + ((V * cgv) >> 16)) + kg;
-                const int tb = cy * ((U * cbu) >> 16) + kb;
+                int su = 2048 + u0 * k0 + u1 * k1 + u2 * k2 + u3 * k3, sv = 2048 + v0 * k0 + v1 * k1 + v2 * k2 + v3 * k3;
+                if (ry) { su += u4 * c14; sv += v4 * c14; }
+                const int U = sat255(sra<12, MH>(su));
+                const int V = sat255(sra<12, MH>(sv));
+                const int tr = cy * sra<16, MH>(V * crv) + kr;
+                const int tg = cy * (sra<16, MH>(U * cgu) + sra<16, MH>(V * cgv)) + kg;
+                const int tb = cy * sra<16, MH>(U * cbu) + kb;
                 const uint4 yy = ry ? yy1 : yy0;
                 const uint32_t yw = q == 0 ? yy.x : q == 1 ? yy.y : q == 2 ? yy.z : yy.w;
                 const int Ya = cy * byte_of(yw, 2 * e), Yb = cy * byte_of(yw, 2 * e + 1);
                 int *r = ry ? r1 : r0, *g = ry ? g1 : g0, *b = ry ? b1 : b0;
-                r[2 * e] = (Ya + (BGR ? tb : tr)) >> 16; g[2 * e] = (Ya + tg) >> 16; b[2 * e] = (Ya + (BGR ? tr : tb)) >> 16;
-                r[2 * e + 1] = (Yb + (BGR ? tb : tr)) >> 16; g[2 * e + 1] = (Yb + tg) >> 16; b[2 * e + 1] = (Yb + (BGR ? tr : tb)) >> 16;
+                r[2 * e] = sra<16, MH>(Ya + (BGR ? tb : tr)); g[2 * e] = sra<16, MH>(Ya + tg); b[2 * e] = sra<16, MH>(Ya + (BGR ? tr : tb));
+                r[2 * e + 1] = sra<16, MH>(Yb + (BGR ? tb : tr)); g[2 * e + 1] = sra<16, MH>(Yb + tg); b[2 * e + 1] = sra<16, MH>(Yb + (BGR ? tr : tb));
             }
         }
         o0[3 * q + 0] = pack4_sat_u8(r0[0], g0[0], b0[0], r0[1]);
@@ -240,6 +249,112 @@ sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
         o1[3 * q + 0] = pack4_sat_u8(r1[0], g1[0], b1[0], r1[1]);
         o1[3 * q + 1] = pack4_sat_u8(g1[1], b1[1], r1[2], g1[2]);
         o1[3 * q + 2] = pack4_sat_u8(b1[2], r1[3], g1[3], b1[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        stg_stream(D + 16 * k, make_uint4(o0[4 * k], o0[4 * k + 1], o0[4 * k + 2], o0[4 * k + 3]));
+        stg_stream(D + a.dstStride + 16 * k, make_uint4(o1[4 * k], o1[4 * k + 1], o1[4 * k + 2], o1[4 * k + 3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FUSED kernel, dp4a variant of the interior fast path: the 4 chroma lines of a column are byte-transposed into one word
+// (2 PRMT per column instead of 4-5 byte extracts -- the 16-lane ALU pipe is the limiter of these kernels) and the 4-tap
+// FIR becomes two IDP4A (coefficient = 256 * hi + lo, lo unsigned byte, hi signed byte) plus one IMAD.  Per row pair the
+// packed taps, the fifth tap and the first chroma line come from a host-built table (SwsPairTaps).
+struct SwsPairTaps { uint32_t lo0, hi0, lo1, hi1; int tap4; int first; int pad0, pad1; };   // 32 bytes per row pair
+
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c)
+{ int d; asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{ int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+// four 32-bit sums -> one word of clip_u8(sum >> 16): the upper half-words of two sums are gathered by one PRMT, clipped
+// two at a time (packed s16 min + relu) and the four low bytes gathered by a third PRMT: 5 ALU-pipe instructions instead
+// of 4 shifts + 2 saturating packs.  Valid because |sum >> 16| < 2^15.
+__device__ __forceinline__ uint32_t pack4_hi16_sat(int w0, int w1, int w2, int w3)
+{
+    const uint32_t h01 = __byte_perm((uint32_t)w0, (uint32_t)w1, 0x7632), h23 = __byte_perm((uint32_t)w2, (uint32_t)w3, 0x7632);
+    const uint32_t c01 = __vimin_s16x2_relu(h01, 0x00FF00FFu), c23 = __vimin_s16x2_relu(h23, 0x00FF00FFu);
+    return __byte_perm(c01, c23, 0x6420);
+}
+
+template <bool BGR>
+__global__ void __launch_bounds__(128)
+sws_fused_rgb24_v3_kernel(SwsDev p, FusedArgs a, const SwsPairTaps *__restrict__ taps)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x;            // group of 16 pixels
+    const int rp = blockIdx.y * 4 + threadIdx.y;             // row pair
+    if (gx * 16 >= p.dstW || rp * 2 >= p.dstH) return;
+    const size_t f = blockIdx.z;
+    const int y0 = rp * 2;
+    const uint8_t *Yp = a.y + f * a.yFrame + (size_t)y0 * a.yStride + gx * 16;
+    const uint8_t *Up = a.u + f * a.uFrame + gx * 8, *Vp = a.v + f * a.vFrame + gx * 8;
+    uint8_t *D = a.dst + f * a.dstFrame + (size_t)y0 * a.dstStride + gx * 48;
+
+    const uint4 tq = __ldg(reinterpret_cast<const uint4 *>(taps + rp));
+    const int2 tz = __ldg(reinterpret_cast<const int2 *>(taps + rp) + 2);
+    const int first = tz.y, tap4 = tz.x;
+    uint2 u[5], v[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const int row = min(max(first + j, 0), p.chrSrcH - 1);
+        u[j] = __ldg(reinterpret_cast<const uint2 *>(Up + (size_t)row * a.uStride));
+        v[j] = __ldg(reinterpret_cast<const uint2 *>(Vp + (size_t)row * a.vStride));
+    }
+    const uint4 yy0 = ldg_stream(Yp), yy1 = ldg_stream(Yp + a.yStride);
+    const int cy = p.k.cy, crv = p.k.crv, cgu = p.k.cgu, cgv = p.k.cgv, cbu = p.k.cbu, kr = p.k.kr, kg = p.k.kg, kb = p.k.kb;
+
+    uint32_t o0[12], o1[12];
+#pragma unroll
+    for (int hq = 0; hq < 2; hq++) {                         // half of the group: 4 chroma columns = 8 pixels
+        // 4x4 byte transposes: TU[c] = (line0, line1, line2, line3) of chroma column c
+        uint32_t TU[4], TV[4];
+        {
+            const uint32_t r0 = hq ? u[0].y : u[0].x, r1 = hq ? u[1].y : u[1].x, r2 = hq ? u[2].y : u[2].x, r3 = hq ? u[3].y : u[3].x;
+            const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140), t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+            TU[0] = __byte_perm(t0, t1, 0x5410); TU[1] = __byte_perm(t0, t1, 0x7632); TU[2] = __byte_perm(t2, t3, 0x5410); TU[3] = __byte_perm(t2, t3, 0x7632);
+        }
+        {
+            const uint32_t r0 = hq ? v[0].y : v[0].x, r1 = hq ? v[1].y : v[1].x, r2 = hq ? v[2].y : v[2].x, r3 = hq ? v[3].y : v[3].x;
+            const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140), t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+            TV[0] = __byte_perm(t0, t1, 0x5410); TV[1] = __byte_perm(t0, t1, 0x7632); TV[2] = __byte_perm(t2, t3, 0x5410); TV[3] = __byte_perm(t2, t3, 0x7632);
+        }
+        const uint32_t u4w = hq ? u[4].y : u[4].x, v4w = hq ? v[4].y : v[4].x;
+#pragma unroll
+        for (int q2 = 0; q2 < 2; q2++) {                     // 4 pixels = 2 chroma columns per step
+            const int q = 2 * hq + q2;
+            int r0[4], g0[4], b0[4], r1[4], g1[4], b1[4];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = 2 * q2 + e;                    // chroma column inside this half
+                const int u4 = byte_of(u4w, c), v4 = byte_of(v4w, c);
+#pragma unroll
+                for (int ry = 0; ry < 2; ry++) {
+                    const uint32_t lo = ry ? tq.z : tq.x, hi = ry ? tq.w : tq.y;
+                    int su = dp4a_us(TU[c], hi, 0) * 256 + dp4a_uu(TU[c], lo, 2048);
+                    int sv = dp4a_us(TV[c], hi, 0) * 256 + dp4a_uu(TV[c], lo, 2048);
+                    if (ry) { su += u4 * tap4; sv += v4 * tap4; }
+                    const int U = sat255(su >> 12), V = sat255(sv >> 12);
+                    const int tr = cy * ((V * crv) >> 16) + kr;
+                    const int tg = cy * (((U * cgu) >> 16) + ((V * cgv) >> 16)) + kg;
+                    const int tb = cy * ((U * cbu) >> 16) + kb;
+                    const uint4 yy = ry ? yy1 : yy0;
+                    const uint32_t yw = q == 0 ? yy.x : q == 1 ? yy.y : q == 2 ? yy.z : yy.w;
+                    const int Ya = cy * byte_of(yw, 2 * e), Yb = cy * byte_of(yw, 2 * e + 1);
+                    // keep the 32-bit sums; the >> 16, the clip and the packing happen four values at a time below
+                    int *r = ry ? r1 : r0, *g = ry ? g1 : g0, *b = ry ? b1 : b0;
+                    r[2 * e] = Ya + (BGR ? tb : tr); g[2 * e] = Ya + tg; b[2 * e] = Ya + (BGR ? tr : tb);
+                    r[2 * e + 1] = Yb + (BGR ? tb : tr); g[2 * e + 1] = Yb + tg; b[2 * e + 1] = Yb + (BGR ? tr : tb);
+                }
+            }
+            o0[3 * q + 0] = pack4_hi16_sat(r0[0], g0[0], b0[0], r0[1]);
+            o0[3 * q + 1] = pack4_hi16_sat(g0[1], b0[1], r0[2], g0[2]);
+            o0[3 * q + 2] = pack4_hi16_sat(b0[2], r0[3], g0[3], b0[3]);
+            o1[3 * q + 0] = pack4_hi16_sat(r1[0], g1[0], b1[0], r1[1]);
+            o1[3 * q + 1] = pack4_hi16_sat(g1[1], b1[1], r1[2], g1[2]);
+            o1[3 * q + 2] = pack4_hi16_sat(b1[2], r1[3], g1[3], b1[3]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -364,6 +479,7 @@ struct SwsCudaContext {
     bool fast_ok = false;       // the fused interior kernel's host-side preconditions on the filter bank hold
     bool fused;                 // horizontal identity + vLum identity + 4-tap vChr -> one kernel
     void *d_tables = nullptr;   // all filter banks in one device allocation
+    void *d_pair_taps = nullptr; // SwsPairTaps[dstH / 2] for the dp4a fused kernel (fast_ok only)
     SwsDev dev;
     int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
     int lumStridePx = 0, chrStridePx = 0;
@@ -444,7 +560,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
         for (int y = 0; y < dstH && ok; y += 2) {
-            if (c->vChr.pos[y] != c->vChr.pos[y + 1]) ok = false;
+            const int f0 = c->vChr.pos[y] > -3 ? c->vChr.pos[y] : -3, f1 = c->vChr.pos[y + 1] > -3 ? c->vChr.pos[y + 1] : -3;
+            if (f1 - f0 != 0 && f1 - f0 != 1) ok = false;       // the pair's windows must start at most one line apart
             for (int r = 0; r < 2 && ok; r++) {
                 int lo = 2048, hi = 2048;
                 for (int j = 0; j < 4; j++) { int k = c->vChr.coef[(size_t)(y + r) * 4 + j]; if (k < 0) lo += 255 * k; else hi += 255 * k; }
@@ -456,6 +573,29 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->copy = !rgb && srcW == dstW && srcH == dstH;
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
+    if (c->fast_ok) {
+        std::vector<SwsPairTaps> pt(dstH / 2);
+        for (int rp = 0; rp < dstH / 2; rp++) {
+            const int y = 2 * rp;
+            const int f0 = c->vChr.pos[y] > -3 ? c->vChr.pos[y] : -3, f1 = c->vChr.pos[y + 1] > -3 ? c->vChr.pos[y + 1] : -3, d1 = f1 - f0;
+            int k0[4], k1[5] = { 0, 0, 0, 0, 0 };
+            for (int j = 0; j < 4; j++) { k0[j] = c->vChr.coef[(size_t)y * 4 + j]; k1[j + d1] = c->vChr.coef[(size_t)(y + 1) * 4 + j]; }
+            SwsPairTaps t = {};
+            for (int j = 0; j < 4; j++) {
+                t.lo0 |= (uint32_t)(k0[j] & 255) << (8 * j); t.hi0 |= (uint32_t)((k0[j] >> 8) & 255) << (8 * j);
+                t.lo1 |= (uint32_t)(k1[j] & 255) << (8 * j); t.hi1 |= (uint32_t)((k1[j] >> 8) & 255) << (8 * j);
+                if ((k0[j] >> 8) < -128 || (k0[j] >> 8) > 127 || (k1[j] >> 8) < -128 || (k1[j] >> 8) > 127) c->fast_ok = false;
+            }
+            t.tap4 = k1[4]; t.first = f0;
+            pt[rp] = t;
+        }
+        if (c->fast_ok) {
+            if (cudaMalloc(&c->d_pair_taps, pt.size() * sizeof(SwsPairTaps)) != cudaSuccess ||
+                cudaMemcpy(c->d_pair_taps, pt.data(), pt.size() * sizeof(SwsPairTaps), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("sws_getContext_cuda", cudaGetLastError()); cudaFree(c->d_tables); delete c; return nullptr;
+            }
+        }
+    }
     if (!c->fused && !c->copy) {
         c->lumStridePx = (dstW + 1 + 7) & ~7;
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
@@ -502,8 +642,14 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
                          !(a.vStride & 7) && !(a.uFrame & 7) && !(a.vFrame & 7) && !((uintptr_t)p.vChrF & 15);
         if (c->fast_ok && a16 && tuning("sws_fused_variant") != 1) {
             dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (p.dstH / 2 + 3) / 4, nframes);
-            if (p.bgr) sws_fused_rgb24_v2_kernel<true><<<g2, b2, 0, st>>>(p, a);
-            else       sws_fused_rgb24_v2_kernel<false><<<g2, b2, 0, st>>>(p, a);
+            if (tuning("sws_fused_variant") != 2) {             // default: the dp4a variant (71.9 % of HBM peak vs 66.1 %)
+                const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
+                if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, st>>>(p, a, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, st>>>(p, a, pt);
+                return check_launch("sws_scale:fused");
+            }
+            const bool mh = tuning("sws_mulhi") == 1;
+            if (p.bgr) { if (mh) sws_fused_rgb24_v2_kernel<true, true><<<g2, b2, 0, st>>>(p, a); else sws_fused_rgb24_v2_kernel<true, false><<<g2, b2, 0, st>>>(p, a); }
+            else       { if (mh) sws_fused_rgb24_v2_kernel<false, true><<<g2, b2, 0, st>>>(p, a); else sws_fused_rgb24_v2_kernel<false, false><<<g2, b2, 0, st>>>(p, a); }
             return check_launch("sws_scale:fused");
         }
         dim3 b(32, 8), g((p.dstW + 255) / 256, (p.dstH + 15) / 16, nframes);
@@ -539,7 +685,7 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
 static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
-    cudaFree(c->d_tables); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
     delete c;
 }
 

@@ -180,11 +180,15 @@ def make_sws_workload(torch, L, stream, rank):
     }
 
 
+H264_PICTURES = 16
+
+
 def make_h264_workload(torch, L, stream, rank):
-    """config 3: one 1920x1088 P picture, 64 slices: MC (put + avg) -> residual add -> deblocking wavefront."""
+    """config 3: 1920x1088 P pictures, 64 slices each: MC (put + avg) -> residual add per picture, then ONE deblocking
+    wavefront launch over the batch of independent pictures (stacked planes)."""
     from libav_b200 import synth
     lib = L.lib
-    mb_w, mb_h = 120, 68
+    mb_w, mb_h, P = 120, 68, H264_PICTURES
     refs = [synth.h264_picture(mb_w, mb_h, seed=11 + rank), synth.h264_picture(mb_w, mb_h, seed=12 + rank)]
     mc = synth.h264_mc_work(mb_w, mb_h, seed=5)
     res, coeffs, nnzc = synth.h264_residual_work(mb_w, mb_h, seed=6)
@@ -192,29 +196,34 @@ def make_h264_workload(torch, L, stream, rank):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
     d_refs = [[t(p) for p in r] for r in refs]
     d_planes = torch.tensor([[p.data_ptr() for p in r] for r in d_refs], dtype=torch.int64).cuda()
-    d_mc, d_res, d_nnz, d_dbk = t(mc), t(res), t(nnzc), t(dbk)
+    d_mc, d_res, d_nnz = t(mc), t(res), t(nnzc)
+    d_dbk = t(np.concatenate([dbk] * P))
     d_coef0 = t(coeffs)
-    d_coef = torch.empty_like(d_coef0)
+    d_coef = [torch.empty_like(d_coef0) for _ in range(P)]
     y, cb, cr = synth.h264_picture(mb_w, mb_h, seed=13)
-    d_y, d_cb, d_cr = t(y), t(cb), t(cr)
-    d_prog = torch.zeros(mb_h, dtype=torch.int32, device="cuda")
     W, H = 16 * mb_w, 16 * mb_h
+    d_y = torch.zeros(P * W * H, dtype=torch.uint8, device="cuda")
+    d_cb = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
+    d_cr = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
+    d_prog = torch.zeros(mb_h * P, dtype=torch.int32, device="cuda")
 
     def run(i):
-        d_coef.copy_(d_coef0)                              # the residual kernel consumes (zeroes) its coefficients
-        L.check(lib.ff_h264_mc_batch_cuda(d_mc.data_ptr(), mc.shape[0], d_planes.data_ptr(), d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(),
-                                          W, W // 2, W, H, stream), "mc")
-        L.check(lib.ff_h264_idct_add_mb_batch_cuda(d_res.data_ptr(), res.shape[0], d_coef.data_ptr(), 768, d_nnz.data_ptr(), d_y.data_ptr(),
-                                                   d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2, stream), "residual")
-        L.check(lib.ff_h264_deblock_picture_cuda(d_dbk.data_ptr(), mb_w, mb_h, d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2,
-                                                 d_prog.data_ptr(), stream), "deblock")
+        for k in range(P):
+            d_coef[k].copy_(d_coef0)                       # the residual kernel consumes (zeroes) its coefficients
+            py, pc = d_y.data_ptr() + k * W * H, k * W * H // 4
+            L.check(lib.ff_h264_mc_batch_cuda(d_mc.data_ptr(), mc.shape[0], d_planes.data_ptr(), py, d_cb.data_ptr() + pc, d_cr.data_ptr() + pc,
+                                              W, W // 2, W, H, stream), "mc")
+            L.check(lib.ff_h264_idct_add_mb_batch_cuda(d_res.data_ptr(), res.shape[0], d_coef[k].data_ptr(), 768, d_nnz.data_ptr(), py,
+                                                       d_cb.data_ptr() + pc, d_cr.data_ptr() + pc, W, W // 2, stream), "residual")
+        L.check(lib.ff_h264_deblock_batch_cuda(d_dbk.data_ptr(), mb_w, mb_h, P, d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2,
+                                               d_prog.data_ptr(), stream), "deblock")
 
-    n_mb = mb_w * mb_h
+    n_mb = mb_w * mb_h * P
     return {
-        "name": "H.264 1080p DSP path: qpel/chroma MC (%d partitions) + idct_add16/add8 + deblock wavefront, 64 synthetic slices, 1 picture per step" % mc.shape[0],
-        "run": run, "run_e2e": None, "pixels": W * H, "alg_bytes": int(n_mb * 2.37e3),
-        "launches_per_step": 4, "kernel": "h264_deblock_kernel", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
-        "l2": "one 3 MB picture: L2 resident by nature (latency-bound wavefront, not a bandwidth test)",
+        "name": "H.264 1080p DSP path: qpel/chroma MC (%d partitions/picture) + idct_add16/add8 + deblock wavefront, 64 synthetic slices, %d pictures per step" % (mc.shape[0], P),
+        "run": run, "run_e2e": None, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
+        "launches_per_step": 4 * P + 1, "kernel": "h264_deblock_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
+        "l2": "%d pictures x 3 MB + coefficients (%d MB) per step" % (P, P * coeffs.nbytes >> 20),
         "keep": (d_refs, d_planes, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog),
     }
 

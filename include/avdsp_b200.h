@@ -162,6 +162,11 @@ typedef struct FFH264DeblockMB {
 } FFH264DeblockMB;
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress /* mb_h uint32, scratch */, void *stream);
+/* n_pictures independent pictures in one launch: their planes are stacked vertically (picture k starts at luma row
+ * k * 16 * mb_h / chroma row k * 8 * mb_h of the same allocations), records likewise (k * mb_w * mb_h);
+ * progress holds mb_h * n_pictures words. */
+int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb,
+                               uint8_t *cr, int linesize, int uvlinesize, uint32_t *progress, void *stream);
 
 /* ---- MECmpContext, motion search, HpelDSPContext, FDCTDSPContext -----------------------------------------
  * me_cmp: n block pairs (cur + cur_off vs ref + ref_off, common stride, height h) through one metric; out[i] is

@@ -207,6 +207,154 @@ h264_deblock_kernel(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Deblocking wavefront, register-resident variant (default).  Same tile, same order, but the four vertical edges of a
+// macroblock are filtered by a lane on ITS OWN ROW held in registers (rows are independent for vertical edges), and the
+// four horizontal edges by a lane on its own COLUMN: two phases and two warp barriers per macroblock instead of eight
+// phases, no shared-memory round trip between edges.  The progress flag for macroblock x - 1 is published (fence + store)
+// just before macroblock x is written back, when the stores it covers have long retired, so the fence is cheap; rows
+// therefore follow three macroblocks behind the row above.  Pictures of a batch are stacked vertically (picture k starts
+// at macroblock row k * rows_pp): the first row of every picture has no row above.
+template <int N> struct Px { uint8_t v[N]; };
+
+__global__ void __launch_bounds__(32)
+h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                       int ls, int uvls, uint32_t *progress)
+{
+    __shared__ __align__(16) uint8_t Y[20 * LT];
+    __shared__ __align__(16) uint8_t C[2][10 * CT];
+    __shared__ FFH264DeblockMB P;
+    const int lane = threadIdx.x, row = blockIdx.x, lrow = row % rows_pp;
+    const bool has_above = lrow > 0;
+    volatile uint32_t *prog = progress;
+    uint8_t *const chroma_plane[2] = { cb, cr };
+
+    for (int x = 0; x < mb_w; x++) {
+        if (has_above) {
+            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
+            __syncwarp();
+        }
+        if (x > 0 && lane < 20) {                              // left context = last 4 columns of the finished neighbour
+            *reinterpret_cast<uint32_t *>(&Y[lane * LT]) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
+            const int p = lane / 10, r = lane % 10;
+            *reinterpret_cast<uint32_t *>(&C[p][r * CT]) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
+        }
+        __syncwarp();
+        if (lane < 20) {
+            const int ry = lane - 4;
+            if (lrow * 16 + ry >= 0) {
+                const uint8_t *g = luma + (size_t)(row * 16 + ry) * ls + x * 16;
+                const uint4 w = make_uint4(ld_cg32(g), ld_cg32(g + 4), ld_cg32(g + 8), ld_cg32(g + 12));
+                *reinterpret_cast<uint32_t *>(&Y[lane * LT + 4]) = w.x; *reinterpret_cast<uint32_t *>(&Y[lane * LT + 8]) = w.y;
+                *reinterpret_cast<uint32_t *>(&Y[lane * LT + 12]) = w.z; *reinterpret_cast<uint32_t *>(&Y[lane * LT + 16]) = w.w;
+            }
+            const int p = lane / 10, r = lane % 10;
+            if (lrow * 8 + r - 2 >= 0) {
+                const uint8_t *g = chroma_plane[p] + (size_t)(row * 8 + r - 2) * uvls + x * 8;
+                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 4]) = ld_cg32(g);
+                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 8]) = ld_cg32(g + 4);
+            }
+        }
+        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
+            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
+        __syncwarp();
+
+        // ---- vertical edges: lane-local rows ----
+        if (lane < 16) {
+            Px<20> r;
+            uint32_t *rw = reinterpret_cast<uint32_t *>(&Y[(4 + lane) * LT]);
+#pragma unroll
+            for (int k = 0; k < 5; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int a = P.alpha[0][e], b = P.beta[0][e];
+                if (a && b) {
+                    if (P.intra[0] >> e & 1) h264_luma_intra_line(&r.v[4 + 4 * e], 1, a, b);
+                    else { const int tc = P.tc0[0][e][lane >> 2]; if (tc >= 0) h264_luma_line(&r.v[4 + 4 * e], 1, a, b, tc); }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
+        } else {
+            const int p = (lane - 16) >> 3, l = (lane - 16) & 7;
+            Px<12> r;
+            uint32_t *rw = reinterpret_cast<uint32_t *>(&C[p][(2 + l) * CT]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
+#pragma unroll
+            for (int ce = 0; ce < 2; ce++) {
+                const int a = P.calpha[p][0][ce], b = P.cbeta[p][0][ce];
+                if (a && b) {
+                    const int in = P.cintra[p][0] >> ce & 1, tc = P.ctc0[p][0][ce][l >> 1];
+                    if (in || tc > 0) h264_chroma_line(&r.v[4 + 4 * ce], 1, a, b, tc, in);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
+        }
+        __syncwarp();
+        // ---- horizontal edges: lane-local columns ----
+        if (lane < 16) {
+            Px<20> c;
+            uint8_t *col = &Y[4 + lane];
+#pragma unroll
+            for (int k = 0; k < 20; k++) c.v[k] = col[k * LT];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int a = P.alpha[1][e], b = P.beta[1][e];
+                if (a && b) {
+                    if (P.intra[1] >> e & 1) h264_luma_intra_line(&c.v[4 + 4 * e], 1, a, b);
+                    else { const int tc = P.tc0[1][e][lane >> 2]; if (tc >= 0) h264_luma_line(&c.v[4 + 4 * e], 1, a, b, tc); }
+                }
+            }
+#pragma unroll
+            for (int k = 1; k < 20; k++) col[k * LT] = c.v[k];
+        } else {
+            const int p = (lane - 16) >> 3, l = (lane - 16) & 7;
+            Px<10> c;
+            uint8_t *col = &C[p][4 + l];
+#pragma unroll
+            for (int k = 0; k < 10; k++) c.v[k] = col[k * CT];
+#pragma unroll
+            for (int ce = 0; ce < 2; ce++) {
+                const int a = P.calpha[p][1][ce], b = P.cbeta[p][1][ce];
+                if (a && b) {
+                    const int in = P.cintra[p][1] >> ce & 1, tc = P.ctc0[p][1][ce][l >> 1];
+                    if (in || tc > 0) h264_chroma_line(&c.v[2 + 4 * ce], 1, a, b, tc, in);
+                }
+            }
+#pragma unroll
+            for (int k = 1; k < 10; k++) col[k * CT] = c.v[k];
+        }
+        __syncwarp();
+
+        // publish macroblock x - 1 (its stores were issued a whole macroblock ago), then write macroblock x back
+        if (x > 0) { __threadfence(); if (lane == 0) prog[row] = x; }
+        const int last = x == mb_w - 1;
+        if (lane < 20) {
+            const int ry = lane - 4;
+            if (ry >= -3 && lrow * 16 + ry >= 0) {
+                uint8_t *g = luma + (size_t)(row * 16 + ry) * ls + x * 16;
+                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT]);
+#pragma unroll
+                for (int k = 0; k < 3; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 4 + 4 * k]);
+                if (last) *reinterpret_cast<uint32_t *>(g + 12) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
+            }
+            const int p = lane / 10, r = lane % 10;
+            if (lrow * 8 + r - 2 >= 0) {
+                uint8_t *g = chroma_plane[p] + (size_t)(row * 8 + r - 2) * uvls + x * 8;
+                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT]);
+                *reinterpret_cast<uint32_t *>(g) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 4]);
+                if (last) *reinterpret_cast<uint32_t *>(g + 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
+            }
+        }
+        __syncwarp();
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) prog[row] = mb_w;
+}
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 int launch_h264_residual(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
@@ -233,16 +381,18 @@ int launch_h264_weight(const FFH264WeightRecord *recs, size_t n, uint8_t *plane,
     h264_weight_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, plane, src, stride);
     return check_launch("h264_weight_batch");
 }
-int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls,
-                        uint32_t *progress, cudaStream_t st)
+int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls,
+                        int uvls, uint32_t *progress, cudaStream_t st)
 {
-    if (mb_w <= 0 || mb_h <= 0) return 0;
+    if (mb_w <= 0 || mb_h <= 0 || n_pictures <= 0) return 0;
     if ((ls & 3) || (uvls & 3) || ((uintptr_t)luma & 3) || ((uintptr_t)cb & 3) || ((uintptr_t)cr & 3)) {
         set_error_msg("h264_deblock_picture", "planes and line sizes must be 4-byte aligned"); return -1;
     }
-    if (mb_h > 148 * 16) { set_error_msg("h264_deblock_picture", "picture too tall for one wavefront launch"); return -1; }
-    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * mb_h, st), "h264_deblock_picture");
-    h264_deblock_kernel<<<mb_h, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
+    const int rows = mb_h * n_pictures;
+    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows, st), "h264_deblock_picture");
+    // rows only ever wait on the row above (a lower block index, dispatched earlier), so any grid size makes progress
+    if (tuning("deblock_variant") == 1 && n_pictures == 1) h264_deblock_kernel<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
+    else h264_deblock_kernel_v2<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
     return check_launch("h264_deblock_picture");
 }
 
@@ -260,5 +410,8 @@ int ff_h264_weight_batch_cuda(const FFH264WeightRecord *recs, size_t n, uint8_t 
 { return launch_h264_weight(recs, n, plane, src, stride, (cudaStream_t)stream); }
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress, void *stream)
-{ return launch_h264_deblock(mbs, mb_w, mb_h, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
+{ return launch_h264_deblock(mbs, mb_w, mb_h, 1, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
+int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                               int linesize, int uvlinesize, uint32_t *progress, void *stream)
+{ return launch_h264_deblock(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
 }

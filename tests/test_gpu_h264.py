@@ -96,3 +96,29 @@ def test_weight_batch(gpu, checker, bi):
     gpu.check(gpu.lib.ff_h264_weight_batch_cuda(d_rec.ptr, rec.shape[0], d_pl.ptr, d_src.ptr if bi else None, 256, None))
     device.sync()
     assert np.array_equal(d_pl.download(np.uint8, plane.shape), want)
+
+
+def test_deblock_batch_of_stacked_pictures(gpu, checker):
+    """Three independent pictures stacked vertically in one launch: each must equal its own serial result, and nothing
+    may leak across the picture seams."""
+    from libav_b200 import device
+    mb_w, mb_h, P = 9, 4, 3
+    rng = np.random.default_rng(9)
+    ys, cbs, crs, recs, want = [], [], [], [], []
+    for k in range(P):
+        base = rng.integers(60, 190)
+        y = np.clip(base + rng.integers(-8, 9, size=(16 * mb_h, 16 * mb_w)), 0, 255).astype(np.uint8)
+        cb = np.clip(base + rng.integers(-8, 9, size=(8 * mb_h, 8 * mb_w)), 0, 255).astype(np.uint8)
+        cr = np.clip(base + rng.integers(-8, 9, size=(8 * mb_h, 8 * mb_w)), 0, 255).astype(np.uint8)
+        rec = synth.h264_deblock_work(mb_w, mb_h, seed=20 + k, slices=1 + k)
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hu.oracle_deblock(checker, rec, mb_w, mb_h, wy, wcb, wcr)
+        ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); want.append((wy, wcb, wcr))
+    Y, CB, CR, R = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs), np.concatenate(recs)
+    d_rec, dy, dcb, dcr = _dev(R), _dev(Y), _dev(CB), _dev(CR)
+    prog = device.DevBuf(4 * mb_h * P)
+    gpu.check(gpu.lib.ff_h264_deblock_batch_cuda(d_rec.ptr, mb_w, mb_h, P, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], prog.ptr, None))
+    device.sync()
+    assert np.array_equal(dy.download(np.uint8, Y.shape), np.concatenate([w[0] for w in want]))
+    assert np.array_equal(dcb.download(np.uint8, CB.shape), np.concatenate([w[1] for w in want]))
+    assert np.array_equal(dcr.download(np.uint8, CR.shape), np.concatenate([w[2] for w in want]))

@@ -120,7 +120,9 @@ int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_
  * (mvx & 7, mvy & 7).  Reference samples outside the picture are edge-replicated by clamped addressing, which is what
  * emulated_edge_mc (libavcodec/videodsp_template.c:27-94) / the decoder's padded edges provide.
  * All `put` records run before all `avg` records (list 0 then list 1, h264_mb.c:322-366); records of the same kind
- * must address disjoint destination pixels. */
+ * must address disjoint destination pixels.  A batch of independent pictures is expressed by stacking them vertically
+ * (destination and reference planes alike): pic_h is the height of ONE picture and a record with y in
+ * [k * pic_h, (k + 1) * pic_h) is clamped to picture k of its reference. */
 typedef struct FFH264MCRecord {
     int16_t x, y;          /* luma position of the partition */
     int16_t mvx, mvy;      /* quarter-pel motion vector */
@@ -161,10 +163,10 @@ typedef struct FFH264DeblockMB {
     uint8_t pad[2];
 } FFH264DeblockMB;
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
-                                 int linesize, int uvlinesize, uint32_t *progress /* mb_h uint32, scratch */, void *stream);
+                                 int linesize, int uvlinesize, uint32_t *progress /* 2 * mb_h uint32, scratch */, void *stream);
 /* n_pictures independent pictures in one launch: their planes are stacked vertically (picture k starts at luma row
  * k * 16 * mb_h / chroma row k * 8 * mb_h of the same allocations), records likewise (k * mb_w * mb_h);
- * progress holds mb_h * n_pictures words. */
+ * progress holds 2 * mb_h * n_pictures words. */
 int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb,
                                uint8_t *cr, int linesize, int uvlinesize, uint32_t *progress, void *stream);
 

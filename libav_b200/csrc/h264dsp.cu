@@ -49,15 +49,15 @@ h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t
 
 // ---------------------------------------------------------------------------------------------------
 struct ClampFetch {
-    const uint8_t *p; int stride, w, h;
+    const uint8_t *p; int stride, w, y0, y1;           // rows [y0, y1] belong to the record's picture
     __device__ __forceinline__ int operator()(int x, int y) const
-    { return __ldg(p + (size_t)min(max(y, 0), h - 1) * stride + min(max(x, 0), w - 1)); }
+    { return __ldg(p + (size_t)min(max(y, y0), y1) * stride + min(max(x, 0), w - 1)); }
 };
 
 __global__ void __launch_bounds__(128)
 h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
                uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph,
-               int pass)
+               int pass)   // ph = height of ONE picture; pictures of a batch are stacked vertically
 {
     const int lane = threadIdx.x & 31;
     size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -67,7 +67,9 @@ h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264Re
     const FFH264RefPlanes ref = refs[r.ref];
     const int mx = r.mvx + r.x * 4, my = r.mvy + r.y * 4;          // quarter-pel position, h264_mb.c:216-217
     const int nl = r.w * r.h, cw = r.w >> 1, chh = r.h >> 1, nc = cw * chh;
-    const ClampFetch Y = { ref.y, ls, pw, ph }, CB = { ref.cb, uvls, pw >> 1, ph >> 1 }, CR = { ref.cr, uvls, pw >> 1, ph >> 1 };
+    const int pic = r.y / ph, ly0 = pic * ph, cy0 = pic * (ph >> 1);
+    const ClampFetch Y = { ref.y, ls, pw, ly0, ly0 + ph - 1 }, CB = { ref.cb, uvls, pw >> 1, cy0, cy0 + (ph >> 1) - 1 },
+                     CR = { ref.cr, uvls, pw >> 1, cy0, cy0 + (ph >> 1) - 1 };
     for (int it = lane; it < nl + 2 * nc; it += 32) {
         if (it < nl) {
             int px = it % r.w, py = it / r.w;
@@ -217,142 +219,124 @@ h264_deblock_kernel(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h,
 // at macroblock row k * rows_pp): the first row of every picture has no row above.
 template <int N> struct Px { uint8_t v[N]; };
 
-__global__ void __launch_bounds__(32)
-h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb, uint8_t *cr,
-                       int ls, int uvls, uint32_t *progress)
+// Luma and chroma are independent planes: blockIdx.y = 0 runs the luma wavefront (16 lines per edge), blockIdx.y = 1 the
+// chroma one (8 cb + 8 cr lines), each with its own progress flags, so neither waits for the other's edge passes.
+template <bool CHROMA>
+__device__ __forceinline__ void deblock_row(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb,
+                                            uint8_t *cr, int ls, int uvls, volatile uint32_t *prog, uint8_t *T, FFH264DeblockMB &P)
 {
-    __shared__ __align__(16) uint8_t Y[20 * LT];
-    __shared__ __align__(16) uint8_t C[2][10 * CT];
-    __shared__ FFH264DeblockMB P;
+    // tile T: luma 20 rows x LT (rows -4..15, cols -4..15), chroma 2 planes x 10 rows x CT (rows -2..7, cols -4..7)
     const int lane = threadIdx.x, row = blockIdx.x, lrow = row % rows_pp;
     const bool has_above = lrow > 0;
-    volatile uint32_t *prog = progress;
-    uint8_t *const chroma_plane[2] = { cb, cr };
+    constexpr int NR = CHROMA ? 20 : 20;            // loader lanes: 20 luma rows, or 2 x 10 chroma rows
+    constexpr int PITCH = CHROMA ? CT : LT, MBW = CHROMA ? 8 : 16, TOP = CHROMA ? 2 : 4;
+    const int pl = CHROMA ? lane / 10 : 0, tr = CHROMA ? lane % 10 : lane;             // loader lane -> (plane, tile row)
+    uint8_t *const plane = CHROMA ? (pl ? cr : cb) : luma;
+    const int pitch_g = CHROMA ? uvls : ls;
+    uint8_t *const trow = T + (CHROMA ? pl * 10 * CT : 0) + tr * PITCH;                 // this loader lane's tile row
+    const bool row_exists = lane < NR && lrow * MBW + tr - TOP >= 0;
+    uint8_t *const grow = plane + (size_t)(row * MBW + tr - TOP) * pitch_g;             // same row in the picture
 
     for (int x = 0; x < mb_w; x++) {
         if (has_above) {
             if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
             __syncwarp();
         }
-        if (x > 0 && lane < 20) {                              // left context = last 4 columns of the finished neighbour
-            *reinterpret_cast<uint32_t *>(&Y[lane * LT]) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
-            const int p = lane / 10, r = lane % 10;
-            *reinterpret_cast<uint32_t *>(&C[p][r * CT]) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
-        }
-        __syncwarp();
-        if (lane < 20) {
-            const int ry = lane - 4;
-            if (lrow * 16 + ry >= 0) {
-                const uint8_t *g = luma + (size_t)(row * 16 + ry) * ls + x * 16;
-                const uint4 w = make_uint4(ld_cg32(g), ld_cg32(g + 4), ld_cg32(g + 8), ld_cg32(g + 12));
-                *reinterpret_cast<uint32_t *>(&Y[lane * LT + 4]) = w.x; *reinterpret_cast<uint32_t *>(&Y[lane * LT + 8]) = w.y;
-                *reinterpret_cast<uint32_t *>(&Y[lane * LT + 12]) = w.z; *reinterpret_cast<uint32_t *>(&Y[lane * LT + 16]) = w.w;
-            }
-            const int p = lane / 10, r = lane % 10;
-            if (lrow * 8 + r - 2 >= 0) {
-                const uint8_t *g = chroma_plane[p] + (size_t)(row * 8 + r - 2) * uvls + x * 8;
-                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 4]) = ld_cg32(g);
-                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 8]) = ld_cg32(g + 4);
+        if (lane < NR) {
+            if (x > 0) *reinterpret_cast<uint32_t *>(trow) = *reinterpret_cast<const uint32_t *>(trow + MBW);   // left context
+            if (row_exists) {
+                const uint8_t *g = grow + x * MBW;
+#pragma unroll
+                for (int k = 0; k < MBW / 4; k++) *reinterpret_cast<uint32_t *>(trow + 4 + 4 * k) = ld_cg32(g + 4 * k);
             }
         }
         if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
             reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
         __syncwarp();
 
-        // ---- vertical edges: lane-local rows ----
         if (lane < 16) {
-            Px<20> r;
-            uint32_t *rw = reinterpret_cast<uint32_t *>(&Y[(4 + lane) * LT]);
+            const int p = CHROMA ? lane >> 3 : 0, l = CHROMA ? lane & 7 : lane;          // filter lane -> (plane, line)
+            uint8_t *const tp = T + (CHROMA ? p * 10 * CT : 0);
+            // ---- vertical edges: this lane's row in registers ----
+            {
+                constexpr int W = CHROMA ? 12 : 20;
+                Px<W> r;
+                uint32_t *rw = reinterpret_cast<uint32_t *>(tp + (TOP + l) * PITCH);
 #pragma unroll
-            for (int k = 0; k < 5; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
+                for (int k = 0; k < W / 4; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int a = P.alpha[0][e], b = P.beta[0][e];
-                if (a && b) {
-                    if (P.intra[0] >> e & 1) h264_luma_intra_line(&r.v[4 + 4 * e], 1, a, b);
-                    else { const int tc = P.tc0[0][e][lane >> 2]; if (tc >= 0) h264_luma_line(&r.v[4 + 4 * e], 1, a, b, tc); }
+                for (int e = 0; e < (CHROMA ? 2 : 4); e++) {
+                    if (!CHROMA) {
+                        const int a = P.alpha[0][e], b = P.beta[0][e];
+                        if (a && b) {
+                            if (P.intra[0] >> e & 1) h264_luma_intra_line(&r.v[4 + 4 * e], 1, a, b);
+                            else { const int tc = P.tc0[0][e][l >> 2]; if (tc >= 0) h264_luma_line(&r.v[4 + 4 * e], 1, a, b, tc); }
+                        }
+                    } else {
+                        const int a = P.calpha[p][0][e], b = P.cbeta[p][0][e];
+                        if (a && b) {
+                            const int in = P.cintra[p][0] >> e & 1, tc = P.ctc0[p][0][e][l >> 1];
+                            if (in || tc > 0) h264_chroma_line(&r.v[4 + 4 * e], 1, a, b, tc, in);
+                        }
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < W / 4; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
             }
+            __syncwarp(0xffffu);
+            // ---- horizontal edges: this lane's column in registers ----
+            {
+                constexpr int H = CHROMA ? 10 : 20;
+                Px<H> c;
+                uint8_t *col = tp + 4 + l;
 #pragma unroll
-            for (int k = 0; k < 5; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
-        } else {
-            const int p = (lane - 16) >> 3, l = (lane - 16) & 7;
-            Px<12> r;
-            uint32_t *rw = reinterpret_cast<uint32_t *>(&C[p][(2 + l) * CT]);
+                for (int k = 0; k < H; k++) c.v[k] = col[k * PITCH];
 #pragma unroll
-            for (int k = 0; k < 3; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
-#pragma unroll
-            for (int ce = 0; ce < 2; ce++) {
-                const int a = P.calpha[p][0][ce], b = P.cbeta[p][0][ce];
-                if (a && b) {
-                    const int in = P.cintra[p][0] >> ce & 1, tc = P.ctc0[p][0][ce][l >> 1];
-                    if (in || tc > 0) h264_chroma_line(&r.v[4 + 4 * ce], 1, a, b, tc, in);
+                for (int e = 0; e < (CHROMA ? 2 : 4); e++) {
+                    if (!CHROMA) {
+                        const int a = P.alpha[1][e], b = P.beta[1][e];
+                        if (a && b) {
+                            if (P.intra[1] >> e & 1) h264_luma_intra_line(&c.v[4 + 4 * e], 1, a, b);
+                            else { const int tc = P.tc0[1][e][l >> 2]; if (tc >= 0) h264_luma_line(&c.v[4 + 4 * e], 1, a, b, tc); }
+                        }
+                    } else {
+                        const int a = P.calpha[p][1][e], b = P.cbeta[p][1][e];
+                        if (a && b) {
+                            const int in = P.cintra[p][1] >> e & 1, tc = P.ctc0[p][1][e][l >> 1];
+                            if (in || tc > 0) h264_chroma_line(&c.v[2 + 4 * e], 1, a, b, tc, in);
+                        }
+                    }
                 }
+#pragma unroll
+                for (int k = 1; k < H; k++) col[k * PITCH] = c.v[k];
             }
-#pragma unroll
-            for (int k = 0; k < 3; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
-        }
-        __syncwarp();
-        // ---- horizontal edges: lane-local columns ----
-        if (lane < 16) {
-            Px<20> c;
-            uint8_t *col = &Y[4 + lane];
-#pragma unroll
-            for (int k = 0; k < 20; k++) c.v[k] = col[k * LT];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int a = P.alpha[1][e], b = P.beta[1][e];
-                if (a && b) {
-                    if (P.intra[1] >> e & 1) h264_luma_intra_line(&c.v[4 + 4 * e], 1, a, b);
-                    else { const int tc = P.tc0[1][e][lane >> 2]; if (tc >= 0) h264_luma_line(&c.v[4 + 4 * e], 1, a, b, tc); }
-                }
-            }
-#pragma unroll
-            for (int k = 1; k < 20; k++) col[k * LT] = c.v[k];
-        } else {
-            const int p = (lane - 16) >> 3, l = (lane - 16) & 7;
-            Px<10> c;
-            uint8_t *col = &C[p][4 + l];
-#pragma unroll
-            for (int k = 0; k < 10; k++) c.v[k] = col[k * CT];
-#pragma unroll
-            for (int ce = 0; ce < 2; ce++) {
-                const int a = P.calpha[p][1][ce], b = P.cbeta[p][1][ce];
-                if (a && b) {
-                    const int in = P.cintra[p][1] >> ce & 1, tc = P.ctc0[p][1][ce][l >> 1];
-                    if (in || tc > 0) h264_chroma_line(&c.v[2 + 4 * ce], 1, a, b, tc, in);
-                }
-            }
-#pragma unroll
-            for (int k = 1; k < 10; k++) col[k * CT] = c.v[k];
         }
         __syncwarp();
 
         // publish macroblock x - 1 (its stores were issued a whole macroblock ago), then write macroblock x back
         if (x > 0) { __threadfence(); if (lane == 0) prog[row] = x; }
-        const int last = x == mb_w - 1;
-        if (lane < 20) {
-            const int ry = lane - 4;
-            if (ry >= -3 && lrow * 16 + ry >= 0) {
-                uint8_t *g = luma + (size_t)(row * 16 + ry) * ls + x * 16;
-                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT]);
+        if (row_exists && tr >= 1) {                            // tile row 0 is read-only context
+            uint8_t *g = grow + x * MBW;
+            if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(trow);
 #pragma unroll
-                for (int k = 0; k < 3; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 4 + 4 * k]);
-                if (last) *reinterpret_cast<uint32_t *>(g + 12) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
-            }
-            const int p = lane / 10, r = lane % 10;
-            if (lrow * 8 + r - 2 >= 0) {
-                uint8_t *g = chroma_plane[p] + (size_t)(row * 8 + r - 2) * uvls + x * 8;
-                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT]);
-                *reinterpret_cast<uint32_t *>(g) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 4]);
-                if (last) *reinterpret_cast<uint32_t *>(g + 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
-            }
+            for (int k = 0; k < MBW / 4 - 1; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(trow + 4 + 4 * k);
+            if (x == mb_w - 1) *reinterpret_cast<uint32_t *>(g + MBW - 4) = *reinterpret_cast<const uint32_t *>(trow + MBW);
         }
         __syncwarp();
     }
     __threadfence();
     __syncwarp();
     if (lane == 0) prog[row] = mb_w;
+}
+
+__global__ void __launch_bounds__(32)
+h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                       int ls, int uvls, uint32_t *progress)
+{
+    __shared__ __align__(16) uint8_t T[20 * LT];
+    __shared__ FFH264DeblockMB P;
+    if (blockIdx.y == 0) deblock_row<false>(mbs, mb_w, rows_pp, luma, cb, cr, ls, uvls, progress, T, P);
+    else                 deblock_row<true>(mbs, mb_w, rows_pp, luma, cb, cr, ls, uvls, progress + gridDim.x, T, P);
 }
 
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
@@ -389,10 +373,10 @@ int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pi
         set_error_msg("h264_deblock_picture", "planes and line sizes must be 4-byte aligned"); return -1;
     }
     const int rows = mb_h * n_pictures;
-    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows, st), "h264_deblock_picture");
+    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows * 2, st), "h264_deblock_picture");
     // rows only ever wait on the row above (a lower block index, dispatched earlier), so any grid size makes progress
     if (tuning("deblock_variant") == 1 && n_pictures == 1) h264_deblock_kernel<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
-    else h264_deblock_kernel_v2<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
+    else h264_deblock_kernel_v2<<<dim3(rows, 2), 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
     return check_launch("h264_deblock_picture");
 }
 

@@ -69,7 +69,7 @@ def test_deblock_wavefront(gpu, checker, mb_w, mb_h, slices):
     hu.oracle_deblock(checker, rec, mb_w, mb_h, wy, wcb, wcr)
     assert not np.array_equal(wy, y)                                    # the test does exercise the filters
     d_rec, dy, dcb, dcr = _dev(rec), _dev(y), _dev(cb), _dev(cr)
-    prog = device.DevBuf(4 * mb_h)
+    prog = device.DevBuf(8 * mb_h)
     gpu.check(gpu.lib.ff_h264_deblock_picture_cuda(d_rec.ptr, mb_w, mb_h, dy.ptr, dcb.ptr, dcr.ptr, y.strides[0], cb.strides[0], prog.ptr, None))
     device.sync()
     assert np.array_equal(dy.download(np.uint8, y.shape), wy)
@@ -116,9 +116,37 @@ def test_deblock_batch_of_stacked_pictures(gpu, checker):
         ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); want.append((wy, wcb, wcr))
     Y, CB, CR, R = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs), np.concatenate(recs)
     d_rec, dy, dcb, dcr = _dev(R), _dev(Y), _dev(CB), _dev(CR)
-    prog = device.DevBuf(4 * mb_h * P)
+    prog = device.DevBuf(8 * mb_h * P)
     gpu.check(gpu.lib.ff_h264_deblock_batch_cuda(d_rec.ptr, mb_w, mb_h, P, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], prog.ptr, None))
     device.sync()
     assert np.array_equal(dy.download(np.uint8, Y.shape), np.concatenate([w[0] for w in want]))
     assert np.array_equal(dcb.download(np.uint8, CB.shape), np.concatenate([w[1] for w in want]))
     assert np.array_equal(dcr.download(np.uint8, CR.shape), np.concatenate([w[2] for w in want]))
+
+
+def test_mc_batch_of_stacked_pictures(gpu, checker):
+    """Two pictures stacked vertically: vectors that leave a picture must be clamped to THAT picture's reference."""
+    from libav_b200 import device
+    mb_w, mb_h, P = 5, 3, 2
+    H = 16 * mb_h
+    refs = [[synth.h264_picture(mb_w, mb_h, seed=30 + 2 * k + r) for r in range(2)] for k in range(P)]
+    recs, wants, outs = [], [], []
+    for k in range(P):
+        rec = synth.h264_mc_work(mb_w, mb_h, seed=40 + k, max_mv=80)
+        y, cb, cr = synth.h264_picture(mb_w, mb_h, seed=50 + k)
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hu.oracle_mc(checker, rec, refs[k], wy, wcb, wcr, pad=64)
+        r2 = rec.copy(); r2["y"] = r2["y"] + k * H
+        recs.append(r2); wants.append((wy, wcb, wcr)); outs.append((y, cb, cr))
+    rec = np.concatenate(recs)
+    stack = lambda idx, r: np.concatenate([refs[k][r][idx] for k in range(P)])
+    dref = [[_dev(stack(i, r)) for i in range(3)] for r in range(2)]
+    planes = np.array([[p.ptr for p in r] for r in dref], dtype=np.uint64)
+    Y, CB, CR = (np.concatenate([o[i] for o in outs]) for i in range(3))
+    d_planes, d_rec, dy, dcb, dcr = _dev(planes), _dev(rec), _dev(Y), _dev(CB), _dev(CR)
+    gpu.check(gpu.lib.ff_h264_mc_batch_cuda(d_rec.ptr, rec.shape[0], d_planes.ptr, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0],
+                                            16 * mb_w, H, None))
+    device.sync()
+    assert np.array_equal(dy.download(np.uint8, Y.shape), np.concatenate([w[0] for w in wants]))
+    assert np.array_equal(dcb.download(np.uint8, CB.shape), np.concatenate([w[1] for w in wants]))
+    assert np.array_equal(dcr.download(np.uint8, CR.shape), np.concatenate([w[2] for w in wants]))

@@ -180,7 +180,7 @@ def make_sws_workload(torch, L, stream, rank):
     }
 
 
-H264_PICTURES = 32
+H264_PICTURES = 30      # 30 x 1088 rows still fit the int16 y of FFH264MCRecord
 
 
 def make_h264_workload(torch, L, stream, rank):

@@ -163,6 +163,90 @@ full_search_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Full search, register-tiled variant (default).  The 48x52 window is stored four times in shared memory, copy s shifted
+// left by s bytes, so every candidate reads ALIGNED words (no funnel shifts), and a thread owns five vertically adjacent
+// candidates of one column: the 20 reference rows it needs are read once (80 LDS.32) and reused by up to five
+// candidates, 320 vabsdiff4 per thread.  33 columns x 7 row groups = 231 of the 256 threads carry work.  Copies are
+// spaced 8 banks apart, which makes the 32 lanes of a warp (consecutive dx) hit 32 different banks.
+constexpr int FS2_ROWW = 12;                                   // words per window row in a shifted copy (48 bytes)
+constexpr int FS2_COPY = FS_WIN * FS2_ROWW + 8;                // words per copy, +8 words = 8 banks of skew
+constexpr int FS2_DYG = 5;
+
+__global__ void __launch_bounds__(256)
+full_search_kernel_v2(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int stride, int w, int h, int mb_y0,
+                      int32_t *__restrict__ out)
+{
+    __shared__ __align__(16) uint32_t raw[FS_WIN * 13];        // 52 bytes per row
+    __shared__ __align__(16) uint32_t win[4 * FS2_COPY];
+    __shared__ unsigned long long best_s[8];
+    const int mbw = w >> 4, mbx = blockIdx.x, mby = mb_y0 + blockIdx.y, t = threadIdx.x;
+    const int px = mbx * 16, py = mby * 16;
+    for (int i = t; i < FS_WIN * 13; i += 256) {
+        const int r = i / 13, c4 = i % 13, gy = min(max(py - FS_R + r, 0), h - 1);
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(ref + (size_t)gy * stride + min(max(px - FS_R + 4 * c4 + k, 0), w - 1)) << (8 * k);
+        raw[i] = v;
+    }
+    uint32_t c[16][4];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(cur + (size_t)(py + r) * stride + px);
+        c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
+    }
+    __syncthreads();
+    for (int i = t; i < 4 * FS_WIN * FS2_ROWW; i += 256) {
+        const int s = i / (FS_WIN * FS2_ROWW), rem = i % (FS_WIN * FS2_ROWW), r = rem / FS2_ROWW, cw = rem % FS2_ROWW;
+        win[s * FS2_COPY + rem] = __funnelshift_r(raw[r * 13 + cw], raw[r * 13 + cw + 1], 8 * s);
+    }
+    __syncthreads();
+
+    const int xmin = max(-px, -FS_R), xmax = min(w - 16 - px, FS_R), ymin = max(-py, -FS_R), ymax = min(h - 16 - py, FS_R);
+    unsigned long long best = ~0ull;
+    if (t < 33 * 7) {
+        const int dxi = t % 33, g = t / 33, dy0 = g * FS2_DYG;                      // candidates (dxi, dy0 .. dy0 + 4), biased by +16
+        const uint32_t *base = &win[(dxi & 3) * FS2_COPY + (dxi >> 2)];
+        unsigned sad[FS2_DYG] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+        for (int rr = 0; rr < 16 + FS2_DYG - 1; rr++) {
+            const int wr = min(dy0 + rr, FS_WIN - 1);                                // rows past the window only feed invalid candidates
+            const uint32_t *row = base + wr * FS2_ROWW;
+            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+#pragma unroll
+            for (int j = 0; j < FS2_DYG; j++) {
+                const int cr = rr - j;
+                if (cr >= 0 && cr < 16) {
+                    sad[j] = __vsadu4(c[cr][0], w0) + sad[j];
+                    sad[j] = __vsadu4(c[cr][1], w1) + sad[j];
+                    sad[j] = __vsadu4(c[cr][2], w2) + sad[j];
+                    sad[j] = __vsadu4(c[cr][3], w3) + sad[j];
+                }
+            }
+        }
+        const int dx = dxi - FS_R;
+#pragma unroll
+        for (int j = 0; j < FS2_DYG; j++) {
+            const int dy = dy0 + j - FS_R;
+            if (dx >= xmin && dx <= xmax && dy >= ymin && dy <= ymax) {
+                const unsigned long long key = ((unsigned long long)sad[j] << 11) | (unsigned)((dy0 + j) * 33 + dxi);
+                best = key < best ? key : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v < best ? v : best; }
+    if ((t & 31) == 0) best_s[t >> 5] = best;
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; k++) best = best_s[k] < best ? best_s[k] : best;
+        const int idx = (int)(best & 2047);
+        int32_t *o = out + 3 * ((size_t)mby * mbw + mbx);
+        o[0] = idx % 33 - FS_R; o[1] = idx / 33 - FS_R; o[2] = (int32_t)(best >> 11);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 hpel_kernel(const FFHpelRecord *__restrict__ recs, size_t n, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, ptrdiff_t st)
 {
@@ -298,7 +382,8 @@ int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int 
     if (mb_y1 <= mb_y0) return 0;
     if (range != FS_R) { set_error_msg("full_search", "only me_range 16 is built"); return -1; }
     if ((w & 15) || (h & 15) || (stride & 15) || ((uintptr_t)cur & 15)) { set_error_msg("full_search", "picture must be MB aligned, cur 16-byte aligned"); return -1; }
-    full_search_kernel<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
+    if (tuning("full_search_variant") == 1) full_search_kernel<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
+    else full_search_kernel_v2<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
     return check_launch("full_search");
 }
 

@@ -364,6 +364,35 @@ sws_fused_rgb24_v3_kernel(SwsDev p, FusedArgs a, const SwsPairTaps *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Unscaled table converter: the SwsFunc the reference installs for same-size yuv420p -> rgb24/bgr24 when SWS_ACCURATE_RND
+// is NOT set and dstH is even (swscale_unscaled.c:1051-1055 -> yuv2rgb_c_24_rgb / _bgr, yuv2rgb.c:126-175, :335-372):
+// chroma is taken from the nearest sample in both directions (no vertical interpolation), then the same tables.
+// It converts dstW & ~1 pixels per row (groups of 8, then 4, then 2: an odd last column is left untouched).
+// thread = one chroma sample = 2x2 pixels.
+__global__ void __launch_bounds__(256)
+sws_unscaled_yuv2rgb24_kernel(SwsDev p, FusedArgs a)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cyy = blockIdx.y;
+    if (cx >= (p.dstW >> 1) || cyy >= (p.dstH >> 1)) return;
+    const size_t f = blockIdx.z;
+    const int U = a.u[f * a.uFrame + (size_t)cyy * a.uStride + cx], V = a.v[f * a.vFrame + (size_t)cyy * a.vStride + cx];
+    const ChromaTerms t = chroma_terms(U, V, p.k);
+    const int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
+#pragma unroll
+    for (int ry = 0; ry < 2; ry++) {
+        const uint8_t *yp = a.y + f * a.yFrame + (size_t)(2 * cyy + ry) * a.yStride + 2 * cx;
+        uint8_t *d = a.dst + f * a.dstFrame + (size_t)(2 * cyy + ry) * a.dstStride + 6 * cx;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int Y = yp[e];
+            d[3 * e + 0] = (uint8_t)clip_u8((p.k.cy * Y + tr) >> 16);
+            d[3 * e + 1] = (uint8_t)clip_u8((p.k.cy * Y + t.tg) >> 16);
+            d[3 * e + 2] = (uint8_t)clip_u8((p.k.cy * Y + tb) >> 16);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // GENERAL path, pass 1: hScale8To15 (swscale.c:133-147) for one plane; thread = (column, row)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -476,6 +505,7 @@ struct SwsCudaContext {
     int dstFormat;
     bool copy = false;          // unscaled yuv420p -> yuv420p: the reference installs a plain plane copy
                                 // (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper), whatever the flags
+    bool table_unscaled = false; // same-size rgb without SWS_ACCURATE_RND, even height: the reference's unscaled yuv2rgb SwsFunc
     bool fast_ok = false;       // the fused interior kernel's host-side preconditions on the filter bank hold
     bool fused;                 // horizontal identity + vLum identity + 4-tap vChr -> one kernel
     void *d_tables = nullptr;   // all filter banks in one device allocation
@@ -531,12 +561,6 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     const bool rgb = dstFormat != FMT_YUV420P;
     if (flags & SWS_FULL_CHR_H_INT) { set_error_msg("sws_getContext_cuda", "SWS_FULL_CHR_H_INT is not taken over"); return nullptr; }
-    if (rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1)) {
-        // the reference would pick its table-driven unscaled converter here (swscale_unscaled.c:1051-1055),
-        // whose output differs from the scaler path; that SwsFunc is not part of this back-end yet
-        set_error_msg("sws_getContext_cuda", "unscaled yuv2rgb without SWS_ACCURATE_RND is not taken over");
-        return nullptr;
-    }
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
     c->dstFormat = dstFormat;
@@ -555,7 +579,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         static const int itu601[4] = { 104597, 132201, 25675, 53279 };     // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT]
         rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
     }
-    c->fused = rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->table_unscaled = rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);   // swscale_unscaled.c:1051-1055
+    c->fused = !c->table_unscaled && rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -596,7 +621,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             }
         }
     }
-    if (!c->fused && !c->copy) {
+    if (!c->fused && !c->copy && !c->table_unscaled) {
         c->lumStridePx = (dstW + 1 + 7) & ~7;
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
         if (cudaMalloc(&c->d_lum, (size_t)c->lumStridePx * srcH * 2) != cudaSuccess ||
@@ -627,6 +652,14 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
                                            cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
             }
         return 0;
+    }
+    if (c->table_unscaled) {
+        FusedArgs a;
+        a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst = dst[0];
+        a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2]; a.dstStride = dstStride[0];
+        a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2]; a.dstFrame = dstFrame[0];
+        sws_unscaled_yuv2rgb24_kernel<<<dim3(((p.dstW >> 1) + 255) / 256, p.dstH >> 1, nframes), 256, 0, st>>>(p, a);
+        return check_launch("sws_scale:unscaled");
     }
     if (c->fused) {
         FusedArgs a;
@@ -760,6 +793,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         // whole pixel pairs are written (one pixel past an odd width) when the caller's stride has room
         size_t wbytes = (size_t)g.dstW * 3;
         if (odd && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;
+        if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * 3;       // that converter leaves an odd last column untouched
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);

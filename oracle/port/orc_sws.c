@@ -317,6 +317,20 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
+    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1)) {
+        /* unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
+         * nearest chroma, dstW & ~1 pixels per row */
+        for (int y = 0; y < dh; y++)
+            for (int i = 0; i < dw >> 1; i++) {
+                int Uv = src[1][(size_t)(y >> 1) * ss[1] + i], Vv = src[2][(size_t)(y >> 1) * ss[2] + i];
+                const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
+                const uint8_t *py = src[0] + (size_t)y * ss[0] + 2 * i;
+                uint8_t *d = dst + (size_t)y * dstride + 6 * i;
+                d[0] = r[py[0]]; d[1] = g[py[0]]; d[2] = b[py[0]]; d[3] = r[py[1]]; d[4] = g[py[1]]; d[5] = b[py[1]];
+            }
+        sws_close(&c);
+        return dh;
+    }
     int lp, cp;
     const int fast = c.flags & F_FAST_BILINEAR;
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);

@@ -77,9 +77,6 @@ def test_unsupported_requests_fail_loudly(gpu):
     assert not L.lib.sws_getContext_cuda(640, 480, 5, 640, 480, 2, 4 | ACC, None, None, None)     # not yuv420p
     assert "YUV420P" in L.last_error()
     L.lib.avb200_clear_error()
-    assert not L.lib.sws_getContext_cuda(640, 480, 0, 640, 480, 2, 4, None, None, None)           # unscaled table path
-    assert "ACCURATE_RND" in L.last_error()
-    L.lib.avb200_clear_error()
     assert not L.lib.sws_getContext_cuda(2, 2, 0, 640, 480, 2, 4 | ACC, None, None, None)
     L.lib.avb200_clear_error()
 
@@ -103,3 +100,19 @@ def test_device_batch_equals_single_frames(gpu, checker):
     assert np.array_equal(out[0], oracle_rgb(checker, frames[0], w, h, 4 | ACC))
     for k in range(1, K):
         assert np.array_equal(out[k], ctx.scale(frames[k])), k
+
+
+def test_unscaled_table_converter(gpu, checker):
+    """same size, no SWS_ACCURATE_RND, even height -> the reference's unscaled yuv2rgb SwsFunc (nearest chroma)"""
+    from libav_b200 import device
+    for (w, h) in ((64, 48), (66, 50), (641, 480), (1920, 1080)):
+        yuv = synth.yuv420p_frame(w, h, 5)
+        for fmt in (device.PIX_FMT_RGB24, device.PIX_FMT_BGR24):
+            ctx = device.SwsContext(w, h, w, h, fmt, 4)
+            assert not ctx.fused
+            got = ctx.scale(yuv, dst_pad=6)
+            want = oracle_rgb(checker, yuv, w, h, 4, pad=6)
+            if fmt == device.PIX_FMT_BGR24:
+                n = (w // 2) * 6
+                want = np.concatenate([want[:, :n].reshape(h, -1, 3)[:, :, ::-1].reshape(h, -1), want[:, n:]], axis=1)
+            assert np.array_equal(got, want), (w, h, fmt)

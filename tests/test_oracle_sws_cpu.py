@@ -121,3 +121,14 @@ def test_frames_match_reference(refo, orc, algo):
         assert ra == rb == dh
         for pa, pb in zip(a, b):
             assert np.array_equal(pa, pb), ("yuv", algo, sw, sh, dw, dh)
+
+
+def test_unscaled_table_converter(refo, orc):
+    """same size, no SWS_ACCURATE_RND, even height: the reference installs yuv2rgb_c_24_rgb (nearest chroma)"""
+    for (w, h) in ((64, 48), (66, 50), (70, 36), (641, 480)):
+        yuv = synth.yuv420p_frame(w, h, 5)
+        ra, a = to_rgb(refo, yuv, w, h, BICUBIC, pad=6)
+        rb, b = to_rgb(orc, yuv, w, h, BICUBIC, pad=6)
+        assert ra == rb == h
+        assert np.array_equal(a, b), (w, h)
+        assert not np.array_equal(a, to_rgb(refo, yuv, w, h, BICUBIC | ACC, pad=6)[1])      # it really is a different path

@@ -48,40 +48,81 @@ h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct ClampFetch {
-    const uint8_t *p; int stride, w, y0, y1;           // rows [y0, y1] belong to the record's picture
-    __device__ __forceinline__ int operator()(int x, int y) const
-    { return __ldg(p + (size_t)min(max(y, y0), y1) * stride + min(max(x, 0), w - 1)); }
-};
+// One warp per partition.  The (w+5) x (h+5) luma patch and the two (w/2+1) x (h/2+1) chroma patches are fetched once
+// (clamped) into the warp's shared-memory slice; the unrounded horizontal 6-tap plane `tmp` (int16, rows -2..h+2) is
+// built cooperatively when the position needs H or HV, then every lane finishes its pixels from shared memory:
+// H = clip((tmp + 16) >> 5), HV = clip((6-tap over tmp + 512) >> 10), V = 6-tap over the patch, F = patch.
+constexpr int MC_PW = 24;                 // luma patch pitch (21 used)
+constexpr int MC_CW = 12;                 // chroma patch pitch (9 used)
+struct MCSmem { uint8_t luma[21 * MC_PW]; int16_t tmp[21 * 16]; uint8_t chroma[2][9 * MC_CW]; };
 
 __global__ void __launch_bounds__(128)
 h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
                uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph,
                int pass)   // ph = height of ONE picture; pictures of a batch are stacked vertically
 {
+    __shared__ MCSmem sm[4];
     const int lane = threadIdx.x & 31;
+    MCSmem &S = sm[threadIdx.x >> 5];
     size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ri >= n) return;
     const FFH264MCRecord r = recs[ri];
     if ((r.avg != 0) != (pass != 0)) return;          // pass 0: every `put`; pass 1: the `avg` second directions
     const FFH264RefPlanes ref = refs[r.ref];
     const int mx = r.mvx + r.x * 4, my = r.mvy + r.y * 4;          // quarter-pel position, h264_mb.c:216-217
-    const int nl = r.w * r.h, cw = r.w >> 1, chh = r.h >> 1, nc = cw * chh;
+    const int w = r.w, h = r.h, cw = w >> 1, chh = h >> 1, fx = mx & 3, fy = my & 3;
     const int pic = r.y / ph, ly0 = pic * ph, cy0 = pic * (ph >> 1);
-    const ClampFetch Y = { ref.y, ls, pw, ly0, ly0 + ph - 1 }, CB = { ref.cb, uvls, pw >> 1, cy0, cy0 + (ph >> 1) - 1 },
-                     CR = { ref.cr, uvls, pw >> 1, cy0, cy0 + (ph >> 1) - 1 };
-    for (int it = lane; it < nl + 2 * nc; it += 32) {
-        if (it < nl) {
-            int px = it % r.w, py = it / r.w;
-            int v = qpel_sample(Y, (mx >> 2) + px, (my >> 2) + py, mx & 3, my & 3);
-            uint8_t *d = dy + (size_t)(r.y + py) * ls + r.x + px;
-            *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
-        } else {
-            int k = it - nl, plane = k >= nc;
-            k -= plane * nc;
-            int px = k % cw, py = k / cw;
-            int v = chroma_sample(plane ? CR : CB, (mx >> 3) + px, (my >> 3) + py, mx & 7, my & 7);
-            uint8_t *d = (plane ? dcr : dcb) + (size_t)((r.y >> 1) + py) * uvls + (r.x >> 1) + px;
+    // ---- fetch patches (edge replication by clamping = emulated_edge_mc) ----
+    {
+        const int bx = (mx >> 2) - 2, by = (my >> 2) - 2, PW = w + 5, PH = h + 5;
+        for (int i = lane; i < PW * PH; i += 32) {
+            const int xx = i % PW, yy = i / PW;
+            S.luma[yy * MC_PW + xx] = __ldg(ref.y + (size_t)min(max(by + yy, ly0), ly0 + ph - 1) * ls + min(max(bx + xx, 0), pw - 1));
+        }
+        const int cbx = mx >> 3, cby = my >> 3, CW = cw + 1, CH = chh + 1;
+        for (int i = lane; i < 2 * CW * CH; i += 32) {
+            const int pl = i >= CW * CH, k = i - pl * CW * CH, xx = k % CW, yy = k / CW;
+            const uint8_t *src = pl ? ref.cr : ref.cb;
+            S.chroma[pl][yy * MC_CW + xx] = __ldg(src + (size_t)min(max(cby + yy, cy0), cy0 + (ph >> 1) - 1) * uvls + min(max(cbx + xx, 0), (pw >> 1) - 1));
+        }
+    }
+    __syncwarp();
+    if (fx) {                                          // horizontal 6-tap, unrounded, rows -2 .. h+2 (tmp row = patch row)
+        for (int i = lane; i < w * (h + 5); i += 32) {
+            const int xx = i % w, yy = i / w;
+            const uint8_t *p = &S.luma[yy * MC_PW + xx + 2];
+            S.tmp[yy * 16 + xx] = (int16_t)((p[0] + p[1]) * 20 - (p[-1] + p[2]) * 5 + (p[-2] + p[3]));
+        }
+        __syncwarp();
+    }
+    // ---- luma ----
+    for (int i = lane; i < w * h; i += 32) {
+        const int px = i % w, py = i / w;
+        const uint8_t *p = &S.luma[(py + 2) * MC_PW + px + 2];          // full-pel sample F(px, py)
+        const int16_t *t = &S.tmp[(py + 2) * 16 + px];
+        auto Hs = [&](int dyy) { return clip_u8((t[dyy * 16] + 16) >> 5); };
+        auto Vs = [&](int dxx) { const uint8_t *q = p + dxx; return clip_u8(((q[0] + q[MC_PW]) * 20 - (q[-MC_PW] + q[2 * MC_PW]) * 5 + (q[-2 * MC_PW] + q[3 * MC_PW]) + 16) >> 5); };
+        auto HVs = [&]() { return clip_u8(((t[0] + t[16]) * 20 - (t[-16] + t[32]) * 5 + (t[-32] + t[48]) + 512) >> 10); };
+        int a, b = -1;                                                   // h264qpel_template.c:380-531
+        if (!fx && !fy) a = p[0];
+        else if (!fy) { a = Hs(0); if (fx != 2) b = p[fx == 3]; }
+        else if (!fx) { a = Vs(0); if (fy != 2) b = p[(fy == 3) * MC_PW]; }
+        else if (fx == 2 && fy == 2) a = HVs();
+        else if (fx == 2) { a = HVs(); b = Hs(fy == 3); }
+        else if (fy == 2) { a = HVs(); b = Vs(fx == 3); }
+        else { a = Hs(fy == 3); b = Vs(fx == 3); }
+        const int v = b < 0 ? a : (a + b + 1) >> 1;
+        uint8_t *d = dy + (size_t)(r.y + py) * ls + r.x + px;
+        *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
+    }
+    // ---- chroma (1/8-pel bilinear, h264chroma_template.c:27-170) ----
+    {
+        const int cfx = mx & 7, cfy = my & 7, A = (8 - cfx) * (8 - cfy), B = cfx * (8 - cfy), Cc = (8 - cfx) * cfy, D = cfx * cfy;
+        for (int i = lane; i < 2 * cw * chh; i += 32) {
+            const int pl = i >= cw * chh, k = i - pl * cw * chh, px = k % cw, py = k / cw;
+            const uint8_t *p = &S.chroma[pl][py * MC_CW + px];
+            const int v = (A * p[0] + B * p[1] + Cc * p[MC_CW] + D * p[MC_CW + 1] + 32) >> 6;
+            uint8_t *d = (pl ? dcr : dcb) + (size_t)((r.y >> 1) + py) * uvls + (r.x >> 1) + px;
             *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
         }
     }

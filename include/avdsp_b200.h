@@ -199,6 +199,14 @@ int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const u
  * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332). */
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream);
 
+/* ---- float FFT / MDCT filterbank (FFTContext, libavcodec/fft.h:73-99); parity contract: 1e-6 relative ------------
+ * ff_fft_batch_cuda: n_transforms independent complex FFTs of 2^nbits points (nbits 1..12), in place, natural order in
+ * and out == the reference's fft_permute followed by fft_calc (forward kernel exp(-2 pi i jk / n), no 1/n).
+ * ff_mdct_batch_cuda: op 0 imdct_half (n/2 in -> n/2 out), 1 imdct_calc (n/2 -> n), 2 mdct_calc (n -> n/2) of size
+ * n = 2^nbits (4..14) with the rotation tables of ff_mdct_init(nbits, inverse, scale) (libavcodec/mdct_template.c:86-92). */
+int ff_fft_batch_cuda(int nbits, int inverse, float *z, size_t n_transforms, void *stream);
+int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float *in, size_t n_transforms, void *stream);
+
 /* ---- libswscale boundary (libswscale/swscale.h:159-207) ------------------------------------------------
  * Same argument lists as sws_getContext / sws_scale / sws_freeContext; pixel formats are the reference's
  * AVPixelFormat values (AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_RGB24 = 2, AV_PIX_FMT_BGR24 = 3), flags the
@@ -247,6 +255,11 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth);
 void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth);
 void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
+/* libavcodec/fft_template.c:152-159, mdct_template.c:58-66 (same shape as ff_fft_init_x86 / ff_mdct_init_x86): called after
+ * ff_fft_init / ff_mdct_init filled the context.  fft_permute stays the reference's; the CUDA fft_calc accepts its revtab
+ * order, the MDCT slots use the context's own tcos / tsin tables. */
+void ff_fft_init_cuda(FFTContext *s);
+void ff_mdct_init_cuda(FFTContext *s);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,31 @@ typedef struct HpelDSPContext {
     op_pixels_func avg_no_rnd_pixels_tab[4];
 } HpelDSPContext;
 
+/* ---- libavcodec/fft.h:36-99 (float build: FFTSample = FFTDouble = float), libavcodec/avfft.h FFTComplex ---- */
+typedef float FFTSample;
+typedef float FFTDouble;    /* float build, libavcodec/fft.h:39 */
+typedef struct FFTComplex { FFTSample re, im; } FFTComplex;
+enum fft_permutation_type { FF_FFT_PERM_DEFAULT, FF_FFT_PERM_SWAP_LSBS, FF_FFT_PERM_AVX };
+enum mdct_permutation_type { FF_MDCT_PERM_NONE, FF_MDCT_PERM_INTERLEAVE };
+typedef struct FFTContext {
+    int nbits;
+    int inverse;
+    uint16_t *revtab;
+    FFTComplex *tmp_buf;
+    int mdct_size;
+    int mdct_bits;
+    FFTSample *tcos;
+    FFTSample *tsin;
+    void (*fft_permute)(struct FFTContext *s, FFTComplex *z);
+    void (*fft_calc)(struct FFTContext *s, FFTComplex *z);
+    void (*imdct_calc)(struct FFTContext *s, FFTSample *output, const FFTSample *input);
+    void (*imdct_half)(struct FFTContext *s, FFTSample *output, const FFTSample *input);
+    void (*mdct_calc)(struct FFTContext *s, FFTSample *output, const FFTSample *input);
+    void (*mdct_calcw)(struct FFTContext *s, FFTDouble *output, const FFTSample *input);
+    enum fft_permutation_type fft_permutation;
+    enum mdct_permutation_type mdct_permutation;
+} FFTContext;
+
 #ifdef __cplusplus
 }
 #endif

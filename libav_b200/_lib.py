@@ -70,6 +70,8 @@ PROTOTYPES = {
     "ff_full_search_cuda": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "ff_hpel_batch_cuda": (i32, [vp, sz, vp, vp, pd, vp]),
     "ff_fdct_batch_cuda": (i32, [i32, vp, sz, vp]),
+    "ff_fft_batch_cuda": (i32, [i32, i32, vp, sz, vp]),
+    "ff_mdct_batch_cuda": (i32, [i32, i32, C.c_double, vp, vp, sz, vp]),
     "sws_getContext_cuda": (vp, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "sws_freeContext_cuda": (None, [vp]),
     "sws_scale_cuda": (i32, [vp, vp, vp, i32, i32, vp, vp]),
@@ -85,6 +87,8 @@ PROTOTYPES = {
     "ff_h264qpel_init_cuda": (None, [vp, i32]),
     "ff_h264chroma_init_cuda": (None, [vp, i32]),
     "ff_hpeldsp_init_cuda": (None, [vp, i32]),
+    "ff_fft_init_cuda": (None, [vp]),
+    "ff_mdct_init_cuda": (None, [vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

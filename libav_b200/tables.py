@@ -82,3 +82,15 @@ op_pixels_func = C.CFUNCTYPE(None, u8p, u8p, pd, C.c_int)
 class HpelDSPContext(C.Structure):          # libavcodec/hpeldsp.h:45-93
     _fields_ = [("put_pixels_tab", (op_pixels_func * 4) * 4), ("avg_pixels_tab", (op_pixels_func * 4) * 4),
                 ("put_no_rnd_pixels_tab", (op_pixels_func * 4) * 4), ("avg_no_rnd_pixels_tab", op_pixels_func * 4)]
+
+
+class FFTContext(C.Structure):              # libavcodec/fft.h:73-99
+    pass
+
+
+_fftc = C.CFUNCTYPE(None, C.POINTER(FFTContext), C.c_void_p)
+_mdctf = C.CFUNCTYPE(None, C.POINTER(FFTContext), C.POINTER(C.c_float), C.POINTER(C.c_float))
+FFTContext._fields_ = [("nbits", C.c_int), ("inverse", C.c_int), ("revtab", C.POINTER(C.c_uint16)), ("tmp_buf", C.c_void_p),
+                       ("mdct_size", C.c_int), ("mdct_bits", C.c_int), ("tcos", C.POINTER(C.c_float)), ("tsin", C.POINTER(C.c_float)),
+                       ("fft_permute", _fftc), ("fft_calc", _fftc), ("imdct_calc", _mdctf), ("imdct_half", _mdctf), ("mdct_calc", _mdctf),
+                       ("mdct_calcw", C.c_void_p), ("fft_permutation", C.c_int), ("mdct_permutation", C.c_int)]

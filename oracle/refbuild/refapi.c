@@ -328,6 +328,17 @@ void ref_imdct_calc(int nbits, double scale, float *out, const float *in)
 void ref_mdct_calc(int nbits, double scale, float *out, const float *in)
 { FFTContext s; INIT(); ff_mdct_init(&s, nbits, 0, scale); s.mdct_calc(&s, out, in); ff_mdct_end(&s); }
 
+/* a live reference FFTContext for the slot tests: ff_fft_init / ff_mdct_init exactly as a codec would call them */
+void *ref_fft_ctx_new(int nbits, int inverse, int mdct, double scale)
+{
+    FFTContext *s = av_mallocz(sizeof(*s));
+    INIT();
+    if ((mdct ? ff_mdct_init(s, nbits, inverse, scale) : ff_fft_init(s, nbits, inverse)) < 0) { av_free(s); return NULL; }
+    return s;
+}
+void ref_fft_ctx_free(void *p, int mdct) { FFTContext *s = p; if (!s) return; if (mdct) ff_mdct_end(s); else ff_fft_end(s); av_free(s); }
+int ref_sizeof_fftcontext(void) { return sizeof(FFTContext); }
+
 /* ---- ABI facts of the reference's tables (sizes and a few offsets), for tests/test_abi_cpu.py ---- */
 #include <stddef.h>
 int ref_abi_info(int32_t *out, int cap)

@@ -1,0 +1,42 @@
+"""CPU: pin the FFT / MDCT restatement (oracle/port/orc_fft.c, double precision core) against the unmodified reference's
+float FFTContext slots in oracle/_ref at the north star's tolerance: 1e-6 relative (to the largest output magnitude).  Same
+sizes as the reference's own FATE targets (tests/fate/fft.mak: 2^4 .. 2^12)."""
+import numpy as np
+import pytest
+
+from oracle.loader import ptr
+
+TOL = 1e-6
+
+
+def rel_err(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("nbits", range(2, 13))
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_fft(orc, refo, nbits, inverse):
+    rng = np.random.default_rng(nbits * 2 + inverse)
+    z = rng.uniform(-1, 1, size=2 << nbits).astype(np.float32)
+    a, b = z.copy(), z.copy()
+    orc.fft(nbits, inverse, ptr(a))
+    refo.fft(nbits, inverse, ptr(b))
+    assert rel_err(a, b) < TOL * max(1, nbits / 4), (nbits, inverse, rel_err(a, b))
+    # and the transform really is the textbook DFT
+    zz = z[0::2].astype(np.complex128) + 1j * z[1::2]
+    want = np.fft.ifft(zz) * zz.size if inverse else np.fft.fft(zz)
+    got = a[0::2].astype(np.complex128) + 1j * a[1::2]
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-7
+
+
+@pytest.mark.parametrize("nbits", range(4, 13))
+@pytest.mark.parametrize("scale", [1.0, -1.0, 1.0 / 32768, 2.5])
+def test_mdct(orc, refo, nbits, scale):
+    rng = np.random.default_rng(nbits)
+    n = 1 << nbits
+    x = rng.uniform(-1, 1, size=n).astype(np.float32)
+    for fn, nin, nout in (("imdct_half", n // 2, n // 2), ("imdct_calc", n // 2, n), ("mdct_calc", n, n // 2)):
+        a, b = np.zeros(nout, np.float32), np.zeros(nout, np.float32)
+        getattr(orc, fn)(nbits, scale, ptr(a), ptr(x[:nin].copy()))
+        getattr(refo, fn)(nbits, scale, ptr(b), ptr(x[:nin].copy()))
+        assert rel_err(a, b) < TOL * max(1, nbits / 4), (fn, nbits, scale, rel_err(a, b))

@@ -183,6 +183,32 @@ def make_sws_workload(torch, L, stream, rank):
 H264_PICTURES = 30      # 30 x 1088 rows still fit the int16 y of FFH264MCRecord
 
 
+def make_sws_up_workload(torch, L, stream, rank):
+    """secondary row of config 5: a genuine rescale, 1920x1080 -> 3840x2160 yuv420p->rgb24 bicubic (general path:
+    hScale8To15 + yuv2rgb24_X vertical pass), 8 frames per step."""
+    from libav_b200 import synth, device
+    sw, sh, dw, dh, K = 1920, 1080, 3840, 2160, 8
+    ysz, csz, osz = sw * sh, (sw // 2) * (sh // 2), dw * dh * 3
+    fr = synth.yuv420p_frame(sw, sh, 7 + rank)
+    d_y = torch.from_numpy(np.concatenate([fr[0].reshape(-1)] * K)).cuda()
+    d_u = torch.from_numpy(np.concatenate([fr[1].reshape(-1)] * K)).cuda()
+    d_v = torch.from_numpy(np.concatenate([fr[2].reshape(-1)] * K)).cuda()
+    d_o = torch.empty(osz * K, dtype=torch.uint8, device="cuda")
+    ctx = device.SwsContext(sw, sh, dw, dh, device.PIX_FMT_RGB24, SWS_FLAGS)
+    assert not ctx.fused
+
+    def run(i):
+        ctx.scale_device([d_y.data_ptr(), d_u.data_ptr(), d_v.data_ptr()], [sw, sw // 2, sw // 2], [d_o.data_ptr()], [dw * 3], nframes=K,
+                         src_frame=[ysz, csz, csz], dst_frame=[osz], stream=stream)
+
+    return {
+        "name": "sws_scale 1920x1080 -> 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact (true rescale), %d frames per step" % K,
+        "run": run, "run_e2e": None, "pixels": dw * dh * K, "alg_bytes": int((sw * sh * 1.5 + dw * dh * 3) * K),
+        "launches_per_step": 4 * K, "kernel": "sws_vscale_rgb24_kernel", "dtype": "int32 (u8 in, u8 out)", "h2d": 0, "d2h": 0,
+        "l2": "%d MiB of output per step" % (osz * K >> 20), "keep": (d_y, d_u, d_v, d_o, ctx),
+    }
+
+
 def make_h264_workload(torch, L, stream, rank):
     """config 3: 1920x1088 P pictures of 64 slices each, a batch of independent pictures stacked vertically per launch:
     MC (put pass + avg pass) -> residual add -> deblocking wavefronts (luma + chroma).  The consumed coefficient arena is
@@ -400,7 +426,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
@@ -449,7 +475,8 @@ def main():
         k, v = kv.split("=")
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
-    makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload}
+    makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
+              "sws_up": make_sws_up_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):

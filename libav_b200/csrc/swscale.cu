@@ -473,6 +473,71 @@ sws_vscale_rgb24_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t
     d[5] = (uint8_t)clip_u8((p.k.cy * Y2 + tb) >> 16);
 }
 
+// pass 1, four outputs per thread, one 8-byte store (dstW % 4 == 0 not required: the line planes are padded to 8)
+__global__ void __launch_bounds__(256)
+sws_hscale8to15_x4_kernel(const uint8_t *__restrict__ src, int srcStride, int16_t *__restrict__ dst, int dstStridePx,
+                          const int16_t *__restrict__ filter, const int32_t *__restrict__ pos, int fs, int dstW, int rows)
+{
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (i0 >= dstW || y >= rows) return;
+    const uint8_t *srow = src + (size_t)y * srcStride;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = min(i0 + k, dstW - 1);
+        const uint8_t *sp = srow + pos[i];
+        const int16_t *f = filter + (size_t)i * fs;
+        int acc = 0;
+        for (int j = 0; j < fs; j++) acc += (int)sp[j] * f[j];
+        v[k] = i0 + k < dstW ? min(acc >> 7, (1 << 15) - 1) : 0;       // columns past dstW stay zero like the reference's line buffer
+    }
+    *reinterpret_cast<uint2 *>(dst + (size_t)y * dstStridePx + i0) = make_uint2(pack16(v[0], v[1]), pack16(v[2], v[3]));
+}
+
+// pass 2, yuv2rgb24_X_c (output.c:936-995) for 8 pixels per thread: 16-byte luma / 8-byte chroma line loads, three 8-byte stores
+__global__ void __launch_bounds__(128)
+sws_vscale_rgb24_x8_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t *__restrict__ chrU,
+                           const int16_t *__restrict__ chrV, int lumStride, int chrStride, uint8_t *__restrict__ dst, int dstStride)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (gx * 8 >= p.dstW || y >= p.dstH) return;
+    const int fl = p.vLumSize, fc = p.vChrSize;
+    const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
+    const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+    int Y[8], U[4], V[4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) Y[k] = 1 << 18;
+#pragma unroll
+    for (int k = 0; k < 4; k++) U[k] = V[k] = 1 << 18;
+    for (int j = 0; j < fl; j++) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(lum + (size_t)line_index(firstL, j, p.srcH) * lumStride + gx * 8);
+        const int c = lf[j];
+        Y[0] += lo16s(w.x) * c; Y[1] += hi16s(w.x) * c; Y[2] += lo16s(w.y) * c; Y[3] += hi16s(w.y) * c;
+        Y[4] += lo16s(w.z) * c; Y[5] += hi16s(w.z) * c; Y[6] += lo16s(w.w) * c; Y[7] += hi16s(w.w) * c;
+    }
+    for (int j = 0; j < fc; j++) {
+        const size_t o = (size_t)line_index(firstC, j, p.chrSrcH) * chrStride + gx * 4;
+        const uint2 wu = *reinterpret_cast<const uint2 *>(chrU + o), wv = *reinterpret_cast<const uint2 *>(chrV + o);
+        const int c = cf[j];
+        U[0] += lo16s(wu.x) * c; U[1] += hi16s(wu.x) * c; U[2] += lo16s(wu.y) * c; U[3] += hi16s(wu.y) * c;
+        V[0] += lo16s(wv.x) * c; V[1] += hi16s(wv.x) * c; V[2] += lo16s(wv.y) * c; V[3] += hi16s(wv.y) * c;
+    }
+    int r[8], g[8], b[8];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int y1 = Y[2 * c] >> 19, y2 = Y[2 * c + 1] >> 19, u = U[c] >> 19, v = V[c] >> 19;
+        clip_if_flagged(y1, y2, u, v);
+        const ChromaTerms t = chroma_terms(u, v, p.k);
+        const int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
+        r[2 * c] = (p.k.cy * y1 + tr) >> 16; g[2 * c] = (p.k.cy * y1 + t.tg) >> 16; b[2 * c] = (p.k.cy * y1 + tb) >> 16;
+        r[2 * c + 1] = (p.k.cy * y2 + tr) >> 16; g[2 * c + 1] = (p.k.cy * y2 + t.tg) >> 16; b[2 * c + 1] = (p.k.cy * y2 + tb) >> 16;
+    }
+    uint2 *d = reinterpret_cast<uint2 *>(dst + (size_t)y * dstStride + (size_t)gx * 24);
+    d[0] = make_uint2(pack4_sat_u8(r[0], g[0], b[0], r[1]), pack4_sat_u8(g[1], b[1], r[2], g[2]));
+    d[1] = make_uint2(pack4_sat_u8(b[2], r[3], g[3], b[3]), pack4_sat_u8(r[4], g[4], b[4], r[5]));
+    d[2] = make_uint2(pack4_sat_u8(g[5], b[5], r[6], g[6]), pack4_sat_u8(b[6], r[7], g[7], b[7]));
+}
+
 // pass 2 for planar 8-bit output: yuv2planeX_8_c / yuv2plane1_8_c (output.c:242-265), dither = 64 everywhere
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
@@ -622,7 +687,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
     }
     if (!c->fused && !c->copy && !c->table_unscaled) {
-        c->lumStridePx = (dstW + 1 + 7) & ~7;
+        c->lumStridePx = (dstW + 1 + 7) & ~7;          // multiples of 8 samples: 16-byte aligned rows for the vector passes
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
         if (cudaMalloc(&c->d_lum, (size_t)c->lumStridePx * srcH * 2) != cudaSuccess ||
             cudaMalloc(&c->d_chrU, (size_t)c->chrStridePx * c->g.chrSrcH * 2) != cudaSuccess ||
@@ -698,9 +763,9 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
             sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
             sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
         } else {
-            sws_hscale8to15_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH);
-            sws_hscale8to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
-            sws_hscale8to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
+            sws_hscale8to15_x4_kernel<<<dim3((p.dstW + 1023) / 1024, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH);
+            sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
+            sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
         }
         if (c->dstFormat == FMT_YUV420P) {
             sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH);
@@ -708,7 +773,12 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
             sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH);
         } else {
             int pairs = (p.dstW + 1) >> 1;
-            sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, dst[0] + f * dstFrame[0], dstStride[0]);
+            uint8_t *d0 = dst[0] + f * dstFrame[0];
+            const bool x_path = !((p.vLumSize == 1 && p.vChrSize <= 2) || (p.vLumSize == 2 && p.vChrSize == 2));
+            if (x_path && !(p.dstW & 7) && !(dstStride[0] & 7) && !((uintptr_t)d0 & 7))
+                sws_vscale_rgb24_x8_kernel<<<dim3((p.dstW / 8 + 127) / 128, p.dstH), 128, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
+            else
+                sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
         }
         if (check_launch("sws_scale:general")) return -1;
     }

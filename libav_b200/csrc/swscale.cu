@@ -22,6 +22,7 @@
 #include "../../include/avdsp_b200.h"
 #include <new>
 #include <vector>
+#include <algorithm>
 #include <limits.h>
 #include <string.h>
 
@@ -559,6 +560,263 @@ sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH
 }
 
 // ---------------------------------------------------------------------------------------------------
+// GENERAL path, fused per tile (default): a CTA owns a 128 x 16 tile of the OUTPUT.  It runs hScale8To15 (or the
+// fast-bilinear variant) for just the source lines its 16 rows' vertical filters touch, keeps those 15-bit lines in
+// shared memory, and runs the vertical filter + output stage from there -- the int16 line planes of the two-pass path
+// never exist in HBM.  Same integer recipe as the two-pass kernels above, which stay as the fallback for filters whose
+// line window does not fit in shared memory (heavy down-scaling).
+// ---------------------------------------------------------------------------------------------------
+constexpr int GT_W = 128, GT_H = 16, GT_THREADS = 256;
+// a shared luma line: the 8 samples of pixel group g live as two 16-byte quads at words 4g and 80 + 4g, so both the
+// column-per-lane stores of the horizontal pass and the two LDS.128 of the vertical pass are bank-conflict free
+constexpr int GT_LW = 144;
+__host__ __device__ constexpr int gt_lum_slot(int col) { return ((col >> 3) << 2) + (col & 3) + ((col >> 2) & 1) * 80; }
+
+// lines [lo, hi] the vertical filters of output rows y0..y1 read (after line_index()'s clamp)
+static inline void tile_line_window(const int32_t *pos, int fs, int y0, int y1, int srcH, int &lo, int &hi)
+{
+    lo = 0x7fffffff; hi = -1;
+    for (int y = y0; y <= y1; y++) {
+        int first = pos[y] > 1 - fs ? pos[y] : 1 - fs, a = first, b = first + fs - 1;
+        a = a < 0 ? 0 : (a > srcH - 1 ? srcH - 1 : a); b = b < 0 ? 0 : (b > srcH - 1 ? srcH - 1 : b);
+        lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+    }
+}
+
+// one column of a tile: horizontally scaled samples of lines lo + r, r = r0, r0 + rstep, ... < n, into out[r * W]
+// (shared lines hold the 15-bit samples as int32 so the vertical pass multiplies them straight from 16-byte loads)
+// FS > 0: compile-time tap count with the coefficients in registers; FS == 0: run-time tap count; FS < 0: fast bilinear
+template <int FS>
+__device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, int srcStride, int lo, int n, int r0, int rstep,
+                                              int32_t *out, int W, int x, int dstW, const int16_t *__restrict__ filter,
+                                              const int32_t *__restrict__ pos, int fs, int srcW, unsigned xInc, int chroma)
+{
+    if (x >= dstW) { for (int r = r0; r < n; r += rstep) out[r * W] = 0; return; }     // the reference's zeroed line tail
+    const int step = rstep * srcStride;
+    if constexpr (FS < 0) {
+        const unsigned xpos = (unsigned)x * xInc, xx = xpos >> 16; const int xa = (xpos & 0xFFFF) >> 9;
+        const unsigned xx1 = min(xx + 1, (unsigned)srcW - 1);
+        const uint8_t *sp = src + (size_t)(lo + r0) * srcStride;
+#pragma unroll 2
+        for (int r = r0; r < n; r += rstep, sp += step) {
+            const int a = sp[xx], b = sp[xx1];
+            out[r * W] = chroma ? a * (xa ^ 127) + b * xa : (a << 7) + (b - a) * xa;
+        }
+    } else if constexpr (FS > 0) {
+        int cf[FS > 0 ? FS : 1];
+        const int16_t *f = filter + (size_t)x * FS;
+#pragma unroll
+        for (int j = 0; j < FS; j++) cf[j] = f[j];
+        const uint8_t *sp = src + pos[x] + (size_t)(lo + r0) * srcStride;
+#pragma unroll 4
+        for (int r = r0; r < n; r += rstep, sp += step) {
+            int acc = 0;
+#pragma unroll
+            for (int j = 0; j < FS; j++) acc += (int)sp[j] * cf[j];
+            out[r * W] = min(acc >> 7, (1 << 15) - 1);
+        }
+    } else {
+        const int16_t *f = filter + (size_t)x * fs;
+        const uint8_t *sp = src + pos[x] + (size_t)(lo + r0) * srcStride;
+        for (int r = r0; r < n; r += rstep, sp += step) {
+            int acc = 0;
+            for (int j = 0; j < fs; j++) acc += (int)sp[j] * f[j];
+            out[r * W] = min(acc >> 7, (1 << 15) - 1);
+        }
+    }
+}
+
+struct TileArgs {
+    const uint8_t *y, *u, *v; uint8_t *dst0, *dst1, *dst2;
+    int yStride, uStride, vStride, dstStride0, dstStride1, dstStride2;
+    size_t yFrame, uFrame, vFrame, dstFrame0, dstFrame1, dstFrame2;
+    int lumRows, chrRows;           // shared-memory line capacity (host: maximum over all tiles)
+    const int2 *lumWin, *chrWin;    // per tile row: (first line, line count) of the vertical filters' window (host table)
+    unsigned lumXInc, chrXInc;      // fast bilinear
+    int vec;                        // output rows / bases are 8-byte aligned
+};
+
+__device__ __forceinline__ void lds8(const int32_t *p, int (&v)[8])
+{
+    const int4 a = *reinterpret_cast<const int4 *>(p), b = *reinterpret_cast<const int4 *>(p + 80);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds4(const int32_t *p, int (&v)[4])
+{
+    const int4 a = *reinterpret_cast<const int4 *>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+
+template <int FSL, int FSC>
+__global__ void __launch_bounds__(GT_THREADS)
+sws_tile_rgb24_kernel(SwsDev p, TileArgs a)
+{
+    extern __shared__ __align__(16) int32_t gt_smem[];
+    int32_t *lumS = gt_smem, *chrUS = gt_smem + a.lumRows * GT_LW;
+    const int chrPlane = a.chrRows * (GT_W / 2);             // V lines follow the U lines
+    const int tid = threadIdx.x, x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H, y1 = min(y0 + GT_H, p.dstH) - 1;
+    const size_t f = blockIdx.z;
+    const int2 lw = a.lumWin[blockIdx.y], cw = a.chrWin[blockIdx.y];
+    const int lumLo = lw.x, chrLo = cw.x;
+    {   // horizontal pass into shared memory
+        const int col = tid & (GT_W - 1);
+        hscale_column<FSL>(a.y + f * a.yFrame, a.yStride, lumLo, lw.y, tid >> 7, 2, lumS + gt_lum_slot(col), GT_LW, x0 + col, p.dstW,
+                           p.hLumF, p.hLumP, p.hLumSize, p.srcW, a.lumXInc, 0);
+        const int ccol = tid & (GT_W / 2 - 1), plane = tid >> 7;
+        hscale_column<FSC>((plane ? a.v + f * a.vFrame : a.u + f * a.uFrame), plane ? a.vStride : a.uStride, chrLo, cw.y,
+                           (tid >> 6) & 1, 2, chrUS + plane * chrPlane + ccol, GT_W / 2, (x0 >> 1) + ccol, p.chrDstW,
+                           p.hChrF, p.hChrP, p.hChrSize, p.chrSrcW, a.chrXInc, 1);
+    }
+    __syncthreads();
+    const int tx = tid & 15, y = y0 + (tid >> 4), x = x0 + 8 * tx;
+    if (y > y1 || x >= p.dstW) return;
+    const int fl = p.vLumSize, fc = p.vChrSize;
+    const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
+    const int32_t *lumT = lumS + 4 * tx - lumLo * GT_LW, *chrT = chrUS + 4 * tx - chrLo * (GT_W / 2);
+    auto LL = [&](int j) { return lumT + line_index(firstL, j, p.srcH) * GT_LW; };
+    auto CC = [&](int j) { return chrT + line_index(firstC, j, p.chrSrcH) * (GT_W / 2); };
+    int Y[8], U[4], V[4], t8[8], t4[4];
+    if (fl == 1 && fc <= 2) {                                  // yuv2rgb24_1_c, output.c:1042-1110
+        const int uvalpha = fc == 1 ? 0 : p.vChrF[2 * y + 1];
+        lds8(LL(0), Y);
+#pragma unroll
+        for (int k = 0; k < 8; k++) Y[k] = clip_u8(Y[k] >> 7);
+        const int32_t *c0 = CC(0);
+        lds4(c0, U); lds4(c0 + chrPlane, V);
+        if (uvalpha < 2048) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { U[k] = clip_u8(U[k] >> 7); V[k] = clip_u8(V[k] >> 7); }
+        } else {
+            const int32_t *c1 = CC(1);
+            lds4(c1, t4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) U[k] = clip_u8((U[k] + t4[k]) >> 8);
+            lds4(c1 + chrPlane, t4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) V[k] = clip_u8((V[k] + t4[k]) >> 8);
+        }
+    } else if (fl == 2 && fc == 2) {                           // yuv2rgb24_2_c, output.c:997-1040
+        const int ya = p.vLumF[2 * y + 1], ua = p.vChrF[2 * y + 1], ya1 = 4096 - ya, ua1 = 4096 - ua;
+        lds8(LL(0), Y); lds8(LL(1), t8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) Y[k] = clip_u8((Y[k] * ya1 + t8[k] * ya) >> 19);
+        const int32_t *c0 = CC(0), *c1 = CC(1);
+        lds4(c0, U); lds4(c1, t4);
+#pragma unroll
+        for (int k = 0; k < 4; k++) U[k] = clip_u8((U[k] * ua1 + t4[k] * ua) >> 19);
+        lds4(c0 + chrPlane, V); lds4(c1 + chrPlane, t4);
+#pragma unroll
+        for (int k = 0; k < 4; k++) V[k] = clip_u8((V[k] * ua1 + t4[k] * ua) >> 19);
+    } else {                                                   // yuv2rgb24_X_c, output.c:936-995
+        const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+#pragma unroll
+        for (int k = 0; k < 8; k++) Y[k] = 1 << 18;
+#pragma unroll
+        for (int k = 0; k < 4; k++) U[k] = V[k] = 1 << 18;
+#pragma unroll 4
+        for (int j = 0; j < fl; j++) {
+            lds8(LL(j), t8); const int c = lf[j];
+#pragma unroll
+            for (int k = 0; k < 8; k++) Y[k] += t8[k] * c;
+        }
+#pragma unroll 4
+        for (int j = 0; j < fc; j++) {
+            const int c = cf[j]; const int32_t *cl = CC(j);
+            lds4(cl, t4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) U[k] += t4[k] * c;
+            lds4(cl + chrPlane, t4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) V[k] += t4[k] * c;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            Y[2 * k] >>= 19; Y[2 * k + 1] >>= 19; U[k] >>= 19; V[k] >>= 19;
+            clip_if_flagged(Y[2 * k], Y[2 * k + 1], U[k], V[k]);
+        }
+    }
+    int r[8], g[8], b[8];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const ChromaTerms t = chroma_terms(U[c], V[c], p.k);
+        const int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int yy = p.k.cy * Y[2 * c + e];
+            r[2 * c + e] = (yy + tr) >> 16; g[2 * c + e] = (yy + t.tg) >> 16; b[2 * c + e] = (yy + tb) >> 16;
+        }
+    }
+    uint8_t *d = a.dst0 + f * a.dstFrame0 + (size_t)y * a.dstStride0 + (size_t)x * 3;
+    if (a.vec && x + 8 <= p.dstW) {
+        uint2 *dv = reinterpret_cast<uint2 *>(d);
+        dv[0] = make_uint2(pack4_sat_u8(r[0], g[0], b[0], r[1]), pack4_sat_u8(g[1], b[1], r[2], g[2]));
+        dv[1] = make_uint2(pack4_sat_u8(b[2], r[3], g[3], b[3]), pack4_sat_u8(r[4], g[4], b[4], r[5]));
+        dv[2] = make_uint2(pack4_sat_u8(g[5], b[5], r[6], g[6]), pack4_sat_u8(b[6], r[7], g[7], b[7]));
+    } else {
+        // the C code writes whole pairs: an odd width's last pair spills one pixel into the row padding when there is room
+        const int wlim = (p.dstW & 1) && a.dstStride0 >= 3 * (p.dstW + 1) ? p.dstW + 1 : p.dstW;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (x + k < wlim) { d[3 * k] = (uint8_t)clip_u8(r[k]); d[3 * k + 1] = (uint8_t)clip_u8(g[k]); d[3 * k + 2] = (uint8_t)clip_u8(b[k]); }
+    }
+}
+
+// planar 8-bit output (yuv2planeX_8_c / yuv2plane1_8_c, output.c:242-265): the same tile scheme for one plane kind;
+// CHROMA: blockIdx.z = 2 * frame + plane
+template <int FS, bool CHROMA>
+__global__ void __launch_bounds__(GT_THREADS)
+sws_tile_plane_kernel(SwsDev p, TileArgs a)
+{
+    extern __shared__ __align__(16) int32_t gt_smem[];
+    const int tid = threadIdx.x, x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+    const int dstW = CHROMA ? p.chrDstW : p.dstW, dstH = CHROMA ? p.chrDstH : p.dstH, srcH = CHROMA ? p.chrSrcH : p.srcH;
+    const int y1 = min(y0 + GT_H, dstH) - 1;
+    const size_t f = CHROMA ? blockIdx.z >> 1 : blockIdx.z; const int plane = CHROMA ? 1 + (blockIdx.z & 1) : 0;
+    const uint8_t *src = plane == 0 ? a.y + f * a.yFrame : plane == 1 ? a.u + f * a.uFrame : a.v + f * a.vFrame;
+    const int srcStride = plane == 0 ? a.yStride : plane == 1 ? a.uStride : a.vStride;
+    uint8_t *dst = plane == 0 ? a.dst0 + f * a.dstFrame0 : plane == 1 ? a.dst1 + f * a.dstFrame1 : a.dst2 + f * a.dstFrame2;
+    const int dstStride = plane == 0 ? a.dstStride0 : plane == 1 ? a.dstStride1 : a.dstStride2;
+    const int16_t *vF = CHROMA ? p.vChrF : p.vLumF; const int32_t *vP = CHROMA ? p.vChrP : p.vLumP;
+    const int fs = CHROMA ? p.vChrSize : p.vLumSize;
+    const int2 win = (CHROMA ? a.chrWin : a.lumWin)[blockIdx.y];
+    const int lo = win.x;
+    {
+        const int col = tid & (GT_W - 1);
+        hscale_column<FS>(src, srcStride, lo, win.y, tid >> 7, 2, gt_smem + gt_lum_slot(col), GT_LW, x0 + col, dstW,
+                          CHROMA ? p.hChrF : p.hLumF, CHROMA ? p.hChrP : p.hLumP, CHROMA ? p.hChrSize : p.hLumSize,
+                          CHROMA ? p.chrSrcW : p.srcW, CHROMA ? a.chrXInc : a.lumXInc, CHROMA);
+    }
+    __syncthreads();
+    const int tx = tid & 15, y = y0 + (tid >> 4), x = x0 + 8 * tx;
+    if (y > y1 || x >= dstW) return;
+    const int first = max(1 - fs, vP[y]);
+    int v[8], t8[8];
+    if (fs == 1) {
+        lds8(gt_smem + (line_index(first, 0, srcH) - lo) * GT_LW + 4 * tx, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (v[k] + 64) >> 7;
+    } else {
+        const int16_t *cf = vF + (size_t)y * fs;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = 64 << 12;
+        for (int j = 0; j < fs; j++) {
+            lds8(gt_smem + (line_index(first, j, srcH) - lo) * GT_LW + 4 * tx, t8); const int c = cf[j];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += t8[k] * c;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] >>= 19;
+    }
+    uint8_t *d = dst + (size_t)y * dstStride + x;
+    if (x + 8 <= dstW && !(((uintptr_t)d) & 7)) {
+        *reinterpret_cast<uint2 *>(d) = make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (x + k < dstW) d[k] = (uint8_t)clip_u8(v[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3 };       // libavutil/pixfmt.h enum values
@@ -578,6 +836,8 @@ struct SwsCudaContext {
     SwsDev dev;
     int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
     int lumStridePx = 0, chrStridePx = 0;
+    int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
+    int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
     // staging for the host-pointer sws_scale_cuda()
     uint8_t *d_src = nullptr, *d_dst = nullptr; size_t src_bytes = 0, dst_bytes = 0;
 };
@@ -687,6 +947,27 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
     }
     if (!c->fused && !c->copy && !c->table_unscaled) {
+        int lr = 0, cr = 0, lo, hi;
+        std::vector<int2> win;
+        for (int y0 = 0; y0 < dstH; y0 += GT_H) {
+            tile_line_window(c->vLum.pos.data(), c->vLum.size, y0, std::min(y0 + GT_H, dstH) - 1, srcH, lo, hi);
+            lr = std::max(lr, hi - lo + 1); win.push_back(make_int2(lo, hi - lo + 1));
+        }
+        const size_t nLumWin = win.size();
+        // vChr has chrDstH entries: dstH of them for packed rgb (no vertical chroma sub-sampling on that side)
+        for (int y0 = 0; y0 < c->g.chrDstH; y0 += GT_H) {
+            tile_line_window(c->vChr.pos.data(), c->vChr.size, y0, std::min(y0 + GT_H, c->g.chrDstH) - 1, c->g.chrSrcH, lo, hi);
+            cr = std::max(cr, hi - lo + 1); win.push_back(make_int2(lo, hi - lo + 1));
+        }
+        const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * GT_W) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
+        if (need <= 96 * 1024) {
+            c->tileLumRows = lr; c->tileChrRows = cr;
+            if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
+                cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("sws_getContext_cuda", cudaGetLastError()); cudaFree(c->d_tables); delete c; return nullptr;
+            }
+            c->tileChrWinOff = nLumWin;
+        }
         c->lumStridePx = (dstW + 1 + 7) & ~7;          // multiples of 8 samples: 16-byte aligned rows for the vector passes
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
         if (cudaMalloc(&c->d_lum, (size_t)c->lumStridePx * srcH * 2) != cudaSuccess ||
@@ -755,7 +1036,49 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
         else         sws_fused_rgb24_kernel<false><<<g, b, 0, st>>>(p, a);    // same arithmetic, byte accesses
         return check_launch("sws_scale:fused");
     }
-    for (int f = 0; f < nframes; f++) {      // general path: frames are serialised on the stream (shared line planes)
+    if (c->tileLumRows && tuning("sws_general_variant") != 1) {       // general path, fused per output tile
+        TileArgs a;
+        a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst0 = dst[0]; a.dst1 = dst[1]; a.dst2 = dst[2];
+        a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2];
+        a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2];
+        a.dstStride0 = dstStride[0]; a.dstFrame0 = dstFrame[0];
+        const bool planar = c->dstFormat == FMT_YUV420P;
+        a.dstStride1 = planar ? dstStride[1] : 0; a.dstStride2 = planar ? dstStride[2] : 0;
+        a.dstFrame1 = planar ? dstFrame[1] : 0; a.dstFrame2 = planar ? dstFrame[2] : 0;
+        a.lumRows = c->tileLumRows; a.chrRows = c->tileChrRows;
+        a.lumWin = c->d_tile_win; a.chrWin = c->d_tile_win + c->tileChrWinOff;
+        a.lumXInc = c->g.lumXInc; a.chrXInc = c->g.chrXInc;
+        a.vec = !((uintptr_t)a.dst0 & 7) && !(a.dstStride0 & 7) && !(a.dstFrame0 & 7);
+        const int fsl = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hLumSize, fsc = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hChrSize;
+        const dim3 gl((p.dstW + GT_W - 1) / GT_W, (p.dstH + GT_H - 1) / GT_H, nframes);
+        if (!planar) {
+            const size_t smem = ((size_t)a.lumRows * GT_LW + (size_t)a.chrRows * GT_W) * 4;
+            auto go = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                kern<<<gl, GT_THREADS, smem, st>>>(p, a);
+            };
+            if (fsl == -1)                  go(sws_tile_rgb24_kernel<-1, -1>);
+            else if (fsl == 2 && fsc == 2)  go(sws_tile_rgb24_kernel<2, 2>);
+            else if (fsl == 4 && fsc == 4)  go(sws_tile_rgb24_kernel<4, 4>);
+            else if (fsl == 8 && fsc == 8)  go(sws_tile_rgb24_kernel<8, 8>);
+            else                            go(sws_tile_rgb24_kernel<0, 0>);
+        } else {
+            const dim3 gc((p.chrDstW + GT_W - 1) / GT_W, (p.chrDstH + GT_H - 1) / GT_H, 2 * nframes);
+            auto go = [&](auto kl, auto kc) {
+                cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                kl<<<gl, GT_THREADS, (size_t)a.lumRows * GT_LW * 4, st>>>(p, a);
+                kc<<<gc, GT_THREADS, (size_t)a.chrRows * GT_LW * 4, st>>>(p, a);
+            };
+            if (fsl == -1)                  go(sws_tile_plane_kernel<-1, false>, sws_tile_plane_kernel<-1, true>);
+            else if (fsl == 2 && fsc == 2)  go(sws_tile_plane_kernel<2, false>, sws_tile_plane_kernel<2, true>);
+            else if (fsl == 4 && fsc == 4)  go(sws_tile_plane_kernel<4, false>, sws_tile_plane_kernel<4, true>);
+            else if (fsl == 8 && fsc == 8)  go(sws_tile_plane_kernel<8, false>, sws_tile_plane_kernel<8, true>);
+            else                            go(sws_tile_plane_kernel<0, false>, sws_tile_plane_kernel<0, true>);
+        }
+        return check_launch("sws_scale:tile");
+    }
+    for (int f = 0; f < nframes; f++) {      // general path, two passes: frames are serialised on the stream (shared line planes)
         const uint8_t *y = src[0] + f * srcFrame[0], *u = src[1] + f * srcFrame[1], *v = src[2] + f * srcFrame[2];
         dim3 b(256);
         if (c->g.flags & SWS_FAST_BILINEAR) {
@@ -788,7 +1111,7 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
 static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
     delete c;
 }
 

@@ -49,27 +49,46 @@ GEOMS = [(352, 288, 640, 480), (640, 480, 352, 288), (96, 96, 64, 128), (100, 37
          (64, 48, 64, 48), (66, 50, 33, 25), (641, 479, 641, 479), (1920, 1080, 3840, 2160)]
 
 
+@pytest.mark.parametrize("variant,pad", [("tile", 6), ("tile", 8), ("two_pass", 6)])
 @pytest.mark.parametrize("algo", list(ALGOS))
-def test_scaling_matches_oracle(gpu, checker, algo):
+def test_scaling_matches_oracle(gpu, checker, algo, variant, pad):
+    """both general-path implementations (fused per output tile = default; two passes through int16 line planes = the
+    fallback for line windows that do not fit in shared memory), byte-store (pad 6) and vector-store (pad 8) rows"""
     from libav_b200 import device
+    from libav_b200._lib import lib
     flags = ALGOS[algo] | ACC
-    for (sw, sh, dw, dh) in GEOMS:
-        if sw * sh > 1500 * 1000 and algo not in ("bicubic", "bilinear"):
-            continue
-        yuv = tuple(synth.pad_rows(pl) for pl in synth.yuv420p_frame(sw, sh, 3))
-        for fmt in (device.PIX_FMT_RGB24, device.PIX_FMT_BGR24, device.PIX_FMT_YUV420P):
-            ctx = device.SwsContext(sw, sh, dw, dh, fmt, flags)
-            got = ctx.scale(yuv, dst_pad=6) if fmt != device.PIX_FMT_YUV420P else ctx.scale(yuv)
-            if fmt == device.PIX_FMT_YUV420P:
-                for a, b in zip(got, oracle_yuv(checker, yuv, dw, dh, flags)):
-                    assert np.array_equal(a, b), (algo, sw, sh, dw, dh, "yuv")
-            else:
-                want = oracle_rgb(checker, yuv, dw, dh, flags, pad=6)
-                if fmt == device.PIX_FMT_BGR24:
-                    w3 = want[:, :((dw + 1) // 2) * 6].reshape(dh, -1, 3)[:, :, ::-1].reshape(dh, -1)
-                    want = np.concatenate([w3, want[:, ((dw + 1) // 2) * 6:]], axis=1)
-                assert np.array_equal(got, want), (algo, sw, sh, dw, dh, fmt)
-            ctx.close()
+    lib.avb200_set_tuning(b"sws_general_variant", 1 if variant == "two_pass" else 0)
+    try:
+        for (sw, sh, dw, dh) in GEOMS:
+            if sw * sh > 1500 * 1000 and algo not in ("bicubic", "bilinear"):
+                continue
+            yuv = tuple(synth.pad_rows(pl) for pl in synth.yuv420p_frame(sw, sh, 3))
+            for fmt in (device.PIX_FMT_RGB24, device.PIX_FMT_BGR24, device.PIX_FMT_YUV420P):
+                if fmt == device.PIX_FMT_YUV420P and pad == 8:
+                    continue
+                ctx = device.SwsContext(sw, sh, dw, dh, fmt, flags)
+                got = ctx.scale(yuv, dst_pad=pad) if fmt != device.PIX_FMT_YUV420P else ctx.scale(yuv)
+                if fmt == device.PIX_FMT_YUV420P:
+                    for a, b in zip(got, oracle_yuv(checker, yuv, dw, dh, flags)):
+                        assert np.array_equal(a, b), (algo, sw, sh, dw, dh, "yuv")
+                else:
+                    want = oracle_rgb(checker, yuv, dw, dh, flags, pad=pad)
+                    if fmt == device.PIX_FMT_BGR24:
+                        w3 = want[:, :((dw + 1) // 2) * 6].reshape(dh, -1, 3)[:, :, ::-1].reshape(dh, -1)
+                        want = np.concatenate([w3, want[:, ((dw + 1) // 2) * 6:]], axis=1)
+                    assert np.array_equal(got, want), (algo, sw, sh, dw, dh, fmt)
+                ctx.close()
+    finally:
+        lib.avb200_set_tuning(b"sws_general_variant", 0)
+
+
+def test_heavy_downscale_falls_back_to_two_passes(gpu, checker):
+    """a 16-row output tile of a 12x vertical reduction needs > 96 KB of source lines: the context must still be bit-exact"""
+    from libav_b200 import device
+    sw, sh, dw, dh = 256, 4800, 128, 100
+    yuv = tuple(synth.pad_rows(pl) for pl in synth.yuv420p_frame(sw, sh, 9))
+    ctx = device.SwsContext(sw, sh, dw, dh, device.PIX_FMT_RGB24, 4 | ACC)
+    assert np.array_equal(ctx.scale(yuv, dst_pad=8), oracle_rgb(checker, yuv, dw, dh, 4 | ACC, pad=8))
 
 
 def test_unsupported_requests_fail_loudly(gpu):

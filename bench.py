@@ -204,7 +204,7 @@ def make_sws_up_workload(torch, L, stream, rank):
     return {
         "name": "sws_scale 1920x1080 -> 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact (true rescale), %d frames per step" % K,
         "run": run, "run_e2e": None, "pixels": dw * dh * K, "alg_bytes": int((sw * sh * 1.5 + dw * dh * 3) * K),
-        "launches_per_step": 4 * K, "kernel": "sws_vscale_rgb24_kernel", "dtype": "int32 (u8 in, u8 out)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 1, "kernel": "sws_tile_rgb24_kernel", "dtype": "int32 (u8 in, u8 out)", "h2d": 0, "d2h": 0,
         "l2": "%d MiB of output per step" % (osz * K >> 20), "keep": (d_y, d_u, d_v, d_o, ctx),
     }
 

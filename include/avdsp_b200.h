@@ -170,6 +170,43 @@ int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h,
 int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb,
                                uint8_t *cr, int linesize, int uvlinesize, uint32_t *progress, void *stream);
 
+/* Deblocking DECISIONS: what loop_filter() -> fill_filter_caches() -> ff_h264_filter_mb()
+ * (libavcodec/h264_slice.c:1972-2262, libavcodec/h264_loopfilter.c:438-846) decide for every macroblock of a
+ * progressive 4:2:0 8-bit picture -- boundary strengths, averaged qp, alpha / beta / tc0 per edge -- computed on the
+ * device from the decoder's side-information arrays, written as the FFH264DeblockMB records the deblocking kernels
+ * above consume.  All pointers are DEVICE pointers to copies of the decoder's own arrays, in the decoder's layouts:
+ *   mb_type, qscale_table, cbp_table, slice_table: [n_pictures * mb_h][mb_w + 1] (mb_stride = mb_w + 1, the extra
+ *       column is the decoder's padding and is never read)          H264Picture.mb_type / qscale_table, H264Context
+ *   non_zero_count: [..][48] per macroblock                          H264Context.non_zero_count
+ *   motion_val[list]: [4 * n_pictures * mb_h][4 * mb_w][2] int16     H264Picture.motion_val, b_stride = 4 * mb_w
+ *   ref_index[list]: [..][4] per macroblock (one per 8x8)            H264Picture.ref_index
+ *   slices[slice_num]: the slice-header values the filter uses and the slice's ref2frm table (h264dec.h:186,538;
+ *       ref2frm[list][2 + ref_index] = identity of the referenced frame, entries 0/1 = -1); at most 32 slice numbers
+ *   chroma_qp_table: PPS.chroma_qp_table[2][64] (h264_ps.h:124)
+ * Pictures of a batch are stacked row-wise; no edge is filtered across a picture boundary.
+ * Not covered: MBAFF / field pictures, 4:2:2 / 4:4:4, high bit depth (the reference's other branches). */
+typedef struct FFH264DeblockSlice {
+    int32_t alpha_c0_offset, beta_offset;   /* sl->slice_alpha_c0_offset, sl->slice_beta_offset */
+    int32_t deblocking_filter;              /* 0 off, 1 every edge, 2 not across slice boundaries */
+    int32_t list_count;                     /* 1 (P) or 2 (B) */
+    int32_t qp_thresh;                      /* sl->qp_thresh, h264_slice.c:1815-1818 */
+    int32_t ref2frm[2][64];
+} FFH264DeblockSlice;
+typedef struct FFH264DeblockInfo {
+    int mb_w, mb_h, n_pictures;
+    const uint32_t *mb_type;
+    const int8_t   *qscale_table;
+    const uint8_t  *non_zero_count;
+    const uint16_t *cbp_table, *slice_table;
+    const int16_t  *motion_val[2];
+    const int8_t   *ref_index[2];
+    const FFH264DeblockSlice *slices;
+    int n_slices;
+    const uint8_t  *chroma_qp_table;
+    int cabac, transform_8x8_mode;          /* PPS.cabac, PPS.transform_8x8_mode */
+} FFH264DeblockInfo;
+int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info /* host struct */, FFH264DeblockMB *out, void *stream);
+
 /* ---- MECmpContext, motion search, HpelDSPContext, FDCTDSPContext -----------------------------------------
  * me_cmp: n block pairs (cur + cur_off vs ref + ref_off, common stride, height h) through one metric; out[i] is
  * what the C slot returns.  kind / sidx / dxy select the slot like the reference's tables (libavcodec/me_cmp.h:39-63):

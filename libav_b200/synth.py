@@ -296,6 +296,94 @@ def h264_deblock_work(mb_w, mb_h, seed=4, slices=1):
     return rec
 
 
+# ---- decoder side information for the deblocking-decision kernel (the reference's own array layouts) ----
+MB_INTRA4x4, MB_INTRA16x16, MB_16x16, MB_16x8, MB_8x16, MB_8x8 = 1, 2, 8, 16, 32, 64
+MB_DIRECT2, MB_SKIP, MB_P0L0, MB_P1L0, MB_P0L1, MB_P1L1, MB_8x8DCT = 0x100, 0x800, 0x1000, 0x2000, 0x4000, 0x8000, 0x01000000
+H264_CHROMA_QP = np.array(list(range(30)) + [29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39], np.uint8)
+
+
+def h264_deblock_info(mb_w, mb_h, seed=5, n_slices=3, bipred=False, cabac=1, t8x8=0, mode=1, qp_lo=10, qp_hi=51,
+                      p_intra=0.15, cb_off=0, cr_off=0):
+    """Random but self-consistent side information of one progressive picture, in the layouts libavcodec keeps it
+    (H264Picture.mb_type / qscale_table / motion_val / ref_index, H264Context.non_zero_count / cbp_table /
+    slice_table / ref2frm, PPS.chroma_qp_table): what ff_h264_deblock_params_cuda and the oracle consume.
+    Motion vectors differ by 0..8 quarter-pels between partitions so the |d| >= 4 rule is exercised both ways."""
+    r = np.random.RandomState(seed)
+    ms, bs = mb_w + 1, 4 * mb_w
+    n = ms * mb_h
+    d = {"mb_w": mb_w, "mb_h": mb_h, "cabac": cabac, "t8x8": t8x8, "n_slices": n_slices}
+    mb_type = np.zeros(n, np.uint32); qp = np.zeros(n, np.int8); nnz = np.zeros((n, 48), np.uint8)
+    cbp = np.zeros(n, np.uint16); sl = np.full(n, 0xFFFF, np.uint16)
+    mv = np.zeros((2, 4 * mb_h, bs, 2), np.int16); ref = np.full((2, n, 4), -1, np.int8)
+    per = -(-mb_w * mb_h // n_slices)
+    for y in range(mb_h):
+        for x in range(mb_w):
+            xy = x + y * ms
+            sl[xy] = (x + y * mb_w) // per
+            qp[xy] = r.randint(qp_lo, qp_hi + 1)
+            dct8 = MB_8x8DCT if (t8x8 and r.rand() < 0.4) else 0
+            if r.rand() < p_intra:
+                mb_type[xy] = (MB_INTRA4x4 | dct8) if r.rand() < 0.6 else MB_INTRA16x16
+                nnz[xy, :16] = r.randint(0, 17, 16)
+                cbp[xy] = r.randint(0, 16) | (r.randint(0, 16) << 12)
+                continue
+            part = [MB_16x16, MB_16x8, MB_8x16, MB_8x8][r.randint(0, 4)]
+            if bipred:
+                use = [[1, 0], [0, 1], [1, 1]][r.randint(0, 3)]
+                if r.rand() < 0.1: use = [1, 1]
+            else:
+                use = [1, 0]
+            t = part | dct8
+            if use[0]: t |= MB_P0L0 | MB_P1L0
+            if use[1]: t |= MB_P0L1 | MB_P1L1
+            if part == MB_16x16 and r.rand() < 0.2: t |= MB_SKIP
+            if bipred and r.rand() < 0.1: t |= MB_DIRECT2
+            mb_type[xy] = t
+            # partition geometry in 4x4 units
+            rects = {MB_16x16: [(0, 0, 4, 4)], MB_16x8: [(0, 0, 4, 2), (0, 2, 4, 2)], MB_8x16: [(0, 0, 2, 4), (2, 0, 2, 4)],
+                     MB_8x8: [(0, 0, 2, 2), (2, 0, 2, 2), (0, 2, 2, 2), (2, 2, 2, 2)]}[part]
+            base = r.randint(-6, 7, 2)
+            for l in range(2):
+                if not use[l]:
+                    continue
+                for (bx, by, bw, bh) in rects:
+                    ri = r.randint(0, 3)
+                    if part == MB_8x8 and r.rand() < 0.5:                       # sub-partitions: per-4x4 vectors
+                        for yy in range(by, by + bh):
+                            for xx in range(bx, bx + bw):
+                                mv[l, 4 * y + yy, 4 * x + xx] = base + r.randint(0, 6, 2)
+                    else:
+                        mv[l, 4 * y + by:4 * y + by + bh, 4 * x + bx:4 * x + bx + bw] = base + r.randint(0, 6, 2)
+                    for yy in range(by // 2, (by + bh + 1) // 2):
+                        for xx in range(bx // 2, (bx + bw + 1) // 2):
+                            ref[l, xy, xx + 2 * yy] = ri
+            coded = r.rand(4) < 0.45                                              # per 8x8 luma
+            for k in range(16):
+                b8 = ((k & 3) >> 1) + 2 * (k >> 3)
+                nnz[xy, k] = r.randint(1, 17) if (coded[b8] and r.rand() < 0.6) else 0
+            c = 0
+            for b8 in range(4):
+                if nnz[xy, [b8 % 2 * 2 + b8 // 2 * 8 + o for o in (0, 1, 4, 5)]].any(): c |= 1 << b8
+            cbp[xy] = c | (r.randint(0, 3) << 4) | ((r.randint(0, 16) << 12) if dct8 else 0)
+    # per-slice parameters: {alpha_c0_offset, beta_offset, deblocking_filter, list_count, qp_thresh, ref2frm[2][64]}
+    sp = np.zeros((n_slices, 133), np.int32)
+    for s in range(n_slices):
+        a, b = 2 * r.randint(-3, 4), 2 * r.randint(-3, 4)
+        r2f = np.full((2, 64), -1, np.int32)
+        ids = r.permutation(6)
+        for l in range(2):
+            for i in range(4):
+                r2f[l, 2 + i] = 4 * int(ids[(i + 2 * l) % 4 if bipred else i % 3]) + 3      # some indices share a frame
+        sp[s, :5] = [a, b, mode, 2 if bipred else 1, 15 - min(a, b) - max(0, cb_off, cr_off)]
+        sp[s, 5:] = r2f.reshape(-1)
+    cqt = np.zeros((2, 64), np.uint8)
+    for t, off in enumerate((cb_off, cr_off)):
+        cqt[t, :52] = H264_CHROMA_QP[np.clip(np.arange(52) + off, 0, 51)]
+    d.update(mb_type=mb_type, qscale=qp, nnz=nnz, cbp=cbp, slice_table=sl, mv0=np.ascontiguousarray(mv[0]), mv1=np.ascontiguousarray(mv[1]),
+             ref0=np.ascontiguousarray(ref[0]), ref1=np.ascontiguousarray(ref[1]), slice_params=sp, chroma_qp_table=cqt)
+    return d
+
+
 MECMP_DT = np.dtype([("cur_off", "<u4"), ("ref_off", "<u4")])
 HPEL_DT = np.dtype([("dst_off", "<u4"), ("src_off", "<u4"), ("tab", "u1"), ("sidx", "u1"), ("dxy", "u1"), ("h", "u1")])
 assert MECMP_DT.itemsize == 8 and HPEL_DT.itemsize == 12

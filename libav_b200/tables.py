@@ -94,3 +94,19 @@ FFTContext._fields_ = [("nbits", C.c_int), ("inverse", C.c_int), ("revtab", C.PO
                        ("mdct_size", C.c_int), ("mdct_bits", C.c_int), ("tcos", C.POINTER(C.c_float)), ("tsin", C.POINTER(C.c_float)),
                        ("fft_permute", _fftc), ("fft_calc", _fftc), ("imdct_calc", _mdctf), ("imdct_half", _mdctf), ("mdct_calc", _mdctf),
                        ("mdct_calcw", C.c_void_p), ("fft_permutation", C.c_int), ("mdct_permutation", C.c_int)]
+
+
+class FFH264DeblockSlice(C.Structure):
+    """include/avdsp_b200.h FFH264DeblockSlice (133 int32)"""
+    _fields_ = [("alpha_c0_offset", C.c_int32), ("beta_offset", C.c_int32), ("deblocking_filter", C.c_int32),
+                ("list_count", C.c_int32), ("qp_thresh", C.c_int32), ("ref2frm", (C.c_int32 * 64) * 2)]
+
+
+class FFH264DeblockInfo(C.Structure):
+    """include/avdsp_b200.h FFH264DeblockInfo (host struct holding device pointers)"""
+    _fields_ = [("mb_w", C.c_int), ("mb_h", C.c_int), ("n_pictures", C.c_int),
+                ("mb_type", C.c_void_p), ("qscale_table", C.c_void_p), ("non_zero_count", C.c_void_p),
+                ("cbp_table", C.c_void_p), ("slice_table", C.c_void_p),
+                ("motion_val", C.c_void_p * 2), ("ref_index", C.c_void_p * 2),
+                ("slices", C.c_void_p), ("n_slices", C.c_int), ("chroma_qp_table", C.c_void_p),
+                ("cabac", C.c_int), ("transform_8x8_mode", C.c_int)]

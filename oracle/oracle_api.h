@@ -61,6 +61,26 @@ void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
  *        6 v_chroma_intra 7 h_chroma_intra ; tc0 ignored for intra */
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
+
+/* Deblocking DECISIONS for one progressive 4:2:0 8-bit picture: what loop_filter() ->
+ * fill_filter_caches() -> ff_h264_filter_mb() (libavcodec/h264_slice.c:2198-2262, :1972-2196,
+ * libavcodec/h264_loopfilter.c:420-846) decide per macroblock -- which edges are filtered with which
+ * (alpha, beta, tc0 | bS 4).  Inputs are the decoder's own side-information arrays in the decoder's layouts:
+ *   mb_type, qscale, cbp, slice_table : [mb_h * mb_stride], mb_stride = mb_w + 1, index mb_x + mb_y * mb_stride
+ *                                       (the extra column is padding and is never read here)
+ *   nnz        : [mb_h * mb_stride][48]   H264Context.non_zero_count (luma 4x4 block k at [k], raster inside the MB)
+ *   mv0 / mv1  : [4 * mb_h][4 * mb_w][2]  H264Picture.motion_val[list], b_stride = 4 * mb_w, quarter-pel
+ *   ref0 / ref1: [mb_h * mb_stride][4]    H264Picture.ref_index[list] per 8x8
+ *   slice_params: per slice_num 133 int32 = { slice_alpha_c0_offset, slice_beta_offset, deblocking_filter,
+ *                 list_count, qp_thresh, ref2frm[2][64] }  (H264SliceContext / H264Context.ref2frm, h264dec.h:186,538)
+ *   chroma_qp_table: PPS.chroma_qp_table[2][64] (h264_ps.h:124)
+ * out: mb_w * mb_h records of 104 bytes, raster order, in the layout of FFH264DeblockMB (include/avdsp_b200.h):
+ *   alpha[2][4] beta[2][4] tc0[2][4][4] intra[2] calpha[2][2][2] cbeta[2][2][2] ctc0[2][2][2][4] cintra[2][2] pad[2];
+ *   an edge that is not filtered has alpha = beta = 0. Returns 0, or -1 for n_slices > 32. */
+int ORC(h264_deblock_params)(int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
+                             const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
+                             const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
+                             const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode, uint8_t *out);
 /* widx: 0..3 = width 16,8,4,2 */
 void ORC(h264_weight)(int widx, uint8_t *block, int stride, int height, int log2_denom,
                       int weight, int offset);

@@ -1,0 +1,49 @@
+"""Deblocking DECISIONS: the plain-C restatement (oracle/port/orc_h264lf.c) against the reference's
+own h264_loopfilter.c (compiled unmodified into oracle/_ref, slots replaced by recorders) on random but self-consistent
+decoder side information -- P and B pictures, several slices, CABAC and CAVLC with the 8x8 transform, both slice-edge
+modes, low-qp pictures that take the threshold shortcut, unequal cb/cr qp offsets."""
+import numpy as np
+import pytest
+
+from libav_b200 import synth
+from oracle.loader import ptr
+
+CASES = [
+    dict(seed=1),
+    dict(seed=2, bipred=True),
+    dict(seed=3, t8x8=1, cabac=1),
+    dict(seed=4, t8x8=1, cabac=0),
+    dict(seed=5, t8x8=1, cabac=0, bipred=True, mode=2, n_slices=5),
+    dict(seed=6, mode=2, n_slices=7, p_intra=0.4),
+    dict(seed=7, qp_lo=0, qp_hi=20),                      # most macroblocks fall under qp_thresh
+    dict(seed=8, cb_off=-3, cr_off=5, bipred=True),       # chroma_qp_diff: cb and cr edges get different thresholds
+    dict(seed=9, p_intra=0.0, qp_lo=30, qp_hi=40),
+    dict(seed=10, mode=0),
+]
+
+
+def run(o, d):
+    out = np.zeros((d["mb_w"] * d["mb_h"], 104), np.uint8)
+    rc = o.h264_deblock_params(d["mb_w"], d["mb_h"], ptr(d["mb_type"]), ptr(d["qscale"]), ptr(d["nnz"]), ptr(d["cbp"]),
+                               ptr(d["slice_table"]), ptr(d["mv0"]), ptr(d["mv1"]), ptr(d["ref0"]), ptr(d["ref1"]),
+                               ptr(d["slice_params"]), d["n_slices"], ptr(d["chroma_qp_table"]), d["cabac"], d["t8x8"], ptr(out))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join("%s%s" % kv for kv in c.items()))
+def test_port_matches_reference_decisions(orc, refo, case):
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    for (mw, mh) in ((11, 9), (1, 1), (2, 5), (20, 3)):
+        d = synth.h264_deblock_info(mw, mh, **case)
+        a, b = run(refo, d), run(orc, d)
+        bad = np.argwhere((a != b).any(axis=1))
+        assert not len(bad), (mw, mh, bad[:4].ravel().tolist(), a[bad[0, 0]].tolist(), b[bad[0, 0]].tolist())
+
+
+def test_decisions_are_not_trivial(orc):
+    d = synth.h264_deblock_info(12, 8, seed=1)
+    rec = run(orc, d).view(synth.DEBLOCK_DT).reshape(-1)
+    assert (rec["alpha"] != 0).mean() > 0.3 and (rec["alpha"] == 0).mean() > 0.05
+    assert rec["intra"].any() and (rec["tc0"] > 0).any() and (rec["tc0"] < 0).any()

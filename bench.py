@@ -271,6 +271,36 @@ def make_h264_workload(torch, L, stream, rank):
     }
 
 
+def make_h264_decide_workload(torch, L, stream, rank):
+    """deblocking decisions (bS / alpha / beta / tc0 per edge) for a batch of stacked 1080p B pictures,
+    from the decoder's side-information arrays resident in HBM to FFH264DeblockMB records in HBM."""
+    from libav_b200 import synth, tables
+    lib = L.lib
+    mb_w, mb_h, P = 120, 68, H264_PICTURES
+    d = synth.h264_deblock_info(mb_w, mb_h, seed=3 + rank, n_slices=8, bipred=True)
+    t = lambda a, reps=P: torch.from_numpy(np.concatenate([np.ascontiguousarray(a)] * reps).view(np.uint8).reshape(-1)).cuda()
+    keep = {k: t(d[k]) for k in ("mb_type", "qscale", "nnz", "cbp", "slice_table", "mv0", "mv1", "ref0", "ref1")}
+    keep["sp"], keep["cq"] = t(d["slice_params"], 1), t(d["chroma_qp_table"], 1)
+    n = mb_w * mb_h * P
+    d_out = torch.empty(n * 104, dtype=torch.uint8, device="cuda")
+    info = tables.FFH264DeblockInfo(mb_w, mb_h, P, keep["mb_type"].data_ptr(), keep["qscale"].data_ptr(), keep["nnz"].data_ptr(),
+                                    keep["cbp"].data_ptr(), keep["slice_table"].data_ptr(),
+                                    (C.c_void_p * 2)(keep["mv0"].data_ptr(), keep["mv1"].data_ptr()),
+                                    (C.c_void_p * 2)(keep["ref0"].data_ptr(), keep["ref1"].data_ptr()), keep["sp"].data_ptr(), 8,
+                                    keep["cq"].data_ptr(), 1, 0)
+
+    def run(i):
+        L.check(lib.ff_h264_deblock_params_cuda(C.byref(info), d_out.data_ptr(), stream), "deblock_params")
+
+    per_mb = 4 + 1 + 48 + 2 + 2 + 2 * 64 + 2 * 4 + 104
+    return {
+        "name": "H.264 deblocking decisions (bS, alpha, beta, tc0) for %d stacked 1080p B pictures of 8 slices" % P,
+        "run": run, "run_e2e": None, "pixels": 256 * n, "alg_bytes": n * per_mb,
+        "launches_per_step": 1, "kernel": "h264_deblock_params_kernel", "dtype": "int32 (decoder side information in, records out)",
+        "h2d": 0, "d2h": 0, "l2": "%d MB of side information + records per step" % (n * per_mb >> 20), "keep": (keep, d_out, info),
+    }
+
+
 def make_me_workload(torch, L, stream, rank):
     """config 4: pix_abs16 full search +-16 over a 1920x1088 luma pair (restricted MVs, lambda 0)."""
     from libav_b200 import synth
@@ -426,7 +456,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
@@ -476,7 +506,7 @@ def main():
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
     makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
-              "sws_up": make_sws_up_workload}
+              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):

@@ -98,6 +98,33 @@ int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, si
  * (libavcodec/h264_mb_template.c:40-, h264_mb.c:204-320, h264_loopfilter.c:238-418).  The batched entry points take
  * the same information as arrays of per-macroblock records plus the picture planes, all DEVICE memory. */
 
+/* Inverse quantisation, alone and fused in front of the simple IDCT: MpegEncContext.dct_unquantize_{mpeg1,mpeg2,h263}_
+ * {intra,inter} (libavcodec/mpegvideo.c:51-270) as used by put_dct() / add_dequant_dct() (mpegvideo.c:1401-1427).
+ *   kind 0 mpeg1_intra  1 mpeg1_inter  2 mpeg2_intra  3 mpeg2_intra_bitexact (mismatch control, what
+ *        AV_CODEC_FLAG_BITEXACT installs, mpegvideo.c:281-282)  4 mpeg2_inter  5 h263_intra  6 h263_inter
+ * One record per block carries what the C functions read from the MpegEncContext for that block.
+ * ff_mpeg_dequant_batch_cuda rewrites the blocks in place (inter kinds leave a block with last_index < 0 untouched,
+ * like add_dequant_dct); ff_mpeg_dequant_idct_batch_cuda = dequantise + ff_simple_idct_put (intra kinds) or
+ * ff_simple_idct_add (inter kinds; blocks with last_index < 0 are skipped) in one kernel, destinations addressed like
+ * ff_simple_idct_batch_cuda.  `tables` is a host struct, everything else device memory. */
+typedef struct FFMpegDequantBlock {
+    uint8_t qscale;
+    int8_t  last_index;    /* s->block_last_index[n] */
+    uint8_t dc_scale;      /* n < 4 ? s->y_dc_scale : s->c_dc_scale (intra kinds) */
+    uint8_t flags;         /* bit 0: s->ac_pred (h263_intra) */
+} FFMpegDequantBlock;
+typedef struct FFMpegDequantTables {
+    uint16_t intra_matrix[64], inter_matrix[64];   /* s->intra_matrix / s->inter_matrix, raster order */
+    uint8_t  permutated[64];                       /* s->intra_scantable.permutated (idctdsp.c:28-47) */
+    uint8_t  raster_end[64];                       /* s->inter_scantable.raster_end */
+    int      alternate_scan, h263_aic;
+} FFMpegDequantTables;
+int ff_mpeg_dequant_batch_cuda(int kind, const FFMpegDequantTables *tables, const FFMpegDequantBlock *recs, int16_t *blocks,
+                               size_t n, void *stream);
+int ff_mpeg_dequant_idct_batch_cuda(int kind, const FFMpegDequantTables *tables, const FFMpegDequantBlock *recs, int16_t *blocks,
+                                    uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row,
+                                    int clear, void *stream);
+
 /* Residual: H264DSPContext.h264_idct_add16 / _add16intra / idct8_add4 (+ h264_idct_add8 for chroma)
  * (libavcodec/h264idct_template.c:174-214).  Record i consumes coeffs + i * coeff_stride (int16; block k of the MB at
  * + 16 * k, luma k = 0..15, cb 16..19, cr 32..35 -- the reference's sl->mb layout) and nnzc + i * 120

@@ -2,6 +2,7 @@
 // the host-buffer end-to-end call, per-block slot functions and the ff_*_init_cuda hooks.
 #include "common.cuh"
 #include "scratch.h"
+#include "idct_dq.h"
 #include "../../include/avdsp_b200.h"
 #include <string.h>
 
@@ -11,6 +12,9 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
 int launch_pixels_clamped(int mode, const int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,
                           ptrdiff_t stride, size_t n, int tiles_per_row, cudaStream_t st);
 int launch_clear_blocks(int16_t *blocks, size_t n_blocks, cudaStream_t st);
+int launch_mpeg_dequant(int kind, const DqTables &t, const uint32_t *recs, int16_t *blocks, size_t n, cudaStream_t st);
+int launch_mpeg_dequant_idct(int kind, const DqTables &t, const uint32_t *recs, int16_t *blocks, uint8_t *frame,
+                             const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row, int clear, cudaStream_t st);
 int launch_fill_blocks(uint8_t *frame, const uint32_t *dst_off, const uint8_t *value, ptrdiff_t stride, int h,
                        int w16, size_t n, cudaStream_t st);
 }
@@ -27,6 +31,35 @@ int ff_pixels_clamped_batch_cuda(int mode, const int16_t *blocks, uint8_t *frame
                                  ptrdiff_t stride, size_t n, int tiles_per_row, void *stream)
 {
     return launch_pixels_clamped(mode, blocks, frame, dst_off, stride, n, tiles_per_row, (cudaStream_t)stream);
+}
+static int dq_tables(const char *who, int kind, const FFMpegDequantTables *t, DqTables &d)
+{
+    if (!t || kind < 0 || kind > 6) { set_error_msg(who, "bad kind / tables"); return -1; }
+    uint8_t seen[64] = { 0 };
+    for (int i = 0; i < 64; i++) {
+        if (t->permutated[i] > 63 || seen[t->permutated[i]]++) { set_error_msg(who, "permutated[] is not a permutation of 0..63"); return -1; }
+        d.rank[t->permutated[i]] = (uint8_t)i;
+        d.raster_end[i] = t->raster_end[i];
+        d.intra[i] = t->intra_matrix[i]; d.inter[i] = t->inter_matrix[i];
+    }
+    d.alternate_scan = t->alternate_scan; d.h263_aic = t->h263_aic;
+    return 0;
+}
+int ff_mpeg_dequant_batch_cuda(int kind, const FFMpegDequantTables *t, const FFMpegDequantBlock *recs, int16_t *blocks, size_t n,
+                               void *stream)
+{
+    DqTables d;
+    if (dq_tables("ff_mpeg_dequant_batch_cuda", kind, t, d)) return -1;
+    return launch_mpeg_dequant(kind, d, reinterpret_cast<const uint32_t *>(recs), blocks, n, (cudaStream_t)stream);
+}
+int ff_mpeg_dequant_idct_batch_cuda(int kind, const FFMpegDequantTables *t, const FFMpegDequantBlock *recs, int16_t *blocks,
+                                    uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row,
+                                    int clear, void *stream)
+{
+    DqTables d;
+    if (dq_tables("ff_mpeg_dequant_idct_batch_cuda", kind, t, d)) return -1;
+    return launch_mpeg_dequant_idct(kind, d, reinterpret_cast<const uint32_t *>(recs), blocks, frame, dst_off, stride, n, tiles_per_row,
+                                    clear, (cudaStream_t)stream);
 }
 int ff_clear_blocks_batch_cuda(int16_t *blocks, size_t n_blocks, void *stream)
 {

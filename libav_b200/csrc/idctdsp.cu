@@ -16,6 +16,8 @@
 // Two tiles per warp are double-buffered so the next group's loads fly during the math.
 // Algorithmic traffic: put 128 B in + 64 B out (+4 B offset) per block; add 256 B; idct 256 B.
 #include "common.cuh"
+#include <type_traits>
+#include "idct_dq.h"
 
 namespace avb {
 
@@ -106,12 +108,70 @@ __device__ __forceinline__ uint4 lds128(unsigned saddr)
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Inverse quantisation in front of the IDCT: MpegEncContext.dct_unquantize_* (libavcodec/mpegvideo.c:51-270) as a
+// per-coefficient rule.  DQ: 0 none, 1 + kind otherwise (kind 0 mpeg1_intra 1 mpeg1_inter 2 mpeg2_intra 3 mpeg2_intra
+// bitexact 4 mpeg2_inter 5 h263_intra 6 h263_inter).  One thread owns one block, so the raster index j is the same in
+// every lane at every unrolled step: matrix[j] and rank[j] are kernel-parameter (constant bank) operands.
+// ---------------------------------------------------------------------------------------------------
+struct DqLane { int qscale, limit, dc_scale, qadd; };
+
+template <int KIND>
+__device__ __forceinline__ DqLane dq_lane(uint32_t rec, const DqTables &T)
+{
+    DqLane L;
+    L.qscale = rec & 255;
+    const int last = (int)(int8_t)(rec >> 8), ac_pred = (rec >> 24) & 1;
+    L.dc_scale = (rec >> 16) & 255;
+    if (KIND >= 5) L.limit = (KIND == 5 && ac_pred) ? 63 : (last < 0 ? -1 : (int)T.raster_end[last]);
+    else           L.limit = ((KIND == 2 || KIND == 3 || KIND == 4) && T.alternate_scan) ? 63 : last;
+    L.qadd = (KIND == 5 && T.h263_aic) ? 0 : (L.qscale - 1) | 1;
+    return L;
+}
+
+template <int KIND>
+__device__ __forceinline__ int dq_coef(int level, int j, const DqTables &T, const DqLane &L, int &sum)
+{
+    constexpr bool INTRA = KIND == 0 || KIND == 2 || KIND == 3 || KIND == 5;
+    if (INTRA && j == 0) return (KIND == 5 && T.h263_aic) ? level : level * L.dc_scale;
+    const int pos = KIND >= 5 ? j : (int)T.rank[j];
+    const int sg = level >> 31, a = (level ^ sg) - sg;
+    int v;
+    if (KIND == 0)                    { v = (a * (L.qscale * (int)T.intra[j])) >> 3; v = (v - 1) | 1; }
+    else if (KIND == 1)               { v = ((2 * a + 1) * (L.qscale * (int)T.inter[j])) >> 4; v = (v - 1) | 1; }
+    else if (KIND == 2 || KIND == 3)  { v = (a * (L.qscale * (int)T.intra[j])) >> 3; }
+    else if (KIND == 4)               { v = ((2 * a + 1) * (L.qscale * (int)T.inter[j])) >> 4; }
+    else                              { v = a * (2 * L.qscale) + L.qadd; }
+    v = (v ^ sg) - sg;
+    const bool coded = pos <= L.limit && level != 0;
+    if (KIND == 3 || KIND == 4) sum += coded ? v : 0;
+    return coded ? v : level;
+}
+
+// one row (8 packed int16) of a block; results are stored back as int16 exactly like the C code's block[j] = level
+template <int KIND>
+__device__ __forceinline__ uint4 dq_row(uint4 w, int r, const DqTables &T, const DqLane &L, int &sum)
+{
+    const uint32_t in[4] = { w.x, w.y, w.z, w.w };
+    uint32_t out[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        out[c] = pack16(dq_coef<KIND>(lo16s(in[c]), 8 * r + 2 * c, T, L, sum), dq_coef<KIND>(hi16s(in[c]), 8 * r + 2 * c + 1, T, L, sum));
+    if ((KIND == 3 || KIND == 4) && r == 7) out[3] ^= (uint32_t)(sum & 1) << 16;       // mismatch control on block[63]
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // MODE 0: put, 1: add, 2: plain (in place int16).  CLEAR: also zero the coefficient block
 // afterwards (fused BlockDSPContext.clear_block, what every caller does next).
-template <int MODE, bool CLEAR, int MINB = 5, bool MH = false>
+// DQ != 0: dequantise (kind DQ - 1) in front of the row pass -- put_dct / add_dequant_dct of libavcodec/mpegvideo.c:1401-1427
+// in one kernel; an `add` block with block_last_index < 0 is skipped like the C code skips it.
+struct DqArgs { const uint32_t *recs; DqTables t; };
+struct NoDq {};
+template <int MODE, bool CLEAR, int MINB = 5, bool MH = false, int DQ = 0>
 __global__ void __launch_bounds__(IDCT_WARPS * 32, MINB)
 simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
-                   const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
+                   const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row,
+                   const typename std::conditional<DQ != 0, DqArgs, NoDq>::type dq = {})
 {
     __shared__ __align__(128) uint4 tile[IDCT_WARPS][2][256];   // 32 blocks x 8 chunks of 16 B
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -157,13 +217,23 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
         if (gn < groups) { issue(gn, tile_s + (buf ^ 4096u)); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncwarp();
 
+        const size_t i = g * 32 + lane;
+        bool live = i < n;
         uint4 row[8];
+        if constexpr (DQ != 0) {
+            const uint32_t rec = live ? dq.recs[i] : 0;
+            const DqLane L = dq_lane<DQ - 1>(rec, dq.t);
+            if (MODE == 1 && (int8_t)(rec >> 8) < 0) live = false;
+            int sum = -1;
 #pragma unroll
-        for (int r = 0; r < 8; r++) row[r] = row_pass<MH>(lds128(tb + rd_base + (((unsigned)r << 4) ^ rd_key)));
+            for (int r = 0; r < 8; r++)
+                row[r] = row_pass<MH>(dq_row<DQ - 1>(lds128(tb + rd_base + (((unsigned)r << 4) ^ rd_key)), r, dq.t, L, sum));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) row[r] = row_pass<MH>(lds128(tb + rd_base + (((unsigned)r << 4) ^ rd_key)));
+        }
         __syncwarp();     // this buffer is free for the load issued two iterations from now
 
-        const size_t i = g * 32 + lane;
-        const bool live = i < n;
         if (MODE == 2) {
             // plain idct: results go back in place as int16, column by column pair
             uint32_t o[8][4];
@@ -316,6 +386,59 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
         simple_idct_kernel<2, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
     }
     return check_launch("simple_idct_batch");
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+mpeg_dequant_kernel(int16_t *__restrict__ blocks, const uint32_t *__restrict__ recs, size_t n, const DqTables T)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t rec = recs[i];
+    if ((KIND == 1 || KIND == 4 || KIND == 6) && (int8_t)(rec >> 8) < 0) return;    // add_dequant_dct leaves such blocks alone
+    const DqLane L = dq_lane<KIND>(rec, T);
+    uint4 *b = reinterpret_cast<uint4 *>(blocks) + i * 8;
+    int sum = -1;
+#pragma unroll
+    for (int r = 0; r < 8; r++) b[r] = dq_row<KIND>(b[r], r, T, L, sum);
+}
+
+int launch_mpeg_dequant(int kind, const DqTables &t, const uint32_t *recs, int16_t *blocks, size_t n, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const int grid = (int)((n + 127) / 128);
+    switch (kind) {
+    case 0: mpeg_dequant_kernel<0><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 1: mpeg_dequant_kernel<1><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 2: mpeg_dequant_kernel<2><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 3: mpeg_dequant_kernel<3><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 4: mpeg_dequant_kernel<4><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 5: mpeg_dequant_kernel<5><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    case 6: mpeg_dequant_kernel<6><<<grid, 128, 0, st>>>(blocks, recs, n, t); break;
+    default: set_error_msg("mpeg_dequant_batch", "bad kind"); return -1;
+    }
+    return check_launch("mpeg_dequant_batch");
+}
+
+// intra kinds run as idct_put, inter kinds as idct_add (put_dct / add_dequant_dct, libavcodec/mpegvideo.c:1401-1427)
+int launch_mpeg_dequant_idct(int kind, const DqTables &t, const uint32_t *recs, int16_t *blocks, uint8_t *frame,
+                             const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row, int clear, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    if (!dst_off && tiles_per_row <= 0) { set_error_msg("mpeg_dequant_idct_batch", "need dst_off or tiles_per_row"); return -1; }
+    const size_t groups = (n + 31) / 32;
+    const int grid = grid_for(groups, IDCT_WARPS, 16);
+    const dim3 b(IDCT_WARPS * 32);
+    DqArgs a; a.recs = recs; a.t = t;
+#define AVB_DQ(K, MODE) \
+    case K: if (clear) simple_idct_kernel<MODE, true, 4, false, K + 1><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row, a); \
+            else       simple_idct_kernel<MODE, false, 4, false, K + 1><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row, a); break;
+    switch (kind) {
+    AVB_DQ(0, 0) AVB_DQ(1, 1) AVB_DQ(2, 0) AVB_DQ(3, 0) AVB_DQ(4, 1) AVB_DQ(5, 0) AVB_DQ(6, 1)
+    default: set_error_msg("mpeg_dequant_idct_batch", "bad kind"); return -1;
+    }
+#undef AVB_DQ
+    return check_launch("mpeg_dequant_idct_batch");
 }
 
 int launch_pixels_clamped(int mode, const int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,

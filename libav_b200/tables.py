@@ -110,3 +110,9 @@ class FFH264DeblockInfo(C.Structure):
                 ("motion_val", C.c_void_p * 2), ("ref_index", C.c_void_p * 2),
                 ("slices", C.c_void_p), ("n_slices", C.c_int), ("chroma_qp_table", C.c_void_p),
                 ("cabac", C.c_int), ("transform_8x8_mode", C.c_int)]
+
+
+class FFMpegDequantTables(C.Structure):
+    """include/avdsp_b200.h FFMpegDequantTables"""
+    _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
+                ("raster_end", C.c_uint8 * 64), ("alternate_scan", C.c_int), ("h263_aic", C.c_int)]

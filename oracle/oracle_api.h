@@ -62,6 +62,17 @@ void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
 
+/* MPEG-1/2/4 and H.263 inverse quantisation of one 8x8 block in place: MpegEncContext.dct_unquantize_*
+ * (libavcodec/mpegvideo.c:51-270), simple-IDCT permutation (none).
+ *   kind 0 mpeg1_intra  1 mpeg1_inter  2 mpeg2_intra  3 mpeg2_intra_bitexact (with mismatch control)  4 mpeg2_inter
+ *        5 h263_intra   6 h263_inter
+ *   n = block number inside the macroblock (< 4: y_dc_scale, else c_dc_scale), last_index = block_last_index[n]. */
+void ORC(mpeg_dequant)(int kind, int16_t *block, int n, int qscale, int last_index, int y_dc_scale, int c_dc_scale,
+                       const uint16_t *intra_matrix, const uint16_t *inter_matrix, int alternate_scan, int h263_aic, int ac_pred);
+/* ScanTable.permutated of intra_scantable and ScanTable.raster_end of inter_scantable (idctdsp.c:28-47,
+ * mpegvideo.c:299-317) for the zigzag (0) or alternate vertical (1) scan */
+void ORC(mpeg_scantables)(int alternate_scan, uint8_t *permutated, uint8_t *raster_end);
+
 /* Deblocking DECISIONS for one progressive 4:2:0 8-bit picture: what loop_filter() ->
  * fill_filter_caches() -> ff_h264_filter_mb() (libavcodec/h264_slice.c:2198-2262, :1972-2196,
  * libavcodec/h264_loopfilter.c:420-846) decide per macroblock -- which edges are filtered with which

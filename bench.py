@@ -301,6 +301,41 @@ def make_h264_decide_workload(torch, L, stream, rank):
     }
 
 
+def make_dequant_idct_workload(torch, L, stream, rank):
+    """SURVEY 8f rank 2 (mpegvideo half): put_dct() in one kernel -- dct_unquantize_mpeg2_intra (bitexact variant, with
+    mismatch control) fused in front of simple_idct_put, same 2^20-block batch and frame as the headline workload."""
+    from libav_b200 import synth, tables
+    lib = L.lib
+    base = synth.dense_blocks(1 << 14, seed=11 + rank) >> 3          # quantised levels
+    blocks_h = synth.tile_large(base, N_BLOCKS)
+    r = np.random.RandomState(5 + rank)
+    rec = np.zeros(N_BLOCKS, np.dtype([("qscale", "u1"), ("last", "i1"), ("dc", "u1"), ("flags", "u1")]))
+    rec["qscale"] = r.randint(1, 32, N_BLOCKS); rec["last"] = r.randint(0, 64, N_BLOCKS); rec["dc"] = 8
+    t = tables.FFMpegDequantTables()
+    perm, rend = synth.zigzag_scan_tables()
+    for k in range(64):
+        t.intra_matrix[k] = t.inter_matrix[k] = 8 + ((k & 7) + (k >> 3)) * 2
+        t.permutated[k], t.raster_end[k] = int(perm[k]), int(rend[k])
+    nbuf = 3
+    d_blocks = [torch.from_numpy(blocks_h).cuda() for _ in range(nbuf)]
+    d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1)).cuda()
+    stride = TILES_PER_ROW * 8
+    rows = (N_BLOCKS // TILES_PER_ROW) * 8
+    d_frame = [torch.zeros((rows, stride), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+
+    def run(i):
+        k = i % nbuf
+        L.check(lib.ff_mpeg_dequant_idct_batch_cuda(3, C.byref(t), d_rec.data_ptr(), d_blocks[k].data_ptr(), d_frame[k].data_ptr(), None,
+                                                    stride, N_BLOCKS, TILES_PER_ROW, 0, stream), "ff_mpeg_dequant_idct_batch_cuda")
+
+    return {
+        "name": "fused dct_unquantize_mpeg2_intra (bitexact) + simple_idct_put, 2^20 blocks per GPU -> 8192x8192 u8 frame",
+        "run": run, "run_e2e": None, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * (IDCT_BYTES_PER_BLOCK + 4),
+        "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false,4,false,4>", "dtype": "int32 (int16 levels in, u8 out)",
+        "h2d": 0, "d2h": 0, "l2": "3 rotating 196 MiB buffer sets", "keep": (d_blocks, d_rec, d_frame, t),
+    }
+
+
 def make_me_workload(torch, L, stream, rank):
     """config 4: pix_abs16 full search +-16 over a 1920x1088 luma pair (restricted MVs, lambda 0)."""
     from libav_b200 import synth
@@ -456,7 +491,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
@@ -506,7 +541,7 @@ def main():
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
     makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
-              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload}
+              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):

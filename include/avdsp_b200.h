@@ -106,7 +106,9 @@ int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, si
  * ff_mpeg_dequant_batch_cuda rewrites the blocks in place (inter kinds leave a block with last_index < 0 untouched,
  * like add_dequant_dct); ff_mpeg_dequant_idct_batch_cuda = dequantise + ff_simple_idct_put (intra kinds) or
  * ff_simple_idct_add (inter kinds; blocks with last_index < 0 are skipped) in one kernel, destinations addressed like
- * ff_simple_idct_batch_cuda.  `tables` is a host struct, everything else device memory. */
+ * ff_simple_idct_batch_cuda.  `tables` is a host struct, everything else device memory.
+ * Domain: any int16 level, qscale <= 112, matrix entries <= 255 (so |level| * qscale * matrix stays below 2^31, as it
+ * does for every conforming stream); outside it the C code's 32-bit wrap-around is not reproduced. */
 typedef struct FFMpegDequantBlock {
     uint8_t qscale;
     int8_t  last_index;    /* s->block_last_index[n] */

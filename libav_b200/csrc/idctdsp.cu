@@ -129,21 +129,31 @@ __device__ __forceinline__ DqLane dq_lane(uint32_t rec, const DqTables &T)
     return L;
 }
 
+// Sign-free forms of the C code's "negate, scale, negate back": with p = level * (qscale * matrix) the magnitude shift is
+// a division that truncates towards zero, u = (p + ((p >> 31) & (2^k - 1))) >> k; MPEG-1's oddification (v - 1) | 1 of
+// the magnitude is (u - 1 - s) | 1 with s = level >> 31.  Exact while |level| * qscale * matrix < 2^31, which holds for
+// every int16 level with qscale <= 112 and 8-bit matrices (what the bitstreams can carry); include/avdsp_b200.h says so.
 template <int KIND>
 __device__ __forceinline__ int dq_coef(int level, int j, const DqTables &T, const DqLane &L, int &sum)
 {
     constexpr bool INTRA = KIND == 0 || KIND == 2 || KIND == 3 || KIND == 5;
     if (INTRA && j == 0) return (KIND == 5 && T.h263_aic) ? level : level * L.dc_scale;
     const int pos = KIND >= 5 ? j : (int)T.rank[j];
-    const int sg = level >> 31, a = (level ^ sg) - sg;
+    const int s = level >> 31;
     int v;
-    if (KIND == 0)                    { v = (a * (L.qscale * (int)T.intra[j])) >> 3; v = (v - 1) | 1; }
-    else if (KIND == 1)               { v = ((2 * a + 1) * (L.qscale * (int)T.inter[j])) >> 4; v = (v - 1) | 1; }
-    else if (KIND == 2 || KIND == 3)  { v = (a * (L.qscale * (int)T.intra[j])) >> 3; }
-    else if (KIND == 4)               { v = ((2 * a + 1) * (L.qscale * (int)T.inter[j])) >> 4; }
-    else                              { v = a * (2 * L.qscale) + L.qadd; }
-    v = (v ^ sg) - sg;
-    const bool coded = pos <= L.limit && level != 0;
+    if (KIND == 0 || KIND == 2 || KIND == 3) {
+        const int p = level * (L.qscale * (int)T.intra[j]);
+        v = (p + ((p >> 31) & 7)) >> 3;
+        if (KIND == 0) v = (v - 1 - s) | 1;
+    } else if (KIND == 1 || KIND == 4) {
+        const int p = (2 * level + 1 + 2 * s) * (L.qscale * (int)T.inter[j]);
+        v = (p + ((p >> 31) & 15)) >> 4;
+        if (KIND == 1) v = (v - 1 - s) | 1;
+    } else {
+        v = level * (2 * L.qscale) + ((L.qadd ^ s) - s);
+    }
+    // a zero level stays zero by itself under the MPEG-2 intra rule; everywhere else it must be kept out explicitly
+    const bool coded = (KIND == 2 || KIND == 3) ? pos <= L.limit : (pos <= L.limit && level != 0);
     if (KIND == 3 || KIND == 4) sum += coded ? v : 0;
     return coded ? v : level;
 }

@@ -384,6 +384,20 @@ def h264_deblock_info(mb_w, mb_h, seed=5, n_slices=3, bipred=False, cabac=1, t8x
     return d
 
 
+def zigzag_scan_tables():
+    """(permutated, raster_end) of the 8x8 zigzag scan for an IDCT without coefficient permutation -- what
+    ff_init_scantable (libavcodec/idctdsp.c:28-47) builds from ff_zigzag_direct: walk the anti-diagonals, even ones
+    upwards (towards the top right), odd ones downwards."""
+    order = []
+    for d in range(15):
+        cells = [(d - x, x) for x in range(8) if 0 <= d - x < 8]          # (row, col), col ascending = walking up-right
+        if d % 2 == 1:
+            cells.reverse()
+        order += [r * 8 + c for r, c in cells]
+    perm = np.array(order, np.uint8)
+    return perm, np.maximum.accumulate(perm).astype(np.uint8)
+
+
 MECMP_DT = np.dtype([("cur_off", "<u4"), ("ref_off", "<u4")])
 HPEL_DT = np.dtype([("dst_off", "<u4"), ("src_off", "<u4"), ("tab", "u1"), ("sidx", "u1"), ("dxy", "u1"), ("h", "u1")])
 assert MECMP_DT.itemsize == 8 and HPEL_DT.itemsize == 12

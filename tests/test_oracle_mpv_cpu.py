@@ -48,3 +48,11 @@ def test_scan_tables(orc, refo):
             p2, e2 = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
             refo.mpeg_scantables(alt, ptr(p2), ptr(e2))
             assert np.array_equal(p, p2) and np.array_equal(e, e2)
+
+
+def test_synthetic_zigzag_equals_the_scan_table(orc):
+    from libav_b200 import synth
+    p, e = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+    orc.mpeg_scantables(0, ptr(p), ptr(e))
+    sp, se = synth.zigzag_scan_tables()
+    assert np.array_equal(sp, p) and np.array_equal(se, e)

@@ -35,6 +35,8 @@ API = {
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),
+    "h264_pred": (None, [i32, i32, vp, vp, i32, i32, pd]),
+    "h264_pred_add": (None, [i32, i32, vp, vp, vp, i32, i32, pd]),
     "h264_weight": (None, [i32, vp, i32, i32, i32, i32, i32]),
     "h264_biweight": (None, [i32, vp, vp, i32, i32, i32, i32, i32, i32]),
     "h264_add_pixels_clear": (None, [i32, vp, vp, i32]),

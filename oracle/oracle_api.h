@@ -62,6 +62,19 @@ void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
 
+/* H.264 intra prediction, H264PredContext for codec H.264, 8 bit, 4:2:0 (libavcodec/h264pred.h:91-110,
+ * h264pred_template.c): the block at `src` is overwritten from its neighbours in the same plane.
+ *   tab 0 pred4x4[mode 0..11]  (topright -> 4 samples, only read by DIAG_DOWN_LEFT / VERT_LEFT)
+ *       1 pred8x8l[mode 0..11] (has_topleft / has_topright as the decoder passes them)
+ *       2 pred8x8[mode 0..10]  (chroma: DC, HOR, VERT, PLANE, LEFT_DC, TOP_DC, DC_128, 4 x "ALZHEIMER" DC)
+ *       3 pred16x16[mode 0..6] (DC, HOR, VERT, PLANE, LEFT_DC, TOP_DC, DC_128) */
+void ORC(h264_pred)(int tab, int mode, uint8_t *src, const uint8_t *topright, int has_topleft, int has_topright, ptrdiff_t stride);
+/* lossless (transform-bypass) vertical / horizontal prediction + residual: tab 0 pred4x4_add  1 pred8x8l_add
+ * 2 pred8x8l_filter_add  3 pred8x8_add (4 blocks at block_offset[0..3])  4 pred16x16_add (16 blocks);
+ * mode 0 vertical, 1 horizontal; the consumed coefficients are zeroed. */
+void ORC(h264_pred_add)(int tab, int mode, uint8_t *pix, const int *block_offset, int16_t *block, int has_topleft,
+                        int has_topright, ptrdiff_t stride);
+
 /* MPEG-1/2/4 and H.263 inverse quantisation of one 8x8 block in place: MpegEncContext.dct_unquantize_*
  * (libavcodec/mpegvideo.c:51-270), simple-IDCT permutation (none).
  *   kind 0 mpeg1_intra  1 mpeg1_inter  2 mpeg2_intra  3 mpeg2_intra_bitexact (with mismatch control)  4 mpeg2_inter

@@ -321,6 +321,8 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth);
 void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth);
 void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
+/* libavcodec/h264pred.h:112-123; takes over codec_id AV_CODEC_ID_H264, bit_depth 8, chroma_format_idc <= 1 */
+void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc);
 /* libavcodec/fft_template.c:152-159, mdct_template.c:58-66 (same shape as ff_fft_init_x86 / ff_mdct_init_x86): called after
  * ff_fft_init / ff_mdct_init filled the context.  fft_permute stays the reference's; the CUDA fft_calc accepts its revtab
  * order, the MDCT slots use the context's own tcos / tsin tables. */

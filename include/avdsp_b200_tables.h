@@ -141,6 +141,20 @@ typedef struct HpelDSPContext {
     op_pixels_func avg_no_rnd_pixels_tab[4];
 } HpelDSPContext;
 
+/* ---- libavcodec/h264pred.h:91-110 ---- */
+typedef struct H264PredContext {
+    void (*pred4x4[9 + 3 + 3])(uint8_t *src, const uint8_t *topright, ptrdiff_t stride);
+    void (*pred8x8l[9 + 3])(uint8_t *src, int topleft, int topright, ptrdiff_t stride);
+    void (*pred8x8[4 + 3 + 4])(uint8_t *src, ptrdiff_t stride);
+    void (*pred16x16[4 + 3 + 2])(uint8_t *src, ptrdiff_t stride);
+    void (*pred4x4_add[2])(uint8_t *pix, int16_t *block, ptrdiff_t stride);
+    void (*pred8x8l_add[2])(uint8_t *pix, int16_t *block, ptrdiff_t stride);
+    void (*pred8x8l_filter_add[2])(uint8_t *pix, int16_t *block, int topleft, int topright, ptrdiff_t stride);
+    void (*pred8x8_add[3])(uint8_t *pix, const int *block_offset, int16_t *block, ptrdiff_t stride);
+    void (*pred16x16_add[3])(uint8_t *pix, const int *block_offset, int16_t *block, ptrdiff_t stride);
+} H264PredContext;
+#define AVB_AV_CODEC_ID_H264 27
+
 /* ---- libavcodec/fft.h:36-99 (float build: FFTSample = FFTDouble = float), libavcodec/avfft.h FFTComplex ---- */
 typedef float FFTSample;
 typedef float FFTDouble;    /* float build, libavcodec/fft.h:39 */

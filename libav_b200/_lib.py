@@ -90,6 +90,7 @@ PROTOTYPES = {
     "ff_h264qpel_init_cuda": (None, [vp, i32]),
     "ff_h264chroma_init_cuda": (None, [vp, i32]),
     "ff_hpeldsp_init_cuda": (None, [vp, i32]),
+    "ff_h264_pred_init_cuda": (None, [vp, i32, i32, i32]),
     "ff_fft_init_cuda": (None, [vp]),
     "ff_mdct_init_cuda": (None, [vp]),
 }

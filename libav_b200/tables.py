@@ -116,3 +116,17 @@ class FFMpegDequantTables(C.Structure):
     """include/avdsp_b200.h FFMpegDequantTables"""
     _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
                 ("raster_end", C.c_uint8 * 64), ("alternate_scan", C.c_int), ("h263_aic", C.c_int)]
+
+
+_p4 = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)
+_p8l = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_ssize_t)
+_p8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t)
+_pa = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)
+_pfa = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_ssize_t)
+_pba = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t)
+
+
+class H264PredContext(C.Structure):         # libavcodec/h264pred.h:91-110
+    _fields_ = [("pred4x4", _p4 * 15), ("pred8x8l", _p8l * 12), ("pred8x8", _p8 * 11), ("pred16x16", _p8 * 9),
+                ("pred4x4_add", _pa * 2), ("pred8x8l_add", _pa * 2), ("pred8x8l_filter_add", _pfa * 2),
+                ("pred8x8_add", _pba * 3), ("pred16x16_add", _pba * 3)]

@@ -25,6 +25,7 @@
 #include "libavcodec/h264qpel.h"
 #include "libavcodec/h264chroma.h"
 #include "libavcodec/hpeldsp.h"
+#include "libavcodec/h264pred.h"
 #include "libavcodec/fft.h"
 #include "libavcodec/dct.h"
 #include "libswscale/swscale.h"
@@ -351,6 +352,8 @@ int ref_abi_info(int32_t *out, int cap)
         offsetof(H264DSPContext, h264_idct_add16), offsetof(H264DSPContext, h264_add_pixels8_clear), offsetof(H264DSPContext, startcode_find_candidate),
         sizeof(H264QpelContext), offsetof(H264QpelContext, avg_h264_qpel_pixels_tab),
         sizeof(H264ChromaContext), sizeof(HpelDSPContext), offsetof(HpelDSPContext, put_no_rnd_pixels_tab), offsetof(HpelDSPContext, avg_no_rnd_pixels_tab),
+        sizeof(H264PredContext), offsetof(H264PredContext, pred8x8l), offsetof(H264PredContext, pred16x16), offsetof(H264PredContext, pred8x8l_filter_add),
+        offsetof(H264PredContext, pred16x16_add),
     };
     int n = sizeof(v) / sizeof(v[0]);
     for (int i = 0; i < n && i < cap; i++) out[i] = v[i];

@@ -12,6 +12,8 @@ int main(void)
         offsetof(H264DSPContext, h264_idct_add16), offsetof(H264DSPContext, h264_add_pixels8_clear), offsetof(H264DSPContext, startcode_find_candidate),
         sizeof(H264QpelContext), offsetof(H264QpelContext, avg_h264_qpel_pixels_tab),
         sizeof(H264ChromaContext), sizeof(HpelDSPContext), offsetof(HpelDSPContext, put_no_rnd_pixels_tab), offsetof(HpelDSPContext, avg_no_rnd_pixels_tab),
+        sizeof(H264PredContext), offsetof(H264PredContext, pred8x8l), offsetof(H264PredContext, pred16x16), offsetof(H264PredContext, pred8x8l_filter_add),
+        offsetof(H264PredContext, pred16x16_add),
     };
     for (unsigned i = 0; i < sizeof(v) / sizeof(v[0]); i++) printf("%ld\n", v[i]);
     return 0;

@@ -143,6 +143,28 @@ int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_
                                    const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
                                    int uvlinesize, void *stream);
 
+/* Intra reconstruction: for every intra macroblock of a picture, H264PredContext prediction interleaved with the
+ * residual exactly as hl_decode_mb() orders them (libavcodec/h264_mb.c:607-731 hl_decode_mb_predict_luma,
+ * h264_mb_template.c:158-197 chroma): intra 4x4 -> per block pred4x4 then idct_add / idct_dc_add; intra 8x8 -> pred8x8l
+ * then idct8_add / idct8_dc_add; intra 16x16 -> pred16x16 then h264_idct_add16intra; chroma pred8x8 on cb and cr then
+ * h264_idct_add8.  One record per macroblock of the picture in raster order (kind 0 = not intra: its pixels, written by
+ * the motion-compensation / residual passes, are only read as neighbours).  Coefficients / nnzc as for
+ * ff_h264_idct_add_mb_batch_cuda (DC transforms already applied); consumed coefficients are zeroed like the C code.
+ * Rows run as a wavefront two macroblocks behind the row above; progress = mb_h * n_pictures uint32 of scratch.
+ * Pictures of a batch are stacked vertically (no prediction across a picture boundary; the records say what is
+ * available).  Not covered: transform bypass (the lossless *_add predictors exist as table slots only), MBAFF. */
+typedef struct FFH264IntraMB {
+    uint8_t  kind;             /* 0 not intra, 1 intra 4x4, 2 intra 4x4 with the 8x8 transform (pred8x8l), 3 intra 16x16 */
+    uint8_t  mode16;           /* sl->intra16x16_pred_mode (kind 3) */
+    uint8_t  chroma_mode;      /* sl->chroma_pred_mode */
+    uint8_t  chroma_residual;  /* != 0: h264_idct_add8 after the chroma prediction (cbp & 0x30) */
+    uint8_t  mode4[16];        /* sl->intra4x4_pred_mode_cache[scan8[i]]; kind 2 reads entries 0, 4, 8, 12 */
+    uint16_t topleft_samples_available, topright_samples_available;   /* h264_mvpred.h:468-508 */
+} FFH264IntraMB;
+int ff_h264_intra_mb_batch_cuda(const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, int16_t *coeffs,
+                                size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                                int linesize, int uvlinesize, uint32_t *progress, void *stream);
+
 /* Motion compensation: H264QpelContext put/avg tabs + H264ChromaContext put/avg tabs driven like mc_dir_part()
  * (libavcodec/h264_mb.c:204-320): one record = one luma partition and its two chroma partitions.  (x, y) is the
  * partition's luma position, (mvx, mvy) the quarter-pel vector; luma_xy = (mvx & 3) + 4 * (mvy & 3), chroma phase

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "ff_h264_deblock_picture_cuda": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
     "ff_h264_deblock_batch_cuda": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
     "ff_h264_deblock_params_cuda": (i32, [vp, vp, vp]),
+    "ff_h264_intra_mb_batch_cuda": (i32, [vp, i32, i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, vp, vp]),
     "ff_mpeg_dequant_batch_cuda": (i32, [i32, vp, vp, vp, sz, vp]),
     "ff_mpeg_dequant_idct_batch_cuda": (i32, [i32, vp, vp, vp, vp, vp, pd, sz, i32, i32, vp]),
     "ff_me_cmp_batch_cuda": (i32, [i32, i32, i32, vp, vp, pd, i32, vp, sz, vp, vp]),

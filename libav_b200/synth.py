@@ -384,6 +384,89 @@ def h264_deblock_info(mb_w, mb_h, seed=5, n_slices=3, bipred=False, cabac=1, t8x
     return d
 
 
+INTRA_DT = np.dtype([("kind", "u1"), ("mode16", "u1"), ("chroma_mode", "u1"), ("chroma_residual", "u1"), ("mode4", "u1", (16,)),
+                     ("topleft", "<u2"), ("topright", "<u2")])
+
+
+def h264_intra_work(mb_w, mb_h, seed=8, p_intra=1.0, p_coded=0.5):
+    """Intra macroblocks of one single-slice picture the way the decoder hands them to hl_decode_mb(): prediction modes
+    already substituted for what is available (check_intra4x4_pred_mode / check_intra_pred_mode, h264_parse.c), the
+    sample-availability masks of fill_decode_caches (h264_mvpred.h:468-508), coefficients in the sl->mb layout with
+    their non_zero_count_cache.  Returns (records, coeffs int16 [n][768], nnzc uint8 [n][120])."""
+    r = np.random.RandomState(seed)
+    n = mb_w * mb_h
+    rec = np.zeros(n, INTRA_DT)
+    coeffs = np.zeros((n, 768), np.int16)
+    nnzc = np.zeros((n, 120), np.uint8)
+
+    def fill_block(m, i, size):
+        """coefficients of 4x4 block i (size 16) or 8x8 block i (size 64, stored at i * 16): nnz in {0, 1 (DC), many}"""
+        u = r.rand()
+        if u > p_coded:
+            return 0
+        if u < p_coded / 3:
+            coeffs[m, 16 * i] = r.randint(-800, 801) or 64
+            return 1
+        coeffs[m, 16 * i:16 * i + size] = (r.randint(-64, 65, size) * (r.rand(size) < 0.4)).astype(np.int16) * 4
+        coeffs[m, 16 * i] = r.randint(-600, 601)
+        return 16
+
+    for y in range(mb_h):
+        for x in range(mb_w):
+            m = x + y * mb_w
+            if r.rand() >= p_intra:
+                continue
+            top, left = y > 0, x > 0
+            tl_mb, tr_mb = top and left, top and x + 1 < mb_w
+            topleft, topm, leftm, topright = 0xFFFF, 0xFFFF, 0xFFFF, 0xEEEA
+            if not top:
+                topleft, topm, topright = 0xB3FF, 0x33FF, 0x26EA
+            if not left:
+                topleft &= 0xDF5F; leftm &= 0x5F5F
+            if not tl_mb:
+                topleft &= 0x7FFF
+            if not tr_mb:
+                topright &= 0xFBFF
+            rec["topleft"][m], rec["topright"][m] = topleft, topright
+            kind = r.randint(1, 4)
+            rec["kind"][m] = kind
+
+            def big_mode(t, l):
+                ok = [0] + ([2] if t else []) + ([1] if l else []) + ([3] if t and l else [])
+                md = ok[r.randint(0, len(ok))]
+                if md == 0:
+                    md = 0 if (t and l) else 4 if l else 5 if t else 6
+                return md
+            rec["chroma_mode"][m] = big_mode(top, left)
+            rec["chroma_residual"][m] = r.rand() < 0.7
+            if kind == 3:
+                rec["mode16"][m] = big_mode(top, left)
+                for i in range(16):
+                    nnzc[m, scan8(i)] = fill_block(m, i, 16)
+                    if nnzc[m, scan8(i)] == 1:                 # add16intra treats "DC only" as nnz 0 + DC (the DC comes from the luma DC transform)
+                        nnzc[m, scan8(i)] = 0
+            else:
+                step = 1 if kind == 1 else 4
+                for i in range(0, 16, step):
+                    t = bool(topm & (0x8000 >> i)); l = bool(leftm & (0x8000 >> i))
+                    ok = [2] + ([0, 3, 7] if t else []) + ([1, 8] if l else []) + ([4, 5, 6] if t and l else [])
+                    md = ok[r.randint(0, len(ok))]
+                    if md == 2:
+                        md = 2 if (t and l) else 9 if l else 10 if t else 11
+                    rec["mode4"][m, i] = md
+                    nz = fill_block(m, i, 16 if kind == 1 else 64)
+                    if kind == 1:
+                        nnzc[m, scan8(i)] = nz
+                    else:
+                        for k in range(4):
+                            nnzc[m, scan8(i + k)] = nz
+            if rec["chroma_residual"][m]:
+                for i in list(range(16, 20)) + list(range(32, 36)):
+                    nz = fill_block(m, i, 16)
+                    nnzc[m, scan8(i)] = 0 if nz == 1 else nz
+    return rec, coeffs, nnzc
+
+
 def zigzag_scan_tables():
     """(permutated, raster_end) of the 8x8 zigzag scan for an IDCT without coefficient permutation -- what
     ff_init_scantable (libavcodec/idctdsp.c:28-47) builds from ff_zigzag_direct: walk the anti-diagonals, even ones

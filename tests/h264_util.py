@@ -107,3 +107,50 @@ def oracle_weight(o, rec, plane, src=None):
         else:
             o.h264_biweight(widx[int(r["w"])], at(plane, r["off"]), at(src, r["off"]), st, int(r["h"]), int(r["log2_denom"]),
                             int(r["weight"]), int(r["weight_src"]), int(r["offset"]))
+
+
+def oracle_intra(o, rec, coeffs, nnzc, mb_w, mb_h, y, cb, cr):
+    """hl_decode_mb() for intra macroblocks (h264_mb.c:607-731, h264_mb_template.c:158-197): prediction and residual block
+    by block through the oracle's H264PredContext / H264DSPContext entries."""
+    ls, uvls = y.strides[0], cb.strides[0]
+    for m in range(mb_w * mb_h):
+        r = rec[m]
+        kind = int(r["kind"])
+        if kind == 0:
+            continue
+        mbx, mby = m % mb_w, m // mb_w
+        mb = coeffs[m]
+        org = mby * 16 * ls + mbx * 16
+        corg = mby * 8 * uvls + mbx * 8
+        if kind in (1, 2):
+            for i in range(0, 16, 1 if kind == 1 else 4):
+                bx, by = (i & 1) + 2 * ((i >> 2) & 1), ((i >> 1) & 1) + 2 * (i >> 3)
+                off = org + 4 * by * ls + 4 * bx
+                mode = int(r["mode4"][i])
+                nnz = int(nnzc[m, synth.scan8(i)])
+                blk = mb[16 * i:]
+                if kind == 1:
+                    tr_ok = (int(r["topright"]) << i) & 0x8000
+                    if mode in (3, 7) and not tr_ok:
+                        tr = np.full(4, y[mby * 16 + 4 * by - 1, mbx * 16 + 4 * bx + 3], np.uint8)
+                        o.h264_pred(0, mode, at(y, off), ptr(tr), 0, 0, ls)
+                    else:
+                        o.h264_pred(0, mode, at(y, off), at(y, off + 4 - ls), 0, 0, ls)
+                    if nnz:
+                        o.h264_idct(2 if (nnz == 1 and blk[0]) else 0, at(y, off), ptr(blk), ls)
+                else:
+                    o.h264_pred(1, mode, at(y, off), None, (int(r["topleft"]) << i) & 0x8000, (int(r["topright"]) << i) & 0x4000, ls)
+                    if nnz:
+                        o.h264_idct(3 if (nnz == 1 and blk[0]) else 1, at(y, off), ptr(blk), ls)
+        else:
+            o.h264_pred(3, int(r["mode16"]), at(y, org), None, 0, 0, ls)
+            bo = np.array([4 * ((i & 1) + 2 * ((i >> 2) & 1)) + 4 * (((i >> 1) & 1) + 2 * (i >> 3)) * ls for i in range(16)] + [0] * 32, np.int32)
+            o.h264_idct_mb(1, at(y, org), None, ptr(bo), ptr(mb), ls, ptr(nnzc[m]))
+        for pl in (cb, cr):
+            o.h264_pred(2, int(r["chroma_mode"]), at(pl, corg), None, 0, 0, uvls)
+        if r["chroma_residual"]:
+            bo = np.zeros(48, np.int32)
+            for k in range(4):
+                bo[16 + k] = bo[32 + k] = 4 * (k & 1) + 4 * (k >> 1) * uvls
+            dst2 = (C.c_void_p * 2)(at(cb, corg), at(cr, corg))
+            o.h264_idct_mb(3, None, dst2, ptr(bo), ptr(mb), uvls, ptr(nnzc[m]))

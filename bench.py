@@ -336,6 +336,49 @@ def make_dequant_idct_workload(torch, L, stream, rank):
     }
 
 
+def make_h264_intra_workload(torch, L, stream, rank):
+    """all-intra 1080p pictures (equal shares of intra 4x4 / 8x8 / 16x16 macroblocks, every prediction
+    mode the availability allows, half of the blocks coded) reconstructed by the prediction + residual wavefront; a batch of
+    independent pictures stacked per launch, the consumed coefficient arena refilled on a side stream."""
+    from libav_b200 import synth
+    lib = L.lib
+    mb_w, mb_h, P = 120, 68, 16
+    W, H = 16 * mb_w, 16 * mb_h
+    rec, coeffs, nnzc = synth.h264_intra_work(mb_w, mb_h, seed=9 + rank)
+    t = lambda a, reps=P: torch.from_numpy(np.concatenate([np.ascontiguousarray(a)] * reps).view(np.uint8).reshape(-1)).cuda()
+    d_rec, d_nnz, d_coef0 = t(rec), t(nnzc), t(coeffs)
+    d_coef = [d_coef0.clone(), d_coef0.clone()]
+    d_y = torch.zeros(P * W * H, dtype=torch.uint8, device="cuda")
+    d_cb = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
+    d_cr = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
+    d_prog = torch.zeros(mb_h * P, dtype=torch.int32, device="cuda")
+    side, main = torch.cuda.Stream(), torch.cuda.current_stream()
+    refilled = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in refilled + consumed:
+        e.record(main)
+
+    def run(i):
+        b = i & 1
+        main.wait_event(refilled[b])
+        L.check(lib.ff_h264_intra_mb_batch_cuda(d_rec.data_ptr(), mb_w, mb_h, P, d_coef[b].data_ptr(), 768, d_nnz.data_ptr(), d_y.data_ptr(),
+                                                d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2, d_prog.data_ptr(), stream), "intra")
+        consumed[b].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(consumed[b])
+            d_coef[b].copy_(d_coef0, non_blocking=True)
+            refilled[b].record(side)
+
+    n_mb = mb_w * mb_h * P
+    return {
+        "name": "H.264 intra reconstruction wavefront: %d all-intra 1080p pictures per step (4x4 / 8x8 / 16x16 mix)" % P,
+        "run": run, "run_e2e": None, "pixels": W * H * P, "alg_bytes": n_mb * (768 * 2 + 384 + 120 + 24),
+        "launches_per_step": 1, "kernel": "h264_intra_kernel", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
+        "l2": "%d MB of coefficients + pixels per step" % (n_mb * (768 * 2 + 384) >> 20),
+        "keep": (d_rec, d_nnz, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
+    }
+
+
 def make_me_workload(torch, L, stream, rank):
     """config 4: pix_abs16 full search +-16 over a 1920x1088 luma pair (restricted MVs, lambda 0)."""
     from libav_b200 import synth
@@ -491,7 +534,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
@@ -541,7 +584,7 @@ def main():
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
     makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
-              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload}
+              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):

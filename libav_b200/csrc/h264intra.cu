@@ -20,15 +20,53 @@ constexpr int LP = 32;        // luma tile: 17 rows x 32; sample (x, y) of the m
 constexpr int CP = 16;        // chroma tile: 9 rows x 16; sample (x, y) at [1 + y][4 + x]
 
 __device__ __forceinline__ uint8_t ld_cg8(const uint8_t *p) { return __ldcg(p); }
+__device__ __forceinline__ int s16i(int v) { return (int)(int16_t)v; }
 
-// raw edges of the n x n block whose top-left sample is tile[r0][c0] (pitch P); `tr_ok`: the top-right samples exist
+// raw edges of the n x n block whose top-left sample is tile[r0][c0] (pitch P), gathered by the whole warp;
+// `tr_ok`: the n samples to the top right exist (otherwise the last top sample is repeated, h264_mb.c:676-686)
 template <int P>
-__device__ __forceinline__ void gather_raw(IntraRaw &r, const uint8_t *tile, int r0, int c0, int n, bool tr_ok)
+__device__ __forceinline__ void gather_raw(IntraRaw &r, const uint8_t *tile, int r0, int c0, int n, bool tr_ok, int lane)
 {
     const uint8_t *top = tile + (r0 - 1) * P + c0;
-    r.corner = top[-1];
-    for (int i = 0; i < n; i++) { r.top[i] = top[i]; r.left[i] = tile[(r0 + i) * P + c0 - 1]; }
-    if (n <= 8) for (int i = n; i < 2 * n; i++) r.top[i] = tr_ok ? top[i] : top[n - 1];
+    if (lane < 16) { if (lane < n || n <= 8) r.top[lane] = top[(lane < n || tr_ok) ? lane : n - 1]; }
+    else if (lane - 16 < n) r.left[lane - 16] = tile[(r0 + lane - 16) * P + c0 - 1];
+    if (lane == 0) r.corner = top[-1];
+}
+
+// filtered 8x8 edges, one entry per lane (PREDICT_8x8_LOAD_*, h264pred_template.c:840-875)
+__device__ __forceinline__ void edges8_parallel(IntraEdges &e, const IntraRaw &r, bool has_tl, bool has_tr, int lane)
+{
+    const uint8_t *t = r.top, *l = r.left;
+    const int c = r.corner;
+    if (lane < 16) {
+        int v;
+        if (lane == 0) v = ip_f3(has_tl ? c : t[0], t[0], t[1]);
+        else if (lane < 7) v = ip_f3(t[lane - 1], t[lane], t[lane + 1]);
+        else if (lane == 7) v = ip_f3(has_tr ? t[8] : t[7], t[7], t[6]);
+        else if (!has_tr) v = t[7];
+        else if (lane < 15) v = ip_f3(t[lane - 1], t[lane], t[lane + 1]);
+        else v = (t[14] + 3 * t[15] + 2) >> 2;
+        e.t[lane + 1] = v;
+    } else if (lane < 24) {
+        const int k = lane - 16;
+        e.l[k + 1] = k == 0 ? ip_f3(has_tl ? c : l[0], l[0], l[1]) : k < 7 ? ip_f3(l[k - 1], l[k], l[k + 1]) : (l[6] + 3 * l[7] + 2) >> 2;
+    } else if (lane == 24) {
+        e.t[0] = e.l[0] = ip_f3(l[0], c, t[0]);
+    }
+}
+
+// 4x4 residual on 16 lanes: lane (x = lane & 3, y = lane >> 2) owns pixel (x, y); returns the value to add (already >> 6)
+__device__ __forceinline__ int idct4_lane(int16_t *co, int *tmp, int lane)
+{
+    const int i = lane & 3, k = lane >> 2;
+    const int c0 = i == 0 ? s16i(co[0] + 32) : co[i], c1 = co[i + 4], c2 = co[i + 8], c3 = co[i + 12];
+    const int z0 = c0 + c2, z1 = c0 - c2, z2 = (c1 >> 1) - c3, z3 = c1 + (c3 >> 1);
+    tmp[i + 4 * k] = s16i(k == 0 ? z0 + z3 : k == 1 ? z1 + z2 : k == 2 ? z1 - z2 : z0 - z3);
+    __syncwarp(0xffff);
+    const int d0 = tmp[4 * i], d1 = tmp[4 * i + 1], d2 = tmp[4 * i + 2], d3 = tmp[4 * i + 3];
+    const int y0 = d0 + d2, y1 = d0 - d2, y2 = (d1 >> 1) - d3, y3 = d1 + (d3 >> 1);
+    co[lane] = 0;
+    return (k == 0 ? y0 + y3 : k == 1 ? y1 + y2 : k == 2 ? y1 - y2 : y0 - y3) >> 6;
 }
 
 __global__ void __launch_bounds__(32)
@@ -37,22 +75,41 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
 {
     __shared__ __align__(16) uint8_t Y[17 * LP];
     __shared__ __align__(16) uint8_t C[2][9 * CP];
-    __shared__ FFH264IntraMB M;
-    __shared__ uint8_t nnzc[120];
+    __shared__ __align__(16) int16_t co[2][768];          // this macroblock's coefficients / the next one's (prefetch)
+    __shared__ __align__(16) FFH264IntraMB Ms[2];
+    __shared__ __align__(16) uint8_t nz[2][128];
     __shared__ IntraRaw raw;
     __shared__ IntraEdges edges;
     __shared__ IntraBig big;
+    __shared__ int tmp[64];
     const int lane = threadIdx.x, row = blockIdx.x, prow = row % rows_pp;      // prow: row inside its picture
     volatile uint32_t *prog = progress;
     uint8_t *const cplane[2] = { cb, cr };
+    const bool co16 = !(coeff_stride & 7) && !((uintptr_t)coeffs & 15);
+
+    // side information and coefficients do not depend on other rows: fetch macroblock x + 1 while x is reconstructed
+    auto fetch = [&](int x, int b) {
+        const size_t m = (size_t)row * mb_w + x;
+        if (lane < 6) cp_async4(reinterpret_cast<uint32_t *>(&Ms[b]) + lane, reinterpret_cast<const uint32_t *>(&mbs[m]) + lane);
+        if (lane < 30) cp_async4(reinterpret_cast<uint32_t *>(nz[b]) + lane, reinterpret_cast<const uint32_t *>(nnzc_all + m * 120) + lane);
+        const int16_t *src = coeffs + m * coeff_stride;
+        if (co16) { for (int i = lane; i < 96; i += 32) cp_async16(reinterpret_cast<uint4 *>(co[b]) + i, reinterpret_cast<const uint4 *>(src) + i, true); }
+        else      { for (int i = lane; i < 384; i += 32) cp_async4(reinterpret_cast<uint32_t *>(co[b]) + i, reinterpret_cast<const uint32_t *>(src) + i); }
+        cp_async_commit();
+    };
+    fetch(0, 0);
 
     for (int x = 0; x < mb_w; x++) {
+        const int cur = x & 1;
+        if (x + 1 < mb_w) { fetch(x + 1, cur ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         if (prow > 0) {
             if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
-            __syncwarp();
         }
+        __syncwarp();
+        const FFH264IntraMB &M = Ms[cur];
+        const uint8_t *nnzc = nz[cur];
+        int16_t *mb = co[cur];
         const size_t m = (size_t)row * mb_w + x;
-        if (lane < (int)(sizeof(FFH264IntraMB) / 4)) reinterpret_cast<uint32_t *>(&M)[lane] = reinterpret_cast<const uint32_t *>(&mbs[m])[lane];
         // the previous macroblock's last column becomes this one's left column (tile column 3), corner included
         if (x > 0) {
             if (lane < 17) Y[lane * LP + 3] = Y[lane * LP + 19];
@@ -62,63 +119,99 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
         // row above: samples x = 0 .. 23 (the last 8 belong to the macroblock up-right)
         if (prow > 0) {
             const uint8_t *g = luma + (size_t)(row * 16 - 1) * ls + x * 16;
-            if (lane < 24 && (lane < 16 || x + 1 < mb_w)) Y[4 + lane] = ld_cg8(g + lane);
-            if (lane < 16) { const int p = lane >> 3, i = lane & 7; C[p][4 + i] = ld_cg8(cplane[p] + (size_t)(row * 8 - 1) * uvls + x * 8 + i); }
-            if (x == 0 && lane == 0) { Y[3] = 0; C[0][3] = C[1][3] = 0; }
+            if (lane < 6 && (lane < 4 || x + 1 < mb_w)) *reinterpret_cast<uint32_t *>(&Y[4 + 4 * lane]) = __ldcg(reinterpret_cast<const uint32_t *>(g) + lane);
+            if (lane >= 8 && lane < 12) {
+                const int p = (lane >> 1) & 1, q = lane & 1;
+                *reinterpret_cast<uint32_t *>(&C[p][4 + 4 * q]) = __ldcg(reinterpret_cast<const uint32_t *>(cplane[p] + (size_t)(row * 8 - 1) * uvls + x * 8) + q);
+            }
+            if (x == 0 && lane == 31) { Y[3] = 0; C[0][3] = C[1][3] = 0; }
         }
         const int kind = M.kind;
         if (kind == 0) {
-            // not ours: only keep what its right / lower neighbours will read (last column, via the tile; the row below
-            // re-reads from memory)
-            for (int i = lane; i < 256; i += 32) Y[(1 + (i >> 4)) * LP + 4 + (i & 15)] = ld_cg8(luma + (size_t)(row * 16 + (i >> 4)) * ls + x * 16 + (i & 15));
-            for (int i = lane; i < 128; i += 32) {
-                const int p = i >> 6, k = i & 63;
-                C[p][(1 + (k >> 3)) * CP + 4 + (k & 7)] = ld_cg8(cplane[p] + (size_t)(row * 8 + (k >> 3)) * uvls + x * 8 + (k & 7));
+            // not ours: only its last column is needed (by the macroblock to the right); the row below re-reads from memory
+            for (int i = lane; i < 64; i += 32)
+                *reinterpret_cast<uint32_t *>(&Y[(1 + (i >> 2)) * LP + 4 + 4 * (i & 3)]) = __ldcg(reinterpret_cast<const uint32_t *>(luma + (size_t)(row * 16 + (i >> 2)) * ls + x * 16) + (i & 3));
+            {
+                const int p = lane >> 4, r = (lane >> 1) & 7, q = lane & 1;
+                *reinterpret_cast<uint32_t *>(&C[p][(1 + r) * CP + 4 + 4 * q]) = __ldcg(reinterpret_cast<const uint32_t *>(cplane[p] + (size_t)(row * 8 + r) * uvls + x * 8) + q);
             }
             __syncwarp();
         } else {
-            for (int i = lane; i < 120; i += 32) nnzc[i] = nnzc_all[m * 120 + i];
             __syncwarp();
-            int16_t *mb = coeffs + m * coeff_stride;
             if (kind == 1) {                                   // intra 4x4: 16 blocks in coding order
                 for (int i = 0; i < 16; i++) {
                     const int bx = (i & 1) + 2 * ((i >> 2) & 1), by = ((i >> 1) & 1) + 2 * (i >> 3);
-                    const int mode = M.mode4[i];
-                    if (lane == 0) {
-                        gather_raw<LP>(raw, Y, 1 + 4 * by, 4 + 4 * bx, 4, (M.topright_samples_available << i) & 0x8000);
-                        intra_edges4(edges, raw);
+                    const int mode = M.mode4[i], r0 = 1 + 4 * by, c0 = 4 + 4 * bx;
+                    const bool tr_ok = (M.topright_samples_available << i) & 0x8000;
+                    // edge arrays straight from the tile: lanes 0..8 -> T(-1..7), lanes 16..20 -> L(-1..3)
+                    if (lane < 9) edges.t[lane] = Y[(r0 - 1) * LP + c0 - 1 + ((lane < 5 || tr_ok) ? lane : 4)];
+                    else if (lane >= 16 && lane < 21) edges.l[lane - 16] = Y[(r0 - 1 + lane - 16) * LP + c0 - 1];
+                    __syncwarp();
+                    const int nnz = nnzc[scan8_of(i)];
+                    int16_t *blk = mb + 16 * i;
+                    const bool dc_only = nnz == 1 && blk[0];
+                    if (lane < 16) {
+                        int v = intra_directional(edges, 4, mode, lane & 3, lane >> 2);
+                        if (nnz) {
+                            if (dc_only) v = clip_u8(v + ((blk[0] + 32) >> 6));
+                            else v = clip_u8(v + idct4_lane(blk, tmp, lane));
+                        }
+                        Y[(r0 + (lane >> 2)) * LP + c0 + (lane & 3)] = (uint8_t)v;
                     }
                     __syncwarp();
-                    if (lane < 16) Y[(1 + 4 * by + (lane >> 2)) * LP + 4 + 4 * bx + (lane & 3)] = (uint8_t)intra_directional(edges, 4, mode, lane & 3, lane >> 2);
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int nnz = nnzc[scan8_of(i)];
-                        uint8_t *d = &Y[(1 + 4 * by) * LP + 4 + 4 * bx];
-                        if (nnz) { if (nnz == 1 && mb[16 * i]) h264_dc_add(d, mb + 16 * i, LP, 4); else h264_idct4_add(d, mb + 16 * i, LP); }
-                    }
-                    __syncwarp();
+                    if (dc_only && lane == 0) blk[0] = 0;
                 }
             } else if (kind == 2) {                            // intra 8x8
                 for (int k = 0; k < 4; k++) {
                     const int i = 4 * k, bx = k & 1, by = k >> 1, mode = M.mode4[i];
-                    if (lane == 0) {
-                        const bool tl = (M.topleft_samples_available << i) & 0x8000, tr = (M.topright_samples_available << i) & 0x4000;
-                        gather_raw<LP>(raw, Y, 1 + 8 * by, 4 + 8 * bx, 8, tr);
-                        intra_edges8(edges, raw, tl, tr);
-                    }
+                    const bool tl = (M.topleft_samples_available << i) & 0x8000, tr = (M.topright_samples_available << i) & 0x4000;
+                    gather_raw<LP>(raw, Y, 1 + 8 * by, 4 + 8 * bx, 8, tr, lane);
+                    __syncwarp();
+                    edges8_parallel(edges, raw, tl, tr, lane);
                     __syncwarp();
                     for (int s = lane; s < 64; s += 32)
                         Y[(1 + 8 * by + (s >> 3)) * LP + 4 + 8 * bx + (s & 7)] = (uint8_t)intra_directional(edges, 8, mode, s & 7, s >> 3);
                     __syncwarp();
-                    if (lane == 0) {
-                        const int nnz = nnzc[scan8_of(i)];
-                        uint8_t *d = &Y[(1 + 8 * by) * LP + 4 + 8 * bx];
-                        if (nnz) { if (nnz == 1 && mb[16 * i]) h264_dc_add(d, mb + 16 * i, LP, 8); else h264_idct8_add(d, mb + 16 * i, LP); }
+                    const int nnz = nnzc[scan8_of(i)];
+                    int16_t *blk = mb + 16 * i;
+                    uint8_t *d = &Y[(1 + 8 * by) * LP + 4 + 8 * bx];
+                    if (nnz) {
+                        if (nnz == 1 && blk[0]) {
+                            const int dc = (blk[0] + 32) >> 6;
+                            for (int s = lane; s < 64; s += 32) { uint8_t *q = d + (s >> 3) * LP + (s & 7); *q = (uint8_t)clip_u8(*q + dc); }
+                            __syncwarp();
+                            if (lane == 0) blk[0] = 0;
+                        } else {
+                            // column pass on 8 lanes, row pass on 8 lanes (h264idct_template.c:69-141), int16 round trip kept
+                            if (lane == 0) blk[0] = (int16_t)(blk[0] + 32);
+                            __syncwarp();
+                            if (lane < 8) {
+                                int v[8], o[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) v[q] = blk[lane + 8 * q];
+                                h264_idct8_1d(v, o);
+#pragma unroll
+                                for (int q = 0; q < 8; q++) blk[lane + 8 * q] = (int16_t)o[q];
+                            }
+                            __syncwarp();
+                            if (lane < 8) {
+                                int v[8], o[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) v[q] = blk[8 * lane + q];
+                                h264_idct8_1d(v, o);
+#pragma unroll
+                                for (int q = 0; q < 8; q++) d[lane + q * LP] = (uint8_t)clip_u8(d[lane + q * LP] + (o[q] >> 6));
+                            }
+                            __syncwarp();
+                            blk[lane] = 0; blk[lane + 32] = 0;
+                        }
                     }
                     __syncwarp();
                 }
             } else {                                           // intra 16x16, then h264_idct_add16intra
-                if (lane == 0) { gather_raw<LP>(raw, Y, 1, 4, 16, false); intra_big_prepare(big, raw, 16); }
+                gather_raw<LP>(raw, Y, 1, 4, 16, false, lane);
+                __syncwarp();
+                if (lane == 0) intra_big_prepare(big, raw, 16);
                 __syncwarp();
                 for (int s = lane; s < 256; s += 32) Y[(1 + (s >> 4)) * LP + 4 + (s & 15)] = (uint8_t)intra_big_sample(big, raw, 16, M.mode16, s & 15, s >> 4);
                 __syncwarp();
@@ -131,7 +224,9 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
             }
             // chroma: pred8x8 on both planes, then h264_idct_add8
             for (int p = 0; p < 2; p++) {
-                if (lane == 0) { gather_raw<CP>(raw, C[p], 1, 4, 8, false); raw.top[8] = 0; intra_big_prepare(big, raw, 8); }
+                gather_raw<CP>(raw, C[p], 1, 4, 8, false, lane);
+                __syncwarp();
+                if (lane == 0) intra_big_prepare(big, raw, 8);
                 __syncwarp();
                 for (int s = lane; s < 64; s += 32) C[p][(1 + (s >> 3)) * CP + 4 + (s & 7)] = (uint8_t)intra_big_sample(big, raw, 8, M.chroma_mode, s & 7, s >> 3);
                 __syncwarp();
@@ -142,7 +237,7 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
                 if (nnzc[scan8_of(i)]) h264_idct4_add(d, mb + 16 * i, CP); else if (mb[16 * i]) h264_dc_add(d, mb + 16 * i, CP, 4);
             }
             __syncwarp();
-            // write the macroblock back
+            // write the macroblock and its (now partly zeroed) coefficients back
             for (int i = lane; i < 64; i += 32) {
                 const int r = i >> 2, q = i & 3;
                 *reinterpret_cast<uint32_t *>(luma + (size_t)(row * 16 + r) * ls + x * 16 + 4 * q) = *reinterpret_cast<const uint32_t *>(&Y[(1 + r) * LP + 4 + 4 * q]);
@@ -151,6 +246,9 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
                 const int p = lane >> 4, r = (lane >> 1) & 7, q = lane & 1;
                 *reinterpret_cast<uint32_t *>(cplane[p] + (size_t)(row * 8 + r) * uvls + x * 8 + 4 * q) = *reinterpret_cast<const uint32_t *>(&C[p][(1 + r) * CP + 4 + 4 * q]);
             }
+            int16_t *gco = coeffs + m * coeff_stride;
+            if (co16) { for (int i = lane; i < 96; i += 32) reinterpret_cast<uint4 *>(gco)[i] = reinterpret_cast<const uint4 *>(mb)[i]; }
+            else      { for (int i = lane; i < 384; i += 32) reinterpret_cast<uint32_t *>(gco)[i] = reinterpret_cast<const uint32_t *>(mb)[i]; }
         }
         // publish: everything this macroblock wrote must be visible before the row below may read it
         __syncwarp();

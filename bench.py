@@ -342,7 +342,7 @@ def make_h264_intra_workload(torch, L, stream, rank):
     independent pictures stacked per launch, the consumed coefficient arena refilled on a side stream."""
     from libav_b200 import synth
     lib = L.lib
-    mb_w, mb_h, P = 120, 68, 16
+    mb_w, mb_h, P = 120, 68, int(os.environ.get("AVB200_INTRA_PICTURES", "48"))
     W, H = 16 * mb_w, 16 * mb_h
     rec, coeffs, nnzc = synth.h264_intra_work(mb_w, mb_h, seed=9 + rank)
     t = lambda a, reps=P: torch.from_numpy(np.concatenate([np.ascontiguousarray(a)] * reps).view(np.uint8).reshape(-1)).cuda()

@@ -286,6 +286,13 @@ int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const u
 /* FDCTDSPContext (libavcodec/fdctdsp.h:26-29), in place over n blocks: which 0 = ff_jpeg_fdct_islow_8, 1 =
  * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332). */
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream);
+/* PixblockDSPContext.get_pixels / diff_pixels (libavcodec/pixblockdsp_template.c:24-66) over n 8x8 blocks, optionally
+ * followed by the forward DCT in the same kernel -- the encoder's "fetch (difference) -> fdct" front end
+ * (mpegvideo_enc.c:1923-2019 dct loop).  Block i reads s1 + off1[i] and, if s2 != NULL, subtracts s2 + off2[i] (off2
+ * NULL = the same offsets); which_fdct < 0 stores the samples / differences, 0..3 select the transform as in
+ * ff_fdct_batch_cuda.  Output: int16 blocks[n][64], row-major. */
+int ff_pixblock_fdct_batch_cuda(int which_fdct, const uint8_t *s1, const uint8_t *s2, const uint32_t *off1, const uint32_t *off2,
+                                ptrdiff_t stride, int16_t *blocks, size_t n, void *stream);
 
 /* ---- float FFT / MDCT filterbank (FFTContext, libavcodec/fft.h:73-99); parity contract: 1e-6 relative ------------
  * ff_fft_batch_cuda: n_transforms independent complex FFTs of 2^nbits points (nbits 1..12), in place, natural order in
@@ -345,6 +352,8 @@ void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth);
 void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
 /* libavcodec/h264pred.h:112-123; takes over codec_id AV_CODEC_ID_H264, bit_depth 8, chroma_format_idc <= 1 */
 void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc);
+/* libavcodec/pixblockdsp.h:37-43; high_bit_depth != 0 leaves the table untouched */
+void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth);
 /* libavcodec/fft_template.c:152-159, mdct_template.c:58-66 (same shape as ff_fft_init_x86 / ff_mdct_init_x86): called after
  * ff_fft_init / ff_mdct_init filled the context.  fft_permute stays the reference's; the CUDA fft_calc accepts its revtab
  * order, the MDCT slots use the context's own tcos / tsin tables. */

@@ -141,6 +141,12 @@ typedef struct HpelDSPContext {
     op_pixels_func avg_no_rnd_pixels_tab[4];
 } HpelDSPContext;
 
+/* ---- libavcodec/pixblockdsp.h:27-35 ---- */
+typedef struct PixblockDSPContext {
+    void (*get_pixels)(int16_t *AVB_RESTRICT block, const uint8_t *pixels, ptrdiff_t stride);
+    void (*diff_pixels)(int16_t *AVB_RESTRICT block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride);
+} PixblockDSPContext;
+
 /* ---- libavcodec/h264pred.h:91-110 ---- */
 typedef struct H264PredContext {
     void (*pred4x4[9 + 3 + 3])(uint8_t *src, const uint8_t *topright, ptrdiff_t stride);

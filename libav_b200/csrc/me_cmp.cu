@@ -357,6 +357,64 @@ __global__ void __launch_bounds__(128) fdct_kernel(int16_t *__restrict__ blocks,
         reinterpret_cast<uint4 *>(b)[r] = make_uint4(pack16(m[r][0], m[r][1]), pack16(m[r][2], m[r][3]), pack16(m[r][4], m[r][5]), pack16(m[r][6], m[r][7]));
 }
 
+// PixblockDSPContext.get_pixels / diff_pixels (pixblockdsp_template.c:24-66), optionally followed by the forward DCT of
+// fdct_kernel in the same thread: the 8x8 samples never exist as an int16 block in memory.  FDCT < 0: store them.
+template <int FDCT>
+__global__ void __launch_bounds__(128)
+pixblock_kernel(const uint8_t *__restrict__ s1, const uint8_t *__restrict__ s2, const uint32_t *__restrict__ off1,
+                const uint32_t *__restrict__ off2, ptrdiff_t stride, int16_t *__restrict__ blocks, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *a = s1 + off1[i], *b = s2 ? s2 + (off2 ? off2[i] : off1[i]) : nullptr;
+    const bool vec = !(((uintptr_t)a | (uintptr_t)b | (uintptr_t)stride) & 7);
+    int m[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int in[8];
+        if (vec) {
+            const uint2 pa = *reinterpret_cast<const uint2 *>(a + r * stride);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { in[k] = byte_of(pa.x, k); in[4 + k] = byte_of(pa.y, k); }
+            if (b) {
+                const uint2 pb = *reinterpret_cast<const uint2 *>(b + r * stride);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { in[k] -= byte_of(pb.x, k); in[4 + k] -= byte_of(pb.y, k); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) in[k] = a[r * stride + k] - (b ? b[r * stride + k] : 0);
+        }
+        if (FDCT < 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) m[r][k] = in[k];
+        } else {
+            int o[8];
+            if (FDCT < 2) islow_1d<4, 9>(in, o); else ifast_1d(in, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) m[r][k] = (int)(int16_t)o[k];
+        }
+    }
+    if (FDCT >= 0) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            int in[8], o[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) in[k] = m[k][c];
+            if (FDCT == 0) islow_1d<-4, 17>(in, o);
+            else if (FDCT == 1) col_248<false>(in, o);
+            else if (FDCT == 2) ifast_1d(in, o);
+            else col_248<true>(in, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) m[k][c] = o[k];
+        }
+    }
+    int16_t *d = blocks + 64 * i;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        reinterpret_cast<uint4 *>(d)[r] = make_uint4(pack16(m[r][0], m[r][1]), pack16(m[r][2], m[r][3]), pack16(m[r][4], m[r][5]), pack16(m[r][6], m[r][7]));
+}
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 }  // namespace avb
@@ -407,6 +465,25 @@ int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
     default: set_error_msg("fdct_batch", "bad transform selector"); return -1;
     }
     return check_launch("fdct_batch");
+}
+
+int ff_pixblock_fdct_batch_cuda(int which_fdct, const uint8_t *s1, const uint8_t *s2, const uint32_t *off1, const uint32_t *off2,
+                                ptrdiff_t stride, int16_t *blocks, size_t n, void *stream)
+{
+    if (!n) return 0;
+    if (!s1 || !off1 || !blocks || ((uintptr_t)blocks & 15)) { set_error_msg("pixblock_fdct_batch", "need s1, off1 and 16-byte aligned blocks"); return -1; }
+    const int grid = (int)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (which_fdct) {
+    case 0: pixblock_kernel<0><<<grid, 128, 0, st>>>(s1, s2, off1, off2, stride, blocks, n); break;
+    case 1: pixblock_kernel<1><<<grid, 128, 0, st>>>(s1, s2, off1, off2, stride, blocks, n); break;
+    case 2: pixblock_kernel<2><<<grid, 128, 0, st>>>(s1, s2, off1, off2, stride, blocks, n); break;
+    case 3: pixblock_kernel<3><<<grid, 128, 0, st>>>(s1, s2, off1, off2, stride, blocks, n); break;
+    default:
+        if (which_fdct >= 0) { set_error_msg("pixblock_fdct_batch", "bad transform selector"); return -1; }
+        pixblock_kernel<-1><<<grid, 128, 0, st>>>(s1, s2, off1, off2, stride, blocks, n); break;
+    }
+    return check_launch("pixblock_fdct_batch");
 }
 
 }  // extern "C"

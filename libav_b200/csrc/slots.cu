@@ -133,6 +133,7 @@ extern "C" {
 int ff_me_cmp_batch_cuda(int, int, int, const uint8_t *, const uint8_t *, ptrdiff_t, int, const FFMECmpRecord *, size_t, int32_t *, void *);
 int ff_hpel_batch_cuda(const FFHpelRecord *, size_t, uint8_t *, const uint8_t *, ptrdiff_t, void *);
 int ff_fdct_batch_cuda(int, int16_t *, size_t, void *);
+int ff_pixblock_fdct_batch_cuda(int, const uint8_t *, const uint8_t *, const uint32_t *, const uint32_t *, ptrdiff_t, int16_t *, size_t, void *);
 int ff_h264_weight_batch_cuda(const FFH264WeightRecord *, size_t, uint8_t *, const uint8_t *, int, void *);
 }
 
@@ -146,6 +147,19 @@ template <int WHICH> void slot_fdct(int16_t *block)
     if (S.up() || ff_fdct_batch_cuda(WHICH, (int16_t *)(S.d + o), 1, S.s) || S.down()) return;
     memcpy(block, S.h + o, 128);
 }
+
+// ---- Pixblock: get_pixels / diff_pixels as a batch of one (two staged 8x8 rectangles, pitch SP) ----
+void slot_pixblock(int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride)
+{
+    Stage S; if (!S.ok()) return;
+    const size_t o1 = S.rect_in(s1, stride, 8, 8), o2 = s2 ? S.rect_in(s2, stride, 8, 8) : 0, ob = S.take(128), oo = S.take(16);
+    uint32_t *offs = (uint32_t *)(S.h + oo); offs[0] = (uint32_t)o1; offs[1] = (uint32_t)o2;
+    if (S.up() || ff_pixblock_fdct_batch_cuda(-1, S.d, s2 ? S.d : nullptr, (const uint32_t *)(S.d + oo), (const uint32_t *)(S.d + oo) + 1, SP,
+                                              (int16_t *)(S.d + ob), 1, S.s) || S.down()) return;
+    memcpy(block, S.h + ob, 128);
+}
+void slot_get_pixels(int16_t *block, const uint8_t *pixels, ptrdiff_t stride) { slot_pixblock(block, pixels, nullptr, stride); }
+void slot_diff_pixels(int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride) { slot_pixblock(block, s1, s2, stride); }
 
 // ---- MECmp ----
 template <int KIND, int SIDX, int DXY> int slot_mecmp(struct MpegEncContext *, uint8_t *a, uint8_t *b, ptrdiff_t stride, int h)
@@ -334,6 +348,12 @@ template <int TAB, int SIDX> void fill_hpel(op_pixels_func *t)
 }  // namespace
 
 extern "C" {
+
+void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth)
+{
+    if (!c || high_bit_depth) return;
+    c->get_pixels = slot_get_pixels; c->diff_pixels = slot_diff_pixels;
+}
 
 void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth)
 {

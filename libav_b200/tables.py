@@ -130,3 +130,8 @@ class H264PredContext(C.Structure):         # libavcodec/h264pred.h:91-110
     _fields_ = [("pred4x4", _p4 * 15), ("pred8x8l", _p8l * 12), ("pred8x8", _p8 * 11), ("pred16x16", _p8 * 9),
                 ("pred4x4_add", _pa * 2), ("pred8x8l_add", _pa * 2), ("pred8x8l_filter_add", _pfa * 2),
                 ("pred8x8_add", _pba * 3), ("pred16x16_add", _pba * 3)]
+
+
+class PixblockDSPContext(C.Structure):      # libavcodec/pixblockdsp.h:27-35
+    _fields_ = [("get_pixels", C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)),
+                ("diff_pixels", C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t))]

@@ -62,6 +62,10 @@ void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
 
+/* PixblockDSPContext (libavcodec/pixblockdsp.h:27-35, pixblockdsp_template.c): kind 0 get_pixels (s2 unused),
+ * kind 1 diff_pixels = s1 - s2; 8x8 samples -> int16 block, row-major */
+void ORC(pixblock)(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride);
+
 /* H.264 intra prediction, H264PredContext for codec H.264, 8 bit, 4:2:0 (libavcodec/h264pred.h:91-110,
  * h264pred_template.c): the block at `src` is overwritten from its neighbours in the same plane.
  *   tab 0 pred4x4[mode 0..11]  (topright -> 4 samples, only read by DIAG_DOWN_LEFT / VERT_LEFT)

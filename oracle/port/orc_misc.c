@@ -245,3 +245,12 @@ int orc_hpel(int tab, int sidx, int dxy, uint8_t *block, const uint8_t *pixels, 
         }
     return 0;
 }
+
+
+/* PixblockDSPContext: get_pixels / diff_pixels, libavcodec/pixblockdsp_template.c:24-66 (8-bit) */
+void orc_pixblock(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride)
+{
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            block[8 * y + x] = kind ? (int16_t)(s1[y * stride + x] - s2[y * stride + x]) : s1[y * stride + x];
+}

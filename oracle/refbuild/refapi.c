@@ -26,6 +26,7 @@
 #include "libavcodec/h264chroma.h"
 #include "libavcodec/hpeldsp.h"
 #include "libavcodec/h264pred.h"
+#include "libavcodec/pixblockdsp.h"
 #include "libavcodec/fft.h"
 #include "libavcodec/dct.h"
 #include "libswscale/swscale.h"
@@ -40,6 +41,7 @@ static H264DSPContext h264;
 static H264QpelContext qpel;
 static H264ChromaContext chroma;
 static HpelDSPContext hpel;
+static PixblockDSPContext pixb;
 
 static void init_all(void)
 {
@@ -59,6 +61,7 @@ static void init_all(void)
     ff_h264dsp_init(&h264, 8, 1);
     ff_h264qpel_init(&qpel, 8);
     ff_h264chroma_init(&chroma, 8);
+    ff_pixblockdsp_init(&pixb, avctx);
     ff_hpeldsp_init(&hpel, AV_CODEC_FLAG_BITEXACT);
     free(avctx);
 }
@@ -342,6 +345,9 @@ int ref_sizeof_fftcontext(void) { return sizeof(FFTContext); }
 
 /* ---- ABI facts of the reference's tables (sizes and a few offsets), for tests/test_abi_cpu.py ---- */
 #include <stddef.h>
+void ref_pixblock(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride)
+{ INIT(); if (kind) pixb.diff_pixels(block, s1, s2, stride); else pixb.get_pixels(block, s1, stride); }
+
 int ref_abi_info(int32_t *out, int cap)
 {
     int32_t v[] = {
@@ -354,6 +360,7 @@ int ref_abi_info(int32_t *out, int cap)
         sizeof(H264ChromaContext), sizeof(HpelDSPContext), offsetof(HpelDSPContext, put_no_rnd_pixels_tab), offsetof(HpelDSPContext, avg_no_rnd_pixels_tab),
         sizeof(H264PredContext), offsetof(H264PredContext, pred8x8l), offsetof(H264PredContext, pred16x16), offsetof(H264PredContext, pred8x8l_filter_add),
         offsetof(H264PredContext, pred16x16_add),
+        sizeof(PixblockDSPContext), offsetof(PixblockDSPContext, diff_pixels),
     };
     int n = sizeof(v) / sizeof(v[0]);
     for (int i = 0; i < n && i < cap; i++) out[i] = v[i];

@@ -42,6 +42,7 @@ def test_header_is_plain_c_and_layout_matches_reference(built, tmp_path):
     assert tables.IDCTDSPContext.idct_permutation.offset == mine[2] and tables.MECmpContext.pix_abs.offset == mine[10]
     assert tables.H264DSPContext.h264_idct_add16.offset == mine[14] and tables.HpelDSPContext.avg_no_rnd_pixels_tab.offset == mine[22]
     assert C.sizeof(tables.H264PredContext) == mine[23] and tables.H264PredContext.pred16x16_add.offset == mine[27]
+    assert C.sizeof(tables.PixblockDSPContext) == mine[28] and tables.PixblockDSPContext.diff_pixels.offset == mine[29]
     from oracle import loader
     r = loader.ref()
     if r is None:

@@ -816,10 +816,29 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
     }
 }
 
+// nv12ToUV_c / nv21ToUV_c (input.c:475-497) for whole planes: one thread splits 4 (U,V) pairs
+__global__ void __launch_bounds__(256)
+sws_split_nv_kernel(const uint8_t *__restrict__ uv, int uvStride, size_t uvFrame, uint8_t *__restrict__ u, uint8_t *__restrict__ v,
+                    int outStride, size_t outFrameU, size_t outFrameV, int w, int h)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= w || y >= h) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *s = uv + f * uvFrame + (size_t)y * uvStride + 2 * x4;
+    uint8_t *du = u + f * outFrameU + (size_t)y * outStride + x4, *dv = v + f * outFrameV + (size_t)y * outStride + x4;
+    if (x4 + 4 <= w && !(((uintptr_t)s) & 7) && !(((uintptr_t)du | (uintptr_t)dv) & 3)) {
+        const uint2 p = *reinterpret_cast<const uint2 *>(s);
+        *reinterpret_cast<uint32_t *>(du) = __byte_perm(p.x, p.y, 0x6420);
+        *reinterpret_cast<uint32_t *>(dv) = __byte_perm(p.x, p.y, 0x7531);
+    } else {
+        for (int k = 0; k < 4 && x4 + k < w; k++) { du[k] = s[2 * k]; dv[k] = s[2 * k + 1]; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
-enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3 };       // libavutil/pixfmt.h enum values
+enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_NV12 = 23, FMT_NV21 = 24 };       // libavutil/pixfmt.h enum values
 
 struct SwsCudaContext {
     SwsGeometry g;
@@ -836,6 +855,8 @@ struct SwsCudaContext {
     SwsDev dev;
     int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
     int lumStridePx = 0, chrStridePx = 0;
+    int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
+    uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the split chroma planes of a batch
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
     // staging for the host-pointer sws_scale_cuda()
@@ -880,7 +901,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                                     const double *param, bool device_side)
 {
     const char *err = nullptr;
-    if (srcFormat != FMT_YUV420P) { set_error_msg("sws_getContext_cuda", "only AV_PIX_FMT_YUV420P sources are taken over"); return nullptr; }
+    if (srcFormat != FMT_YUV420P && srcFormat != FMT_NV12 && srcFormat != FMT_NV21) {
+        set_error_msg("sws_getContext_cuda", "only AV_PIX_FMT_YUV420P / NV12 / NV21 sources are taken over"); return nullptr;
+    }
     if (dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && dstFormat != FMT_YUV420P) {
         set_error_msg("sws_getContext_cuda", "destination must be RGB24, BGR24 or YUV420P"); return nullptr;
     }
@@ -889,6 +912,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
     c->dstFormat = dstFormat;
+    c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err)) goto fail;
     {
@@ -904,7 +928,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         static const int itu601[4] = { 104597, 132201, 25675, 53279 };     // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT]
         rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
     }
-    c->table_unscaled = rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);   // swscale_unscaled.c:1051-1055
+    // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
+    c->table_unscaled = !c->srcNV && rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
     c->fused = !c->table_unscaled && rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
@@ -985,7 +1010,49 @@ fail:
     return nullptr;
 }
 
+static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                      uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st);
+
+// semi-planar sources: split the interleaved chroma plane, then everything is the planar path.  Same-size planar output is
+// the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy + a split of srcW/2 x srcH/2 samples.
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                      uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
+{
+    if (!c->srcNV) return run_planar(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
+    if (nframes <= 0) return 0;
+    const SwsDev &p = c->dev;
+    const int swap = c->srcNV == 2;
+    if (c->copy) {
+        const int w = p.srcW / 2, h = p.srcH / 2;
+        for (int f = 0; f < nframes; f++)
+            AVB_CUDA(cudaMemcpy2DAsync(dst[0] + f * dstFrame[0], dstStride[0], src[0] + f * srcFrame[0], srcStride[0], p.srcW, p.srcH,
+                                       cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
+        if (w > 0 && h > 0) {
+            if (dstStride[1] != dstStride[2]) { set_error_msg("sws_scale", "nv12 -> planar copy needs equal chroma pitches"); return -1; }
+            sws_split_nv_kernel<<<dim3((w + 1023) / 1024, h, nframes), 256, 0, st>>>(src[1], srcStride[1], srcFrame[1], dst[swap ? 2 : 1], dst[swap ? 1 : 2],
+                                                                                 dstStride[1], dstFrame[swap ? 2 : 1], dstFrame[swap ? 1 : 2], w, h);
+        }
+        return check_launch("sws_scale:nv12 copy");
+    }
+    const int pitch = (p.chrSrcW + 15) & ~15;
+    const size_t plane = (size_t)pitch * p.chrSrcH, need = 2 * plane * nframes;
+    if (c->nv_bytes < need) {
+        AVB_CUDA(cudaStreamSynchronize(st), "sws_scale:nv12");         // an earlier batch may still read the old planes
+        cudaFree(c->d_nv); c->d_nv = nullptr; c->nv_bytes = 0;
+        AVB_CUDA(cudaMalloc(&c->d_nv, need), "sws_scale:nv12");
+        c->nv_bytes = need;
+    }
+    uint8_t *U = c->d_nv, *V = c->d_nv + plane * nframes;
+    sws_split_nv_kernel<<<dim3((p.chrSrcW + 1023) / 1024, p.chrSrcH, nframes), 256, 0, st>>>(src[1], srcStride[1], srcFrame[1], swap ? V : U, swap ? U : V,
+                                                                                          pitch, plane, plane, p.chrSrcW, p.chrSrcH);
+    if (check_launch("sws_scale:nv12 split")) return -1;
+    const uint8_t *s3[3] = { src[0], U, V };
+    const int st3[3] = { srcStride[0], pitch, pitch };
+    const size_t fr3[3] = { srcFrame[0], plane, plane };
+    return run_planar(c, s3, st3, fr3, dst, dstStride, dstFrame, nframes, st);
+}
+
+static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
     const SwsDev &p = c->dev;
@@ -1111,7 +1178,7 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
 static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_nv); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
     delete c;
 }
 
@@ -1135,7 +1202,7 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
 {
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
-    if (!src || !dst || !src[0] || !src[1] || !src[2] || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
+    if (!src || !dst || !src[0] || !src[1] || (!c->srcNV && !src[2]) || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     static const size_t zero3[3] = { 0, 0, 0 };
     if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
                    nframes, (cudaStream_t)stream)) return -1;
@@ -1150,21 +1217,22 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
     const bool rgb = c->dstFormat != FMT_YUV420P;
-    if (!srcSlice || !dst || !srcSlice[0] || !srcSlice[1] || !srcSlice[2] || !srcStride[0] || !srcStride[1] || !srcStride[2] ||
+    const bool nv = c->srcNV != 0;
+    if (!srcSlice || !dst || !srcSlice[0] || !srcSlice[1] || (!nv && !srcSlice[2]) || !srcStride[0] || !srcStride[1] || (!nv && !srcStride[2]) ||
         !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dst[2] || !dstStride[1] || !dstStride[2]))) {
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
     if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
-    if (srcStride[0] < 0 || srcStride[1] < 0 || srcStride[2] < 0 || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
+    if (srcStride[0] < 0 || srcStride[1] < 0 || (!nv && srcStride[2] < 0) || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
     ScratchLock lk;
     cudaStream_t *st = scratch().streams();
     if (!st) return 0;
     cudaStream_t s = st[0];
     const SwsGeometry &g = c->g;
     // device staging: tight, aligned pitches
-    const int yP = (g.srcW + 15) & ~15, cP = (g.chrSrcW + 15) & ~15;
+    const int yP = (g.srcW + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW + 15) & ~15;
     const size_t yB = (size_t)yP * g.srcH, cB = (size_t)cP * g.chrSrcH;
-    const size_t needS = yB + 2 * cB;
+    const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW + 15) & ~15, dcP = (g.chrDstW + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
@@ -1175,8 +1243,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     uint8_t *dd[3] = { c->d_dst, c->d_dst + dB, c->d_dst + dB + dcB };
     const int dsS[3] = { yP, cP, cP }, ddS[3] = { dP, dcP, dcP };
     if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
         set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
     }
     static const size_t zero3[3] = { 0, 0, 0 };
@@ -1190,8 +1258,10 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, g.chrDstW, g.chrDstH, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, g.chrDstW, g.chrDstH, cudaMemcpyDeviceToHost, s);
+        // nv12ToPlanarWrapper splits srcW / 2 x srcH / 2 samples: an odd last column / row of the caller's planes stays untouched
+        const int cw = (nv && c->copy) ? g.srcW / 2 : g.chrDstW, ch = (nv && c->copy) ? g.srcH / 2 : g.chrDstH;
+        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("sws_scale_cuda:d2h", e); return 0; }

@@ -93,7 +93,7 @@ def idct_put_tiles(blocks, tiles_per_row, mode=0, frame=None, use_offsets=False,
 # ---------------------------------------------------------------------------------------------------
 # libswscale boundary
 # ---------------------------------------------------------------------------------------------------
-PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24 = 0, 2, 3
+PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24, PIX_FMT_NV12, PIX_FMT_NV21 = 0, 2, 3, 23, 24
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
 SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400
 SWS_ACCURATE_RND, SWS_BITEXACT = 0x40000, 0x80000
@@ -103,9 +103,10 @@ class SwsContext:
     """sws_getContext_cuda / sws_scale_cuda / sws_freeContext_cuda with numpy planes (HOST pointers), plus the
     device-pointer batch call."""
 
-    def __init__(self, src_w, src_h, dst_w, dst_h, dst_fmt=PIX_FMT_RGB24, flags=SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT):
+    def __init__(self, src_w, src_h, dst_w, dst_h, dst_fmt=PIX_FMT_RGB24, flags=SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT,
+                 src_fmt=PIX_FMT_YUV420P):
         self.src_w, self.src_h, self.dst_w, self.dst_h, self.dst_fmt = src_w, src_h, dst_w, dst_h, dst_fmt
-        self.ctx = lib.sws_getContext_cuda(src_w, src_h, PIX_FMT_YUV420P, dst_w, dst_h, dst_fmt, flags, None, None, None)
+        self.ctx = lib.sws_getContext_cuda(src_w, src_h, src_fmt, dst_w, dst_h, dst_fmt, flags, None, None, None)
         if not self.ctx:
             L.check(-1, "sws_getContext_cuda")
 
@@ -114,9 +115,10 @@ class SwsContext:
         return bool(lib.sws_is_fused_cuda(self.ctx))
 
     def scale(self, yuv, dst_pad=0):
-        """Host-pointer drop-in call: (Y, U, V) uint8 arrays (any row stride) -> rgb (h, 3w [+pad]) or 3 planes."""
-        src = (C.c_void_p * 4)(*[a.ctypes.data for a in yuv], None)
-        sst = (C.c_int * 4)(*[a.strides[0] for a in yuv], 0)
+        """Host-pointer drop-in call: (Y, U, V) -- or (Y, UV) for nv12 / nv21 -- uint8 arrays (any row stride) -> rgb
+        (h, 3w [+pad]) or 3 planes."""
+        src = (C.c_void_p * 4)(*([a.ctypes.data for a in yuv] + [None] * (4 - len(yuv))))
+        sst = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0] * (4 - len(yuv))))
         if self.dst_fmt == PIX_FMT_YUV420P:
             out = [np.zeros((self.dst_h, self.dst_w), np.uint8),
                    np.zeros(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), np.uint8),
@@ -131,11 +133,11 @@ class SwsContext:
         return out[0] if len(out) == 1 else out
 
     def scale_device(self, d_src, src_strides, d_dst, dst_strides, nframes=1, src_frame=None, dst_frame=None, stream=None):
-        src = (C.c_void_p * 3)(*d_src)
-        sst = (C.c_int * 3)(*src_strides)
+        src = (C.c_void_p * 3)(*(list(d_src) + [None] * (3 - len(d_src))))
+        sst = (C.c_int * 3)(*(list(src_strides) + [0] * (3 - len(src_strides))))
         dst = (C.c_void_p * 3)(*(list(d_dst) + [None] * (3 - len(d_dst))))
         dstr = (C.c_int * 3)(*(list(dst_strides) + [0] * (3 - len(dst_strides))))
-        sf = (C.c_size_t * 3)(*src_frame) if src_frame else None
+        sf = (C.c_size_t * 3)(*(list(src_frame) + [0] * (3 - len(src_frame)))) if src_frame else None
         df = (C.c_size_t * 3)(*(list(dst_frame) + [0] * (3 - len(dst_frame)))) if dst_frame else None
         r = lib.sws_scale_frames_cuda(self.ctx, src, sst, sf, dst, dstr, df, nframes, stream)
         if r < 0:

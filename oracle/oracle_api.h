@@ -159,6 +159,11 @@ int ORC(sws_yuv420p_to_yuv420p)(const uint8_t *const src[3], const int src_strid
  * which: 0 hLum, 1 hChr, 2 vLum, 3 vChr.  Fills filter (int16, n*fsize) and pos (int32, n), where
  * n = number of output samples of that axis (returned in *n_out); returns fsize (<0 on error).
  * filter_align is forced to 1 (the padding taps are zero under SWS_BITEXACT). */
+/* Semi-planar sources: sws_getContext(sw, sh, AV_PIX_FMT_NV12 / NV21, dw, dh, dst_fmt, flags) + sws_scale of one frame
+ * (chroma read through nv12ToUV_c / nv21ToUV_c, libswscale/input.c:475-497; same-size planar output through
+ * nv12ToPlanarWrapper, swscale_unscaled.c:160-181).  dst_fmt 2 = rgb24 (dst[0] only), 0 = yuv420p.  Returns lines written. */
+int ORC(sws_nv12)(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
+                  uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags);
 int ORC(sws_get_filter)(int which, int to_rgb, int src_w, int src_h, int dst_w, int dst_h, int flags,
                         int16_t *filter, int32_t *pos, int cap, int *n_out);
 /* yuv->rgb 24 bpp LUTs (yuv2rgb.c:671-863) with the default colourspace (ITU601, limited range):

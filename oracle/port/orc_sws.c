@@ -420,3 +420,37 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     sws_close(&c);
     return dh;
 }
+
+
+/* Semi-planar sources: nvXXtoUV_c (libswscale/input.c:475-497) in front of the planar path.  A same-size planar
+ * destination is the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy and a split of
+ * srcW/2 x srcH/2 chroma samples; an rgb destination always runs swscale() for these sources (the unscaled table
+ * converter is only installed for planar yuv, swscale_unscaled.c:1051-1055). */
+int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
+                 uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
+{
+    if (dst_fmt == 0 && sw == dw && sh == dh) {
+        for (int r = 0; r < sh; r++) memcpy(dst[0] + (size_t)r * dstride[0], y + (size_t)r * ystride, sw);
+        for (int r = 0; r < sh / 2; r++)
+            for (int x = 0; x < sw / 2; x++) {
+                dst[nv21 ? 2 : 1][(size_t)r * dstride[nv21 ? 2 : 1] + x] = uv[(size_t)r * uvstride + 2 * x];
+                dst[nv21 ? 1 : 2][(size_t)r * dstride[nv21 ? 1 : 2] + x] = uv[(size_t)r * uvstride + 2 * x + 1];
+            }
+        return sh;
+    }
+    const int cw = (sw + 1) >> 1, ch = (sh + 1) >> 1, pitch = cw + 16;
+    uint8_t *u = malloc((size_t)pitch * ch * 2), *v = u + (size_t)pitch * ch;
+    if (!u) return -1;
+    memset(u, 0, (size_t)pitch * ch * 2);
+    for (int r = 0; r < ch; r++)
+        for (int x = 0; x < cw; x++) {
+            (nv21 ? v : u)[(size_t)r * pitch + x] = uv[(size_t)r * uvstride + 2 * x];
+            (nv21 ? u : v)[(size_t)r * pitch + x] = uv[(size_t)r * uvstride + 2 * x + 1];
+        }
+    const uint8_t *src[3] = { y, u, v };
+    const int ss[3] = { ystride, pitch, pitch };
+    int r = dst_fmt == 2 ? orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst[0], dstride[0], dw, dh, flags | 0x40000)
+                         : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    free(u);
+    return r;
+}

@@ -281,6 +281,21 @@ int ref_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     sws_freeContext(c);
     return r;
 }
+int ref_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
+                 uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
+{
+    INIT();
+    struct SwsContext *c = sws_getContext(sw, sh, nv21 ? AV_PIX_FMT_NV21 : AV_PIX_FMT_NV12, dw, dh,
+                                          dst_fmt == 2 ? AV_PIX_FMT_RGB24 : AV_PIX_FMT_YUV420P, flags, NULL, NULL, NULL);
+    if (!c) return -1;
+    uint8_t *d[4] = { dst[0], dst_fmt == 2 ? NULL : dst[1], dst_fmt == 2 ? NULL : dst[2], NULL };
+    int ds[4] = { dstride[0], dst_fmt == 2 ? 0 : dstride[1], dst_fmt == 2 ? 0 : dstride[2], 0 };
+    const uint8_t *s[4] = { y, uv, NULL, NULL };
+    int sst[4] = { ystride, uvstride, 0, 0 };
+    int r = sws_scale(c, s, sst, 0, sh, d, ds);
+    sws_freeContext(c);
+    return r;
+}
 int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,
                        int32_t *pos, int cap, int *n_out)
 {

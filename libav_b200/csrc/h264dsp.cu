@@ -56,48 +56,42 @@ constexpr int MC_PW = 24;                 // luma patch pitch (21 used)
 constexpr int MC_CW = 12;                 // chroma patch pitch (9 used)
 struct MCSmem { uint8_t luma[21 * MC_PW]; int16_t tmp[21 * 16]; uint8_t chroma[2][9 * MC_CW]; };
 
-__global__ void __launch_bounds__(128)
-h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
-               uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph,
-               int pass)   // ph = height of ONE picture; pictures of a batch are stacked vertically
+// The partition width is a template parameter (the switch on r.w is warp uniform): every index split below is a shift or
+// a division by a constant -- with run-time widths the integer divisions were most of the kernel.
+template <int W>
+__device__ __forceinline__ void mc_partition(MCSmem &S, const FFH264MCRecord &r, const FFH264RefPlanes &ref, uint8_t *__restrict__ dy,
+                                             uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph, int lane)
 {
-    __shared__ MCSmem sm[4];
-    const int lane = threadIdx.x & 31;
-    MCSmem &S = sm[threadIdx.x >> 5];
-    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ri >= n) return;
-    const FFH264MCRecord r = recs[ri];
-    if ((r.avg != 0) != (pass != 0)) return;          // pass 0: every `put`; pass 1: the `avg` second directions
-    const FFH264RefPlanes ref = refs[r.ref];
+    constexpr int PW = W + 5, CW = W / 2 + 1, cw = W / 2;
     const int mx = r.mvx + r.x * 4, my = r.mvy + r.y * 4;          // quarter-pel position, h264_mb.c:216-217
-    const int w = r.w, h = r.h, cw = w >> 1, chh = h >> 1, fx = mx & 3, fy = my & 3;
+    const int h = r.h, chh = h >> 1, fx = mx & 3, fy = my & 3;
     const int pic = r.y / ph, ly0 = pic * ph, cy0 = pic * (ph >> 1);
     // ---- fetch patches (edge replication by clamping = emulated_edge_mc) ----
     {
-        const int bx = (mx >> 2) - 2, by = (my >> 2) - 2, PW = w + 5, PH = h + 5;
+        const int bx = (mx >> 2) - 2, by = (my >> 2) - 2, PH = h + 5;
         for (int i = lane; i < PW * PH; i += 32) {
-            const int xx = i % PW, yy = i / PW;
+            const int yy = i / PW, xx = i - yy * PW;
             S.luma[yy * MC_PW + xx] = __ldg(ref.y + (size_t)min(max(by + yy, ly0), ly0 + ph - 1) * ls + min(max(bx + xx, 0), pw - 1));
         }
-        const int cbx = mx >> 3, cby = my >> 3, CW = cw + 1, CH = chh + 1;
-        for (int i = lane; i < 2 * CW * CH; i += 32) {
-            const int pl = i >= CW * CH, k = i - pl * CW * CH, xx = k % CW, yy = k / CW;
+        const int cbx = mx >> 3, cby = my >> 3, CH = chh + 1, per = CW * CH;
+        for (int i = lane; i < 2 * per; i += 32) {
+            const int pl = i >= per, k = i - pl * per, yy = k / CW, xx = k - yy * CW;
             const uint8_t *src = pl ? ref.cr : ref.cb;
             S.chroma[pl][yy * MC_CW + xx] = __ldg(src + (size_t)min(max(cby + yy, cy0), cy0 + (ph >> 1) - 1) * uvls + min(max(cbx + xx, 0), (pw >> 1) - 1));
         }
     }
     __syncwarp();
     if (fx) {                                          // horizontal 6-tap, unrounded, rows -2 .. h+2 (tmp row = patch row)
-        for (int i = lane; i < w * (h + 5); i += 32) {
-            const int xx = i % w, yy = i / w;
+        for (int i = lane; i < W * (h + 5); i += 32) {
+            const int xx = i % W, yy = i / W;
             const uint8_t *p = &S.luma[yy * MC_PW + xx + 2];
             S.tmp[yy * 16 + xx] = (int16_t)((p[0] + p[1]) * 20 - (p[-1] + p[2]) * 5 + (p[-2] + p[3]));
         }
         __syncwarp();
     }
     // ---- luma ----
-    for (int i = lane; i < w * h; i += 32) {
-        const int px = i % w, py = i / w;
+    for (int i = lane; i < W * h; i += 32) {
+        const int px = i % W, py = i / W;
         const uint8_t *p = &S.luma[(py + 2) * MC_PW + px + 2];          // full-pel sample F(px, py)
         const int16_t *t = &S.tmp[(py + 2) * 16 + px];
         auto Hs = [&](int dyy) { return clip_u8((t[dyy * 16] + 16) >> 5); };
@@ -118,14 +112,33 @@ h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264Re
     // ---- chroma (1/8-pel bilinear, h264chroma_template.c:27-170) ----
     {
         const int cfx = mx & 7, cfy = my & 7, A = (8 - cfx) * (8 - cfy), B = cfx * (8 - cfy), Cc = (8 - cfx) * cfy, D = cfx * cfy;
-        for (int i = lane; i < 2 * cw * chh; i += 32) {
-            const int pl = i >= cw * chh, k = i - pl * cw * chh, px = k % cw, py = k / cw;
+        const int per = cw * chh;
+        for (int i = lane; i < 2 * per; i += 32) {
+            const int pl = i >= per, k = i - pl * per, px = k % cw, py = k / cw;
             const uint8_t *p = &S.chroma[pl][py * MC_CW + px];
             const int v = (A * p[0] + B * p[1] + Cc * p[MC_CW] + D * p[MC_CW + 1] + 32) >> 6;
             uint8_t *d = (pl ? dcr : dcb) + (size_t)((r.y >> 1) + py) * uvls + (r.x >> 1) + px;
             *d = (uint8_t)(r.avg ? (*d + v + 1) >> 1 : v);
         }
     }
+}
+
+__global__ void __launch_bounds__(128)
+h264_mc_kernel(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
+               uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph,
+               int pass)   // ph = height of ONE picture; pictures of a batch are stacked vertically
+{
+    __shared__ MCSmem sm[4];
+    const int lane = threadIdx.x & 31;
+    MCSmem &S = sm[threadIdx.x >> 5];
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFH264MCRecord r = recs[ri];
+    if ((r.avg != 0) != (pass != 0)) return;          // pass 0: every `put`; pass 1: the `avg` second directions
+    const FFH264RefPlanes ref = refs[r.ref];
+    if (r.w == 16)     mc_partition<16>(S, r, ref, dy, dcb, dcr, ls, uvls, pw, ph, lane);
+    else if (r.w == 8) mc_partition<8>(S, r, ref, dy, dcb, dcr, ls, uvls, pw, ph, lane);
+    else               mc_partition<4>(S, r, ref, dy, dcb, dcr, ls, uvls, pw, ph, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------

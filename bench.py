@@ -613,6 +613,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_secondary:
         r = {"idct_put": cpu_idct, "sws4k": cpu_sws, "me": cpu_me}.get(args.workload, cpu_idct)(ncores)
         cpu = {"value": r["pixels"] / r["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        if args.workload == "idct_put":                   # SURVEY 8d also asks for the one-thread number
+            r1 = cpu_idct(1, reps=3)
+            cpu["single_thread"] = {"value": r1["pixels"] / r1["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": 1, "sample": r1["sample"]}
+        cpu["note"] = ("portable C build of the reference (ARCH_X86 = 0, av_set_cpu_flags_mask(0)): its x86 SIMD needs nasm / inline asm "
+                       "templates this recipe does not enable")
 
     if world > 1:
         dist.barrier()

@@ -283,6 +283,13 @@ int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int 
 typedef struct FFHpelRecord { uint32_t dst_off, src_off; uint8_t tab, sidx, dxy, h; } FFHpelRecord;
 int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream);
 
+/* QpelDSPContext (libavcodec/qpeldsp.h:69-73): MPEG-4 quarter-pel motion compensation, n blocks per launch.
+ * kind 0 put_qpel_pixels_tab, 1 put_no_rnd_qpel_pixels_tab, 2 avg_qpel_pixels_tab; sidx 0 = 16x16, 1 = 8x8;
+ * mc = x + 4 * y quarter-pel phase (the table index, qpeldsp.c:734-752).  dst and src share `stride` like the C slots;
+ * records of one launch must address disjoint destination blocks. */
+typedef struct FFQpelRecord { uint32_t dst_off, src_off; uint8_t kind, sidx, mc, pad; } FFQpelRecord;
+int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream);
+
 /* FDCTDSPContext (libavcodec/fdctdsp.h:26-29), in place over n blocks: which 0 = ff_jpeg_fdct_islow_8, 1 =
  * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332). */
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream);
@@ -354,6 +361,8 @@ void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
 void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc);
 /* libavcodec/pixblockdsp.h:37-43; high_bit_depth != 0 leaves the table untouched */
 void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth);
+/* libavcodec/qpeldsp.h:75-77 */
+void ff_qpeldsp_init_cuda(QpelDSPContext *c);
 /* libavcodec/fft_template.c:152-159, mdct_template.c:58-66 (same shape as ff_fft_init_x86 / ff_mdct_init_x86): called after
  * ff_fft_init / ff_mdct_init filled the context.  fft_permute stays the reference's; the CUDA fft_calc accepts its revtab
  * order, the MDCT slots use the context's own tcos / tsin tables. */

@@ -125,6 +125,13 @@ typedef struct H264QpelContext {
     qpel_mc_func avg_h264_qpel_pixels_tab[4][16];
 } H264QpelContext;
 
+/* ---- libavcodec/qpeldsp.h:69-73 (qpel_mc_func as above) ---- */
+typedef struct QpelDSPContext {
+    qpel_mc_func put_qpel_pixels_tab[2][16];
+    qpel_mc_func avg_qpel_pixels_tab[2][16];
+    qpel_mc_func put_no_rnd_qpel_pixels_tab[2][16];
+} QpelDSPContext;
+
 /* ---- libavcodec/h264chroma.h:25-30 ---- */
 typedef void (*h264_chroma_mc_func)(uint8_t *dst, uint8_t *src, ptrdiff_t srcStride, int h, int x, int y);
 typedef struct H264ChromaContext {

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "ff_h264_deblock_batch_cuda": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
     "ff_h264_deblock_params_cuda": (i32, [vp, vp, vp]),
     "ff_h264_intra_mb_batch_cuda": (i32, [vp, i32, i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, vp, vp]),
+    "ff_mpeg4_qpel_batch_cuda": (i32, [vp, sz, vp, vp, pd, vp]),
     "ff_pixblock_fdct_batch_cuda": (i32, [i32, vp, vp, vp, vp, pd, vp, sz, vp]),
     "ff_mpeg_dequant_batch_cuda": (i32, [i32, vp, vp, vp, sz, vp]),
     "ff_mpeg_dequant_idct_batch_cuda": (i32, [i32, vp, vp, vp, vp, vp, pd, sz, i32, i32, vp]),
@@ -93,6 +94,7 @@ PROTOTYPES = {
     "ff_h264chroma_init_cuda": (None, [vp, i32]),
     "ff_hpeldsp_init_cuda": (None, [vp, i32]),
     "ff_h264_pred_init_cuda": (None, [vp, i32, i32, i32]),
+    "ff_qpeldsp_init_cuda": (None, [vp]),
     "ff_pixblockdsp_init_cuda": (None, [vp, C.c_uint]),
     "ff_fft_init_cuda": (None, [vp]),
     "ff_mdct_init_cuda": (None, [vp]),

@@ -415,6 +415,63 @@ pixblock_kernel(const uint8_t *__restrict__ s1, const uint8_t *__restrict__ s2, 
         reinterpret_cast<uint4 *>(d)[r] = make_uint4(pack16(m[r][0], m[r][1]), pack16(m[r][2], m[r][3]), pack16(m[r][4], m[r][5]), pack16(m[r][6], m[r][7]));
 }
 
+// QpelDSPContext: MPEG-4 quarter-pel MC (libavcodec/qpeldsp.c:39-700), warp per record.  The (N+1) x (N+1) source patch
+// goes to shared memory, then the horizontal phase plane Hx (N+1 rows, 8-bit after its own rounding, exactly the C code's
+// halfH), then every lane finishes its pixels with the vertical phase: one formula for all 16 positions, 8-tap
+// (-1 3 -6 20 20 -6 3 -1) with the sample index mirrored at both ends of the block.
+struct QpelSmem { uint8_t f[17 * 20]; uint8_t hx[17 * 16]; };
+
+template <int N>
+__device__ __forceinline__ int qpel8tap(const uint8_t *s, int step, int i)
+{
+    auto m = [&](int j) { return (int)s[(j < 0 ? -1 - j : j > N ? 2 * N + 1 - j : j) * step]; };
+    return (m(i) + m(i + 1)) * 20 - (m(i - 1) + m(i + 2)) * 6 + (m(i - 2) + m(i + 3)) * 3 - (m(i - 3) + m(i + 4));
+}
+
+template <int N>
+__device__ __forceinline__ void qpel_record(QpelSmem &S, const FFQpelRecord &r, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                            ptrdiff_t stride, int lane)
+{
+    const int x = r.mc & 3, y = r.mc >> 2, rnd = r.kind == 1 ? 15 : 16, up = r.kind == 1 ? 0 : 1;
+    const int rows = y ? N + 1 : N, cols = x ? N + 1 : N;
+    const uint8_t *sp = src + r.src_off;
+    for (int i = lane; i < rows * cols; i += 32) { const int rr = i / cols, cc = i - rr * cols; S.f[rr * 20 + cc] = sp[rr * stride + cc]; }
+    __syncwarp();
+    for (int i = lane; i < rows * N; i += 32) {
+        const int rr = i / N, cc = i % N;
+        int v = S.f[rr * 20 + cc];
+        if (x) {
+            const int h = clip_u8((qpel8tap<N>(&S.f[rr * 20], 1, cc) + rnd) >> 5);
+            v = x == 2 ? h : (S.f[rr * 20 + cc + (x == 3)] + h + up) >> 1;
+        }
+        S.hx[rr * 16 + cc] = (uint8_t)v;
+    }
+    __syncwarp();
+    uint8_t *dp = dst + r.dst_off;
+    for (int i = lane; i < N * N; i += 32) {
+        const int rr = i / N, cc = i % N;
+        int v = S.hx[rr * 16 + cc];
+        if (y) {
+            const int vv = clip_u8((qpel8tap<N>(&S.hx[cc], 16, rr) + rnd) >> 5);
+            v = y == 2 ? vv : (S.hx[(rr + (y == 3)) * 16 + cc] + vv + up) >> 1;
+        }
+        uint8_t *d = dp + rr * stride + cc;
+        *d = (uint8_t)(r.kind == 2 ? (*d + v + 1) >> 1 : v);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+mpeg4_qpel_kernel(const FFQpelRecord *__restrict__ recs, size_t n, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, ptrdiff_t stride)
+{
+    __shared__ QpelSmem sm[4];
+    const int lane = threadIdx.x & 31;
+    const size_t ri = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFQpelRecord r = recs[ri];
+    if (r.sidx) qpel_record<8>(sm[threadIdx.x >> 5], r, dst, src, stride, lane);
+    else        qpel_record<16>(sm[threadIdx.x >> 5], r, dst, src, stride, lane);
+}
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 }  // namespace avb
@@ -465,6 +522,13 @@ int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
     default: set_error_msg("fdct_batch", "bad transform selector"); return -1;
     }
     return check_launch("fdct_batch");
+}
+
+int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream)
+{
+    if (!n) return 0;
+    mpeg4_qpel_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(recs, n, dst, src, stride);
+    return check_launch("mpeg4_qpel_batch");
 }
 
 int ff_pixblock_fdct_batch_cuda(int which_fdct, const uint8_t *s1, const uint8_t *s2, const uint32_t *off1, const uint32_t *off2,

@@ -133,6 +133,7 @@ extern "C" {
 int ff_me_cmp_batch_cuda(int, int, int, const uint8_t *, const uint8_t *, ptrdiff_t, int, const FFMECmpRecord *, size_t, int32_t *, void *);
 int ff_hpel_batch_cuda(const FFHpelRecord *, size_t, uint8_t *, const uint8_t *, ptrdiff_t, void *);
 int ff_fdct_batch_cuda(int, int16_t *, size_t, void *);
+int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *, size_t, uint8_t *, const uint8_t *, ptrdiff_t, void *);
 int ff_pixblock_fdct_batch_cuda(int, const uint8_t *, const uint8_t *, const uint32_t *, const uint32_t *, ptrdiff_t, int16_t *, size_t, void *);
 int ff_h264_weight_batch_cuda(const FFH264WeightRecord *, size_t, uint8_t *, const uint8_t *, int, void *);
 }
@@ -191,6 +192,22 @@ template <int TAB, int SIDX, int DXY> void slot_hpel(uint8_t *block, const uint8
     if (S.up() || ff_hpel_batch_cuda((const FFHpelRecord *)(S.d + orec), 1, S.d + od, S.d + os, SP, S.s) || S.down()) return;
     S.rect_out(block, ls, w, h, od);
 }
+
+// ---- MPEG-4 qpel: stages exactly the rows / columns the C function of that phase reads ----
+template <int KIND, int SIDX, int MC> void slot_mpeg4_qpel(uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    Stage S; if (!S.ok()) return;
+    const int n = 16 >> SIDX, rows = (MC >> 2) ? n + 1 : n, cols = (MC & 3) ? n + 1 : n;
+    size_t od = S.rect_in(dst, stride, n, n), os = S.rect_in(src, stride, cols, rows), orec = S.take(16);
+    FFQpelRecord r = { 0, 0, (uint8_t)KIND, (uint8_t)SIDX, (uint8_t)MC, 0 };
+    memcpy(S.h + orec, &r, sizeof(r));
+    if (S.up() || ff_mpeg4_qpel_batch_cuda((const FFQpelRecord *)(S.d + orec), 1, S.d + od, S.d + os, SP, S.s) || S.down()) return;
+    S.rect_out(dst, stride, n, n, od);
+}
+template <int KIND, int SIDX, int MC> struct FillMpeg4Qpel {
+    static void go(qpel_mc_func *t) { t[MC] = slot_mpeg4_qpel<KIND, SIDX, MC>; FillMpeg4Qpel<KIND, SIDX, MC - 1>::go(t); }
+};
+template <int KIND, int SIDX> struct FillMpeg4Qpel<KIND, SIDX, -1> { static void go(qpel_mc_func *) {} };
 
 // ---- H.264 qpel / chroma ----
 template <int AVG, int SIDX, int MC> void slot_qpel(uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
@@ -348,6 +365,14 @@ template <int TAB, int SIDX> void fill_hpel(op_pixels_func *t)
 }  // namespace
 
 extern "C" {
+
+void ff_qpeldsp_init_cuda(QpelDSPContext *c)
+{
+    if (!c) return;
+    FillMpeg4Qpel<0, 0, 15>::go(c->put_qpel_pixels_tab[0]);        FillMpeg4Qpel<0, 1, 15>::go(c->put_qpel_pixels_tab[1]);
+    FillMpeg4Qpel<1, 0, 15>::go(c->put_no_rnd_qpel_pixels_tab[0]); FillMpeg4Qpel<1, 1, 15>::go(c->put_no_rnd_qpel_pixels_tab[1]);
+    FillMpeg4Qpel<2, 0, 15>::go(c->avg_qpel_pixels_tab[0]);        FillMpeg4Qpel<2, 1, 15>::go(c->avg_qpel_pixels_tab[1]);
+}
 
 void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth)
 {

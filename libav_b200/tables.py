@@ -135,3 +135,8 @@ class H264PredContext(C.Structure):         # libavcodec/h264pred.h:91-110
 class PixblockDSPContext(C.Structure):      # libavcodec/pixblockdsp.h:27-35
     _fields_ = [("get_pixels", C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)),
                 ("diff_pixels", C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t))]
+
+
+class QpelDSPContext(C.Structure):          # libavcodec/qpeldsp.h:69-73
+    _fields_ = [("put_qpel_pixels_tab", (qpel_mc_func * 16) * 2), ("avg_qpel_pixels_tab", (qpel_mc_func * 16) * 2),
+                ("put_no_rnd_qpel_pixels_tab", (qpel_mc_func * 16) * 2)]

@@ -37,6 +37,7 @@ API = {
     "mpeg_scantables": (None, [i32, vp, vp]),
     "h264_pred": (None, [i32, i32, vp, vp, i32, i32, pd]),
     "h264_pred_add": (None, [i32, i32, vp, vp, vp, i32, i32, pd]),
+    "mpeg4_qpel": (None, [i32, i32, i32, vp, vp, pd]),
     "pixblock": (None, [i32, vp, vp, vp, pd]),
     "h264_weight": (None, [i32, vp, i32, i32, i32, i32, i32]),
     "h264_biweight": (None, [i32, vp, vp, i32, i32, i32, i32, i32, i32]),

@@ -62,6 +62,11 @@ void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
 
+/* QpelDSPContext (libavcodec/qpeldsp.h:69-73, qpeldsp.c:39-766): MPEG-4 quarter-pel motion compensation.
+ * kind 0 put_qpel_pixels_tab, 1 put_no_rnd_qpel_pixels_tab, 2 avg_qpel_pixels_tab; sidx 0 = 16x16, 1 = 8x8;
+ * mc = x + 4 * y quarter-pel phase.  dst and src share `stride`; reads rows 0..N and columns 0..N of src. */
+void ORC(mpeg4_qpel)(int kind, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+
 /* PixblockDSPContext (libavcodec/pixblockdsp.h:27-35, pixblockdsp_template.c): kind 0 get_pixels (s2 unused),
  * kind 1 diff_pixels = s1 - s2; 8x8 samples -> int16 block, row-major */
 void ORC(pixblock)(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride);

@@ -254,3 +254,43 @@ void orc_pixblock(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2
         for (int x = 0; x < 8; x++)
             block[8 * y + x] = kind ? (int16_t)(s1[y * stride + x] - s2[y * stride + x]) : s1[y * stride + x];
 }
+
+
+/* QpelDSPContext: MPEG-4 quarter-pel MC (libavcodec/qpeldsp.c:39-700), one evaluation for all 16 phases:
+ *   L(s, i)  = 8-tap (-1 3 -6 20 20 -6 3 -1) over s[0..N] with the indices mirrored at both ends (:46-126)
+ *   Hx(r, c) = phase x of row r: F, avg(F, H), H, avg(F shifted by one, H), H = clip((L + rnd) >> 5)
+ *   out(c, r)= phase y over the column of Hx: Hx, avg(Hx, V), V, avg(Hx one row down, V), V = clip((L over Hx + rnd) >> 5)
+ * rnd = 16 (15 for the no_rnd table), the inner averages round up (down for no_rnd), the avg table finally averages
+ * with dst rounding up. */
+static int q_tap(const int *s, int n, int i)
+{
+#define QM(j) s[(j) < 0 ? -1 - (j) : (j) > n ? 2 * n + 1 - (j) : (j)]
+    return (QM(i) + QM(i + 1)) * 20 - (QM(i - 1) + QM(i + 2)) * 6 + (QM(i - 2) + QM(i + 3)) * 3 - (QM(i - 3) + QM(i + 4));
+#undef QM
+}
+static inline int q_clip(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+
+void orc_mpeg4_qpel(int kind, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    const int n = sidx ? 8 : 16, x = mc & 3, y = mc >> 2, rnd = kind == 1 ? 15 : 16, up = kind == 1 ? 0 : 1;
+    int hx[17][16], line[17];
+    const int rows = y ? n + 1 : n;
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < n; c++) {
+            if (!x) { hx[r][c] = src[r * stride + c]; continue; }
+            for (int k = 0; k <= n; k++) line[k] = src[r * stride + k];
+            const int h = q_clip((q_tap(line, n, c) + rnd) >> 5);
+            hx[r][c] = x == 2 ? h : (src[r * stride + c + (x == 3)] + h + up) >> 1;
+        }
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) {
+            int v = hx[r][c];
+            if (y) {
+                for (int k = 0; k <= n; k++) line[k] = hx[k][c];
+                const int vv = q_clip((q_tap(line, n, r) + rnd) >> 5);
+                v = y == 2 ? vv : (hx[r + (y == 3)][c] + vv + up) >> 1;
+            }
+            uint8_t *d = dst + r * stride + c;
+            *d = (uint8_t)(kind == 2 ? (*d + v + 1) >> 1 : v);
+        }
+}

@@ -27,6 +27,7 @@
 #include "libavcodec/hpeldsp.h"
 #include "libavcodec/h264pred.h"
 #include "libavcodec/pixblockdsp.h"
+#include "libavcodec/qpeldsp.h"
 #include "libavcodec/fft.h"
 #include "libavcodec/dct.h"
 #include "libswscale/swscale.h"
@@ -42,6 +43,7 @@ static H264QpelContext qpel;
 static H264ChromaContext chroma;
 static HpelDSPContext hpel;
 static PixblockDSPContext pixb;
+static QpelDSPContext mqpel;
 
 static void init_all(void)
 {
@@ -62,6 +64,7 @@ static void init_all(void)
     ff_h264qpel_init(&qpel, 8);
     ff_h264chroma_init(&chroma, 8);
     ff_pixblockdsp_init(&pixb, avctx);
+    ff_qpeldsp_init(&mqpel);
     ff_hpeldsp_init(&hpel, AV_CODEC_FLAG_BITEXACT);
     free(avctx);
 }
@@ -360,6 +363,11 @@ int ref_sizeof_fftcontext(void) { return sizeof(FFTContext); }
 
 /* ---- ABI facts of the reference's tables (sizes and a few offsets), for tests/test_abi_cpu.py ---- */
 #include <stddef.h>
+void ref_mpeg4_qpel(int kind, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    INIT();
+    (kind == 0 ? mqpel.put_qpel_pixels_tab : kind == 1 ? mqpel.put_no_rnd_qpel_pixels_tab : mqpel.avg_qpel_pixels_tab)[sidx][mc](dst, src, stride);
+}
 void ref_pixblock(int kind, int16_t *block, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride)
 { INIT(); if (kind) pixb.diff_pixels(block, s1, s2, stride); else pixb.get_pixels(block, s1, stride); }
 
@@ -376,6 +384,7 @@ int ref_abi_info(int32_t *out, int cap)
         sizeof(H264PredContext), offsetof(H264PredContext, pred8x8l), offsetof(H264PredContext, pred16x16), offsetof(H264PredContext, pred8x8l_filter_add),
         offsetof(H264PredContext, pred16x16_add),
         sizeof(PixblockDSPContext), offsetof(PixblockDSPContext, diff_pixels),
+        sizeof(QpelDSPContext), offsetof(QpelDSPContext, put_no_rnd_qpel_pixels_tab),
     };
     int n = sizeof(v) / sizeof(v[0]);
     for (int i = 0; i < n && i < cap; i++) out[i] = v[i];

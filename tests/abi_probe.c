@@ -15,6 +15,7 @@ int main(void)
         sizeof(H264PredContext), offsetof(H264PredContext, pred8x8l), offsetof(H264PredContext, pred16x16), offsetof(H264PredContext, pred8x8l_filter_add),
         offsetof(H264PredContext, pred16x16_add),
         sizeof(PixblockDSPContext), offsetof(PixblockDSPContext, diff_pixels),
+        sizeof(QpelDSPContext), offsetof(QpelDSPContext, put_no_rnd_qpel_pixels_tab),
     };
     for (unsigned i = 0; i < sizeof(v) / sizeof(v[0]); i++) printf("%ld\n", v[i]);
     return 0;

@@ -43,6 +43,7 @@ def test_header_is_plain_c_and_layout_matches_reference(built, tmp_path):
     assert tables.H264DSPContext.h264_idct_add16.offset == mine[14] and tables.HpelDSPContext.avg_no_rnd_pixels_tab.offset == mine[22]
     assert C.sizeof(tables.H264PredContext) == mine[23] and tables.H264PredContext.pred16x16_add.offset == mine[27]
     assert C.sizeof(tables.PixblockDSPContext) == mine[28] and tables.PixblockDSPContext.diff_pixels.offset == mine[29]
+    assert C.sizeof(tables.QpelDSPContext) == mine[30] and tables.QpelDSPContext.put_no_rnd_qpel_pixels_tab.offset == mine[31]
     from oracle import loader
     r = loader.ref()
     if r is None:

@@ -129,7 +129,7 @@ def make_idct_workload(torch, L, stream, rank):
     return {
         "name": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
         "run": run, "run_e2e": run_e2e, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * IDCT_BYTES_PER_BLOCK,
-        "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false>", "dtype": "int32 (int16 in, u8 out)",
+        "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false>",  "dtype": "int32 (int16 in, u8 out)",
         "h2d": N_BLOCKS * 128, "d2h": rows * stride,
         "l2": "3 rotating 192 MiB buffer sets (inputs larger than the 126 MB L2)",
         "keep": (d_blocks, d_frame, h_blocks, h_frame),

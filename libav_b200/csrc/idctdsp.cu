@@ -17,6 +17,7 @@
 // Algorithmic traffic: put 128 B in + 64 B out (+4 B offset) per block; add 256 B; idct 256 B.
 #include "common.cuh"
 #include <type_traits>
+#include <cuda.h>            // CUtensorMap only; the encoder is looked up at run time (no libcuda link dependency)
 #include "idct_dq.h"
 
 namespace avb {
@@ -177,13 +178,19 @@ __device__ __forceinline__ uint4 dq_row(uint4 w, int r, const DqTables &T, const
 // in one kernel; an `add` block with block_last_index < 0 is skipped like the C code skips it.
 struct DqArgs { const uint32_t *recs; DqTables t; };
 struct NoDq {};
-template <int MODE, bool CLEAR, int MINB = 5, bool MH = false, int DQ = 0>
+struct NoTma {};
+// TMA: the warp's 4 KB group arrives by ONE cp.async.bulk.tensor issued by lane 0 (2-D tensor map over the block array,
+// box 32 blocks x 128 B, SWIZZLE_128B = the same chunk ^ (block & 7) layout the cp.async path builds by hand) and is
+// awaited on an mbarrier, instead of eight cp.async per lane.
+template <int MODE, bool CLEAR, int MINB = 5, bool MH = false, int DQ = 0, bool TMA = false>
 __global__ void __launch_bounds__(IDCT_WARPS * 32, MINB)
 simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
                    const uint32_t *__restrict__ dst_off, ptrdiff_t stride, size_t n, int tiles_per_row,
-                   const typename std::conditional<DQ != 0, DqArgs, NoDq>::type dq = {})
+                   const typename std::conditional<DQ != 0, DqArgs, NoDq>::type dq = {},
+                   const __grid_constant__ typename std::conditional<TMA, CUtensorMap, NoTma>::type tmap = {})
 {
-    __shared__ __align__(128) uint4 tile[IDCT_WARPS][2][256];   // 32 blocks x 8 chunks of 16 B
+    __shared__ __align__(1024) uint4 tile[IDCT_WARPS][2][256];  // 32 blocks x 8 chunks of 16 B (1 KB alignment: TMA swizzle atom)
+    __shared__ __align__(8) uint64_t mbar[IDCT_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t groups = (n + 31) / 32;
     const size_t gstride = (size_t)gridDim.x * IDCT_WARPS;
@@ -196,7 +203,26 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
     const unsigned wr_even = (unsigned)(l3 * 8 + (lc ^ l3)) * 16, wr_odd = (unsigned)(l3 * 8 + (lc ^ (4 + l3))) * 16;
     const unsigned rd_base = (unsigned)lane * 128, rd_key = (unsigned)lc << 4;
 
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(&mbar[warp][0]);
+    if constexpr (TMA) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_s) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_s + 8) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     auto issue = [&](size_t grp, unsigned tb) {
+        if constexpr (TMA) {
+            if (lane == 0) {
+                const unsigned mb = mbar_s + ((tb - tile_s) >> 9);                 // buffer 0 -> +0, buffer 1 (4096) -> +8
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the buffer was last touched by ordinary loads
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(4096) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             :: "r"(tb), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"((int)(grp * 32)), "r"(mb) : "memory");
+            }
+            return;
+        }
         const char *src = reinterpret_cast<const char *>(blocks) + grp * 4096 + lane * 16;
         if (grp * 32 + 32 <= n) {
 #pragma unroll
@@ -219,12 +245,19 @@ simple_idct_kernel(int16_t *__restrict__ blocks, uint8_t *__restrict__ frame,
         step_q = (unsigned)(st / (unsigned)tiles_per_row); step_r = (unsigned)(st - (size_t)step_q * (unsigned)tiles_per_row);
     }
 
-    unsigned buf = 0;
+    unsigned buf = 0, uses = 0;
     if (g < groups) issue(g, tile_s);
-    for (; g < groups; g += gstride, buf ^= 4096u) {
+    for (; g < groups; g += gstride, buf ^= 4096u, uses++) {
         const size_t gn = g + gstride;
         const unsigned tb = tile_s + buf;
-        if (gn < groups) { issue(gn, tile_s + (buf ^ 4096u)); cp_async_wait<1>(); } else cp_async_wait<0>();
+        if constexpr (TMA) {
+            if (gn < groups) issue(gn, tile_s + (buf ^ 4096u));
+            const unsigned mb = mbar_s + (buf >> 9), parity = (uses >> 1) & 1;      // k-th use of a buffer completes phase k
+            asm volatile("{\n.reg .pred p;\nIDCT_TMA_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra IDCT_TMA_DONE_%=;\nbra IDCT_TMA_WAIT_%=;\nIDCT_TMA_DONE_%=:\n}"
+                         :: "r"(mb), "r"(parity) : "memory");
+        } else {
+            if (gn < groups) { issue(gn, tile_s + (buf ^ 4096u)); cp_async_wait<1>(); } else cp_async_wait<0>();
+        }
         __syncwarp();
 
         const size_t i = g * 32 + lane;
@@ -370,6 +403,28 @@ static int grid_for(size_t work_items, int per_cta, int ctas_per_sm)
     return (int)(need < cap ? need : cap);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+static bool make_block_tensor_map(CUtensorMap *tm, const int16_t *blocks, size_t n)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeFn)p;
+        else cudaGetLastError();
+    }
+    if (!fn) return false;
+    const cuuint64_t dims[2] = { 64, (cuuint64_t)n }, strides[1] = { 128 };
+    const cuuint32_t box[2] = { 64, 32 }, estr[2] = { 1, 1 };
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void *)blocks, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride,
                        size_t n, int tiles_per_row, int clear, cudaStream_t st)
 {
@@ -382,6 +437,15 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
     // the shorter per-CTA loops even out the tail
     int grid = grid_for(groups, IDCT_WARPS, tuning("idct_grid_mult") > 0 ? tuning("idct_grid_mult") : 16);
     dim3 b(IDCT_WARPS * 32);
+    // idct_put (the headline path) fetches through TMA by default; idct_tma = 2 selects the cp.async fetch (same arithmetic,
+    // same throughput: 1.634 Tpix/s either way), which also serves when the driver has no tensor-map encoder
+    if (mode == 0 && !clear && tuning("idct_tma") != 2 && minb != 4 && minb != 6 && !tuning("idct_mulhi") && !((uintptr_t)blocks & 15)) {
+        CUtensorMap tm;
+        if (make_block_tensor_map(&tm, blocks, n)) {
+            simple_idct_kernel<0, false, 5, false, 0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row, NoDq{}, tm);
+            return check_launch("simple_idct_batch");
+        }
+    }
     if (mode == 0) {
         if (clear) simple_idct_kernel<0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else if (minb == 4) simple_idct_kernel<0, false, 4><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);

@@ -51,6 +51,26 @@ def test_idct_batch_matches_oracle(gpu, checker, name, mode):
         assert np.array_equal(got, want_b if mode == 2 else want_f), (name, mode, use_off)
 
 
+@pytest.mark.parametrize("name", ["dense", "extreme", "ragged", "one"])
+def test_cp_async_variant_matches_oracle(gpu, checker, name):
+    """idct_put fetches its groups by TMA (cp.async.bulk.tensor, SWIZZLE_128B tensor map) by default; this pins the
+    cp.async fetch that the add / in-place / fused-clear modes use, on the put path as well"""
+    from libav_b200 import device
+    blocks = _cases()[name]
+    n = blocks.shape[0]
+    tpr = 37 if n > 37 else 1
+    stride = tpr * 8
+    frame = np.random.default_rng(2).integers(0, 256, size=(((n + tpr - 1) // tpr) * 8, stride), dtype=np.uint8)
+    off = device.tile_offsets(n, tpr, stride)
+    _, want = _oracle_batch(checker, 0, blocks, frame, off, stride)
+    gpu.lib.avb200_set_tuning(b"idct_tma", 2)
+    try:
+        got = device.idct_put_tiles(blocks, tpr, mode=0, frame=frame, use_offsets=False)
+    finally:
+        gpu.lib.avb200_set_tuning(b"idct_tma", 0)
+    assert np.array_equal(got, want), name
+
+
 def test_fused_clear_zeroes_coefficients(gpu, checker):
     from libav_b200 import device
     blocks = synth.dense_blocks(5000, seed=3)

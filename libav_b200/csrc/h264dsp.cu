@@ -16,34 +16,69 @@
 namespace avb {
 
 // ---------------------------------------------------------------------------------------------------
+// The macroblock's 1536 B of coefficients and its 384 pixels are staged in the warp's shared-memory slice with coalesced
+// vector loads, transformed there (one lane per 4x4 / 8x8 block, as the C dispatchers iterate), and written back with
+// vector stores -- the per-lane 32-byte-strided global accesses of the first version kept 4 of 32 lanes busy and the rest
+// of the time waiting on memory.
+struct ResSmem { __align__(16) int16_t co[768]; __align__(16) uint8_t y[16 * 16]; __align__(16) uint8_t c[2][8 * 8]; };
+
 __global__ void __launch_bounds__(128)
 h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
                      const uint8_t *__restrict__ nnzc, uint8_t *__restrict__ luma, uint8_t *__restrict__ cb,
                      uint8_t *__restrict__ cr, int ls, int uvls)
 {
+    __shared__ ResSmem sm[4];
     const int lane = threadIdx.x & 31;
+    ResSmem &S = sm[threadIdx.x >> 5];
     size_t mb = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (mb >= n) return;
     const FFH264ResidualMB r = mbs[mb];
-    int16_t *c = coeffs + mb * coeff_stride;
+    int16_t *gc = coeffs + mb * coeff_stride;
     const uint8_t *nz = nnzc + mb * 120;
-    if (lane < 16) {
+    const bool do_luma = r.luma_mode <= 2, do_chroma = r.chroma != 0;
+    if (!do_luma && !do_chroma) return;
+    const bool vec = !(coeff_stride & 7) && !((uintptr_t)coeffs & 15);
+    const bool pix4 = !((ls | uvls) & 3) && !((r.luma_off | r.chroma_off) & 3) && !(((uintptr_t)luma | (uintptr_t)cb | (uintptr_t)cr) & 3);
+    // ---- stage ----
+    if (vec) { for (int i = lane; i < 96; i += 32) reinterpret_cast<uint4 *>(S.co)[i] = reinterpret_cast<const uint4 *>(gc)[i]; }
+    else     { for (int i = lane; i < 768; i += 32) S.co[i] = gc[i]; }
+    if (pix4) {
+        if (do_luma) for (int i = lane; i < 64; i += 32) reinterpret_cast<uint32_t *>(S.y)[i] = *reinterpret_cast<const uint32_t *>(luma + r.luma_off + (size_t)(i >> 2) * ls + 4 * (i & 3));
+        if (do_chroma) { const int p = lane >> 4, k = lane & 15; reinterpret_cast<uint32_t *>(S.c[p])[k] = *reinterpret_cast<const uint32_t *>((p ? cr : cb) + r.chroma_off + (size_t)(k >> 1) * uvls + 4 * (k & 1)); }
+    } else {
+        if (do_luma) for (int i = lane; i < 256; i += 32) S.y[i] = luma[r.luma_off + (size_t)(i >> 4) * ls + (i & 15)];
+        if (do_chroma) for (int i = lane; i < 128; i += 32) { const int p = i >> 6, k = i & 63; S.c[p][k] = (p ? cr : cb)[r.chroma_off + (size_t)(k >> 3) * uvls + (k & 7)]; }
+    }
+    __syncwarp();
+    // ---- transform in shared memory ----
+    if (lane < 16 && do_luma) {
         const int i = lane;
-        uint8_t *d = luma + r.luma_off + blk_x(i) + blk_y(i) * ls;
-        int16_t *b = c + 16 * i;
+        uint8_t *d = S.y + blk_x(i) + blk_y(i) * 16;
+        int16_t *b = S.co + 16 * i;
         const int nnz = nz[scan8_of(i)];
         if (r.luma_mode == 0) {                                   // h264_idct_add16, h264idct_template.c:174-183
-            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, ls, 4); else h264_idct4_add(d, b, ls); }
+            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, 16, 4); else h264_idct4_add(d, b, 16); }
         } else if (r.luma_mode == 1) {                            // h264_idct_add16intra, :185-191
-            if (nnz) h264_idct4_add(d, b, ls); else if (b[0]) h264_dc_add(d, b, ls, 4);
-        } else if (r.luma_mode == 2 && (i & 3) == 0) {            // h264_idct8_add4, :193-202
-            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, ls, 8); else h264_idct8_add(d, b, ls); }
+            if (nnz) h264_idct4_add(d, b, 16); else if (b[0]) h264_dc_add(d, b, 16, 4);
+        } else if ((i & 3) == 0) {                                // h264_idct8_add4, :193-202
+            if (nnz) { if (nnz == 1 && b[0]) h264_dc_add(d, b, 16, 8); else h264_idct8_add(d, b, 16); }
         }
-    } else if (lane < 24 && r.chroma) {                           // h264_idct_add8, :204-214
+    } else if (lane >= 16 && lane < 24 && do_chroma) {            // h264_idct_add8, :204-214
         const int plane = (lane - 16) >> 2, k = (lane - 16) & 3, i = 16 + 16 * plane + k;
-        uint8_t *d = (plane ? cr : cb) + r.chroma_off + blk_x(k) + blk_y(k) * uvls;
-        int16_t *b = c + 16 * i;
-        if (nz[scan8_of(i)]) h264_idct4_add(d, b, uvls); else if (b[0]) h264_dc_add(d, b, uvls, 4);
+        uint8_t *d = S.c[plane] + blk_x(k) + blk_y(k) * 8;
+        int16_t *b = S.co + 16 * i;
+        if (nz[scan8_of(i)]) h264_idct4_add(d, b, 8); else if (b[0]) h264_dc_add(d, b, 8, 4);
+    }
+    __syncwarp();
+    // ---- write back ----
+    if (vec) { for (int i = lane; i < 96; i += 32) reinterpret_cast<uint4 *>(gc)[i] = reinterpret_cast<const uint4 *>(S.co)[i]; }
+    else     { for (int i = lane; i < 768; i += 32) gc[i] = S.co[i]; }
+    if (pix4) {
+        if (do_luma) for (int i = lane; i < 64; i += 32) *reinterpret_cast<uint32_t *>(luma + r.luma_off + (size_t)(i >> 2) * ls + 4 * (i & 3)) = reinterpret_cast<const uint32_t *>(S.y)[i];
+        if (do_chroma) { const int p = lane >> 4, k = lane & 15; *reinterpret_cast<uint32_t *>((p ? cr : cb) + r.chroma_off + (size_t)(k >> 1) * uvls + 4 * (k & 1)) = reinterpret_cast<const uint32_t *>(S.c[p])[k]; }
+    } else {
+        if (do_luma) for (int i = lane; i < 256; i += 32) luma[r.luma_off + (size_t)(i >> 4) * ls + (i & 15)] = S.y[i];
+        if (do_chroma) for (int i = lane; i < 128; i += 32) { const int p = i >> 6, k = i & 63; (p ? cr : cb)[r.chroma_off + (size_t)(k >> 3) * uvls + (k & 7)] = S.c[p][k]; }
     }
 }
 

@@ -143,6 +143,19 @@ int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_
                                    const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
                                    int uvlinesize, void *stream);
 
+/* DC transforms + dequantisation, the step hl_decode_mb() runs before the residual of a macroblock:
+ * H264DSPContext.h264_luma_dc_dequant_idct (intra 16x16; libavcodec/h264_mb.c:714-719, h264idct_template.c:242-275) from
+ * the macroblock's 16 luma DC levels (sl->mb_luma_dc, luma_dc + 16 * i) into the DC positions of its coefficient arena, and
+ * h264_chroma_dc_dequant_idct (h264_mb_template.c:182-189, h264idct_template.c:304-324) in place on cb (coeffs + 256) and
+ * cr (+ 512).  A qmul of 0 skips that transform (the C code's non_zero_count_cache[...DC_BLOCK_INDEX] test).  Run it on the
+ * stream ahead of ff_h264_idct_add_mb_batch_cuda / ff_h264_intra_mb_batch_cuda. */
+typedef struct FFH264DCRecord {
+    uint32_t luma_qmul;        /* pps->dequant4_coeff[0][qscale][0], 0 = no luma DC block */
+    uint32_t chroma_qmul[2];   /* pps->dequant4_coeff[1 + (intra ? 0 : 3)][chroma_qp[0]][0], [2 + ...][chroma_qp[1]][0]; 0 = none */
+} FFH264DCRecord;
+int ff_h264_dc_dequant_batch_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
+                                  void *stream);
+
 /* Intra reconstruction: for every intra macroblock of a picture, H264PredContext prediction interleaved with the
  * residual exactly as hl_decode_mb() orders them (libavcodec/h264_mb.c:607-731 hl_decode_mb_predict_luma,
  * h264_mb_template.c:158-197 chroma): intra 4x4 -> per block pred4x4 then idct_add / idct_dc_add; intra 8x8 -> pred8x8l

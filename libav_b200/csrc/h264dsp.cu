@@ -82,6 +82,27 @@ h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t
     }
 }
 
+// DC transforms + dequantisation ahead of the residual passes: what hl_decode_mb() does before the IDCTs
+// (h264_mb.c:714-719 h264_luma_dc_dequant_idct for intra 16x16, h264_mb_template.c:182-189 chroma_dc_dequant_idct).
+// Thread per macroblock; only the 16 + 8 DC positions of its coefficient arena are touched.
+__global__ void __launch_bounds__(128)
+h264_dc_dequant_kernel(const FFH264DCRecord *__restrict__ recs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
+                       const int16_t *__restrict__ luma_dc)
+{
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const FFH264DCRecord r = recs[m];
+    int16_t *mb = coeffs + m * coeff_stride;
+    if (r.luma_qmul) {
+        int16_t in[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) in[i] = luma_dc[16 * m + i];
+        h264_luma_dc_dequant(mb, in, (int)r.luma_qmul);
+    }
+    if (r.chroma_qmul[0]) h264_chroma_dc_dequant(mb + 256, (int)r.chroma_qmul[0]);
+    if (r.chroma_qmul[1]) h264_chroma_dc_dequant(mb + 512, (int)r.chroma_qmul[1]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One warp per partition.  The (w+5) x (h+5) luma patch and the two (w/2+1) x (h/2+1) chroma patches are fetched once
 // (clamped) into the warp's shared-memory slice; the unrounded horizontal 6-tap plane `tmp` (int16, rows -2..h+2) is
@@ -481,6 +502,13 @@ int ff_h264_mc_batch_cuda(const FFH264MCRecord *recs, size_t n, const FFH264RefP
 { return launch_h264_mc(recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream); }
 int ff_h264_weight_batch_cuda(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, void *stream)
 { return launch_h264_weight(recs, n, plane, src, stride, (cudaStream_t)stream); }
+int ff_h264_dc_dequant_batch_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
+                                  void *stream)
+{
+    if (!n) return 0;
+    h264_dc_dequant_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(recs, n, coeffs, coeff_stride, luma_dc);
+    return check_launch("ff_h264_dc_dequant_batch_cuda");
+}
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress, void *stream)
 { return launch_h264_deblock(mbs, mb_w, mb_h, 1, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }

@@ -150,3 +150,30 @@ def test_mc_batch_of_stacked_pictures(gpu, checker):
     assert np.array_equal(dy.download(np.uint8, Y.shape), np.concatenate([w[0] for w in wants]))
     assert np.array_equal(dcb.download(np.uint8, CB.shape), np.concatenate([w[1] for w in wants]))
     assert np.array_equal(dcr.download(np.uint8, CR.shape), np.concatenate([w[2] for w in wants]))
+
+
+def test_dc_dequant_batch(gpu, checker):
+    """luma / chroma DC transforms + dequantisation over a coefficient arena, against the oracle's two slot functions"""
+    from libav_b200 import device
+    from oracle.loader import ptr
+    r = np.random.RandomState(77)
+    n = 5000
+    coeffs = r.randint(-2000, 2001, (n, 768)).astype(np.int16)
+    luma_dc = r.randint(-2000, 2001, (n, 16)).astype(np.int16)
+    rec = np.zeros(n, np.dtype([("luma_qmul", "<u4"), ("chroma_qmul", "<u4", (2,))]))
+    rec["luma_qmul"] = r.randint(0, 4, n) * r.randint(16, 4000, n)          # a quarter of the macroblocks have no luma DC block
+    rec["chroma_qmul"] = (r.randint(0, 3, (n, 2)) > 0) * r.randint(16, 4000, (n, 2))
+    want = coeffs.copy()
+    for m in range(n):
+        if rec["luma_qmul"][m]:
+            checker.h264_luma_dc_dequant_idct(ptr(want[m]), ptr(luma_dc[m].copy()), int(rec["luma_qmul"][m]))
+        for p in range(2):
+            if rec["chroma_qmul"][m, p]:
+                blk = np.ascontiguousarray(want[m, 256 * (p + 1):256 * (p + 2)])
+                checker.h264_chroma_dc_dequant_idct(ptr(blk), int(rec["chroma_qmul"][m, p]))
+                want[m, 256 * (p + 1):256 * (p + 2)] = blk
+    d_c, d_l, d_r = _dev(coeffs), _dev(luma_dc), _dev(rec)
+    gpu.check(gpu.lib.ff_h264_dc_dequant_batch_cuda(d_r.ptr, n, d_c.ptr, 768, d_l.ptr, None))
+    device.sync()
+    got = d_c.download(np.int16, coeffs.shape)
+    assert np.array_equal(got, want), np.argwhere((got != want).any(axis=1))[:4].ravel().tolist()

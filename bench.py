@@ -215,15 +215,18 @@ def make_h264_workload(torch, L, stream, rank):
     refilled on a side stream (the role the entropy decoder plays), double-buffered against the compute stream."""
     from libav_b200 import synth
     lib = L.lib
-    mb_w, mb_h, P = 120, 68, H264_PICTURES
+    G = max(1, int(os.environ.get("AVB200_H264_GROUPS", "2")))         # groups of H264_PICTURES stacked pictures per step
+    mb_w, mb_h, P = 120, 68, H264_PICTURES * G
     W, H = 16 * mb_w, 16 * mb_h
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
     refs = [synth.h264_picture(mb_w, mb_h, seed=11 + rank), synth.h264_picture(mb_w, mb_h, seed=12 + rank)]
     d_refs = [[t(np.concatenate([p] * P)) for p in r] for r in refs]              # reference pictures, stacked like the output
     d_planes = torch.tensor([[p.data_ptr() for p in r] for r in d_refs], dtype=torch.int64).cuda()
+    d_planes_g = [torch.tensor([[r[0].data_ptr() + gi * H264_PICTURES * W * H, r[1].data_ptr() + gi * H264_PICTURES * W * H // 4,
+                                 r[2].data_ptr() + gi * H264_PICTURES * W * H // 4] for r in d_refs], dtype=torch.int64).cuda() for gi in range(G)]
     mc1 = synth.h264_mc_work(mb_w, mb_h, seed=5)
     mcs = []
-    for k in range(P):
+    for k in range(H264_PICTURES):                         # FFH264MCRecord.y is int16: MC runs per group of 30 stacked pictures
         m = mc1.copy(); m["y"] = m["y"] + k * H; mcs.append(m)
     mc = np.concatenate(mcs)
     res1, coeffs, nnzc = synth.h264_residual_work(mb_w, mb_h, seed=6)
@@ -249,8 +252,10 @@ def make_h264_workload(torch, L, stream, rank):
     def run(i):
         b = i & 1
         main.wait_event(refilled[b])
-        L.check(lib.ff_h264_mc_batch_cuda(d_mc.data_ptr(), mc.shape[0], d_planes.data_ptr(), d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(),
-                                          W, W // 2, W, H, stream), "mc")
+        for gi in range(G):
+            yo, co = gi * H264_PICTURES * W * H, gi * H264_PICTURES * W * H // 4
+            L.check(lib.ff_h264_mc_batch_cuda(d_mc.data_ptr(), mc.shape[0], d_planes_g[gi].data_ptr(), d_y.data_ptr() + yo, d_cb.data_ptr() + co,
+                                              d_cr.data_ptr() + co, W, W // 2, W, H, stream), "mc")
         L.check(lib.ff_h264_idct_add_mb_batch_cuda(d_res.data_ptr(), res.shape[0], d_coef[b].data_ptr(), 768, d_nnz.data_ptr(), d_y.data_ptr(),
                                                    d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2, stream), "residual")
         consumed[b].record(main)
@@ -265,9 +270,9 @@ def make_h264_workload(torch, L, stream, rank):
     return {
         "name": "H.264 1080p DSP path: qpel/chroma MC (%d partitions/picture) + idct_add16/add8 + deblock wavefront, 64 synthetic slices per picture, %d pictures per step" % (mc1.shape[0], P),
         "run": run, "run_e2e": None, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
-        "launches_per_step": 4, "kernel": "h264_deblock_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 2 + 2 * G, "kernel": "h264_deblock_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
         "l2": "%d pictures per step: %d MB of pixels + %d MB of coefficients, larger than the 126 MB L2" % (P, P * W * H * 3 // 2 >> 20, d_coef0.numel() >> 20),
-        "keep": (d_refs, d_planes, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
+        "keep": (d_refs, d_planes, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
     }
 
 

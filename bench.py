@@ -554,20 +554,22 @@ def main():
         if rank != 0:
             return 0
         steps = min(steps, 20)
-        if args.workload == "h264":
-            print(json.dumps({"impl": "reference", "unavailable": "no batched CPU driver for the H.264 DSP composite yet (per-slot parity is in tests/)"}))
+        if args.workload not in ("idct_put", "sws4k", "me"):
+            print(json.dumps({"impl": "reference", "unavailable": "no batched CPU driver for workload %s (its per-function parity against the reference is in tests/)" % args.workload}))
             return 0
         fn = {"idct_put": cpu_idct, "sws4k": cpu_sws, "me": cpu_me}[args.workload]
         fn(ncores, reps=1)                                    # warm-up pass (page in, spin up threads)
         r = fn(ncores, reps=steps)
         mpix = r["pixels"] / r["sec_per_step"] / 1e6
-        name = {"idct_put": "batched simple_idct_put 8x8, 2^20 dense int16 blocks -> 8192x8192 u8 frame",
-                "sws4k": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact",
-                "me": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16"}[args.workload]
+        # the same workload names as the GPU arm's config.workload (the driver pairs the two lines by them)
+        name = {"idct_put": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
+                "sws4k": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % SWS_FRAMES,
+                "me": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16, whole frame per GPU"}[args.workload]
         print(json.dumps({
             "impl": "reference", "metric": "Mpixels/s", "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": {"workload": name, "host_threads": ncores},
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": {"workload": name, "per_gpu_batch": "one batch of the same shape on the host cores (a bounded sample: %s)" % r["sample"],
+                                                                     "host_threads": ncores, "idct_algo": "FF_IDCT_SIMPLE", "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
             "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,

@@ -40,3 +40,14 @@ def test_mdct(orc, refo, nbits, scale):
         getattr(orc, fn)(nbits, scale, ptr(a), ptr(x[:nin].copy()))
         getattr(refo, fn)(nbits, scale, ptr(b), ptr(x[:nin].copy()))
         assert rel_err(a, b) < TOL * max(1, nbits / 4), (fn, nbits, scale, rel_err(a, b))
+
+
+def test_fate_fft_targets_pass_on_the_compiled_reference():
+    """tests/golden/fate_fft.txt is written by oracle/refbuild/run_fft_selftest.sh: the reference's own
+    libavcodec/tests/fft program, linked against oracle/_ref, run for fate-{fft,ifft,mdct,imdct}-{4..12}; it applies
+    FATE's 1e-3 threshold itself.  The oracle the GPU kernels are held to (1e-6 against that same library) sits
+    three orders of magnitude inside it."""
+    import os
+    lines = [l.split() for l in open(os.path.join(os.path.dirname(__file__), "golden", "fate_fft.txt")) if not l.startswith("#")]
+    assert len(lines) == 36 and all(rc == "0" for _, rc in lines)
+    assert {n for n, _ in lines} == {"fate-%s-%d" % (k, n) for k in ("fft", "ifft", "mdct", "imdct") for n in range(4, 13)}

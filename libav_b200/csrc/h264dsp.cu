@@ -347,21 +347,28 @@ __device__ __forceinline__ void deblock_row(const FFH264DeblockMB *__restrict__ 
     const bool row_exists = lane < NR && lrow * MBW + tr - TOP >= 0;
     uint8_t *const grow = plane + (size_t)(row * MBW + tr - TOP) * pitch_g;             // same row in the picture
 
+    bool prev_top = false;                                  // did the previous macroblock filter its top edge?
     for (int x = 0; x < mb_w; x++) {
-        if (has_above) {
+        // the parameters do not depend on other rows: fetch them first, they say whether this macroblock touches the row above
+        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
+            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
+        __syncwarp();
+        // Only the top (horizontal, edge 0) filter reads or writes pixels of the row above.  When it is off -- first row, or a
+        // slice boundary with disable_deblocking_filter_idc 2 -- this macroblock neither waits for that row nor stores into it.
+        const bool top = has_above && (CHROMA ? ((P.calpha[0][1][0] && P.cbeta[0][1][0]) || (P.calpha[1][1][0] && P.cbeta[1][1][0]))
+                                              : (P.alpha[1][0] && P.beta[1][0]));
+        if (top) {
             if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
             __syncwarp();
         }
         if (lane < NR) {
             if (x > 0) *reinterpret_cast<uint32_t *>(trow) = *reinterpret_cast<const uint32_t *>(trow + MBW);   // left context
-            if (row_exists) {
+            if (row_exists && (top || tr >= TOP)) {
                 const uint8_t *g = grow + x * MBW;
 #pragma unroll
                 for (int k = 0; k < MBW / 4; k++) *reinterpret_cast<uint32_t *>(trow + 4 + 4 * k) = ld_cg32(g + 4 * k);
             }
         }
-        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
-            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
         __syncwarp();
 
         if (lane < 16) {
@@ -427,11 +434,15 @@ __device__ __forceinline__ void deblock_row(const FFH264DeblockMB *__restrict__ 
         if (x > 0) { __threadfence(); if (lane == 0) prog[row] = x; }
         if (row_exists && tr >= 1) {                            // tile row 0 is read-only context
             uint8_t *g = grow + x * MBW;
-            if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(trow);
+            const bool own = tr >= TOP;                         // rows above the macroblock row are stored only by whoever filtered them
+            if (x > 0 && (own || prev_top)) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(trow);
+            if (own || top) {
 #pragma unroll
-            for (int k = 0; k < MBW / 4 - 1; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(trow + 4 + 4 * k);
-            if (x == mb_w - 1) *reinterpret_cast<uint32_t *>(g + MBW - 4) = *reinterpret_cast<const uint32_t *>(trow + MBW);
+                for (int k = 0; k < MBW / 4 - 1; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(trow + 4 + 4 * k);
+                if (x == mb_w - 1) *reinterpret_cast<uint32_t *>(g + MBW - 4) = *reinterpret_cast<const uint32_t *>(trow + MBW);
+            }
         }
+        prev_top = top;
         __syncwarp();
     }
     __threadfence();

@@ -102,29 +102,34 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
     for (int x = 0; x < mb_w; x++) {
         const int cur = x & 1;
         if (x + 1 < mb_w) { fetch(x + 1, cur ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-        if (prow > 0) {
-            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
-        }
         __syncwarp();
         const FFH264IntraMB &M = Ms[cur];
         const uint8_t *nnzc = nz[cur];
         int16_t *mb = co[cur];
         const size_t m = (size_t)row * mb_w + x;
-        // the previous macroblock's last column becomes this one's left column (tile column 3), corner included
+        // only an intra macroblock reads the row above; the others neither wait for it nor look at it
+        const bool needs_above = prow > 0 && M.kind != 0;
+        if (needs_above) {
+            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
+            __syncwarp();
+        }
+        // the previous macroblock's last column becomes this one's left column (tile column 3)
         if (x > 0) {
             if (lane < 17) Y[lane * LP + 3] = Y[lane * LP + 19];
             if (lane < 18) { const int p = lane / 9, r = lane % 9; C[p][r * CP + 3] = C[p][r * CP + 11]; }
         }
         __syncwarp();
-        // row above: samples x = 0 .. 23 (the last 8 belong to the macroblock up-right)
-        if (prow > 0) {
+        // row above: samples x = -1 .. 23 (the corner, this macroblock's 16, and 8 of the macroblock up-right)
+        if (needs_above) {
             const uint8_t *g = luma + (size_t)(row * 16 - 1) * ls + x * 16;
             if (lane < 6 && (lane < 4 || x + 1 < mb_w)) *reinterpret_cast<uint32_t *>(&Y[4 + 4 * lane]) = __ldcg(reinterpret_cast<const uint32_t *>(g) + lane);
             if (lane >= 8 && lane < 12) {
                 const int p = (lane >> 1) & 1, q = lane & 1;
                 *reinterpret_cast<uint32_t *>(&C[p][4 + 4 * q]) = __ldcg(reinterpret_cast<const uint32_t *>(cplane[p] + (size_t)(row * 8 - 1) * uvls + x * 8) + q);
             }
-            if (x == 0 && lane == 31) { Y[3] = 0; C[0][3] = C[1][3] = 0; }
+            if (lane == 31) Y[3] = x > 0 ? ld_cg8(g - 1) : 0;
+            if (lane == 30) C[0][3] = x > 0 ? ld_cg8(cb + (size_t)(row * 8 - 1) * uvls + x * 8 - 1) : 0;
+            if (lane == 29) C[1][3] = x > 0 ? ld_cg8(cr + (size_t)(row * 8 - 1) * uvls + x * 8 - 1) : 0;
         }
         const int kind = M.kind;
         if (kind == 0) {

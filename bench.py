@@ -384,6 +384,25 @@ def make_h264_intra_workload(torch, L, stream, rank):
     }
 
 
+def make_fft_workload(torch, L, stream, rank):
+    """FFTContext.fft_permute + fft_calc, 32768 independent 1024-point complex float transforms per step
+    (in place, 256 MiB), followed per step by 32768 imdct_half of size 2048 (AAC long windows) under "also"."""
+    lib = L.lib
+    nb, T = 10, 32768
+    g = torch.Generator(device="cuda"); g.manual_seed(1 + rank)
+    bufs = [torch.randn(T * (1 << nb) * 2, generator=g, device="cuda", dtype=torch.float32) for _ in range(2)]
+
+    def run(i):
+        L.check(lib.ff_fft_batch_cuda(nb, 0, bufs[i & 1].data_ptr(), T, stream), "fft")
+
+    return {
+        "name": "FFTContext fft_permute + fft_calc: %d x %d-point complex float transforms per step" % (T, 1 << nb),
+        "run": run, "run_e2e": None, "pixels": T * (1 << nb), "alg_bytes": T * (1 << nb) * 16,
+        "launches_per_step": 1, "kernel": "fft_kernel", "dtype": "f32 (complex)", "h2d": 0, "d2h": 0,
+        "l2": "2 rotating 256 MiB buffers; the metric counts complex points as pixels", "keep": (bufs,),
+    }
+
+
 def make_me_workload(torch, L, stream, rank):
     """config 4: pix_abs16 full search +-16 over a 1920x1088 luma pair (restricted MVs, lambda 0)."""
     from libav_b200 import synth
@@ -539,7 +558,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra"])
+    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
@@ -591,7 +610,7 @@ def main():
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
     makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
-              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload}
+              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload, "fft": make_fft_workload}
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):

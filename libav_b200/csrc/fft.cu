@@ -20,18 +20,41 @@ namespace avb {
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place radix-2 DIT on bit-reversed data in shared memory; tw[k] = exp(sign * 2 pi i k / n), k < n / 2
+// in-place DIT on bit-reversed data in shared memory; tw[k] = exp(sign * 2 pi i k / n), k < n / 2.
+// Two radix-2 stages are fused per pass (a thread carries its four points through both in registers: the same
+// butterflies in the same order as stage-by-stage radix 2, so the result is bit-identical to it), which halves the
+// shared-memory round trips and barriers; an odd log2(n) starts with one plain radix-2 stage.
 __device__ __forceinline__ void fft_smem(float2 *s, int nbits, const float2 *__restrict__ tw)
 {
     const int n = 1 << nbits;
-    for (int st = 0; st < nbits; st++) {
-        const int half = 1 << st, tstep = n >> (st + 1);
+    int st = 0;
+    if (nbits & 1) {
         __syncthreads();
-        for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {
-            const int k = b & (half - 1), i = ((b >> st) << (st + 1)) + k;
-            const float2 w = __ldg(&tw[k * tstep]), a = s[i], t = cmul(s[i + half], w);
-            s[i] = make_float2(a.x + t.x, a.y + t.y);
-            s[i + half] = make_float2(a.x - t.x, a.y - t.y);
+        for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {        // stage 0: half = 1, twiddle 1
+            const float2 a = s[2 * b], t = s[2 * b + 1];
+            s[2 * b] = make_float2(a.x + t.x, a.y + t.y);
+            s[2 * b + 1] = make_float2(a.x - t.x, a.y - t.y);
+        }
+        st = 1;
+    }
+    for (; st < nbits; st += 2) {
+        const int half = 1 << st, t1 = n >> (st + 1), t2 = n >> (st + 2);
+        __syncthreads();
+        for (int b = threadIdx.x; b < n / 4; b += blockDim.x) {
+            const int k = b & (half - 1), i0 = ((b >> st) << (st + 2)) + k;
+            const float2 w1 = __ldg(&tw[k * t1]), w2 = __ldg(&tw[k * t2]), w3 = __ldg(&tw[(k + half) * t2]);
+            float2 x0 = s[i0], x1 = s[i0 + half], x2 = s[i0 + 2 * half], x3 = s[i0 + 3 * half];
+            // stage st: (x0, x1) and (x2, x3), both with w1
+            float2 t = cmul(x1, w1);
+            x1 = make_float2(x0.x - t.x, x0.y - t.y); x0 = make_float2(x0.x + t.x, x0.y + t.y);
+            t = cmul(x3, w1);
+            x3 = make_float2(x2.x - t.x, x2.y - t.y); x2 = make_float2(x2.x + t.x, x2.y + t.y);
+            // stage st + 1: (x0, x2) with w2, (x1, x3) with w3
+            t = cmul(x2, w2);
+            x2 = make_float2(x0.x - t.x, x0.y - t.y); x0 = make_float2(x0.x + t.x, x0.y + t.y);
+            t = cmul(x3, w3);
+            x3 = make_float2(x1.x - t.x, x1.y - t.y); x1 = make_float2(x1.x + t.x, x1.y + t.y);
+            s[i0] = x0; s[i0 + half] = x1; s[i0 + 2 * half] = x2; s[i0 + 3 * half] = x3;
         }
     }
     __syncthreads();

@@ -65,6 +65,7 @@ struct FusedArgs {
     const uint8_t *y, *u, *v; uint8_t *dst;
     int yStride, uStride, vStride, dstStride;
     size_t yFrame, uFrame, vFrame, dstFrame;      // byte distance between consecutive frames of a batch
+    int rp0 = 0, rp1 = 0x7fffffff;                 // row-pair range of this launch (the dp4a kernel; bands of the host pipeline)
 };
 
 // one output row of 8 pixels from 8 luma bytes and 4 already filtered (U,V) pairs -> 6 packed words
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(128)
 sws_fused_rgb24_v3_kernel(SwsDev p, FusedArgs a, const SwsPairTaps *__restrict__ taps)
 {
     const int gx = blockIdx.x * 32 + threadIdx.x;            // group of 16 pixels
-    const int rp = blockIdx.y * 4 + threadIdx.y;             // row pair
-    if (gx * 16 >= p.dstW || rp * 2 >= p.dstH) return;
+    const int rp = a.rp0 + blockIdx.y * 4 + threadIdx.y;     // row pair
+    if (gx * 16 >= p.dstW || rp >= a.rp1) return;
     const size_t f = blockIdx.z;
     const int y0 = rp * 2;
     const uint8_t *Yp = a.y + f * a.yFrame + (size_t)y0 * a.yStride + gx * 16;
@@ -1090,6 +1091,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (p.dstH / 2 + 3) / 4, nframes);
             if (tuning("sws_fused_variant") != 2) {             // default: the dp4a variant (71.9 % of HBM peak vs 66.1 %)
                 const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
+                a.rp0 = 0; a.rp1 = p.dstH / 2;
                 if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, st>>>(p, a, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, st>>>(p, a, pt);
                 return check_launch("sws_scale:fused");
             }
@@ -1242,6 +1244,40 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const uint8_t *ds[3] = { c->d_src, c->d_src + yB, c->d_src + yB + cB };
     uint8_t *dd[3] = { c->d_dst, c->d_dst + dB, c->d_dst + dB + dcB };
     const int dsS[3] = { yP, cP, cP }, ddS[3] = { dP, dcP, dcP };
+    // Same-size rgb (the dp4a fused kernel): the frame goes through in bands of rows on three streams, so the upload of band
+    // k + 1, the kernel of band k and the download of band k - 1 overlap -- the call is PCIe bound and PCIe is full duplex.
+    // A band re-uploads the few chroma lines it shares with its neighbours (identical bytes), so bands need no cross-stream order.
+    if (c->fused && c->fast_ok && !nv && rgb && !odd && tuning("sws_fused_variant") != 1 && tuning("sws_fused_variant") != 2 &&
+        tuning("sws_host_bands") != 1 && g.dstH >= 64 && !((uintptr_t)c->dev.vChrF & 15)) {
+        const SwsDev &p = c->dev;
+        const int pairs = g.dstH / 2, nb = tuning("sws_host_bands") > 1 ? tuning("sws_host_bands") : 3, per = ((pairs + nb - 1) / nb + 3) & ~3;
+        int k = 0;
+        for (int rp0 = 0; rp0 < pairs; rp0 += per, k = (k + 1) % 3) {
+            const int rp1 = rp0 + per < pairs ? rp0 + per : pairs, y0 = 2 * rp0, y1 = 2 * rp1;
+            cudaStream_t sb = st[k];
+            int clo = c->vChr.pos[y0] > -3 ? c->vChr.pos[y0] : -3, chi = (c->vChr.pos[y1 - 1] > -3 ? c->vChr.pos[y1 - 1] : -3) + 4;
+            clo = clo < 0 ? 0 : clo; chi = chi > g.chrSrcH - 1 ? g.chrSrcH - 1 : chi;
+            if (cudaMemcpy2DAsync((void *)(ds[0] + (size_t)y0 * yP), yP, srcSlice[0] + (size_t)y0 * srcStride[0], srcStride[0], g.srcW, y1 - y0, cudaMemcpyHostToDevice, sb) != cudaSuccess ||
+                cudaMemcpy2DAsync((void *)(ds[1] + (size_t)clo * cP), cP, srcSlice[1] + (size_t)clo * srcStride[1], srcStride[1], g.chrSrcW, chi - clo + 1, cudaMemcpyHostToDevice, sb) != cudaSuccess ||
+                cudaMemcpy2DAsync((void *)(ds[2] + (size_t)clo * cP), cP, srcSlice[2] + (size_t)clo * srcStride[2], srcStride[2], g.chrSrcW, chi - clo + 1, cudaMemcpyHostToDevice, sb) != cudaSuccess) {
+                set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
+            }
+            FusedArgs a;
+            a.y = ds[0]; a.u = ds[1]; a.v = ds[2]; a.dst = dd[0];
+            a.yStride = yP; a.uStride = cP; a.vStride = cP; a.dstStride = dP;
+            a.yFrame = a.uFrame = a.vFrame = a.dstFrame = 0;
+            a.rp0 = rp0; a.rp1 = rp1;
+            const dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (rp1 - rp0 + 3) / 4, 1);
+            const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
+            if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, sb>>>(p, a, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, sb>>>(p, a, pt);
+            if (check_launch("sws_scale_cuda:band")) return 0;
+            if (cudaMemcpy2DAsync(dst[0] + (size_t)y0 * dstStride[0], dstStride[0], dd[0] + (size_t)y0 * dP, dP, (size_t)g.dstW * 3, y1 - y0, cudaMemcpyDeviceToHost, sb) != cudaSuccess) {
+                set_error("sws_scale_cuda:d2h", cudaGetLastError()); return 0;
+            }
+        }
+        for (int q = 0; q < 3; q++) if (cudaStreamSynchronize(st[q]) != cudaSuccess) { set_error("sws_scale_cuda:sync", cudaGetLastError()); return 0; }
+        return g.dstH;
+    }
     if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {

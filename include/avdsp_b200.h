@@ -278,8 +278,11 @@ int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info /* host struct */,
  *        1 sad[sidx]   2 sse[sidx] (sidx 2 = 4 wide)   3 hadamard8_diff[sidx]   4 vsad[0]   5 vsse[0]
  *        6 nsse[sidx] (weight 8: the NULL-context default, me_cmp.c:331)   7 hadamard8_diff[4 + sidx] (intra)
  *        8 vsad[4 + sidx] (intra)   9 vsse[4 + sidx] (intra)   10 sum_abs_dctelem (cur_off in bytes into int16 blocks)
- * The encoder-state metrics (dct_sad, quant_psnr, bit, rd, dct_max, dct264_sad: me_cmp.c:538-782) need a live
- * MpegEncContext and are not taken over. */
+ *       11 dct_sad[sidx]   12 dct_max[sidx]   13 dct264_sad[sidx]   (me_cmp.c:538-621; for 11 / 12 `dxy` names the
+ *          FDCTDSPContext.fdct the encoder context holds: 0 = ff_jpeg_fdct_islow_8, 2 = ff_fdct_ifast)
+ * These three only dereference the MpegEncContext's DSP tables, so the batch call covers them; their table slots are
+ * left to the C code (a slot cannot know which fdct the caller's context selected).  quant_psnr, bit and rd
+ * (me_cmp.c:623-782) need the quantiser and VLC length tables of a live encoder and are not taken over. */
 typedef struct FFMECmpRecord { uint32_t cur_off, ref_off; } FFMECmpRecord;
 int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
                          const FFMECmpRecord *recs, size_t n, int32_t *out, void *stream);

@@ -472,6 +472,65 @@ mpeg4_qpel_kernel(const FFQpelRecord *__restrict__ recs, size_t n, uint8_t *__re
     else        qpel_record<16>(sm[threadIdx.x >> 5], r, dst, src, stride, lane);
 }
 
+// Encoder-state metrics that only need the DSP tables (me_cmp.c:538-621): kind 11 dct_sad, 12 dct_max (diff_pixels ->
+// FDCTDSPContext.fdct -> sum / max of |coefficient|; dxy selects the transform: 0 islow, 2 ifast), 13 dct264_sad (diff ->
+// H.264 8x8 forward transform rows then columns -> sum of |result|).  Warp per record, one lane per 8x8 quadrant.
+__device__ __forceinline__ void dct264_1d(const int (&v)[8], int (&o)[8])
+{
+    const int s07 = v[0] + v[7], s16 = v[1] + v[6], s25 = v[2] + v[5], s34 = v[3] + v[4];
+    const int a0 = s07 + s34, a1 = s16 + s25, a2 = s07 - s34, a3 = s16 - s25;
+    const int d07 = v[0] - v[7], d16 = v[1] - v[6], d25 = v[2] - v[5], d34 = v[3] - v[4];
+    const int a4 = d16 + d25 + (d07 + (d07 >> 1)), a5 = d07 - d34 - (d25 + (d25 >> 1));
+    const int a6 = d07 + d34 - (d16 + (d16 >> 1)), a7 = d16 - d25 + (d34 + (d34 >> 1));
+    o[0] = a0 + a1; o[1] = a4 + (a7 >> 2); o[2] = a2 + (a3 >> 1); o[3] = a5 + (a6 >> 2);
+    o[4] = a0 - a1; o[5] = a6 - (a5 >> 2); o[6] = (a2 >> 1) - a3; o[7] = (a4 >> 2) - a7;
+}
+
+template <int T>   // T 0 islow, 2 ifast, 4 h264
+__device__ __forceinline__ int dct_metric_block(const uint8_t *a, const uint8_t *b, ptrdiff_t st, bool want_max)
+{
+    int m[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int in[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) in[k] = a[r * st + k] - b[r * st + k];
+        if (T == 0) islow_1d<4, 9>(in, o); else if (T == 2) ifast_1d(in, o); else dct264_1d(in, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[r][k] = (int)(int16_t)o[k];
+    }
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int in[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) in[k] = m[k][c];
+        if (T == 0) islow_1d<-4, 17>(in, o); else if (T == 2) ifast_1d(in, o); else dct264_1d(in, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int v = T == 4 ? o[k] : (int)(int16_t)o[k]; s = want_max ? max(s, iabs_m(v)) : s + iabs_m(v); }
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(128)
+me_cmp_dct_kernel(int kind, int sidx, int fdct_sel, const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, ptrdiff_t st, int h,
+                  const FFMECmpRecord *__restrict__ recs, size_t n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    size_t ri = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const int nblk = sidx == 0 ? (h == 16 ? 4 : 2) : 1;
+    int s = 0;
+    if (lane < nblk) {
+        const uint8_t *a = cur + recs[ri].cur_off + (lane & 1) * 8 + (lane >> 1) * 8 * st, *b = ref + recs[ri].ref_off + (lane & 1) * 8 + (lane >> 1) * 8 * st;
+        if (kind == 13) s = dct_metric_block<4>(a, b, st, false);
+        else if (fdct_sel == 2) s = dct_metric_block<2>(a, b, st, kind == 12);
+        else s = dct_metric_block<0>(a, b, st, kind == 12);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[ri] = s;
+}
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 }  // namespace avb
@@ -485,9 +544,10 @@ int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const 
     if (!n) return 0;
     const bool ok = (kind == 0 && sidx <= 1 && dxy >= 0 && dxy <= 3) || (kind == 1 && sidx <= 1) || (kind == 2 && sidx <= 2) ||
                     ((kind == 3 || kind == 7) && sidx <= 1) || ((kind == 4 || kind == 5) && sidx == 0) || (kind == 6 && sidx <= 1) ||
-                    ((kind == 8 || kind == 9) && sidx <= 1) || kind == 10;
+                    ((kind == 8 || kind == 9) && sidx <= 1) || kind == 10 || (kind >= 11 && kind <= 13 && sidx <= 1 && (h == 8 || (h == 16 && sidx == 0)));
     if (!ok || sidx < 0) { set_error_msg("me_cmp_batch", "this (kind, size) slot is NULL in the reference table as well"); return -1; }
-    me_cmp_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(kind, sidx, dxy, cur, ref, stride, h, recs, n, out);
+    if (kind >= 11) me_cmp_dct_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(kind, sidx, dxy, cur, ref, stride, h, recs, n, out);
+    else me_cmp_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(kind, sidx, dxy, cur, ref, stride, h, recs, n, out);
     return check_launch("me_cmp_batch");
 }
 

@@ -182,6 +182,40 @@ int orc_me_cmp(int kind, int sidx, int dxy, const uint8_t *a, const uint8_t *b, 
         return s + iabs(s2) * 8;
     }
     case 10: { const int16_t *c = (const int16_t *)a; for (int i = 0; i < 64; i++) s += iabs(c[i]); return s; }
+    case 11: case 12: case 13: {
+        /* encoder-state metrics that only need the DSP tables: dct_sad8x8_c / dct_max8x8_c (me_cmp.c:538-548, :606-621)
+         * = diff_pixels -> fdsp.fdct (dxy: 0 islow, 2 ifast) -> sum / max of |coefficient|; dct264_sad8x8_c (:551-603) =
+         * diff -> the H.264 8x8 forward transform, rows then columns, sum of |result|.  16-wide = sum over the 8x8
+         * quadrants the wrapper visits (WRAPPER8_16_SQ, :859-874: two for h == 8, four for h == 16). */
+        if (sidx > 1) return -1;
+        const int nblk = sidx == 0 ? (h == 16 ? 4 : 2) : 1;
+        for (int q = 0; q < nblk; q++) {
+            const uint8_t *pa = a + (q & 1) * 8 + (q >> 1) * 8 * st, *pb = b + (q & 1) * 8 + (q >> 1) * 8 * st;
+            int16_t t[64];
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) t[8 * y + x] = (int16_t)(pa[y * st + x] - pb[y * st + x]);
+            if (kind != 13) {
+                orc_fdct(dxy == 2 ? 2 : 0, t);
+                int m = 0;
+                for (int i = 0; i < 64; i++) { if (kind == 11) s += iabs(t[i]); else if (iabs(t[i]) > m) m = iabs(t[i]); }
+                s += m;
+            } else {
+                for (int pass = 0; pass < 2; pass++)
+                    for (int i = 0; i < 8; i++) {
+                        int v[8], o[8];
+                        for (int k = 0; k < 8; k++) v[k] = pass ? t[8 * k + i] : t[8 * i + k];
+                        const int s07 = v[0] + v[7], s16 = v[1] + v[6], s25 = v[2] + v[5], s34 = v[3] + v[4];
+                        const int a0 = s07 + s34, a1 = s16 + s25, a2 = s07 - s34, a3 = s16 - s25;
+                        const int d07 = v[0] - v[7], d16 = v[1] - v[6], d25 = v[2] - v[5], d34 = v[3] - v[4];
+                        const int a4 = d16 + d25 + (d07 + (d07 >> 1)), a5 = d07 - d34 - (d25 + (d25 >> 1));
+                        const int a6 = d07 + d34 - (d16 + (d16 >> 1)), a7 = d16 - d25 + (d34 + (d34 >> 1));
+                        o[0] = a0 + a1; o[1] = a4 + (a7 >> 2); o[2] = a2 + (a3 >> 1); o[3] = a5 + (a6 >> 2);
+                        o[4] = a0 - a1; o[5] = a6 - (a5 >> 2); o[6] = (a2 >> 1) - a3; o[7] = (a4 >> 2) - a7;
+                        for (int k = 0; k < 8; k++) { if (pass) s += iabs(o[k]); else t[8 * i + k] = (int16_t)o[k]; }
+                    }
+            }
+        }
+        return s;
+    }
     }
     return -1;
 }

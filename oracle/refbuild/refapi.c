@@ -206,6 +206,7 @@ int ref_me_cmp(int kind, int sidx, int dxy, const uint8_t *b1, const uint8_t *b2
     case 8: f = mecc.vsad[4 + sidx]; break;
     case 9: f = mecc.vsse[4 + sidx]; break;
     case 10: return mecc.sum_abs_dctelem((int16_t *)p1);
+    case 11: case 12: case 13: { extern int ref_me_cmp_enc(int, int, int, uint8_t *, uint8_t *, ptrdiff_t, int); return ref_me_cmp_enc(kind, sidx, dxy, p1, p2, stride, h); }
     }
     if (!f) return -1;
     return f(NULL, p1, p2, stride, h);

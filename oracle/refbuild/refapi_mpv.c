@@ -74,3 +74,32 @@ void ref_mpeg_scantables(int alternate_scan, uint8_t *permutated, uint8_t *raste
     memcpy(raster_end, s->inter_scantable.raster_end, 64);
     pthread_mutex_unlock(&mu);
 }
+
+
+/* Encoder-state me_cmp metrics that only dereference the context's DSP tables (me_cmp.c:538-621): dct_sad, dct_max,
+ * dct264_sad.  The MpegEncContext carries pdsp / fdsp / mecc exactly as ff_mpv_encode_init() fills them
+ * (mpegvideo_enc.c:742-747); fdct_sel 0 = FF_DCT_AUTO (islow), 2 = FF_DCT_FASTINT (ifast). */
+#include "libavcodec/me_cmp.h"
+static MpegEncContext *enc_ctx[2];
+int ref_me_cmp_enc(int kind, int sidx, int fdct_sel, uint8_t *b1, uint8_t *b2, ptrdiff_t stride, int h)
+{
+    pthread_mutex_lock(&mu);
+    MpegEncContext *s = enc_ctx[fdct_sel == 2];
+    if (!s) {
+        AVCodecContext *avctx = calloc(1, sizeof(*avctx));
+        av_set_cpu_flags_mask(0);
+        avctx->bits_per_raw_sample = 8;
+        avctx->dct_algo = fdct_sel == 2 ? FF_DCT_FASTINT : FF_DCT_AUTO;
+        s = av_mallocz(sizeof(*s));
+        s->avctx = avctx;
+        ff_pixblockdsp_init(&s->pdsp, avctx);
+        ff_fdctdsp_init(&s->fdsp, avctx);
+        ff_me_cmp_init_static();
+        ff_me_cmp_init(&s->mecc, avctx);
+        enc_ctx[fdct_sel == 2] = s;
+    }
+    me_cmp_func f = kind == 11 ? s->mecc.dct_sad[sidx] : kind == 12 ? s->mecc.dct_max[sidx] : s->mecc.dct264_sad[sidx];
+    int r = f ? f(s, b1, b2, stride, h) : -1;
+    pthread_mutex_unlock(&mu);
+    return r;
+}

@@ -122,3 +122,26 @@ def test_fdct_batch(gpu, checker, which):
     gpu.check(gpu.lib.ff_fdct_batch_cuda(which, d.ptr, 5000, None))
     device.sync()
     assert np.array_equal(d.download(np.int16, blocks.shape), want)
+
+
+@pytest.mark.parametrize("kind", [11, 12, 13])
+def test_me_cmp_dct_metrics(gpu, checker, kind):
+    """dct_sad / dct_max / dct264_sad: the encoder-state metrics that only need the DSP tables, batch call vs checker"""
+    from libav_b200 import device
+    r = np.random.RandomState(kind)
+    w, h = 176, 144
+    cur = r.randint(0, 256, (h, w)).astype(np.uint8)
+    ref = np.clip(cur.astype(int) + r.randint(-20, 21, cur.shape), 0, 255).astype(np.uint8)
+    n = 600
+    rec = np.zeros(n, synth.MECMP_DT)
+    rec["cur_off"] = r.randint(0, h - 16, n) * w + r.randint(0, w - 16, n)
+    rec["ref_off"] = r.randint(0, h - 16, n) * w + r.randint(0, w - 16, n)
+    d_c, d_r, d_rec = device.DevBuf.from_numpy(cur), device.DevBuf.from_numpy(ref), device.DevBuf.from_numpy(rec)
+    out = device.DevBuf(4 * n)
+    for sidx, hh in ((0, 16), (0, 8), (1, 8)):
+        for sel in ((0, 2) if kind != 13 else (0,)):
+            gpu.check(gpu.lib.ff_me_cmp_batch_cuda(kind, sidx, sel, d_c.ptr, d_r.ptr, w, hh, d_rec.ptr, n, out.ptr, None))
+            device.sync()
+            got = out.download(np.int32, (n,))
+            want = np.array([checker.me_cmp(kind, sidx, sel, cur.ctypes.data + int(q["cur_off"]), ref.ctypes.data + int(q["ref_off"]), w, hh) for q in rec], np.int32)
+            assert np.array_equal(got, want), (kind, sidx, hh, sel, np.flatnonzero(got != want)[:5].tolist())

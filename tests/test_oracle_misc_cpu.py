@@ -79,3 +79,20 @@ def test_hpel(orc, refo, tab):
                 rb = refo.hpel(tab, sidx, dxy, ptr(b), ptr(pix), 40, h)
                 assert ra == rb, (tab, sidx, dxy)
                 assert np.array_equal(a, b), (tab, sidx, dxy, h)
+
+
+def test_dct_metrics_port_matches_reference(orc, refo):
+    """dct_sad / dct_max / dct264_sad (me_cmp.c:538-621): the port against the reference's functions called with an
+    MpegEncContext that carries pdsp / fdsp / mecc like an encoder's, both fdct selections, 16x16 / 16x8 / 8x8"""
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.RandomState(1)
+    for it in range(120):
+        a = rng.randint(0, 256, (40, 48)).astype(np.uint8)
+        b = rng.randint(0, 256, (40, 48)).astype(np.uint8) if it % 3 else np.clip(a.astype(int) + rng.randint(-6, 7, a.shape), 0, 255).astype(np.uint8)
+        for kind in (11, 12, 13):
+            for sidx, h in ((0, 16), (0, 8), (1, 8)):
+                for sel in ((0, 2) if kind != 13 else (0,)):
+                    x = refo.me_cmp(kind, sidx, sel, a.ctypes.data + 8, b.ctypes.data + 8, 48, h)
+                    y = orc.me_cmp(kind, sidx, sel, a.ctypes.data + 8, b.ctypes.data + 8, 48, h)
+                    assert x == y and x >= 0, (kind, sidx, h, sel, x, y)

@@ -256,6 +256,11 @@ void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int 
     cgu = (cgu * contrast * saturation) >> 32;
     cgv = (cgv * contrast * saturation) >> 32;
     oy -= 256 * (int64_t)brightness;
+    {   // roundToInt16(), yuv2rgb.c:659-669, then the (int16_t) casts of :735-740
+        auto r16 = [](int64_t f) { int r = (int)((f + (1 << 15)) >> 16); return (int)(int16_t)(r < -0x7FFF ? 0x8000 : r > 0x7FFF ? 0x7FFF : r); };
+        k.fy_coeff = r16(cy << 13); k.fy_offset = r16(oy << 9);
+        k.fv2r = r16(crv << 13); k.fv2g = r16(cgv << 13); k.fu2g = r16(cgu << 13); k.fu2b = r16(cbu << 13);
+    }
     crv = ((crv << 16) + 0x8000) / cy;
     cbu = ((cbu << 16) + 0x8000) / cy;
     cgu = ((cgu << 16) + 0x8000) / cy;

@@ -43,6 +43,8 @@ struct RgbConstants {      // r = clip_u8((cy * (Y + ar + ((V * crv) >> 16)) + k
     int crv, cgu, cgv, cbu;
     int ar, agu, agv, ab;  // yoffs - (crv >> 9), yoffs - (cgu >> 9), -(cgv >> 9), yoffs - (cbu >> 9)
     int kr, kg, kb;        // cy * ar + k1, cy * (agu + agv) + k1, cy * ab + k1: the additive terms with the offsets folded in
+    // SWS_FULL_CHR_H_INT output stage (output.c:1165-1240): c->yuv2rgb_{y_coeff,y_offset,v2r,v2g,u2g,u2b}_coeff, yuv2rgb.c:735-740
+    int fy_coeff, fy_offset, fv2r, fv2g, fu2g, fu2b;
 };
 void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int brightness, int contrast, int saturation);
 

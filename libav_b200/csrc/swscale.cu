@@ -35,6 +35,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     const int32_t *hLumP, *hChrP, *vLumP, *vChrP;
     RgbConstants k;
     int bgr;
+    int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
 };
 
 struct ChromaTerms { int tr, tg, tb; };
@@ -56,6 +57,15 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V, const RgbConst
 __device__ __forceinline__ void clip_if_flagged(int &y1, int &y2, int &u, int &v)
 {
     if ((y1 | y2 | u | v) & 0x100) { y1 = clip_u8(y1); y2 = clip_u8(y2); u = clip_u8(u); v = clip_u8(v); }
+}
+
+// yuv2rgb24_full_X_c's pixel (output.c:1193-1225): 30-bit fixed-point matrix on Y, U - 128, V - 128 (all << 9 here)
+__device__ __forceinline__ void full_pixel(int Y, int U, int V, const RgbConstants &k, int bgr, uint8_t *d)
+{
+    Y = (Y - k.fy_offset) * k.fy_coeff + (1 << 21);
+    int R = Y + V * k.fv2r, G = Y + V * k.fv2g + U * k.fu2g, B = Y + U * k.fu2b;
+    if ((R | G | B) & 0xC0000000) { R = min(max(R, 0), 0x3FFFFFFF); G = min(max(G, 0), 0x3FFFFFFF); B = min(max(B, 0), 0x3FFFFFFF); }
+    d[bgr ? 2 : 0] = (uint8_t)(R >> 22); d[1] = (uint8_t)(G >> 22); d[bgr ? 0 : 2] = (uint8_t)(B >> 22);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -540,6 +550,25 @@ sws_vscale_rgb24_x8_kernel(SwsDev p, const int16_t *__restrict__ lum, const int1
     d[2] = make_uint2(pack4_sat_u8(g[5], b[5], r[6], g[6]), pack4_sat_u8(b[6], r[7], g[7], b[7]));
 }
 
+// pass 2, SWS_FULL_CHR_H_INT: yuv2rgb24_full_X_c (output.c:1165-1240), thread = (pixel, output row)
+__global__ void __launch_bounds__(256)
+sws_vscale_rgb24_full_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t *__restrict__ chrU,
+                             const int16_t *__restrict__ chrV, int lumStride, int chrStride, uint8_t *__restrict__ dst, int dstStride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= p.dstW || y >= p.dstH) return;
+    const int fl = p.vLumSize, fc = p.vChrSize;
+    const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
+    const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+    int Y = 0, U = -128 * (1 << 19), V = -128 * (1 << 19);
+    for (int j = 0; j < fl; j++) Y += lum[(size_t)line_index(firstL, j, p.srcH) * lumStride + i] * lf[j];
+    for (int j = 0; j < fc; j++) {
+        const size_t o = (size_t)line_index(firstC, j, p.chrSrcH) * chrStride + i;
+        U += chrU[o] * cf[j]; V += chrV[o] * cf[j];
+    }
+    full_pixel(Y >> 10, U >> 10, V >> 10, p.k, p.bgr, dst + (size_t)y * dstStride + (size_t)i * 3);
+}
+
 // pass 2 for planar 8-bit output: yuv2planeX_8_c / yuv2plane1_8_c (output.c:242-265), dither = 64 everywhere
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
@@ -648,13 +677,13 @@ __device__ __forceinline__ void lds4(const int32_t *p, int (&v)[4])
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
 
-template <int FSL, int FSC>
+template <int FSL, int FSC, bool FULL = false>
 __global__ void __launch_bounds__(GT_THREADS)
 sws_tile_rgb24_kernel(SwsDev p, TileArgs a)
 {
     extern __shared__ __align__(16) int32_t gt_smem[];
     int32_t *lumS = gt_smem, *chrUS = gt_smem + a.lumRows * GT_LW;
-    const int chrPlane = a.chrRows * (GT_W / 2);             // V lines follow the U lines
+    const int chrPlane = a.chrRows * (FULL ? GT_LW : GT_W / 2);   // V lines follow the U lines
     const int tid = threadIdx.x, x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H, y1 = min(y0 + GT_H, p.dstH) - 1;
     const size_t f = blockIdx.z;
     const int2 lw = a.lumWin[blockIdx.y], cw = a.chrWin[blockIdx.y];
@@ -663,10 +692,17 @@ sws_tile_rgb24_kernel(SwsDev p, TileArgs a)
         const int col = tid & (GT_W - 1);
         hscale_column<FSL>(a.y + f * a.yFrame, a.yStride, lumLo, lw.y, tid >> 7, 2, lumS + gt_lum_slot(col), GT_LW, x0 + col, p.dstW,
                            p.hLumF, p.hLumP, p.hLumSize, p.srcW, a.lumXInc, 0);
-        const int ccol = tid & (GT_W / 2 - 1), plane = tid >> 7;
-        hscale_column<FSC>((plane ? a.v + f * a.vFrame : a.u + f * a.uFrame), plane ? a.vStride : a.uStride, chrLo, cw.y,
-                           (tid >> 6) & 1, 2, chrUS + plane * chrPlane + ccol, GT_W / 2, (x0 >> 1) + ccol, p.chrDstW,
-                           p.hChrF, p.hChrP, p.hChrSize, p.chrSrcW, a.chrXInc, 1);
+        const int plane = tid >> 7;
+        if (FULL) {                      // one chroma sample per pixel: each plane is as wide as the luma tile, same quad layout
+            hscale_column<FSC>((plane ? a.v + f * a.vFrame : a.u + f * a.uFrame), plane ? a.vStride : a.uStride, chrLo, cw.y, 0, 1,
+                               chrUS + plane * chrPlane + gt_lum_slot(col), GT_LW, x0 + col, p.chrDstW,
+                               p.hChrF, p.hChrP, p.hChrSize, p.chrSrcW, a.chrXInc, 1);
+        } else {
+            const int ccol = tid & (GT_W / 2 - 1);
+            hscale_column<FSC>((plane ? a.v + f * a.vFrame : a.u + f * a.uFrame), plane ? a.vStride : a.uStride, chrLo, cw.y,
+                               (tid >> 6) & 1, 2, chrUS + plane * chrPlane + ccol, GT_W / 2, (x0 >> 1) + ccol, p.chrDstW,
+                               p.hChrF, p.hChrP, p.hChrSize, p.chrSrcW, a.chrXInc, 1);
+        }
     }
     __syncthreads();
     const int tx = tid & 15, y = y0 + (tid >> 4), x = x0 + 8 * tx;
@@ -675,6 +711,31 @@ sws_tile_rgb24_kernel(SwsDev p, TileArgs a)
     const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
     const int32_t *lumT = lumS + 4 * tx - lumLo * GT_LW, *chrT = chrUS + 4 * tx - chrLo * (GT_W / 2);
     auto LL = [&](int j) { return lumT + line_index(firstL, j, p.srcH) * GT_LW; };
+    if (FULL) {                                                // yuv2rgb24_full_X_c, output.c:1165-1240
+        const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+        const int32_t *chrF = chrUS + 4 * tx - chrLo * GT_LW;
+        int Y[8], U[8], V[8], t8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { Y[k] = 0; U[k] = V[k] = -128 * (1 << 19); }
+        for (int j = 0; j < fl; j++) {
+            lds8(LL(j), t8); const int c = lf[j];
+#pragma unroll
+            for (int k = 0; k < 8; k++) Y[k] += t8[k] * c;
+        }
+        for (int j = 0; j < fc; j++) {
+            const int c = cf[j]; const int32_t *cl = chrF + line_index(firstC, j, p.chrSrcH) * GT_LW;
+            lds8(cl, t8);
+#pragma unroll
+            for (int k = 0; k < 8; k++) U[k] += t8[k] * c;
+            lds8(cl + chrPlane, t8);
+#pragma unroll
+            for (int k = 0; k < 8; k++) V[k] += t8[k] * c;
+        }
+        uint8_t *d = a.dst0 + f * a.dstFrame0 + (size_t)y * a.dstStride0 + (size_t)x * 3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (x + k < p.dstW) full_pixel(Y[k] >> 10, U[k] >> 10, V[k] >> 10, p.k, p.bgr, d + 3 * k);
+        return;
+    }
     auto CC = [&](int j) { return chrT + line_index(firstC, j, p.chrSrcH) * (GT_W / 2); };
     int Y[8], U[4], V[4], t8[8], t4[4];
     if (fl == 1 && fc <= 2) {                                  // yuv2rgb24_1_c, output.c:1042-1110
@@ -895,6 +956,7 @@ static int upload_tables(SwsCudaContext *c)
     d.vChrF = (const int16_t *)(base + off[6]); d.vChrP = (const int32_t *)(base + off[7]);
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
+    d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && c->dstFormat != FMT_YUV420P;
     return 0;
 }
 
@@ -909,7 +971,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "destination must be RGB24, BGR24 or YUV420P"); return nullptr;
     }
     const bool rgb = dstFormat != FMT_YUV420P;
-    if (flags & SWS_FULL_CHR_H_INT) { set_error_msg("sws_getContext_cuda", "SWS_FULL_CHR_H_INT is not taken over"); return nullptr; }
+    if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
     c->dstFormat = dstFormat;
@@ -931,7 +993,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
     c->table_unscaled = !c->srcNV && rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
-    c->fused = !c->table_unscaled && rgb && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->fused = !c->table_unscaled && rgb && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -985,7 +1047,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             tile_line_window(c->vChr.pos.data(), c->vChr.size, y0, std::min(y0 + GT_H, c->g.chrDstH) - 1, c->g.chrSrcH, lo, hi);
             cr = std::max(cr, hi - lo + 1); win.push_back(make_int2(lo, hi - lo + 1));
         }
-        const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * GT_W) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
+        const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
+        const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
         if (need <= 96 * 1024) {
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
@@ -1121,12 +1184,18 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         const int fsl = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hLumSize, fsc = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hChrSize;
         const dim3 gl((p.dstW + GT_W - 1) / GT_W, (p.dstH + GT_H - 1) / GT_H, nframes);
         if (!planar) {
-            const size_t smem = ((size_t)a.lumRows * GT_LW + (size_t)a.chrRows * GT_W) * 4;
+            const size_t smem = ((size_t)a.lumRows * GT_LW + (size_t)a.chrRows * (p.full ? 2 * GT_LW : GT_W)) * 4;
             auto go = [&](auto kern) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
                 kern<<<gl, GT_THREADS, smem, st>>>(p, a);
             };
-            if (fsl == -1)                  go(sws_tile_rgb24_kernel<-1, -1>);
+            if (p.full) {
+                if (fsl == -1)                 go(sws_tile_rgb24_kernel<-1, -1, true>);
+                else if (fsl == 4 && fsc == 4) go(sws_tile_rgb24_kernel<4, 4, true>);
+                else if (fsl == 8 && fsc == 8) go(sws_tile_rgb24_kernel<8, 8, true>);
+                else                           go(sws_tile_rgb24_kernel<0, 0, true>);
+            }
+            else if (fsl == -1)             go(sws_tile_rgb24_kernel<-1, -1>);
             else if (fsl == 2 && fsc == 2)  go(sws_tile_rgb24_kernel<2, 2>);
             else if (fsl == 4 && fsc == 4)  go(sws_tile_rgb24_kernel<4, 4>);
             else if (fsl == 8 && fsc == 8)  go(sws_tile_rgb24_kernel<8, 8>);
@@ -1167,7 +1236,9 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
             const bool x_path = !((p.vLumSize == 1 && p.vChrSize <= 2) || (p.vLumSize == 2 && p.vChrSize == 2));
-            if (x_path && !(p.dstW & 7) && !(dstStride[0] & 7) && !((uintptr_t)d0 & 7))
+            if (p.full)
+                sws_vscale_rgb24_full_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
+            else if (x_path && !(p.dstW & 7) && !(dstStride[0] & 7) && !((uintptr_t)d0 & 7))
                 sws_vscale_rgb24_x8_kernel<<<dim3((p.dstW / 8 + 127) / 128, p.dstH), 128, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
             else
                 sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
@@ -1289,7 +1360,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     if (rgb) {
         // whole pixel pairs are written (one pixel past an odd width) when the caller's stride has room
         size_t wbytes = (size_t)g.dstW * 3;
-        if (odd && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;
+        if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;      // (full chroma writes single pixels)
         if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * 3;       // that converter leaves an odd last column untouched
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {

@@ -211,10 +211,11 @@ static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags
     int algo = flags & (F_POINT | F_AREA | F_BILINEAR | F_FAST_BILINEAR | F_BICUBIC | F_X | F_GAUSS | F_LANCZOS | F_SINC | F_SPLINE | F_BICUBLIN);
     if (!algo) flags |= (dw < sw && dh < sh) ? F_GAUSS : (dw > sw && dh > sh) ? F_SINC : F_LANCZOS;
     else if (algo & (algo - 1)) return -1;
-    if (sw < 4 || sh < 1 || dw < 8 || dh < 1 || (flags & F_FULL_CHR_H_INT)) return -1;
+    if (sw < 4 || sh < 1 || dw < 8 || dh < 1 || ((flags & F_FULL_CHR_H_INT) && !rgb)) return -1;
     c->srcW = sw; c->srcH = sh; c->dstW = dw; c->dstH = dh; c->flags = flags; c->rgb = rgb;
     c->chrSrcW = (sw + 1) >> 1; c->chrSrcH = (sh + 1) >> 1;
-    c->chrDstW = (dw + 1) >> 1; c->chrDstH = rgb ? dh : (dh + 1) >> 1;
+    /* packed RGB shares a chroma sample between two pixels unless SWS_FULL_CHR_H_INT asks for one per pixel (utils.c:998-1014) */
+    c->chrDstW = (rgb && (flags & F_FULL_CHR_H_INT)) ? dw : (dw + 1) >> 1; c->chrDstH = rgb ? dh : (dh + 1) >> 1;
     int lx = (int)((((int64_t)sw << 16) + (dw >> 1)) / dw), ly = (int)((((int64_t)sh << 16) + (dh >> 1)) / dh);
     int cx = (int)((((int64_t)c->chrSrcW << 16) + (c->chrDstW >> 1)) / c->chrDstW);
     int cyi = (int)((((int64_t)c->chrSrcH << 16) + (c->chrDstH >> 1)) / c->chrDstH);
@@ -337,6 +338,40 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
     const int fl = c.vl.taps, fc = c.vc.taps;
+    if (flags & F_FULL_CHR_H_INT) {
+        /* yuv2rgb24_full_X_c (output.c:1165-1240): one chroma sample per pixel, 30-bit fixed point colour matrix with the
+         * coefficients of ff_yuv2rgb_c_init_tables (yuv2rgb.c:735-740); always the X variant (output.c:1392-1460) */
+        int64_t kcy = ((int64_t)(1 << 16) * 255) / 219, koy = 16 << 16;
+        static const int itu601[4] = { 104597, 132201, 25675, 53279 };
+#define R16(f) ((int16_t)({ int r_ = (int)(((int64_t)(f) + (1 << 15)) >> 16); r_ < -0x7FFF ? -0x8000 : r_ > 0x7FFF ? 0x7FFF : r_; }))
+        const int y_coeff = R16(kcy << 13), y_offset = R16(koy << 9), v2r = R16((int64_t)itu601[0] << 13), v2g = R16(-(int64_t)itu601[3] << 13),
+                  u2g = R16(-(int64_t)itu601[2] << 13), u2b = R16((int64_t)itu601[1] << 13);
+#undef R16
+        for (int y = 0; y < dh; y++) {
+            int firstL = c.vl.pos[y] > 1 - fl ? c.vl.pos[y] : 1 - fl;
+            int firstC = c.vc.pos[y] > 1 - fc ? c.vc.pos[y] : 1 - fc;
+            const int16_t *lf = c.vl.coef + (size_t)y * fl, *cf = c.vc.coef + (size_t)y * fc;
+            uint8_t *d = dst + (size_t)y * dstride;
+            for (int i = 0; i < dw; i++) {
+                int Y = 0, Uv = -128 * (1 << 19), Vv = -128 * (1 << 19);
+                for (int j = 0; j < fl; j++) Y += L[(size_t)rowsel(firstL, j, sh) * lp + i] * lf[j];
+                for (int j = 0; j < fc; j++) {
+                    Uv += U[(size_t)rowsel(firstC, j, c.chrSrcH) * cp + i] * cf[j];
+                    Vv += V[(size_t)rowsel(firstC, j, c.chrSrcH) * cp + i] * cf[j];
+                }
+                Y >>= 10; Uv >>= 10; Vv >>= 10;
+                Y = (Y - y_offset) * y_coeff + (1 << 21);
+                int R = Y + Vv * v2r, G = Y + Vv * v2g + Uv * u2g, B = Y + Uv * u2b;
+                if ((R | G | B) & 0xC0000000) {
+                    R = R < 0 ? 0 : R > 0x3FFFFFFF ? 0x3FFFFFFF : R; G = G < 0 ? 0 : G > 0x3FFFFFFF ? 0x3FFFFFFF : G; B = B < 0 ? 0 : B > 0x3FFFFFFF ? 0x3FFFFFFF : B;
+                }
+                d[3 * i] = (uint8_t)(R >> 22); d[3 * i + 1] = (uint8_t)(G >> 22); d[3 * i + 2] = (uint8_t)(B >> 22);
+            }
+        }
+        free(L); free(U); free(V);
+        sws_close(&c);
+        return dh;
+    }
     for (int y = 0; y < dh; y++) {
         int firstL = c.vl.pos[y] > 1 - fl ? c.vl.pos[y] : 1 - fl;
         int firstC = c.vc.pos[y] > 1 - fc ? c.vc.pos[y] : 1 - fc;

@@ -135,3 +135,28 @@ def test_unscaled_table_converter(gpu, checker):
                 n = (w // 2) * 6
                 want = np.concatenate([want[:, :n].reshape(h, -1, 3)[:, :, ::-1].reshape(h, -1), want[:, n:]], axis=1)
             assert np.array_equal(got, want), (w, h, fmt)
+
+
+@pytest.mark.parametrize("variant", ["tile", "two_pass"])
+def test_full_chroma_interpolation(gpu, checker, variant):
+    """SWS_FULL_CHR_H_INT: yuv2rgb24_full_X_c through both general-path implementations, rgb24 and bgr24, odd sizes"""
+    from libav_b200 import device
+    from libav_b200._lib import lib
+    FULL = 0x2000
+    lib.avb200_set_tuning(b"sws_general_variant", 1 if variant == "two_pass" else 0)
+    try:
+        for (sw, sh, dw, dh) in [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (100, 37, 333, 211), (641, 479, 641, 479), (1920, 1080, 1280, 720)]:
+            yuv = tuple(synth.pad_rows(pl) for pl in synth.yuv420p_frame(sw, sh, 3))
+            for flags in (4 | ACC, 2 | ACC, 0x10 | ACC, 1 | ACC):
+                if sw * sh > 1500 * 1000 and flags != (4 | ACC):
+                    continue
+                want = oracle_rgb(checker, yuv, dw, dh, flags | FULL, pad=6)
+                for fmt in (device.PIX_FMT_RGB24, device.PIX_FMT_BGR24):
+                    ctx = device.SwsContext(sw, sh, dw, dh, fmt, flags | FULL)
+                    assert not ctx.fused
+                    got = ctx.scale(yuv, dst_pad=6)
+                    w2 = want if fmt == device.PIX_FMT_RGB24 else np.concatenate([want[:, :dw * 3].reshape(dh, -1, 3)[:, :, ::-1].reshape(dh, -1), want[:, dw * 3:]], axis=1)
+                    assert np.array_equal(got, w2), (variant, sw, sh, dw, dh, hex(flags), fmt, np.argwhere(got != w2)[:3].tolist())
+                    ctx.close()
+    finally:
+        lib.avb200_set_tuning(b"sws_general_variant", 0)

@@ -132,3 +132,23 @@ def test_unscaled_table_converter(refo, orc):
         assert ra == rb == h
         assert np.array_equal(a, b), (w, h)
         assert not np.array_equal(a, to_rgb(refo, yuv, w, h, BICUBIC | ACC, pad=6)[1])      # it really is a different path
+
+
+def test_full_chroma_interpolation_port_matches_reference(orc, refo):
+    """SWS_FULL_CHR_H_INT (yuv2rgb24_full_X_c): one chroma sample per pixel and the 30-bit colour matrix"""
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    import ctypes as C
+    from libav_b200 import synth
+    from oracle.loader import ptr
+    FULL = 0x2000
+    for (w, h, dw, dh) in [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (100, 37, 333, 211), (66, 50, 33, 25), (641, 479, 641, 479)]:
+        yuv = tuple(synth.pad_rows(pl) for pl in synth.yuv420p_frame(w, h, 3))
+        p, s = (C.c_void_p * 3)(*[a.ctypes.data for a in yuv]), (C.c_int * 3)(*[a.strides[0] for a in yuv])
+        for fl in (4 | 0xC0000, 2 | 0xC0000, 4, 0x10 | 0xC0000, 1 | 0xC0000, 0x200 | 0xC0000):
+            outs = []
+            for o in (refo, orc):
+                dst = np.full((dh, dw * 3 + 6), 9, np.uint8)
+                assert o.sws_yuv420p_to_rgb24(p, s, w, h, ptr(dst), dst.strides[0], dw, dh, fl | FULL) == dh
+                outs.append(dst)
+            assert np.array_equal(outs[0], outs[1]), (w, h, dw, dh, hex(fl))

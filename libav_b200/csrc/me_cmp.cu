@@ -181,12 +181,19 @@ full_search_kernel_v2(const uint8_t *__restrict__ cur, const uint8_t *__restrict
     __shared__ unsigned long long best_s[8];
     const int mbw = w >> 4, mbx = blockIdx.x, mby = mb_y0 + blockIdx.y, t = threadIdx.x;
     const int px = mbx * 16, py = mby * 16;
-    for (int i = t; i < FS_WIN * 13; i += 256) {
-        const int r = i / 13, c4 = i % 13, gy = min(max(py - FS_R + r, 0), h - 1);
-        uint32_t v = 0;
+    // a window that lies inside the picture (all but the border macroblocks) is fetched as aligned words
+    const bool interior = px >= FS_R && px + 36 <= w && py >= FS_R && py + 32 <= h && !((stride | (int)(uintptr_t)ref) & 3);
+    if (interior) {
+        const uint8_t *g = ref + (size_t)(py - FS_R) * stride + px - FS_R;
+        for (int i = t; i < FS_WIN * 13; i += 256) { const int r = i / 13, c4 = i - r * 13; raw[i] = __ldg(reinterpret_cast<const uint32_t *>(g + (size_t)r * stride) + c4); }
+    } else {
+        for (int i = t; i < FS_WIN * 13; i += 256) {
+            const int r = i / 13, c4 = i % 13, gy = min(max(py - FS_R + r, 0), h - 1);
+            uint32_t v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(ref + (size_t)gy * stride + min(max(px - FS_R + 4 * c4 + k, 0), w - 1)) << (8 * k);
-        raw[i] = v;
+            for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(ref + (size_t)gy * stride + min(max(px - FS_R + 4 * c4 + k, 0), w - 1)) << (8 * k);
+            raw[i] = v;
+        }
     }
     uint32_t c[16][4];
 #pragma unroll

@@ -169,7 +169,8 @@ full_search_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ 
 // candidates, 320 vabsdiff4 per thread.  33 columns x 7 row groups = 231 of the 256 threads carry work.  Copies are
 // spaced 8 banks apart, which makes the 32 lanes of a warp (consecutive dx) hit 32 different banks.
 constexpr int FS2_ROWW = 12;                                   // words per window row in a shifted copy (48 bytes)
-constexpr int FS2_COPY = FS_WIN * FS2_ROWW + 8;                // words per copy, +8 words = 8 banks of skew
+constexpr int FS2_ROWS = FS_WIN + 2;                            // two spare rows: the last row group reads past the window (those candidates are invalid)
+constexpr int FS2_COPY = FS2_ROWS * FS2_ROWW + 8;              // words per copy, +8 words = 8 banks of skew
 constexpr int FS2_DYG = 5;
 
 __global__ void __launch_bounds__(256)
@@ -216,17 +217,18 @@ full_search_kernel_v2(const uint8_t *__restrict__ cur, const uint8_t *__restrict
         unsigned sad[FS2_DYG] = { 0, 0, 0, 0, 0 };
 #pragma unroll
         for (int rr = 0; rr < 16 + FS2_DYG - 1; rr++) {
-            const int wr = min(dy0 + rr, FS_WIN - 1);                                // rows past the window only feed invalid candidates
-            const uint32_t *row = base + wr * FS2_ROWW;
+            const uint32_t *row = base + (dy0 + rr) * FS2_ROWW;                      // rows 48, 49 (spare) only feed invalid candidates
             const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
 #pragma unroll
             for (int j = 0; j < FS2_DYG; j++) {
                 const int cr = rr - j;
                 if (cr >= 0 && cr < 16) {
-                    sad[j] = __vsadu4(c[cr][0], w0) + sad[j];
-                    sad[j] = __vsadu4(c[cr][1], w1) + sad[j];
-                    sad[j] = __vsadu4(c[cr][2], w2) + sad[j];
-                    sad[j] = __vsadu4(c[cr][3], w3) + sad[j];
+                    // the accumulate is part of the instruction (VABSDIFF4 ... .ADD); written as `__vsadu4() + acc` the compiler
+                    // split half of them into a separate IADD3 on the same (ALU) pipe
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(sad[j]) : "r"(c[cr][0]), "r"(w0));
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(sad[j]) : "r"(c[cr][1]), "r"(w1));
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(sad[j]) : "r"(c[cr][2]), "r"(w2));
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(sad[j]) : "r"(c[cr][3]), "r"(w3));
                 }
             }
         }

@@ -170,7 +170,8 @@ full_search_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ 
 // spaced 8 banks apart, which makes the 32 lanes of a warp (consecutive dx) hit 32 different banks.
 constexpr int FS2_ROWW = 12;                                   // words per window row in a shifted copy (48 bytes)
 constexpr int FS2_ROWS = FS_WIN + 2;                            // two spare rows: the last row group reads past the window (those candidates are invalid)
-constexpr int FS2_COPY = FS2_ROWS * FS2_ROWW + 8;              // words per copy, +8 words = 8 banks of skew
+constexpr int FS2_COPY = FS2_ROWS * FS2_ROWW + 16;             // words per copy; 616 = 8 (mod 32): consecutive copies sit 8 banks apart
+static_assert(FS2_COPY % 32 == 8, "the four shifted copies must start 8 banks apart");
 constexpr int FS2_DYG = 5;
 
 __global__ void __launch_bounds__(256)

@@ -183,11 +183,20 @@ full_search_kernel_v2(const uint8_t *__restrict__ cur, const uint8_t *__restrict
     __shared__ unsigned long long best_s[8];
     const int mbw = w >> 4, mbx = blockIdx.x, mby = mb_y0 + blockIdx.y, t = threadIdx.x;
     const int px = mbx * 16, py = mby * 16;
-    // a window that lies inside the picture (all but the border macroblocks) is fetched as aligned words
+    // A window that lies inside the picture (all but the border macroblocks) is fetched as aligned words, and the four
+    // byte-shifted copies are produced straight from the two words a thread loaded (no staging pass, one barrier).
     const bool interior = px >= FS_R && px + 36 <= w && py >= FS_R && py + 32 <= h && !((stride | (int)(uintptr_t)ref) & 3);
     if (interior) {
         const uint8_t *g = ref + (size_t)(py - FS_R) * stride + px - FS_R;
-        for (int i = t; i < FS_WIN * 13; i += 256) { const int r = i / 13, c4 = i - r * 13; raw[i] = __ldg(reinterpret_cast<const uint32_t *>(g + (size_t)r * stride) + c4); }
+        for (int i = t; i < FS_WIN * FS2_ROWW; i += 256) {
+            const int r = i / FS2_ROWW, cw = i - r * FS2_ROWW;
+            const uint32_t *gp = reinterpret_cast<const uint32_t *>(g + (size_t)r * stride) + cw;
+            const uint32_t a = __ldg(gp), b = __ldg(gp + 1);
+            win[i] = a;
+            win[FS2_COPY + i] = __funnelshift_r(a, b, 8);
+            win[2 * FS2_COPY + i] = __funnelshift_r(a, b, 16);
+            win[3 * FS2_COPY + i] = __funnelshift_r(a, b, 24);
+        }
     } else {
         for (int i = t; i < FS_WIN * 13; i += 256) {
             const int r = i / 13, c4 = i % 13, gy = min(max(py - FS_R + r, 0), h - 1);
@@ -196,17 +205,17 @@ full_search_kernel_v2(const uint8_t *__restrict__ cur, const uint8_t *__restrict
             for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(ref + (size_t)gy * stride + min(max(px - FS_R + 4 * c4 + k, 0), w - 1)) << (8 * k);
             raw[i] = v;
         }
+        __syncthreads();
+        for (int i = t; i < 4 * FS_WIN * FS2_ROWW; i += 256) {
+            const int s = i / (FS_WIN * FS2_ROWW), rem = i % (FS_WIN * FS2_ROWW), r = rem / FS2_ROWW, cw = rem % FS2_ROWW;
+            win[s * FS2_COPY + rem] = __funnelshift_r(raw[r * 13 + cw], raw[r * 13 + cw + 1], 8 * s);
+        }
     }
     uint32_t c[16][4];
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const uint4 v = *reinterpret_cast<const uint4 *>(cur + (size_t)(py + r) * stride + px);
         c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
-    }
-    __syncthreads();
-    for (int i = t; i < 4 * FS_WIN * FS2_ROWW; i += 256) {
-        const int s = i / (FS_WIN * FS2_ROWW), rem = i % (FS_WIN * FS2_ROWW), r = rem / FS2_ROWW, cw = rem % FS2_ROWW;
-        win[s * FS2_COPY + rem] = __funnelshift_r(raw[r * 13 + cw], raw[r * 13 + cw + 1], 8 * s);
     }
     __syncthreads();
 

@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # Some test modules import the ctypes binding at collection time: in a fresh checkout (built artefacts are not tracked)
+    # build before collecting.  A no-op when everything is up to date; on the GPU box the prebuilt files travelled.
+    import __graft_entry__ as g
+    g.build()
 
 
 @pytest.fixture(scope="session")

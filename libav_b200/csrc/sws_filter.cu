@@ -217,7 +217,8 @@ int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, 
     return 0;
 }
 
-int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool dst_is_rgb, int flags, const char **err)
+int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool dst_is_rgb, int flags, const char **err,
+                    int chrSrcHSub, int chrSrcVSub)
 {
     int algos = flags & (SWS_POINT | SWS_AREA | SWS_BILINEAR | SWS_FAST_BILINEAR | SWS_BICUBIC | SWS_X | SWS_GAUSS |
                          SWS_LANCZOS | SWS_SINC | SWS_SPLINE | SWS_BICUBLIN);
@@ -230,7 +231,7 @@ int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool
     g.srcW = srcW; g.srcH = srcH; g.dstW = dstW; g.dstH = dstH; g.flags = flags;
     g.lumXInc = (int)((((int64_t)srcW << 16) + (dstW >> 1)) / dstW);
     g.lumYInc = (int)((((int64_t)srcH << 16) + (dstH >> 1)) / dstH);
-    g.chrSrcHSub = 1; g.chrSrcVSub = 1;                       // yuv420p
+    g.chrSrcHSub = chrSrcHSub; g.chrSrcVSub = chrSrcVSub;     // getSubSampleFactors(), utils.c:983
     if (dst_is_rgb) { g.chrDstHSub = (flags & SWS_FULL_CHR_H_INT) ? 0 : 1; g.chrDstVSub = 0; }   // :1013-1014
     else            { g.chrDstHSub = 1; g.chrDstVSub = 1; }
     g.chrSrcVSub += (flags & 0x30000) >> 16;                  // SWS_SRC_V_CHR_DROP

@@ -900,7 +900,8 @@ sws_split_nv_kernel(const uint8_t *__restrict__ uv, int uvStride, size_t uvFrame
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
-enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_NV12 = 23, FMT_NV21 = 24 };       // libavutil/pixfmt.h enum values
+enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
+       FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31 };       // libavutil/pixfmt.h enum values
 
 struct SwsCudaContext {
     SwsGeometry g;
@@ -917,6 +918,7 @@ struct SwsCudaContext {
     SwsDev dev;
     int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
     int lumStridePx = 0, chrStridePx = 0;
+    bool src422 = false;        // the unscaled table converter reads the even chroma line of a 4:2:2 source for both rows (yuv2rgb.c:133-136)
     int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the split chroma planes of a batch
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
@@ -964,8 +966,19 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                                     const double *param, bool device_side)
 {
     const char *err = nullptr;
-    if (srcFormat != FMT_YUV420P && srcFormat != FMT_NV12 && srcFormat != FMT_NV21) {
-        set_error_msg("sws_getContext_cuda", "only AV_PIX_FMT_YUV420P / NV12 / NV21 sources are taken over"); return nullptr;
+    int hs = 1, vs = 1;                                       // source chroma sub-sampling, libavutil/pixdesc.c log2_chroma_w / _h
+    switch (srcFormat) {
+    case FMT_YUV420P: case FMT_NV12: case FMT_NV21: break;
+    case FMT_YUV422P: vs = 0; break;
+    case FMT_YUV444P: hs = 0; vs = 0; break;
+    case FMT_YUV410P: hs = 2; vs = 2; break;
+    case FMT_YUV411P: hs = 2; vs = 0; break;
+    case FMT_YUV440P: hs = 0; break;
+    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21"); return nullptr;
+    }
+    if (srcFormat == FMT_YUV410P && dstFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !(flags & SWS_BITEXACT)) {
+        set_error_msg("sws_getContext_cuda", "yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper: not taken over");
+        return nullptr;
     }
     if (dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && dstFormat != FMT_YUV420P) {
         set_error_msg("sws_getContext_cuda", "destination must be RGB24, BGR24 or YUV420P"); return nullptr;
@@ -977,7 +990,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->dstFormat = dstFormat;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
-    if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err)) goto fail;
+    c->src422 = srcFormat == FMT_YUV422P;
+    if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err, hs, vs)) goto fail;
     {
         const int fl = c->g.flags;
         const int lumFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BICUBIC) : fl;
@@ -992,7 +1006,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
-    c->table_unscaled = !c->srcNV && rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
+    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
     c->fused = !c->table_unscaled && rgb && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
@@ -1008,7 +1022,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         c->fast_ok = ok;
     }
-    c->copy = !rgb && srcW == dstW && srcH == dstH;
+    c->copy = !rgb && srcW == dstW && srcH == dstH && hs == 1 && vs == 1;      // same format (or nv12 / nv21, split on the way)
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
     if (c->fast_ok) {
@@ -1133,7 +1147,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
     if (c->table_unscaled) {
         FusedArgs a;
         a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst = dst[0];
-        a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2]; a.dstStride = dstStride[0];
+        a.yStride = srcStride[0]; a.uStride = srcStride[1] << (c->src422 ? 1 : 0); a.vStride = srcStride[2] << (c->src422 ? 1 : 0); a.dstStride = dstStride[0];
         a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2]; a.dstFrame = dstFrame[0];
         sws_unscaled_yuv2rgb24_kernel<<<dim3(((p.dstW >> 1) + 255) / 256, p.dstH >> 1, nframes), 256, 0, st>>>(p, a);
         return check_launch("sws_scale:unscaled");

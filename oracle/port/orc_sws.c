@@ -33,6 +33,7 @@
 #define F_SPLINE 0x400
 #define F_FULL_CHR_H_INT 0x2000
 #define F_ACCURATE_RND 0x40000
+#define F_BITEXACT 0x80000
 #define PARAM_DEFAULT 123456.0
 
 typedef struct { int taps, n; int16_t *coef; int32_t *pos; } bank_t;
@@ -205,6 +206,9 @@ static int make_bank(bank_t *b, int xinc, int slen, int dlen, int one, int flags
 static void free_bank(bank_t *b) { free(b->coef); free(b->pos); memset(b, 0, sizeof(*b)); }
 static void sws_close(sws_t *c) { free_bank(&c->hl); free_bank(&c->hc); free_bank(&c->vl); free_bank(&c->vc); }
 
+/* chroma sub-sampling of the planar 8-bit source being converted (log2): 4:2:0 unless orc_sws_planar() says otherwise */
+static __thread int g_hs = 1, g_vs = 1;
+
 static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags)
 {
     memset(c, 0, sizeof(*c));
@@ -213,7 +217,7 @@ static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags
     else if (algo & (algo - 1)) return -1;
     if (sw < 4 || sh < 1 || dw < 8 || dh < 1 || ((flags & F_FULL_CHR_H_INT) && !rgb)) return -1;
     c->srcW = sw; c->srcH = sh; c->dstW = dw; c->dstH = dh; c->flags = flags; c->rgb = rgb;
-    c->chrSrcW = (sw + 1) >> 1; c->chrSrcH = (sh + 1) >> 1;
+    c->chrSrcW = -((-sw) >> g_hs); c->chrSrcH = -((-sh) >> g_vs);
     /* packed RGB shares a chroma sample between two pixels unless SWS_FULL_CHR_H_INT asks for one per pixel (utils.c:998-1014) */
     c->chrDstW = (rgb && (flags & F_FULL_CHR_H_INT)) ? dw : (dw + 1) >> 1; c->chrDstH = rgb ? dh : (dh + 1) >> 1;
     int lx = (int)((((int64_t)sw << 16) + (dw >> 1)) / dw), ly = (int)((((int64_t)sh << 16) + (dh >> 1)) / dh);
@@ -318,12 +322,15 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
-    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1)) {
-        /* unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
+    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1) {
+        /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
+         * i.e. both rows of a pair read the even chroma line)
+         * unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
          * nearest chroma, dstW & ~1 pixels per row */
         for (int y = 0; y < dh; y++)
             for (int i = 0; i < dw >> 1; i++) {
-                int Uv = src[1][(size_t)(y >> 1) * ss[1] + i], Vv = src[2][(size_t)(y >> 1) * ss[2] + i];
+                const int crow = (y >> 1) << (1 - g_vs);
+                int Uv = src[1][(size_t)crow * ss[1] + i], Vv = src[2][(size_t)crow * ss[2] + i];
                 const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
                 const uint8_t *py = src[0] + (size_t)y * ss[0] + 2 * i;
                 uint8_t *d = dst + (size_t)y * dstride + 6 * i;
@@ -434,7 +441,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh) {       /* unscaled same-format special converter: plain plane copy
+    if (sw == dw && sh == dh && g_hs == 1 && g_vs == 1) {       /* unscaled same-format special converter: plain plane copy
                                          (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
@@ -487,5 +494,28 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
     int r = dst_fmt == 2 ? orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst[0], dstride[0], dw, dh, flags | 0x40000)
                          : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
     free(u);
+    return r;
+}
+
+
+/* Planar 8-bit YUV sources of any chroma sub-sampling (getSubSampleFactors, utils.c:983): the same pipeline with
+ * chrSrcW / chrSrcH derived from the format.  src_fmt: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6,
+ * YUV411P 7, YUV440P 31. */
+int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
+                   uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
+{
+    int hs, vs;
+    switch (src_fmt) {
+    case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;
+    case 6: hs = 2; vs = 2; break;  case 7: hs = 2; vs = 0; break;  case 31: hs = 0; vs = 1; break;
+    default: return -1;
+    }
+    /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
+     * rgb2rgb.c planar2x): not restated */
+    if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT)) return -1;
+    g_hs = hs; g_vs = vs;
+    int r = dst_fmt == 2 ? orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst[0], dstride[0], dw, dh, flags)
+                         : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    g_hs = 1; g_vs = 1;
     return r;
 }

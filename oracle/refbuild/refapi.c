@@ -285,6 +285,21 @@ int ref_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     sws_freeContext(c);
     return r;
 }
+int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
+                   uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
+{
+    INIT();
+    struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, dst_fmt == 2 ? AV_PIX_FMT_RGB24 : AV_PIX_FMT_YUV420P,
+                                          flags, NULL, NULL, NULL);
+    if (!c) return -1;
+    uint8_t *d[4] = { dst[0], dst_fmt == 2 ? NULL : dst[1], dst_fmt == 2 ? NULL : dst[2], NULL };
+    int ds[4] = { dstride[0], dst_fmt == 2 ? 0 : dstride[1], dst_fmt == 2 ? 0 : dstride[2], 0 };
+    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
+    int sst[4] = { ss[0], ss[1], ss[2], 0 };
+    int r = sws_scale(c, s, sst, 0, sh, d, ds);
+    sws_freeContext(c);
+    return r;
+}
 int ref_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
                  uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {

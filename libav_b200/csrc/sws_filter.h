@@ -13,7 +13,7 @@ namespace avb {
 enum {   // libswscale/swscale.h:57-83
     SWS_FAST_BILINEAR = 1, SWS_BILINEAR = 2, SWS_BICUBIC = 4, SWS_X = 8, SWS_POINT = 0x10, SWS_AREA = 0x20,
     SWS_BICUBLIN = 0x40, SWS_GAUSS = 0x80, SWS_SINC = 0x100, SWS_LANCZOS = 0x200, SWS_SPLINE = 0x400,
-    SWS_FULL_CHR_H_INT = 0x2000, SWS_ACCURATE_RND = 0x40000, SWS_BITEXACT = 0x80000,
+    SWS_FULL_CHR_H_INT = 0x2000, SWS_FULL_CHR_H_INP = 0x4000, SWS_ACCURATE_RND = 0x40000, SWS_BITEXACT = 0x80000,
 };
 constexpr double SWS_PARAM_DEFAULT = 123456;
 

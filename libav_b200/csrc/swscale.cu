@@ -898,10 +898,126 @@ sws_split_nv_kernel(const uint8_t *__restrict__ uv, int uvStride, size_t uvFrame
 }
 
 // ---------------------------------------------------------------------------------------------------
+// packed sources: the reference's input readers (lumToYV12 / chrToYV12, libswscale/input.c) for whole frames, in front of
+// the planar kernels.  The readers run on 8-bit samples and produce 8-bit planes (formatConvBuffer, swscale.c:120-160).
+// ---------------------------------------------------------------------------------------------------
+namespace rd {            // input.c:38-47
+constexpr int SH = 15;
+constexpr int BY = (int)(0.114 * 219 / 255 * (1 << SH) + 0.5), BV = -(int)(0.081 * 224 / 255 * (1 << SH) + 0.5), BU = (int)(0.500 * 224 / 255 * (1 << SH) + 0.5);
+constexpr int GY = (int)(0.587 * 219 / 255 * (1 << SH) + 0.5), GV = -(int)(0.419 * 224 / 255 * (1 << SH) + 0.5), GU = -(int)(0.331 * 224 / 255 * (1 << SH) + 0.5);
+constexpr int RY = (int)(0.299 * 219 / 255 * (1 << SH) + 0.5), RV = (int)(0.500 * 224 / 255 * (1 << SH) + 0.5), RU = -(int)(0.169 * 224 / 255 * (1 << SH) + 0.5);
+}
+
+// KIND 1: rgb24 / bgr24 (rgb24ToY_c, rgb24ToUV_c, rgb24ToUV_half_c and the bgr24 twins, input.c:539-625; `ro` / `bo` are the byte
+// offsets of red and blue), 2: yuyv422 (yuy2ToY_c, yuy2ToUV_c, :369-387), 3: uyvy422 (uyvyToY_c, uyvyToUV_c, :456-473).
+// One thread reads one pixel pair.  For an odd width the reference's chroma readers read one pixel past the row; those bytes
+// are read here too whenever they lie inside the frame (row padding or the next row), else the pair's first pixel is repeated.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+sws_read_packed_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
+                       uint8_t *__restrict__ V, int yPitch, int cPitch, size_t yPlane, size_t cPlane, int w, int h, int ro, int bo, int half)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (2 * i >= w) return;
+    const size_t f = blockIdx.z;
+    constexpr int BPP = KIND == 1 ? 3 : 2;
+    const uint8_t *s = src + f * srcFrame + (size_t)y * srcStride + (size_t)i * 2 * BPP;
+    uint8_t *dy = Y + f * yPlane + (size_t)y * yPitch + 2 * i;
+    uint8_t *du = U + f * cPlane + (size_t)y * cPitch, *dv = V + f * cPlane + (size_t)y * cPitch;
+    const bool second = 2 * i + 1 < w;
+    const bool readable = second || y < h - 1 || (2 * i + 2) * BPP <= srcStride;
+    if (KIND == 1) {
+        using namespace rd;
+        const int r0 = s[ro], g0 = s[1], b0 = s[bo];
+        int r1 = r0, g1 = g0, b1 = b0;
+        if (readable) { r1 = s[3 + ro]; g1 = s[4]; b1 = s[3 + bo]; }
+        dy[0] = (uint8_t)((RY * r0 + GY * g0 + BY * b0 + (33 << (SH - 1))) >> SH);
+        if (second) dy[1] = (uint8_t)((RY * r1 + GY * g1 + BY * b1 + (33 << (SH - 1))) >> SH);
+        if (half) {
+            const int r = r0 + r1, g = g0 + g1, b = b0 + b1;
+            du[i] = (uint8_t)((RU * r + GU * g + BU * b + (257 << SH)) >> (SH + 1));
+            dv[i] = (uint8_t)((RV * r + GV * g + BV * b + (257 << SH)) >> (SH + 1));
+        } else {
+            du[2 * i] = (uint8_t)((RU * r0 + GU * g0 + BU * b0 + (257 << (SH - 1))) >> SH);
+            dv[2 * i] = (uint8_t)((RV * r0 + GV * g0 + BV * b0 + (257 << (SH - 1))) >> SH);
+            if (second) {
+                du[2 * i + 1] = (uint8_t)((RU * r1 + GU * g1 + BU * b1 + (257 << (SH - 1))) >> SH);
+                dv[2 * i + 1] = (uint8_t)((RV * r1 + GV * g1 + BV * b1 + (257 << (SH - 1))) >> SH);
+            }
+        }
+    } else {
+        const int yo = KIND == 2 ? 0 : 1, co = KIND == 2 ? 1 : 0;
+        dy[0] = s[yo];
+        if (second) dy[1] = s[2 + yo];
+        du[i] = s[co];
+        dv[i] = readable ? s[2 + co] : s[co];
+    }
+}
+
+// the reference's unscaled special converters for these sources (swscale_unscaled.c:1063-1072,1140-1145):
+// rgb24 <-> bgr24 (rgbToRgbWrapper -> rgb24tobgr24, rgb2rgb_template.c) and the same-format copy (packedCopyWrapper); only the
+// w x h pixels are written (the reference's whole-buffer variants also convert the row padding when the strides match)
+__global__ void __launch_bounds__(256)
+sws_rgb24_shuffle_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
+                         int w, int h, int swap)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *s = src + blockIdx.z * srcFrame + (size_t)y * srcStride + 3 * x;
+    uint8_t *d = dst + blockIdx.z * dstFrame + (size_t)y * dstStride + 3 * x;
+    const uint8_t a = s[0], b = s[1], c = s[2];
+    d[0] = swap ? c : a; d[1] = b; d[2] = swap ? a : c;
+}
+
+// bgr24ToYv12Wrapper -> rgb24toyv12_c (rgb2rgb_template.c:638-693, 8-bit coefficients rgb2rgb.c:111-120): chroma from the first
+// pixel of each pair of the even rows only; width >> 1 pairs, so an odd last column stays untouched.  One thread per pair and row.
+__global__ void __launch_bounds__(256)
+sws_bgr24_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
+                      uint8_t *__restrict__ V, int yStride, int cStride, size_t yFrame, size_t uFrame, size_t vFrame, int w, int h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= (w >> 1)) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *s = src + f * srcFrame + (size_t)y * srcStride + 6 * i;
+    uint8_t *dy = Y + f * yFrame + (size_t)y * yStride + 2 * i;
+    const int b0 = s[0], g0 = s[1], r0 = s[2], b1 = s[3], g1 = s[4], r1 = s[5];
+    dy[0] = (uint8_t)(((66 * r0 + 129 * g0 + 25 * b0) >> 8) + 16);
+    dy[1] = (uint8_t)(((66 * r1 + 129 * g1 + 25 * b1) >> 8) + 16);
+    if (!(y & 1)) {
+        U[f * uFrame + (size_t)(y >> 1) * cStride + i] = (uint8_t)(((-37 * r0 - 73 * g0 + 112 * b0) >> 8) + 128);
+        V[f * vFrame + (size_t)(y >> 1) * cStride + i] = (uint8_t)(((112 * r0 - 93 * g0 - 17 * b0) >> 8) + 128);
+    }
+}
+
+// yuyvToYuv420Wrapper / uyvyToYuv420Wrapper -> yuyvtoyuv420_c / uyvytoyuv420_c (rgb2rgb_template.c:854-910): luma of every row,
+// chroma = the mean (truncating) of the two rows of a pair; h / 2 chroma rows.  One thread per pixel pair and row.
+__global__ void __launch_bounds__(256)
+sws_yuyv_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
+                     uint8_t *__restrict__ V, int yStride, int cStride, size_t yFrame, size_t uFrame, size_t vFrame, int w, int h, int uyvy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (2 * i >= w) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *s = src + f * srcFrame + (size_t)y * srcStride + 4 * i;
+    uint8_t *dy = Y + f * yFrame + (size_t)y * yStride + 2 * i;
+    const int yo = uyvy ? 1 : 0, co = uyvy ? 0 : 1;
+    const bool second = 2 * i + 1 < w;
+    dy[0] = s[yo];
+    if (second) dy[1] = s[2 + yo];
+    if (y & 1) {
+        const uint8_t *p = s - srcStride;
+        // the V sample one pixel past an odd width lies in the row padding or in the next row (the reference reads it too)
+        const int v0 = p[2 + co], v1 = (second || 4 * i + 4 <= srcStride || y < h - 1) ? s[2 + co] : s[co];
+        U[f * uFrame + (size_t)(y >> 1) * cStride + i] = (uint8_t)((p[co] + s[co]) >> 1);
+        V[f * vFrame + (size_t)(y >> 1) * cStride + i] = (uint8_t)((v0 + v1) >> 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
-enum { FMT_YUV420P = 0, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
-       FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31 };       // libavutil/pixfmt.h enum values
+enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
+       FMT_UYVY422 = 15, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31 };       // libavutil/pixfmt.h enum values
 
 struct SwsCudaContext {
     SwsGeometry g;
@@ -920,7 +1036,11 @@ struct SwsCudaContext {
     int lumStridePx = 0, chrStridePx = 0;
     bool src422 = false;        // the unscaled table converter reads the even chroma line of a 4:2:2 source for both rows (yuv2rgb.c:133-136)
     int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
-    uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the split chroma planes of a batch
+    int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422: the input readers (input.c) write planes first
+    int pkR = 0, pkB = 2;       //   byte offsets of red and blue
+    int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
+                                // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p
+    uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
     // staging for the host-pointer sws_scale_cuda()
@@ -974,7 +1094,20 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     case FMT_YUV410P: hs = 2; vs = 2; break;
     case FMT_YUV411P: hs = 2; vs = 0; break;
     case FMT_YUV440P: hs = 0; break;
-    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21"); return nullptr;
+    case FMT_YUYV422: case FMT_UYVY422: vs = 0; break;
+    case FMT_RGB24: case FMT_BGR24: {                         // utils.c:1021-1034: every other pixel for chroma unless told / forced otherwise
+        const int chrDstHSub = (dstFormat == FMT_YUV420P || !(flags & SWS_FULL_CHR_H_INT)) ? 1 : 0;
+        hs = (!(flags & SWS_FULL_CHR_H_INP) && ((dstW >> chrDstHSub) <= (srcW >> 1) || (flags & SWS_FAST_BILINEAR))) ? 1 : 0;
+        vs = 0;
+        break;
+    }
+    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21, yuyv422, uyvy422, rgb24, bgr24"); return nullptr;
+    }
+    const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
+    const bool unscaled = srcW == dstW && srcH == dstH;
+    if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1)) {
+        set_error_msg("sws_getContext_cuda", "bgr24 -> yuv420p of the same size without SWS_ACCURATE_RND is the reference's rgb24toyv12, which needs an even height");
+        return nullptr;
     }
     if (srcFormat == FMT_YUV410P && dstFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !(flags & SWS_BITEXACT)) {
         set_error_msg("sws_getContext_cuda", "yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper: not taken over");
@@ -991,6 +1124,13 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P;
+    c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : 0;
+    c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR;
+    if (unscaled) {                                           // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
+        if (srcRgb && dstFormat != FMT_YUV420P) c->special = srcFormat == dstFormat ? 1 : 2;
+        else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
+        else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
+    }
     if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err, hs, vs)) goto fail;
     {
         const int fl = c->g.flags;
@@ -1092,10 +1232,55 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st);
 
 // semi-planar sources: split the interleaved chroma plane, then everything is the planar path.  Same-size planar output is
+// Packed sources (rgb24 / bgr24 / yuyv422 / uyvy422): the reference's unscaled special converters where it installs them, else the
+// input readers into planes (one pre-pass, + srcW * srcH * (1 + 2 / 2^hs) bytes written and read again) and the planar kernels.
+static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                      uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
+{
+    if (nframes <= 0) return 0;
+    const SwsDev &p = c->dev;
+    const int w = p.srcW, h = p.srcH;
+    if (c->special == 1 || c->special == 2) {
+        sws_rgb24_shuffle_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dstStride[0], dstFrame[0], w, h, c->special == 2);
+        return check_launch("sws_scale:rgb24 shuffle");
+    }
+    if (c->special >= 3) {
+        if (dstStride[1] != dstStride[2]) { set_error_msg("sws_scale", "packed -> yuv420p needs equal chroma pitches"); return -1; }
+        if (c->special == 3) {
+            if (w >> 1) sws_bgr24_yv12_kernel<<<dim3(((w >> 1) + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dst[1], dst[2], dstStride[0], dstStride[1],
+                                                                                                    dstFrame[0], dstFrame[1], dstFrame[2], w, h);
+        } else {
+            sws_yuyv_yv12_kernel<<<dim3(((w + 1) / 2 + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dst[1], dst[2], dstStride[0], dstStride[1],
+                                                                                         dstFrame[0], dstFrame[1], dstFrame[2], w, h, c->special == 5);
+        }
+        return check_launch("sws_scale:packed -> yuv420p");
+    }
+    const int yPitch = (w + 15) & ~15, cPitch = (p.chrSrcW + 15) & ~15;
+    const size_t yPlane = (size_t)yPitch * h, cPlane = (size_t)cPitch * p.chrSrcH, need = (yPlane + 2 * cPlane) * nframes;
+    if (c->nv_bytes < need) {
+        AVB_CUDA(cudaStreamSynchronize(st), "sws_scale:reader");       // an earlier batch may still read the old planes
+        cudaFree(c->d_nv); c->d_nv = nullptr; c->nv_bytes = 0;
+        AVB_CUDA(cudaMalloc(&c->d_nv, need), "sws_scale:reader");
+        c->nv_bytes = need;
+    }
+    uint8_t *Y = c->d_nv, *U = Y + yPlane * nframes, *V = U + cPlane * nframes;
+    const dim3 grid(((w + 1) / 2 + 255) / 256, h, nframes);
+    const int half = p.chrSrcW != w;
+    if (c->srcPacked == 1)      sws_read_packed_kernel<1><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkB, half);
+    else if (c->srcPacked == 2) sws_read_packed_kernel<2><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 1);
+    else                        sws_read_packed_kernel<3><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 1);
+    if (check_launch("sws_scale:reader")) return -1;
+    const uint8_t *s3[3] = { Y, U, V };
+    const int st3[3] = { yPitch, cPitch, cPitch };
+    const size_t fr3[3] = { yPlane, cPlane, cPlane };
+    return run_planar(c, s3, st3, fr3, dst, dstStride, dstFrame, nframes, st);
+}
+
 // the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy + a split of srcW/2 x srcH/2 samples.
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
+    if (c->srcPacked) return run_packed(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
     if (!c->srcNV) return run_planar(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
     if (nframes <= 0) return 0;
     const SwsDev &p = c->dev;
@@ -1289,7 +1474,7 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
 {
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
-    if (!src || !dst || !src[0] || !src[1] || (!c->srcNV && !src[2]) || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
+    if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     static const size_t zero3[3] = { 0, 0, 0 };
     if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
                    nframes, (cudaStream_t)stream)) return -1;
@@ -1304,21 +1489,23 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
     const bool rgb = c->dstFormat != FMT_YUV420P;
-    const bool nv = c->srcNV != 0;
-    if (!srcSlice || !dst || !srcSlice[0] || !srcSlice[1] || (!nv && !srcSlice[2]) || !srcStride[0] || !srcStride[1] || (!nv && !srcStride[2]) ||
+    const bool nv = c->srcNV != 0, pk = c->srcPacked != 0;
+    if (!srcSlice || !dst || !srcSlice[0] || !srcStride[0] || (!pk && (!srcSlice[1] || !srcStride[1] || (!nv && (!srcSlice[2] || !srcStride[2])))) ||
         !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dst[2] || !dstStride[1] || !dstStride[2]))) {
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
     if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
-    if (srcStride[0] < 0 || srcStride[1] < 0 || (!nv && srcStride[2] < 0) || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
+    if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
     ScratchLock lk;
     cudaStream_t *st = scratch().streams();
     if (!st) return 0;
     cudaStream_t s = st[0];
     const SwsGeometry &g = c->g;
     // device staging: tight, aligned pitches
-    const int yP = (g.srcW + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW + 15) & ~15;
-    const size_t yB = (size_t)yP * g.srcH, cB = (size_t)cP * g.chrSrcH;
+    // (a packed source keeps the caller's pitch: the chroma readers look one pixel past an odd width, into the padding or the next row)
+    const int pkBpp = c->srcPacked == 1 ? 3 : 2;
+    const int yP = pk ? srcStride[0] : (g.srcW + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW + 15) & ~15;
+    const size_t yB = (size_t)yP * g.srcH, cB = pk ? 0 : (size_t)cP * g.chrSrcH;
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW + 15) & ~15, dcP = (g.chrDstW + 15) & ~15;
@@ -1363,7 +1550,13 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         for (int q = 0; q < 3; q++) if (cudaStreamSynchronize(st[q]) != cudaSuccess) { set_error("sws_scale_cuda:sync", cudaGetLastError()); return 0; }
         return g.dstH;
     }
-    if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+    if (pk) {
+        size_t rowB = (size_t)g.srcW * pkBpp;
+        if ((g.srcW & 1) && rowB + pkBpp <= (size_t)srcStride[0]) rowB += pkBpp;       // the pixel the readers look at past an odd width
+        if (cudaMemcpyAsync((void *)ds[0], srcSlice[0], (size_t)(g.srcH - 1) * srcStride[0] + rowB, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+            set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
+        }
+    } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
         (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
         set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
@@ -1376,11 +1569,14 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         size_t wbytes = (size_t)g.dstW * 3;
         if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;      // (full chroma writes single pixels)
         if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * 3;       // that converter leaves an odd last column untouched
+        if (c->special) wbytes = (size_t)g.dstW * 3;
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {
-        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);
-        // nv12ToPlanarWrapper splits srcW / 2 x srcH / 2 samples: an odd last column / row of the caller's planes stays untouched
-        const int cw = (nv && c->copy) ? g.srcW / 2 : g.chrDstW, ch = (nv && c->copy) ? g.srcH / 2 : g.chrDstH;
+        // rgb24toyv12_c converts whole pixel pairs only
+        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, c->special == 3 ? g.dstW & ~1 : g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);
+        // nv12ToPlanarWrapper splits srcW / 2 x srcH / 2 samples: an odd last column / row of the caller's planes stays untouched;
+        // the packed -> yuv420p converters write srcH / 2 chroma rows
+        const int cw = ((nv && c->copy) || c->special == 3) ? g.srcW / 2 : g.chrDstW, ch = ((nv && c->copy) || c->special >= 3) ? g.srcH / 2 : g.chrDstH;
         if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
     }

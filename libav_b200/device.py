@@ -114,17 +114,17 @@ class SwsContext:
     def fused(self):
         return bool(lib.sws_is_fused_cuda(self.ctx))
 
-    def scale(self, yuv, dst_pad=0):
-        """Host-pointer drop-in call: (Y, U, V) -- or (Y, UV) for nv12 / nv21 -- uint8 arrays (any row stride) -> rgb
-        (h, 3w [+pad]) or 3 planes."""
+    def scale(self, yuv, dst_pad=0, fill=0):
+        """Host-pointer drop-in call: (Y, U, V) -- (Y, UV) for nv12 / nv21, (packed,) for yuyv422 / uyvy422 / rgb24 / bgr24 --
+        uint8 arrays (any row stride) -> rgb (h, 3w [+pad]) or 3 planes, pre-filled with `fill`."""
         src = (C.c_void_p * 4)(*([a.ctypes.data for a in yuv] + [None] * (4 - len(yuv))))
         sst = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0] * (4 - len(yuv))))
         if self.dst_fmt == PIX_FMT_YUV420P:
-            out = [np.zeros((self.dst_h, self.dst_w), np.uint8),
-                   np.zeros(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), np.uint8),
-                   np.zeros(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), np.uint8)]
+            out = [np.full((self.dst_h, self.dst_w), fill, np.uint8),
+                   np.full(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), fill, np.uint8),
+                   np.full(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), fill, np.uint8)]
         else:
-            out = [np.zeros((self.dst_h, self.dst_w * 3 + dst_pad), np.uint8)]
+            out = [np.full((self.dst_h, self.dst_w * 3 + dst_pad), fill, np.uint8)]
         dst = (C.c_void_p * 4)(*([a.ctypes.data for a in out] + [None] * (4 - len(out))))
         dstr = (C.c_int * 4)(*([a.strides[0] for a in out] + [0] * (4 - len(out))))
         r = lib.sws_scale_cuda(self.ctx, src, sst, 0, self.src_h, dst, dstr)

@@ -164,9 +164,10 @@ int ORC(sws_yuv420p_to_yuv420p)(const uint8_t *const src[3], const int src_strid
  * which: 0 hLum, 1 hChr, 2 vLum, 3 vChr.  Fills filter (int16, n*fsize) and pos (int32, n), where
  * n = number of output samples of that axis (returned in *n_out); returns fsize (<0 on error).
  * filter_align is forced to 1 (the padding taps are zero under SWS_BITEXACT). */
-/* Planar 8-bit YUV sources of any chroma sub-sampling: src_fmt = AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6,
- * YUV411P 7, YUV440P 31 (libavutil/pixfmt.h); dst_fmt 2 = rgb24 (dst[0] only), 0 = yuv420p.  One frame through
- * sws_getContext + sws_scale; returns the lines written. */
+/* Any source format the product takes over.  Planar 8-bit YUV of any chroma sub-sampling: src_fmt = AV_PIX_FMT_YUV420P 0, YUV422P 4,
+ * YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31; packed (src[0] / ss[0] only): YUYV422 1, RGB24 2, BGR24 3, UYVY422 15
+ * (libavutil/pixfmt.h).  dst_fmt 2 = rgb24, 3 = bgr24 (dst[0] only), 0 = yuv420p.  One frame through sws_getContext + sws_scale;
+ * returns the lines written. */
 int ORC(sws_planar)(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                     uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags);
 /* Semi-planar sources: sws_getContext(sw, sh, AV_PIX_FMT_NV12 / NV21, dw, dh, dst_fmt, flags) + sws_scale of one frame

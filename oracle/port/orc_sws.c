@@ -498,23 +498,153 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
 }
 
 
-/* Planar 8-bit YUV sources of any chroma sub-sampling (getSubSampleFactors, utils.c:983): the same pipeline with
- * chrSrcW / chrSrcH derived from the format.  src_fmt: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6,
- * YUV411P 7, YUV440P 31. */
+/* rgb24 output helper for the bgr24 destination: the two only differ in byte order (output.c:1008-1040) */
+static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt, uint8_t *dst, int dstride, int dw, int dh, int flags)
+{
+    if (dst_fmt == 2) return orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    const int pitch = (dw + 1) * 3;
+    uint8_t *t = malloc((size_t)pitch * dh);
+    if (!t) return -1;
+    int r = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, t, pitch, dw, dh, flags);
+    for (int y = 0; r == dh && y < dh; y++)
+        for (int x = 0; x < dw; x++)
+            for (int k = 0; k < 3; k++) dst[(size_t)y * dstride + 3 * x + k] = t[(size_t)y * pitch + 3 * x + 2 - k];
+    free(t);
+    return r;
+}
+
+/* input.c:38-47 */
+#define RSH 15
+#define C_BY  ((int)(0.114 * 219 / 255 * (1 << RSH) + 0.5))
+#define C_BV (-(int)(0.081 * 224 / 255 * (1 << RSH) + 0.5))
+#define C_BU  ((int)(0.500 * 224 / 255 * (1 << RSH) + 0.5))
+#define C_GY  ((int)(0.587 * 219 / 255 * (1 << RSH) + 0.5))
+#define C_GV (-(int)(0.419 * 224 / 255 * (1 << RSH) + 0.5))
+#define C_GU (-(int)(0.331 * 224 / 255 * (1 << RSH) + 0.5))
+#define C_RY  ((int)(0.299 * 219 / 255 * (1 << RSH) + 0.5))
+#define C_RV  ((int)(0.500 * 224 / 255 * (1 << RSH) + 0.5))
+#define C_RU (-(int)(0.169 * 224 / 255 * (1 << RSH) + 0.5))
+
+/* Packed sources.  src_fmt: AV_PIX_FMT_YUYV422 1, RGB24 2, BGR24 3, UYVY422 15.
+ *  - same size: the reference installs special converters (swscale_unscaled.c:1063-1072,1140-1145,1152-1176): rgb24 <-> bgr24
+ *    (rgb24tobgr24) and the same-format copy; bgr24 -> yuv420p without SWS_ACCURATE_RND = rgb24toyv12_c (rgb2rgb_template.c:638-693,
+ *    8-bit coefficients rgb2rgb.c:111-120); yuyv422 / uyvy422 -> yuv420p = yuyvtoyuv420_c / uyvytoyuv420_c (:854-910);
+ *  - otherwise swscale() with the input readers in front (input.c:369-387,456-473,539-625): 8-bit planes, chroma at half width for
+ *    rgb unless SWS_FULL_CHR_H_INP or an up-scale asks for every pixel (utils.c:1021-1034), one chroma line per source line. */
+static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, int sh, int dst_fmt, uint8_t *const dst[3],
+                         const int ds[3], int dw, int dh, int flags)
+{
+    const int rgb_src = src_fmt == 2 || src_fmt == 3, ro = src_fmt == 3 ? 2 : 0, bo = 2 - ro;
+    if (sw == dw && sh == dh) {
+        if (rgb_src && dst_fmt != 0) {
+            for (int y = 0; y < sh; y++)
+                for (int x = 0; x < sw; x++)
+                    for (int k = 0; k < 3; k++)
+                        dst[0][(size_t)y * ds[0] + 3 * x + k] = src[(size_t)y * stride + 3 * x + (src_fmt == dst_fmt ? k : 2 - k)];
+            return sh;
+        }
+        if (src_fmt == 3 && dst_fmt == 0 && !(flags & F_ACCURATE_RND)) {
+            if (sh & 1) return -1;                           /* the reference's loop converts rows in pairs */
+            for (int y = 0; y < sh; y++)
+                for (int i = 0; i < (sw >> 1); i++)
+                    for (int k = 0; k < 2; k++) {
+                        const uint8_t *p = src + (size_t)y * stride + 6 * i + 3 * k;
+                        const int b = p[0], g = p[1], r = p[2];
+                        dst[0][(size_t)y * ds[0] + 2 * i + k] = (uint8_t)(((66 * r + 129 * g + 25 * b) >> 8) + 16);
+                        if (!(y & 1) && !k) {
+                            dst[1][(size_t)(y >> 1) * ds[1] + i] = (uint8_t)(((-37 * r - 73 * g + 112 * b) >> 8) + 128);
+                            dst[2][(size_t)(y >> 1) * ds[2] + i] = (uint8_t)(((112 * r - 93 * g - 17 * b) >> 8) + 128);
+                        }
+                    }
+            return sh;
+        }
+        if (!rgb_src && dst_fmt == 0) {
+            const int yo = src_fmt == 15, co = 1 - yo, cw = (sw + 1) >> 1;
+            for (int y = 0; y < sh; y++) {
+                const uint8_t *s = src + (size_t)y * stride, *p = s - stride;
+                for (int x = 0; x < sw; x++) dst[0][(size_t)y * ds[0] + x] = s[2 * x + yo];
+                if (y & 1)
+                    for (int i = 0; i < cw; i++) {
+                        const int ok = 2 * i + 1 < sw || 4 * i + 4 <= stride || y < sh - 1;
+                        dst[1][(size_t)(y >> 1) * ds[1] + i] = (uint8_t)((p[4 * i + co] + s[4 * i + co]) >> 1);
+                        dst[2][(size_t)(y >> 1) * ds[2] + i] = (uint8_t)((p[4 * i + 2 + co] + (ok ? s[4 * i + 2 + co] : s[4 * i + co])) >> 1);
+                    }
+            }
+            return sh;
+        }
+    }
+    int hs = 1;
+    if (rgb_src) {
+        const int chr_dst_hsub = (dst_fmt == 0 || !(flags & F_FULL_CHR_H_INT)) ? 1 : 0;
+        hs = (!(flags & 0x4000) && ((dw >> chr_dst_hsub) <= (sw >> 1) || (flags & 1))) ? 1 : 0;
+    }
+    const int cw = -((-sw) >> hs), yp = sw + 16, cp = cw + 16;
+    uint8_t *Y = calloc((size_t)yp * sh + 2 * (size_t)cp * sh, 1), *U = Y + (size_t)yp * sh, *V = U + (size_t)cp * sh;
+    if (!Y) return -1;
+    for (int y = 0; y < sh; y++) {
+        const uint8_t *row = src + (size_t)y * stride;
+        for (int i = 0; 2 * i < sw; i++) {
+            const int second = 2 * i + 1 < sw;
+            const int bpp = rgb_src ? 3 : 2;
+            const int ok = second || y < sh - 1 || (2 * i + 2) * bpp <= stride;   /* the sample past an odd width is inside the frame */
+            const uint8_t *s = row + 2 * i * bpp;
+            if (rgb_src) {
+                const int r0 = s[ro], g0 = s[1], b0 = s[bo];
+                const int r1 = ok ? s[3 + ro] : r0, g1 = ok ? s[4] : g0, b1 = ok ? s[3 + bo] : b0;
+                Y[(size_t)y * yp + 2 * i] = (uint8_t)((C_RY * r0 + C_GY * g0 + C_BY * b0 + (33 << (RSH - 1))) >> RSH);
+                if (second) Y[(size_t)y * yp + 2 * i + 1] = (uint8_t)((C_RY * r1 + C_GY * g1 + C_BY * b1 + (33 << (RSH - 1))) >> RSH);
+                if (hs) {
+                    const int r = r0 + r1, g = g0 + g1, b = b0 + b1;
+                    U[(size_t)y * cp + i] = (uint8_t)((C_RU * r + C_GU * g + C_BU * b + (257 << RSH)) >> (RSH + 1));
+                    V[(size_t)y * cp + i] = (uint8_t)((C_RV * r + C_GV * g + C_BV * b + (257 << RSH)) >> (RSH + 1));
+                } else {
+                    U[(size_t)y * cp + 2 * i] = (uint8_t)((C_RU * r0 + C_GU * g0 + C_BU * b0 + (257 << (RSH - 1))) >> RSH);
+                    V[(size_t)y * cp + 2 * i] = (uint8_t)((C_RV * r0 + C_GV * g0 + C_BV * b0 + (257 << (RSH - 1))) >> RSH);
+                    if (second) {
+                        U[(size_t)y * cp + 2 * i + 1] = (uint8_t)((C_RU * r1 + C_GU * g1 + C_BU * b1 + (257 << (RSH - 1))) >> RSH);
+                        V[(size_t)y * cp + 2 * i + 1] = (uint8_t)((C_RV * r1 + C_GV * g1 + C_BV * b1 + (257 << (RSH - 1))) >> RSH);
+                    }
+                }
+            } else {
+                const int yo = src_fmt == 15, co = 1 - yo;
+                Y[(size_t)y * yp + 2 * i] = s[yo];
+                if (second) Y[(size_t)y * yp + 2 * i + 1] = s[2 + yo];
+                U[(size_t)y * cp + i] = s[co];
+                V[(size_t)y * cp + i] = ok ? s[2 + co] : s[co];
+            }
+        }
+    }
+    const uint8_t *pl[3] = { Y, U, V };
+    const int ss[3] = { yp, cp, cp };
+    g_hs = hs; g_vs = 0;
+    /* (the unscaled table converter is only installed for planar yuv sources: keep the port off that branch) */
+    int r = dst_fmt != 0 ? to_rgb_or_bgr(pl, ss, sw, sh, dst_fmt, dst[0], ds[0], dw, dh, flags | F_ACCURATE_RND)
+                         : orc_sws_yuv420p_to_yuv420p(pl, ss, sw, sh, dst, ds, dw, dh, flags);
+    g_hs = 1; g_vs = 1;
+    free(Y);
+    return r;
+}
+
+/* Any source format the product takes over, to rgb24 (dst_fmt 2), bgr24 (3) or yuv420p (0).  Planar 8-bit YUV sources of any chroma
+ * sub-sampling (getSubSampleFactors, utils.c:983) run the same pipeline with chrSrcW / chrSrcH derived from the format.
+ * src_fmt: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31; packed: YUYV422 1, RGB24 2, BGR24 3,
+ * UYVY422 15 (src[0] / ss[0] only). */
 int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs;
+    if (dst_fmt != 0 && dst_fmt != 2 && dst_fmt != 3) return -1;
     switch (src_fmt) {
     case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;
     case 6: hs = 2; vs = 2; break;  case 7: hs = 2; vs = 0; break;  case 31: hs = 0; vs = 1; break;
+    case 1: case 2: case 3: case 15: return packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
     default: return -1;
     }
     /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
      * rgb2rgb.c planar2x): not restated */
     if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT)) return -1;
     g_hs = hs; g_vs = vs;
-    int r = dst_fmt == 2 ? orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst[0], dstride[0], dw, dh, flags)
+    int r = dst_fmt != 0 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
                          : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
     g_hs = 1; g_vs = 1;
     return r;

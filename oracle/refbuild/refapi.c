@@ -289,13 +289,13 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     INIT();
-    struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, dst_fmt == 2 ? AV_PIX_FMT_RGB24 : AV_PIX_FMT_YUV420P,
-                                          flags, NULL, NULL, NULL);
+    const int packed_src = src_fmt == AV_PIX_FMT_YUYV422 || src_fmt == AV_PIX_FMT_UYVY422 || src_fmt == AV_PIX_FMT_RGB24 || src_fmt == AV_PIX_FMT_BGR24;
+    struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
-    uint8_t *d[4] = { dst[0], dst_fmt == 2 ? NULL : dst[1], dst_fmt == 2 ? NULL : dst[2], NULL };
-    int ds[4] = { dstride[0], dst_fmt == 2 ? 0 : dstride[1], dst_fmt == 2 ? 0 : dstride[2], 0 };
-    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
-    int sst[4] = { ss[0], ss[1], ss[2], 0 };
+    uint8_t *d[4] = { dst[0], dst_fmt ? NULL : dst[1], dst_fmt ? NULL : dst[2], NULL };
+    int ds[4] = { dstride[0], dst_fmt ? 0 : dstride[1], dst_fmt ? 0 : dstride[2], 0 };
+    const uint8_t *s[4] = { src[0], packed_src ? NULL : src[1], packed_src ? NULL : src[2], NULL };
+    int sst[4] = { ss[0], packed_src ? 0 : ss[1], packed_src ? 0 : ss[2], 0 };
     int r = sws_scale(c, s, sst, 0, sh, d, ds);
     sws_freeContext(c);
     return r;

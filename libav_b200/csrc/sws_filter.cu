@@ -218,7 +218,7 @@ int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, 
 }
 
 int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool dst_is_rgb, int flags, const char **err,
-                    int chrSrcHSub, int chrSrcVSub)
+                    int chrSrcHSub, int chrSrcVSub, int chrDstHSub, int chrDstVSub)
 {
     int algos = flags & (SWS_POINT | SWS_AREA | SWS_BILINEAR | SWS_FAST_BILINEAR | SWS_BICUBIC | SWS_X | SWS_GAUSS |
                          SWS_LANCZOS | SWS_SINC | SWS_SPLINE | SWS_BICUBLIN);
@@ -233,7 +233,7 @@ int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool
     g.lumYInc = (int)((((int64_t)srcH << 16) + (dstH >> 1)) / dstH);
     g.chrSrcHSub = chrSrcHSub; g.chrSrcVSub = chrSrcVSub;     // getSubSampleFactors(), utils.c:983
     if (dst_is_rgb) { g.chrDstHSub = (flags & SWS_FULL_CHR_H_INT) ? 0 : 1; g.chrDstVSub = 0; }   // :1013-1014
-    else            { g.chrDstHSub = 1; g.chrDstVSub = 1; }
+    else            { g.chrDstHSub = chrDstHSub; g.chrDstVSub = chrDstVSub; }
     g.chrSrcVSub += (flags & 0x30000) >> 16;                  // SWS_SRC_V_CHR_DROP
     g.chrSrcW = -((-srcW) >> g.chrSrcHSub);
     g.chrSrcH = -((-srcH) >> g.chrSrcVSub);

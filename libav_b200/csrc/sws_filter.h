@@ -35,9 +35,9 @@ struct SwsGeometry {
     int lumXInc, lumYInc, chrXInc, chrYInc;
     int flags;
 };
-// planar 8-bit yuv source; dst_is_rgb selects packed 24-bit RGB (chroma shared by pixel pairs) or planar yuv420p
+// planar 8-bit yuv source; dst_is_rgb selects packed 24-bit RGB (chroma shared by pixel pairs) or planar yuv of the given sub-sampling
 int derive_geometry(SwsGeometry &g, int srcW, int srcH, int dstW, int dstH, bool dst_is_rgb, int flags, const char **err,
-                    int chrSrcHSub = 1, int chrSrcVSub = 1);     // source chroma sub-sampling (log2), 4:2:0 by default
+                    int chrSrcHSub = 1, int chrSrcVSub = 1, int chrDstHSub = 1, int chrDstVSub = 1);     // source chroma sub-sampling (log2), 4:2:0 by default
 
 struct RgbConstants {      // r = clip_u8((cy * (Y + ar + ((V * crv) >> 16)) + k1) >> 16), etc.
     int cy, k1;

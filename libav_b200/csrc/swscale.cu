@@ -36,7 +36,17 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     RgbConstants k;
     int bgr;
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
+    int dstBits;                      // planar destinations: 8, or 9 / 10 (little-endian 16-bit samples, yuv2planeX_10_c)
 };
+
+// yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64 everywhere) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) are one
+// recipe in the output depth: plane1 (v + (1 << (14 - bits))) >> (15 - bits), planeX ((1 << (26 - bits)) + sum) >> (27 - bits),
+// clipped to `bits` bits
+__device__ __forceinline__ int plane_clip(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
+__device__ __forceinline__ void plane_store(uint8_t *row, int x, int v, int bits)
+{
+    if (bits == 8) row[x] = (uint8_t)v; else reinterpret_cast<uint16_t *>(row)[x] = (uint16_t)v;
+}
 
 struct ChromaTerms { int tr, tg, tb; };
 
@@ -569,24 +579,24 @@ sws_vscale_rgb24_full_kernel(SwsDev p, const int16_t *__restrict__ lum, const in
     full_pixel(Y >> 10, U >> 10, V >> 10, p.k, p.bgr, dst + (size_t)y * dstStride + (size_t)i * 3);
 }
 
-// pass 2 for planar 8-bit output: yuv2planeX_8_c / yuv2plane1_8_c (output.c:242-265), dither = 64 everywhere
+// pass 2 for planar output (see plane_store above)
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
-                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH)
+                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (i >= dstW || y >= dstH) return;
     const int first = max(1 - fs, pos[y]);
     int val;
     if (fs == 1) {
-        val = (src[(size_t)line_index(first, 0, srcH) * srcStride + i] + 64) >> 7;
+        val = (src[(size_t)line_index(first, 0, srcH) * srcStride + i] + (1 << (14 - bits))) >> (15 - bits);
     } else {
         const int16_t *f = filter + (size_t)y * fs;
-        val = 64 << 12;
+        val = 1 << (26 - bits);
         for (int j = 0; j < fs; j++) val += src[(size_t)line_index(first, j, srcH) * srcStride + i] * f[j];
-        val >>= 19;
+        val >>= 27 - bits;
     }
-    dst[(size_t)y * dstStride + i] = (uint8_t)clip_u8(val);
+    plane_store(dst + (size_t)y * dstStride, i, plane_clip(val, bits), bits);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -853,21 +863,33 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
     if (y > y1 || x >= dstW) return;
     const int first = max(1 - fs, vP[y]);
     int v[8], t8[8];
+    const int bits = p.dstBits;
     if (fs == 1) {
         lds8(gt_smem + (line_index(first, 0, srcH) - lo) * GT_LW + 4 * tx, v);
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (v[k] + 64) >> 7;
+        for (int k = 0; k < 8; k++) v[k] = (v[k] + (1 << (14 - bits))) >> (15 - bits);
     } else {
         const int16_t *cf = vF + (size_t)y * fs;
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = 64 << 12;
+        for (int k = 0; k < 8; k++) v[k] = 1 << (26 - bits);
         for (int j = 0; j < fs; j++) {
             lds8(gt_smem + (line_index(first, j, srcH) - lo) * GT_LW + 4 * tx, t8); const int c = cf[j];
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] += t8[k] * c;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] >>= 19;
+        for (int k = 0; k < 8; k++) v[k] >>= 27 - bits;
+    }
+    if (bits != 8) {
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + (size_t)y * dstStride) + x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = plane_clip(v[k], bits);
+        if (x + 8 <= dstW && !(((uintptr_t)d16) & 15))
+            *reinterpret_cast<uint4 *>(d16) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        else
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (x + k < dstW) d16[k] = (uint16_t)v[k];
+        return;
     }
     uint8_t *d = dst + (size_t)y * dstStride + x;
     if (x + 8 <= dstW && !(((uintptr_t)d) & 7)) {
@@ -1013,11 +1035,60 @@ sws_yuyv_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcF
     }
 }
 
+// planarCopyWrapper, 8-bit source plane -> 9 / 10-bit plane (swscale_unscaled.c:946-971): limited-range luma and both chroma
+// planes are plain shifts
+__global__ void __launch_bounds__(256)
+sws_copy_plane_up_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
+                         int w, int h, int shift)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    reinterpret_cast<uint16_t *>(dst + blockIdx.z * dstFrame + (size_t)y * dstStride)[x] =
+        (uint16_t)(src[blockIdx.z * srcFrame + (size_t)y * srcStride + x] << shift);
+}
+
+// yuyvToYuv422Wrapper / uyvyToYuv422Wrapper -> yuyvtoyuv422_c / uyvytoyuv422_c (rgb2rgb_template.c:873-888,912-927): one thread per pixel pair
+__global__ void __launch_bounds__(256)
+sws_yuyv_yuv422p_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
+                        uint8_t *__restrict__ V, int yStride, int cStride, size_t yFrame, size_t uFrame, size_t vFrame, int w, int h, int uyvy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (2 * i >= w) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *s = src + f * srcFrame + (size_t)y * srcStride + 4 * i;
+    uint8_t *dy = Y + f * yFrame + (size_t)y * yStride + 2 * i;
+    const int yo = uyvy ? 1 : 0, co = uyvy ? 0 : 1;
+    const bool second = 2 * i + 1 < w;
+    dy[0] = s[yo];
+    if (second) dy[1] = s[2 + yo];
+    U[f * uFrame + (size_t)y * cStride + i] = s[co];
+    V[f * vFrame + (size_t)y * cStride + i] = (second || 4 * i + 4 <= srcStride || y < h - 1) ? s[2 + co] : s[co];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
-       FMT_UYVY422 = 15, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31 };       // libavutil/pixfmt.h enum values
+       FMT_UYVY422 = 15, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
+       FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
+
+// planar yuv destination: chroma sub-sampling (log2) and sample depth; false for anything else
+static bool planar_dst(int fmt, int *hs, int *vs, int *bits)
+{
+    *bits = 8;
+    switch (fmt) {
+    case FMT_YUV420P: *hs = 1; *vs = 1; return true;
+    case FMT_YUV422P: *hs = 1; *vs = 0; return true;
+    case FMT_YUV444P: *hs = 0; *vs = 0; return true;
+    case FMT_YUV410P: *hs = 2; *vs = 2; return true;
+    case FMT_YUV411P: *hs = 2; *vs = 0; return true;
+    case FMT_YUV440P: *hs = 0; *vs = 1; return true;
+    case FMT_YUV420P9: case FMT_YUV420P10: *hs = 1; *vs = 1; *bits = fmt == FMT_YUV420P9 ? 9 : 10; return true;
+    case FMT_YUV422P9: case FMT_YUV422P10: *hs = 1; *vs = 0; *bits = fmt == FMT_YUV422P9 ? 9 : 10; return true;
+    case FMT_YUV444P9: case FMT_YUV444P10: *hs = 0; *vs = 0; *bits = fmt == FMT_YUV444P9 ? 9 : 10; return true;
+    }
+    return false;
+}
 
 struct SwsCudaContext {
     SwsGeometry g;
@@ -1039,7 +1110,9 @@ struct SwsCudaContext {
     int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422: the input readers (input.c) write planes first
     int pkR = 0, pkB = 2;       //   byte offsets of red and blue
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
-                                // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p
+                                // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
+    bool planar = false;        // planar yuv destination (else packed rgb24 / bgr24)
+    int dstBits = 8;
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
@@ -1078,7 +1151,8 @@ static int upload_tables(SwsCudaContext *c)
     d.vChrF = (const int16_t *)(base + off[6]); d.vChrP = (const int32_t *)(base + off[7]);
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
-    d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && c->dstFormat != FMT_YUV420P;
+    d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
+    d.dstBits = c->dstBits;
     return 0;
 }
 
@@ -1086,6 +1160,12 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                                     const double *param, bool device_side)
 {
     const char *err = nullptr;
+    int dhs = 1, dvs = 0, dbits = 8;
+    const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits);
+    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24) {
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10-bit LE 420p 422p 444p");
+        return nullptr;
+    }
     int hs = 1, vs = 1;                                       // source chroma sub-sampling, libavutil/pixdesc.c log2_chroma_w / _h
     switch (srcFormat) {
     case FMT_YUV420P: case FMT_NV12: case FMT_NV21: break;
@@ -1096,7 +1176,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     case FMT_YUV440P: hs = 0; break;
     case FMT_YUYV422: case FMT_UYVY422: vs = 0; break;
     case FMT_RGB24: case FMT_BGR24: {                         // utils.c:1021-1034: every other pixel for chroma unless told / forced otherwise
-        const int chrDstHSub = (dstFormat == FMT_YUV420P || !(flags & SWS_FULL_CHR_H_INT)) ? 1 : 0;
+        const int chrDstHSub = planar ? dhs : (flags & SWS_FULL_CHR_H_INT) ? 0 : 1;
         hs = (!(flags & SWS_FULL_CHR_H_INP) && ((dstW >> chrDstHSub) <= (srcW >> 1) || (flags & SWS_FAST_BILINEAR))) ? 1 : 0;
         vs = 0;
         break;
@@ -1113,25 +1193,23 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper: not taken over");
         return nullptr;
     }
-    if (dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && dstFormat != FMT_YUV420P) {
-        set_error_msg("sws_getContext_cuda", "destination must be RGB24, BGR24 or YUV420P"); return nullptr;
-    }
-    const bool rgb = dstFormat != FMT_YUV420P;
+    const bool rgb = !planar;
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->dstFormat = dstFormat;
+    c->dstFormat = dstFormat; c->planar = planar; c->dstBits = dbits;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P;
     c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : 0;
     c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR;
     if (unscaled) {                                           // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
-        if (srcRgb && dstFormat != FMT_YUV420P) c->special = srcFormat == dstFormat ? 1 : 2;
+        if (srcRgb && rgb) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
         else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
+        else if (srcYuy && dstFormat == FMT_YUV422P) c->special = srcFormat == FMT_YUYV422 ? 6 : 7;
     }
-    if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err, hs, vs)) goto fail;
+    if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err, hs, vs, dhs, dvs)) goto fail;
     {
         const int fl = c->g.flags;
         const int lumFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BICUBIC) : fl;
@@ -1162,7 +1240,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         c->fast_ok = ok;
     }
-    c->copy = !rgb && srcW == dstW && srcH == dstH && hs == 1 && vs == 1;      // same format (or nv12 / nv21, split on the way)
+    // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
+    // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
+    c->copy = planar && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P);
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
     if (c->fast_ok) {
@@ -1246,14 +1326,17 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
     }
     if (c->special >= 3) {
         if (dstStride[1] != dstStride[2]) { set_error_msg("sws_scale", "packed -> yuv420p needs equal chroma pitches"); return -1; }
-        if (c->special == 3) {
+        if (c->special >= 6) {
+            sws_yuyv_yuv422p_kernel<<<dim3(((w + 1) / 2 + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dst[1], dst[2], dstStride[0], dstStride[1],
+                                                                                            dstFrame[0], dstFrame[1], dstFrame[2], w, h, c->special == 7);
+        } else if (c->special == 3) {
             if (w >> 1) sws_bgr24_yv12_kernel<<<dim3(((w >> 1) + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dst[1], dst[2], dstStride[0], dstStride[1],
                                                                                                     dstFrame[0], dstFrame[1], dstFrame[2], w, h);
         } else {
             sws_yuyv_yv12_kernel<<<dim3(((w + 1) / 2 + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dst[1], dst[2], dstStride[0], dstStride[1],
                                                                                          dstFrame[0], dstFrame[1], dstFrame[2], w, h, c->special == 5);
         }
-        return check_launch("sws_scale:packed -> yuv420p");
+        return check_launch("sws_scale:packed -> planar");
     }
     const int yPitch = (w + 15) & ~15, cPitch = (p.chrSrcW + 15) & ~15;
     const size_t yPlane = (size_t)yPitch * h, cPlane = (size_t)cPitch * p.chrSrcH, need = (yPlane + 2 * cPlane) * nframes;
@@ -1320,6 +1403,13 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
 {
     const SwsDev &p = c->dev;
     if (nframes <= 0) return 0;
+    if (c->copy && p.dstBits != 8) {
+        for (int pl = 0; pl < 3; pl++) {
+            const int w = pl ? p.chrSrcW : p.srcW, h = pl ? p.chrSrcH : p.srcH;
+            sws_copy_plane_up_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[pl], srcStride[pl], srcFrame[pl], dst[pl], dstStride[pl], dstFrame[pl], w, h, p.dstBits - 8);
+        }
+        return check_launch("sws_scale:copy");
+    }
     if (c->copy) {
         for (int f = 0; f < nframes; f++)
             for (int pl = 0; pl < 3; pl++) {
@@ -1373,7 +1463,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2];
         a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2];
         a.dstStride0 = dstStride[0]; a.dstFrame0 = dstFrame[0];
-        const bool planar = c->dstFormat == FMT_YUV420P;
+        const bool planar = c->planar;
         a.dstStride1 = planar ? dstStride[1] : 0; a.dstStride2 = planar ? dstStride[2] : 0;
         a.dstFrame1 = planar ? dstFrame[1] : 0; a.dstFrame2 = planar ? dstFrame[2] : 0;
         a.lumRows = c->tileLumRows; a.chrRows = c->tileChrRows;
@@ -1427,10 +1517,10 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
             sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
         }
-        if (c->dstFormat == FMT_YUV420P) {
-            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH);
+        if (c->planar) {
+            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits);
         } else {
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
@@ -1488,7 +1578,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
 {
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
-    const bool rgb = c->dstFormat != FMT_YUV420P;
+    const bool rgb = !c->planar;
     const bool nv = c->srcNV != 0, pk = c->srcPacked != 0;
     if (!srcSlice || !dst || !srcSlice[0] || !srcStride[0] || (!pk && (!srcSlice[1] || !srcStride[1] || (!nv && (!srcSlice[2] || !srcStride[2])))) ||
         !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dst[2] || !dstStride[1] || !dstStride[2]))) {
@@ -1508,7 +1598,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t yB = (size_t)yP * g.srcH, cB = pk ? 0 : (size_t)cP * g.chrSrcH;
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
-    const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW + 15) & ~15, dcP = (g.chrDstW + 15) & ~15;
+    const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
+    const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
     if (c->src_bytes < needS) { cudaFree(c->d_src); c->d_src = nullptr; if (cudaMalloc(&c->d_src, needS) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->src_bytes = needS; }
@@ -1573,12 +1664,13 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {
         // rgb24toyv12_c converts whole pixel pairs only
-        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, c->special == 3 ? g.dstW & ~1 : g.dstW, g.dstH, cudaMemcpyDeviceToHost, s);
+        e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, (size_t)(c->special == 3 ? g.dstW & ~1 : g.dstW) * sB, g.dstH, cudaMemcpyDeviceToHost, s);
         // nv12ToPlanarWrapper splits srcW / 2 x srcH / 2 samples: an odd last column / row of the caller's planes stays untouched;
         // the packed -> yuv420p converters write srcH / 2 chroma rows
-        const int cw = ((nv && c->copy) || c->special == 3) ? g.srcW / 2 : g.chrDstW, ch = ((nv && c->copy) || c->special >= 3) ? g.srcH / 2 : g.chrDstH;
-        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, cw, ch, cudaMemcpyDeviceToHost, s);
+        const int cw = ((nv && c->copy) || c->special == 3) ? g.srcW / 2 : g.chrDstW;
+        const int ch = ((nv && c->copy) || (c->special >= 3 && c->special <= 5)) ? g.srcH / 2 : g.chrDstH;
+        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, (size_t)cw * sB, ch, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, (size_t)cw * sB, ch, cudaMemcpyDeviceToHost, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("sws_scale_cuda:d2h", e); return 0; }

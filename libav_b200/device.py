@@ -94,6 +94,10 @@ def idct_put_tiles(blocks, tiles_per_row, mode=0, frame=None, use_offsets=False,
 # libswscale boundary
 # ---------------------------------------------------------------------------------------------------
 PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24, PIX_FMT_NV12, PIX_FMT_NV21 = 0, 2, 3, 23, 24
+PIX_FMT_YUYV422, PIX_FMT_UYVY422 = 1, 15
+# planar yuv formats (libavutil/pixfmt.h values): (log2 chroma width, log2 chroma height, bits per sample; > 8 = little-endian uint16)
+PLANAR_FORMATS = {0: (1, 1, 8), 4: (1, 0, 8), 5: (0, 0, 8), 6: (2, 2, 8), 7: (2, 0, 8), 31: (0, 1, 8),
+                  62: (1, 1, 9), 64: (1, 1, 10), 72: (1, 0, 9), 66: (1, 0, 10), 68: (0, 0, 9), 70: (0, 0, 10)}
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
 SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400
 SWS_ACCURATE_RND, SWS_BITEXACT = 0x40000, 0x80000
@@ -119,10 +123,11 @@ class SwsContext:
         uint8 arrays (any row stride) -> rgb (h, 3w [+pad]) or 3 planes, pre-filled with `fill`."""
         src = (C.c_void_p * 4)(*([a.ctypes.data for a in yuv] + [None] * (4 - len(yuv))))
         sst = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0] * (4 - len(yuv))))
-        if self.dst_fmt == PIX_FMT_YUV420P:
-            out = [np.full((self.dst_h, self.dst_w), fill, np.uint8),
-                   np.full(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), fill, np.uint8),
-                   np.full(((self.dst_h + 1) // 2, (self.dst_w + 1) // 2), fill, np.uint8)]
+        if self.dst_fmt in PLANAR_FORMATS:
+            hs, vs, bits = PLANAR_FORMATS[self.dst_fmt]
+            dt = np.uint8 if bits == 8 else np.dtype("<u2")
+            cw, ch = -((-self.dst_w) >> hs), -((-self.dst_h) >> vs)
+            out = [np.full((self.dst_h, self.dst_w), fill, dt), np.full((ch, cw), fill, dt), np.full((ch, cw), fill, dt)]
         else:
             out = [np.full((self.dst_h, self.dst_w * 3 + dst_pad), fill, np.uint8)]
         dst = (C.c_void_p * 4)(*([a.ctypes.data for a in out] + [None] * (4 - len(out))))

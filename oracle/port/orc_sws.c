@@ -208,6 +208,9 @@ static void sws_close(sws_t *c) { free_bank(&c->hl); free_bank(&c->hc); free_ban
 
 /* chroma sub-sampling of the planar 8-bit source being converted (log2): 4:2:0 unless orc_sws_planar() says otherwise */
 static __thread int g_hs = 1, g_vs = 1;
+/* the planar destination: chroma sub-sampling (log2) and sample depth (8, or 9 / 10 in little-endian 16-bit samples) */
+static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8;
+static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
 
 static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags)
 {
@@ -219,7 +222,7 @@ static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags
     c->srcW = sw; c->srcH = sh; c->dstW = dw; c->dstH = dh; c->flags = flags; c->rgb = rgb;
     c->chrSrcW = -((-sw) >> g_hs); c->chrSrcH = -((-sh) >> g_vs);
     /* packed RGB shares a chroma sample between two pixels unless SWS_FULL_CHR_H_INT asks for one per pixel (utils.c:998-1014) */
-    c->chrDstW = (rgb && (flags & F_FULL_CHR_H_INT)) ? dw : (dw + 1) >> 1; c->chrDstH = rgb ? dh : (dh + 1) >> 1;
+    c->chrDstW = rgb ? ((flags & F_FULL_CHR_H_INT) ? dw : (dw + 1) >> 1) : -((-dw) >> g_dhs); c->chrDstH = rgb ? dh : -((-dh) >> g_dvs);
     int lx = (int)((((int64_t)sw << 16) + (dw >> 1)) / dw), ly = (int)((((int64_t)sh << 16) + (dh >> 1)) / dh);
     int cx = (int)((((int64_t)c->chrSrcW << 16) + (c->chrDstW >> 1)) / c->chrDstW);
     int cyi = (int)((((int64_t)c->chrSrcH << 16) + (c->chrDstH >> 1)) / c->chrDstH);
@@ -419,19 +422,24 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     return dh;
 }
 
+/* yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) in one recipe:
+ * the rounding constants and shifts only depend on the output depth */
 static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t *dst, int dstride, int w, int h)
 {
+    const int bits = g_dbits, top = (1 << bits) - 1;
     for (int y = 0; y < h; y++) {
         int fs = b->taps, first = b->pos[y] > 1 - fs ? b->pos[y] : 1 - fs;
         for (int i = 0; i < w; i++) {
             int v;
-            if (fs == 1) v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + 64) >> 7;
+            if (fs == 1) v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + (1 << (14 - bits))) >> (15 - bits);
             else {
-                v = 64 << 12;
+                v = 1 << (26 - bits);
                 for (int j = 0; j < fs; j++) v += s[(size_t)rowsel(first, j, sh) * pitch + i] * b->coef[(size_t)y * fs + j];
-                v >>= 19;
+                v >>= 27 - bits;
             }
-            dst[(size_t)y * dstride + i] = u8clip(v);
+            v = v < 0 ? 0 : v > top ? top : v;
+            if (bits == 8) dst[(size_t)y * dstride + i] = (uint8_t)v;
+            else { dst[(size_t)y * dstride + 2 * i] = (uint8_t)v; dst[(size_t)y * dstride + 2 * i + 1] = (uint8_t)(v >> 8); }
         }
     }
 }
@@ -441,11 +449,17 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh && g_hs == 1 && g_vs == 1) {       /* unscaled same-format special converter: plain plane copy
-                                         (utils.c:1043-1054 -> swscale_unscaled.c planarCopyWrapper) */
+    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy) {   /* unscaled, same sub-sampling: planarCopyWrapper (utils.c:1043-1054,
+                                         swscale_unscaled.c:793-1020); 8 -> 9 / 10 bits is a plain shift for limited-range sources (:946-971) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
-            for (int y = 0; y < h; y++) memcpy(dst[p] + (size_t)y * ds[p], src[p] + (size_t)y * ss[p], w);
+            for (int y = 0; y < h; y++) {
+                if (g_dbits == 8) { memcpy(dst[p] + (size_t)y * ds[p], src[p] + (size_t)y * ss[p], w); continue; }
+                for (int x = 0; x < w; x++) {
+                    const int v = src[p][(size_t)y * ss[p] + x] << (g_dbits - 8);
+                    dst[p][(size_t)y * ds[p] + 2 * x] = (uint8_t)v; dst[p][(size_t)y * ds[p] + 2 * x + 1] = (uint8_t)(v >> 8);
+                }
+            }
         }
         sws_close(&c);
         return dh;
@@ -468,6 +482,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
  * destination is the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy and a split of
  * srcW/2 x srcH/2 chroma samples; an rgb destination always runs swscale() for these sources (the unscaled table
  * converter is only installed for planar yuv, swscale_unscaled.c:1051-1055). */
+static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt, uint8_t *dst, int dstride, int dw, int dh, int flags);
 int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
                  uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
@@ -491,8 +506,10 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
         }
     const uint8_t *src[3] = { y, u, v };
     const int ss[3] = { ystride, pitch, pitch };
-    int r = dst_fmt == 2 ? orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst[0], dstride[0], dw, dh, flags | 0x40000)
-                         : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    g_nocopy = 1;
+    int r = dst_fmt == 2 || dst_fmt == 3 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
+                                         : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    g_nocopy = 0;
     free(u);
     return r;
 }
@@ -535,8 +552,9 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
                          const int ds[3], int dw, int dh, int flags)
 {
     const int rgb_src = src_fmt == 2 || src_fmt == 3, ro = src_fmt == 3 ? 2 : 0, bo = 2 - ro;
+    const int rgb_dst = dst_fmt == 2 || dst_fmt == 3;
     if (sw == dw && sh == dh) {
-        if (rgb_src && dst_fmt != 0) {
+        if (rgb_src && rgb_dst) {
             for (int y = 0; y < sh; y++)
                 for (int x = 0; x < sw; x++)
                     for (int k = 0; k < 3; k++)
@@ -558,6 +576,19 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
                     }
             return sh;
         }
+        if (!rgb_src && dst_fmt == 4) {                     /* yuyvtoyuv422_c / uyvytoyuv422_c (rgb2rgb_template.c:873-888,912-927) */
+            const int yo = src_fmt == 15, co = 1 - yo, cw = (sw + 1) >> 1;
+            for (int y = 0; y < sh; y++) {
+                const uint8_t *s = src + (size_t)y * stride;
+                for (int x = 0; x < sw; x++) dst[0][(size_t)y * ds[0] + x] = s[2 * x + yo];
+                for (int i = 0; i < cw; i++) {
+                    const int ok = 2 * i + 1 < sw || 4 * i + 4 <= stride || y < sh - 1;
+                    dst[1][(size_t)y * ds[1] + i] = s[4 * i + co];
+                    dst[2][(size_t)y * ds[2] + i] = ok ? s[4 * i + 2 + co] : s[4 * i + co];
+                }
+            }
+            return sh;
+        }
         if (!rgb_src && dst_fmt == 0) {
             const int yo = src_fmt == 15, co = 1 - yo, cw = (sw + 1) >> 1;
             for (int y = 0; y < sh; y++) {
@@ -575,7 +606,7 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     }
     int hs = 1;
     if (rgb_src) {
-        const int chr_dst_hsub = (dst_fmt == 0 || !(flags & F_FULL_CHR_H_INT)) ? 1 : 0;
+        const int chr_dst_hsub = !rgb_dst ? g_dhs : (flags & F_FULL_CHR_H_INT) ? 0 : 1;
         hs = (!(flags & 0x4000) && ((dw >> chr_dst_hsub) <= (sw >> 1) || (flags & 1))) ? 1 : 0;
     }
     const int cw = -((-sw) >> hs), yp = sw + 16, cp = cw + 16;
@@ -618,34 +649,57 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     const int ss[3] = { yp, cp, cp };
     g_hs = hs; g_vs = 0;
     /* (the unscaled table converter is only installed for planar yuv sources: keep the port off that branch) */
-    int r = dst_fmt != 0 ? to_rgb_or_bgr(pl, ss, sw, sh, dst_fmt, dst[0], ds[0], dw, dh, flags | F_ACCURATE_RND)
-                         : orc_sws_yuv420p_to_yuv420p(pl, ss, sw, sh, dst, ds, dw, dh, flags);
+    int r = rgb_dst ? to_rgb_or_bgr(pl, ss, sw, sh, dst_fmt, dst[0], ds[0], dw, dh, flags | F_ACCURATE_RND)
+                    : orc_sws_yuv420p_to_yuv420p(pl, ss, sw, sh, dst, ds, dw, dh, flags);
     g_hs = 1; g_vs = 1;
     free(Y);
     return r;
 }
 
-/* Any source format the product takes over, to rgb24 (dst_fmt 2), bgr24 (3) or yuv420p (0).  Planar 8-bit YUV sources of any chroma
+/* planar destinations: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31, and the little-endian
+ * YUV420P9 62, YUV420P10 64, YUV422P10 66, YUV444P9 68, YUV444P10 70, YUV422P9 72 */
+static int planar_dst(int fmt, int *hs, int *vs, int *bits)
+{
+    *bits = 8;
+    switch (fmt) {
+    case 0: *hs = 1; *vs = 1; return 1;   case 4: *hs = 1; *vs = 0; return 1;   case 5: *hs = 0; *vs = 0; return 1;
+    case 6: *hs = 2; *vs = 2; return 1;   case 7: *hs = 2; *vs = 0; return 1;   case 31: *hs = 0; *vs = 1; return 1;
+    case 62: case 64: *hs = 1; *vs = 1; *bits = fmt == 62 ? 9 : 10; return 1;
+    case 72: case 66: *hs = 1; *vs = 0; *bits = fmt == 72 ? 9 : 10; return 1;
+    case 68: case 70: *hs = 0; *vs = 0; *bits = fmt == 68 ? 9 : 10; return 1;
+    }
+    return 0;
+}
+
+/* Any source format the product takes over, to rgb24 (dst_fmt 2), bgr24 (3) or a planar yuv format (planar_dst above).  Planar 8-bit YUV sources of any chroma
  * sub-sampling (getSubSampleFactors, utils.c:983) run the same pipeline with chrSrcW / chrSrcH derived from the format.
  * src_fmt: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31; packed: YUYV422 1, RGB24 2, BGR24 3,
  * UYVY422 15 (src[0] / ss[0] only). */
 int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
-    int hs, vs;
-    if (dst_fmt != 0 && dst_fmt != 2 && dst_fmt != 3) return -1;
+    int hs, vs, r;
+    const int rgb = dst_fmt == 2 || dst_fmt == 3;
+    if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
     case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;
     case 6: hs = 2; vs = 2; break;  case 7: hs = 2; vs = 0; break;  case 31: hs = 0; vs = 1; break;
-    case 1: case 2: case 3: case 15: return packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
-    default: return -1;
+    case 23: case 24:                                   /* src[0] luma, src[1] interleaved chroma */
+        r = orc_sws_nv12(src_fmt == 24, src[0], ss[0], src[1], ss[1], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+        g_dhs = g_dvs = 1; g_dbits = 8;
+        return r;
+    case 1: case 2: case 3: case 15:
+        r = packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+        g_dhs = g_dvs = 1; g_dbits = 8;
+        return r;
+    default: g_dhs = g_dvs = 1; g_dbits = 8; return -1;
     }
     /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
      * rgb2rgb.c planar2x): not restated */
     if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT)) return -1;
     g_hs = hs; g_vs = vs;
-    int r = dst_fmt != 0 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
-                         : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
-    g_hs = 1; g_vs = 1;
+    r = rgb ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
+            : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    g_hs = 1; g_vs = 1; g_dhs = g_dvs = 1; g_dbits = 8;
     return r;
 }

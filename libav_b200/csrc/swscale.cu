@@ -36,7 +36,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     RgbConstants k;
     int bgr;
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
-    int dstBits;                      // planar destinations: 8, or 9 / 10 (little-endian 16-bit samples, yuv2planeX_10_c)
+    int dstBits;                      // planar destinations: 8, 9 / 10 (little-endian 16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
 };
 
 // yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64 everywhere) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) are one
@@ -629,8 +629,8 @@ static inline void tile_line_window(const int32_t *pos, int fs, int y0, int y1, 
 template <int FS>
 __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, int srcStride, int lo, int n, int r0, int rstep,
                                               int32_t *out, int W, int x, int dstW, const int16_t *__restrict__ filter,
-                                              const int32_t *__restrict__ pos, int fs, int srcW, unsigned xInc, int chroma)
-{
+                                              const int32_t *__restrict__ pos, int fs, int srcW, unsigned xInc, int chroma, int sh = 7)
+{   // sh: 7 = hScale8To15_c, 3 = hScale8To19_c (16-bit destinations; swscale.c:62-100)
     if (x >= dstW) { for (int r = r0; r < n; r += rstep) out[r * W] = 0; return; }     // the reference's zeroed line tail
     const int step = rstep * srcStride;
     if constexpr (FS < 0) {
@@ -653,7 +653,7 @@ __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, i
             int acc = 0;
 #pragma unroll
             for (int j = 0; j < FS; j++) acc += (int)sp[j] * cf[j];
-            out[r * W] = min(acc >> 7, (1 << 15) - 1);
+            out[r * W] = min(acc >> sh, (1 << (22 - sh)) - 1);
         }
     } else {
         const int16_t *f = filter + (size_t)x * fs;
@@ -661,7 +661,7 @@ __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, i
         for (int r = r0; r < n; r += rstep, sp += step) {
             int acc = 0;
             for (int j = 0; j < fs; j++) acc += (int)sp[j] * f[j];
-            out[r * W] = min(acc >> 7, (1 << 15) - 1);
+            out[r * W] = min(acc >> sh, (1 << (22 - sh)) - 1);
         }
     }
 }
@@ -856,7 +856,7 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
         const int col = tid & (GT_W - 1);
         hscale_column<FS>(src, srcStride, lo, win.y, tid >> 7, 2, gt_smem + gt_lum_slot(col), GT_LW, x0 + col, dstW,
                           CHROMA ? p.hChrF : p.hLumF, CHROMA ? p.hChrP : p.hLumP, CHROMA ? p.hChrSize : p.hLumSize,
-                          CHROMA ? p.chrSrcW : p.srcW, CHROMA ? a.chrXInc : a.lumXInc, CHROMA);
+                          CHROMA ? p.chrSrcW : p.srcW, CHROMA ? a.chrXInc : a.lumXInc, CHROMA, p.dstBits == 16 ? 3 : 7);
     }
     __syncthreads();
     const int tx = tid & 15, y = y0 + (tid >> 4), x = x0 + 8 * tx;
@@ -864,6 +864,32 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
     const int first = max(1 - fs, vP[y]);
     int v[8], t8[8];
     const int bits = p.dstBits;
+    if (bits == 16) {            // yuv2plane1_16_c / yuv2planeX_16_c (output.c:136-172) on the 19-bit lines
+        if (fs == 1) {
+            lds8(gt_smem + (line_index(first, 0, srcH) - lo) * GT_LW + 4 * tx, v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = min(max((v[k] + 4) >> 3, 0), 65535);
+        } else {
+            const int16_t *cf = vF + (size_t)y * fs;
+            unsigned acc[8];      // the reference biases the sum by -0x40000000 so it stays inside 32 bits; wrap-around arithmetic here
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = (1u << 14) - 0x40000000u;
+            for (int j = 0; j < fs; j++) {
+                lds8(gt_smem + (line_index(first, j, srcH) - lo) * GT_LW + 4 * tx, t8); const int c = cf[j];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += (unsigned)(t8[k] * c);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = min(max((int)acc[k] >> 15, -32768), 32767) + 0x8000;
+        }
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + (size_t)y * dstStride) + x;
+        if (x + 8 <= dstW && !(((uintptr_t)d16) & 15))
+            *reinterpret_cast<uint4 *>(d16) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        else
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (x + k < dstW) d16[k] = (uint16_t)v[k];
+        return;
+    }
     if (fs == 1) {
         lds8(gt_smem + (line_index(first, 0, srcH) - lo) * GT_LW + 4 * tx, v);
 #pragma unroll
@@ -1036,15 +1062,15 @@ sws_yuyv_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcF
 }
 
 // planarCopyWrapper, 8-bit source plane -> 9 / 10-bit plane (swscale_unscaled.c:946-971): limited-range luma and both chroma
-// planes are plain shifts
+// planes are plain shifts; -> 16-bit plane (:984-992): the byte twice
 __global__ void __launch_bounds__(256)
 sws_copy_plane_up_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
                          int w, int h, int shift)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    reinterpret_cast<uint16_t *>(dst + blockIdx.z * dstFrame + (size_t)y * dstStride)[x] =
-        (uint16_t)(src[blockIdx.z * srcFrame + (size_t)y * srcStride + x] << shift);
+    const int v = src[blockIdx.z * srcFrame + (size_t)y * srcStride + x];
+    reinterpret_cast<uint16_t *>(dst + blockIdx.z * dstFrame + (size_t)y * dstStride)[x] = (uint16_t)(shift == 8 ? v * 257 : v << shift);
 }
 
 // yuyvToYuv422Wrapper / uyvyToYuv422Wrapper -> yuyvtoyuv422_c / uyvytoyuv422_c (rgb2rgb_template.c:873-888,912-927): one thread per pixel pair
@@ -1070,7 +1096,7 @@ sws_yuyv_yuv422p_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
        FMT_UYVY422 = 15, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
-       FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
+       FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
 // planar yuv destination: chroma sub-sampling (log2) and sample depth; false for anything else
 static bool planar_dst(int fmt, int *hs, int *vs, int *bits)
@@ -1086,6 +1112,9 @@ static bool planar_dst(int fmt, int *hs, int *vs, int *bits)
     case FMT_YUV420P9: case FMT_YUV420P10: *hs = 1; *vs = 1; *bits = fmt == FMT_YUV420P9 ? 9 : 10; return true;
     case FMT_YUV422P9: case FMT_YUV422P10: *hs = 1; *vs = 0; *bits = fmt == FMT_YUV422P9 ? 9 : 10; return true;
     case FMT_YUV444P9: case FMT_YUV444P10: *hs = 0; *vs = 0; *bits = fmt == FMT_YUV444P9 ? 9 : 10; return true;
+    case FMT_YUV420P16: *hs = 1; *vs = 1; *bits = 16; return true;
+    case FMT_YUV422P16: *hs = 1; *vs = 0; *bits = 16; return true;
+    case FMT_YUV444P16: *hs = 0; *vs = 0; *bits = 16; return true;
     }
     return false;
 }
@@ -1163,7 +1192,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     int dhs = 1, dvs = 0, dbits = 8;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits);
     if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10-bit LE 420p 422p 444p");
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit LE 420p 422p 444p");
         return nullptr;
     }
     int hs = 1, vs = 1;                                       // source chroma sub-sampling, libavutil/pixdesc.c log2_chroma_w / _h
@@ -1290,6 +1319,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                 set_error("sws_getContext_cuda", cudaGetLastError()); cudaFree(c->d_tables); delete c; return nullptr;
             }
             c->tileChrWinOff = nLumWin;
+        }
+        if (dbits == 16 && !c->tileLumRows) {      // the two-pass fallback keeps 15-bit lines in int16 planes
+            set_error_msg("sws_getContext_cuda", "16-bit destination: the vertical filter window does not fit in shared memory (19-bit lines exist only there)");
+            cudaFree(c->d_tables); delete c; return nullptr;
         }
         c->lumStridePx = (dstW + 1 + 7) & ~7;          // multiples of 8 samples: 16-byte aligned rows for the vector passes
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
@@ -1457,7 +1490,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         else         sws_fused_rgb24_kernel<false><<<g, b, 0, st>>>(p, a);    // same arithmetic, byte accesses
         return check_launch("sws_scale:fused");
     }
-    if (c->tileLumRows && tuning("sws_general_variant") != 1) {       // general path, fused per output tile
+    if (c->tileLumRows && (tuning("sws_general_variant") != 1 || p.dstBits == 16)) {       // general path, fused per output tile
         TileArgs a;
         a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst0 = dst[0]; a.dst1 = dst[1]; a.dst2 = dst[2];
         a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2];
@@ -1470,7 +1503,9 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         a.lumWin = c->d_tile_win; a.chrWin = c->d_tile_win + c->tileChrWinOff;
         a.lumXInc = c->g.lumXInc; a.chrXInc = c->g.chrXInc;
         a.vec = !((uintptr_t)a.dst0 & 7) && !(a.dstStride0 & 7) && !(a.dstFrame0 & 7);
-        const int fsl = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hLumSize, fsc = (c->g.flags & SWS_FAST_BILINEAR) ? -1 : p.hChrSize;
+        // (the fast-bilinear line functions only exist for 15-bit lines: a 16-bit destination gets the designed filter, swscale.c:728-741)
+        const bool fastb = (c->g.flags & SWS_FAST_BILINEAR) && p.dstBits != 16;
+        const int fsl = fastb ? -1 : p.hLumSize, fsc = fastb ? -1 : p.hChrSize;
         const dim3 gl((p.dstW + GT_W - 1) / GT_W, (p.dstH + GT_H - 1) / GT_H, nframes);
         if (!planar) {
             const size_t smem = ((size_t)a.lumRows * GT_LW + (size_t)a.chrRows * (p.full ? 2 * GT_LW : GT_W)) * 4;

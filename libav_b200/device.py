@@ -97,7 +97,8 @@ PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24, PIX_FMT_NV12, PIX_FMT_NV21 = 0, 2
 PIX_FMT_YUYV422, PIX_FMT_UYVY422 = 1, 15
 # planar yuv formats (libavutil/pixfmt.h values): (log2 chroma width, log2 chroma height, bits per sample; > 8 = little-endian uint16)
 PLANAR_FORMATS = {0: (1, 1, 8), 4: (1, 0, 8), 5: (0, 0, 8), 6: (2, 2, 8), 7: (2, 0, 8), 31: (0, 1, 8),
-                  62: (1, 1, 9), 64: (1, 1, 10), 72: (1, 0, 9), 66: (1, 0, 10), 68: (0, 0, 9), 70: (0, 0, 10)}
+                  62: (1, 1, 9), 64: (1, 1, 10), 72: (1, 0, 9), 66: (1, 0, 10), 68: (0, 0, 9), 70: (0, 0, 10),
+                  47: (1, 1, 16), 49: (1, 0, 16), 51: (0, 0, 16)}
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
 SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400
 SWS_ACCURATE_RND, SWS_BITEXACT = 0x40000, 0x80000

@@ -316,6 +316,22 @@ static int16_t *hpass(const uint8_t *src, int stride, int rows, const bank_t *b,
     return out;
 }
 
+/* hScale8To19_c (swscale.c:62-80): the lines a 16-bit destination is filtered from */
+static int32_t *hpass19(const uint8_t *src, int stride, int rows, const bank_t *b, int *pitch)
+{
+    int p = b->n + 2;
+    int32_t *out = calloc((size_t)p * rows, sizeof(*out));
+    for (int y = 0; y < rows; y++)
+        for (int i = 0; i < b->n; i++) {
+            int v = 0;
+            for (int j = 0; j < b->taps; j++) v += src[(size_t)y * stride + b->pos[i] + j] * b->coef[(size_t)i * b->taps + j];
+            v >>= 3;
+            out[(size_t)y * p + i] = v > (1 << 19) - 1 ? (1 << 19) - 1 : v;
+        }
+    *pitch = p;
+    return out;
+}
+
 static int rowsel(int first, int j, int h) { int r = first + j; return r < 0 ? 0 : r > h - 1 ? h - 1 : r; }
 
 int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst, int dstride,
@@ -444,6 +460,27 @@ static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t
     }
 }
 
+/* yuv2plane1_16_c / yuv2planeX_16_c (output.c:136-172), little-endian */
+static void vplane16(const int32_t *s, int pitch, int sh, const bank_t *b, uint8_t *dst, int dstride, int w, int h)
+{
+    for (int y = 0; y < h; y++) {
+        int fs = b->taps, first = b->pos[y] > 1 - fs ? b->pos[y] : 1 - fs;
+        for (int i = 0; i < w; i++) {
+            int v;
+            if (fs == 1) {
+                v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + 4) >> 3;
+                v = v < 0 ? 0 : v > 65535 ? 65535 : v;
+            } else {
+                uint32_t acc = (1u << 14) - 0x40000000u;      /* the reference's bias keeps the sum inside 32 bits */
+                for (int j = 0; j < fs; j++) acc += (uint32_t)(s[(size_t)rowsel(first, j, sh) * pitch + i] * b->coef[(size_t)y * fs + j]);
+                v = (int32_t)acc >> 15;
+                v = (v < -32768 ? -32768 : v > 32767 ? 32767 : v) + 0x8000;
+            }
+            dst[(size_t)y * dstride + 2 * i] = (uint8_t)v; dst[(size_t)y * dstride + 2 * i + 1] = (uint8_t)(v >> 8);
+        }
+    }
+}
+
 int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *const dst[3],
                                const int ds[3], int dw, int dh, int flags)
 {
@@ -456,7 +493,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
             for (int y = 0; y < h; y++) {
                 if (g_dbits == 8) { memcpy(dst[p] + (size_t)y * ds[p], src[p] + (size_t)y * ss[p], w); continue; }
                 for (int x = 0; x < w; x++) {
-                    const int v = src[p][(size_t)y * ss[p] + x] << (g_dbits - 8);
+                    const int v = g_dbits == 16 ? src[p][(size_t)y * ss[p] + x] * 257 : src[p][(size_t)y * ss[p] + x] << (g_dbits - 8);
                     dst[p][(size_t)y * ds[p] + 2 * x] = (uint8_t)v; dst[p][(size_t)y * ds[p] + 2 * x + 1] = (uint8_t)(v >> 8);
                 }
             }
@@ -465,6 +502,15 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
         return dh;
     }
     int lp, cp;
+    if (g_dbits == 16) {                /* 19-bit lines; no fast-bilinear line functions at this depth (swscale.c:728-741) */
+        int32_t *L = hpass19(src[0], ss[0], sh, &c.hl, &lp), *U = hpass19(src[1], ss[1], c.chrSrcH, &c.hc, &cp), *V = hpass19(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+        vplane16(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
+        vplane16(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
+        vplane16(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH);
+        free(L); free(U); free(V);
+        sws_close(&c);
+        return dh;
+    }
     const int fast = c.flags & F_FAST_BILINEAR;
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
@@ -647,11 +693,11 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     }
     const uint8_t *pl[3] = { Y, U, V };
     const int ss[3] = { yp, cp, cp };
-    g_hs = hs; g_vs = 0;
-    /* (the unscaled table converter is only installed for planar yuv sources: keep the port off that branch) */
+    g_hs = hs; g_vs = 0; g_nocopy = 1;
+    /* (the unscaled table converter and planarCopyWrapper are only installed for planar yuv sources: keep the port off those branches) */
     int r = rgb_dst ? to_rgb_or_bgr(pl, ss, sw, sh, dst_fmt, dst[0], ds[0], dw, dh, flags | F_ACCURATE_RND)
                     : orc_sws_yuv420p_to_yuv420p(pl, ss, sw, sh, dst, ds, dw, dh, flags);
-    g_hs = 1; g_vs = 1;
+    g_hs = 1; g_vs = 1; g_nocopy = 0;
     free(Y);
     return r;
 }
@@ -667,6 +713,9 @@ static int planar_dst(int fmt, int *hs, int *vs, int *bits)
     case 62: case 64: *hs = 1; *vs = 1; *bits = fmt == 62 ? 9 : 10; return 1;
     case 72: case 66: *hs = 1; *vs = 0; *bits = fmt == 72 ? 9 : 10; return 1;
     case 68: case 70: *hs = 0; *vs = 0; *bits = fmt == 68 ? 9 : 10; return 1;
+    case 47: *hs = 1; *vs = 1; *bits = 16; return 1;      /* YUV420P16LE, YUV422P16LE 49, YUV444P16LE 51 */
+    case 49: *hs = 1; *vs = 0; *bits = 16; return 1;
+    case 51: *hs = 0; *vs = 0; *bits = 16; return 1;
     }
     return 0;
 }

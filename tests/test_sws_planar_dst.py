@@ -1,6 +1,6 @@
-"""Planar yuv destinations other than yuv420p: 8-bit 422p / 444p / 410p / 411p / 440p and the little-endian 9 / 10-bit 420p /
-422p / 444p (yuv2planeX_10_c / yuv2plane1_10_c, output.c:183-213; planarCopyWrapper's 8 -> 9 / 10 bit shift,
-swscale_unscaled.c:946-971; yuyvtoyuv422_c / uyvytoyuv422_c).  CPU: port vs the compiled reference; GPU: product vs checker."""
+"""Planar yuv destinations other than yuv420p: 8-bit 422p / 444p / 410p / 411p / 440p and the little-endian 9 / 10 / 16-bit 420p /
+422p / 444p (yuv2planeX_10_c / yuv2plane1_10_c, output.c:183-213; yuv2planeX_16_c on hScale8To19_c lines, :136-172; planarCopyWrapper's
+8 -> 9 / 10 / 16 bit conversions, swscale_unscaled.c:946-992; yuyvtoyuv422_c / uyvytoyuv422_c).  CPU: port vs the compiled reference; GPU: product vs checker."""
 import ctypes as C
 
 import numpy as np
@@ -10,10 +10,10 @@ from libav_b200 import synth
 from libav_b200.device import PLANAR_FORMATS
 
 SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 23: None, 1: None, 2: None, 15: None}
-DST = [4, 5, 6, 7, 31, 62, 64, 66, 68, 70, 72]
+DST = [4, 5, 6, 7, 31, 62, 64, 66, 68, 70, 72, 47, 49, 51]
 GEOMS = [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (101, 37, 333, 211), (66, 50, 33, 25)]
 ACC = 0x40000 | 0x80000
-FLAGS = (4 | ACC, 2 | 0x80000, 0x10 | ACC, 0x200 | ACC)
+FLAGS = (4 | ACC, 2 | 0x80000, 0x10 | ACC, 0x200 | ACC, 1 | ACC)
 
 
 def source(fmt, w, h, seed):
@@ -37,6 +37,13 @@ def outputs(dfmt, dw, dh, pad=3):
     return [np.full((dh, dw + pad), 7, dt), np.full((ch, cw + pad), 7, dt), np.full((ch, cw + pad), 7, dt)]
 
 
+def undefined_edge(fmt, flags, sw, dw, dfmt):
+    """fast-bilinear up-scaling of a source that goes through the reference's uncleared formatConvBuffer: its last pixels
+    depend on uninitialised memory (tests/test_sws_packed_sources.py covers everything but that edge)"""
+    chroma_up = -((-dw) >> PLANAR_FORMATS[dfmt][0]) > (sw + 1) // 2          # all four have half-width chroma lines
+    return bool(flags & 1) and fmt in (23, 1, 2, 15) and (dw > sw or chroma_up) and PLANAR_FORMATS[dfmt][2] != 16
+
+
 def run(o, fmt, pl, w, h, dfmt, dw, dh, flags):
     out = outputs(dfmt, dw, dh)
     sp = (C.c_void_p * 3)(*([a.ctypes.data for a in pl] + [None] * (3 - len(pl))))
@@ -53,6 +60,8 @@ def test_port_matches_reference(orc, refo, dfmt):
         for (w, h, dw, dh) in GEOMS:
             pl = source(fmt, w, h, 3)
             for flags in FLAGS:
+                if undefined_edge(fmt, flags, w, dw, dfmt):
+                    continue
                 a, b = run(refo, fmt, pl, w, h, dfmt, dw, dh, flags), run(orc, fmt, pl, w, h, dfmt, dw, dh, flags)
                 assert a[0] == b[0] == dh and all(np.array_equal(x, y) for x, y in zip(a[1], b[1])), (fmt, dfmt, w, h, dw, dh, hex(flags))
 
@@ -65,7 +74,7 @@ def test_gpu_matches_checker(gpu, checker, dfmt):
         for (w, h, dw, dh) in GEOMS + [(1280, 720, 1920, 1080)]:
             pl = source(fmt, w, h, 5)
             for flags in FLAGS:
-                if w * h > 500000 and flags != 4 | ACC:
+                if (w * h > 500000 and flags != 4 | ACC) or undefined_edge(fmt, flags, w, dw, dfmt):
                     continue
                 rc, want = run(checker, fmt, pl, w, h, dfmt, dw, dh, flags)
                 assert rc == dh
@@ -80,5 +89,5 @@ def test_gpu_matches_checker(gpu, checker, dfmt):
 def test_refusals_are_loud(gpu):
     from libav_b200 import device
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 64, 48, 47, 4)          # yuv420p16le: 19-bit intermediates are not taken over
+        device.SwsContext(64, 48, 64, 48, 48, 4)          # yuv420p16be
     gpu.lib.avb200_clear_error()

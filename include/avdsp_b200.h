@@ -271,6 +271,35 @@ typedef struct FFH264DeblockInfo {
 } FFH264DeblockInfo;
 int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info /* host struct */, FFH264DeblockMB *out, void *stream);
 
+/* The flush point of a decoder back-end: the CPU parses and entropy-decodes, RECORDS the work of a batch of
+ * pictures (or of the slices decoded so far) in the arrays below, and flushes it with one call.  The stages run on `stream` in
+ * the order hl_decode_mb() (libavcodec/h264_mb_template.c:40-260: inter prediction, weighted prediction, DC transforms,
+ * residual; intra prediction interleaved with its residual) and loop_filter() (libavcodec/h264_slice.c:1972-2066) impose; the
+ * call returns without synchronising.  Every array is a DEVICE pointer (deblock_info is a host struct of device pointers), a
+ * NULL array / zero count skips its stage.  Per-macroblock arrays (dc, residual, intra, deblock_records, the coefficient arena
+ * coeffs + i * coeff_stride, nnzc + i * 120) have one entry per macroblock of the batch in raster order, pictures stacked:
+ * a macroblock that takes no part in a stage says so in its record (residual luma_mode 3 / chroma 0 for intra and skipped
+ * macroblocks, intra kind 0 for inter ones, dc qmul 0).  Planes: n_pictures pictures stacked vertically, 16 * mb_h luma rows
+ * each.  progress: 2 * mb_h * n_pictures uint32 of scratch. */
+typedef struct FFH264PictureWork {
+    int mb_w, mb_h, n_pictures;
+    uint8_t *luma, *cb, *cr;                 /* the pictures being reconstructed */
+    int linesize, uvlinesize;
+    const FFH264MCRecord *mc; size_t n_mc;   /* ff_h264_mc_batch_cuda; pic_w / pic_h = 16 * mb_w / 16 * mb_h */
+    const FFH264RefPlanes *refs;
+    const FFH264WeightRecord *weight[3]; size_t n_weight[3];   /* per plane: ff_h264_weight_batch_cuda */
+    const uint8_t *weight_src[3];            /* bi-weighting: the plane holding the second prediction, else NULL */
+    int16_t *coeffs; size_t coeff_stride;    /* coefficient arena, consumed (zeroed) like the C functions do */
+    const uint8_t *nnzc;
+    const FFH264DCRecord *dc; const int16_t *luma_dc;          /* ff_h264_dc_dequant_batch_cuda */
+    const FFH264ResidualMB *residual;        /* ff_h264_idct_add_mb_batch_cuda */
+    const FFH264IntraMB *intra;              /* ff_h264_intra_mb_batch_cuda */
+    const FFH264DeblockInfo *deblock_info;   /* host struct: decisions are derived on the device into deblock_records */
+    FFH264DeblockMB *deblock_records;        /* with deblock_info NULL: records the caller already filled; NULL = no loop filter */
+    uint32_t *progress;
+} FFH264PictureWork;
+int ff_h264_flush_pictures_cuda(const FFH264PictureWork *work /* host struct */, void *stream);
+
 /* ---- MECmpContext, motion search, HpelDSPContext, FDCTDSPContext -----------------------------------------
  * me_cmp: n block pairs (cur + cur_off vs ref + ref_off, common stride, height h) through one metric; out[i] is
  * what the C slot returns.  kind / sidx / dxy select the slot like the reference's tables (libavcodec/me_cmp.h:39-63):

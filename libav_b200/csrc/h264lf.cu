@@ -221,3 +221,37 @@ extern "C" int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info, FFH264
     h264_deblock_params_kernel<<<(2 * n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, out, n);
     return check_launch("ff_h264_deblock_params_cuda");
 }
+
+// The decoder back-end's flush point: everything the CPU recorded for a batch of pictures / slices, run in the
+// order hl_decode_mb() (libavcodec/h264_mb_template.c:40-260) and loop_filter() (h264_slice.c:1972-2066) impose.  Pure stream
+// ordering of the batch entry points -- no host synchronisation; an error of any stage stops the flush.
+extern "C" int ff_h264_flush_pictures_cuda(const FFH264PictureWork *w, void *stream)
+{
+    if (!w || w->mb_w <= 0 || w->mb_h <= 0 || w->n_pictures <= 0 || !w->luma || !w->cb || !w->cr) {
+        set_error_msg("ff_h264_flush_pictures_cuda", "bad arguments"); return -1;
+    }
+    const size_t n_mb = (size_t)w->mb_w * w->mb_h * w->n_pictures;
+    // 1. inter prediction: every put partition, then every avg partition (h264_mb.c:322-366)
+    if (w->n_mc && ff_h264_mc_batch_cuda(w->mc, w->n_mc, w->refs, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, 16 * w->mb_w, 16 * w->mb_h, stream)) return -1;
+    // 2. explicit / implicit weighted prediction on the predicted blocks (h264_mb.c:368-460), plane by plane
+    for (int pl = 0; pl < 3; pl++) {
+        uint8_t *plane = pl == 0 ? w->luma : pl == 1 ? w->cb : w->cr;
+        if (w->n_weight[pl] && ff_h264_weight_batch_cuda(w->weight[pl], w->n_weight[pl], plane, w->weight_src[pl], pl ? w->uvlinesize : w->linesize, stream)) return -1;
+    }
+    // 3. DC transforms + dequantisation into the coefficient arena, 4. residual of the inter macroblocks
+    if (w->dc && ff_h264_dc_dequant_batch_cuda(w->dc, n_mb, w->coeffs, w->coeff_stride, w->luma_dc, stream)) return -1;
+    if (w->residual && ff_h264_idct_add_mb_batch_cuda(w->residual, n_mb, w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, stream)) return -1;
+    // 5. intra macroblocks: prediction interleaved with their residual, as a wavefront over the reconstructed neighbours
+    if (w->intra && ff_h264_intra_mb_batch_cuda(w->intra, w->mb_w, w->mb_h, w->n_pictures, w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
+                                                w->linesize, w->uvlinesize, w->progress, stream)) return -1;
+    // 6. deblocking decisions from the side information, 7. the loop filter
+    if (w->deblock_info) {
+        if (!w->deblock_records || w->deblock_info->mb_w != w->mb_w || w->deblock_info->mb_h != w->mb_h || w->deblock_info->n_pictures != w->n_pictures) {
+            set_error_msg("ff_h264_flush_pictures_cuda", "deblock_info does not describe this batch"); return -1;
+        }
+        if (ff_h264_deblock_params_cuda(w->deblock_info, w->deblock_records, stream)) return -1;
+    }
+    if (w->deblock_records && ff_h264_deblock_batch_cuda(w->deblock_records, w->mb_w, w->mb_h, w->n_pictures, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize,
+                                                         w->progress, stream)) return -1;
+    return 0;
+}

@@ -112,6 +112,17 @@ class FFH264DeblockInfo(C.Structure):
                 ("cabac", C.c_int), ("transform_8x8_mode", C.c_int)]
 
 
+class FFH264PictureWork(C.Structure):
+    """include/avdsp_b200.h FFH264PictureWork (host struct holding device pointers): ff_h264_flush_pictures_cuda"""
+    _fields_ = [("mb_w", C.c_int), ("mb_h", C.c_int), ("n_pictures", C.c_int),
+                ("luma", C.c_void_p), ("cb", C.c_void_p), ("cr", C.c_void_p), ("linesize", C.c_int), ("uvlinesize", C.c_int),
+                ("mc", C.c_void_p), ("n_mc", C.c_size_t), ("refs", C.c_void_p),
+                ("weight", C.c_void_p * 3), ("n_weight", C.c_size_t * 3), ("weight_src", C.c_void_p * 3),
+                ("coeffs", C.c_void_p), ("coeff_stride", C.c_size_t), ("nnzc", C.c_void_p),
+                ("dc", C.c_void_p), ("luma_dc", C.c_void_p), ("residual", C.c_void_p), ("intra", C.c_void_p),
+                ("deblock_info", C.POINTER(FFH264DeblockInfo)), ("deblock_records", C.c_void_p), ("progress", C.c_void_p)]
+
+
 class FFMpegDequantTables(C.Structure):
     """include/avdsp_b200.h FFMpegDequantTables"""
     _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),

@@ -1195,6 +1195,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit LE 420p 422p 444p");
         return nullptr;
     }
+    if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
+        set_error_msg("sws_getContext_cuda", "SWS_SRC_V_CHR_DROP (skipping source chroma lines) is not taken over"); return nullptr;
+    }
     int hs = 1, vs = 1;                                       // source chroma sub-sampling, libavutil/pixdesc.c log2_chroma_w / _h
     switch (srcFormat) {
     case FMT_YUV420P: case FMT_NV12: case FMT_NV21: break;

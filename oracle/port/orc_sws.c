@@ -219,6 +219,7 @@ static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags
     if (!algo) flags |= (dw < sw && dh < sh) ? F_GAUSS : (dw > sw && dh > sh) ? F_SINC : F_LANCZOS;
     else if (algo & (algo - 1)) return -1;
     if (sw < 4 || sh < 1 || dw < 8 || dh < 1 || ((flags & F_FULL_CHR_H_INT) && !rgb)) return -1;
+    if (flags & 0x30000) return -1;                          /* SWS_SRC_V_CHR_DROP_MASK: not restated */
     c->srcW = sw; c->srcH = sh; c->dstW = dw; c->dstH = dh; c->flags = flags; c->rgb = rgb;
     c->chrSrcW = -((-sw) >> g_hs); c->chrSrcH = -((-sh) >> g_vs);
     /* packed RGB shares a chroma sample between two pixels unless SWS_FULL_CHR_H_INT asks for one per pixel (utils.c:998-1014) */

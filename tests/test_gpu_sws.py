@@ -98,6 +98,9 @@ def test_unsupported_requests_fail_loudly(gpu):
     L.lib.avb200_clear_error()
     assert not L.lib.sws_getContext_cuda(2, 2, 0, 640, 480, 2, 4 | ACC, None, None, None)
     L.lib.avb200_clear_error()
+    assert not L.lib.sws_getContext_cuda(640, 480, 0, 320, 240, 2, 4 | ACC | 0x10000, None, None, None)     # SWS_SRC_V_CHR_DROP
+    assert "CHR_DROP" in L.last_error()
+    L.lib.avb200_clear_error()
 
 
 def test_device_batch_equals_single_frames(gpu, checker):

@@ -42,7 +42,8 @@ def picture_work(mb_w, mb_h, seed, p_intra):
     wrec["off"] = (mbs // mb_w) * 16 * (16 * mb_w) + (mbs % mb_w) * 16
     wrec["w"] = 16; wrec["h"] = 16; wrec["log2_denom"] = r.randint(0, 7, wrec.shape[0])
     wrec["weight"] = r.randint(-60, 100, wrec.shape[0]); wrec["offset"] = r.randint(-20, 21, wrec.shape[0])
-    info = synth.h264_deblock_info(mb_w, mb_h, seed=seed + 4, n_slices=3, bipred=True, t8x8=1, cabac=1)
+    # (one set of slice headers per flush: every picture of the batch gets the same side information, its pixels differ)
+    info = synth.h264_deblock_info(mb_w, mb_h, seed=mb_w + 4, n_slices=3, bipred=True, t8x8=1, cabac=1)
     return dict(intra=intra, res=res, coeffs=np.ascontiguousarray(coeffs), nnzc=np.ascontiguousarray(nnzc), mc=mc, dc=dc, luma_dc=luma_dc, weight=wrec,
                 info=info)
 

@@ -36,16 +36,18 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     RgbConstants k;
     int bgr;
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
-    int dstBits;                      // planar destinations: 8, 9 / 10 (little-endian 16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
+    int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
+    int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
 };
 
 // yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64 everywhere) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) are one
 // recipe in the output depth: plane1 (v + (1 << (14 - bits))) >> (15 - bits), planeX ((1 << (26 - bits)) + sum) >> (27 - bits),
 // clipped to `bits` bits
 __device__ __forceinline__ int plane_clip(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
-__device__ __forceinline__ void plane_store(uint8_t *row, int x, int v, int bits)
+__device__ __forceinline__ int swap16_if(int v, int be) { return be ? ((v >> 8) | (v << 8)) & 0xFFFF : v; }
+__device__ __forceinline__ void plane_store(uint8_t *row, int x, int v, int bits, int be)
 {
-    if (bits == 8) row[x] = (uint8_t)v; else reinterpret_cast<uint16_t *>(row)[x] = (uint16_t)v;
+    if (bits == 8) row[x] = (uint8_t)v; else reinterpret_cast<uint16_t *>(row)[x] = (uint16_t)swap16_if(v, be);
 }
 
 struct ChromaTerms { int tr, tg, tb; };
@@ -582,7 +584,7 @@ sws_vscale_rgb24_full_kernel(SwsDev p, const int16_t *__restrict__ lum, const in
 // pass 2 for planar output (see plane_store above)
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
-                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits)
+                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits, int be)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (i >= dstW || y >= dstH) return;
@@ -596,7 +598,7 @@ sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH
         for (int j = 0; j < fs; j++) val += src[(size_t)line_index(first, j, srcH) * srcStride + i] * f[j];
         val >>= 27 - bits;
     }
-    plane_store(dst + (size_t)y * dstStride, i, plane_clip(val, bits), bits);
+    plane_store(dst + (size_t)y * dstStride, i, plane_clip(val, bits), bits, be);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -882,6 +884,8 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = min(max((int)acc[k] >> 15, -32768), 32767) + 0x8000;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = swap16_if(v[k], p.dstBE);
         uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + (size_t)y * dstStride) + x;
         if (x + 8 <= dstW && !(((uintptr_t)d16) & 15))
             *reinterpret_cast<uint4 *>(d16) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
@@ -909,7 +913,7 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
     if (bits != 8) {
         uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + (size_t)y * dstStride) + x;
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = plane_clip(v[k], bits);
+        for (int k = 0; k < 8; k++) v[k] = swap16_if(plane_clip(v[k], bits), p.dstBE);
         if (x + 8 <= dstW && !(((uintptr_t)d16) & 15))
             *reinterpret_cast<uint4 *>(d16) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
         else
@@ -1065,12 +1069,12 @@ sws_yuyv_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcF
 // planes are plain shifts; -> 16-bit plane (:984-992): the byte twice
 __global__ void __launch_bounds__(256)
 sws_copy_plane_up_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
-                         int w, int h, int shift)
+                         int w, int h, int shift, int be)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const int v = src[blockIdx.z * srcFrame + (size_t)y * srcStride + x];
-    reinterpret_cast<uint16_t *>(dst + blockIdx.z * dstFrame + (size_t)y * dstStride)[x] = (uint16_t)(shift == 8 ? v * 257 : v << shift);
+    reinterpret_cast<uint16_t *>(dst + blockIdx.z * dstFrame + (size_t)y * dstStride)[x] = (uint16_t)swap16_if(shift == 8 ? v * 257 : v << shift, be);
 }
 
 // yuyvToYuv422Wrapper / uyvyToYuv422Wrapper -> yuyvtoyuv422_c / uyvytoyuv422_c (rgb2rgb_template.c:873-888,912-927): one thread per pixel pair
@@ -1099,9 +1103,13 @@ enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV42
        FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
 // planar yuv destination: chroma sub-sampling (log2) and sample depth; false for anything else
-static bool planar_dst(int fmt, int *hs, int *vs, int *bits)
+static bool planar_dst(int fmt, int *hs, int *vs, int *bits, int *be)
 {
-    *bits = 8;
+    *bits = 8; *be = 0;
+    switch (fmt) {               // big-endian twins: 9 / 10-bit LE - 1, 16-bit LE + 1
+    case 61: case 63: case 65: case 67: case 69: case 71: *be = 1; fmt += 1; break;
+    case 48: case 50: case 52: *be = 1; fmt -= 1; break;
+    }
     switch (fmt) {
     case FMT_YUV420P: *hs = 1; *vs = 1; return true;
     case FMT_YUV422P: *hs = 1; *vs = 0; return true;
@@ -1141,7 +1149,7 @@ struct SwsCudaContext {
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
     bool planar = false;        // planar yuv destination (else packed rgb24 / bgr24)
-    int dstBits = 8;
+    int dstBits = 8, dstBE = 0;
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
@@ -1181,7 +1189,7 @@ static int upload_tables(SwsCudaContext *c)
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE;
     return 0;
 }
 
@@ -1189,10 +1197,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                                     const double *param, bool device_side)
 {
     const char *err = nullptr;
-    int dhs = 1, dvs = 0, dbits = 8;
-    const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits);
+    int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
+    const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit LE 420p 422p 444p");
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1229,7 +1237,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->dstFormat = dstFormat; c->planar = planar; c->dstBits = dbits;
+    c->dstFormat = dstFormat; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P;
@@ -1442,7 +1450,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
     if (c->copy && p.dstBits != 8) {
         for (int pl = 0; pl < 3; pl++) {
             const int w = pl ? p.chrSrcW : p.srcW, h = pl ? p.chrSrcH : p.srcH;
-            sws_copy_plane_up_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[pl], srcStride[pl], srcFrame[pl], dst[pl], dstStride[pl], dstFrame[pl], w, h, p.dstBits - 8);
+            sws_copy_plane_up_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[pl], srcStride[pl], srcFrame[pl], dst[pl], dstStride[pl], dstFrame[pl], w, h, p.dstBits - 8, p.dstBE);
         }
         return check_launch("sws_scale:copy");
     }
@@ -1556,9 +1564,9 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
         }
         if (c->planar) {
-            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits);
+            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits, p.dstBE);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE);
         } else {
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];

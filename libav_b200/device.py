@@ -99,6 +99,9 @@ PIX_FMT_YUYV422, PIX_FMT_UYVY422 = 1, 15
 PLANAR_FORMATS = {0: (1, 1, 8), 4: (1, 0, 8), 5: (0, 0, 8), 6: (2, 2, 8), 7: (2, 0, 8), 31: (0, 1, 8),
                   62: (1, 1, 9), 64: (1, 1, 10), 72: (1, 0, 9), 66: (1, 0, 10), 68: (0, 0, 9), 70: (0, 0, 10),
                   47: (1, 1, 16), 49: (1, 0, 16), 51: (0, 0, 16)}
+PLANAR_FORMATS.update({f - 1: PLANAR_FORMATS[f] for f in (62, 64, 72, 66, 68, 70)})     # big-endian twins
+PLANAR_FORMATS.update({f + 1: PLANAR_FORMATS[f] for f in (47, 49, 51)})
+PLANAR_BE = {61, 63, 71, 65, 67, 69, 48, 50, 52}
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
 SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400
 SWS_ACCURATE_RND, SWS_BITEXACT = 0x40000, 0x80000
@@ -126,7 +129,7 @@ class SwsContext:
         sst = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0] * (4 - len(yuv))))
         if self.dst_fmt in PLANAR_FORMATS:
             hs, vs, bits = PLANAR_FORMATS[self.dst_fmt]
-            dt = np.uint8 if bits == 8 else np.dtype("<u2")
+            dt = np.uint8 if bits == 8 else np.dtype(">u2" if self.dst_fmt in PLANAR_BE else "<u2")
             cw, ch = -((-self.dst_w) >> hs), -((-self.dst_h) >> vs)
             out = [np.full((self.dst_h, self.dst_w), fill, dt), np.full((ch, cw), fill, dt), np.full((ch, cw), fill, dt)]
         else:

@@ -209,7 +209,8 @@ static void sws_close(sws_t *c) { free_bank(&c->hl); free_bank(&c->hc); free_ban
 /* chroma sub-sampling of the planar 8-bit source being converted (log2): 4:2:0 unless orc_sws_planar() says otherwise */
 static __thread int g_hs = 1, g_vs = 1;
 /* the planar destination: chroma sub-sampling (log2) and sample depth (8, or 9 / 10 in little-endian 16-bit samples) */
-static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8;
+static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8, g_dbe = 0;
+static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; } else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); } }
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
 
 static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags)
@@ -456,7 +457,7 @@ static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t
             }
             v = v < 0 ? 0 : v > top ? top : v;
             if (bits == 8) dst[(size_t)y * dstride + i] = (uint8_t)v;
-            else { dst[(size_t)y * dstride + 2 * i] = (uint8_t)v; dst[(size_t)y * dstride + 2 * i + 1] = (uint8_t)(v >> 8); }
+            else put16(dst + (size_t)y * dstride + 2 * i, v);
         }
     }
 }
@@ -477,7 +478,7 @@ static void vplane16(const int32_t *s, int pitch, int sh, const bank_t *b, uint8
                 v = (int32_t)acc >> 15;
                 v = (v < -32768 ? -32768 : v > 32767 ? 32767 : v) + 0x8000;
             }
-            dst[(size_t)y * dstride + 2 * i] = (uint8_t)v; dst[(size_t)y * dstride + 2 * i + 1] = (uint8_t)(v >> 8);
+            put16(dst + (size_t)y * dstride + 2 * i, v);
         }
     }
 }
@@ -495,7 +496,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
                 if (g_dbits == 8) { memcpy(dst[p] + (size_t)y * ds[p], src[p] + (size_t)y * ss[p], w); continue; }
                 for (int x = 0; x < w; x++) {
                     const int v = g_dbits == 16 ? src[p][(size_t)y * ss[p] + x] * 257 : src[p][(size_t)y * ss[p] + x] << (g_dbits - 8);
-                    dst[p][(size_t)y * ds[p] + 2 * x] = (uint8_t)v; dst[p][(size_t)y * ds[p] + 2 * x + 1] = (uint8_t)(v >> 8);
+                    put16(dst[p] + (size_t)y * ds[p] + 2 * x, v);
                 }
             }
         }
@@ -707,7 +708,11 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
  * YUV420P9 62, YUV420P10 64, YUV422P10 66, YUV444P9 68, YUV444P10 70, YUV422P9 72 */
 static int planar_dst(int fmt, int *hs, int *vs, int *bits)
 {
-    *bits = 8;
+    *bits = 8; g_dbe = 0;
+    switch (fmt) {               /* big-endian twins: 9 / 10-bit LE - 1, 16-bit LE + 1 */
+    case 61: case 63: case 65: case 67: case 69: case 71: g_dbe = 1; fmt += 1; break;
+    case 48: case 50: case 52: g_dbe = 1; fmt -= 1; break;
+    }
     switch (fmt) {
     case 0: *hs = 1; *vs = 1; return 1;   case 4: *hs = 1; *vs = 0; return 1;   case 5: *hs = 0; *vs = 0; return 1;
     case 6: *hs = 2; *vs = 2; return 1;   case 7: *hs = 2; *vs = 0; return 1;   case 31: *hs = 0; *vs = 1; return 1;
@@ -736,13 +741,13 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     case 6: hs = 2; vs = 2; break;  case 7: hs = 2; vs = 0; break;  case 31: hs = 0; vs = 1; break;
     case 23: case 24:                                   /* src[0] luma, src[1] interleaved chroma */
         r = orc_sws_nv12(src_fmt == 24, src[0], ss[0], src[1], ss[1], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
-        g_dhs = g_dvs = 1; g_dbits = 8;
+        g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
     case 1: case 2: case 3: case 15:
         r = packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
-        g_dhs = g_dvs = 1; g_dbits = 8;
+        g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
-    default: g_dhs = g_dvs = 1; g_dbits = 8; return -1;
+    default: g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0; return -1;
     }
     /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
      * rgb2rgb.c planar2x): not restated */
@@ -750,6 +755,6 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     g_hs = hs; g_vs = vs;
     r = rgb ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
             : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
-    g_hs = 1; g_vs = 1; g_dhs = g_dvs = 1; g_dbits = 8;
+    g_hs = 1; g_vs = 1; g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
     return r;
 }

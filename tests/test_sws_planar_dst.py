@@ -7,10 +7,10 @@ import numpy as np
 import pytest
 
 from libav_b200 import synth
-from libav_b200.device import PLANAR_FORMATS
+from libav_b200.device import PLANAR_BE, PLANAR_FORMATS
 
 SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 23: None, 1: None, 2: None, 15: None}
-DST = [4, 5, 6, 7, 31, 62, 64, 66, 68, 70, 72, 47, 49, 51]
+DST = [4, 5, 6, 7, 31, 62, 64, 66, 68, 70, 72, 47, 49, 51, 61, 65, 69, 48, 52]
 GEOMS = [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (101, 37, 333, 211), (66, 50, 33, 25)]
 ACC = 0x40000 | 0x80000
 FLAGS = (4 | ACC, 2 | 0x80000, 0x10 | ACC, 0x200 | ACC, 1 | ACC)
@@ -32,7 +32,7 @@ def source(fmt, w, h, seed):
 
 def outputs(dfmt, dw, dh, pad=3):
     hs, vs, bits = PLANAR_FORMATS[dfmt]
-    dt = np.uint8 if bits == 8 else np.dtype("<u2")
+    dt = np.uint8 if bits == 8 else np.dtype(">u2" if dfmt in PLANAR_BE else "<u2")
     cw, ch = -((-dw) >> hs), -((-dh) >> vs)
     return [np.full((dh, dw + pad), 7, dt), np.full((ch, cw + pad), 7, dt), np.full((ch, cw + pad), 7, dt)]
 
@@ -89,5 +89,5 @@ def test_gpu_matches_checker(gpu, checker, dfmt):
 def test_refusals_are_loud(gpu):
     from libav_b200 import device
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 64, 48, 48, 4)          # yuv420p16be
+        device.SwsContext(64, 48, 64, 48, 33, 4)          # yuva420p
     gpu.lib.avb200_clear_error()

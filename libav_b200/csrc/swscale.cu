@@ -1065,6 +1065,22 @@ sws_yuyv_yv12_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcF
     }
 }
 
+// 32-bit packed rgb destinations (argb, rgba, abgr, bgra): the colour tables of the 32-bit output functions hold the same 8-bit
+// channel values as the 24-bit ones plus a constant alpha of 255 (yuv2rgb.c:763-800, output.c:1040-1075,1230-1260), so the rgb24
+// result is expanded: `ro` / `go` / `bo` / `ao` are the byte positions inside a destination pixel.  One thread per pixel.
+__global__ void __launch_bounds__(256)
+sws_expand_rgb32_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
+                        int w, int ro, int go, int bo, int ao)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *s = src + blockIdx.z * srcFrame + (size_t)y * srcStride + 3 * x;
+    const uint32_t v = ((uint32_t)s[0] << (8 * ro)) | ((uint32_t)s[1] << (8 * go)) | ((uint32_t)s[2] << (8 * bo)) | (255u << (8 * ao));
+    uint8_t *d = dst + blockIdx.z * dstFrame + (size_t)y * dstStride + 4 * x;
+    if (!((uintptr_t)d & 3)) *reinterpret_cast<uint32_t *>(d) = v;
+    else { d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24); }
+}
+
 // planarCopyWrapper, 8-bit source plane -> 9 / 10-bit plane (swscale_unscaled.c:946-971): limited-range luma and both chroma
 // planes are plain shifts; -> 16-bit plane (:984-992): the byte twice
 __global__ void __launch_bounds__(256)
@@ -1099,7 +1115,7 @@ sws_yuyv_yuv422p_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
 // context
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
-       FMT_UYVY422 = 15, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
+       FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
        FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
 // planar yuv destination: chroma sub-sampling (log2) and sample depth; false for anything else
@@ -1148,7 +1164,9 @@ struct SwsCudaContext {
     int pkR = 0, pkB = 2;       //   byte offsets of red and blue
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
-    bool planar = false;        // planar yuv destination (else packed rgb24 / bgr24)
+    bool planar = false;        // planar yuv destination (else packed rgb)
+    int dst32 = 0;              // argb / rgba / abgr / bgra destination (the pixel format value): rgb24 into d_rgb, then expanded
+    uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
@@ -1199,8 +1217,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     const char *err = nullptr;
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
-    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
+    const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
+    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32) {
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1225,6 +1244,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
     const bool unscaled = srcW == dstW && srcH == dstH;
+    if (srcRgb && dst32 && unscaled) {                        // rgbToRgbWrapper's 24 <-> 32 bit converters (swscale_unscaled.c:591-710)
+        set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> 32-bit rgb of the same size is the reference's rgb2rgb converter family: not taken over");
+        return nullptr;
+    }
     if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1)) {
         set_error_msg("sws_getContext_cuda", "bgr24 -> yuv420p of the same size without SWS_ACCURATE_RND is the reference's rgb24toyv12, which needs an even height");
         return nullptr;
@@ -1237,7 +1260,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->dstFormat = dstFormat; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
+    c->dstFormat = dstFormat; c->dst32 = dst32 ? dstFormat : 0; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P;
@@ -1404,8 +1427,42 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
 }
 
 // the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy + a split of srcW/2 x srcH/2 samples.
+static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st);
+
+// 32-bit rgb destinations: the rgb24 pipeline into a scratch picture, then one expansion pass (+ 6 B per pixel of traffic; fusing the
+// 4-byte store into every output kernel is the next step for this format family)
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
+{
+    if (!c->dst32) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
+    if (nframes <= 0) return 0;
+    const SwsDev &p = c->dev;
+    const int pitch = ((p.dstW + 1) * 3 + 15) & ~15;
+    const size_t frame = (size_t)pitch * p.dstH, need = frame * nframes;
+    if (c->rgb_bytes < need) {
+        AVB_CUDA(cudaStreamSynchronize(st), "sws_scale:rgb32");
+        cudaFree(c->d_rgb); c->d_rgb = nullptr; c->rgb_bytes = 0;
+        AVB_CUDA(cudaMalloc(&c->d_rgb, need), "sws_scale:rgb32");
+        c->rgb_bytes = need;
+    }
+    uint8_t *const d3[3] = { c->d_rgb, nullptr, nullptr };
+    const int s3[3] = { pitch, 0, 0 };
+    const size_t f3[3] = { frame, 0, 0 };
+    if (run_frames_24(c, src, srcStride, srcFrame, d3, s3, f3, nframes, st)) return -1;
+    // what the 24-bit functions write: whole pixel pairs (one pixel past an odd width when the row has room), single pixels with
+    // SWS_FULL_CHR_H_INT, and the unscaled table converter leaves an odd last column alone
+    int w = p.dstW;
+    if (c->table_unscaled) w &= ~1;
+    else if ((w & 1) && !p.full && dstStride[0] >= 4 * (w + 1)) w++;
+    static const int order[4][4] = { { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };    // argb, rgba, abgr, bgra: r g b a positions
+    const int *o = order[c->dst32 - FMT_ARGB];
+    sws_expand_rgb32_kernel<<<dim3((w + 255) / 256, p.dstH, nframes), 256, 0, st>>>(c->d_rgb, pitch, frame, dst[0], dstStride[0], dstFrame[0], w, o[0], o[1], o[2], o[3]);
+    return check_launch("sws_scale:rgb32");
+}
+
+static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
+                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
     if (c->srcPacked) return run_packed(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
     if (!c->srcNV) return run_planar(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
@@ -1586,7 +1643,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
 static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_nv); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
     delete c;
 }
 
@@ -1645,7 +1702,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
-    const int dP = rgb ? ((g.dstW + odd) * 3 + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB + 15) & ~15;
+    const int pxB = c->dst32 ? 4 : 3;                       // bytes per packed rgb pixel
+    const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
     if (c->src_bytes < needS) { cudaFree(c->d_src); c->d_src = nullptr; if (cudaMalloc(&c->d_src, needS) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->src_bytes = needS; }
@@ -1656,7 +1714,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     // Same-size rgb (the dp4a fused kernel): the frame goes through in bands of rows on three streams, so the upload of band
     // k + 1, the kernel of band k and the download of band k - 1 overlap -- the call is PCIe bound and PCIe is full duplex.
     // A band re-uploads the few chroma lines it shares with its neighbours (identical bytes), so bands need no cross-stream order.
-    if (c->fused && c->fast_ok && !nv && rgb && !odd && tuning("sws_fused_variant") != 1 && tuning("sws_fused_variant") != 2 &&
+    if (c->fused && c->fast_ok && !nv && rgb && !c->dst32 && !odd && tuning("sws_fused_variant") != 1 && tuning("sws_fused_variant") != 2 &&
         tuning("sws_host_bands") != 1 && g.dstH >= 64 && !((uintptr_t)c->dev.vChrF & 15)) {
         const SwsDev &p = c->dev;
         const int pairs = g.dstH / 2, nb = tuning("sws_host_bands") > 1 ? tuning("sws_host_bands") : 3, per = ((pairs + nb - 1) / nb + 3) & ~3;
@@ -1703,9 +1761,9 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     cudaError_t e;
     if (rgb) {
         // whole pixel pairs are written (one pixel past an odd width) when the caller's stride has room
-        size_t wbytes = (size_t)g.dstW * 3;
-        if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + 3) wbytes += 3;      // (full chroma writes single pixels)
-        if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * 3;       // that converter leaves an odd last column untouched
+        size_t wbytes = (size_t)g.dstW * pxB;
+        if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + pxB) wbytes += pxB;      // (full chroma writes single pixels)
+        if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * pxB;       // that converter leaves an odd last column untouched
         if (c->special) wbytes = (size_t)g.dstW * 3;
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {

@@ -95,6 +95,8 @@ def idct_put_tiles(blocks, tiles_per_row, mode=0, frame=None, use_offsets=False,
 # ---------------------------------------------------------------------------------------------------
 PIX_FMT_YUV420P, PIX_FMT_RGB24, PIX_FMT_BGR24, PIX_FMT_NV12, PIX_FMT_NV21 = 0, 2, 3, 23, 24
 PIX_FMT_YUYV422, PIX_FMT_UYVY422 = 1, 15
+PIX_FMT_ARGB, PIX_FMT_RGBA, PIX_FMT_ABGR, PIX_FMT_BGRA = 25, 26, 27, 28
+RGB32_FORMATS = (25, 26, 27, 28)
 # planar yuv formats (libavutil/pixfmt.h values): (log2 chroma width, log2 chroma height, bits per sample; > 8 = little-endian uint16)
 PLANAR_FORMATS = {0: (1, 1, 8), 4: (1, 0, 8), 5: (0, 0, 8), 6: (2, 2, 8), 7: (2, 0, 8), 31: (0, 1, 8),
                   62: (1, 1, 9), 64: (1, 1, 10), 72: (1, 0, 9), 66: (1, 0, 10), 68: (0, 0, 9), 70: (0, 0, 10),
@@ -133,7 +135,7 @@ class SwsContext:
             cw, ch = -((-self.dst_w) >> hs), -((-self.dst_h) >> vs)
             out = [np.full((self.dst_h, self.dst_w), fill, dt), np.full((ch, cw), fill, dt), np.full((ch, cw), fill, dt)]
         else:
-            out = [np.full((self.dst_h, self.dst_w * 3 + dst_pad), fill, np.uint8)]
+            out = [np.full((self.dst_h, self.dst_w * (4 if self.dst_fmt in RGB32_FORMATS else 3) + dst_pad), fill, np.uint8)]
         dst = (C.c_void_p * 4)(*([a.ctypes.data for a in out] + [None] * (4 - len(out))))
         dstr = (C.c_int * 4)(*([a.strides[0] for a in out] + [0] * (4 - len(out))))
         r = lib.sws_scale_cuda(self.ctx, src, sst, 0, self.src_h, dst, dstr)

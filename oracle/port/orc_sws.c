@@ -555,7 +555,7 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
     const uint8_t *src[3] = { y, u, v };
     const int ss[3] = { ystride, pitch, pitch };
     g_nocopy = 1;
-    int r = dst_fmt == 2 || dst_fmt == 3 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
+    int r = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
                                          : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
     g_nocopy = 0;
     free(u);
@@ -570,10 +570,29 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
     const int pitch = (dw + 1) * 3;
     uint8_t *t = malloc((size_t)pitch * dh);
     if (!t) return -1;
+    memset(t, 0, (size_t)pitch * dh);
     int r = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, t, pitch, dw, dh, flags);
-    for (int y = 0; r == dh && y < dh; y++)
-        for (int x = 0; x < dw; x++)
-            for (int k = 0; k < 3; k++) dst[(size_t)y * dstride + 3 * x + k] = t[(size_t)y * pitch + 3 * x + 2 - k];
+    if (dst_fmt == 3) {
+        for (int y = 0; r == dh && y < dh; y++)
+            for (int x = 0; x < dw; x++)
+                for (int k = 0; k < 3; k++) dst[(size_t)y * dstride + 3 * x + k] = t[(size_t)y * pitch + 3 * x + 2 - k];
+    } else {
+        /* argb 25, rgba 26, abgr 27, bgra 28: the 32-bit colour tables hold the 24-bit channel values plus alpha 255
+         * (yuv2rgb.c:763-800).  Like the 24-bit functions: whole pixel pairs (one pixel past an odd width), single pixels with
+         * SWS_FULL_CHR_H_INT, and the unscaled table converter (same size, no SWS_ACCURATE_RND, even height, 4:2:0 / 4:2:2
+         * planar source) leaves an odd last column alone */
+        static const int order[4][4] = { { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };
+        const int *o = order[dst_fmt - 25];
+        int w = dw;
+        if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1) w &= ~1;
+        else if ((w & 1) && !(flags & F_FULL_CHR_H_INT) && dstride >= 4 * (w + 1)) w++;
+        for (int y = 0; r == dh && y < dh; y++)
+            for (int x = 0; x < w; x++) {
+                uint8_t *d = dst + (size_t)y * dstride + 4 * x;
+                const uint8_t *p = t + (size_t)y * pitch + 3 * x;
+                d[o[0]] = p[0]; d[o[1]] = p[1]; d[o[2]] = p[2]; d[o[3]] = 255;
+            }
+    }
     free(t);
     return r;
 }
@@ -600,7 +619,8 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
                          const int ds[3], int dw, int dh, int flags)
 {
     const int rgb_src = src_fmt == 2 || src_fmt == 3, ro = src_fmt == 3 ? 2 : 0, bo = 2 - ro;
-    const int rgb_dst = dst_fmt == 2 || dst_fmt == 3;
+    const int rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
     if (sw == dw && sh == dh) {
         if (rgb_src && rgb_dst) {
             for (int y = 0; y < sh; y++)
@@ -734,7 +754,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
-    const int rgb = dst_fmt == 2 || dst_fmt == 3;
+    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
     case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;

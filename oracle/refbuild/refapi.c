@@ -292,7 +292,7 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     const int packed_src = src_fmt == AV_PIX_FMT_YUYV422 || src_fmt == AV_PIX_FMT_UYVY422 || src_fmt == AV_PIX_FMT_RGB24 || src_fmt == AV_PIX_FMT_BGR24;
     struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
-    const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24;
+    const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA);
     uint8_t *d[4] = { dst[0], packed_dst ? NULL : dst[1], packed_dst ? NULL : dst[2], NULL };
     int ds[4] = { dstride[0], packed_dst ? 0 : dstride[1], packed_dst ? 0 : dstride[2], 0 };
     const uint8_t *s[4] = { src[0], packed_src ? NULL : src[1], packed_src ? NULL : src[2], NULL };

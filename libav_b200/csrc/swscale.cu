@@ -1244,6 +1244,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
     const bool unscaled = srcW == dstW && srcH == dstH;
+    if (dstFormat == FMT_ABGR && (flags & SWS_FULL_CHR_H_INT)) {  // output.c:1231-1237 advances the pointer twice per abgr pixel and runs off the row
+        set_error_msg("sws_getContext_cuda", "abgr with SWS_FULL_CHR_H_INT: the reference's output function overruns the destination; there is no result to match");
+        return nullptr;
+    }
     if (srcRgb && dst32 && unscaled) {                        // rgbToRgbWrapper's 24 <-> 32 bit converters (swscale_unscaled.c:591-710)
         set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> 32-bit rgb of the same size is the reference's rgb2rgb converter family: not taken over");
         return nullptr;

@@ -755,6 +755,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
 {
     int hs, vs, r;
     const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT)) return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
     case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;

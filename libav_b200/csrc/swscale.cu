@@ -960,29 +960,30 @@ constexpr int GY = (int)(0.587 * 219 / 255 * (1 << SH) + 0.5), GV = -(int)(0.419
 constexpr int RY = (int)(0.299 * 219 / 255 * (1 << SH) + 0.5), RV = (int)(0.500 * 224 / 255 * (1 << SH) + 0.5), RU = -(int)(0.169 * 224 / 255 * (1 << SH) + 0.5);
 }
 
-// KIND 1: rgb24 / bgr24 (rgb24ToY_c, rgb24ToUV_c, rgb24ToUV_half_c and the bgr24 twins, input.c:539-625; `ro` / `bo` are the byte
-// offsets of red and blue), 2: yuyv422 (yuy2ToY_c, yuy2ToUV_c, :369-387), 3: uyvy422 (uyvyToY_c, uyvyToUV_c, :456-473).
+// KIND 1: rgb24 / bgr24 (rgb24ToY_c, rgb24ToUV_c, rgb24ToUV_half_c and the bgr24 twins, input.c:539-625; `ro` / `go` / `bo` are the byte
+// offsets of red, green and blue), KIND 4: argb / rgba / abgr / bgra (the rgb16_32ToY / ToUV / ToUV_half templates, input.c:230-330:
+// the same sums on the 8-bit channels, scaled by 2^8 on both sides of the shift), 2: yuyv422 (yuy2ToY_c, yuy2ToUV_c, :369-387), 3: uyvy422 (uyvyToY_c, uyvyToUV_c, :456-473).
 // One thread reads one pixel pair.  For an odd width the reference's chroma readers read one pixel past the row; those bytes
 // are read here too whenever they lie inside the frame (row padding or the next row), else the pair's first pixel is repeated.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 sws_read_packed_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
-                       uint8_t *__restrict__ V, int yPitch, int cPitch, size_t yPlane, size_t cPlane, int w, int h, int ro, int bo, int half)
+                       uint8_t *__restrict__ V, int yPitch, int cPitch, size_t yPlane, size_t cPlane, int w, int h, int ro, int go, int bo, int half)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (2 * i >= w) return;
     const size_t f = blockIdx.z;
-    constexpr int BPP = KIND == 1 ? 3 : 2;
+    constexpr int BPP = KIND == 1 ? 3 : KIND == 4 ? 4 : 2;
     const uint8_t *s = src + f * srcFrame + (size_t)y * srcStride + (size_t)i * 2 * BPP;
     uint8_t *dy = Y + f * yPlane + (size_t)y * yPitch + 2 * i;
     uint8_t *du = U + f * cPlane + (size_t)y * cPitch, *dv = V + f * cPlane + (size_t)y * cPitch;
     const bool second = 2 * i + 1 < w;
     const bool readable = second || y < h - 1 || (2 * i + 2) * BPP <= srcStride;
-    if (KIND == 1) {
+    if (KIND == 1 || KIND == 4) {
         using namespace rd;
-        const int r0 = s[ro], g0 = s[1], b0 = s[bo];
+        const int r0 = s[ro], g0 = s[go], b0 = s[bo];
         int r1 = r0, g1 = g0, b1 = b0;
-        if (readable) { r1 = s[3 + ro]; g1 = s[4]; b1 = s[3 + bo]; }
+        if (readable) { r1 = s[BPP + ro]; g1 = s[BPP + go]; b1 = s[BPP + bo]; }
         dy[0] = (uint8_t)((RY * r0 + GY * g0 + BY * b0 + (33 << (SH - 1))) >> SH);
         if (second) dy[1] = (uint8_t)((RY * r1 + GY * g1 + BY * b1 + (33 << (SH - 1))) >> SH);
         if (half) {
@@ -1118,6 +1119,8 @@ enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV42
        FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
        FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
+static bool unscaled0(int sw, int sh, int dw, int dh) { return sw == dw && sh == dh; }
+
 // planar yuv destination: chroma sub-sampling (log2) and sample depth; false for anything else
 static bool planar_dst(int fmt, int *hs, int *vs, int *bits, int *be)
 {
@@ -1160,8 +1163,8 @@ struct SwsCudaContext {
     int lumStridePx = 0, chrStridePx = 0;
     bool src422 = false;        // the unscaled table converter reads the even chroma line of a 4:2:2 source for both rows (yuv2rgb.c:133-136)
     int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
-    int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422: the input readers (input.c) write planes first
-    int pkR = 0, pkB = 2;       //   byte offsets of red and blue
+    int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422, 4 argb / rgba / abgr / bgra: the input readers (input.c) write planes first
+    int pkR = 0, pkG = 1, pkB = 2;   //   byte offsets of red, green and blue
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
     bool planar = false;        // planar yuv destination (else packed rgb)
@@ -1234,13 +1237,18 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     case FMT_YUV411P: hs = 2; vs = 0; break;
     case FMT_YUV440P: hs = 0; break;
     case FMT_YUYV422: case FMT_UYVY422: vs = 0; break;
-    case FMT_RGB24: case FMT_BGR24: {                         // utils.c:1021-1034: every other pixel for chroma unless told / forced otherwise
+    case FMT_RGB24: case FMT_BGR24: case FMT_ARGB: case FMT_RGBA: case FMT_ABGR: case FMT_BGRA: {   // utils.c:1021-1034: every other pixel for chroma unless told / forced otherwise
         const int chrDstHSub = planar ? dhs : (flags & SWS_FULL_CHR_H_INT) ? 0 : 1;
         hs = (!(flags & SWS_FULL_CHR_H_INP) && ((dstW >> chrDstHSub) <= (srcW >> 1) || (flags & SWS_FAST_BILINEAR))) ? 1 : 0;
         vs = 0;
         break;
     }
-    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21, yuyv422, uyvy422, rgb24, bgr24"); return nullptr;
+    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21, yuyv422, uyvy422, rgb24, bgr24, argb, rgba, abgr, bgra"); return nullptr;
+    }
+    const bool src32 = srcFormat >= FMT_ARGB && srcFormat <= FMT_BGRA;
+    if (src32 && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar))) {
+        // 32 -> 32 bit: the reference scales the alpha plane too; same size -> packed rgb: rgbToRgbWrapper's converters (swscale_unscaled.c:591-710)
+        set_error_msg("sws_getContext_cuda", "32-bit rgb source: only planar yuv destinations and scaled rgb24 / bgr24 are taken over"); return nullptr;
     }
     const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
     const bool unscaled = srcW == dstW && srcH == dstH;
@@ -1268,8 +1276,12 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P;
-    c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : 0;
+    c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : src32 ? 4 : 0;
     c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR;
+    if (src32) {
+        static const int rgbpos[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };       // argb, rgba, abgr, bgra
+        c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
+    }
     if (unscaled) {                                           // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
         if (srcRgb && rgb) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
@@ -1420,9 +1432,10 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
     uint8_t *Y = c->d_nv, *U = Y + yPlane * nframes, *V = U + cPlane * nframes;
     const dim3 grid(((w + 1) / 2 + 255) / 256, h, nframes);
     const int half = p.chrSrcW != w;
-    if (c->srcPacked == 1)      sws_read_packed_kernel<1><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkB, half);
-    else if (c->srcPacked == 2) sws_read_packed_kernel<2><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 1);
-    else                        sws_read_packed_kernel<3><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 1);
+    if (c->srcPacked == 1)      sws_read_packed_kernel<1><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkG, c->pkB, half);
+    else if (c->srcPacked == 4) sws_read_packed_kernel<4><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkG, c->pkB, half);
+    else if (c->srcPacked == 2) sws_read_packed_kernel<2><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 0, 1);
+    else                        sws_read_packed_kernel<3><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 0, 1);
     if (check_launch("sws_scale:reader")) return -1;
     const uint8_t *s3[3] = { Y, U, V };
     const int st3[3] = { yPitch, cPitch, cPitch };
@@ -1700,7 +1713,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const SwsGeometry &g = c->g;
     // device staging: tight, aligned pitches
     // (a packed source keeps the caller's pitch: the chroma readers look one pixel past an odd width, into the padding or the next row)
-    const int pkBpp = c->srcPacked == 1 ? 3 : 2;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2;
     const int yP = pk ? srcStride[0] : (g.srcW + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW + 15) & ~15;
     const size_t yB = (size_t)yP * g.srcH, cB = pk ? 0 : (size_t)cP * g.chrSrcH;
     const size_t needS = yB + (nv ? 1 : 2) * cB;

@@ -618,11 +618,19 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
 static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, int sh, int dst_fmt, uint8_t *const dst[3],
                          const int ds[3], int dw, int dh, int flags)
 {
-    const int rgb_src = src_fmt == 2 || src_fmt == 3, ro = src_fmt == 3 ? 2 : 0, bo = 2 - ro;
+    /* byte positions of r, g, b: rgb24, bgr24, and argb 25 / rgba 26 / abgr 27 / bgra 28 (rgb16_32ToY / ToUV / ToUV_half templates,
+     * input.c:230-330: the same sums on the 8-bit channels, both sides of the shift scaled by 2^8) */
+    static const int pos32[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };
+    const int src32 = src_fmt >= 25 && src_fmt <= 28;
+    const int rgb_src = src_fmt == 2 || src_fmt == 3 || src32;
+    const int ro = src32 ? pos32[src_fmt - 25][0] : src_fmt == 3 ? 2 : 0, go = src32 ? pos32[src_fmt - 25][1] : 1, bo = src32 ? pos32[src_fmt - 25][2] : 2 - ro;
+    const int rgb_bpp = src32 ? 4 : 3;
     const int rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
     if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
+    /* 32-bit sources: 32 -> 32 bit scales the alpha plane as well, same size -> packed rgb is the rgb2rgb family: neither is restated */
+    if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && rgb_dst))) return -1;
     if (sw == dw && sh == dh) {
-        if (rgb_src && rgb_dst) {
+        if (rgb_src && !src32 && rgb_dst) {
             for (int y = 0; y < sh; y++)
                 for (int x = 0; x < sw; x++)
                     for (int k = 0; k < 3; k++)
@@ -684,12 +692,12 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
         const uint8_t *row = src + (size_t)y * stride;
         for (int i = 0; 2 * i < sw; i++) {
             const int second = 2 * i + 1 < sw;
-            const int bpp = rgb_src ? 3 : 2;
+            const int bpp = rgb_src ? rgb_bpp : 2;
             const int ok = second || y < sh - 1 || (2 * i + 2) * bpp <= stride;   /* the sample past an odd width is inside the frame */
             const uint8_t *s = row + 2 * i * bpp;
             if (rgb_src) {
-                const int r0 = s[ro], g0 = s[1], b0 = s[bo];
-                const int r1 = ok ? s[3 + ro] : r0, g1 = ok ? s[4] : g0, b1 = ok ? s[3 + bo] : b0;
+                const int r0 = s[ro], g0 = s[go], b0 = s[bo];
+                const int r1 = ok ? s[rgb_bpp + ro] : r0, g1 = ok ? s[rgb_bpp + go] : g0, b1 = ok ? s[rgb_bpp + bo] : b0;
                 Y[(size_t)y * yp + 2 * i] = (uint8_t)((C_RY * r0 + C_GY * g0 + C_BY * b0 + (33 << (RSH - 1))) >> RSH);
                 if (second) Y[(size_t)y * yp + 2 * i + 1] = (uint8_t)((C_RY * r1 + C_GY * g1 + C_BY * b1 + (33 << (RSH - 1))) >> RSH);
                 if (hs) {
@@ -764,7 +772,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         r = orc_sws_nv12(src_fmt == 24, src[0], ss[0], src[1], ss[1], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
-    case 1: case 2: case 3: case 15:
+    case 1: case 2: case 3: case 15: case 25: case 26: case 27: case 28:
         r = packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;

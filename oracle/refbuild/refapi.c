@@ -289,7 +289,8 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     INIT();
-    const int packed_src = src_fmt == AV_PIX_FMT_YUYV422 || src_fmt == AV_PIX_FMT_UYVY422 || src_fmt == AV_PIX_FMT_RGB24 || src_fmt == AV_PIX_FMT_BGR24;
+    const int packed_src = src_fmt == AV_PIX_FMT_YUYV422 || src_fmt == AV_PIX_FMT_UYVY422 || src_fmt == AV_PIX_FMT_RGB24 || src_fmt == AV_PIX_FMT_BGR24 ||
+                           (src_fmt >= AV_PIX_FMT_ARGB && src_fmt <= AV_PIX_FMT_BGRA);
     struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
     const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA);

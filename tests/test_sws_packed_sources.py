@@ -1,4 +1,4 @@
-"""Packed sources (yuyv422, uyvy422, rgb24, bgr24) -> rgb24 / bgr24 / yuv420p: the reference's input readers (libswscale/input.c)
+"""Packed sources (yuyv422, uyvy422, rgb24, bgr24, argb, rgba, abgr, bgra) -> rgb24 / bgr24 / yuv420p: the reference's input readers (libswscale/input.c)
 in front of the scaler, and its unscaled special converters (rgb24 <-> bgr24, rgb24toyv12_c, yuyvtoyuv420_c / uyvytoyuv420_c).
 CPU: port vs the compiled reference; GPU: product vs checker, host-pointer and device-pointer (batched) calls."""
 import ctypes as C
@@ -8,7 +8,7 @@ import pytest
 
 from libav_b200 import synth
 
-BPP = {1: 2, 15: 2, 2: 3, 3: 3}
+BPP = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
 GEOMS = [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (101, 37, 333, 211), (67, 51, 67, 51), (66, 50, 33, 25),
          (64, 48, 160, 48)]
 ACC = 0x40000 | 0x80000
@@ -43,6 +43,8 @@ def combos(fmt):
                     continue
                 if fmt == 3 and dfmt == 0 and (w, h) == (dw, dh) and not flags & 0x40000 and h & 1:
                     continue        # rgb24toyv12_c converts rows in pairs: an odd height is refused
+                if fmt >= 25 and dfmt and (w, h) == (dw, dh):
+                    continue        # 32-bit rgb -> packed rgb of the same size: the rgb2rgb converter family, refused
                 yield w, h, dw, dh, flags, dfmt
 
 
@@ -60,7 +62,7 @@ def fast_bilinear_margin(flags, sw, dw):
     return 2 * -(-dw // sw) + 2 if (flags & 1) and dw > sw else 0
 
 
-@pytest.mark.parametrize("fmt", [1, 15, 2, 3])
+@pytest.mark.parametrize("fmt", [1, 15, 2, 3, 25, 26, 27, 28])
 def test_port_matches_reference(orc, refo, fmt):
     if refo is None:
         pytest.skip("oracle/_ref not built (no /root/reference here)")
@@ -90,7 +92,7 @@ def test_port_tight_rows(orc, refo):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fmt", [1, 15, 2, 3])
+@pytest.mark.parametrize("fmt", [1, 15, 2, 3, 25, 26, 27, 28])
 def test_gpu_matches_checker(gpu, checker, orc, fmt):
     from libav_b200 import device
     for (w, h, dw, dh, flags, dfmt) in combos(fmt):
@@ -143,5 +145,8 @@ def test_refusals_are_loud(gpu):
         device.SwsContext(64, 49, 64, 49, device.PIX_FMT_YUV420P, 4, src_fmt=3)      # rgb24toyv12_c with an odd height
     gpu.lib.avb200_clear_error()
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 64, 48, device.PIX_FMT_RGB24, 4, src_fmt=26)      # rgba
+        device.SwsContext(64, 48, 64, 48, device.PIX_FMT_RGB24, 4, src_fmt=26)      # rgba -> rgb24 of the same size: rgb2rgb family
+    gpu.lib.avb200_clear_error()
+    with pytest.raises(Exception):
+        device.SwsContext(64, 48, 128, 96, 28, 4, src_fmt=26)                        # rgba -> bgra: the alpha plane would be scaled too
     gpu.lib.avb200_clear_error()

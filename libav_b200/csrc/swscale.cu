@@ -37,6 +37,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int bgr;
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
     int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
+    int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
 };
 
@@ -584,7 +585,7 @@ sws_vscale_rgb24_full_kernel(SwsDev p, const int16_t *__restrict__ lum, const in
 // pass 2 for planar output (see plane_store above)
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
-                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits, int be)
+                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits, int be, int step = 1)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (i >= dstW || y >= dstH) return;
@@ -598,7 +599,7 @@ sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH
         for (int j = 0; j < fs; j++) val += src[(size_t)line_index(first, j, srcH) * srcStride + i] * f[j];
         val >>= 27 - bits;
     }
-    plane_store(dst + (size_t)y * dstStride, i, plane_clip(val, bits), bits, be);
+    plane_store(dst + (size_t)y * dstStride, i * step, plane_clip(val, bits), bits, be);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -921,6 +922,12 @@ sws_tile_plane_kernel(SwsDev p, TileArgs a)
             for (int k = 0; k < 8; k++) if (x + k < dstW) d16[k] = (uint16_t)v[k];
         return;
     }
+    if (CHROMA && p.chrStep == 2) {          // nv12 / nv21: this plane's samples go to every other byte
+        uint8_t *d2 = dst + (size_t)y * dstStride + 2 * x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (x + k < dstW) d2[2 * k] = (uint8_t)clip_u8(v[k]);
+        return;
+    }
     uint8_t *d = dst + (size_t)y * dstStride + x;
     if (x + 8 <= dstW && !(((uintptr_t)d) & 7)) {
         *reinterpret_cast<uint2 *>(d) = make_uint2(pack4_sat_u8(v[0], v[1], v[2], v[3]), pack4_sat_u8(v[4], v[5], v[6], v[7]));
@@ -1082,6 +1089,18 @@ sws_expand_rgb32_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
     else { d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24); }
 }
 
+// planarToNv12Wrapper (swscale_unscaled.c:138-156): interleaveBytes of srcW / 2 x srcH / 2 chroma samples (an odd last column / row stays untouched)
+__global__ void __launch_bounds__(256)
+sws_interleave_kernel(const uint8_t *__restrict__ a, int aStride, size_t aFrame, const uint8_t *__restrict__ b, int bStride, size_t bFrame,
+                      uint8_t *__restrict__ dst, int dstStride, size_t dstFrame, int w)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    uint8_t *d = dst + blockIdx.z * dstFrame + (size_t)y * dstStride + 2 * x;
+    d[0] = a[blockIdx.z * aFrame + (size_t)y * aStride + x];
+    d[1] = b[blockIdx.z * bFrame + (size_t)y * bStride + x];
+}
+
 // planarCopyWrapper, 8-bit source plane -> 9 / 10-bit plane (swscale_unscaled.c:946-971): limited-range luma and both chroma
 // planes are plain shifts; -> 16-bit plane (:984-992): the byte twice
 __global__ void __launch_bounds__(256)
@@ -1130,6 +1149,7 @@ static bool planar_dst(int fmt, int *hs, int *vs, int *bits, int *be)
     case 48: case 50: case 52: *be = 1; fmt -= 1; break;
     }
     switch (fmt) {
+    case FMT_NV12: case FMT_NV21:                          // luma plane + one interleaved chroma plane
     case FMT_YUV420P: *hs = 1; *vs = 1; return true;
     case FMT_YUV422P: *hs = 1; *vs = 0; return true;
     case FMT_YUV444P: *hs = 0; *vs = 0; return true;
@@ -1171,6 +1191,8 @@ struct SwsCudaContext {
     int dst32 = 0;              // argb / rgba / abgr / bgra destination (the pixel format value): rgb24 into d_rgb, then expanded
     uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
+    int dstNV = 0;              // 1 nv12, 2 nv21 destination
+    bool nvcopy = false;        // yuv420p -> nv12 / nv21 of the same size: planarToNv12Wrapper
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
     int2 *d_tile_win = nullptr; size_t tileChrWinOff = 0;
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
@@ -1210,7 +1232,7 @@ static int upload_tables(SwsCudaContext *c)
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits; d.dstBE = c->dstBE;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1;
     return 0;
 }
 
@@ -1245,6 +1267,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21, yuyv422, uyvy422, rgb24, bgr24, argb, rgba, abgr, bgra"); return nullptr;
     }
+    if ((srcFormat == FMT_NV12 || srcFormat == FMT_NV21) && (dstFormat == FMT_NV12 || dstFormat == FMT_NV21) && srcW == dstW && srcH == dstH) {
+        set_error_msg("sws_getContext_cuda", "nv12 / nv21 -> nv12 / nv21 of the same size (the reference's plane copy skips the chroma plane there) is not taken over"); return nullptr;
+    }
     const bool src32 = srcFormat >= FMT_ARGB && srcFormat <= FMT_BGRA;
     if (src32 && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar))) {
         // 32 -> 32 bit: the reference scales the alpha plane too; same size -> packed rgb: rgbToRgbWrapper's converters (swscale_unscaled.c:591-710)
@@ -1272,6 +1297,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
+    c->dstNV = dstFormat == FMT_NV12 ? 1 : dstFormat == FMT_NV21 ? 2 : 0;
     c->dstFormat = dstFormat; c->dst32 = dst32 ? dstFormat : 0; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
@@ -1321,7 +1347,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
-    c->copy = planar && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P);
+    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P);
+    c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
     if (c->fast_ok) {
@@ -1445,7 +1472,8 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
 
 // the reference's nv12ToPlanarWrapper (swscale_unscaled.c:160-181): luma copy + a split of srcW/2 x srcH/2 samples.
 static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
-                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st);
+                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st,
+                         uint8_t *const *remapped = nullptr);
 
 // 32-bit rgb destinations: the rgb24 pipeline into a scratch picture, then one expansion pass (+ 6 B per pixel of traffic; fusing the
 // 4-byte store into every output kernel is the next step for this format family)
@@ -1479,8 +1507,26 @@ static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int 
 }
 
 static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
-                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
+                         uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st,
+                         uint8_t *const *remapped)
 {
+    if (c->dstNV && !remapped) {       // an nv12 / nv21 destination: U and V are the even / odd bytes of plane 1 (chrStep 2 in the kernels)
+        if (c->nvcopy) {
+            const SwsDev &q = c->dev;
+            if (nframes <= 0) return 0;
+            for (int f = 0; f < nframes; f++)
+                AVB_CUDA(cudaMemcpy2DAsync(dst[0] + f * dstFrame[0], dstStride[0], src[0] + f * srcFrame[0], srcStride[0], q.srcW, q.srcH, cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
+            const int sw = c->dstNV == 2;
+            if (q.srcW / 2 > 0 && q.srcH / 2 > 0)
+                sws_interleave_kernel<<<dim3((q.srcW / 2 + 255) / 256, q.srcH / 2, nframes), 256, 0, st>>>(src[sw ? 2 : 1], srcStride[sw ? 2 : 1], srcFrame[sw ? 2 : 1], src[sw ? 1 : 2],
+                                                                                                     srcStride[sw ? 1 : 2], srcFrame[sw ? 1 : 2], dst[1], dstStride[1], dstFrame[1], q.srcW / 2);
+            return check_launch("sws_scale:planar -> nv12");
+        }
+        uint8_t *const d3[3] = { dst[0], dst[1] + (c->dstNV == 2 ? 1 : 0), dst[1] + (c->dstNV == 2 ? 0 : 1) };
+        const int s3[3] = { dstStride[0], dstStride[1], dstStride[1] };
+        const size_t f3[3] = { dstFrame[0], dstFrame[1], dstFrame[1] };
+        return run_frames_24(c, src, srcStride, srcFrame, d3, s3, f3, nframes, st, d3);
+    }
     if (c->srcPacked) return run_packed(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
     if (!c->srcNV) return run_planar(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
     if (nframes <= 0) return 0;
@@ -1639,8 +1685,8 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         }
         if (c->planar) {
             sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits, p.dstBE);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep);
         } else {
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
@@ -1684,7 +1730,7 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
 {
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
-    if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0]) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
+    if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0] || (c->planar && (!dst[1] || (!c->dstNV && !dst[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     static const size_t zero3[3] = { 0, 0, 0 };
     if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
                    nframes, (cudaStream_t)stream)) return -1;
@@ -1701,7 +1747,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const bool rgb = !c->planar;
     const bool nv = c->srcNV != 0, pk = c->srcPacked != 0;
     if (!srcSlice || !dst || !srcSlice[0] || !srcStride[0] || (!pk && (!srcSlice[1] || !srcStride[1] || (!nv && (!srcSlice[2] || !srcStride[2])))) ||
-        !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dst[2] || !dstStride[1] || !dstStride[2]))) {
+        !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dstStride[1] || (!c->dstNV && (!dst[2] || !dstStride[2]))))) {
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
     if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
@@ -1720,7 +1766,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const int odd = g.dstW & 1;
     const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
     const int pxB = c->dst32 ? 4 : 3;                       // bytes per packed rgb pixel
-    const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB + 15) & ~15;
+    const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB * (c->dstNV ? 2 : 1) + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
     if (c->src_bytes < needS) { cudaFree(c->d_src); c->d_src = nullptr; if (cudaMalloc(&c->d_src, needS) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->src_bytes = needS; }
@@ -1788,10 +1834,10 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, (size_t)(c->special == 3 ? g.dstW & ~1 : g.dstW) * sB, g.dstH, cudaMemcpyDeviceToHost, s);
         // nv12ToPlanarWrapper splits srcW / 2 x srcH / 2 samples: an odd last column / row of the caller's planes stays untouched;
         // the packed -> yuv420p converters write srcH / 2 chroma rows
-        const int cw = ((nv && c->copy) || c->special == 3) ? g.srcW / 2 : g.chrDstW;
-        const int ch = ((nv && c->copy) || (c->special >= 3 && c->special <= 5)) ? g.srcH / 2 : g.chrDstH;
-        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, (size_t)cw * sB, ch, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, (size_t)cw * sB, ch, cudaMemcpyDeviceToHost, s);
+        const int cw = ((nv && c->copy) || c->special == 3 || c->nvcopy) ? g.srcW / 2 : g.chrDstW;
+        const int ch = ((nv && c->copy) || (c->special >= 3 && c->special <= 5) || c->nvcopy) ? g.srcH / 2 : g.chrDstH;
+        if (e == cudaSuccess && cw && ch) e = cudaMemcpy2DAsync(dst[1], dstStride[1], dd[1], dcP, (size_t)cw * sB * (c->dstNV ? 2 : 1), ch, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && cw && ch && !c->dstNV) e = cudaMemcpy2DAsync(dst[2], dstStride[2], dd[2], dcP, (size_t)cw * sB, ch, cudaMemcpyDeviceToHost, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("sws_scale_cuda:d2h", e); return 0; }

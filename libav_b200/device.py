@@ -129,7 +129,9 @@ class SwsContext:
         uint8 arrays (any row stride) -> rgb (h, 3w [+pad]) or 3 planes, pre-filled with `fill`."""
         src = (C.c_void_p * 4)(*([a.ctypes.data for a in yuv] + [None] * (4 - len(yuv))))
         sst = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0] * (4 - len(yuv))))
-        if self.dst_fmt in PLANAR_FORMATS:
+        if self.dst_fmt in (PIX_FMT_NV12, PIX_FMT_NV21):
+            out = [np.full((self.dst_h, self.dst_w), fill, np.uint8), np.full(((self.dst_h + 1) // 2, 2 * ((self.dst_w + 1) // 2)), fill, np.uint8)]
+        elif self.dst_fmt in PLANAR_FORMATS:
             hs, vs, bits = PLANAR_FORMATS[self.dst_fmt]
             dt = np.uint8 if bits == 8 else np.dtype(">u2" if self.dst_fmt in PLANAR_BE else "<u2")
             cw, ch = -((-self.dst_w) >> hs), -((-self.dst_h) >> vs)

@@ -211,6 +211,7 @@ static __thread int g_hs = 1, g_vs = 1;
 /* the planar destination: chroma sub-sampling (log2) and sample depth (8, or 9 / 10 in little-endian 16-bit samples) */
 static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8, g_dbe = 0;
 static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; } else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); } }
+static __thread int g_nospecial;    /* an nv12 / nv21 destination computed through the planar path: no yuv420p-only special converters */
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
 
 static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags)
@@ -629,7 +630,7 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
     /* 32-bit sources: 32 -> 32 bit scales the alpha plane as well, same size -> packed rgb is the rgb2rgb family: neither is restated */
     if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && rgb_dst))) return -1;
-    if (sw == dw && sh == dh) {
+    if (sw == dw && sh == dh && !g_nospecial) {
         if (rgb_src && !src32 && rgb_dst) {
             for (int y = 0; y < sh; y++)
                 for (int x = 0; x < sw; x++)
@@ -758,7 +759,49 @@ static int planar_dst(int fmt, int *hs, int *vs, int *bits)
  * sub-sampling (getSubSampleFactors, utils.c:983) run the same pipeline with chrSrcW / chrSrcH derived from the format.
  * src_fmt: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31; packed: YUYV422 1, RGB24 2, BGR24 3,
  * UYVY422 15 (src[0] / ss[0] only). */
+static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
+                   uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags);
+
+/* nv12 (23) / nv21 (24) destinations: yuv2nv12cX_c (output.c:267-303) is yuv2planeX_8_c on both chroma planes, written
+ * interleaved (the dither is the constant 64 for 8-bit sources, swscale.c:395-399); yuv420p of the same size goes through
+ * planarToNv12Wrapper (swscale_unscaled.c:138-156, srcW / 2 x srcH / 2 chroma samples). */
 int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
+                   uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
+{
+    if (dst_fmt != 23 && dst_fmt != 24) return sws_any(src_fmt, src, ss, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+    const int swap = dst_fmt == 24;
+    if (sw == dw && sh == dh) {
+        if (src_fmt == 23 || src_fmt == 24) return -1;         /* the reference's plane copy skips the chroma plane there */
+        if (src_fmt == 0) {
+            for (int y = 0; y < sh; y++) memcpy(dst[0] + (size_t)y * dstride[0], src[0] + (size_t)y * ss[0], sw);
+            for (int y = 0; y < sh / 2; y++)
+                for (int x = 0; x < sw / 2; x++) {
+                    dst[1][(size_t)y * dstride[1] + 2 * x + swap] = src[1][(size_t)y * ss[1] + x];
+                    dst[1][(size_t)y * dstride[1] + 2 * x + 1 - swap] = src[2][(size_t)y * ss[2] + x];
+                }
+            return sh;
+        }
+    }
+    const int cw = (dw + 1) >> 1, ch = (dh + 1) >> 1;
+    uint8_t *u = malloc((size_t)cw * ch * 2), *v = u + (size_t)cw * ch;
+    if (!u) return -1;
+    uint8_t *const d3[3] = { dst[0], u, v };
+    const int s3[3] = { dstride[0], cw, cw };
+    /* (the inner call's destination "yuv420p" must not take the unscaled special converters the reference only installs for a real
+     * yuv420p destination: yuyvtoyuv420, rgb24toyv12 ...) */
+    g_nospecial = 1;
+    int r = sws_any(src_fmt, src, ss, sw, sh, 0, d3, s3, dw, dh, flags);
+    g_nospecial = 0;
+    for (int y = 0; r == dh && y < ch; y++)
+        for (int x = 0; x < cw; x++) {
+            dst[1][(size_t)y * dstride[1] + 2 * x + swap] = u[(size_t)y * cw + x];
+            dst[1][(size_t)y * dstride[1] + 2 * x + 1 - swap] = v[(size_t)y * cw + x];
+        }
+    free(u);
+    return r;
+}
+
+static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
@@ -780,7 +823,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     }
     /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
      * rgb2rgb.c planar2x): not restated */
-    if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT)) return -1;
+    if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT) && !g_nospecial) return -1;
     g_hs = hs; g_vs = vs;
     r = rgb ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
             : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);

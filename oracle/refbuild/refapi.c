@@ -294,8 +294,9 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
     const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA);
-    uint8_t *d[4] = { dst[0], packed_dst ? NULL : dst[1], packed_dst ? NULL : dst[2], NULL };
-    int ds[4] = { dstride[0], packed_dst ? 0 : dstride[1], packed_dst ? 0 : dstride[2], 0 };
+    const int nv_dst = dst_fmt == AV_PIX_FMT_NV12 || dst_fmt == AV_PIX_FMT_NV21;
+    uint8_t *d[4] = { dst[0], packed_dst ? NULL : dst[1], packed_dst || nv_dst ? NULL : dst[2], NULL };
+    int ds[4] = { dstride[0], packed_dst ? 0 : dstride[1], packed_dst || nv_dst ? 0 : dstride[2], 0 };
     const uint8_t *s[4] = { src[0], packed_src ? NULL : src[1], packed_src ? NULL : src[2], NULL };
     int sst[4] = { ss[0], packed_src ? 0 : ss[1], packed_src ? 0 : ss[2], 0 };
     int r = sws_scale(c, s, sst, 0, sh, d, ds);

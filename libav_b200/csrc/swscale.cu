@@ -37,6 +37,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int bgr;
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
     int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
+    int pk422;                        // packed 4:2:2 destination: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576)
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
 };
@@ -485,6 +486,13 @@ sws_vscale_rgb24_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t
         for (int j = 0; j < fc; j++) { U += CU(j) * cf[j]; V += CV(j) * cf[j]; }
         Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
         clip_if_flagged(Y1, Y2, U, V);
+    }
+    if (p.pk422) {             // the same four values, stored instead of converted (output_pixels, output.c:448-467)
+        uint8_t *d = dst + (size_t)y * dstStride + (size_t)i * 4;
+        const bool room = has2 || dstStride >= 2 * (p.dstW + 1);      // odd width: the pair's second half needs room in the row
+        if (p.pk422 == 1) { d[0] = (uint8_t)Y1; d[1] = (uint8_t)U; if (room) { d[2] = (uint8_t)Y2; d[3] = (uint8_t)V; } }
+        else              { d[0] = (uint8_t)U; d[1] = (uint8_t)Y1; if (room) { d[2] = (uint8_t)V; d[3] = (uint8_t)Y2; } }
+        return;
     }
     ChromaTerms t = chroma_terms(U, V, p.k);
     int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
@@ -1089,6 +1097,21 @@ sws_expand_rgb32_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
     else { d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24); }
 }
 
+// yuv422pToYuy2Wrapper / yuv422pToUyvyWrapper and planarToYuy2Wrapper / planarToUyvyWrapper (swscale_unscaled.c:183-225 ->
+// yuvPlanartoyuy2_c / yuvPlanartouyvy_c, rgb2rgb_template.c:322-420): width >> 1 pixel pairs per row, luma row y with chroma row y >> vshift
+__global__ void __launch_bounds__(256)
+sws_planar_to_422_kernel(const uint8_t *__restrict__ Y, int yStride, size_t yFrame, const uint8_t *__restrict__ U, const uint8_t *__restrict__ V,
+                         int cStride, size_t uFrame, size_t vFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame, int w, int vshift, int uyvy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= (w >> 1)) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *py = Y + f * yFrame + (size_t)y * yStride + 2 * i;
+    const uint8_t u = U[f * uFrame + (size_t)(y >> vshift) * cStride + i], v = V[f * vFrame + (size_t)(y >> vshift) * cStride + i];
+    uint8_t *d = dst + f * dstFrame + (size_t)y * dstStride + 4 * i;
+    if (uyvy) { d[0] = u; d[1] = py[0]; d[2] = v; d[3] = py[1]; } else { d[0] = py[0]; d[1] = u; d[2] = py[1]; d[3] = v; }
+}
+
 // planarToNv12Wrapper (swscale_unscaled.c:138-156): interleaveBytes of srcW / 2 x srcH / 2 chroma samples (an odd last column / row stays untouched)
 __global__ void __launch_bounds__(256)
 sws_interleave_kernel(const uint8_t *__restrict__ a, int aStride, size_t aFrame, const uint8_t *__restrict__ b, int bStride, size_t bFrame,
@@ -1191,6 +1214,8 @@ struct SwsCudaContext {
     int dst32 = 0;              // argb / rgba / abgr / bgra destination (the pixel format value): rgb24 into d_rgb, then expanded
     uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
+    int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
+    int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
     int dstNV = 0;              // 1 nv12, 2 nv21 destination
     bool nvcopy = false;        // yuv420p -> nv12 / nv21 of the same size: planarToNv12Wrapper
     uint8_t *d_nv = nullptr; size_t nv_bytes = 0;   // the planes the pre-pass of a batch writes (split nv chroma, reader output)
@@ -1232,7 +1257,7 @@ static int upload_tables(SwsCudaContext *c)
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422;
     return 0;
 }
 
@@ -1243,8 +1268,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
-    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
+    const int pk422 = dstFormat == FMT_YUYV422 ? 1 : dstFormat == FMT_UYVY422 ? 2 : 0;
+    if (pk422) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
+    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422) {
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1271,7 +1298,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "nv12 / nv21 -> nv12 / nv21 of the same size (the reference's plane copy skips the chroma plane there) is not taken over"); return nullptr;
     }
     const bool src32 = srcFormat >= FMT_ARGB && srcFormat <= FMT_BGRA;
-    if (src32 && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar))) {
+    if (src32 && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar && !pk422))) {
         // 32 -> 32 bit: the reference scales the alpha plane too; same size -> packed rgb: rgbToRgbWrapper's converters (swscale_unscaled.c:591-710)
         set_error_msg("sws_getContext_cuda", "32-bit rgb source: only planar yuv destinations and scaled rgb24 / bgr24 are taken over"); return nullptr;
     }
@@ -1297,6 +1324,12 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
+    c->pk422 = pk422;
+    if (pk422 && srcW == dstW && srcH == dstH) {               // swscale_unscaled.c:1123-1139,1152-1176
+        if (srcFormat == FMT_YUV422P) c->to422 = 1;
+        else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
+        else if (srcFormat == dstFormat) c->to422 = 3;
+    }
     c->dstNV = dstFormat == FMT_NV12 ? 1 : dstFormat == FMT_NV21 ? 2 : 0;
     c->dstFormat = dstFormat; c->dst32 = dst32 ? dstFormat : 0; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
@@ -1309,7 +1342,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
     if (unscaled) {                                           // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
-        if (srcRgb && rgb) c->special = srcFormat == dstFormat ? 1 : 2;
+        if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
         else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
         else if (srcYuy && dstFormat == FMT_YUV422P) c->special = srcFormat == FMT_YUYV422 ? 6 : 7;
@@ -1329,8 +1362,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
-    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
-    c->fused = !c->table_unscaled && rgb && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
+    c->fused = !c->table_unscaled && rgb && !pk422 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -1374,7 +1407,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             }
         }
     }
-    if (!c->fused && !c->copy && !c->table_unscaled) {
+    if (!c->fused && !c->copy && !c->table_unscaled && !c->to422) {
         int lr = 0, cr = 0, lo, hi;
         std::vector<int2> win;
         for (int y0 = 0; y0 < dstH; y0 += GT_H) {
@@ -1389,7 +1422,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
         const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
-        if (need <= 96 * 1024) {
+        if (need <= 96 * 1024 && !pk422) {          // (the packed 4:2:2 output stage only exists in the two-pass path so far)
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1510,6 +1543,25 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
                          uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st,
                          uint8_t *const *remapped)
 {
+    if (c->to422) {
+        const SwsDev &q = c->dev;
+        if (nframes <= 0) return 0;
+        if (c->to422 == 3) {
+            for (int f = 0; f < nframes; f++)
+                AVB_CUDA(cudaMemcpy2DAsync(dst[0] + f * dstFrame[0], dstStride[0], src[0] + f * srcFrame[0], srcStride[0], (size_t)q.srcW * 2, q.srcH, cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
+            return 0;
+        }
+        if (srcStride[1] != srcStride[2]) { set_error_msg("sws_scale", "planar -> packed 4:2:2 needs equal chroma pitches"); return -1; }
+        // the reference's 64-bit loop converts two pairs per step (rgb2rgb_template.c:374-386): an odd pair count is rounded up and the extra
+        // pair reads / writes past the nominal width -- reproduced when every row involved has room for it
+        const int pairs = q.srcW >> 1, pairs_r = (pairs + 1) & ~1;
+        const bool extra = pairs_r > pairs && dstStride[0] >= 4 * pairs_r && srcStride[0] >= 2 * pairs_r && srcStride[1] >= pairs_r;
+        const int np = extra ? pairs_r : pairs;
+        if (np)
+            sws_planar_to_422_kernel<<<dim3((np + 255) / 256, q.srcH, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], src[1], src[2], srcStride[1], srcFrame[1], srcFrame[2],
+                                                                                          dst[0], dstStride[0], dstFrame[0], 2 * np, c->to422 == 2 ? 1 : 0, c->pk422 == 2);
+        return check_launch("sws_scale:planar -> packed 4:2:2");
+    }
     if (c->dstNV && !remapped) {       // an nv12 / nv21 destination: U and V are the even / odd bytes of plane 1 (chrStep 2 in the kernels)
         if (c->nvcopy) {
             const SwsDev &q = c->dev;
@@ -1691,7 +1743,9 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
             const bool x_path = !((p.vLumSize == 1 && p.vChrSize <= 2) || (p.vLumSize == 2 && p.vChrSize == 2));
-            if (p.full)
+            if (p.pk422)
+                sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
+            else if (p.full)
                 sws_vscale_rgb24_full_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
             else if (x_path && !(p.dstW & 7) && !(dstStride[0] & 7) && !((uintptr_t)d0 & 7))
                 sws_vscale_rgb24_x8_kernel<<<dim3((p.dstW / 8 + 127) / 128, p.dstH), 128, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
@@ -1765,7 +1819,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
-    const int pxB = c->dst32 ? 4 : 3;                       // bytes per packed rgb pixel
+    const int pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;        // bytes per packed pixel
     const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB * (c->dstNV ? 2 : 1) + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
@@ -1808,15 +1862,25 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         for (int q = 0; q < 3; q++) if (cudaStreamSynchronize(st[q]) != cudaSuccess) { set_error("sws_scale_cuda:sync", cudaGetLastError()); return 0; }
         return g.dstH;
     }
+    // planar -> packed 4:2:2 converters: the rounded-up last pair reads the samples just past the width (see run_frames_24)
+    int upX = 0, upCX = 0;
+    if (c->to422 == 1 || c->to422 == 2) {
+        const int pairs = g.srcW >> 1, pairs_r = (pairs + 1) & ~1;
+        if (pairs_r > pairs && dstStride[0] >= 4 * pairs_r && srcStride[0] >= 2 * pairs_r && srcStride[1] >= pairs_r && srcStride[2] >= pairs_r) {
+            upX = 2 * pairs_r - g.srcW; upCX = pairs_r - g.chrSrcW;
+            if (upX < 0) upX = 0;
+            if (upCX < 0) upCX = 0;
+        }
+    }
     if (pk) {
         size_t rowB = (size_t)g.srcW * pkBpp;
         if ((g.srcW & 1) && rowB + pkBpp <= (size_t)srcStride[0]) rowB += pkBpp;       // the pixel the readers look at past an odd width
         if (cudaMemcpyAsync((void *)ds[0], srcSlice[0], (size_t)(g.srcH - 1) * srcStride[0] + rowB, cudaMemcpyHostToDevice, s) != cudaSuccess) {
             set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
         }
-    } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
+    } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW + upX, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW + upCX, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW + upCX, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
         set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
     }
     static const size_t zero3[3] = { 0, 0, 0 };
@@ -1828,6 +1892,11 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + pxB) wbytes += pxB;      // (full chroma writes single pixels)
         if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * pxB;       // that converter leaves an odd last column untouched
         if (c->special) wbytes = (size_t)g.dstW * 3;
+        if (c->to422) {          // (see run_frames_24: an odd pair count is rounded up when the rows have room)
+            const int pairs = g.dstW >> 1, pairs_r = (pairs + 1) & ~1;
+            const bool extra = pairs_r > pairs && dstStride[0] >= 4 * pairs_r && srcStride[0] >= 2 * pairs_r && srcStride[1] >= pairs_r && srcStride[2] >= pairs_r;
+            wbytes = c->to422 == 3 ? (size_t)g.dstW * 2 : (size_t)(extra ? pairs_r : pairs) * 4;
+        }
         e = cudaMemcpy2DAsync(dst[0], dstStride[0], dd[0], dP, wbytes, g.dstH, cudaMemcpyDeviceToHost, s);
     } else {
         // rgb24toyv12_c converts whole pixel pairs only

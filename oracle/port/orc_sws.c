@@ -211,6 +211,7 @@ static __thread int g_hs = 1, g_vs = 1;
 /* the planar destination: chroma sub-sampling (log2) and sample depth (8, or 9 / 10 in little-endian 16-bit samples) */
 static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8, g_dbe = 0;
 static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; } else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); } }
+static __thread int g_pk422;        /* packed 4:2:2 destination of the "rgb" entry point: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576) */
 static __thread int g_nospecial;    /* an nv12 / nv21 destination computed through the planar path: no yuv420p-only special converters */
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
 
@@ -344,7 +345,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
-    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1) {
+    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422) {
         /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
          * i.e. both rows of a pair read the even chroma line)
          * unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
@@ -430,6 +431,12 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
                 for (j = 0; j < fc; j++) { Uv += CHU(j) * cf[j]; Vv += CHV(j) * cf[j]; }
                 Y1 >>= 19; Y2 >>= 19; Uv >>= 19; Vv >>= 19;
                 if ((Y1 | Y2 | Uv | Vv) & 0x100) { Y1 = u8clip(Y1); Y2 = u8clip(Y2); Uv = u8clip(Uv); Vv = u8clip(Vv); }
+            }
+            if (g_pk422) {      /* output_pixels (output.c:448-467): the four values are stored, not converted */
+                const int room = 2 * i + 1 < dw || dstride >= 2 * (dw + 1);
+                if (g_pk422 == 1) { d[4 * i] = (uint8_t)Y1; d[4 * i + 1] = (uint8_t)Uv; if (room) { d[4 * i + 2] = (uint8_t)Y2; d[4 * i + 3] = (uint8_t)Vv; } }
+                else              { d[4 * i] = (uint8_t)Uv; d[4 * i + 1] = (uint8_t)Y1; if (room) { d[4 * i + 2] = (uint8_t)Vv; d[4 * i + 3] = (uint8_t)Y2; } }
+                continue;
             }
             const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
             d[6 * i + 0] = r[Y1]; d[6 * i + 1] = g[Y1]; d[6 * i + 2] = b[Y1];
@@ -556,7 +563,7 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
     const uint8_t *src[3] = { y, u, v };
     const int ss[3] = { ystride, pitch, pitch };
     g_nocopy = 1;
-    int r = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
+    int r = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || dst_fmt == 1 || dst_fmt == 15 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
                                          : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
     g_nocopy = 0;
     free(u);
@@ -568,6 +575,12 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
 static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt, uint8_t *dst, int dstride, int dw, int dh, int flags)
 {
     if (dst_fmt == 2) return orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    if (dst_fmt == 1 || dst_fmt == 15) {          /* yuyv422 / uyvy422: the packed output stage without the colour conversion */
+        g_pk422 = dst_fmt == 1 ? 1 : 2;
+        int r422 = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags & ~F_FULL_CHR_H_INT);
+        g_pk422 = 0;
+        return r422;
+    }
     const int pitch = (dw + 1) * 3;
     uint8_t *t = malloc((size_t)pitch * dh);
     if (!t) return -1;
@@ -626,12 +639,13 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     const int rgb_src = src_fmt == 2 || src_fmt == 3 || src32;
     const int ro = src32 ? pos32[src_fmt - 25][0] : src_fmt == 3 ? 2 : 0, go = src32 ? pos32[src_fmt - 25][1] : 1, bo = src32 ? pos32[src_fmt - 25][2] : 2 - ro;
     const int rgb_bpp = src32 ? 4 : 3;
-    const int rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    const int real_rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    const int rgb_dst = real_rgb_dst || dst_fmt == 1 || dst_fmt == 15;       /* packed destinations share the output stage */
     if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
     /* 32-bit sources: 32 -> 32 bit scales the alpha plane as well, same size -> packed rgb is the rgb2rgb family: neither is restated */
-    if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && rgb_dst))) return -1;
+    if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && real_rgb_dst))) return -1;
     if (sw == dw && sh == dh && !g_nospecial) {
-        if (rgb_src && !src32 && rgb_dst) {
+        if (rgb_src && !src32 && real_rgb_dst) {
             for (int y = 0; y < sh; y++)
                 for (int x = 0; x < sw; x++)
                     for (int k = 0; k < 3; k++)
@@ -683,7 +697,7 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     }
     int hs = 1;
     if (rgb_src) {
-        const int chr_dst_hsub = !rgb_dst ? g_dhs : (flags & F_FULL_CHR_H_INT) ? 0 : 1;
+        const int chr_dst_hsub = !rgb_dst ? g_dhs : ((flags & F_FULL_CHR_H_INT) && real_rgb_dst) ? 0 : 1;
         hs = (!(flags & 0x4000) && ((dw >> chr_dst_hsub) <= (sw >> 1) || (flags & 1))) ? 1 : 0;
     }
     const int cw = -((-sw) >> hs), yp = sw + 16, cp = cw + 16;
@@ -805,7 +819,32 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
-    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    const int pk = dst_fmt == 1 || dst_fmt == 15;
+    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk;
+    if (pk && sw == dw && sh == dh) {
+        /* the reference's unscaled converters to packed 4:2:2 (swscale_unscaled.c:1123-1139,1152-1176): from yuv422p always, from yuv420p
+         * with the fast-bilinear / point flags (yuvPlanartoyuy2_c, rgb2rgb_template.c:322-420: width >> 1 pairs), same format = copy */
+        const int vshift = src_fmt == 0 ? 1 : 0, uyvy = dst_fmt == 15;
+        if (src_fmt == 4 || (src_fmt == 0 && (flags & (F_FAST_BILINEAR | F_POINT)))) {
+            /* the 64-bit build of the loop (HAVE_FAST_64BIT, :374-386) converts two pairs per step: an odd width >> 1 is rounded up, the
+             * extra pair reads / writes past the nominal width (here: when the rows have room for it) */
+            const int pairs = sw >> 1, pairs_r = (pairs + 1) & ~1;
+            const int extra = pairs_r > pairs && dstride[0] >= 4 * pairs_r && ss[0] >= 2 * pairs_r && ss[1] >= pairs_r && ss[2] >= pairs_r;
+            for (int y = 0; y < sh; y++)
+                for (int i = 0; i < (extra ? pairs_r : pairs); i++) {
+                    uint8_t *d = dst[0] + (size_t)y * dstride[0] + 4 * i;
+                    const uint8_t *py = src[0] + (size_t)y * ss[0] + 2 * i;
+                    const uint8_t u = src[1][(size_t)(y >> vshift) * ss[1] + i], v = src[2][(size_t)(y >> vshift) * ss[2] + i];
+                    if (uyvy) { d[0] = u; d[1] = py[0]; d[2] = v; d[3] = py[1]; } else { d[0] = py[0]; d[1] = u; d[2] = py[1]; d[3] = v; }
+                }
+            return sh;
+        }
+        if (src_fmt == dst_fmt) {
+            for (int y = 0; y < sh; y++) memcpy(dst[0] + (size_t)y * dstride[0], src[0] + (size_t)y * ss[0], (size_t)sw * 2);
+            return sh;
+        }
+    }
+    if (pk) flags &= ~F_FULL_CHR_H_INT;
     if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT)) return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {

@@ -293,7 +293,8 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                            (src_fmt >= AV_PIX_FMT_ARGB && src_fmt <= AV_PIX_FMT_BGRA);
     struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
-    const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA);
+    const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA) ||
+                           dst_fmt == AV_PIX_FMT_YUYV422 || dst_fmt == AV_PIX_FMT_UYVY422;
     const int nv_dst = dst_fmt == AV_PIX_FMT_NV12 || dst_fmt == AV_PIX_FMT_NV21;
     uint8_t *d[4] = { dst[0], packed_dst ? NULL : dst[1], packed_dst || nv_dst ? NULL : dst[2], NULL };
     int ds[4] = { dstride[0], packed_dst ? 0 : dstride[1], packed_dst || nv_dst ? 0 : dstride[2], 0 };

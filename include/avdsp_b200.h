@@ -375,6 +375,13 @@ typedef struct SwsContextCUDA SwsContextCUDA;
 SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
                                     void *srcFilter, void *dstFilter, const double *param);
 void sws_freeContext_cuda(SwsContextCUDA *ctx);
+/* sws_setColorspaceDetails (libswscale/swscale.h:269-271, utils.c:807-835) for packed rgb destinations: inv_table = the four
+ * yuv -> rgb coefficients (ff_yuv2rgb_coeffs[], e.g. SWS_CS_ITU709 = { 117504, 138453, 13954, 34903 }), srcRange 1 = full-range
+ * (JPEG) yuv, brightness / contrast / saturation in 16.16 fixed point (0, 1 << 16, 1 << 16 = neutral).  Returns 0, or -1 for a yuv
+ * destination (like the reference) and for settings that would index outside the reference's 1024-entry colour table.  The
+ * full-range source formats yuvj420p = 12, yuvj422p = 13, yuvj444p = 14 are taken over as sources of rgb destinations. */
+int sws_setColorspaceDetails_cuda(SwsContextCUDA *ctx, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                  int brightness, int contrast, int saturation);
 int  sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY,
                     int srcSliceH, uint8_t *const dst[], const int dstStride[]);
 int  sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], const int srcStride[3],

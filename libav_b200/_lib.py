@@ -82,6 +82,7 @@ PROTOTYPES = {
     "ff_mdct_batch_cuda": (i32, [i32, i32, C.c_double, vp, vp, sz, vp]),
     "sws_getContext_cuda": (vp, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "sws_freeContext_cuda": (None, [vp]),
+    "sws_setColorspaceDetails_cuda": (i32, [vp, vp, i32, vp, i32, i32, i32, i32]),
     "sws_scale_cuda": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "sws_scale_frames_cuda": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "sws_is_fused_cuda": (i32, [vp]),

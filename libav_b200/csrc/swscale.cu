@@ -1158,7 +1158,7 @@ sws_yuyv_yuv422p_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
 // context
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
-       FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
+       FMT_YUVJ420P = 12, FMT_YUVJ422P = 13, FMT_YUVJ444P = 14, FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
        FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
 static bool unscaled0(int sw, int sh, int dw, int dh) { return sw == dw && sh == dh; }
@@ -1214,6 +1214,7 @@ struct SwsCudaContext {
     int dst32 = 0;              // argb / rgba / abgr / bgra destination (the pixel format value): rgb24 into d_rgb, then expanded
     uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
+    int srcRange = 0;           // 1 = full-range (JPEG) source, sws_setColorspaceDetails / a yuvj source format
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
     int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
     int dstNV = 0;              // 1 nv12, 2 nv21 destination
@@ -1265,6 +1266,11 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
                                     const double *param, bool device_side)
 {
     const char *err = nullptr;
+    // handle_jpeg() (utils.c:855-873): the full-range planar formats are their limited-range twins with srcRange = 1
+    int srcRange = 0;
+    if (srcFormat == FMT_YUVJ420P) { srcFormat = FMT_YUV420P; srcRange = 1; }
+    else if (srcFormat == FMT_YUVJ422P) { srcFormat = FMT_YUV422P; srcRange = 1; }
+    else if (srcFormat == FMT_YUVJ444P) { srcFormat = FMT_YUV444P; srcRange = 1; }
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
@@ -1321,6 +1327,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         return nullptr;
     }
     const bool rgb = !planar;
+    if (srcRange && (planar || pk422)) {                      // swscale.c:748-765: lumRangeFromJpeg_c / chrRangeFromJpeg_c between the two passes
+        set_error_msg("sws_getContext_cuda", "full-range (yuvj) source to a limited-range yuv destination needs the range conversion: not taken over");
+        return nullptr;
+    }
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
@@ -1359,7 +1369,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     {
         static const int itu601[4] = { 104597, 132201, 25675, 53279 };     // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT]
-        rgb_constants(c->k, itu601, 0, 0, 1 << 16, 1 << 16);             // sws_getContext defaults, utils.c:1366-1368
+        rgb_constants(c->k, itu601, srcRange, 0, 1 << 16, 1 << 16);      // sws_getContext defaults, utils.c:1366-1368
+        c->srcRange = srcRange;
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
     c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
@@ -1778,6 +1789,30 @@ SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW,
 }
 
 void sws_freeContext_cuda(SwsContextCUDA *ctx) { destroy((SwsCudaContext *)ctx); }
+
+// sws_setColorspaceDetails (libswscale/utils.c:807-835): new yuv -> rgb constants (ff_yuv2rgb_c_init_tables, yuv2rgb.c:671-863) for a
+// packed rgb destination; -1 for yuv destinations like the reference, and -1 (nothing changed) for what is not taken over.
+int sws_setColorspaceDetails_cuda(SwsContextCUDA *ctx, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                  int brightness, int contrast, int saturation)
+{
+    SwsCudaContext *c = (SwsCudaContext *)ctx;
+    (void)table; (void)dstRange;                  // only read by the yuv -> yuv range conversion (not taken over) and rgb sources' fixed readers
+    if (!c || !inv_table) { set_error_msg("sws_setColorspaceDetails_cuda", "NULL argument"); return -1; }
+    if (c->planar || c->pk422) return -1;         // isYUV(dstFormat): the reference returns -1 as well (utils.c:821-822)
+    if (c->special) return 0;                     // rgb -> rgb copies / swaps never look at the tables
+    RgbConstants k;
+    rgb_constants(k, inv_table, srcRange != 0, brightness, contrast, saturation);
+    if (k.cy <= 0) { set_error_msg("sws_setColorspaceDetails_cuda", "contrast must be positive"); return -1; }
+    // the reference indexes a 1024-entry table with Y + offset(U, V): the settings must keep every index inside it
+    const int lo[3] = { k.ar + (int)std::min<int64_t>(0, (255LL * k.crv) >> 16), k.agu + k.agv + (int)std::min<int64_t>(0, (255LL * k.cgu) >> 16) + (int)std::min<int64_t>(0, (255LL * k.cgv) >> 16),
+                        k.ab + (int)std::min<int64_t>(0, (255LL * k.cbu) >> 16) };
+    const int hi[3] = { k.ar + (int)std::max<int64_t>(0, (255LL * k.crv) >> 16), k.agu + k.agv + (int)std::max<int64_t>(0, (255LL * k.cgu) >> 16) + (int)std::max<int64_t>(0, (255LL * k.cgv) >> 16),
+                        k.ab + (int)std::max<int64_t>(0, (255LL * k.cbu) >> 16) };
+    for (int ch = 0; ch < 3; ch++)
+        if (lo[ch] < 0 || hi[ch] + 255 > 1023) { set_error_msg("sws_setColorspaceDetails_cuda", "these settings index outside the reference's colour table"); return -1; }
+    c->k = k; c->dev.k = k; c->srcRange = srcRange != 0;
+    return 0;
+}
 
 int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrameStride[3],
                           uint8_t *const dst[3], const int dstStride[3], const size_t dstFrameStride[3], int nframes, void *stream)

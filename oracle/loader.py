@@ -49,6 +49,7 @@ API = {
     "full_search": (None, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32]),
     "sws_yuv420p_to_rgb24": (i32, [vp, vp, i32, i32, vp, i32, i32, i32, i32]),
     "sws_yuv420p_to_yuv420p": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32]),
+    "sws_set_colorspace": (None, [vp, i32, i32, i32, i32]),
     "sws_planar": (i32, [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32]),
     "sws_nv12": (i32, [i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "sws_get_filter": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),

@@ -168,6 +168,9 @@ int ORC(sws_yuv420p_to_yuv420p)(const uint8_t *const src[3], const int src_strid
  * YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31; packed (src[0] / ss[0] only): YUYV422 1, RGB24 2, BGR24 3, UYVY422 15
  * (libavutil/pixfmt.h).  dst_fmt 2 = rgb24, 3 = bgr24 (dst[0] only), 0 = yuv420p.  One frame through sws_getContext + sws_scale;
  * returns the lines written. */
+/* colour settings for the following sws_planar calls (sws_setColorspaceDetails, utils.c:807-835): inv_table = ff_yuv2rgb_coeffs[] row,
+ * src_range 1 = full-range yuv, brightness / contrast / saturation in 16.16; NULL restores sws_getContext's defaults */
+void ORC(sws_set_colorspace)(const int inv_table[4], int src_range, int brightness, int contrast, int saturation);
 int ORC(sws_planar)(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                     uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags);
 /* Semi-planar sources: sws_getContext(sw, sh, AV_PIX_FMT_NV12 / NV21, dw, dh, dst_fmt, flags) + sws_scale of one frame

@@ -254,15 +254,38 @@ int orc_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, in
     return taps;
 }
 
-/* yuv2rgb.c:633-658, :671-863 with inv_table = ITU601, limited range, neutral brightness/contrast/saturation */
+/* the colour settings of sws_setColorspaceDetails (utils.c:807-835); defaults = sws_getContext's (ITU601, limited range, neutral) */
+static __thread struct { int inv[4], full_range, brightness, contrast, saturation; } g_cs = { { 104597, 132201, 25675, 53279 }, 0, 0, 1 << 16, 1 << 16 };
+static __thread int g_cs_jpeg;       /* a yuvj source format forces full range for one call */
+
+void orc_sws_set_colorspace(const int inv_table[4], int src_range, int brightness, int contrast, int saturation)
+{
+    static const int itu601[4] = { 104597, 132201, 25675, 53279 };
+    memcpy(g_cs.inv, inv_table ? inv_table : itu601, sizeof(g_cs.inv));
+    g_cs.full_range = inv_table ? src_range != 0 : 0; g_cs.brightness = inv_table ? brightness : 0;
+    g_cs.contrast = inv_table ? contrast : 1 << 16; g_cs.saturation = inv_table ? saturation : 1 << 16;
+}
+
+/* ff_yuv2rgb_c_init_tables' scalar part (yuv2rgb.c:671-734): cy, oy and the four chroma coefficients before the division by cy */
+static void cs_coeffs(int64_t *cy, int64_t *oy, int64_t *crv, int64_t *cbu, int64_t *cgu, int64_t *cgv, int *yoffs)
+{
+    const int full = g_cs.full_range || g_cs_jpeg;
+    *crv = g_cs.inv[0]; *cbu = g_cs.inv[1]; *cgu = -g_cs.inv[2]; *cgv = -g_cs.inv[3];
+    *cy = 1 << 16; *oy = 0; *yoffs = full ? 384 : 326;
+    if (!full) { *cy = (*cy * 255) / 219; *oy = 16 << 16; }
+    else { *crv = (*crv * 224) / 255; *cbu = (*cbu * 224) / 255; *cgu = (*cgu * 224) / 255; *cgv = (*cgv * 224) / 255; }
+    *cy = (*cy * g_cs.contrast) >> 16;
+    *crv = (*crv * g_cs.contrast * g_cs.saturation) >> 32; *cbu = (*cbu * g_cs.contrast * g_cs.saturation) >> 32;
+    *cgu = (*cgu * g_cs.contrast * g_cs.saturation) >> 32; *cgv = (*cgv * g_cs.contrast * g_cs.saturation) >> 32;
+    *oy -= 256 * (int64_t)g_cs.brightness;
+}
+
+/* yuv2rgb.c:633-658, :671-863 */
 void orc_sws_rgb24_tables(uint8_t *ytab, int32_t *rv, int32_t *gu, int32_t *gv, int32_t *bu)
 {
-    const int yoffs = 326;
-    int64_t crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279;
-    int64_t cy = ((1LL << 16) * 255) / 219, oy = 16 << 16, yb;
-    cy = (cy * 65536) >> 16;
-    crv = (crv * 65536 * 65536) >> 32; cbu = (cbu * 65536 * 65536) >> 32;
-    cgu = (cgu * 65536 * 65536) >> 32; cgv = (cgv * 65536 * 65536) >> 32;
+    int yoffs;
+    int64_t crv, cbu, cgu, cgv, cy, oy, yb;
+    cs_coeffs(&cy, &oy, &crv, &cbu, &cgu, &cgv, &yoffs);
     crv = ((crv << 16) + 0x8000) / cy; cbu = ((cbu << 16) + 0x8000) / cy;
     cgu = ((cgu * 65536) + 0x8000) / cy; cgv = ((cgv * 65536) + 0x8000) / cy;
     yb = -(384 << 16) - oy;
@@ -371,11 +394,11 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (flags & F_FULL_CHR_H_INT) {
         /* yuv2rgb24_full_X_c (output.c:1165-1240): one chroma sample per pixel, 30-bit fixed point colour matrix with the
          * coefficients of ff_yuv2rgb_c_init_tables (yuv2rgb.c:735-740); always the X variant (output.c:1392-1460) */
-        int64_t kcy = ((int64_t)(1 << 16) * 255) / 219, koy = 16 << 16;
-        static const int itu601[4] = { 104597, 132201, 25675, 53279 };
+        int64_t kcy, koy, kcrv, kcbu, kcgu, kcgv; int kyoffs;
+        cs_coeffs(&kcy, &koy, &kcrv, &kcbu, &kcgu, &kcgv, &kyoffs);
 #define R16(f) ((int16_t)({ int r_ = (int)(((int64_t)(f) + (1 << 15)) >> 16); r_ < -0x7FFF ? -0x8000 : r_ > 0x7FFF ? 0x7FFF : r_; }))
-        const int y_coeff = R16(kcy << 13), y_offset = R16(koy << 9), v2r = R16((int64_t)itu601[0] << 13), v2g = R16(-(int64_t)itu601[3] << 13),
-                  u2g = R16(-(int64_t)itu601[2] << 13), u2b = R16((int64_t)itu601[1] << 13);
+        const int y_coeff = R16(kcy << 13), y_offset = R16(koy << 9), v2r = R16(kcrv << 13), v2g = R16(kcgv << 13),
+                  u2g = R16(kcgu << 13), u2b = R16(kcbu << 13);
 #undef R16
         for (int y = 0; y < dh; y++) {
             int firstL = c.vl.pos[y] > 1 - fl ? c.vl.pos[y] : 1 - fl;
@@ -820,6 +843,13 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
 {
     int hs, vs, r;
     const int pk = dst_fmt == 1 || dst_fmt == 15;
+    if (src_fmt >= 12 && src_fmt <= 14) {           /* yuvj420p / 422p / 444p: handle_jpeg() (utils.c:855-873), srcRange = 1 */
+        if (!(dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28))) return -1;      /* yuv destinations would need the range conversion */
+        g_cs_jpeg = 1;
+        r = sws_any(src_fmt == 12 ? 0 : src_fmt == 13 ? 4 : 5, src, ss, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+        g_cs_jpeg = 0;
+        return r;
+    }
     const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk;
     if (pk && sw == dw && sh == dh) {
         /* the reference's unscaled converters to packed 4:2:2 (swscale_unscaled.c:1123-1139,1152-1176): from yuv422p always, from yuv420p

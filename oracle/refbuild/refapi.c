@@ -285,6 +285,13 @@ int ref_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     sws_freeContext(c);
     return r;
 }
+static int g_cs_set, g_cs_inv[4], g_cs_range, g_cs_b, g_cs_c, g_cs_s;
+void ref_sws_set_colorspace(const int inv_table[4], int src_range, int brightness, int contrast, int saturation)
+{
+    g_cs_set = inv_table != NULL;
+    if (inv_table) memcpy(g_cs_inv, inv_table, sizeof(g_cs_inv));
+    g_cs_range = src_range; g_cs_b = brightness; g_cs_c = contrast; g_cs_s = saturation;
+}
 int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt,
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
@@ -293,6 +300,7 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                            (src_fmt >= AV_PIX_FMT_ARGB && src_fmt <= AV_PIX_FMT_BGRA);
     struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
     if (!c) return -1;
+    if (g_cs_set && sws_setColorspaceDetails(c, g_cs_inv, g_cs_range, g_cs_inv, 0, g_cs_b, g_cs_c, g_cs_s) < 0) { sws_freeContext(c); return -2; }
     const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA) ||
                            dst_fmt == AV_PIX_FMT_YUYV422 || dst_fmt == AV_PIX_FMT_UYVY422;
     const int nv_dst = dst_fmt == AV_PIX_FMT_NV12 || dst_fmt == AV_PIX_FMT_NV21;

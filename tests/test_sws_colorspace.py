@@ -90,7 +90,8 @@ def test_gpu_refusals(gpu):
     assert gpu.lib.sws_setColorspaceDetails_cuda(ctx.ctx, tab, 0, tab, 0, 0, 1 << 16, 1 << 16) == -1
     ctx.close()
     ctx = device.SwsContext(64, 48, 128, 96, 2, 4)
-    assert gpu.lib.sws_setColorspaceDetails_cuda(ctx.ctx, tab, 0, tab, 0, 0, 1 << 20, 1 << 16) == -1      # contrast 16: leaves the colour table
+    assert gpu.lib.sws_setColorspaceDetails_cuda(ctx.ctx, tab, 0, tab, 0, 0, 1 << 16, 1 << 20) == -1      # saturation 16: leaves the colour table
+    assert "colour table" in gpu.last_error()
     gpu.lib.avb200_clear_error()
     ctx.close()
     with pytest.raises(Exception):

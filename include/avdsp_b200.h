@@ -393,6 +393,11 @@ int  sws_is_fused_cuda(SwsContextCUDA *ctx);   /* 1 when the single-kernel same-
 int  sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags,
                            int16_t *filter, int32_t *pos, int cap, int *n_out);
 void sws_debug_rgb_constants_cuda(int32_t out[10]);
+/* what sws_getContext_cuda would decide, computed on the host only: 1 = taken over (out[0] path: 1 plane copy, 2 unscaled table
+ * converter, 3 fused same-size kernel, 4 general scaler, 5 packed-source special converter, 6 planar -> packed 4:2:2 converter,
+ * 7 yuv420p -> nv12 interleave; out[1..4] chrSrcW chrSrcH chrDstW chrDstH; out[5] source pre-pass 0 / 1 nv split / 2 reader;
+ * out[6] destination bits per sample (planar) or bytes per pixel (packed); out[7] full-range source), 0 = refused */
+int  sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[8]);
 
 /* ------------------------------------------------------------------ 3. table hooks --------------- */
 /* One more arch behind ff_idctdsp_init()'s dispatch (libavcodec/idctdsp.c:183-188; same shape as

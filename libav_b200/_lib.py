@@ -88,6 +88,7 @@ PROTOTYPES = {
     "sws_is_fused_cuda": (i32, [vp]),
     "sws_debug_filter_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "sws_debug_rgb_constants_cuda": (None, [vp]),
+    "sws_debug_plan_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp]),
     "ff_idctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
     "ff_blockdsp_init_cuda": (None, [vp]),
     "ff_fdctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),

@@ -1966,6 +1966,25 @@ int sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int
     delete c;
     return fs;
 }
+// What sws_getContext_cuda() decides for a request, without touching a device (CPU tests of the format / refusal rules):
+// returns 1 and fills out[] when the request is taken over, 0 (with the error string set) when it is refused.
+//   out[0] path: 1 plane copy (planarCopyWrapper / nv12ToPlanarWrapper), 2 unscaled table converter, 3 fused same-size kernel,
+//          4 general scaler (tile kernel or two passes), 5 packed-source special converter, 6 planar -> packed 4:2:2 converter,
+//          7 yuv420p -> nv12 / nv21 interleave
+//   out[1..4] chrSrcW, chrSrcH, chrDstW, chrDstH   out[5] source pre-pass: 0 none, 1 nv split, 2 packed reader
+//   out[6] destination sample bits (planar) or bytes per pixel (packed)   out[7] full-range source
+int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[8])
+{
+    SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
+    if (!c) return 0;
+    out[0] = c->to422 ? 6 : c->nvcopy ? 7 : c->special ? 5 : c->copy ? 1 : c->table_unscaled ? 2 : c->fused ? 3 : 4;
+    out[1] = c->g.chrSrcW; out[2] = c->g.chrSrcH; out[3] = c->g.chrDstW; out[4] = c->g.chrDstH;
+    out[5] = c->srcPacked ? 2 : c->srcNV ? 1 : 0;
+    out[6] = c->planar ? c->dstBits : c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    out[7] = c->srcRange;
+    delete c;
+    return 1;
+}
 void sws_debug_rgb_constants_cuda(int32_t out[10])
 {
     static const int itu601[4] = { 104597, 132201, 25675, 53279 };

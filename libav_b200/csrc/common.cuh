@@ -18,6 +18,12 @@ int  check_launch(const char *where);   // cudaGetLastError() -> sticky error, r
         if (e__ != cudaSuccess) { avb::set_error(where, e__); return -1; } \
     } while (0)
 
+// Kernel launch.  The product always expands to the <<<>>> form; tests/hostsim/ (test infrastructure, CPU suite) defines this
+// macro first and compiles the thread-independent slot kernels as host C++ so that the slot plumbing is checked without a GPU.
+#ifndef AVB_LAUNCH
+#define AVB_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 int sm_count();                 // multiprocessor count of the current device (cached)
 int tuning(const char *key);    // experiment knob set through avb200_set_tuning(); 0 when unset
 

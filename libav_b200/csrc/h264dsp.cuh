@@ -116,6 +116,23 @@ __device__ inline void h264_chroma_dc_dequant(int16_t *b, int qmul)
     b[32] = (int16_t)(((a - c) * qmul) >> 7); b[48] = (int16_t)(((e - bb) * qmul) >> 7);
 }
 
+// 4:2:2 chroma DC (h264idct_template.c:277-302): 2 (across) x 4 (down) Hadamard over the eight DC values, which sit 16 coefficients
+// apart in the macroblock's coefficient array; (v * qmul + 128) >> 8 like the luma DC
+__device__ inline void h264_chroma422_dc_dequant(int16_t *b, int qmul)
+{
+    int t[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { t[2 * i] = b[32 * i] + b[32 * i + 16]; t[2 * i + 1] = b[32 * i] - b[32 * i + 16]; }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int z0 = t[i] + t[4 + i], z1 = t[i] - t[4 + i], z2 = t[2 + i] - t[6 + i], z3 = t[2 + i] + t[6 + i];
+        b[16 * i + 0]  = (int16_t)(((z0 + z3) * qmul + 128) >> 8);
+        b[16 * i + 32] = (int16_t)(((z1 + z2) * qmul + 128) >> 8);
+        b[16 * i + 64] = (int16_t)(((z1 - z2) * qmul + 128) >> 8);
+        b[16 * i + 96] = (int16_t)(((z0 - z3) * qmul + 128) >> 8);
+    }
+}
+
 // ---- deblocking: one line across an edge; `px` = distance between samples across the edge -------------------
 __device__ inline void h264_luma_line(uint8_t *q, int px, int alpha, int beta, int tc0)
 {

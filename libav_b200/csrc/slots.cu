@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(32) slot_kernel(SlotArgs s)
             else h264_dc_add(s.p0, s.blk, SP, s.a == 2 ? 4 : 8);
         }
         break;
-    case OP_H264_IDCT_MB: {                   // a = which (0 add16, 1 add16intra, 2 idct8_add4, 3 add8), b = pitch
+    case OP_H264_IDCT_MB: {                   // a = which (0 add16, 1 add16intra, 2 idct8_add4, 3 add8, 4 add8_422), b = pitch
         const int which = s.a, pitch = s.b;
         if (which < 3 && lane < 16) {
             int16_t *blk = s.blk + 16 * lane;
@@ -50,25 +50,28 @@ __global__ void __launch_bounds__(32) slot_kernel(SlotArgs s)
             if (which == 0) { if (nnz) { if (nnz == 1 && blk[0]) h264_dc_add(d, blk, pitch, 4); else h264_idct4_add(d, blk, pitch); } }
             else if (which == 1) { if (nnz) h264_idct4_add(d, blk, pitch); else if (blk[0]) h264_dc_add(d, blk, pitch, 4); }
             else if ((lane & 3) == 0 && nnz) { if (nnz == 1 && blk[0]) h264_dc_add(d, blk, pitch, 8); else h264_idct8_add(d, blk, pitch); }
-        } else if (which == 3 && lane < 8) {
-            const int plane = lane >> 2, i = 16 + 16 * plane + (lane & 3);
+        } else if (which >= 3 && lane < (which == 4 ? 16 : 8)) {
+            // 4:2:0: four blocks per plane.  4:2:2 (h264idct_template.c:216-236): eight, the lower four keep their coefficients at
+            // block i but are addressed through scan8[i + 4] / block_offset[i + 4]
+            const int per = which == 4 ? 8 : 4, plane = lane / per, k = lane % per;
+            const int i = 16 + 16 * plane + k, e = k >= 4 ? i + 4 : i;
             int16_t *blk = s.blk + 16 * i;
-            uint8_t *d = (plane ? s.p1 : s.p0) + s.off[i];
-            if (s.nnzc[scan8_of(i)]) h264_idct4_add(d, blk, pitch); else if (blk[0]) h264_dc_add(d, blk, pitch, 4);
+            uint8_t *d = (plane ? s.p1 : s.p0) + s.off[e];
+            if (s.nnzc[scan8_of(e)]) h264_idct4_add(d, blk, pitch); else if (blk[0]) h264_dc_add(d, blk, pitch, 4);
         }
     } break;
     case OP_H264_LUMA_DC: if (lane == 0) h264_luma_dc_dequant(s.blk, s.blk + 256, s.a); break;
-    case OP_H264_CHROMA_DC: if (lane == 0) h264_chroma_dc_dequant(s.blk, s.a); break;
+    case OP_H264_CHROMA_DC: if (lane == 0) { if (s.b) h264_chroma422_dc_dequant(s.blk, s.a); else h264_chroma_dc_dequant(s.blk, s.a); } break;    // b = 4:2:2
     case OP_H264_ADD_PIXELS: {                // a = n (4 / 8): dst += block (wraps, no clip), block cleared
         const int n = s.a;
         for (int i = lane; i < n * n; i += 32) { uint8_t *d = s.p0 + (i / n) * SP + i % n; *d = (uint8_t)(*d + s.blk[i]); s.blk[i] = 0; }
     } break;
-    case OP_H264_LOOP: {                      // a = which (oracle numbering), b = alpha, c = beta; p0 -> q0 sample
-        const int which = s.a, horiz_edge = !(which & 1), chroma = which >= 4, intra = (which & 2) != 0;
-        const int across = horiz_edge ? SP : 1, along = horiz_edge ? 1 : SP, lines = chroma ? 8 : 16;
+    case OP_H264_LOOP: {                      // a = kind bits (1 horizontal edge, 2 chroma, 4 intra), b = alpha, c = beta, d = lines; p0 -> q0 sample
+        const bool horiz_edge = s.a & 1, chroma = s.a & 2, intra = s.a & 4;
+        const int across = horiz_edge ? SP : 1, along = horiz_edge ? 1 : SP, lines = s.d;      // a tc0 entry covers lines / 4 of them
         if (lane < lines) {
             uint8_t *q = s.p0 + lane * along;
-            const int tc = s.tc0[lane / (chroma ? 2 : 4)];
+            const int tc = s.tc0[lane / (lines >> 2)];
             if (!chroma) { if (intra) h264_luma_intra_line(q, across, s.b, s.c); else if (tc >= 0) h264_luma_line(q, across, s.b, s.c, tc); }
             else if (intra || tc > 0) h264_chroma_line(q, across, s.b, s.c, tc, intra);
         }
@@ -121,7 +124,7 @@ struct Stage {
         AVB_CUDA(cudaStreamSynchronize(s), "slot:sync");
         return 0;
     }
-    int run(const SlotArgs &a) { slot_kernel<<<1, 32, 0, s>>>(a); return check_launch("slot"); }
+    int run(const SlotArgs &a) { AVB_LAUNCH(slot_kernel, 1, 32, 0, s)(a); return check_launch("slot"); }
 };
 
 }  // namespace avb
@@ -251,16 +254,20 @@ template <int WIDX> void slot_biweight(uint8_t *dst, uint8_t *src, int stride, i
     if (S.up() || ff_h264_weight_batch_cuda((const FFH264WeightRecord *)(S.d + orec), 1, S.d + od, S.d + os, SP, S.s) || S.down()) return;
     S.rect_out(dst, stride, w, height, od);
 }
-// WHICH: 0 v_luma 1 h_luma 2 v_luma_intra 3 h_luma_intra 4 v_chroma 5 h_chroma 6 v_chroma_intra 7 h_chroma_intra
+// WHICH: 0 v_luma 1 h_luma 2 v_luma_intra 3 h_luma_intra 4 v_chroma 5 h_chroma 6 v_chroma_intra 7 h_chroma_intra, then the h_ variants
+// that differ only in the lines per tc0 entry (h264dsp_template.c:158-163,222-229,272-283,314-328): 8 luma_mbaff 9 luma_mbaff_intra
+// 10 chroma_mbaff 11 chroma_mbaff_intra 12 chroma422 13 chroma422_intra 14 chroma422_mbaff 15 chroma422_mbaff_intra
 template <int WHICH> void loop_filter_impl(uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0)
 {
     Stage S; if (!S.ok()) return;
-    const bool horiz_edge = !(WHICH & 1), chroma = WHICH >= 4;
-    const int lines = chroma ? 8 : 16, reach = chroma ? 2 : 4;       // samples touched on each side of the edge
+    constexpr bool ext = WHICH >= 8;
+    constexpr bool horiz_edge = !ext && !(WHICH & 1), chroma = ext ? WHICH >= 10 : WHICH >= 4, intra = ext ? (WHICH & 1) != 0 : (WHICH & 2) != 0;
+    constexpr int ext_lines[8] = { 8, 8, 4, 4, 16, 16, 8, 8 };
+    constexpr int lines = ext ? ext_lines[WHICH & 7] : chroma ? 8 : 16, reach = chroma ? 2 : 4;       // samples touched on each side of the edge
     const int w = horiz_edge ? lines : 2 * reach, h = horiz_edge ? 2 * reach : lines;
     uint8_t *org = horiz_edge ? pix - reach * stride : pix - reach;
     size_t o = S.rect_in(org, stride, w, h);
-    SlotArgs a = {}; a.op = OP_H264_LOOP; a.a = WHICH; a.b = alpha; a.c = beta;
+    SlotArgs a = {}; a.op = OP_H264_LOOP; a.a = (horiz_edge ? 1 : 0) | (chroma ? 2 : 0) | (intra ? 4 : 0); a.b = alpha; a.c = beta; a.d = lines;
     a.p0 = S.d + o + (horiz_edge ? reach * SP : reach);
     if (tc0) memcpy(a.tc0, tc0, 4);
     if (S.up() || S.run(a) || S.down()) return;
@@ -280,47 +287,51 @@ template <int WHICH> void slot_h264_idct(uint8_t *dst, int16_t *block, int strid
     S.rect_out(dst, stride, n, n, od);
     memcpy(block, S.h + ob, coefs * 2);                        // idct zeroes the block, dc_add only block[0]
 }
-// per-MB dispatchers: the caller's block_offset[] is honoured by staging the bounding rectangle of the blocks
+// per-MB dispatchers: the caller's block_offset[] is honoured by staging the bounding rectangle of the blocks.
+// WHICH: 0 add16, 1 add16intra, 2 idct8_add4, 3 add8 (4:2:0), 4 add8_422
 template <int WHICH> void idct_mb_impl(uint8_t *dst, uint8_t **dst2, const int *bo, int16_t *block, int stride, const uint8_t *nnzc)
 {
     Stage S; if (!S.ok()) return;
     if (stride <= 0) { set_error_msg("h264_idct_add16 slot", "non-positive stride is not taken over"); return; }
-    const int nb = WHICH == 2 ? 8 : 4, first = WHICH == 3 ? 16 : 0, count = WHICH == 3 ? 4 : 16, step = WHICH == 2 ? 4 : 1;
+    constexpr int nb = WHICH == 2 ? 8 : 4, planes = WHICH >= 3 ? 2 : 1;
+    constexpr int ncoef = (WHICH == 3 ? 36 : WHICH == 4 ? 40 : 16) * 16;       // coefficients up to the last block the C function may touch
+    // the block_offset[] / scan8[] entries the C function reads
+    int ent[16], n_ent = 0;
+    if (WHICH <= 1) for (int i = 0; i < 16; i++) ent[n_ent++] = i;
+    else if (WHICH == 2) for (int i = 0; i < 16; i += 4) ent[n_ent++] = i;
+    else for (int p = 0; p < 2; p++) for (int k = 0; k < (WHICH == 4 ? 8 : 4); k++) ent[n_ent++] = 16 + 16 * p + (k >= 4 ? k + 4 : k);
     int W = 0, H = 0;
-    const int planes = WHICH == 3 ? 2 : 1;
-    for (int p = 0; p < planes; p++)
-        for (int k = 0; k < count; k += step) {
-            int i = first + 16 * p + k;
-            if (bo[i] < 0) { set_error_msg("h264_idct_add16 slot", "negative block offsets are not taken over"); return; }
-            int x = bo[i] % stride + nb, y = bo[i] / stride + nb;
-            if (x > W) W = x;
-            if (y > H) H = y;
-        }
+    for (int n = 0; n < n_ent; n++) {
+        const int i = ent[n];
+        if (bo[i] < 0) { set_error_msg("h264_idct_add16 slot", "negative block offsets are not taken over"); return; }
+        int x = bo[i] % stride + nb, y = bo[i] / stride + nb;
+        if (x > W) W = x;
+        if (y > H) H = y;
+    }
     const int pitch = (W + 15) & ~15;
     if ((size_t)pitch * H * planes + 2048 > Stage::CAP) { set_error_msg("h264_idct_add16 slot", "block offsets span too large a rectangle"); return; }
     size_t od[2];
     for (int p = 0; p < planes; p++) {
         od[p] = S.take((size_t)pitch * H);
-        const uint8_t *src = WHICH == 3 ? dst2[p] : dst;
+        const uint8_t *src = WHICH >= 3 ? dst2[p] : dst;
         for (int y = 0; y < H; y++) memcpy(S.h + od[p] + (size_t)y * pitch, src + (size_t)y * stride, W);
     }
     size_t ob = S.take(48 * 16 * 2);
-    memcpy(S.h + ob, block, 48 * 16 * 2 > 0 ? (WHICH == 3 ? 36 : 16) * 16 * 2 : 0);
+    memcpy(S.h + ob, block, ncoef * 2);
     SlotArgs a = {}; a.op = OP_H264_IDCT_MB; a.a = WHICH; a.b = pitch; a.p0 = S.d + od[0]; a.p1 = planes == 2 ? S.d + od[1] : nullptr;
     a.blk = (int16_t *)(S.d + ob);
     for (int i = 0; i < 48; i++) a.off[i] = 0;
-    for (int p = 0; p < planes; p++)
-        for (int k = 0; k < count; k += step) { int i = first + 16 * p + k; a.off[i] = (bo[i] / stride) * pitch + bo[i] % stride; }
+    for (int n = 0; n < n_ent; n++) { const int i = ent[n]; a.off[i] = (bo[i] / stride) * pitch + bo[i] % stride; }
     memcpy(a.nnzc, nnzc, 120);
     if (S.up() || S.run(a) || S.down()) return;
     for (int p = 0; p < planes; p++) {
-        uint8_t *d = WHICH == 3 ? dst2[p] : dst;
+        uint8_t *d = WHICH >= 3 ? dst2[p] : dst;
         for (int y = 0; y < H; y++) memcpy(d + (size_t)y * stride, S.h + od[p] + (size_t)y * pitch, W);
     }
-    memcpy(block, S.h + ob, (WHICH == 3 ? 36 : 16) * 16 * 2);
+    memcpy(block, S.h + ob, ncoef * 2);
 }
 template <int WHICH> void slot_idct_mb(uint8_t *dst, const int *bo, int16_t *block, int stride, const uint8_t nnzc[15 * 8]) { idct_mb_impl<WHICH>(dst, nullptr, bo, block, stride, nnzc); }
-void slot_idct_add8(uint8_t **dst, const int *bo, int16_t *block, int stride, const uint8_t nnzc[15 * 8]) { idct_mb_impl<3>(nullptr, dst, bo, block, stride, nnzc); }
+template <int WHICH> void slot_idct_add8(uint8_t **dst, const int *bo, int16_t *block, int stride, const uint8_t nnzc[15 * 8]) { idct_mb_impl<WHICH>(nullptr, dst, bo, block, stride, nnzc); }
 
 void slot_luma_dc(int16_t *output, int16_t *input, int qmul)
 {
@@ -331,14 +342,16 @@ void slot_luma_dc(int16_t *output, int16_t *input, int qmul)
     if (S.up() || S.run(a) || S.down()) return;
     memcpy(output, S.h + o, 512);
 }
-void slot_chroma_dc(int16_t *block, int qmul)
+// C422 = 0: the 2x2 transform touches block[0 / 16 / 32 / 48]; C422 = 1: the 2x4 transform touches block[16 k], k < 8
+template <int C422> void slot_chroma_dc(int16_t *block, int qmul)
 {
     Stage S; if (!S.ok()) return;
-    size_t o = S.take(128);
-    memcpy(S.h + o, block, 128);
-    SlotArgs a = {}; a.op = OP_H264_CHROMA_DC; a.a = qmul; a.blk = (int16_t *)(S.d + o);
+    constexpr size_t bytes = C422 ? 113 * 2 : 128;
+    size_t o = S.take(256);
+    memcpy(S.h + o, block, bytes);
+    SlotArgs a = {}; a.op = OP_H264_CHROMA_DC; a.a = qmul; a.b = C422; a.blk = (int16_t *)(S.d + o);
     if (S.up() || S.run(a) || S.down()) return;
-    memcpy(block, S.h + o, 128);
+    memcpy(block, S.h + o, bytes);
 }
 template <int N> void slot_add_pixels_clear(uint8_t *dst, int16_t *block, int stride)
 {
@@ -406,21 +419,29 @@ void ff_me_cmp_init_cuda(MECmpContext *c)
 
 void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc)
 {
-    if (bit_depth != 8 || chroma_format_idc > 1) return;                 // 9/10-bit and 4:2:2 stay on the C path
+    if (bit_depth != 8) return;                                           // the 9 / 10-bit templates stay on the C path
+    const bool c420 = chroma_format_idc <= 1;                             // the reference's own test, h264dsp.c:81-122
     c->weight_h264_pixels_tab[0] = slot_weight<0>; c->weight_h264_pixels_tab[1] = slot_weight<1>;
     c->weight_h264_pixels_tab[2] = slot_weight<2>; c->weight_h264_pixels_tab[3] = slot_weight<3>;
     c->biweight_h264_pixels_tab[0] = slot_biweight<0>; c->biweight_h264_pixels_tab[1] = slot_biweight<1>;
     c->biweight_h264_pixels_tab[2] = slot_biweight<2>; c->biweight_h264_pixels_tab[3] = slot_biweight<3>;
     c->h264_v_loop_filter_luma = slot_loop<0>; c->h264_h_loop_filter_luma = slot_loop<1>;
+    c->h264_h_loop_filter_luma_mbaff = slot_loop<8>;
     c->h264_v_loop_filter_luma_intra = slot_loop_intra<2>; c->h264_h_loop_filter_luma_intra = slot_loop_intra<3>;
-    c->h264_v_loop_filter_chroma = slot_loop<4>; c->h264_h_loop_filter_chroma = slot_loop<5>;
-    c->h264_v_loop_filter_chroma_intra = slot_loop_intra<6>; c->h264_h_loop_filter_chroma_intra = slot_loop_intra<7>;
-    // the mbaff variants, h264_loop_filter_strength (NULL in C, h264dsp.c:124) and startcode_find_candidate are left alone
+    c->h264_h_loop_filter_luma_mbaff_intra = slot_loop_intra<9>;
+    c->h264_v_loop_filter_chroma = slot_loop<4>;
+    c->h264_h_loop_filter_chroma = c420 ? slot_loop<5> : slot_loop<12>;
+    c->h264_h_loop_filter_chroma_mbaff = c420 ? slot_loop<10> : slot_loop<14>;
+    c->h264_v_loop_filter_chroma_intra = slot_loop_intra<6>;
+    c->h264_h_loop_filter_chroma_intra = c420 ? slot_loop_intra<7> : slot_loop_intra<13>;
+    c->h264_h_loop_filter_chroma_mbaff_intra = c420 ? slot_loop_intra<11> : slot_loop_intra<15>;
+    // h264_loop_filter_strength (NULL in C, h264dsp.c:124) and startcode_find_candidate are left alone
     c->h264_idct_add = slot_h264_idct<0>; c->h264_idct8_add = slot_h264_idct<1>;
     c->h264_idct_dc_add = slot_h264_idct<2>; c->h264_idct8_dc_add = slot_h264_idct<3>;
     c->h264_idct_add16 = slot_idct_mb<0>; c->h264_idct_add16intra = slot_idct_mb<1>; c->h264_idct8_add4 = slot_idct_mb<2>;
-    c->h264_idct_add8 = slot_idct_add8;
-    c->h264_luma_dc_dequant_idct = slot_luma_dc; c->h264_chroma_dc_dequant_idct = slot_chroma_dc;
+    c->h264_idct_add8 = c420 ? slot_idct_add8<3> : slot_idct_add8<4>;
+    c->h264_luma_dc_dequant_idct = slot_luma_dc;
+    c->h264_chroma_dc_dequant_idct = c420 ? slot_chroma_dc<0> : slot_chroma_dc<1>;
     c->h264_add_pixels8_clear = slot_add_pixels_clear<8>; c->h264_add_pixels4_clear = slot_add_pixels_clear<4>;
 }
 

@@ -31,6 +31,7 @@ API = {
     "h264_idct_mb": (None, [i32, vp, vp, vp, vp, i32, vp]),
     "h264_luma_dc_dequant_idct": (None, [vp, vp, i32]),
     "h264_chroma_dc_dequant_idct": (None, [vp, i32]),
+    "h264_chroma422_dc_dequant_idct": (None, [vp, i32]),
     "h264_loop_filter": (None, [i32, vp, i32, i32, i32, vp]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),

@@ -52,13 +52,17 @@ void ORC(fdct)(int which, int16_t *block);
 /* ---- H264DSPContext (libavcodec/h264dsp.h:41-117), 8-bit ---- */
 /* which: 0 idct_add, 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add */
 void ORC(h264_idct)(int which, uint8_t *dst, int16_t *block, int stride);
-/* which: 0 idct_add16, 1 idct_add16intra, 2 idct8_add4, 3 idct_add8 (dst2 = {cb, cr}) */
+/* which: 0 idct_add16, 1 idct_add16intra, 2 idct8_add4, 3 idct_add8 (dst2 = {cb, cr}), 4 idct_add8_422 (the table entry for
+ * chroma_format_idc 2, h264dsp.c:81-84) */
 void ORC(h264_idct_mb)(int which, uint8_t *dst, uint8_t **dst2, const int *block_offset,
                        int16_t *block, int stride, const uint8_t *nnzc);
 void ORC(h264_luma_dc_dequant_idct)(int16_t *output, int16_t *input, int qmul);
 void ORC(h264_chroma_dc_dequant_idct)(int16_t *block, int qmul);
+void ORC(h264_chroma422_dc_dequant_idct)(int16_t *block, int qmul);   /* the chroma_format_idc 2 entry, h264dsp.c:87-90 */
 /* which: 0 v_luma 1 h_luma 2 v_luma_intra 3 h_luma_intra 4 v_chroma 5 h_chroma
- *        6 v_chroma_intra 7 h_chroma_intra ; tc0 ignored for intra */
+ *        6 v_chroma_intra 7 h_chroma_intra ; tc0 ignored for intra
+ *        8 h_luma_mbaff 9 h_luma_mbaff_intra 10 h_chroma_mbaff 11 h_chroma_mbaff_intra, and the chroma_format_idc 2 entries
+ *        12 h_chroma422 13 h_chroma422_intra 14 h_chroma422_mbaff 15 h_chroma422_mbaff_intra (h264dsp.c:104-122) */
 void ORC(h264_loop_filter)(int which, uint8_t *pix, int stride, int alpha, int beta,
                            const int8_t *tc0);
 

@@ -114,12 +114,16 @@ void orc_h264_idct_mb(int which, uint8_t *dst, uint8_t **dst2, const int *bo, in
             if (nnz == 1 && b[0]) dc_add(dst + bo[i], b, stride, 8); else idct8_add(dst + bo[i], b, stride);
         }
     } else {
-        for (int j = 1; j < 3; j++)
-            for (int i = 16 * j; i < 16 * j + 4; i++) {
-                int16_t *b = block + 16 * i;
-                if (nnzc[scan8_of(i)]) idct4_add(dst2[j - 1] + bo[i], b, stride);
-                else if (b[0]) dc_add(dst2[j - 1] + bo[i], b, stride, 4);
-            }
+        /* which 3: idct_add8 (4:2:0, four blocks per plane); which 4: idct_add8_422 -- the lower four blocks of a plane keep
+         * their coefficients at block i but their nnz / offset entries live four places further (h264idct_template.c:216-236) */
+        for (int half = 0; half < (which == 4 ? 2 : 1); half++)
+            for (int j = 1; j < 3; j++)
+                for (int k = 0; k < 4; k++) {
+                    int i = 16 * j + 4 * half + k, e = i + 4 * half;
+                    int16_t *b = block + 16 * i;
+                    if (nnzc[scan8_of(e)]) idct4_add(dst2[j - 1] + bo[e], b, stride);
+                    else if (b[0]) dc_add(dst2[j - 1] + bo[e], b, stride, 4);
+                }
     }
 }
 
@@ -147,6 +151,20 @@ void orc_h264_chroma_dc_dequant_idct(int16_t *b, int qmul)
     int e = a - bb; a += bb; bb = c - d; c += d;
     b[0] = (int16_t)(((a + c) * qmul) >> 7);  b[16] = (int16_t)(((e + bb) * qmul) >> 7);
     b[32] = (int16_t)(((a - c) * qmul) >> 7); b[48] = (int16_t)(((e - bb) * qmul) >> 7);
+}
+
+/* 4:2:2 chroma DC: 2 (across) x 4 (down) Hadamard, the eight DC values sit 16 coefficients apart (h264idct_template.c:277-302) */
+void orc_h264_chroma422_dc_dequant_idct(int16_t *b, int qmul)
+{
+    int t[8];
+    for (int i = 0; i < 4; i++) { t[2 * i] = b[32 * i] + b[32 * i + 16]; t[2 * i + 1] = b[32 * i] - b[32 * i + 16]; }
+    for (int i = 0; i < 2; i++) {
+        int z0 = t[i] + t[4 + i], z1 = t[i] - t[4 + i], z2 = t[2 + i] - t[6 + i], z3 = t[2 + i] + t[6 + i];
+        b[16 * i + 0]  = (int16_t)(((z0 + z3) * qmul + 128) >> 8);
+        b[16 * i + 32] = (int16_t)(((z1 + z2) * qmul + 128) >> 8);
+        b[16 * i + 64] = (int16_t)(((z1 - z2) * qmul + 128) >> 8);
+        b[16 * i + 96] = (int16_t)(((z0 - z3) * qmul + 128) >> 8);
+    }
 }
 
 void orc_h264_add_pixels_clear(int w8, uint8_t *dst, int16_t *block, int stride)
@@ -222,12 +240,17 @@ static void chroma_line(uint8_t *q, int px, int alpha, int beta, int tc, int int
     }
 }
 
+/* which 0..7: the 4:2:0 frame filters; 8..15: the h_ (vertical-edge) variants that only differ in the number of lines per tc0 entry
+ * (h264dsp_template.c:158-163, 222-229, 272-283, 314-328): 8 luma_mbaff 9 luma_mbaff_intra 10 chroma_mbaff 11 chroma_mbaff_intra
+ * 12 chroma422 13 chroma422_intra 14 chroma422_mbaff 15 chroma422_mbaff_intra */
 void orc_h264_loop_filter(int which, uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0)
 {
-    int horiz_edge = !(which & 1);            /* v_* filters: samples across the edge are `stride` apart */
+    static const uint8_t ext_lines[8] = { 8, 8, 4, 4, 16, 16, 8, 8 };
+    int ext = which >= 8;
+    int horiz_edge = !ext && !(which & 1);    /* v_* filters: samples across the edge are `stride` apart */
     int across = horiz_edge ? stride : 1, along = horiz_edge ? 1 : stride;
-    int chroma = which >= 4, intra = (which & 2) != 0;
-    int lines = chroma ? 8 : 16, per_group = chroma ? 2 : 4;
+    int chroma = ext ? which >= 10 : which >= 4, intra = ext ? (which & 1) : (which & 2) != 0;
+    int lines = ext ? ext_lines[which - 8] : chroma ? 8 : 16, per_group = lines / 4;
     for (int l = 0; l < lines; l++) {
         uint8_t *q = pix + l * along;
         int g = l / per_group;

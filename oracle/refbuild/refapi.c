@@ -38,7 +38,7 @@ static IDCTDSPContext idsp;
 static FDCTDSPContext fdsp_islow, fdsp_ifast;
 static BlockDSPContext bdsp;
 static MECmpContext mecc;
-static H264DSPContext h264;
+static H264DSPContext h264, h264_422;     /* chroma_format_idc 1 and 2 */
 static H264QpelContext qpel;
 static H264ChromaContext chroma;
 static HpelDSPContext hpel;
@@ -61,6 +61,7 @@ static void init_all(void)
     ff_me_cmp_init_static();
     ff_me_cmp_init(&mecc, avctx);
     ff_h264dsp_init(&h264, 8, 1);
+    ff_h264dsp_init(&h264_422, 8, 2);
     ff_h264qpel_init(&qpel, 8);
     ff_h264chroma_init(&chroma, 8);
     ff_pixblockdsp_init(&pixb, avctx);
@@ -136,11 +137,13 @@ void ref_h264_idct_mb(int which, uint8_t *dst, uint8_t **dst2, const int *bo, in
     case 0: h264.h264_idct_add16(dst, bo, block, stride, nnzc); break;
     case 1: h264.h264_idct_add16intra(dst, bo, block, stride, nnzc); break;
     case 2: h264.h264_idct8_add4(dst, bo, block, stride, nnzc); break;
-    default: h264.h264_idct_add8(dst2, bo, block, stride, nnzc); break;
+    case 3: h264.h264_idct_add8(dst2, bo, block, stride, nnzc); break;
+    default: h264_422.h264_idct_add8(dst2, bo, block, stride, nnzc); break;     /* ff_h264_idct_add8_422 */
     }
 }
 void ref_h264_luma_dc_dequant_idct(int16_t *o, int16_t *i, int q) { INIT(); h264.h264_luma_dc_dequant_idct(o, i, q); }
 void ref_h264_chroma_dc_dequant_idct(int16_t *b, int q) { INIT(); h264.h264_chroma_dc_dequant_idct(b, q); }
+void ref_h264_chroma422_dc_dequant_idct(int16_t *b, int q) { INIT(); h264_422.h264_chroma_dc_dequant_idct(b, q); }
 void ref_h264_loop_filter(int which, uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0)
 {
     INIT();
@@ -153,7 +156,15 @@ void ref_h264_loop_filter(int which, uint8_t *pix, int stride, int alpha, int be
     case 4: h264.h264_v_loop_filter_chroma(pix, stride, alpha, beta, t); break;
     case 5: h264.h264_h_loop_filter_chroma(pix, stride, alpha, beta, t); break;
     case 6: h264.h264_v_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
-    default: h264.h264_h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 7: h264.h264_h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 8: h264.h264_h_loop_filter_luma_mbaff(pix, stride, alpha, beta, t); break;
+    case 9: h264.h264_h_loop_filter_luma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 10: h264.h264_h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, t); break;
+    case 11: h264.h264_h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 12: h264_422.h264_h_loop_filter_chroma(pix, stride, alpha, beta, t); break;              /* chroma422 */
+    case 13: h264_422.h264_h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 14: h264_422.h264_h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, t); break;        /* chroma422_mbaff */
+    default: h264_422.h264_h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
     }
 }
 void ref_h264_weight(int widx, uint8_t *b, int stride, int h, int ld, int w, int off)

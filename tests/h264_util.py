@@ -22,6 +22,40 @@ def block_offsets(ls, uvls):
     return bo
 
 
+def block_offsets_422(uvls):
+    """block_offset[] entries ff_h264_idct_add8_422 reads: chroma blocks 16..19 / 32..35 (upper 8 rows) and 24..27 / 40..43
+    (lower 8 rows) of an 8x16 chroma macroblock"""
+    bo = np.zeros(48, dtype=np.int32)
+    for i in range(4):
+        bo[16 + i] = bo[32 + i] = 4 * (i & 1) + 4 * ((i >> 1) & 1) * uvls
+        bo[24 + i] = bo[40 + i] = 4 * (i & 1) + (8 + 4 * ((i >> 1) & 1)) * uvls
+    return bo
+
+
+def scan8(i):
+    plane, k = i >> 4, i & 15
+    return 4 + (k & 1) + 2 * ((k >> 2) & 1) + 8 * (1 + ((k >> 1) & 1) + 2 * (k >> 3) + 5 * plane)
+
+
+def residual_422(seed):
+    """coefficients (48 x 16 int16, sl->mb layout) and non_zero_count_cache for one 4:2:2 macroblock's chroma: per 4x4 block
+    nothing / DC only with nnz 0 (the dc_add branch) / full block, like the decoder leaves them after the chroma DC transform"""
+    rng = np.random.default_rng(1000 + seed)
+    coeffs = np.zeros((48, 16), np.int16)
+    nnzc = np.zeros(120, np.uint8)
+    for plane in (1, 2):
+        for k in range(8):
+            i = 16 * plane + k                        # coefficient block
+            e = i + 4 if k >= 4 else i                # cache / offset entry
+            kind = int(rng.integers(0, 3))
+            if kind == 1:
+                coeffs[i, 0] = rng.integers(-2000, 2000)
+            elif kind == 2:
+                coeffs[i] = rng.integers(-600, 600, size=16)
+                nnzc[scan8(e)] = rng.integers(1, 16)
+    return coeffs, nnzc
+
+
 def oracle_residual(o, rec, coeffs, nnzc, y, cb, cr):
     ls, uvls = y.strides[0], cb.strides[0]
     bo = block_offsets(ls, uvls)

@@ -8,7 +8,7 @@ import pytest
 
 from libav_b200 import synth
 from oracle.loader import ptr
-from h264_util import at, block_offsets
+from h264_util import at, block_offsets, block_offsets_422, residual_422
 
 
 def both(orc, refo, fn, make_args):
@@ -69,6 +69,11 @@ def test_dc_dequant(orc, refo):
         orc.h264_chroma_dc_dequant_idct(ptr(a), q)
         refo.h264_chroma_dc_dequant_idct(ptr(b), q)
         assert np.array_equal(a, b)
+        blk = rng.integers(-3000, 3000, size=128).astype(np.int16)        # 4:2:2: eight DC values, 16 coefficients apart
+        a, b = blk.copy(), blk.copy()
+        orc.h264_chroma422_dc_dequant_idct(ptr(a), q)
+        refo.h264_chroma422_dc_dequant_idct(ptr(b), q)
+        assert np.array_equal(a, b) and not np.array_equal(a, blk)
 
 
 def test_add_pixels_clear_and_weight(orc, refo):
@@ -100,7 +105,7 @@ def test_add_pixels_clear_and_weight(orc, refo):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("which", range(8))
+@pytest.mark.parametrize("which", range(16))        # 8..15: mbaff and chroma_format_idc 2 entries
 def test_loop_filters(orc, refo, which):
     rng = np.random.default_rng(which)
     for it in range(300):

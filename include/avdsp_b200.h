@@ -398,6 +398,9 @@ void sws_debug_rgb_constants_cuda(int32_t out[10]);
  * 7 yuv420p -> nv12 interleave; out[1..4] chrSrcW chrSrcH chrDstW chrDstH; out[5] source pre-pass 0 / 1 nv split / 2 reader;
  * out[6] destination bits per sample (planar) or bytes per pixel (packed); out[7] full-range source), 0 = refused */
 int  sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[8]);
+/* what the per-line slots (section 3, ff_sws_init_swscale_cuda) would know about that context: 25 int32 (19 colour constants, flags,
+ * planar, destination bits, big endian, packed target, nv12 / nv21); returns the count, 0 = refused.  Host only. */
+int  sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32]);
 
 /* ------------------------------------------------------------------ 3. table hooks --------------- */
 /* One more arch behind ff_idctdsp_init()'s dispatch (libavcodec/idctdsp.c:183-188; same shape as
@@ -429,6 +432,37 @@ void ff_qpeldsp_init_cuda(QpelDSPContext *c);
  * order, the MDCT slots use the context's own tcos / tsin tables. */
 void ff_fft_init_cuda(FFTContext *s);
 void ff_mdct_init_cuda(FFTContext *s);
+
+
+/* libswscale's per-line slots: what sws_init_swscale() and its arch hooks (ff_sws_init_swscale_x86 / _ppc, libswscale/swscale.c:723-783)
+ * install in a SwsContext (the function-pointer fields of libswscale/swscale_internal.h:312-330,478-535), with the reference's
+ * signatures (swscale_internal.h:62-110) and HOST pointers.  `struct SwsContext` stays opaque to this library: it is only the key under
+ * which ff_sws_init_swscale_cuda() remembers which SwsContextCUDA (destination format, colour constants) a slot call belongs to.
+ * Filled like the reference fills them for an 8-bit source: hyScale / hcScale = hScale8To15_c (hScale8To19_c for a 16-bit destination),
+ * hyscale_fast / hcscale_fast only with SWS_FAST_BILINEAR (and not for 16-bit destinations), yuv2plane1 / yuv2planeX by destination depth
+ * (8, 9, 10, 16; LE / BE), yuv2nv12cX for nv12 / nv21, yuv2packed1 / 2 / X for rgb24 bgr24 argb rgba abgr bgra yuyv422 uyvy422 (only
+ * yuv2packedX with SWS_FULL_CHR_H_INT, output.c:1392-1472); entries the reference leaves NULL are set to NULL.  Each call is a batch of
+ * one line on the GPU (stage, copy, kernel, copy back, synchronise): plumbing and parity, like the DSP table slots -- whole frames go
+ * through sws_scale_cuda / sws_scale_frames_cuda. */
+struct SwsContext;
+typedef struct SwsLineSlotsCUDA {
+    void (*hyScale)(struct SwsContext *c, int16_t *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize);
+    void (*hcScale)(struct SwsContext *c, int16_t *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize);
+    void (*hyscale_fast)(struct SwsContext *c, int16_t *dst, int dstWidth, const uint8_t *src, int srcW, int xInc);
+    void (*hcscale_fast)(struct SwsContext *c, int16_t *dst1, int16_t *dst2, int dstWidth, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc);
+    void (*yuv2plane1)(const int16_t *src, uint8_t *dest, int dstW, const uint8_t *dither, int offset);
+    void (*yuv2planeX)(const int16_t *filter, int filterSize, const int16_t **src, uint8_t *dest, int dstW, const uint8_t *dither, int offset);
+    void (*yuv2nv12cX)(struct SwsContext *c, const int16_t *chrFilter, int chrFilterSize, const int16_t **chrUSrc, const int16_t **chrVSrc,
+                       uint8_t *dest, int dstW);
+    void (*yuv2packed1)(struct SwsContext *c, const int16_t *lumSrc, const int16_t *chrUSrc[2], const int16_t *chrVSrc[2], const int16_t *alpSrc,
+                        uint8_t *dest, int dstW, int uvalpha, int y);
+    void (*yuv2packed2)(struct SwsContext *c, const int16_t *lumSrc[2], const int16_t *chrUSrc[2], const int16_t *chrVSrc[2],
+                        const int16_t *alpSrc[2], uint8_t *dest, int dstW, int yalpha, int uvalpha, int y);
+    void (*yuv2packedX)(struct SwsContext *c, const int16_t *lumFilter, const int16_t **lumSrc, int lumFilterSize, const int16_t *chrFilter,
+                        const int16_t **chrUSrc, const int16_t **chrVSrc, int chrFilterSize, const int16_t **alpSrc, uint8_t *dest, int dstW, int y);
+} SwsLineSlotsCUDA;
+/* 0, or -1 (sticky error) for a NULL argument.  The registration lasts until sws_freeContext_cuda(cuda). */
+int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cuda, SwsLineSlotsCUDA *slots);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "sws_debug_filter_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "sws_debug_rgb_constants_cuda": (None, [vp]),
     "sws_debug_plan_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp]),
+    "sws_debug_slot_view_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp]),
     "ff_idctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
     "ff_blockdsp_init_cuda": (None, [vp]),
     "ff_fdctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
@@ -102,6 +103,7 @@ PROTOTYPES = {
     "ff_pixblockdsp_init_cuda": (None, [vp, C.c_uint]),
     "ff_fft_init_cuda": (None, [vp]),
     "ff_mdct_init_cuda": (None, [vp]),
+    "ff_sws_init_swscale_cuda": (i32, [vp, vp, vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

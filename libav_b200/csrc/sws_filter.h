@@ -49,4 +49,17 @@ struct RgbConstants {      // r = clip_u8((cy * (Y + ar + ((V * crv) >> 16)) + k
 };
 void rgb_constants(RgbConstants &k, const int inv_table[4], int full_range, int brightness, int contrast, int saturation);
 
+
+// what the per-line SwsContext slots (sws_slots.cu) need to know about a context made by sws_getContext_cuda (swscale.cu)
+struct SwsSlotView {
+    RgbConstants k;
+    int flags;
+    int planar;        // planar / semi-planar yuv destination
+    int dstBits, dstBE;
+    int target;        // packed destinations: 0 rgb24, 1 bgr24, 2 yuyv422, 3 uyvy422, 4 argb, 5 rgba, 6 abgr, 7 bgra; -1 for planar
+    int dstNV;         // 1 nv12, 2 nv21
+};
+bool sws_slot_view(const void *ctx, SwsSlotView &v);      // false for NULL
+void sws_slots_forget(const void *ctx);                   // sws_freeContext_cuda: drop the registrations of this context
+
 }  // namespace avb

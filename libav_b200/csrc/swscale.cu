@@ -22,6 +22,7 @@
 #include "../../include/avdsp_b200.h"
 #include <new>
 #include <vector>
+#include "sws_dev.cuh"
 #include <algorithm>
 #include <limits.h>
 #include <string.h>
@@ -41,46 +42,6 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
 };
-
-// yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64 everywhere) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) are one
-// recipe in the output depth: plane1 (v + (1 << (14 - bits))) >> (15 - bits), planeX ((1 << (26 - bits)) + sum) >> (27 - bits),
-// clipped to `bits` bits
-__device__ __forceinline__ int plane_clip(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
-__device__ __forceinline__ int swap16_if(int v, int be) { return be ? ((v >> 8) | (v << 8)) & 0xFFFF : v; }
-__device__ __forceinline__ void plane_store(uint8_t *row, int x, int v, int bits, int be)
-{
-    if (bits == 8) row[x] = (uint8_t)v; else reinterpret_cast<uint16_t *>(row)[x] = (uint16_t)swap16_if(v, be);
-}
-
-struct ChromaTerms { int tr, tg, tb; };
-
-// per (U,V): the additive term of each channel, so a pixel costs one IMAD + shift per channel
-__device__ __forceinline__ ChromaTerms chroma_terms(int U, int V, const RgbConstants &k)
-{
-    int ro = k.ar + ((V * k.crv) >> 16);
-    int go = k.agu + ((U * k.cgu) >> 16) + k.agv + ((V * k.cgv) >> 16);
-    int bo = k.ab + ((U * k.cbu) >> 16);
-    ChromaTerms t;
-    t.tr = k.cy * ro + k.k1;
-    t.tg = k.cy * go + k.k1;
-    t.tb = k.cy * bo + k.k1;
-    return t;
-}
-
-// the "clip only when bit 8 is set somewhere" rule of yuv2rgb_X_c_template (output.c:966-971)
-__device__ __forceinline__ void clip_if_flagged(int &y1, int &y2, int &u, int &v)
-{
-    if ((y1 | y2 | u | v) & 0x100) { y1 = clip_u8(y1); y2 = clip_u8(y2); u = clip_u8(u); v = clip_u8(v); }
-}
-
-// yuv2rgb24_full_X_c's pixel (output.c:1193-1225): 30-bit fixed-point matrix on Y, U - 128, V - 128 (all << 9 here)
-__device__ __forceinline__ void full_pixel(int Y, int U, int V, const RgbConstants &k, int bgr, uint8_t *d)
-{
-    Y = (Y - k.fy_offset) * k.fy_coeff + (1 << 21);
-    int R = Y + V * k.fv2r, G = Y + V * k.fv2g + U * k.fu2g, B = Y + U * k.fu2b;
-    if ((R | G | B) & 0xC0000000) { R = min(max(R, 0), 0x3FFFFFFF); G = min(max(G, 0), 0x3FFFFFFF); B = min(max(B, 0), 0x3FFFFFFF); }
-    d[bgr ? 2 : 0] = (uint8_t)(R >> 22); d[1] = (uint8_t)(G >> 22); d[bgr ? 0 : 2] = (uint8_t)(B >> 22);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // FUSED kernel: horizontal identity, vLum identity, 4-tap vertical chroma.
@@ -1775,6 +1736,15 @@ static void destroy(SwsCudaContext *c)
     delete c;
 }
 
+bool sws_slot_view(const void *ctx, SwsSlotView &v)
+{
+    const SwsCudaContext *c = (const SwsCudaContext *)ctx;
+    if (!c) return false;
+    v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
+    v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
+    return true;
+}
+
 }  // namespace avb
 
 using namespace avb;
@@ -1788,7 +1758,7 @@ SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW,
     return (SwsContextCUDA *)make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, param, true);
 }
 
-void sws_freeContext_cuda(SwsContextCUDA *ctx) { destroy((SwsCudaContext *)ctx); }
+void sws_freeContext_cuda(SwsContextCUDA *ctx) { sws_slots_forget(ctx); destroy((SwsCudaContext *)ctx); }
 
 // sws_setColorspaceDetails (libswscale/utils.c:807-835): new yuv -> rgb constants (ff_yuv2rgb_c_init_tables, yuv2rgb.c:671-863) for a
 // packed rgb destination; -1 for yuv destinations like the reference, and -1 (nothing changed) for what is not taken over.
@@ -1984,6 +1954,19 @@ int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, i
     out[7] = c->srcRange;
     delete c;
     return 1;
+}
+// The SwsSlotView (sws_filter.h) sws_getContext_cuda() would hand to the per-line slots, as 25 int32, computed on the host only:
+// 19 colour constants, flags, planar, dstBits, dstBE, packed target, dstNV.  Returns the count, 0 when the request is refused.
+int sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32])
+{
+    static_assert(sizeof(SwsSlotView) == 25 * sizeof(int32_t), "SwsSlotView is 25 ints");
+    SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
+    if (!c) return 0;
+    SwsSlotView v;
+    sws_slot_view(c, v);
+    memcpy(out, &v, sizeof(v));
+    delete c;
+    return 25;
 }
 void sws_debug_rgb_constants_cuda(int32_t out[10])
 {

@@ -151,3 +151,16 @@ class PixblockDSPContext(C.Structure):      # libavcodec/pixblockdsp.h:27-35
 class QpelDSPContext(C.Structure):          # libavcodec/qpeldsp.h:69-73
     _fields_ = [("put_qpel_pixels_tab", (qpel_mc_func * 16) * 2), ("avg_qpel_pixels_tab", (qpel_mc_func * 16) * 2),
                 ("put_no_rnd_qpel_pixels_tab", (qpel_mc_func * 16) * 2)]
+
+
+_vp, _i = C.c_void_p, C.c_int
+
+
+class SwsLineSlotsCUDA(C.Structure):        # include/avdsp_b200.h SwsLineSlotsCUDA: the SwsContext per-line slots (swscale_internal.h:312-330,478-535)
+    _fields_ = [("hyScale", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _vp, _vp, _i)), ("hcScale", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _vp, _vp, _i)),
+                ("hyscale_fast", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _i, _i)), ("hcscale_fast", C.CFUNCTYPE(None, _vp, _vp, _vp, _i, _vp, _vp, _i, _i)),
+                ("yuv2plane1", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _i)), ("yuv2planeX", C.CFUNCTYPE(None, _vp, _i, _vp, _vp, _i, _vp, _i)),
+                ("yuv2nv12cX", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _vp, _vp, _i)),
+                ("yuv2packed1", C.CFUNCTYPE(None, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i)),
+                ("yuv2packed2", C.CFUNCTYPE(None, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i)),
+                ("yuv2packedX", C.CFUNCTYPE(None, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i))]

@@ -53,6 +53,11 @@ API = {
     "sws_set_colorspace": (None, [vp, i32, i32, i32, i32]),
     "sws_planar": (i32, [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32]),
     "sws_nv12": (i32, [i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
+    "sws_line_hscale": (i32, [i32, i32, vp, i32, vp, vp, vp, i32]),
+    "sws_line_hfast": (i32, [i32, vp, vp, i32, vp, vp, i32, i32]),
+    "sws_line_plane": (i32, [i32, vp, i32, vp, vp, i32, vp, i32]),
+    "sws_line_nv12": (i32, [i32, vp, i32, vp, vp, vp, i32]),
+    "sws_line_packed": (i32, [i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32]),
     "sws_get_filter": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "sws_rgb24_tables": (None, [vp, vp, vp, vp, vp]),
     "fft": (None, [i32, i32, vp]),

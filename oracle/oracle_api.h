@@ -125,6 +125,23 @@ void ORC(h264_biweight)(int widx, uint8_t *dst, uint8_t *src, int stride, int he
                         int log2_denom, int weightd, int weights, int offset);
 void ORC(h264_add_pixels_clear)(int w8, uint8_t *dst, int16_t *block, int stride);
 
+/* ---- SwsContext per-line slots (libswscale/swscale_internal.h:62-110,312-330,478-535): the functions sws_init_swscale()
+ * (swscale.c:723-769) / ff_sws_init_output_funcs() (output.c:1357-1590) install in a context for a yuv420p source, the destination
+ * format dst_fmt (AV_PIX_FMT_* value) and `flags`, called on caller-made lines.  The colour settings of sws_set_colorspace apply.
+ *   hscale:  hyScale = hcScale = hScale8To15_c (dst int16[dstW]) or hScale8To19_c (dst int32[dstW]) when dst_fmt is 16-bit planar
+ *   hfast:   hyscale_fast_c (chroma 0: dst1 / src1 only) or hcscale_fast_c (chroma 1)
+ *   plane:   yuv2plane1 (filterSize 0, src[0]) / yuv2planeX of dst_fmt's depth; lines are int16, int32 for 16-bit destinations
+ *   nv12:    yuv2nv12cX_c (dst_fmt nv12 / nv21), chrDither8 = 64
+ *   packed:  kind 1 yuv2packed1 (lumSrc[0], chr*[0..1], uvalpha), 2 yuv2packed2 (two lines each, yalpha / uvalpha), 0 yuv2packedX
+ * Returns 0, -1 when the reference would not install that slot (or the request is outside what the port restates). */
+int ORC(sws_line_hscale)(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize);
+int ORC(sws_line_hfast)(int chroma, int16_t *dst1, int16_t *dst2, int dstW, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc);
+int ORC(sws_line_plane)(int dst_fmt, const int16_t *filter, int filterSize, const void *const *src, uint8_t *dest, int dstW, const uint8_t *dither, int offset);
+int ORC(sws_line_nv12)(int dst_fmt, const int16_t *chrFilter, int chrFilterSize, const int16_t *const *chrU, const int16_t *const *chrV, uint8_t *dest, int chrDstW);
+int ORC(sws_line_packed)(int dst_fmt, int flags, int kind, const int16_t *lumFilter, const int16_t *const *lumSrc, int lumFilterSize,
+                         const int16_t *chrFilter, const int16_t *const *chrU, const int16_t *const *chrV, int chrFilterSize,
+                         uint8_t *dest, int dstW, int yalpha, int uvalpha, int y);
+
 /* ---- H264QpelContext / H264ChromaContext (h264qpel.h:27-30, h264chroma.h:25-30) ---- */
 /* sidx 0..3 = 16,8,4,2 ; mc = (mx&3) + 4*(my&3) */
 void ORC(h264_qpel)(int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);

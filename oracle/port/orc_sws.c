@@ -899,3 +899,157 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     g_hs = 1; g_vs = 1; g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
     return r;
 }
+
+/* ---- SwsContext per-line slots -------------------------------------------------------------------------------------------------
+ * The functions sws_init_swscale() / ff_sws_init_output_funcs() install (swscale.c:723-769, output.c:1357-1590), restated per line. */
+int orc_sws_line_hscale(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize)
+{
+    int hs, vs, bits;
+    (void)flags;
+    const int wide = planar_dst(dst_fmt, &hs, &vs, &bits) && bits == 16;      /* hScale8To19_c (swscale.c:149-164) feeds the 16-bit output functions */
+    for (int i = 0; i < dstW; i++) {
+        int val = 0;
+        for (int j = 0; j < filterSize; j++) val += src[filterPos[i] + j] * filter[filterSize * i + j];
+        if (wide) ((int32_t *)dst)[i] = (val >> 3) < (1 << 19) - 1 ? val >> 3 : (1 << 19) - 1;
+        else      ((int16_t *)dst)[i] = (int16_t)((val >> 7) < (1 << 15) - 1 ? val >> 7 : (1 << 15) - 1);      /* swscale.c:133-147 */
+    }
+    return 0;
+}
+
+int orc_sws_line_hfast(int chroma, int16_t *dst1, int16_t *dst2, int dstW, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc)
+{
+    (void)srcW;                            /* swscale.c:238-250, 286-299: the loops never look at srcW */
+    unsigned xpos = 0;
+    for (int i = 0; i < dstW; i++, xpos += (unsigned)xInc) {
+        const unsigned xx = xpos >> 16, xa = (xpos & 0xFFFF) >> 9;
+        if (!chroma) dst1[i] = (int16_t)((src1[xx] << 7) + (src1[xx + 1] - src1[xx]) * (int)xa);
+        else {
+            dst1[i] = (int16_t)(src1[xx] * (int)(xa ^ 127) + src1[xx + 1] * (int)xa);
+            dst2[i] = (int16_t)(src2[xx] * (int)(xa ^ 127) + src2[xx + 1] * (int)xa);
+        }
+    }
+    return 0;
+}
+
+int orc_sws_line_plane(int dst_fmt, const int16_t *filter, int filterSize, const void *const *src, uint8_t *dest, int dstW, const uint8_t *dither, int offset)
+{
+    int hs, vs, bits = 8;
+    if (!planar_dst(dst_fmt, &hs, &vs, &bits)) { bits = 8; g_dbe = 0; }      /* packed and nv12 / nv21 destinations get the 8-bit functions (output.c:1385-1390) */
+    const int be = g_dbe;
+    for (int i = 0; i < dstW; i++) {
+        int v;
+        if (bits == 8) {                   /* output.c:242-265 */
+            if (!filterSize) v = (((const int16_t *)src[0])[i] + dither[(i + offset) & 7]) >> 7;
+            else {
+                v = dither[(i + offset) & 7] << 12;
+                for (int j = 0; j < filterSize; j++) v += ((const int16_t *)src[j])[i] * filter[j];
+                v >>= 19;
+            }
+            dest[i] = u8clip(v);
+            continue;
+        }
+        if (bits == 16) {                  /* output.c:136-172 on 19-bit int32 lines */
+            if (!filterSize) { v = (((const int32_t *)src[0])[i] + 4) >> 3; v = v < 0 ? 0 : v > 65535 ? 65535 : v; }
+            else {
+                unsigned acc = (1u << 14) - 0x40000000u;
+                for (int j = 0; j < filterSize; j++) acc += (unsigned)(((const int32_t *)src[j])[i] * filter[j]);
+                v = (int)acc >> 15; v = (v < -32768 ? -32768 : v > 32767 ? 32767 : v) + 0x8000;
+            }
+        } else {                           /* output.c:183-213 */
+            if (!filterSize) v = (((const int16_t *)src[0])[i] + (1 << (14 - bits))) >> (15 - bits);
+            else {
+                v = 1 << (26 - bits);
+                for (int j = 0; j < filterSize; j++) v += ((const int16_t *)src[j])[i] * filter[j];
+                v >>= 27 - bits;
+            }
+            v = v < 0 ? 0 : v > (1 << bits) - 1 ? (1 << bits) - 1 : v;
+        }
+        if (be) { dest[2 * i] = (uint8_t)(v >> 8); dest[2 * i + 1] = (uint8_t)v; } else { dest[2 * i] = (uint8_t)v; dest[2 * i + 1] = (uint8_t)(v >> 8); }
+    }
+    return 0;
+}
+
+int orc_sws_line_nv12(int dst_fmt, const int16_t *chrFilter, int chrFilterSize, const int16_t *const *chrU, const int16_t *const *chrV, uint8_t *dest, int chrDstW)
+{
+    if (dst_fmt != 23 && dst_fmt != 24) return -1;          /* output.c:1388-1389 */
+    for (int i = 0; i < chrDstW; i++) {                     /* output.c:267-303, chrDither8 = 64 */
+        int u = 64 << 12, v = 64 << 12;
+        for (int j = 0; j < chrFilterSize; j++) { u += chrU[j][i] * chrFilter[j]; v += chrV[j][i] * chrFilter[j]; }
+        dest[2 * i + (dst_fmt == 24)] = u8clip(u >> 19);
+        dest[2 * i + (dst_fmt != 24)] = u8clip(v >> 19);
+    }
+    return 0;
+}
+
+int orc_sws_line_packed(int dst_fmt, int flags, int kind, const int16_t *lumFilter, const int16_t *const *lumSrc, int lumFilterSize,
+                        const int16_t *chrFilter, const int16_t *const *chrU, const int16_t *const *chrV, int chrFilterSize,
+                        uint8_t *dest, int dstW, int yalpha, int uvalpha, int y)
+{
+    (void)y;
+    const int is422 = dst_fmt == 1 || dst_fmt == 15, is32 = dst_fmt >= 25 && dst_fmt <= 28;
+    if (!is422 && !is32 && dst_fmt != 2 && dst_fmt != 3) return -1;
+    /* byte positions of r, g, b (and alpha = 255) in a pixel: rgb24, bgr24, argb, rgba, abgr, bgra */
+    const int bpp = is32 ? 4 : 3;
+    const int ro = dst_fmt == 2 ? 0 : dst_fmt == 3 ? 2 : dst_fmt == 25 ? 1 : dst_fmt == 26 ? 0 : dst_fmt == 27 ? 3 : 2;
+    const int go = is32 ? (dst_fmt <= 26 ? ro + 1 : ro - 1) : 1;
+    const int bo = dst_fmt == 2 ? 2 : dst_fmt == 3 ? 0 : dst_fmt == 25 ? 3 : dst_fmt == 26 ? 2 : dst_fmt == 27 ? 1 : 0;
+    const int ao = dst_fmt == 26 || dst_fmt == 28 ? 3 : 0;
+    if ((flags & 0x2000) && !is422) {                      /* SWS_FULL_CHR_H_INT: yuv2rgb_full_X_c_template (output.c:1165-1250), only yuv2packedX exists */
+        if (kind) return -1;
+        int64_t kcy, koy, kcrv, kcbu, kcgu, kcgv; int kyoffs;
+        cs_coeffs(&kcy, &koy, &kcrv, &kcbu, &kcgu, &kcgv, &kyoffs);
+#define R16(f) ((int16_t)({ int r_ = (int)(((int64_t)(f) + (1 << 15)) >> 16); r_ < -0x7FFF ? -0x8000 : r_ > 0x7FFF ? 0x7FFF : r_; }))
+        const int y_coeff = R16(kcy << 13), y_offset = R16(koy << 9), v2r = R16(kcrv << 13), v2g = R16(kcgv << 13), u2g = R16(kcgu << 13), u2b = R16(kcbu << 13);
+#undef R16
+        for (int i = 0; i < dstW; i++) {
+            int Y = 0, U = -128 * (1 << 19), V = -128 * (1 << 19);
+            for (int j = 0; j < lumFilterSize; j++) Y += lumSrc[j][i] * lumFilter[j];
+            for (int j = 0; j < chrFilterSize; j++) { U += chrU[j][i] * chrFilter[j]; V += chrV[j][i] * chrFilter[j]; }
+            Y >>= 10; U >>= 10; V >>= 10;
+            Y = (Y - y_offset) * y_coeff + (1 << 21);
+            int R = Y + V * v2r, G = Y + V * v2g + U * u2g, B = Y + U * u2b;
+            if ((R | G | B) & 0xC0000000) {
+                R = R < 0 ? 0 : R > 0x3FFFFFFF ? 0x3FFFFFFF : R; G = G < 0 ? 0 : G > 0x3FFFFFFF ? 0x3FFFFFFF : G; B = B < 0 ? 0 : B > 0x3FFFFFFF ? 0x3FFFFFFF : B;
+            }
+            uint8_t *d = dest + (size_t)bpp * i;
+            d[ro] = (uint8_t)(R >> 22); d[go] = (uint8_t)(G >> 22); d[bo] = (uint8_t)(B >> 22);
+            if (is32) d[ao] = 255;
+        }
+        return 0;
+    }
+    uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
+    orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
+    for (int i = 0; i < (dstW + 1) >> 1; i++) {
+        int Y1, Y2, U, V;
+        if (kind == 1) {                                    /* output.c:1042-1110 / 531-576 */
+            Y1 = lumSrc[0][2 * i] >> 7; Y2 = lumSrc[0][2 * i + 1] >> 7;
+            if (uvalpha < 2048) { U = chrU[0][i] >> 7; V = chrV[0][i] >> 7; }
+            else { U = (chrU[0][i] + chrU[1][i]) >> 8; V = (chrV[0][i] + chrV[1][i]) >> 8; }
+            Y1 = u8clip(Y1); Y2 = u8clip(Y2); U = u8clip(U); V = u8clip(V);
+        } else if (kind == 2) {                             /* output.c:997-1040 / 498-529 */
+            const int ya1 = 4096 - yalpha, ua1 = 4096 - uvalpha;
+            Y1 = (lumSrc[0][2 * i] * ya1 + lumSrc[1][2 * i] * yalpha) >> 19;
+            Y2 = (lumSrc[0][2 * i + 1] * ya1 + lumSrc[1][2 * i + 1] * yalpha) >> 19;
+            U = (chrU[0][i] * ua1 + chrU[1][i] * uvalpha) >> 19;
+            V = (chrV[0][i] * ua1 + chrV[1][i] * uvalpha) >> 19;
+            Y1 = u8clip(Y1); Y2 = u8clip(Y2); U = u8clip(U); V = u8clip(V);
+        } else {                                            /* output.c:936-995 / 456-496 */
+            Y1 = Y2 = U = V = 1 << 18;
+            for (int j = 0; j < lumFilterSize; j++) { Y1 += lumSrc[j][2 * i] * lumFilter[j]; Y2 += lumSrc[j][2 * i + 1] * lumFilter[j]; }
+            for (int j = 0; j < chrFilterSize; j++) { U += chrU[j][i] * chrFilter[j]; V += chrV[j][i] * chrFilter[j]; }
+            Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
+            if ((Y1 | Y2 | U | V) & 0x100) { Y1 = u8clip(Y1); Y2 = u8clip(Y2); U = u8clip(U); V = u8clip(V); }
+        }
+        if (is422) {
+            uint8_t *d = dest + 4 * (size_t)i;
+            if (dst_fmt == 1) { d[0] = (uint8_t)Y1; d[1] = (uint8_t)U; d[2] = (uint8_t)Y2; d[3] = (uint8_t)V; }
+            else              { d[0] = (uint8_t)U; d[1] = (uint8_t)Y1; d[2] = (uint8_t)V; d[3] = (uint8_t)Y2; }
+            continue;
+        }
+        const uint8_t *r = ytab + rv[V], *g = ytab + gu[U] + gv[V], *b = ytab + bu[U];
+        uint8_t *d = dest + (size_t)bpp * 2 * i;
+        d[ro] = r[Y1]; d[go] = g[Y1]; d[bo] = b[Y1]; d[bpp + ro] = r[Y2]; d[bpp + go] = g[Y2]; d[bpp + bo] = b[Y2];
+        if (is32) d[ao] = d[bpp + ao] = 255;
+    }
+    return 0;
+}

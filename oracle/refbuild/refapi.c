@@ -338,6 +338,66 @@ int ref_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
     sws_freeContext(c);
     return r;
 }
+/* ---- per-line slots: the function pointers the reference itself installed in a (scaling) context ---- */
+static struct SwsContext *line_ctx(int dst_fmt, int flags)
+{
+    INIT();
+    struct SwsContext *c = sws_getContext(64, 48, AV_PIX_FMT_YUV420P, 96, 80, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
+    if (!c) return NULL;
+    if (g_cs_set) sws_setColorspaceDetails(c, g_cs_inv, g_cs_range, g_cs_inv, 0, g_cs_b, g_cs_c, g_cs_s);     /* -1 (nothing changed) for yuv destinations, utils.c:821-822 */
+    static const uint8_t pb_64[8] = { 64, 64, 64, 64, 64, 64, 64, 64 };
+    c->lumDither8 = c->chrDither8 = pb_64;               /* what swscale() sets for every 8-bit source before the first line (swscale.c:445-447) */
+    return c;
+}
+int ref_sws_line_hscale(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize)
+{
+    struct SwsContext *c = line_ctx(dst_fmt, flags);
+    if (!c) return -1;
+    c->hyScale(c, dst, dstW, src, filter, filterPos, filterSize);
+    int same = c->hcScale == c->hyScale;
+    sws_freeContext(c);
+    return same ? 0 : -1;
+}
+int ref_sws_line_hfast(int chroma, int16_t *dst1, int16_t *dst2, int dstW, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc)
+{
+    struct SwsContext *c = line_ctx(AV_PIX_FMT_YUV420P, SWS_FAST_BILINEAR);
+    if (!c || !c->hyscale_fast || !c->hcscale_fast) { sws_freeContext(c); return -1; }
+    if (chroma) c->hcscale_fast(c, dst1, dst2, dstW, src1, src2, srcW, xInc);
+    else        c->hyscale_fast(c, dst1, dstW, src1, srcW, xInc);
+    sws_freeContext(c);
+    return 0;
+}
+int ref_sws_line_plane(int dst_fmt, const int16_t *filter, int filterSize, const void *const *src, uint8_t *dest, int dstW, const uint8_t *dither, int offset)
+{
+    struct SwsContext *c = line_ctx(dst_fmt, SWS_BICUBIC);
+    if (!c) return -1;
+    if (filterSize) c->yuv2planeX(filter, filterSize, (const int16_t **)src, dest, dstW, dither, offset);
+    else            c->yuv2plane1((const int16_t *)src[0], dest, dstW, dither, offset);
+    sws_freeContext(c);
+    return 0;
+}
+int ref_sws_line_nv12(int dst_fmt, const int16_t *chrFilter, int chrFilterSize, const int16_t *const *chrU, const int16_t *const *chrV, uint8_t *dest, int chrDstW)
+{
+    struct SwsContext *c = line_ctx(dst_fmt, SWS_BICUBIC);
+    if (!c || !c->yuv2nv12cX) { sws_freeContext(c); return -1; }
+    c->yuv2nv12cX(c, chrFilter, chrFilterSize, (const int16_t **)chrU, (const int16_t **)chrV, dest, chrDstW);
+    sws_freeContext(c);
+    return 0;
+}
+int ref_sws_line_packed(int dst_fmt, int flags, int kind, const int16_t *lumFilter, const int16_t *const *lumSrc, int lumFilterSize,
+                        const int16_t *chrFilter, const int16_t *const *chrU, const int16_t *const *chrV, int chrFilterSize,
+                        uint8_t *dest, int dstW, int yalpha, int uvalpha, int y)
+{
+    struct SwsContext *c = line_ctx(dst_fmt, flags);
+    if (!c) return -1;
+    int r = 0;
+    if (kind == 1) { if (c->yuv2packed1) c->yuv2packed1(c, lumSrc[0], (const int16_t **)chrU, (const int16_t **)chrV, NULL, dest, dstW, uvalpha, y); else r = -1; }
+    else if (kind == 2) { if (c->yuv2packed2) c->yuv2packed2(c, (const int16_t **)lumSrc, (const int16_t **)chrU, (const int16_t **)chrV, NULL, dest, dstW, yalpha, uvalpha, y); else r = -1; }
+    else { if (c->yuv2packedX) c->yuv2packedX(c, lumFilter, (const int16_t **)lumSrc, lumFilterSize, chrFilter, (const int16_t **)chrU, (const int16_t **)chrV, chrFilterSize, NULL, dest, dstW, y); else r = -1; }
+    sws_freeContext(c);
+    return r;
+}
+
 int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,
                        int32_t *pos, int cap, int *n_out)
 {

@@ -91,7 +91,3 @@ def test_h264_qpel_and_chroma_slots(gpu, checker):
 
 def test_h264dsp_slots(gpu, checker):
     slot_cases.h264dsp_cases(gpu.lib, gpu.last_error, checker)
-
-
-def test_h264dsp_slots_422(gpu, checker):
-    slot_cases.h264dsp_422_cases(gpu.lib, gpu.last_error, checker)

@@ -17,12 +17,14 @@ LIB = os.path.join(HERE, "libslots_hostsim.so")
 @pytest.fixture(scope="module")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
-    deps = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "shim", "cuda_runtime.h")] + \
-        [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h")] + \
+    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp")]
+    deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h")] + \
+        [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h", "sws_slots.cu", "sws_dev.cuh",
+                                                               "sws_filter.cu", "sws_filter.h")] + \
         [os.path.join(root, "include", f) for f in ("avdsp_b200.h", "avdsp_b200_tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", os.path.join(HERE, "shim"), "-Wno-unknown-pragmas",
-                        "-o", LIB, os.path.join(HERE, "slots_hostsim.cpp")], check=True)
+                        "-o", LIB] + srcs, check=True)
     lib = C.CDLL(LIB)
     lib.avb200_last_error.restype = C.c_char_p
     return lib
@@ -52,4 +54,58 @@ def test_batched_kernels_are_not_simulated(sim):
     pix = np.zeros((16, 32), np.uint8)
     c.weight_h264_pixels_tab[0](slot_cases.P(pix), 32, 8, 5, 37, -3)
     assert "not simulated" in sim.avb200_last_error().decode()
+    sim.avb200_clear_error()
+
+
+def test_sws_line_slots(sim, refo):
+    """libswscale's per-line slots (libav_b200/csrc/sws_slots.cu, host-compiled) against the functions the compiled reference installs;
+    the context view comes from the PRODUCT library's host-only set-up (sws_debug_slot_view_cuda)."""
+    import numpy as np
+    import libav_b200._lib as prod
+    import sws_line_cases as L
+    sim.hostsim_sws_context.restype = C.c_void_p
+    sim.hostsim_sws_free.argtypes = [C.c_void_p]
+
+    def run(colourspace):
+        def make_ctx(dst_fmt, flags):
+            view = np.zeros(32, np.int32)
+            assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, dst_fmt, flags, view.ctypes.data) == 25, (dst_fmt, flags, prod.last_error())
+            if colourspace:                  # sws_setColorspaceDetails_cuda needs a live context; the constants are the product's own host code
+                k = np.zeros(32, np.int32)
+                assert sim.hostsim_rgb_constants(k.ctypes.data, (C.c_int * 4)(*colourspace[0]), *colourspace[1:]) == 19
+                view[:19] = k[:19]
+            return sim.hostsim_sws_context(view.ctypes.data), sim.hostsim_sws_free
+        calls = L.SlotCalls(sim, make_ctx, last_error_of(sim))
+        try:
+            return L.compare(calls, L.OracleCalls(refo), seed=3 if colourspace else 4)
+        finally:
+            calls.close()
+    assert run(None) > 150
+    refo.sws_set_colorspace((C.c_int * 4)(*L.FCC), 0, 3000, 70000, 60000)
+    try:
+        assert run((L.FCC, 0, 3000, 70000, 60000)) > 150
+    finally:
+        refo.sws_set_colorspace(None, 0, 0, 0, 0)
+    assert sim.avb200_last_error().decode() == ""
+
+
+def test_sws_line_slot_registration(sim):
+    """a slot called for a SwsContext that was never registered (or whose SwsContextCUDA was freed) fails loudly"""
+    import numpy as np
+    import libav_b200._lib as prod
+    import sws_line_cases as L
+    from libav_b200 import tables
+    sim.hostsim_sws_context.restype = C.c_void_p
+    sim.hostsim_sws_free.argtypes = [C.c_void_p]
+    t = tables.SwsLineSlotsCUDA()
+    assert sim.ff_sws_init_swscale_cuda(None, None, C.byref(t)) == -1
+    sim.avb200_clear_error()
+    view = np.zeros(32, np.int32)
+    assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, 2, 4, view.ctypes.data) == 25
+    ctx = sim.hostsim_sws_context(view.ctypes.data)
+    assert sim.ff_sws_init_swscale_cuda(C.c_void_p(0x7000), C.c_void_p(ctx), C.byref(t)) == 0
+    sim.hostsim_sws_free(ctx)
+    lum, cu, out = np.zeros(64, np.int16), np.zeros(64, np.int16), np.full(256, 9, np.uint8)
+    t.yuv2packed1(C.c_void_p(0x7000), L.vp(lum), L.ptrs([cu, cu]), L.ptrs([cu, cu]), None, L.vp(out), 16, 0, 0)
+    assert "not registered" in sim.avb200_last_error().decode() and (out == 9).all()
     sim.avb200_clear_error()

@@ -1,0 +1,66 @@
+"""GPU: slots added while no GPU box was at hand (developed against tests/hostsim/, see tests/test_hostsim_slots_cpu.py): the
+chroma_format_idc 2 entries of H264DSPContext and libswscale's per-line SwsContext slots.  Same cases as the host simulation, now
+through the product library on a B200.  (The file name sorts last on purpose: `pytest -x` reaches these after every older test.)"""
+import ctypes as C
+
+import pytest
+
+import slot_cases
+import sws_line_cases as L
+
+pytestmark = pytest.mark.gpu
+
+
+def test_h264dsp_slots_422(gpu, checker):
+    slot_cases.h264dsp_422_cases(gpu.lib, gpu.last_error, checker)
+
+
+def make_ctx_factory(gpu):
+    def make_ctx(dst_fmt, flags):
+        ctx = gpu.lib.sws_getContext_cuda(64, 48, 0, 96, 80, dst_fmt, flags, None, None, None)
+        assert ctx, (dst_fmt, flags, gpu.last_error())
+        return ctx, gpu.lib.sws_freeContext_cuda
+    return make_ctx
+
+
+def test_sws_line_slots(gpu, checker):
+    calls = L.SlotCalls(gpu.lib, make_ctx_factory(gpu), gpu.last_error)
+    try:
+        assert L.compare(calls, L.OracleCalls(checker), seed=5) > 150
+    finally:
+        calls.close()
+    assert gpu.last_error() == ""
+
+
+def test_sws_line_slots_colourspace(gpu, checker):
+    """sws_setColorspaceDetails_cuda on the registered context is seen by the packed slots"""
+    tab = (C.c_int * 4)(*L.FCC)
+
+    def make_ctx(dst_fmt, flags):
+        ctx, free = make_ctx_factory(gpu)(dst_fmt, flags)
+        if dst_fmt in L.PACKED_FMTS and dst_fmt not in (1, 15):
+            assert gpu.lib.sws_setColorspaceDetails_cuda(ctx, tab, 0, tab, 0, 3000, 70000, 60000) == 0
+        return ctx, free
+    calls = L.SlotCalls(gpu.lib, make_ctx, gpu.last_error)
+    checker.sws_set_colorspace(tab, 0, 3000, 70000, 60000)
+    try:
+        assert L.compare(calls, L.OracleCalls(checker), seed=6) > 150
+    finally:
+        checker.sws_set_colorspace(None, 0, 0, 0, 0)
+        calls.close()
+    assert gpu.last_error() == ""
+
+
+def test_sws_line_slot_refusals(gpu):
+    from libav_b200 import tables
+    t = tables.SwsLineSlotsCUDA()
+    assert gpu.lib.ff_sws_init_swscale_cuda(None, None, C.byref(t)) == -1
+    gpu.lib.avb200_clear_error()
+    ctx = gpu.lib.sws_getContext_cuda(64, 48, 0, 96, 80, 2, 4, None, None, None)
+    assert gpu.lib.ff_sws_init_swscale_cuda(C.c_void_p(0x7000), ctx, C.byref(t)) == 0
+    gpu.lib.sws_freeContext_cuda(ctx)                       # the registration ends with the context
+    import numpy as np
+    lum, cu, out = np.zeros(64, np.int16), np.zeros(64, np.int16), np.zeros(256, np.uint8)
+    t.yuv2packed1(C.c_void_p(0x7000), L.vp(lum), L.ptrs([cu, cu]), L.ptrs([cu, cu]), None, L.vp(out), 16, 0, 0)
+    assert "not registered" in gpu.last_error()
+    gpu.lib.avb200_clear_error()

@@ -398,8 +398,8 @@ void sws_debug_rgb_constants_cuda(int32_t out[10]);
  * 7 yuv420p -> nv12 interleave; out[1..4] chrSrcW chrSrcH chrDstW chrDstH; out[5] source pre-pass 0 / 1 nv split / 2 reader;
  * out[6] destination bits per sample (planar) or bytes per pixel (packed); out[7] full-range source), 0 = refused */
 int  sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[8]);
-/* what the per-line slots (section 3, ff_sws_init_swscale_cuda) would know about that context: 25 int32 (19 colour constants, flags,
- * planar, destination bits, big endian, packed target, nv12 / nv21); returns the count, 0 = refused.  Host only. */
+/* what the per-line slots (section 3, ff_sws_init_swscale_cuda) would know about that context: 26 int32 (19 colour constants, flags,
+ * planar, destination bits, big endian, packed target, nv12 / nv21, range conversion); returns the count, 0 = refused.  Host only. */
 int  sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32]);
 
 /* ------------------------------------------------------------------ 3. table hooks --------------- */
@@ -460,6 +460,10 @@ typedef struct SwsLineSlotsCUDA {
                         const int16_t *alpSrc[2], uint8_t *dest, int dstW, int yalpha, int uvalpha, int y);
     void (*yuv2packedX)(struct SwsContext *c, const int16_t *lumFilter, const int16_t **lumSrc, int lumFilterSize, const int16_t *chrFilter,
                         const int16_t **chrUSrc, const int16_t **chrVSrc, int chrFilterSize, const int16_t **alpSrc, uint8_t *dest, int dstW, int y);
+    /* set when the context converts between full-range (yuvj) and limited-range yuv (swscale.c:748-757): lum / chrRangeFromJpeg_c or
+     * lum / chrRangeToJpeg_c on 15-bit lines, in place; NULL otherwise */
+    void (*lumConvertRange)(int16_t *dst, int width);
+    void (*chrConvertRange)(int16_t *dst1, int16_t *dst2, int width);
 } SwsLineSlotsCUDA;
 /* 0, or -1 (sticky error) for a NULL argument.  The registration lasts until sws_freeContext_cuda(cuda). */
 int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cuda, SwsLineSlotsCUDA *slots);

@@ -58,7 +58,11 @@ struct SwsSlotView {
     int dstBits, dstBE;
     int target;        // packed destinations: 0 rgb24, 1 bgr24, 2 yuyv422, 3 uyvy422, 4 argb, 5 rgba, 6 abgr, 7 bgra; -1 for planar
     int dstNV;         // 1 nv12, 2 nv21
+    int rangeConv;     // 1 full -> limited, 2 limited -> full range on the hscaled lines (yuv destinations), else 0
 };
+// lum / chrRange{From,To}Jpeg_c (swscale.c:166-197) in place on `rows` lines of `w` 15-bit samples, `stridePx` samples apart (device memory):
+// kind 0 lumFromJpeg, 1 chrFromJpeg, 2 lumToJpeg, 3 chrToJpeg.  Defined in sws_slots.cu; 0 / -1
+int sws_launch_range(int16_t *plane, int stridePx, int w, int rows, int kind, cudaStream_t stream);
 bool sws_slot_view(const void *ctx, SwsSlotView &v);      // false for NULL
 void sws_slots_forget(const void *ctx);                   // sws_freeContext_cuda: drop the registrations of this context
 

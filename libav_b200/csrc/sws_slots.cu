@@ -156,6 +156,31 @@ __global__ void __launch_bounds__(256) sws_line_kernel(SwsLineArgs s)
     }
 }
 
+// lumRangeFromJpeg_c / chrRangeFromJpeg_c / lumRangeToJpeg_c / chrRangeToJpeg_c (swscale.c:166-197), in place on 15-bit lines:
+// the frame path runs it over its hscaled line planes, the lumConvertRange / chrConvertRange slots over one (two) staged line(s)
+__device__ __forceinline__ int range_sample(int v, int kind)
+{
+    switch (kind) {
+    case 0: return (v * 14071 + 33561947) >> 14;
+    case 1: return (v * 1799 + 4081085) >> 11;
+    case 2: return (min(v, 30189) * 19077 - 39057361) >> 14;
+    default: return (min(v, 30775) * 4663 - 9289992) >> 12;
+    }
+}
+__global__ void __launch_bounds__(256) sws_range_kernel(int16_t *plane, int stridePx, int w, int rows, int kind)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= rows) return;
+    int16_t *p = plane + (size_t)y * stridePx + x;
+    *p = (int16_t)range_sample(*p, kind);
+}
+int sws_launch_range(int16_t *plane, int stridePx, int w, int rows, int kind, cudaStream_t stream)
+{
+    if (w <= 0 || rows <= 0) return 0;
+    AVB_LAUNCH(sws_range_kernel, dim3((w + 255) / 256, rows), dim3(256), 0, stream)(plane, stridePx, w, rows, kind);
+    return check_launch("sws range conversion");
+}
+
 // ---- registry: struct SwsContext * (opaque key) -> the context made by sws_getContext_cuda ------------------
 static std::mutex g_reg_mu;
 static std::vector<std::pair<const void *, const void *>> g_reg;
@@ -330,6 +355,23 @@ void slot_packedX(struct SwsContext *c, const int16_t *lumFilter, const int16_t 
     packed_impl(c, 0, lumFilter, lumSrc, lumFilterSize, chrFilter, chrUSrc, chrVSrc, chrFilterSize, dest, dstW, 0);
 }
 
+// ---- range conversion: c->lumConvertRange(dst, width) / c->chrConvertRange(dstU, dstV, width), in place ----
+template <int KIND> void range_impl(int16_t *d1, int16_t *d2, int width)
+{
+    if (width <= 0) return;
+    const size_t line = (size_t)width * 2, stride = al16(line);
+    LineStage S; if (!S.ok(2 * stride)) return;
+    const size_t o1 = S.put(d1, line), o2 = d2 ? S.put(d2, line) : o1;
+    if (S.used > S.cap) return;
+    if (cudaMemcpyAsync(S.d, S.h, S.used, cudaMemcpyHostToDevice, S.s) != cudaSuccess) { set_error("sws range slot:h2d", cudaGetLastError()); return; }
+    if (sws_launch_range((int16_t *)(S.d + o1), (int)(stride / 2), width, d2 ? 2 : 1, KIND, S.s)) return;
+    if (cudaMemcpyAsync(S.h, S.d, S.used, cudaMemcpyDeviceToHost, S.s) != cudaSuccess || cudaStreamSynchronize(S.s) != cudaSuccess) { set_error("sws range slot:d2h", cudaGetLastError()); return; }
+    memcpy(d1, S.h + o1, line);
+    if (d2) memcpy(d2, S.h + o2, line);
+}
+template <int KIND> void slot_lum_range(int16_t *dst, int width) { range_impl<KIND>(dst, nullptr, width); }
+template <int KIND> void slot_chr_range(int16_t *dstU, int16_t *dstV, int width) { range_impl<KIND>(dstU, dstV, width); }
+
 }  // namespace
 
 extern "C" int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cuda, SwsLineSlotsCUDA *t)
@@ -356,5 +398,7 @@ extern "C" int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cu
         t->yuv2packedX = slot_packedX;
         if (!full) { t->yuv2packed1 = slot_packed1; t->yuv2packed2 = slot_packed2; }
     }
+    if (v.rangeConv == 1)      { t->lumConvertRange = slot_lum_range<0>; t->chrConvertRange = slot_chr_range<1>; }     // swscale.c:748-757
+    else if (v.rangeConv == 2) { t->lumConvertRange = slot_lum_range<2>; t->chrConvertRange = slot_chr_range<3>; }
     return 0;
 }

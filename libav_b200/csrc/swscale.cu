@@ -1119,7 +1119,7 @@ sws_yuyv_yuv422p_kernel(const uint8_t *__restrict__ src, int srcStride, size_t s
 // context
 // ---------------------------------------------------------------------------------------------------
 enum { FMT_YUV420P = 0, FMT_YUYV422 = 1, FMT_RGB24 = 2, FMT_BGR24 = 3, FMT_YUV422P = 4, FMT_YUV444P = 5, FMT_YUV410P = 6, FMT_YUV411P = 7,
-       FMT_YUVJ420P = 12, FMT_YUVJ422P = 13, FMT_YUVJ444P = 14, FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
+       FMT_YUVJ420P = 12, FMT_YUVJ422P = 13, FMT_YUVJ444P = 14, FMT_YUVJ440P = 32, FMT_UYVY422 = 15, FMT_ARGB = 25, FMT_RGBA = 26, FMT_ABGR = 27, FMT_BGRA = 28, FMT_NV12 = 23, FMT_NV21 = 24, FMT_YUV440P = 31,
        FMT_YUV420P16 = 47, FMT_YUV422P16 = 49, FMT_YUV444P16 = 51, FMT_YUV420P9 = 62, FMT_YUV420P10 = 64, FMT_YUV422P10 = 66, FMT_YUV444P9 = 68, FMT_YUV444P10 = 70, FMT_YUV422P9 = 72 };  // libavutil/pixfmt.h (LE)
 
 static bool unscaled0(int sw, int sh, int dw, int dh) { return sw == dw && sh == dh; }
@@ -1176,6 +1176,7 @@ struct SwsCudaContext {
     uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
     int srcRange = 0;           // 1 = full-range (JPEG) source, sws_setColorspaceDetails / a yuvj source format
+    int rangeConv = 0;          // yuv destination of the other range: 1 lum / chrRangeFromJpeg_c, 2 lum / chrRangeToJpeg_c on the hscaled lines (two-pass path)
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
     int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
     int dstNV = 0;              // 1 nv12, 2 nv21 destination
@@ -1228,10 +1229,17 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
 {
     const char *err = nullptr;
     // handle_jpeg() (utils.c:855-873): the full-range planar formats are their limited-range twins with srcRange = 1
-    int srcRange = 0;
-    if (srcFormat == FMT_YUVJ420P) { srcFormat = FMT_YUV420P; srcRange = 1; }
-    else if (srcFormat == FMT_YUVJ422P) { srcFormat = FMT_YUV422P; srcRange = 1; }
-    else if (srcFormat == FMT_YUVJ444P) { srcFormat = FMT_YUV444P; srcRange = 1; }
+    int srcRange = 0, dstRange = 0;
+    auto handle_jpeg = [](int &fmt) {
+        switch (fmt) {
+        case FMT_YUVJ420P: fmt = FMT_YUV420P; return 1;
+        case FMT_YUVJ422P: fmt = FMT_YUV422P; return 1;
+        case FMT_YUVJ444P: fmt = FMT_YUV444P; return 1;
+        case FMT_YUVJ440P: fmt = FMT_YUV440P; return 1;
+        }
+        return 0;
+    };
+    srcRange = handle_jpeg(srcFormat); dstRange = handle_jpeg(dstFormat);
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
@@ -1283,14 +1291,21 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "bgr24 -> yuv420p of the same size without SWS_ACCURATE_RND is the reference's rgb24toyv12, which needs an even height");
         return nullptr;
     }
-    if (srcFormat == FMT_YUV410P && dstFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !(flags & SWS_BITEXACT)) {
+    if (srcFormat == FMT_YUV410P && dstFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !(flags & SWS_BITEXACT) && srcRange == dstRange) {
         set_error_msg("sws_getContext_cuda", "yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper: not taken over");
         return nullptr;
     }
     const bool rgb = !planar;
-    if (srcRange && (planar || pk422)) {                      // swscale.c:748-765: lumRangeFromJpeg_c / chrRangeFromJpeg_c between the two passes
-        set_error_msg("sws_getContext_cuda", "full-range (yuvj) source to a limited-range yuv destination needs the range conversion: not taken over");
-        return nullptr;
+    // swscale.c:748-765: a yuv destination of the other range gets lum / chrRangeFromJpeg_c (1) or ...ToJpeg_c (2) between the two passes,
+    // and none of the unscaled special converters (utils.c:1043-1044)
+    const int rangeConv = (srcRange != dstRange && (planar || pk422)) ? (srcRange ? 1 : 2) : 0;
+    if (rangeConv) {
+        const bool planarSrc = srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P || srcFormat == FMT_YUV444P || srcFormat == FMT_YUV410P ||
+                               srcFormat == FMT_YUV411P || srcFormat == FMT_YUV440P;
+        if (!planarSrc || !planar || dstFormat == FMT_NV12 || dstFormat == FMT_NV21 || dbits == 16) {
+            set_error_msg("sws_getContext_cuda", "range conversion (full-range yuvj <-> limited-range yuv) is taken over for planar 8-bit sources and planar 8 / 9 / 10-bit destinations only");
+            return nullptr;
+        }
     }
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
@@ -1352,7 +1367,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
-    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P);
+    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv;
+    c->rangeConv = rangeConv;
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
@@ -1394,7 +1410,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
         const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
-        if (need <= 96 * 1024 && !pk422) {          // (the packed 4:2:2 output stage only exists in the two-pass path so far)
+        if (need <= 96 * 1024 && !pk422 && !rangeConv) {          // (the packed 4:2:2 output stage and the range conversion only exist in the two-pass path so far)
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1707,6 +1723,11 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
             sws_hscale8to15_x4_kernel<<<dim3((p.chrDstW + 1023) / 1024, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH);
         }
+        if (c->rangeConv) {                 // hyscale() / hcscale() call c->lumConvertRange / chrConvertRange on every converted line (swscale.c:223-225, 270-272)
+            if (sws_launch_range(c->d_lum, c->lumStridePx, p.dstW, p.srcH, c->rangeConv == 1 ? 0 : 2, st) ||
+                sws_launch_range(c->d_chrU, c->chrStridePx, p.chrDstW, p.chrSrcH, c->rangeConv == 1 ? 1 : 3, st) ||
+                sws_launch_range(c->d_chrV, c->chrStridePx, p.chrDstW, p.chrSrcH, c->rangeConv == 1 ? 1 : 3, st)) return -1;
+        }
         if (c->planar) {
             sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits, p.dstBE);
             sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep);
@@ -1740,6 +1761,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
 {
     const SwsCudaContext *c = (const SwsCudaContext *)ctx;
     if (!c) return false;
+    v.rangeConv = c->rangeConv;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
@@ -1955,18 +1977,18 @@ int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, i
     delete c;
     return 1;
 }
-// The SwsSlotView (sws_filter.h) sws_getContext_cuda() would hand to the per-line slots, as 25 int32, computed on the host only:
-// 19 colour constants, flags, planar, dstBits, dstBE, packed target, dstNV.  Returns the count, 0 when the request is refused.
+// The SwsSlotView (sws_filter.h) sws_getContext_cuda() would hand to the per-line slots, as 26 int32, computed on the host only:
+// 19 colour constants, flags, planar, dstBits, dstBE, packed target, dstNV, range conversion.  Returns the count, 0 when the request is refused.
 int sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32])
 {
-    static_assert(sizeof(SwsSlotView) == 25 * sizeof(int32_t), "SwsSlotView is 25 ints");
+    static_assert(sizeof(SwsSlotView) == 26 * sizeof(int32_t), "SwsSlotView is 26 ints");
     SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
     if (!c) return 0;
     SwsSlotView v;
     sws_slot_view(c, v);
     memcpy(out, &v, sizeof(v));
     delete c;
-    return 25;
+    return 26;
 }
 void sws_debug_rgb_constants_cuda(int32_t out[10])
 {

@@ -103,6 +103,7 @@ PLANAR_FORMATS = {0: (1, 1, 8), 4: (1, 0, 8), 5: (0, 0, 8), 6: (2, 2, 8), 7: (2,
                   47: (1, 1, 16), 49: (1, 0, 16), 51: (0, 0, 16)}
 PLANAR_FORMATS.update({f - 1: PLANAR_FORMATS[f] for f in (62, 64, 72, 66, 68, 70)})     # big-endian twins
 PLANAR_FORMATS.update({f + 1: PLANAR_FORMATS[f] for f in (47, 49, 51)})
+PLANAR_FORMATS.update({12: (1, 1, 8), 13: (1, 0, 8), 14: (0, 0, 8), 32: (0, 1, 8)})     # full-range (yuvj) twins of 420p 422p 444p 440p
 PLANAR_BE = {61, 63, 71, 65, 67, 69, 48, 50, 52}
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_X, SWS_POINT, SWS_AREA = 1, 2, 4, 8, 0x10, 0x20
 SWS_BICUBLIN, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x40, 0x80, 0x100, 0x200, 0x400

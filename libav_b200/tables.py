@@ -163,4 +163,5 @@ class SwsLineSlotsCUDA(C.Structure):        # include/avdsp_b200.h SwsLineSlotsC
                 ("yuv2nv12cX", C.CFUNCTYPE(None, _vp, _vp, _i, _vp, _vp, _vp, _i)),
                 ("yuv2packed1", C.CFUNCTYPE(None, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i)),
                 ("yuv2packed2", C.CFUNCTYPE(None, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i)),
-                ("yuv2packedX", C.CFUNCTYPE(None, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i))]
+                ("yuv2packedX", C.CFUNCTYPE(None, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i)),
+                ("lumConvertRange", C.CFUNCTYPE(None, _vp, _i)), ("chrConvertRange", C.CFUNCTYPE(None, _vp, _vp, _i))]

@@ -134,6 +134,9 @@ void ORC(h264_add_pixels_clear)(int w8, uint8_t *dst, int16_t *block, int stride
  *   nv12:    yuv2nv12cX_c (dst_fmt nv12 / nv21), chrDither8 = 64
  *   packed:  kind 1 yuv2packed1 (lumSrc[0], chr*[0..1], uvalpha), 2 yuv2packed2 (two lines each, yalpha / uvalpha), 0 yuv2packedX
  * Returns 0, -1 when the reference would not install that slot (or the request is outside what the port restates). */
+/*   range:   kind 0 lumRangeFromJpeg_c (dst1), 1 chrRangeFromJpeg_c (dst1, dst2), 2 lumRangeToJpeg_c, 3 chrRangeToJpeg_c: c->lumConvertRange /
+ *            c->chrConvertRange of a yuvj420p -> yuv420p (0, 1) or yuv420p -> yuvj420p (2, 3) context (swscale.c:166-197,748-757) */
+int ORC(sws_line_range)(int kind, int16_t *dst1, int16_t *dst2, int width);
 int ORC(sws_line_hscale)(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize);
 int ORC(sws_line_hfast)(int chroma, int16_t *dst1, int16_t *dst2, int dstW, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc);
 int ORC(sws_line_plane)(int dst_fmt, const int16_t *filter, int filterSize, const void *const *src, uint8_t *dest, int dstW, const uint8_t *dither, int offset);

@@ -361,6 +361,23 @@ static int32_t *hpass19(const uint8_t *src, int stride, int rows, const bank_t *
 
 static int rowsel(int first, int j, int h) { int r = first + j; return r < 0 ? 0 : r > h - 1 ? h - 1 : r; }
 
+/* Range conversion between the horizontal and the vertical pass (c->lumConvertRange / chrConvertRange, swscale.c:166-197 installed at
+ * :748-765 when srcRange != dstRange and the destination is not rgb): 1 = full (yuvj) -> limited, 2 = limited -> full, 15-bit lines */
+static __thread int g_range;
+static int16_t range_sample(int v, int kind, int chroma)
+{
+    if (kind == 1) return (int16_t)(chroma ? (v * 1799 + 4081085) >> 11 : (v * 14071 + 33561947) >> 14);
+    if (chroma) { v = v < 30775 ? v : 30775; return (int16_t)((v * 4663 - 9289992) >> 12); }
+    v = v < 30189 ? v : 30189;
+    return (int16_t)((v * 19077 - 39057361) >> 14);
+}
+static void range_lines(int16_t *p, int pitch, int rows, int w, int chroma)
+{
+    if (!g_range) return;
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < w; x++) p[(size_t)y * pitch + x] = range_sample(p[(size_t)y * pitch + x], g_range, chroma);
+}
+
 int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst, int dstride,
                              int dw, int dh, int flags)
 {
@@ -519,7 +536,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy) {   /* unscaled, same sub-sampling: planarCopyWrapper (utils.c:1043-1054,
+    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
                                          swscale_unscaled.c:793-1020); 8 -> 9 / 10 bits is a plain shift for limited-range sources (:946-971) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
@@ -536,6 +553,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     }
     int lp, cp;
     if (g_dbits == 16) {                /* 19-bit lines; no fast-bilinear line functions at this depth (swscale.c:728-741) */
+        if (g_range) { sws_close(&c); return -1; }      /* (the *Range*16_c variants are not restated) */
         int32_t *L = hpass19(src[0], ss[0], sh, &c.hl, &lp), *U = hpass19(src[1], ss[1], c.chrSrcH, &c.hc, &cp), *V = hpass19(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
         vplane16(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
         vplane16(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
@@ -548,6 +566,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    range_lines(L, lp, sh, dw, 0); range_lines(U, cp, c.chrSrcH, c.chrDstW, 1); range_lines(V, cp, c.chrSrcH, c.chrDstW, 1);
     vplane(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
     vplane(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
     vplane(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH);
@@ -843,11 +862,27 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
 {
     int hs, vs, r;
     const int pk = dst_fmt == 1 || dst_fmt == 15;
-    if (src_fmt >= 12 && src_fmt <= 14) {           /* yuvj420p / 422p / 444p: handle_jpeg() (utils.c:855-873), srcRange = 1 */
-        if (!(dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28))) return -1;      /* yuv destinations would need the range conversion */
-        g_cs_jpeg = 1;
-        r = sws_any(src_fmt == 12 ? 0 : src_fmt == 13 ? 4 : 5, src, ss, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
-        g_cs_jpeg = 0;
+    /* handle_jpeg() (utils.c:855-873) on both sides: yuvj420p 12 / 422p 13 / 444p 14 / 440p 32 are their limited-range twins with
+     * srcRange / dstRange = 1.  An rgb destination folds the source range into its colour tables; a yuv destination of the other range
+     * gets the range conversion (restated for planar 8-bit sources to planar 8 / 9 / 10-bit destinations), of the same range nothing. */
+    const int src_j = (src_fmt >= 12 && src_fmt <= 14) || src_fmt == 32, dst_j = (dst_fmt >= 12 && dst_fmt <= 14) || dst_fmt == 32;
+    if (src_j || dst_j) {
+        const int sf = src_fmt == 12 ? 0 : src_fmt == 13 ? 4 : src_fmt == 14 ? 5 : src_fmt == 32 ? 31 : src_fmt;
+        const int df = dst_fmt == 12 ? 0 : dst_fmt == 13 ? 4 : dst_fmt == 14 ? 5 : dst_fmt == 32 ? 31 : dst_fmt;
+        const int dst_rgb = df == 2 || df == 3 || (df >= 25 && df <= 28);
+        if (dst_rgb) {
+            g_cs_jpeg = 1;
+            r = sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
+            g_cs_jpeg = 0;
+            return r;
+        }
+        if (src_j == dst_j) return sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
+        int h2, v2, b2;
+        const int planar_src = sf == 0 || sf == 4 || sf == 5 || sf == 6 || sf == 7 || sf == 31;
+        if (!planar_src || g_nospecial || !planar_dst(df, &h2, &v2, &b2) || b2 == 16) { g_dbe = 0; return -1; }
+        g_range = src_j ? 1 : 2;
+        r = sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
+        g_range = 0;
         return r;
     }
     const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk;
@@ -892,7 +927,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     }
     /* yuv410p -> yuv420p of the same size without SWS_BITEXACT is the reference's yvu9ToYv12Wrapper (swscale_unscaled.c:1057-1061,
      * rgb2rgb.c planar2x): not restated */
-    if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT) && !g_nospecial) return -1;
+    if (src_fmt == 6 && dst_fmt == 0 && sw == dw && sh == dh && !(flags & F_BITEXACT) && !g_nospecial && !g_range) return -1;
     g_hs = hs; g_vs = vs;
     r = rgb ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags)
             : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
@@ -902,6 +937,15 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
 
 /* ---- SwsContext per-line slots -------------------------------------------------------------------------------------------------
  * The functions sws_init_swscale() / ff_sws_init_output_funcs() install (swscale.c:723-769, output.c:1357-1590), restated per line. */
+int orc_sws_line_range(int kind, int16_t *dst1, int16_t *dst2, int width)
+{
+    for (int i = 0; i < width; i++) {
+        dst1[i] = range_sample(dst1[i], kind < 2 ? 1 : 2, kind & 1);
+        if (kind & 1) dst2[i] = range_sample(dst2[i], kind < 2 ? 1 : 2, 1);
+    }
+    return 0;
+}
+
 int orc_sws_line_hscale(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize)
 {
     int hs, vs, bits;

@@ -349,6 +349,16 @@ static struct SwsContext *line_ctx(int dst_fmt, int flags)
     c->lumDither8 = c->chrDither8 = pb_64;               /* what swscale() sets for every 8-bit source before the first line (swscale.c:445-447) */
     return c;
 }
+int ref_sws_line_range(int kind, int16_t *dst1, int16_t *dst2, int width)
+{
+    INIT();
+    struct SwsContext *c = sws_getContext(64, 48, kind < 2 ? AV_PIX_FMT_YUVJ420P : AV_PIX_FMT_YUV420P, 96, 80,
+                                          kind < 2 ? AV_PIX_FMT_YUV420P : AV_PIX_FMT_YUVJ420P, SWS_BICUBIC, NULL, NULL, NULL);
+    if (!c || !c->lumConvertRange || !c->chrConvertRange) { sws_freeContext(c); return -1; }
+    if (kind & 1) c->chrConvertRange(dst1, dst2, width); else c->lumConvertRange(dst1, width);
+    sws_freeContext(c);
+    return 0;
+}
 int ref_sws_line_hscale(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize)
 {
     struct SwsContext *c = line_ctx(dst_fmt, flags);

@@ -123,6 +123,14 @@ def run_packed(call, case):
     return out
 
 
+def range_cases(rng):
+    for kind in range(4):
+        for width in (37, 200):
+            a = rng.integers(-300, 32768, size=width + 4).astype(np.int16)
+            a[:3] = (32767, 30189, 30775)
+            yield kind, width, a, rng.integers(-300, 32768, size=width + 4).astype(np.int16)
+
+
 # ---- the two kinds of callee -------------------------------------------------------------------------------------------------
 class OracleCalls:
     """the oracle entry points (oracle/oracle_api.h sws_line_*)"""
@@ -142,6 +150,9 @@ class OracleCalls:
     def nv12(self, fmt, cf, fs, cu, cv, out, width):
         assert self.o.sws_line_nv12(fmt, ptr(cf), fs, ptrs(cu), ptrs(cv), ptr(out), width) == 0
 
+    def range(self, kind, d1, d2, width):
+        assert self.o.sws_line_range(kind, ptr(d1), ptr(d2), width) == 0
+
     def packed(self, fmt, flags, kind, lf, lum, cf, cu, cv, out, width, yalpha, uvalpha):
         assert self.o.sws_line_packed(fmt, flags, kind, ptr(lf), ptrs(lum), len(lum), ptr(cf), ptrs(cu), ptrs(cv), len(cu), ptr(out), width,
                                       yalpha, uvalpha, 5) == 0
@@ -154,11 +165,11 @@ class SlotCalls:
         self.lib, self.make_ctx, self.last_error = lib, make_ctx, last_error
         self.cache = {}
 
-    def slots(self, dst_fmt, flags):
+    def slots(self, dst_fmt, flags, src_fmt=0):
         from libav_b200 import tables
-        key = (dst_fmt, flags)
+        key = (dst_fmt, flags, src_fmt)
         if key not in self.cache:
-            ctx, free = self.make_ctx(dst_fmt, flags)
+            ctx, free = self.make_ctx(dst_fmt, flags) if not src_fmt else self.make_ctx(dst_fmt, flags, src_fmt)
             t = tables.SwsLineSlotsCUDA()
             handle = C.c_void_p(0x5000 + 16 * len(self.cache))         # stands for the caller's struct SwsContext *
             assert self.lib.ff_sws_init_swscale_cuda(handle, C.c_void_p(ctx), C.byref(t)) == 0
@@ -173,7 +184,7 @@ class SlotCalls:
     def hscale(self, dst_fmt, out, dst_w, src, filt, pos, fs):
         h, t = self.slots(dst_fmt, BICUBIC)
         t.hyScale(h, vp(out), dst_w, vp(src), vp(filt), vp(pos), fs)
-        assert C.cast(t.hcScale, C.c_void_p).value == C.cast(t.hyScale, C.c_void_p).value and not t.hyscale_fast
+        assert C.cast(t.hcScale, C.c_void_p).value == C.cast(t.hyScale, C.c_void_p).value and not t.hyscale_fast and not t.lumConvertRange
 
     def hfast(self, chroma, d1, d2, dst_w, s1, s2, src_w, x_inc):
         h, t = self.slots(0, FAST)
@@ -193,6 +204,13 @@ class SlotCalls:
     def nv12(self, fmt, cf, fs, cu, cv, out, width):
         h, t = self.slots(fmt, BICUBIC)
         t.yuv2nv12cX(h, vp(cf), fs, ptrs(cu), ptrs(cv), vp(out), width)
+
+    def range(self, kind, d1, d2, width):
+        h, t = self.slots(0 if kind < 2 else 12, BICUBIC, src_fmt=12 if kind < 2 else 0)       # yuvj420p -> yuv420p / yuv420p -> yuvj420p
+        if kind & 1:
+            t.chrConvertRange(vp(d1), vp(d2), width)
+        else:
+            t.lumConvertRange(vp(d1), width)
 
     def packed(self, fmt, flags, kind, lf, lum, cf, cu, cv, out, width, yalpha, uvalpha):
         h, t = self.slots(fmt, flags)
@@ -231,6 +249,14 @@ def compare(a, b, seed=0, colourspace=None):
             c.nv12(fmt, cf, fs, cu, cv, out, width)
             outs.append(out)
         assert np.array_equal(outs[0], outs[1]), ("nv12", fmt, fs, width); n += 1
+    for (kind, width, l1, l2) in range_cases(rng):
+        outs = []
+        for c in (a, b):
+            d1, d2 = l1.copy(), l2.copy()
+            c.range(kind, d1, d2, width)
+            outs.append((d1, d2))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), ("range", kind, width)
+        assert np.array_equal(outs[0][0][width:], l1[width:]) and ((kind & 1) or np.array_equal(outs[0][1], l2)); n += 1
     for case in packed_cases(rng):
         x, y = run_packed(a.packed, case), run_packed(b.packed, case)
         assert np.array_equal(x, y), ("packed",) + case[:4] + (np.argwhere(x != y)[:4].tolist(),); n += 1

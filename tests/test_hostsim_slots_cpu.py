@@ -67,9 +67,9 @@ def test_sws_line_slots(sim, refo):
     sim.hostsim_sws_free.argtypes = [C.c_void_p]
 
     def run(colourspace):
-        def make_ctx(dst_fmt, flags):
+        def make_ctx(dst_fmt, flags, src_fmt=0):
             view = np.zeros(32, np.int32)
-            assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, dst_fmt, flags, view.ctypes.data) == 25, (dst_fmt, flags, prod.last_error())
+            assert prod.lib.sws_debug_slot_view_cuda(64, 48, src_fmt, 96, 80, dst_fmt, flags, view.ctypes.data) == 26, (dst_fmt, flags, prod.last_error())
             if colourspace:                  # sws_setColorspaceDetails_cuda needs a live context; the constants are the product's own host code
                 k = np.zeros(32, np.int32)
                 assert sim.hostsim_rgb_constants(k.ctypes.data, (C.c_int * 4)(*colourspace[0]), *colourspace[1:]) == 19
@@ -101,7 +101,7 @@ def test_sws_line_slot_registration(sim):
     assert sim.ff_sws_init_swscale_cuda(None, None, C.byref(t)) == -1
     sim.avb200_clear_error()
     view = np.zeros(32, np.int32)
-    assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, 2, 4, view.ctypes.data) == 25
+    assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, 2, 4, view.ctypes.data) == 26
     ctx = sim.hostsim_sws_context(view.ctypes.data)
     assert sim.ff_sws_init_swscale_cuda(C.c_void_p(0x7000), C.c_void_p(ctx), C.byref(t)) == 0
     sim.hostsim_sws_free(ctx)

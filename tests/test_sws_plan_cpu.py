@@ -9,10 +9,10 @@ import pytest
 from libav_b200.device import PLANAR_FORMATS
 
 ACC = 0x40000 | 0x80000
-PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0)}
+PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0), 32: (0, 1)}
 PACKED_SRC = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
 SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24]
-DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24]
+DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24, 12, 14, 32]        # 12 14 32: full-range (yuvj) planar
 GEOMS = [(64, 48, 64, 48), (66, 50, 66, 50), (64, 48, 96, 80), (96, 80, 64, 48)]
 FLAGS = (4 | ACC, 4, 0x10, 1 | ACC, 2 | ACC | 0x2000, 2)
 
@@ -99,6 +99,8 @@ def test_paths_and_geometry(built):
     assert P(64, 48, 23, 32, 24, 2, 4 | 0x2000)[1][1:6] == [32, 24, 32, 24, 1]
     assert P(64, 48, 12, 96, 80, 2, 4)[1][7] == 1 and P(64, 48, 0, 96, 80, 2, 4)[1][7] == 0
     assert [P(64, 48, 0, 96, 80, d, 4)[1][6] for d in (0, 62, 64, 47, 2, 26, 1)] == [8, 9, 10, 16, 3, 4, 2]
+    # a yuv destination of the other range: the scaler even at the same size (no plane copy, utils.c:1043-1044); same range: still the copy
+    assert P(64, 48, 12, 64, 48, 0, 4)[1][0] == 4 and P(64, 48, 0, 64, 48, 12, 4)[1][0] == 4 and P(64, 48, 12, 64, 48, 12, 4)[1][0] == 1 and P(64, 48, 13, 64, 48, 66, 4)[1][0] == 4
 
 
 def test_refusals_carry_a_reason(built):
@@ -107,7 +109,7 @@ def test_refusals_carry_a_reason(built):
     cases = [((64, 48, 8, 64, 48, 2, 4), "sources taken over"), ((64, 48, 0, 64, 48, 33, 4), "destinations taken over"),
              ((64, 48, 0, 96, 80, 2, 4 | 0x10000), "CHR_DROP"), ((64, 48, 0, 96, 80, 27, 4 | 0x2000), "abgr"),
              ((64, 48, 26, 64, 48, 2, 4), "32-bit rgb source"), ((64, 48, 2, 64, 48, 26, 4), "rgb2rgb"), ((64, 49, 3, 64, 49, 0, 4), "even height"),
-             ((64, 48, 12, 96, 80, 0, 4), "range conversion"), ((64, 48, 23, 64, 48, 24, 4), "nv12"), ((64, 48, 6, 64, 48, 0, 4), "yvu9ToYv12Wrapper"),
+             ((64, 48, 12, 96, 80, 23, 4), "range conversion"), ((64, 48, 23, 96, 80, 12, 4), "range conversion"), ((64, 48, 12, 96, 80, 47, 4), "range conversion"), ((64, 48, 23, 64, 48, 24, 4), "nv12"), ((64, 48, 6, 64, 48, 0, 4), "yvu9ToYv12Wrapper"),
              ((2, 2, 0, 64, 48, 2, 4), ""), ((64, 48, 0, 96, 80, 2, 4 | 2), "")]
     for args, reason in cases:
         assert L.lib.sws_debug_plan_cuda(*args, out) == 0, args

@@ -16,8 +16,8 @@ def test_h264dsp_slots_422(gpu, checker):
 
 
 def make_ctx_factory(gpu):
-    def make_ctx(dst_fmt, flags):
-        ctx = gpu.lib.sws_getContext_cuda(64, 48, 0, 96, 80, dst_fmt, flags, None, None, None)
+    def make_ctx(dst_fmt, flags, src_fmt=0):
+        ctx = gpu.lib.sws_getContext_cuda(64, 48, src_fmt, 96, 80, dst_fmt, flags, None, None, None)
         assert ctx, (dst_fmt, flags, gpu.last_error())
         return ctx, gpu.lib.sws_freeContext_cuda
     return make_ctx
@@ -36,8 +36,8 @@ def test_sws_line_slots_colourspace(gpu, checker):
     """sws_setColorspaceDetails_cuda on the registered context is seen by the packed slots"""
     tab = (C.c_int * 4)(*L.FCC)
 
-    def make_ctx(dst_fmt, flags):
-        ctx, free = make_ctx_factory(gpu)(dst_fmt, flags)
+    def make_ctx(dst_fmt, flags, src_fmt=0):
+        ctx, free = make_ctx_factory(gpu)(dst_fmt, flags, src_fmt)
         if dst_fmt in L.PACKED_FMTS and dst_fmt not in (1, 15):
             assert gpu.lib.sws_setColorspaceDetails_cuda(ctx, tab, 0, tab, 0, 3000, 70000, 60000) == 0
         return ctx, free
@@ -64,3 +64,23 @@ def test_sws_line_slot_refusals(gpu):
     t.yuv2packed1(C.c_void_p(0x7000), L.vp(lum), L.ptrs([cu, cu]), L.ptrs([cu, cu]), None, L.vp(out), 16, 0, 0)
     assert "not registered" in gpu.last_error()
     gpu.lib.avb200_clear_error()
+
+
+def test_sws_range_conversion_frames(gpu, checker):
+    """full-range (yuvj) <-> limited-range planar yuv through sws_scale_cuda: the two-pass path with the range kernel between the passes"""
+    import numpy as np
+    from libav_b200 import device
+    import test_sws_range_cpu as R
+    from test_sws_planar_dst import run
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in list(R.cases()) + [(12, 0, 1280, 720, 1920, 1080, 4 | R.ACC), (0, 12, 1920, 1080, 1280, 720, 4 | R.ACC)]:
+        pl = R.planes(sf, w, h, 21)
+        rc, want = run(checker, sf, pl, w, h, df, dw, dh, flags)
+        assert rc == dh
+        ctx = device.SwsContext(w, h, dw, dh, df, flags, src_fmt=sf)
+        got = ctx.scale(pl, fill=7)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b[:, :a.shape[1]]), (sf, df, w, h, dw, dh, hex(flags))
+        ctx.close()
+        n += 1
+    assert n > 400 and gpu.last_error() == ""

@@ -33,6 +33,15 @@ API = {
     "h264_chroma_dc_dequant_idct": (None, [vp, i32]),
     "h264_chroma422_dc_dequant_idct": (None, [vp, i32]),
     "h264_loop_filter": (None, [i32, vp, i32, i32, i32, vp]),
+    "h264_hbd_idct": (None, [i32, i32, vp, vp, i32]),
+    "h264_hbd_idct_mb": (None, [i32, i32, vp, vp, vp, vp, i32, vp]),
+    "h264_hbd_dc_dequant": (None, [i32, i32, vp, vp, i32]),
+    "h264_hbd_add_pixels_clear": (None, [i32, i32, vp, vp, i32]),
+    "h264_hbd_weight": (None, [i32, i32, vp, i32, i32, i32, i32, i32]),
+    "h264_hbd_biweight": (None, [i32, i32, vp, vp, i32, i32, i32, i32, i32, i32]),
+    "h264_hbd_loop_filter": (None, [i32, i32, vp, i32, i32, i32, vp]),
+    "h264_hbd_qpel": (None, [i32, i32, i32, i32, vp, vp, pd]),
+    "h264_hbd_chroma": (None, [i32, i32, i32, vp, vp, pd, i32, i32, i32]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),

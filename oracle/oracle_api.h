@@ -145,6 +145,19 @@ int ORC(sws_line_packed)(int dst_fmt, int flags, int kind, const int16_t *lumFil
                          const int16_t *chrFilter, const int16_t *const *chrU, const int16_t *const *chrV, int chrFilterSize,
                          uint8_t *dest, int dstW, int yalpha, int uvalpha, int y);
 
+/* ---- the 9 / 10-bit instances of H264DSPContext / H264QpelContext / H264ChromaContext (ff_h264dsp_init(c, bits, idc), ff_h264qpel_init(c, bits),
+ * ff_h264chroma_init(c, bits); bit_depth_template.c:49-67: uint16 samples, int32 coefficients).  `which` / `widx` / `sidx` / `mc` number the
+ * entries like the 8-bit functions above; strides are in BYTES; dc_dequant kind 0 luma (out, in), 1 chroma 4:2:0, 2 chroma 4:2:2 (in place in `out`) */
+void ORC(h264_hbd_idct)(int bits, int which, uint8_t *dst, int32_t *block, int stride);
+void ORC(h264_hbd_idct_mb)(int bits, int which, uint8_t *dst, uint8_t **dst2, const int *block_offset, int32_t *block, int stride, const uint8_t *nnzc);
+void ORC(h264_hbd_dc_dequant)(int bits, int kind, int32_t *out, int32_t *in, int qmul);
+void ORC(h264_hbd_add_pixels_clear)(int bits, int w8, uint8_t *dst, int32_t *block, int stride);
+void ORC(h264_hbd_weight)(int bits, int widx, uint8_t *block, int stride, int height, int log2_denom, int weight, int offset);
+void ORC(h264_hbd_biweight)(int bits, int widx, uint8_t *dst, uint8_t *src, int stride, int height, int log2_denom, int weightd, int weights, int offset);
+void ORC(h264_hbd_loop_filter)(int bits, int which, uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0);
+void ORC(h264_hbd_qpel)(int bits, int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+void ORC(h264_hbd_chroma)(int bits, int avg, int widx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int h, int x, int y);
+
 /* ---- H264QpelContext / H264ChromaContext (h264qpel.h:27-30, h264chroma.h:25-30) ---- */
 /* sidx 0..3 = 16,8,4,2 ; mc = (mx&3) + 4*(my&3) */
 void ORC(h264_qpel)(int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);

@@ -1,0 +1,149 @@
+"""Cases for the 9 / 10-bit H.264 DSP entries (uint16 samples, int32 coefficients), shared by the oracle pinning, the host simulation
+and the GPU tests.  A `callee` maps the oracle's entry names (oracle/oracle_api.h h264_hbd_*) to callables with the oracle's argument
+order; tests/test_oracle_h264_hbd_cpu.py passes the two oracles, the slot tests an adapter over the product's tables.  TEST INFRASTRUCTURE."""
+import ctypes as C
+
+import numpy as np
+
+from h264_util import block_offsets, block_offsets_422, scan8
+
+
+def vp(a, off=0):
+    return C.c_void_p(a.ctypes.data + int(off))
+
+
+def residual(rng, which, bits):
+    """48 x 16 int32 coefficients + nnz cache for one macroblock: per block nothing / DC only / full, as the dispatchers distinguish them"""
+    coeffs = np.zeros((48, 16), np.int32)
+    nnzc = np.zeros(120, np.uint8)
+    amp = 600 << (bits - 8)
+    if which == 2:
+        for i in range(0, 16, 4):
+            kind = int(rng.integers(0, 3))
+            if kind == 1:
+                coeffs[i, 0] = rng.integers(-amp, amp); nnzc[scan8(i)] = 1
+            elif kind == 2:
+                coeffs[i:i + 4] = rng.integers(-amp // 4, amp // 4, size=(4, 16)); nnzc[scan8(i)] = rng.integers(2, 16)
+        return coeffs, nnzc
+    blocks = range(16) if which < 2 else [16 + 16 * p + k for p in (0, 1) for k in range(8 if which == 4 else 4)]
+    for i in blocks:
+        e = i + 4 if (which == 4 and (i & 15) >= 4) else i
+        kind = int(rng.integers(0, 4))
+        if kind == 1:                           # DC only; add16 takes the dc path for nnz == 1, the intra / chroma dispatchers for nnz == 0
+            coeffs[i, 0] = rng.integers(-amp, amp)
+            nnzc[scan8(e)] = 1 if which == 0 else 0
+        elif kind == 2:
+            coeffs[i] = rng.integers(-amp // 4, amp // 4, size=16); nnzc[scan8(e)] = rng.integers(1, 16)
+        elif kind == 3 and which == 0:
+            nnzc[scan8(e)] = 1                  # nnz == 1 with a zero DC: the full transform of a zero block
+    return coeffs, nnzc
+
+
+def compare(a, b, bits, seed=0):
+    """every entry through callee a and callee b on identical inputs; outputs AND clobbered inputs must agree"""
+    rng = np.random.default_rng(seed + bits)
+    top = (1 << bits) - 1
+    n = 0
+    pixels = lambda shape: rng.integers(0, top + 1, size=shape).astype(np.uint16)
+    # single-block transforms
+    for which in range(4):
+        for it in range(12):
+            nco = 64 if which in (1, 3) else 16
+            blk = rng.integers(-(2000 << (bits - 8)), 2000 << (bits - 8), size=nco).astype(np.int32)
+            if it == 0:
+                blk[:] = rng.integers(-(1 << 20), 1 << 20, size=nco)
+            pix = pixels((8, 32))
+            res = []
+            for c in (a, b):
+                p, k = pix.copy(), blk.copy()
+                c.h264_hbd_idct(bits, which, vp(p, 16), vp(k), 64)
+                res.append((p, k))
+            assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]), ("idct", bits, which, it); n += 1
+    # per-macroblock dispatchers (which 4 = add8_422)
+    for which in range(5):
+        bo = 2 * (block_offsets_422(24) if which == 4 else block_offsets(48, 24))        # byte offsets of 16-bit samples
+        for it in range(8):
+            coeffs, nnzc = residual(rng, which, bits)
+            yp, cb, cr = pixels((16, 48)), pixels((16, 24)), pixels((16, 24))
+            res = []
+            for c in (a, b):
+                y2, b2, r2, k = yp.copy(), cb.copy(), cr.copy(), coeffs.copy()
+                d2 = (C.c_void_p * 2)(b2.ctypes.data + 16, r2.ctypes.data + 16)
+                c.h264_hbd_idct_mb(bits, which, vp(y2, 32), d2, vp(bo), vp(k), 96 if which < 3 else 48, vp(nnzc))
+                res.append((y2, b2, r2, k))
+            for u, v in zip(*res):
+                assert np.array_equal(u, v), ("idct_mb", bits, which, it)
+            n += 1
+    # DC transforms
+    for kind in range(3):
+        for q in [777, 1, 4000] + [int(v) for v in rng.integers(1, 4000, size=10)]:
+            inp = rng.integers(-3000 << (bits - 8), 3000 << (bits - 8), size=16).astype(np.int32)
+            blk = rng.integers(-3000 << (bits - 8), 3000 << (bits - 8), size=256).astype(np.int32)
+            res = []
+            for c in (a, b):
+                o, i2 = blk.copy(), inp.copy()
+                c.h264_hbd_dc_dequant(bits, kind, vp(o), vp(i2), q)
+                res.append((o, i2))
+            assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and not np.array_equal(res[0][0], blk), ("dc", bits, kind, q); n += 1
+    # bypass add
+    for w8 in (0, 1):
+        nn = 8 if w8 else 4
+        blk = rng.integers(-300 << (bits - 8), 300 << (bits - 8), size=nn * nn).astype(np.int32)
+        pix = pixels((8, 16))
+        res = []
+        for c in (a, b):
+            p, k = pix.copy(), blk.copy()
+            c.h264_hbd_add_pixels_clear(bits, w8, vp(p), vp(k), 32)
+            res.append((p, k))
+        assert np.array_equal(res[0][0], res[1][0]) and not res[0][1].any() and not res[1][1].any(); n += 1
+    # weighted prediction
+    for widx in range(4):
+        for it in range(6):
+            ld, w, off, ws = int(rng.integers(0, 8)), int(rng.integers(-128, 128)), int(rng.integers(-128, 128)), int(rng.integers(-128, 128))
+            hgt = int(rng.choice([2, 4, 8, 16]))
+            pix, src = pixels((16, 32)), pixels((16, 32))
+            res = []
+            for c in (a, b):
+                p, q = pix.copy(), pix.copy()
+                c.h264_hbd_weight(bits, widx, vp(p), 64, hgt, ld, w, off)
+                c.h264_hbd_biweight(bits, widx, vp(q), vp(src), 64, hgt, ld, w, ws, off)
+                res.append((p, q))
+            assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]), ("weight", bits, widx, it); n += 1
+    # loop filters
+    for which in range(16):
+        for it in range(10):
+            base = rng.integers(0, top + 1)
+            pix = np.clip(base + rng.integers(-10 << (bits - 8), (10 << (bits - 8)) + 1, size=(24, 32)), 0, top).astype(np.uint16)
+            alpha, beta = int(rng.integers(1, 200)), int(rng.integers(1, 19))
+            tc0 = rng.integers(-1, 12, size=4).astype(np.int8)
+            res = []
+            for c in (a, b):
+                p = pix.copy()
+                c.h264_hbd_loop_filter(bits, which, vp(p, 2 * (4 * 32 + 8)), 64, alpha, beta, vp(tc0))
+                res.append(p)
+            assert np.array_equal(res[0], res[1]), ("loop", bits, which, it); n += 1
+    # motion compensation
+    for avg in (0, 1):
+        for sidx in range(3 if avg else 4):
+            nn = 16 >> sidx
+            for mc in range(16):
+                src, dst = pixels((nn + 8, 48)), pixels((nn, 48))
+                if mc == 10:
+                    src[:] = top                 # the centre position at full scale: the largest intermediate sums
+                res = []
+                for c in (a, b):
+                    d = dst.copy()
+                    c.h264_hbd_qpel(bits, avg, sidx, mc, vp(d, 8), vp(src, 2 * (3 * 48 + 8)), 96)
+                    res.append(d)
+                assert np.array_equal(res[0], res[1]), ("qpel", bits, avg, sidx, mc); n += 1
+        for widx in range(3):
+            for (fx, fy) in ((0, 0), (3, 0), (0, 5), (7, 7), (1, 6)):
+                h = 8 >> widx
+                src, dst = pixels((h + 2, 32)), pixels((h, 32))
+                res = []
+                for c in (a, b):
+                    d = dst.copy()
+                    c.h264_hbd_chroma(bits, avg, widx, vp(d), vp(src, 4), 64, h, fx, fy)
+                    res.append(d)
+                assert np.array_equal(res[0], res[1]), ("chroma", bits, avg, widx, fx, fy); n += 1
+    return n

@@ -129,6 +129,12 @@ struct Stage {
 
 }  // namespace avb
 
+namespace avb {      // slots_hbd.cu: the 9 / 10-bit instances
+void h264dsp_init_hbd(H264DSPContext *c, int bits, int chroma_format_idc);
+void h264qpel_init_hbd(H264QpelContext *c, int bits);
+void h264chroma_init_hbd(H264ChromaContext *c, int bits);
+}
+
 using namespace avb;
 
 // batched launchers reused as "batch of one"
@@ -419,7 +425,8 @@ void ff_me_cmp_init_cuda(MECmpContext *c)
 
 void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc)
 {
-    if (bit_depth != 8) return;                                           // the 9 / 10-bit templates stay on the C path
+    if (bit_depth == 9 || bit_depth == 10) { h264dsp_init_hbd(c, bit_depth, chroma_format_idc); return; }
+    if (bit_depth != 8) return;                                           // other depths do not exist for H.264 here (h264dsp.c:126-136 maps them to 8)
     const bool c420 = chroma_format_idc <= 1;                             // the reference's own test, h264dsp.c:81-122
     c->weight_h264_pixels_tab[0] = slot_weight<0>; c->weight_h264_pixels_tab[1] = slot_weight<1>;
     c->weight_h264_pixels_tab[2] = slot_weight<2>; c->weight_h264_pixels_tab[3] = slot_weight<3>;
@@ -447,6 +454,7 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
 
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth)
 {
+    if (bit_depth == 9 || bit_depth == 10) { h264qpel_init_hbd(c, bit_depth); return; }
     if (bit_depth != 8) return;
     fill_qpel<0, 0>(c->put_h264_qpel_pixels_tab[0]); fill_qpel<0, 1>(c->put_h264_qpel_pixels_tab[1]);
     fill_qpel<0, 2>(c->put_h264_qpel_pixels_tab[2]); fill_qpel<0, 3>(c->put_h264_qpel_pixels_tab[3]);
@@ -456,6 +464,7 @@ void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth)
 
 void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth)
 {
+    if (bit_depth == 9 || bit_depth == 10) { h264chroma_init_hbd(c, bit_depth); return; }
     if (bit_depth != 8) return;
     c->put_h264_chroma_pixels_tab[0] = slot_chroma<0, 0>; c->put_h264_chroma_pixels_tab[1] = slot_chroma<0, 1>; c->put_h264_chroma_pixels_tab[2] = slot_chroma<0, 2>;
     c->avg_h264_chroma_pixels_tab[0] = slot_chroma<1, 0>; c->avg_h264_chroma_pixels_tab[1] = slot_chroma<1, 1>; c->avg_h264_chroma_pixels_tab[2] = slot_chroma<1, 2>;

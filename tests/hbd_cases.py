@@ -147,3 +147,76 @@ def compare(a, b, bits, seed=0):
                     res.append(d)
                 assert np.array_equal(res[0], res[1]), ("chroma", bits, avg, widx, fx, fy); n += 1
     return n
+
+
+class TableCallee:
+    """the oracle's h264_hbd_* entry names served by the product's tables: ff_h264dsp_init_cuda(c, bits, idc), ff_h264qpel_init_cuda(c, bits),
+    ff_h264chroma_init_cuda(c, bits) of `lib` (the product library on a GPU, or the host simulation)"""
+
+    def __init__(self, lib):
+        from libav_b200 import tables
+        self.t = {}
+        for bits in (9, 10):
+            d1, d2, q, ch = tables.H264DSPContext(), tables.H264DSPContext(), tables.H264QpelContext(), tables.H264ChromaContext()
+            lib.ff_h264dsp_init_cuda(C.byref(d1), bits, 1); lib.ff_h264dsp_init_cuda(C.byref(d2), bits, 2)
+            lib.ff_h264qpel_init_cuda(C.byref(q), bits); lib.ff_h264chroma_init_cuda(C.byref(ch), bits)
+            assert d1.h264_idct_add and d2.h264_idct_add8 and q.put_h264_qpel_pixels_tab[0][0] and ch.put_h264_chroma_pixels_tab[0], bits
+            self.t[bits] = (d1, d2, q, ch)
+
+    @staticmethod
+    def u8(v):
+        return C.cast(v, C.POINTER(C.c_uint8))
+
+    @staticmethod
+    def i16(v):
+        return C.cast(v, C.POINTER(C.c_int16))
+
+    def h264_hbd_idct(self, bits, which, dst, block, stride):
+        d = self.t[bits][0]
+        (d.h264_idct_add, d.h264_idct8_add, d.h264_idct_dc_add, d.h264_idct8_dc_add)[which](self.u8(dst), self.i16(block), stride)
+
+    def h264_hbd_idct_mb(self, bits, which, dst, dst2, bo, block, stride, nnzc):
+        d = self.t[bits][1 if which == 4 else 0]
+        bo, nn = C.cast(bo, C.POINTER(C.c_int)), self.u8(nnzc)
+        if which < 3:
+            (d.h264_idct_add16, d.h264_idct_add16intra, d.h264_idct8_add4)[which](self.u8(dst), bo, self.i16(block), stride, nn)
+        else:
+            u8p = C.POINTER(C.c_uint8)
+            d.h264_idct_add8((u8p * 2)(C.cast(dst2[0], u8p), C.cast(dst2[1], u8p)), bo, self.i16(block), stride, nn)
+
+    def h264_hbd_dc_dequant(self, bits, kind, out, inp, qmul):
+        if kind == 0:
+            self.t[bits][0].h264_luma_dc_dequant_idct(self.i16(out), self.i16(inp), qmul)
+        else:
+            self.t[bits][kind - 1].h264_chroma_dc_dequant_idct(self.i16(out), qmul)
+
+    def h264_hbd_add_pixels_clear(self, bits, w8, dst, block, stride):
+        d = self.t[bits][0]
+        (d.h264_add_pixels8_clear if w8 else d.h264_add_pixels4_clear)(self.u8(dst), self.i16(block), stride)
+
+    def h264_hbd_weight(self, bits, widx, block, stride, height, ld, w, off):
+        self.t[bits][0].weight_h264_pixels_tab[widx](self.u8(block), stride, height, ld, w, off)
+
+    def h264_hbd_biweight(self, bits, widx, dst, src, stride, height, ld, wd, ws, off):
+        self.t[bits][0].biweight_h264_pixels_tab[widx](self.u8(dst), self.u8(src), stride, height, ld, wd, ws, off)
+
+    def h264_hbd_loop_filter(self, bits, which, pix, stride, alpha, beta, tc0):
+        d = self.t[bits][1 if which >= 12 else 0]
+        i8 = C.cast(tc0, C.POINTER(C.c_int8))
+        lf = {0: d.h264_v_loop_filter_luma, 1: d.h264_h_loop_filter_luma, 4: d.h264_v_loop_filter_chroma, 5: d.h264_h_loop_filter_chroma, 12: d.h264_h_loop_filter_chroma,
+              8: d.h264_h_loop_filter_luma_mbaff, 10: d.h264_h_loop_filter_chroma_mbaff, 14: d.h264_h_loop_filter_chroma_mbaff}
+        lfi = {2: d.h264_v_loop_filter_luma_intra, 3: d.h264_h_loop_filter_luma_intra, 6: d.h264_v_loop_filter_chroma_intra, 7: d.h264_h_loop_filter_chroma_intra,
+               13: d.h264_h_loop_filter_chroma_intra, 9: d.h264_h_loop_filter_luma_mbaff_intra, 11: d.h264_h_loop_filter_chroma_mbaff_intra,
+               15: d.h264_h_loop_filter_chroma_mbaff_intra}
+        if which in lf:
+            lf[which](self.u8(pix), stride, alpha, beta, i8)
+        else:
+            lfi[which](self.u8(pix), stride, alpha, beta)
+
+    def h264_hbd_qpel(self, bits, avg, sidx, mc, dst, src, stride):
+        q = self.t[bits][2]
+        (q.avg_h264_qpel_pixels_tab if avg else q.put_h264_qpel_pixels_tab)[sidx][mc](self.u8(dst), self.u8(src), stride)
+
+    def h264_hbd_chroma(self, bits, avg, widx, dst, src, stride, h, x, y):
+        ch = self.t[bits][3]
+        (ch.avg_h264_chroma_pixels_tab if avg else ch.put_h264_chroma_pixels_tab)[widx](self.u8(dst), self.u8(src), stride, h, x, y)

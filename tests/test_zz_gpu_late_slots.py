@@ -84,3 +84,10 @@ def test_sws_range_conversion_frames(gpu, checker):
         ctx.close()
         n += 1
     assert n > 400 and gpu.last_error() == ""
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+def test_h264_high_bit_depth_slots(gpu, checker, bits):
+    import hbd_cases
+    assert hbd_cases.compare(hbd_cases.TableCallee(gpu.lib), checker, bits, seed=3) > 400
+    assert gpu.last_error() == ""

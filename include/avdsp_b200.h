@@ -80,6 +80,11 @@ int ff_simple_idct_batch_cuda(int mode, int16_t *blocks, uint8_t *frame, const u
 int ff_pixels_clamped_batch_cuda(int mode, const int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,
                                  ptrdiff_t stride, size_t n, int tiles_per_row, void *stream);
 
+/* ff_simple_idct_put_10 / _add_10 / _10 (libavcodec/simple_idct_template.c, BIT_DEPTH 10; idctdsp.c:151-155) over n blocks: mode 0 put, 1 add,
+ * 2 in place; block i -> the 8 x 8 16-bit samples at frame + dst_off[i] (bytes), rows `stride` bytes apart.  The blocks are left as the C
+ * functions leave them.  Functional path for 10-bit content (thread per block), not tuned like the 8-bit kernel. */
+int ff_simple_idct10_batch_cuda(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride, size_t n, void *stream);
+
 /* BlockDSPContext.clear_block / clear_blocks over n_blocks * 64 coefficients (blockdsp.c:29-37) and
  * fill_block_tab[w16 ? 0 : 1] over n records (blockdsp.c:39-58). */
 int ff_clear_blocks_batch_cuda(int16_t *blocks, size_t n_blocks, void *stream);
@@ -406,7 +411,8 @@ int  sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int d
 /* One more arch behind ff_idctdsp_init()'s dispatch (libavcodec/idctdsp.c:183-188; same shape as
  * ff_idctdsp_init_x86, libavcodec/idctdsp.h:109-110).  AVCodecContext is opaque to this library, so the
  * two fields the hook needs are passed by value (INTEGRATION.md shows the one-line caller).
- * Only idct_algo FF_IDCT_SIMPLE/FF_IDCT_AUTO at 8 bit is taken over; anything else leaves `c` untouched. */
+ * Taken over: idct_algo FF_IDCT_SIMPLE / FF_IDCT_AUTO at 8 bit, and bits_per_raw_sample 10 (ff_simple_idct_*_10 whatever idct_algo says,
+ * idctdsp.c:151-155); anything else leaves `c` untouched. */
 void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
 void ff_blockdsp_init_cuda(BlockDSPContext *c);   /* libavcodec/blockdsp.c:60-74 */
 /* libavcodec/fdctdsp.c:27-50 (same shape as ff_fdctdsp_init_x86): dct_algo FF_DCT_AUTO / FF_DCT_INT -> islow,

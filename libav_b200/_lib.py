@@ -57,6 +57,7 @@ PROTOTYPES = {
     "avb200_event_sync": (i32, [vp]),
     "avb200_event_elapsed_ms": (C.c_float, [vp, vp]),
     "ff_simple_idct_batch_cuda": (i32, [i32, vp, vp, vp, pd, sz, i32, i32, vp]),
+    "ff_simple_idct10_batch_cuda": (i32, [i32, vp, vp, vp, pd, sz, vp]),
     "ff_pixels_clamped_batch_cuda": (i32, [i32, vp, vp, vp, pd, sz, i32, vp]),
     "ff_clear_blocks_batch_cuda": (i32, [vp, sz, vp]),
     "ff_fill_blocks_batch_cuda": (i32, [vp, vp, vp, pd, i32, i32, sz, vp]),

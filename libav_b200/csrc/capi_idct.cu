@@ -213,11 +213,20 @@ void slot_fill8(uint8_t *b, uint8_t v, ptrdiff_t ls, int h) { slot_fill(b, v, ls
 
 }  // namespace
 
+namespace avb { void idct10_install(IDCTDSPContext *c); }      // idct10.cu
+
 extern "C" {
 
 void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, unsigned high_bit_depth)
 {
-    if (high_bit_depth || bits_per_raw_sample > 8) return;              // 9/10-bit: not taken over (yet)
+    if (bits_per_raw_sample == 10) {                                    // idctdsp.c:151-155: the 10-bit simple IDCT whatever idct_algo says;
+        idct10_install(c);                                              // the three pixel-clamp entries are the 8-bit functions at every depth (:175-177)
+        c->put_pixels_clamped        = slot_put_pixels_clamped;
+        c->put_signed_pixels_clamped = slot_put_signed_pixels_clamped;
+        c->add_pixels_clamped        = slot_add_pixels_clamped;
+        return;
+    }
+    if (high_bit_depth || bits_per_raw_sample > 8) return;              // 9 / 12-bit ...: the reference falls through to its 8-bit table there; not taken over
     c->put_pixels_clamped        = slot_put_pixels_clamped;
     c->put_signed_pixels_clamped = slot_put_signed_pixels_clamped;
     c->add_pixels_clamped        = slot_add_pixels_clamped;

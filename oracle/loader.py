@@ -19,6 +19,7 @@ API = {
     "simple_idct_put": (None, [vp, pd, vp]),
     "simple_idct_add": (None, [vp, pd, vp]),
     "simple_idct": (None, [vp]),
+    "simple_idct10": (None, [i32, vp, pd, vp]),
     "put_pixels_clamped": (None, [vp, vp, pd]),
     "put_signed_pixels_clamped": (None, [vp, vp, pd]),
     "add_pixels_clamped": (None, [vp, vp, pd]),

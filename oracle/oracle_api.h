@@ -38,6 +38,10 @@ void ORC(clear_block)(int16_t *block);
 void ORC(clear_blocks)(int16_t *blocks);
 void ORC(fill_block)(int w16, uint8_t *block, uint8_t value, ptrdiff_t stride, int h);
 
+/* the 10-bit instance (ff_simple_idct_put_10 / _add_10 / _10, simple_idct_template.c BIT_DEPTH == 10: 16-bit samples, `stride` in bytes),
+ * what ff_idctdsp_init installs for bits_per_raw_sample == 10 (idctdsp.c:151-155).  mode 0 put, 1 add, 2 in place (dst ignored) */
+void ORC(simple_idct10)(int mode, uint8_t *dst, ptrdiff_t stride, int16_t *block);
+
 /* batch driver used for parity at scale and for CPU timing: block i -> frame + dst_off[i].
  * mode 0 = idct_put, 1 = idct_add, 2 = idct (in place, frame ignored).
  * nthreads > 1 splits the block range over pthreads. The blocks array is clobbered exactly

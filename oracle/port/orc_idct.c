@@ -165,3 +165,56 @@ void orc_idct_batch(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *d
     }
     if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
 }
+
+/* ---- the 10-bit instance: simple_idct_template.c with BIT_DEPTH 10 (:63-78: 17-bit constants, ROW_SHIFT 15, COL_SHIFT 20, DC_SHIFT 1,
+ * plain int multiplies); 16-bit samples clipped to 10 bits.  Same structure as the 8-bit functions: the DC-only row shortcut
+ * (row[0] << 1 broadcast, :94-106), int16 write-back between the passes, column rounding folded into the DC term (:176). */
+static void idct10_rows(int16_t *b)
+{
+    enum { W1 = 90901, W2 = 85627, W3 = 77062, W4 = 65535, W5 = 51491, W6 = 35468, W7 = 18081 };
+    for (int r = 0; r < 8; r++) {
+        int16_t *row = b + 8 * r;
+        if (!(row[1] | row[2] | row[3] | row[4] | row[5] | row[6] | row[7])) {
+            const int16_t v = (int16_t)((row[0] * 2) & 0xffff);
+            for (int k = 0; k < 8; k++) row[k] = v;
+            continue;
+        }
+        int a0 = W4 * row[0] + (1 << 14), a1 = a0, a2 = a0, a3 = a0;
+        a0 += W2 * row[2]; a1 += W6 * row[2]; a2 -= W6 * row[2]; a3 -= W2 * row[2];
+        int b0 = W1 * row[1] + W3 * row[3], b1 = W3 * row[1] - W7 * row[3], b2 = W5 * row[1] - W1 * row[3], b3 = W7 * row[1] - W5 * row[3];
+        if (row[4] | row[5] | row[6] | row[7]) {
+            a0 += W4 * row[4] + W6 * row[6]; a1 += -W4 * row[4] - W2 * row[6]; a2 += -W4 * row[4] + W2 * row[6]; a3 += W4 * row[4] - W6 * row[6];
+            b0 += W5 * row[5] + W7 * row[7]; b1 += -W1 * row[5] - W5 * row[7]; b2 += W7 * row[5] + W3 * row[7]; b3 += W3 * row[5] - W1 * row[7];
+        }
+        row[0] = (int16_t)((a0 + b0) >> 15); row[7] = (int16_t)((a0 - b0) >> 15); row[1] = (int16_t)((a1 + b1) >> 15); row[6] = (int16_t)((a1 - b1) >> 15);
+        row[2] = (int16_t)((a2 + b2) >> 15); row[5] = (int16_t)((a2 - b2) >> 15); row[3] = (int16_t)((a3 + b3) >> 15); row[4] = (int16_t)((a3 - b3) >> 15);
+    }
+}
+static void idct10_col(const int16_t *col, int out[8])
+{
+    enum { W1 = 90901, W2 = 85627, W3 = 77062, W4 = 65535, W5 = 51491, W6 = 35468, W7 = 18081 };
+    int a0 = W4 * (col[0] + ((1 << 19) / W4)), a1 = a0, a2 = a0, a3 = a0;
+    a0 += W2 * col[16]; a1 += W6 * col[16]; a2 -= W6 * col[16]; a3 -= W2 * col[16];
+    int b0 = W1 * col[8] + W3 * col[24], b1 = W3 * col[8] - W7 * col[24], b2 = W5 * col[8] - W1 * col[24], b3 = W7 * col[8] - W5 * col[24];
+    a0 += W4 * col[32]; a1 -= W4 * col[32]; a2 -= W4 * col[32]; a3 += W4 * col[32];
+    b0 += W5 * col[40]; b1 -= W1 * col[40]; b2 += W7 * col[40]; b3 += W3 * col[40];
+    a0 += W6 * col[48]; a1 -= W2 * col[48]; a2 += W2 * col[48]; a3 -= W6 * col[48];
+    b0 += W7 * col[56]; b1 -= W5 * col[56]; b2 += W3 * col[56]; b3 -= W1 * col[56];
+    out[0] = (a0 + b0) >> 20; out[1] = (a1 + b1) >> 20; out[2] = (a2 + b2) >> 20; out[3] = (a3 + b3) >> 20;
+    out[4] = (a3 - b3) >> 20; out[5] = (a2 - b2) >> 20; out[6] = (a1 - b1) >> 20; out[7] = (a0 - b0) >> 20;
+}
+void orc_simple_idct10(int mode, uint8_t *dst, ptrdiff_t stride, int16_t *block)
+{
+    uint16_t *d = (uint16_t *)dst;
+    const ptrdiff_t st = stride / 2;
+    idct10_rows(block);
+    for (int i = 0; i < 8; i++) {
+        int o[8];
+        idct10_col(block + i, o);
+        for (int k = 0; k < 8; k++) {
+            if (mode == 2) { block[i + 8 * k] = (int16_t)o[k]; continue; }
+            int v = mode == 1 ? d[i + k * st] + o[k] : o[k];
+            d[i + k * st] = (uint16_t)(v < 0 ? 0 : v > 1023 ? 1023 : v);
+        }
+    }
+}

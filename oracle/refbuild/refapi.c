@@ -34,7 +34,7 @@
 #include "libswscale/swscale_internal.h"
 
 static pthread_once_t once = PTHREAD_ONCE_INIT;
-static IDCTDSPContext idsp;
+static IDCTDSPContext idsp, idsp10;      /* bits_per_raw_sample 8 and 10 */
 static FDCTDSPContext fdsp_islow, fdsp_ifast;
 static BlockDSPContext bdsp;
 static MECmpContext mecc;
@@ -54,6 +54,9 @@ static void init_all(void)
     avctx->flags               = AV_CODEC_FLAG_BITEXACT;
     avctx->dct_algo            = FF_DCT_INT;
     ff_idctdsp_init(&idsp, avctx);
+    avctx->bits_per_raw_sample = 10;
+    ff_idctdsp_init(&idsp10, avctx);
+    avctx->bits_per_raw_sample = 8;
     ff_fdctdsp_init(&fdsp_islow, avctx);
     avctx->dct_algo = FF_DCT_FASTINT;
     ff_fdctdsp_init(&fdsp_ifast, avctx);
@@ -74,6 +77,8 @@ static void init_all(void)
 void ref_simple_idct_put(uint8_t *d, ptrdiff_t s, int16_t *b) { INIT(); idsp.idct_put(d, s, b); }
 void ref_simple_idct_add(uint8_t *d, ptrdiff_t s, int16_t *b) { INIT(); idsp.idct_add(d, s, b); }
 void ref_simple_idct(int16_t *b) { INIT(); idsp.idct(b); }
+void ref_simple_idct10(int mode, uint8_t *d, ptrdiff_t s, int16_t *b)
+{ INIT(); if (mode == 0) idsp10.idct_put(d, s, b); else if (mode == 1) idsp10.idct_add(d, s, b); else idsp10.idct(b); }
 void ref_put_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.put_pixels_clamped(b, p, s); }
 void ref_put_signed_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.put_signed_pixels_clamped(b, p, s); }
 void ref_add_pixels_clamped(const int16_t *b, uint8_t *p, ptrdiff_t s) { INIT(); idsp.add_pixels_clamped(b, p, s); }

@@ -17,10 +17,10 @@ LIB = os.path.join(HERE, "libslots_hostsim.so")
 @pytest.fixture(scope="module")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
-    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp")]
+    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp"), os.path.join(HERE, "idct10_hostsim.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h")] + \
         [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h", "sws_slots.cu", "sws_dev.cuh",
-                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh")] + \
+                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu")] + \
         [os.path.join(root, "include", f) for f in ("avdsp_b200.h", "avdsp_b200_tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", os.path.join(HERE, "shim"), "-Wno-unknown-pragmas",
@@ -118,3 +118,22 @@ def test_h264_high_bit_depth_slots(sim, refo, bits):
     import hbd_cases
     assert hbd_cases.compare(hbd_cases.TableCallee(sim), refo, bits, seed=2) > 400
     assert sim.avb200_last_error().decode() == ""
+
+
+def test_simple_idct10(sim, refo):
+    """the 10-bit simple IDCT (libav_b200/csrc/idct10.cu, host-compiled): the three table entries and the batched entry point"""
+    import numpy as np
+    import idct10_cases
+    from libav_b200 import tables
+    t = tables.IDCTDSPContext()
+    sim.hostsim_idctdsp_init10(C.byref(t))
+    assert idct10_cases.slot_cases(t, refo) == 360
+    sim.ff_simple_idct10_batch_cuda.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_size_t, C.c_void_p]
+
+    def run_batch(mode, blk, frame, off):          # host simulation: "device memory" is host memory
+        assert sim.ff_simple_idct10_batch_cuda(mode, blk.ctypes.data, frame.ctypes.data, off.ctypes.data, frame.strides[0], len(blk), None) == 0
+        return blk, frame
+    for mode in range(3):
+        idct10_cases.batch_case(run_batch, refo, mode)
+    assert sim.ff_simple_idct10_batch_cuda(3, None, None, None, 0, 0, None) == -1
+    sim.avb200_clear_error()

@@ -91,3 +91,31 @@ def test_h264_high_bit_depth_slots(gpu, checker, bits):
     import hbd_cases
     assert hbd_cases.compare(hbd_cases.TableCallee(gpu.lib), checker, bits, seed=3) > 400
     assert gpu.last_error() == ""
+
+
+def test_simple_idct10(gpu, checker):
+    """ff_idctdsp_init_cuda(c, idct_algo, 10, 1): the 10-bit simple IDCT entries, and ff_simple_idct10_batch_cuda on device buffers"""
+    import numpy as np
+    import idct10_cases
+    from libav_b200 import tables
+    lib = gpu.lib
+    t = tables.IDCTDSPContext()
+    lib.ff_idctdsp_init_cuda(C.byref(t), 0, 10, 1)
+    assert idct10_cases.slot_cases(t, checker) == 360
+    assert t.put_pixels_clamped and t.add_pixels_clamped
+
+    def run_batch(mode, blk, frame, off):
+        bufs = []
+        for a in (blk, frame, off):
+            d = lib.avb200_malloc(a.nbytes)
+            assert d and lib.avb200_memcpy_h2d(d, a.ctypes.data, a.nbytes, None) == 0
+            bufs.append(d)
+        assert lib.ff_simple_idct10_batch_cuda(mode, bufs[0], bufs[1], bufs[2], frame.strides[0], len(blk), None) == 0
+        assert lib.avb200_memcpy_d2h(blk.ctypes.data, bufs[0], blk.nbytes, None) == 0 and lib.avb200_memcpy_d2h(frame.ctypes.data, bufs[1], frame.nbytes, None) == 0
+        assert lib.avb200_device_sync() == 0
+        for d in bufs:
+            lib.avb200_free(d)
+        return blk, frame
+    for mode in range(3):
+        idct10_cases.batch_case(run_batch, checker, mode)
+    assert gpu.last_error() == ""

@@ -175,13 +175,17 @@ template <> struct Fill7<-1> { static void go(H264PredContext *) {} };
 }  // namespace
 }  // namespace avb
 
+namespace avb { void h264pred_init_hbd(H264PredContext *h, int bits); }
+
 using namespace avb;
 
 // libavcodec/h264pred.h:112-113 / the per-arch hooks :114-123.  Takes over codec H.264 (AV_CODEC_ID_H264 = 27), 8 bit,
-// chroma_format_idc <= 1; anything else leaves the table as the C init filled it.
+// chroma_format_idc <= 1 -- and the 9 / 10-bit instances through h264pred_hbd.cu; anything else leaves the table as the C init filled it.
 extern "C" void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc)
 {
-    if (!h || codec_id != 27 || bit_depth != 8 || chroma_format_idc > 1) return;
+    if (!h || codec_id != 27 || chroma_format_idc > 1) return;
+    if (bit_depth == 9 || bit_depth == 10) { h264pred_init_hbd(h, bit_depth); return; }      // h264pred_hbd.cu
+    if (bit_depth != 8) return;
     Fill12<11>::go(h); Fill11<10>::go(h); Fill7<6>::go(h);
     h->pred4x4_add[0] = s_add4<0>;   h->pred4x4_add[1] = s_add4<1>;
     h->pred8x8l_add[0] = s_add8l<0>; h->pred8x8l_add[1] = s_add8l<1>;

@@ -1,0 +1,247 @@
+// libav_b200/csrc/h264pred_hbd.cu -- the 9 / 10-bit instances of H264PredContext (libavcodec/h264pred.h:91-110; h264pred_template.c with
+// BIT_DEPTH > 8: uint16 samples, int32 residual in the lossless *_add functions) for codec H.264, 4:2:0, as per-call table slots.
+// Same edge-array formulas as h264pred.cuh (its directional expression is reused as is); what the depth changes: the DC_128 family
+// predicts 1 << (bits - 1), plane prediction clips to `bits` bits, the lossless running sums wrap in 16 bits.  A slot gathers the
+// neighbours the C function of that mode reads (host pointers, strides in bytes), runs one small kernel and scatters the block back.
+// Every thread derives its sample from the raw neighbours on its own (no shared memory, no barrier): the file also compiles for
+// tests/hostsim/.  There is no batched high-bit-depth intra path yet.
+#include "h264pred.cuh"
+#include "scratch.h"
+#include "../../include/avdsp_b200.h"
+#include <string.h>
+
+namespace avb {
+
+struct PredJobH {
+    int bits, tab, mode, has_tl, has_tr;   // tab 0 pred4x4, 1 pred8x8l, 2 pred8x8, 3 pred16x16; 4.. lossless add kinds
+    uint16_t top[16], left[16], corner, pad;
+    int nblocks;
+    int off[16];                           // lossless 8x8 / 16x16: block offsets (samples) inside the staged rectangle (pitch 32)
+};
+
+__device__ inline void hbd_edges(IntraEdges &e, const PredJobH &j)
+{
+    const uint16_t *t = j.top, *l = j.left;
+    const int c = j.corner;
+    if (j.tab == 0 || j.tab == 4) {                        // raw edges of a 4x4 block
+        e.t[0] = e.l[0] = c;
+        for (int i = 0; i < 8; i++) e.t[i + 1] = t[i];
+        for (int i = 0; i < 4; i++) e.l[i + 1] = l[i];
+        return;
+    }
+    // 8x8 luma: low-pass filtered with the availability rules of PREDICT_8x8_LOAD_* (h264pred_template.c:840-875)
+    e.t[1] = ip_f3(j.has_tl ? c : t[0], t[0], t[1]);
+    for (int i = 1; i < 7; i++) e.t[i + 1] = ip_f3(t[i - 1], t[i], t[i + 1]);
+    e.t[8] = ip_f3(j.has_tr ? t[8] : t[7], t[7], t[6]);
+    if (j.has_tr) {
+        for (int i = 8; i < 15; i++) e.t[i + 1] = ip_f3(t[i - 1], t[i], t[i + 1]);
+        e.t[16] = (t[14] + 3 * t[15] + 2) >> 2;
+    } else {
+        for (int i = 8; i < 16; i++) e.t[i + 1] = t[7];
+    }
+    e.l[1] = ip_f3(j.has_tl ? c : l[0], l[0], l[1]);
+    for (int i = 1; i < 7; i++) e.l[i + 1] = ip_f3(l[i - 1], l[i], l[i + 1]);
+    e.l[8] = (l[6] + 3 * l[7] + 2) >> 2;
+    e.t[0] = e.l[0] = ip_f3(l[0], c, t[0]);
+}
+
+// pred8x8 (chroma, n = 8, modes 0..10) and pred16x16 (n = 16, modes 0..6) from raw edges (h264pred_template.c:330-797)
+__device__ inline int hbd_big_sample(const PredJobH &j, int n, int x, int y)
+{
+    const int mode = j.mode, mid = 1 << (j.bits - 1);
+    if (mode == 1) return j.left[y];
+    if (mode == 2) return j.top[x];
+    if (mode == 6) return mid;
+    if (mode == 3) {
+        const int h = n / 2;
+        int H = 0, V = 0;
+        for (int k = 1; k <= h; k++) {
+            const int tl = h - 1 - k < 0 ? j.corner : j.top[h - 1 - k], ll = h - 1 - k < 0 ? j.corner : j.left[h - 1 - k];
+            H += k * (j.top[h - 1 + k] - tl); V += k * (j.left[h - 1 + k] - ll);
+        }
+        if (n == 8) { H = (17 * H + 16) >> 5; V = (17 * V + 16) >> 5; } else { H = (5 * H + 32) >> 6; V = (5 * V + 32) >> 6; }
+        const int a = 16 * (j.left[n - 1] + j.top[n - 1] + 1) - (h - 1) * (V + H);
+        return min(max((a + x * H + y * V) >> 5, 0), (1 << j.bits) - 1);
+    }
+    int st[4] = { 0, 0, 0, 0 }, sl[4] = { 0, 0, 0, 0 };
+    for (int i = 0; i < n; i++) { st[i >> 2] += j.top[i]; sl[i >> 2] += j.left[i]; }
+    if (n == 16) {
+        const int T = st[0] + st[1] + st[2] + st[3], L = sl[0] + sl[1] + sl[2] + sl[3];
+        return mode == 0 ? (T + L + 16) >> 5 : mode == 4 ? (L + 8) >> 4 : (T + 8) >> 4;
+    }
+    const int q = (x >> 2) + 2 * (y >> 2), t0 = st[0], t1 = st[1], l0 = sl[0], l1 = sl[1];
+    const int dc_q[4] = { (t0 + l0 + 4) >> 3, (t1 + 2) >> 2, (l1 + 2) >> 2, (t1 + l1 + 4) >> 3 };
+    const int top_q = (((q & 1) ? t1 : t0) + 2) >> 2, left_q = (((q >> 1) ? l1 : l0) + 2) >> 2;
+    switch (mode) {
+    case 0: return dc_q[q];
+    case 4: return left_q;
+    case 5: return top_q;
+    case 7: return q == 0 ? dc_q[0] : top_q;
+    case 8: return q == 0 ? top_q : dc_q[q];
+    case 9: return q < 2 ? left_q : mid;
+    default: return q < 2 ? mid : left_q;
+    }
+}
+
+// out: n x n samples (pitch n)
+__global__ void __launch_bounds__(256) pred_hbd_kernel(PredJobH j, uint16_t *__restrict__ out)
+{
+    const int n = j.tab == 0 ? 4 : j.tab == 3 ? 16 : 8, t = threadIdx.x;
+    if (t >= n * n) return;
+    const int x = t % n, y = t / n;
+    int v;
+    if (j.tab < 2) {
+        if (j.mode == 11) v = 1 << (j.bits - 1);
+        else { IntraEdges e; hbd_edges(e, j); v = intra_directional(e, n, j.mode, x, y); }
+    } else v = hbd_big_sample(j, n, x, y);
+    out[t] = (uint16_t)v;
+}
+
+// lossless vertical / horizontal prediction + residual (h264pred_template.c:1123-1354).  rect: staged 17 x 17 neighbourhood (row 0 = the
+// row above, column 0 = the column to the left), pitch 32 samples.  The C code runs the blocks one after the other (a block below /
+// right of another starts from that block's output), so one thread walks them in that order.
+__global__ void __launch_bounds__(32) pred_add_hbd_kernel(PredJobH j, uint16_t *__restrict__ rect, int32_t *__restrict__ block)
+{
+    if (threadIdx.x) return;
+    const int kind = j.tab - 4, horizontal = j.mode, n = (kind == 1 || kind == 2) ? 8 : 4;
+    IntraEdges e;
+    if (kind == 2) hbd_edges(e, j);
+    for (int b = 0; b < j.nblocks; b++) {
+        uint16_t *p = rect + 32 + 1 + (kind >= 3 ? j.off[b] : 0);
+        int32_t *blk = block + b * n * n;
+        for (int i = 0; i < n; i++) {
+            int v = kind == 2 ? (horizontal ? e.l[i + 1] : e.t[i + 1]) : (horizontal ? p[-1 + i * 32] : p[i - 32]);
+            for (int k = 0; k < n; k++) {
+                const int ci = horizontal ? i * n + k : k * n + i;
+                v = (v + blk[ci]) & 0xffff;
+                p[horizontal ? k + i * 32 : i + k * 32] = (uint16_t)v;
+                blk[ci] = 0;
+            }
+        }
+    }
+}
+
+namespace {
+
+struct PHStage {
+    ScratchLock lk;
+    uint8_t *h = nullptr, *d = nullptr;
+    cudaStream_t s = nullptr;
+    bool ok() {
+        Scratch &S = scratch();
+        h = (uint8_t *)S.pinned2(64 * 1024); d = (uint8_t *)S.dev(9, 64 * 1024);
+        cudaStream_t *st = S.streams();
+        if (!h || !d || !st) return false;
+        s = st[0];
+        return true;
+    }
+};
+inline const uint16_t *px(const uint8_t *p) { return (const uint16_t *)p; }
+
+template <int BITS> void predict(int tab, int mode, uint8_t *src, const uint8_t *topright, int has_tl, int has_tr, ptrdiff_t st)
+{
+    PHStage S; if (!S.ok()) return;
+    PredJobH j; memset(&j, 0, sizeof(j));
+    j.bits = BITS; j.tab = tab; j.mode = mode; j.has_tl = has_tl != 0; j.has_tr = has_tr != 0;
+    const int n = tab == 0 ? 4 : tab == 3 ? 16 : 8;
+    bool top = false, left = false, corner = false, tr = false;
+    int nleft = n;
+    if (tab < 2) {
+        const int nd = intra_needs(mode);
+        top = nd & 1; left = nd & 2; corner = nd & 4; tr = nd & 8;
+        if (tab == 1) {                                       // the edge filters look one sample further only when told they may
+            if ((top || left) && has_tl) corner = true;
+            tr = top && has_tr;
+        }
+    } else if (tab == 2) {
+        top = mode == 0 || mode == 2 || mode == 3 || mode == 5 || mode == 7 || mode == 8;
+        left = mode == 0 || mode == 1 || mode == 3 || mode == 4 || mode >= 7;
+        corner = mode == 3;
+        if (mode == 7) nleft = 4;
+    } else {
+        top = mode == 0 || mode == 2 || mode == 3 || mode == 5;
+        left = mode == 0 || mode == 1 || mode == 3 || mode == 4;
+        corner = mode == 3;
+    }
+    if (top) memcpy(j.top, src - st, (size_t)n * 2);
+    if (tr) { if (tab == 0) memcpy(j.top + 4, topright, 8); else memcpy(j.top + 8, src - st + 16, (intra_needs(mode) & 8) ? 16 : 2); }
+    if (left) for (int i = 0; i < nleft; i++) j.left[i] = *px(src - 2 + i * st);
+    if (corner) j.corner = *px(src - 2 - st);
+    AVB_LAUNCH(pred_hbd_kernel, 1, 256, 0, S.s)(j, (uint16_t *)S.d);
+    if (check_launch("h264_pred slot (high bit depth)")) return;
+    if (cudaMemcpyAsync(S.h, S.d, 512, cudaMemcpyDeviceToHost, S.s) != cudaSuccess || cudaStreamSynchronize(S.s) != cudaSuccess) {
+        set_error("h264_pred slot (high bit depth)", cudaGetLastError()); return;
+    }
+    for (int y = 0; y < n; y++) memcpy(src + y * st, S.h + (size_t)y * n * 2, (size_t)n * 2);
+}
+
+template <int BITS> void predict_add(int kind, int horizontal, uint8_t *pix, const int *block_offset, int16_t *block, int has_tl, int has_tr, ptrdiff_t st)
+{
+    PHStage S; if (!S.ok()) return;
+    PredJobH j; memset(&j, 0, sizeof(j));
+    j.bits = BITS; j.tab = 4 + kind; j.mode = horizontal; j.has_tl = has_tl != 0; j.has_tr = has_tr != 0;
+    const int n = (kind == 1 || kind == 2) ? 8 : 4, nb = kind == 3 ? 4 : kind == 4 ? 16 : 1, span = kind == 4 ? 16 : 8;
+    j.nblocks = nb;
+    for (int b = 0; b < nb; b++) {                         // byte offsets in the caller's pitch -> sample offsets in the staged pitch (32)
+        const int o = kind >= 3 ? block_offset[b] : 0, oy = (int)(o / st), ox = (int)(o - oy * st) / 2;
+        j.off[b] = oy * 32 + ox;
+    }
+    uint16_t *rect = (uint16_t *)S.h;                      // 17 rows x 32 samples: row 0 / column 0 = the neighbours
+    memset(rect, 0, 17 * 32 * 2);
+    const int ext = kind >= 3 ? span : n;
+    if (kind == 2) {                                       // filtered edges: the same gather as pred8x8l vertical / horizontal
+        if (!horizontal) { memcpy(j.top, pix - st, 16); if (has_tr) j.top[8] = *px(pix + 16 - st); }
+        else for (int i = 0; i < 8; i++) j.left[i] = *px(pix - 2 + i * st);
+        if (has_tl) j.corner = *px(pix - 2 - st);
+    }
+    if (!horizontal) memcpy(rect + 1, pix - st, (size_t)ext * 2);
+    else for (int i = 0; i < ext; i++) rect[32 * (i + 1)] = *px(pix - 2 + i * st);
+    for (int y = 0; y < ext; y++) memcpy(rect + 32 * (y + 1) + 1, pix + y * st, (size_t)ext * 2);
+    const size_t rbytes = 17 * 32 * 2, cbytes = (size_t)nb * n * n * 4;
+    memcpy(S.h + 2048, block, cbytes);
+    if (cudaMemcpyAsync(S.d, S.h, 2048 + cbytes, cudaMemcpyHostToDevice, S.s) != cudaSuccess) { set_error("h264_pred_add slot (high bit depth)", cudaGetLastError()); return; }
+    AVB_LAUNCH(pred_add_hbd_kernel, 1, 32, 0, S.s)(j, (uint16_t *)S.d, (int32_t *)(S.d + 2048));
+    if (check_launch("h264_pred_add slot (high bit depth)")) return;
+    if (cudaMemcpyAsync(S.h, S.d, 2048 + cbytes, cudaMemcpyDeviceToHost, S.s) != cudaSuccess || cudaStreamSynchronize(S.s) != cudaSuccess) {
+        set_error("h264_pred_add slot (high bit depth)", cudaGetLastError()); return;
+    }
+    (void)rbytes;
+    for (int y = 0; y < ext; y++) memcpy(pix + y * st, rect + 32 * (y + 1) + 1, (size_t)ext * 2);
+    memcpy(block, S.h + 2048, cbytes);
+}
+
+template <int B, int MODE> void s_pred4x4(uint8_t *src, const uint8_t *topright, ptrdiff_t stride) { predict<B>(0, MODE, src, topright, 0, 0, stride); }
+template <int B, int MODE> void s_pred8x8l(uint8_t *src, int tl, int tr, ptrdiff_t stride) { predict<B>(1, MODE, src, nullptr, tl, tr, stride); }
+template <int B, int MODE> void s_pred8x8(uint8_t *src, ptrdiff_t stride) { predict<B>(2, MODE, src, nullptr, 0, 0, stride); }
+template <int B, int MODE> void s_pred16x16(uint8_t *src, ptrdiff_t stride) { predict<B>(3, MODE, src, nullptr, 0, 0, stride); }
+template <int B, int HOR> void s_add4(uint8_t *pix, int16_t *block, ptrdiff_t stride) { predict_add<B>(0, HOR, pix, nullptr, block, 0, 0, stride); }
+template <int B, int HOR> void s_add8l(uint8_t *pix, int16_t *block, ptrdiff_t stride) { predict_add<B>(1, HOR, pix, nullptr, block, 0, 0, stride); }
+template <int B, int HOR> void s_add8lf(uint8_t *pix, int16_t *block, int tl, int tr, ptrdiff_t stride) { predict_add<B>(2, HOR, pix, nullptr, block, tl, tr, stride); }
+template <int B, int HOR> void s_add8(uint8_t *pix, const int *bo, int16_t *block, ptrdiff_t stride) { predict_add<B>(3, HOR, pix, bo, block, 0, 0, stride); }
+template <int B, int HOR> void s_add16(uint8_t *pix, const int *bo, int16_t *block, ptrdiff_t stride) { predict_add<B>(4, HOR, pix, bo, block, 0, 0, stride); }
+
+template <int B, int M> struct Fill12 {
+    static void go(H264PredContext *h) { h->pred4x4[M] = s_pred4x4<B, M>; h->pred8x8l[M] = s_pred8x8l<B, M>; Fill12<B, M - 1>::go(h); }
+};
+template <int B> struct Fill12<B, -1> { static void go(H264PredContext *) {} };
+template <int B, int M> struct Fill11 { static void go(H264PredContext *h) { h->pred8x8[M] = s_pred8x8<B, M>; Fill11<B, M - 1>::go(h); } };
+template <int B> struct Fill11<B, -1> { static void go(H264PredContext *) {} };
+template <int B, int M> struct Fill7 { static void go(H264PredContext *h) { h->pred16x16[M] = s_pred16x16<B, M>; Fill7<B, M - 1>::go(h); } };
+template <int B> struct Fill7<B, -1> { static void go(H264PredContext *) {} };
+
+template <int B> void install(H264PredContext *h)
+{
+    Fill12<B, 11>::go(h); Fill11<B, 10>::go(h); Fill7<B, 6>::go(h);
+    h->pred4x4_add[0] = s_add4<B, 0>;   h->pred4x4_add[1] = s_add4<B, 1>;
+    h->pred8x8l_add[0] = s_add8l<B, 0>; h->pred8x8l_add[1] = s_add8l<B, 1>;
+    h->pred8x8l_filter_add[0] = s_add8lf<B, 0>; h->pred8x8l_filter_add[1] = s_add8lf<B, 1>;
+    h->pred8x8_add[2] = s_add8<B, 0>;   h->pred8x8_add[1] = s_add8<B, 1>;          // [VERT_PRED8x8 = 2], [HOR_PRED8x8 = 1]
+    h->pred16x16_add[2] = s_add16<B, 0>; h->pred16x16_add[1] = s_add16<B, 1>;
+}
+
+}  // namespace
+
+// ff_h264_pred_init_cuda (h264pred.cu) for bit_depth 9 and 10
+void h264pred_init_hbd(H264PredContext *h, int bits) { if (bits == 9) install<9>(h); else install<10>(h); }
+
+}  // namespace avb

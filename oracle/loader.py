@@ -43,6 +43,8 @@ API = {
     "h264_hbd_loop_filter": (None, [i32, i32, vp, i32, i32, i32, vp]),
     "h264_hbd_qpel": (None, [i32, i32, i32, i32, vp, vp, pd]),
     "h264_hbd_chroma": (None, [i32, i32, i32, vp, vp, pd, i32, i32, i32]),
+    "h264_hbd_pred": (None, [i32, i32, i32, vp, vp, i32, i32, pd]),
+    "h264_hbd_pred_add": (None, [i32, i32, i32, vp, vp, vp, i32, i32, pd]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),

@@ -161,6 +161,9 @@ void ORC(h264_hbd_biweight)(int bits, int widx, uint8_t *dst, uint8_t *src, int 
 void ORC(h264_hbd_loop_filter)(int bits, int which, uint8_t *pix, int stride, int alpha, int beta, const int8_t *tc0);
 void ORC(h264_hbd_qpel)(int bits, int avg, int sidx, int mc, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
 void ORC(h264_hbd_chroma)(int bits, int avg, int widx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int h, int x, int y);
+/* H264PredContext for codec H.264, 9 / 10 bit, 4:2:0: tab / mode as h264_pred and h264_pred_add above; block_offset[] and stride in bytes */
+void ORC(h264_hbd_pred)(int bits, int tab, int mode, uint8_t *src, const uint8_t *topright, int has_topleft, int has_topright, ptrdiff_t stride);
+void ORC(h264_hbd_pred_add)(int bits, int tab, int mode, uint8_t *pix, const int *block_offset, int32_t *block, int has_topleft, int has_topright, ptrdiff_t stride);
 
 /* ---- H264QpelContext / H264ChromaContext (h264qpel.h:27-30, h264chroma.h:25-30) ---- */
 /* sidx 0..3 = 16,8,4,2 ; mc = (mx&3) + 4*(my&3) */

@@ -10,6 +10,8 @@
 #include "libavcodec/h264dsp.h"
 #include "libavcodec/h264qpel.h"
 #include "libavcodec/h264chroma.h"
+#include "libavcodec/avcodec.h"
+#include "libavcodec/h264pred.h"
 #define ORC_PREFIX ref_
 #include "../oracle_api.h"
 
@@ -17,12 +19,14 @@ static pthread_once_t once = PTHREAD_ONCE_INIT;
 static H264DSPContext dsp[2][2];          /* [bits 9 / 10][chroma_format_idc 1 / 2] */
 static H264QpelContext qpel[2];
 static H264ChromaContext chroma[2];
+static H264PredContext pred[2];
 static void init_all(void)
 {
     av_set_cpu_flags_mask(0);
     for (int b = 0; b < 2; b++) {
         ff_h264dsp_init(&dsp[b][0], 9 + b, 1); ff_h264dsp_init(&dsp[b][1], 9 + b, 2);
         ff_h264qpel_init(&qpel[b], 9 + b); ff_h264chroma_init(&chroma[b], 9 + b);
+        ff_h264_pred_init(&pred[b], AV_CODEC_ID_H264, 9 + b, 1);
     }
 }
 #define D(bits, idc2) (pthread_once(&once, init_all), &dsp[(bits) - 9][idc2])
@@ -87,4 +91,29 @@ void ref_h264_hbd_chroma(int bits, int avg, int widx, uint8_t *dst, uint8_t *src
 {
     pthread_once(&once, init_all);
     (avg ? chroma[bits - 9].avg_h264_chroma_pixels_tab : chroma[bits - 9].put_h264_chroma_pixels_tab)[widx](dst, src, stride, h, x, y);
+}
+
+void ref_h264_hbd_pred(int bits, int tab, int mode, uint8_t *src, const uint8_t *topright, int has_topleft, int has_topright, ptrdiff_t stride)
+{
+    pthread_once(&once, init_all);
+    H264PredContext *h = &pred[bits - 9];
+    switch (tab) {
+    case 0: h->pred4x4[mode](src, topright, stride); break;
+    case 1: h->pred8x8l[mode](src, has_topleft, has_topright, stride); break;
+    case 2: h->pred8x8[mode](src, stride); break;
+    default: h->pred16x16[mode](src, stride); break;
+    }
+}
+void ref_h264_hbd_pred_add(int bits, int tab, int mode, uint8_t *pix, const int *block_offset, int32_t *block, int has_topleft, int has_topright, ptrdiff_t stride)
+{
+    pthread_once(&once, init_all);
+    H264PredContext *h = &pred[bits - 9];
+    int16_t *b = (int16_t *)block;
+    switch (tab) {
+    case 0: h->pred4x4_add[mode](pix, b, stride); break;
+    case 1: h->pred8x8l_add[mode](pix, b, stride); break;
+    case 2: h->pred8x8l_filter_add[mode](pix, b, has_topleft, has_topright, stride); break;
+    case 3: h->pred8x8_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, b, stride); break;
+    default: h->pred16x16_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, b, stride); break;
+    }
 }

@@ -146,6 +146,49 @@ def compare(a, b, bits, seed=0):
                     c.h264_hbd_chroma(bits, avg, widx, vp(d), vp(src, 4), 64, h, fx, fy)
                     res.append(d)
                 assert np.array_equal(res[0], res[1]), ("chroma", bits, avg, widx, fx, fy); n += 1
+    n += pred_compare(a, b, bits, rng)
+    return n
+
+
+PRED_TABS = {0: (4, 12), 1: (8, 12), 2: (8, 11), 3: (16, 7)}
+
+
+def pred_compare(a, b, bits, rng):
+    """H264PredContext: every mode of pred4x4 / pred8x8l (all has_topleft / has_topright pairs) / pred8x8 / pred16x16 and the ten lossless
+    *_add predictors on 64-sample-wide pictures of 16-bit samples; whole pictures are compared (a stray write shows)"""
+    top, stride, n = (1 << bits) - 1, 128, 0
+    for tab, (size, modes) in PRED_TABS.items():
+        for it in range(10):
+            img = rng.integers(0, top + 1, size=(48, 64)).astype(np.uint16)
+            if it % 4 == 0:
+                img[:] = rng.choice([0, top, top // 2])        # flat pictures: plane prediction clipping
+                img[::3, ::5] = rng.integers(0, top + 1)
+            x, y = 16 + 4 * int(rng.integers(0, 3)), 16 + 4 * int(rng.integers(0, 3))
+            trbuf = img[y - 1, x + size:x + size + 4].copy() if it & 1 else np.full(4, img[y - 1, x + size - 1], np.uint16)
+            for mode in range(modes):
+                for tl, tr in ((0, 0), (1, 1), (1, 0), (0, 1)) if tab == 1 else ((0, 0),):
+                    res = []
+                    for c in (a, b):
+                        p = img.copy()
+                        c.h264_hbd_pred(bits, tab, mode, vp(p, 2 * (y * 64 + x)), vp(trbuf), tl, tr, stride)
+                        res.append(p)
+                    assert np.array_equal(res[0], res[1]), ("pred", bits, tab, mode, tl, tr, np.argwhere(res[0] != res[1])[:4].tolist()); n += 1
+    for tab in range(5):
+        nco = {0: 16, 1: 64, 2: 64, 3: 64, 4: 256}[tab]
+        chroma = tab == 3
+        bo = np.array([2 * (4 * ((k & 1) if chroma else (k & 1) + 2 * ((k >> 2) & 1)) + 4 * ((k >> 1) if chroma else ((k >> 1) & 1) + 2 * (k >> 3)) * 64)
+                       for k in range(4 if chroma else 16)], np.int32)              # frame-macroblock offsets in bytes
+        for it in range(12):
+            img = rng.integers(0, top + 1, size=(48, 64)).astype(np.uint16)
+            blk = rng.integers(-300 << (bits - 8), (300 << (bits - 8)) + 1, size=nco).astype(np.int32)
+            for mode in (0, 1):
+                for tl, tr in ((0, 0), (1, 1), (1, 0), (0, 1)) if tab == 2 else ((0, 0),):
+                    res = []
+                    for c in (a, b):
+                        p, k = img.copy(), blk.copy()
+                        c.h264_hbd_pred_add(bits, tab, mode, vp(p, 2 * (16 * 64 + 16)), vp(bo), vp(k), tl, tr, stride)
+                        res.append((p, k))
+                    assert np.array_equal(res[0][0], res[1][0]) and not res[0][1].any() and not res[1][1].any(), ("pred_add", bits, tab, mode, tl, tr); n += 1
     return n
 
 
@@ -153,9 +196,18 @@ class TableCallee:
     """the oracle's h264_hbd_* entry names served by the product's tables: ff_h264dsp_init_cuda(c, bits, idc), ff_h264qpel_init_cuda(c, bits),
     ff_h264chroma_init_cuda(c, bits) of `lib` (the product library on a GPU, or the host simulation)"""
 
-    def __init__(self, lib):
+    def __init__(self, lib, pred_init=None):
+        """pred_init(table, bits): fills an H264PredContext; default = the product's ff_h264_pred_init_cuda(h, AV_CODEC_ID_H264, bits, 1)"""
         from libav_b200 import tables
-        self.t = {}
+        self.t, self.p = {}, {}
+        for bits in (9, 10):
+            h = tables.H264PredContext()
+            if pred_init:
+                pred_init(C.byref(h), bits)
+            else:
+                lib.ff_h264_pred_init_cuda(C.byref(h), 27, bits, 1)
+            assert h.pred4x4[0] and h.pred16x16[3] and h.pred8x8_add[2], bits
+            self.p[bits] = h
         for bits in (9, 10):
             d1, d2, q, ch = tables.H264DSPContext(), tables.H264DSPContext(), tables.H264QpelContext(), tables.H264ChromaContext()
             lib.ff_h264dsp_init_cuda(C.byref(d1), bits, 1); lib.ff_h264dsp_init_cuda(C.byref(d2), bits, 2)
@@ -220,3 +272,27 @@ class TableCallee:
     def h264_hbd_chroma(self, bits, avg, widx, dst, src, stride, h, x, y):
         ch = self.t[bits][3]
         (ch.avg_h264_chroma_pixels_tab if avg else ch.put_h264_chroma_pixels_tab)[widx](self.u8(dst), self.u8(src), stride, h, x, y)
+
+    def h264_hbd_pred(self, bits, tab, mode, src, topright, tl, tr, stride):
+        h = self.p[bits]
+        if tab == 0:
+            h.pred4x4[mode](src, topright, stride)
+        elif tab == 1:
+            h.pred8x8l[mode](src, tl, tr, stride)
+        elif tab == 2:
+            h.pred8x8[mode](src, stride)
+        else:
+            h.pred16x16[mode](src, stride)
+
+    def h264_hbd_pred_add(self, bits, tab, mode, pix, bo, block, tl, tr, stride):
+        h = self.p[bits]
+        if tab == 0:
+            h.pred4x4_add[mode](pix, block, stride)
+        elif tab == 1:
+            h.pred8x8l_add[mode](pix, block, stride)
+        elif tab == 2:
+            h.pred8x8l_filter_add[mode](pix, block, tl, tr, stride)
+        elif tab == 3:
+            h.pred8x8_add[1 if mode else 2](pix, bo, block, stride)          # [HOR_PRED8x8 = 1], [VERT_PRED8x8 = 2]
+        else:
+            h.pred16x16_add[1 if mode else 2](pix, bo, block, stride)

@@ -17,10 +17,10 @@ LIB = os.path.join(HERE, "libslots_hostsim.so")
 @pytest.fixture(scope="module")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
-    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp"), os.path.join(HERE, "idct10_hostsim.cpp")]
+    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp"), os.path.join(HERE, "idct10_hostsim.cpp"), os.path.join(HERE, "h264pred_hbd_hostsim.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h")] + \
         [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h", "sws_slots.cu", "sws_dev.cuh",
-                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu")] + \
+                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu", "h264pred_hbd.cu", "h264pred.cuh")] + \
         [os.path.join(root, "include", f) for f in ("avdsp_b200.h", "avdsp_b200_tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", os.path.join(HERE, "shim"), "-Wno-unknown-pragmas",
@@ -113,10 +113,11 @@ def test_sws_line_slot_registration(sim):
 
 @pytest.mark.parametrize("bits", [9, 10])
 def test_h264_high_bit_depth_slots(sim, refo, bits):
-    """the 9 / 10-bit instances of H264DSPContext / H264QpelContext / H264ChromaContext (libav_b200/csrc/slots_hbd.cu, host-compiled) against
+    """the 9 / 10-bit instances of H264DSPContext / H264QpelContext / H264ChromaContext / H264PredContext (libav_b200/csrc/slots_hbd.cu,
+    h264pred_hbd.cu, host-compiled) against
     the tables the compiled reference fills for those depths"""
     import hbd_cases
-    assert hbd_cases.compare(hbd_cases.TableCallee(sim), refo, bits, seed=2) > 400
+    assert hbd_cases.compare(hbd_cases.TableCallee(sim, pred_init=sim.hostsim_h264_pred_init_hbd), refo, bits, seed=2) > 800
     assert sim.avb200_last_error().decode() == ""
 
 

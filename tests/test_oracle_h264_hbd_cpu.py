@@ -7,4 +7,4 @@ import hbd_cases
 
 @pytest.mark.parametrize("bits", [9, 10])
 def test_port_matches_reference(orc, refo, bits):
-    assert hbd_cases.compare(orc, refo, bits, seed=1) > 400
+    assert hbd_cases.compare(orc, refo, bits, seed=1) > 800

@@ -341,7 +341,8 @@ typedef struct FFQpelRecord { uint32_t dst_off, src_off; uint8_t kind, sidx, mc,
 int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream);
 
 /* FDCTDSPContext (libavcodec/fdctdsp.h:26-29), in place over n blocks: which 0 = ff_jpeg_fdct_islow_8, 1 =
- * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332). */
+ * ff_fdct248_islow_8 (jfdctint_template.c:260-398), 2 = ff_fdct_ifast, 3 = ff_fdct_ifast248 (jfdctfst.c:207-332), 4 = ff_jpeg_fdct_islow_10,
+ * 5 = ff_fdct248_islow_10 (the BIT_DEPTH 10 instances: PASS1_BITS 1, OUT_SHIFT 2; thread per block, untuned). */
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream);
 /* PixblockDSPContext.get_pixels / diff_pixels (libavcodec/pixblockdsp_template.c:24-66) over n 8x8 blocks, optionally
  * followed by the forward DCT in the same kernel -- the encoder's "fetch (difference) -> fdct" front end
@@ -416,7 +417,7 @@ int  sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int d
 void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
 void ff_blockdsp_init_cuda(BlockDSPContext *c);   /* libavcodec/blockdsp.c:60-74 */
 /* libavcodec/fdctdsp.c:27-50 (same shape as ff_fdctdsp_init_x86): dct_algo FF_DCT_AUTO / FF_DCT_INT -> islow,
- * FF_DCT_FASTINT -> ifast; FF_DCT_FAAN and 10-bit are left to the C path */
+ * FF_DCT_FASTINT -> ifast; bits_per_raw_sample 10 -> jpeg_fdct_islow_10 / fdct248_islow_10; FF_DCT_FAAN is left to the C path */
 void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
 /* libavcodec/me_cmp.c:895-944: every slot ff_me_cmp_init fills except the encoder-state metrics */
 void ff_me_cmp_init_cuda(MECmpContext *c);

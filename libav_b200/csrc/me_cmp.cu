@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "../../include/avdsp_b200.h"
 
+namespace avb { int fdct10_launch(int which, int16_t *blocks, size_t n, cudaStream_t st); }      // fdct10.cu
+
 namespace avb {
 
 __device__ __forceinline__ int iabs_m(int v) { return v < 0 ? -v : v; }
@@ -590,6 +592,7 @@ int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const u
 
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
 {
+    using avb::fdct10_launch;
     if (!n) return 0;
     const int grid = (int)((n + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
@@ -598,6 +601,7 @@ int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
     case 1: fdct_kernel<1><<<grid, 128, 0, st>>>(blocks, n); break;
     case 2: fdct_kernel<2><<<grid, 128, 0, st>>>(blocks, n); break;
     case 3: fdct_kernel<3><<<grid, 128, 0, st>>>(blocks, n); break;
+    case 4: case 5: return fdct10_launch(which, blocks, n, st);          // the 10-bit instances, fdct10.cu
     default: set_error_msg("fdct_batch", "bad transform selector"); return -1;
     }
     return check_launch("fdct_batch");

@@ -401,7 +401,8 @@ void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth)
 
 void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth)
 {
-    if (high_bit_depth || bits_per_raw_sample > 8) return;               // libavcodec/fdctdsp.c:27-38: 10-bit variants stay on the C path
+    if (bits_per_raw_sample == 10) { c->fdct = slot_fdct<4>; c->fdct248 = slot_fdct<5>; return; }      // fdctdsp.c:31-33: the 10-bit islow pair whatever dct_algo says
+    if (high_bit_depth || bits_per_raw_sample > 8) return;               // other depths: the reference falls through to its 8-bit functions; not taken over
     if (dct_algo == AVB_FF_DCT_FASTINT) { c->fdct = slot_fdct<2>; c->fdct248 = slot_fdct<3>; }
     else if (dct_algo == AVB_FF_DCT_AUTO || dct_algo == AVB_FF_DCT_INT) { c->fdct = slot_fdct<0>; c->fdct248 = slot_fdct<1>; }
     // FF_DCT_FAAN (float) is not taken over

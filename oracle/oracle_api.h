@@ -50,7 +50,7 @@ void ORC(idct_batch)(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *
                      ptrdiff_t stride, size_t n, int nthreads);
 
 /* ---- FDCTDSPContext (libavcodec/fdctdsp.h:26-29): 0 = jpeg_fdct_islow_8, 1 = fdct248_islow_8,
- *      2 = fdct_ifast, 3 = fdct_ifast248 */
+ *      2 = fdct_ifast, 3 = fdct_ifast248, 4 = jpeg_fdct_islow_10, 5 = fdct248_islow_10 (bits_per_raw_sample == 10, fdctdsp.c:31-33) */
 void ORC(fdct)(int which, int16_t *block);
 
 /* ---- H264DSPContext (libavcodec/h264dsp.h:41-117), 8-bit ---- */

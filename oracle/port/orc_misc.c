@@ -42,18 +42,18 @@ static void islow_1d(const int in[8], int out[8], int up, int dn)
     out[1] = rshift_round(t7 + z1 + z4, dn);
 }
 /* 2-4-8 column pass (two interleaved 4-point DCTs), jfdctint_template.c:342-398 */
-static void islow_248_col(const int in[8], int out[8])
+static void islow_248_col(const int in[8], int out[8], int sh, int dn)       /* sh = OUT_SHIFT, dn = CONST_BITS + OUT_SHIFT */
 {
     int a0 = in[0] + in[1], a1 = in[2] + in[3], a2 = in[4] + in[5], a3 = in[6] + in[7];
     int b0 = in[0] - in[1], b1 = in[2] - in[3], b2 = in[4] - in[5], b3 = in[6] - in[7];
     int e0 = a0 + a3, e1 = a1 + a2, e2 = a1 - a2, e3 = a0 - a3, z;
-    out[0] = rshift_round(e0 + e1, 4); out[4] = rshift_round(e0 - e1, 4);
+    out[0] = rshift_round(e0 + e1, sh); out[4] = rshift_round(e0 - e1, sh);
     z = (e2 + e3) * K0541;
-    out[2] = rshift_round(z + e3 * K0765, 17); out[6] = rshift_round(z - e2 * K1847, 17);
+    out[2] = rshift_round(z + e3 * K0765, dn); out[6] = rshift_round(z - e2 * K1847, dn);
     e0 = b0 + b3; e1 = b1 + b2; e2 = b1 - b2; e3 = b0 - b3;
-    out[1] = rshift_round(e0 + e1, 4); out[5] = rshift_round(e0 - e1, 4);
+    out[1] = rshift_round(e0 + e1, sh); out[5] = rshift_round(e0 - e1, sh);
     z = (e2 + e3) * K0541;
-    out[3] = rshift_round(z + e3 * K0765, 17); out[7] = rshift_round(z - e2 * K1847, 17);
+    out[3] = rshift_round(z + e3 * K0765, dn); out[7] = rshift_round(z - e2 * K1847, dn);
 }
 /* AAN "ifast": products are shifted down by 8 without rounding and truncated to int16 (jfdctfst.c MULTIPLY) */
 static inline int fmul(int v, int k) { return (int16_t)((v * k) >> 8); }
@@ -82,17 +82,19 @@ static void ifast_248_col(const int in[8], int out[8])
 
 void orc_fdct(int which, int16_t *b)
 {
+    /* which 4 / 5: jpeg_fdct_islow_10 / fdct248_islow_10 -- the same code with PASS1_BITS 1, OUT_SHIFT 2 (jfdctint_template.c:126-130) */
+    const int ten = which >= 4, p1 = ten ? 1 : 4, osh = ten ? 2 : 4;
     int in[8], out[8];
     for (int r = 0; r < 8; r++) {                 /* rows: results go back as int16 */
         for (int k = 0; k < 8; k++) in[k] = b[8 * r + k];
-        if (which < 2) islow_1d(in, out, 4, 9); else ifast_1d(in, out);
+        if (which < 2 || ten) islow_1d(in, out, p1, 13 - p1); else ifast_1d(in, out);
         for (int k = 0; k < 8; k++) b[8 * r + k] = (int16_t)out[k];
     }
     for (int c = 0; c < 8; c++) {
         for (int k = 0; k < 8; k++) in[k] = b[8 * k + c];
         switch (which) {
-        case 0: islow_1d(in, out, -4, 17); break;
-        case 1: islow_248_col(in, out); break;
+        case 0: case 4: islow_1d(in, out, -osh, 13 + osh); break;
+        case 1: case 5: islow_248_col(in, out, osh, 13 + osh); break;
         case 2: ifast_1d(in, out); break;
         default: ifast_248_col(in, out); break;
         }

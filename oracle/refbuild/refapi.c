@@ -35,7 +35,7 @@
 
 static pthread_once_t once = PTHREAD_ONCE_INIT;
 static IDCTDSPContext idsp, idsp10;      /* bits_per_raw_sample 8 and 10 */
-static FDCTDSPContext fdsp_islow, fdsp_ifast;
+static FDCTDSPContext fdsp_islow, fdsp_ifast, fdsp10;
 static BlockDSPContext bdsp;
 static MECmpContext mecc;
 static H264DSPContext h264, h264_422;     /* chroma_format_idc 1 and 2 */
@@ -56,6 +56,7 @@ static void init_all(void)
     ff_idctdsp_init(&idsp, avctx);
     avctx->bits_per_raw_sample = 10;
     ff_idctdsp_init(&idsp10, avctx);
+    ff_fdctdsp_init(&fdsp10, avctx);
     avctx->bits_per_raw_sample = 8;
     ff_fdctdsp_init(&fdsp_islow, avctx);
     avctx->dct_algo = FF_DCT_FASTINT;
@@ -120,7 +121,9 @@ void ref_fdct(int which, int16_t *block)
     case 0: fdsp_islow.fdct(block); break;
     case 1: fdsp_islow.fdct248(block); break;
     case 2: fdsp_ifast.fdct(block); break;
-    default: fdsp_ifast.fdct248(block); break;
+    case 3: fdsp_ifast.fdct248(block); break;
+    case 4: fdsp10.fdct(block); break;            /* ff_jpeg_fdct_islow_10, fdctdsp.c:31-33 */
+    default: fdsp10.fdct248(block); break;
     }
 }
 

@@ -14,6 +14,7 @@ uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
 #include "../../libav_b200/csrc/slots.cu"
+#include "../../libav_b200/csrc/fdct10.cu"
 
 namespace avb {
 static std::string g_err;
@@ -40,7 +41,12 @@ void avb200_clear_error(void) { avb::g_err.clear(); }
 #define NOT_SIMULATED(name) { avb::set_error_msg(name, "batched kernel: not simulated on the host"); return -1; }
 int ff_me_cmp_batch_cuda(int, int, int, const uint8_t *, const uint8_t *, ptrdiff_t, int, const FFMECmpRecord *, size_t, int32_t *, void *) NOT_SIMULATED("ff_me_cmp_batch_cuda")
 int ff_hpel_batch_cuda(const FFHpelRecord *, size_t, uint8_t *, const uint8_t *, ptrdiff_t, void *) NOT_SIMULATED("ff_hpel_batch_cuda")
-int ff_fdct_batch_cuda(int, int16_t *, size_t, void *) NOT_SIMULATED("ff_fdct_batch_cuda")
+// the 8-bit transforms are warp kernels (me_cmp.cu, not simulated); the 10-bit ones are thread-per-block (fdct10.cu, included below)
+int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
+{
+    if (which == 4 || which == 5) return avb::fdct10_launch(which, blocks, n, (cudaStream_t)stream);
+    NOT_SIMULATED("ff_fdct_batch_cuda")
+}
 int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *, size_t, uint8_t *, const uint8_t *, ptrdiff_t, void *) NOT_SIMULATED("ff_mpeg4_qpel_batch_cuda")
 int ff_pixblock_fdct_batch_cuda(int, const uint8_t *, const uint8_t *, const uint32_t *, const uint32_t *, ptrdiff_t, int16_t *, size_t, void *) NOT_SIMULATED("ff_pixblock_fdct_batch_cuda")
 int ff_h264_weight_batch_cuda(const FFH264WeightRecord *, size_t, uint8_t *, const uint8_t *, int, void *) NOT_SIMULATED("ff_h264_weight_batch_cuda")

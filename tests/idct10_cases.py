@@ -61,3 +61,23 @@ def batch_case(run_batch, checker, mode, n=5000, seed=1):
         checker.simple_idct10(mode, C.c_void_p(want_f.ctypes.data + int(off[i])), frame.strides[0], C.c_void_p(want_b.ctypes.data + 128 * i))
     assert np.array_equal(got_b, want_b) and np.array_equal(got_f, want_f), mode
     assert mode == 2 or not np.array_equal(got_f, frame)
+
+
+def fdct10_cases(table, run_batch, checker, seed=0):
+    """FDCTDSPContext for bits_per_raw_sample 10 (ff_jpeg_fdct_islow_10 / ff_fdct248_islow_10): the two slots, and ff_fdct_batch_cuda(4 | 5);
+    run_batch(which, blocks (n, 64) int16) -> blocks after the call"""
+    rng = np.random.default_rng(seed)
+    i16p = C.POINTER(C.c_int16)
+    for it in range(60):
+        blk = (rng.integers(-1023, 1024, 64) if it % 3 else rng.integers(0, 1024, 64)).astype(np.int16)
+        for slot, which in ((table.fdct, 4), (table.fdct248, 5)):
+            a, b = blk.copy(), blk.copy()
+            slot(C.cast(a.ctypes.data, i16p))
+            checker.fdct(which, ptr(b))
+            assert np.array_equal(a, b), (which, it)
+    for which in (4, 5):
+        blk = rng.integers(-1023, 1024, size=(3000, 64)).astype(np.int16)
+        want = blk.copy()
+        for i in range(len(want)):
+            checker.fdct(which, C.c_void_p(want.ctypes.data + 128 * i))
+        assert np.array_equal(run_batch(which, blk.copy()), want), which

@@ -20,7 +20,7 @@ def sim(built):
     srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp"), os.path.join(HERE, "idct10_hostsim.cpp"), os.path.join(HERE, "h264pred_hbd_hostsim.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h")] + \
         [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h", "sws_slots.cu", "sws_dev.cuh",
-                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu", "h264pred_hbd.cu", "h264pred.cuh")] + \
+                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu", "h264pred_hbd.cu", "h264pred.cuh", "fdct10.cu")] + \
         [os.path.join(root, "include", f) for f in ("avdsp_b200.h", "avdsp_b200_tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", os.path.join(HERE, "shim"), "-Wno-unknown-pragmas",
@@ -138,3 +138,18 @@ def test_simple_idct10(sim, refo):
         idct10_cases.batch_case(run_batch, refo, mode)
     assert sim.ff_simple_idct10_batch_cuda(3, None, None, None, 0, 0, None) == -1
     sim.avb200_clear_error()
+
+
+def test_fdct10(sim, refo):
+    """ff_fdctdsp_init_cuda(c, dct_algo, 10, 1): the 10-bit accurate forward DCT pair (libav_b200/csrc/fdct10.cu through slots.cu, host-compiled)"""
+    import idct10_cases
+    from libav_b200 import tables
+    t = tables.FDCTDSPContext()
+    sim.ff_fdctdsp_init_cuda(C.byref(t), 0, 10, 1)
+    sim.ff_fdct_batch_cuda.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+
+    def run_batch(which, blk):
+        assert sim.ff_fdct_batch_cuda(which, blk.ctypes.data, len(blk), None) == 0
+        return blk
+    idct10_cases.fdct10_cases(t, run_batch, refo)
+    assert sim.avb200_last_error().decode() == ""

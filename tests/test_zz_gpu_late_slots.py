@@ -119,3 +119,21 @@ def test_simple_idct10(gpu, checker):
     for mode in range(3):
         idct10_cases.batch_case(run_batch, checker, mode)
     assert gpu.last_error() == ""
+
+
+def test_fdct10(gpu, checker):
+    import idct10_cases
+    from libav_b200 import tables
+    lib = gpu.lib
+    t = tables.FDCTDSPContext()
+    lib.ff_fdctdsp_init_cuda(C.byref(t), 0, 10, 1)
+
+    def run_batch(which, blk):
+        d = lib.avb200_malloc(blk.nbytes)
+        assert d and lib.avb200_memcpy_h2d(d, blk.ctypes.data, blk.nbytes, None) == 0
+        assert lib.ff_fdct_batch_cuda(which, d, len(blk), None) == 0
+        assert lib.avb200_memcpy_d2h(blk.ctypes.data, d, blk.nbytes, None) == 0 and lib.avb200_device_sync() == 0
+        lib.avb200_free(d)
+        return blk
+    idct10_cases.fdct10_cases(t, run_batch, checker)
+    assert gpu.last_error() == ""

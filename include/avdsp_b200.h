@@ -429,7 +429,8 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth);
 void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth);
 void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags);
-/* libavcodec/h264pred.h:112-123; takes over codec_id AV_CODEC_ID_H264, bit_depth 8 / 9 / 10 (16-bit samples, int32 residual), chroma_format_idc <= 1 */
+/* libavcodec/h264pred.h:112-123; takes over codec_id AV_CODEC_ID_H264, bit_depth 8 / 9 / 10 (16-bit samples, int32 residual above 8);
+ * chroma_format_idc > 1 installs the 8 x 16 chroma functions in pred8x8[] / pred8x8_add[] like h264pred.c:477-563 */
 void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc);
 /* libavcodec/pixblockdsp.h:37-43; high_bit_depth != 0 leaves the table untouched */
 void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth);

@@ -175,7 +175,7 @@ template <> struct Fill7<-1> { static void go(H264PredContext *) {} };
 }  // namespace
 }  // namespace avb
 
-namespace avb { void h264pred_init_hbd(H264PredContext *h, int bits); }
+namespace avb { void h264pred_init_hbd(H264PredContext *h, int bits); void h264pred_install_422(H264PredContext *h, int bits); }
 
 using namespace avb;
 
@@ -183,13 +183,17 @@ using namespace avb;
 // chroma_format_idc <= 1 -- and the 9 / 10-bit instances through h264pred_hbd.cu; anything else leaves the table as the C init filled it.
 extern "C" void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc)
 {
-    if (!h || codec_id != 27 || chroma_format_idc > 1) return;
-    if (bit_depth == 9 || bit_depth == 10) { h264pred_init_hbd(h, bit_depth); return; }      // h264pred_hbd.cu
-    if (bit_depth != 8) return;
+    if (!h || codec_id != 27 || (bit_depth != 8 && bit_depth != 9 && bit_depth != 10)) return;
+    if (bit_depth != 8) {                                     // h264pred_hbd.cu
+        h264pred_init_hbd(h, bit_depth);
+        if (chroma_format_idc > 1) h264pred_install_422(h, bit_depth);
+        return;
+    }
     Fill12<11>::go(h); Fill11<10>::go(h); Fill7<6>::go(h);
     h->pred4x4_add[0] = s_add4<0>;   h->pred4x4_add[1] = s_add4<1>;
     h->pred8x8l_add[0] = s_add8l<0>; h->pred8x8l_add[1] = s_add8l<1>;
     h->pred8x8l_filter_add[0] = s_add8lf<0>; h->pred8x8l_filter_add[1] = s_add8lf<1>;
     h->pred8x8_add[2] = s_add8<0>;   h->pred8x8_add[1] = s_add8<1>;        // [VERT_PRED8x8 = 2], [HOR_PRED8x8 = 1]
     h->pred16x16_add[2] = s_add16<0>; h->pred16x16_add[1] = s_add16<1>;
+    if (chroma_format_idc > 1) h264pred_install_422(h, 8);    // h264pred.c:477-563: the pred8x8[] / pred8x8_add[] entries become the 8 x 16 functions
 }

@@ -83,10 +83,44 @@ __device__ inline int hbd_big_sample(const PredJobH &j, int n, int x, int y)
     }
 }
 
-// out: n x n samples (pitch n)
+// chroma_format_idc 2: sample (x, y) of an 8 x 16 chroma block, modes 0..10 of pred8x8[] (h264pred_template.c:502-838): the DC family per
+// 4 x 4 quadrant (2 across, 4 down), plane prediction with an 8-tap vertical gradient
+__device__ inline int hbd_sample_8x16(const PredJobH &j, int x, int y)
+{
+    const int mode = j.mode, mid = 1 << (j.bits - 1);
+    if (mode == 1) return j.left[y];
+    if (mode == 2) return j.top[x];
+    if (mode == 6) return mid;
+    if (mode == 3) {
+        int H = 0, V = 0;
+        for (int k = 1; k <= 4; k++) H += k * (j.top[3 + k] - (3 - k < 0 ? j.corner : j.top[3 - k]));
+        for (int k = 1; k <= 8; k++) V += k * (j.left[7 + k] - (7 - k < 0 ? j.corner : j.left[7 - k]));
+        H = (17 * H + 16) >> 5; V = (5 * V + 32) >> 6;
+        const int a = 16 * (j.left[15] + j.top[7] + 1) - 7 * V - 3 * H;
+        return min(max((a + x * H + y * V) >> 5, 0), (1 << j.bits) - 1);
+    }
+    int t0 = 0, t1 = 0, l[4] = { 0, 0, 0, 0 };
+    for (int i = 0; i < 4; i++) { t0 += j.top[i]; t1 += j.top[4 + i]; }
+    for (int i = 0; i < 16; i++) l[i >> 2] += j.left[i];
+    const int c = x >> 2, r = y >> 2;
+    const int dc = !c ? (!r ? (t0 + l[0] + 4) >> 3 : (l[r] + 2) >> 2) : (!r ? (t1 + 2) >> 2 : (t1 + l[r] + 4) >> 3);
+    const int ldc = (l[r] + 2) >> 2, tdc = ((c ? t1 : t0) + 2) >> 2;
+    switch (mode) {
+    case 0: return dc;
+    case 4: return ldc;
+    case 5: return tdc;
+    case 7: return (!c && !r) ? (t0 + l[0] + 4) >> 3 : tdc;          // top_dc, then pred4x4_dc on the first block
+    case 8: return (!c && !r) ? (t0 + 2) >> 2 : dc;                  // dc, then pred4x4_top_dc on the first block
+    case 9: return r == 1 ? mid : ldc;                               // left_dc, then 128 on the two blocks of the second row
+    default: return r == 0 ? mid : ldc;                              // left_dc, then 128 on the two blocks of the first row
+    }
+}
+
+// out: n x n samples (pitch n); tab 5: 8 x 16 samples (pitch 8)
 __global__ void __launch_bounds__(256) pred_hbd_kernel(PredJobH j, uint16_t *__restrict__ out)
 {
     const int n = j.tab == 0 ? 4 : j.tab == 3 ? 16 : 8, t = threadIdx.x;
+    if (j.tab == 5) { if (t < 128) out[t] = (uint16_t)hbd_sample_8x16(j, t & 7, t >> 3); return; }
     if (t >= n * n) return;
     const int x = t % n, y = t / n;
     int v;
@@ -104,6 +138,7 @@ __global__ void __launch_bounds__(32) pred_add_hbd_kernel(PredJobH j, uint16_t *
 {
     if (threadIdx.x) return;
     const int kind = j.tab - 4, horizontal = j.mode, n = (kind == 1 || kind == 2) ? 8 : 4;
+    const int mask = j.bits > 8 ? 0xffff : 0xff;               // the running sum wraps in the sample type (8-bit jobs only come from the 4:2:2 entries)
     IntraEdges e;
     if (kind == 2) hbd_edges(e, j);
     for (int b = 0; b < j.nblocks; b++) {
@@ -113,7 +148,7 @@ __global__ void __launch_bounds__(32) pred_add_hbd_kernel(PredJobH j, uint16_t *
             int v = kind == 2 ? (horizontal ? e.l[i + 1] : e.t[i + 1]) : (horizontal ? p[-1 + i * 32] : p[i - 32]);
             for (int k = 0; k < n; k++) {
                 const int ci = horizontal ? i * n + k : k * n + i;
-                v = (v + blk[ci]) & 0xffff;
+                v = (v + blk[ci]) & mask;
                 p[horizontal ? k + i * 32 : i + k * 32] = (uint16_t)v;
                 blk[ci] = 0;
             }
@@ -210,6 +245,69 @@ template <int BITS> void predict_add(int kind, int horizontal, uint8_t *pix, con
     memcpy(block, S.h + 2048, cbytes);
 }
 
+// ---- chroma_format_idc 2: the 8 x 16 pred8x8[] entries and the two pred8x8_add[] entries, bit depth 8 / 9 / 10 ----
+// (samples are widened to 16 bits in the job / staged rectangle and narrowed on the way back for 8-bit pictures)
+template <int BITS> inline int lds(const uint8_t *p, ptrdiff_t byte_off) { return BITS > 8 ? *(const uint16_t *)(p + byte_off) : p[byte_off]; }
+template <int BITS> inline void sts(uint8_t *p, ptrdiff_t byte_off, int v) { if (BITS > 8) *(uint16_t *)(p + byte_off) = (uint16_t)v; else p[byte_off] = (uint8_t)v; }
+
+template <int BITS, int MODE> void s_pred8x16(uint8_t *src, ptrdiff_t st)
+{
+    PHStage S; if (!S.ok()) return;
+    constexpr int SB = BITS > 8 ? 2 : 1;
+    PredJobH j; memset(&j, 0, sizeof(j));
+    j.bits = BITS; j.tab = 5; j.mode = MODE;
+    constexpr bool top = MODE == 0 || MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7 || MODE == 8;
+    constexpr bool left = MODE == 0 || MODE == 1 || MODE == 3 || MODE == 4 || MODE >= 7;
+    constexpr int nleft = MODE == 7 ? 4 : 16;                 // L0T only looks at the first block's left column
+    if (top) for (int i = 0; i < 8; i++) j.top[i] = (uint16_t)lds<BITS>(src, -st + i * SB);
+    if (left) for (int i = 0; i < nleft; i++) j.left[i] = (uint16_t)lds<BITS>(src, i * st - SB);
+    if (MODE == 3) j.corner = (uint16_t)lds<BITS>(src, -st - SB);
+    AVB_LAUNCH(pred_hbd_kernel, 1, 256, 0, S.s)(j, (uint16_t *)S.d);
+    if (check_launch("h264_pred slot (4:2:2)")) return;
+    if (cudaMemcpyAsync(S.h, S.d, 256, cudaMemcpyDeviceToHost, S.s) != cudaSuccess || cudaStreamSynchronize(S.s) != cudaSuccess) {
+        set_error("h264_pred slot (4:2:2)", cudaGetLastError()); return;
+    }
+    const uint16_t *o = (const uint16_t *)S.h;
+    for (int y = 0; y < 16; y++) for (int x = 0; x < 8; x++) sts<BITS>(src, y * st + x * SB, o[8 * y + x]);
+}
+template <int BITS, int HOR> void s_add8x16(uint8_t *pix, const int *block_offset, int16_t *block, ptrdiff_t st)
+{
+    PHStage S; if (!S.ok()) return;
+    constexpr int SB = BITS > 8 ? 2 : 1;
+    PredJobH j; memset(&j, 0, sizeof(j));
+    j.bits = BITS; j.tab = 4 + 3; j.mode = HOR; j.nblocks = 8;          // the kernel's kind 3: 4 x 4 blocks at j.off[]
+    int maxx = 0, maxy = 0;
+    for (int b = 0; b < 8; b++) {
+        const int o = block_offset[b < 4 ? b : b + 4], oy = (int)(o / st), ox = (int)(o - oy * st) / SB;
+        if (o < 0 || ox + 4 > 31 || oy + 4 > 16) { set_error_msg("h264_pred8x16_add slot", "block offsets outside the 8 x 16 chroma block are not taken over"); return; }
+        j.off[b] = oy * 32 + ox;
+        if (ox + 4 > maxx) maxx = ox + 4;
+        if (oy + 4 > maxy) maxy = oy + 4;
+    }
+    uint16_t *rect = (uint16_t *)S.h;                                   // 17 rows x 32 samples: row 0 / column 0 = the neighbours
+    memset(rect, 0, 17 * 32 * 2);
+    if (!HOR) for (int x = 0; x < maxx; x++) rect[1 + x] = (uint16_t)lds<BITS>(pix, -st + x * SB);
+    else for (int y = 0; y < maxy; y++) rect[32 * (y + 1)] = (uint16_t)lds<BITS>(pix, y * st - SB);
+    for (int y = 0; y < maxy; y++) for (int x = 0; x < maxx; x++) rect[32 * (y + 1) + 1 + x] = (uint16_t)lds<BITS>(pix, y * st + x * SB);
+    int32_t *cb = (int32_t *)(S.h + 2048);
+    for (int i = 0; i < 128; i++) cb[i] = BITS > 8 ? ((const int32_t *)block)[i] : block[i];
+    if (cudaMemcpyAsync(S.d, S.h, 2048 + 512, cudaMemcpyHostToDevice, S.s) != cudaSuccess) { set_error("h264_pred8x16_add slot", cudaGetLastError()); return; }
+    AVB_LAUNCH(pred_add_hbd_kernel, 1, 32, 0, S.s)(j, (uint16_t *)S.d, (int32_t *)(S.d + 2048));
+    if (check_launch("h264_pred8x16_add slot")) return;
+    if (cudaMemcpyAsync(S.h, S.d, 2048 + 512, cudaMemcpyDeviceToHost, S.s) != cudaSuccess || cudaStreamSynchronize(S.s) != cudaSuccess) {
+        set_error("h264_pred8x16_add slot", cudaGetLastError()); return;
+    }
+    for (int y = 0; y < maxy; y++) for (int x = 0; x < maxx; x++) sts<BITS>(pix, y * st + x * SB, rect[32 * (y + 1) + 1 + x]);
+    for (int i = 0; i < 128; i++) { if (BITS > 8) ((int32_t *)block)[i] = cb[i]; else block[i] = (int16_t)cb[i]; }
+}
+template <int B, int M> struct Fill422 { static void go(H264PredContext *h) { h->pred8x8[M] = s_pred8x16<B, M>; Fill422<B, M - 1>::go(h); } };
+template <int B> struct Fill422<B, -1> { static void go(H264PredContext *) {} };
+template <int B> void install422(H264PredContext *h)
+{
+    Fill422<B, 10>::go(h);
+    h->pred8x8_add[2] = s_add8x16<B, 0>; h->pred8x8_add[1] = s_add8x16<B, 1>;        // [VERT_PRED8x8 = 2], [HOR_PRED8x8 = 1]
+}
+
 template <int B, int MODE> void s_pred4x4(uint8_t *src, const uint8_t *topright, ptrdiff_t stride) { predict<B>(0, MODE, src, topright, 0, 0, stride); }
 template <int B, int MODE> void s_pred8x8l(uint8_t *src, int tl, int tr, ptrdiff_t stride) { predict<B>(1, MODE, src, nullptr, tl, tr, stride); }
 template <int B, int MODE> void s_pred8x8(uint8_t *src, ptrdiff_t stride) { predict<B>(2, MODE, src, nullptr, 0, 0, stride); }
@@ -243,5 +341,7 @@ template <int B> void install(H264PredContext *h)
 
 // ff_h264_pred_init_cuda (h264pred.cu) for bit_depth 9 and 10
 void h264pred_init_hbd(H264PredContext *h, int bits) { if (bits == 9) install<9>(h); else install<10>(h); }
+// chroma_format_idc > 1 (h264pred.c:477-563): the chroma entries become the 8 x 16 functions; bits 8 / 9 / 10
+void h264pred_install_422(H264PredContext *h, int bits) { if (bits == 8) install422<8>(h); else if (bits == 9) install422<9>(h); else install422<10>(h); }
 
 }  // namespace avb

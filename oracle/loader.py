@@ -45,6 +45,8 @@ API = {
     "h264_hbd_chroma": (None, [i32, i32, i32, vp, vp, pd, i32, i32, i32]),
     "h264_hbd_pred": (None, [i32, i32, i32, vp, vp, i32, i32, pd]),
     "h264_hbd_pred_add": (None, [i32, i32, i32, vp, vp, vp, i32, i32, pd]),
+    "h264_pred422": (None, [i32, i32, vp, pd]),
+    "h264_pred422_add": (None, [i32, i32, vp, vp, vp, pd]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),

@@ -164,6 +164,11 @@ void ORC(h264_hbd_chroma)(int bits, int avg, int widx, uint8_t *dst, uint8_t *sr
 /* H264PredContext for codec H.264, 9 / 10 bit, 4:2:0: tab / mode as h264_pred and h264_pred_add above; block_offset[] and stride in bytes */
 void ORC(h264_hbd_pred)(int bits, int tab, int mode, uint8_t *src, const uint8_t *topright, int has_topleft, int has_topright, ptrdiff_t stride);
 void ORC(h264_hbd_pred_add)(int bits, int tab, int mode, uint8_t *pix, const int *block_offset, int32_t *block, int has_topleft, int has_topright, ptrdiff_t stride);
+/* chroma_format_idc 2: the pred8x8[] / pred8x8_add[] entries become the 8 x 16 functions (h264pred.c:477-563, h264pred_template.c:502-838,
+ * 1326-1354).  bits 8 (uint8 samples, int16 residual) / 9 / 10 (uint16, int32); mode = the pred8x8[] index 0..10; add_mode 0 vertical,
+ * 1 horizontal; stride and block_offset[] in bytes */
+void ORC(h264_pred422)(int bits, int mode, uint8_t *src, ptrdiff_t stride);
+void ORC(h264_pred422_add)(int bits, int add_mode, uint8_t *pix, const int *block_offset, void *block, ptrdiff_t stride);
 
 /* ---- H264QpelContext / H264ChromaContext (h264qpel.h:27-30, h264chroma.h:25-30) ---- */
 /* sidx 0..3 = 16,8,4,2 ; mc = (mx&3) + 4*(my&3) */

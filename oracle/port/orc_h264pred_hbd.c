@@ -172,3 +172,71 @@ void orc_h264_hbd_pred_add(int bits, int tab, int mode, uint8_t *pixp, const int
         }
     }
 }
+
+/* ---- chroma_format_idc 2: 8 x 16 chroma blocks (h264pred_template.c:502-838), bits 8 / 9 / 10 ------------------------------------------
+ * One expression per sample from the row above (top[0..7], corner) and the column to the left (left[0..15]): the DC family works per
+ * 4 x 4 quadrant (2 across, 4 down), plane prediction has an 8-tap vertical gradient (:804-838). */
+static int ld(const uint8_t *p, int bits, ptrdiff_t byte_off) { return bits > 8 ? *(const uint16_t *)(p + byte_off) : p[byte_off]; }
+static void stp(uint8_t *p, int bits, ptrdiff_t byte_off, int v) { if (bits > 8) *(uint16_t *)(p + byte_off) = (uint16_t)v; else p[byte_off] = (uint8_t)v; }
+
+void orc_h264_pred422(int bits, int mode, uint8_t *src, ptrdiff_t st)
+{
+    const int sb = bits > 8 ? 2 : 1, mid = 1 << (bits - 1), maxv = (1 << bits) - 1;
+    int top[8], left[16], corner, out[16][8];
+    const int rt = mode == 0 || mode == 2 || mode == 3 || mode == 5 || mode == 7 || mode == 8;
+    const int rl = mode == 0 || mode == 1 || mode == 3 || mode == 4 || mode >= 7;
+    const int nl = mode == 7 ? 4 : 16;
+    memset(top, 0, sizeof(top)); memset(left, 0, sizeof(left));
+    if (rt) for (int i = 0; i < 8; i++) top[i] = ld(src, bits, -st + i * sb);
+    if (rl) for (int i = 0; i < nl; i++) left[i] = ld(src, bits, i * st - sb);
+    corner = mode == 3 ? ld(src, bits, -st - sb) : 0;
+    int t0 = 0, t1 = 0, l[4] = { 0, 0, 0, 0 }, H = 0, V = 0, a = 0;
+    for (int i = 0; i < 4; i++) { t0 += top[i]; t1 += top[4 + i]; }
+    for (int i = 0; i < 16; i++) l[i >> 2] += left[i];
+    if (mode == 3) {
+        for (int k = 1; k <= 4; k++) H += k * (top[3 + k] - (3 - k < 0 ? corner : top[3 - k]));
+        for (int k = 1; k <= 8; k++) V += k * (left[7 + k] - (7 - k < 0 ? corner : left[7 - k]));
+        H = (17 * H + 16) >> 5; V = (5 * V + 32) >> 6;
+        a = 16 * (left[15] + top[7] + 1) - 7 * V - 3 * H;
+    }
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 8; x++) {
+            const int c = x >> 2, r = y >> 2;
+            const int dc = !c ? (!r ? (t0 + l[0] + 4) >> 3 : (l[r] + 2) >> 2) : (!r ? (t1 + 2) >> 2 : (t1 + l[r] + 4) >> 3);     /* pred8x16_dc, :673-720 */
+            const int ldc = (l[r] + 2) >> 2, tdc = ((c ? t1 : t0) + 2) >> 2;
+            int v;
+            switch (mode) {
+            case 0: v = dc; break;
+            case 1: v = left[y]; break;
+            case 2: v = top[x]; break;
+            case 3: v = (a + x * H + y * V) >> 5; v = v < 0 ? 0 : v > maxv ? maxv : v; break;
+            case 4: v = ldc; break;
+            case 5: v = tdc; break;
+            case 6: v = mid; break;
+            case 7: v = (!c && !r) ? (t0 + l[0] + 4) >> 3 : tdc; break;      /* top_dc, then pred4x4_dc on the first block */
+            case 8: v = (!c && !r) ? (t0 + 2) >> 2 : dc; break;              /* dc, then pred4x4_top_dc on the first block */
+            case 9: v = r == 1 ? mid : ldc; break;                           /* left_dc, then 128 on the two blocks of the second row */
+            default: v = r == 0 ? mid : ldc; break;                          /* left_dc, then 128 on the two blocks of the first row */
+            }
+            out[y][x] = v;
+        }
+    for (int y = 0; y < 16; y++) for (int x = 0; x < 8; x++) stp(src, bits, y * st + x * sb, out[y][x]);
+}
+
+/* pred8x16_vertical_add / _horizontal_add (:1326-1354): eight 4 x 4 blocks, the lower four through block_offset[i + 4] */
+void orc_h264_pred422_add(int bits, int add_mode, uint8_t *pix, const int *block_offset, void *block, ptrdiff_t st)
+{
+    const int sb = bits > 8 ? 2 : 1, mask = bits > 8 ? 0xffff : 0xff;
+    for (int b = 0; b < 8; b++) {
+        uint8_t *p = pix + block_offset[b < 4 ? b : b + 4];
+        for (int i = 0; i < 4; i++) {
+            int v = add_mode ? ld(p, bits, i * st - sb) : ld(p, bits, -st + i * sb);
+            for (int k = 0; k < 4; k++) {
+                const int ci = 16 * b + (add_mode ? i * 4 + k : k * 4 + i);
+                v = (v + (bits > 8 ? ((int32_t *)block)[ci] : ((int16_t *)block)[ci])) & mask;
+                stp(p, bits, add_mode ? i * st + k * sb : k * st + i * sb, v);
+            }
+        }
+        if (bits > 8) memset((int32_t *)block + 16 * b, 0, 64); else memset((int16_t *)block + 16 * b, 0, 32);
+    }
+}

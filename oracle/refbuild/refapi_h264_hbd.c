@@ -19,14 +19,16 @@ static pthread_once_t once = PTHREAD_ONCE_INIT;
 static H264DSPContext dsp[2][2];          /* [bits 9 / 10][chroma_format_idc 1 / 2] */
 static H264QpelContext qpel[2];
 static H264ChromaContext chroma[2];
-static H264PredContext pred[2];
+static H264PredContext pred[2], pred422[3];      /* pred422: chroma_format_idc 2 at 8 / 9 / 10 bit */
 static void init_all(void)
 {
     av_set_cpu_flags_mask(0);
+    ff_h264_pred_init(&pred422[0], AV_CODEC_ID_H264, 8, 2);
     for (int b = 0; b < 2; b++) {
         ff_h264dsp_init(&dsp[b][0], 9 + b, 1); ff_h264dsp_init(&dsp[b][1], 9 + b, 2);
         ff_h264qpel_init(&qpel[b], 9 + b); ff_h264chroma_init(&chroma[b], 9 + b);
         ff_h264_pred_init(&pred[b], AV_CODEC_ID_H264, 9 + b, 1);
+        ff_h264_pred_init(&pred422[1 + b], AV_CODEC_ID_H264, 9 + b, 2);
     }
 }
 #define D(bits, idc2) (pthread_once(&once, init_all), &dsp[(bits) - 9][idc2])
@@ -116,4 +118,15 @@ void ref_h264_hbd_pred_add(int bits, int tab, int mode, uint8_t *pix, const int 
     case 3: h->pred8x8_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, b, stride); break;
     default: h->pred16x16_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, b, stride); break;
     }
+}
+
+void ref_h264_pred422(int bits, int mode, uint8_t *src, ptrdiff_t stride)
+{
+    pthread_once(&once, init_all);
+    pred422[bits - 8].pred8x8[mode](src, stride);
+}
+void ref_h264_pred422_add(int bits, int add_mode, uint8_t *pix, const int *block_offset, void *block, ptrdiff_t stride)
+{
+    pthread_once(&once, init_all);
+    pred422[bits - 8].pred8x8_add[add_mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, (int16_t *)block, stride);
 }

@@ -153,6 +153,40 @@ def compare(a, b, bits, seed=0):
 PRED_TABS = {0: (4, 12), 1: (8, 12), 2: (8, 11), 3: (16, 7)}
 
 
+def pred422_compare(a, b, bits, seed=0):
+    """chroma_format_idc 2: the 8 x 16 pred8x8[] entries and the two pred8x8_add[] entries, bits 8 / 9 / 10"""
+    rng = np.random.default_rng(seed + 100 * bits)
+    top, sb, n = (1 << bits) - 1, 2 if bits > 8 else 1, 0
+    dt, ct = (np.uint16, np.int32) if bits > 8 else (np.uint8, np.int16)
+    stride = 64 * sb
+    for it in range(14):
+        img = rng.integers(0, top + 1, size=(48, 64)).astype(dt)
+        if it % 4 == 0:
+            img[:] = rng.choice([0, top, top // 2])
+            img[::3, ::5] = rng.integers(0, top + 1)
+        x, y = 16 + 4 * int(rng.integers(0, 3)), 16 + 4 * int(rng.integers(0, 3))
+        for mode in range(11):
+            res = []
+            for c in (a, b):
+                p = img.copy()
+                c.h264_pred422(bits, mode, vp(p, sb * (y * 64 + x)), stride)
+                res.append(p)
+            assert np.array_equal(res[0], res[1]), ("pred422", bits, mode, np.argwhere(res[0] != res[1])[:4].tolist()); n += 1
+        bo = np.zeros(16, np.int32)
+        for k in range(4):
+            bo[k] = sb * (4 * (k & 1) + 4 * (k >> 1) * 64)
+            bo[8 + k] = sb * (4 * (k & 1) + (8 + 4 * (k >> 1)) * 64)
+        blk = rng.integers(-300 << (bits - 8), (300 << (bits - 8)) + 1, size=128).astype(ct)
+        for add_mode in (0, 1):
+            res = []
+            for c in (a, b):
+                p, k = img.copy(), blk.copy()
+                c.h264_pred422_add(bits, add_mode, vp(p, sb * (16 * 64 + 16)), vp(bo), vp(k), stride)
+                res.append((p, k))
+            assert np.array_equal(res[0][0], res[1][0]) and not res[0][1].any() and not res[1][1].any(), ("pred422_add", bits, add_mode); n += 1
+    return n
+
+
 def pred_compare(a, b, bits, rng):
     """H264PredContext: every mode of pred4x4 / pred8x8l (all has_topleft / has_topright pairs) / pred8x8 / pred16x16 and the ten lossless
     *_add predictors on 64-sample-wide pictures of 16-bit samples; whole pictures are compared (a stray write shows)"""
@@ -296,3 +330,22 @@ class TableCallee:
             h.pred8x8_add[1 if mode else 2](pix, bo, block, stride)          # [HOR_PRED8x8 = 1], [VERT_PRED8x8 = 2]
         else:
             h.pred16x16_add[1 if mode else 2](pix, bo, block, stride)
+
+
+class Pred422Callee:
+    """h264_pred422 / h264_pred422_add served by an H264PredContext filled for chroma_format_idc 2: fill(table_ref, bits)"""
+
+    def __init__(self, fill):
+        from libav_b200 import tables
+        self.h = {}
+        for bits in (8, 9, 10):
+            h = tables.H264PredContext()
+            fill(C.byref(h), bits)
+            assert all(C.cast(h.pred8x8[m], C.c_void_p).value for m in range(11)) and h.pred8x8_add[1] and h.pred8x8_add[2], bits
+            self.h[bits] = h
+
+    def h264_pred422(self, bits, mode, src, stride):
+        self.h[bits].pred8x8[mode](src, stride)
+
+    def h264_pred422_add(self, bits, add_mode, pix, bo, block, stride):
+        self.h[bits].pred8x8_add[1 if add_mode else 2](pix, bo, block, stride)

@@ -5,3 +5,4 @@
 
 // ff_h264_pred_init_cuda() itself lives in h264pred.cu (its 8-bit kernels use shared memory); this is the branch it takes for 9 / 10 bit
 extern "C" void hostsim_h264_pred_init_hbd(H264PredContext *h, int bits) { avb::h264pred_init_hbd(h, bits); }
+extern "C" void hostsim_h264_pred_install_422(H264PredContext *h, int bits) { avb::h264pred_install_422(h, bits); }

@@ -23,7 +23,6 @@ def hpc(gpu):
 def test_other_codecs_are_left_alone(gpu):
     h = tables.H264PredContext()
     gpu.lib.ff_h264_pred_init_cuda(C.byref(h), 27, 12, 1)       # (9 / 10 bit are taken over: tests/test_zz_gpu_late_slots.py)
-    gpu.lib.ff_h264_pred_init_cuda(C.byref(h), 27, 8, 2)        # 4:2:2: the pred8x16 family is not
     gpu.lib.ff_h264_pred_init_cuda(C.byref(h), 139, 8, 1)
     assert not any(C.cast(f, C.c_void_p).value for f in h.pred4x4)
 

@@ -153,3 +153,11 @@ def test_fdct10(sim, refo):
         return blk
     idct10_cases.fdct10_cases(t, run_batch, refo)
     assert sim.avb200_last_error().decode() == ""
+
+
+@pytest.mark.parametrize("bits", [8, 9, 10])
+def test_h264_pred_422(sim, refo, bits):
+    """chroma_format_idc 2: the 8 x 16 entries of pred8x8[] / pred8x8_add[] (libav_b200/csrc/h264pred_hbd.cu, host-compiled), 8 / 9 / 10 bit"""
+    import hbd_cases
+    assert hbd_cases.pred422_compare(hbd_cases.Pred422Callee(sim.hostsim_h264_pred_install_422), refo, bits, seed=2) > 150
+    assert sim.avb200_last_error().decode() == ""

@@ -137,3 +137,17 @@ def test_fdct10(gpu, checker):
         return blk
     idct10_cases.fdct10_cases(t, run_batch, checker)
     assert gpu.last_error() == ""
+
+
+@pytest.mark.parametrize("bits", [8, 9, 10])
+def test_h264_pred_422(gpu, checker, bits):
+    """ff_h264_pred_init_cuda(h, AV_CODEC_ID_H264, bits, 2): the chroma entries are the 8 x 16 functions; the luma entries stay what they are at idc 1"""
+    import hbd_cases
+    from libav_b200 import tables
+    fill = lambda h, b: gpu.lib.ff_h264_pred_init_cuda(h, 27, b, 2)
+    assert hbd_cases.pred422_compare(hbd_cases.Pred422Callee(fill), checker, bits, seed=3) > 150
+    h1, h2 = tables.H264PredContext(), tables.H264PredContext()
+    gpu.lib.ff_h264_pred_init_cuda(C.byref(h1), 27, bits, 1); gpu.lib.ff_h264_pred_init_cuda(C.byref(h2), 27, bits, 2)
+    same = lambda a, b: C.cast(a, C.c_void_p).value == C.cast(b, C.c_void_p).value
+    assert same(h1.pred4x4[3], h2.pred4x4[3]) and same(h1.pred16x16[3], h2.pred16x16[3]) and not same(h1.pred8x8[0], h2.pred8x8[0])
+    assert gpu.last_error() == ""

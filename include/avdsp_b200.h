@@ -423,7 +423,7 @@ void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_samp
 void ff_me_cmp_init_cuda(MECmpContext *c);
 /* libavcodec/h264dsp.c:57-143, h264qpel.c:36-89, h264chroma.c:32-55, hpeldsp.c:338-366.  bit_depth 8, and 9 / 10 (the reference's BIT_DEPTH > 8
  * instances: uint8_t * arguments point at uint16 samples, int16_t * at int32 coefficients, strides stay in bytes).  ff_h264dsp_init_cuda fills
- * every entry ff_h264dsp_init fills (mbaff loop filters included) except startcode_find_candidate; chroma_format_idc > 1 selects the
+ * every entry ff_h264dsp_init fills (mbaff loop filters and startcode_find_candidate included); chroma_format_idc > 1 selects the
  * 4:2:2 entries (idct_add8_422, the 2x4 chroma DC transform, the 16-line h_ chroma filters) exactly like h264dsp.c:81-122 */
 void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc);
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth);

@@ -127,9 +127,38 @@ struct Stage {
     int run(const SlotArgs &a) { AVB_LAUNCH(slot_kernel, 1, 32, 0, s)(a); return check_launch("slot"); }
 };
 
+// H264DSPContext.startcode_find_candidate = ff_startcode_find_candidate_c (libavcodec/startcode.c:31-59): index of the first zero byte, `size`
+// when there is none before it.  Thread per byte, the smallest index wins through atomicMin.
+__global__ void __launch_bounds__(256) startcode_kernel(const uint8_t *__restrict__ buf, int size, int *__restrict__ first)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < size && !buf[i]) atomicMin(first, i);
+}
+int startcode_find_candidate_cuda(const uint8_t *buf, int size)
+{
+    if (size <= 0) return 0;
+    ScratchLock lk;
+    Scratch &S = scratch();
+    const size_t need = (size_t)size + 64;
+    uint8_t *h = (uint8_t *)S.pinned2(need), *d = (uint8_t *)S.dev(4, need);
+    cudaStream_t *st = S.streams();
+    if (!h || !d || !st) return size;
+    const size_t off = ((size_t)size + 15) & ~(size_t)15;            // the result word sits after the bytes
+    memcpy(h, buf, size);
+    memcpy(h + off, &size, 4);
+    if (cudaMemcpyAsync(d, h, off + 4, cudaMemcpyHostToDevice, st[0]) != cudaSuccess) { set_error("startcode slot:h2d", cudaGetLastError()); return size; }
+    AVB_LAUNCH(startcode_kernel, dim3((unsigned)((size + 255) / 256)), dim3(256), 0, st[0])(d, size, (int *)(d + off));
+    if (check_launch("startcode slot")) return size;
+    int r = size;
+    if (cudaMemcpyAsync(h + off, d + off, 4, cudaMemcpyDeviceToHost, st[0]) != cudaSuccess || cudaStreamSynchronize(st[0]) != cudaSuccess) { set_error("startcode slot:d2h", cudaGetLastError()); return size; }
+    memcpy(&r, h + off, 4);
+    return r;
+}
+
 }  // namespace avb
 
 namespace avb {      // slots_hbd.cu: the 9 / 10-bit instances
+static int slot_startcode(const uint8_t *buf, int size) { return startcode_find_candidate_cuda(buf, size); }
 void h264dsp_init_hbd(H264DSPContext *c, int bits, int chroma_format_idc);
 void h264qpel_init_hbd(H264QpelContext *c, int bits);
 void h264chroma_init_hbd(H264ChromaContext *c, int bits);
@@ -426,7 +455,7 @@ void ff_me_cmp_init_cuda(MECmpContext *c)
 
 void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc)
 {
-    if (bit_depth == 9 || bit_depth == 10) { h264dsp_init_hbd(c, bit_depth, chroma_format_idc); return; }
+    if (bit_depth == 9 || bit_depth == 10) { h264dsp_init_hbd(c, bit_depth, chroma_format_idc); c->startcode_find_candidate = slot_startcode; return; }
     if (bit_depth != 8) return;                                           // other depths do not exist for H.264 here (h264dsp.c:126-136 maps them to 8)
     const bool c420 = chroma_format_idc <= 1;                             // the reference's own test, h264dsp.c:81-122
     c->weight_h264_pixels_tab[0] = slot_weight<0>; c->weight_h264_pixels_tab[1] = slot_weight<1>;
@@ -443,7 +472,8 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
     c->h264_v_loop_filter_chroma_intra = slot_loop_intra<6>;
     c->h264_h_loop_filter_chroma_intra = c420 ? slot_loop_intra<7> : slot_loop_intra<13>;
     c->h264_h_loop_filter_chroma_mbaff_intra = c420 ? slot_loop_intra<11> : slot_loop_intra<15>;
-    // h264_loop_filter_strength (NULL in C, h264dsp.c:124) and startcode_find_candidate are left alone
+    // h264_loop_filter_strength stays NULL like in C (h264dsp.c:124)
+    c->startcode_find_candidate = slot_startcode;                         // h264dsp.c:137, every bit depth
     c->h264_idct_add = slot_h264_idct<0>; c->h264_idct8_add = slot_h264_idct<1>;
     c->h264_idct_dc_add = slot_h264_idct<2>; c->h264_idct8_dc_add = slot_h264_idct<3>;
     c->h264_idct_add16 = slot_idct_mb<0>; c->h264_idct_add16intra = slot_idct_mb<1>; c->h264_idct8_add4 = slot_idct_mb<2>;

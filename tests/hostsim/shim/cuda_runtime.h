@@ -54,6 +54,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
     }
     return r;
 }
+static inline int atomicMin(int *p, int v) { const int old = *p; if (v < old) *p = v; return old; }      /* threads run one after the other here */
 static inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }
 

@@ -121,8 +121,24 @@ def h264dsp_cases(lib, last_error, checker, weights=True):
              c.h264_v_loop_filter_chroma, c.h264_h_loop_filter_chroma, c.h264_v_loop_filter_chroma_intra, c.h264_h_loop_filter_chroma_intra,
              c.h264_h_loop_filter_luma_mbaff, c.h264_h_loop_filter_luma_mbaff_intra, c.h264_h_loop_filter_chroma_mbaff, c.h264_h_loop_filter_chroma_mbaff_intra]
     loop_filter_cases(rng, checker, [(which, slot, bool(which & 2) if which < 8 else bool(which & 1)) for which, slot in enumerate(slots)])
-    assert not c.h264_loop_filter_strength and not c.startcode_find_candidate      # left to the caller, as documented
+    assert not c.h264_loop_filter_strength                                          # NULL in C too (h264dsp.c:124)
+    assert c.startcode_find_candidate                                               # (exercised by startcode_cases from the late / hostsim tests)
     assert last_error() == ""
+
+
+def startcode_cases(rng, slot):
+    """ff_startcode_find_candidate_c (libavcodec/startcode.c:31-59): the index of the first zero byte, `size` when there is none before it"""
+    for size in (1, 7, 8, 9, 255, 256, 257, 5000, 100001):
+        buf = rng.integers(1, 256, size=size + 64, dtype=np.uint8)
+        assert slot(P(buf), size) == size                          # no zero at all
+        buf[size:] = 0
+        assert slot(P(buf), size) == size                          # zeros only in the padding
+        for pos in sorted({0, size // 2, size - 1}):
+            b2 = buf.copy()
+            b2[pos] = 0
+            b2[min(pos + 3, size - 1)] = 0
+            assert slot(P(b2), size) == pos, (size, pos)
+    assert slot(P(np.zeros(16, np.uint8)), 0) == 0
 
 
 def loop_filter_cases(rng, checker, cases, iters=12):

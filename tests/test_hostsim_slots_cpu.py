@@ -42,6 +42,16 @@ def test_h264dsp_slots(sim, checker):
     slot_cases.h264dsp_cases(sim, last_error_of(sim), checker, weights=False)
 
 
+def test_startcode_slot(sim):
+    import numpy as np
+    from libav_b200 import tables
+    for bits in (8, 10):
+        c = tables.H264DSPContext()
+        sim.ff_h264dsp_init_cuda(C.byref(c), bits, 1)
+        slot_cases.startcode_cases(np.random.default_rng(bits), c.startcode_find_candidate)
+    assert sim.avb200_last_error().decode() == ""
+
+
 def test_h264dsp_slots_422(sim, checker):
     slot_cases.h264dsp_422_cases(sim, last_error_of(sim), checker)
 

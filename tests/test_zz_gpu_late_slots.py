@@ -151,3 +151,13 @@ def test_h264_pred_422(gpu, checker, bits):
     same = lambda a, b: C.cast(a, C.c_void_p).value == C.cast(b, C.c_void_p).value
     assert same(h1.pred4x4[3], h2.pred4x4[3]) and same(h1.pred16x16[3], h2.pred16x16[3]) and not same(h1.pred8x8[0], h2.pred8x8[0])
     assert gpu.last_error() == ""
+
+
+def test_startcode_slot(gpu):
+    import numpy as np
+    from libav_b200 import tables
+    for bits in (8, 10):
+        c = tables.H264DSPContext()
+        gpu.lib.ff_h264dsp_init_cuda(C.byref(c), bits, 1)
+        slot_cases.startcode_cases(np.random.default_rng(bits), c.startcode_find_candidate)
+    assert gpu.last_error() == ""

@@ -76,3 +76,27 @@ def test_product_does_not_link_or_import_the_oracle():
                 assert "oracle_api.h" not in txt and "liboracle" not in txt and "libavref" not in txt or f == "build.py", f
     out = subprocess.check_output(["ldd", os.path.join(ROOT, "libav_b200", "libavdsp_b200.so")]).decode()
     assert "oracle" not in out and "avref" not in out
+
+
+def test_null_and_zero_arguments_fail_loudly_not_fatally(built):
+    """every batched / scaler entry point called with NULL pointers and zero (then small non-zero) counts, without a GPU: an error return
+    or an empty success, never a crash (run in a child process so that a crash would be a test failure, not the end of the suite)"""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import libav_b200._lib as L
+names = [n for n in L.PROTOTYPES if n.startswith("ff_") and n.endswith("_cuda") and "init" not in n] + \
+        ["sws_scale_cuda", "sws_scale_frames_cuda", "sws_setColorspaceDetails_cuda", "sws_is_fused_cuda", "sws_freeContext_cuda"]
+for name in names:
+    res, args = L.PROTOTYPES[name]
+    for variant in (0, 4):
+        vals = [None if a in (C.c_void_p, C.c_char_p) else 1.0 if a == C.c_double else variant for a in args]
+        r = getattr(L.lib, name)(*vals)
+        assert r in (None, 0, -1), (name, variant, r)
+        L.lib.avb200_clear_error()
+print("ok", len(names))
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.startswith("ok"), (p.returncode, p.stdout[-300:], p.stderr[-300:])

@@ -1818,6 +1818,50 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
     return c->g.dstH * nframes;
 }
 
+// Bottom-up pictures (negative strides, e.g. after a vertical flip that only negates linesize; the reference handles them like any
+// other stride, swscale_unscaled.c:1212-1340): the planes with a negative stride are copied row by row into top-down host buffers of the
+// same pitch, the call below runs on those, and destination planes are copied back the same way (pre-filled with the caller's bytes so
+// that what a converter leaves untouched stays untouched).  Rows are copied with a few bytes past the nominal width -- the bytes the
+// top-down path may look at or write (odd widths, pair rounding) -- never more than the pitch.
+static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    const SwsGeometry &g = c->g;
+    const bool pk = c->srcPacked != 0, nv = c->srcNV != 0, rgb = !c->planar;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
+    const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH }, dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
+    const size_t srcW[3] = { (size_t)g.srcW * (pk ? pkBpp : 1), (size_t)g.chrSrcW * (nv ? 2 : 1), (size_t)g.chrSrcW };
+    const size_t dstW[3] = { (size_t)g.dstW * (rgb ? pxB : sB), (size_t)g.chrDstW * (c->dstNV ? 2 : sB), (size_t)g.chrDstW * sB };
+    std::vector<uint8_t> sbuf[3], dbuf[3];
+    const uint8_t *s2[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint8_t *d2[4] = { nullptr, nullptr, nullptr, nullptr };
+    int ss[4] = { 0, 0, 0, 0 }, ds[4] = { 0, 0, 0, 0 };
+    size_t drow[3] = { 0, 0, 0 };
+    for (int p = 0; p < nsrc; p++) {
+        s2[p] = srcSlice[p]; ss[p] = srcStride[p];
+        if (srcStride[p] >= 0) continue;
+        const size_t pitch = (size_t)(-(ptrdiff_t)srcStride[p]), row = std::min(pitch, srcW[p] + 16);
+        sbuf[p].assign(pitch * srcRows[p] + 16, 0);
+        for (int y = 0; y < srcRows[p]; y++) memcpy(sbuf[p].data() + y * pitch, srcSlice[p] + (ptrdiff_t)y * srcStride[p], row);
+        s2[p] = sbuf[p].data(); ss[p] = (int)pitch;
+    }
+    for (int p = 0; p < ndst; p++) {
+        d2[p] = dst[p]; ds[p] = dstStride[p];
+        if (dstStride[p] >= 0) continue;
+        const size_t pitch = (size_t)(-(ptrdiff_t)dstStride[p]);
+        drow[p] = std::min(pitch, dstW[p] + 16);
+        dbuf[p].assign(pitch * dstRows[p] + 16, 0);
+        for (int y = 0; y < dstRows[p]; y++) memcpy(dbuf[p].data() + y * pitch, dst[p] + (ptrdiff_t)y * dstStride[p], drow[p]);
+        d2[p] = dbuf[p].data(); ds[p] = (int)pitch;
+    }
+    const int r = sws_scale_cuda((SwsContextCUDA *)c, s2, ss, 0, srcSliceH, d2, ds);
+    if (r <= 0) return r;
+    for (int p = 0; p < ndst; p++)
+        if (dstStride[p] < 0)
+            for (int y = 0; y < dstRows[p]; y++) memcpy(dst[p] + (ptrdiff_t)y * dstStride[p], dbuf[p].data() + (size_t)y * ds[p], drow[p]);
+    return r;
+}
+
 // Host-pointer drop-in for sws_scale() (libswscale/swscale_unscaled.c:1212-1340): whole frames only.
 // Returns the number of output lines like the reference, 0 on bad arguments.
 int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY, int srcSliceH,
@@ -1832,7 +1876,9 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
     if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
-    if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0) { set_error_msg("sws_scale_cuda", "negative strides are not taken over"); return 0; }
+    if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0 ||
+        (!rgb && (dstStride[1] < 0 || (!c->dstNV && dstStride[2] < 0))))
+        return sws_scale_cuda_flipped(c, srcSlice, srcStride, srcSliceH, dst, dstStride);
     ScratchLock lk;
     cudaStream_t *st = scratch().streams();
     if (!st) return 0;

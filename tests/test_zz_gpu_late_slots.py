@@ -161,3 +161,48 @@ def test_startcode_slot(gpu):
         gpu.lib.ff_h264dsp_init_cuda(C.byref(c), bits, 1)
         slot_cases.startcode_cases(np.random.default_rng(bits), c.startcode_find_candidate)
     assert gpu.last_error() == ""
+
+
+def test_sws_scale_negative_strides(gpu):
+    """bottom-up pictures (negative strides on either side) give the bytes of the same picture stored top-down; what the converters leave
+    untouched (row padding) stays untouched"""
+    import numpy as np
+    from test_sws_planar_dst import source
+    lib = gpu.lib
+    for (sf, df, w, h, dw, dh, flags) in [(0, 2, 64, 48, 96, 80, 4), (0, 2, 66, 50, 66, 50, 4 | 0x40000), (0, 0, 101, 37, 64, 48, 4), (4, 5, 64, 48, 64, 48, 2),
+                                           (1, 2, 64, 48, 96, 80, 4), (0, 28, 64, 48, 33, 25, 4), (0, 23, 64, 48, 96, 80, 4)]:
+        ctx = lib.sws_getContext_cuda(w, h, sf, dw, dh, df, flags, None, None, None)
+        assert ctx, (sf, df, gpu.last_error())
+        pl = source(sf, w, h, 31)
+        if df in (2, 28):
+            outs = [np.full((dh, dw * (4 if df == 28 else 3) + 24), 9, np.uint8)]
+        elif df == 23:
+            outs = [np.full((dh, dw + 8), 9, np.uint8), np.full(((dh + 1) // 2, 2 * ((dw + 1) // 2) + 8), 9, np.uint8)]
+        else:
+            cw, ch = (dw, dh) if df == 5 else ((dw + 1) // 2, (dh + 1) // 2)
+            outs = [np.full((dh, dw + 8), 9, np.uint8), np.full((ch, cw + 8), 9, np.uint8), np.full((ch, cw + 8), 9, np.uint8)]
+
+        def call(src, dst):
+            sp = (C.c_void_p * 4)(*([a.ctypes.data for a in src] + [None] * (4 - len(src))))
+            ss = (C.c_int * 4)(*([a.strides[0] for a in src] + [0] * (4 - len(src))))
+            dp = (C.c_void_p * 4)(*([a.ctypes.data for a in dst] + [None] * (4 - len(dst))))
+            ds = (C.c_int * 4)(*([a.strides[0] for a in dst] + [0] * (4 - len(dst))))
+            assert lib.sws_scale_cuda(ctx, sp, ss, 0, h, dp, ds) == dh, gpu.last_error()
+        want = [o.copy() for o in outs]
+        call(pl, want)
+        # the same pictures stored bottom-up: flipped copies viewed through negative strides
+        src_up = [np.ascontiguousarray(a[::-1])[::-1] for a in pl]
+        got_store = [np.ascontiguousarray(o[::-1]) for o in outs]
+        got = [g[::-1] for g in got_store]
+        assert all(a.strides[0] < 0 for a in src_up + got)
+        call(src_up, got)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (sf, df, w, h, dw, dh)
+        # mixed: top-down source, bottom-up destination
+        got_store = [np.ascontiguousarray(o[::-1]) for o in outs]
+        got = [g[::-1] for g in got_store]
+        call(pl, got)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), ("mixed", sf, df)
+        lib.sws_freeContext_cuda(ctx)
+    assert gpu.last_error() == ""

@@ -28,10 +28,11 @@ static Scratch g_scratch;
 static std::recursive_mutex g_mu;
 Scratch &scratch() { return g_scratch; }
 std::recursive_mutex &scratch_mutex() { return g_mu; }
-static void *grow(void *&p, size_t &n, size_t bytes) { if (n < bytes) { free(p); p = calloc(1, bytes); n = bytes; } return p; }
-void *Scratch::dev(int slot, size_t bytes) { return grow(d_[slot], dn_[slot], bytes); }
+// real device / pinned allocations come back uninitialised: poison them so that a kernel reading bytes nobody staged cannot pass by luck
+static void *grow(void *&p, size_t &n, size_t bytes) { if (n < bytes) { free(p); p = malloc(bytes); memset(p, 0xA7, bytes); n = bytes; } return p; }
+void *Scratch::dev(int slot, size_t bytes) { void *p = grow(d_[slot], dn_[slot], bytes); memset(p, 0xA7, bytes); return p; }      // (every call: contents are undefined)
 void *Scratch::pinned(size_t bytes) { return grow(h_, hn_, bytes); }
-void *Scratch::pinned2(size_t bytes) { return grow(h2_, h2n_, bytes); }
+void *Scratch::pinned2(size_t bytes) { void *p = grow(h2_, h2n_, bytes); memset(p, 0x5B, bytes); return p; }
 cudaStream_t *Scratch::streams() { return st_; }
 }  // namespace avb
 

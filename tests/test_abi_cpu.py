@@ -100,3 +100,18 @@ print("ok", len(names))
 ''' % ROOT
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.startswith("ok"), (p.returncode, p.stdout[-300:], p.stderr[-300:])
+
+
+def test_reference_side_binding_compiles(built):
+    """examples/reference_binding/dsp_init_cuda.c -- the glue INTEGRATION.md describes -- against the reference's OWN headers: every hook
+    prototype and every slot assignment is type-checked with the reference's struct definitions (needs /root/reference; skipped on the GPU box)"""
+    ref, cfg = "/root/reference", os.path.join(ROOT, "oracle", "_ref", "cfg")
+    if not os.path.isdir(ref) or not os.path.exists(os.path.join(cfg, "config.h")):
+        pytest.skip("no reference tree here")
+    src = os.path.join(ROOT, "examples", "reference_binding", "dsp_init_cuda.c")
+    r = subprocess.run(["gcc", "-std=c99", "-c", "-Wall", "-Werror", "-Wno-unused-function", "-Wno-attributes", "-I", cfg, "-I", ref, src, "-o", os.devnull],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # the slot table declared there with the reference's typedefs has the layout of the one in include/avdsp_b200.h
+    from libav_b200 import tables
+    assert C.sizeof(tables.SwsLineSlotsCUDA) == 12 * C.sizeof(C.c_void_p)

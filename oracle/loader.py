@@ -73,6 +73,11 @@ API = {
     "sws_line_plane": (i32, [i32, vp, i32, vp, vp, i32, vp, i32]),
     "sws_line_nv12": (i32, [i32, vp, i32, vp, vp, vp, i32]),
     "sws_line_packed": (i32, [i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32]),
+    "sws_open": (vp, [i32, i32, i32, i32, i32, i32, i32]),
+    "sws_set_slots": (i32, [vp, vp]),
+    "sws_slot_mask": (i32, [vp]),
+    "sws_run": (i32, [vp, vp, vp, i32, vp, vp]),
+    "sws_close": (None, [vp]),
     "sws_get_filter": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "sws_rgb24_tables": (None, [vp, vp, vp, vp, vp]),
     "fft": (None, [i32, i32, vp]),

@@ -416,6 +416,53 @@ int ref_sws_line_packed(int dst_fmt, int flags, int kind, const int16_t *lumFilt
     return r;
 }
 
+/* ---- the reference's own scheduler with foreign per-line slots: sws_getContext() -> the caller replaces the slot fields ->
+ * sws_scale().  Used to show that the product's SwsContext slots are a drop-in under the UNMODIFIED swscale() line loop
+ * (tests/test_sws_dropin_cpu.py: host simulation; tests/test_zz_gpu_late_slots.py: the product library).  Only in _ref. ---- */
+void *ref_sws_open(int src_fmt, int sw, int sh, int dst_fmt, int dw, int dh, int flags)
+{
+    INIT();
+    return sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
+}
+/* slots: the 12 pointers of SwsLineSlotsCUDA (include/avdsp_b200.h) in its order; NULL entries leave the C function in place.
+ * Returns how many fields were replaced, -1 if the table asks for a slot the reference itself does not have for this context. */
+int ref_sws_set_slots(void *ctx, void *const slots[12])
+{
+    struct SwsContext *c = ctx;
+    int n = 0;
+    if ((slots[2] && !c->hyscale_fast) || (slots[6] && !c->yuv2nv12cX) || (slots[7] && !c->yuv2packed1) || (slots[8] && !c->yuv2packed2) ||
+        (slots[9] && !c->yuv2packedX) || (slots[10] && !c->lumConvertRange)) return -1;
+    if (slots[0])  { c->hyScale = slots[0]; n++; }
+    if (slots[1])  { c->hcScale = slots[1]; n++; }
+    if (slots[2])  { c->hyscale_fast = slots[2]; n++; }
+    if (slots[3])  { c->hcscale_fast = slots[3]; n++; }
+    if (slots[4])  { c->yuv2plane1 = slots[4]; n++; }
+    if (slots[5])  { c->yuv2planeX = slots[5]; n++; }
+    if (slots[6])  { c->yuv2nv12cX = slots[6]; n++; }
+    if (slots[7])  { c->yuv2packed1 = slots[7]; n++; }
+    if (slots[8])  { c->yuv2packed2 = slots[8]; n++; }
+    if (slots[9])  { c->yuv2packedX = slots[9]; n++; }
+    if (slots[10]) { c->lumConvertRange = slots[10]; n++; }
+    if (slots[11]) { c->chrConvertRange = slots[11]; n++; }
+    /* which slots the reference has installed itself (bit i = slot i non-NULL): the product's table must install the same set */
+    return n;
+}
+int ref_sws_slot_mask(void *ctx)
+{
+    struct SwsContext *c = ctx;
+    return (c->hyScale ? 1 : 0) | (c->hcScale ? 2 : 0) | (c->hyscale_fast ? 4 : 0) | (c->hcscale_fast ? 8 : 0) | (c->yuv2plane1 ? 16 : 0) |
+           (c->yuv2planeX ? 32 : 0) | (c->yuv2nv12cX ? 64 : 0) | (c->yuv2packed1 ? 128 : 0) | (c->yuv2packed2 ? 256 : 0) | (c->yuv2packedX ? 512 : 0) |
+           (c->lumConvertRange ? 1024 : 0) | (c->chrConvertRange ? 2048 : 0);
+}
+int ref_sws_run(void *ctx, const uint8_t *const src[3], const int ss[3], int sh, uint8_t *const dst[3], const int dstride[3])
+{
+    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
+    int sst[4] = { ss[0], ss[1], ss[2], 0 }, ds[4] = { dstride[0], dstride[1], dstride[2], 0 };
+    uint8_t *d[4] = { dst[0], dst[1], dst[2], NULL };
+    return sws_scale(ctx, s, sst, 0, sh, d, ds);
+}
+void ref_sws_close(void *ctx) { sws_freeContext(ctx); }
+
 int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,
                        int32_t *pos, int cap, int *n_out)
 {

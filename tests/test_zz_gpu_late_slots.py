@@ -206,3 +206,16 @@ def test_sws_scale_negative_strides(gpu):
             assert np.array_equal(a, b), ("mixed", sf, df)
         lib.sws_freeContext_cuda(ctx)
     assert gpu.last_error() == ""
+
+
+def test_sws_slots_under_the_reference_scheduler(gpu, refo):
+    """the product's per-line slots installed in real reference SwsContexts and driven by the reference's unmodified swscale()
+    (tests/sws_dropin_cases.py); needs the compiled reference, which travels to the GPU box as oracle/_ref"""
+    import sws_dropin_cases as D
+
+    def make_ctx(sf, w, h, df, dw, dh, flags):
+        ctx = gpu.lib.sws_getContext_cuda(w, h, sf, dw, dh, df, flags, None, None, None)
+        assert ctx, (sf, df, hex(flags), gpu.last_error())
+        return ctx
+    assert D.check(refo, gpu.lib, make_ctx, gpu.lib.sws_freeContext_cuda, geoms=D.GEOMS[:3]) == 46
+    assert gpu.last_error() == ""

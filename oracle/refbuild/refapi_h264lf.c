@@ -152,10 +152,13 @@ static int gather_caches(const H264Context *h, H264SliceContext *sl, int mb_type
     return 0;
 }
 
-int ref_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
-                            const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
-                            const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
-                            const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode, uint8_t *out)
+/* table == NULL: the recorders above (decisions into `out`).  table != NULL: an H264DSPContext whose loop-filter entries are called on the
+ * real picture planes Y / Cb / Cr (pitches ls / uvls) with the pointers loop_filter() passes (h264_slice.c:2198-2262), `out` unused. */
+static int run_driver(const H264DSPContext *table, uint8_t *Y, uint8_t *Cb, uint8_t *Cr, int ls, int uvls,
+                      int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
+                      const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
+                      const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
+                      const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode, uint8_t *out)
 {
     const int ms = mb_w + 1, pad = 2 * ms + 1, n = ms * mb_h;
     H264Context *h = calloc(1, sizeof(*h));
@@ -202,13 +205,14 @@ int ref_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
     h->h264dsp.h264_h_loop_filter_chroma       = r_h_chroma;   h->h264dsp.h264_v_loop_filter_chroma       = r_v_chroma;
     h->h264dsp.h264_h_loop_filter_chroma_intra = r_h_chroma_i; h->h264dsp.h264_v_loop_filter_chroma_intra = r_v_chroma_i;
     h->h264dsp.h264_loop_filter_strength = NULL;               /* what ff_h264dsp_init leaves in the C build */
+    if (table) h->h264dsp = *table;
 
-    memset(out, 0, (size_t)104 * mb_w * mb_h);
+    if (!table) memset(out, 0, (size_t)104 * mb_w * mb_h);
     for (y = 0; y < mb_h; y++)
         for (x = 0; x < mb_w; x++) {
             const int xy = x + y * ms, type = h->cur_pic.mb_type[xy];
             const int32_t *sp = slice_params + 133 * h->slice_table[xy];
-            cur_rec = out + (size_t)104 * (x + y * mb_w);
+            if (!table) cur_rec = out + (size_t)104 * (x + y * mb_w);
             sl->mb_xy = xy; sl->mb_x = x; sl->mb_y = y;
             sl->slice_num = h->slice_table[xy];
             sl->slice_alpha_c0_offset = sp[0]; sl->slice_beta_offset = sp[1];
@@ -217,9 +221,34 @@ int ref_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
                 continue;
             sl->chroma_qp[0] = pps->chroma_qp_table[0][h->cur_pic.qscale_table[xy] & 63];
             sl->chroma_qp[1] = pps->chroma_qp_table[1][h->cur_pic.qscale_table[xy] & 63];
-            ff_h264_filter_mb_fast(h, sl, x, y, fake_y, fake_cb, fake_cr, REC_LS, REC_UVLS);
+            if (table) ff_h264_filter_mb_fast(h, sl, x, y, Y + 16 * (x + (size_t)y * ls), Cb + 8 * (x + (size_t)y * uvls), Cr + 8 * (x + (size_t)y * uvls), ls, uvls);
+            else       ff_h264_filter_mb_fast(h, sl, x, y, fake_y, fake_cb, fake_cr, REC_LS, REC_UVLS);
         }
     for (l = 0; l < 2; l++) free(t_ref[l]);
     free(t_b); free(t_nnz); free(t_cbp); free(t_slice); free(t_qp); free(t_type); free(sps); free(pps); free(sl); free(h);
     return 0;
+}
+
+int ref_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
+                            const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
+                            const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
+                            const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode, uint8_t *out)
+{
+    return run_driver(NULL, NULL, NULL, NULL, 0, 0, mb_w, mb_h, mb_type, qscale, nnz, cbp, slice_table, mv0, mv1, ref0, ref1, slice_params, n_slices,
+                      chroma_qp_table, cabac, transform_8x8_mode, out);
+}
+
+/* The reference's own deblocking driver (ff_h264_filter_mb_fast -> ff_h264_filter_mb, raster order like loop_filter()) filtering a real
+ * picture in place through the loop-filter entries of `table` -- an H264DSPContext filled by anybody: NULL = ff_h264dsp_init(8, 1), the
+ * reference's C functions; otherwise e.g. the table ff_h264dsp_init_cuda() filled (tests/h264_dropin_cases.py).  Only in _ref. */
+int ref_h264_deblock_picture_with(const void *table, uint8_t *Y, uint8_t *Cb, uint8_t *Cr, int ls, int uvls,
+                                  int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
+                                  const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
+                                  const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
+                                  const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode)
+{
+    H264DSPContext c_table;
+    if (!table) { ff_h264dsp_init(&c_table, 8, 1); table = &c_table; }
+    return run_driver(table, Y, Cb, Cr, ls, uvls, mb_w, mb_h, mb_type, qscale, nnz, cbp, slice_table, mv0, mv1, ref0, ref1, slice_params, n_slices,
+                      chroma_qp_table, cabac, transform_8x8_mode, NULL);
 }

@@ -219,3 +219,11 @@ def test_sws_slots_under_the_reference_scheduler(gpu, refo):
         return ctx
     assert D.check(refo, gpu.lib, make_ctx, gpu.lib.sws_freeContext_cuda, geoms=D.GEOMS[:3]) == 46
     assert gpu.last_error() == ""
+
+
+def test_loop_filter_slots_under_the_reference_driver(gpu, refo):
+    """the reference's own deblocking driver (h264_loopfilter.c, unmodified, in oracle/_ref) filtering pictures through the product's
+    H264DSPContext slots: tests/h264_dropin_cases.py"""
+    import h264_dropin_cases as D
+    assert D.check(refo, gpu.lib, sizes=((6, 4), (1, 1))) == 12
+    assert gpu.last_error() == ""

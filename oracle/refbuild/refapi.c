@@ -127,6 +127,10 @@ void ref_fdct(int which, int16_t *block)
     }
 }
 
+/* ff_set_cmp() (libavcodec/me_cmp.c:365-417), the reference's own selection of the six compare functions of a kind out of ANY MECmpContext --
+ * e.g. the one ff_me_cmp_init_cuda() filled (tests/test_me_cmp_select_cpu.py).  Only in _ref. */
+void ref_me_cmp_select(void *table, int type, void *out[6]) { INIT(); ff_set_cmp((MECmpContext *)table, (me_cmp_func *)out, type); }
+
 void ref_h264_idct(int which, uint8_t *dst, int16_t *block, int stride)
 {
     INIT();

@@ -227,3 +227,23 @@ def test_loop_filter_slots_under_the_reference_driver(gpu, refo):
     import h264_dropin_cases as D
     assert D.check(refo, gpu.lib, sizes=((6, 4), (1, 1))) == 12
     assert gpu.last_error() == ""
+
+
+def test_me_cmp_functions_selected_by_the_reference(gpu, refo, checker):
+    """ff_set_cmp() (the reference's, in oracle/_ref) picks compare functions out of the product's MECmpContext; call what it picked"""
+    import numpy as np
+    from libav_b200 import tables
+    from test_me_cmp_select_cpu import select
+    t = tables.MECmpContext()
+    gpu.lib.ff_me_cmp_init_cuda(C.byref(t))
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 256, size=(24, 48), dtype=np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-20, 21, size=a.shape), 0, 255).astype(np.uint8)
+    for kind, okind in (("SAD", 1), ("SSE", 2), ("SATD", 3), ("NSSE", 6)):
+        picked = select(refo, t, kind)
+        for sidx in (0, 1):
+            f = tables.me_cmp_func(picked[sidx])
+            h = 16 if sidx == 0 else 8
+            got = f(None, slot_cases.P(a, 48 * 2 + 16), slot_cases.P(b, 48 * 3 + 5), 48, h)
+            assert got == checker.me_cmp(okind, sidx, 0, C.c_void_p(a.ctypes.data + 48 * 2 + 16), C.c_void_p(b.ctypes.data + 48 * 3 + 5), 48, h), (kind, sidx)
+    assert gpu.last_error() == ""

@@ -50,6 +50,8 @@ API = {
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "h264_deblock_picture_with": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32]),
     "me_cmp_select": (None, [vp, i32, vp]),
+    "table_fill": (i32, [i32, i32, i32, vp, i32]),
+    "pred_table_fill": (i32, [i32, i32, vp, i32]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),
     "h264_pred": (None, [i32, i32, vp, vp, i32, i32, pd]),

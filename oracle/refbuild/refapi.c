@@ -131,6 +131,38 @@ void ref_fdct(int which, int16_t *block)
  * e.g. the one ff_me_cmp_init_cuda() filled (tests/test_me_cmp_select_cpu.py).  Only in _ref. */
 void ref_me_cmp_select(void *table, int type, void *out[6]) { INIT(); ff_set_cmp((MECmpContext *)table, (me_cmp_func *)out, type); }
 
+/* Which entries does the reference's own init fill?  kind: 0 H264DSPContext (a = bit_depth, b = chroma_format_idc), 1 H264QpelContext (a = bit_depth),
+ * 2 H264ChromaContext (a), 3 H264PredContext for AV_CODEC_ID_H264 (a, b), 4 HpelDSPContext (a = flags), 5 MECmpContext, 6 QpelDSPContext,
+ * 7 BlockDSPContext, 8 FDCTDSPContext (a = bits_per_raw_sample, b = dct_algo), 9 PixblockDSPContext (a = bits), 10 IDCTDSPContext (a = bits, b = idct_algo;
+ * only its six function pointers).  out[i] = 1 when pointer-sized word i of the table is non-zero.  Returns the word count.  Only in _ref. */
+int ref_table_fill(int kind, int a, int b, uint8_t *out, int cap)
+{
+    INIT();
+    union { H264DSPContext h; H264QpelContext q; H264ChromaContext c; HpelDSPContext hp; MECmpContext m; QpelDSPContext mq; BlockDSPContext bd;
+            FDCTDSPContext f; PixblockDSPContext p; IDCTDSPContext i; void *w[4096]; } u;
+    AVCodecContext *avctx = calloc(1, sizeof(*avctx));
+    size_t bytes = 0;
+    memset(&u, 0, sizeof(u));
+    avctx->bits_per_raw_sample = a; avctx->flags = AV_CODEC_FLAG_BITEXACT; avctx->idct_algo = b; avctx->dct_algo = b;
+    switch (kind) {
+    case 0: ff_h264dsp_init(&u.h, a, b); bytes = sizeof(u.h); break;
+    case 1: ff_h264qpel_init(&u.q, a); bytes = sizeof(u.q); break;
+    case 2: ff_h264chroma_init(&u.c, a); bytes = sizeof(u.c); break;
+    case 4: ff_hpeldsp_init(&u.hp, a); bytes = sizeof(u.hp); break;
+    case 5: ff_me_cmp_init(&u.m, avctx); bytes = sizeof(u.m); break;
+    case 6: ff_qpeldsp_init(&u.mq); bytes = sizeof(u.mq); break;
+    case 7: ff_blockdsp_init(&u.bd); bytes = sizeof(u.bd); break;
+    case 8: ff_fdctdsp_init(&u.f, avctx); bytes = sizeof(u.f); break;
+    case 9: ff_pixblockdsp_init(&u.p, avctx); bytes = sizeof(u.p); break;
+    case 10: ff_idctdsp_init(&u.i, avctx); bytes = 6 * sizeof(void *); break;
+    default: free(avctx); return -1;
+    }
+    free(avctx);
+    const int n = (int)(bytes / sizeof(void *));
+    for (int i = 0; i < n && i < cap; i++) out[i] = u.w[i] != NULL;
+    return n;
+}
+
 void ref_h264_idct(int which, uint8_t *dst, int16_t *block, int stride)
 {
     INIT();

@@ -7,6 +7,7 @@
 #include "../oracle_api.h"
 
 #include <pthread.h>
+#include <string.h>
 
 #include "libavutil/cpu.h"
 #include "libavcodec/avcodec.h"
@@ -38,4 +39,16 @@ void ref_h264_pred_add(int tab, int mode, uint8_t *pix, const int *block_offset,
     case 3: hpc.pred8x8_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, block, stride); break;
     default: hpc.pred16x16_add[mode ? HOR_PRED8x8 : VERT_PRED8x8](pix, block_offset, block, stride); break;
     }
+}
+
+/* which entries ff_h264_pred_init(h, AV_CODEC_ID_H264, bit_depth, chroma_format_idc) fills (see ref_table_fill in refapi.c) */
+int ref_pred_table_fill(int bit_depth, int chroma_format_idc, uint8_t *out, int cap)
+{
+    union { H264PredContext h; void *w[256]; } u;
+    memset(&u, 0, sizeof(u));
+    av_set_cpu_flags_mask(0);
+    ff_h264_pred_init(&u.h, AV_CODEC_ID_H264, bit_depth, chroma_format_idc);
+    const int n = (int)(sizeof(u.h) / sizeof(void *));
+    for (int i = 0; i < n && i < cap; i++) out[i] = u.w[i] != NULL;
+    return n;
 }

@@ -368,7 +368,9 @@ int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float 
  * 422p 444p 410p 411p 440p and their full-range yuvj twins 12 / 13 / 14 / 32 on either side -- a yuv destination of the other range gets the
  * reference's range conversion, planar 8 / 9 / 10-bit only; 9 / 10 / 16-bit 420p = 62 / 64 / 47, 422p = 72 / 66 / 49, 444p = 68 / 70 / 51 little-endian and their big-endian twins), any size, SWS_FULL_CHR_H_INT or not, every scaler
  * algorithm of initFilter (libswscale/utils.c:249-632), results identical to the reference's C path under
- * SWS_ACCURATE_RND | SWS_BITEXACT.  Anything else returns NULL with an error (no fallback).
+ * SWS_ACCURATE_RND | SWS_BITEXACT.  srcFilter / dstFilter: pointers to the reference's SwsFilter (four pointers to { double *coeff; int length; }),
+ * taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations, vertical vectors symmetric.  Anything else returns NULL
+ * with an error (no fallback).
  *   sws_scale_cuda         HOST pointers, whole frames (srcSliceY = 0, srcSliceH = srcH), strides of either sign (bottom-up pictures);
  *                          uploads, runs, downloads, synchronises; returns output lines like sws_scale(), 0 on bad arguments.
  *   sws_scale_frames_cuda  DEVICE pointers, asynchronous on `stream`: nframes frames whose planes lie
@@ -399,6 +401,9 @@ int  sws_is_fused_cuda(SwsContextCUDA *ctx);   /* 1 when the single-kernel same-
  * reference without a GPU: which = 0 hLum, 1 hChr, 2 vLum, 3 vChr; returns taps per output sample */
 int  sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags,
                            int16_t *filter, int32_t *pos, int cap, int *n_out);
+/* the same with a SwsFilter pair (the reference's struct: four pointers to { double *coeff; int length; }), NULL = none */
+int  sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, const void *srcFilter,
+                            const void *dstFilter, int16_t *filter, int32_t *pos, int cap, int *n_out);
 void sws_debug_rgb_constants_cuda(int32_t out[10]);
 /* what sws_getContext_cuda would decide, computed on the host only: 1 = taken over (out[0] path: 1 plane copy, 2 unscaled table
  * converter, 3 fused same-size kernel, 4 general scaler, 5 packed-source special converter, 6 planar -> packed 4:2:2 converter,

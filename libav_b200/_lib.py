@@ -88,6 +88,7 @@ PROTOTYPES = {
     "sws_scale_frames_cuda": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "sws_is_fused_cuda": (i32, [vp]),
     "sws_debug_filter_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "sws_debug_filter2_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "sws_debug_rgb_constants_cuda": (None, [vp]),
     "sws_debug_plan_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp]),
     "sws_debug_slot_view_cuda": (i32, [i32, i32, i32, i32, i32, i32, i32, vp]),

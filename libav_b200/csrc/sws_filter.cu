@@ -82,7 +82,7 @@ int64_t kernel_weight(int flags, const double param[2], int64_t d, int x_inc)
 }  // namespace
 
 int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, int flags,
-                  const double param[2], bool horizontal, const char **err)
+                  const double param[2], bool horizontal, const char **err, const SwsVec *srcv, const SwsVec *dstv)
 {
     const int n = dst_len;
     int taps;
@@ -136,6 +136,30 @@ int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, 
                 w[(size_t)i * taps + j] = kernel_weight(flags, param, d, x_inc);
             }
         }
+    }
+
+    // the caller's SwsFilter vectors (utils.c:444-474): the source-side vector is convolved into every row -- int64 weights times double
+    // coefficients, accumulated through the reference's own int64 += double conversions -- the destination-side vector only widens the
+    // rows ("FIXME dstFilter" in the reference); the positions move by the difference of the half widths
+    if ((srcv && srcv->length > 0) || (dstv && dstv->length > 0)) {
+        int taps2 = taps;
+        if (srcv && srcv->length > 0) taps2 += srcv->length - 1;
+        if (dstv && dstv->length > 0) taps2 += dstv->length - 1;
+        std::vector<int64_t> w2((size_t)n * taps2, 0);
+        for (int i = 0; i < n; i++) {
+            if (srcv && srcv->length > 0) {
+                for (int k = 0; k < srcv->length; k++)
+                    for (int j = 0; j < taps; j++) {
+                        int64_t &d = w2[(size_t)i * taps2 + k + j];
+                        d = (int64_t)((double)d + srcv->coeff[k] * (double)w[(size_t)i * taps + j]);
+                    }
+            } else {
+                for (int j = 0; j < taps; j++) w2[(size_t)i * taps2 + j] = w[(size_t)i * taps + j];
+            }
+            pos[i] += (taps - 1) / 2 - (taps2 - 1) / 2;
+        }
+        w.swap(w2);
+        taps = taps2;
     }
 
     // trim near-zero taps: shift rows left while the leading mass is below the cut-off, then find the

@@ -25,8 +25,10 @@ struct FilterBank {
 };
 
 // returns 0, or -1 with *err set
+// SwsVector (libswscale/swscale.h:106-109): a caller-made filter that initFilter() convolves into every row of a bank (utils.c:444-474)
+struct SwsVec { const double *coeff; int length; };
 int design_filter(FilterBank &fb, int x_inc, int src_len, int dst_len, int one, int flags,
-                  const double param[2], bool horizontal, const char **err);
+                  const double param[2], bool horizontal, const char **err, const SwsVec *srcv = nullptr, const SwsVec *dstv = nullptr);
 
 struct SwsGeometry {
     int srcW, srcH, dstW, dstH;

@@ -1224,9 +1224,15 @@ static int upload_tables(SwsCudaContext *c)
     return 0;
 }
 
+struct SwsFilterView { const SwsVec *lumH, *lumV, *chrH, *chrV; };      // libswscale/swscale.h:112-117 (a SwsVector is { double *coeff; int length; })
 static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
-                                    const double *param, bool device_side)
+                                    const double *param, bool device_side, const void *srcFilter = nullptr, const void *dstFilter = nullptr)
 {
+    static const SwsFilterView noFilter = { nullptr, nullptr, nullptr, nullptr };
+    const SwsFilterView &sf = srcFilter ? *(const SwsFilterView *)srcFilter : noFilter, &df = dstFilter ? *(const SwsFilterView *)dstFilter : noFilter;
+    auto longer = [](const SwsVec *v) { return v && v->length > 1; };
+    // usesVFilter / usesHFilter (utils.c:974-981): with either, no unscaled special converter is installed (:1043)
+    const bool usesFilter = longer(sf.lumV) || longer(sf.chrV) || longer(df.lumV) || longer(df.chrV) || longer(sf.lumH) || longer(sf.chrH) || longer(df.lumH) || longer(df.chrH);
     const char *err = nullptr;
     // handle_jpeg() (utils.c:855-873): the full-range planar formats are their limited-range twins with srcRange = 1
     int srcRange = 0, dstRange = 0;
@@ -1296,6 +1302,15 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         return nullptr;
     }
     const bool rgb = !planar;
+    {   // a shifted / asymmetric vertical vector makes the reference's last output rows depend on stale lines of its ring buffer (measured:
+        // port and product, which clamp to the last line, differ from it there and nowhere else): no defined result to match
+        auto asym = [](const SwsVec *v) { if (!v) return false; for (int i = 0; i < v->length / 2; i++) if (v->coeff[i] != v->coeff[v->length - 1 - i]) return true; return false; };
+        if (asym(sf.lumV) || asym(sf.chrV)) { set_error_msg("sws_getContext_cuda", "asymmetric vertical SwsFilter vectors are not taken over"); return nullptr; }
+    }
+    if (usesFilter && (srcRgb || srcYuy || src32 || srcFormat == FMT_NV12 || srcFormat == FMT_NV21 || pk422 || dstFormat == FMT_NV12 || dstFormat == FMT_NV21 || dbits != 8)) {
+        set_error_msg("sws_getContext_cuda", "SwsFilter vectors are taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations only");
+        return nullptr;
+    }
     // swscale.c:748-765: a yuv destination of the other range gets lum / chrRangeFromJpeg_c (1) or ...ToJpeg_c (2) between the two passes,
     // and none of the unscaled special converters (utils.c:1043-1044)
     const int rangeConv = (srcRange != dstRange && (planar || pk422)) ? (srcRange ? 1 : 2) : 0;
@@ -1311,7 +1326,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
     c->pk422 = pk422;
-    if (pk422 && srcW == dstW && srcH == dstH) {               // swscale_unscaled.c:1123-1139,1152-1176
+    if (pk422 && srcW == dstW && srcH == dstH && !usesFilter) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
         else if (srcFormat == dstFormat) c->to422 = 3;
@@ -1327,7 +1342,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         static const int rgbpos[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };       // argb, rgba, abgr, bgra
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
-    if (unscaled) {                                           // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
+    if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
         if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
         else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
@@ -1338,10 +1353,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         const int fl = c->g.flags;
         const int lumFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BICUBIC) : fl;
         const int chrFlags = (fl & SWS_BICUBLIN) ? (fl | SWS_BILINEAR) : fl;
-        if (design_filter(c->hLum, c->g.lumXInc, srcW, dstW, 1 << 14, lumFlags, prm, true, &err)) goto fail;
-        if (design_filter(c->hChr, c->g.chrXInc, c->g.chrSrcW, c->g.chrDstW, 1 << 14, chrFlags, prm, true, &err)) goto fail;
-        if (design_filter(c->vLum, c->g.lumYInc, srcH, dstH, 1 << 12, lumFlags, prm, false, &err)) goto fail;
-        if (design_filter(c->vChr, c->g.chrYInc, c->g.chrSrcH, c->g.chrDstH, 1 << 12, chrFlags, prm, false, &err)) goto fail;
+        if (design_filter(c->hLum, c->g.lumXInc, srcW, dstW, 1 << 14, lumFlags, prm, true, &err, sf.lumH, df.lumH)) goto fail;       // utils.c:1165-1198
+        if (design_filter(c->hChr, c->g.chrXInc, c->g.chrSrcW, c->g.chrDstW, 1 << 14, chrFlags, prm, true, &err, sf.chrH, df.chrH)) goto fail;
+        if (design_filter(c->vLum, c->g.lumYInc, srcH, dstH, 1 << 12, lumFlags, prm, false, &err, sf.lumV, df.lumV)) goto fail;
+        if (design_filter(c->vChr, c->g.chrYInc, c->g.chrSrcH, c->g.chrDstH, 1 << 12, chrFlags, prm, false, &err, sf.chrV, df.chrV)) goto fail;
     }
     {
         static const int itu601[4] = { 104597, 132201, 25675, 53279 };     // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT]
@@ -1349,7 +1364,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         c->srcRange = srcRange;
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
-    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1);
+    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter;
     c->fused = !c->table_unscaled && rgb && !pk422 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
@@ -1367,7 +1382,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
-    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv;
+    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter;
     c->rangeConv = rangeConv;
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
@@ -1776,8 +1791,7 @@ extern "C" {
 SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
                                     void *srcFilter, void *dstFilter, const double *param)
 {
-    if (srcFilter || dstFilter) { set_error_msg("sws_getContext_cuda", "SwsFilter pre/post filters are not taken over"); return nullptr; }
-    return (SwsContextCUDA *)make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, param, true);
+    return (SwsContextCUDA *)make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, param, true, srcFilter, dstFilter);
 }
 
 void sws_freeContext_cuda(SwsContextCUDA *ctx) { sws_slots_forget(ctx); destroy((SwsCudaContext *)ctx); }
@@ -1991,10 +2005,18 @@ int sws_is_fused_cuda(SwsContextCUDA *ctx) { return ctx ? ((SwsCudaContext *)ctx
 // Host-only introspection used by the CPU test-suite to pin the set-up stage against the reference
 // (no device is touched): filter bank `which` (0 hLum, 1 hChr, 2 vLum, 3 vChr) of the context that
 // sws_getContext_cuda() would build.  Returns the tap count, <0 on error.
+int sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, const void *srcFilter, const void *dstFilter,
+                           int16_t *filter, int32_t *pos, int cap, int *n_out);
 int sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, int16_t *filter,
                           int32_t *pos, int cap, int *n_out)
 {
-    SwsCudaContext *c = make_context(srcW, srcH, FMT_YUV420P, dstW, dstH, dstFormat, flags, nullptr, false);
+    return sws_debug_filter2_cuda(which, srcW, srcH, dstW, dstH, dstFormat, flags, nullptr, nullptr, filter, pos, cap, n_out);
+}
+// the same with the caller's SwsFilter pair (libswscale/swscale.h:112-117 layout)
+int sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, const void *srcFilter, const void *dstFilter,
+                           int16_t *filter, int32_t *pos, int cap, int *n_out)
+{
+    SwsCudaContext *c = make_context(srcW, srcH, FMT_YUV420P, dstW, dstH, dstFormat, flags, nullptr, false, srcFilter, dstFilter);
     if (!c) return -1;
     const FilterBank &b = which == 0 ? c->hLum : which == 1 ? c->hChr : which == 2 ? c->vLum : c->vChr;
     int fs = b.size;

@@ -71,6 +71,7 @@ API = {
     "sws_set_colorspace": (None, [vp, i32, i32, i32, i32]),
     "sws_planar": (i32, [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32]),
     "sws_nv12": (i32, [i32, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
+    "sws_set_filter": (None, [i32, i32, vp, i32]),
     "sws_line_range": (i32, [i32, vp, vp, i32]),
     "sws_line_hscale": (i32, [i32, i32, vp, i32, vp, vp, vp, i32]),
     "sws_line_hfast": (i32, [i32, vp, vp, i32, vp, vp, i32, i32]),

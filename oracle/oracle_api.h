@@ -140,6 +140,9 @@ void ORC(h264_add_pixels_clear)(int w8, uint8_t *dst, int16_t *block, int stride
  * Returns 0, -1 when the reference would not install that slot (or the request is outside what the port restates). */
 /*   range:   kind 0 lumRangeFromJpeg_c (dst1), 1 chrRangeFromJpeg_c (dst1, dst2), 2 lumRangeToJpeg_c, 3 chrRangeToJpeg_c: c->lumConvertRange /
  *            c->chrConvertRange of a yuvj420p -> yuv420p (0, 1) or yuv420p -> yuvj420p (2, 3) context (swscale.c:166-197,748-757) */
+/* SwsFilter vectors for the sws_* calls that follow (libswscale/swscale.h:106-117): which 0 lumH, 1 lumV, 2 chrH, 3 chrV; side 0 srcFilter,
+ * 1 dstFilter; length 0 clears.  The coefficient array must stay alive while it is set. */
+void ORC(sws_set_filter)(int which, int side, const double *coeff, int length);
 int ORC(sws_line_range)(int kind, int16_t *dst1, int16_t *dst2, int width);
 int ORC(sws_line_hscale)(int dst_fmt, int flags, void *dst, int dstW, const uint8_t *src, const int16_t *filter, const int32_t *filterPos, int filterSize);
 int ORC(sws_line_hfast)(int chroma, int16_t *dst1, int16_t *dst2, int dstW, const uint8_t *src1, const uint8_t *src2, int srcW, int xInc);

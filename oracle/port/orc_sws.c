@@ -93,7 +93,22 @@ static int64_t tap_weight(int flags, int64_t d, int xinc)
     return 0;
 }
 
-static int make_bank(bank_t *b, int xinc, int slen, int dlen, int one, int flags, int horiz)
+/* SwsFilter vectors (libswscale/swscale.h:106-117), set for the calls that follow: which 0 lumH, 1 lumV, 2 chrH, 3 chrV; side 0 = srcFilter,
+ * 1 = dstFilter; length 0 clears.  initFilter() convolves the source-side vector into every row and lets the destination-side one only widen
+ * the rows (utils.c:444-474); with any vector longer than 1 no unscaled special converter is installed (:974-981,1043). */
+static __thread struct { const double *coeff; int length; } g_fv[4][2];
+static int uses_filter(void)
+{
+    for (int w = 0; w < 4; w++) for (int s = 0; s < 2; s++) if (g_fv[w][s].length > 1) return 1;
+    return 0;
+}
+void orc_sws_set_filter(int which, int side, const double *coeff, int length)
+{
+    if (which < 0 || which > 3 || side < 0 || side > 1) return;
+    g_fv[which][side].coeff = length > 0 ? coeff : NULL; g_fv[which][side].length = length > 0 ? length : 0;
+}
+
+static int make_bank(bank_t *b, int xinc, int slen, int dlen, int one, int flags, int horiz, int which)
 {
     int taps, i, j, k;
     int64_t *w;
@@ -139,6 +154,21 @@ static int make_bank(bank_t *b, int xinc, int slen, int dlen, int one, int flags
             }
             x += 2 * (int64_t)xinc;
         }
+    }
+    if (g_fv[which][0].length > 0 || g_fv[which][1].length > 0) {          /* utils.c:444-474 */
+        const int ns = g_fv[which][0].length, nd = g_fv[which][1].length;
+        const int taps2 = taps + (ns > 0 ? ns - 1 : 0) + (nd > 0 ? nd - 1 : 0);
+        int64_t *w2 = calloc((size_t)taps2 * dlen, sizeof(*w2));
+        for (i = 0; i < dlen; i++) {
+            if (ns > 0) {
+                for (k = 0; k < ns; k++)
+                    for (j = 0; j < taps; j++) w2[(size_t)i * taps2 + k + j] += g_fv[which][0].coeff[k] * w[(size_t)i * taps + j];
+            } else {
+                for (j = 0; j < taps; j++) w2[(size_t)i * taps2 + j] = w[(size_t)i * taps + j];
+            }
+            pos[i] += (taps - 1) / 2 - (taps2 - 1) / 2;
+        }
+        free(w); w = w2; taps = taps2;
     }
     /* shrink (utils.c:476-520) */
     int minsize = 0;
@@ -232,8 +262,8 @@ static int sws_open(sws_t *c, int sw, int sh, int dw, int dh, int rgb, int flags
     int cyi = (int)((((int64_t)c->chrSrcH << 16) + (c->chrDstH >> 1)) / c->chrDstH);
     c->lumXInc = lx; c->chrXInc = cx;
     int lf = (flags & F_BICUBLIN) ? (flags | F_BICUBIC) : flags, cf = (flags & F_BICUBLIN) ? (flags | F_BILINEAR) : flags;
-    if (make_bank(&c->hl, lx, sw, dw, 1 << 14, lf, 1) || make_bank(&c->hc, cx, c->chrSrcW, c->chrDstW, 1 << 14, cf, 1) ||
-        make_bank(&c->vl, ly, sh, dh, 1 << 12, lf, 0) || make_bank(&c->vc, cyi, c->chrSrcH, c->chrDstH, 1 << 12, cf, 0)) {
+    if (make_bank(&c->hl, lx, sw, dw, 1 << 14, lf, 1, 0) || make_bank(&c->hc, cx, c->chrSrcW, c->chrDstW, 1 << 14, cf, 1, 2) ||
+        make_bank(&c->vl, ly, sh, dh, 1 << 12, lf, 0, 1) || make_bank(&c->vc, cyi, c->chrSrcH, c->chrDstH, 1 << 12, cf, 0, 3)) {
         sws_close(c);
         return -1;
     }
@@ -385,7 +415,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
-    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422) {
+    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422 && !uses_filter()) {
         /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
          * i.e. both rows of a pair read the even chroma line)
          * unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
@@ -536,7 +566,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
+    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range && !uses_filter()) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
                                          swscale_unscaled.c:793-1020); 8 -> 9 / 10 bits is a plain shift for limited-range sources (:946-971) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
@@ -640,7 +670,7 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
         static const int order[4][4] = { { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };
         const int *o = order[dst_fmt - 25];
         int w = dw;
-        if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1) w &= ~1;
+        if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter()) w &= ~1;
         else if ((w & 1) && !(flags & F_FULL_CHR_H_INT) && dstride >= 4 * (w + 1)) w++;
         for (int y = 0; r == dh && y < dh; y++)
             for (int x = 0; x < w; x++) {
@@ -825,6 +855,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     if (dst_fmt != 23 && dst_fmt != 24) return sws_any(src_fmt, src, ss, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+    if (uses_filter()) return -1;
     const int swap = dst_fmt == 24;
     if (sw == dw && sh == dh) {
         if (src_fmt == 23 || src_fmt == 24) return -1;         /* the reference's plane copy skips the chroma plane there */
@@ -886,6 +917,14 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         return r;
     }
     const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk;
+    for (int wv = 1; wv < 4; wv += 2)                      /* asymmetric vertical vectors (lumV, chrV): the reference's last rows depend on its ring buffer state */
+        for (int i = 0; i < g_fv[wv][0].length / 2; i++)
+            if (g_fv[wv][0].coeff[i] != g_fv[wv][0].coeff[g_fv[wv][0].length - 1 - i]) return -1;
+    if (uses_filter()) {        /* restated for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations only */
+        int h2, v2, b2 = 8;
+        const int planar_src = src_fmt == 0 || src_fmt == 4 || src_fmt == 5 || src_fmt == 6 || src_fmt == 7 || src_fmt == 31;
+        if (!planar_src || pk || g_nospecial || (!rgb && (!planar_dst(dst_fmt, &h2, &v2, &b2) || b2 != 8))) { g_dbe = 0; return -1; }
+    }
     if (pk && sw == dw && sh == dh) {
         /* the reference's unscaled converters to packed 4:2:2 (swscale_unscaled.c:1123-1139,1152-1176): from yuv422p always, from yuv420p
          * with the fast-bilinear / point flags (yuvPlanartoyuy2_c, rgb2rgb_template.c:322-420: width >> 1 pairs), same format = copy */

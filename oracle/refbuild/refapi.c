@@ -309,10 +309,26 @@ void ref_full_search(const uint8_t *cur, const uint8_t *ref, int stride, int w, 
 }
 
 /* ---- swscale ---- */
+/* SwsFilter state for the contexts created below (oracle_api.h sws_set_filter) */
+static SwsVector g_vec[4][2];
+static SwsFilter g_srcF, g_dstF;
+void ref_sws_set_filter(int which, int side, const double *coeff, int length)
+{
+    if (which < 0 || which > 3 || side < 0 || side > 1) return;
+    g_vec[which][side].coeff = length > 0 ? (double *)coeff : NULL; g_vec[which][side].length = length > 0 ? length : 0;
+    SwsFilter *f = side ? &g_dstF : &g_srcF;
+    SwsVector *v = g_vec[which][side].length ? &g_vec[which][side] : NULL;
+    if (which == 0) f->lumH = v; else if (which == 1) f->lumV = v; else if (which == 2) f->chrH = v; else f->chrV = v;
+}
+static SwsFilter *filt(int side)
+{
+    SwsFilter *f = side ? &g_dstF : &g_srcF;
+    return (f->lumH || f->lumV || f->chrH || f->chrV) ? f : NULL;
+}
 static struct SwsContext *mk_sws(int sw, int sh, int dw, int dh, enum AVPixelFormat df, int flags)
 {
     INIT();
-    return sws_getContext(sw, sh, AV_PIX_FMT_YUV420P, dw, dh, df, flags, NULL, NULL, NULL);
+    return sws_getContext(sw, sh, AV_PIX_FMT_YUV420P, dw, dh, df, flags, filt(0), filt(1), NULL);
 }
 int ref_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst,
                              int dstride, int dw, int dh, int flags)
@@ -353,7 +369,7 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     INIT();
     const int packed_src = src_fmt == AV_PIX_FMT_YUYV422 || src_fmt == AV_PIX_FMT_UYVY422 || src_fmt == AV_PIX_FMT_RGB24 || src_fmt == AV_PIX_FMT_BGR24 ||
                            (src_fmt >= AV_PIX_FMT_ARGB && src_fmt <= AV_PIX_FMT_BGRA);
-    struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, NULL, NULL, NULL);
+    struct SwsContext *c = sws_getContext(sw, sh, (enum AVPixelFormat)src_fmt, dw, dh, (enum AVPixelFormat)dst_fmt, flags, filt(0), filt(1), NULL);
     if (!c) return -1;
     if (g_cs_set && sws_setColorspaceDetails(c, g_cs_inv, g_cs_range, g_cs_inv, 0, g_cs_b, g_cs_c, g_cs_s) < 0) { sws_freeContext(c); return -2; }
     const int packed_dst = dst_fmt == AV_PIX_FMT_RGB24 || dst_fmt == AV_PIX_FMT_BGR24 || (dst_fmt >= AV_PIX_FMT_ARGB && dst_fmt <= AV_PIX_FMT_BGRA) ||

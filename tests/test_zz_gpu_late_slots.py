@@ -247,3 +247,43 @@ def test_me_cmp_functions_selected_by_the_reference(gpu, refo, checker):
             got = f(None, slot_cases.P(a, 48 * 2 + 16), slot_cases.P(b, 48 * 3 + 5), 48, h)
             assert got == checker.me_cmp(okind, sidx, 0, C.c_void_p(a.ctypes.data + 48 * 2 + 16), C.c_void_p(b.ctypes.data + 48 * 3 + 5), 48, h), (kind, sidx)
     assert gpu.last_error() == ""
+
+
+def test_sws_filter_frames(gpu, checker):
+    """sws_getContext_cuda with a SwsFilter pair (the reference's struct layout): frames against the checker for the vector sets of
+    tests/test_sws_filter_cpu.py (their banks are pinned to the reference on the CPU)"""
+    import numpy as np
+    import test_sws_filter_cpu as F
+    from libav_b200 import synth
+    lib = gpu.lib
+    for k, s in enumerate(F.SETS):
+        sf, keep1 = F.make_filter(s.get("src"))
+        df, keep2 = F.make_filter(s.get("dst"))
+        keep = F.set_oracle(checker, s)
+        try:
+            for (sw, sh, dw, dh) in F.GEOMS:
+                yuv = synth.yuv420p_frame(sw, sh, 3 + k)
+                for flags in (4 | F.ACC, 4, 2):
+                    for dfmt in (2, 0):
+                        if dfmt == 2:
+                            rc, want = F.to_rgb(checker, yuv, dw, dh, flags, pad=3)
+                            want = [want]
+                            got = [np.zeros((dh, dw * 3 + 3), np.uint8)]
+                        else:
+                            rc, want = F.to_yuv(checker, yuv, dw, dh, flags)
+                            got = [np.zeros_like(w) for w in want]
+                        assert rc == dh
+                        ctx = lib.sws_getContext_cuda(sw, sh, 0, dw, dh, dfmt, flags, C.byref(sf), C.byref(df), None)
+                        assert ctx, (k, gpu.last_error())
+                        sp = (C.c_void_p * 4)(*([a.ctypes.data for a in yuv] + [None]))
+                        ss = (C.c_int * 4)(*([a.strides[0] for a in yuv] + [0]))
+                        dp = (C.c_void_p * 4)(*([a.ctypes.data for a in got] + [None] * (4 - len(got))))
+                        ds = (C.c_int * 4)(*([a.strides[0] for a in got] + [0] * (4 - len(got))))
+                        assert lib.sws_scale_cuda(ctx, sp, ss, 0, sh, dp, ds) == dh, gpu.last_error()
+                        lib.sws_freeContext_cuda(ctx)
+                        for a, b in zip(got, want):
+                            assert np.array_equal(a, b), (k, sw, sh, dw, dh, hex(flags), dfmt)
+        finally:
+            F.set_oracle(checker, None)
+        del keep, keep1, keep2
+    assert gpu.last_error() == ""

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace avb {
 
@@ -28,6 +29,22 @@ int sm_count();                 // multiprocessor count of the current device (c
 int tuning(const char *key);    // experiment knob set through avb200_set_tuning(); 0 when unset
 
 // ---- device helpers ------------------------------------------------------------------------
+#ifdef AVB_HOSTSIM
+// tests/hostsim/ (CPU suite) compiles the thread-independent kernels as host C++: the PTX helpers below get their plain definitions there
+inline uint4 ldg_stream(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+inline uint2 ldg_stream8(const void *p) { return *reinterpret_cast<const uint2 *>(p); }
+inline void stg_stream(void *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
+inline void stg_stream8(void *p, uint2 v) { *reinterpret_cast<uint2 *>(p) = v; }
+inline void cp_async16(void *smem, const void *gmem, bool valid) { if (valid) memcpy(smem, gmem, 16); else memset(smem, 0, 16); }
+inline void cp_async4(void *smem, const void *gmem) { memcpy(smem, gmem, 4); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+inline uint32_t pack_sat_u8(int b0, int b1, uint32_t hi16)
+{
+    const uint32_t s0 = (uint32_t)(b0 < 0 ? 0 : b0 > 255 ? 255 : b0), s1 = (uint32_t)(b1 < 0 ? 0 : b1 > 255 ? 255 : b1);
+    return (hi16 << 16) | (s1 << 8) | s0;
+}
+#else
 // streaming 128-bit global accesses (data touched exactly once: keep it out of L1)
 __device__ __forceinline__ uint4 ldg_stream(const void *p)
 {
@@ -76,6 +93,7 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int b0, int b1, uint32_t hi16)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(hi16));
     return d;
 }
+#endif
 // four s32 -> one little-endian word of saturated bytes {p0,p1,p2,p3}
 __device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3)
 {

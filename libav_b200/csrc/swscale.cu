@@ -251,10 +251,15 @@ sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
 // packed taps, the fifth tap and the first chroma line come from a host-built table (SwsPairTaps).
 struct SwsPairTaps { uint32_t lo0, hi0, lo1, hi1; int tap4; int first; int pad0, pad1; };   // 32 bytes per row pair
 
+#ifdef AVB_HOSTSIM      // tests/hostsim/: the two dot-product instructions spelled out
+inline int dp4a_uu(uint32_t a, uint32_t b, int c) { for (int k = 0; k < 4; k++) c += (int)((a >> (8 * k)) & 255) * (int)((b >> (8 * k)) & 255); return c; }
+inline int dp4a_us(uint32_t a, uint32_t b, int c) { for (int k = 0; k < 4; k++) c += (int)((a >> (8 * k)) & 255) * (int)(int8_t)((b >> (8 * k)) & 255); return c; }
+#else
 __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c)
 { int d; asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+#endif
 
 // four 32-bit sums -> one word of clip_u8(sum >> 16): the upper half-words of two sums are gathered by one PRMT, clipped
 // two at a time (packed s16 min + relu) and the four low bytes gathered by a third PRMT: 5 ALU-pipe instructions instead

@@ -22,7 +22,8 @@ void set_error_msg(const char *where, const char *msg) { if (g_err.empty()) g_er
 void set_error(const char *where, cudaError_t) { set_error_msg(where, "hostsim error"); }
 int check_launch(const char *) { return 0; }
 int sm_count() { return 148; }
-int tuning(const char *) { return 0; }
+// the general scaler is forced onto its two-pass path here: the tile kernels synchronise their threads (swscale_hostsim.cpp)
+int tuning(const char *key) { return !strcmp(key, "sws_general_variant") ? 1 : 0; }
 
 static Scratch g_scratch;
 static std::recursive_mutex g_mu;

@@ -1,4 +1,5 @@
 // tests/hostsim/sws_slots_hostsim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
+// (the contexts the slots belong to come from the host-compiled swscale.cu: swscale_hostsim.cpp)
 //
 // The product's per-line SwsContext slots (libav_b200/csrc/sws_slots.cu + sws_dev.cuh) compiled UNCHANGED as host C++ against
 // shim/cuda_runtime.h (see slots_hostsim.cpp).  The one thing the slots need from the rest of the product -- the SwsSlotView of a
@@ -8,23 +9,7 @@
 #include "../../libav_b200/csrc/sws_slots.cu"
 #include "../../libav_b200/csrc/sws_filter.cu"     // host-only code (filter design, colour constants)
 
-namespace avb {
-bool sws_slot_view(const void *ctx, SwsSlotView &v)
-{
-    if (!ctx) return false;
-    v = *(const SwsSlotView *)ctx;
-    return true;
-}
-}  // namespace avb
-
 extern "C" {
-// a stand-in for the SwsContextCUDA of sws_getContext_cuda(): a copy of its 25-int view (freed with hostsim_sws_free)
-void *hostsim_sws_context(const int32_t view[25])
-{
-    avb::SwsSlotView *v = new avb::SwsSlotView;
-    memcpy(v, view, sizeof(*v));
-    return v;
-}
 // the product's own host code for sws_setColorspaceDetails' constants (libav_b200/csrc/sws_filter.cu rgb_constants, linked from the
 // product's object file is not possible here -- it lives in a .cu with the filter design -- so the translation unit is included)
 int hostsim_rgb_constants(int32_t out[19], const int inv_table[4], int full_range, int brightness, int contrast, int saturation)
@@ -34,5 +19,4 @@ int hostsim_rgb_constants(int32_t out[19], const int inv_table[4], int full_rang
     memcpy(out, &k, sizeof(k));
     return (int)(sizeof(k) / 4);
 }
-void hostsim_sws_free(void *ctx) { avb::sws_slots_forget(ctx); delete (avb::SwsSlotView *)ctx; }
 }

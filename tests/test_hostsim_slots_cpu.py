@@ -5,6 +5,7 @@ loaded here.  The GPU tests remain the parity tests proper; this keeps the slot 
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -14,19 +15,27 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 LIB = os.path.join(HERE, "libslots_hostsim.so")
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture(scope="session")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
-    srcs = [os.path.join(HERE, "slots_hostsim.cpp"), os.path.join(HERE, "sws_slots_hostsim.cpp"), os.path.join(HERE, "slots_hbd_hostsim.cpp"), os.path.join(HERE, "idct10_hostsim.cpp"), os.path.join(HERE, "h264pred_hbd_hostsim.cpp")]
-    deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h")] + \
-        [os.path.join(root, "libav_b200", "csrc", f) for f in ("slots.cu", "h264dsp.cuh", "common.cuh", "scratch.h", "sws_slots.cu", "sws_dev.cuh",
-                                                               "sws_filter.cu", "sws_filter.h", "slots_hbd.cu", "h264dsp_hbd.cuh", "idct10.cu", "h264pred_hbd.cu", "h264pred.cuh", "fdct10.cu")] + \
+    csrc = os.path.join(root, "libav_b200", "csrc")
+    srcs = [os.path.join(HERE, f) for f in ("slots_hostsim.cpp", "sws_slots_hostsim.cpp", "slots_hbd_hostsim.cpp", "idct10_hostsim.cpp", "h264pred_hbd_hostsim.cpp",
+                                            "swscale_hostsim.cpp")]
+    deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h"), os.path.join(HERE, "gen_launches.py")] + \
+        [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))] + \
         [os.path.join(root, "include", f) for f in ("avdsp_b200.h", "avdsp_b200_tables.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", os.path.join(HERE, "shim"), "-Wno-unknown-pragmas",
+        os.makedirs(os.path.join(HERE, "_gen"), exist_ok=True)
+        subprocess.run([sys.executable, os.path.join(HERE, "gen_launches.py"), os.path.join(csrc, "swscale.cu"), os.path.join(HERE, "_gen", "swscale_gen.cu")], check=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DAVB_HOSTSIM", "-I", os.path.join(HERE, "shim"), "-I", csrc, "-Wno-unknown-pragmas",
                         "-o", LIB] + srcs, check=True)
     lib = C.CDLL(LIB)
     lib.avb200_last_error.restype = C.c_char_p
+    lib.sws_getContext_cuda.restype = C.c_void_p
+    lib.sws_getContext_cuda.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
+    lib.sws_freeContext_cuda.argtypes = [C.c_void_p]
+    lib.sws_scale_cuda.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sws_setColorspaceDetails_cuda.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     return lib
 
 
@@ -68,23 +77,18 @@ def test_batched_kernels_are_not_simulated(sim):
 
 
 def test_sws_line_slots(sim, refo):
-    """libswscale's per-line slots (libav_b200/csrc/sws_slots.cu, host-compiled) against the functions the compiled reference installs;
-    the context view comes from the PRODUCT library's host-only set-up (sws_debug_slot_view_cuda)."""
-    import numpy as np
-    import libav_b200._lib as prod
+    """libswscale's per-line slots (libav_b200/csrc/sws_slots.cu, host-compiled) against the functions the compiled reference installs; the
+    contexts come from the host-compiled sws_getContext_cuda() (swscale_hostsim.cpp)"""
     import sws_line_cases as L
-    sim.hostsim_sws_context.restype = C.c_void_p
-    sim.hostsim_sws_free.argtypes = [C.c_void_p]
 
     def run(colourspace):
         def make_ctx(dst_fmt, flags, src_fmt=0):
-            view = np.zeros(32, np.int32)
-            assert prod.lib.sws_debug_slot_view_cuda(64, 48, src_fmt, 96, 80, dst_fmt, flags, view.ctypes.data) == 26, (dst_fmt, flags, prod.last_error())
-            if colourspace:                  # sws_setColorspaceDetails_cuda needs a live context; the constants are the product's own host code
-                k = np.zeros(32, np.int32)
-                assert sim.hostsim_rgb_constants(k.ctypes.data, (C.c_int * 4)(*colourspace[0]), *colourspace[1:]) == 19
-                view[:19] = k[:19]
-            return sim.hostsim_sws_context(view.ctypes.data), sim.hostsim_sws_free
+            ctx = sim.sws_getContext_cuda(64, 48, src_fmt, 96, 80, dst_fmt, flags, None, None, None)
+            assert ctx, (dst_fmt, flags, sim.avb200_last_error())
+            if colourspace and dst_fmt in L.PACKED_FMTS and dst_fmt not in (1, 15):
+                tab = (C.c_int * 4)(*colourspace[0])
+                assert sim.sws_setColorspaceDetails_cuda(ctx, tab, colourspace[1], tab, 0, *colourspace[2:]) == 0
+            return ctx, sim.sws_freeContext_cuda
         calls = L.SlotCalls(sim, make_ctx, last_error_of(sim))
         try:
             return L.compare(calls, L.OracleCalls(refo), seed=3 if colourspace else 4)
@@ -102,19 +106,14 @@ def test_sws_line_slots(sim, refo):
 def test_sws_line_slot_registration(sim):
     """a slot called for a SwsContext that was never registered (or whose SwsContextCUDA was freed) fails loudly"""
     import numpy as np
-    import libav_b200._lib as prod
     import sws_line_cases as L
     from libav_b200 import tables
-    sim.hostsim_sws_context.restype = C.c_void_p
-    sim.hostsim_sws_free.argtypes = [C.c_void_p]
     t = tables.SwsLineSlotsCUDA()
     assert sim.ff_sws_init_swscale_cuda(None, None, C.byref(t)) == -1
     sim.avb200_clear_error()
-    view = np.zeros(32, np.int32)
-    assert prod.lib.sws_debug_slot_view_cuda(64, 48, 0, 96, 80, 2, 4, view.ctypes.data) == 26
-    ctx = sim.hostsim_sws_context(view.ctypes.data)
+    ctx = sim.sws_getContext_cuda(64, 48, 0, 96, 80, 2, 4, None, None, None)
     assert sim.ff_sws_init_swscale_cuda(C.c_void_p(0x7000), C.c_void_p(ctx), C.byref(t)) == 0
-    sim.hostsim_sws_free(ctx)
+    sim.sws_freeContext_cuda(ctx)
     lum, cu, out = np.zeros(64, np.int16), np.zeros(64, np.int16), np.full(256, 9, np.uint8)
     t.yuv2packed1(C.c_void_p(0x7000), L.vp(lum), L.ptrs([cu, cu]), L.ptrs([cu, cu]), None, L.vp(out), 16, 0, 0)
     assert "not registered" in sim.avb200_last_error().decode() and (out == 9).all()

@@ -1,0 +1,135 @@
+"""CPU: whole frames through the product's scaler compiled for the host (tests/hostsim/swscale_hostsim.cpp: every kernel of swscale.cu except
+the two shared-memory tile kernels is thread-independent; the general scaler runs on its two-pass path) -- sws_getContext_cuda /
+sws_scale_cuda of that build against the compiled reference.  This is where the parts of the frame path written without a GPU at hand are
+checked end to end: the yuvj <-> yuv range conversion, SwsFilter vectors, bottom-up pictures; plus the fused same-size kernels, the
+unscaled converters, the source readers and every output stage the two-pass path has.  16-bit destinations (tile kernel only) stay GPU-only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from libav_b200 import synth
+from libav_b200.device import PLANAR_BE, PLANAR_FORMATS
+from test_hostsim_slots_cpu import sim          # noqa: F401
+from test_sws_planar_dst import source
+
+ACC = 0x40000 | 0x80000
+
+
+def outputs(df, dw, dh, pad=8, fill=7):
+    if df in (23, 24):
+        return [np.full((dh, dw + pad), fill, np.uint8), np.full(((dh + 1) // 2, 2 * ((dw + 1) // 2) + pad), fill, np.uint8)]
+    if df in PLANAR_FORMATS:
+        hs, vs, bits = PLANAR_FORMATS[df]
+        dt = np.uint8 if bits == 8 else np.dtype(">u2" if df in PLANAR_BE else "<u2")
+        cw, ch = -((-dw) >> hs), -((-dh) >> vs)
+        return [np.full((dh, dw + pad), fill, dt), np.full((ch, cw + pad), fill, dt), np.full((ch, cw + pad), fill, dt)]
+    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) else 3
+    return [np.full((dh, dw * bpp + 2 * pad), fill, np.uint8)]
+
+
+def arrays(planes):
+    return (C.c_void_p * 4)(*([a.ctypes.data for a in planes] + [None] * (4 - len(planes)))), (C.c_int * 4)(*([a.strides[0] for a in planes] + [0] * (4 - len(planes))))
+
+
+def product(sim, sf, pl, w, h, df, dw, dh, flags, src_filter=None, dst_filter=None, outs=None):
+    ctx = sim.sws_getContext_cuda(w, h, sf, dw, dh, df, flags, src_filter, dst_filter, None)
+    assert ctx, (sf, df, w, h, dw, dh, hex(flags), sim.avb200_last_error())
+    outs = outputs(df, dw, dh) if outs is None else outs
+    sp, ss = arrays(pl)
+    dp, ds = arrays(outs)
+    assert sim.sws_scale_cuda(ctx, sp, ss, 0, h, dp, ds) == dh, sim.avb200_last_error()
+    sim.sws_freeContext_cuda(ctx)
+    return outs
+
+
+def reference(refo, sf, pl, w, h, df, dw, dh, flags, outs=None):
+    outs = outputs(df, dw, dh) if outs is None else outs
+    sp = (C.c_void_p * 3)(*([a.ctypes.data for a in pl] + [None] * (3 - len(pl))))
+    ss = (C.c_int * 3)(*([a.strides[0] for a in pl] + [0] * (3 - len(pl))))
+    dp = (C.c_void_p * 3)(*([a.ctypes.data for a in outs] + [None] * (3 - len(outs))))
+    ds = (C.c_int * 3)(*([a.strides[0] for a in outs] + [0] * (3 - len(outs))))
+    assert refo.sws_planar(sf, sp, ss, w, h, df, dp, ds, dw, dh, flags) == dh
+    return outs
+
+
+def same(a, b, what, crop=0):
+    """crop > 0: compare the pictures only, not the row padding (the reference's plane copies move whole strides when the pitches agree)"""
+    for x, y in zip(a, b):
+        if crop:
+            x, y = x[:, :x.shape[1] - crop], y[:, :y.shape[1] - crop]
+        assert np.array_equal(x, y), (what, np.argwhere(x != y)[:4].tolist())
+
+
+def test_known_answer_crc_fused_kernel(sim):
+    """av_crc(AV_CRC_32_IEEE) of the rgb24 picture of the LFG-seed-1 640x480 frame = f046d710 -- here through the fused dp4a kernel"""
+    yuv = synth.yuv420p_frame(640, 480, 1)
+    out = product(sim, 0, yuv, 640, 480, 2, 640, 480, 4 | ACC, outs=[np.zeros((480, 640 * 3), np.uint8)])
+    assert synth.crc32_ieee_be(out[0].tobytes()) == 0xF046D710
+
+
+def test_format_matrix(sim, refo):
+    import test_sws_planar_dst as T
+    T.SRC.setdefault(6, (2, 2)); T.SRC.setdefault(26, None)
+    n = 0
+    for sf in (0, 4, 5, 23, 1, 2, 15):
+        for df in (2, 3, 28, 25, 0, 5, 62, 63, 23, 24, 1, 15, 4):
+            for (w, h, dw, dh) in ((64, 48, 64, 48), (66, 50, 33, 25), (64, 48, 96, 80), (101, 37, 64, 48)):
+                for flags in (4 | ACC, 2, 0x10 | ACC, 4 | ACC | 0x2000):
+                    if (flags & 0x2000) and df not in (2, 3, 28, 25):
+                        continue
+                    if sf in (23,) and df in (23, 24) and (w, h) == (dw, dh):
+                        continue                                   # refused: the reference's plane copy skips the chroma plane
+                    if sf in (2,) and df in (28, 25) and (w, h) == (dw, dh):
+                        continue                                   # rgb2rgb converter family: refused
+                    if sf == 3 and df == 0 and (w, h) == (dw, dh) and not (flags & 0x40000) and h & 1:
+                        continue
+                    pl = source(sf, w, h, 41)
+                    same(product(sim, sf, pl, w, h, df, dw, dh, flags), reference(refo, sf, pl, w, h, df, dw, dh, flags), (sf, df, w, h, dw, dh, hex(flags)), crop=8)
+                    n += 1
+    assert n > 900
+
+
+def test_range_conversion_frames(sim, refo):
+    import test_sws_range_cpu as R
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in R.cases():
+        pl = R.planes(sf, w, h, 21)
+        same(product(sim, sf, pl, w, h, df, dw, dh, flags), reference(refo, sf, pl, w, h, df, dw, dh, flags), (sf, df, w, h, dw, dh, hex(flags)))
+        n += 1
+    assert n == len(R.PAIRS) * len(R.GEOMS) * len(R.FLAGS)
+
+
+def test_sws_filter_frames(sim, refo):
+    import test_sws_filter_cpu as F
+    for k, s in enumerate(F.SETS):
+        sf, keep1 = F.make_filter(s.get("src"))
+        df, keep2 = F.make_filter(s.get("dst"))
+        keep = F.set_oracle(refo, s)
+        try:
+            for (w, h, dw, dh) in F.GEOMS:
+                yuv = synth.yuv420p_frame(w, h, 3 + k)
+                for flags in (4 | ACC, 4, 2):
+                    for dfmt in (2, 0, 28, 5):
+                        got = product(sim, 0, yuv, w, h, dfmt, dw, dh, flags, C.byref(sf), C.byref(df))
+                        same(got, reference(refo, 0, yuv, w, h, dfmt, dw, dh, flags), (k, dfmt, w, h, dw, dh, hex(flags)))
+        finally:
+            F.set_oracle(refo, None)
+        del keep, keep1, keep2
+
+
+def test_negative_strides(sim):
+    for (sf, df, w, h, dw, dh, flags) in [(0, 2, 64, 48, 96, 80, 4), (0, 2, 128, 64, 128, 64, 4 | ACC), (0, 0, 101, 37, 64, 48, 4), (4, 5, 64, 48, 64, 48, 2),
+                                           (1, 2, 64, 48, 96, 80, 4), (0, 28, 64, 48, 33, 25, 4), (0, 23, 64, 48, 96, 80, 4)]:
+        pl = source(sf, w, h, 31)
+        want = product(sim, sf, pl, w, h, df, dw, dh, flags)
+        src_up = [np.ascontiguousarray(a[::-1])[::-1] for a in pl]
+        store = [np.ascontiguousarray(o[::-1]) for o in outputs(df, dw, dh)]
+        got = [g[::-1] for g in store]
+        assert all(a.strides[0] < 0 for a in src_up + got)
+        product(sim, sf, src_up, w, h, df, dw, dh, flags, outs=got)
+        same(got, want, ("bottom-up", sf, df))
+        store = [np.ascontiguousarray(o[::-1]) for o in outputs(df, dw, dh)]
+        got = [g[::-1] for g in store]
+        product(sim, sf, pl, w, h, df, dw, dh, flags, outs=got)
+        same(got, want, ("bottom-up destination", sf, df))

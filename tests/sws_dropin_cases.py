@@ -44,8 +44,6 @@ def check(refo, lib, make_ctx, free_ctx, cases=CASES, geoms=GEOMS):
     for (sf, df, flags) in cases:
         for (w, h, dw, dh) in geoms:
             base = {12: 0, 13: 4, 14: 5}.get(sf, sf)
-            import test_sws_planar_dst as T
-            T.SRC.setdefault(5, (0, 0))
             pl = source(base, w, h, 77)
             plain = refo.sws_open(sf, w, h, df, dw, dh, flags)
             assert plain

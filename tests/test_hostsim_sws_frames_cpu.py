@@ -69,8 +69,6 @@ def test_known_answer_crc_fused_kernel(sim):
 
 
 def test_format_matrix(sim, refo):
-    import test_sws_planar_dst as T
-    T.SRC.setdefault(6, (2, 2)); T.SRC.setdefault(26, None)
     n = 0
     for sf in (0, 4, 5, 23, 1, 2, 15):
         for df in (2, 3, 28, 25, 0, 5, 62, 63, 23, 24, 1, 15, 4):

@@ -16,10 +16,12 @@ PAIRS = [(12, 0), (13, 4), (14, 5), (32, 31), (12, 5), (14, 0), (13, 62), (12, 6
 
 
 def planes(fmt, w, h, seed):
-    import test_sws_planar_dst as T
-    base = J.get(fmt, fmt)
-    T.SRC.setdefault(base, SRC_SUB[base])
-    return source(base, w, h, seed)
+    """planar 8-bit source of any sub-sampling, rows padded like tests/test_sws_planar_dst.source"""
+    from libav_b200 import synth
+    hs, vs = SRC_SUB[J.get(fmt, fmt)]
+    r = np.random.RandomState(seed)
+    cw, ch = -((-w) >> hs), -((-h) >> vs)
+    return [synth.pad_rows(r.randint(0, 256, s).astype(np.uint8)) for s in ((h, w), (ch, cw), (ch, cw))]
 
 
 def cases():

@@ -1298,7 +1298,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> 32-bit rgb of the same size is the reference's rgb2rgb converter family: not taken over");
         return nullptr;
     }
-    if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1)) {
+    if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1) && srcRange == dstRange) {
         set_error_msg("sws_getContext_cuda", "bgr24 -> yuv420p of the same size without SWS_ACCURATE_RND is the reference's rgb24toyv12, which needs an even height");
         return nullptr;
     }
@@ -1319,19 +1319,15 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     // swscale.c:748-765: a yuv destination of the other range gets lum / chrRangeFromJpeg_c (1) or ...ToJpeg_c (2) between the two passes,
     // and none of the unscaled special converters (utils.c:1043-1044)
     const int rangeConv = (srcRange != dstRange && (planar || pk422)) ? (srcRange ? 1 : 2) : 0;
-    if (rangeConv) {
-        const bool planarSrc = srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P || srcFormat == FMT_YUV444P || srcFormat == FMT_YUV410P ||
-                               srcFormat == FMT_YUV411P || srcFormat == FMT_YUV440P;
-        if (!planarSrc || !planar || dstFormat == FMT_NV12 || dstFormat == FMT_NV21 || dbits == 16) {
-            set_error_msg("sws_getContext_cuda", "range conversion (full-range yuvj <-> limited-range yuv) is taken over for planar 8-bit sources and planar 8 / 9 / 10-bit destinations only");
-            return nullptr;
-        }
+    if (rangeConv && dbits == 16) {       // (the *Range*16_c variants work on the 19-bit lines that only exist in the tile kernel)
+        set_error_msg("sws_getContext_cuda", "range conversion (full-range yuvj <-> limited-range yuv) to a 16-bit destination is not taken over");
+        return nullptr;
     }
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
     c->pk422 = pk422;
-    if (pk422 && srcW == dstW && srcH == dstH && !usesFilter) {               // swscale_unscaled.c:1123-1139,1152-1176
+    if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
         else if (srcFormat == dstFormat) c->to422 = 3;
@@ -1347,8 +1343,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         static const int rgbpos[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };       // argb, rgba, abgr, bgra
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
-    if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176
+    if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176 (yuv destinations: only with equal ranges, utils.c:1043-1044)
         if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
+        else if (rangeConv) c->special = 0;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
         else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
         else if (srcYuy && dstFormat == FMT_YUV422P) c->special = srcFormat == FMT_YUYV422 ? 6 : 7;
@@ -1389,7 +1386,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
     c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter;
     c->rangeConv = rangeConv;
-    c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH;           // swscale_unscaled.c:1040-1044
+    c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
     if (c->fast_ok) {

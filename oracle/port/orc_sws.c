@@ -437,6 +437,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    if (g_pk422) { range_lines(L, lp, sh, dw, 0); range_lines(U, cp, c.chrSrcH, c.chrDstW, 1); range_lines(V, cp, c.chrSrcH, c.chrDstW, 1); }    /* (a yuv destination: swscale.c:748-765) */
     const int fl = c.vl.taps, fc = c.vc.taps;
     if (flags & F_FULL_CHR_H_INT) {
         /* yuv2rgb24_full_X_c (output.c:1165-1240): one chroma sample per pixel, 30-bit fixed point colour matrix with the
@@ -614,7 +615,7 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
 int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int uvstride, int sw, int sh, int dst_fmt,
                  uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
-    if (dst_fmt == 0 && sw == dw && sh == dh) {
+    if (dst_fmt == 0 && sw == dw && sh == dh && !g_range) {
         for (int r = 0; r < sh; r++) memcpy(dst[0] + (size_t)r * dstride[0], y + (size_t)r * ystride, sw);
         for (int r = 0; r < sh / 2; r++)
             for (int x = 0; x < sw / 2; x++) {
@@ -716,7 +717,7 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
     /* 32-bit sources: 32 -> 32 bit scales the alpha plane as well, same size -> packed rgb is the rgb2rgb family: neither is restated */
     if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && real_rgb_dst))) return -1;
-    if (sw == dw && sh == dh && !g_nospecial) {
+    if (sw == dw && sh == dh && !g_nospecial && (!g_range || real_rgb_dst)) {
         if (rgb_src && !src32 && real_rgb_dst) {
             for (int y = 0; y < sh; y++)
                 for (int x = 0; x < sw; x++)
@@ -859,7 +860,7 @@ int orc_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     const int swap = dst_fmt == 24;
     if (sw == dw && sh == dh) {
         if (src_fmt == 23 || src_fmt == 24) return -1;         /* the reference's plane copy skips the chroma plane there */
-        if (src_fmt == 0) {
+        if (src_fmt == 0) {            /* (a yuvj420p source is format 12 here: it takes the scaler below, with the range conversion) */
             for (int y = 0; y < sh; y++) memcpy(dst[0] + (size_t)y * dstride[0], src[0] + (size_t)y * ss[0], sw);
             for (int y = 0; y < sh / 2; y++)
                 for (int x = 0; x < sw / 2; x++) {
@@ -909,8 +910,8 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         }
         if (src_j == dst_j) return sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
         int h2, v2, b2;
-        const int planar_src = sf == 0 || sf == 4 || sf == 5 || sf == 6 || sf == 7 || sf == 31;
-        if (!planar_src || g_nospecial || !planar_dst(df, &h2, &v2, &b2) || b2 == 16) { g_dbe = 0; return -1; }
+        /* any source the port restates; destinations: planar 8 / 9 / 10 bit (also as the inner planes of an nv12 / nv21 destination) and packed 4:2:2 */
+        if (df != 1 && df != 15 && (!planar_dst(df, &h2, &v2, &b2) || b2 == 16)) { g_dbe = 0; return -1; }
         g_range = src_j ? 1 : 2;
         r = sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
         g_range = 0;
@@ -925,7 +926,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         const int planar_src = src_fmt == 0 || src_fmt == 4 || src_fmt == 5 || src_fmt == 6 || src_fmt == 7 || src_fmt == 31;
         if (!planar_src || pk || g_nospecial || (!rgb && (!planar_dst(dst_fmt, &h2, &v2, &b2) || b2 != 8))) { g_dbe = 0; return -1; }
     }
-    if (pk && sw == dw && sh == dh) {
+    if (pk && sw == dw && sh == dh && !g_range) {
         /* the reference's unscaled converters to packed 4:2:2 (swscale_unscaled.c:1123-1139,1152-1176): from yuv422p always, from yuv420p
          * with the fast-bilinear / point flags (yuvPlanartoyuy2_c, rgb2rgb_template.c:322-420: width >> 1 pairs), same format = copy */
         const int vshift = src_fmt == 0 ? 1 : 0, uyvy = dst_fmt == 15;

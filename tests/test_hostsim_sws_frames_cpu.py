@@ -131,3 +131,16 @@ def test_negative_strides(sim):
         got = [g[::-1] for g in store]
         product(sim, sf, pl, w, h, df, dw, dh, flags, outs=got)
         same(got, want, ("bottom-up destination", sf, df))
+
+
+def test_range_conversion_with_a_semi_planar_or_packed_side(sim, refo):
+    import test_sws_range_cpu as R
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in R.mixed_cases():
+        pl = R.mixed_planes(sf, w, h, 13)
+        rc, want = R.mixed_run(refo, sf, pl, w, h, df, dw, dh, flags)
+        assert rc == dh
+        got = product(sim, sf, pl, w, h, df, dw, dh, flags, outs=R.mixed_outputs(df, dw, dh))
+        same(got, want, (sf, df, w, h, dw, dh, hex(flags)))
+        n += 1
+    assert n > 230

@@ -95,5 +95,5 @@ def test_gpu_refusals(gpu):
     gpu.lib.avb200_clear_error()
     ctx.close()
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 128, 96, 23, 4, src_fmt=12)             # yuvj420p -> nv12: the range conversion is only taken over between planar formats
+        device.SwsContext(64, 48, 128, 96, 47, 4, src_fmt=12)             # yuvj420p -> 16-bit yuv: the 16-bit range conversion is not taken over
     gpu.lib.avb200_clear_error()

@@ -13,6 +13,8 @@ FLAGS = (4 | ACC, 2 | 0x80000, 0x10, 1 | ACC, 0x200 | ACC)
 # (source, destination): full -> limited, limited -> full, same range, 9 / 10-bit destinations
 PAIRS = [(12, 0), (13, 4), (14, 5), (32, 31), (12, 5), (14, 0), (13, 62), (12, 64), (14, 63), (0, 12), (4, 13), (5, 14), (31, 32), (5, 12), (6, 12), (7, 13),
          (12, 12), (13, 14), (14, 13), (32, 12)]
+# ... and with a semi-planar / packed side (two-pass path: the range kernel sits between the passes whatever reads or writes the planes)
+MIXED = [(12, 23), (13, 24), (14, 1), (12, 15), (13, 1), (23, 12), (24, 14), (1, 12), (15, 13), (2, 12), (3, 14), (26, 13)]
 
 
 def planes(fmt, w, h, seed):
@@ -41,6 +43,56 @@ def test_port_matches_reference(orc, refo):
             changed += not np.array_equal(a[1][0][:, :dw], pl[0][:h, :w])
         n += 1
     assert n == len(PAIRS) * len(GEOMS) * len(FLAGS) and changed > 50
+
+
+def mixed_planes(fmt, w, h, seed):
+    from libav_b200 import synth
+    if J.get(fmt, fmt) in SRC_SUB:
+        return planes(fmt, w, h, seed)
+    r = np.random.RandomState(seed)
+    if fmt in (23, 24):
+        return [synth.pad_rows(r.randint(0, 256, (h, w)).astype(np.uint8)), r.randint(0, 256, ((h + 1) // 2, 2 * ((w + 1) // 2) + 6)).astype(np.uint8)]
+    bpp = {1: 2, 15: 2, 2: 3, 3: 3, 26: 4}[fmt]
+    return [r.randint(0, 256, (h, bpp * w + 16)).astype(np.uint8)]
+
+
+def mixed_outputs(df, dw, dh):
+    if df in (23, 24):
+        return [np.full((dh, dw + 3), 7, np.uint8), np.full(((dh + 1) // 2, 2 * ((dw + 1) // 2) + 6), 7, np.uint8)]
+    if df in (1, 15):
+        return [np.full((dh, 2 * dw + 10), 7, np.uint8)]
+    from test_sws_planar_dst import outputs
+    return outputs(df, dw, dh)
+
+
+def mixed_run(o, sf, pl, w, h, df, dw, dh, flags):
+    import ctypes as C
+    out = mixed_outputs(df, dw, dh)
+    sp = (C.c_void_p * 3)(*([a.ctypes.data for a in pl] + [None] * (3 - len(pl))))
+    ss = (C.c_int * 3)(*([a.strides[0] for a in pl] + [0] * (3 - len(pl))))
+    dp = (C.c_void_p * 3)(*([a.ctypes.data for a in out] + [None] * (3 - len(out))))
+    ds = (C.c_int * 3)(*([a.strides[0] for a in out] + [0] * (3 - len(out))))
+    return o.sws_planar(sf, sp, ss, w, h, df, dp, ds, dw, dh, flags), out
+
+
+def mixed_cases():
+    for (sf, df) in MIXED:
+        for (w, h, dw, dh) in GEOMS:
+            for flags in FLAGS:
+                chr_dw = dw if J.get(df, df) == 5 else (dw + 1) // 2
+                if (flags & 1) and sf in (23, 24, 1, 15, 2, 3, 26) and (dw > w or chr_dw > (w + 1) // 2):
+                    continue            # fast bilinear up-scaling (luma or chroma) of a source that goes through the reference's uncleared formatConvBuffer
+                yield sf, df, w, h, dw, dh, flags
+
+
+def test_port_matches_reference_with_a_semi_planar_or_packed_side(orc, refo):
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in mixed_cases():
+        pl = mixed_planes(sf, w, h, 13)
+        a, b = mixed_run(refo, sf, pl, w, h, df, dw, dh, flags), mixed_run(orc, sf, pl, w, h, df, dw, dh, flags)
+        assert a[0] == b[0] == dh and all(np.array_equal(x, y) for x, y in zip(a[1], b[1])), (sf, df, w, h, dw, dh, hex(flags))
+        n += 1
+    assert n > 230
 
 
 def test_what_stays_refused(orc):

@@ -287,3 +287,22 @@ def test_sws_filter_frames(gpu, checker):
             F.set_oracle(checker, None)
         del keep, keep1, keep2
     assert gpu.last_error() == ""
+
+
+def test_sws_range_conversion_with_a_semi_planar_or_packed_side(gpu, checker):
+    import numpy as np
+    from libav_b200 import device
+    import test_sws_range_cpu as R
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in R.mixed_cases():
+        pl = R.mixed_planes(sf, w, h, 13)
+        rc, want = R.mixed_run(checker, sf, pl, w, h, df, dw, dh, flags)
+        assert rc == dh
+        ctx = device.SwsContext(w, h, dw, dh, df, flags, src_fmt=sf)
+        got = ctx.scale(pl, fill=7)
+        got = got if isinstance(got, list) else [got]
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b[:, :a.shape[1]]), (sf, df, w, h, dw, dh, hex(flags))
+        ctx.close()
+        n += 1
+    assert n > 230 and gpu.last_error() == ""

@@ -41,6 +41,8 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int pk422;                        // packed 4:2:2 destination: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576)
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
+    int srcBits, srcBE;               // 9 / 10 / 16-bit planar sources: 16-bit words (byte-swapped when big-endian), hScale16To15_c; else 8
+    int dither;                       // those sources dither their 8-bit planar outputs (should_dither, swscale.c:389-390,553-556)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -556,20 +558,50 @@ sws_vscale_rgb24_full_kernel(SwsDev p, const int16_t *__restrict__ lum, const in
     full_pixel(Y >> 10, U >> 10, V >> 10, p.k, p.bgr, dst + (size_t)y * dstStride + (size_t)i * 3);
 }
 
-// pass 2 for planar output (see plane_store above)
+// GENERAL path, pass 1 for 9 / 10 / 16-bit planar sources: hScale16To15_c (swscale.c:110-131): 16-bit words (byte-swapped first for the
+// big-endian formats: input.c bswap16Y_c / bswap16UV_c), products shifted down by depth - 1; thread = (column, row)
+__global__ void __launch_bounds__(256)
+sws_hscale16to15_kernel(const uint8_t *__restrict__ src, int srcStride, int16_t *__restrict__ dst, int dstStridePx,
+                        const int16_t *__restrict__ filter, const int32_t *__restrict__ pos, int fs, int dstW, int rows, int bits, int be)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= dstW || y >= rows) return;
+    const uint16_t *s = reinterpret_cast<const uint16_t *>(src + (size_t)y * srcStride) + pos[i];
+    const int16_t *f = filter + (size_t)i * fs;
+    int val = 0;
+    for (int j = 0; j < fs; j++) val += swap16_if(s[j], be) * f[j];
+    dst[(size_t)y * dstStridePx + i] = (int16_t)min(val >> (bits - 1), (1 << 15) - 1);
+}
+
+// ff_dither_8x8_128[row][col] (swscale.c:38-47) is a bit-interleaved ordered-dither matrix: affine over GF(2) in the bits of row and column
+__device__ __forceinline__ int dither128(int row, int col)
+{
+    int v = 18;
+    if (row & 1) v ^= 32;
+    if (row & 2) v ^= 8;
+    if (row & 4) v ^= 2;
+    if (col & 1) v ^= 48;
+    if (col & 2) v ^= 12;
+    if (col & 4) v ^= 3;
+    return 2 * v;
+}
+
+// pass 2 for planar output (see plane_store above); dither: 8-bit output of a high-bit-depth source, lumDither8 / chrDither8 with offset doff
 __global__ void __launch_bounds__(256)
 sws_vscale_plane_kernel(const int16_t *__restrict__ src, int srcStride, int srcH, const int16_t *__restrict__ filter,
-                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits, int be, int step = 1)
+                        const int32_t *__restrict__ pos, int fs, uint8_t *__restrict__ dst, int dstStride, int dstW, int dstH, int bits, int be, int step = 1,
+                        int dither = 0, int doff = 0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (i >= dstW || y >= dstH) return;
     const int first = max(1 - fs, pos[y]);
     int val;
+    const int dth = (dither && bits == 8) ? dither128(y & 7, (i + doff) & 7) : 1 << (14 - bits);      // 64 for plain 8-bit output
     if (fs == 1) {
-        val = (src[(size_t)line_index(first, 0, srcH) * srcStride + i] + (1 << (14 - bits))) >> (15 - bits);
+        val = (src[(size_t)line_index(first, 0, srcH) * srcStride + i] + dth) >> (15 - bits);
     } else {
         const int16_t *f = filter + (size_t)y * fs;
-        val = 1 << (26 - bits);
+        val = bits == 8 ? dth << 12 : 1 << (26 - bits);
         for (int j = 0; j < fs; j++) val += src[(size_t)line_index(first, j, srcH) * srcStride + i] * f[j];
         val >>= 27 - bits;
     }
@@ -1181,6 +1213,7 @@ struct SwsCudaContext {
     uint8_t *d_rgb = nullptr; size_t rgb_bytes = 0;
     int dstBits = 8, dstBE = 0;
     int srcRange = 0;           // 1 = full-range (JPEG) source, sws_setColorspaceDetails / a yuvj source format
+    int srcBits = 8, srcBE = 0; // 9 / 10 / 16-bit planar source (16-bit words; hScale16To15_c in the two-pass path)
     int rangeConv = 0;          // yuv destination of the other range: 1 lum / chrRangeFromJpeg_c, 2 lum / chrRangeToJpeg_c on the hscaled lines (two-pass path)
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
     int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
@@ -1226,6 +1259,7 @@ static int upload_tables(SwsCudaContext *c)
     d.bgr = c->dstFormat == FMT_BGR24;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
     d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422;
+    d.srcBits = c->srcBits; d.srcBE = c->srcBE; d.dither = c->srcBits > 8;
     return 0;
 }
 
@@ -1251,6 +1285,21 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         return 0;
     };
     srcRange = handle_jpeg(srcFormat); dstRange = handle_jpeg(dstFormat);
+    // 9 / 10 / 16-bit planar sources (LE values of libavutil/pixfmt.h; big-endian twins: 9 / 10-bit LE - 1, 16-bit LE + 1)
+    int srcBits = 8, srcBE = 0;
+    {
+        int f = srcFormat;
+        if (f == 61 || f == 63 || f == 65 || f == 67 || f == 69 || f == 71) { srcBE = 1; f += 1; }
+        else if (f == 48 || f == 50 || f == 52) { srcBE = 1; f -= 1; }
+        switch (f) {
+        case FMT_YUV420P9: srcBits = 9; srcFormat = FMT_YUV420P; break;   case FMT_YUV420P10: srcBits = 10; srcFormat = FMT_YUV420P; break;
+        case FMT_YUV420P16: srcBits = 16; srcFormat = FMT_YUV420P; break; case FMT_YUV422P9: srcBits = 9; srcFormat = FMT_YUV422P; break;
+        case FMT_YUV422P10: srcBits = 10; srcFormat = FMT_YUV422P; break; case FMT_YUV422P16: srcBits = 16; srcFormat = FMT_YUV422P; break;
+        case FMT_YUV444P9: srcBits = 9; srcFormat = FMT_YUV444P; break;   case FMT_YUV444P10: srcBits = 10; srcFormat = FMT_YUV444P; break;
+        case FMT_YUV444P16: srcBits = 16; srcFormat = FMT_YUV444P; break;
+        default: srcBE = 0; break;
+        }
+    }
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
@@ -1323,11 +1372,21 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "range conversion (full-range yuvj <-> limited-range yuv) to a 16-bit destination is not taken over");
         return nullptr;
     }
+    if (srcBits > 8) {
+        const char *why = nullptr;
+        if (usesFilter) why = "SwsFilter vectors with a 9 / 10 / 16-bit source are not taken over";
+        else if (rangeConv) why = "range conversion from a 9 / 10 / 16-bit source is not taken over";
+        else if (planar && dbits == 16) why = "9 / 10 / 16-bit source to a 16-bit destination (hScale16To19_c lines) is not taken over";
+        // same size and sub-sampling, planar destination: planarCopyWrapper with its own depth conversions (swscale_unscaled.c:793-1020)
+        else if (planar && dstFormat != FMT_NV12 && dstFormat != FMT_NV21 && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs)
+            why = "9 / 10 / 16-bit source to a planar destination of the same size and sub-sampling is the reference's planarCopyWrapper: not taken over";
+        if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
+    }
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->pk422 = pk422;
-    if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv) {               // swscale_unscaled.c:1123-1139,1152-1176
+    c->pk422 = pk422; c->srcBits = srcBits; c->srcBE = srcBE;
+    if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv && srcBits == 8) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
         else if (srcFormat == dstFormat) c->to422 = 3;
@@ -1336,7 +1395,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->dstFormat = dstFormat; c->dst32 = dst32 ? dstFormat : 0; c->planar = planar; c->dstBits = dbits; c->dstBE = dbe;
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
-    c->src422 = srcFormat == FMT_YUV422P;
+    c->src422 = srcFormat == FMT_YUV422P && srcBits == 8;
     c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : src32 ? 4 : 0;
     c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR;
     if (src32) {
@@ -1366,8 +1425,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         c->srcRange = srcRange;
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
-    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter;
-    c->fused = !c->table_unscaled && rgb && !pk422 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8;
+    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -1384,9 +1443,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
-    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter;
+    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter && srcBits == 8;
     c->rangeConv = rangeConv;
-    c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv;           // swscale_unscaled.c:1040-1044
+    c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv && srcBits == 8;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { delete c; return nullptr; }
     if (c->fast_ok) {
@@ -1427,7 +1486,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
         const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
-        if (need <= 96 * 1024 && !pk422 && !rangeConv) {          // (the packed 4:2:2 output stage and the range conversion only exist in the two-pass path so far)
+        if (need <= 96 * 1024 && !pk422 && !rangeConv && srcBits == 8) {          // (the packed 4:2:2 output stage and the range conversion only exist in the two-pass path so far)
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1731,7 +1790,11 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
     for (int f = 0; f < nframes; f++) {      // general path, two passes: frames are serialised on the stream (shared line planes)
         const uint8_t *y = src[0] + f * srcFrame[0], *u = src[1] + f * srcFrame[1], *v = src[2] + f * srcFrame[2];
         dim3 b(256);
-        if (c->g.flags & SWS_FAST_BILINEAR) {
+        if (p.srcBits > 8) {                  // no fast-bilinear line functions for these sources (swscale.c:733-743): the designed bank
+            sws_hscale16to15_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH, p.srcBits, p.srcBE);
+            sws_hscale16to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH, p.srcBits, p.srcBE);
+            sws_hscale16to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH, p.srcBits, p.srcBE);
+        } else if (c->g.flags & SWS_FAST_BILINEAR) {
             sws_hscale_fast_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.srcW, p.dstW, p.srcH, c->g.lumXInc, 0);
             sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
             sws_hscale_fast_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.chrSrcW, p.chrDstW, p.chrSrcH, c->g.chrXInc, 1);
@@ -1746,9 +1809,9 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
                 sws_launch_range(c->d_chrV, c->chrStridePx, p.chrDstW, p.chrSrcH, c->rangeConv == 1 ? 1 : 3, st)) return -1;
         }
         if (c->planar) {
-            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits, p.dstBE);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep);
-            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep);
+            sws_vscale_plane_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(c->d_lum, c->lumStridePx, p.srcH, p.vLumF, p.vLumP, p.vLumSize, dst[0] + f * dstFrame[0], dstStride[0], p.dstW, p.dstH, p.dstBits, p.dstBE, 1, p.dither, 0);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrU, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[1] + f * dstFrame[1], dstStride[1], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep, p.dither, 0);
+            sws_vscale_plane_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrDstH), b, 0, st>>>(c->d_chrV, c->chrStridePx, p.chrSrcH, p.vChrF, p.vChrP, p.vChrSize, dst[2] + f * dstFrame[2], dstStride[2], p.chrDstW, p.chrDstH, p.dstBits, p.dstBE, p.chrStep, p.dither, 3);      // chrDither8 with offset 3 for V (swscale.c:636-644)
         } else {
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
@@ -1846,7 +1909,8 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
     const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;
     const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
     const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH }, dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
-    const size_t srcW[3] = { (size_t)g.srcW * (pk ? pkBpp : 1), (size_t)g.chrSrcW * (nv ? 2 : 1), (size_t)g.chrSrcW };
+    const size_t sS = c->srcBits > 8 ? 2 : 1;
+    const size_t srcW[3] = { (size_t)g.srcW * (pk ? pkBpp : sS), (size_t)g.chrSrcW * (nv ? 2 : sS), (size_t)g.chrSrcW * sS };
     const size_t dstW[3] = { (size_t)g.dstW * (rgb ? pxB : sB), (size_t)g.chrDstW * (c->dstNV ? 2 : sB), (size_t)g.chrDstW * sB };
     std::vector<uint8_t> sbuf[3], dbuf[3];
     const uint8_t *s2[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -1903,7 +1967,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     // device staging: tight, aligned pitches
     // (a packed source keeps the caller's pitch: the chroma readers look one pixel past an odd width, into the padding or the next row)
     const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2;
-    const int yP = pk ? srcStride[0] : (g.srcW + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW + 15) & ~15;
+    const int sS = c->srcBits > 8 ? 2 : 1;                  // bytes per source sample (planar 9 / 10 / 16-bit sources)
+    const int yP = pk ? srcStride[0] : (g.srcW * sS + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW * sS + 15) & ~15;
     const size_t yB = (size_t)yP * g.srcH, cB = pk ? 0 : (size_t)cP * g.chrSrcH;
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
@@ -1967,9 +2032,9 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         if (cudaMemcpyAsync((void *)ds[0], srcSlice[0], (size_t)(g.srcH - 1) * srcStride[0] + rowB, cudaMemcpyHostToDevice, s) != cudaSuccess) {
             set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
         }
-    } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], g.srcW + upX, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (nv ? 2 : 1) * g.chrSrcW + upCX, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], g.chrSrcW + upCX, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
+    } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], (size_t)(g.srcW + upX) * sS, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpy2DAsync((void *)ds[1], cP, srcSlice[1], srcStride[1], (size_t)((nv ? 2 : 1) * g.chrSrcW + upCX) * sS, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        (!nv && cudaMemcpy2DAsync((void *)ds[2], cP, srcSlice[2], srcStride[2], (size_t)(g.chrSrcW + upCX) * sS, g.chrSrcH, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
         set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
     }
     static const size_t zero3[3] = { 0, 0, 0 };

@@ -358,6 +358,27 @@ static int16_t *hfast(const uint8_t *src, int stride, int rows, int sw, int dw, 
 }
 
 /* hScale8To15_c over a whole plane into (rows x (n + 2)) int16, trailing columns zero like the zeroed line buffers */
+/* 9 / 10 / 16-bit planar sources (hScale16To15_c, swscale.c:110-131: samples in 16-bit words, shifted down by depth - 1; big-endian formats are
+ * byte-swapped by the input stage first, input.c bswap16Y_c / bswap16UV_c) and the ordered dither their 8-bit planar outputs get
+ * (should_dither, swscale.c:389-390,553-556): ff_dither_8x8_128[row & 7][(i + offset) & 7], a bit-interleaved 8 x 8 matrix */
+static __thread int g_sbits = 8, g_sbe;
+static int dither128(int row, int col)
+{
+    int v = 18;
+    if (row & 1) v ^= 32;
+    if (row & 2) v ^= 8;
+    if (row & 4) v ^= 2;
+    if (col & 1) v ^= 48;
+    if (col & 2) v ^= 12;
+    if (col & 4) v ^= 3;
+    return 2 * v;
+}
+static int sample_at(const uint8_t *src, size_t byte_row, int x)
+{
+    if (g_sbits == 8) return src[byte_row + x];
+    const uint8_t *p = src + byte_row + 2 * (size_t)x;
+    return g_sbe ? (p[0] << 8) | p[1] : p[0] | (p[1] << 8);
+}
 static int16_t *hpass(const uint8_t *src, int stride, int rows, const bank_t *b, int *pitch)
 {
     int p = b->n + 2;
@@ -365,8 +386,8 @@ static int16_t *hpass(const uint8_t *src, int stride, int rows, const bank_t *b,
     for (int y = 0; y < rows; y++)
         for (int i = 0; i < b->n; i++) {
             int v = 0;
-            for (int j = 0; j < b->taps; j++) v += src[(size_t)y * stride + b->pos[i] + j] * b->coef[(size_t)i * b->taps + j];
-            v >>= 7;
+            for (int j = 0; j < b->taps; j++) v += sample_at(src, (size_t)y * stride, b->pos[i] + j) * b->coef[(size_t)i * b->taps + j];
+            v >>= g_sbits == 8 ? 7 : g_sbits - 1;
             out[(size_t)y * p + i] = (int16_t)(v > 32767 ? 32767 : v);
         }
     *pitch = p;
@@ -415,7 +436,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
-    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422 && !uses_filter()) {
+    if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422 && !uses_filter() && g_sbits == 8) {
         /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
          * i.e. both rows of a pair read the even chroma line)
          * unscaled table converter yuv2rgb_c_24_rgb (yuv2rgb.c:126-175, :335-372; chosen at swscale_unscaled.c:1051-1055):
@@ -433,7 +454,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
         return dh;
     }
     int lp, cp;
-    const int fast = c.flags & F_FAST_BILINEAR;
+    const int fast = (c.flags & F_FAST_BILINEAR) && g_sbits == 8;      /* the fast line functions only exist for 8-bit sources (swscale.c:733-739) */
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
@@ -521,16 +542,17 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
 
 /* yuv2plane1_8_c / yuv2planeX_8_c (output.c:242-265, dither 64) and yuv2plane1_10_c / yuv2planeX_10_c (:183-213) in one recipe:
  * the rounding constants and shifts only depend on the output depth */
-static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t *dst, int dstride, int w, int h)
+static void vplane(const int16_t *s, int pitch, int sh, const bank_t *b, uint8_t *dst, int dstride, int w, int h, int doff)
 {
     const int bits = g_dbits, top = (1 << bits) - 1;
     for (int y = 0; y < h; y++) {
         int fs = b->taps, first = b->pos[y] > 1 - fs ? b->pos[y] : 1 - fs;
         for (int i = 0; i < w; i++) {
             int v;
-            if (fs == 1) v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + (1 << (14 - bits))) >> (15 - bits);
+            const int dth = (bits == 8 && g_sbits > 8) ? dither128(y & 7, (i + doff) & 7) : 1 << (14 - bits);      /* 64 for 8-bit output without dithering */
+            if (fs == 1) v = (s[(size_t)rowsel(first, 0, sh) * pitch + i] + dth) >> (15 - bits);
             else {
-                v = 1 << (26 - bits);
+                v = bits == 8 ? dth << 12 : 1 << (26 - bits);
                 for (int j = 0; j < fs; j++) v += s[(size_t)rowsel(first, j, sh) * pitch + i] * b->coef[(size_t)y * fs + j];
                 v >>= 27 - bits;
             }
@@ -567,7 +589,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range && !uses_filter()) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
+    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range && !uses_filter() && g_sbits == 8) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
                                          swscale_unscaled.c:793-1020); 8 -> 9 / 10 bits is a plain shift for limited-range sources (:946-971) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
@@ -593,14 +615,14 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
         sws_close(&c);
         return dh;
     }
-    const int fast = c.flags & F_FAST_BILINEAR;
+    const int fast = (c.flags & F_FAST_BILINEAR) && g_sbits == 8;      /* the fast line functions only exist for 8-bit sources (swscale.c:733-739) */
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
     range_lines(L, lp, sh, dw, 0); range_lines(U, cp, c.chrSrcH, c.chrDstW, 1); range_lines(V, cp, c.chrSrcH, c.chrDstW, 1);
-    vplane(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
-    vplane(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
-    vplane(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH);
+    vplane(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh, 0);
+    vplane(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH, 0);
+    vplane(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH, 3);      /* chrDither8 with offset 3 for V (swscale.c:636-644) */
     free(L); free(U); free(V);
     sws_close(&c);
     return dh;
@@ -671,7 +693,7 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
         static const int order[4][4] = { { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };
         const int *o = order[dst_fmt - 25];
         int w = dw;
-        if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter()) w &= ~1;
+        if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter() && g_sbits == 8) w &= ~1;
         else if ((w & 1) && !(flags & F_FULL_CHR_H_INT) && dstride >= 4 * (w + 1)) w++;
         for (int y = 0; r == dh && y < dh; y++)
             for (int x = 0; x < w; x++) {
@@ -894,6 +916,31 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
 {
     int hs, vs, r;
     const int pk = dst_fmt == 1 || dst_fmt == 15;
+    {   /* 9 / 10 / 16-bit planar sources: yuv420p 62 64 47, yuv422p 72 66 49, yuv444p 68 70 51 (LE), big-endian twins -1 / +1 */
+        int f = src_fmt, be = 0, bits = 0, base = -1;
+        if (f == 61 || f == 63 || f == 65 || f == 67 || f == 69 || f == 71) { be = 1; f += 1; }
+        else if (f == 48 || f == 50 || f == 52) { be = 1; f -= 1; }
+        switch (f) {
+        case 62: base = 0; bits = 9; break;   case 64: base = 0; bits = 10; break;  case 47: base = 0; bits = 16; break;
+        case 72: base = 4; bits = 9; break;   case 66: base = 4; bits = 10; break;  case 49: base = 4; bits = 16; break;
+        case 68: base = 5; bits = 9; break;   case 70: base = 5; bits = 10; break;  case 51: base = 5; bits = 16; break;
+        }
+        if (base >= 0 && g_sbits == 8) {
+            int h2, v2, b2 = 8;
+            const int rgbd = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28), pkd = dst_fmt == 1 || dst_fmt == 15, nvd = g_nospecial;
+            const int shs = base == 5 ? 0 : 1, svs = base == 0 ? 1 : 0;
+            if (uses_filter()) return -1;
+            if (!rgbd && !pkd) {
+                if (!planar_dst(dst_fmt, &h2, &v2, &b2) || b2 == 16) { g_dbe = 0; return -1; }        /* 19-bit lines: not restated for these sources */
+                /* same size and sub-sampling: planarCopyWrapper with its own depth conversions (swscale_unscaled.c:793-1020), not restated */
+                if (sw == dw && sh == dh && !nvd && h2 == shs && v2 == svs) { g_dbe = 0; return -1; }
+            }
+            g_sbits = bits; g_sbe = be;
+            r = sws_any(base, src, ss, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+            g_sbits = 8; g_sbe = 0;
+            return r;
+        }
+    }
     /* handle_jpeg() (utils.c:855-873) on both sides: yuvj420p 12 / 422p 13 / 444p 14 / 440p 32 are their limited-range twins with
      * srcRange / dstRange = 1.  An rgb destination folds the source range into its colour tables; a yuv destination of the other range
      * gets the range conversion (restated for planar 8-bit sources to planar 8 / 9 / 10-bit destinations), of the same range nothing. */
@@ -926,7 +973,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         const int planar_src = src_fmt == 0 || src_fmt == 4 || src_fmt == 5 || src_fmt == 6 || src_fmt == 7 || src_fmt == 31;
         if (!planar_src || pk || g_nospecial || (!rgb && (!planar_dst(dst_fmt, &h2, &v2, &b2) || b2 != 8))) { g_dbe = 0; return -1; }
     }
-    if (pk && sw == dw && sh == dh && !g_range) {
+    if (pk && sw == dw && sh == dh && !g_range && g_sbits == 8) {
         /* the reference's unscaled converters to packed 4:2:2 (swscale_unscaled.c:1123-1139,1152-1176): from yuv422p always, from yuv420p
          * with the fast-bilinear / point flags (yuvPlanartoyuy2_c, rgb2rgb_template.c:322-420: width >> 1 pairs), same format = copy */
         const int vshift = src_fmt == 0 ? 1 : 0, uyvy = dst_fmt == 15;

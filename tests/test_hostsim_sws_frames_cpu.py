@@ -144,3 +144,22 @@ def test_range_conversion_with_a_semi_planar_or_packed_side(sim, refo):
         same(got, want, (sf, df, w, h, dw, dh, hex(flags)))
         n += 1
     assert n > 230
+
+
+def test_high_bit_depth_sources(sim, refo):
+    """9 / 10 / 16-bit planar sources (hScale16To15 in the two-pass path, ordered dither on 8-bit planar / nv12 outputs)"""
+    import test_sws_hbd_sources_cpu as H
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in H.cases():
+        pl = H.planes(sf, w, h, 5)
+        rc, want = H.run(refo, sf, pl, w, h, df, dw, dh, flags)
+        assert rc == dh
+        got = product(sim, sf, pl, w, h, df, dw, dh, flags, outs=H.outputs(df, dw, dh))
+        same(got, want, (sf, df, w, h, dw, dh, hex(flags)))
+        n += 1
+    assert n > 2000
+    # what stays refused, with a reason
+    for (sf, df, w, h, dw, dh) in ((64, 64, 64, 48, 64, 48), (64, 0, 64, 48, 64, 48), (64, 47, 64, 48, 96, 80), (64, 12, 64, 48, 96, 80)):
+        assert not sim.sws_getContext_cuda(w, h, sf, dw, dh, df, 4, None, None, None)
+        assert sim.avb200_last_error()
+        sim.avb200_clear_error()

@@ -11,7 +11,8 @@ from libav_b200.device import PLANAR_FORMATS
 ACC = 0x40000 | 0x80000
 PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0), 32: (0, 1)}
 PACKED_SRC = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
-SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24]
+HBD_SRC = [62, 63, 64, 48, 66, 70]                       # 9 / 10 / 16-bit planar sources (a sample; every one in tests/test_sws_hbd_sources_cpu.py)
+SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24] + HBD_SRC
 DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24, 12, 14, 32]        # 12 14 32: full-range (yuvj) planar
 GEOMS = [(64, 48, 64, 48), (66, 50, 66, 50), (64, 48, 96, 80), (96, 80, 64, 48)]
 FLAGS = (4 | ACC, 4, 0x10, 1 | ACC, 2 | ACC | 0x2000, 2)
@@ -26,6 +27,9 @@ def plan(L, sw, sh, sf, dw, dh, df, flags):
 
 
 def source(fmt, w, h):
+    if fmt in HBD_SRC:
+        import test_sws_hbd_sources_cpu as H
+        return H.planes(fmt, w, h, 3)
     r = np.random.RandomState(fmt * 7 + w)
     if fmt in PACKED_SRC:
         return [r.randint(0, 256, (h + 1, PACKED_SRC[fmt] * w + 16)).astype(np.uint8)]

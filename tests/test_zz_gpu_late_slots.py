@@ -306,3 +306,28 @@ def test_sws_range_conversion_with_a_semi_planar_or_packed_side(gpu, checker):
         ctx.close()
         n += 1
     assert n > 230 and gpu.last_error() == ""
+
+
+def test_sws_high_bit_depth_sources(gpu, checker):
+    """9 / 10 / 16-bit planar sources through sws_scale_cuda (tests/test_sws_hbd_sources_cpu.py cases; host-simulated on the CPU)"""
+    import numpy as np
+    import test_sws_hbd_sources_cpu as H
+    lib = gpu.lib
+    n = 0
+    for (sf, df, w, h, dw, dh, flags) in H.cases((64, 63, 62, 47, 66, 70, 69)):
+        pl = H.planes(sf, w, h, 5)
+        rc, want = H.run(checker, sf, pl, w, h, df, dw, dh, flags)
+        assert rc == dh
+        ctx = lib.sws_getContext_cuda(w, h, sf, dw, dh, df, flags, None, None, None)
+        assert ctx, (sf, df, gpu.last_error())
+        got = H.outputs(df, dw, dh)
+        sp = (C.c_void_p * 4)(*([a.ctypes.data for a in pl] + [None]))
+        ss = (C.c_int * 4)(*([a.strides[0] for a in pl] + [0]))
+        dp = (C.c_void_p * 4)(*([a.ctypes.data for a in got] + [None] * (4 - len(got))))
+        ds = (C.c_int * 4)(*([a.strides[0] for a in got] + [0] * (4 - len(got))))
+        assert lib.sws_scale_cuda(ctx, sp, ss, 0, h, dp, ds) == dh, gpu.last_error()
+        lib.sws_freeContext_cuda(ctx)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (sf, df, w, h, dw, dh, hex(flags))
+        n += 1
+    assert n > 1000 and gpu.last_error() == ""

@@ -371,8 +371,12 @@ int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float 
  * SWS_ACCURATE_RND | SWS_BITEXACT.  srcFilter / dstFilter: pointers to the reference's SwsFilter (four pointers to { double *coeff; int length; }),
  * taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations, vertical vectors symmetric.  Anything else returns NULL
  * with an error (no fallback).
- *   sws_scale_cuda         HOST pointers, whole frames (srcSliceY = 0, srcSliceH = srcH), strides of either sign (bottom-up pictures);
- *                          uploads, runs, downloads, synchronises; returns output lines like sws_scale(), 0 on bad arguments.
+ *   sws_scale_cuda         HOST pointers; whole frames (srcSliceY = 0, srcSliceH = srcH) with strides of either sign (bottom-up pictures), or
+ *                          slices like sws_scale() takes them (swscale_unscaled.c:1212-1340): srcSlice[] at source row srcSliceY, dst[] at the
+ *                          top of the picture, top-down and contiguous, boundaries on whole chroma rows, positive strides; each call returns
+ *                          (and writes) the rows the reference's loop completes with the same slices (swscale.c:483-485), at the cost of a
+ *                          whole-frame pass per slice.  Uploads, runs, downloads, synchronises; returns output lines like sws_scale(),
+ *                          0 on bad arguments.
  *   sws_scale_frames_cuda  DEVICE pointers, asynchronous on `stream`: nframes frames whose planes lie
  *                          *_frame_stride[] bytes apart (NULL = a single frame); returns lines written or -1.
  *                          For odd dstW the reference writes whole pixel pairs (libswscale/output.c:947); that

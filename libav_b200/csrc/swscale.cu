@@ -1224,6 +1224,8 @@ struct SwsCudaContext {
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
     // staging for the host-pointer sws_scale_cuda()
     uint8_t *d_src = nullptr, *d_dst = nullptr; size_t src_bytes = 0, dst_bytes = 0;
+    // slices (sws_scale_cuda_sliced): the source rows received so far, the next expected source row, the output rows already returned
+    std::vector<uint8_t> sliceSrc[3]; int slicePitch[3] = { 0, 0, 0 }; int sliceNextY = 0, sliceDstY = 0;
 };
 
 static bool is_identity(const FilterBank &b, int one)
@@ -1942,7 +1944,103 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
     return r;
 }
 
-// Host-pointer drop-in for sws_scale() (libswscale/swscale_unscaled.c:1212-1340): whole frames only.
+// Slices (libswscale/swscale_unscaled.c:1212-1340 sws_scale, libswscale/swscale.c:323-721 swscale): srcSlice[] points at source row
+// srcSliceY (chroma row srcSliceY >> chrSrcVSubSample), dst[] at the top of the destination picture, and each call returns the output
+// rows it completed.  The rows received so far are kept in the context; a call runs the frame pipeline over them and hands back the rows
+// the reference would have finished with the same slices: for its scaler loop all dstY whose last luma line (of the chroma-aligned row
+// group, lastLumSrcY2) and last chroma line lie inside the rows received ("enough_lines", swscale.c:483-485), for its unscaled converters
+// the rows of the slice itself.  Top-down, contiguous slices only (srcSliceY == 0 restarts a picture); a slice costs a whole-frame pass.
+static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY, int srcSliceH,
+                                 uint8_t *const dst[], const int dstStride[])
+{
+    const SwsGeometry &g = c->g;
+    const bool pk = c->srcPacked != 0, nv = c->srcNV != 0, rgb = !c->planar;
+    const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
+    if (srcSliceY < 0 || srcSliceH < 0 || srcSliceY + srcSliceH > g.srcH) { set_error_msg("sws_scale_cuda", "slice outside the picture"); return 0; }
+    for (int p = 0; p < nsrc; p++) if (srcStride[p] < 0) { set_error_msg("sws_scale_cuda", "slices of bottom-up pictures are not taken over"); return 0; }
+    for (int p = 0; p < ndst; p++) if (dstStride[p] < 0) { set_error_msg("sws_scale_cuda", "slices of bottom-up pictures are not taken over"); return 0; }
+    if (srcSliceY == 0) { c->sliceNextY = 0; c->sliceDstY = 0; }
+    else if (srcSliceY != c->sliceNextY) {
+        // (the reference also takes bottom-up slice orders, and answers "Slices start in the middle!" to a first slice that touches neither end)
+        set_error_msg("sws_scale_cuda", "slices are taken over top-down and contiguous only"); return 0;
+    }
+    const int end = srcSliceY + srcSliceH;
+    const bool rowMapped = c->copy || c->table_unscaled || c->special || c->to422 || c->nvcopy;
+    {
+        // a slice boundary inside a source chroma row makes the reference's scaler loop address rows before the slice (it has no check for it);
+        // the unscaled converters work on whole chroma row groups of either side
+        int sub = g.chrSrcVSub;
+        if (rowMapped) {
+            sub = sub > g.chrDstVSub ? sub : g.chrDstVSub;
+            if (c->table_unscaled || c->special == 3 || c->to422 == 2) sub = sub > 1 ? sub : 1;
+        }
+        const int m = (1 << sub) - 1;
+        if ((srcSliceY & m) || ((srcSliceH & m) && end != g.srcH)) { set_error_msg("sws_scale_cuda", "slice not aligned to the chroma rows"); return 0; }
+    }
+    // keep the rows
+    const int sS = c->srcBits > 8 ? 2 : 1, pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2;
+    const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH };
+    const size_t srcWB[3] = { (size_t)g.srcW * (pk ? pkBpp : sS), (size_t)g.chrSrcW * (nv ? 2 : 1) * sS, (size_t)g.chrSrcW * sS };
+    const int cY0 = srcSliceY >> g.chrSrcVSub, cY1 = -((-end) >> g.chrSrcVSub);
+    for (int p = 0; p < nsrc; p++) {
+        const size_t pitch = (size_t)srcStride[p];
+        if (c->sliceSrc[p].size() != pitch * srcRows[p] + 16 || c->slicePitch[p] != srcStride[p]) {
+            if (srcSliceY != 0) { set_error_msg("sws_scale_cuda", "the source pitch changed between slices"); return 0; }
+            c->sliceSrc[p].assign(pitch * srcRows[p] + 16, 0);
+            c->slicePitch[p] = srcStride[p];
+        }
+        const int y0 = p ? cY0 : srcSliceY, y1 = p ? (cY1 < srcRows[p] ? cY1 : srcRows[p]) : end;
+        const size_t row = pitch < srcWB[p] + 16 ? pitch : srcWB[p] + 16;
+        for (int y = y0; y < y1; y++) memcpy(c->sliceSrc[p].data() + (size_t)y * pitch, srcSlice[p] + (size_t)(y - y0) * pitch, row);
+    }
+    // the output rows this slice completes
+    int dstY0, dstY1;
+    if (rowMapped) { dstY0 = srcSliceY; dstY1 = end; }
+    else {
+        const int cdv = g.chrDstVSub, vL = c->vLum.size, vC = c->vChr.size;
+        dstY0 = c->sliceDstY;
+        for (dstY1 = dstY0; dstY1 < g.dstH; dstY1++) {
+            const int grp = dstY1 | ((1 << cdv) - 1), last = grp < g.dstH - 1 ? grp : g.dstH - 1;
+            const int fl = c->vLum.pos[last] > 1 - vL ? c->vLum.pos[last] : 1 - vL, fc = c->vChr.pos[dstY1 >> cdv] > 1 - vC ? c->vChr.pos[dstY1 >> cdv] : 1 - vC;
+            const int ll = (g.srcH < fl + vL ? g.srcH : fl + vL) - 1, lc = (g.chrSrcH < fc + vC ? g.chrSrcH : fc + vC) - 1;
+            if (!(ll < end && lc < cY1)) break;
+        }
+    }
+    c->sliceNextY = end == g.srcH ? 0 : end;
+    c->sliceDstY = end == g.srcH ? 0 : dstY1;
+    const int ret = rowMapped ? srcSliceH : dstY1 - dstY0;
+    if (dstY1 <= dstY0) return ret;
+    // the frame pipeline over the rows so far, into a copy of the caller's picture; the finished rows go back
+    const int sB = c->dstBits > 8 ? 2 : 1, pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    const int dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
+    const size_t dstWB[3] = { (size_t)g.dstW * (rgb ? pxB : sB), (size_t)g.chrDstW * (c->dstNV ? 2 : sB), (size_t)g.chrDstW * sB };
+    std::vector<uint8_t> dbuf[3];
+    const uint8_t *s2[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint8_t *d2[4] = { nullptr, nullptr, nullptr, nullptr };
+    int ss[4] = { 0, 0, 0, 0 }, ds[4] = { 0, 0, 0, 0 };
+    size_t drow[3] = { 0, 0, 0 };
+    for (int p = 0; p < nsrc; p++) { s2[p] = c->sliceSrc[p].data(); ss[p] = srcStride[p]; }
+    for (int p = 0; p < ndst; p++) {
+        const size_t pitch = (size_t)dstStride[p];
+        drow[p] = pitch < dstWB[p] + 16 ? pitch : dstWB[p] + 16;
+        dbuf[p].assign(pitch * dstRows[p] + 16, 0);
+        for (int y = 0; y < dstRows[p]; y++) memcpy(dbuf[p].data() + (size_t)y * pitch, dst[p] + (size_t)y * pitch, drow[p]);
+        d2[p] = dbuf[p].data(); ds[p] = dstStride[p];
+    }
+    if (sws_scale_cuda((SwsContextCUDA *)c, s2, ss, 0, g.srcH, d2, ds) <= 0) return 0;
+    c->sliceNextY = end == g.srcH ? 0 : end;          // (the whole-frame call above restarted the slice state)
+    c->sliceDstY = end == g.srcH ? 0 : dstY1;
+    const int s = 1 << g.chrDstVSub;
+    for (int p = 0; p < ndst; p++) {
+        const int y0 = p ? (dstY0 + s - 1) >> g.chrDstVSub : dstY0;
+        int y1 = p ? (dstY1 + s - 1) >> g.chrDstVSub : dstY1;
+        if (y1 > dstRows[p]) y1 = dstRows[p];
+        for (int y = y0; y < y1; y++) memcpy(dst[p] + (size_t)y * ds[p], dbuf[p].data() + (size_t)y * ds[p], drow[p]);
+    }
+    return ret;
+}
+
+// Host-pointer drop-in for sws_scale() (libswscale/swscale_unscaled.c:1212-1340): whole frames, or top-down slices (above).
 // Returns the number of output lines like the reference, 0 on bad arguments.
 int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY, int srcSliceH,
                    uint8_t *const dst[], const int dstStride[])
@@ -1955,7 +2053,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dstStride[1] || (!c->dstNV && (!dst[2] || !dstStride[2]))))) {
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
-    if (srcSliceY != 0 || srcSliceH != c->g.srcH) { set_error_msg("sws_scale_cuda", "only whole-frame slices are taken over"); return 0; }
+    if (srcSliceY != 0 || srcSliceH != c->g.srcH) return sws_scale_cuda_sliced(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
+    c->sliceNextY = 0; c->sliceDstY = 0;
     if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0 ||
         (!rgb && (dstStride[1] < 0 || (!c->dstNV && dstStride[2] < 0))))
         return sws_scale_cuda_flipped(c, srcSlice, srcStride, srcSliceH, dst, dstStride);

@@ -82,6 +82,7 @@ API = {
     "sws_set_slots": (i32, [vp, vp]),
     "sws_slot_mask": (i32, [vp]),
     "sws_run": (i32, [vp, vp, vp, i32, vp, vp]),
+    "sws_run_slice": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "sws_close": (None, [vp]),
     "sws_get_filter": (i32, [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "sws_rgb24_tables": (None, [vp, vp, vp, vp, vp]),

@@ -513,6 +513,14 @@ int ref_sws_run(void *ctx, const uint8_t *const src[3], const int ss[3], int sh,
     uint8_t *d[4] = { dst[0], dst[1], dst[2], NULL };
     return sws_scale(ctx, s, sst, 0, sh, d, ds);
 }
+/* one slice: src[] points at source row y0 (chroma row y0 >> chrSrcVSubSample), dst[] at the top of the picture */
+int ref_sws_run_slice(void *ctx, const uint8_t *const src[3], const int ss[3], int y0, int sh, uint8_t *const dst[3], const int dstride[3])
+{
+    const uint8_t *s[4] = { src[0], src[1], src[2], NULL };
+    int sst[4] = { ss[0], ss[1], ss[2], 0 }, ds[4] = { dstride[0], dstride[1], dstride[2], 0 };
+    uint8_t *d[4] = { dst[0], dst[1], dst[2], NULL };
+    return sws_scale(ctx, s, sst, y0, sh, d, ds);
+}
 void ref_sws_close(void *ctx) { sws_freeContext(ctx); }
 
 int ref_sws_get_filter(int which, int to_rgb, int sw, int sh, int dw, int dh, int flags, int16_t *filter,

@@ -331,3 +331,24 @@ def test_sws_high_bit_depth_sources(gpu, checker):
             assert np.array_equal(a, b), (sf, df, w, h, dw, dh, hex(flags))
         n += 1
     assert n > 1000 and gpu.last_error() == ""
+
+
+def test_sws_scale_slices(gpu, refo):
+    """sws_scale() slice by slice (tests/test_hostsim_sws_slices_cpu.py has the CPU twin): per call the return value and the whole destination
+    picture against the compiled reference given the same slices -- through the tile kernels here"""
+    import test_hostsim_sws_slices_cpu as S
+    ACC = 0x40000 | 0x80000
+    n = 0
+    for sf, df in ((0, 2), (0, 0), (4, 0), (5, 28), (0, 23), (23, 0), (2, 0), (0, 1), (0, 63)):
+        for (w, h, dw, dh) in ((64, 48, 96, 80), (66, 50, 33, 25), (64, 48, 64, 48)):
+            for flags in (4 | ACC, 2):
+                if (w, h) == (dw, dh) and not (flags & ACC == ACC and sf in (0, 4, 5) and df in (2, 28)):
+                    continue
+                for plan in S.plans(h, 1 << S.VSUB.get(sf, 0)):
+                    S.compare(gpu.lib, refo, sf, df, w, h, dw, dh, flags, plan)
+                    n += 1
+    for sf, df, flags, align in ((0, 0, 4, 2), (0, 2, 4, 2), (0, 23, 4, 2), (23, 0, 4, 2), (2, 3, 4, 1), (3, 0, 4, 2), (1, 0, 4, 2), (4, 1, 4, 1), (0, 62, 4, 2)):
+        for plan in S.plans(48, align):
+            S.compare(gpu.lib, refo, sf, df, 64, 48, 64, 48, flags, plan)
+            n += 1
+    assert n > 100 and gpu.last_error() == ""

@@ -17,11 +17,17 @@ from test_hostsim_sws_frames_cpu import ACC, arrays, outputs
 from libav_b200 import synth
 from test_sws_planar_dst import source as _source
 
-VSUB = {0: 1, 4: 0, 5: 0, 23: 1, 24: 1, 12: 1, 13: 0, 14: 0, 6: 2, 7: 0, 8: 1, 62: 1, 63: 1, 64: 0}
+VSUB = {61: 1, 47: 1, 48: 1, 66: 0, 70: 0, 0: 1, 4: 0, 5: 0, 23: 1, 24: 1, 12: 1, 13: 0, 14: 0, 6: 2, 7: 0, 8: 1, 62: 1, 63: 1, 64: 1}
 
 
 def source(sf, w, h, seed):
     r = np.random.RandomState(seed)
+    if sf in (62, 61, 64, 63, 47, 48, 66, 70):
+        import test_sws_hbd_sources_cpu as H
+        return H.planes(sf, w, h, seed)
+    if sf in (12, 13, 14):
+        import test_sws_range_cpu as R
+        return R.planes(sf, w, h, seed)
     if sf == 3:
         return [r.randint(0, 256, (h, 3 * w + 10)).astype(np.uint8)]
     if sf == 6:
@@ -92,6 +98,21 @@ def test_scaler_loop_slices(sim, refo):
                     compare(sim, refo, sf, df, w, h, dw, dh, flags, plan)
                     n += 1
     assert n > 200
+
+
+def test_range_conversion_and_deep_source_slices(sim, refo):
+    """the two-pass-only stages under slices: yuvj <-> yuv range conversion on the scaled lines, 9 / 10 / 16-bit sources (hScale16To15_c)"""
+    import test_sws_hbd_sources_cpu as H
+    n = 0
+    for sf, df in ((12, 0), (0, 12), (14, 4), (12, 2), (64, 0), (62, 2), (47, 5), (63, 28), (64, 62)):
+        for (w, h, dw, dh) in ((64, 48, 96, 80), (66, 50, 33, 25), (64, 48, 64, 48)):
+            for flags in (4 | ACC, 2):
+                if sf > 40 and not H.taken(sf, df, w, h, dw, dh, flags):
+                    continue                                         # (their same-size plane copies are refused at sws_getContext_cuda)
+                for plan in plans(h, 1 << VSUB.get(sf, 0)):
+                    compare(sim, refo, sf, df, w, h, dw, dh, flags, plan)
+                    n += 1
+    assert n > 140
 
 
 def test_unscaled_converter_slices(sim, refo):

@@ -23,6 +23,7 @@
 #include <new>
 #include <vector>
 #include "sws_dev.cuh"
+#include "sws_fused.h"
 #include <algorithm>
 #include <limits.h>
 #include <string.h>
@@ -48,12 +49,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
 // ---------------------------------------------------------------------------------------------------
 // FUSED kernel: horizontal identity, vLum identity, 4-tap vertical chroma.
 // ---------------------------------------------------------------------------------------------------
-struct FusedArgs {
-    const uint8_t *y, *u, *v; uint8_t *dst;
-    int yStride, uStride, vStride, dstStride;
-    size_t yFrame, uFrame, vFrame, dstFrame;      // byte distance between consecutive frames of a batch
-    int rp0 = 0, rp1 = 0x7fffffff;                 // row-pair range of this launch (the dp4a kernel; bands of the host pipeline)
-};
+// (FusedArgs: sws_fused.h)
 
 // one output row of 8 pixels from 8 luma bytes and 4 already filtered (U,V) pairs -> 6 packed words
 __device__ __forceinline__ void rgb_row8(uint2 yy, const int (&U)[4], const int (&V)[4], const RgbConstants &k, int bgr,
@@ -160,94 +156,13 @@ sws_fused_rgb24_kernel(SwsDev p, FusedArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// FUSED kernel, interior fast path: a thread owns 16 pixels x 2 rows (one LDG.128 of luma per row, one LDG.64 per
-// chroma line) and walks its 8 chroma columns once, producing both rows from the same extracted bytes.
-// Preconditions checked on the host (else the kernel above runs): 16-byte aligned planes / pitches, dstW % 16 == 0,
-// dstH even, the chroma windows of the two rows of every pair start at most one line apart, and the filter bank cannot
-// push U,V outside
-// (-256, 512) -- then clipping each value on its own is identical to the reference's "clip all four if any has bit 8
-// set" (output.c:966-971) because an in-range value is unchanged by av_clip_uint8.
-// Per pixel pair and row: 8 IMAD + 2 shifts + 2 clamps for the FIR, 12 for the colour terms, 17 for the two pixels.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sat255(int v) { return __vimin_s32_relu(v, 255); }       // max(min(v, 255), 0), one VIMNMX
-
-template <bool BGR, bool MH>
-__global__ void __launch_bounds__(128)
-sws_fused_rgb24_v2_kernel(SwsDev p, FusedArgs a)
-{
-    const int gx = blockIdx.x * 32 + threadIdx.x;            // group of 16 pixels
-    const int rp = blockIdx.y * 4 + threadIdx.y;             // row pair
-    if (gx * 16 >= p.dstW || rp * 2 >= p.dstH) return;
-    const size_t f = blockIdx.z;
-    const int y0 = rp * 2;
-    const uint8_t *Yp = a.y + f * a.yFrame + (size_t)y0 * a.yStride + gx * 16;
-    const uint8_t *Up = a.u + f * a.uFrame + gx * 8, *Vp = a.v + f * a.vFrame + gx * 8;
-    uint8_t *D = a.dst + f * a.dstFrame + (size_t)y0 * a.dstStride + gx * 48;
-
-    // The two rows of a pair use chroma windows that start at the same line or one line apart (host-checked): five
-    // lines are loaded and row 1 runs a 5-tap filter whose first or last tap is zero.
-    const int first = max(-3, p.vChrP[y0]);
-    const int d1 = max(-3, p.vChrP[y0 + 1]) - first;         // 0 or 1
-    uint2 u[5], v[5];
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const int row = min(max(first + j, 0), p.chrSrcH - 1);
-        u[j] = __ldg(reinterpret_cast<const uint2 *>(Up + (size_t)row * a.uStride));
-        v[j] = __ldg(reinterpret_cast<const uint2 *>(Vp + (size_t)row * a.vStride));
-    }
-    const uint4 yy0 = ldg_stream(Yp), yy1 = ldg_stream(Yp + a.yStride);
-    const uint4 cf = __ldg(reinterpret_cast<const uint4 *>(p.vChrF + (size_t)y0 * 4));   // 2 rows x 4 int16 taps
-    const int c00 = lo16s(cf.x), c01 = hi16s(cf.x), c02 = lo16s(cf.y), c03 = hi16s(cf.y);
-    const int t0 = lo16s(cf.z), t1 = hi16s(cf.z), t2 = lo16s(cf.w), t3 = hi16s(cf.w);
-    const int c10 = d1 ? 0 : t0, c11 = d1 ? t0 : t1, c12 = d1 ? t1 : t2, c13 = d1 ? t2 : t3, c14 = d1 ? t3 : 0;
-    const int cy = p.k.cy, crv = p.k.crv, cgu = p.k.cgu, cgv = p.k.cgv, cbu = p.k.cbu, kr = p.k.kr, kg = p.k.kg, kb = p.k.kb;
-
-    uint32_t o0[12], o1[12];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {                            // 4 pixels = 2 chroma columns per step
-        int r0[4], g0[4], b0[4], r1[4], g1[4], b1[4];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int c = 2 * q + e;                         // chroma column 0..7
-            const int u0 = byte_of(c < 4 ? u[0].x : u[0].y, c & 3), u1 = byte_of(c < 4 ? u[1].x : u[1].y, c & 3);
-            const int u2 = byte_of(c < 4 ? u[2].x : u[2].y, c & 3), u3 = byte_of(c < 4 ? u[3].x : u[3].y, c & 3);
-            const int v0 = byte_of(c < 4 ? v[0].x : v[0].y, c & 3), v1 = byte_of(c < 4 ? v[1].x : v[1].y, c & 3);
-            const int v2 = byte_of(c < 4 ? v[2].x : v[2].y, c & 3), v3 = byte_of(c < 4 ? v[3].x : v[3].y, c & 3);
-            const int u4 = byte_of(c < 4 ? u[4].x : u[4].y, c & 3), v4 = byte_of(c < 4 ? v[4].x : v[4].y, c & 3);
-#pragma unroll
-            for (int ry = 0; ry < 2; ry++) {
-                const int k0 = ry ? c10 : c00, k1 = ry ? c11 : c01, k2 = ry ? c12 : c02, k3 = ry ? c13 : c03;
-                int su = 2048 + u0 * k0 + u1 * k1 + u2 * k2 + u3 * k3, sv = 2048 + v0 * k0 + v1 * k1 + v2 * k2 + v3 * k3;
-                if (ry) { su += u4 * c14; sv += v4 * c14; }
-                const int U = sat255(sra<12, MH>(su));
-                const int V = sat255(sra<12, MH>(sv));
-                const int tr = cy * sra<16, MH>(V * crv) + kr;
-                const int tg = cy * (sra<16, MH>(U * cgu) + sra<16, MH>(V * cgv)) + kg;
-                const int tb = cy * sra<16, MH>(U * cbu) + kb;
-                const uint4 yy = ry ? yy1 : yy0;
-                const uint32_t yw = q == 0 ? yy.x : q == 1 ? yy.y : q == 2 ? yy.z : yy.w;
-                const int Ya = cy * byte_of(yw, 2 * e), Yb = cy * byte_of(yw, 2 * e + 1);
-                int *r = ry ? r1 : r0, *g = ry ? g1 : g0, *b = ry ? b1 : b0;
-                r[2 * e] = sra<16, MH>(Ya + (BGR ? tb : tr)); g[2 * e] = sra<16, MH>(Ya + tg); b[2 * e] = sra<16, MH>(Ya + (BGR ? tr : tb));
-                r[2 * e + 1] = sra<16, MH>(Yb + (BGR ? tb : tr)); g[2 * e + 1] = sra<16, MH>(Yb + tg); b[2 * e + 1] = sra<16, MH>(Yb + (BGR ? tr : tb));
-            }
-        }
-        o0[3 * q + 0] = pack4_sat_u8(r0[0], g0[0], b0[0], r0[1]);
-        o0[3 * q + 1] = pack4_sat_u8(g0[1], b0[1], r0[2], g0[2]);
-        o0[3 * q + 2] = pack4_sat_u8(b0[2], r0[3], g0[3], b0[3]);
-        o1[3 * q + 0] = pack4_sat_u8(r1[0], g1[0], b1[0], r1[1]);
-        o1[3 * q + 1] = pack4_sat_u8(g1[1], b1[1], r1[2], g1[2]);
-        o1[3 * q + 2] = pack4_sat_u8(b1[2], r1[3], g1[3], b1[3]);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        stg_stream(D + 16 * k, make_uint4(o0[4 * k], o0[4 * k + 1], o0[4 * k + 2], o0[4 * k + 3]));
-        stg_stream(D + a.dstStride + 16 * k, make_uint4(o1[4 * k], o1[4 * k + 1], o1[4 * k + 2], o1[4 * k + 3]));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// FUSED kernel, dp4a variant of the interior fast path: the 4 chroma lines of a column are byte-transposed into one word
+// FUSED kernel, interior fast path (LDG variant; the TMA-staged kernel of sws_fused_tma.cu runs instead whenever tensor maps can
+// describe the planes).  A thread owns 16 pixels x 2 rows (one LDG.128 of luma per row, one LDG.64 per chroma line).
+// Preconditions checked on the host (else the kernel above runs): 16-byte aligned planes / pitches, dstW % 16 == 0, dstH even, the
+// chroma windows of the two rows of every pair start at most one line apart, and the filter bank cannot push U,V outside (-256, 512)
+// -- then clipping each value on its own is identical to the reference's "clip all four if any has bit 8 set" (output.c:966-971)
+// because an in-range value is unchanged by av_clip_uint8.
+// The 4 chroma lines of a column are byte-transposed into one word
 // (2 PRMT per column instead of 4-5 byte extracts -- the 16-lane ALU pipe is the limiter of these kernels) and the 4-tap
 // FIR becomes two IDP4A (coefficient = 256 * hi + lo, lo unsigned byte, hi signed byte) plus one IMAD.  Per row pair the
 // packed taps, the fifth tap and the first chroma line come from a host-built table (SwsPairTaps).
@@ -262,16 +177,6 @@ __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c)
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 #endif
-
-// four 32-bit sums -> one word of clip_u8(sum >> 16): the upper half-words of two sums are gathered by one PRMT, clipped
-// two at a time (packed s16 min + relu) and the four low bytes gathered by a third PRMT: 5 ALU-pipe instructions instead
-// of 4 shifts + 2 saturating packs.  Valid because |sum >> 16| < 2^15.
-__device__ __forceinline__ uint32_t pack4_hi16_sat(int w0, int w1, int w2, int w3)
-{
-    const uint32_t h01 = __byte_perm((uint32_t)w0, (uint32_t)w1, 0x7632), h23 = __byte_perm((uint32_t)w2, (uint32_t)w3, 0x7632);
-    const uint32_t c01 = __vimin_s16x2_relu(h01, 0x00FF00FFu), c23 = __vimin_s16x2_relu(h23, 0x00FF00FFu);
-    return __byte_perm(c01, c23, 0x6420);
-}
 
 template <bool BGR>
 __global__ void __launch_bounds__(128)
@@ -1199,6 +1104,8 @@ struct SwsCudaContext {
     bool fused;                 // horizontal identity + vLum identity + 4-tap vChr -> one kernel
     void *d_tables = nullptr;   // all filter banks in one device allocation
     void *d_pair_taps = nullptr; // SwsPairTaps[dstH / 2] for the dp4a fused kernel (fast_ok only)
+    void *d_pair_taps_t = nullptr; // SwsPairTapsT[dstH / 2] for the TMA fused kernel (tma_ok only)
+    bool tma_ok = false;        // every four-pair tile of the TMA kernel reaches at most eight chroma lines
     SwsDev dev;
     int16_t *d_lum = nullptr, *d_chrU = nullptr, *d_chrV = nullptr;   // general path line planes
     int lumStridePx = 0, chrStridePx = 0;
@@ -1227,6 +1134,13 @@ struct SwsCudaContext {
     // slices (sws_scale_cuda_sliced): the source rows received so far, the next expected source row, the output rows already returned
     std::vector<uint8_t> sliceSrc[3]; int slicePitch[3] = { 0, 0, 0 }; int sliceNextY = 0, sliceDstY = 0;
 };
+
+static void destroy(SwsCudaContext *c)
+{
+    if (!c) return;
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    delete c;
+}
 
 static bool is_identity(const FilterBank &b, int one)
 {
@@ -1449,7 +1363,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->rangeConv = rangeConv;
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv && srcBits == 8;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
-    if (upload_tables(c)) { delete c; return nullptr; }
+    if (upload_tables(c)) { destroy(c); return nullptr; }
     if (c->fast_ok) {
         std::vector<SwsPairTaps> pt(dstH / 2);
         for (int rp = 0; rp < dstH / 2; rp++) {
@@ -1469,8 +1383,42 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         if (c->fast_ok) {
             if (cudaMalloc(&c->d_pair_taps, pt.size() * sizeof(SwsPairTaps)) != cudaSuccess ||
                 cudaMemcpy(c->d_pair_taps, pt.data(), pt.size() * sizeof(SwsPairTaps), cudaMemcpyHostToDevice) != cudaSuccess) {
-                set_error("sws_getContext_cuda", cudaGetLastError()); cudaFree(c->d_tables); delete c; return nullptr;
+                set_error("sws_getContext_cuda", cudaGetLastError()); destroy(c); return nullptr;
             }
+        }
+    }
+    if (c->fast_ok) {            // the TMA kernel's table: per pair the int16 tap pairs of both rows, per four-pair tile its chroma line window
+        const int pairs = dstH / 2, chrH = c->g.chrSrcH;
+        std::vector<SwsPairTapsT> pt(pairs);
+        bool ok = true;
+        for (int rp = 0; rp < pairs; rp++) {
+            SwsPairTapsT &t = pt[rp];
+            const int16_t *k0 = &c->vChr.coef[(size_t)(2 * rp) * 4], *k1 = k0 + 4;
+            t.k01_0 = (uint16_t)k0[0] | (uint32_t)(uint16_t)k0[1] << 16; t.k23_0 = (uint16_t)k0[2] | (uint32_t)(uint16_t)k0[3] << 16;
+            t.k01_1 = (uint16_t)k1[0] | (uint32_t)(uint16_t)k1[1] << 16; t.k23_1 = (uint16_t)k1[2] | (uint32_t)(uint16_t)k1[3] << 16;
+            t.first0 = c->vChr.pos[2 * rp] > -3 ? c->vChr.pos[2 * rp] : -3;
+            t.first1 = c->vChr.pos[2 * rp + 1] > -3 ? c->vChr.pos[2 * rp + 1] : -3;
+        }
+        auto clampl = [&](int l) { return l < 0 ? 0 : l > chrH - 1 ? chrH - 1 : l; };
+        for (int t0 = 0; t0 < pairs && ok; t0 += 4) {
+            const int t1 = std::min(t0 + 4, pairs);
+            int lo = INT_MAX, hi = INT_MIN;
+            for (int rp = t0; rp < t1; rp++)
+                for (int r = 0; r < 2; r++) {
+                    const int f = r ? pt[rp].first1 : pt[rp].first0;
+                    lo = std::min(lo, clampl(f)); hi = std::max(hi, clampl(f + 3));
+                }
+            if (hi - lo > 7) ok = false;
+            bool interior = t1 - t0 == 4 && lo + 7 <= chrH - 1;
+            for (int rp = t0; rp < t1 && interior; rp++) interior = pt[rp].first0 == lo + (rp - t0) && pt[rp].first1 == pt[rp].first0 + 1;
+            for (int rp = t0; rp < t1; rp++) { pt[rp].base = lo; pt[rp].interior = interior; }
+        }
+        if (ok && pairs > 0) {
+            if (cudaMalloc(&c->d_pair_taps_t, pt.size() * sizeof(SwsPairTapsT)) != cudaSuccess ||
+                cudaMemcpy(c->d_pair_taps_t, pt.data(), pt.size() * sizeof(SwsPairTapsT), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("sws_getContext_cuda", cudaGetLastError()); destroy(c); return nullptr;
+            }
+            c->tma_ok = true;
         }
     }
     if (!c->fused && !c->copy && !c->table_unscaled && !c->to422) {
@@ -1492,13 +1440,13 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
-                set_error("sws_getContext_cuda", cudaGetLastError()); cudaFree(c->d_tables); delete c; return nullptr;
+                set_error("sws_getContext_cuda", cudaGetLastError()); destroy(c); return nullptr;
             }
             c->tileChrWinOff = nLumWin;
         }
         if (dbits == 16 && !c->tileLumRows) {      // the two-pass fallback keeps 15-bit lines in int16 planes
             set_error_msg("sws_getContext_cuda", "16-bit destination: the vertical filter window does not fit in shared memory (19-bit lines exist only there)");
-            cudaFree(c->d_tables); delete c; return nullptr;
+            destroy(c); return nullptr;
         }
         c->lumStridePx = (dstW + 1 + 7) & ~7;          // multiples of 8 samples: 16-byte aligned rows for the vector passes
         c->chrStridePx = (c->g.chrDstW + 7) & ~7;
@@ -1506,8 +1454,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             cudaMalloc(&c->d_chrU, (size_t)c->chrStridePx * c->g.chrSrcH * 2) != cudaSuccess ||
             cudaMalloc(&c->d_chrV, (size_t)c->chrStridePx * c->g.chrSrcH * 2) != cudaSuccess) {
             set_error("sws_getContext_cuda", cudaGetLastError());
-            cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_tables);
-            delete c; return nullptr;
+            destroy(c); return nullptr;
         }
     }
     return c;
@@ -1680,6 +1627,26 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
     return run_planar(c, s3, st3, fr3, dst, dstStride, dstFrame, nframes, st);
 }
 
+// the interior fast path of the fused same-size kernel over row pairs [a.rp0, a.rp1): TMA-staged (sws_fused_tma.cu) when tensor maps can
+// describe the planes, else the LDG kernel
+static int launch_fused_fast(SwsCudaContext *c, const FusedArgs &a, int nframes, cudaStream_t st)
+{
+    const SwsDev &p = c->dev;
+#ifndef AVB_HOSTSIM
+    if (c->tma_ok && tuning("sws_fused_variant") != 3) {
+        const int r = sws_fused_tma_launch(p.k, p.bgr, p.dstW, p.dstH, p.chrSrcW, p.chrSrcH, a, (const SwsPairTapsT *)c->d_pair_taps_t, nframes, st);
+        if (r <= 0) return r;
+    }
+#endif
+    const int rp1 = a.rp1 < p.dstH / 2 ? a.rp1 : p.dstH / 2;
+    if (rp1 <= a.rp0) return 0;
+    dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (rp1 - a.rp0 + 3) / 4, nframes);
+    FusedArgs a2 = a; a2.rp1 = rp1;
+    const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
+    if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, st>>>(p, a2, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, st>>>(p, a2, pt);
+    return check_launch("sws_scale:fused");
+}
+
 static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
@@ -1722,17 +1689,8 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
                          !(a.yFrame & 15) && !(a.dstFrame & 15) && !((uintptr_t)a.u & 7) && !((uintptr_t)a.v & 7) && !(a.uStride & 7) &&
                          !(a.vStride & 7) && !(a.uFrame & 7) && !(a.vFrame & 7) && !((uintptr_t)p.vChrF & 15);
         if (c->fast_ok && a16 && tuning("sws_fused_variant") != 1) {
-            dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (p.dstH / 2 + 3) / 4, nframes);
-            if (tuning("sws_fused_variant") != 2) {             // default: the dp4a variant (71.9 % of HBM peak vs 66.1 %)
-                const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
-                a.rp0 = 0; a.rp1 = p.dstH / 2;
-                if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, st>>>(p, a, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, st>>>(p, a, pt);
-                return check_launch("sws_scale:fused");
-            }
-            const bool mh = tuning("sws_mulhi") == 1;
-            if (p.bgr) { if (mh) sws_fused_rgb24_v2_kernel<true, true><<<g2, b2, 0, st>>>(p, a); else sws_fused_rgb24_v2_kernel<true, false><<<g2, b2, 0, st>>>(p, a); }
-            else       { if (mh) sws_fused_rgb24_v2_kernel<false, true><<<g2, b2, 0, st>>>(p, a); else sws_fused_rgb24_v2_kernel<false, false><<<g2, b2, 0, st>>>(p, a); }
-            return check_launch("sws_scale:fused");
+            a.rp0 = 0; a.rp1 = p.dstH / 2;
+            return launch_fused_fast(c, a, nframes, st);
         }
         dim3 b(32, 8), g((p.dstW + 255) / 256, (p.dstH + 15) / 16, nframes);
         if (aligned) sws_fused_rgb24_kernel<true><<<g, b, 0, st>>>(p, a);
@@ -1830,13 +1788,6 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         if (check_launch("sws_scale:general")) return -1;
     }
     return 0;
-}
-
-static void destroy(SwsCudaContext *c)
-{
-    if (!c) return;
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
-    delete c;
 }
 
 bool sws_slot_view(const void *ctx, SwsSlotView &v)
@@ -2084,7 +2035,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     // Same-size rgb (the dp4a fused kernel): the frame goes through in bands of rows on three streams, so the upload of band
     // k + 1, the kernel of band k and the download of band k - 1 overlap -- the call is PCIe bound and PCIe is full duplex.
     // A band re-uploads the few chroma lines it shares with its neighbours (identical bytes), so bands need no cross-stream order.
-    if (c->fused && c->fast_ok && !nv && rgb && !c->dst32 && !odd && tuning("sws_fused_variant") != 1 && tuning("sws_fused_variant") != 2 &&
+    if (c->fused && c->fast_ok && !nv && rgb && !c->dst32 && !odd && tuning("sws_fused_variant") != 1 &&
         tuning("sws_host_bands") != 1 && g.dstH >= 64 && !((uintptr_t)c->dev.vChrF & 15)) {
         const SwsDev &p = c->dev;
         const int pairs = g.dstH / 2, nb = tuning("sws_host_bands") > 1 ? tuning("sws_host_bands") : 3, per = ((pairs + nb - 1) / nb + 3) & ~3;
@@ -2104,10 +2055,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
             a.yStride = yP; a.uStride = cP; a.vStride = cP; a.dstStride = dP;
             a.yFrame = a.uFrame = a.vFrame = a.dstFrame = 0;
             a.rp0 = rp0; a.rp1 = rp1;
-            const dim3 b2(32, 4), g2((p.dstW / 16 + 31) / 32, (rp1 - rp0 + 3) / 4, 1);
-            const SwsPairTaps *pt = (const SwsPairTaps *)c->d_pair_taps;
-            if (p.bgr) sws_fused_rgb24_v3_kernel<true><<<g2, b2, 0, sb>>>(p, a, pt); else sws_fused_rgb24_v3_kernel<false><<<g2, b2, 0, sb>>>(p, a, pt);
-            if (check_launch("sws_scale_cuda:band")) return 0;
+            if (launch_fused_fast(c, a, 1, sb)) return 0;
             if (cudaMemcpy2DAsync(dst[0] + (size_t)y0 * dstStride[0], dstStride[0], dd[0] + (size_t)y0 * dP, dP, (size_t)g.dstW * 3, y1 - y0, cudaMemcpyDeviceToHost, sb) != cudaSuccess) {
                 set_error("sws_scale_cuda:d2h", cudaGetLastError()); return 0;
             }

@@ -1,0 +1,142 @@
+"""GPU parity of the same-size yuv420p -> rgb24 / bgr24 fast path (config 5's kernel): the TMA-staged kernel of
+csrc/sws_fused_tma.cu in each of its shapes (term tables in shared memory / arithmetic terms, 4 / 12 / 16 warps per CTA) and the LDG
+kernel it falls back to, byte for byte against the CPU checker (the compiled reference's sws_scale when oracle/_ref exists):
+ragged widths (not a multiple of the 256-pixel tile), heights whose row pairs do not fill the last 8-row tile, the clamped chroma
+windows at the top and bottom of the plane, multi-frame device batches (every frame compared), the banded host-pointer call."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from libav_b200 import synth
+from oracle.loader import ptr
+
+pytestmark = pytest.mark.gpu
+FLAGS = 4 | 0x40000 | 0x80000
+
+# (tuning knobs) -> which kernel runs
+VARIANTS = {
+    "tma_lut": {},                                              # the default
+    "tma_lut_w4": {"sws_tma_warps": 4},
+    "tma_lut_w16": {"sws_tma_warps": 16},
+    "tma_arith": {"sws_tma_lut": 2, "sws_tma_warps": 12},
+    "ldg": {"sws_fused_variant": 3},
+}
+KNOBS = ("sws_tma_warps", "sws_tma_lut", "sws_fused_variant", "sws_host_bands")
+
+
+def _set(gpu, knobs):
+    for k in KNOBS:
+        gpu.lib.avb200_set_tuning(k.encode(), int(knobs.get(k, 0)))
+
+
+def oracle_packed(o, yuv, w, h, fmt):
+    dst = [np.zeros((h, w * 3), np.uint8)]
+    sp = (C.c_void_p * 3)(*[a.ctypes.data for a in yuv]); ss = (C.c_int * 3)(*[a.strides[0] for a in yuv])
+    dp = (C.c_void_p * 3)(dst[0].ctypes.data, None, None); ds = (C.c_int * 3)(w * 3, 0, 0)
+    assert o.sws_planar(0, sp, ss, w, h, fmt, dp, ds, w, h, FLAGS) == h
+    return dst[0]
+
+
+def device_frames(ctx, frames, w, h):
+    """the device-pointer batch call over len(frames) frames laid out frame after frame"""
+    from libav_b200 import device
+    K = len(frames)
+    ysz, csz, osz = w * h, (w // 2) * (h // 2), w * h * 3
+    d_y = device.DevBuf(ysz * K); d_u = device.DevBuf(csz * K); d_v = device.DevBuf(csz * K); d_o = device.DevBuf(osz * K)
+    d_y.upload(np.concatenate([f[0].reshape(-1) for f in frames]))
+    d_u.upload(np.concatenate([f[1].reshape(-1) for f in frames]))
+    d_v.upload(np.concatenate([f[2].reshape(-1) for f in frames]))
+    d_o.upload(np.full(osz * K, 0xA5, np.uint8))
+    ctx.scale_device([d_y.ptr, d_u.ptr, d_v.ptr], [w, w // 2, w // 2], [d_o.ptr], [w * 3], nframes=K, src_frame=[ysz, csz, csz], dst_frame=[osz])
+    device.sync()
+    return d_o.download(np.uint8, (K, h, w * 3))
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("w,h", [(640, 480), (1936, 1082), (272, 66), (256, 16), (16, 8), (3840, 2160), (4096, 2176), (528, 8)])
+def test_fused_variants_match_the_reference(gpu, checker, variant, w, h):
+    from libav_b200 import device
+    _set(gpu, VARIANTS[variant])
+    try:
+        for fmt in (device.PIX_FMT_RGB24, device.PIX_FMT_BGR24):
+            yuv = synth.yuv420p_frame(w, h, 3 + w + fmt)
+            ctx = device.SwsContext(w, h, w, h, fmt, FLAGS)
+            assert ctx.fused
+            want = oracle_packed(checker, yuv, w, h, fmt)
+            assert np.array_equal(device_frames(ctx, [yuv], w, h)[0], want), "device call"
+            assert np.array_equal(ctx.scale(yuv), want), "host call (banded above 64 rows)"
+            ctx.close()
+    finally:
+        _set(gpu, {})
+
+
+def test_extreme_samples_and_flat_pictures(gpu, checker):
+    """all-0 / all-255 planes and the four corners of (Y, U, V) drive the chroma FIR to its overshoot (the clip in front of the term
+    tables) and the output stage to both ends of its clip"""
+    from libav_b200 import device
+    w, h = 512, 64
+    r = np.random.RandomState(5)
+    cases = []
+    for yv, uv, vv in ((0, 0, 0), (255, 255, 255), (0, 255, 0), (255, 0, 255), (16, 128, 128), (235, 240, 16)):
+        cases.append([np.full((h, w), yv, np.uint8), np.full((h // 2, w // 2), uv, np.uint8), np.full((h // 2, w // 2), vv, np.uint8)])
+    cases.append([r.choice([0, 255], (h, w)).astype(np.uint8), r.choice([0, 255], (h // 2, w // 2)).astype(np.uint8), r.choice([0, 255], (h // 2, w // 2)).astype(np.uint8)])
+    for variant in ("tma_lut", "tma_arith", "ldg"):
+        _set(gpu, VARIANTS[variant])
+        try:
+            ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, FLAGS)
+            got = device_frames(ctx, cases, w, h)
+            for k, yuv in enumerate(cases):
+                assert np.array_equal(got[k], oracle_packed(checker, yuv, w, h, device.PIX_FMT_RGB24)), (variant, k)
+            ctx.close()
+        finally:
+            _set(gpu, {})
+
+
+def test_config5_batch_every_frame_against_the_reference(gpu, checker):
+    """config 5's per-GPU batch as bench.py launches it: 16 4K frames in one launch, each of them compared with the checker"""
+    from libav_b200 import device
+    w, h, K = 3840, 2160, 16
+    frames = [synth.yuv420p_frame(w, h, 1 + k) for k in range(K)]
+    ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, FLAGS)
+    out = device_frames(ctx, frames, w, h)
+    assert synth.crc32_ieee_be(out[0].tobytes()) == 0xE1558C0A          # SURVEY 8d's known answer for the seed-1 frame
+    for k in range(K):
+        assert np.array_equal(out[k], oracle_packed(checker, frames[k], w, h, device.PIX_FMT_RGB24)), k
+    ctx.close()
+
+
+@pytest.mark.parametrize("bands", [1, 2, 3, 5])
+def test_host_call_bands(gpu, checker, bands):
+    """sws_scale_cuda sends a frame through in row bands on three streams; every band count gives the same picture"""
+    from libav_b200 import device
+    w, h = 1920, 1080
+    yuv = synth.yuv420p_frame(w, h, 77)
+    want = oracle_packed(checker, yuv, w, h, device.PIX_FMT_RGB24)
+    _set(gpu, {"sws_host_bands": bands})
+    try:
+        ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, FLAGS)
+        for _ in range(2):
+            assert np.array_equal(ctx.scale(yuv, fill=0x5A), want)
+        ctx.close()
+    finally:
+        _set(gpu, {})
+
+
+def test_colorspace_details_reach_the_term_tables(gpu, checker):
+    """sws_setColorspaceDetails changes the constants the CTA builds its tables from"""
+    from libav_b200 import device
+    w, h = 768, 96
+    yuv = synth.yuv420p_frame(w, h, 9)
+    for tab, rng, bri, con, sat in (((117504, 138453, 13954, 34903), 1, 0, 1 << 16, 1 << 16),      # ff_yuv2rgb_coeffs[SWS_CS_ITU709], full range
+                                    ((117579, 136230, 16907, 35559), 1, -4000, 60000, 80000)):     # SMPTE 240M + brightness / contrast / saturation
+        t = (C.c_int * 4)(*tab)
+        ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, FLAGS)
+        assert gpu.lib.sws_setColorspaceDetails_cuda(ctx.ctx, t, rng, t, 0, bri, con, sat) == 0
+        checker.sws_set_colorspace(t, rng, bri, con, sat)
+        try:
+            want = oracle_packed(checker, yuv, w, h, device.PIX_FMT_RGB24)
+        finally:
+            checker.sws_set_colorspace(None, 0, 0, 0, 0)
+        assert np.array_equal(device_frames(ctx, [yuv], w, h)[0], want), tab
+        ctx.close()

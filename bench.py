@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the B200 DSP/scaler hot path (contract: see the task statement / DESIGN.md).
+"""bench.py -- throughput of the B200 DSP/scaler hot path (contract: see the task statement / DESIGN.md section 6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload idct_put|sws4k] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sws4k|h264|idct_put|me|...] [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input that is already resident in HBM:
-  idct_put (default, BASELINE.json configs[1]): IDCTDSPContext.idct_put (FF_IDCT_SIMPLE) over 2^20 dense
-            int16 blocks per GPU into an 8192x8192 frame                       -> 64 output pixels per block
-  sws4k    (configs[4] shape, one GPU's share): sws_scale 3840x2160 yuv420p->rgb24, bicubic|accurate_rnd|
-            bitexact, 16 frames per launch                                     -> 8.29 Mpixel per frame
-Every rank (one per GPU, torchrun) runs the same per-GPU batch: weak scaling, no data-path collective.
-`value` is device time (CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
-the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region).  The secondary workload is
-reported under "workloads".  --impl reference times the reference's CPU path (oracle/_ref, else the oracle
-port) on all host cores for the same workload.
+BASELINE.json's metric is "Mpixels/s: H.264 1080p decode DSP + 4K yuv420p->rgb24 swscale"; one "step" = one pass of the hot path over
+one batch of synthetic input that is already resident in HBM:
+  sws4k    (default; configs[4], one GPU's share): sws_scale 3840x2160 yuv420p->rgb24, bicubic|accurate_rnd|bitexact, 16 frames
+           per launch                                                            -> 8.29 Mpixel per frame
+  h264     (configs[2]): 1920x1088 P pictures of 64 slices, qpel/chroma MC -> idct_add16/add8 -> deblock, 60 pictures per step
+  idct_put (configs[1]): IDCTDSPContext.idct_put (FF_IDCT_SIMPLE) over 2^20 dense int16 blocks into an 8192x8192 frame
+  me       (configs[3]): pix_abs16 full search +-16 over a 1920x1088 luma pair; with --gpus N the frame's macroblock rows are
+           split over the ranks (strong scaling) and the motion-vector field is gathered with ncclAllGather on device buffers
+Every other workload runs the same per-GPU batch on every rank (weak scaling, no data-path collective).  `value` is device time
+(CUDA events on the launching stream, max over ranks); `e2e` is the same metric through the host-buffer C-ABI call (pinned host
+memory, H2D + D2H inside the timed region).  After the timed region (never inside it) the bytes the workload produced are compared
+with the CPU checker ("verified").  The line ends with "secondary": {workload: [Mpixels/s, fraction of the HBM roofline]} for the other
+workloads and "cpu": their reference-C figures.  --impl reference times the reference's own CPU implementation (oracle/_ref: the
+x86 inline-asm build when present, else the portable-C build, else the port) on all host cores for the same workload.
 """
 import argparse
 import ctypes as C
@@ -126,9 +130,22 @@ def make_idct_workload(torch, L, stream, rank):
                                                    N_BLOCKS, TILES_PER_ROW), "ff_simple_idct_batch_host_cuda")
         return int(h_frame[0, 0])                          # the step's result is read on the host
 
+    def verify():
+        """all 2^20 blocks of the last step's frame against the CPU checker"""
+        o, kind = cpu_oracle()
+        from oracle.loader import ptr
+        want = np.zeros((rows, stride), np.uint8)
+        i = np.arange(N_BLOCKS, dtype=np.uint64)
+        off = ((i // TILES_PER_ROW) * 8 * stride + (i % TILES_PER_ROW) * 8).astype(np.uint32)
+        o.idct_batch(0, ptr(blocks_h.copy()), ptr(want), ptr(off), stride, N_BLOCKS, os.cpu_count() or 1)
+        for k in range(nbuf):
+            if not np.array_equal(d_frame[k].cpu().numpy(), want):
+                raise SystemExit("bench.py: idct_put output differs from the %s checker (buffer %d)" % (kind, k))
+        return "all 2^20 blocks of each of the %d frames == %s" % (nbuf, kind)
+
     return {
         "name": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
-        "run": run, "run_e2e": run_e2e, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * IDCT_BYTES_PER_BLOCK,
+        "run": run, "run_e2e": run_e2e, "verify": verify, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * IDCT_BYTES_PER_BLOCK,
         "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false>",  "dtype": "int32 (int16 in, u8 out)",
         "h2d": N_BLOCKS * 128, "d2h": rows * stride,
         "l2": "3 rotating 192 MiB buffer sets (inputs larger than the 126 MB L2)",
@@ -170,9 +187,29 @@ def make_sws_workload(torch, L, stream, rank):
                 L.check(-1, "sws_scale_cuda")
         return int(ho[0, 0])
 
+    def verify():
+        """first, second and last frame of the last launch + the frame of the host-pointer arm against the CPU checker"""
+        o, kind = cpu_oracle()
+        from oracle.loader import ptr
+        want = []
+        for fr in frames:
+            w_ = np.zeros((h, w * 3), np.uint8)
+            sp = (C.c_void_p * 3)(*[a.ctypes.data for a in fr]); ss = (C.c_int * 3)(w, w // 2, w // 2)
+            if o.sws_yuv420p_to_rgb24(sp, ss, w, h, ptr(w_), w * 3, w, h, SWS_FLAGS) != h:
+                raise SystemExit("bench.py: the CPU checker refused the frame")
+            want.append(w_)
+        for k in range(nbuf):
+            got = d_o[k].cpu().numpy().reshape(K, h, w * 3)
+            for j in (0, 1, K - 1):
+                if not np.array_equal(got[j], want[j % 2]):
+                    raise SystemExit("bench.py: sws4k frame %d of buffer %d differs from the %s checker" % (j, k, kind))
+        if not np.array_equal(ho.numpy(), want[0]):
+            raise SystemExit("bench.py: sws_scale_cuda (host buffers) differs from the %s checker" % kind)
+        return "frames 0, 1, %d of each of the %d output batches and the host-call frame == %s" % (K - 1, nbuf, kind)
+
     return {
         "name": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % K,
-        "run": run, "run_e2e": run_e2e, "pixels": w * h * K, "alg_bytes": int(w * h * K * SWS_BYTES_PER_PIXEL),
+        "run": run, "run_e2e": run_e2e, "verify": verify, "pixels": w * h * K, "alg_bytes": int(w * h * K * SWS_BYTES_PER_PIXEL),
         "launches_per_step": 1, "kernel": "sws_fused_rgb24_v3_kernel", "dtype": "int32 (u8 in, u8 out)",
         "h2d": int(w * h * 1.5) * K, "d2h": osz * K,
         "l2": "2 rotating %d MiB buffer sets (inputs+outputs larger than the 126 MB L2)" % ((ysz + 2 * csz + osz) * K >> 20),
@@ -211,37 +248,37 @@ def make_sws_up_workload(torch, L, stream, rank):
 
 def make_h264_workload(torch, L, stream, rank):
     """config 3: 1920x1088 P pictures of 64 slices each, a batch of independent pictures stacked vertically per launch:
-    MC (put pass + avg pass) -> residual add -> deblocking wavefronts (luma + chroma).  The consumed coefficient arena is
-    refilled on a side stream (the role the entropy decoder plays), double-buffered against the compute stream."""
+    MC (put pass + avg pass) -> residual add -> deblocking.  The consumed coefficient arena is refilled on a side stream (the role the
+    entropy decoder plays), double-buffered against the compute stream.  synth.h264_config3_picture is also what the CPU arm runs."""
     from libav_b200 import synth
     lib = L.lib
     G = max(1, int(os.environ.get("AVB200_H264_GROUPS", "2")))         # groups of H264_PICTURES stacked pictures per step
-    mb_w, mb_h, P = 120, 68, H264_PICTURES * G
+    pic = synth.h264_config3_picture(120, 68, 64, seed=rank)
+    mb_w, mb_h, P = pic["mb_w"], pic["mb_h"], H264_PICTURES * G
     W, H = 16 * mb_w, 16 * mb_h
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
-    refs = [synth.h264_picture(mb_w, mb_h, seed=11 + rank), synth.h264_picture(mb_w, mb_h, seed=12 + rank)]
+    refs = pic["refs"]
     d_refs = [[t(np.concatenate([p] * P)) for p in r] for r in refs]              # reference pictures, stacked like the output
-    d_planes = torch.tensor([[p.data_ptr() for p in r] for r in d_refs], dtype=torch.int64).cuda()
     d_planes_g = [torch.tensor([[r[0].data_ptr() + gi * H264_PICTURES * W * H, r[1].data_ptr() + gi * H264_PICTURES * W * H // 4,
                                  r[2].data_ptr() + gi * H264_PICTURES * W * H // 4] for r in d_refs], dtype=torch.int64).cuda() for gi in range(G)]
-    mc1 = synth.h264_mc_work(mb_w, mb_h, seed=5)
+    mc1 = pic["mc"]
     mcs = []
     for k in range(H264_PICTURES):                         # FFH264MCRecord.y is int16: MC runs per group of 30 stacked pictures
         m = mc1.copy(); m["y"] = m["y"] + k * H; mcs.append(m)
     mc = np.concatenate(mcs)
-    res1, coeffs, nnzc = synth.h264_residual_work(mb_w, mb_h, seed=6)
+    res1, coeffs, nnzc = pic["res"], pic["coeffs"], pic["nnzc"]
     ress = []
     for k in range(P):
         r = res1.copy(); r["luma_off"] = r["luma_off"] + k * W * H; r["chroma_off"] = r["chroma_off"] + k * W * H // 4; ress.append(r)
     res = np.concatenate(ress)
-    dbk = synth.h264_deblock_work(mb_w, mb_h, seed=7, slices=64)
+    dbk = pic["dbk"]
     d_mc, d_res, d_nnz, d_dbk = t(mc), t(res), t(np.concatenate([nnzc] * P)), t(np.concatenate([dbk] * P))
     d_coef0 = t(np.concatenate([coeffs] * P))
     d_coef = [d_coef0.clone(), d_coef0.clone()]
     d_y = torch.zeros(P * W * H, dtype=torch.uint8, device="cuda")
     d_cb = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
     d_cr = torch.zeros(P * W * H // 4, dtype=torch.uint8, device="cuda")
-    d_prog = torch.zeros(2 * mb_h * P, dtype=torch.int32, device="cuda")
+    d_prog = torch.zeros(2 * mb_h * P + 64, dtype=torch.int32, device="cuda")
     side = torch.cuda.Stream()
     main = torch.cuda.current_stream()
     refilled = [torch.cuda.Event(), torch.cuda.Event()]
@@ -266,13 +303,26 @@ def make_h264_workload(torch, L, stream, rank):
             d_coef[b].copy_(d_coef0, non_blocking=True)
             refilled[b].record(side)
 
+    def verify():
+        """every reconstructed picture of the last step against the reference's own tables driven over the same records on the host"""
+        o, kind = cpu_oracle()
+        if not o.has("h264_pictures"):
+            return None
+        y, cb, cr, co = np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), coeffs.copy()
+        cpu_h264_run(o, pic, 1, y, cb, cr, co, os.cpu_count() or 1)
+        gy, gcb, gcr = d_y.cpu().numpy().reshape(P, H, W), d_cb.cpu().numpy().reshape(P, H // 2, W // 2), d_cr.cpu().numpy().reshape(P, H // 2, W // 2)
+        for k in range(P):
+            if not (np.array_equal(gy[k], y) and np.array_equal(gcb[k], cb) and np.array_equal(gcr[k], cr)):
+                raise SystemExit("bench.py: h264 picture %d differs from the %s checker" % (k, kind))
+        return "all %d reconstructed pictures (luma + both chroma planes) == %s driver" % (P, kind)
+
     n_mb = mb_w * mb_h * P
     return {
-        "name": "H.264 1080p DSP path: qpel/chroma MC (%d partitions/picture) + idct_add16/add8 + deblock wavefront, 64 synthetic slices per picture, %d pictures per step" % (mc1.shape[0], P),
-        "run": run, "run_e2e": None, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
+        "name": NAMES["h264"],
+        "run": run, "run_e2e": None, "verify": verify, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
         "launches_per_step": 2 + 2 * G, "kernel": "h264_deblock_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
-        "l2": "%d pictures per step: %d MB of pixels + %d MB of coefficients, larger than the 126 MB L2" % (P, P * W * H * 3 // 2 >> 20, d_coef0.numel() >> 20),
-        "keep": (d_refs, d_planes, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
+        "l2": "%d pictures (%d MC partitions each) per step: %d MB of pixels + %d MB of coefficients, larger than the 126 MB L2" % (P, mc1.shape[0], P * W * H * 3 // 2 >> 20, d_coef0.numel() >> 20),
+        "keep": (d_refs, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
     }
 
 
@@ -416,12 +466,66 @@ def make_me_workload(torch, L, stream, rank):
     def run(i):
         L.check(lib.ff_full_search_cuda(d_cur.data_ptr(), d_ref.data_ptr(), w, w, h, 16, 0, h // 16, d_out.data_ptr(), stream), "full_search")
 
+    def verify():
+        o, kind = cpu_oracle()
+        from oracle.loader import ptr
+        want = np.zeros(3 * n_mb, np.int32)
+        o.full_search(ptr(cur), ptr(ref), w, w, h, 16, 0, h // 16, ptr(want), os.cpu_count() or 1)
+        if not np.array_equal(d_out.cpu().numpy(), want):
+            raise SystemExit("bench.py: full-search motion field differs from the %s checker" % kind)
+        return "all %d (mx, my, sad) triples == %s" % (n_mb, kind)
+
     return {
         "name": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16, whole frame per GPU",
-        "run": run, "run_e2e": None, "pixels": w * h, "alg_bytes": 2 * w * h + 12 * n_mb,
+        "run": run, "run_e2e": None, "verify": verify, "pixels": w * h, "alg_bytes": 2 * w * h + 12 * n_mb,
         "launches_per_step": 1, "kernel": "full_search_kernel", "dtype": "u8 (vabsdiff4)", "h2d": 0, "d2h": 0,
         "l2": "4 MB working set, ALU/shared-memory bound (2.27 G abs-diff-accumulate per frame), HBM fraction reported for completeness",
         "keep": (d_cur, d_ref, d_out),
+    }
+
+
+def make_me_sharded_workload(torch, dist, L, stream, rank, world):
+    """config 4 as BASELINE states it: ONE 1920x1088 frame pair, its 68 macroblock rows split over the ranks (each rank holds only its
+    rows of `cur` and those rows +-16 of `ref`), the per-rank pieces of the motion-vector field gathered on every rank with ncclAllGather
+    on device buffers inside the timed step.  Strong scaling: the work is fixed, `value` = the frame's pixels / max-over-ranks time."""
+    from libav_b200 import synth, shard
+    lib = L.lib
+    w, h = 1920, 1088
+    mb_w, mb_h = w // 16, h // 16
+    cur, ref = synth.me_frames(w, h, seed=1)                       # the same frame on every rank: each uploads its shard only
+    y0, y1 = shard.mb_row_range(mb_h, rank, world)
+    lo, hi = max(0, 16 * y0 - 16), min(h, 16 * y1 + 16)
+    rows_max = -(-mb_h // world)
+    d_cur = torch.from_numpy(np.ascontiguousarray(cur[16 * y0:16 * y1])).cuda()
+    d_ref = torch.from_numpy(np.ascontiguousarray(ref[lo:hi])).cuda()
+    d_loc = torch.zeros(rows_max * mb_w * 3, dtype=torch.int32, device="cuda")
+    d_all = torch.zeros(world * rows_max * mb_w * 3, dtype=torch.int32, device="cuda")
+    # the call addresses rows by their position in the frame: hand it the (virtual) origin of each shard's frame
+    p_cur, p_ref, p_out = d_cur.data_ptr() - 16 * y0 * w, d_ref.data_ptr() - lo * w, d_loc.data_ptr() - 12 * y0 * mb_w
+
+    def run(i):
+        if y1 > y0:
+            L.check(lib.ff_full_search_cuda(p_cur, p_ref, w, w, h, 16, y0, y1, p_out, stream), "full_search")
+        dist.all_gather_into_tensor(d_all, d_loc)                  # NCCL all-gather, device to device, on the current stream
+
+    def verify():
+        o, kind = cpu_oracle()
+        from oracle.loader import ptr
+        want = np.zeros((mb_h, mb_w * 3), np.int32)
+        o.full_search(ptr(cur), ptr(ref), w, w, h, 16, 0, mb_h, ptr(want), os.cpu_count() or 1)
+        got = d_all.cpu().numpy().reshape(world, rows_max, mb_w * 3)
+        for r in range(world):
+            a, b = shard.mb_row_range(mb_h, r, world)
+            if not np.array_equal(got[r, :b - a], want[a:b]):
+                raise SystemExit("bench.py: gathered motion field differs from the %s checker in rank %d's rows" % (kind, r))
+        return "the gathered field of all %d macroblocks (as rank 0 holds it after ncclAllGather) == %s" % (mb_w * mb_h, kind)
+
+    return {
+        "name": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16, frame-shard over %d GPUs + ncclAllGather of the motion field" % world,
+        "run": run, "run_e2e": None, "verify": verify, "scaling": "strong", "pixels": w * h, "alg_bytes": 2 * w * h + 12 * mb_w * mb_h,
+        "launches_per_step": 1, "kernel": "full_search_kernel", "dtype": "u8 (vabsdiff4)", "h2d": 0, "d2h": 0,
+        "l2": "4 MB working set, ALU/shared-memory bound (2.27 G abs-diff-accumulate per frame), HBM fraction reported for completeness",
+        "keep": (d_cur, d_ref, d_loc, d_all),
     }
 
 
@@ -474,6 +578,7 @@ def time_e2e(torch, dist, wl, steps, warmup, world):
 # CPU legs (the only place bench.py touches oracle/)
 # ----------------------------------------------------------------------------------------------------
 def cpu_oracle():
+    """the parity checker: the compiled reference's portable-C build, else the port"""
     from oracle import loader
     r = loader.ref()
     if r is not None:
@@ -481,11 +586,26 @@ def cpu_oracle():
     return loader.port(), "port"
 
 
-def cpu_idct(nthreads, seconds=3.0, reps=None):
+def cpu_timing_arms():
+    """[(library, kind, label)] to time: the reference's x86 inline-asm build (what a default build of the reference runs on this host
+    without an external assembler: psadbw SAD, MMX simple IDCT under FF_IDCT_AUTO, MMX hpel / blockdsp; every H.264 slot, hScale and
+    the bit-exact rgb24 output stage stay C there because their SIMD is external nasm code) and its portable-C build."""
+    from oracle import loader
+    arms = []
+    if loader.ref_simd() is not None:
+        arms.append((loader.ref_simd(), "reference", "x86 inline-asm SIMD build (cpu flags unmasked, FF_IDCT_AUTO)"))
+    if loader.ref() is not None:
+        arms.append((loader.ref(), "reference", "portable C build (ARCH_X86 = 0, av_set_cpu_flags_mask(0))"))
+    if not arms:
+        arms.append((loader.port(), "port", "plain-C restatement (oracle/port)"))
+    return arms
+
+
+def cpu_idct(nthreads, seconds=3.0, reps=None, arm=None):
     """reference C ff_simple_idct_put_8 over the full 2^20-block workload, all host threads; median of reps."""
     from libav_b200 import synth
     from oracle.loader import ptr
-    o, kind = cpu_oracle()
+    o, kind = arm[:2] if arm else cpu_oracle()
     base = synth.tile_large(synth.dense_blocks(1 << 14, seed=1), N_BLOCKS)
     stride = TILES_PER_ROW * 8
     frame = np.zeros((N_BLOCKS // TILES_PER_ROW * 8, stride), dtype=np.uint8)
@@ -503,11 +623,11 @@ def cpu_idct(nthreads, seconds=3.0, reps=None):
             "pixels": N_BLOCKS * 64}
 
 
-def cpu_sws(nthreads, seconds=3.0, reps=None, frames_per_thread=1):
+def cpu_sws(nthreads, seconds=3.0, reps=None, arm=None, frames_per_thread=1):
     """reference sws_scale 4K yuv420p->rgb24 on all host threads (one context per thread, one frame each)."""
     from libav_b200 import synth
     from oracle.loader import ptr
-    o, kind = cpu_oracle()
+    o, kind = arm[:2] if arm else cpu_oracle()
     w, h = SWS_W, SWS_H
     yuv = synth.yuv420p_frame(w, h, 1)
     src = (C.c_void_p * 3)(*[a.ctypes.data for a in yuv])
@@ -533,11 +653,11 @@ def cpu_sws(nthreads, seconds=3.0, reps=None, frames_per_thread=1):
             "pixels": w * h * nthreads * frames_per_thread}
 
 
-def cpu_me(nthreads, seconds=3.0, reps=None):
+def cpu_me(nthreads, seconds=3.0, reps=None, arm=None):
     """reference pix_abs16 (C) driven by the full-search loop over a 1920x1088 frame, MB rows split over host threads."""
     from libav_b200 import synth
     from oracle.loader import ptr
-    o, kind = cpu_oracle()
+    o, kind = arm[:2] if arm else cpu_oracle()
     w, h = 1920, 1088
     cur, ref = synth.me_frames(w, h, seed=1)
     out = np.zeros(3 * (w // 16) * (h // 16), np.int32)
@@ -552,14 +672,82 @@ def cpu_me(nthreads, seconds=3.0, reps=None):
             "pixels": w * h}
 
 
+def cpu_h264_run(o, pic, P, y, cb, cr, coeffs, nthreads):
+    from oracle.loader import ptr
+    refs = (C.c_void_p * 6)(*[p.ctypes.data for r in pic["refs"] for p in r])
+    if o.h264_pictures(ptr(pic["mc"]), ptr(pic["mc_first"]), ptr(pic["res"]), ptr(pic["dbk"]), ptr(pic["nnzc"]), ptr(coeffs), refs, 2,
+                       ptr(y), ptr(cb), ptr(cr), y.strides[0], cb.strides[0], pic["mb_w"], pic["mb_h"], P, pic["slices"], nthreads) != 0:
+        raise SystemExit("bench.py: the CPU H.264 driver refused its arguments")
+
+
+def cpu_h264(nthreads, seconds=3.0, reps=None, arm=None):
+    """config 3 on the host: the reference's H264DSPContext / H264QpelContext / H264ChromaContext / VideoDSPContext tables over the same
+    synthetic pictures (MC -> idct_add16 / add8 per macroblock, loop filter per slice; the 64 slices of every picture are independent
+    work units handed to pthreads).  A bounded sample: as many pictures per pass as two per thread ... at most the GPU step's 60."""
+    from libav_b200 import synth
+    o, kind = arm[:2] if arm else cpu_oracle()
+    if not o.has("h264_pictures"):
+        return None
+    pic = synth.h264_config3_picture(120, 68, 64, seed=0)
+    W, H = 16 * pic["mb_w"], 16 * pic["mb_h"]
+    P = max(2, min(60, (2 * nthreads + 63) // 64))
+    y, cb, cr = np.zeros((P * H, W), np.uint8), np.zeros((P * H // 2, W // 2), np.uint8), np.zeros((P * H // 2, W // 2), np.uint8)
+    co0 = np.concatenate([pic["coeffs"]] * P)
+    times = []
+    t_all = time.perf_counter()
+    while (len(times) < reps) if reps else (time.perf_counter() - t_all < seconds or len(times) < 3):
+        co = co0.copy()                                   # the residual functions consume (zero) their coefficients: refill outside the timing
+        t0 = time.perf_counter()
+        cpu_h264_run(o, pic, P, y, cb, cr, co, nthreads)
+        times.append(time.perf_counter() - t0)
+    return {"sec_per_step": float(np.median(times)), "kind": kind, "cores": nthreads, "reps": len(times),
+            "sample": "%d 1920x1088 pictures x 64 slices per pass, slices handed to %d pthreads, median of %d passes" % (P, nthreads, len(times)),
+            "pixels": W * H * P}
+
+
+def bind_to_gpu_numa_node(index):
+    """One rank drives one GPU: run this process on the CPUs next to that GPU and prefer their memory node, BEFORE the pinned staging
+    buffers are allocated -- with four ranks per socket copying at once the host side is the limiter of the end-to-end arm."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = open(dev + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        if node >= 0:
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
+            libc.syscall(238, 1, C.byref(mask), C.c_ulong(64))       # set_mempolicy(MPOL_PREFERRED, {node})
+        return {"numa_node": node, "cpus": cpus}
+    except Exception as e:                                            # containers without sysfs / NVML: stay unbound
+        return {"numa_node": None, "error": str(e)[:80]}
+
+
+CPU_LEGS = {"idct_put": cpu_idct, "sws4k": cpu_sws, "me": cpu_me, "h264": cpu_h264}
+NAMES = {"idct_put": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
+         "sws4k": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % SWS_FRAMES,
+         "me": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16, whole frame per GPU",
+         "h264": "H.264 1080p DSP path: qpel/chroma MC + idct_add16/add8 + deblock, 64 synthetic slices per picture"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="idct_put", choices=["idct_put", "sws4k", "h264", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft"])
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workload and the CPU baseline")
+    ap.add_argument("--workload", default="sws4k", choices=["sws4k", "h264", "idct_put", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads and the CPU baselines")
+    ap.add_argument("--no-verify", action="store_true", help="skip the post-timing comparison with the CPU checker")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -573,28 +761,29 @@ def main():
         if rank != 0:
             return 0
         steps = min(steps, 20)
-        if args.workload not in ("idct_put", "sws4k", "me"):
+        fn = CPU_LEGS.get(args.workload)
+        arm = cpu_timing_arms()[0]
+        if fn is None or (args.workload == "h264" and not arm[0].has("h264_pictures")):
             print(json.dumps({"impl": "reference", "unavailable": "no batched CPU driver for workload %s (its per-function parity against the reference is in tests/)" % args.workload}))
             return 0
-        fn = {"idct_put": cpu_idct, "sws4k": cpu_sws, "me": cpu_me}[args.workload]
-        fn(ncores, reps=1)                                    # warm-up pass (page in, spin up threads)
-        r = fn(ncores, reps=steps)
+        fn(ncores, reps=1, arm=arm)                           # warm-up pass (page in, spin up threads)
+        r = fn(ncores, reps=steps, arm=arm)
         mpix = r["pixels"] / r["sec_per_step"] / 1e6
         # the same workload names as the GPU arm's config.workload (the driver pairs the two lines by them)
-        name = {"idct_put": "batched simple_idct_put 8x8, 2^20 dense int16 blocks per GPU -> 8192x8192 u8 frame",
-                "sws4k": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % SWS_FRAMES,
-                "me": "me_cmp pix_abs16 SAD full search, 1920x1088, range 16, whole frame per GPU"}[args.workload]
         print(json.dumps({
             "impl": "reference", "metric": "Mpixels/s", "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": {"workload": name, "per_gpu_batch": "one batch of the same shape on the host cores (a bounded sample: %s)" % r["sample"],
-                                                                     "host_threads": ncores, "idct_algo": "FF_IDCT_SIMPLE", "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
-            "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": NAMES[args.workload], "per_gpu_batch": "one batch of the same shape on the host cores (a bounded sample: %s)" % r["sample"],
+                       "host_threads": ncores, "build": arm[2], "idct_algo": "FF_IDCT_SIMPLE (C build) / FF_IDCT_AUTO (x86 build)",
+                       "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
+            "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "build": arm[2]},
             "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }))
         return 0
 
+    numa = bind_to_gpu_numa_node(local_rank)                  # before torch / the library allocate their pinned staging buffers
     import torch
     import torch.distributed as dist
     import libav_b200._lib as L
@@ -609,41 +798,64 @@ def main():
         k, v = kv.split("=")
         L.lib.avb200_set_tuning(k.encode(), int(v))
 
-    makers = {"idct_put": make_idct_workload, "sws4k": make_sws_workload, "h264": make_h264_workload, "me": make_me_workload,
-              "sws_up": make_sws_up_workload, "h264_decide": make_h264_decide_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload, "fft": make_fft_workload}
+    makers = {"sws4k": make_sws_workload, "h264": make_h264_workload, "idct_put": make_idct_workload, "me": make_me_workload,
+              "sws_up": make_sws_up_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload,
+              "fft": make_fft_workload, "h264_decide": make_h264_decide_workload}
+    if args.workload == "me" and world > 1:
+        makers["me"] = make_me_sharded_workload
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
     results = {}
     for idx, wname in enumerate(order):
-        wl = makers[wname](torch, L, stream, rank)
+        sharded = wname == "me" and makers[wname] is make_me_sharded_workload
+        wl = makers[wname](torch, dist, L, stream, rank, world) if sharded else makers[wname](torch, L, stream, rank)
+        st = steps if idx == 0 else max(5, min(steps, 30))   # the secondaries get a shorter timed region
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        ms = time_gpu(torch, dist, wl, steps, warmup, world, sampler)
-        e2e_steps = max(1, min(steps, 5))
+        ms = time_gpu(torch, dist, wl, st, warmup, world, sampler)
+        e2e_steps = max(1, min(st, 5))
         e2e_sec = time_e2e(torch, dist, wl, e2e_steps, warmup, world) if wl["run_e2e"] else None
-        ms_step = ms / steps
-        mpix = wl["pixels"] * world / (ms_step * 1e-3) / 1e6
+        verified = None
+        if not args.no_verify and wl.get("verify") and rank == 0:
+            torch.cuda.synchronize()
+            verified = wl["verify"]()
+        ms_step = ms / st
+        strong = wl.get("scaling") == "strong"
+        mpix = wl["pixels"] * (1 if strong else world) / (ms_step * 1e-3) / 1e6
         gbs = wl["alg_bytes"] / (ms_step * 1e-3) / 1e9
         results[wname] = {
-            "workload": wl["name"], "value": mpix, "ms_per_step": ms_step,
+            "workload": wl["name"], "value": mpix, "ms_per_step": ms_step, "steps": st, "scaling": wl.get("scaling", "weak"),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          "traffic": traffic_for(wl["kernel"]), "kernel": wl["kernel"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": wl["alg_bytes"]},
             "e2e": ({"value": wl["pixels"] * world / (e2e_sec / e2e_steps) / 1e6, "unit": "Mpixels/s",
                      "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps} if e2e_sec else None),
-            "gpu_launches": wl["launches_per_step"] * steps * world,
+            "gpu_launches": wl["launches_per_step"] * st * world, "verified": verified,
             "clocks": sampler.summary() if sampler else None, "dtype": wl["dtype"], "l2": wl["l2"],
         }
         del wl
         torch.cuda.empty_cache()
 
-    cpu = None
+    cpu, cpu_others = None, {}
     if rank == 0 and world == 1 and not args.no_secondary:
-        r = {"idct_put": cpu_idct, "sws4k": cpu_sws, "me": cpu_me}.get(args.workload, cpu_idct)(ncores)
-        cpu = {"value": r["pixels"] / r["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        if args.workload == "idct_put":                   # SURVEY 8d also asks for the one-thread number
-            r1 = cpu_idct(1, reps=3)
-            cpu["single_thread"] = {"value": r1["pixels"] / r1["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": 1, "sample": r1["sample"]}
-        cpu["note"] = ("portable C build of the reference (ARCH_X86 = 0, av_set_cpu_flags_mask(0)): its x86 SIMD needs nasm / inline asm "
-                       "templates this recipe does not enable")
+        arms = cpu_timing_arms()
+        leg = CPU_LEGS.get(args.workload, cpu_sws)
+        r = leg(ncores, arm=arms[0])
+        cpu = {"value": r["pixels"] / r["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "build": arms[0][2]}
+        for o_, kind_, label in arms[1:]:                     # the same leg on the other build(s) of the reference
+            r2 = leg(ncores, seconds=2.0, arm=(o_, kind_, label))
+            if r2:
+                cpu.setdefault("other_builds", []).append({"build": label, "value": r2["pixels"] / r2["sec_per_step"] / 1e6, "cores": r2["cores"]})
+        r1 = leg(1, reps=2, arm=arms[0])                      # SURVEY 8d also asks for the one-thread number
+        if r1:
+            cpu["single_thread"] = {"value": r1["pixels"] / r1["sec_per_step"] / 1e6, "unit": "Mpixels/s", "cores": 1}
+        cpu["note"] = ("x86 build = the reference's inline-asm SIMD (psadbw SAD, MMX simple IDCT / hpel / blockdsp); all H.264 slots, hScale and "
+                       "the bit-exact rgb24 output stage are C in it too: their SIMD is external nasm code and no assembler exists here")
+        for wname, fn in CPU_LEGS.items():                    # reference figures of the other headline workloads, all host threads
+            if wname == args.workload or wname not in results:
+                continue
+            r3 = fn(ncores, seconds=2.0, arm=arms[0])
+            if r3:
+                cpu_others[wname] = round(r3["pixels"] / r3["sec_per_step"] / 1e6, 1)
 
     if world > 1:
         dist.barrier()
@@ -652,13 +864,17 @@ def main():
         m = results[args.workload]
         line = {
             "metric": "Mpixels/s", "value": m["value"], "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": m["scaling"], "vs_baseline": None,
             "dtype": m["dtype"], "data": "synthetic",
-            "config": {"workload": m["workload"], "per_gpu_batch": "identical on every rank (weak scaling, no collective on the data path)",
+            "config": {"workload": m["workload"], "per_gpu_batch": ("one frame's macroblock rows split over the ranks, ncclAllGather of the motion field" if m["scaling"] == "strong"
+                                                                    else "identical on every rank (weak scaling, no collective on the data path)"),
                        "l2": m["l2"], "idct_algo": "FF_IDCT_SIMPLE", "sws_flags": "SWS_BICUBIC|SWS_ACCURATE_RND|SWS_BITEXACT"},
             "tuning": args.tune, "roofline": m["roofline"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
-            "cpu_baseline": cpu,
-            "workloads": {k: {kk: vv for kk, vv in v.items()} for k, v in results.items() if k != args.workload},
+            "verified": m["verified"], "numa": numa, "cpu_baseline": cpu,
+            # compact tail: [Mpixels/s on this many GPUs, fraction of the HBM roofline, verified against the checker]
+            "secondary": {k: [round(v["value"], 1), round(v["roofline"]["frac"], 4), bool(v["verified"])] for k, v in results.items() if k != args.workload},
+            "secondary_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in results.items() if k != args.workload},
+            "cpu": cpu_others,
         }
         print(json.dumps(line))
     return 0

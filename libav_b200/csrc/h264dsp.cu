@@ -224,101 +224,6 @@ constexpr int CT = 16;      // chroma tile pitch (12 columns used: -4 .. 7)
 
 __device__ __forceinline__ uint32_t ld_cg32(const uint8_t *p) { return __ldcg(reinterpret_cast<const uint32_t *>(p)); }
 
-__global__ void __launch_bounds__(32)
-h264_deblock_kernel(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
-                    int ls, int uvls, uint32_t *progress)
-{
-    __shared__ __align__(16) uint8_t Y[20 * LT];
-    __shared__ __align__(16) uint8_t C[2][10 * CT];
-    __shared__ FFH264DeblockMB P;
-    const int lane = threadIdx.x, row = blockIdx.x;
-    volatile uint32_t *prog = progress;
-    uint8_t *const chroma_plane[2] = { cb, cr };
-
-    for (int x = 0; x < mb_w; x++) {
-        // wait until the row above has finished macroblock x + 1 (its left edge touches MB x's right columns)
-        if (row > 0) {
-            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
-            __syncwarp();
-        }
-        // left context: the previous macroblock's last 4 columns (luma 12..15, chroma 4..7) become columns -4..-1
-        if (x > 0 && lane < 20) {
-            *reinterpret_cast<uint32_t *>(&Y[lane * LT]) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
-            const int p = lane / 10, r = lane % 10;
-            *reinterpret_cast<uint32_t *>(&C[p][r * CT]) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
-        }
-        __syncwarp();
-        // load columns 0..15 (luma) / 0..7 (chroma); rows above the picture do not exist
-        if (lane < 20) {
-            const int ry = lane - 4, gy = row * 16 + ry;
-            if (gy >= 0) {
-                const uint8_t *g = luma + (size_t)gy * ls + x * 16;
-#pragma unroll
-                for (int k = 0; k < 4; k++) *reinterpret_cast<uint32_t *>(&Y[lane * LT + 4 + 4 * k]) = ld_cg32(g + 4 * k);
-            }
-            const int p = lane / 10, r = lane % 10, cy = row * 8 + r - 2;
-            if (cy >= 0) {
-                const uint8_t *g = chroma_plane[p] + (size_t)cy * uvls + x * 8;
-                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 4]) = ld_cg32(g);
-                *reinterpret_cast<uint32_t *>(&C[p][r * CT + 8]) = ld_cg32(g + 4);
-            }
-        }
-        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
-            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
-        __syncwarp();
-
-        // vertical edges (filter across x), then horizontal edges (filter across y): h264_loopfilter.c:397-415
-#pragma unroll 1
-        for (int dir = 0; dir < 2; dir++) {
-#pragma unroll 1
-            for (int e = 0; e < 4; e++) {
-                if (lane < 16) {
-                    const int a = P.alpha[dir][e], b = P.beta[dir][e];
-                    if (a && b) {
-                        uint8_t *q = dir == 0 ? &Y[(4 + lane) * LT + 4 + 4 * e] : &Y[(4 + 4 * e) * LT + 4 + lane];
-                        const int px = dir == 0 ? 1 : LT;
-                        if (P.intra[dir] >> e & 1) h264_luma_intra_line(q, px, a, b);
-                        else { const int tc = P.tc0[dir][e][lane >> 2]; if (tc >= 0) h264_luma_line(q, px, a, b, tc); }
-                    }
-                } else if (!(e & 1)) {
-                    const int p = (lane - 16) >> 3, l = (lane - 16) & 7, ce = e >> 1;
-                    const int a = P.calpha[p][dir][ce], b = P.cbeta[p][dir][ce];
-                    if (a && b) {
-                        uint8_t *q = dir == 0 ? &C[p][(2 + l) * CT + 4 + 4 * ce] : &C[p][(2 + 4 * ce) * CT + 4 + l];
-                        const int px = dir == 0 ? 1 : CT;
-                        const int in = P.cintra[p][dir] >> ce & 1, tc = P.ctc0[p][dir][ce][l >> 1];
-                        if (in || tc > 0) h264_chroma_line(q, px, a, b, tc, in);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-
-        // write back what is final for this row: columns -4..11 (all 20 at the end of the row), rows -3..15
-        const int last = x == mb_w - 1;
-        if (lane < 20) {
-            const int ry = lane - 4, gy = row * 16 + ry;
-            if (ry >= -3 && gy >= 0) {
-                uint8_t *g = luma + (size_t)gy * ls + x * 16;
-                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT]);
-#pragma unroll
-                for (int k = 0; k < 3; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 4 + 4 * k]);
-                if (last) *reinterpret_cast<uint32_t *>(g + 12) = *reinterpret_cast<const uint32_t *>(&Y[lane * LT + 16]);
-            }
-            const int p = lane / 10, r = lane % 10, cy = row * 8 + r - 2;
-            if (cy >= 0) {
-                uint8_t *g = chroma_plane[p] + (size_t)cy * uvls + x * 8;
-                if (x > 0) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT]);
-                *reinterpret_cast<uint32_t *>(g) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 4]);
-                if (last) *reinterpret_cast<uint32_t *>(g + 4) = *reinterpret_cast<const uint32_t *>(&C[p][r * CT + 8]);
-            }
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) prog[row] = x + 1;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Deblocking wavefront, register-resident variant (default).  Same tile, same order, but the four vertical edges of a
 // macroblock are filtered by a lane on ITS OWN ROW held in registers (rows are independent for vertical edges), and the
@@ -460,6 +365,9 @@ h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int ro
     else                 deblock_row<true>(mbs, mb_w, rows_pp, luma, cb, cr, ls, uvls, progress + gridDim.x, T, P);
 }
 
+int launch_h264_deblock_v3(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls,
+                           int uvls, uint32_t *progress, cudaStream_t st);       // h264_deblock.cu
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 int launch_h264_residual(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
@@ -493,11 +401,12 @@ int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pi
     if ((ls & 3) || (uvls & 3) || ((uintptr_t)luma & 3) || ((uintptr_t)cb & 3) || ((uintptr_t)cr & 3)) {
         set_error_msg("h264_deblock_picture", "planes and line sizes must be 4-byte aligned"); return -1;
     }
+    // default: the paired-row, register-resident wavefront of h264_deblock.cu; deblock_variant = 2 keeps the one-warp-per-row
+    // kernel above for comparison (profiling knob)
+    if (tuning("deblock_variant") != 2) return launch_h264_deblock_v3(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, ls, uvls, progress, st);
     const int rows = mb_h * n_pictures;
     AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows * 2, st), "h264_deblock_picture");
-    // rows only ever wait on the row above (a lower block index, dispatched earlier), so any grid size makes progress
-    if (tuning("deblock_variant") == 1 && n_pictures == 1) h264_deblock_kernel<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
-    else h264_deblock_kernel_v2<<<dim3(rows, 2), 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
+    h264_deblock_kernel_v2<<<dim3(rows, 2), 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
     return check_launch("h264_deblock_picture");
 }
 

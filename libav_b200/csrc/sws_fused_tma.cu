@@ -8,8 +8,10 @@
 //     outside the plane) into the warp's own double-buffered stage and are awaited on the warp's own mbarrier: no CTA-wide barrier
 //     exists after start-up, the tile after the current one is always in flight.  Warps are persistent and stride over the tiles of all
 //     frames of the batch.
-//   * a thread owns 16 pixels x 4 rows.  The six chroma lines its two row pairs need are byte-transposed once (window 0-3), the
-//     windows of the next rows are one PRMT away (drop the oldest line, append the next); the 4-tap FIR is two IDP.2A on int16 taps.
+//   * a thread owns 16 pixels x 4 rows (row pairs `half` and `half + 2` of the tile).  The seven chroma lines they need are
+//     byte-transposed once (window 0-3), the windows of the next rows are one PRMT away (drop the oldest line, append the next); the
+//     4-tap FIR is two IDP.2A on int16 taps.
+//   * the rows leave through shared memory: four 768-byte rows per cp.async.bulk.tensor store (whole 128-byte lines per request).
 //   * the per-(U, V) additive terms  cy * ((V * crv) >> 16) + kr,  cy * ((V * cgv) >> 16),  cy * ((U * cbu) >> 16) + kb,
 //     cy * ((U * cgu) >> 16) + kg  come from two 256-entry tables in shared memory, built by the CTA from the context's constants
 //     with exactly these formulas, 16 copies of each 8-byte entry so that every lane of a half-warp reads its own bank pair
@@ -25,6 +27,7 @@ namespace {
 
 constexpr int FT_STAGE = 4096;                  // Y 8 rows x 256 B | U 8 lines x 128 B | V 8 lines x 128 B
 constexpr int FT_LUT = 2 * 256 * 16 * 8;        // table by V {tr, tgv}, table by U {tb, tgu}: 256 entries x 16 lane copies x 8 B
+constexpr int FT_OUT = 4 * 768;                 // output staging: four 768-byte rows (half a tile) per bulk tensor store
 
 struct FusedTmaArgs {
     uint8_t *dst; int dstStride; size_t dstFrame;
@@ -87,22 +90,18 @@ __device__ __forceinline__ void row16(const uint32_t (&TU)[8], const uint32_t (&
     }
 }
 
-__device__ __forceinline__ void store_row(uint8_t *d, const uint32_t (&o)[12])
-{
-#pragma unroll
-    for (int j = 0; j < 3; j++) stg_stream(d + 16 * j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
-}
-
 template <bool BGR, bool LUT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 sws_fused_rgb24_tma_kernel(const RgbConstants k, const FusedTmaArgs a, const SwsPairTapsT *__restrict__ taps,
-                           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV)
+                           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+                           const __grid_constant__ CUtensorMap tmD)
 {
     extern __shared__ __align__(1024) uint8_t ft_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(ft_smem);
     const unsigned stage_s = smem_s + (LUT ? FT_LUT : 0) + warp * 2 * FT_STAGE;
-    const unsigned mbar_s = smem_s + (LUT ? FT_LUT : 0) + WARPS * 2 * FT_STAGE + warp * 16;
+    const unsigned out_s = smem_s + (LUT ? FT_LUT : 0) + WARPS * 2 * FT_STAGE + warp * FT_OUT;
+    const unsigned mbar_s = smem_s + (LUT ? FT_LUT : 0) + WARPS * (2 * FT_STAGE + FT_OUT) + warp * 16;
 
     if (LUT) {                          // the two term tables, every entry 16 times (one copy per lane of a half-warp)
         uint2 *lut = reinterpret_cast<uint2 *>(ft_smem);
@@ -122,101 +121,124 @@ sws_fused_rgb24_tma_kernel(const RgbConstants k, const FusedTmaArgs a, const Sws
 
     int item = blockIdx.x * WARPS + warp;
     if (item >= a.nitems) return;
-    int tx = item % a.tilesX, ty, f;
-    { const int t2 = item / a.tilesX; ty = t2 % a.nTy; f = t2 / a.nTy; }
     const int wstride = gridDim.x * WARPS;
-
-    auto issue = [&](int txx, int tyy, int ff, unsigned st) {
+    // three tiles are known at any time: the one being computed (c), the one in flight (n) and the one whose table words are being
+    // fetched (m); every table read is issued a whole tile before its value is used
+    int ctx = item % a.tilesX, cty, cf;
+    { const int t2 = item / a.tilesX; cty = t2 % a.nTy; cf = t2 / a.nTy; }
+    auto advance = [&](int &tx, int &ty, int &f) {
+        tx += a.stepX; f += a.stepF;
+        if (tx >= a.tilesX) { tx -= a.tilesX; ty++; }
+        ty += a.stepTy;
+        if (ty >= a.nTy) { ty -= a.nTy; f++; }
+    };
+    auto tile_words = [&](int ty) { return __ldg(reinterpret_cast<const int2 *>(&taps[a.rp0 + 4 * ty].base)); };   // (base, interior)
+    auto issue = [&](int tx, int ty, int f, int base, unsigned st) {
         if (lane == 0) {
-            const int rpT = a.rp0 + 4 * tyy;
-            const int base = __ldg(&taps[rpT].base);
             const unsigned mb = mbar_s + (st ? 8u : 0u), dst = stage_s + st * FT_STAGE;
             fence_proxy_async();                              // the stage was last read by ordinary shared loads
             mbar_expect_tx(mb, FT_STAGE);
-            tma_load_3d(dst, &tmY, txx * 256, 2 * rpT, ff, mb);
-            tma_load_3d(dst + 2048, &tmU, txx * 128, base, ff, mb);
-            tma_load_3d(dst + 3072, &tmV, txx * 128, base, ff, mb);
+            tma_load_3d(dst, &tmY, tx * 256, 2 * (a.rp0 + 4 * ty), f, mb);
+            tma_load_3d(dst + 2048, &tmU, tx * 128, base, f, mb);
+            tma_load_3d(dst + 3072, &tmV, tx * 128, base, f, mb);
         }
     };
+    int2 cw = tile_words(cty);
+    issue(ctx, cty, cf, cw.x, 0);
+    int ntx = ctx, nty = cty, nf = cf;
+    advance(ntx, nty, nf);
+    int2 nw = item + wstride < a.nitems ? tile_words(nty) : make_int2(0, 0);
 
-    issue(tx, ty, f, 0);
     unsigned st = 0, uses = 0;
     for (; item < a.nitems; item += wstride, st ^= 1u, uses++) {
-        // coordinates of the warp's next tile; its bytes start travelling before this tile is touched
-        int ntx = tx + a.stepX, nty = ty, nf = f + a.stepF;
-        if (ntx >= a.tilesX) { ntx -= a.tilesX; nty++; }
-        nty += a.stepTy;
-        if (nty >= a.nTy) { nty -= a.nTy; nf++; }
-        if (item + wstride < a.nitems) issue(ntx, nty, nf, st ^ 1u);
+        if (item + wstride < a.nitems) issue(ntx, nty, nf, nw.x, st ^ 1u);       // the next tile's bytes start travelling before this one is touched
+        int mtx = ntx, mty = nty, mf = nf;
+        advance(mtx, mty, mf);
+        const int2 mw = (long long)item + 2ll * wstride < a.nitems ? tile_words(mty) : make_int2(0, 0);
 
-        const int rpT = a.rp0 + 4 * ty;
-        const int interior = __ldg(&taps[rpT].interior);
+        const int rpT = a.rp0 + 4 * cty;
         mbar_wait(mbar_s + (st ? 8u : 0u), (uses >> 1) & 1u);                   // k-th use of a stage completes its phase k
         const unsigned sY = stage_s + st * FT_STAGE, sU = sY + 2048, sV = sY + 3072;
-        const int x = tx * 256 + cg * 16, row0 = 2 * rpT + 4 * half;
-        uint8_t *D = a.dst + (size_t)f * a.dstFrame + (size_t)row0 * a.dstStride + (size_t)x * 3;
-        const bool xin = x < a.dstW;
-
-        if (interior) {
-            uint4 yy[4];
-            uint2 ul[6], vl[6];
+        // Rows leave the warp four at a time: the half-warps' first pairs are tile rows 0-3, their second pairs rows 4-7.  A row is staged
+        // in the warp's 4 x 768-byte slab; one bulk tensor store writes the four rows (whole 128-byte lines: three 16-byte STG per lane
+        // 48 bytes apart cost twice the L1 -> L2 write transactions, measured).  Columns past the width / rows past the range are clipped
+        // by the tensor map.
+        auto stage_row = [&](int slot, const uint32_t (&o)[12]) {
 #pragma unroll
-            for (int r = 0; r < 4; r++) yy[r] = lds128(sY + (4 * half + r) * 256 + cg * 16);
-#pragma unroll
-            for (int j = 0; j < 6; j++) { ul[j] = lds64(sU + (2 * half + j) * 128 + cg * 8); vl[j] = lds64(sV + (2 * half + j) * 128 + cg * 8); }
-            const uint4 tA = __ldg(reinterpret_cast<const uint4 *>(taps + rpT + 2 * half)), tB = __ldg(reinterpret_cast<const uint4 *>(taps + rpT + 2 * half + 1));
+            for (int j = 0; j < 3; j++) sts128(out_s + slot * 768 + cg * 48 + 16 * j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+        };
+        auto slab_free = [&]() { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); };       // the previous store has read the slab
+        auto flush = [&](int g) {
+            fence_proxy_async();
             __syncwarp();
-            // windows of the thread's four rows: lines 0-3, 1-4, 1-4, 2-5 of its six
-            uint32_t W0U[8], W1U[8], W2U[8], W0V[8], W1V[8], W2V[8];
-            transpose4(ul[0].x, ul[1].x, ul[2].x, ul[3].x, W0U); transpose4(ul[0].y, ul[1].y, ul[2].y, ul[3].y, W0U + 4);
-            transpose4(vl[0].x, vl[1].x, vl[2].x, vl[3].x, W0V); transpose4(vl[0].y, vl[1].y, vl[2].y, vl[3].y, W0V + 4);
-            slide4(W0U, ul[4].x, W1U); slide4(W0U + 4, ul[4].y, W1U + 4); slide4(W1U, ul[5].x, W2U); slide4(W1U + 4, ul[5].y, W2U + 4);
-            slide4(W0V, vl[4].x, W1V); slide4(W0V + 4, vl[4].y, W1V + 4); slide4(W1V, vl[5].x, W2V); slide4(W1V + 4, vl[5].y, W2V + 4);
-            uint32_t o[12];
-            row16<BGR, LUT>(W0U, W0V, tA.x, tA.y, yy[0], k, lutU_s, lutV_s, o);
-            if (xin) store_row(D, o);
-            row16<BGR, LUT>(W1U, W1V, tA.z, tA.w, yy[1], k, lutU_s, lutV_s, o);
-            if (xin) store_row(D + a.dstStride, o);
-            row16<BGR, LUT>(W1U, W1V, tB.x, tB.y, yy[2], k, lutU_s, lutV_s, o);
-            if (xin) store_row(D + 2 * (size_t)a.dstStride, o);
-            row16<BGR, LUT>(W2U, W2V, tB.z, tB.w, yy[3], k, lutU_s, lutV_s, o);
-            if (xin) store_row(D + 3 * (size_t)a.dstStride, o);
+            if (lane == 0) { tma_store_3d(&tmD, ctx * 192, 2 * rpT + 4 * g, cf, out_s); bulk_commit(); }
+        };
+
+        if (cw.y) {
+            // interior tile: pair q of the tile filters chroma lines q .. q + 3 (first row) and q + 1 .. q + 4 (second row) of the stage.
+            // This thread's pairs are `half` and `half + 2`: seven lines, four windows one line apart
+            uint4 yy[4];
+            uint2 ul[7], vl[7];
+#pragma unroll
+            for (int r = 0; r < 4; r++) yy[r] = lds128(sY + (2 * half + (r & 1) + 4 * (r >> 1)) * 256 + cg * 16);
+#pragma unroll
+            for (int j = 0; j < 7; j++) { ul[j] = lds64(sU + (half + j) * 128 + cg * 8); vl[j] = lds64(sV + (half + j) * 128 + cg * 8); }
+            const uint4 tA = __ldg(reinterpret_cast<const uint4 *>(taps + rpT + half)), tB = __ldg(reinterpret_cast<const uint4 *>(taps + rpT + half + 2));
+            __syncwarp();
+            uint32_t WU[8], WV[8], XU[8], XV[8], o[12];
+            transpose4(ul[0].x, ul[1].x, ul[2].x, ul[3].x, WU); transpose4(ul[0].y, ul[1].y, ul[2].y, ul[3].y, WU + 4);
+            transpose4(vl[0].x, vl[1].x, vl[2].x, vl[3].x, WV); transpose4(vl[0].y, vl[1].y, vl[2].y, vl[3].y, WV + 4);
+            slab_free();
+            row16<BGR, LUT>(WU, WV, tA.x, tA.y, yy[0], k, lutU_s, lutV_s, o); stage_row(2 * half, o);
+            slide4(WU, ul[4].x, XU); slide4(WU + 4, ul[4].y, XU + 4); slide4(WV, vl[4].x, XV); slide4(WV + 4, vl[4].y, XV + 4);
+            row16<BGR, LUT>(XU, XV, tA.z, tA.w, yy[1], k, lutU_s, lutV_s, o); stage_row(2 * half + 1, o);
+            flush(0);
+            slide4(XU, ul[5].x, WU); slide4(XU + 4, ul[5].y, WU + 4); slide4(XV, vl[5].x, WV); slide4(XV + 4, vl[5].y, WV + 4);
+            row16<BGR, LUT>(WU, WV, tB.x, tB.y, yy[2], k, lutU_s, lutV_s, o);
+            slab_free();
+            stage_row(2 * half, o);
+            slide4(WU, ul[6].x, XU); slide4(WU + 4, ul[6].y, XU + 4); slide4(WV, vl[6].x, XV); slide4(WV + 4, vl[6].y, XV + 4);
+            row16<BGR, LUT>(XU, XV, tB.z, tB.w, yy[3], k, lutU_s, lutV_s, o); stage_row(2 * half + 1, o);
+            flush(1);
         } else {
             // plane edges and ragged tiles: every row fetches its own four (clamped) lines
-            const int base = __ldg(&taps[rpT].base);
 #pragma unroll 1
             for (int r = 0; r < 4; r++) {
-                const int row = row0 + r;
-                if (row >= a.rowEnd) break;                                       // rowEnd <= dstH: the pair below has a table entry
+                const int trow = 2 * half + (r & 1) + 4 * (r >> 1);
+                const int row = min(2 * rpT + trow, a.rowEnd - 1);               // rows past the launch's range compute a discarded duplicate: the loop stays warp-uniform
                 const SwsPairTapsT *t = taps + (row >> 1);
-                const uint2 kk = __ldg(reinterpret_cast<const uint2 *>(t) + (r & 1));
-                const int first = __ldg(&t->first0 + (r & 1));
+                const uint2 kk = __ldg(reinterpret_cast<const uint2 *>(t) + (row & 1));
+                const int first = __ldg(&t->first0 + (row & 1));
                 uint2 ul[4], vl[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const int line = min(max(first + j, 0), a.chrSrcH - 1) - base;   // 0..7, host-checked
+                    const int line = min(max(min(max(first + j, 0), a.chrSrcH - 1) - cw.x, 0), 7);   // 0..7 (host-checked for rows inside the range)
                     ul[j] = lds64(sU + line * 128 + cg * 8); vl[j] = lds64(sV + line * 128 + cg * 8);
                 }
-                const uint4 yy = lds128(sY + (4 * half + r) * 256 + cg * 16);
+                const uint4 yy = lds128(sY + trow * 256 + cg * 16);
                 uint32_t TU[8], TV[8], o[12];
                 transpose4(ul[0].x, ul[1].x, ul[2].x, ul[3].x, TU); transpose4(ul[0].y, ul[1].y, ul[2].y, ul[3].y, TU + 4);
                 transpose4(vl[0].x, vl[1].x, vl[2].x, vl[3].x, TV); transpose4(vl[0].y, vl[1].y, vl[2].y, vl[3].y, TV + 4);
                 row16<BGR, LUT>(TU, TV, kk.x, kk.y, yy, k, lutU_s, lutV_s, o);
-                if (xin) store_row(D + (size_t)r * a.dstStride, o);
+                if (!(r & 1)) slab_free();
+                stage_row(trow & 3, o);
+                if (r & 1) flush(r >> 1);
             }
             __syncwarp();
         }
-        tx = ntx; ty = nty; f = nf;
+        ctx = ntx; cty = nty; cf = nf; cw = nw;
+        ntx = mtx; nty = mty; nf = mf; nw = mw;
     }
+    if (lane == 0) bulk_wait<0>();
 }
 
 }  // namespace
 
 template <bool BGR, bool LUT, int WARPS>
 static int launch_variant(const RgbConstants &k, const FusedTmaArgs &fa, const SwsPairTapsT *taps, const CUtensorMap &tmY, const CUtensorMap &tmU,
-                          const CUtensorMap &tmV, int grid, cudaStream_t st)
+                          const CUtensorMap &tmV, const CUtensorMap &tmD, int grid, cudaStream_t st)
 {
-    const size_t smem = (LUT ? FT_LUT : 0) + (size_t)WARPS * 2 * FT_STAGE + WARPS * 16;
+    const size_t smem = (LUT ? FT_LUT : 0) + (size_t)WARPS * (2 * FT_STAGE + FT_OUT) + WARPS * 16;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(sws_fused_rgb24_tma_kernel<BGR, LUT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -224,7 +246,7 @@ static int launch_variant(const RgbConstants &k, const FusedTmaArgs &fa, const S
         }
         attr_done = true;
     }
-    sws_fused_rgb24_tma_kernel<BGR, LUT, WARPS><<<grid, WARPS * 32, smem, st>>>(k, fa, taps, tmY, tmU, tmV);
+    sws_fused_rgb24_tma_kernel<BGR, LUT, WARPS><<<grid, WARPS * 32, smem, st>>>(k, fa, taps, tmY, tmU, tmV, tmD);
     return check_launch("sws_scale:fused tma");
 }
 
@@ -240,8 +262,13 @@ int sws_fused_tma_launch(const RgbConstants &k, int bgr, int dstW, int dstH, int
     if ((a.yStride | a.uStride | a.vStride | a.dstStride) & 15) return 1;
     if (nframes > 1 && ((a.yFrame | a.uFrame | a.vFrame | a.dstFrame) & 15)) return 1;
     if (a.yStride <= 0 || a.uStride <= 0 || a.vStride <= 0) return 1;
-    CUtensorMap tmY, tmU, tmV;
+    CUtensorMap tmY, tmU, tmV, tmD;
     {
+        // the destination as 32-bit words: a 256-pixel row of a tile is 768 bytes = 192 words (a box side is at most 256 elements)
+        const cuuint64_t dD[3] = { (cuuint64_t)dstW * 3 / 4, (cuuint64_t)(2 * rp1), (cuuint64_t)nframes };
+        const cuuint64_t sD[2] = { (cuuint64_t)a.dstStride, nframes > 1 ? (cuuint64_t)a.dstFrame : (cuuint64_t)a.dstStride * dstH };
+        const cuuint32_t bD[3] = { 192, 4, 1 };
+        if (a.dstStride <= 0 || !tma_encode(&tmD, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, a.dst, dD, sD, bD)) return 1;
         const cuuint64_t dY[3] = { (cuuint64_t)dstW, (cuuint64_t)dstH, (cuuint64_t)nframes };
         const cuuint64_t dC[3] = { (cuuint64_t)chrSrcW, (cuuint64_t)chrSrcH, (cuuint64_t)nframes };
         const cuuint64_t sY[2] = { (cuuint64_t)a.yStride, nframes > 1 ? (cuuint64_t)a.yFrame : (cuuint64_t)a.yStride * dstH };
@@ -260,19 +287,19 @@ int sws_fused_tma_launch(const RgbConstants &k, int bgr, int dstW, int dstH, int
     const long long nitems = (long long)nframes * fa.nTy * fa.tilesX;
     if (nitems > 0x7fffffff / 2) return 1;
     fa.nitems = (int)nitems;
-    // tuning knobs (profiling): sws_tma_warps 4 / 12 / 16, sws_tma_lut 2 = arithmetic terms instead of the shared-memory tables
+    // tuning knobs (profiling): sws_tma_warps 4 / 12 / 14, sws_tma_lut 2 = arithmetic terms instead of the shared-memory tables
     const bool lut = tuning("sws_tma_lut") != 2;
     int warps = tuning("sws_tma_warps");
-    if (warps != 4 && warps != 12 && warps != 16) warps = nitems >= 12 * 2 * sm_count() ? 12 : 4;
-    if (!lut && warps == 16) warps = 12;
+    if (warps != 4 && warps != 12 && warps != 14) warps = nitems >= 12 * 2 * sm_count() ? 12 : 4;
+    if (!lut && warps == 14) warps = 12;
     const int ctas_per_sm = warps == 4 ? 2 : 1;
     long long grid = (nitems + warps - 1) / warps;
     if (grid > (long long)sm_count() * ctas_per_sm) grid = (long long)sm_count() * ctas_per_sm;
     const long long wstride = grid * warps;
     fa.stepX = (int)(wstride % fa.tilesX);
     { const long long t2 = wstride / fa.tilesX; fa.stepTy = (int)(t2 % fa.nTy); fa.stepF = (int)(t2 / fa.nTy); }
-#define AVB_FT_GO(L, W) (bgr ? launch_variant<true, L, W>(k, fa, taps, tmY, tmU, tmV, (int)grid, st) : launch_variant<false, L, W>(k, fa, taps, tmY, tmU, tmV, (int)grid, st))
-    if (lut) return warps == 4 ? AVB_FT_GO(true, 4) : warps == 16 ? AVB_FT_GO(true, 16) : AVB_FT_GO(true, 12);
+#define AVB_FT_GO(L, W) (bgr ? launch_variant<true, L, W>(k, fa, taps, tmY, tmU, tmV, tmD, (int)grid, st) : launch_variant<false, L, W>(k, fa, taps, tmY, tmU, tmV, tmD, (int)grid, st))
+    if (lut) return warps == 4 ? AVB_FT_GO(true, 4) : warps == 14 ? AVB_FT_GO(true, 14) : AVB_FT_GO(true, 12);
     return warps == 4 ? AVB_FT_GO(false, 4) : AVB_FT_GO(false, 12);
 #undef AVB_FT_GO
 }

@@ -51,6 +51,17 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst_s, const CUtensorMap *t
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(dst_s), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(mbar_s) : "memory");
 }
+// shared -> global bulk tensor store (bulk async-group completion); the source must have been made visible with fence_proxy_async()
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int x, int y, int z, unsigned src_s)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(src_s) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void sts128(unsigned a, uint4 v)
+{ asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ uint4 lds128(unsigned a)
 { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory"); return r; }
 __device__ __forceinline__ uint2 lds64(unsigned a)

@@ -493,3 +493,17 @@ def me_frames(w, h, seed=1, shift=(3, -5), noise=3):
     rng = np.random.default_rng(seed)
     cur = np.roll(ref, shift, axis=(0, 1)).astype(np.int64) + rng.integers(-noise, noise + 1, size=(h, w))
     return np.clip(cur, 0, 255).astype(np.uint8), ref
+
+
+def h264_config3_picture(mb_w=120, mb_h=68, slices=64, seed=0):
+    """BASELINE config 3, one synthetic P picture: two reference pictures, quarter-pel MC records for every partition, residual
+    records + coefficient arena, per-edge deblocking records with `slices` slices (disable_deblocking_filter_idc = 2: no edge crosses
+    a slice), and mc_first[m] = index of macroblock m's first MC record (records are in macroblock raster order)."""
+    refs = [h264_picture(mb_w, mb_h, seed=11 + seed), h264_picture(mb_w, mb_h, seed=12 + seed)]
+    mc = h264_mc_work(mb_w, mb_h, seed=5 + seed)
+    res, coeffs, nnzc = h264_residual_work(mb_w, mb_h, seed=6 + seed)
+    dbk = h264_deblock_work(mb_w, mb_h, seed=7 + seed, slices=slices)
+    mb_of = (mc["y"].astype(np.int64) // 16) * mb_w + mc["x"].astype(np.int64) // 16
+    assert np.all(np.diff(mb_of) >= 0)
+    mc_first = np.searchsorted(mb_of, np.arange(mb_w * mb_h + 1)).astype(np.uint32)
+    return dict(mb_w=mb_w, mb_h=mb_h, slices=slices, refs=refs, mc=mc, mc_first=mc_first, res=res, coeffs=coeffs, nnzc=nnzc, dbk=dbk)

@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_PATH = os.path.join(_HERE, "liboracle_port.so")
 REF_PATH = os.path.join(_HERE, "_ref", "libavref.so")
+REF_SIMD_PATH = os.path.join(_HERE, "_ref", "libavref_simd.so")
 
 vp, sz, i32, pd, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_ssize_t, C.c_double
 
@@ -49,6 +50,7 @@ API = {
     "h264_pred422_add": (None, [i32, i32, vp, vp, vp, pd]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "h264_deblock_picture_with": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32]),
+    "h264_pictures": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]),
     "me_cmp_select": (None, [vp, i32, vp]),
     "table_fill": (i32, [i32, i32, i32, vp, i32]),
     "pred_table_fill": (i32, [i32, i32, vp, i32]),
@@ -127,6 +129,15 @@ def ref():
     if "ref" not in _cache:
         _cache["ref"] = Oracle(REF_PATH, "ref_") if os.path.exists(REF_PATH) else None
     return _cache["ref"]
+
+
+def ref_simd():
+    """TIMING ONLY: the same unmodified reference sources configured the way its own configure does on this x86-64 host without an
+    external assembler (ARCH_X86, inline-asm MMX / SSE2 / SSSE3 on, cpu flags unmasked, idct_algo FF_IDCT_AUTO) -- bench.py's
+    "x86 SIMD" CPU figure.  Never a parity oracle (the MMX IDCT is a different algorithm).  None when it has not been built."""
+    if "ref_simd" not in _cache:
+        _cache["ref_simd"] = Oracle(REF_SIMD_PATH, "ref_") if os.path.exists(REF_SIMD_PATH) else None
+    return _cache["ref_simd"]
 
 
 def ptr(a):

@@ -12,6 +12,7 @@ import os, re, sys
 
 REF = sys.argv[1]
 OUT = sys.argv[2]
+SIMD = len(sys.argv) > 3 and sys.argv[3] == "simd"     # the timing-only x86 flavour (oracle/_ref/libavref_simd.so), see Makefile
 
 ONES = set("""
 HAVE_FAST_64BIT HAVE_FAST_CLZ HAVE_FAST_CMOV HAVE_FAST_UNALIGNED
@@ -32,6 +33,15 @@ CONFIG_FFT CONFIG_MDCT CONFIG_RDFT CONFIG_DCT CONFIG_SWSCALE CONFIG_AVUTIL CONFI
 CONFIG_SMALL_NOT
 """.split())
 ONES.discard("CONFIG_SMALL_NOT")
+if SIMD:
+    # what the reference's configure finds on an x86-64 gcc host when no external assembler is present (--disable-x86asm): the
+    # inline-asm MMX / MMXEXT / SSE / SSE2 / SSSE3 code is compiled in and selected at run time from cpuid; every *_EXTERNAL stays 0
+    ONES |= set("""
+    ARCH_X86 ARCH_X86_64 HAVE_INLINE_ASM HAVE_MMX HAVE_MMXEXT HAVE_SSE HAVE_SSE2 HAVE_SSE3 HAVE_SSSE3
+    HAVE_MMX_INLINE HAVE_MMXEXT_INLINE HAVE_SSE_INLINE HAVE_SSE2_INLINE HAVE_SSE3_INLINE HAVE_SSSE3_INLINE
+    HAVE_XMM_CLOBBERS HAVE_EBP_AVAILABLE HAVE_EBX_AVAILABLE HAVE_INLINE_ASM_LABELS HAVE_INLINE_ASM_NONLOCAL_LABELS
+    HAVE_INLINE_ASM_DIRECT_SYMBOL_REFS HAVE_I686 HAVE_RDTSC
+    """.split())
 
 tok = re.compile(r"\b((?:ARCH|HAVE|CONFIG)_[A-Z0-9_]+)\b")
 names = set()
@@ -42,6 +52,9 @@ for sub in ("libavutil", "libavcodec", "libswscale", "compat"):
                 with open(os.path.join(root, f), errors="replace") as fh:
                     names.update(tok.findall(fh.read()))
 names |= ONES
+# the x86 cpu-flag macros are token-pasted (libavutil/x86/cpu.h, cpu_internal.h): name every (extension, flavour) pair explicitly
+for ext in "MMX MMXEXT SSE SSE2 SSE3 SSSE3 SSE4 SSE42 AVX AVX2 XOP FMA3 FMA4 AMD3DNOW AMD3DNOWEXT".split():
+    names |= {"HAVE_" + ext, "HAVE_%s_EXTERNAL" % ext, "HAVE_%s_INLINE" % ext}
 os.makedirs(os.path.join(OUT, "libavutil"), exist_ok=True)
 with open(os.path.join(OUT, "config.h"), "w") as o:
     o.write("/* written by oracle/refbuild/gen_config.py - not the reference's configure */\n")

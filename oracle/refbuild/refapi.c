@@ -48,10 +48,16 @@ static QpelDSPContext mqpel;
 static void init_all(void)
 {
     AVCodecContext *avctx = calloc(1, sizeof(*avctx));
+#ifdef REF_SIMD                           /* oracle/_ref/libavref_simd.so, TIMING ONLY: the tables a default-configured decoder gets on this host */
+    avctx->idct_algo           = FF_IDCT_AUTO;
+#else
     av_set_cpu_flags_mask(0);             /* what FATE's -cpuflags 0 does: portable C only */
     avctx->idct_algo           = FF_IDCT_SIMPLE;
+#endif
     avctx->bits_per_raw_sample = 8;
+#ifndef REF_SIMD
     avctx->flags               = AV_CODEC_FLAG_BITEXACT;
+#endif
     avctx->dct_algo            = FF_DCT_INT;
     ff_idctdsp_init(&idsp, avctx);
     avctx->bits_per_raw_sample = 10;
@@ -261,7 +267,9 @@ int ref_me_cmp(int kind, int sidx, int dxy, const uint8_t *b1, const uint8_t *b2
     case 8: f = mecc.vsad[4 + sidx]; break;
     case 9: f = mecc.vsse[4 + sidx]; break;
     case 10: return mecc.sum_abs_dctelem((int16_t *)p1);
+#ifndef REF_SIMD      /* (the timing-only flavour does not link the encoder-context shim) */
     case 11: case 12: case 13: { extern int ref_me_cmp_enc(int, int, int, uint8_t *, uint8_t *, ptrdiff_t, int); return ref_me_cmp_enc(kind, sidx, dxy, p1, p2, stride, h); }
+#endif
     }
     if (!f) return -1;
     return f(NULL, p1, p2, stride, h);

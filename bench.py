@@ -210,7 +210,7 @@ def make_sws_workload(torch, L, stream, rank):
     return {
         "name": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % K,
         "run": run, "run_e2e": run_e2e, "verify": verify, "pixels": w * h * K, "alg_bytes": int(w * h * K * SWS_BYTES_PER_PIXEL),
-        "launches_per_step": 1, "kernel": "sws_fused_rgb24_v3_kernel", "dtype": "int32 (u8 in, u8 out)",
+        "launches_per_step": 1, "kernel": "sws_fused_rgb24_tma_kernel", "dtype": "int32 (u8 in, u8 out)",
         "h2d": int(w * h * 1.5) * K, "d2h": osz * K,
         "l2": "2 rotating %d MiB buffer sets (inputs+outputs larger than the 126 MB L2)" % ((ysz + 2 * csz + osz) * K >> 20),
         "keep": (d_y, d_u, d_v, d_o, ctx, hy, hu, hv, ho),
@@ -320,7 +320,7 @@ def make_h264_workload(torch, L, stream, rank):
     return {
         "name": NAMES["h264"],
         "run": run, "run_e2e": None, "verify": verify, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
-        "launches_per_step": 2 + 2 * G, "kernel": "h264_deblock_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 2 + 2 * G, "kernel": "h264_mc_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
         "l2": "%d pictures (%d MC partitions each) per step: %d MB of pixels + %d MB of coefficients, larger than the 126 MB L2" % (P, mc1.shape[0], P * W * H * 3 // 2 >> 20, d_coef0.numel() >> 20),
         "keep": (d_refs, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
     }

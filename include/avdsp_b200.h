@@ -15,8 +15,9 @@
  *                                       (libavcodec/idctdsp.c:183-188 etc.); they are for plumbing and
  *                                       parity, not speed.
  * Error convention: the reference slots return void.  Every entry point here that can fail
- * returns 0 / -1 and records the first failure in a sticky string (avb200_last_error()); slot functions
- * record it too.  There is NO CPU fallback: without a B200 every call fails loudly.
+ * returns 0 / -1 and records a message (avb200_last_error()); slot functions record it too.  The first CUDA FAILURE sticks until
+ * avb200_clear_error(); a REFUSAL (a request this library does not take over: the caller keeps its C path) is held only until a
+ * failure arrives, so routine refusals never hide a real fault.  There is NO CPU fallback: without a B200 every call fails loudly.
  */
 #ifndef AVDSP_B200_H
 #define AVDSP_B200_H

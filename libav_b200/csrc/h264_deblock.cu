@@ -14,7 +14,8 @@
 //     register-only chain; back through the tile the rows are stored.  Two warp barriers per macroblock, no other synchronisation.
 //   * everything a macroblock needs from memory is requested one macroblock ahead (its own lines, its parameter record); the lines
 //     of the row above -- needed only when the top edge is filtered -- are requested before the vertical pass and used after it.
-//   * rows of a picture follow each other as a wavefront: a row publishes how many of its macroblocks are final (release store),
+//   * rows of a picture follow each other as a wavefront: a row publishes how many of its macroblocks are final (release store, issued
+//     one macroblock late so that its fence finds the stores it covers already retired),
 //     the row below polls that word (acquire load) only for macroblocks whose top edge is filtered -- slice boundaries with
 //     disable_deblocking_filter_idc = 2 never wait.  Rows are handed out by an atomic ticket in wavefront order, so the row a warp
 //     may wait for is always held by a warp that is already running: no dependence on the order CTAs are dispatched in.
@@ -28,6 +29,8 @@ namespace {
 __device__ __forceinline__ uint32_t ld_cg(const uint8_t *p) { return __ldcg(reinterpret_cast<const uint32_t *>(p)); }
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{ uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
 { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
@@ -130,8 +133,19 @@ __device__ __forceinline__ void deblock_pair(const DeblockArgs &a, int pair, uin
     }
     __syncwarp();
 
+    // A release store costs a full memory barrier (it waits for every outstanding access of the warp), so the row only publishes when
+    // the row below will look: the leader reads, one macroblock ahead, whether the macroblock below filters its top edge.
+    const bool watch = valid && hl == 0 && lrow + 1 < a.rows_pp;
+    const uint32_t *const below = reinterpret_cast<const uint32_t *>(recs + a.mb_w);
+    bool pub = false;                                                                     // publish at this iteration?
     for (int x = 0; x < a.mb_w; x++) {
         const uint8_t *P = reinterpret_cast<const uint8_t *>(parm + (x & 1) * DB_PARAM_WORDS);
+        uint32_t bw[4] = { 0, 0, 0, 0 };                                                  // the top-edge alpha / beta words of the macroblock below
+        if (watch) {
+            const uint32_t *r = below + (size_t)x * DB_PARAM_WORDS;
+            if (!CH) { bw[0] = __ldg(r + 1); bw[1] = __ldg(r + 3); }                      // alpha[1][0..3], beta[1][0..3]
+            else { bw[0] = __ldg(r + 13); bw[1] = __ldg(r + 15); bw[2] = __ldg(r + 14); bw[3] = __ldg(r + 16); }   // bytes 52, 60, 56, 64
+        }
         // ---- requests for the next macroblock (consumed at the end of this iteration) ----
         uint32_t nxt[W / 4], np0 = 0, np1 = 0;
         const bool more = valid && x + 1 < a.mb_w;
@@ -142,14 +156,18 @@ __device__ __forceinline__ void deblock_pair(const DeblockArgs &a, int pair, uin
             np0 = __ldg(r + hl);
             if (hl + 16 < DB_PARAM_WORDS) np1 = __ldg(r + hl + 16);
         }
-        // ---- does the top edge touch the row above?  then that row must have finished macroblock x + 1 ----
+        // ---- does the top edge touch the row above?  then that row's macroblock x must be final ----
         bool top;
         if (!CH) top = has_above && P[4] && P[12];                                       // alpha[1][0], beta[1][0]
         else     top = has_above && ((P[50 + 2] && P[58 + 2]) || (P[50 + 4 + 2] && P[58 + 4 + 2]));   // calpha / cbeta [plane][1][0] of either plane
         {
-            const uint32_t need = (uint32_t)min(x + 2, a.mb_w);
-            bool ok = !top || hl != 0 || ld_acquire(prog + row - 1) >= need;
-            while (!__all_sync(0xffffffffu, ok)) ok = !top || hl != 0 || ld_acquire(prog + row - 1) >= need;
+            // poll with relaxed loads (an acquire load invalidates the SM's L1 every time); one acquire load once the word is there
+            // the row above publishes v once its macroblocks < v are final (their last columns included): this top edge needs macroblock x
+            const uint32_t need = (uint32_t)min(x + 1, a.mb_w);
+            const bool poll = top && hl == 0;
+            bool ok = !poll || ld_relaxed(prog + row - 1) >= need;
+            while (!__all_sync(0xffffffffu, ok)) ok = !poll || ld_relaxed(prog + row - 1) >= need;
+            if (poll) (void)ld_acquire(prog + row - 1);
             __syncwarp();                                     // the leaders' acquire loads are ordered before every lane's loads of the row above
         }
         uint32_t topw[W / 4];
@@ -217,6 +235,10 @@ __device__ __forceinline__ void deblock_pair(const DeblockArgs &a, int pair, uin
         __syncwarp();
 
         // ---- rows out: the macroblock's own lines, and the lines above when the top edge ran ----
+        // First publish what is already out: macroblocks < x are final (this iteration's vertical pass has just rewritten the last
+        // columns of macroblock x - 1); their stores were issued long ago and are ordered before this point by the barriers above, so
+        // the release fence finds them retired instead of waiting for the stores that follow.
+        if (pub) st_release(prog + row, (uint32_t)x);
         if (valid) {
 #pragma unroll
             for (int k = 0; k < W / 4; k++) {
@@ -237,9 +259,12 @@ __device__ __forceinline__ void deblock_pair(const DeblockArgs &a, int pair, uin
         }
 #pragma unroll
         for (int k = 0; k < W / 4; k++) cur[k] = nxt[k];
-        __syncwarp();                                         // orders the lanes' stores before the release below, and the tile's reuse
-        if (valid && hl == 0) st_release(prog + row, (uint32_t)(x + 1));
+        // macroblock x of the row below waits for the value x + 1, which the next iteration publishes
+        if (!CH) pub = watch && (bw[0] & 255u) && (bw[1] & 255u);
+        else     pub = watch && (((bw[0] & 255u) && (bw[1] & 255u)) || ((bw[2] & 255u) && (bw[3] & 255u)));
+        __syncwarp();                                         // the tile and the parameter buffer may be reused
     }
+    if (valid && hl == 0) st_release(prog + row, (uint32_t)a.mb_w);  // (after the barrier that ended the last iteration: every lane's stores are ordered before it)
 }
 
 __global__ void __launch_bounds__(DB_WARPS * 32, 8)

@@ -368,6 +368,12 @@ h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int ro
 int launch_h264_deblock_v3(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls,
                            int uvls, uint32_t *progress, cudaStream_t st);       // h264_deblock.cu
 
+int launch_h264_mc_v2(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dy, uint8_t *dcb, uint8_t *dcr,
+                      int ls, int uvls, int pw, int ph, cudaStream_t st);                  // h264_mc.cu
+
+int launch_h264_residual_v2(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
+                            uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, cudaStream_t st);      // h264_residual.cu
+
 static int warps_grid(size_t n, int warps_per_cta) { return (int)((n + warps_per_cta - 1) / warps_per_cta); }
 
 int launch_h264_residual(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
@@ -375,6 +381,12 @@ int launch_h264_residual(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs,
 {
     if (!n) return 0;
     if (coeff_stride < 16 * 36) { set_error_msg("h264_idct_add_mb_batch", "coeff_stride must cover blocks 0..35 (>= 576)"); return -1; }
+    // default: lane per block in registers, touching only what the C dispatchers touch (h264_residual.cu); residual_variant = 2 keeps
+    // the shared-memory staged kernel, which also serves unaligned arenas / planes and records whose offsets are not multiples of 4
+    if (tuning("residual_variant") != 2) {
+        const int r = launch_h264_residual_v2(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, ls, uvls, st);
+        if (r <= 0) return r;
+    }
     h264_residual_kernel<<<warps_grid(n, 4), 128, 0, st>>>(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, ls, uvls);
     return check_launch("h264_idct_add_mb_batch");
 }
@@ -382,6 +394,12 @@ int launch_h264_mc(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *
                    int ls, int uvls, int pw, int ph, cudaStream_t st)
 {
     if (!n) return 0;
+    // default: one thread per 4x4 block on packed bytes (h264_mc.cu); mc_variant = 2 keeps the warp-per-partition kernel below, which
+    // also serves destinations whose planes the word stores cannot address
+    if (tuning("mc_variant") != 2) {
+        const int r = launch_h264_mc_v2(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, st);
+        if (r <= 0) return r;
+    }
     // bi-prediction is put (list 0) then avg (list 1) on the same pixels (h264_mb.c:322-366): two ordered passes
     // over the record array keep that order without any ordering requirement on the records themselves
     h264_mc_kernel<<<warps_grid(n, 4), 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, 0);

@@ -432,14 +432,13 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
     if (mode < 0 || mode > 2) { set_error_msg("simple_idct_batch", "bad mode"); return -1; }
     if (mode != 2 && !dst_off && tiles_per_row <= 0) { set_error_msg("simple_idct_batch", "need dst_off or tiles_per_row"); return -1; }
     size_t groups = (n + 31) / 32;
-    const int minb = tuning("idct_min_blocks");            // profiling knob: resident CTAs per SM the kernel is compiled for
     // 16 CTAs per SM in the grid (about 3 waves of the 5 resident ones): measured +4 % over exactly one persistent wave,
     // the shorter per-CTA loops even out the tail
-    int grid = grid_for(groups, IDCT_WARPS, tuning("idct_grid_mult") > 0 ? tuning("idct_grid_mult") : 16);
+    int grid = grid_for(groups, IDCT_WARPS, 16);
     dim3 b(IDCT_WARPS * 32);
-    // idct_put (the headline path) fetches through TMA by default; idct_tma = 2 selects the cp.async fetch (same arithmetic,
-    // same throughput: 1.634 Tpix/s either way), which also serves when the driver has no tensor-map encoder
-    if (mode == 0 && !clear && tuning("idct_tma") != 2 && minb != 4 && minb != 6 && !tuning("idct_mulhi") && !((uintptr_t)blocks & 15)) {
+    // idct_put (the headline path) fetches through TMA; the cp.async fetch (same arithmetic, same throughput) serves unaligned block
+    // arrays and drivers without a tensor-map encoder (idct_tma = 2 forces it: the parity tests run both fetches)
+    if (mode == 0 && !clear && tuning("idct_tma") != 2 && !((uintptr_t)blocks & 15)) {
         CUtensorMap tm;
         if (make_block_tensor_map(&tm, blocks, n)) {
             simple_idct_kernel<0, false, 5, false, 0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row, NoDq{}, tm);
@@ -448,10 +447,6 @@ int launch_simple_idct(int mode, int16_t *blocks, uint8_t *frame, const uint32_t
     }
     if (mode == 0) {
         if (clear) simple_idct_kernel<0, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
-        else if (minb == 4) simple_idct_kernel<0, false, 4><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
-        else if (minb == 6) simple_idct_kernel<0, false, 6><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
-        else if (tuning("idct_mulhi") == 1) simple_idct_kernel<0, false, 5, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
-        else if (tuning("idct_mulhi") == 2) simple_idct_kernel<0, false, 4, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
         else       simple_idct_kernel<0, false><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);
     } else if (mode == 1) {
         if (clear) simple_idct_kernel<1, true><<<grid, b, 0, st>>>(blocks, frame, dst_off, stride, n, tiles_per_row);

@@ -103,69 +103,8 @@ me_cmp_kernel(int kind, int sidx, int dxy, const uint8_t *__restrict__ cur, cons
 // ---------------------------------------------------------------------------------------------------
 constexpr int FS_R = 16, FS_WIN = 48, FS_PITCH = 52;          // search range, window edge, smem pitch (words: 13)
 
-__global__ void __launch_bounds__(256)
-full_search_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int stride, int w, int h, int mb_y0,
-                   int32_t *__restrict__ out)
-{
-    __shared__ __align__(16) uint8_t win[FS_WIN * FS_PITCH];
-    __shared__ unsigned long long best_s[8];
-    const int mbw = w >> 4, mbx = blockIdx.x, mby = mb_y0 + blockIdx.y, t = threadIdx.x;
-    const int px = mbx * 16, py = mby * 16;
-    // 48x48 window around the block, addresses clamped into the picture (clipped candidates never read the clamped part)
-    for (int i = t; i < FS_WIN * (FS_WIN / 4); i += 256) {
-        int r = i / (FS_WIN / 4), c4 = i % (FS_WIN / 4);
-        int gy = min(max(py - FS_R + r, 0), h - 1);
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int gx = min(max(px - FS_R + 4 * c4 + k, 0), w - 1);
-            v |= (uint32_t)__ldg(ref + (size_t)gy * stride + gx) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t *>(&win[r * FS_PITCH + 4 * c4]) = v;
-    }
-    uint32_t c[16][4];
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(cur + (size_t)(py + r) * stride + px);
-        c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
-    }
-    __syncthreads();
-    // get_limits(): the block must stay inside the picture (motion_est.c:537-540), then +-range
-    const int xmin = max(-px, -FS_R), xmax = min(w - 16 - px, FS_R), ymin = max(-py, -FS_R), ymax = min(h - 16 - py, FS_R);
-    unsigned long long best = ~0ull;
-    for (int idx = t; idx < 33 * 33; idx += 256) {
-        const int dy = idx / 33 - FS_R, dx = idx % 33 - FS_R;
-        if (dx < xmin || dx > xmax || dy < ymin || dy > ymax) continue;
-        const uint8_t *wp = &win[(dy + FS_R) * FS_PITCH + ((dx + FS_R) & ~3)];
-        const int sh = ((dx + FS_R) & 3) * 8;
-        unsigned sad = 0;
-#pragma unroll
-        for (int r = 0; r < 16; r++) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(wp + r * FS_PITCH);
-            uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
-            sad = __vsadu4(c[r][0], __funnelshift_r(w0, w1, sh)) + sad;
-            sad = __vsadu4(c[r][1], __funnelshift_r(w1, w2, sh)) + sad;
-            sad = __vsadu4(c[r][2], __funnelshift_r(w2, w3, sh)) + sad;
-            sad = __vsadu4(c[r][3], __funnelshift_r(w3, w4, sh)) + sad;
-        }
-        unsigned long long key = ((unsigned long long)sad << 11) | (unsigned)idx;   // strict <, first in raster order wins
-        best = key < best ? key : best;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v < best ? v : best; }
-    if ((t & 31) == 0) best_s[t >> 5] = best;
-    __syncthreads();
-    if (t == 0) {
-#pragma unroll
-        for (int k = 1; k < 8; k++) best = best_s[k] < best ? best_s[k] : best;
-        const int idx = (int)(best & 2047);
-        int32_t *o = out + 3 * ((size_t)mby * mbw + mbx);
-        o[0] = idx % 33 - FS_R; o[1] = idx / 33 - FS_R; o[2] = (int32_t)(best >> 11);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Full search, register-tiled variant (default).  The 48x52 window is stored four times in shared memory, copy s shifted
+// Full search, register-tiled.  The 48x52 window is stored four times in shared memory, copy s shifted
 // left by s bytes, so every candidate reads ALIGNED words (no funnel shifts), and a thread owns five vertically adjacent
 // candidates of one column: the 20 reference rows it needs are read once (80 LDS.32) and reused by up to five
 // candidates, 320 vabsdiff4 per thread.  33 columns x 7 row groups = 231 of the 256 threads carry work.  Copies are
@@ -578,8 +517,7 @@ int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int 
     if (mb_y1 <= mb_y0) return 0;
     if (range != FS_R) { set_error_msg("full_search", "only me_range 16 is built"); return -1; }
     if ((w & 15) || (h & 15) || (stride & 15) || ((uintptr_t)cur & 15)) { set_error_msg("full_search", "picture must be MB aligned, cur 16-byte aligned"); return -1; }
-    if (tuning("full_search_variant") == 1) full_search_kernel<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
-    else full_search_kernel_v2<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
+    full_search_kernel_v2<<<dim3(w >> 4, mb_y1 - mb_y0), 256, 0, (cudaStream_t)stream>>>(cur, ref, stride, w, h, mb_y0, out);
     return check_launch("full_search");
 }
 

@@ -13,16 +13,22 @@ namespace avb {
 
 static std::mutex g_mu;
 static std::string g_err;
+static bool g_err_is_fault = false;          // g_err holds a CUDA failure (sticks) rather than a refusal (replaceable)
 static int g_sms = 0;
 static void (*g_log_cb)(int level, const char *msg) = nullptr;
 
-void set_error_msg(const char *where, const char *msg)
+// Two kinds of message share the channel.  A REFUSAL ("format not taken over", bad arguments: the caller falls back to its C path, which
+// a drop-in caller does routinely) is kept only until something more important arrives; a FAULT (a CUDA call failed -- the void DSP
+// slots have no other way to report it) sticks and replaces a refusal, so that avb200_last_error() never hides a real failure behind
+// an earlier benign message.
+static void record(const char *where, const char *msg, bool fault)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_err.empty()) g_err = std::string(where) + ": " + msg;   // first error sticks
-    if (g_log_cb) g_log_cb(16 /* AV_LOG_ERROR */, (std::string(where) + ": " + msg).c_str());
+    if (g_err.empty() || (fault && !g_err_is_fault)) { g_err = std::string(where) + ": " + msg; g_err_is_fault = fault; }
+    if (g_log_cb) g_log_cb(fault ? 16 /* AV_LOG_ERROR */ : 24 /* AV_LOG_WARNING */, (std::string(where) + ": " + msg).c_str());
 }
-void set_error(const char *where, cudaError_t e) { set_error_msg(where, cudaGetErrorString(e)); }
+void set_error_msg(const char *where, const char *msg) { record(where, msg, false); }
+void set_error(const char *where, cudaError_t e) { record(where, cudaGetErrorString(e), true); }
 int check_launch(const char *where)
 {
     cudaError_t e = cudaGetLastError();
@@ -89,7 +95,7 @@ const char *avb200_last_error(void)
     copy = g_err;
     return copy.c_str();
 }
-void avb200_clear_error(void) { std::lock_guard<std::mutex> lk(g_mu); g_err.clear(); }
+void avb200_clear_error(void) { std::lock_guard<std::mutex> lk(g_mu); g_err.clear(); g_err_is_fault = false; }
 void avb200_set_log_callback(void (*cb)(int, const char *)) { g_log_cb = cb; }
 
 void *avb200_malloc(size_t bytes)

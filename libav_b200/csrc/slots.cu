@@ -205,7 +205,9 @@ template <int KIND, int SIDX, int DXY> int slot_mecmp(struct MpegEncContext *, u
 {
     Stage S; if (!S.ok()) return 0;
     const int w = SIDX == 0 ? 16 : SIDX == 1 ? 8 : 4;
-    size_t oa = S.rect_in(a, stride, w, h), ob = S.rect_in(b, stride, w + 1, h + 1), orec = S.take(8), oout = S.take(16);
+    // exactly what the C function of this slot reads: one more column only for x2, one more row only for y2 (me_cmp.c:109-307) --
+    // at the right / bottom edge of a frame without edge rows anything more lies outside the caller's buffer
+    size_t oa = S.rect_in(a, stride, w, h), ob = S.rect_in(b, stride, w + (KIND == 0 ? DXY & 1 : 0), h + (KIND == 0 ? DXY >> 1 : 0)), orec = S.take(8), oout = S.take(16);
     memset(S.h + orec, 0, 8);
     if (S.up() || ff_me_cmp_batch_cuda(KIND, SIDX, DXY, S.d + oa, S.d + ob, SP, h, (const FFMECmpRecord *)(S.d + orec), 1, (int32_t *)(S.d + oout), S.s) || S.down()) return 0;
     int32_t r; memcpy(&r, S.h + oout, 4); return r;
@@ -224,7 +226,7 @@ template <int TAB, int SIDX, int DXY> void slot_hpel(uint8_t *block, const uint8
 {
     Stage S; if (!S.ok()) return;
     const int w = 16 >> SIDX;
-    size_t od = S.rect_in(block, ls, w, h), os = S.rect_in(pixels, ls, w + 1, h + 1), orec = S.take(16);
+    size_t od = S.rect_in(block, ls, w, h), os = S.rect_in(pixels, ls, w + (DXY & 1), h + (DXY >> 1)), orec = S.take(16);     // (hpeldsp.c:38-366 reads no more)
     FFHpelRecord r = { 0, 0, (uint8_t)TAB, (uint8_t)SIDX, (uint8_t)DXY, (uint8_t)h };
     memcpy(S.h + orec, &r, sizeof(r));
     if (S.up() || ff_hpel_batch_cuda((const FFHpelRecord *)(S.d + orec), 1, S.d + od, S.d + os, SP, S.s) || S.down()) return;

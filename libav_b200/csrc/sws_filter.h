@@ -61,6 +61,7 @@ struct SwsSlotView {
     int target;        // packed destinations: 0 rgb24, 1 bgr24, 2 yuyv422, 3 uyvy422, 4 argb, 5 rgba, 6 abgr, 7 bgra; -1 for planar
     int dstNV;         // 1 nv12, 2 nv21
     int rangeConv;     // 1 full -> limited, 2 limited -> full range on the hscaled lines (yuv destinations), else 0
+    int srcBits;       // 8, or 9 / 10 / 16 for the planar high-bit-depth sources (their line functions are hScale16To15_c / ...To19_c)
 };
 // lum / chrRange{From,To}Jpeg_c (swscale.c:166-197) in place on `rows` lines of `w` 15-bit samples, `stridePx` samples apart (device memory):
 // kind 0 lumFromJpeg, 1 chrFromJpeg, 2 lumToJpeg, 3 chrToJpeg.  Defined in sws_slots.cu; 0 / -1

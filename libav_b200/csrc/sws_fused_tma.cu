@@ -300,7 +300,7 @@ int sws_fused_tma_launch(const RgbConstants &k, int bgr, int dstW, int dstH, int
     { const long long t2 = wstride / fa.tilesX; fa.stepTy = (int)(t2 % fa.nTy); fa.stepF = (int)(t2 / fa.nTy); }
 #define AVB_FT_GO(L, W) (bgr ? launch_variant<true, L, W>(k, fa, taps, tmY, tmU, tmV, tmD, (int)grid, st) : launch_variant<false, L, W>(k, fa, taps, tmY, tmU, tmV, tmD, (int)grid, st))
     if (lut) return warps == 4 ? AVB_FT_GO(true, 4) : warps == 14 ? AVB_FT_GO(true, 14) : AVB_FT_GO(true, 12);
-    return warps == 4 ? AVB_FT_GO(false, 4) : AVB_FT_GO(false, 12);
+    return AVB_FT_GO(false, 12);
 #undef AVB_FT_GO
 }
 

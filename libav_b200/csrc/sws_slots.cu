@@ -385,6 +385,11 @@ extern "C" int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cu
         if (!found) g_reg.emplace_back(c, cuda);
     }
     memset(t, 0, sizeof(*t));
+    // 9 / 10 / 16-bit sources: the reference installs hScale16To15_c / hScale16To19_c (swscale.c:744-745) and feeds the 8-bit output
+    // functions an ordered-dither row per output line that lives in its own SwsContext (chrDither8 / lumDither8, swscale.c:554-555),
+    // which this hook cannot see.  Those contexts are NOT taken over line by line: every slot stays NULL (the caller keeps its C
+    // functions) and the refusal is reported; the whole-frame calls sws_scale_cuda / sws_scale_frames_cuda serve them.
+    if (v.srcBits > 8) { set_error_msg("ff_sws_init_swscale_cuda", "high-bit-depth source: the per-line slots are not taken over (use the frame calls)"); return -1; }
     const bool d16 = v.planar && v.dstBits == 16;
     t->hyScale = t->hcScale = d16 ? slot_hscale<19> : slot_hscale<15>;                    // swscale.c:733-743
     if ((v.flags & SWS_FAST_BILINEAR) && !d16) { t->hyscale_fast = slot_hyscale_fast; t->hcscale_fast = slot_hcscale_fast; }

@@ -1794,7 +1794,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
 {
     const SwsCudaContext *c = (const SwsCudaContext *)ctx;
     if (!c) return false;
-    v.rangeConv = c->rangeConv;
+    v.rangeConv = c->rangeConv; v.srcBits = c->srcBits;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
@@ -2163,14 +2163,14 @@ int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, i
 // 19 colour constants, flags, planar, dstBits, dstBE, packed target, dstNV, range conversion.  Returns the count, 0 when the request is refused.
 int sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32])
 {
-    static_assert(sizeof(SwsSlotView) == 26 * sizeof(int32_t), "SwsSlotView is 26 ints");
+    static_assert(sizeof(SwsSlotView) == 27 * sizeof(int32_t), "SwsSlotView is 27 ints");
     SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
     if (!c) return 0;
     SwsSlotView v;
     sws_slot_view(c, v);
     memcpy(out, &v, sizeof(v));
     delete c;
-    return 26;
+    return 27;
 }
 void sws_debug_rgb_constants_cuda(int32_t out[10])
 {

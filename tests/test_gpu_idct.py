@@ -195,3 +195,23 @@ def test_full_size_properties(gpu, checker):
     assert np.array_equal(tiles[:16384].reshape(-1), want)
     added = device.idct_put_tiles(blocks, tpr, mode=1, frame=np.zeros_like(frame))
     assert np.array_equal(added, frame)
+
+
+@pytest.mark.parametrize("gen", ["dense", "dct0", "sparse"])
+def test_config2_every_block_against_the_checker(gpu, checker, gen):
+    """BASELINE config 2 at its full size, every one of the 2^20 blocks compared with the CPU checker (all host threads), for the
+    three distributions SURVEY 8d names: dense uniform, dct.c test 0, dct.c test 1 (sparse)"""
+    from libav_b200 import device
+    import os
+    n, tpr = 1 << 20, 1024
+    if gen == "dense":
+        blocks = synth.dense_blocks(n, seed=3)
+    else:
+        blocks = synth.tile_large(synth.dct_test_blocks(0 if gen == "dct0" else 1, 1 << 16), n)
+        blocks = np.ascontiguousarray(blocks + (np.arange(n, dtype=np.int16)[:, None] & 1))      # every copy differs from its neighbours
+    stride = tpr * 8
+    off = device.tile_offsets(n, tpr, stride)
+    want = np.zeros(((n // tpr) * 8, stride), np.uint8)
+    checker.idct_batch(0, ptr(blocks.copy()), ptr(want), ptr(off), stride, n, os.cpu_count() or 1)
+    got = device.idct_put_tiles(blocks, tpr)
+    assert np.array_equal(got, want)

@@ -21,6 +21,7 @@ h264_mc_kernel_v2(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH26
 {
     __shared__ int s_off[4][33];
     __shared__ uint16_t s_edge[4][64];                     // deferred edge blocks (ordinals)
+    __shared__ const uint8_t *s_pl[4][32][3];               // the record's reference planes (read once per record, not once per block)
     __shared__ uint32_t s_rec[4][32][4];                   // x | y << 16, mvx | mvy << 16, w | h << 8 | avg << 16 | ref << 24, first luma row of the record's picture
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t r0 = ((size_t)blockIdx.x * 4 + warp) * 32;
@@ -34,6 +35,10 @@ h264_mc_kernel_v2(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH26
             const int w = w2 & 255, h = (w2 >> 8) & 255, avg = (w2 >> 16) & 255;
             if ((avg != 0) == (pass != 0)) nb = (w >> 2) * (h >> 2);
             ly0 = (uint32_t)(((int)(int16_t)(w0 >> 16) / ph) * ph);
+            if (nb) {
+                const FFH264RefPlanes rp = refs[w2 >> 24];
+                s_pl[warp][lane][0] = rp.y; s_pl[warp][lane][1] = rp.cb; s_pl[warp][lane][2] = rp.cr;
+            }
         }
         s_rec[warp][lane][0] = w0; s_rec[warp][lane][1] = w1; s_rec[warp][lane][2] = w2; s_rec[warp][lane][3] = ly0;
     }
@@ -57,7 +62,7 @@ h264_mc_kernel_v2(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH26
         const uint32_t w0 = s_rec[warp][j][0], w1 = s_rec[warp][j][1], w2 = s_rec[warp][j][2];
         const int ly0 = (int)s_rec[warp][j][3];
         const int rx = (int16_t)(w0 & 0xffff), ry = (int16_t)(w0 >> 16), mvx = (int16_t)(w1 & 0xffff), mvy = (int16_t)(w1 >> 16);
-        const int rw = w2 & 255, avg = (w2 >> 16) & 255, ref = w2 >> 24;
+        const int rw = w2 & 255, avg = (w2 >> 16) & 255;
         const int b = q - s_off[warp][j], bw = rw >> 2;
         const int by = bw == 4 ? b >> 2 : bw == 2 ? b >> 1 : b, bx = b - by * bw;
         const int x = rx + 4 * bx, y = ry + 4 * by, mx = mvx + 4 * x, my = mvy + 4 * y;
@@ -65,9 +70,8 @@ h264_mc_kernel_v2(const FFH264MCRecord *__restrict__ recs, size_t n, const FFH26
         McPlanes pl = { nullptr, nullptr, nullptr };
         bool inside = false;
         if (live) {
-            const FFH264RefPlanes rp = refs[ref];
-            pl.y = rp.y; pl.cb = rp.cb; pl.cr = rp.cr;
-            const bool aligned = !(((uintptr_t)rp.y | (uintptr_t)rp.cb | (uintptr_t)rp.cr | (uintptr_t)ls | (uintptr_t)uvls) & 3);
+            pl.y = s_pl[warp][j][0]; pl.cb = s_pl[warp][j][1]; pl.cr = s_pl[warp][j][2];
+            const bool aligned = !(((uintptr_t)pl.y | (uintptr_t)pl.cb | (uintptr_t)pl.cr | (uintptr_t)ls | (uintptr_t)uvls) & 3);
             inside = mc_block_inside(pw, ph, ly0, mx, my, aligned);
         }
         const bool mine = live && (EDGE || inside);                   // (the interior pass leaves edge blocks to the deferred pass)

@@ -42,12 +42,14 @@ __device__ __forceinline__ uint32_t mc_avg4(uint32_t a, uint32_t b) { return (a 
 
 // 6-tap over eight consecutive samples held as (w0 = samples 0..3, w1 = samples 4..7) + sample 8 in byte 0 of w2:
 // out[c] = s[c] - 5 s[c+1] + 20 s[c+2] + 20 s[c+3] - 5 s[c+4] + s[c+5], c = 0..3
+// (+ RND: the rounding constant rides in the accumulator of the first dot product)
+template <int RND>
 __device__ __forceinline__ void mc_tap6(uint32_t w0, uint32_t w1, uint32_t w2, int (&out)[4])
 {
-    out[0] = mc_dp4a_us(w1, AVB_TAPS(-5, 1, 0, 0), mc_dp4a_us(w0, AVB_TAPS(1, -5, 20, 20), 0));
-    out[1] = mc_dp4a_us(w1, AVB_TAPS(20, -5, 1, 0), mc_dp4a_us(w0, AVB_TAPS(0, 1, -5, 20), 0));
-    out[2] = mc_dp4a_us(w1, AVB_TAPS(20, 20, -5, 1), mc_dp4a_us(w0, AVB_TAPS(0, 0, 1, -5), 0));
-    out[3] = mc_dp4a_us(w2, AVB_TAPS(1, 0, 0, 0), mc_dp4a_us(w1, AVB_TAPS(-5, 20, 20, -5), mc_dp4a_us(w0, AVB_TAPS(0, 0, 0, 1), 0)));
+    out[0] = mc_dp4a_us(w1, AVB_TAPS(-5, 1, 0, 0), mc_dp4a_us(w0, AVB_TAPS(1, -5, 20, 20), RND));
+    out[1] = mc_dp4a_us(w1, AVB_TAPS(20, -5, 1, 0), mc_dp4a_us(w0, AVB_TAPS(0, 1, -5, 20), RND));
+    out[2] = mc_dp4a_us(w1, AVB_TAPS(20, 20, -5, 1), mc_dp4a_us(w0, AVB_TAPS(0, 0, 1, -5), RND));
+    out[3] = mc_dp4a_us(w2, AVB_TAPS(1, 0, 0, 0), mc_dp4a_us(w1, AVB_TAPS(-5, 20, 20, -5), mc_dp4a_us(w0, AVB_TAPS(0, 0, 0, 1), RND)));
 }
 // rows r0..r3 hold 4 columns each: out[c] = (r0.c, r1.c, r2.c, r3.c)
 __device__ __forceinline__ void mc_transpose4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t (&out)[4])
@@ -119,7 +121,7 @@ __device__ __forceinline__ void mc_block(const McPlanes &ref, uint8_t *__restric
         int h[9][4];
 #pragma unroll
         for (int r = 0; r < 9; r++)
-            if (need_j || (r >= 2 && r <= 6)) mc_tap6(W0[r], W1[r], W2[r], h[r]);
+            if (need_j || (r >= 2 && r <= 6)) mc_tap6<0>(W0[r], W1[r], W2[r], h[r]);
 #pragma unroll
         for (int k = 0; k < 5; k++) Hp[k] = mc_round_pack<16, 5>(h[2 + k]);      // rows 0 .. 4, rounded
         if (need_j) {
@@ -144,11 +146,11 @@ __device__ __forceinline__ void mc_block(const McPlanes &ref, uint8_t *__restric
         mc_transpose4(C[4], C[5], C[6], C[7], T1);
         int v[4][4];                                                  // [column][row]
 #pragma unroll
-        for (int c = 0; c < 4; c++) mc_tap6(T0[c], T1[c], __byte_perm(C[8], 0u, 0x4440 + c), v[c]);
+        for (int c = 0; c < 4; c++) mc_tap6<16>(T0[c], T1[c], __byte_perm(C[8], 0u, 0x4440 + c), v[c]);
 #pragma unroll
         for (int yy = 0; yy < 4; yy++) {
             const int row[4] = { v[0][yy], v[1][yy], v[2][yy], v[3][yy] };
-            Vw[yy] = mc_round_pack<16, 5>(row);
+            Vw[yy] = mc_round_pack<0, 5>(row);
         }
     }
     // ---- the position picks one component or the mean of two (h264qpel_template.c:380-531) ----

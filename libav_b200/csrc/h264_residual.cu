@@ -55,6 +55,12 @@ __device__ __forceinline__ void st_px(uint8_t *p, uint32_t v, bool al)
     else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 }
 
+// One warp per macroblock.  Two code paths, each executed once by all the lanes that have work (a warp that let every lane branch on
+// its own block kind ran 5 of 32 threads per instruction):
+//   4x4 path   lanes 0-15 = the luma blocks of an idct_add16 / add16intra macroblock, lanes 16-23 = the cb / cr blocks; the full
+//              transform and the DC-only shortcut are computed side by side and selected per lane
+//   8x8 path   a transform-8x8 macroblock: 8 lanes per block (32 busy lanes); a lane owns coefficient row t, then column t, then row t
+//              again, then pixel row t -- the three transposes go through 4 x 144 bytes of shared memory
 __global__ void __launch_bounds__(128)
 h264_residual_kernel_v2(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
                         const uint8_t *__restrict__ nnzc, uint8_t *__restrict__ luma, uint8_t *__restrict__ cb,
@@ -63,113 +69,95 @@ h264_residual_kernel_v2(const FFH264ResidualMB *__restrict__ mbs, size_t n, int1
     const int lane = threadIdx.x & 31;
     const size_t mb = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (mb >= n) return;
-    const uint2 rw = __ldg(reinterpret_cast<const uint2 *>(mbs + mb));       // luma_off, chroma_off
-    const uint32_t rm = __ldg(reinterpret_cast<const uint32_t *>(mbs + mb) + 2);
+    const uint32_t *rp = reinterpret_cast<const uint32_t *>(mbs + mb);      // (12-byte records: word loads)
+    const uint2 rw = make_uint2(__ldg(rp), __ldg(rp + 1));                   // luma_off, chroma_off
+    const uint32_t rm = __ldg(rp + 2);
     const int mode = rm & 255, chroma = (rm >> 8) & 255;
     const bool al = !((rw.x | rw.y) & 3u);
     int16_t *gc = coeffs + mb * coeff_stride;
     const uint8_t *nz = nnzc + mb * 120;
 
-    if (lane < 16 && mode <= 1) {                                   // h264_idct_add16 (:174-183) / h264_idct_add16intra (:185-191)
-        const int i = lane, nnz = __ldg(nz + scan8_of(i));
-        int16_t *b = gc + 16 * i;
-        uint8_t *d = luma + rw.x + blk_x(i) + (size_t)blk_y(i) * ls;
-        int kind = 0;                                               // 1 full transform, 2 DC only
-        uint32_t w0 = 0;
-        if (nnz) { w0 = *reinterpret_cast<const uint32_t *>(b); kind = (mode == 0 && nnz == 1 && (w0 & 0xffffu)) ? 2 : 1; }
-        else if (mode == 1) { w0 = *reinterpret_cast<const uint32_t *>(b); kind = (w0 & 0xffffu) ? 2 : 0; }
-        if (kind) {
-            uint32_t px[4];
-#pragma unroll
-            for (int y = 0; y < 4; y++) px[y] = ld_px(d + (size_t)y * ls, al);
-            if (kind == 1) {
-                const uint4 c0 = *reinterpret_cast<const uint4 *>(b), c1 = *reinterpret_cast<const uint4 *>(b + 8);
-                idct4_add_regs(c0, c1, px);
-                *reinterpret_cast<uint4 *>(b) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4 *>(b + 8) = make_uint4(0, 0, 0, 0);
-            } else {
-                const int dc = (lo16s(w0) + 32) >> 6;
-#pragma unroll
-                for (int y = 0; y < 4; y++) px[y] = add_clip4(px[y], dc, dc, dc, dc);
-                b[0] = 0;
-            }
-#pragma unroll
-            for (int y = 0; y < 4; y++) st_px(d + (size_t)y * ls, px[y], al);
-        }
-    } else if (lane < 4 && mode == 2) {                             // h264_idct8_add4 (:193-202): blocks 0, 4, 8, 12
-        const int i = 4 * lane, nnz = __ldg(nz + scan8_of(i));
-        if (nnz) {
-            int16_t *b = gc + 16 * i;
-            uint8_t *d = luma + rw.x + blk_x(i) + (size_t)blk_y(i) * ls;
-            uint32_t px[8][2];
-#pragma unroll
-            for (int y = 0; y < 8; y++) { px[y][0] = ld_px(d + (size_t)y * ls, al); px[y][1] = ld_px(d + (size_t)y * ls + 4, al); }
-            const int b0 = b[0];
-            if (nnz == 1 && b0) {                                   // ff_h264_idct8_dc_add
-                const int dc = (b0 + 32) >> 6;
-#pragma unroll
-                for (int y = 0; y < 8; y++) { px[y][0] = add_clip4(px[y][0], dc, dc, dc, dc); px[y][1] = add_clip4(px[y][1], dc, dc, dc, dc); }
-                b[0] = 0;
-            } else {                                                // ff_h264_idct8_add: columns, int16 write-back, rows
-                int c[64];
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(b + 8 * k);
-                    c[8 * k] = lo16s(q.x); c[8 * k + 1] = hi16s(q.x); c[8 * k + 2] = lo16s(q.y); c[8 * k + 3] = hi16s(q.y);
-                    c[8 * k + 4] = lo16s(q.z); c[8 * k + 5] = hi16s(q.z); c[8 * k + 6] = lo16s(q.w); c[8 * k + 7] = hi16s(q.w);
-                }
-                c[0] = s16(c[0] + 32);
-#pragma unroll
-                for (int x = 0; x < 8; x++) {
-                    int v[8], o[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = c[x + 8 * k];
-                    h264_idct8_1d(v, o);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) c[x + 8 * k] = s16(o[k]);
-                }
-#pragma unroll
-                for (int x = 0; x < 8; x++) {                       // row x of the coefficient block -> pixel COLUMN x
-                    int v[8], o[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = c[8 * x + k];
-                    h264_idct8_1d(v, o);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) c[8 * x + k] = o[k] >> 6;       // (reuse: c[8 x + k] = what pixel (column x, row k) gains)
-                }
-#pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    px[y][0] = add_clip4(px[y][0], c[y], c[8 + y], c[16 + y], c[24 + y]);
-                    px[y][1] = add_clip4(px[y][1], c[32 + y], c[40 + y], c[48 + y], c[56 + y]);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) *reinterpret_cast<uint4 *>(b + 8 * k) = make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int y = 0; y < 8; y++) { st_px(d + (size_t)y * ls, px[y][0], al); st_px(d + (size_t)y * ls + 4, px[y][1], al); }
-        }
-    } else if (lane >= 16 && lane < 24 && chroma) {                 // h264_idct_add8 (:204-214): blocks 16..19 (cb), 32..35 (cr)
-        const int plane = (lane - 16) >> 2, k = (lane - 16) & 3, i = 16 + 16 * plane + k;
-        int16_t *b = gc + 16 * i;
-        uint8_t *d = (plane ? cr : cb) + rw.y + blk_x(k) + (size_t)blk_y(k) * uvls;
+#ifndef AVB_HOSTSIM
+    if (mode == 2) {                                                // h264_idct8_add4 (:193-202): blocks 0, 4, 8, 12
+        __shared__ __align__(16) int16_t tr[4][4][72];              // [warp][block][8 rows x 8 + 8 pad]: 144 bytes per block keeps the groups on different banks
+        const int g = lane >> 3, t = lane & 7, i = 4 * g;
+        int16_t (&T)[72] = tr[threadIdx.x >> 5][g];
         const int nnz = __ldg(nz + scan8_of(i));
-        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(b);
-        const int kind = nnz ? 1 : (w0 & 0xffffu) ? 2 : 0;
-        if (kind) {
-            uint32_t px[4];
+        int16_t *b = gc + 16 * i;
+        uint8_t *d = luma + rw.x + blk_x(i) + (size_t)(blk_y(i) + t) * ls;         // this lane's pixel row
+        const int b0 = nnz ? (int)b[0] : 0;
+        const int kind = !nnz ? 0 : (nnz == 1 && b0) ? 2 : 1;       // uniform over the block's 8 lanes
+        uint32_t p0 = 0, p1 = 0;
+        if (kind) { p0 = ld_px(d, al); p1 = ld_px(d + 4, al); }
+        int gain[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (kind == 1) q = *reinterpret_cast<const uint4 *>(b + 8 * t);          // coefficient row t
+        if (kind == 1 && t == 0) q.x = (q.x & 0xffff0000u) | (uint32_t)(uint16_t)(lo16s(q.x) + 32);   // block[0] += 32 (int16)
+        *reinterpret_cast<uint4 *>(&T[8 * t]) = q;
+        __syncwarp();
+        int v[8], o[8];
 #pragma unroll
-            for (int y = 0; y < 4; y++) px[y] = ld_px(d + (size_t)y * uvls, al);
-            if (kind == 1) {
+        for (int k = 0; k < 8; k++) v[k] = T[8 * k + t];            // column t
+        h264_idct8_1d(v, o);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) T[8 * k + t] = (int16_t)o[k];   // written back as int16 like the C code
+        __syncwarp();
+        {
+            const uint4 r = *reinterpret_cast<const uint4 *>(&T[8 * t]);         // row t of the half-transformed block
+            v[0] = lo16s(r.x); v[1] = hi16s(r.x); v[2] = lo16s(r.y); v[3] = hi16s(r.y); v[4] = lo16s(r.z); v[5] = hi16s(r.z); v[6] = lo16s(r.w); v[7] = hi16s(r.w);
+        }
+        h264_idct8_1d(v, o);                                        // o[k] >> 6 is what pixel (column t, row k) gains
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) T[8 * k + t] = (int16_t)(o[k] >> 6);
+        __syncwarp();
+        {
+            const uint4 r = *reinterpret_cast<const uint4 *>(&T[8 * t]);         // pixel row t
+            gain[0] = lo16s(r.x); gain[1] = hi16s(r.x); gain[2] = lo16s(r.y); gain[3] = hi16s(r.y); gain[4] = lo16s(r.z); gain[5] = hi16s(r.z); gain[6] = lo16s(r.w); gain[7] = hi16s(r.w);
+        }
+        if (kind == 2) {                                            // ff_h264_idct8_dc_add
+            const int dc = (b0 + 32) >> 6;
+#pragma unroll
+            for (int k = 0; k < 8; k++) gain[k] = dc;
+        }
+        if (kind) {
+            st_px(d, add_clip4(p0, gain[0], gain[1], gain[2], gain[3]), al);
+            st_px(d + 4, add_clip4(p1, gain[4], gain[5], gain[6], gain[7]), al);
+            if (kind == 1) *reinterpret_cast<uint4 *>(b + 8 * t) = make_uint4(0, 0, 0, 0);
+            else if (t == 0) b[0] = 0;
+        }
+    }
+#endif
+    // ---- 4x4 blocks: luma (h264_idct_add16 :174-183, h264_idct_add16intra :185-191) and chroma (h264_idct_add8 :204-214) ----
+    {
+        const bool is_luma = lane < 16;
+        const int plane = (lane - 16) >> 2, k = is_luma ? lane : (lane - 16) & 3;
+        const int i = is_luma ? lane : 16 + 16 * plane + k;
+        const bool mine = is_luma ? mode <= 1 : (lane < 24 && chroma);
+        if (mine) {
+            int16_t *b = gc + 16 * i;
+            const int pitch = is_luma ? ls : uvls;
+            uint8_t *d = (is_luma ? luma + rw.x : (plane ? cr : cb) + rw.y) + blk_x(k) + (size_t)blk_y(k) * pitch;
+            const int nnz = __ldg(nz + scan8_of(i));
+            const bool dc_rule_inter = is_luma && mode == 0;        // idct_add16: DC-only shortcut only when nnz == 1; the others: when nnz == 0
+            int kind = 0;                                           // 1 full transform, 2 DC only
+            uint32_t w0 = 0;
+            if (nnz || !dc_rule_inter) w0 = *reinterpret_cast<const uint32_t *>(b);
+            if (nnz) kind = (dc_rule_inter && nnz == 1 && (w0 & 0xffffu)) ? 2 : 1;
+            else if (!dc_rule_inter) kind = (w0 & 0xffffu) ? 2 : 0;
+            if (kind) {
+                uint32_t px[4], pd[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++) pd[y] = px[y] = ld_px(d + (size_t)y * pitch, al);
                 const uint4 c0 = *reinterpret_cast<const uint4 *>(b), c1 = *reinterpret_cast<const uint4 *>(b + 8);
-                idct4_add_regs(c0, c1, px);
-                *reinterpret_cast<uint4 *>(b) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4 *>(b + 8) = make_uint4(0, 0, 0, 0);
-            } else {
+                idct4_add_regs(c0, c1, px);                         // (computed for DC-only lanes too: the warp runs it anyway)
                 const int dc = (lo16s(w0) + 32) >> 6;
 #pragma unroll
-                for (int y = 0; y < 4; y++) px[y] = add_clip4(px[y], dc, dc, dc, dc);
-                b[0] = 0;
+                for (int y = 0; y < 4; y++) st_px(d + (size_t)y * pitch, kind == 1 ? px[y] : add_clip4(pd[y], dc, dc, dc, dc), al);
+                if (kind == 1) { *reinterpret_cast<uint4 *>(b) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4 *>(b + 8) = make_uint4(0, 0, 0, 0); }
+                else b[0] = 0;
             }
-#pragma unroll
-            for (int y = 0; y < 4; y++) st_px(d + (size_t)y * uvls, px[y], al);
         }
     }
 }

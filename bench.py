@@ -168,13 +168,24 @@ def make_sws_workload(torch, L, stream, rank):
     d_o = [torch.empty(osz * K, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     ctx = device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, SWS_FLAGS)
     assert ctx.fused
-    # end-to-end arm: one frame per call through the host-pointer sws_scale_cuda (the reference's own call shape)
+    # end-to-end arm: one frame per call through the host-pointer sws_scale_cuda (the reference's own call shape), from T host threads
+    # with a context each -- config 5's "concurrent streams"; the CPU arm runs one context per host thread the same way.  A call must
+    # return a finished picture, so a single caller leaves both PCIe directions idle between frames.
+    T = max(1, min(K, int(os.environ.get("AVB200_E2E_STREAMS", "4"))))
     hy, hu, hv = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in frames[0]]
     ho = torch.empty((h, w * 3), dtype=torch.uint8).pin_memory()
+    e2e_ctx = [ctx] + [device.SwsContext(w, h, w, h, device.PIX_FMT_RGB24, SWS_FLAGS) for _ in range(T - 1)]
+    e2e_out = [ho] + [torch.empty((h, w * 3), dtype=torch.uint8).pin_memory() for _ in range(T - 1)]
     src = (C.c_void_p * 4)(hy.data_ptr(), hu.data_ptr(), hv.data_ptr(), None)
     sst = (C.c_int * 4)(w, w // 2, w // 2, 0)
-    dst = (C.c_void_p * 4)(ho.data_ptr(), None, None, None)
+    dsts = [(C.c_void_p * 4)(o.data_ptr(), None, None, None) for o in e2e_out]
     dstr = (C.c_int * 4)(w * 3, 0, 0, 0)
+    e2e_err = []
+
+    def e2e_worker(t):
+        for _ in range(t, K, T):
+            if L.lib.sws_scale_cuda(e2e_ctx[t].ctx, src, sst, 0, h, dsts[t], dstr) != h:
+                e2e_err.append(t)
 
     def run(i):
         k = i % nbuf
@@ -182,10 +193,13 @@ def make_sws_workload(torch, L, stream, rank):
                          [w * 3], nframes=K, src_frame=[ysz, csz, csz], dst_frame=[osz], stream=stream)
 
     def run_e2e(i):
-        for _ in range(K):
-            if L.lib.sws_scale_cuda(ctx.ctx, src, sst, 0, h, dst, dstr) != h:
-                L.check(-1, "sws_scale_cuda")
-        return int(ho[0, 0])
+        ths = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(1, T)]
+        [t.start() for t in ths]
+        e2e_worker(0)
+        [t.join() for t in ths]
+        if e2e_err:
+            L.check(-1, "sws_scale_cuda")
+        return int(ho[0, 0]) + sum(int(o[h - 1, 0]) for o in e2e_out)        # every caller's picture is read on the host
 
     def verify():
         """first, second and last frame of the last launch + the frame of the host-pointer arm against the CPU checker"""
@@ -203,9 +217,10 @@ def make_sws_workload(torch, L, stream, rank):
             for j in (0, 1, K - 1):
                 if not np.array_equal(got[j], want[j % 2]):
                     raise SystemExit("bench.py: sws4k frame %d of buffer %d differs from the %s checker" % (j, k, kind))
-        if not np.array_equal(ho.numpy(), want[0]):
-            raise SystemExit("bench.py: sws_scale_cuda (host buffers) differs from the %s checker" % kind)
-        return "frames 0, 1, %d of each of the %d output batches and the host-call frame == %s" % (K - 1, nbuf, kind)
+        for o_ in e2e_out:
+            if not np.array_equal(o_.numpy(), want[0]):
+                raise SystemExit("bench.py: sws_scale_cuda (host buffers) differs from the %s checker" % kind)
+        return "frames 0, 1, %d of each of the %d output batches and the %d host-call pictures == %s" % (K - 1, nbuf, T, kind)
 
     return {
         "name": "sws_scale 3840x2160 yuv420p->rgb24 bicubic|accurate_rnd|bitexact, %d frames per launch per GPU" % K,
@@ -213,7 +228,7 @@ def make_sws_workload(torch, L, stream, rank):
         "launches_per_step": 1, "kernel": "sws_fused_rgb24_tma_kernel", "dtype": "int32 (u8 in, u8 out)",
         "h2d": int(w * h * 1.5) * K, "d2h": osz * K,
         "l2": "2 rotating %d MiB buffer sets (inputs+outputs larger than the 126 MB L2)" % ((ysz + 2 * csz + osz) * K >> 20),
-        "keep": (d_y, d_u, d_v, d_o, ctx, hy, hu, hv, ho),
+        "keep": (d_y, d_u, d_v, d_o, ctx, hy, hu, hv, ho, e2e_ctx, e2e_out, dsts), "e2e_streams": T,
     }
 
 
@@ -286,18 +301,34 @@ def make_h264_workload(torch, L, stream, rank):
     for e in refilled + consumed:
         e.record(main)
 
+    # The groups are independent pictures: each runs its own MC -> residual -> deblock chain on its own stream (the decoder threads
+    # of the reference would be one per picture too), so the latency-bound wavefront of one group overlaps the other group's kernels.
+    chains = [main] + [torch.cuda.Stream() for _ in range(G - 1)] if os.environ.get("AVB200_H264_CHAINS", "1") != "0" else [main] * G
+    fork, joined = torch.cuda.Event(), [torch.cuda.Event() for _ in range(G)]
+    n_g = mb_w * mb_h * H264_PICTURES                          # macroblocks per group
+
     def run(i):
         b = i & 1
         main.wait_event(refilled[b])
+        fork.record(main)
         for gi in range(G):
+            st = chains[gi]
+            if st is not main:
+                st.wait_event(fork)
+            sp = st.cuda_stream
             yo, co = gi * H264_PICTURES * W * H, gi * H264_PICTURES * W * H // 4
             L.check(lib.ff_h264_mc_batch_cuda(d_mc.data_ptr(), mc.shape[0], d_planes_g[gi].data_ptr(), d_y.data_ptr() + yo, d_cb.data_ptr() + co,
-                                              d_cr.data_ptr() + co, W, W // 2, W, H, stream), "mc")
-        L.check(lib.ff_h264_idct_add_mb_batch_cuda(d_res.data_ptr(), res.shape[0], d_coef[b].data_ptr(), 768, d_nnz.data_ptr(), d_y.data_ptr(),
-                                                   d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2, stream), "residual")
+                                              d_cr.data_ptr() + co, W, W // 2, W, H, sp), "mc")
+            L.check(lib.ff_h264_idct_add_mb_batch_cuda(d_res.data_ptr() + gi * n_g * 12, n_g, d_coef[b].data_ptr() + gi * n_g * 1536, 768,
+                                                       d_nnz.data_ptr() + gi * n_g * 120, d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2, sp), "residual")
+            L.check(lib.ff_h264_deblock_batch_cuda(d_dbk.data_ptr() + gi * n_g * 104, mb_w, mb_h, H264_PICTURES, d_y.data_ptr() + yo, d_cb.data_ptr() + co,
+                                                   d_cr.data_ptr() + co, W, W // 2, d_prog.data_ptr() + gi * 8 * mb_h * H264_PICTURES, sp), "deblock")
+            if st is not main:
+                joined[gi].record(st)
+        for gi in range(G):
+            if chains[gi] is not main:
+                main.wait_event(joined[gi])
         consumed[b].record(main)
-        L.check(lib.ff_h264_deblock_batch_cuda(d_dbk.data_ptr(), mb_w, mb_h, P, d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(), W, W // 2,
-                                               d_prog.data_ptr(), stream), "deblock")
         with torch.cuda.stream(side):                      # refill the arena this step consumed while the next step runs
             side.wait_event(consumed[b])
             d_coef[b].copy_(d_coef0, non_blocking=True)
@@ -320,9 +351,9 @@ def make_h264_workload(torch, L, stream, rank):
     return {
         "name": NAMES["h264"],
         "run": run, "run_e2e": None, "verify": verify, "pixels": W * H * P, "alg_bytes": int(n_mb * 2.37e3),
-        "launches_per_step": 2 + 2 * G, "kernel": "h264_mc_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 4 * G, "kernel": "h264_mc_kernel_v2", "dtype": "int32 (u8 / int16 in, u8 out)", "h2d": 0, "d2h": 0,
         "l2": "%d pictures (%d MC partitions each) per step: %d MB of pixels + %d MB of coefficients, larger than the 126 MB L2" % (P, mc1.shape[0], P * W * H * 3 // 2 >> 20, d_coef0.numel() >> 20),
-        "keep": (d_refs, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed),
+        "keep": (d_refs, d_planes_g, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr, d_prog, side, refilled, consumed, chains, fork, joined),
     }
 
 
@@ -388,6 +419,35 @@ def make_dequant_idct_workload(torch, L, stream, rank):
         "run": run, "run_e2e": None, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * (IDCT_BYTES_PER_BLOCK + 4),
         "launches_per_step": 1, "kernel": "simple_idct_kernel<0,false,4,false,4>", "dtype": "int32 (int16 levels in, u8 out)",
         "h2d": 0, "d2h": 0, "l2": "3 rotating 196 MiB buffer sets", "keep": (d_blocks, d_rec, d_frame, t),
+    }
+
+
+def make_idct10_workload(torch, L, stream, rank):
+    """the 10-bit instance of IDCTDSPContext.idct_put (ff_simple_idct_put_10, bits_per_raw_sample 10): 2^20 blocks -> 8192x8192 16-bit
+    samples.  The blocks are modified in place (the C functions leave the row pass there): 384 B of traffic per block."""
+    from libav_b200 import synth
+    lib = L.lib
+    base = synth.dense_blocks(1 << 14, seed=21 + rank) >> 1
+    blocks_h = synth.tile_large(base, N_BLOCKS)
+    nbuf = 2
+    d_blocks0 = torch.from_numpy(blocks_h).cuda()
+    d_blocks = [d_blocks0.clone() for _ in range(nbuf)]
+    stride = TILES_PER_ROW * 16
+    i = np.arange(N_BLOCKS, dtype=np.uint64)
+    off = ((i // TILES_PER_ROW) * 8 * stride + (i % TILES_PER_ROW) * 16).astype(np.uint32)
+    d_off = torch.from_numpy(off.view(np.int32)).cuda()
+    d_frame = [torch.zeros(N_BLOCKS * 64, dtype=torch.int16, device="cuda") for _ in range(nbuf)]
+
+    def run(i):
+        k = i % nbuf
+        L.check(lib.ff_simple_idct10_batch_cuda(0, d_blocks[k].data_ptr(), d_frame[k].data_ptr(), d_off.data_ptr(), stride, N_BLOCKS, stream), "idct10")
+
+    return {
+        "name": "batched simple_idct_put_10 (10-bit), 2^20 int16 blocks per GPU -> 8192x8192 16-bit frame",
+        "run": run, "run_e2e": None, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * 384,
+        "launches_per_step": 1, "kernel": "simple_idct10_kernel", "dtype": "int32 (int16 in, u16 out)", "h2d": 0, "d2h": 0,
+        "l2": "2 rotating 384 MiB buffer sets (the row pass is written back over the coefficients, as the C functions leave it)",
+        "keep": (d_blocks0, d_blocks, d_off, d_frame),
     }
 
 
@@ -745,7 +805,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sws4k", choices=["sws4k", "h264", "idct_put", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft"])
+    ap.add_argument("--workload", default="sws4k", choices=["sws4k", "h264", "idct_put", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft", "idct10"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads and the CPU baselines")
     ap.add_argument("--no-verify", action="store_true", help="skip the post-timing comparison with the CPU checker")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
@@ -807,7 +867,7 @@ def main():
 
     makers = {"sws4k": make_sws_workload, "h264": make_h264_workload, "idct_put": make_idct_workload, "me": make_me_workload,
               "sws_up": make_sws_up_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload,
-              "fft": make_fft_workload, "h264_decide": make_h264_decide_workload}
+              "fft": make_fft_workload, "h264_decide": make_h264_decide_workload, "idct10": make_idct10_workload}
     if args.workload == "me" and world > 1:
         makers["me"] = make_me_sharded_workload
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])
@@ -834,7 +894,8 @@ def main():
                          "traffic": traffic_for(wl["kernel"]), "kernel": wl["kernel"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": wl["alg_bytes"]},
             "e2e": ({"value": wl["pixels"] * world / (e2e_sec / e2e_steps) / 1e6, "unit": "Mpixels/s",
-                     "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps} if e2e_sec else None),
+                     "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
+                     "host_threads": wl.get("e2e_streams", 1)} if e2e_sec else None),
             "gpu_launches": wl["launches_per_step"] * st * world, "verified": verified,
             "clocks": sampler.summary() if sampler else None, "dtype": wl["dtype"], "l2": wl["l2"],
         }

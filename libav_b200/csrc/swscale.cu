@@ -1131,6 +1131,7 @@ struct SwsCudaContext {
     int tileLumRows = 0, tileChrRows = 0;  // fused-tile general path: shared-memory line capacity; 0 = window too large, two passes
     // staging for the host-pointer sws_scale_cuda()
     uint8_t *d_src = nullptr, *d_dst = nullptr; size_t src_bytes = 0, dst_bytes = 0;
+    cudaStream_t streams[3] = {}; bool streams_ok = false;
     // slices (sws_scale_cuda_sliced): the source rows received so far, the next expected source row, the output rows already returned
     std::vector<uint8_t> sliceSrc[3]; int slicePitch[3] = { 0, 0, 0 }; int sliceNextY = 0, sliceDstY = 0;
 };
@@ -1138,6 +1139,7 @@ struct SwsCudaContext {
 static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
+    if (c->streams_ok) for (int i = 0; i < 3; i++) cudaStreamDestroy(c->streams[i]);
     cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
     delete c;
 }
@@ -2009,9 +2011,15 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0 ||
         (!rgb && (dstStride[1] < 0 || (!c->dstNV && dstStride[2] < 0))))
         return sws_scale_cuda_flipped(c, srcSlice, srcStride, srcSliceH, dst, dstStride);
-    ScratchLock lk;
-    cudaStream_t *st = scratch().streams();
-    if (!st) return 0;
+    // the context's own three streams: like the reference's SwsContext a context serves one thread at a time (swscale.c:393-398), and
+    // contexts of different threads run concurrently -- eight streams keep both PCIe directions busy where one leaves bubbles between
+    // the frames (the host-pointer call must return a finished picture)
+    if (!c->streams_ok) {
+        for (int i = 0; i < 3; i++)
+            if (cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) { set_error("sws_scale_cuda:streams", cudaGetLastError()); return 0; }
+        c->streams_ok = true;
+    }
+    cudaStream_t *st = c->streams;
     cudaStream_t s = st[0];
     const SwsGeometry &g = c->g;
     // device staging: tight, aligned pitches

@@ -103,6 +103,42 @@ void all_hooks_take_the_reference_types(IDCTDSPContext *a, FDCTDSPContext *b, Bl
     ff_mdct_init_cuda(l);
 }
 
+/* ---- MECmpContext.quant_psnr / bit / rd: called from ff_mpv_encode_init() after the quantiser, the matrices and the
+ *      codec's VLC length tables are in place (mpegvideo_enc.c:742-849).  The view holds pointers INTO the context, so the slots follow
+ *      qscale / mb_intra as the macroblock loop changes them. ---- */
+#include "libavcodec/dct.h"
+#include "libavcodec/mpegvideo.h"
+typedef struct FFMECmpEncView {
+    const int *qscale, *y_dc_scale, *h263_aic, *intra_quant_bias, *inter_quant_bias, *ac_esc_length;
+    int *mb_intra, *block_last_index;
+    int (*const *q_intra_matrix)[64], (*const *q_inter_matrix)[64];
+    const uint16_t *intra_matrix, *inter_matrix;
+    const uint8_t *scantable;
+    uint8_t *const *intra_ac_vlc_length, *const *intra_ac_vlc_last_length, *const *inter_ac_vlc_length, *const *inter_ac_vlc_last_length;
+    const uint8_t *const *luma_dc_vlc_length;
+    int fdct, dequant, idct_perm_none, plain_quantiser;
+} FFMECmpEncView;
+int ff_me_cmp_enc_init_cuda(MECmpContext *c, struct MpegEncContext *s, const FFMECmpEncView *view);
+int ff_mpv_encode_init_cuda(MpegEncContext *s)
+{
+    FFMECmpEncView v = {
+        .qscale = &s->qscale, .y_dc_scale = &s->y_dc_scale, .h263_aic = &s->h263_aic,
+        .intra_quant_bias = &s->intra_quant_bias, .inter_quant_bias = &s->inter_quant_bias, .ac_esc_length = &s->ac_esc_length,
+        .mb_intra = &s->mb_intra, .block_last_index = s->block_last_index,
+        .q_intra_matrix = &s->q_intra_matrix, .q_inter_matrix = &s->q_inter_matrix,
+        .intra_matrix = s->intra_matrix, .inter_matrix = s->inter_matrix, .scantable = s->intra_scantable.scantable,
+        .intra_ac_vlc_length = &s->intra_ac_vlc_length, .intra_ac_vlc_last_length = &s->intra_ac_vlc_last_length,
+        .inter_ac_vlc_length = &s->inter_ac_vlc_length, .inter_ac_vlc_last_length = &s->inter_ac_vlc_last_length,
+        .luma_dc_vlc_length = (const uint8_t *const *)&s->luma_dc_vlc_length,
+        .fdct = s->fdsp.fdct == ff_fdct_ifast ? 2 : s->fdsp.fdct == ff_jpeg_fdct_islow_8 ? 0 : -1,
+        .dequant = s->dct_unquantize_inter == s->dct_unquantize_h263_inter ? 3 :
+                   s->dct_unquantize_inter == s->dct_unquantize_mpeg2_inter ? 1 + !!(s->avctx->flags & AV_CODEC_FLAG_BITEXACT) : 0,
+        .idct_perm_none = s->idsp.perm_type == FF_IDCT_PERM_NONE,
+        .plain_quantiser = s->fast_dct_quantize == ff_dct_quantize_c && !s->dct_error_sum,
+    };
+    return ff_me_cmp_enc_init_cuda(&s->mecc, s, &v);      /* -1: the C functions ff_me_cmp_init() installed stay */
+}
+
 /* ---- libswscale: the whole-frame SwsFunc and the per-line slots ---- */
 static int swscale_cuda(SwsContext *c, const uint8_t *src[], int srcStride[], int srcSliceY, int srcSliceH, uint8_t *dst[], int dstStride[])
 {

@@ -317,10 +317,41 @@ int ff_h264_flush_pictures_cuda(const FFH264PictureWork *work /* host struct */,
  *          FDCTDSPContext.fdct the encoder context holds: 0 = ff_jpeg_fdct_islow_8, 2 = ff_fdct_ifast)
  * These three only dereference the MpegEncContext's DSP tables, so the batch call covers them; their table slots are
  * left to the C code (a slot cannot know which fdct the caller's context selected).  quant_psnr, bit and rd
- * (me_cmp.c:623-782) need the quantiser and VLC length tables of a live encoder and are not taken over. */
+ * (me_cmp.c:621-782) need the quantiser and VLC length tables of a live encoder: see ff_me_cmp_enc_batch_cuda below. */
 typedef struct FFMECmpRecord { uint32_t cur_off, ref_off; } FFMECmpRecord;
 int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
                          const FFMECmpRecord *recs, size_t n, int32_t *out, void *stream);
+
+/* quant_psnr / bit / rd (libavcodec/me_cmp.c:621-782: quant_psnr8x8_c, bit8x8_c, rd8x8_c and their 16-wide wrappers :883-885): the three
+ * metrics that run the encoder's own quantiser on the difference block -- s->fast_dct_quantize = ff_dct_quantize_c
+ * (libavcodec/mpegvideo_enc.c:773-777, :4371-4450: forward DCT, DC division, biased threshold quantiser in scan order) -- then count
+ * VLC bits from the codec's run / level length tables (bit, rd) and / or reconstruct through s->dct_unquantize_intra / _inter
+ * (libavcodec/mpegvideo.c:51-270) and the simple IDCT (quant_psnr, rd).  FFMECmpEncState = the MpegEncContext fields they read, by value
+ * (q_*_matrix = the row of s->q_intra_matrix / s->q_inter_matrix for `qscale`, as ff_convert_matrix() built it, mpegvideo_enc.c:84-160);
+ * FFMECmpVlcTables = the codec's static length tables (HOST pointers; [64 * 128] indexed UNI_AC_ENC_INDEX(run, level + 64), the DC table
+ * [512] indexed level + 256; may be NULL for quant_psnr, which reads none).  The IDCT is the table's own: FF_IDCT_PERM_NONE
+ * (what ff_idctdsp_init_cuda installs), so scantable serves the quantiser and the bit counter alike.
+ *   kind 14 quant_psnr (always quantises as an inter block, like the C code)   15 bit   16 rd;   sidx 0 = 16 wide (h 16 or 8), 1 = 8x8
+ *   out[i] = the slot's return value; last_index[i] (optional) = s->block_last_index[0] as the C function leaves it.
+ * A DC level outside the DC table (|level| > 255: impossible for 8-bit differences with dc_scale >= 1) is clamped to its ends. */
+typedef struct FFMECmpEncState {
+    int32_t fdct;                  /* s->fdsp.fdct: 0 ff_jpeg_fdct_islow_8, 2 ff_fdct_ifast */
+    int32_t dequant;               /* s->dct_unquantize_intra / _inter (mpegvideo_enc.c:1613-1622): 0 mpeg1, 1 mpeg2, 2 mpeg2 under
+                                      AV_CODEC_FLAG_BITEXACT (mismatch control on intra blocks too), 3 h263 */
+    int32_t qscale, mb_intra, y_dc_scale, h263_aic;
+    int32_t intra_quant_bias, inter_quant_bias, ac_esc_length;
+    int32_t q_intra_matrix[64], q_inter_matrix[64];
+    uint16_t intra_matrix[64], inter_matrix[64];   /* s->intra_matrix / s->inter_matrix (the inverse quantisers' side) */
+    uint8_t scantable[64];                         /* s->intra_scantable.scantable */
+} FFMECmpEncState;
+typedef struct FFMECmpVlcTables {
+    const uint8_t *intra_ac_vlc_length, *intra_ac_vlc_last_length, *inter_ac_vlc_length, *inter_ac_vlc_last_length, *luma_dc_vlc_length;
+} FFMECmpVlcTables;
+/* device-resident copy of one encoder state (one per (qscale, mb_intra) a batch uses); NULL + avb200_last_error() on failure */
+void *ff_me_cmp_enc_state_cuda(const FFMECmpEncState *state, const FFMECmpVlcTables *vlc);
+void ff_me_cmp_enc_state_free_cuda(void *enc_state);
+int ff_me_cmp_enc_batch_cuda(int kind, int sidx, const void *enc_state, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
+                             const FFMECmpRecord *recs, size_t n, int32_t *out, int32_t *last_index, void *stream);
 
 /* Exhaustive search (libavcodec/motion_est_template.c:620-655) for every 16x16 macroblock of rows [mb_y0, mb_y1):
  * candidates within +-range (16) clipped so the block stays inside the picture (get_limits, motion_est.c:517-548),
@@ -432,6 +463,24 @@ void ff_blockdsp_init_cuda(BlockDSPContext *c);   /* libavcodec/blockdsp.c:60-74
 void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth);
 /* libavcodec/me_cmp.c:895-944: every slot ff_me_cmp_init fills except the encoder-state metrics */
 void ff_me_cmp_init_cuda(MECmpContext *c);
+/* MECmpContext.quant_psnr[0..1] / bit[0..1] / rd[0..1] as slots.  They read a LIVE encoder context through `view`: host pointers to the
+ * fields of the MpegEncContext `s` the C functions read (and the two they write: mb_intra, block_last_index[0]), filled once by the glue
+ * with the reference's own headers (examples/reference_binding/dsp_init_cuda.c); every call snapshots them, so qscale / mb_intra may change
+ * between macroblocks like in the encoder loop.  `s` is only the key the slots find their view by (struct MpegEncContext stays opaque).
+ * Returns 0, or -1 (table untouched) for a state the kernels do not cover: a permuting IDCT, denoise_dct (s->dct_error_sum), trellis. */
+typedef struct FFMECmpEncView {
+    const int *qscale, *y_dc_scale, *h263_aic, *intra_quant_bias, *inter_quant_bias, *ac_esc_length;
+    int *mb_intra, *block_last_index;
+    int (*const *q_intra_matrix)[64], (*const *q_inter_matrix)[64];     /* &s->q_intra_matrix, &s->q_inter_matrix */
+    const uint16_t *intra_matrix, *inter_matrix;
+    const uint8_t *scantable;                                            /* s->intra_scantable.scantable */
+    uint8_t *const *intra_ac_vlc_length, *const *intra_ac_vlc_last_length, *const *inter_ac_vlc_length, *const *inter_ac_vlc_last_length;
+    const uint8_t *const *luma_dc_vlc_length;                            /* &s->intra_ac_vlc_length ... (codec init may set them later) */
+    int fdct, dequant;                                                   /* as in FFMECmpEncState (the glue compares function pointers) */
+    int idct_perm_none, plain_quantiser;                                 /* s->idsp.perm_type == FF_IDCT_PERM_NONE; fast_dct_quantize == ff_dct_quantize_c && !dct_error_sum */
+} FFMECmpEncView;
+int ff_me_cmp_enc_init_cuda(MECmpContext *c, struct MpegEncContext *s, const FFMECmpEncView *view);
+void ff_me_cmp_enc_uninit_cuda(struct MpegEncContext *s);
 /* libavcodec/h264dsp.c:57-143, h264qpel.c:36-89, h264chroma.c:32-55, hpeldsp.c:338-366.  bit_depth 8, and 9 / 10 (the reference's BIT_DEPTH > 8
  * instances: uint8_t * arguments point at uint16 samples, int16_t * at int32 coefficients, strides stay in bytes).  ff_h264dsp_init_cuda fills
  * every entry ff_h264dsp_init fills (mbaff loop filters and startcode_find_candidate included); chroma_format_idc > 1 selects the

@@ -76,6 +76,9 @@ PROTOTYPES = {
     "ff_mpeg_dequant_batch_cuda": (i32, [i32, vp, vp, vp, sz, vp]),
     "ff_mpeg_dequant_idct_batch_cuda": (i32, [i32, vp, vp, vp, vp, vp, pd, sz, i32, i32, vp]),
     "ff_me_cmp_batch_cuda": (i32, [i32, i32, i32, vp, vp, pd, i32, vp, sz, vp, vp]),
+    "ff_me_cmp_enc_state_cuda": (vp, [vp, vp]),
+    "ff_me_cmp_enc_state_free_cuda": (None, [vp]),
+    "ff_me_cmp_enc_batch_cuda": (i32, [i32, i32, vp, vp, vp, pd, i32, vp, sz, vp, vp, vp]),
     "ff_full_search_cuda": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "ff_hpel_batch_cuda": (i32, [vp, sz, vp, vp, pd, vp]),
     "ff_fdct_batch_cuda": (i32, [i32, vp, sz, vp]),
@@ -96,6 +99,8 @@ PROTOTYPES = {
     "ff_blockdsp_init_cuda": (None, [vp]),
     "ff_fdctdsp_init_cuda": (None, [vp, i32, i32, C.c_uint]),
     "ff_me_cmp_init_cuda": (None, [vp]),
+    "ff_me_cmp_enc_init_cuda": (i32, [vp, vp, vp]),
+    "ff_me_cmp_enc_uninit_cuda": (None, [vp]),
     "ff_h264dsp_init_cuda": (None, [vp, i32, i32]),
     "ff_h264qpel_init_cuda": (None, [vp, i32]),
     "ff_h264chroma_init_cuda": (None, [vp, i32]),

@@ -129,6 +129,28 @@ class FFMpegDequantTables(C.Structure):
                 ("raster_end", C.c_uint8 * 64), ("alternate_scan", C.c_int), ("h263_aic", C.c_int)]
 
 
+class FFMECmpEncState(C.Structure):
+    """include/avdsp_b200.h FFMECmpEncState: the MpegEncContext fields quant_psnr / bit / rd read (me_cmp.c:621-782)"""
+    _fields_ = [("fdct", C.c_int32), ("dequant", C.c_int32), ("qscale", C.c_int32), ("mb_intra", C.c_int32), ("y_dc_scale", C.c_int32),
+                ("h263_aic", C.c_int32), ("intra_quant_bias", C.c_int32), ("inter_quant_bias", C.c_int32), ("ac_esc_length", C.c_int32),
+                ("q_intra_matrix", C.c_int32 * 64), ("q_inter_matrix", C.c_int32 * 64), ("intra_matrix", C.c_uint16 * 64),
+                ("inter_matrix", C.c_uint16 * 64), ("scantable", C.c_uint8 * 64)]
+
+
+class FFMECmpVlcTables(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("intra_ac_vlc_length", "intra_ac_vlc_last_length", "inter_ac_vlc_length", "inter_ac_vlc_last_length",
+                                          "luma_dc_vlc_length")]
+
+
+class FFMECmpEncView(C.Structure):
+    """include/avdsp_b200.h FFMECmpEncView: host pointers into a live MpegEncContext"""
+    _fields_ = [(n, C.c_void_p) for n in ("qscale", "y_dc_scale", "h263_aic", "intra_quant_bias", "inter_quant_bias", "ac_esc_length", "mb_intra",
+                                          "block_last_index", "q_intra_matrix", "q_inter_matrix", "intra_matrix", "inter_matrix", "scantable",
+                                          "intra_ac_vlc_length", "intra_ac_vlc_last_length", "inter_ac_vlc_length", "inter_ac_vlc_last_length",
+                                          "luma_dc_vlc_length")] + \
+        [(n, C.c_int) for n in ("fdct", "dequant", "idct_perm_none", "plain_quantiser")]
+
+
 _p4 = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)
 _p8l = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_ssize_t)
 _p8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t)

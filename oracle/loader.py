@@ -16,6 +16,16 @@ REF_SIMD_PATH = os.path.join(_HERE, "_ref", "libavref_simd.so")
 
 vp, sz, i32, pd, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_ssize_t, C.c_double
 
+class OrcEncState(C.Structure):
+    """oracle_api.h OrcEncState: the MpegEncContext fields quant_psnr / bit / rd read (me_cmp.c:621-782)."""
+    _fields_ = [("fdct_sel", C.c_int32), ("dequant", C.c_int32), ("qscale", C.c_int32), ("mb_intra", C.c_int32), ("y_dc_scale", C.c_int32),
+                ("c_dc_scale", C.c_int32), ("h263_aic", C.c_int32), ("ac_pred", C.c_int32), ("alternate_scan", C.c_int32),
+                ("intra_quant_bias", C.c_int32), ("inter_quant_bias", C.c_int32), ("ac_esc_length", C.c_int32),
+                ("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64),
+                ("intra_ac_vlc_length", C.c_void_p), ("intra_ac_vlc_last_length", C.c_void_p), ("inter_ac_vlc_length", C.c_void_p),
+                ("inter_ac_vlc_last_length", C.c_void_p), ("luma_dc_vlc_length", C.c_void_p)]
+
+
 API = {
     "simple_idct_put": (None, [vp, pd, vp]),
     "simple_idct_add": (None, [vp, pd, vp]),
@@ -56,6 +66,8 @@ API = {
     "pred_table_fill": (i32, [i32, i32, vp, i32]),
     "mpeg_dequant": (None, [i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32]),
     "mpeg_scantables": (None, [i32, vp, vp]),
+    "me_cmp_quant": (i32, [i32, i32, vp, vp, vp, pd, i32, vp]),
+    "enc_qmatrices": (None, [vp, vp, vp, vp]),
     "h264_pred": (None, [i32, i32, vp, vp, i32, i32, pd]),
     "h264_pred_add": (None, [i32, i32, vp, vp, vp, i32, i32, pd]),
     "mpeg4_qpel": (None, [i32, i32, i32, vp, vp, pd]),

@@ -103,6 +103,25 @@ void ORC(mpeg_dequant)(int kind, int16_t *block, int n, int qscale, int last_ind
  * mpegvideo.c:299-317) for the zigzag (0) or alternate vertical (1) scan */
 void ORC(mpeg_scantables)(int alternate_scan, uint8_t *permutated, uint8_t *raster_end);
 
+/* ---- MECmpContext.quant_psnr / bit / rd (libavcodec/me_cmp.c:621-782): the three comparison functions that run the encoder's own
+ * quantiser (s->fast_dct_quantize = ff_dct_quantize_c, libavcodec/mpegvideo_enc.c:4371-4450), count VLC bits from the codec's
+ * length tables and / or reconstruct through s->dct_unquantize_* and the simple IDCT.  OrcEncState = the MpegEncContext fields they read.
+ *   kind 14 quant_psnr, 15 bit, 16 rd; sidx 0 = the 16-wide wrappers (h 16 or 8), 1 = 8x8 (h 8)
+ *   side[0] = s->block_last_index[0] after the call, side[1] = s->mb_intra after the call (quant_psnr clears it) */
+typedef struct OrcEncState {
+    int32_t fdct_sel;        /* s->fdsp.fdct: 0 ff_jpeg_fdct_islow_8 (FF_DCT_AUTO), 2 ff_fdct_ifast (FF_DCT_FASTINT) */
+    int32_t dequant;         /* s->dct_unquantize_intra / _inter (mpegvideo_enc.c:1613-1622): 0 mpeg1, 1 mpeg2, 2 mpeg2 with AV_CODEC_FLAG_BITEXACT, 3 h263 */
+    int32_t qscale, mb_intra, y_dc_scale, c_dc_scale, h263_aic, ac_pred, alternate_scan;
+    int32_t intra_quant_bias, inter_quant_bias, ac_esc_length;
+    uint16_t intra_matrix[64], inter_matrix[64];
+    const uint8_t *intra_ac_vlc_length, *intra_ac_vlc_last_length, *inter_ac_vlc_length, *inter_ac_vlc_last_length;   /* [64 * 128], UNI_AC_ENC_INDEX */
+    const uint8_t *luma_dc_vlc_length;                                                                               /* [512] */
+} OrcEncState;
+int ORC(me_cmp_quant)(int kind, int sidx, const OrcEncState *st, uint8_t *b1, uint8_t *b2, ptrdiff_t stride, int h, int32_t *side);
+/* s->q_intra_matrix[qscale] / s->q_inter_matrix[qscale] as ff_convert_matrix() builds them (mpegvideo_enc.c:84-160), and
+ * s->intra_scantable.scantable (the order the quantiser walks) */
+void ORC(enc_qmatrices)(const OrcEncState *st, int32_t *q_intra, int32_t *q_inter, uint8_t *scantable);
+
 /* Deblocking DECISIONS for one progressive 4:2:0 8-bit picture: what loop_filter() ->
  * fill_filter_caches() -> ff_h264_filter_mb() (libavcodec/h264_slice.c:2198-2262, :1972-2196,
  * libavcodec/h264_loopfilter.c:420-846) decide per macroblock -- which edges are filtered with which

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libslots_hostsim.so")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
     csrc = os.path.join(root, "libav_b200", "csrc")
-    srcs = [os.path.join(HERE, f) for f in ("slots_hostsim.cpp", "sws_slots_hostsim.cpp", "slots_hbd_hostsim.cpp", "idct10_hostsim.cpp", "h264pred_hbd_hostsim.cpp",
+    srcs = [os.path.join(HERE, f) for f in ("slots_hostsim.cpp", "sws_slots_hostsim.cpp", "slots_hbd_hostsim.cpp", "idct10_hostsim.cpp", "h264pred_hbd_hostsim.cpp", "me_cmp_enc_hostsim.cpp",
                                             "swscale_hostsim.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h"), os.path.join(HERE, "gen_launches.py")] + \
         [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))] + \
@@ -162,6 +162,39 @@ def test_fdct10(sim, refo):
         return blk
     idct10_cases.fdct10_cases(t, run_batch, refo)
     assert sim.avb200_last_error().decode() == ""
+
+
+def _enc_protos(lib):
+    lib.ff_me_cmp_enc_state_cuda.restype = C.c_void_p
+    lib.ff_me_cmp_enc_state_cuda.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ff_me_cmp_enc_state_free_cuda.argtypes = [C.c_void_p]
+    lib.ff_me_cmp_enc_batch_cuda.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ff_me_cmp_enc_init_cuda.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ff_me_cmp_enc_uninit_cuda.argtypes = [C.c_void_p]
+
+
+def test_me_cmp_quant_metrics_batch(sim, refo, orc):
+    """quant_psnr / bit / rd (libav_b200/csrc/me_cmp_enc.cu, host-compiled): the batched call against the compiled reference's me_cmp.c"""
+    import numpy as np
+    import enc_cases
+    _enc_protos(sim)
+
+    def run_batch(kind, sidx, handle, cur, ref, recs, h):      # host simulation: "device memory" is host memory
+        out, last = np.zeros(len(recs), np.int32), np.zeros(len(recs), np.int32)
+        assert sim.ff_me_cmp_enc_batch_cuda(kind, sidx, handle, cur.ctypes.data, ref.ctypes.data, cur.strides[0], h, recs.ctypes.data, len(recs),
+                                            out.ctypes.data, last.ctypes.data, None) == 0
+        return out, last
+    assert enc_cases.batch_cases(sim, run_batch, refo, orc, n=16) > 6000
+    assert sim.ff_me_cmp_enc_batch_cuda(13, 0, None, None, None, 0, 8, None, 0, None, None, None) == -1
+    sim.avb200_clear_error()
+
+
+def test_me_cmp_quant_metrics_slots(sim, refo, orc):
+    """ff_me_cmp_enc_init_cuda: MECmpContext.quant_psnr / bit / rd over a live (changing) encoder state, host-compiled"""
+    import enc_cases
+    _enc_protos(sim)
+    assert enc_cases.slot_cases(sim, refo, orc) > 800
+    sim.avb200_clear_error()
 
 
 @pytest.mark.parametrize("bits", [8, 9, 10])

@@ -352,3 +352,35 @@ def test_sws_scale_slices(gpu, refo):
             S.compare(gpu.lib, refo, sf, df, 64, 48, 64, 48, flags, plan)
             n += 1
     assert n > 100 and gpu.last_error() == ""
+
+
+def test_me_cmp_quant_metrics_batch(gpu, checker, orc):
+    """MECmpContext.quant_psnr / bit / rd (libav_b200/csrc/me_cmp_enc.cu): ff_me_cmp_enc_batch_cuda on device buffers, every encoder state x
+    metric x block size against the compiled reference's me_cmp.c:621-782 (with its own ff_dct_quantize_c / dct_unquantize_*_c)"""
+    import numpy as np
+    import enc_cases
+    lib = gpu.lib
+
+    def run_batch(kind, sidx, handle, cur, ref, recs, h):
+        out, last = np.zeros(len(recs), np.int32), np.zeros(len(recs), np.int32)
+        bufs = []
+        for a in (cur, ref, recs, out, last):
+            d = lib.avb200_malloc(a.nbytes)
+            assert d and lib.avb200_memcpy_h2d(d, a.ctypes.data, a.nbytes, None) == 0
+            bufs.append(d)
+        assert lib.ff_me_cmp_enc_batch_cuda(kind, sidx, handle, bufs[0], bufs[1], cur.strides[0], h, bufs[2], len(recs), bufs[3], bufs[4], None) == 0, gpu.last_error()
+        assert lib.avb200_memcpy_d2h(out.ctypes.data, bufs[3], out.nbytes, None) == 0 and lib.avb200_memcpy_d2h(last.ctypes.data, bufs[4], last.nbytes, None) == 0
+        assert lib.avb200_device_sync() == 0
+        for d in bufs:
+            lib.avb200_free(d)
+        return out, last
+    assert enc_cases.batch_cases(lib, run_batch, checker, orc, n=200) > 80000
+    assert lib.ff_me_cmp_enc_batch_cuda(13, 0, None, None, None, 0, 8, None, 0, None, None, None) == -1
+    lib.avb200_clear_error()
+
+
+def test_me_cmp_quant_metrics_slots(gpu, checker, orc):
+    """ff_me_cmp_enc_init_cuda: the six table entries over a live encoder state (return values and the context fields the C functions write)"""
+    import enc_cases
+    assert enc_cases.slot_cases(gpu.lib, checker, orc) > 800
+    assert gpu.last_error() == ""

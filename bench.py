@@ -445,7 +445,7 @@ def make_idct10_workload(torch, L, stream, rank):
     return {
         "name": "batched simple_idct_put_10 (10-bit), 2^20 int16 blocks per GPU -> 8192x8192 16-bit frame",
         "run": run, "run_e2e": None, "pixels": N_BLOCKS * 64, "alg_bytes": N_BLOCKS * 384,
-        "launches_per_step": 1, "kernel": "simple_idct10_kernel", "dtype": "int32 (int16 in, u16 out)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 1, "kernel": "simple_idct10_staged_kernel<0>", "dtype": "int32 (int16 in, u16 out)", "h2d": 0, "d2h": 0,
         "l2": "2 rotating 384 MiB buffer sets (the row pass is written back over the coefficients, as the C functions leave it)",
         "keep": (d_blocks0, d_blocks, d_off, d_frame),
     }

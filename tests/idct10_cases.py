@@ -47,14 +47,20 @@ def slot_cases(table, checker, seed=0):
     return n
 
 
-def batch_case(run_batch, checker, mode, n=5000, seed=1):
-    """run_batch(mode, blocks (n, 64) int16, frame (rows, 8 * tiles) uint16, dst_off uint32[n]) -> (blocks, frame) after the call"""
+def batch_case(run_batch, checker, mode, n=5000, seed=1, pad=4, shift=0):
+    """run_batch(mode, blocks (n, 64) int16, frame (rows, 8 * tiles) uint16, dst_off uint32[n]) -> (blocks, frame) after the call.
+    pad 4: a pitch that is not a multiple of 16 bytes (thread-per-block kernel); pad 8: 16-byte rows (the staged kernel), `shift` samples
+    of offset on every third block put those on its sample-store path"""
     rng = np.random.default_rng(seed + mode)
     blk = blocks(rng, n)
     tiles = 64
     rows = 8 * ((n + tiles - 1) // tiles)
-    frame = rng.integers(0, 1024, size=(rows, 8 * tiles + 4)).astype(np.uint16)
-    off = np.array([(i // tiles) * 8 * frame.strides[0] + (i % tiles) * 16 for i in range(n)], np.uint32)
+    frame = rng.integers(0, 1024, size=(rows, 8 * tiles + pad)).astype(np.uint16)
+    off = np.array([(i // tiles) * 8 * frame.strides[0] + (i % tiles) * 16 + (2 * shift if i % 3 == 1 and i % tiles < tiles - 1 else 0) for i in range(n)], np.uint32)
+    if shift:       # shifted blocks overlap their right neighbour: keep one of each pair (the C order would decide otherwise)
+        keep = np.array([i % 3 != 2 or i % tiles == 0 for i in range(n)])
+        blk, off = np.ascontiguousarray(blk[keep]), np.ascontiguousarray(off[keep])
+        n = len(blk)
     got_b, got_f = run_batch(mode, blk.copy(), frame.copy(), off)
     want_b, want_f = blk.copy(), frame.copy()
     for i in range(n):

@@ -145,6 +145,8 @@ def test_simple_idct10(sim, refo):
         return blk, frame
     for mode in range(3):
         idct10_cases.batch_case(run_batch, refo, mode)
+        idct10_cases.batch_case(run_batch, refo, mode, n=1003, pad=8)
+        idct10_cases.batch_case(run_batch, refo, mode, n=1000, pad=8, shift=1, seed=7)
     assert sim.ff_simple_idct10_batch_cuda(3, None, None, None, 0, 0, None) == -1
     sim.avb200_clear_error()
 

@@ -117,7 +117,10 @@ def test_simple_idct10(gpu, checker):
             lib.avb200_free(d)
         return blk, frame
     for mode in range(3):
-        idct10_cases.batch_case(run_batch, checker, mode)
+        idct10_cases.batch_case(run_batch, checker, mode)                       # pitch 1032: the thread-per-block kernel
+        idct10_cases.batch_case(run_batch, checker, mode, n=5003, pad=8)        # 16-byte rows: the staged kernel, ragged last group
+        idct10_cases.batch_case(run_batch, checker, mode, n=4000, pad=8, shift=1, seed=7)   # ... with blocks off the 16-byte grid
+        idct10_cases.batch_case(run_batch, checker, mode, n=100000, pad=8, seed=3)          # more groups than resident warps
     assert gpu.last_error() == ""
 
 

@@ -240,6 +240,22 @@ int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h,
 int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb,
                                uint8_t *cr, int linesize, int uvlinesize, uint32_t *progress, void *stream);
 
+/* The same three stages for 9 / 10-bit pictures (the BIT_DEPTH > 8 instances, libavcodec/bit_depth_template.c:49-67: uint16 samples,
+ * int32 coefficients -- coeffs / coeff_stride count int32 elements, 16 per block like the 8-bit layout; every pitch and every record
+ * offset stays in BYTES) and, for the residual and the motion compensation, chroma_format_idc 2 (4:2:2: 8 x 16 chroma macroblocks,
+ * h264_idct_add8_422 h264idct_template.c:216-236, chroma vectors at full vertical resolution h264_mb.c:287-316).  Records, order rules
+ * and picture stacking are those of the 8-bit calls above; alpha / beta / tc0 in FFH264DeblockMB are the 8-bit-scale table values the
+ * decisions produce (the filters scale them by 2^(bit_depth - 8) like h264dsp_template.c:110-113,240).  Field pictures of a frame are
+ * pictures in their own right here: pass the field's first row and twice the frame's pitch.  MBAFF frames are not covered. */
+int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264ResidualMB *mbs, size_t n, int32_t *coeffs,
+                                       size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
+                                       int uvlinesize, void *stream);
+int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs,
+                              uint8_t *dst_y, uint8_t *dst_cb, uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h,
+                              void *stream);
+int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma,
+                                   uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream);
+
 /* Deblocking DECISIONS: what loop_filter() -> fill_filter_caches() -> ff_h264_filter_mb()
  * (libavcodec/h264_slice.c:1972-2262, libavcodec/h264_loopfilter.c:438-846) decide for every macroblock of a
  * progressive 4:2:0 8-bit picture -- boundary strengths, averaged qp, alpha / beta / tc0 per edge -- computed on the

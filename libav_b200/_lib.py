@@ -76,6 +76,9 @@ PROTOTYPES = {
     "ff_mpeg_dequant_batch_cuda": (i32, [i32, vp, vp, vp, sz, vp]),
     "ff_mpeg_dequant_idct_batch_cuda": (i32, [i32, vp, vp, vp, vp, vp, pd, sz, i32, i32, vp]),
     "ff_me_cmp_batch_cuda": (i32, [i32, i32, i32, vp, vp, pd, i32, vp, sz, vp, vp]),
+    "ff_h264_idct_add_mb_batch_hbd_cuda": (i32, [i32, i32, vp, sz, vp, sz, vp, vp, vp, vp, i32, i32, vp]),
+    "ff_h264_mc_batch_hbd_cuda": (i32, [i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ff_h264_deblock_batch_hbd_cuda": (i32, [i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
     "ff_me_cmp_enc_state_cuda": (vp, [vp, vp]),
     "ff_me_cmp_enc_state_free_cuda": (None, [vp]),
     "ff_me_cmp_enc_batch_cuda": (i32, [i32, i32, vp, vp, vp, pd, i32, vp, sz, vp, vp, vp]),

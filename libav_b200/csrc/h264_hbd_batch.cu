@@ -1,0 +1,258 @@
+// libav_b200/csrc/h264_hbd_batch.cu -- the batched H.264 calls for 9 / 10-bit pictures (uint16 samples, int32 coefficients: the
+// BIT_DEPTH > 8 instances of libavcodec/bit_depth_template.c:49-67) and for chroma_format_idc 2 (4:2:2) content:
+//
+//   ff_h264_idct_add_mb_batch_hbd_cuda   h264_idct_add16 / add16intra / idct8_add4 / idct_add8 / idct_add8_422 per macroblock
+//                                        (libavcodec/h264idct_template.c:174-236), 4:2:0 and 4:2:2
+//   ff_h264_mc_batch_hbd_cuda            mc_dir_part() (libavcodec/h264_mb.c:204-320): H264QpelContext + H264ChromaContext put / avg with
+//                                        emulated_edge_mc, 4:2:0 and 4:2:2 (chroma rows at full vertical resolution, :287-316)
+//   ff_h264_deblock_batch_hbd_cuda       the loop filters of libavcodec/h264dsp_template.c:104-328 over whole pictures in the reference's
+//                                        serial raster order (h264_loopfilter.c:397-415), 4:2:0
+//
+// These are the FUNCTIONAL batched paths for that content, built from the per-sample arithmetic of h264dsp_hbd.cuh (the one the table
+// slots of slots_hbd.cu use); they are not shaped like the 8-bit kernels (h264_mc.cu / h264_residual.cu / h264_deblock.cu), which
+// live on packed bytes.  Mapping:
+//   residual   warp per macroblock, lane per transform block exactly as the C dispatchers iterate (lanes never communicate)
+//   MC         warp per partition record, lanes stride over its luma and chroma samples, every reference sample through a clamped fetch
+//              (= emulated_edge_mc); `put` records in pass 0, `avg` records in pass 1 (two ordered launches)
+//   deblock    one CTA per picture, its warps take macroblock rows round-robin and run them as a wavefront (a row stays two macroblocks
+//              behind the row above): progress counters live in SHARED memory, so no inter-CTA ordering, fence or dispatch-order
+//              assumption exists; all warps of a CTA are resident, rows are taken in increasing order, hence no deadlock.  Within a
+//              macroblock: 16 luma + 8 cb + 8 cr lanes filter the vertical edges line by line, then the horizontal ones column by
+//              column (h264_loopfilter.c:238-395 order per plane).
+// A picture of a batch starts `pic_h` luma rows after the previous one in the same planes (like the 8-bit calls).
+#include "h264dsp.cuh"
+#include "h264dsp_hbd.cuh"
+#include "../../include/avdsp_b200.h"
+
+namespace avb {
+
+namespace {
+
+using hbd::px;
+
+__device__ __forceinline__ px *at_bytes(uint8_t *plane, size_t off) { return reinterpret_cast<px *>(plane + off); }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+h264_residual_hbd_kernel(int bits, int c422, const FFH264ResidualMB *__restrict__ mbs, size_t n, int32_t *__restrict__ coeffs, size_t coeff_stride,
+                         const uint8_t *__restrict__ nnzc, uint8_t *__restrict__ luma, uint8_t *__restrict__ cb, uint8_t *__restrict__ cr, int ls, int uvls)
+{
+    using namespace hbd;
+    const int lane = threadIdx.x & 31;
+    const size_t mb = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (mb >= n) return;
+    const FFH264ResidualMB r = mbs[mb];
+    int32_t *gc = coeffs + mb * coeff_stride;
+    const uint8_t *nz = nnzc + mb * 120;
+    const int lsp = ls >> 1, uvlsp = uvls >> 1;                     // row distance in samples
+    if (lane < 16) {
+        if (r.luma_mode > 2) return;
+        const int i = lane;
+        px *d = at_bytes(luma, r.luma_off) + blk_x(i) + (size_t)blk_y(i) * lsp;
+        int32_t *b = gc + 16 * i;
+        const int nnz = nz[scan8_of(i)];
+        if (r.luma_mode == 0)      { if (nnz) { if (nnz == 1 && b[0]) dc_add(bits, d, b, lsp, 4); else idct4_add(bits, d, b, lsp); } }       // :174-183
+        else if (r.luma_mode == 1) { if (nnz) idct4_add(bits, d, b, lsp); else if (b[0]) dc_add(bits, d, b, lsp, 4); }                       // :185-191
+        else if ((i & 3) == 0 && nnz) { if (nnz == 1 && b[0]) dc_add(bits, d, b, lsp, 8); else idct8_add(bits, d, b, lsp); }                 // :193-202
+    } else if (r.chroma) {
+        // 4:2:0 (:204-214): blocks 16..19 / 32..35.  4:2:2 (:216-236): eight per plane; the lower four keep their coefficients at block i
+        // but are addressed through scan8[i + 4] / block_offset[i + 4] (rows 8..15 of the 8 x 16 chroma macroblock)
+        const int per = c422 ? 8 : 4, t = lane - 16;
+        if (t >= 2 * per) return;
+        const int plane = t / per, k = t % per, i = 16 + 16 * plane + k, e = k >= 4 ? i + 4 : i, ke = e & 15;
+        px *d = at_bytes(plane ? cr : cb, r.chroma_off) + blk_x(ke) + (size_t)blk_y(ke) * uvlsp;
+        int32_t *b = gc + 16 * i;
+        if (nz[scan8_of(e)]) idct4_add(bits, d, b, uvlsp); else if (b[0]) dc_add(bits, d, b, uvlsp, 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// clamped sample fetch = emulated_edge_mc (replicated borders); [y0, y0 + h) are the rows of the record's own picture
+struct EdgeFetch {
+    const px *p; int st, w, h, y0;
+    __device__ __forceinline__ int operator()(int x, int y) const { return p[(size_t)min(max(y, y0), y0 + h - 1) * st + min(max(x, 0), w - 1)]; }
+};
+__device__ __forceinline__ int tap6f(const EdgeFetch &S, int x, int y, int dx, int dy)
+{ return (S(x, y) + S(x + dx, y + dy)) * 20 - (S(x - dx, y - dy) + S(x + 2 * dx, y + 2 * dy)) * 5 + (S(x - 2 * dx, y - 2 * dy) + S(x + 3 * dx, y + 3 * dy)); }
+__device__ __forceinline__ int qh(int bits, const EdgeFetch &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 1, 0) + 16) >> 5, bits); }
+__device__ __forceinline__ int qv(int bits, const EdgeFetch &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 0, 1) + 16) >> 5, bits); }
+__device__ inline int qhv(int bits, const EdgeFetch &S, int x, int y)
+{
+    int t[6];
+    for (int k = 0; k < 6; k++) t[k] = tap6f(S, x, y + k - 2, 1, 0);
+    return hbd::clipb(((t[2] + t[3]) * 20 - (t[1] + t[4]) * 5 + (t[0] + t[5]) + 512) >> 10, bits);
+}
+// the sixteen quarter-sample positions (h264qpel_template.c:380-531)
+__device__ inline int qpel_at(int bits, const EdgeFetch &S, int x, int y, int fx, int fy)
+{
+    int a, b = -1;
+    if (!fx && !fy) a = S(x, y);
+    else if (!fy) { a = qh(bits, S, x, y); if (fx != 2) b = S(x + (fx == 3), y); }
+    else if (!fx) { a = qv(bits, S, x, y); if (fy != 2) b = S(x, y + (fy == 3)); }
+    else if (fx == 2 && fy == 2) a = qhv(bits, S, x, y);
+    else if (fx == 2) { a = qhv(bits, S, x, y); b = qh(bits, S, x, y + (fy == 3)); }
+    else if (fy == 2) { a = qhv(bits, S, x, y); b = qv(bits, S, x + (fx == 3), y); }
+    else { a = qh(bits, S, x, y + (fy == 3)); b = qv(bits, S, x + (fx == 3), y); }
+    return b < 0 ? a : (a + b + 1) >> 1;
+}
+
+__global__ void __launch_bounds__(128)
+h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
+                   uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph, int pass)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t ri = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFH264MCRecord r = recs[ri];
+    if ((r.avg != 0) != (pass != 0)) return;
+    const FFH264RefPlanes ref = refs[r.ref];
+    const int lsp = ls >> 1, uvlsp = uvls >> 1;
+    const int ly0 = ((int)r.y / ph) * ph;                                   // first luma row of the record's picture in the stacked planes
+    const int mx = (int)r.mvx + 4 * (int)r.x, my = (int)r.mvy + 4 * (int)r.y, w = r.w, h = r.h;
+    {   // ---- luma ----
+        const EdgeFetch S = { reinterpret_cast<const px *>(ref.y), lsp, pw, ph, ly0 };
+        px *d0 = reinterpret_cast<px *>(dy) + (size_t)r.y * lsp + r.x;
+        for (int i = lane; i < w * h; i += 32) {
+            const int x = i % w, y = i / w;
+            const int v = qpel_at(bits, S, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
+            px *d = d0 + (size_t)y * lsp + x;
+            *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+        }
+    }
+    {   // ---- chroma: eighth-sample bilinear (h264chroma_template.c:27-173); 4:2:2 keeps the luma's vertical resolution (h264_mb.c:287-316) ----
+        const int cw = w >> 1, ch = c422 ? h : h >> 1, cph = c422 ? ph : ph >> 1, cy0 = c422 ? ly0 : ly0 >> 1;
+        const int sx = mx >> 3, sy = c422 ? my >> 2 : my >> 3, fx = mx & 7, fy = c422 ? (my << 1) & 7 : my & 7;
+        const int dx0 = r.x >> 1, dy0 = c422 ? (int)r.y : r.y >> 1;
+        const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), Cc = (8 - fx) * fy, D = fx * fy;
+        for (int i = lane; i < 2 * cw * ch; i += 32) {
+            const int pl = i / (cw * ch), k = i % (cw * ch), x = k % cw, y = k / cw;
+            const EdgeFetch S = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
+            int v = A * S(sx + x, sy + y);
+            if (B) v += B * S(sx + x + 1, sy + y);
+            if (Cc) v += Cc * S(sx + x, sy + y + 1);
+            if (D) v += D * S(sx + x + 1, sy + y + 1);
+            v = (v + 32) >> 6;
+            px *d = reinterpret_cast<px *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
+            *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+        }
+    }
+}
+
+#ifndef AVB_HOSTSIM      // (the wavefront synchronises warps: not part of tests/hostsim/, GPU tests only)
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int DB_WARPS = 16;
+
+__global__ void __launch_bounds__(DB_WARPS * 32)
+h264_deblock_hbd_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
+{
+    using namespace hbd;
+    extern __shared__ int prog_s[];                                  // macroblocks finished per row of this CTA's picture
+    volatile int *prog = prog_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pic = blockIdx.x, sh = bits - 8;
+    for (int i = threadIdx.x; i < mb_h; i += blockDim.x) prog_s[i] = 0;
+    __syncthreads();
+    const int lsp = ls >> 1, uvlsp = uvls >> 1;
+    px *const Y = reinterpret_cast<px *>(luma) + (size_t)pic * mb_h * 16 * lsp;
+    px *const Cb = reinterpret_cast<px *>(cb) + (size_t)pic * mb_h * 8 * uvlsp, *const Cr = reinterpret_cast<px *>(cr) + (size_t)pic * mb_h * 8 * uvlsp;
+    const bool is_luma = lane < 16;
+    const int p = (lane - 16) >> 3, l = is_luma ? lane : (lane - 16) & 7;       // chroma plane, line / column inside the macroblock
+    for (int row = warp; row < mb_h; row += DB_WARPS) {
+        for (int x = 0; x < mb_w; x++) {
+            if (row > 0) {
+                // the row above must be done with macroblock x + 1: its left-edge filter still reads and writes columns 13..15 of the
+                // macroblock above this one (raster order of the reference)
+                const int need = min(x + 2, mb_w);
+                if (lane == 0) while (prog[row - 1] < need) { }
+                __syncwarp();
+                __threadfence_block();
+            }
+            const FFH264DeblockMB &P = mbs[((size_t)pic * mb_h + row) * mb_w + x];
+            px *const base = is_luma ? Y + (size_t)row * 16 * lsp + x * 16 : (p ? Cr : Cb) + (size_t)row * 8 * uvlsp + x * 8;
+            const int st = is_luma ? lsp : uvlsp;
+            for (int dir = 0; dir < 2; dir++) {
+                // dir 0: vertical edges, this lane's line; dir 1: horizontal edges, this lane's column
+                px *const line = dir == 0 ? base + (size_t)l * st : base + l;
+                const int across = dir == 0 ? 1 : st;
+                if (is_luma) {
+                    for (int e = 0; e < 4; e++) {
+                        const int a = P.alpha[dir][e], b = P.beta[dir][e];
+                        if (!a || !b) continue;
+                        px *q = line + (size_t)4 * e * across;
+                        if (P.intra[dir] >> e & 1) luma_intra_line(q, across, a << sh, b << sh);
+                        else { const int tc = P.tc0[dir][e][l >> 2]; if (tc >= 0) luma_line(bits, q, across, a << sh, b << sh, tc << sh); }       // h264dsp_template.c:110-113
+                    }
+                } else {
+                    for (int e = 0; e < 2; e++) {
+                        const int a = P.calpha[p][dir][e], b = P.cbeta[p][dir][e];
+                        if (!a || !b) continue;
+                        px *q = line + (size_t)4 * e * across;
+                        if (P.cintra[p][dir] >> e & 1) chroma_line(bits, q, across, a << sh, b << sh, 0, 1);
+                        else { const int tc = ((P.ctc0[p][dir][e][l >> 1] - 1) << sh) + 1; if (tc > 0) chroma_line(bits, q, across, a << sh, b << sh, tc, 0); }   // :240
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+            }
+            if (lane == 0) prog[row] = x + 1;
+        }
+    }
+}
+
+#endif
+
+bool hbd_args_ok(const char *where, int bit_depth, int chroma_format_idc, int ls, int uvls, const void *a, const void *b, const void *c)
+{
+    if (bit_depth != 9 && bit_depth != 10) { set_error_msg(where, "bit_depth must be 9 or 10 (8-bit pictures take the calls without _hbd)"); return false; }
+    if (chroma_format_idc != 1 && chroma_format_idc != 2) { set_error_msg(where, "chroma_format_idc must be 1 (4:2:0) or 2 (4:2:2)"); return false; }
+    if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)ls | (uintptr_t)uvls) & 1) { set_error_msg(where, "16-bit samples need even plane addresses and pitches"); return false; }
+    return true;
+}
+
+}  // namespace
+}  // namespace avb
+
+using namespace avb;
+
+extern "C" {
+
+int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264ResidualMB *mbs, size_t n, int32_t *coeffs, size_t coeff_stride,
+                                       const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
+{
+    const char *where = "ff_h264_idct_add_mb_batch_hbd_cuda";
+    if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (n && (!mbs || !coeffs || !nnzc || !luma || !cb || !cr)) { set_error_msg(where, "NULL argument"); return -1; }
+    if (!n) return 0;
+    AVB_LAUNCH(h264_residual_hbd_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, mbs, n, coeffs, coeff_stride, nnzc,
+                                                                                                            luma, cb, cr, linesize, uvlinesize);
+    return check_launch(where) ? -1 : 0;
+}
+
+int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y,
+                              uint8_t *dst_cb, uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h, void *stream)
+{
+    const char *where = "ff_h264_mc_batch_hbd_cuda";
+    if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, dst_y, dst_cb, dst_cr)) return -1;
+    if (n && (!recs || !refs || !dst_y || !dst_cb || !dst_cr)) { set_error_msg(where, "NULL argument"); return -1; }
+    if (pic_w <= 0 || pic_h <= 0 || (pic_w & 1) || (pic_h & 1)) { set_error_msg(where, "picture size must be positive and even"); return -1; }
+    if (!n) return 0;
+    for (int pass = 0; pass < 2; pass++)
+        AVB_LAUNCH(h264_mc_hbd_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr,
+                                                                                                          linesize, uvlinesize, pic_w, pic_h, pass);
+    return check_launch(where) ? -1 : 0;
+}
+
+#ifndef AVB_HOSTSIM
+int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr,
+                                   int linesize, int uvlinesize, void *stream)
+{
+    const char *where = "ff_h264_deblock_batch_hbd_cuda";
+    if (!hbd_args_ok(where, bit_depth, 1, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (!mbs || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
+    if (!n_pictures) return 0;
+    h264_deblock_hbd_kernel<<<(unsigned)n_pictures, DB_WARPS * 32, (size_t)mb_h * sizeof(int), (cudaStream_t)stream>>>(bit_depth, mbs, mb_w, mb_h, luma, cb, cr,
+                                                                                                                    linesize, uvlinesize);
+    return check_launch(where) ? -1 : 0;
+}
+#endif
+
+}  // extern "C"

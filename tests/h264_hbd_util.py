@@ -1,0 +1,138 @@
+"""9 / 10-bit (and 4:2:2) pictures for the batched H.264 calls (libav_b200/csrc/h264_hbd_batch.cu): generators and the picture-level
+checker that applies the CPU oracle's per-block functions (the reference's own BIT_DEPTH > 8 instances) in the reference's order.
+TEST INFRASTRUCTURE."""
+import ctypes as C
+
+import numpy as np
+
+from libav_b200 import synth
+from oracle.loader import ptr
+from h264_util import at, scan8
+
+
+def picture(mb_w, mb_h, bits, c422, seed):
+    rng = np.random.default_rng(seed)
+    w, h = 16 * mb_w, 16 * mb_h
+    ch = h if c422 else h // 2
+    return (rng.integers(0, 1 << bits, (h, w)).astype(np.uint16), rng.integers(0, 1 << bits, (ch, w // 2)).astype(np.uint16),
+            rng.integers(0, 1 << bits, (ch, w // 2)).astype(np.uint16))
+
+
+def block_offsets(ls, uvls, c422):
+    """block_offset[] in BYTES for 16-bit samples (h264_slice.c:486-493 with pixel_shift 1): luma 0..15, chroma 16.. / 32.. (4:2:2: the entries
+    ff_h264_idct_add8_422 reads, 16..19 and 24..27 per plane)"""
+    bo = np.zeros(48, dtype=np.int32)
+    for i in range(16):
+        bo[i] = 2 * 4 * ((i & 1) + 2 * ((i >> 2) & 1)) + 4 * (((i >> 1) & 1) + 2 * (i >> 3)) * ls
+    for i in range(4):
+        bo[16 + i] = bo[32 + i] = 2 * 4 * (i & 1) + 4 * ((i >> 1) & 1) * uvls
+        if c422:
+            bo[24 + i] = bo[40 + i] = 2 * 4 * (i & 1) + (8 + 4 * ((i >> 1) & 1)) * uvls
+    return bo
+
+
+def residual_work(mb_w, mb_h, bits, c422, y, cb, seed):
+    """records (byte offsets for these planes), int32 coefficients (n, 768), nnzc (n, 120)"""
+    rng = np.random.default_rng(seed)
+    n = mb_w * mb_h
+    rec = np.zeros(n, dtype=synth.RESIDUAL_DT)
+    mbx, mby = np.arange(n) % mb_w, np.arange(n) // mb_w
+    rec["luma_off"] = mby * 16 * y.strides[0] + mbx * 32
+    rec["chroma_off"] = mby * (16 if c422 else 8) * cb.strides[0] + mbx * 16
+    rec["luma_mode"] = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=n)
+    rec["chroma"] = rng.integers(0, 2, size=n)
+    coeffs = np.zeros((n, 768), dtype=np.int32)
+    nnzc = np.zeros((n, 120), dtype=np.uint8)
+    sc = 1 << (bits - 8)
+    chroma_blocks = [16, 17, 18, 19, 32, 33, 34, 35] + ([20, 21, 22, 23, 36, 37, 38, 39] if c422 else [])
+    for m in range(n):
+        mode = int(rec["luma_mode"][m])
+        blocks = list(range(0, 16, 4)) if mode == 2 else list(range(16))
+        for i in blocks + chroma_blocks:
+            sz = 64 if (mode == 2 and i < 16) else 16
+            kind = rng.integers(0, 4) if rng.random() < 0.75 else 0       # 0 none, 1 dc only (nnz 0), 2 dc (nnz 1), 3 full
+            if kind == 0:
+                continue
+            e = i + 4 if (i & 15) >= 4 and i >= 16 else i                  # 4:2:2 lower half: nnz lives at scan8[i + 4]
+            if kind in (1, 2):
+                coeffs[m, 16 * i] = rng.integers(-2000 * sc, 2000 * sc)
+                nnzc[m, scan8(e)] = 0 if kind == 1 else 1
+            else:
+                coeffs[m, 16 * i:16 * i + sz] = rng.integers(-300 * sc, 300 * sc, size=sz)
+                nnzc[m, scan8(e)] = rng.integers(2, 17)
+    return rec, coeffs, nnzc
+
+
+def oracle_residual(o, bits, c422, rec, coeffs, nnzc, y, cb, cr):
+    ls, uvls = y.strides[0], cb.strides[0]
+    bo = block_offsets(ls, uvls, c422)
+    for m in range(rec.shape[0]):
+        r = rec[m]
+        blk, nz = coeffs[m], nnzc[m]
+        if r["luma_mode"] < 3:
+            o.h264_hbd_idct_mb(bits, int(r["luma_mode"]), at(y, r["luma_off"]), None, ptr(bo), ptr(blk), ls, ptr(nz))
+        if r["chroma"]:
+            d2 = (C.c_void_p * 2)(cb.ctypes.data + int(r["chroma_off"]), cr.ctypes.data + int(r["chroma_off"]))
+            o.h264_hbd_idct_mb(bits, 4 if c422 else 3, None, d2, ptr(bo), ptr(blk), uvls, ptr(nz))
+
+
+def oracle_mc(o, bits, c422, rec, refs, y, cb, cr, pad=48):
+    """refs: list of (y, cb, cr) uint16 planes; emulated_edge_mc = edge-replicated padding of the reference planes"""
+    pr = [tuple(np.pad(p, pad, mode="edge") for p in r) for r in refs]
+    sizes = {16: 0, 8: 1, 4: 2, 2: 3}
+    for r in rec:
+        ry, rcb, rcr = pr[int(r["ref"])]
+        mx, my = int(r["mvx"]) + 4 * int(r["x"]), int(r["mvy"]) + 4 * int(r["y"])
+        w, h, avg = int(r["w"]), int(r["h"]), int(r["avg"])
+        mc = (mx & 3) + 4 * (my & 3)
+        n = min(w, h)
+        for (ox, oy) in [(a, b) for b in range(0, h, n) for a in range(0, w, n)]:     # square calls (h264_mb.c:248-250)
+            dst = at(y, (int(r["y"]) + oy) * y.strides[0] + 2 * (int(r["x"]) + ox))
+            win = np.zeros((n + 5, y.strides[0] // 2), np.uint16)                       # source window at the destination's pitch
+            sy, sx = (my >> 2) + oy - 2 + pad, (mx >> 2) + ox - 2 + pad
+            win[:, :n + 5] = ry[sy:sy + n + 5, sx:sx + n + 5]
+            o.h264_hbd_qpel(bits, avg, sizes[n], mc, dst, at(win, 2 * win.strides[0] + 4), y.strides[0])
+        cw, chh = w // 2, (h if c422 else h // 2)
+        sy, sx = ((my >> 2) if c422 else (my >> 3)) + pad, (mx >> 3) + pad
+        fy = ((my << 1) & 7) if c422 else (my & 7)
+        for (pl, rp) in ((cb, rcb), (cr, rcr)):
+            win = np.zeros((chh + 1, pl.strides[0] // 2), np.uint16)
+            win[:, :cw + 1] = rp[sy:sy + chh + 1, sx:sx + cw + 1]
+            dst = at(pl, (int(r["y"]) if c422 else int(r["y"]) // 2) * pl.strides[0] + 2 * (int(r["x"]) // 2))
+            o.h264_hbd_chroma(bits, avg, {8: 0, 4: 1, 2: 2}[cw], dst, ptr(win), pl.strides[0], chh, mx & 7, fy)
+
+
+def oracle_deblock(o, bits, rec, mb_w, mb_h, y, cb, cr):
+    ls, uvls = y.strides[0], cb.strides[0]
+    for m in range(mb_w * mb_h):
+        r = rec[m]
+        mbx, mby = m % mb_w, m // mb_w
+        for d in (0, 1):
+            for e in range(4):
+                a, b = int(r["alpha"][d, e]), int(r["beta"][d, e])
+                if a and b:
+                    off = (mby * 16 + (4 * e if d else 0)) * ls + 2 * (mbx * 16 + (0 if d else 4 * e))
+                    intra = (int(r["intra"][d]) >> e) & 1
+                    tc = np.ascontiguousarray(r["tc0"][d, e])
+                    o.h264_hbd_loop_filter(bits, (1 if d == 0 else 0) + (2 if intra else 0), at(y, off), ls, a, b, ptr(tc))
+                if not (e & 1):
+                    ce = e >> 1
+                    for p, pl in enumerate((cb, cr)):
+                        a, b = int(r["calpha"][p, d, ce]), int(r["cbeta"][p, d, ce])
+                        if a and b:
+                            off = (mby * 8 + (4 * ce if d else 0)) * uvls + 2 * (mbx * 8 + (0 if d else 4 * ce))
+                            intra = (int(r["cintra"][p, d]) >> ce) & 1
+                            tc = np.ascontiguousarray(r["ctc0"][p, d, ce])
+                            o.h264_hbd_loop_filter(bits, 4 + (1 if d == 0 else 0) + (2 if intra else 0), at(pl, off), uvls, a, b, ptr(tc))
+
+
+def smooth_picture(mb_w, mb_h, bits, seed):
+    """smooth content + noise so that a large share of the edges really gets filtered"""
+    rng = np.random.default_rng(seed)
+    sc = 1 << (bits - 8)
+
+    def plane(shape):
+        base = rng.integers(40, 200, size=(shape[0] // 8 + 1, shape[1] // 8 + 1))
+        up = np.kron(base, np.ones((8, 8), dtype=np.int64))[:shape[0], :shape[1]]
+        return np.clip(sc * (up + rng.integers(-6, 7, size=shape)) + rng.integers(0, sc, size=shape), 0, (1 << bits) - 1).astype(np.uint16)
+    return plane((16 * mb_h, 16 * mb_w)), plane((8 * mb_h, 8 * mb_w)), plane((8 * mb_h, 8 * mb_w))

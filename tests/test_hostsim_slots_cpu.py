@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libslots_hostsim.so")
 def sim(built):
     root = os.path.dirname(os.path.dirname(HERE))
     csrc = os.path.join(root, "libav_b200", "csrc")
-    srcs = [os.path.join(HERE, f) for f in ("slots_hostsim.cpp", "sws_slots_hostsim.cpp", "slots_hbd_hostsim.cpp", "idct10_hostsim.cpp", "h264pred_hbd_hostsim.cpp", "me_cmp_enc_hostsim.cpp",
+    srcs = [os.path.join(HERE, f) for f in ("slots_hostsim.cpp", "sws_slots_hostsim.cpp", "slots_hbd_hostsim.cpp", "idct10_hostsim.cpp", "h264pred_hbd_hostsim.cpp", "me_cmp_enc_hostsim.cpp", "h264_hbd_hostsim.cpp",
                                             "swscale_hostsim.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "cuda_runtime.h"), os.path.join(HERE, "gen_launches.py")] + \
         [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))] + \
@@ -204,4 +204,35 @@ def test_h264_pred_422(sim, refo, bits):
     """chroma_format_idc 2: the 8 x 16 entries of pred8x8[] / pred8x8_add[] (libav_b200/csrc/h264pred_hbd.cu, host-compiled), 8 / 9 / 10 bit"""
     import hbd_cases
     assert hbd_cases.pred422_compare(hbd_cases.Pred422Callee(sim.hostsim_h264_pred_install_422), refo, bits, seed=2) > 150
+    assert sim.avb200_last_error().decode() == ""
+
+
+@pytest.mark.parametrize("c422", [0, 1])
+@pytest.mark.parametrize("bits", [9, 10])
+def test_h264_hbd_batch_residual_and_mc(sim, refo, bits, c422):
+    """ff_h264_idct_add_mb_batch_hbd_cuda / ff_h264_mc_batch_hbd_cuda (libav_b200/csrc/h264_hbd_batch.cu, host-compiled) on 9 / 10-bit pictures,
+    4:2:0 and 4:2:2, against the compiled reference's BIT_DEPTH > 8 functions applied in the reference's order"""
+    import numpy as np
+    import h264_hbd_util as hh
+    from libav_b200 import synth
+    sim.ff_h264_idct_add_mb_batch_hbd_cuda.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]
+    sim.ff_h264_mc_batch_hbd_cuda.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
+    for mb_w, mb_h in ((3, 2), (7, 5)):
+        y, cb, cr = hh.picture(mb_w, mb_h, bits, c422, seed=5)
+        rec, coeffs, nnzc = hh.residual_work(mb_w, mb_h, bits, c422, y, cb, seed=mb_w + bits)
+        wy, wcb, wcr, wco = y.copy(), cb.copy(), cr.copy(), coeffs.copy()
+        hh.oracle_residual(refo, bits, c422, rec, wco, nnzc, wy, wcb, wcr)
+        assert sim.ff_h264_idct_add_mb_batch_hbd_cuda(bits, 1 + c422, rec.ctypes.data, len(rec), coeffs.ctypes.data, 768, nnzc.ctypes.data, y.ctypes.data,
+                                                      cb.ctypes.data, cr.ctypes.data, y.strides[0], cb.strides[0], None) == 0
+        assert np.array_equal(y, wy) and np.array_equal(cb, wcb) and np.array_equal(cr, wcr) and np.array_equal(coeffs, wco)
+        refs = [hh.picture(mb_w, mb_h, bits, c422, seed=11), hh.picture(mb_w, mb_h, bits, c422, seed=12)]
+        mrec = synth.h264_mc_work(mb_w, mb_h, seed=mb_h + bits, max_mv=64 if mb_w > 4 else 24, avg_second=True)
+        y, cb, cr = hh.picture(mb_w, mb_h, bits, c422, seed=13)
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hh.oracle_mc(refo, bits, c422, mrec, refs, wy, wcb, wcr)
+        planes = np.array([[p.ctypes.data for p in r] for r in refs], dtype=np.uint64)
+        assert sim.ff_h264_mc_batch_hbd_cuda(bits, 1 + c422, mrec.ctypes.data, len(mrec), planes.ctypes.data, y.ctypes.data, cb.ctypes.data, cr.ctypes.data,
+                                             y.strides[0], cb.strides[0], 16 * mb_w, 16 * mb_h, None) == 0
+        assert np.array_equal(y, wy), "luma"
+        assert np.array_equal(cb, wcb) and np.array_equal(cr, wcr), "chroma"
     assert sim.avb200_last_error().decode() == ""

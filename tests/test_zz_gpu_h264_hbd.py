@@ -1,0 +1,90 @@
+"""GPU parity for the batched H.264 calls on 9 / 10-bit and 4:2:2 pictures (libav_b200/csrc/h264_hbd_batch.cu) against the CPU oracle's
+BIT_DEPTH > 8 instances applied macroblock by macroblock in the reference's order (tests/h264_hbd_util.py).  Sorted last: written after the
+rest of the suite had been green on a B200."""
+import numpy as np
+import pytest
+
+from libav_b200 import synth
+import h264_hbd_util as hh
+
+pytestmark = pytest.mark.gpu
+SIZES = [(3, 2), (7, 5), (20, 12)]
+
+
+def _dev(a):
+    from libav_b200 import device
+    return device.DevBuf.from_numpy(a)
+
+
+@pytest.mark.parametrize("c422", [0, 1])
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("mb_w,mb_h", SIZES)
+def test_residual_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
+    from libav_b200 import device
+    y, cb, cr = hh.picture(mb_w, mb_h, bits, c422, seed=5)
+    rec, coeffs, nnzc = hh.residual_work(mb_w, mb_h, bits, c422, y, cb, seed=mb_w + bits)
+    wy, wcb, wcr, wco = y.copy(), cb.copy(), cr.copy(), coeffs.copy()
+    hh.oracle_residual(checker, bits, c422, rec, wco, nnzc, wy, wcb, wcr)
+    assert not np.array_equal(wy, y) and not np.array_equal(wcb, cb)
+    d = [_dev(x) for x in (rec, coeffs, nnzc, y, cb, cr)]
+    gpu.check(gpu.lib.ff_h264_idct_add_mb_batch_hbd_cuda(bits, 1 + c422, d[0].ptr, rec.shape[0], d[1].ptr, 768, d[2].ptr, d[3].ptr, d[4].ptr, d[5].ptr,
+                                                         y.strides[0], cb.strides[0], None))
+    device.sync()
+    assert np.array_equal(d[3].download(np.uint16, y.shape), wy)
+    assert np.array_equal(d[4].download(np.uint16, cb.shape), wcb)
+    assert np.array_equal(d[5].download(np.uint16, cr.shape), wcr)
+    assert np.array_equal(d[1].download(np.int32, coeffs.shape), wco)      # consumed coefficients are zeroed identically
+
+
+@pytest.mark.parametrize("c422", [0, 1])
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("mb_w,mb_h", SIZES)
+def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
+    from libav_b200 import device
+    refs = [hh.picture(mb_w, mb_h, bits, c422, seed=11), hh.picture(mb_w, mb_h, bits, c422, seed=12)]
+    rec = synth.h264_mc_work(mb_w, mb_h, seed=mb_h + bits, max_mv=64 if mb_w > 4 else 24, avg_second=True)
+    y, cb, cr = hh.picture(mb_w, mb_h, bits, c422, seed=13)
+    wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+    hh.oracle_mc(checker, bits, c422, rec, refs, wy, wcb, wcr)
+    dref = [[_dev(p) for p in r] for r in refs]
+    planes = np.array([[p.ptr for p in r] for r in dref], dtype=np.uint64)
+    d_planes, d_rec = _dev(planes), _dev(rec)
+    dy, dcb, dcr = _dev(y), _dev(cb), _dev(cr)
+    gpu.check(gpu.lib.ff_h264_mc_batch_hbd_cuda(bits, 1 + c422, d_rec.ptr, rec.shape[0], d_planes.ptr, dy.ptr, dcb.ptr, dcr.ptr, y.strides[0], cb.strides[0],
+                                                16 * mb_w, 16 * mb_h, None))
+    device.sync()
+    assert np.array_equal(dy.download(np.uint16, y.shape), wy)
+    assert np.array_equal(dcb.download(np.uint16, cb.shape), wcb)
+    assert np.array_equal(dcr.download(np.uint16, cr.shape), wcr)
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("mb_w,mb_h,slices,P", [(3, 2, 1, 1), (7, 5, 4, 2), (20, 12, 1, 3), (40, 36, 8, 2)])
+def test_deblock_batch_hbd(gpu, checker, mb_w, mb_h, slices, P, bits):
+    """P stacked pictures, rows of one picture as a wavefront inside one CTA: every picture must equal its own serial result"""
+    from libav_b200 import device
+    ys, cbs, crs, recs, want = [], [], [], [], []
+    for k in range(P):
+        y, cb, cr = hh.smooth_picture(mb_w, mb_h, bits, seed=100 * mb_w + k)
+        rec = synth.h264_deblock_work(mb_w, mb_h, seed=slices + k, slices=slices)
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hh.oracle_deblock(checker, bits, rec, mb_w, mb_h, wy, wcb, wcr)
+        assert not np.array_equal(wy, y) and not np.array_equal(wcb, cb)
+        ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); want.append((wy, wcb, wcr))
+    Y, CB, CR, R = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs), np.concatenate(recs)
+    d_rec, dy, dcb, dcr = _dev(R), _dev(Y), _dev(CB), _dev(CR)
+    gpu.check(gpu.lib.ff_h264_deblock_batch_hbd_cuda(bits, d_rec.ptr, mb_w, mb_h, P, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], None))
+    device.sync()
+    gy, gcb, gcr = dy.download(np.uint16, Y.shape), dcb.download(np.uint16, CB.shape), dcr.download(np.uint16, CR.shape)
+    for k in range(P):
+        assert np.array_equal(gy[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][0]), k
+        assert np.array_equal(gcb[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][1]), k
+        assert np.array_equal(gcr[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][2]), k
+
+
+def test_hbd_refusals(gpu):
+    lib = gpu.lib
+    assert lib.ff_h264_idct_add_mb_batch_hbd_cuda(8, 1, None, 0, None, 768, None, None, None, None, 64, 32, None) == -1
+    assert lib.ff_h264_mc_batch_hbd_cuda(10, 3, None, 0, None, None, None, None, 64, 32, 16, 16, None) == -1
+    assert lib.ff_h264_deblock_batch_hbd_cuda(10, None, 1, 1, 1, None, None, None, 64, 32, None) == -1
+    lib.avb200_clear_error()

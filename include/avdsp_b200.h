@@ -270,7 +270,8 @@ int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, in
  *       ref2frm[list][2 + ref_index] = identity of the referenced frame, entries 0/1 = -1); at most 32 slice numbers
  *   chroma_qp_table: PPS.chroma_qp_table[2][64] (h264_ps.h:124)
  * Pictures of a batch are stacked row-wise; no edge is filtered across a picture boundary.
- * Not covered: MBAFF / field pictures, 4:2:2 / 4:4:4, high bit depth (the reference's other branches). */
+ * Field pictures (PAFF) are covered through field_picture; not covered: MBAFF frames, the chroma edges of 4:2:2 / 4:4:4 (the records
+ * themselves are bit-depth agnostic: ff_h264_deblock_batch_hbd_cuda takes them for 9 / 10-bit pictures). */
 typedef struct FFH264DeblockSlice {
     int32_t alpha_c0_offset, beta_offset;   /* sl->slice_alpha_c0_offset, sl->slice_beta_offset */
     int32_t deblocking_filter;              /* 0 off, 1 every edge, 2 not across slice boundaries */
@@ -290,6 +291,9 @@ typedef struct FFH264DeblockInfo {
     int n_slices;
     const uint8_t  *chroma_qp_table;
     int cabac, transform_8x8_mode;          /* PPS.cabac, PPS.transform_8x8_mode */
+    int field_picture;                      /* h->picture_structure != PICT_FRAME: the pictures are fields (every mb_type carries
+                                               MB_TYPE_INTERLACED): vertical vector limit 2, bS 3 on horizontal intra macroblock edges
+                                               (h264_loopfilter.c:551-557,723) */
 } FFH264DeblockInfo;
 int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info /* host struct */, FFH264DeblockMB *out, void *stream);
 

@@ -24,7 +24,7 @@ __constant__ uint8_t c_tc0[52][3] = {
     {1,1,2},{1,1,2},{1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},
     {4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20},{11,15,23},{13,17,25} };
 
-enum : uint32_t { T_INTRA = 7, T_16x16 = 8, T_8x16 = 32, T_DCT8 = 0x01000000 };
+enum : uint32_t { T_INTRA = 7, T_16x16 = 8, T_8x16 = 32, T_INTERLACED = 0x80, T_DCT8 = 0x01000000 };
 __device__ __forceinline__ uint32_t uses_list(uint32_t t, int l) { return t & (0x3000u << (2 * l)); }
 
 struct Blk { int nz, ref0, ref1; int mv0, mv1; };          // mv = packed (x, y) int16 pair
@@ -61,22 +61,22 @@ __device__ __forceinline__ Blk fetch_block(const LfPic &p, int xy, int bx4, int 
     return b;
 }
 
-__device__ __forceinline__ int mv_far(int a, int b)          // |dx| >= 4 or |dy| >= 4 (frame macroblocks: mvy_limit 4)
+__device__ __forceinline__ int mv_far(int a, int b, int ylim)    // |dx| >= 4 or |dy| >= mvy_limit (4; 2 for the macroblocks of a field, h264_loopfilter.c:723)
 {
     const int dx = lo16s(a) - lo16s(b), dy = hi16s(a) - hi16s(b);
-    return (abs(dx) >= 4) | (abs(dy) >= 4);
+    return (abs(dx) >= 4) | (abs(dy) >= ylim);
 }
 
 // check_mv(), h264_loopfilter.c:438-469
-__device__ __forceinline__ int motion_differs(const Blk &a, const Blk &b, int lists)
+__device__ __forceinline__ int motion_differs(const Blk &a, const Blk &b, int lists, int ylim)
 {
     int v = a.ref0 != b.ref0;
-    if (!v && a.ref0 != -1) v = mv_far(a.mv0, b.mv0);
+    if (!v && a.ref0 != -1) v = mv_far(a.mv0, b.mv0, ylim);
     if (lists == 2) {
-        if (!v) v = (a.ref1 != b.ref1) | mv_far(a.mv1, b.mv1);
+        if (!v) v = (a.ref1 != b.ref1) | mv_far(a.mv1, b.mv1, ylim);
         if (v) {
             if ((a.ref0 != b.ref1) | (a.ref1 != b.ref0)) return 1;
-            return mv_far(a.mv0, b.mv1) | mv_far(a.mv1, b.mv0);
+            return mv_far(a.mv0, b.mv1, ylim) | mv_far(a.mv1, b.mv0, ylim);
         }
     }
     return v;
@@ -137,6 +137,7 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
         const bool is_intra = type & T_INTRA;
         const int edges = (mask_edge == 3 && !is_intra && !(p.i.cbp_table[xy] & 15)) ? 1 : 4;
         const uint32_t par0 = type & (T_16x16 | (T_8x16 >> dir));
+        const int ylim = (type & T_INTERLACED) ? 2 : 4;
         const int cq0 = p.i.chroma_qp_table[qp], cq1 = p.i.chroma_qp_table[64 + qp];
         const int bx4 = 4 * x, by4 = 4 * row, nbx4 = dir ? bx4 : bx4 - 4, nby4 = dir ? by4 - 4 : by4;
         for (int e = 0; e < edges; e++) {
@@ -144,7 +145,8 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
             if (e && (type & T_DCT8) && (e & 1)) continue;
             int bS[4];
             if (e == 0 && ((type | mt) & T_INTRA)) {
-                bS[0] = bS[1] = bS[2] = bS[3] = 4;
+                // 4, but 3 across the horizontal macroblock edges of a field picture (h264_loopfilter.c:551-557)
+                bS[0] = bS[1] = bS[2] = bS[3] = (((type | mt) & T_INTERLACED) && !(p.i.field_picture && dir == 0)) ? 3 : 4;
             } else if (is_intra) {
                 bS[0] = bS[1] = bS[2] = bS[3] = 3;
             } else {
@@ -154,14 +156,14 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
                     const Blk a = fetch_block(p, xy, bx4, by4, dir ? 0 : e, dir ? e : 0, type, 0);
                     const Blk b = e ? fetch_block(p, xy, bx4, by4, dir ? 0 : e - 1, dir ? e - 1 : 0, type, 0)
                                     : fetch_block(p, nxy, nbx4, nby4, dir ? 0 : 3, dir ? 3 : 0, mt, dir ? 1 : 2);
-                    whole = motion_differs(a, b, lists);
+                    whole = motion_differs(a, b, lists, ylim);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const Blk a = fetch_block(p, xy, bx4, by4, dir ? k : e, dir ? e : k, type, 0);
                     const Blk b = e ? fetch_block(p, xy, bx4, by4, dir ? k : e - 1, dir ? e - 1 : k, type, 0)
                                     : fetch_block(p, nxy, nbx4, nby4, dir ? k : 3, dir ? 3 : k, mt, dir ? 1 : 2);
-                    bS[k] = (a.nz | b.nz) ? 2 : whole >= 0 ? whole : motion_differs(a, b, lists);
+                    bS[k] = (a.nz | b.nz) ? 2 : whole >= 0 ? whole : motion_differs(a, b, lists, ylim);
                 }
             }
             if (!(bS[0] + bS[1] + bS[2] + bS[3])) continue;

@@ -141,6 +141,9 @@ int ORC(h264_deblock_params)(int mb_w, int mb_h, const uint32_t *mb_type, const 
                              const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
                              const int8_t *ref0, const int8_t *ref1, const int32_t *slice_params, int n_slices,
                              const uint8_t *chroma_qp_table, int cabac, int transform_8x8_mode, uint8_t *out);
+/* the pictures of the following h264_deblock_params / h264_deblock_picture_with calls are fields (h->picture_structure != PICT_FRAME; their
+ * mb_type entries must carry MB_TYPE_INTERLACED, 0x80): mvy_limit 2, bS 3 on horizontal intra macroblock edges (h264_loopfilter.c:551-557,723) */
+void ORC(h264_deblock_picture_structure)(int field_picture);
 /* widx: 0..3 = width 16,8,4,2 */
 void ORC(h264_weight)(int widx, uint8_t *block, int stride, int height, int log2_denom,
                       int weight, int offset);

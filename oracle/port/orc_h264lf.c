@@ -16,7 +16,12 @@
 #include <string.h>
 #include "../oracle_api.h"
 
-enum { T_INTRA = 7, T_16x16 = 8, T_16x8 = 16, T_8x16 = 32, T_DCT8 = 0x01000000 };
+enum { T_INTRA = 7, T_16x16 = 8, T_16x8 = 16, T_8x16 = 32, T_INTERLACED = 0x80, T_DCT8 = 0x01000000 };
+
+/* h->picture_structure != PICT_FRAME for the pictures that follow (PAFF field pictures: every macroblock type carries MB_TYPE_INTERLACED) */
+static int g_field_picture;
+void orc_h264_deblock_picture_structure(int field_picture) { g_field_picture = field_picture != 0; }
+static int g_ylim = 4;          /* mvy_limit of the macroblock being decided (h264_loopfilter.c:723) */
 #define USES(t, l) ((t) & (0x3000 << (2 * (l))))
 
 static const uint8_t alpha_std[52] = {
@@ -68,20 +73,21 @@ static Blk block_of(const Pic *p, int x, int y, int bx, int by, uint32_t type, i
 }
 
 static int far(int a, int b) { int d = a - b; return d >= 4 || d <= -4; }
+static int far_y(int a, int b) { int d = a - b; return d >= g_ylim || d <= -g_ylim; }
 
 /* check_mv(), h264_loopfilter.c:438-469 */
 static int motion_differs(const Blk *a, const Blk *b, int list_count)
 {
     int v = a->ref[0] != b->ref[0];
     if (!v && a->ref[0] != -1)
-        v = far(a->mvx[0], b->mvx[0]) | far(a->mvy[0], b->mvy[0]);
+        v = far(a->mvx[0], b->mvx[0]) | far_y(a->mvy[0], b->mvy[0]);
     if (list_count == 2) {
         if (!v)
-            v = (a->ref[1] != b->ref[1]) | far(a->mvx[1], b->mvx[1]) | far(a->mvy[1], b->mvy[1]);
+            v = (a->ref[1] != b->ref[1]) | far(a->mvx[1], b->mvx[1]) | far_y(a->mvy[1], b->mvy[1]);
         if (v) {
             if ((a->ref[0] != b->ref[1]) | (a->ref[1] != b->ref[0]))
                 return 1;
-            return far(a->mvx[0], b->mvx[1]) | far(a->mvy[0], b->mvy[1]) | far(a->mvx[1], b->mvx[0]) | far(a->mvy[1], b->mvy[0]);
+            return far(a->mvx[0], b->mvx[1]) | far_y(a->mvy[0], b->mvy[1]) | far(a->mvx[1], b->mvx[0]) | far_y(a->mvy[1], b->mvy[0]);
         }
     }
     return v;
@@ -154,8 +160,10 @@ int orc_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
                     int bS[4], sum = 0;
                     if (e == 0 && !mt) continue;
                     if (e && (type & T_DCT8) && (e & 1)) continue;
+                    g_ylim = (type & T_INTERLACED) ? 2 : 4;
                     if (e == 0 && ((type | mt) & T_INTRA)) {
-                        bS[0] = bS[1] = bS[2] = bS[3] = 4;
+                        /* 3 across the horizontal macroblock edges of a field picture, 4 otherwise (h264_loopfilter.c:551-557) */
+                        bS[0] = bS[1] = bS[2] = bS[3] = (((type | mt) & T_INTERLACED) && !(g_field_picture && dir == 0)) ? 3 : 4;
                     } else if (type & T_INTRA) {
                         bS[0] = bS[1] = bS[2] = bS[3] = 3;
                     } else {

@@ -152,6 +152,11 @@ static int gather_caches(const H264Context *h, H264SliceContext *sl, int mb_type
     return 0;
 }
 
+/* PAFF field pictures: h->picture_structure for the pictures that follow (the caller's mb_type entries then carry MB_TYPE_INTERLACED, as
+ * ff_h264_decode_mb_* leave them in a field picture); MBAFF is not driven */
+static int g_field_picture;
+void ref_h264_deblock_picture_structure(int field_picture) { g_field_picture = field_picture != 0; }
+
 /* table == NULL: the recorders above (decisions into `out`).  table != NULL: an H264DSPContext whose loop-filter entries are called on the
  * real picture planes Y / Cb / Cr (pitches ls / uvls) with the pointers loop_filter() passes (h264_slice.c:2198-2262), `out` unused. */
 static int run_driver(const H264DSPContext *table, uint8_t *Y, uint8_t *Cb, uint8_t *Cr, int ls, int uvls,
@@ -192,7 +197,7 @@ static int run_driver(const H264DSPContext *table, uint8_t *Y, uint8_t *Cb, uint
     h->mb2b_xy = t_b + pad;
     h->cur_pic.motion_val[0] = (int16_t (*)[2])mv0; h->cur_pic.motion_val[1] = (int16_t (*)[2])mv1;
     h->cur_pic.ref_index[0] = t_ref[0] + 4 * pad; h->cur_pic.ref_index[1] = t_ref[1] + 4 * pad;
-    h->picture_structure = PICT_FRAME;
+    h->picture_structure = g_field_picture ? PICT_TOP_FIELD : PICT_FRAME;
     pps->cabac = cabac; pps->transform_8x8_mode = transform_8x8_mode;
     memcpy(pps->chroma_qp_table, chroma_qp_table, 128);
     pps->chroma_qp_diff = memcmp(chroma_qp_table, chroma_qp_table + 64, 64) != 0;

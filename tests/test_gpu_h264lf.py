@@ -20,7 +20,7 @@ def _dev(a):
     return device.DevBuf.from_numpy(np.ascontiguousarray(a))
 
 
-def gpu_params(gpu, infos):
+def gpu_params(gpu, infos, field=0):
     """infos: list of per-picture dicts of equal geometry (stacked row-wise into one call)"""
     from libav_b200 import device
     d0 = infos[0]
@@ -32,10 +32,26 @@ def gpu_params(gpu, infos):
     info = tables.FFH264DeblockInfo(d0["mb_w"], d0["mb_h"], len(infos), keep["mb_type"].ptr, keep["qscale"].ptr, keep["nnz"].ptr,
                                     keep["cbp"].ptr, keep["slice_table"].ptr, (C.c_void_p * 2)(keep["mv0"].ptr, keep["mv1"].ptr),
                                     (C.c_void_p * 2)(keep["ref0"].ptr, keep["ref1"].ptr), keep["sp"].ptr, d0["n_slices"], keep["cq"].ptr,
-                                    d0["cabac"], d0["t8x8"])
+                                    d0["cabac"], d0["t8x8"], field)
     gpu.check(gpu.lib.ff_h264_deblock_params_cuda(C.byref(info), out.ptr, None))
     device.sync()
     return out.download(np.uint8, (n, 104)), out
+
+
+def test_field_picture_decisions(gpu, checker):
+    """FFH264DeblockInfo.field_picture: the fields of a PAFF frame as pictures of their own (h264_loopfilter.c:551-557,723)"""
+    from test_oracle_h264lf_cpu import FIELD_CASES, as_field
+    for case in FIELD_CASES:
+        for (mw, mh) in ((11, 9), (2, 5), (40, 17)):
+            d = as_field(synth.h264_deblock_info(mw, mh, **case))
+            try:
+                checker.h264_deblock_picture_structure(1)
+                want = oracle_run(checker, d)
+            finally:
+                checker.h264_deblock_picture_structure(0)
+            got, _ = gpu_params(gpu, [d], field=1)
+            bad = np.argwhere((got[:, :102] != want[:, :102]).any(axis=1))
+            assert not len(bad), (case, mw, mh, bad[:4].ravel().tolist(), got[bad[0, 0]].tolist(), want[bad[0, 0]].tolist())
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join("%s%s" % kv for kv in c.items()))

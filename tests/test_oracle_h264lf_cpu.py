@@ -42,6 +42,36 @@ def test_port_matches_reference_decisions(orc, refo, case):
         assert not len(bad), (mw, mh, bad[:4].ravel().tolist(), a[bad[0, 0]].tolist(), b[bad[0, 0]].tolist())
 
 
+FIELD_CASES = [dict(seed=21), dict(seed=22, bipred=True, t8x8=1, cabac=0, n_slices=4), dict(seed=23, p_intra=0.5, mode=2, n_slices=5)]
+
+
+def as_field(d):
+    """the same side information as one field of a PAFF frame: every macroblock type carries MB_TYPE_INTERLACED (mpegutils.h:58)"""
+    d = dict(d)
+    d["mb_type"] = d["mb_type"] | np.uint32(0x80) * (d["mb_type"] != 0)
+    return d
+
+
+@pytest.mark.parametrize("case", FIELD_CASES, ids=lambda c: "-".join("%s%s" % kv for kv in c.items()))
+def test_field_pictures(orc, refo, case):
+    """picture_structure != PICT_FRAME: vertical vector limit 2, bS 3 on horizontal intra macroblock edges (h264_loopfilter.c:551-557,723)"""
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    differs = 0
+    for (mw, mh) in ((11, 9), (2, 5), (20, 3)):
+        frame = synth.h264_deblock_info(mw, mh, **case)
+        d = as_field(frame)
+        try:
+            refo.h264_deblock_picture_structure(1); orc.h264_deblock_picture_structure(1)
+            a, b = run(refo, d), run(orc, d)
+        finally:
+            refo.h264_deblock_picture_structure(0); orc.h264_deblock_picture_structure(0)
+        bad = np.argwhere((a != b).any(axis=1))
+        assert not len(bad), (mw, mh, bad[:4].ravel().tolist(), a[bad[0, 0]].tolist(), b[bad[0, 0]].tolist())
+        differs += int((a != run(refo, frame)).any())
+    assert differs                       # the field rules do change decisions
+
+
 def test_decisions_are_not_trivial(orc):
     d = synth.h264_deblock_info(12, 8, seed=1)
     rec = run(orc, d).view(synth.DEBLOCK_DT).reshape(-1)

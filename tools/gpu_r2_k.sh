@@ -3,6 +3,8 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_zz_gpu_late_slots.py -m gpu -q -x -k "idct10 or fdct10 or quant_metrics" > gpurun_out/r2k_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2k_tests.log
 grep -v QMAT_SHIFT gpurun_out/r2k_tests.log | tail -15 | cut -c1-400
+timeout 900 python -m pytest tests/test_zz_gpu_h264_hbd.py -m gpu -q > gpurun_out/r2k_tests_hbd.log 2>&1; echo "rc=$?" >> gpurun_out/r2k_tests_hbd.log
+tail -15 gpurun_out/r2k_tests_hbd.log | cut -c1-400
 timeout 600 python bench.py --no-secondary --steps 30 --warmup 5 --workload idct10 > gpurun_out/r2k_bench_idct10.json 2> gpurun_out/r2k_bench_idct10.err
 python - <<'PY'
 import json

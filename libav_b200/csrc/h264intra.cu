@@ -71,7 +71,7 @@ __device__ __forceinline__ int idct4_lane(int16_t *co, int *tmp, int lane)
 
 __global__ void __launch_bounds__(32)
 h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, int16_t *__restrict__ coeffs, size_t coeff_stride,
-                  const uint8_t *__restrict__ nnzc_all, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, uint32_t *progress)
+                  const uint8_t *__restrict__ nnzc_all, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, uint32_t *progress, uint32_t *ticket)
 {
     __shared__ __align__(16) uint8_t Y[17 * LP];
     __shared__ __align__(16) uint8_t C[2][9 * CP];
@@ -82,7 +82,13 @@ h264_intra_kernel(const FFH264IntraMB *__restrict__ mbs, int mb_w, int rows_pp, 
     __shared__ IntraEdges edges;
     __shared__ IntraBig big;
     __shared__ int tmp[64];
-    const int lane = threadIdx.x, row = blockIdx.x, prow = row % rows_pp;      // prow: row inside its picture
+    // rows are handed out by an atomic ticket in the order CTAs START: whoever holds row r knows that row r - 1 has been taken by a CTA that
+    // is running or done, whatever order the hardware dispatches block indices in
+    const int lane = threadIdx.x;
+    int row = 0;
+    if (lane == 0) row = (int)atomicAdd(ticket, 1u);
+    row = __shfl_sync(0xffffffffu, row, 0);
+    const int prow = row % rows_pp;                                            // prow: row inside its picture
     volatile uint32_t *prog = progress;
     uint8_t *const cplane[2] = { cb, cr };
     const bool co16 = !(coeff_stride & 7) && !((uintptr_t)coeffs & 15);
@@ -277,7 +283,12 @@ extern "C" int ff_h264_intra_mb_batch_cuda(const FFH264IntraMB *mbs, int mb_w, i
     cudaStream_t st = (cudaStream_t)stream;
     const int rows = mb_h * n_pictures;
     AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows, st), "ff_h264_intra_mb_batch_cuda");
-    // a row only ever waits on the row above (a lower block index, dispatched earlier), so any grid size makes progress
-    h264_intra_kernel<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, progress);
+    // a row only ever waits on the row above, which holds a lower ticket (taken by a CTA that started earlier), so any grid size makes progress
+    static uint32_t *tickets = nullptr;                    // a small ring of counters: launches on different streams may overlap
+    static unsigned next = 0;
+    if (!tickets) AVB_CUDA(cudaMalloc(&tickets, 64 * sizeof(uint32_t)), "ff_h264_intra_mb_batch_cuda:tickets");
+    uint32_t *ticket = tickets + (next++ % 64);
+    AVB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st), "ff_h264_intra_mb_batch_cuda");
+    h264_intra_kernel<<<rows, 32, 0, st>>>(mbs, mb_w, mb_h, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, progress, ticket);
     return check_launch("ff_h264_intra_mb_batch_cuda");
 }

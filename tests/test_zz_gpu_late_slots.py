@@ -386,4 +386,5 @@ def test_me_cmp_quant_metrics_slots(gpu, checker, orc):
     """ff_me_cmp_enc_init_cuda: the six table entries over a live encoder state (return values and the context fields the C functions write)"""
     import enc_cases
     assert enc_cases.slot_cases(gpu.lib, checker, orc) > 800
-    assert gpu.last_error() == ""
+    assert "not taken over" in gpu.last_error()          # (the refusal slot_cases() ends with; nothing else was recorded)
+    gpu.lib.avb200_clear_error()

@@ -25,11 +25,13 @@ extern "C" {
 int ff_simple_idct_batch_cuda(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride,
                               size_t n, int tiles_per_row, int clear, void *stream)
 {
+    avb::enter();
     return launch_simple_idct(mode, blocks, frame, dst_off, stride, n, tiles_per_row, clear, (cudaStream_t)stream);
 }
 int ff_pixels_clamped_batch_cuda(int mode, const int16_t *blocks, uint8_t *frame, const uint32_t *dst_off,
                                  ptrdiff_t stride, size_t n, int tiles_per_row, void *stream)
 {
+    avb::enter();
     return launch_pixels_clamped(mode, blocks, frame, dst_off, stride, n, tiles_per_row, (cudaStream_t)stream);
 }
 static int dq_tables(const char *who, int kind, const FFMpegDequantTables *t, DqTables &d)
@@ -48,6 +50,7 @@ static int dq_tables(const char *who, int kind, const FFMpegDequantTables *t, Dq
 int ff_mpeg_dequant_batch_cuda(int kind, const FFMpegDequantTables *t, const FFMpegDequantBlock *recs, int16_t *blocks, size_t n,
                                void *stream)
 {
+    avb::enter();
     DqTables d;
     if (dq_tables("ff_mpeg_dequant_batch_cuda", kind, t, d)) return -1;
     return launch_mpeg_dequant(kind, d, reinterpret_cast<const uint32_t *>(recs), blocks, n, (cudaStream_t)stream);
@@ -56,6 +59,7 @@ int ff_mpeg_dequant_idct_batch_cuda(int kind, const FFMpegDequantTables *t, cons
                                     uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row,
                                     int clear, void *stream)
 {
+    avb::enter();
     DqTables d;
     if (dq_tables("ff_mpeg_dequant_idct_batch_cuda", kind, t, d)) return -1;
     return launch_mpeg_dequant_idct(kind, d, reinterpret_cast<const uint32_t *>(recs), blocks, frame, dst_off, stride, n, tiles_per_row,
@@ -63,11 +67,13 @@ int ff_mpeg_dequant_idct_batch_cuda(int kind, const FFMpegDequantTables *t, cons
 }
 int ff_clear_blocks_batch_cuda(int16_t *blocks, size_t n_blocks, void *stream)
 {
+    avb::enter();
     return launch_clear_blocks(blocks, n_blocks, (cudaStream_t)stream);
 }
 int ff_fill_blocks_batch_cuda(uint8_t *frame, const uint32_t *dst_off, const uint8_t *value, ptrdiff_t stride, int h,
                               int w16, size_t n, void *stream)
 {
+    avb::enter();
     return launch_fill_blocks(frame, dst_off, value, stride, h, w16, n, (cudaStream_t)stream);
 }
 
@@ -75,6 +81,7 @@ int ff_fill_blocks_batch_cuda(uint8_t *frame, const uint32_t *dst_off, const uin
 int ff_simple_idct_batch_host_cuda(int mode, int16_t *blocks, uint8_t *frame, size_t frame_bytes,
                                    const uint32_t *dst_off, ptrdiff_t stride, size_t n, int tiles_per_row)
 {
+    avb::enter();
     if (n == 0) return 0;
     if (mode < 0 || mode > 2) { set_error_msg("simple_idct_batch_host", "bad mode"); return -1; }
     ScratchLock lk;
@@ -219,6 +226,7 @@ extern "C" {
 
 void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, unsigned high_bit_depth)
 {
+    avb::enter();
     if (bits_per_raw_sample == 10) {                                    // idctdsp.c:151-155: the 10-bit simple IDCT whatever idct_algo says;
         idct10_install(c);                                              // the three pixel-clamp entries are the 8-bit functions at every depth (:175-177)
         c->put_pixels_clamped        = slot_put_pixels_clamped;
@@ -243,6 +251,7 @@ void ff_idctdsp_init_cuda(IDCTDSPContext *c, int idct_algo, int bits_per_raw_sam
 
 void ff_blockdsp_init_cuda(BlockDSPContext *c)
 {
+    avb::enter();
     c->clear_block       = slot_clear_block;
     c->clear_blocks      = slot_clear_blocks;
     c->fill_block_tab[0] = slot_fill16;

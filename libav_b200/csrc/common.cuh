@@ -25,6 +25,7 @@ int  check_launch(const char *where);   // cudaGetLastError() -> sticky error, r
 #define AVB_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
 #endif
 
+void enter();                   // make the device avb200_init() chose current in the calling thread (first statement of every public entry point)
 int sm_count();                 // multiprocessor count of the current device (cached)
 int tuning(const char *key);    // experiment knob set through avb200_set_tuning(); 0 when unset
 

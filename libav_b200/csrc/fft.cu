@@ -194,10 +194,11 @@ using namespace avb;
 extern "C" {
 
 int ff_fft_batch_cuda(int nbits, int inverse, float *z, size_t n_transforms, void *stream)
-{ return launch_fft(nbits, inverse, z, n_transforms, nullptr, (cudaStream_t)stream); }
+{ avb::enter(); return launch_fft(nbits, inverse, z, n_transforms, nullptr, (cudaStream_t)stream); }
 
 int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float *in, size_t n_transforms, void *stream)
 {
+    avb::enter();
     if (!n_transforms) return 0;
     if (nbits < 4 || nbits > 14) { set_error_msg("mdct_batch", "nbits 4..14"); return -1; }
     const float *rot = rotations(nbits, scale);
@@ -244,11 +245,13 @@ static void slot_mdct_calc(FFTContext *s, FFTSample *o, const FFTSample *i) { md
 
 void ff_fft_init_cuda(FFTContext *s)
 {
+    avb::enter();
     if (s->nbits < 1 || s->nbits > 12) return;
     s->fft_calc = slot_fft_calc;                   // fft_permute stays the reference's: fft_calc accepts its revtab order
 }
 void ff_mdct_init_cuda(FFTContext *s)
 {
+    avb::enter();
     if (s->mdct_bits < 4 || s->mdct_bits > 14 || s->mdct_permutation != FF_MDCT_PERM_NONE) return;
     s->imdct_calc = slot_imdct_calc; s->imdct_half = slot_imdct_half; s->mdct_calc = slot_mdct_calc;
     s->mdct_calcw = slot_mdct_calc;                // float build: mdct_calcw == mdct_calc (mdct_template.c:68)

@@ -218,6 +218,7 @@ extern "C" {
 int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264ResidualMB *mbs, size_t n, int32_t *coeffs, size_t coeff_stride,
                                        const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
 {
+    avb::enter();
     const char *where = "ff_h264_idct_add_mb_batch_hbd_cuda";
     if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, luma, cb, cr)) return -1;
     if (n && (!mbs || !coeffs || !nnzc || !luma || !cb || !cr)) { set_error_msg(where, "NULL argument"); return -1; }
@@ -230,6 +231,7 @@ int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, con
 int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y,
                               uint8_t *dst_cb, uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h, void *stream)
 {
+    avb::enter();
     const char *where = "ff_h264_mc_batch_hbd_cuda";
     if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, dst_y, dst_cb, dst_cr)) return -1;
     if (n && (!recs || !refs || !dst_y || !dst_cb || !dst_cr)) { set_error_msg(where, "NULL argument"); return -1; }
@@ -245,6 +247,7 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
 int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                    int linesize, int uvlinesize, void *stream)
 {
+    avb::enter();
     const char *where = "ff_h264_deblock_batch_hbd_cuda";
     if (!hbd_args_ok(where, bit_depth, 1, linesize, uvlinesize, luma, cb, cr)) return -1;
     if (!mbs || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }

@@ -434,23 +434,24 @@ using namespace avb;
 extern "C" {
 int ff_h264_idct_add_mb_batch_cuda(const FFH264ResidualMB *mbs, size_t n, int16_t *coeffs, size_t coeff_stride, const uint8_t *nnzc,
                                    uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
-{ return launch_h264_residual(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream); }
+{ avb::enter(); return launch_h264_residual(mbs, n, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream); }
 int ff_h264_mc_batch_cuda(const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y, uint8_t *dst_cb,
                           uint8_t *dst_cr, int linesize, int uvlinesize, int pic_w, int pic_h, void *stream)
-{ return launch_h264_mc(recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream); }
+{ avb::enter(); return launch_h264_mc(recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream); }
 int ff_h264_weight_batch_cuda(const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, void *stream)
-{ return launch_h264_weight(recs, n, plane, src, stride, (cudaStream_t)stream); }
+{ avb::enter(); return launch_h264_weight(recs, n, plane, src, stride, (cudaStream_t)stream); }
 int ff_h264_dc_dequant_batch_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
                                   void *stream)
 {
+    avb::enter();
     if (!n) return 0;
     h264_dc_dequant_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(recs, n, coeffs, coeff_stride, luma_dc);
     return check_launch("ff_h264_dc_dequant_batch_cuda");
 }
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress, void *stream)
-{ return launch_h264_deblock(mbs, mb_w, mb_h, 1, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
+{ avb::enter(); return launch_h264_deblock(mbs, mb_w, mb_h, 1, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
 int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                int linesize, int uvlinesize, uint32_t *progress, void *stream)
-{ return launch_h264_deblock(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
+{ avb::enter(); return launch_h264_deblock(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, linesize, uvlinesize, progress, (cudaStream_t)stream); }
 }

@@ -276,6 +276,7 @@ extern "C" int ff_h264_intra_mb_batch_cuda(const FFH264IntraMB *mbs, int mb_w, i
                                            size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                            int linesize, int uvlinesize, uint32_t *progress, void *stream)
 {
+    avb::enter();
     if (mb_w <= 0 || mb_h <= 0 || n_pictures <= 0) return 0;
     if ((linesize & 3) || (uvlinesize & 3) || ((uintptr_t)luma & 3) || ((uintptr_t)cb & 3) || ((uintptr_t)cr & 3)) {
         set_error_msg("ff_h264_intra_mb_batch_cuda", "planes and pitches must be 4-byte aligned"); return -1;

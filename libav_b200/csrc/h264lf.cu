@@ -214,6 +214,7 @@ using namespace avb;
 
 extern "C" int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info, FFH264DeblockMB *out, void *stream)
 {
+    avb::enter();
     if (!info || !out || info->mb_w <= 0 || info->mb_h <= 0 || info->n_pictures <= 0 || info->n_slices <= 0 || info->n_slices > 32) {
         set_error_msg("ff_h264_deblock_params_cuda", "bad arguments (1..32 slices per call: the reference keeps 32 ref2frm tables)");
         return -1;
@@ -229,6 +230,7 @@ extern "C" int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info, FFH264
 // ordering of the batch entry points -- no host synchronisation; an error of any stage stops the flush.
 extern "C" int ff_h264_flush_pictures_cuda(const FFH264PictureWork *w, void *stream)
 {
+    avb::enter();
     if (!w || w->mb_w <= 0 || w->mb_h <= 0 || w->n_pictures <= 0 || !w->luma || !w->cb || !w->cr) {
         set_error_msg("ff_h264_flush_pictures_cuda", "bad arguments"); return -1;
     }

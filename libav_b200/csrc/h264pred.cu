@@ -183,6 +183,7 @@ using namespace avb;
 // chroma_format_idc <= 1 -- and the 9 / 10-bit instances through h264pred_hbd.cu; anything else leaves the table as the C init filled it.
 extern "C" void ff_h264_pred_init_cuda(H264PredContext *h, int codec_id, const int bit_depth, const int chroma_format_idc)
 {
+    avb::enter();
     if (!h || codec_id != 27 || (bit_depth != 8 && bit_depth != 9 && bit_depth != 10)) return;
     if (bit_depth != 8) {                                     // h264pred_hbd.cu
         h264pred_init_hbd(h, bit_depth);

@@ -261,6 +261,7 @@ using namespace avb;
 
 extern "C" int ff_simple_idct10_batch_cuda(int mode, int16_t *blocks, uint8_t *frame, const uint32_t *dst_off, ptrdiff_t stride, size_t n, void *stream)
 {
+    avb::enter();
     if (mode < 0 || mode > 2 || (n && !blocks) || (mode != 2 && n && (!frame || !dst_off)) || (stride & 1)) {
         set_error_msg("ff_simple_idct10_batch_cuda", "bad argument"); return -1;
     }

@@ -451,6 +451,7 @@ extern "C" {
 int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
                          const FFMECmpRecord *recs, size_t n, int32_t *out, void *stream)
 {
+    avb::enter();
     if (!n) return 0;
     const bool ok = (kind == 0 && sidx <= 1 && dxy >= 0 && dxy <= 3) || (kind == 1 && sidx <= 1) || (kind == 2 && sidx <= 2) ||
                     ((kind == 3 || kind == 7) && sidx <= 1) || ((kind == 4 || kind == 5) && sidx == 0) || (kind == 6 && sidx <= 1) ||
@@ -464,6 +465,7 @@ int ff_me_cmp_batch_cuda(int kind, int sidx, int dxy, const uint8_t *cur, const 
 int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int w, int h, int range, int mb_y0, int mb_y1,
                         int32_t *out, void *stream)
 {
+    avb::enter();
     if (mb_y1 <= mb_y0) return 0;
     if (range != FS_R) { set_error_msg("full_search", "only me_range 16 is built"); return -1; }
     if ((w & 15) || (h & 15) || (stride & 15) || ((uintptr_t)cur & 15)) { set_error_msg("full_search", "picture must be MB aligned, cur 16-byte aligned"); return -1; }
@@ -473,6 +475,7 @@ int ff_full_search_cuda(const uint8_t *cur, const uint8_t *ref, int stride, int 
 
 int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream)
 {
+    avb::enter();
     if (!n) return 0;
     hpel_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(recs, n, dst, src, stride);
     return check_launch("hpel_batch");
@@ -480,6 +483,7 @@ int ff_hpel_batch_cuda(const FFHpelRecord *recs, size_t n, uint8_t *dst, const u
 
 int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
 {
+    avb::enter();
     using avb::fdct10_launch;
     if (!n) return 0;
     const int grid = (int)((n + 127) / 128);
@@ -497,6 +501,7 @@ int ff_fdct_batch_cuda(int which, int16_t *blocks, size_t n, void *stream)
 
 int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *recs, size_t n, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, void *stream)
 {
+    avb::enter();
     if (!n) return 0;
     mpeg4_qpel_kernel<<<warps_grid(n, 4), 128, 0, (cudaStream_t)stream>>>(recs, n, dst, src, stride);
     return check_launch("mpeg4_qpel_batch");
@@ -505,6 +510,7 @@ int ff_mpeg4_qpel_batch_cuda(const FFQpelRecord *recs, size_t n, uint8_t *dst, c
 int ff_pixblock_fdct_batch_cuda(int which_fdct, const uint8_t *s1, const uint8_t *s2, const uint32_t *off1, const uint32_t *off2,
                                 ptrdiff_t stride, int16_t *blocks, size_t n, void *stream)
 {
+    avb::enter();
     if (!n) return 0;
     if (!s1 || !off1 || !blocks || ((uintptr_t)blocks & 15)) { set_error_msg("pixblock_fdct_batch", "need s1, off1 and 16-byte aligned blocks"); return -1; }
     const int grid = (int)((n + 127) / 128);

@@ -296,6 +296,7 @@ extern "C" {
 
 void *ff_me_cmp_enc_state_cuda(const FFMECmpEncState *state, const FFMECmpVlcTables *vlc)
 {
+    avb::enter();
     if (!state_ok(state, "ff_me_cmp_enc_state_cuda")) return nullptr;
     EncDev e;
     memset(&e, 0, sizeof(e));
@@ -311,11 +312,12 @@ void *ff_me_cmp_enc_state_cuda(const FFMECmpEncState *state, const FFMECmpVlcTab
     return dev;
 }
 
-void ff_me_cmp_enc_state_free_cuda(void *enc_state) { if (enc_state) cudaFree(enc_state); }
+void ff_me_cmp_enc_state_free_cuda(void *enc_state) { avb::enter(); if (enc_state) cudaFree(enc_state); }
 
 int ff_me_cmp_enc_batch_cuda(int kind, int sidx, const void *enc_state, const uint8_t *cur, const uint8_t *ref, ptrdiff_t stride, int h,
                              const FFMECmpRecord *recs, size_t n, int32_t *out, int32_t *last_index, void *stream)
 {
+    avb::enter();
     if (kind < 14 || kind > 16 || sidx < 0 || sidx > 1 || !(h == 8 || (h == 16 && sidx == 0)) || !enc_state || (n && (!cur || !ref || !recs || !out))) {
         set_error_msg("ff_me_cmp_enc_batch_cuda", "bad argument (kind 14..16, sidx 0 | 1, h 8 or 16 for sidx 0)"); return -1;
     }
@@ -324,6 +326,7 @@ int ff_me_cmp_enc_batch_cuda(int kind, int sidx, const void *enc_state, const ui
 
 int ff_me_cmp_enc_init_cuda(MECmpContext *c, struct MpegEncContext *s, const FFMECmpEncView *view)
 {
+    avb::enter();
     if (!c || !s || !view) { set_error_msg("ff_me_cmp_enc_init_cuda", "NULL argument"); return -1; }
     const void *need[] = { view->qscale, view->y_dc_scale, view->h263_aic, view->intra_quant_bias, view->inter_quant_bias, view->ac_esc_length, view->mb_intra,
                            view->block_last_index, view->q_intra_matrix, view->q_inter_matrix, view->intra_matrix, view->inter_matrix, view->scantable,
@@ -340,6 +343,6 @@ int ff_me_cmp_enc_init_cuda(MECmpContext *c, struct MpegEncContext *s, const FFM
     return 0;
 }
 
-void ff_me_cmp_enc_uninit_cuda(struct MpegEncContext *s) { std::lock_guard<std::mutex> lk(g_view_mu); g_views.erase(s); }
+void ff_me_cmp_enc_uninit_cuda(struct MpegEncContext *s) { avb::enter(); std::lock_guard<std::mutex> lk(g_view_mu); g_views.erase(s); }
 
 }  // extern "C"

@@ -29,6 +29,15 @@ static void record(const char *where, const char *msg, bool fault)
 }
 void set_error_msg(const char *where, const char *msg) { record(where, msg, false); }
 void set_error(const char *where, cudaError_t e) { record(where, cudaGetErrorString(e), true); }
+// The device avb200_init() chose.  CUDA's current device is PER THREAD and starts at 0: a caller thread the library has not seen yet
+// (decoder frame threads, a scaler per worker thread) would otherwise launch onto device 0 with pointers, streams and tensor maps of
+// device g_device -- "invalid argument" on every rank but the first.  Every public entry point calls enter() first.
+static int g_device = -1;
+void enter()
+{
+    static thread_local int t_dev = -2;
+    if (g_device >= 0 && t_dev != g_device) { if (cudaSetDevice(g_device) == cudaSuccess) t_dev = g_device; else cudaGetLastError(); }
+}
 int check_launch(const char *where)
 {
     cudaError_t e = cudaGetLastError();
@@ -85,6 +94,7 @@ int avb200_init(int device)
     AVB_CUDA(cudaGetDeviceProperties(&p, device), "avb200_init");
     if (p.major != 10) { set_error_msg("avb200_init", "kernels are built for sm_100a only"); return -1; }
     g_sms = p.multiProcessorCount;
+    g_device = device;
     return 0;
 }
 

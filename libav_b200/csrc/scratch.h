@@ -26,6 +26,7 @@ struct Scratch {
 };
 Scratch &scratch();
 std::recursive_mutex &scratch_mutex();
-struct ScratchLock { ScratchLock() { scratch_mutex().lock(); } ~ScratchLock() { scratch_mutex().unlock(); } };
+void enter();
+struct ScratchLock { ScratchLock() { enter(); scratch_mutex().lock(); } ~ScratchLock() { scratch_mutex().unlock(); } };
 
 }  // namespace avb

@@ -418,6 +418,7 @@ extern "C" {
 
 void ff_qpeldsp_init_cuda(QpelDSPContext *c)
 {
+    avb::enter();
     if (!c) return;
     FillMpeg4Qpel<0, 0, 15>::go(c->put_qpel_pixels_tab[0]);        FillMpeg4Qpel<0, 1, 15>::go(c->put_qpel_pixels_tab[1]);
     FillMpeg4Qpel<1, 0, 15>::go(c->put_no_rnd_qpel_pixels_tab[0]); FillMpeg4Qpel<1, 1, 15>::go(c->put_no_rnd_qpel_pixels_tab[1]);
@@ -426,12 +427,14 @@ void ff_qpeldsp_init_cuda(QpelDSPContext *c)
 
 void ff_pixblockdsp_init_cuda(PixblockDSPContext *c, unsigned high_bit_depth)
 {
+    avb::enter();
     if (!c || high_bit_depth) return;
     c->get_pixels = slot_get_pixels; c->diff_pixels = slot_diff_pixels;
 }
 
 void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample, unsigned high_bit_depth)
 {
+    avb::enter();
     if (bits_per_raw_sample == 10) { c->fdct = slot_fdct<4>; c->fdct248 = slot_fdct<5>; return; }      // fdctdsp.c:31-33: the 10-bit islow pair whatever dct_algo says
     if (high_bit_depth || bits_per_raw_sample > 8) return;               // other depths: the reference falls through to its 8-bit functions; not taken over
     if (dct_algo == AVB_FF_DCT_FASTINT) { c->fdct = slot_fdct<2>; c->fdct248 = slot_fdct<3>; }
@@ -441,6 +444,7 @@ void ff_fdctdsp_init_cuda(FDCTDSPContext *c, int dct_algo, int bits_per_raw_samp
 
 void ff_me_cmp_init_cuda(MECmpContext *c)
 {
+    avb::enter();
     // mirrors the assignments of ff_me_cmp_init (libavcodec/me_cmp.c:895-944); slots that need encoder state
     // (dct_sad, dct_max, dct264_sad, quant_psnr, rd, bit) keep whatever the caller installed
     c->sum_abs_dctelem = slot_sum_abs_dctelem;
@@ -457,6 +461,7 @@ void ff_me_cmp_init_cuda(MECmpContext *c)
 
 void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chroma_format_idc)
 {
+    avb::enter();
     if (bit_depth == 9 || bit_depth == 10) { h264dsp_init_hbd(c, bit_depth, chroma_format_idc); c->startcode_find_candidate = slot_startcode; return; }
     if (bit_depth != 8) return;                                           // other depths do not exist for H.264 here (h264dsp.c:126-136 maps them to 8)
     const bool c420 = chroma_format_idc <= 1;                             // the reference's own test, h264dsp.c:81-122
@@ -487,6 +492,7 @@ void ff_h264dsp_init_cuda(H264DSPContext *c, const int bit_depth, const int chro
 
 void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth)
 {
+    avb::enter();
     if (bit_depth == 9 || bit_depth == 10) { h264qpel_init_hbd(c, bit_depth); return; }
     if (bit_depth != 8) return;
     fill_qpel<0, 0>(c->put_h264_qpel_pixels_tab[0]); fill_qpel<0, 1>(c->put_h264_qpel_pixels_tab[1]);
@@ -497,6 +503,7 @@ void ff_h264qpel_init_cuda(H264QpelContext *c, int bit_depth)
 
 void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth)
 {
+    avb::enter();
     if (bit_depth == 9 || bit_depth == 10) { h264chroma_init_hbd(c, bit_depth); return; }
     if (bit_depth != 8) return;
     c->put_h264_chroma_pixels_tab[0] = slot_chroma<0, 0>; c->put_h264_chroma_pixels_tab[1] = slot_chroma<0, 1>; c->put_h264_chroma_pixels_tab[2] = slot_chroma<0, 2>;
@@ -505,6 +512,7 @@ void ff_h264chroma_init_cuda(H264ChromaContext *c, int bit_depth)
 
 void ff_hpeldsp_init_cuda(HpelDSPContext *c, int flags)
 {
+    avb::enter();
     (void)flags;
     fill_hpel<0, 0>(c->put_pixels_tab[0]); fill_hpel<0, 1>(c->put_pixels_tab[1]); fill_hpel<0, 2>(c->put_pixels_tab[2]); fill_hpel<0, 3>(c->put_pixels_tab[3]);
     fill_hpel<1, 0>(c->avg_pixels_tab[0]); fill_hpel<1, 1>(c->avg_pixels_tab[1]); fill_hpel<1, 2>(c->avg_pixels_tab[2]); fill_hpel<1, 3>(c->avg_pixels_tab[3]);

@@ -376,6 +376,7 @@ template <int KIND> void slot_chr_range(int16_t *dstU, int16_t *dstV, int width)
 
 extern "C" int ff_sws_init_swscale_cuda(struct SwsContext *c, SwsContextCUDA *cuda, SwsLineSlotsCUDA *t)
 {
+    avb::enter();
     SwsSlotView v;
     if (!c || !t || !sws_slot_view(cuda, v)) { set_error_msg("ff_sws_init_swscale_cuda", "NULL argument"); return -1; }
     {

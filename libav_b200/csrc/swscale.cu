@@ -40,6 +40,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int full;                         // SWS_FULL_CHR_H_INT: one chroma sample per output pixel, yuv2rgb24_full_X_c
     int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
     int pk422;                        // packed 4:2:2 destination: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576)
+    int rgb16;                        // 15 / 16 / 12-bpp destination: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (yuv2rgb_write, output.c:869-902)
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
     int srcBits, srcBE;               // 9 / 10 / 16-bit planar sources: 16-bit words (byte-swapped when big-endian), hScale16To15_c; else 8
@@ -368,6 +369,33 @@ sws_vscale_rgb24_kernel(SwsDev p, const int16_t *__restrict__ lum, const int16_t
         return;
     }
     ChromaTerms t = chroma_terms(U, V, p.k);
+    if (p.rgb16) {
+        // yuv2rgb_write for 565 / 555 / 444 (output.c:869-902): r[Y + dr] + g[Y + dg] + b[Y + db] with the 2 x 2 (4 x 4 for 444) ordered
+        // dither added to the table INDEX; the tables hold the 8-bit channel value cut to 5 / 6 / 4 bits at its bit position
+        // (yuv2rgb.c:806-844), byte-swapped for the big-endian formats -- the fields do not overlap, so the sum swaps as a whole
+        const int kind = (p.rgb16 & 7) - 1, fmt = kind >> 1, bgr = kind & 1;                  // fmt 0 565, 1 555, 2 444
+        int d8a, d8b, dga, dgb, dba, dbb;                                                      // (dr1, dr2), (dg1, dg2), (db1, db2)
+        if (fmt == 2) {
+            const int a0 = 0x070B0408, a1 = 0x0D010E02, a2 = 0x0509060A, a3 = 0x0F030C00;      // ff_dither_4x4_16 rows, bytes [0] [1] [2] [3] (output.c:48-53)
+            const int r0 = (y & 3) == 0 ? a0 : (y & 3) == 1 ? a1 : (y & 3) == 2 ? a2 : a3, yb = (y & 3) ^ 3, r1 = yb == 0 ? a0 : yb == 1 ? a1 : yb == 2 ? a2 : a3;
+            d8a = r0 & 255; d8b = (r0 >> 8) & 255; dga = d8b; dgb = d8a; dba = r1 & 255; dbb = (r1 >> 8) & 255;
+        } else {
+            const int e = y & 1;                                                               // dither_2x2_8 = { { 6, 2 }, { 0, 4 } }, dither_2x2_4 = { { 1, 3 }, { 2, 0 } } (output.c:38-46)
+            d8a = e ? 0 : 6; d8b = e ? 4 : 2; dba = e ? 6 : 0; dbb = e ? 2 : 4;
+            if (fmt == 0) { dga = e ? 2 : 1; dgb = e ? 0 : 3; } else { dga = d8b; dgb = d8a; }
+        }
+        const int rs = fmt == 2 ? 4 : 3, gs = fmt == 0 ? 2 : fmt == 1 ? 3 : 4, gb = fmt == 2 ? 4 : 5, hb = fmt == 0 ? 11 : fmt == 1 ? 10 : 8;
+        const int rb = bgr ? 0 : hb, bb = bgr ? hb : 0;
+        auto px = [&](int Y, int dr, int dg, int db) -> uint32_t {
+            const uint32_t v = (uint32_t)(clip_u8((p.k.cy * (Y + dr) + t.tr) >> 16) >> rs) << rb | (uint32_t)(clip_u8((p.k.cy * (Y + dg) + t.tg) >> 16) >> gs) << gb |
+                               (uint32_t)(clip_u8((p.k.cy * (Y + db) + t.tb) >> 16) >> rs) << bb;
+            return (p.rgb16 & 8) ? ((v >> 8) | (v << 8)) & 0xffffu : v;
+        };
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + (size_t)y * dstStride) + 2 * i;
+        d16[0] = (uint16_t)px(Y1, d8a, dga, dba);
+        if (has2 || dstStride >= 2 * (p.dstW + 1)) d16[1] = (uint16_t)px(Y2, d8b, dgb, dbb);
+        return;
+    }
     int tr = p.bgr ? t.tb : t.tr, tb = p.bgr ? t.tr : t.tb;
     uint8_t *d = dst + (size_t)y * dstStride + (size_t)i * 6;
     d[0] = (uint8_t)clip_u8((p.k.cy * Y1 + tr) >> 16);
@@ -1123,6 +1151,7 @@ struct SwsCudaContext {
     int srcBits = 8, srcBE = 0; // 9 / 10 / 16-bit planar source (16-bit words; hScale16To15_c in the two-pass path)
     int rangeConv = 0;          // yuv destination of the other range: 1 lum / chrRangeFromJpeg_c, 2 lum / chrRangeToJpeg_c on the hscaled lines (two-pass path)
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
+    int rgb16 = 0;              // rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 destination (SwsDev::rgb16)
     int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
     int dstNV = 0;              // 1 nv12, 2 nv21 destination
     bool nvcopy = false;        // yuv420p -> nv12 / nv21 of the same size: planarToNv12Wrapper
@@ -1176,7 +1205,7 @@ static int upload_tables(SwsCudaContext *c)
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422; d.rgb16 = c->rgb16;
     d.srcBits = c->srcBits; d.srcBE = c->srcBE; d.dither = c->srcBits > 8;
     return 0;
 }
@@ -1222,9 +1251,15 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
     const int pk422 = dstFormat == FMT_YUYV422 ? 1 : dstFormat == FMT_UYVY422 ? 2 : 0;
-    if (pk422) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
-    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
+    int rgb16 = 0;                                           // libavutil/pixfmt.h: RGB565BE 36 LE 37, RGB555BE 38 LE 39, BGR565BE 40 LE 41, BGR555BE 42 LE 43, RGB444LE 54 BE 55, BGR444LE 56 BE 57
+    switch (dstFormat) {
+    case 37: rgb16 = 1; break; case 36: rgb16 = 1 | 8; break; case 41: rgb16 = 2; break; case 40: rgb16 = 2 | 8; break;
+    case 39: rgb16 = 3; break; case 38: rgb16 = 3 | 8; break; case 43: rgb16 = 4; break; case 42: rgb16 = 4 | 8; break;
+    case 54: rgb16 = 5; break; case 55: rgb16 = 5 | 8; break; case 56: rgb16 = 6; break; case 57: rgb16 = 6 | 8; break;
+    }
+    if (pk422 || rgb16) flags &= ~SWS_FULL_CHR_H_INT;        // only 24 / 32-bit packed RGB knows the flag (utils.c:998-1014)
+    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422 && !rgb16) {
+        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 (LE and BE), yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1274,6 +1309,16 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         return nullptr;
     }
     const bool rgb = !planar;
+    if (rgb16) {
+        // the 15 / 16 / 12-bpp destinations exist where swscale()'s packed output stage runs (yuv2rgb16_X / _2 / _1 ..., output.c:1321-1326);
+        // the reference's other routes to them are separate converter families that are not taken over
+        const char *why = nullptr;
+        if (srcRgb || src32 || srcYuy) why = "15 / 16 / 12-bpp rgb destinations are taken over for planar / semi-planar yuv sources only";
+        else if ((srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && unscaled && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8)
+            why = "same-size yuv -> 15 / 16 / 12-bpp rgb without SWS_ACCURATE_RND is the reference's ordered-dither table converter (yuv2rgb.c:377-573): not taken over";
+        else if (usesFilter) why = "SwsFilter vectors with a 15 / 16 / 12-bpp destination are not taken over";
+        if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
+    }
     {   // a shifted / asymmetric vertical vector makes the reference's last output rows depend on stale lines of its ring buffer (measured:
         // port and product, which clamp to the last line, differ from it there and nowhere else): no defined result to match
         auto asym = [](const SwsVec *v) { if (!v) return false; for (int i = 0; i < v->length / 2; i++) if (v->coeff[i] != v->coeff[v->length - 1 - i]) return true; return false; };
@@ -1303,7 +1348,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->pk422 = pk422; c->srcBits = srcBits; c->srcBE = srcBE;
+    c->pk422 = pk422; c->rgb16 = rgb16; c->srcBits = srcBits; c->srcBE = srcBE;
     if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv && srcBits == 8) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
@@ -1344,7 +1389,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
     c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8;
-    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !rgb16 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -1438,7 +1483,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
         const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
-        if (need <= 96 * 1024 && !pk422 && !rangeConv && srcBits == 8) {          // (the packed 4:2:2 output stage and the range conversion only exist in the two-pass path so far)
+        if (need <= 96 * 1024 && !pk422 && !rgb16 && !rangeConv && srcBits == 8) {          // (the packed 4:2:2 / 16-bpp output stages and the range conversion only exist in the two-pass path so far)
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1778,7 +1823,7 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
             int pairs = (p.dstW + 1) >> 1;
             uint8_t *d0 = dst[0] + f * dstFrame[0];
             const bool x_path = !((p.vLumSize == 1 && p.vChrSize <= 2) || (p.vLumSize == 2 && p.vChrSize == 2));
-            if (p.pk422)
+            if (p.pk422 || p.rgb16)
                 sws_vscale_rgb24_kernel<<<dim3((pairs + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
             else if (p.full)
                 sws_vscale_rgb24_full_kernel<<<dim3((p.dstW + 255) / 256, p.dstH), b, 0, st>>>(p, c->d_lum, c->d_chrU, c->d_chrV, c->lumStridePx, c->chrStridePx, d0, dstStride[0]);
@@ -1798,6 +1843,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
     if (!c) return false;
     v.rangeConv = c->rangeConv; v.srcBits = c->srcBits;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
+    if (c->rgb16) return false;            // (the per-line slots do not cover the 15 / 16 / 12-bpp output stage: the hook leaves the C slots)
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
 }
@@ -1811,16 +1857,18 @@ extern "C" {
 SwsContextCUDA *sws_getContext_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
                                     void *srcFilter, void *dstFilter, const double *param)
 {
+    avb::enter();
     return (SwsContextCUDA *)make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, param, true, srcFilter, dstFilter);
 }
 
-void sws_freeContext_cuda(SwsContextCUDA *ctx) { sws_slots_forget(ctx); destroy((SwsCudaContext *)ctx); }
+void sws_freeContext_cuda(SwsContextCUDA *ctx) { avb::enter(); sws_slots_forget(ctx); destroy((SwsCudaContext *)ctx); }
 
 // sws_setColorspaceDetails (libswscale/utils.c:807-835): new yuv -> rgb constants (ff_yuv2rgb_c_init_tables, yuv2rgb.c:671-863) for a
 // packed rgb destination; -1 for yuv destinations like the reference, and -1 (nothing changed) for what is not taken over.
 int sws_setColorspaceDetails_cuda(SwsContextCUDA *ctx, const int inv_table[4], int srcRange, const int table[4], int dstRange,
                                   int brightness, int contrast, int saturation)
 {
+    avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     (void)table; (void)dstRange;                  // only read by the yuv -> yuv range conversion (not taken over) and rgb sources' fixed readers
     if (!c || !inv_table) { set_error_msg("sws_setColorspaceDetails_cuda", "NULL argument"); return -1; }
@@ -1843,6 +1891,7 @@ int sws_setColorspaceDetails_cuda(SwsContextCUDA *ctx, const int inv_table[4], i
 int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrameStride[3],
                           uint8_t *const dst[3], const int dstStride[3], const size_t dstFrameStride[3], int nframes, void *stream)
 {
+    avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
     if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0] || (c->planar && (!dst[1] || (!c->dstNV && !dst[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
@@ -1861,7 +1910,7 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
 {
     const SwsGeometry &g = c->g;
     const bool pk = c->srcPacked != 0, nv = c->srcNV != 0, rgb = !c->planar;
-    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
     const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH }, dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
     const size_t sS = c->srcBits > 8 ? 2 : 1;
@@ -1964,7 +2013,7 @@ static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlic
     const int ret = rowMapped ? srcSliceH : dstY1 - dstY0;
     if (dstY1 <= dstY0) return ret;
     // the frame pipeline over the rows so far, into a copy of the caller's picture; the finished rows go back
-    const int sB = c->dstBits > 8 ? 2 : 1, pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    const int sB = c->dstBits > 8 ? 2 : 1, pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     const int dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
     const size_t dstWB[3] = { (size_t)g.dstW * (rgb ? pxB : sB), (size_t)g.chrDstW * (c->dstNV ? 2 : sB), (size_t)g.chrDstW * sB };
     std::vector<uint8_t> dbuf[3];
@@ -1998,6 +2047,7 @@ static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlic
 int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const int srcStride[], int srcSliceY, int srcSliceH,
                    uint8_t *const dst[], const int dstStride[])
 {
+    avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
     const bool rgb = !c->planar;
@@ -2031,7 +2081,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
-    const int pxB = c->pk422 ? 2 : c->dst32 ? 4 : 3;        // bytes per packed pixel
+    const int pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;        // bytes per packed pixel
     const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB * (c->dstNV ? 2 : 1) + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
@@ -2122,7 +2172,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     return g.dstH;
 }
 
-int sws_is_fused_cuda(SwsContextCUDA *ctx) { return ctx ? ((SwsCudaContext *)ctx)->fused : 0; }
+int sws_is_fused_cuda(SwsContextCUDA *ctx) { avb::enter(); return ctx ? ((SwsCudaContext *)ctx)->fused : 0; }
 
 // Host-only introspection used by the CPU test-suite to pin the set-up stage against the reference
 // (no device is touched): filter bank `which` (0 hLum, 1 hChr, 2 vLum, 3 vChr) of the context that
@@ -2132,12 +2182,14 @@ int sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, in
 int sws_debug_filter_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, int16_t *filter,
                           int32_t *pos, int cap, int *n_out)
 {
+    avb::enter();
     return sws_debug_filter2_cuda(which, srcW, srcH, dstW, dstH, dstFormat, flags, nullptr, nullptr, filter, pos, cap, n_out);
 }
 // the same with the caller's SwsFilter pair (libswscale/swscale.h:112-117 layout)
 int sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, const void *srcFilter, const void *dstFilter,
                            int16_t *filter, int32_t *pos, int cap, int *n_out)
 {
+    avb::enter();
     SwsCudaContext *c = make_context(srcW, srcH, FMT_YUV420P, dstW, dstH, dstFormat, flags, nullptr, false, srcFilter, dstFilter);
     if (!c) return -1;
     const FilterBank &b = which == 0 ? c->hLum : which == 1 ? c->hChr : which == 2 ? c->vLum : c->vChr;
@@ -2157,12 +2209,13 @@ int sws_debug_filter2_cuda(int which, int srcW, int srcH, int dstW, int dstH, in
 //   out[6] destination sample bits (planar) or bytes per pixel (packed)   out[7] full-range source
 int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[8])
 {
+    avb::enter();
     SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
     if (!c) return 0;
     out[0] = c->to422 ? 6 : c->nvcopy ? 7 : c->special ? 5 : c->copy ? 1 : c->table_unscaled ? 2 : c->fused ? 3 : 4;
     out[1] = c->g.chrSrcW; out[2] = c->g.chrSrcH; out[3] = c->g.chrDstW; out[4] = c->g.chrDstH;
     out[5] = c->srcPacked ? 2 : c->srcNV ? 1 : 0;
-    out[6] = c->planar ? c->dstBits : c->pk422 ? 2 : c->dst32 ? 4 : 3;
+    out[6] = c->planar ? c->dstBits : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     out[7] = c->srcRange;
     delete c;
     return 1;
@@ -2171,6 +2224,7 @@ int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, i
 // 19 colour constants, flags, planar, dstBits, dstBE, packed target, dstNV, range conversion.  Returns the count, 0 when the request is refused.
 int sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags, int32_t out[32])
 {
+    avb::enter();
     static_assert(sizeof(SwsSlotView) == 27 * sizeof(int32_t), "SwsSlotView is 27 ints");
     SwsCudaContext *c = make_context(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, nullptr, false);
     if (!c) return 0;
@@ -2182,6 +2236,7 @@ int sws_debug_slot_view_cuda(int srcW, int srcH, int srcFormat, int dstW, int ds
 }
 void sws_debug_rgb_constants_cuda(int32_t out[10])
 {
+    avb::enter();
     static const int itu601[4] = { 104597, 132201, 25675, 53279 };
     RgbConstants k;
     rgb_constants(k, itu601, 0, 0, 1 << 16, 1 << 16);

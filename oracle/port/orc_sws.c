@@ -241,6 +241,8 @@ static __thread int g_hs = 1, g_vs = 1;
 /* the planar destination: chroma sub-sampling (log2) and sample depth (8, or 9 / 10 in little-endian 16-bit samples) */
 static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8, g_dbe = 0;
 static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; } else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); } }
+#define IS_RGB16(f) (((f) >= 36 && (f) <= 43) || ((f) >= 54 && (f) <= 57))     /* rgb565 / 555 / bgr565 / 555 (36-43), rgb444 / bgr444 (54-57), LE and BE */
+static __thread int g_rgb16;        /* 15 / 16 / 12-bpp destination of the "rgb" entry point: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (output.c:869-902) */
 static __thread int g_pk422;        /* packed 4:2:2 destination of the "rgb" entry point: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576) */
 static __thread int g_nospecial;    /* an nv12 / nv21 destination computed through the planar path: no yuv420p-only special converters */
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
@@ -436,6 +438,10 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (sws_open(&c, sw, sh, dw, dh, 1, flags)) return -1;
     uint8_t ytab[1024]; int32_t rv[256], gu[256], gv[256], bu[256];
     orc_sws_rgb24_tables(ytab, rv, gu, gv, bu);
+    if (g_rgb16 && sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter() && g_sbits == 8) {
+        sws_close(&c);          /* the ordered-dither table converters yuv2rgb_c_16 / _15 / _12_ordered_dither (yuv2rgb.c:377-573): not restated */
+        return -1;
+    }
     if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422 && !uses_filter() && g_sbits == 8) {
         /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
          * i.e. both rows of a pair read the even chroma line)
@@ -531,6 +537,28 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
                 continue;
             }
             const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
+            if (g_rgb16) {
+                /* yuv2rgb_write (output.c:869-902): the channel tables of these depths hold the 8-bit value cut down to its field
+                 * (yuv2rgb.c:806-844) and are indexed with an ordered dither added: 2 x 2 for 565 / 555, 4 x 4 for 444 */
+                static const uint8_t d2x2_4[2][2] = { { 1, 3 }, { 2, 0 } }, d2x2_8[2][2] = { { 6, 2 }, { 0, 4 } };
+                static const uint8_t d4x4[4][2] = { { 8, 4 }, { 2, 14 }, { 10, 6 }, { 0, 12 } };
+                const int kind = (g_rgb16 & 7) - 1, fmt = kind >> 1, isbgr = kind & 1;
+                int dr[2], dg[2], db[2];
+                for (int k = 0; k < 2; k++) {
+                    if (fmt == 0)      { dr[k] = d2x2_8[y & 1][k]; dg[k] = d2x2_4[y & 1][k];     db[k] = d2x2_8[(y & 1) ^ 1][k]; }
+                    else if (fmt == 1) { dr[k] = d2x2_8[y & 1][k]; dg[k] = d2x2_8[y & 1][k ^ 1]; db[k] = d2x2_8[(y & 1) ^ 1][k]; }
+                    else               { dr[k] = d4x4[y & 3][k];   dg[k] = d4x4[y & 3][k ^ 1];   db[k] = d4x4[(y & 3) ^ 3][k]; }
+                }
+                const int rs = fmt == 2 ? 4 : 3, gs = fmt == 0 ? 2 : fmt == 1 ? 3 : 4, gpos = fmt == 2 ? 4 : 5, hi = fmt == 0 ? 11 : fmt == 1 ? 10 : 8;
+                const int Yk[2] = { Y1, Y2 };
+                for (int k = 0; k < 2; k++) {
+                    if (k && !(2 * i + 1 < dw || dstride >= 2 * (dw + 1))) break;
+                    unsigned v = (unsigned)(r[Yk[k] + dr[k]] >> rs) << (isbgr ? 0 : hi) | (unsigned)(g[Yk[k] + dg[k]] >> gs) << gpos | (unsigned)(b[Yk[k] + db[k]] >> rs) << (isbgr ? hi : 0);
+                    if (g_rgb16 & 8) v = ((v >> 8) | (v << 8)) & 0xffff;
+                    d[4 * i + 2 * k] = (uint8_t)v; d[4 * i + 2 * k + 1] = (uint8_t)(v >> 8);
+                }
+                continue;
+            }
             d[6 * i + 0] = r[Y1]; d[6 * i + 1] = g[Y1]; d[6 * i + 2] = b[Y1];
             if (2 * i + 1 < dw || dstride >= 3 * (dw + 1)) { d[6 * i + 3] = r[Y2]; d[6 * i + 4] = g[Y2]; d[6 * i + 5] = b[Y2]; }
         }
@@ -658,7 +686,7 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
     const uint8_t *src[3] = { y, u, v };
     const int ss[3] = { ystride, pitch, pitch };
     g_nocopy = 1;
-    int r = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || dst_fmt == 1 || dst_fmt == 15 ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
+    int r = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || dst_fmt == 1 || dst_fmt == 15 || IS_RGB16(dst_fmt) ? to_rgb_or_bgr(src, ss, sw, sh, dst_fmt, dst[0], dstride[0], dw, dh, flags | 0x40000)
                                          : orc_sws_yuv420p_to_yuv420p(src, ss, sw, sh, dst, dstride, dw, dh, flags);
     g_nocopy = 0;
     free(u);
@@ -670,6 +698,21 @@ int orc_sws_nv12(int nv21, const uint8_t *y, int ystride, const uint8_t *uv, int
 static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, int sh, int dst_fmt, uint8_t *dst, int dstride, int dw, int dh, int flags)
 {
     if (dst_fmt == 2) return orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags);
+    {   /* rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444, LE and BE (libavutil/pixfmt.h 36-43, 54-57) */
+        int k16 = 0;
+        switch (dst_fmt) {
+        case 37: k16 = 1; break; case 36: k16 = 1 | 8; break; case 41: k16 = 2; break; case 40: k16 = 2 | 8; break;
+        case 39: k16 = 3; break; case 38: k16 = 3 | 8; break; case 43: k16 = 4; break; case 42: k16 = 4 | 8; break;
+        case 54: k16 = 5; break; case 55: k16 = 5 | 8; break; case 56: k16 = 6; break; case 57: k16 = 6 | 8; break;
+        }
+        if (k16) {
+            if (uses_filter()) return -1;
+            g_rgb16 = k16;
+            int r16 = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags & ~F_FULL_CHR_H_INT);
+            g_rgb16 = 0;
+            return r16;
+        }
+    }
     if (dst_fmt == 1 || dst_fmt == 15) {          /* yuyv422 / uyvy422: the packed output stage without the colour conversion */
         g_pk422 = dst_fmt == 1 ? 1 : 2;
         int r422 = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags & ~F_FULL_CHR_H_INT);
@@ -927,7 +970,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         }
         if (base >= 0 && g_sbits == 8) {
             int h2, v2, b2 = 8;
-            const int rgbd = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28), pkd = dst_fmt == 1 || dst_fmt == 15, nvd = g_nospecial;
+            const int rgbd = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || IS_RGB16(dst_fmt), pkd = dst_fmt == 1 || dst_fmt == 15, nvd = g_nospecial;
             const int shs = base == 5 ? 0 : 1, svs = base == 0 ? 1 : 0;
             if (uses_filter()) return -1;
             if (!rgbd && !pkd) {
@@ -948,7 +991,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     if (src_j || dst_j) {
         const int sf = src_fmt == 12 ? 0 : src_fmt == 13 ? 4 : src_fmt == 14 ? 5 : src_fmt == 32 ? 31 : src_fmt;
         const int df = dst_fmt == 12 ? 0 : dst_fmt == 13 ? 4 : dst_fmt == 14 ? 5 : dst_fmt == 32 ? 31 : dst_fmt;
-        const int dst_rgb = df == 2 || df == 3 || (df >= 25 && df <= 28);
+        const int dst_rgb = df == 2 || df == 3 || (df >= 25 && df <= 28) || IS_RGB16(df);
         if (dst_rgb) {
             g_cs_jpeg = 1;
             r = sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
@@ -964,7 +1007,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         g_range = 0;
         return r;
     }
-    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk;
+    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk || IS_RGB16(dst_fmt);
     for (int wv = 1; wv < 4; wv += 2)                      /* asymmetric vertical vectors (lumV, chrV): the reference's last rows depend on its ring buffer state */
         for (int i = 0; i < g_fv[wv][0].length / 2; i++)
             if (g_fv[wv][0].coeff[i] != g_fv[wv][0].coeff[g_fv[wv][0].length - 1 - i]) return -1;
@@ -996,7 +1039,8 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
             return sh;
         }
     }
-    if (pk) flags &= ~F_FULL_CHR_H_INT;
+    if (pk || IS_RGB16(dst_fmt)) flags &= ~F_FULL_CHR_H_INT;
+    if (IS_RGB16(dst_fmt) && uses_filter()) return -1;
     if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT)) return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
@@ -1007,6 +1051,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
     case 1: case 2: case 3: case 15: case 25: case 26: case 27: case 28:
+        if (IS_RGB16(dst_fmt)) return -1;              /* (rgb2rgb converter families and readers in front of the 16-bpp output stage: not restated) */
         r = packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;

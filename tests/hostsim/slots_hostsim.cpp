@@ -21,6 +21,7 @@ static std::string g_err;
 void set_error_msg(const char *where, const char *msg) { if (g_err.empty()) g_err = std::string(where) + ": " + msg; }
 void set_error(const char *where, cudaError_t) { set_error_msg(where, "hostsim error"); }
 int check_launch(const char *) { return 0; }
+void enter() {}
 int sm_count() { return 148; }
 // the general scaler is forced onto its two-pass path here: the tile kernels synchronise their threads (swscale_hostsim.cpp)
 int tuning(const char *key) { return !strcmp(key, "sws_general_variant") ? 1 : 0; }

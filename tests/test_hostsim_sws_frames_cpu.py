@@ -24,7 +24,7 @@ def outputs(df, dw, dh, pad=8, fill=7):
         dt = np.uint8 if bits == 8 else np.dtype(">u2" if df in PLANAR_BE else "<u2")
         cw, ch = -((-dw) >> hs), -((-dh) >> vs)
         return [np.full((dh, dw + pad), fill, dt), np.full((ch, cw + pad), fill, dt), np.full((ch, cw + pad), fill, dt)]
-    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) else 3
+    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) or 36 <= df <= 43 or 54 <= df <= 57 else 3
     return [np.full((dh, dw * bpp + 2 * pad), fill, np.uint8)]
 
 
@@ -86,6 +86,31 @@ def test_format_matrix(sim, refo):
                     same(product(sim, sf, pl, w, h, df, dw, dh, flags), reference(refo, sf, pl, w, h, df, dw, dh, flags), (sf, df, w, h, dw, dh, hex(flags)), crop=8)
                     n += 1
     assert n > 900
+
+
+def test_rgb16_destinations(sim, refo):
+    """rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444, LE and BE (tests/test_sws_rgb16_dst.py): the dithered 16-bpp output stage of the
+    two-pass path, every source it is taken over for, full-range sources and 10-bit sources included"""
+    import test_sws_rgb16_dst as R
+    n = 0
+    for df in R.DST:
+        for (sf, w, h, dw, dh, flags) in R.combos(df):
+            if n % 3 and (w, h, dw, dh) != (67, 50, 67, 50):
+                n += 1
+                continue                         # (a third of the matrix per format: the port covers all of it against the reference)
+            pl = source(sf, w, h, 43)
+            same(product(sim, sf, pl, w, h, df, dw, dh, flags), reference(refo, sf, pl, w, h, df, dw, dh, flags), (sf, df, w, h, dw, dh, hex(flags)), crop=8)
+            n += 1
+    assert n > 1000
+    import test_sws_hbd_sources_cpu as H
+    for sf in (12, 64):                          # yuvj420p (the range folds into the colour constants), yuv420p10le (hScale16To15 lines)
+        for df in (37, 43, 55):
+            pl = source(0, 66, 50, 44) if sf == 12 else H.planes(sf, 66, 50, 5)
+            same(product(sim, sf, pl, 66, 50, df, 100, 80, 4 | ACC), reference(refo, sf, pl, 66, 50, df, 100, 80, 4 | ACC), (sf, df), crop=8)
+    # refusals: the ordered-dither table converter's case, packed rgb sources, the per-line slots
+    for args in ((64, 48, 0, 64, 48, 37, 4), (64, 48, 2, 128, 96, 37, 4 | ACC), (64, 48, 1, 128, 96, 41, 4 | ACC)):
+        assert not sim.sws_getContext_cuda(*args, None, None, None)
+        sim.avb200_clear_error()
 
 
 def test_range_conversion_frames(sim, refo):

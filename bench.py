@@ -451,6 +451,52 @@ def make_idct10_workload(torch, L, stream, rank):
     }
 
 
+def make_h264_hbd_workload(torch, L, stream, rank):
+    """config 3's chain on 10-bit pictures (the BIT_DEPTH 10 instances: uint16 samples, int32 coefficients): 30 stacked 1920x1088 pictures of 64
+    slices per step through ff_h264_mc_batch_hbd_cuda -> ff_h264_idct_add_mb_batch_hbd_cuda -> ff_h264_deblock_batch_hbd_cuda (the functional
+    kernels of csrc/h264_hbd_batch.cu).  Same records as the 8-bit workload, byte offsets doubled."""
+    from libav_b200 import synth
+    lib = L.lib
+    pic = synth.h264_config3_picture(120, 68, 64, seed=rank)
+    mb_w, mb_h, P = pic["mb_w"], pic["mb_h"], H264_PICTURES
+    W, H = 16 * mb_w, 16 * mb_h
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    up = lambda p8: (p8.astype(np.uint16) << 2) | (p8.astype(np.uint16) >> 6)
+    d_refs = [[t(np.concatenate([up(p)] * P)) for p in r] for r in pic["refs"]]
+    d_planes = torch.tensor([[r[0].data_ptr(), r[1].data_ptr(), r[2].data_ptr()] for r in d_refs], dtype=torch.int64).cuda()
+    mcs = []
+    for k in range(P):
+        m = pic["mc"].copy(); m["y"] = m["y"] + k * H; mcs.append(m)
+    mc = np.concatenate(mcs)
+    ress = []
+    for k in range(P):
+        r = pic["res"].copy(); r["luma_off"] = 2 * (r["luma_off"] + k * W * H); r["chroma_off"] = 2 * (r["chroma_off"] + k * W * H // 4); ress.append(r)
+    res = np.concatenate(ress)
+    n = mb_w * mb_h * P
+    d_mc, d_res, d_nnz, d_dbk = t(mc), t(res), t(np.concatenate([pic["nnzc"]] * P)), t(np.concatenate([pic["dbk"]] * P))
+    d_coef0 = t(np.concatenate([pic["coeffs"].astype(np.int32) * 4] * P))
+    d_coef = d_coef0.clone()
+    d_y = torch.zeros(P * W * H * 2, dtype=torch.uint8, device="cuda")
+    d_cb = torch.zeros(P * W * H // 2, dtype=torch.uint8, device="cuda")
+    d_cr = torch.zeros(P * W * H // 2, dtype=torch.uint8, device="cuda")
+
+    def run(i):
+        d_coef.copy_(d_coef0, non_blocking=True)               # (inside the step: the arena the residual pass consumes)
+        L.check(lib.ff_h264_mc_batch_hbd_cuda(10, 1, d_mc.data_ptr(), mc.shape[0], d_planes.data_ptr(), d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(),
+                                              2 * W, W, W, H, stream), "mc hbd")
+        L.check(lib.ff_h264_idct_add_mb_batch_hbd_cuda(10, 1, d_res.data_ptr(), n, d_coef.data_ptr(), 768, d_nnz.data_ptr(), d_y.data_ptr(), d_cb.data_ptr(),
+                                                       d_cr.data_ptr(), 2 * W, W, stream), "residual hbd")
+        L.check(lib.ff_h264_deblock_batch_hbd_cuda(10, d_dbk.data_ptr(), mb_w, mb_h, P, d_y.data_ptr(), d_cb.data_ptr(), d_cr.data_ptr(), 2 * W, W, stream), "deblock hbd")
+
+    return {
+        "name": "H.264 1080p DSP path on 10-bit pictures (functional kernels): MC + residual + deblock, %d stacked 64-slice pictures per step" % P,
+        "run": run, "run_e2e": None, "pixels": P * W * H, "alg_bytes": n * (2 * 768 + 3 * 1536 + 104 + 1536),
+        "launches_per_step": 4, "kernel": "h264_deblock_hbd_kernel", "dtype": "int32 (u16 samples, int32 coefficients)", "h2d": 0, "d2h": 0,
+        "l2": "%d MiB of pictures + coefficients per step" % ((P * W * H * 3 + n * 3072) >> 20),
+        "keep": (d_refs, d_planes, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr),
+    }
+
+
 def make_h264_intra_workload(torch, L, stream, rank):
     """all-intra 1080p pictures (equal shares of intra 4x4 / 8x8 / 16x16 macroblocks, every prediction
     mode the availability allows, half of the blocks coded) reconstructed by the prediction + residual wavefront; a batch of
@@ -805,7 +851,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sws4k", choices=["sws4k", "h264", "idct_put", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft", "idct10"])
+    ap.add_argument("--workload", default="sws4k", choices=["sws4k", "h264", "idct_put", "me", "sws_up", "h264_decide", "dequant_idct", "h264_intra", "fft", "idct10", "h264_hbd"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads and the CPU baselines")
     ap.add_argument("--no-verify", action="store_true", help="skip the post-timing comparison with the CPU checker")
     ap.add_argument("--tune", action="append", default=[], help="kernel-variant knob key=value (avb200_set_tuning), profiling only")
@@ -867,7 +913,7 @@ def main():
 
     makers = {"sws4k": make_sws_workload, "h264": make_h264_workload, "idct_put": make_idct_workload, "me": make_me_workload,
               "sws_up": make_sws_up_workload, "dequant_idct": make_dequant_idct_workload, "h264_intra": make_h264_intra_workload,
-              "fft": make_fft_workload, "h264_decide": make_h264_decide_workload, "idct10": make_idct10_workload}
+              "fft": make_fft_workload, "h264_decide": make_h264_decide_workload, "idct10": make_idct10_workload, "h264_hbd": make_h264_hbd_workload}
     if args.workload == "me" and world > 1:
         makers["me"] = make_me_sharded_workload
     order = [args.workload] + ([w for w in makers if w != args.workload] if not args.no_secondary else [])

@@ -2,8 +2,8 @@
 # round 2: the driver's 8-GPU launch of both arms (torchrun, one rank per GPU), to look at the end-to-end scaling after the NUMA binding
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r2s_topo.txt 2>&1
-for n in 8; do
-  ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r2s_bench_n$n.json 2> gpurun_out/r2s_bench_n$n.err ) 2> gpurun_out/r2s_bench_n$n.time
+for n in 2 8; do
+  ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 --no-secondary > gpurun_out/r2s_bench_n$n.json 2> gpurun_out/r2s_bench_n$n.err ) 2> gpurun_out/r2s_bench_n$n.time
   tail -3 gpurun_out/r2s_bench_n$n.time
   python - $n <<'PY'
 import json, sys

@@ -5,10 +5,7 @@
 //              rows read-modify-written, consumed coefficients zeroed (parity also holds on the coefficient buffer).
 //   MC         one warp per partition record, lanes stride over the partition's luma + 2 x chroma samples; reference
 //              samples come through a clamped fetch (replaces emulated_edge_mc), read-only path, L1-resident window.
-//   deblock    one warp per macroblock ROW, rows run as a wavefront two macroblocks behind the row above (progress
-//              counters in global memory), so the serial raster order of the reference is reproduced exactly.
-//              A macroblock lives in shared memory while its 8 luma + 4 chroma edge passes run: lanes 0-15 own the 16
-//              luma lines of an edge, lanes 16-23 / 24-31 the 8 cb / cr lines.
+//   deblock    h264_deblock.cu (paired-row register-resident wavefront, rows handed out by an atomic ticket)
 // All arithmetic is in h264dsp.cuh.
 #include "h264dsp.cuh"
 #include "../../include/avdsp_b200.h"
@@ -218,153 +215,8 @@ h264_weight_kernel(const FFH264WeightRecord *__restrict__ recs, size_t n, uint8_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Deblocking wavefront.
-constexpr int LT = 24;      // luma tile pitch   (20 columns used: -4 .. 15)
-constexpr int CT = 16;      // chroma tile pitch (12 columns used: -4 .. 7)
-
-__device__ __forceinline__ uint32_t ld_cg32(const uint8_t *p) { return __ldcg(reinterpret_cast<const uint32_t *>(p)); }
-
-// ---------------------------------------------------------------------------------------------------
-// Deblocking wavefront, register-resident variant (default).  Same tile, same order, but the four vertical edges of a
-// macroblock are filtered by a lane on ITS OWN ROW held in registers (rows are independent for vertical edges), and the
-// four horizontal edges by a lane on its own COLUMN: two phases and two warp barriers per macroblock instead of eight
-// phases, no shared-memory round trip between edges.  The progress flag for macroblock x - 1 is published (fence + store)
-// just before macroblock x is written back, when the stores it covers have long retired, so the fence is cheap; rows
-// therefore follow three macroblocks behind the row above.  Pictures of a batch are stacked vertically (picture k starts
-// at macroblock row k * rows_pp): the first row of every picture has no row above.
-template <int N> struct Px { uint8_t v[N]; };
-
-// Luma and chroma are independent planes: blockIdx.y = 0 runs the luma wavefront (16 lines per edge), blockIdx.y = 1 the
-// chroma one (8 cb + 8 cr lines), each with its own progress flags, so neither waits for the other's edge passes.
-template <bool CHROMA>
-__device__ __forceinline__ void deblock_row(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb,
-                                            uint8_t *cr, int ls, int uvls, volatile uint32_t *prog, uint8_t *T, FFH264DeblockMB &P)
-{
-    // tile T: luma 20 rows x LT (rows -4..15, cols -4..15), chroma 2 planes x 10 rows x CT (rows -2..7, cols -4..7)
-    const int lane = threadIdx.x, row = blockIdx.x, lrow = row % rows_pp;
-    const bool has_above = lrow > 0;
-    constexpr int NR = CHROMA ? 20 : 20;            // loader lanes: 20 luma rows, or 2 x 10 chroma rows
-    constexpr int PITCH = CHROMA ? CT : LT, MBW = CHROMA ? 8 : 16, TOP = CHROMA ? 2 : 4;
-    const int pl = CHROMA ? lane / 10 : 0, tr = CHROMA ? lane % 10 : lane;             // loader lane -> (plane, tile row)
-    uint8_t *const plane = CHROMA ? (pl ? cr : cb) : luma;
-    const int pitch_g = CHROMA ? uvls : ls;
-    uint8_t *const trow = T + (CHROMA ? pl * 10 * CT : 0) + tr * PITCH;                 // this loader lane's tile row
-    const bool row_exists = lane < NR && lrow * MBW + tr - TOP >= 0;
-    uint8_t *const grow = plane + (size_t)(row * MBW + tr - TOP) * pitch_g;             // same row in the picture
-
-    bool prev_top = false;                                  // did the previous macroblock filter its top edge?
-    for (int x = 0; x < mb_w; x++) {
-        // the parameters do not depend on other rows: fetch them first, they say whether this macroblock touches the row above
-        if (lane < (int)(sizeof(FFH264DeblockMB) / 4))
-            reinterpret_cast<uint32_t *>(&P)[lane] = reinterpret_cast<const uint32_t *>(&mbs[(size_t)row * mb_w + x])[lane];
-        __syncwarp();
-        // Only the top (horizontal, edge 0) filter reads or writes pixels of the row above.  When it is off -- first row, or a
-        // slice boundary with disable_deblocking_filter_idc 2 -- this macroblock neither waits for that row nor stores into it.
-        const bool top = has_above && (CHROMA ? ((P.calpha[0][1][0] && P.cbeta[0][1][0]) || (P.calpha[1][1][0] && P.cbeta[1][1][0]))
-                                              : (P.alpha[1][0] && P.beta[1][0]));
-        if (top) {
-            if (lane == 0) { const uint32_t need = min(x + 2, mb_w); while (prog[row - 1] < need) { } }
-            __syncwarp();
-        }
-        if (lane < NR) {
-            if (x > 0) *reinterpret_cast<uint32_t *>(trow) = *reinterpret_cast<const uint32_t *>(trow + MBW);   // left context
-            if (row_exists && (top || tr >= TOP)) {
-                const uint8_t *g = grow + x * MBW;
-#pragma unroll
-                for (int k = 0; k < MBW / 4; k++) *reinterpret_cast<uint32_t *>(trow + 4 + 4 * k) = ld_cg32(g + 4 * k);
-            }
-        }
-        __syncwarp();
-
-        if (lane < 16) {
-            const int p = CHROMA ? lane >> 3 : 0, l = CHROMA ? lane & 7 : lane;          // filter lane -> (plane, line)
-            uint8_t *const tp = T + (CHROMA ? p * 10 * CT : 0);
-            // ---- vertical edges: this lane's row in registers ----
-            {
-                constexpr int W = CHROMA ? 12 : 20;
-                Px<W> r;
-                uint32_t *rw = reinterpret_cast<uint32_t *>(tp + (TOP + l) * PITCH);
-#pragma unroll
-                for (int k = 0; k < W / 4; k++) { const uint32_t w = rw[k]; r.v[4 * k] = (uint8_t)w; r.v[4 * k + 1] = (uint8_t)(w >> 8); r.v[4 * k + 2] = (uint8_t)(w >> 16); r.v[4 * k + 3] = (uint8_t)(w >> 24); }
-#pragma unroll
-                for (int e = 0; e < (CHROMA ? 2 : 4); e++) {
-                    if (!CHROMA) {
-                        const int a = P.alpha[0][e], b = P.beta[0][e];
-                        if (a && b) {
-                            if (P.intra[0] >> e & 1) h264_luma_intra_line(&r.v[4 + 4 * e], 1, a, b);
-                            else { const int tc = P.tc0[0][e][l >> 2]; if (tc >= 0) h264_luma_line(&r.v[4 + 4 * e], 1, a, b, tc); }
-                        }
-                    } else {
-                        const int a = P.calpha[p][0][e], b = P.cbeta[p][0][e];
-                        if (a && b) {
-                            const int in = P.cintra[p][0] >> e & 1, tc = P.ctc0[p][0][e][l >> 1];
-                            if (in || tc > 0) h264_chroma_line(&r.v[4 + 4 * e], 1, a, b, tc, in);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < W / 4; k++) rw[k] = r.v[4 * k] | (r.v[4 * k + 1] << 8) | (r.v[4 * k + 2] << 16) | ((uint32_t)r.v[4 * k + 3] << 24);
-            }
-            __syncwarp(0xffffu);
-            // ---- horizontal edges: this lane's column in registers ----
-            {
-                constexpr int H = CHROMA ? 10 : 20;
-                Px<H> c;
-                uint8_t *col = tp + 4 + l;
-#pragma unroll
-                for (int k = 0; k < H; k++) c.v[k] = col[k * PITCH];
-#pragma unroll
-                for (int e = 0; e < (CHROMA ? 2 : 4); e++) {
-                    if (!CHROMA) {
-                        const int a = P.alpha[1][e], b = P.beta[1][e];
-                        if (a && b) {
-                            if (P.intra[1] >> e & 1) h264_luma_intra_line(&c.v[4 + 4 * e], 1, a, b);
-                            else { const int tc = P.tc0[1][e][l >> 2]; if (tc >= 0) h264_luma_line(&c.v[4 + 4 * e], 1, a, b, tc); }
-                        }
-                    } else {
-                        const int a = P.calpha[p][1][e], b = P.cbeta[p][1][e];
-                        if (a && b) {
-                            const int in = P.cintra[p][1] >> e & 1, tc = P.ctc0[p][1][e][l >> 1];
-                            if (in || tc > 0) h264_chroma_line(&c.v[2 + 4 * e], 1, a, b, tc, in);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 1; k < H; k++) col[k * PITCH] = c.v[k];
-            }
-        }
-        __syncwarp();
-
-        // publish macroblock x - 1 (its stores were issued a whole macroblock ago), then write macroblock x back
-        if (x > 0) { __threadfence(); if (lane == 0) prog[row] = x; }
-        if (row_exists && tr >= 1) {                            // tile row 0 is read-only context
-            uint8_t *g = grow + x * MBW;
-            const bool own = tr >= TOP;                         // rows above the macroblock row are stored only by whoever filtered them
-            if (x > 0 && (own || prev_top)) *reinterpret_cast<uint32_t *>(g - 4) = *reinterpret_cast<const uint32_t *>(trow);
-            if (own || top) {
-#pragma unroll
-                for (int k = 0; k < MBW / 4 - 1; k++) *reinterpret_cast<uint32_t *>(g + 4 * k) = *reinterpret_cast<const uint32_t *>(trow + 4 + 4 * k);
-                if (x == mb_w - 1) *reinterpret_cast<uint32_t *>(g + MBW - 4) = *reinterpret_cast<const uint32_t *>(trow + MBW);
-            }
-        }
-        prev_top = top;
-        __syncwarp();
-    }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) prog[row] = mb_w;
-}
-
-__global__ void __launch_bounds__(32)
-h264_deblock_kernel_v2(const FFH264DeblockMB *__restrict__ mbs, int mb_w, int rows_pp, uint8_t *luma, uint8_t *cb, uint8_t *cr,
-                       int ls, int uvls, uint32_t *progress)
-{
-    __shared__ __align__(16) uint8_t T[20 * LT];
-    __shared__ FFH264DeblockMB P;
-    if (blockIdx.y == 0) deblock_row<false>(mbs, mb_w, rows_pp, luma, cb, cr, ls, uvls, progress, T, P);
-    else                 deblock_row<true>(mbs, mb_w, rows_pp, luma, cb, cr, ls, uvls, progress + gridDim.x, T, P);
-}
-
+// Deblocking wavefront: h264_deblock.cu (the one-warp-per-row kernel that lived here relied on CTAs being dispatched in block-index order and
+// is gone).
 int launch_h264_deblock_v3(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls,
                            int uvls, uint32_t *progress, cudaStream_t st);       // h264_deblock.cu
 
@@ -419,13 +271,8 @@ int launch_h264_deblock(const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pi
     if ((ls & 3) || (uvls & 3) || ((uintptr_t)luma & 3) || ((uintptr_t)cb & 3) || ((uintptr_t)cr & 3)) {
         set_error_msg("h264_deblock_picture", "planes and line sizes must be 4-byte aligned"); return -1;
     }
-    // default: the paired-row, register-resident wavefront of h264_deblock.cu; deblock_variant = 2 keeps the one-warp-per-row
-    // kernel above for comparison (profiling knob)
-    if (tuning("deblock_variant") != 2) return launch_h264_deblock_v3(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, ls, uvls, progress, st);
-    const int rows = mb_h * n_pictures;
-    AVB_CUDA(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * rows * 2, st), "h264_deblock_picture");
-    h264_deblock_kernel_v2<<<dim3(rows, 2), 32, 0, st>>>(mbs, mb_w, mb_h, luma, cb, cr, ls, uvls, progress);
-    return check_launch("h264_deblock_picture");
+    // the paired-row, register-resident wavefront of h264_deblock.cu (rows handed out by an atomic ticket)
+    return launch_h264_deblock_v3(mbs, mb_w, mb_h, n_pictures, luma, cb, cr, ls, uvls, progress, st);
 }
 
 }  // namespace avb

@@ -491,7 +491,7 @@ def make_h264_hbd_workload(torch, L, stream, rank):
     return {
         "name": "H.264 1080p DSP path on 10-bit pictures (functional kernels): MC + residual + deblock, %d stacked 64-slice pictures per step" % P,
         "run": run, "run_e2e": None, "pixels": P * W * H, "alg_bytes": n * (2 * 768 + 3 * 1536 + 104 + 1536),
-        "launches_per_step": 4, "kernel": "h264_deblock_hbd_kernel", "dtype": "int32 (u16 samples, int32 coefficients)", "h2d": 0, "d2h": 0,
+        "launches_per_step": 4, "kernel": "h264_deblock_generic_kernel", "dtype": "int32 (u16 samples, int32 coefficients)", "h2d": 0, "d2h": 0,
         "l2": "%d MiB of pictures + coefficients per step" % ((P * W * H * 3 + n * 3072) >> 20),
         "keep": (d_refs, d_planes, d_mc, d_res, d_nnz, d_dbk, d_coef0, d_coef, d_y, d_cb, d_cr),
     }

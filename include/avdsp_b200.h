@@ -255,6 +255,18 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
                               void *stream);
 int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma,
                                    uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream);
+/* chroma_format_idc 2, bit depth 8 / 9 / 10: the 8 x 16 chroma macroblock has two vertical edges of sixteen lines (the 104-byte record's
+ * calpha / cbeta / ctc0 / cintra [plane][0][edge]: h264_h_loop_filter_chroma422, a tc0 entry per four lines) and FOUR horizontal edges, one per
+ * luma edge at chroma rows 0, 4, 8, 12 (h264_loopfilter.c:633,693-700: also inside 8x8-transform macroblocks), carried by a second record per
+ * macroblock; luma is filtered from the 104-byte record as always ([plane][1][..] of its chroma fields is not read). */
+typedef struct FFH264DeblockChroma422 {
+    uint8_t alpha[2][4], beta[2][4];   /* [plane cb / cr][edge] */
+    int8_t  tc0[2][4][4];              /* as passed to h264_v_loop_filter_chroma (already + 1), <= 0 = group not filtered */
+    uint8_t intra[2];                  /* bit e: edge e uses the intra (bS 4) filter */
+    uint8_t pad[2];
+} FFH264DeblockChroma422;
+int ff_h264_deblock_batch_422_cuda(int bit_depth, const FFH264DeblockMB *mbs, const FFH264DeblockChroma422 *chroma422, int mb_w, int mb_h,
+                                   int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream);
 
 /* Deblocking DECISIONS: what loop_filter() -> fill_filter_caches() -> ff_h264_filter_mb()
  * (libavcodec/h264_slice.c:1972-2262, libavcodec/h264_loopfilter.c:438-846) decide for every macroblock of a
@@ -270,7 +282,7 @@ int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, in
  *       ref2frm[list][2 + ref_index] = identity of the referenced frame, entries 0/1 = -1); at most 32 slice numbers
  *   chroma_qp_table: PPS.chroma_qp_table[2][64] (h264_ps.h:124)
  * Pictures of a batch are stacked row-wise; no edge is filtered across a picture boundary.
- * Field pictures (PAFF) are covered through field_picture; not covered: MBAFF frames, the chroma edges of 4:2:2 / 4:4:4 (the records
+ * Field pictures (PAFF) are covered through field_picture, 4:2:2 through chroma422; not covered: MBAFF frames, 4:4:4 (the records
  * themselves are bit-depth agnostic: ff_h264_deblock_batch_hbd_cuda takes them for 9 / 10-bit pictures). */
 typedef struct FFH264DeblockSlice {
     int32_t alpha_c0_offset, beta_offset;   /* sl->slice_alpha_c0_offset, sl->slice_beta_offset */
@@ -294,6 +306,8 @@ typedef struct FFH264DeblockInfo {
     int field_picture;                      /* h->picture_structure != PICT_FRAME: the pictures are fields (every mb_type carries
                                                MB_TYPE_INTERLACED): vertical vector limit 2, bS 3 on horizontal intra macroblock edges
                                                (h264_loopfilter.c:551-557,723) */
+    FFH264DeblockChroma422 *chroma422;      /* device pointer, NULL for 4:2:0; else chroma_format_idc 2: the horizontal chroma edges of
+                                               macroblock m are written to chroma422[m] instead of the 104-byte record's [plane][1][..] */
 } FFH264DeblockInfo;
 int ff_h264_deblock_params_cuda(const FFH264DeblockInfo *info /* host struct */, FFH264DeblockMB *out, void *stream);
 

@@ -14,11 +14,11 @@
 //   residual   warp per macroblock, lane per transform block exactly as the C dispatchers iterate (lanes never communicate)
 //   MC         warp per partition record, lanes stride over its luma and chroma samples, every reference sample through a clamped fetch
 //              (= emulated_edge_mc); `put` records in pass 0, `avg` records in pass 1 (two ordered launches)
-//   deblock    one CTA per picture, its warps take macroblock rows round-robin and run them as a wavefront (a row stays two macroblocks
-//              behind the row above): progress counters live in SHARED memory, so no inter-CTA ordering, fence or dispatch-order
-//              assumption exists; all warps of a CTA are resident, rows are taken in increasing order, hence no deadlock.  Within a
-//              macroblock: 16 luma + 8 cb + 8 cr lanes filter the vertical edges line by line, then the horizontal ones column by
-//              column (h264_loopfilter.c:238-395 order per plane).
+//   deblock    one CTA per picture and plane kind (luma; cb + cr), its warps take macroblock rows round-robin and run them as a wavefront (a
+//              row stays two macroblocks behind the row above): progress counters live in SHARED memory, so no inter-CTA ordering, fence
+//              or dispatch-order assumption exists; all warps of a CTA are resident, rows are taken in increasing order, hence no
+//              deadlock.  Within a macroblock: 16 lanes filter the vertical edges line by line, then the horizontal ones column by column
+//              (h264_loopfilter.c:238-395 order per plane); the next macroblock's record and sample rows are prefetched meanwhile.
 // A picture of a batch starts `pic_h` luma rows after the previous one in the same planes (like the 8-bit calls).
 #include "h264dsp.cuh"
 #include "h264dsp_hbd.cuh"
@@ -142,22 +142,68 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int DB_WARPS = 16;
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
+// the loop-filter slots on one line across an edge, by sample type: 8-bit = h264dsp.cuh, 9 / 10-bit = h264dsp_hbd.cuh (alpha / beta / tc0
+// scaled by 2^(bits - 8) like h264dsp_template.c:110-113,240); ctc = the chroma slots' tc0 argument (already + 1)
+template <typename PX> struct LineFilter;
+template <> struct LineFilter<uint8_t> {
+    static __device__ __forceinline__ void luma(int, uint8_t *q, int ps, int a, int b, int tc0, bool intra)
+    { if (intra) h264_luma_intra_line(q, ps, a, b); else if (tc0 >= 0) h264_luma_line(q, ps, a, b, tc0); }
+    static __device__ __forceinline__ void chroma(int, uint8_t *q, int ps, int a, int b, int ctc, bool intra)
+    { if (intra || ctc > 0) h264_chroma_line(q, ps, a, b, ctc, intra); }
+};
+template <> struct LineFilter<uint16_t> {
+    static __device__ __forceinline__ void luma(int bits, uint16_t *q, int ps, int a, int b, int tc0, bool intra)
+    { const int sh = bits - 8; if (intra) hbd::luma_intra_line(q, ps, a << sh, b << sh); else if (tc0 >= 0) hbd::luma_line(bits, q, ps, a << sh, b << sh, tc0 << sh); }
+    static __device__ __forceinline__ void chroma(int bits, uint16_t *q, int ps, int a, int b, int ctc, bool intra)
+    {
+        const int sh = bits - 8;
+        if (intra) hbd::chroma_line(bits, q, ps, a << sh, b << sh, 0, 1);
+        else { const int tc = ((ctc - 1) << sh) + 1; if (tc > 0) hbd::chroma_line(bits, q, ps, a << sh, b << sh, tc, 0); }
+    }
+};
+
+// blockIdx.x = picture, blockIdx.y = 0 luma / 1 chroma: the planes are independent (h264_loopfilter.c filters them edge by edge side by
+// side, but no sample of one plane depends on another), so each gets its own CTA, its own wavefront and its own progress counters.
+// Luma: lanes 0..15 = the 16 lines / columns of a macroblock.  Chroma 4:2:0: lanes 0..7 cb, 8..15 cr.  Chroma 4:2:2 (8 x 16 macroblocks):
+// vertical edges = 16 lines per plane on all 32 lanes (two edges, the 104-byte record's fields, a tc0 entry per four lines), horizontal
+// edges = 8 columns per plane on 16 lanes, FOUR edges (rows 0, 4, 8, 12; one per luma edge, h264_loopfilter.c:693-700) from the 52-byte
+// FFH264DeblockChroma422 record.  While macroblock x is filtered the records and the sample rows of macroblock x + 1 are prefetched into
+// L1 (first touches otherwise cost a DRAM round trip per macroblock on the critical path of the wavefront; the CTA is the only writer of
+// its picture, so the SM's L1 stays coherent).
+template <typename PX, bool C422>
 __global__ void __launch_bounds__(DB_WARPS * 32)
-h264_deblock_hbd_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
+h264_deblock_generic_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, const FFH264DeblockChroma422 *__restrict__ ext, int mb_w, int mb_h,
+                            uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
 {
-    using namespace hbd;
-    extern __shared__ int prog_s[];                                  // macroblocks finished per row of this CTA's picture
+    extern __shared__ int prog_s[];                                  // macroblocks finished per row of this CTA's picture and plane kind
     volatile int *prog = prog_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pic = blockIdx.x, sh = bits - 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pic = blockIdx.x;
+    const bool is_luma = blockIdx.y == 0;
     for (int i = threadIdx.x; i < mb_h; i += blockDim.x) prog_s[i] = 0;
     __syncthreads();
-    const int lsp = ls >> 1, uvlsp = uvls >> 1;
-    px *const Y = reinterpret_cast<px *>(luma) + (size_t)pic * mb_h * 16 * lsp;
-    px *const Cb = reinterpret_cast<px *>(cb) + (size_t)pic * mb_h * 8 * uvlsp, *const Cr = reinterpret_cast<px *>(cr) + (size_t)pic * mb_h * 8 * uvlsp;
-    const bool is_luma = lane < 16;
-    const int p = (lane - 16) >> 3, l = is_luma ? lane : (lane - 16) & 7;       // chroma plane, line / column inside the macroblock
+    const int st = (is_luma ? ls : uvls) / (int)sizeof(PX);           // row distance in samples
+    const int mbw_px = is_luma ? 16 : 8, mbh_px = is_luma ? 16 : (C422 ? 16 : 8);
+    PX *const yplane = reinterpret_cast<PX *>(luma) + (size_t)pic * mb_h * 16 * st;
+    PX *const cplane[2] = { reinterpret_cast<PX *>(cb) + (size_t)pic * mb_h * mbh_px * st, reinterpret_cast<PX *>(cr) + (size_t)pic * mb_h * mbh_px * st };
+    // prefetch role of this lane: a sample row of the next macroblock (luma: rows 0..15 on lanes 0..15, the four rows above on 16..19;
+    // chroma: plane lane >> 4, rows 0..mbh - 1, the two rows above on the lanes left over in 4:2:0)
+    const int pf_plane = is_luma ? 0 : lane >> 4;
+    int pf_row = is_luma ? (lane < 16 ? lane : lane < 20 ? 15 - lane : 99) : ((lane & 15) < mbh_px ? (lane & 15) : (lane & 15) < mbh_px + 2 ? mbh_px - 1 - (lane & 15) : 99);
     for (int row = warp; row < mb_h; row += DB_WARPS) {
-        for (int x = 0; x < mb_w; x++) {
+        PX *const rbase_y = yplane + (size_t)row * 16 * st;
+        PX *const rbase_c[2] = { cplane[0] + (size_t)row * mbh_px * st, cplane[1] + (size_t)row * mbh_px * st };
+        PX *const pf_base = is_luma ? rbase_y : rbase_c[pf_plane];
+        const size_t mrow = ((size_t)pic * mb_h + row) * mb_w;
+        const bool pf_ok = pf_row != 99 && (pf_row >= 0 || row > 0);
+        for (int x = -1; x < mb_w; x++) {
+            if (x + 1 < mb_w) {                                       // macroblock x + 1: sample rows, the 104-byte record (4 sectors), the 52-byte one (2)
+                if (pf_ok) prefetch_l1(pf_base + (ptrdiff_t)pf_row * st + (x + 1) * mbw_px);
+                if (lane < 4) prefetch_l1(reinterpret_cast<const char *>(mbs + mrow + x + 1) + 32 * lane);
+                else if (C422 && !is_luma && lane < 6) prefetch_l1(reinterpret_cast<const char *>(ext + mrow + x + 1) + 32 * (lane - 4));
+            }
+            if (x < 0) continue;
             if (row > 0) {
                 // the row above must be done with macroblock x + 1: its left-edge filter still reads and writes columns 13..15 of the
                 // macroblock above this one (raster order of the reference)
@@ -166,28 +212,40 @@ h264_deblock_hbd_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, int m
                 __syncwarp();
                 __threadfence_block();
             }
-            const FFH264DeblockMB &P = mbs[((size_t)pic * mb_h + row) * mb_w + x];
-            px *const base = is_luma ? Y + (size_t)row * 16 * lsp + x * 16 : (p ? Cr : Cb) + (size_t)row * 8 * uvlsp + x * 8;
-            const int st = is_luma ? lsp : uvlsp;
+            const FFH264DeblockMB &P = mbs[mrow + x];
             for (int dir = 0; dir < 2; dir++) {
-                // dir 0: vertical edges, this lane's line; dir 1: horizontal edges, this lane's column
-                px *const line = dir == 0 ? base + (size_t)l * st : base + l;
-                const int across = dir == 0 ? 1 : st;
+                // dir 0: vertical edges, a lane = a line; dir 1: horizontal edges, a lane = a column
                 if (is_luma) {
-                    for (int e = 0; e < 4; e++) {
-                        const int a = P.alpha[dir][e], b = P.beta[dir][e];
-                        if (!a || !b) continue;
-                        px *q = line + (size_t)4 * e * across;
-                        if (P.intra[dir] >> e & 1) luma_intra_line(q, across, a << sh, b << sh);
-                        else { const int tc = P.tc0[dir][e][l >> 2]; if (tc >= 0) luma_line(bits, q, across, a << sh, b << sh, tc << sh); }       // h264dsp_template.c:110-113
+                    if (lane < 16) {
+                        PX *const line = dir == 0 ? rbase_y + (size_t)lane * st + x * 16 : rbase_y + x * 16 + lane;
+                        const int across = dir == 0 ? 1 : st;
+                        for (int e = 0; e < 4; e++) {
+                            const int a = P.alpha[dir][e], b = P.beta[dir][e];
+                            if (a && b) LineFilter<PX>::luma(bits, line + (size_t)4 * e * across, across, a, b, P.tc0[dir][e][lane >> 2], P.intra[dir] >> e & 1);
+                        }
                     }
-                } else {
+                } else if (C422 && dir == 0) {
+                    const int p = lane >> 4, l = lane & 15;                                 // 16 lines per plane
+                    PX *const line = rbase_c[p] + (size_t)l * st + x * 8;
                     for (int e = 0; e < 2; e++) {
-                        const int a = P.calpha[p][dir][e], b = P.cbeta[p][dir][e];
-                        if (!a || !b) continue;
-                        px *q = line + (size_t)4 * e * across;
-                        if (P.cintra[p][dir] >> e & 1) chroma_line(bits, q, across, a << sh, b << sh, 0, 1);
-                        else { const int tc = ((P.ctc0[p][dir][e][l >> 1] - 1) << sh) + 1; if (tc > 0) chroma_line(bits, q, across, a << sh, b << sh, tc, 0); }   // :240
+                        const int a = P.calpha[p][0][e], b = P.cbeta[p][0][e];
+                        if (a && b) LineFilter<PX>::chroma(bits, line + 4 * e, 1, a, b, P.ctc0[p][0][e][l >> 2], P.cintra[p][0] >> e & 1);
+                    }
+                } else if (lane < 16) {
+                    const int p = lane >> 3, l = lane & 7;
+                    PX *const line = dir == 0 ? rbase_c[p] + (size_t)l * st + x * 8 : rbase_c[p] + x * 8 + l;
+                    const int across = dir == 0 ? 1 : st;
+                    if (C422) {                                                              // four horizontal edges from the 4:2:2 record
+                        const FFH264DeblockChroma422 &X = ext[mrow + x];
+                        for (int e = 0; e < 4; e++) {
+                            const int a = X.alpha[p][e], b = X.beta[p][e];
+                            if (a && b) LineFilter<PX>::chroma(bits, line + (size_t)4 * e * across, across, a, b, X.tc0[p][e][l >> 1], X.intra[p] >> e & 1);
+                        }
+                    } else {
+                        for (int e = 0; e < 2; e++) {
+                            const int a = P.calpha[p][dir][e], b = P.cbeta[p][dir][e];
+                            if (a && b) LineFilter<PX>::chroma(bits, line + (size_t)4 * e * across, across, a, b, P.ctc0[p][dir][e][l >> 1], P.cintra[p][dir] >> e & 1);
+                        }
                     }
                 }
                 __syncwarp();
@@ -244,17 +302,40 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
 }
 
 #ifndef AVB_HOSTSIM
+static int launch_deblock_generic(const char *where, int bit_depth, const FFH264DeblockMB *mbs, const FFH264DeblockChroma422 *ext, int mb_w, int mb_h, int n_pictures,
+                                  uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, cudaStream_t st)
+{
+    if (!mbs || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
+    if (!n_pictures) return 0;
+    const dim3 grid((unsigned)n_pictures, 2);
+    const size_t smem = (size_t)mb_h * sizeof(int);
+    if (bit_depth == 8) {
+        if (ext) h264_deblock_generic_kernel<uint8_t, true><<<grid, DB_WARPS * 32, smem, st>>>(8, mbs, ext, mb_w, mb_h, luma, cb, cr, ls, uvls);
+        else     h264_deblock_generic_kernel<uint8_t, false><<<grid, DB_WARPS * 32, smem, st>>>(8, mbs, ext, mb_w, mb_h, luma, cb, cr, ls, uvls);
+    } else {
+        if (ext) h264_deblock_generic_kernel<uint16_t, true><<<grid, DB_WARPS * 32, smem, st>>>(bit_depth, mbs, ext, mb_w, mb_h, luma, cb, cr, ls, uvls);
+        else     h264_deblock_generic_kernel<uint16_t, false><<<grid, DB_WARPS * 32, smem, st>>>(bit_depth, mbs, ext, mb_w, mb_h, luma, cb, cr, ls, uvls);
+    }
+    return check_launch(where) ? -1 : 0;
+}
+
 int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                    int linesize, int uvlinesize, void *stream)
 {
     avb::enter();
     const char *where = "ff_h264_deblock_batch_hbd_cuda";
     if (!hbd_args_ok(where, bit_depth, 1, linesize, uvlinesize, luma, cb, cr)) return -1;
-    if (!mbs || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
-    if (!n_pictures) return 0;
-    h264_deblock_hbd_kernel<<<(unsigned)n_pictures, DB_WARPS * 32, (size_t)mb_h * sizeof(int), (cudaStream_t)stream>>>(bit_depth, mbs, mb_w, mb_h, luma, cb, cr,
-                                                                                                                    linesize, uvlinesize);
-    return check_launch(where) ? -1 : 0;
+    return launch_deblock_generic(where, bit_depth, mbs, nullptr, mb_w, mb_h, n_pictures, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream);
+}
+
+int ff_h264_deblock_batch_422_cuda(int bit_depth, const FFH264DeblockMB *mbs, const FFH264DeblockChroma422 *chroma422, int mb_w, int mb_h, int n_pictures,
+                                   uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
+{
+    avb::enter();
+    const char *where = "ff_h264_deblock_batch_422_cuda";
+    if (bit_depth != 8 && !hbd_args_ok(where, bit_depth, 2, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (!chroma422) { set_error_msg(where, "the 4:2:2 records are NULL"); return -1; }
+    return launch_deblock_generic(where, bit_depth, mbs, chroma422, mb_w, mb_h, n_pictures, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream);
 }
 #endif
 

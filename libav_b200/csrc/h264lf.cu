@@ -116,6 +116,10 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
     int8_t tc0[4][4] = {};
     uint8_t calpha[2][2] = {}, cbeta[2][2] = {}, cintra[2] = { 0, 0 };
     int8_t ctc0[2][2][4] = {};
+    // chroma_format_idc 2: the four horizontal chroma edges (this thread's when dir == 1) go to the 4:2:2 record
+    const bool c422h = p.i.chroma422 != nullptr && dir == 1;
+    uint8_t xalpha[2][4] = {}, xbeta[2][4] = {}, xintra[2] = { 0, 0 };
+    int8_t xtc0[2][4][4] = {};
 
     const int sn = p.i.slice_table[xy];
     const FFH264DeblockSlice &sl = p.i.slices[sn];
@@ -142,7 +146,8 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
         const int bx4 = 4 * x, by4 = 4 * row, nbx4 = dir ? bx4 : bx4 - 4, nby4 = dir ? by4 - 4 : by4;
         for (int e = 0; e < edges; e++) {
             if (e == 0 && !mt) continue;
-            if (e && (type & T_DCT8) && (e & 1)) continue;
+            const bool deblock_edge = !(e && (type & T_DCT8) && (e & 1));      // inside an 8x8 transform block there is no luma edge; 4:2:2 chroma still has one (h264_loopfilter.c:633)
+            if (!deblock_edge && !c422h) continue;
             int bS[4];
             if (e == 0 && ((type | mt) & T_INTRA)) {
                 // 4, but 3 across the horizontal macroblock edges of a field picture (h264_loopfilter.c:551-557)
@@ -174,11 +179,19 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
                 qc0 = (cq0 + p.i.chroma_qp_table[qn] + 1) >> 1;
                 qc1 = (cq1 + p.i.chroma_qp_table[64 + qn] + 1) >> 1;
             }
-            const EdgeOut L = edge_params(bS, ql, offa, offb, e == 0, 0);
-            alpha[e] = L.alpha; beta[e] = L.beta; intra |= (uint8_t)L.intra << e;
+            if (deblock_edge) {
+                const EdgeOut L = edge_params(bS, ql, offa, offb, e == 0, 0);
+                alpha[e] = L.alpha; beta[e] = L.beta; intra |= (uint8_t)L.intra << e;
 #pragma unroll
-            for (int k = 0; k < 4; k++) tc0[e][k] = L.tc[k];
-            if (!(e & 1)) {
+                for (int k = 0; k < 4; k++) tc0[e][k] = L.tc[k];
+            }
+            if (c422h) {
+                const EdgeOut C0 = edge_params(bS, qc0, offa, offb, e == 0, 1), C1 = edge_params(bS, qc1, offa, offb, e == 0, 1);
+                xalpha[0][e] = C0.alpha; xbeta[0][e] = C0.beta; xintra[0] |= (uint8_t)C0.intra << e;
+                xalpha[1][e] = C1.alpha; xbeta[1][e] = C1.beta; xintra[1] |= (uint8_t)C1.intra << e;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { xtc0[0][e][k] = C0.tc[k]; xtc0[1][e][k] = C1.tc[k]; }
+            } else if (!(e & 1)) {
                 const EdgeOut C0 = edge_params(bS, qc0, offa, offb, e == 0, 1), C1 = edge_params(bS, qc1, offa, offb, e == 0, 1);
                 const int ce = e >> 1;
                 calpha[0][ce] = C0.alpha; cbeta[0][ce] = C0.beta; cintra[0] |= (uint8_t)C0.intra << ce;
@@ -206,6 +219,19 @@ h264_deblock_params_kernel(LfPic p, FFH264DeblockMB *__restrict__ out, int n_mbs
         }
     }
     rec.pad[dir] = 0;
+    if (c422h) {
+        FFH264DeblockChroma422 &x = p.i.chroma422[m];
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            x.intra[pl] = xintra[pl]; x.pad[pl] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                x.alpha[pl][e] = xalpha[pl][e]; x.beta[pl][e] = xbeta[pl][e];
+#pragma unroll
+                for (int k = 0; k < 4; k++) x.tc0[pl][e][k] = xtc0[pl][e][k];
+            }
+        }
+    }
 }
 
 }  // namespace avb

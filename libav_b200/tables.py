@@ -109,7 +109,7 @@ class FFH264DeblockInfo(C.Structure):
                 ("cbp_table", C.c_void_p), ("slice_table", C.c_void_p),
                 ("motion_val", C.c_void_p * 2), ("ref_index", C.c_void_p * 2),
                 ("slices", C.c_void_p), ("n_slices", C.c_int), ("chroma_qp_table", C.c_void_p),
-                ("cabac", C.c_int), ("transform_8x8_mode", C.c_int), ("field_picture", C.c_int)]
+                ("cabac", C.c_int), ("transform_8x8_mode", C.c_int), ("field_picture", C.c_int), ("chroma422", C.c_void_p)]
 
 
 class FFH264PictureWork(C.Structure):

@@ -59,6 +59,7 @@ API = {
     "h264_pred422": (None, [i32, i32, vp, pd]),
     "h264_pred422_add": (None, [i32, i32, vp, vp, vp, pd]),
     "h264_deblock_picture_structure": (None, [i32]),
+    "h264_deblock_chroma422": (None, [vp]),
     "h264_deblock_params": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "h264_deblock_picture_with": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32]),
     "h264_pictures": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]),

@@ -144,6 +144,10 @@ int ORC(h264_deblock_params)(int mb_w, int mb_h, const uint32_t *mb_type, const 
 /* the pictures of the following h264_deblock_params / h264_deblock_picture_with calls are fields (h->picture_structure != PICT_FRAME; their
  * mb_type entries must carry MB_TYPE_INTERLACED, 0x80): mvy_limit 2, bS 3 on horizontal intra macroblock edges (h264_loopfilter.c:551-557,723) */
 void ORC(h264_deblock_picture_structure)(int field_picture);
+/* chroma_format_idc 2 for the following h264_deblock_params calls while ext != NULL: the four horizontal chroma edges of every macroblock
+ * (chroma rows 0, 4, 8, 12; h264_loopfilter.c:633,693-700) are written to ext + 52 * mb as alpha[2 planes][4], beta[2][4], tc0[2][4][4], intra[2], pad[2];
+ * the 104-byte record keeps luma and the vertical chroma edges (whose tc0 entries then cover four of sixteen lines) */
+void ORC(h264_deblock_chroma422)(uint8_t *ext);
 /* widx: 0..3 = width 16,8,4,2 */
 void ORC(h264_weight)(int widx, uint8_t *block, int stride, int height, int log2_denom,
                       int weight, int offset);

@@ -21,6 +21,11 @@ enum { T_INTRA = 7, T_16x16 = 8, T_16x8 = 16, T_8x16 = 32, T_INTERLACED = 0x80, 
 /* h->picture_structure != PICT_FRAME for the pictures that follow (PAFF field pictures: every macroblock type carries MB_TYPE_INTERLACED) */
 static int g_field_picture;
 void orc_h264_deblock_picture_structure(int field_picture) { g_field_picture = field_picture != 0; }
+/* chroma_format_idc 2: the horizontal chroma edges (four per macroblock: chroma rows 0, 4, 8, 12 of the 8 x 16 block, one per luma edge,
+ * h264_loopfilter.c:633,693-700) go to a second record per macroblock, 52 bytes: alpha[2 planes][4], beta[2][4], tc0[2][4][4], intra[2], pad[2];
+ * the vertical ones keep the 4:2:0 fields (each tc0 entry then covers four of the sixteen lines) */
+static uint8_t *g_ext422;
+void orc_h264_deblock_chroma422(uint8_t *ext) { g_ext422 = ext; }
 static int g_ylim = 4;          /* mvy_limit of the macroblock being decided (h264_loopfilter.c:723) */
 #define USES(t, l) ((t) & (0x3000 << (2 * (l))))
 
@@ -113,6 +118,19 @@ static void emit(uint8_t *rec, int chroma, int dir, int e, const int bS[4], int 
     else
         *pi |= 1 << bit;
 }
+/* a horizontal chroma edge of a 4:2:2 macroblock -> the extension record */
+static void emit422(uint8_t *ext, int plane, int e, const int bS[4], int qp, int offa, int offb, int may_be_intra)
+{
+    const int ia = idx51(qp + offa), ib = idx51(qp + offb);
+    const int alpha = ia < 0 ? 0 : alpha_std[ia], beta = ib < 0 ? 0 : beta_std[ib];
+    if (!alpha || !beta) return;
+    ext[4 * plane + e] = alpha; ext[8 + 4 * plane + e] = beta;
+    int8_t *pt = (int8_t *)ext + 16 + 16 * plane + 4 * e;
+    if (bS[0] < 4 || !may_be_intra)
+        for (int i = 0; i < 4; i++) pt[i] = (bS[i] ? (int)tc0_std[ia][bS[i] - 1] : -1) + 1;
+    else
+        ext[48 + plane] |= 1 << e;
+}
 
 int orc_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const int8_t *qscale, const uint8_t *nnz,
                             const uint16_t *cbp, const uint16_t *slice_table, const int16_t *mv0, const int16_t *mv1,
@@ -124,9 +142,11 @@ int orc_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
               { mv0, mv1 }, { ref0, ref1 }, slice_params, chroma_qp_table };
     if (n_slices > 32) return -1;
     memset(out, 0, (size_t)104 * mb_w * mb_h);
+    if (g_ext422) memset(g_ext422, 0, (size_t)52 * mb_w * mb_h);
     for (int y = 0; y < mb_h; y++)
         for (int x = 0; x < mb_w; x++) {
             const int xy = x + y * p.ms, sn = slice_table[xy];
+            uint8_t *ext = g_ext422 ? g_ext422 + (size_t)52 * (x + y * mb_w) : NULL;
             const int32_t *sp = slice_params + 133 * sn;
             const int offa = sp[0], offb = sp[1], mode = sp[2], lists = sp[3], th = sp[4];
             const uint32_t type = mb_type[xy];
@@ -159,7 +179,8 @@ int orc_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
                 for (int e = 0; e < edges; e++) {
                     int bS[4], sum = 0;
                     if (e == 0 && !mt) continue;
-                    if (e && (type & T_DCT8) && (e & 1)) continue;
+                    const int deblock_edge = !(e && (type & T_DCT8) && (e & 1));     /* inside an 8x8 transform block: no luma edge; 4:2:2 chroma still has one (:633) */
+                    if (!deblock_edge && !(ext && dir == 1)) continue;
                     g_ylim = (type & T_INTERLACED) ? 2 : 4;
                     if (e == 0 && ((type | mt) & T_INTRA)) {
                         /* 3 across the horizontal macroblock edges of a field picture, 4 otherwise (h264_loopfilter.c:551-557) */
@@ -187,12 +208,14 @@ int orc_h264_deblock_params(int mb_w, int mb_h, const uint32_t *mb_type, const i
                     if (!sum) continue;
                     if (e == 0) {
                         const int qn = qscale[nx + ny * p.ms];
+                        const int qa0 = (cq[0] + chroma_qp_table[qn] + 1) >> 1, qa1 = (cq[1] + chroma_qp_table[64 + qn] + 1) >> 1;
                         emit(rec, 0, dir, 0, bS, (qp + qn + 1) >> 1, offa, offb, 1);
-                        emit(rec, 1, dir, 0, bS, (cq[0] + chroma_qp_table[qn] + 1) >> 1, offa, offb, 1);
-                        emit(rec, 2, dir, 0, bS, (cq[1] + chroma_qp_table[64 + qn] + 1) >> 1, offa, offb, 1);
+                        if (ext && dir == 1) { emit422(ext, 0, 0, bS, qa0, offa, offb, 1); emit422(ext, 1, 0, bS, qa1, offa, offb, 1); }
+                        else { emit(rec, 1, dir, 0, bS, qa0, offa, offb, 1); emit(rec, 2, dir, 0, bS, qa1, offa, offb, 1); }
                     } else {
-                        emit(rec, 0, dir, e, bS, qp, offa, offb, 0);
-                        if (!(e & 1)) { emit(rec, 1, dir, e, bS, cq[0], offa, offb, 0); emit(rec, 2, dir, e, bS, cq[1], offa, offb, 0); }
+                        if (deblock_edge) emit(rec, 0, dir, e, bS, qp, offa, offb, 0);
+                        if (ext && dir == 1) { emit422(ext, 0, e, bS, cq[0], offa, offb, 0); emit422(ext, 1, e, bS, cq[1], offa, offb, 0); }
+                        else if (!(e & 1)) { emit(rec, 1, dir, e, bS, cq[0], offa, offb, 0); emit(rec, 2, dir, e, bS, cq[1], offa, offb, 0); }
                     }
                 }
             }

@@ -23,7 +23,10 @@
 
 /* ---- recorders --------------------------------------------------------------------------------------------- */
 enum { REC_LS = 64, REC_UVLS = 32 };                 /* fake picture pitches: offsets identify the edge */
-static uint8_t fake_y[16 * REC_LS], fake_cb[8 * REC_UVLS], fake_cr[8 * REC_UVLS];
+static uint8_t fake_y[16 * REC_LS], fake_cb[16 * REC_UVLS], fake_cr[16 * REC_UVLS];       /* (16 chroma rows: 4:2:2) */
+static uint8_t *cur_ext;                             /* 4:2:2: the 52-byte record of the horizontal chroma edges, NULL for 4:2:0 */
+static uint8_t *g_ext422;
+void ref_h264_deblock_chroma422(uint8_t *ext) { g_ext422 = ext; }
 static uint8_t *cur_rec;                             /* 104-byte record being written (layout: oracle_api.h) */
 
 enum { O_ALPHA = 0, O_BETA = 8, O_TC0 = 16, O_INTRA = 48, O_CALPHA = 50, O_CBETA = 58, O_CTC0 = 66, O_CINTRA = 98 };
@@ -40,6 +43,12 @@ static void rec_chroma(int dir, uint8_t *pix, int alpha, int beta, const int8_t 
 {
     int plane = pix >= fake_cr && pix < fake_cr + sizeof(fake_cr);
     int off = (int)(pix - (plane ? fake_cr : fake_cb)), e = dir ? off / (4 * REC_UVLS) : off / 4;
+    if (cur_ext && dir) {                            /* chroma_format_idc 2: rows 0, 4, 8, 12 of the 8 x 16 chroma macroblock */
+        cur_ext[4 * plane + e] = alpha; cur_ext[8 + 4 * plane + e] = beta;
+        if (tc0) memcpy(cur_ext + 16 + 16 * plane + 4 * e, tc0, 4);
+        else     cur_ext[48 + plane] |= 1 << e;
+        return;
+    }
     int i = (plane * 2 + dir) * 2 + e;
     cur_rec[O_CALPHA + i] = alpha;
     cur_rec[O_CBETA + i]  = beta;
@@ -201,7 +210,7 @@ static int run_driver(const H264DSPContext *table, uint8_t *Y, uint8_t *Cb, uint
     pps->cabac = cabac; pps->transform_8x8_mode = transform_8x8_mode;
     memcpy(pps->chroma_qp_table, chroma_qp_table, 128);
     pps->chroma_qp_diff = memcmp(chroma_qp_table, chroma_qp_table + 64, 64) != 0;
-    sps->bit_depth_luma = 8; sps->chroma_format_idc = 1;
+    sps->bit_depth_luma = 8; sps->chroma_format_idc = (g_ext422 && !table) ? 2 : 1;
     h->ps.pps = pps; h->ps.sps = sps;
     for (s = 0; s < n_slices; s++)
         memcpy(h->ref2frm[s], slice_params + 133 * s + 5, sizeof(h->ref2frm[s]));
@@ -213,11 +222,12 @@ static int run_driver(const H264DSPContext *table, uint8_t *Y, uint8_t *Cb, uint
     if (table) h->h264dsp = *table;
 
     if (!table) memset(out, 0, (size_t)104 * mb_w * mb_h);
+    if (!table && g_ext422) memset(g_ext422, 0, (size_t)52 * mb_w * mb_h);
     for (y = 0; y < mb_h; y++)
         for (x = 0; x < mb_w; x++) {
             const int xy = x + y * ms, type = h->cur_pic.mb_type[xy];
             const int32_t *sp = slice_params + 133 * h->slice_table[xy];
-            if (!table) cur_rec = out + (size_t)104 * (x + y * mb_w);
+            if (!table) { cur_rec = out + (size_t)104 * (x + y * mb_w); cur_ext = g_ext422 ? g_ext422 + (size_t)52 * (x + y * mb_w) : NULL; }
             sl->mb_xy = xy; sl->mb_x = x; sl->mb_y = y;
             sl->slice_num = h->slice_table[xy];
             sl->slice_alpha_c0_offset = sp[0]; sl->slice_beta_offset = sp[1];

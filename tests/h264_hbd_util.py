@@ -136,3 +136,66 @@ def smooth_picture(mb_w, mb_h, bits, seed):
         up = np.kron(base, np.ones((8, 8), dtype=np.int64))[:shape[0], :shape[1]]
         return np.clip(sc * (up + rng.integers(-6, 7, size=shape)) + rng.integers(0, sc, size=shape), 0, (1 << bits) - 1).astype(np.uint16)
     return plane((16 * mb_h, 16 * mb_w)), plane((8 * mb_h, 8 * mb_w)), plane((8 * mb_h, 8 * mb_w))
+
+
+# ---- 4:2:2 deblocking (8 / 9 / 10 bit): the 52-byte record of the four horizontal chroma edges ------------------------------------------
+CHROMA422_DT = np.dtype([("alpha", "u1", (2, 4)), ("beta", "u1", (2, 4)), ("tc0", "i1", (2, 4, 4)), ("intra", "u1", (2,)), ("pad", "u1", (2,))])
+assert CHROMA422_DT.itemsize == 52
+
+
+def deblock422_work(mb_w, mb_h, seed, slices=1):
+    """(104-byte records, 52-byte records) with random per-edge parameters in the ranges of the reference's tables; picture- and slice-boundary
+    edges carry alpha 0 like synth.h264_deblock_work makes them"""
+    rec = synth.h264_deblock_work(mb_w, mb_h, seed=seed, slices=slices)
+    rng = np.random.default_rng(1000 + seed)
+    n = mb_w * mb_h
+    ext = np.zeros(n, CHROMA422_DT)
+    ext["alpha"] = rng.integers(0, 120, (n, 2, 4)); ext["beta"] = rng.integers(0, 19, (n, 2, 4))
+    ext["tc0"] = rng.integers(0, 11, (n, 2, 4, 4)); ext["intra"] = rng.integers(0, 2, (n, 2))       # only edge 0 may be intra
+    ext["alpha"][:, :, 0] = np.where(rec["alpha"][:, 1, 0][:, None] == 0, 0, ext["alpha"][:, :, 0])   # top edge off where the luma one is (boundaries)
+    rec["calpha"][:, :, 1, :] = 0                                                                      # not read in 4:2:2
+    return rec, ext
+
+
+def oracle_deblock422(o, bits, rec, ext, mb_w, mb_h, y, cb, cr):
+    """luma from the 104-byte record; chroma: vertical edges = h_loop_filter_chroma422 (16 lines, which 12 / 13), horizontal edges = the four
+    v_loop_filter_chroma calls of h264_loopfilter.c:693-700 (which 4 / 6), in the reference's order: per direction, edge by edge"""
+    ls, uvls, sb = y.strides[0], cb.strides[0], (1 if bits == 8 else 2)
+    lf = (lambda which, p, st, a, b, tc: o.h264_loop_filter(which, p, st, a, b, tc)) if bits == 8 else \
+         (lambda which, p, st, a, b, tc: o.h264_hbd_loop_filter(bits, which, p, st, a, b, tc))
+    for m in range(mb_w * mb_h):
+        r, x = rec[m], ext[m]
+        mbx, mby = m % mb_w, m // mb_w
+        for d in (0, 1):
+            for e in range(4):
+                a, b = int(r["alpha"][d, e]), int(r["beta"][d, e])
+                if a and b:
+                    off = (mby * 16 + (4 * e if d else 0)) * ls + sb * (mbx * 16 + (0 if d else 4 * e))
+                    intra = (int(r["intra"][d]) >> e) & 1
+                    lf((1 if d == 0 else 0) + (2 if intra else 0), at(y, off), ls, a, b, ptr(np.ascontiguousarray(r["tc0"][d, e])))
+                for p, pl in enumerate((cb, cr)):
+                    if d == 0 and not (e & 1):
+                        ce = e >> 1
+                        a, b = int(r["calpha"][p, 0, ce]), int(r["cbeta"][p, 0, ce])
+                        if a and b:
+                            off = mby * 16 * uvls + sb * (mbx * 8 + 4 * ce)
+                            intra = (int(r["cintra"][p, 0]) >> ce) & 1
+                            lf(13 if intra else 12, at(pl, off), uvls, a, b, ptr(np.ascontiguousarray(r["ctc0"][p, 0, ce])))
+                    elif d == 1:
+                        a, b = int(x["alpha"][p, e]), int(x["beta"][p, e])
+                        if a and b:
+                            off = (mby * 16 + 4 * e) * uvls + sb * mbx * 8
+                            intra = (int(x["intra"][p]) >> e) & 1
+                            lf(6 if intra else 4, at(pl, off), uvls, a, b, ptr(np.ascontiguousarray(x["tc0"][p, e])))
+
+
+def smooth_picture422(mb_w, mb_h, bits, seed):
+    rng = np.random.default_rng(seed)
+    sc = 1 << (bits - 8)
+
+    def plane(shape):
+        base = rng.integers(40, 200, size=(shape[0] // 8 + 1, shape[1] // 8 + 1))
+        up = np.kron(base, np.ones((8, 8), dtype=np.int64))[:shape[0], :shape[1]]
+        v = np.clip(sc * (up + rng.integers(-6, 7, size=shape)) + rng.integers(0, sc, size=shape), 0, (1 << bits) - 1)
+        return v.astype(np.uint8 if bits == 8 else np.uint16)
+    return plane((16 * mb_h, 16 * mb_w)), plane((16 * mb_h, 8 * mb_w)), plane((16 * mb_h, 8 * mb_w))

@@ -20,7 +20,7 @@ def _dev(a):
     return device.DevBuf.from_numpy(np.ascontiguousarray(a))
 
 
-def gpu_params(gpu, infos, field=0):
+def gpu_params(gpu, infos, field=0, chroma422=None):
     """infos: list of per-picture dicts of equal geometry (stacked row-wise into one call)"""
     from libav_b200 import device
     d0 = infos[0]
@@ -32,7 +32,7 @@ def gpu_params(gpu, infos, field=0):
     info = tables.FFH264DeblockInfo(d0["mb_w"], d0["mb_h"], len(infos), keep["mb_type"].ptr, keep["qscale"].ptr, keep["nnz"].ptr,
                                     keep["cbp"].ptr, keep["slice_table"].ptr, (C.c_void_p * 2)(keep["mv0"].ptr, keep["mv1"].ptr),
                                     (C.c_void_p * 2)(keep["ref0"].ptr, keep["ref1"].ptr), keep["sp"].ptr, d0["n_slices"], keep["cq"].ptr,
-                                    d0["cabac"], d0["t8x8"], field)
+                                    d0["cabac"], d0["t8x8"], field, chroma422)
     gpu.check(gpu.lib.ff_h264_deblock_params_cuda(C.byref(info), out.ptr, None))
     device.sync()
     return out.download(np.uint8, (n, 104)), out

@@ -72,6 +72,40 @@ def test_field_pictures(orc, refo, case):
     assert differs                       # the field rules do change decisions
 
 
+C422_CASES = [dict(seed=31), dict(seed=32, bipred=True, t8x8=1, cabac=1, n_slices=4), dict(seed=33, t8x8=1, cabac=0, mode=2, n_slices=5),
+              dict(seed=34, p_intra=0.5, cb_off=-4, cr_off=6), dict(seed=35, qp_lo=0, qp_hi=24, t8x8=1)]
+
+
+def run422(o, d):
+    """chroma_format_idc 2: (104-byte records, 52-byte records of the four horizontal chroma edges)"""
+    ext = np.full((d["mb_w"] * d["mb_h"], 52), 0xEE, np.uint8)
+    try:
+        o.h264_deblock_chroma422(ptr(ext))
+        rec = run(o, d)
+    finally:
+        o.h264_deblock_chroma422(None)
+    return rec, ext
+
+
+@pytest.mark.parametrize("case", C422_CASES, ids=lambda c: "-".join("%s%s" % kv for kv in c.items()))
+def test_chroma422(orc, refo, case):
+    """4:2:2: a horizontal chroma edge per luma edge, also inside 8x8-transform macroblocks (h264_loopfilter.c:633,693-700)"""
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    inner = 0
+    for (mw, mh) in ((11, 9), (2, 5), (20, 3)):
+        d = synth.h264_deblock_info(mw, mh, **case)
+        (a, ea), (b, eb) = run422(refo, d), run422(orc, d)
+        bad = np.argwhere((a != b).any(axis=1))
+        assert not len(bad), (mw, mh, bad[:4].ravel().tolist(), a[bad[0, 0]].tolist(), b[bad[0, 0]].tolist())
+        bad = np.argwhere((ea != eb).any(axis=1))
+        assert not len(bad), ("ext", mw, mh, bad[:4].ravel().tolist(), ea[bad[0, 0]].tolist(), eb[bad[0, 0]].tolist())
+        a420 = run(refo, d)
+        assert np.array_equal(a[:, :50], a420[:, :50])                  # luma decisions do not depend on the chroma format
+        inner += int(ea[:, [1, 3, 5, 7]].any())                          # alpha of the edges that exist only in 4:2:2
+    assert inner
+
+
 def test_decisions_are_not_trivial(orc):
     d = synth.h264_deblock_info(12, 8, seed=1)
     rec = run(orc, d).view(synth.DEBLOCK_DT).reshape(-1)

@@ -88,3 +88,47 @@ def test_hbd_refusals(gpu):
     assert lib.ff_h264_mc_batch_hbd_cuda(10, 3, None, 0, None, None, None, None, 64, 32, 16, 16, None) == -1
     assert lib.ff_h264_deblock_batch_hbd_cuda(10, None, 1, 1, 1, None, None, None, 64, 32, None) == -1
     lib.avb200_clear_error()
+
+
+@pytest.mark.parametrize("bits", [8, 9, 10])
+@pytest.mark.parametrize("mb_w,mb_h,slices,P", [(3, 2, 1, 1), (7, 5, 4, 2), (20, 12, 1, 3), (40, 36, 8, 2)])
+def test_deblock_batch_422(gpu, checker, mb_w, mb_h, slices, P, bits):
+    """chroma_format_idc 2: two 16-line vertical and four horizontal chroma edges per macroblock (8 / 9 / 10 bit), stacked pictures"""
+    from libav_b200 import device
+    dt = np.uint8 if bits == 8 else np.uint16
+    ys, cbs, crs, recs, exts, want = [], [], [], [], [], []
+    for k in range(P):
+        y, cb, cr = hh.smooth_picture422(mb_w, mb_h, bits, seed=100 * mb_w + k)
+        rec, ext = hh.deblock422_work(mb_w, mb_h, seed=slices + k, slices=slices)
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hh.oracle_deblock422(checker, bits, rec, ext, mb_w, mb_h, wy, wcb, wcr)
+        assert not np.array_equal(wy, y) and not np.array_equal(wcb, cb)
+        ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); exts.append(ext); want.append((wy, wcb, wcr))
+    Y, CB, CR, R, X = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs), np.concatenate(recs), np.concatenate(exts)
+    d_rec, d_ext, dy, dcb, dcr = _dev(R), _dev(X), _dev(Y), _dev(CB), _dev(CR)
+    gpu.check(gpu.lib.ff_h264_deblock_batch_422_cuda(bits, d_rec.ptr, d_ext.ptr, mb_w, mb_h, P, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], None))
+    device.sync()
+    gy, gcb, gcr = dy.download(dt, Y.shape), dcb.download(dt, CB.shape), dcr.download(dt, CR.shape)
+    for k in range(P):
+        assert np.array_equal(gy[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][0]), k
+        assert np.array_equal(gcb[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][1]), k
+        assert np.array_equal(gcr[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][2]), k
+
+
+def test_chroma422_decisions(gpu, checker):
+    """FFH264DeblockInfo.chroma422: the decisions of a 4:2:2 picture (h264_loopfilter.c:633,693-700) against the reference's own h264_loopfilter.c"""
+    import ctypes as C
+    from libav_b200 import device, tables
+    from test_oracle_h264lf_cpu import C422_CASES, run422
+    from test_gpu_h264lf import gpu_params
+    for case in C422_CASES:
+        for (mw, mh) in ((11, 9), (2, 5), (40, 17)):
+            d = synth.h264_deblock_info(mw, mh, **case)
+            want, want_ext = run422(checker, d)
+            ext = device.DevBuf(52 * mw * mh); ext.fill(0xCD)
+            got, _ = gpu_params(gpu, [d], chroma422=ext.ptr)
+            bad = np.argwhere((got[:, :102] != want[:, :102]).any(axis=1))
+            assert not len(bad), (case, mw, mh, bad[:4].ravel().tolist(), got[bad[0, 0]].tolist(), want[bad[0, 0]].tolist())
+            gext = ext.download(np.uint8, (mw * mh, 52))
+            bad = np.argwhere((gext[:, :50] != want_ext[:, :50]).any(axis=1))
+            assert not len(bad), ("ext", case, mw, mh, bad[:4].ravel().tolist(), gext[bad[0, 0]].tolist(), want_ext[bad[0, 0]].tolist())

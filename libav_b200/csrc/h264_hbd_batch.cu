@@ -72,18 +72,24 @@ struct EdgeFetch {
     const px *p; int st, w, h, y0;
     __device__ __forceinline__ int operator()(int x, int y) const { return p[(size_t)min(max(y, y0), y0 + h - 1) * st + min(max(x, 0), w - 1)]; }
 };
-__device__ __forceinline__ int tap6f(const EdgeFetch &S, int x, int y, int dx, int dy)
+// the (w + 5) x (h + 5) luma patch (or a (w / 2 + 1) x (ch + 1) chroma patch) of a partition staged in shared memory: sample (x, y) of the
+// reference plane sits at p[(y - y0) * pitch + (x - x0)]
+struct PatchFetch {
+    const px *p; int pitch, x0, y0;
+    __device__ __forceinline__ int operator()(int x, int y) const { return p[(y - y0) * pitch + (x - x0)]; }
+};
+template <class F> __device__ __forceinline__ int tap6f(const F &S, int x, int y, int dx, int dy)
 { return (S(x, y) + S(x + dx, y + dy)) * 20 - (S(x - dx, y - dy) + S(x + 2 * dx, y + 2 * dy)) * 5 + (S(x - 2 * dx, y - 2 * dy) + S(x + 3 * dx, y + 3 * dy)); }
-__device__ __forceinline__ int qh(int bits, const EdgeFetch &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 1, 0) + 16) >> 5, bits); }
-__device__ __forceinline__ int qv(int bits, const EdgeFetch &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 0, 1) + 16) >> 5, bits); }
-__device__ inline int qhv(int bits, const EdgeFetch &S, int x, int y)
+template <class F> __device__ __forceinline__ int qh(int bits, const F &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 1, 0) + 16) >> 5, bits); }
+template <class F> __device__ __forceinline__ int qv(int bits, const F &S, int x, int y) { return hbd::clipb((tap6f(S, x, y, 0, 1) + 16) >> 5, bits); }
+template <class F> __device__ inline int qhv(int bits, const F &S, int x, int y)
 {
     int t[6];
     for (int k = 0; k < 6; k++) t[k] = tap6f(S, x, y + k - 2, 1, 0);
     return hbd::clipb(((t[2] + t[3]) * 20 - (t[1] + t[4]) * 5 + (t[0] + t[5]) + 512) >> 10, bits);
 }
 // the sixteen quarter-sample positions (h264qpel_template.c:380-531)
-__device__ inline int qpel_at(int bits, const EdgeFetch &S, int x, int y, int fx, int fy)
+template <class F> __device__ inline int qpel_at(int bits, const F &S, int x, int y, int fx, int fy)
 {
     int a, b = -1;
     if (!fx && !fy) a = S(x, y);
@@ -95,13 +101,30 @@ __device__ inline int qpel_at(int bits, const EdgeFetch &S, int x, int y, int fx
     else { a = qh(bits, S, x, y + (fy == 3)); b = qv(bits, S, x + (fx == 3), y); }
     return b < 0 ? a : (a + b + 1) >> 1;
 }
+template <class F> __device__ __forceinline__ int chroma_at(const F &S, int x, int y, int A, int B, int Cc, int D)
+{
+    int v = A * S(x, y);
+    if (B) v += B * S(x + 1, y);
+    if (Cc) v += Cc * S(x, y + 1);
+    if (D) v += D * S(x + 1, y + 1);
+    return (v + 32) >> 6;
+}
 
+// STAGED: the warp first copies the clamped patches into its slice of shared memory (one global load per patch sample instead of 6 .. 36
+// per output sample), then every lane filters from there.  !STAGED: every tap is a clamped global load -- the same arithmetic with no
+// communication between lanes, which is what tests/hostsim/ compiles.
+constexpr int MCH_LP = 24, MCH_CP = 12;           // patch pitches in samples (21 x 21 luma, 9 x 17 chroma per plane)
+template <bool STAGED>
 __global__ void __launch_bounds__(128)
 h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
                    uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph, int pass)
 {
-    const int lane = threadIdx.x & 31;
-    const size_t ri = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+#ifndef AVB_HOSTSIM
+    __shared__ px s_luma[STAGED ? 4 : 1][STAGED ? 21 * MCH_LP : 1];
+    __shared__ px s_chroma[STAGED ? 4 : 1][2][STAGED ? 17 * MCH_CP : 1];
+#endif
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ri = (size_t)blockIdx.x * 4 + warp;
     if (ri >= n) return;
     const FFH264MCRecord r = recs[ri];
     if ((r.avg != 0) != (pass != 0)) return;
@@ -109,32 +132,53 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
     const int lsp = ls >> 1, uvlsp = uvls >> 1;
     const int ly0 = ((int)r.y / ph) * ph;                                   // first luma row of the record's picture in the stacked planes
     const int mx = (int)r.mvx + 4 * (int)r.x, my = (int)r.mvy + 4 * (int)r.y, w = r.w, h = r.h;
-    {   // ---- luma ----
-        const EdgeFetch S = { reinterpret_cast<const px *>(ref.y), lsp, pw, ph, ly0 };
-        px *d0 = reinterpret_cast<px *>(dy) + (size_t)r.y * lsp + r.x;
+    // chroma: eighth-sample bilinear (h264chroma_template.c:27-173); 4:2:2 keeps the luma's vertical resolution (h264_mb.c:287-316)
+    const int cw = w >> 1, ch = c422 ? h : h >> 1, cph = c422 ? ph : ph >> 1, cy0 = c422 ? ly0 : ly0 >> 1;
+    const int sx = mx >> 3, sy = c422 ? my >> 2 : my >> 3, fx = mx & 7, fy = c422 ? (my << 1) & 7 : my & 7;
+    const int dx0 = r.x >> 1, dy0 = c422 ? (int)r.y : r.y >> 1;
+    const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), Cc = (8 - fx) * fy, D = fx * fy;
+    const EdgeFetch GY = { reinterpret_cast<const px *>(ref.y), lsp, pw, ph, ly0 };
+    px *d0 = reinterpret_cast<px *>(dy) + (size_t)r.y * lsp + r.x;
+    (void)warp;
+#ifndef AVB_HOSTSIM
+    if (STAGED) {
+        const int lx0 = (mx >> 2) - 2, lyy0 = (my >> 2) - 2;
+        for (int i = lane; i < (w + 5) * (h + 5); i += 32) { const int c = i % (w + 5), rr = i / (w + 5); s_luma[warp][rr * MCH_LP + c] = (px)GY(lx0 + c, lyy0 + rr); }
+        for (int i = lane; i < 2 * (cw + 1) * (ch + 1); i += 32) {
+            const int pl = i / ((cw + 1) * (ch + 1)), k = i % ((cw + 1) * (ch + 1)), c = k % (cw + 1), rr = k / (cw + 1);
+            const EdgeFetch GC = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
+            s_chroma[warp][pl][rr * MCH_CP + c] = (px)GC(sx + c, sy + rr);
+        }
+        __syncwarp();
+        const PatchFetch SY = { s_luma[warp], MCH_LP, lx0, lyy0 };
         for (int i = lane; i < w * h; i += 32) {
             const int x = i % w, y = i / w;
-            const int v = qpel_at(bits, S, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
+            const int v = qpel_at(bits, SY, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
             px *d = d0 + (size_t)y * lsp + x;
             *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
         }
-    }
-    {   // ---- chroma: eighth-sample bilinear (h264chroma_template.c:27-173); 4:2:2 keeps the luma's vertical resolution (h264_mb.c:287-316) ----
-        const int cw = w >> 1, ch = c422 ? h : h >> 1, cph = c422 ? ph : ph >> 1, cy0 = c422 ? ly0 : ly0 >> 1;
-        const int sx = mx >> 3, sy = c422 ? my >> 2 : my >> 3, fx = mx & 7, fy = c422 ? (my << 1) & 7 : my & 7;
-        const int dx0 = r.x >> 1, dy0 = c422 ? (int)r.y : r.y >> 1;
-        const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), Cc = (8 - fx) * fy, D = fx * fy;
         for (int i = lane; i < 2 * cw * ch; i += 32) {
             const int pl = i / (cw * ch), k = i % (cw * ch), x = k % cw, y = k / cw;
-            const EdgeFetch S = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
-            int v = A * S(sx + x, sy + y);
-            if (B) v += B * S(sx + x + 1, sy + y);
-            if (Cc) v += Cc * S(sx + x, sy + y + 1);
-            if (D) v += D * S(sx + x + 1, sy + y + 1);
-            v = (v + 32) >> 6;
+            const PatchFetch SC = { s_chroma[warp][pl], MCH_CP, sx, sy };
+            const int v = chroma_at(SC, sx + x, sy + y, A, B, Cc, D);
             px *d = reinterpret_cast<px *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
             *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
         }
+        return;
+    }
+#endif
+    for (int i = lane; i < w * h; i += 32) {
+        const int x = i % w, y = i / w;
+        const int v = qpel_at(bits, GY, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
+        px *d = d0 + (size_t)y * lsp + x;
+        *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+    }
+    for (int i = lane; i < 2 * cw * ch; i += 32) {
+        const int pl = i / (cw * ch), k = i % (cw * ch), x = k % cw, y = k / cw;
+        const EdgeFetch GC = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
+        const int v = chroma_at(GC, sx + x, sy + y, A, B, Cc, D);
+        px *d = reinterpret_cast<px *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
+        *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
     }
 }
 
@@ -296,8 +340,15 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
     if (pic_w <= 0 || pic_h <= 0 || (pic_w & 1) || (pic_h & 1)) { set_error_msg(where, "picture size must be positive and even"); return -1; }
     if (!n) return 0;
     for (int pass = 0; pass < 2; pass++)
-        AVB_LAUNCH(h264_mc_hbd_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr,
-                                                                                                          linesize, uvlinesize, pic_w, pic_h, pass);
+#ifdef AVB_HOSTSIM
+        AVB_LAUNCH(h264_mc_hbd_kernel<false>, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr,
+                                                                                                                 linesize, uvlinesize, pic_w, pic_h, pass);
+#else
+        if (tuning("mc_hbd_staged") == 2)       // (test knob: the clamped-global-load form of the same arithmetic, the one tests/hostsim/ runs)
+            h264_mc_hbd_kernel<false><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
+        else
+            h264_mc_hbd_kernel<true><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
+#endif
     return check_launch(where) ? -1 : 0;
 }
 

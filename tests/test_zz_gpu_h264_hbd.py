@@ -36,11 +36,14 @@ def test_residual_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
     assert np.array_equal(d[1].download(np.int32, coeffs.shape), wco)      # consumed coefficients are zeroed identically
 
 
+@pytest.mark.parametrize("staged", [0, 2])
 @pytest.mark.parametrize("c422", [0, 1])
 @pytest.mark.parametrize("bits", [9, 10])
 @pytest.mark.parametrize("mb_w,mb_h", SIZES)
-def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
+def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422, staged):
+    """staged 0: the default kernel (patches staged in shared memory); 2: the clamped-global-load form of the same arithmetic (tests/hostsim/ runs it)"""
     from libav_b200 import device
+    gpu.lib.avb200_set_tuning(b"mc_hbd_staged", staged)
     refs = [hh.picture(mb_w, mb_h, bits, c422, seed=11), hh.picture(mb_w, mb_h, bits, c422, seed=12)]
     rec = synth.h264_mc_work(mb_w, mb_h, seed=mb_h + bits, max_mv=64 if mb_w > 4 else 24, avg_second=True)
     y, cb, cr = hh.picture(mb_w, mb_h, bits, c422, seed=13)
@@ -53,6 +56,7 @@ def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
     gpu.check(gpu.lib.ff_h264_mc_batch_hbd_cuda(bits, 1 + c422, d_rec.ptr, rec.shape[0], d_planes.ptr, dy.ptr, dcb.ptr, dcr.ptr, y.strides[0], cb.strides[0],
                                                 16 * mb_w, 16 * mb_h, None))
     device.sync()
+    gpu.lib.avb200_set_tuning(b"mc_hbd_staged", 0)
     assert np.array_equal(dy.download(np.uint16, y.shape), wy)
     assert np.array_equal(dcb.download(np.uint16, cb.shape), wcb)
     assert np.array_equal(dcr.download(np.uint16, cr.shape), wcr)

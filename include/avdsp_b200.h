@@ -255,6 +255,13 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
                               void *stream);
 int ff_h264_deblock_batch_hbd_cuda(int bit_depth, const FFH264DeblockMB *mbs, int mb_w, int mb_h, int n_pictures, uint8_t *luma,
                                    uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream);
+/* weighted prediction and the DC transforms for the same pictures: weight_h264_pixels / biweight_h264_pixels at 9 / 10 bit (the record's offset is
+ * in 8-bit units and scaled by 2^(bit_depth - 8) like h264dsp_template.c:39,70; `off` and `stride` in bytes) and h264_luma_dc_dequant_idct /
+ * h264_chroma_dc_dequant_idct / h264_chroma422_dc_dequant_idct on int32 coefficients (h264idct_template.c:242-324; luma_dc = 16 int32 per macroblock) */
+int ff_h264_weight_batch_hbd_cuda(int bit_depth, const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src /* NULL = uni */,
+                                  int stride, void *stream);
+int ff_h264_dc_dequant_batch_hbd_cuda(int chroma_format_idc, const FFH264DCRecord *recs, size_t n, int32_t *coeffs, size_t coeff_stride,
+                                      const int32_t *luma_dc, void *stream);
 /* chroma_format_idc 2, bit depth 8 / 9 / 10: the 8 x 16 chroma macroblock has two vertical edges of sixteen lines (the 104-byte record's
  * calpha / cbeta / ctc0 / cintra [plane][0][edge]: h264_h_loop_filter_chroma422, a tc0 entry per four lines) and FOUR horizontal edges, one per
  * luma edge at chroma rows 0, 4, 8, 12 (h264_loopfilter.c:633,693-700: also inside 8x8-transform macroblocks), carried by a second record per

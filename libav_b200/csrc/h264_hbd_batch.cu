@@ -182,6 +182,45 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
     }
 }
 
+// weight_h264_pixels / biweight_h264_pixels at 9 / 10 bit (h264dsp_template.c:30-98: the offset is scaled by 2^(bits - 8), :39,70): warp per record
+__global__ void __launch_bounds__(128)
+h264_weight_hbd_kernel(int bits, const FFH264WeightRecord *__restrict__ recs, size_t n, uint8_t *__restrict__ plane, const uint8_t *__restrict__ src, int stride)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t ri = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ri >= n) return;
+    const FFH264WeightRecord r = recs[ri];
+    const int ld = r.log2_denom, sp = stride >> 1;
+    int off = (int)r.offset * (1 << (bits - 8));
+    if (!src) { off *= 1 << ld; if (ld) off += 1 << (ld - 1); }
+    else off = ((off + 1) | 1) << ld;
+    px *d0 = reinterpret_cast<px *>(plane + r.off);
+    const px *s0 = src ? reinterpret_cast<const px *>(src + r.off) : nullptr;
+    for (int it = lane; it < r.w * r.h; it += 32) {
+        const size_t o = (size_t)(it / r.w) * sp + it % r.w;
+        const int v = s0 ? ((int)s0[o] * r.weight_src + (int)d0[o] * r.weight + off) >> (ld + 1) : ((int)d0[o] * r.weight + off) >> ld;
+        d0[o] = (px)hbd::clipb(v, bits);
+    }
+}
+
+// h264_luma_dc_dequant_idct / h264_chroma_dc_dequant_idct / h264_chroma422_dc_dequant_idct on int32 coefficients (h264idct_template.c:242-324), the
+// step hl_decode_mb() runs before the residual of a macroblock: thread per macroblock, only the DC positions of its arena are touched
+__global__ void __launch_bounds__(128)
+h264_dc_dequant_hbd_kernel(int c422, const FFH264DCRecord *__restrict__ recs, size_t n, int32_t *__restrict__ coeffs, size_t coeff_stride, const int32_t *__restrict__ luma_dc)
+{
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const FFH264DCRecord r = recs[m];
+    int32_t *mb = coeffs + m * coeff_stride;
+    if (r.luma_qmul) {
+        int32_t in[16];
+        for (int i = 0; i < 16; i++) in[i] = luma_dc[16 * m + i];
+        hbd::luma_dc_dequant(mb, in, (int)r.luma_qmul);
+    }
+    for (int pl = 0; pl < 2; pl++)
+        if (r.chroma_qmul[pl]) { if (c422) hbd::chroma422_dc_dequant(mb + 256 * (pl + 1), (int)r.chroma_qmul[pl]); else hbd::chroma_dc_dequant(mb + 256 * (pl + 1), (int)r.chroma_qmul[pl]); }
+}
+
 #ifndef AVB_HOSTSIM      // (the wavefront synchronises warps: not part of tests/hostsim/, GPU tests only)
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int DB_WARPS = 16;
@@ -349,6 +388,28 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
         else
             h264_mc_hbd_kernel<true><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
 #endif
+    return check_launch(where) ? -1 : 0;
+}
+
+int ff_h264_weight_batch_hbd_cuda(int bit_depth, const FFH264WeightRecord *recs, size_t n, uint8_t *plane, const uint8_t *src, int stride, void *stream)
+{
+    avb::enter();
+    const char *where = "ff_h264_weight_batch_hbd_cuda";
+    if (!hbd_args_ok(where, bit_depth, 1, stride, 0, plane, src, nullptr)) return -1;
+    if (n && (!recs || !plane)) { set_error_msg(where, "NULL argument"); return -1; }
+    if (!n) return 0;
+    AVB_LAUNCH(h264_weight_hbd_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, recs, n, plane, src, stride);
+    return check_launch(where) ? -1 : 0;
+}
+
+int ff_h264_dc_dequant_batch_hbd_cuda(int chroma_format_idc, const FFH264DCRecord *recs, size_t n, int32_t *coeffs, size_t coeff_stride, const int32_t *luma_dc, void *stream)
+{
+    avb::enter();
+    const char *where = "ff_h264_dc_dequant_batch_hbd_cuda";
+    if (chroma_format_idc != 1 && chroma_format_idc != 2) { set_error_msg(where, "chroma_format_idc must be 1 or 2"); return -1; }
+    if (n && (!recs || !coeffs || !luma_dc)) { set_error_msg(where, "NULL argument"); return -1; }
+    if (!n) return 0;
+    AVB_LAUNCH(h264_dc_dequant_hbd_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, (cudaStream_t)stream)(chroma_format_idc == 2, recs, n, coeffs, coeff_stride, luma_dc);
     return check_launch(where) ? -1 : 0;
 }
 

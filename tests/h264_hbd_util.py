@@ -199,3 +199,49 @@ def smooth_picture422(mb_w, mb_h, bits, seed):
         v = np.clip(sc * (up + rng.integers(-6, 7, size=shape)) + rng.integers(0, sc, size=shape), 0, (1 << bits) - 1)
         return v.astype(np.uint8 if bits == 8 else np.uint16)
     return plane((16 * mb_h, 16 * mb_w)), plane((16 * mb_h, 8 * mb_w)), plane((16 * mb_h, 8 * mb_w))
+
+
+# ---- weighted prediction and DC transforms at 9 / 10 bit ------------------------------------------------------------------------------------
+def weight_dc_cases(run_weight, run_dc, o, bits):
+    """run_weight(bits, rec, plane, src | None) -> plane after ff_h264_weight_batch_hbd_cuda; run_dc(c422, recs, coeffs, luma_dc) -> coeffs after
+    ff_h264_dc_dequant_batch_hbd_cuda; both against the oracle's BIT_DEPTH > 8 functions"""
+    rng = np.random.default_rng(bits)
+    widx = {16: 0, 8: 1, 4: 2, 2: 3}
+    for bi in (0, 1):
+        plane = rng.integers(0, 1 << bits, size=(128, 256)).astype(np.uint16)
+        src = rng.integers(0, 1 << bits, size=(128, 256)).astype(np.uint16)
+        recs = []
+        for by in range(0, 128, 16):
+            for bx in range(0, 256, 16):
+                w = int(rng.choice([16, 8, 4, 2]))
+                recs.append(((by * 256 + bx) * 2, w, int(rng.choice([2, 4, 8, 16])), int(rng.integers(0, 8)), 0, int(rng.integers(-128, 128)),
+                             int(rng.integers(-128, 128)), int(rng.integers(-128, 128)), 0))
+        rec = np.array(recs, dtype=synth.WEIGHT_DT)
+        want = plane.copy()
+        st = want.strides[0]
+        for r in rec:
+            if bi:
+                o.h264_hbd_biweight(bits, widx[int(r["w"])], at(want, r["off"]), at(src, r["off"]), st, int(r["h"]), int(r["log2_denom"]), int(r["weight"]),
+                                    int(r["weight_src"]), int(r["offset"]))
+            else:
+                o.h264_hbd_weight(bits, widx[int(r["w"])], at(want, r["off"]), st, int(r["h"]), int(r["log2_denom"]), int(r["weight"]), int(r["offset"]))
+        got = run_weight(bits, rec, plane.copy(), src if bi else None)
+        assert not np.array_equal(want, plane) and np.array_equal(got, want), ("weight", bits, bi, np.argwhere(got != want)[:4].tolist())
+    DC_DT = np.dtype([("luma_qmul", "<u4"), ("chroma_qmul", "<u4", (2,))])
+    for c422 in (0, 1):
+        n = 300
+        recs = np.zeros(n, DC_DT)
+        recs["luma_qmul"] = np.where(rng.random(n) < 0.6, rng.integers(16, 4000, n), 0)
+        recs["chroma_qmul"] = np.where(rng.random((n, 2)) < 0.6, rng.integers(16, 4000, (n, 2)), 0)
+        sc = 1 << (bits - 8)
+        coeffs = rng.integers(-300 * sc, 300 * sc, size=(n, 768)).astype(np.int32)
+        luma_dc = rng.integers(-2000 * sc, 2000 * sc, size=(n, 16)).astype(np.int32)
+        want = coeffs.copy()
+        for m in range(n):
+            if recs["luma_qmul"][m]:
+                o.h264_hbd_dc_dequant(bits, 0, at(want, m * 768 * 4), ptr(luma_dc[m].copy()), int(recs["luma_qmul"][m]))
+            for pl in range(2):
+                if recs["chroma_qmul"][m, pl]:
+                    o.h264_hbd_dc_dequant(bits, 2 if c422 else 1, at(want, (m * 768 + 256 * (pl + 1)) * 4), None, int(recs["chroma_qmul"][m, pl]))
+        got = run_dc(c422, recs, coeffs.copy(), luma_dc)
+        assert not np.array_equal(want, coeffs) and np.array_equal(got, want), ("dc", bits, c422, np.argwhere(got != want)[:4].tolist())

@@ -236,3 +236,21 @@ def test_h264_hbd_batch_residual_and_mc(sim, refo, bits, c422):
         assert np.array_equal(y, wy), "luma"
         assert np.array_equal(cb, wcb) and np.array_equal(cr, wcr), "chroma"
     assert sim.avb200_last_error().decode() == ""
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+def test_h264_hbd_batch_weight_and_dc(sim, refo, bits):
+    """ff_h264_weight_batch_hbd_cuda / ff_h264_dc_dequant_batch_hbd_cuda (host-compiled) against the compiled reference's BIT_DEPTH > 8 functions"""
+    import h264_hbd_util as hh
+    sim.ff_h264_weight_batch_hbd_cuda.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    sim.ff_h264_dc_dequant_batch_hbd_cuda.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+
+    def run_weight(b, rec, plane, src):
+        assert sim.ff_h264_weight_batch_hbd_cuda(b, rec.ctypes.data, len(rec), plane.ctypes.data, src.ctypes.data if src is not None else None, plane.strides[0], None) == 0
+        return plane
+
+    def run_dc(c422, recs, coeffs, luma_dc):
+        assert sim.ff_h264_dc_dequant_batch_hbd_cuda(1 + c422, recs.ctypes.data, len(recs), coeffs.ctypes.data, 768, luma_dc.ctypes.data, None) == 0
+        return coeffs
+    hh.weight_dc_cases(run_weight, run_dc, refo, bits)
+    assert sim.avb200_last_error().decode() == ""

@@ -136,3 +136,23 @@ def test_chroma422_decisions(gpu, checker):
             gext = ext.download(np.uint8, (mw * mh, 52))
             bad = np.argwhere((gext[:, :50] != want_ext[:, :50]).any(axis=1))
             assert not len(bad), ("ext", case, mw, mh, bad[:4].ravel().tolist(), gext[bad[0, 0]].tolist(), want_ext[bad[0, 0]].tolist())
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+def test_weight_and_dc_batch_hbd(gpu, checker, bits):
+    from libav_b200 import device
+    lib = gpu.lib
+
+    def run_weight(b, rec, plane, src):
+        d_rec, d_pl = _dev(rec), _dev(plane)
+        d_src = _dev(src) if src is not None else None
+        gpu.check(lib.ff_h264_weight_batch_hbd_cuda(b, d_rec.ptr, rec.shape[0], d_pl.ptr, d_src.ptr if d_src else None, plane.strides[0], None))
+        device.sync()
+        return d_pl.download(np.uint16, plane.shape)
+
+    def run_dc(c422, recs, coeffs, luma_dc):
+        d_rec, d_co, d_dc = _dev(recs), _dev(coeffs), _dev(luma_dc)
+        gpu.check(lib.ff_h264_dc_dequant_batch_hbd_cuda(1 + c422, d_rec.ptr, recs.shape[0], d_co.ptr, 768, d_dc.ptr, None))
+        device.sync()
+        return d_co.download(np.int32, coeffs.shape)
+    hh.weight_dc_cases(run_weight, run_dc, checker, bits)

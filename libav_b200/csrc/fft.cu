@@ -2,9 +2,9 @@
 //   fft_permute + fft_calc           libavcodec/fft_template.c:186-194, :140-346  (natural-order DFT, no 1/n)
 //   imdct_half / imdct_calc / mdct_calc   libavcodec/mdct_template.c:95-214, rotation tables as ff_mdct_init (:86-92)
 // Contract for this row: 1e-6 relative to the reference's float result (north star), not bit-exactness.
-// One CTA per transform: the sequence is bit-reversed into shared memory, log2(n) radix-2 passes with twiddles read from
-// a per-size table computed in double on the host (so the only float rounding is the butterflies'), MDCT pre/post
-// rotations fused around the core.  HBM traffic is one read and one write of the data: 16 B per complex point.
+// One CTA per transform: the sequence is bit-reversed into (bank-swizzled) shared memory, log2(n) radix-2 stages -- four per pass, 16 points per
+// thread in registers -- with twiddles read from a per-size table computed in double on the host (so the only float rounding is the
+// butterflies'), MDCT pre/post rotations fused around the core.  HBM traffic is one read and one write of the data: 16 B per complex point.
 #include "common.cuh"
 #include "scratch.h"
 #include "../../include/avdsp_b200.h"
@@ -20,42 +20,52 @@ namespace avb {
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place DIT on bit-reversed data in shared memory; tw[k] = exp(sign * 2 pi i k / n), k < n / 2.
-// Two radix-2 stages are fused per pass (a thread carries its four points through both in registers: the same
-// butterflies in the same order as stage-by-stage radix 2, so the result is bit-identical to it), which halves the
-// shared-memory round trips and barriers; an odd log2(n) starts with one plain radix-2 stage.
+// Shared-memory index swizzle: element i lives at i ^ ((i >> 4) & 15).  A thread of the 16-point pass reads elements 16 b + m (one stride of
+// 128 bytes per lane: without the swizzle all 32 lanes hit the same two banks), the bit-reversed scatter writes elements that differ in their
+// top bits only; with it both spread over the banks, and every later pass (consecutive k per lane) stays a permutation inside 16 elements.
+__device__ __forceinline__ int sw(int i) { return i ^ ((i >> 4) & 15); }
+
+// One pass = F radix-2 DIT stages (st .. st + F - 1) on 2^F points carried in registers: the same butterflies in the same order as stage-by-stage
+// radix 2, so the result is bit-identical to it.  Stage st + q pairs (m, m + 2^q); element i0 + m * half sits at offset k + (m mod 2^q) * half
+// inside its group of that stage, which is its twiddle index (times n >> (stage + 1)).
+template <int F>
+__device__ __forceinline__ void fft_pass(float2 *s, int n, int st, const float2 *__restrict__ tw)
+{
+    constexpr int P = 1 << F;
+    const int half = 1 << st;
+    for (int b = threadIdx.x; b < (n >> F); b += blockDim.x) {
+        const int k = b & (half - 1), i0 = ((b >> st) << (st + F)) + k;
+        float2 x[P];
+#pragma unroll
+        for (int m = 0; m < P; m++) x[m] = s[sw(i0 + m * half)];
+#pragma unroll
+        for (int q = 0; q < F; q++) {
+            const int tstep = n >> (st + q + 1);
+#pragma unroll
+            for (int m = 0; m < P; m++) {
+                if (m & (1 << q)) continue;
+                const float2 w = __ldg(&tw[(k + (m & ((1 << q) - 1)) * half) * tstep]);
+                const float2 t = cmul(x[m + (1 << q)], w);
+                x[m + (1 << q)] = make_float2(x[m].x - t.x, x[m].y - t.y);
+                x[m] = make_float2(x[m].x + t.x, x[m].y + t.y);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < P; m++) s[sw(i0 + m * half)] = x[m];
+    }
+}
+
+// in-place DIT on bit-reversed (and swizzled) data in shared memory; tw[k] = exp(sign * 2 pi i k / n), k < n / 2.  Four stages per pass while
+// that many remain (16 points per thread: a 1024-point transform is three passes and two barriers instead of five and five), then 3 / 2 / 1.
 __device__ __forceinline__ void fft_smem(float2 *s, int nbits, const float2 *__restrict__ tw)
 {
     const int n = 1 << nbits;
     int st = 0;
-    if (nbits & 1) {
+    while (st < nbits) {
+        const int rem = nbits - st, f = rem >= 4 ? (rem == 5 ? 3 : 4) : rem;
         __syncthreads();
-        for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {        // stage 0: half = 1, twiddle 1
-            const float2 a = s[2 * b], t = s[2 * b + 1];
-            s[2 * b] = make_float2(a.x + t.x, a.y + t.y);
-            s[2 * b + 1] = make_float2(a.x - t.x, a.y - t.y);
-        }
-        st = 1;
-    }
-    for (; st < nbits; st += 2) {
-        const int half = 1 << st, t1 = n >> (st + 1), t2 = n >> (st + 2);
-        __syncthreads();
-        for (int b = threadIdx.x; b < n / 4; b += blockDim.x) {
-            const int k = b & (half - 1), i0 = ((b >> st) << (st + 2)) + k;
-            const float2 w1 = __ldg(&tw[k * t1]), w2 = __ldg(&tw[k * t2]), w3 = __ldg(&tw[(k + half) * t2]);
-            float2 x0 = s[i0], x1 = s[i0 + half], x2 = s[i0 + 2 * half], x3 = s[i0 + 3 * half];
-            // stage st: (x0, x1) and (x2, x3), both with w1
-            float2 t = cmul(x1, w1);
-            x1 = make_float2(x0.x - t.x, x0.y - t.y); x0 = make_float2(x0.x + t.x, x0.y + t.y);
-            t = cmul(x3, w1);
-            x3 = make_float2(x2.x - t.x, x2.y - t.y); x2 = make_float2(x2.x + t.x, x2.y + t.y);
-            // stage st + 1: (x0, x2) with w2, (x1, x3) with w3
-            t = cmul(x2, w2);
-            x2 = make_float2(x0.x - t.x, x0.y - t.y); x0 = make_float2(x0.x + t.x, x0.y + t.y);
-            t = cmul(x3, w3);
-            x3 = make_float2(x1.x - t.x, x1.y - t.y); x1 = make_float2(x1.x + t.x, x1.y + t.y);
-            s[i0] = x0; s[i0 + half] = x1; s[i0 + 2 * half] = x2; s[i0 + 3 * half] = x3;
-        }
+        if (f == 4) fft_pass<4>(s, n, st, tw); else if (f == 3) fft_pass<3>(s, n, st, tw); else if (f == 2) fft_pass<2>(s, n, st, tw); else fft_pass<1>(s, n, st, tw);
+        st += f;
     }
     __syncthreads();
 }
@@ -66,9 +76,9 @@ __global__ void fft_kernel(float2 *__restrict__ z, int nbits, const float2 *__re
     extern __shared__ float2 sm[];
     const int n = 1 << nbits;
     float2 *zz = z + (size_t)blockIdx.x * n;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) sm[bitrev(j, nbits)] = zz[revtab ? revtab[j] : j];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sm[sw(bitrev(j, nbits))] = zz[revtab ? revtab[j] : j];
     fft_smem(sm, nbits, tw);
-    for (int j = threadIdx.x; j < n; j += blockDim.x) zz[j] = sm[j];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) zz[j] = sm[sw(j)];
 }
 
 // op 0 imdct_half (in n/2 -> out n/2), 1 imdct_calc (n/2 -> n), 2 mdct_calc (n -> n/2); FFT of n/4 points inside.
@@ -84,22 +94,22 @@ __global__ void mdct_kernel(int op, int nbits, float *__restrict__ out, const fl
     if (op < 2) {                                              // pre rotation, mdct_template.c:109-117
         for (int k = threadIdx.x; k < n4; k += blockDim.x) {
             const float a = x[n2 - 1 - 2 * k], b = x[2 * k], c = tcos[k], s = tsin[k];
-            sm[bitrev(k, fb)] = make_float2(a * c - b * s, a * s + b * c);
+            sm[sw(bitrev(k, fb))] = make_float2(a * c - b * s, a * s + b * c);
         }
     } else {                                                   // :163-175
         for (int i = threadIdx.x; i < n8; i += blockDim.x) {
             float re = -x[2 * i + n3] - x[n3 - 1 - 2 * i], im = -x[n4 + 2 * i] + x[n4 - 1 - 2 * i];
             float c = -tcos[i], s = tsin[i];
-            sm[bitrev(i, fb)] = make_float2(re * c - im * s, re * s + im * c);
+            sm[sw(bitrev(i, fb))] = make_float2(re * c - im * s, re * s + im * c);
             re = x[2 * i] - x[n2 - 1 - 2 * i]; im = -x[n2 + 2 * i] - x[n - 1 - 2 * i];
             c = -tcos[n8 + i]; s = tsin[n8 + i];
-            sm[bitrev(n8 + i, fb)] = make_float2(re * c - im * s, re * s + im * c);
+            sm[sw(bitrev(n8 + i, fb))] = make_float2(re * c - im * s, re * s + im * c);
         }
     }
     fft_smem(sm, fb, tw);
     float *half = op == 1 ? y + n4 : y;                        // imdct_calc builds its middle half first (:139)
     for (int k = threadIdx.x; k < n8; k += blockDim.x) {
-        const float2 za = sm[n8 - k - 1], zb = sm[n8 + k];
+        const float2 za = sm[sw(n8 - k - 1)], zb = sm[sw(n8 + k)];
         float r0, i0, r1, i1;
         if (op < 2) {                                          // :120-130
             float a = za.y, b = za.x, c = tsin[n8 - k - 1], s = tcos[n8 - k - 1];
@@ -166,7 +176,7 @@ static const float *rotations(int nbits, double scale)
     g_rot[key] = d;
     return d;
 }
-static int threads_for(int points) { int t = points / 2; return t < 32 ? 32 : t > 256 ? 256 : t; }
+static int threads_for(int points) { int t = points / 16; return t < 32 ? 32 : t > 256 ? 256 : t; }      // a thread carries 16 points through four stages
 
 int launch_fft(int nbits, int inverse, float *z, size_t n_tr, const uint16_t *d_revtab, cudaStream_t st)
 {

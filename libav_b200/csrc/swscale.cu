@@ -1152,6 +1152,10 @@ struct SwsCudaContext {
     int rangeConv = 0;          // yuv destination of the other range: 1 lum / chrRangeFromJpeg_c, 2 lum / chrRangeToJpeg_c on the hscaled lines (two-pass path)
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
     int rgb16 = 0;              // rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 destination (SwsDev::rgb16)
+    bool gray = false;          // gray8 destination: the luma plane of the planar conversion (swscale.c:618-630 skips the chroma of a gray destination, the
+                                // unscaled copy takes plane 0 only, swscale_unscaled.c:1155); the chroma planes go to scratch nobody reads
+    uint8_t *d_gray[2] = { nullptr, nullptr }; int grayPitch = 0;
+    std::vector<uint8_t> h_gray[2];
     int to422 = 0;              // its unscaled special converters: 1 from yuv422p, 2 from yuv420p (fast-bilinear / point flags only), 3 same-format copy
     int dstNV = 0;              // 1 nv12, 2 nv21 destination
     bool nvcopy = false;        // yuv420p -> nv12 / nv21 of the same size: planarToNv12Wrapper
@@ -1169,7 +1173,7 @@ static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
     if (c->streams_ok) for (int i = 0; i < 3; i++) cudaStreamDestroy(c->streams[i]);
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst);
+    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_gray[0]); cudaFree(c->d_gray[1]);
     delete c;
 }
 
@@ -1247,6 +1251,17 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         default: srcBE = 0; break;
         }
     }
+    // gray8 (AV_PIX_FMT_GRAY8 = 8): only luma exists; it is the luma plane of the conversion to a planar yuv picture -- of the source's own
+    // sub-sampling when the source is planar 8-bit yuv, so that the same-size case is the reference's plane copy for every such source
+    // (isPlanarYUV(src) && isGray(dst), swscale_unscaled.c:1155) -- whose chroma planes are written to scratch
+    bool gray = false;
+    if (dstFormat == 8) {
+        gray = true;
+        switch (srcFormat) {
+        case FMT_YUV420P: case FMT_YUV422P: case FMT_YUV444P: case FMT_YUV410P: case FMT_YUV411P: case FMT_YUV440P: dstFormat = srcFormat; break;
+        default: dstFormat = FMT_YUV420P; break;
+        }
+    }
     int dhs = 1, dvs = 0, dbits = 8, dbe = 0;
     const bool planar = planar_dst(dstFormat, &dhs, &dvs, &dbits, &dbe);
     const bool dst32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
@@ -1259,7 +1274,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     if (pk422 || rgb16) flags &= ~SWS_FULL_CHR_H_INT;        // only 24 / 32-bit packed RGB knows the flag (utils.c:998-1014)
     if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422 && !rgb16) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: rgb24, bgr24, argb, rgba, abgr, bgra, rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 (LE and BE), yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
+        set_error_msg("sws_getContext_cuda", "destinations taken over: gray8, rgb24, bgr24, argb, rgba, abgr, bgra, rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 (LE and BE), yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1348,7 +1363,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->pk422 = pk422; c->rgb16 = rgb16; c->srcBits = srcBits; c->srcBE = srcBE;
+    c->pk422 = pk422; c->rgb16 = rgb16; c->gray = gray; c->srcBits = srcBits; c->srcBE = srcBE;
     if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv && srcBits == 8) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
@@ -1411,6 +1426,11 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv && srcBits == 8;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { destroy(c); return nullptr; }
+    if (c->gray) {
+        c->grayPitch = (c->g.chrDstW + 63) & ~31;
+        for (int k = 0; k < 2; k++)
+            if (cudaMalloc(&c->d_gray[k], (size_t)c->grayPitch * (c->g.chrDstH + 2)) != cudaSuccess) { set_error("sws_getContext_cuda", cudaGetLastError()); destroy(c); return nullptr; }
+    }
     if (c->fast_ok) {
         std::vector<SwsPairTaps> pt(dstH / 2);
         for (int rp = 0; rp < dstH / 2; rp++) {
@@ -1843,7 +1863,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
     if (!c) return false;
     v.rangeConv = c->rangeConv; v.srcBits = c->srcBits;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
-    if (c->rgb16) return false;            // (the per-line slots do not cover the 15 / 16 / 12-bpp output stage: the hook leaves the C slots)
+    if (c->rgb16 || c->gray) return false; // (the per-line slots do not cover the 15 / 16 / 12-bpp output stage: the hook leaves the C slots)
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
 }
@@ -1894,8 +1914,16 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
     avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
-    if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0] || (c->planar && (!dst[1] || (!c->dstNV && !dst[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     static const size_t zero3[3] = { 0, 0, 0 };
+    if (c->gray && dst && dst[0] && dstStride) {      // chroma to scratch (every frame of the batch into the same two planes: nobody reads them)
+        uint8_t *const d3[3] = { dst[0], c->d_gray[0], c->d_gray[1] };
+        const int ds3[3] = { dstStride[0], c->grayPitch, c->grayPitch };
+        const size_t df3[3] = { dstFrameStride ? dstFrameStride[0] : 0, 0, 0 };
+        if (!src || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
+        if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, d3, ds3, df3, nframes, (cudaStream_t)stream)) return -1;
+        return c->g.dstH * nframes;
+    }
+    if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0] || (c->planar && (!dst[1] || (!c->dstNV && !dst[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
                    nframes, (cudaStream_t)stream)) return -1;
     return c->g.dstH * nframes;
@@ -2050,6 +2078,18 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
+    if (c->gray && dst && dst[0] && dstStride) {        // (a gray8 caller's dst[] has one plane; `gray` is cleared around the inner call)
+        // the chroma planes of the planar conversion go to host scratch of the context (they are computed and dropped)
+        const size_t bytes = (size_t)c->grayPitch * (c->g.chrDstH + 2);
+        for (int k = 0; k < 2; k++) if (c->h_gray[k].size() < bytes) c->h_gray[k].resize(bytes);
+        uint8_t *const d3[4] = { dst[0], c->h_gray[0].data(), c->h_gray[1].data(), nullptr };
+        const int ds3[4] = { dstStride[0], dstStride[0] < 0 ? -c->grayPitch : c->grayPitch, dstStride[0] < 0 ? -c->grayPitch : c->grayPitch, 0 };
+        if (dstStride[0] < 0) {              // bottom-up: the scratch planes are addressed from their last row like the caller's plane
+            uint8_t *const d3f[4] = { dst[0], c->h_gray[0].data() + (size_t)c->grayPitch * (c->g.chrDstH - 1), c->h_gray[1].data() + (size_t)c->grayPitch * (c->g.chrDstH - 1), nullptr };
+            c->gray = false; const int r = sws_scale_cuda(ctx, srcSlice, srcStride, srcSliceY, srcSliceH, d3f, ds3); c->gray = true; return r;
+        }
+        c->gray = false; const int r = sws_scale_cuda(ctx, srcSlice, srcStride, srcSliceY, srcSliceH, d3, ds3); c->gray = true; return r;
+    }
     const bool rgb = !c->planar;
     const bool nv = c->srcNV != 0, pk = c->srcPacked != 0;
     if (!srcSlice || !dst || !srcSlice[0] || !srcStride[0] || (!pk && (!srcSlice[1] || !srcStride[1] || (!nv && (!srcSlice[2] || !srcStride[2])))) ||

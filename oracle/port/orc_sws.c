@@ -958,6 +958,26 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
+    if (dst_fmt == 8) {
+        /* gray8: luma only.  swscale() skips the chroma of a gray destination (swscale.c:618-630) and the same-size case is the plane copy for
+         * every planar yuv source (isPlanarYUV(src) && isGray(dst), swscale_unscaled.c:1155): the luma plane of the conversion to a planar
+         * picture of the source's own sub-sampling (4:2:0 for the other sources), chroma into scratch */
+        int df = (src_fmt == 0 || src_fmt == 4 || src_fmt == 5 || src_fmt == 6 || src_fmt == 7 || src_fmt == 31) ? src_fmt : 0;
+        {   /* 9 / 10 / 16-bit planar sources count as planar yuv too: at the same size the reference runs planarCopyWrapper's depth conversion
+             * (not restated: the twin of the source's sub-sampling makes the refusal below apply) */
+            int f = src_fmt;
+            if (f == 61 || f == 63 || f == 65 || f == 67 || f == 69 || f == 71) f += 1; else if (f == 48 || f == 50 || f == 52) f -= 1;
+            if (f == 72 || f == 66 || f == 49) df = 4; else if (f == 68 || f == 70 || f == 51) df = 5;
+        }
+        const int pitch = dw + 64;
+        uint8_t *tmp = calloc((size_t)pitch * (dh + 2), 2);
+        if (!tmp) return -1;
+        uint8_t *const d3[3] = { dst[0], tmp, tmp + (size_t)pitch * (dh + 2) };
+        const int ds3[3] = { dstride[0], pitch, pitch };
+        r = sws_any(src_fmt, src, ss, sw, sh, df, d3, ds3, dw, dh, flags);
+        free(tmp);
+        return r;
+    }
     const int pk = dst_fmt == 1 || dst_fmt == 15;
     {   /* 9 / 10 / 16-bit planar sources: yuv420p 62 64 47, yuv422p 72 66 49, yuv444p 68 70 51 (LE), big-endian twins -1 / +1 */
         int f = src_fmt, be = 0, bits = 0, base = -1;

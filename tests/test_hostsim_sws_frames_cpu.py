@@ -24,7 +24,7 @@ def outputs(df, dw, dh, pad=8, fill=7):
         dt = np.uint8 if bits == 8 else np.dtype(">u2" if df in PLANAR_BE else "<u2")
         cw, ch = -((-dw) >> hs), -((-dh) >> vs)
         return [np.full((dh, dw + pad), fill, dt), np.full((ch, cw + pad), fill, dt), np.full((ch, cw + pad), fill, dt)]
-    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) or 36 <= df <= 43 or 54 <= df <= 57 else 3
+    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) or 36 <= df <= 43 or 54 <= df <= 57 else 1 if df == 8 else 3
     return [np.full((dh, dw * bpp + 2 * pad), fill, np.uint8)]
 
 
@@ -111,6 +111,19 @@ def test_rgb16_destinations(sim, refo):
     for args in ((64, 48, 0, 64, 48, 37, 4), (64, 48, 2, 128, 96, 37, 4 | ACC), (64, 48, 1, 128, 96, 41, 4 | ACC)):
         assert not sim.sws_getContext_cuda(*args, None, None, None)
         sim.avb200_clear_error()
+
+
+def test_gray8_destination(sim, refo):
+    """gray8 (tests/test_sws_gray_dst.py): the luma plane of the planar conversion, chroma into the context's scratch"""
+    import test_sws_gray_dst as G
+    n = 0
+    for (sf, w, h, dw, dh, flags) in G.combos():
+        pl = G.planes(sf, w, h, 47)
+        got = product(sim, sf, pl, w, h, 8, dw, dh, flags)
+        want = reference(refo, sf, pl, w, h, 8, dw, dh, flags)
+        assert np.array_equal(got[0][:, :dw], want[0][:, :dw]) and (got[0][:, dw:] == 7).all(), (sf, w, h, dw, dh, hex(flags), np.argwhere(got[0] != want[0])[:4].tolist())
+        n += 1
+    assert n > 200
 
 
 def test_range_conversion_frames(sim, refo):

@@ -262,6 +262,11 @@ int ff_h264_weight_batch_hbd_cuda(int bit_depth, const FFH264WeightRecord *recs,
                                   int stride, void *stream);
 int ff_h264_dc_dequant_batch_hbd_cuda(int chroma_format_idc, const FFH264DCRecord *recs, size_t n, int32_t *coeffs, size_t coeff_stride,
                                       const int32_t *luma_dc, void *stream);
+/* intra reconstruction at 9 / 10 bit (4:2:0): ff_h264_intra_mb_batch_cuda's records and order, uint16 samples, int32 coefficients; no scratch
+ * argument (the wavefront's progress lives in shared memory, one CTA per picture) */
+int ff_h264_intra_mb_batch_hbd_cuda(int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, int32_t *coeffs,
+                                    size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
+                                    int uvlinesize, void *stream);
 /* chroma_format_idc 2, bit depth 8 / 9 / 10: the 8 x 16 chroma macroblock has two vertical edges of sixteen lines (the 104-byte record's
  * calpha / cbeta / ctc0 / cintra [plane][0][edge]: h264_h_loop_filter_chroma422, a tc0 entry per four lines) and FOUR horizontal edges, one per
  * luma edge at chroma rows 0, 4, 8, 12 (h264_loopfilter.c:633,693-700: also inside 8x8-transform macroblocks), carried by a second record per

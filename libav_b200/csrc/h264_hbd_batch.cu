@@ -22,6 +22,7 @@
 // A picture of a batch starts `pic_h` luma rows after the previous one in the same planes (like the 8-bit calls).
 #include "h264dsp.cuh"
 #include "h264dsp_hbd.cuh"
+#include "h264pred_hbd.cuh"
 #include "../../include/avdsp_b200.h"
 
 namespace avb {
@@ -339,6 +340,129 @@ h264_deblock_generic_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Intra reconstruction at 9 / 10 bit, 4:2:0: hl_decode_mb() for the intra macroblocks of a batch of pictures (h264_mb.c:607-731 luma,
+// h264_mb_template.c:158-197 chroma) -- per block pred4x4 / pred8x8l then its residual, pred16x16 then h264_idct_add16intra, pred8x8 on cb
+// and cr then h264_idct_add8 -- in raster order.  One CTA per picture, its warps take macroblock rows round-robin as a wavefront two
+// macroblocks behind the row above (prediction reaches left, up-left, up and up-right), progress in shared memory like the deblocking
+// kernel above.  Every lane collects the block's neighbours itself (the table slots' PredJobH) and derives its samples from them;
+// lane 0 (or a lane per 4x4 block) adds the residual; the warp synchronises between a block's prediction, its residual and the next block.
+__device__ __forceinline__ void intra_job_neighbours(PredJobH &j, const px *P, int st, int nt, int nl, bool tr_ok, int ax, int ay, int y0)
+{   // P = the block's first sample at absolute (ax, ay); [y0, ..) = the picture's rows.  nt top samples (4 or 8 more when tr_ok), nl left samples
+    const bool top = ay - 1 >= y0, left = ax - 1 >= 0;
+    for (int k = 0; k < nt; k++) j.top[k] = top ? P[-st + k] : 0;
+    for (int k = nt; k < 2 * nt && k < 16; k++) j.top[k] = (top && tr_ok) ? P[-st + k] : j.top[nt - 1];
+    for (int k = 0; k < nl; k++) j.left[k] = left ? P[(ptrdiff_t)k * st - 1] : 0;
+    j.corner = (top && left) ? P[-st - 1] : 0;
+}
+
+__global__ void __launch_bounds__(DB_WARPS * 32)
+h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w, int mb_h, int32_t *__restrict__ coeffs, size_t coeff_stride,
+                      const uint8_t *__restrict__ nnzc_all, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
+{
+    using namespace hbd;
+    extern __shared__ int prog_s[];
+    volatile int *prog = prog_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pic = blockIdx.x;
+    for (int i = threadIdx.x; i < mb_h; i += blockDim.x) prog_s[i] = 0;
+    __syncthreads();
+    const int lsp = ls >> 1, uvlsp = uvls >> 1, y0 = pic * mb_h * 16, cy0 = pic * mb_h * 8;
+    px *const Y = reinterpret_cast<px *>(luma), *const C2[2] = { reinterpret_cast<px *>(cb), reinterpret_cast<px *>(cr) };
+    for (int row = warp; row < mb_h; row += DB_WARPS) {
+        for (int x = 0; x < mb_w; x++) {
+            const size_t m = ((size_t)pic * mb_h + row) * mb_w + x;
+            const FFH264IntraMB M = mbs[m];
+            if (M.kind) {
+                if (row > 0) {
+                    const int need = min(x + 2, mb_w);                 // up-right neighbour finished
+                    if (lane == 0) while (prog[row - 1] < need) { }
+                    __syncwarp();
+                    __threadfence_block();
+                }
+                int32_t *mb = coeffs + m * coeff_stride;
+                const uint8_t *nnzc = nnzc_all + m * 120;
+                const int ax0 = x * 16, ay0 = y0 + row * 16;
+                PredJobH j;
+                j.bits = bits; j.has_tl = j.has_tr = 0; j.nblocks = 0;
+                if (M.kind == 1) {                                      // intra 4x4: 16 blocks in coding order
+                    for (int i = 0; i < 16; i++) {
+                        const int bx = blk_x(i), by = blk_y(i), mode = M.mode4[i];
+                        px *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
+                        const bool tr_ok = (M.topright_samples_available << i) & 0x8000;
+                        j.tab = 0; j.mode = mode;
+                        intra_job_neighbours(j, P, lsp, 4, 4, tr_ok, ax0 + bx, ay0 + by, y0);
+                        int v = 0;
+                        if (lane < 16) {
+                            if (mode == 11) v = 1 << (bits - 1);
+                            else { IntraEdges e; hbd_edges(e, j); v = intra_directional(e, 4, mode, lane & 3, lane >> 2); }
+                        }
+                        __syncwarp();                                   // every lane has read its neighbours
+                        if (lane < 16) P[(size_t)(lane >> 2) * lsp + (lane & 3)] = (px)v;
+                        __syncwarp();
+                        const int nnz = nnzc[scan8_of(i)];
+                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) dc_add(bits, P, mb + 16 * i, lsp, 4); else idct4_add(bits, P, mb + 16 * i, lsp); }
+                        __syncwarp();
+                    }
+                } else if (M.kind == 2) {                               // intra 8x8 (pred8x8l)
+                    for (int k = 0; k < 4; k++) {
+                        const int i = 4 * k, bx = 8 * (k & 1), by = 8 * (k >> 1), mode = M.mode4[i];
+                        px *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
+                        j.tab = 1; j.mode = mode;
+                        j.has_tl = ((M.topleft_samples_available << i) & 0x8000) != 0; j.has_tr = ((M.topright_samples_available << i) & 0x4000) != 0;
+                        intra_job_neighbours(j, P, lsp, 8, 8, j.has_tr, ax0 + bx, ay0 + by, y0);
+                        int v[2];
+                        {
+                            IntraEdges e;
+                            if (mode != 11) hbd_edges(e, j);
+                            for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; v[q] = mode == 11 ? 1 << (bits - 1) : intra_directional(e, 8, mode, sidx & 7, sidx >> 3); }
+                        }
+                        __syncwarp();
+                        for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * lsp + (sidx & 7)] = (px)v[q]; }
+                        __syncwarp();
+                        const int nnz = nnzc[scan8_of(i)];
+                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) dc_add(bits, P, mb + 16 * i, lsp, 8); else idct8_add(bits, P, mb + 16 * i, lsp); }
+                        __syncwarp();
+                    }
+                    j.has_tl = j.has_tr = 0;
+                } else {                                                // intra 16x16, then h264_idct_add16intra
+                    px *P = Y + (size_t)ay0 * lsp + ax0;
+                    j.tab = 3; j.mode = M.mode16;
+                    intra_job_neighbours(j, P, lsp, 16, 16, false, ax0, ay0, y0);
+                    int v[8];
+                    for (int q = 0; q < 8; q++) { const int sidx = lane + 32 * q; v[q] = hbd_big_sample(j, 16, sidx & 15, sidx >> 4); }
+                    __syncwarp();
+                    for (int q = 0; q < 8; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 4) * lsp + (sidx & 15)] = (px)v[q]; }
+                    __syncwarp();
+                    if (lane < 16) {
+                        px *d = P + (size_t)blk_y(lane) * lsp + blk_x(lane);
+                        if (nnzc[scan8_of(lane)]) idct4_add(bits, d, mb + 16 * lane, lsp); else if (mb[16 * lane]) dc_add(bits, d, mb + 16 * lane, lsp, 4);
+                    }
+                    __syncwarp();
+                }
+                // chroma: pred8x8 on both planes, then h264_idct_add8
+                for (int pl = 0; pl < 2; pl++) {
+                    px *P = C2[pl] + (size_t)(cy0 + row * 8) * uvlsp + x * 8;
+                    j.tab = 2; j.mode = M.chroma_mode;
+                    intra_job_neighbours(j, P, uvlsp, 8, 8, false, x * 8, cy0 + row * 8, cy0);
+                    int v[2];
+                    for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; v[q] = hbd_big_sample(j, 8, sidx & 7, sidx >> 3); }
+                    __syncwarp();
+                    for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * uvlsp + (sidx & 7)] = (px)v[q]; }
+                }
+                __syncwarp();
+                if (M.chroma_residual && lane < 8) {
+                    const int pl = lane >> 2, k = lane & 3, i = 16 + 16 * pl + k;
+                    px *d = C2[pl] + (size_t)(cy0 + row * 8 + 4 * (k >> 1)) * uvlsp + x * 8 + 4 * (k & 1);
+                    if (nnzc[scan8_of(i)]) idct4_add(bits, d, mb + 16 * i, uvlsp); else if (mb[16 * i]) dc_add(bits, d, mb + 16 * i, uvlsp, 4);
+                }
+                __syncwarp();
+                __threadfence_block();
+            }
+            if (lane == 0) prog[row] = x + 1;
+        }
+    }
+}
+
 #endif
 
 bool hbd_args_ok(const char *where, int bit_depth, int chroma_format_idc, int ls, int uvls, const void *a, const void *b, const void *c)
@@ -412,6 +536,21 @@ int ff_h264_dc_dequant_batch_hbd_cuda(int chroma_format_idc, const FFH264DCRecor
     AVB_LAUNCH(h264_dc_dequant_hbd_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, (cudaStream_t)stream)(chroma_format_idc == 2, recs, n, coeffs, coeff_stride, luma_dc);
     return check_launch(where) ? -1 : 0;
 }
+
+#ifndef AVB_HOSTSIM
+int ff_h264_intra_mb_batch_hbd_cuda(int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, int32_t *coeffs, size_t coeff_stride,
+                                    const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
+{
+    avb::enter();
+    const char *where = "ff_h264_intra_mb_batch_hbd_cuda";
+    if (!hbd_args_ok(where, bit_depth, 1, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (!mbs || !coeffs || !nnzc || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
+    if (!n_pictures) return 0;
+    h264_intra_hbd_kernel<<<(unsigned)n_pictures, DB_WARPS * 32, (size_t)mb_h * sizeof(int), (cudaStream_t)stream>>>(bit_depth, mbs, mb_w, mb_h, coeffs, coeff_stride, nnzc,
+                                                                                                                  luma, cb, cr, linesize, uvlinesize);
+    return check_launch(where) ? -1 : 0;
+}
+#endif
 
 #ifndef AVB_HOSTSIM
 static int launch_deblock_generic(const char *where, int bit_depth, const FFH264DeblockMB *mbs, const FFH264DeblockChroma422 *ext, int mb_w, int mb_h, int n_pictures,

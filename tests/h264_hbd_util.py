@@ -245,3 +245,54 @@ def weight_dc_cases(run_weight, run_dc, o, bits):
                     o.h264_hbd_dc_dequant(bits, 2 if c422 else 1, at(want, (m * 768 + 256 * (pl + 1)) * 4), None, int(recs["chroma_qmul"][m, pl]))
         got = run_dc(c422, recs, coeffs.copy(), luma_dc)
         assert not np.array_equal(want, coeffs) and np.array_equal(got, want), ("dc", bits, c422, np.argwhere(got != want)[:4].tolist())
+
+
+# ---- intra reconstruction at 9 / 10 bit ---------------------------------------------------------------------------------------------------
+def oracle_intra(o, bits, rec, coeffs, nnzc, mb_w, mb_h, y, cb, cr):
+    """hl_decode_mb() for intra macroblocks (h264_mb.c:607-731, h264_mb_template.c:158-197) through the oracle's BIT_DEPTH > 8 H264PredContext /
+    H264DSPContext entries, block by block (tests/h264_util.py::oracle_intra for 16-bit samples; strides and offsets in bytes)"""
+    ls, uvls = y.strides[0], cb.strides[0]
+    for m in range(mb_w * mb_h):
+        r = rec[m]
+        kind = int(r["kind"])
+        if kind == 0:
+            continue
+        mbx, mby = m % mb_w, m // mb_w
+        mb = coeffs[m]
+        org = mby * 16 * ls + mbx * 32
+        corg = mby * 8 * uvls + mbx * 16
+        if kind in (1, 2):
+            for i in range(0, 16, 1 if kind == 1 else 4):
+                bx, by = (i & 1) + 2 * ((i >> 2) & 1), ((i >> 1) & 1) + 2 * (i >> 3)
+                off = org + 4 * by * ls + 8 * bx
+                mode = int(r["mode4"][i])
+                nnz = int(nnzc[m, synth.scan8(i)])
+                blk = mb[16 * i:]
+                if kind == 1:
+                    tr_ok = (int(r["topright"]) << i) & 0x8000
+                    if mode in (3, 7) and not tr_ok:
+                        tr = np.full(4, y[mby * 16 + 4 * by - 1, mbx * 16 + 4 * bx + 3], np.uint16)
+                        o.h264_hbd_pred(bits, 0, mode, at(y, off), ptr(tr), 0, 0, ls)
+                    else:
+                        o.h264_hbd_pred(bits, 0, mode, at(y, off), at(y, off + 8 - ls), 0, 0, ls)
+                    if nnz:
+                        o.h264_hbd_idct(bits, 2 if (nnz == 1 and blk[0]) else 0, at(y, off), ptr(blk), ls)
+                else:
+                    o.h264_hbd_pred(bits, 1, mode, at(y, off), None, (int(r["topleft"]) << i) & 0x8000, (int(r["topright"]) << i) & 0x4000, ls)
+                    if nnz:
+                        o.h264_hbd_idct(bits, 3 if (nnz == 1 and blk[0]) else 1, at(y, off), ptr(blk), ls)
+        else:
+            o.h264_hbd_pred(bits, 3, int(r["mode16"]), at(y, org), None, 0, 0, ls)
+            bo = block_offsets(ls, uvls, 0)
+            o.h264_hbd_idct_mb(bits, 1, at(y, org), None, ptr(bo), ptr(mb), ls, ptr(nnzc[m]))
+        for pl in (cb, cr):
+            o.h264_hbd_pred(bits, 2, int(r["chroma_mode"]), at(pl, corg), None, 0, 0, uvls)
+        if r["chroma_residual"]:
+            bo = block_offsets(ls, uvls, 0)
+            dst2 = (C.c_void_p * 2)(cb.ctypes.data + corg, cr.ctypes.data + corg)
+            o.h264_hbd_idct_mb(bits, 3, None, dst2, ptr(bo), ptr(mb), uvls, ptr(nnzc[m]))
+
+
+def intra_work(mb_w, mb_h, bits, seed, p_intra=1.0):
+    rec, coeffs, nnzc = synth.h264_intra_work(mb_w, mb_h, seed=seed, p_intra=p_intra)
+    return rec, coeffs.astype(np.int32) * (1 << (bits - 8)), nnzc

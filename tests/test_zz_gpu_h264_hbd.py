@@ -156,3 +156,29 @@ def test_weight_and_dc_batch_hbd(gpu, checker, bits):
         device.sync()
         return d_co.download(np.int32, coeffs.shape)
     hh.weight_dc_cases(run_weight, run_dc, checker, bits)
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("mb_w,mb_h,P,p_intra", [(3, 2, 1, 1.0), (7, 5, 2, 1.0), (20, 12, 2, 0.6), (40, 30, 3, 1.0)])
+def test_intra_batch_hbd(gpu, checker, mb_w, mb_h, P, p_intra, bits):
+    """ff_h264_intra_mb_batch_hbd_cuda: all-intra and mixed pictures, stacked; samples and consumed coefficients against the oracle chain"""
+    from libav_b200 import device
+    ys, cbs, crs, recs, cos, nzs, want = [], [], [], [], [], [], []
+    for k in range(P):
+        y, cb, cr = hh.picture(mb_w, mb_h, bits, 0, seed=50 + k)
+        rec, coeffs, nnzc = hh.intra_work(mb_w, mb_h, bits, seed=mb_w + k, p_intra=p_intra)
+        wy, wcb, wcr, wco = y.copy(), cb.copy(), cr.copy(), coeffs.copy()
+        hh.oracle_intra(checker, bits, rec, wco, nnzc, mb_w, mb_h, wy, wcb, wcr)
+        assert not np.array_equal(wy, y)
+        ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); cos.append(coeffs); nzs.append(nnzc); want.append((wy, wcb, wcr, wco))
+    Y, CB, CR = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs)
+    R, CO, NZ = np.concatenate(recs), np.concatenate(cos), np.concatenate(nzs)
+    d_rec, d_co, d_nz, dy, dcb, dcr = _dev(R), _dev(CO), _dev(NZ), _dev(Y), _dev(CB), _dev(CR)
+    gpu.check(gpu.lib.ff_h264_intra_mb_batch_hbd_cuda(bits, d_rec.ptr, mb_w, mb_h, P, d_co.ptr, 768, d_nz.ptr, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], None))
+    device.sync()
+    gy, gcb, gcr, gco = dy.download(np.uint16, Y.shape), dcb.download(np.uint16, CB.shape), dcr.download(np.uint16, CR.shape), d_co.download(np.int32, CO.shape)
+    n = mb_w * mb_h
+    for k in range(P):
+        assert np.array_equal(gy[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][0]), (k, np.argwhere(gy[16 * mb_h * k:16 * mb_h * (k + 1)] != want[k][0])[:4].tolist())
+        assert np.array_equal(gcb[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][1]) and np.array_equal(gcr[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][2]), k
+        assert np.array_equal(gco[n * k:n * (k + 1)], want[k][3]), k

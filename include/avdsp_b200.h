@@ -349,6 +349,9 @@ typedef struct FFH264PictureWork {
     const FFH264DeblockInfo *deblock_info;   /* host struct: decisions are derived on the device into deblock_records */
     FFH264DeblockMB *deblock_records;        /* with deblock_info NULL: records the caller already filled; NULL = no loop filter */
     uint32_t *progress;
+    int bit_depth, chroma_format_idc;        /* 0 = 8 / 1.  9 / 10-bit pictures (int32 coeffs / luma_dc behind the same pointers) and 4:2:2 chroma at
+                                                9 / 10 bit run the *_hbd_cuda / *_422_cuda stages in the same order (progress is not used then) */
+    const FFH264DeblockChroma422 *deblock_chroma422;   /* 4:2:2 with caller-filled deblock_records: their second record array */
 } FFH264PictureWork;
 int ff_h264_flush_pictures_cuda(const FFH264PictureWork *work /* host struct */, void *stream);
 

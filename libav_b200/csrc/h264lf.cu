@@ -261,6 +261,37 @@ extern "C" int ff_h264_flush_pictures_cuda(const FFH264PictureWork *w, void *str
         set_error_msg("ff_h264_flush_pictures_cuda", "bad arguments"); return -1;
     }
     const size_t n_mb = (size_t)w->mb_w * w->mb_h * w->n_pictures;
+    const int depth = w->bit_depth ? w->bit_depth : 8, idc = w->chroma_format_idc ? w->chroma_format_idc : 1;
+    if (depth != 8 || idc != 1) {
+        // 9 / 10-bit pictures and / or 4:2:2 chroma: the same order through the kernels of h264_hbd_batch.cu (coeffs / luma_dc hold int32 at 9 / 10 bit)
+        if ((depth != 8 && depth != 9 && depth != 10) || (idc != 1 && idc != 2)) { set_error_msg("ff_h264_flush_pictures_cuda", "bit_depth 8 / 9 / 10, chroma_format_idc 1 / 2"); return -1; }
+        if (depth == 8) { set_error_msg("ff_h264_flush_pictures_cuda", "8-bit 4:2:2 pictures: MC / residual have no batched 8-bit 4:2:2 kernels (use bit_depth 9 / 10 or the table slots)"); return -1; }
+        if (idc == 2 && w->intra) { set_error_msg("ff_h264_flush_pictures_cuda", "4:2:2 intra reconstruction is not batched (table slots)"); return -1; }
+        if (w->n_mc && ff_h264_mc_batch_hbd_cuda(depth, idc, w->mc, w->n_mc, w->refs, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, 16 * w->mb_w, 16 * w->mb_h, stream)) return -1;
+        for (int pl = 0; pl < 3; pl++) {
+            uint8_t *plane = pl == 0 ? w->luma : pl == 1 ? w->cb : w->cr;
+            if (w->n_weight[pl] && ff_h264_weight_batch_hbd_cuda(depth, w->weight[pl], w->n_weight[pl], plane, w->weight_src[pl], pl ? w->uvlinesize : w->linesize, stream)) return -1;
+        }
+        if (w->dc && ff_h264_dc_dequant_batch_hbd_cuda(idc, w->dc, n_mb, (int32_t *)w->coeffs, w->coeff_stride, (const int32_t *)w->luma_dc, stream)) return -1;
+        if (w->residual && ff_h264_idct_add_mb_batch_hbd_cuda(depth, idc, w->residual, n_mb, (int32_t *)w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
+                                                              w->linesize, w->uvlinesize, stream)) return -1;
+        if (w->intra && ff_h264_intra_mb_batch_hbd_cuda(depth, w->intra, w->mb_w, w->mb_h, w->n_pictures, (int32_t *)w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
+                                                        w->linesize, w->uvlinesize, stream)) return -1;
+        if (w->deblock_info) {
+            if (!w->deblock_records || w->deblock_info->mb_w != w->mb_w || w->deblock_info->mb_h != w->mb_h || w->deblock_info->n_pictures != w->n_pictures ||
+                (idc == 2) != (w->deblock_info->chroma422 != nullptr)) {
+                set_error_msg("ff_h264_flush_pictures_cuda", "deblock_info does not describe this batch"); return -1;
+            }
+            if (ff_h264_deblock_params_cuda(w->deblock_info, w->deblock_records, stream)) return -1;
+        }
+        if (w->deblock_records) {
+            if (idc == 2) {
+                const FFH264DeblockChroma422 *x = w->deblock_info ? w->deblock_info->chroma422 : w->deblock_chroma422;
+                if (ff_h264_deblock_batch_422_cuda(depth, w->deblock_records, x, w->mb_w, w->mb_h, w->n_pictures, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, stream)) return -1;
+            } else if (ff_h264_deblock_batch_hbd_cuda(depth, w->deblock_records, w->mb_w, w->mb_h, w->n_pictures, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, stream)) return -1;
+        }
+        return 0;
+    }
     // 1. inter prediction: every put partition, then every avg partition (h264_mb.c:322-366)
     if (w->n_mc && ff_h264_mc_batch_cuda(w->mc, w->n_mc, w->refs, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, 16 * w->mb_w, 16 * w->mb_h, stream)) return -1;
     // 2. explicit / implicit weighted prediction on the predicted blocks (h264_mb.c:368-460), plane by plane

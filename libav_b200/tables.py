@@ -120,7 +120,8 @@ class FFH264PictureWork(C.Structure):
                 ("weight", C.c_void_p * 3), ("n_weight", C.c_size_t * 3), ("weight_src", C.c_void_p * 3),
                 ("coeffs", C.c_void_p), ("coeff_stride", C.c_size_t), ("nnzc", C.c_void_p),
                 ("dc", C.c_void_p), ("luma_dc", C.c_void_p), ("residual", C.c_void_p), ("intra", C.c_void_p),
-                ("deblock_info", C.POINTER(FFH264DeblockInfo)), ("deblock_records", C.c_void_p), ("progress", C.c_void_p)]
+                ("deblock_info", C.POINTER(FFH264DeblockInfo)), ("deblock_records", C.c_void_p), ("progress", C.c_void_p),
+                ("bit_depth", C.c_int), ("chroma_format_idc", C.c_int), ("deblock_chroma422", C.c_void_p)]
 
 
 class FFMpegDequantTables(C.Structure):

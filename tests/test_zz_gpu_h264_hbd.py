@@ -182,3 +182,78 @@ def test_intra_batch_hbd(gpu, checker, mb_w, mb_h, P, p_intra, bits):
         assert np.array_equal(gy[16 * mb_h * k:16 * mb_h * (k + 1)], want[k][0]), (k, np.argwhere(gy[16 * mb_h * k:16 * mb_h * (k + 1)] != want[k][0])[:4].tolist())
         assert np.array_equal(gcb[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][1]) and np.array_equal(gcr[8 * mb_h * k:8 * mb_h * (k + 1)], want[k][2]), k
         assert np.array_equal(gco[n * k:n * (k + 1)], want[k][3]), k
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("mb_w,mb_h,P,p_intra", [(7, 5, 1, 0.3), (20, 12, 2, 0.25)])
+def test_flush_hbd_equals_the_chained_checker(gpu, checker, mb_w, mb_h, P, p_intra, bits):
+    """ff_h264_flush_pictures_cuda with bit_depth 9 / 10: MC -> weighted prediction -> DC transforms -> residual -> intra -> decisions -> loop filter in one
+    call, against the CPU checker's BIT_DEPTH > 8 functions chained in the same order on the same records"""
+    import ctypes as C
+    from libav_b200 import device, tables
+    from oracle.loader import ptr
+    from test_gpu_h264flush import picture_work
+    from test_oracle_h264lf_cpu import run as oracle_decisions
+    sc = 1 << (bits - 8)
+    refs = [hh.picture(mb_w, mb_h, bits, 0, seed=11), hh.picture(mb_w, mb_h, bits, 0, seed=12)]
+    works = [picture_work(mb_w, mb_h, 100 * k + mb_w, p_intra) for k in range(P)]
+    pics = [hh.picture(mb_w, mb_h, bits, 0, seed=50 + k) for k in range(P)]
+    ls, uvls = pics[0][0].strides[0], pics[0][1].strides[0]
+    want, want_co = [], []
+    for w, (y, cb, cr) in zip(works, pics):
+        w["coeffs"] = w["coeffs"].astype(np.int32) * sc
+        w["luma_dc"] = w["luma_dc"].astype(np.int32) * sc
+        w["res"]["luma_off"] *= 2; w["res"]["chroma_off"] *= 2; w["weight"]["off"] *= 2       # byte offsets for 16-bit samples
+        wy, wcb, wcr = y.copy(), cb.copy(), cr.copy()
+        hh.oracle_mc(checker, bits, 0, w["mc"], refs, wy, wcb, wcr)
+        for r in w["weight"]:
+            checker.h264_hbd_weight(bits, 0, hh.at(wy, r["off"]), ls, int(r["h"]), int(r["log2_denom"]), int(r["weight"]), int(r["offset"]))
+        co = w["coeffs"].copy()
+        for m in range(co.shape[0]):
+            if w["dc"]["luma_qmul"][m]:
+                checker.h264_hbd_dc_dequant(bits, 0, hh.at(co, m * 768 * 4), ptr(w["luma_dc"][m].copy()), int(w["dc"]["luma_qmul"][m]))
+            for p in range(2):
+                if w["dc"]["chroma_qmul"][m, p]:
+                    checker.h264_hbd_dc_dequant(bits, 1, hh.at(co, (m * 768 + 256 * (p + 1)) * 4), None, int(w["dc"]["chroma_qmul"][m, p]))
+        hh.oracle_residual(checker, bits, 0, w["res"], co, w["nnzc"], wy, wcb, wcr)
+        hh.oracle_intra(checker, bits, w["intra"], co, w["nnzc"], mb_w, mb_h, wy, wcb, wcr)
+        rec = oracle_decisions(checker, w["info"]).view(synth.DEBLOCK_DT).reshape(-1)
+        hh.oracle_deblock(checker, bits, rec, mb_w, mb_h, wy, wcb, wcr)
+        want.append((wy, wcb, wcr)); want_co.append(co)
+    Y, CB, CR = (np.concatenate([p[i] for p in pics]) for i in range(3))
+    cat = lambda k: np.concatenate([w[k] for w in works])
+    mc, res, wrec = [], [], []
+    for k, w in enumerate(works):
+        m = w["mc"].copy(); m["y"] += 16 * mb_h * k; mc.append(m)
+        r = w["res"].copy(); r["luma_off"] += 16 * mb_h * k * ls; r["chroma_off"] += 8 * mb_h * k * uvls; res.append(r)
+        t = w["weight"].copy(); t["off"] += 16 * mb_h * k * ls; wrec.append(t)
+    mc, res, wrec = np.concatenate(mc), np.concatenate(res), np.concatenate(wrec)
+    mc = np.concatenate([mc[mc["avg"] == 0], mc[mc["avg"] != 0]])
+    dref = [[_dev(np.concatenate([p] * P)) for p in r] for r in refs]
+    d_planes = _dev(np.array([[p.ptr for p in r] for r in dref], dtype=np.uint64))
+    infos = [w["info"] for w in works]
+    catinfo = lambda k: np.concatenate([d[k] for d in infos], axis=0)
+    keep = {k: _dev(catinfo(k)) for k in ("mb_type", "qscale", "nnz", "cbp", "slice_table", "mv0", "mv1", "ref0", "ref1")}
+    keep["sp"] = _dev(infos[0]["slice_params"]); keep["cq"] = _dev(infos[0]["chroma_qp_table"])
+    info = tables.FFH264DeblockInfo(mb_w, mb_h, P, keep["mb_type"].ptr, keep["qscale"].ptr, keep["nnz"].ptr, keep["cbp"].ptr, keep["slice_table"].ptr,
+                                    (C.c_void_p * 2)(keep["mv0"].ptr, keep["mv1"].ptr), (C.c_void_p * 2)(keep["ref0"].ptr, keep["ref1"].ptr),
+                                    keep["sp"].ptr, infos[0]["n_slices"], keep["cq"].ptr, infos[0]["cabac"], infos[0]["t8x8"])
+    n = mb_w * mb_h * P
+    d = dict(y=_dev(Y), cb=_dev(CB), cr=_dev(CR), mc=_dev(mc), res=_dev(res), w=_dev(wrec), co=_dev(cat("coeffs")), nz=_dev(cat("nnzc")),
+             dc=_dev(cat("dc")), ldc=_dev(cat("luma_dc")), intra=_dev(cat("intra")), rec=device.DevBuf(n * 104))
+    work = tables.FFH264PictureWork()
+    work.mb_w, work.mb_h, work.n_pictures = mb_w, mb_h, P
+    work.luma, work.cb, work.cr, work.linesize, work.uvlinesize = d["y"].ptr, d["cb"].ptr, d["cr"].ptr, ls, uvls
+    work.mc, work.n_mc, work.refs = d["mc"].ptr, mc.shape[0], d_planes.ptr
+    work.weight[0], work.n_weight[0] = d["w"].ptr, wrec.shape[0]
+    work.coeffs, work.coeff_stride, work.nnzc = d["co"].ptr, 768, d["nz"].ptr
+    work.dc, work.luma_dc, work.residual, work.intra = d["dc"].ptr, d["ldc"].ptr, d["res"].ptr, d["intra"].ptr
+    work.deblock_info, work.deblock_records = C.pointer(info), d["rec"].ptr
+    work.bit_depth, work.chroma_format_idc = bits, 1
+    gpu.check(gpu.lib.ff_h264_flush_pictures_cuda(C.byref(work), None))
+    device.sync()
+    gy, gcb, gcr = d["y"].download(np.uint16, Y.shape), d["cb"].download(np.uint16, CB.shape), d["cr"].download(np.uint16, CR.shape)
+    wy = np.concatenate([w[0] for w in want])
+    assert np.array_equal(gy, wy), np.argwhere(gy != wy)[:5].tolist()
+    assert np.array_equal(gcb, np.concatenate([w[1] for w in want])) and np.array_equal(gcr, np.concatenate([w[2] for w in want]))
+    assert np.array_equal(d["co"].download(np.int32, (n, 768)), np.concatenate(want_co))

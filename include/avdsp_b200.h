@@ -161,6 +161,10 @@ typedef struct FFH264DCRecord {
 } FFH264DCRecord;
 int ff_h264_dc_dequant_batch_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
                                   void *stream);
+/* 8-bit 4:2:2 pictures: the chroma transform is h264_chroma422_dc_dequant_idct (the 2 x 4 DC block, h264idct_template.c:271-306, installed for
+ * chroma_format_idc 2 at h264dsp.c:87-90); luma as above */
+int ff_h264_dc_dequant_batch_422_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
+                                      void *stream);
 
 /* Intra reconstruction: for every intra macroblock of a picture, H264PredContext prediction interleaved with the
  * residual exactly as hl_decode_mb() orders them (libavcodec/h264_mb.c:607-731 hl_decode_mb_predict_luma,
@@ -246,7 +250,9 @@ int ff_h264_deblock_batch_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, i
  * h264_idct_add8_422 h264idct_template.c:216-236, chroma vectors at full vertical resolution h264_mb.c:287-316).  Records, order rules
  * and picture stacking are those of the 8-bit calls above; alpha / beta / tc0 in FFH264DeblockMB are the 8-bit-scale table values the
  * decisions produce (the filters scale them by 2^(bit_depth - 8) like h264dsp_template.c:110-113,240).  Field pictures of a frame are
- * pictures in their own right here: pass the field's first row and twice the frame's pitch.  MBAFF frames are not covered. */
+ * pictures in their own right here: pass the field's first row and twice the frame's pitch.  MBAFF frames are not covered.
+ * The residual and the motion compensation also take bit_depth 8 with chroma_format_idc 2 (8-bit 4:2:2 pictures: uint8 samples, and `coeffs`
+ * then points at int16 coefficients, coeff_stride counting int16); 8-bit 4:2:0 stays with the calls without _hbd, which refuse nothing here. */
 int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264ResidualMB *mbs, size_t n, int32_t *coeffs,
                                        size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
                                        int uvlinesize, void *stream);
@@ -350,7 +356,8 @@ typedef struct FFH264PictureWork {
     FFH264DeblockMB *deblock_records;        /* with deblock_info NULL: records the caller already filled; NULL = no loop filter */
     uint32_t *progress;
     int bit_depth, chroma_format_idc;        /* 0 = 8 / 1.  9 / 10-bit pictures (int32 coeffs / luma_dc behind the same pointers) and 4:2:2 chroma at
-                                                9 / 10 bit run the *_hbd_cuda / *_422_cuda stages in the same order (progress is not used then) */
+                                                8 / 9 / 10 bit run the *_hbd_cuda / *_422_cuda stages in the same order (progress is not used then;
+                                                4:2:2 pictures with intra records are refused) */
     const FFH264DeblockChroma422 *deblock_chroma422;   /* 4:2:2 with caller-filled deblock_records: their second record array */
 } FFH264PictureWork;
 int ff_h264_flush_pictures_cuda(const FFH264PictureWork *work /* host struct */, void *stream);

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "ff_h264_deblock_params_cuda": (i32, [vp, vp, vp]),
     "ff_h264_flush_pictures_cuda": (i32, [vp, vp]),
     "ff_h264_dc_dequant_batch_cuda": (i32, [vp, sz, vp, sz, vp, vp]),
+    "ff_h264_dc_dequant_batch_422_cuda": (i32, [vp, sz, vp, sz, vp, vp]),
     "ff_h264_intra_mb_batch_cuda": (i32, [vp, i32, i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, vp, vp]),
     "ff_mpeg4_qpel_batch_cuda": (i32, [vp, sz, vp, vp, pd, vp]),
     "ff_pixblock_fdct_batch_cuda": (i32, [i32, vp, vp, vp, vp, pd, vp, sz, vp]),

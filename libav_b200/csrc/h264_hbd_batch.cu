@@ -31,52 +31,67 @@ namespace {
 
 using hbd::px;
 
-__device__ __forceinline__ px *at_bytes(uint8_t *plane, size_t off) { return reinterpret_cast<px *>(plane + off); }
+// the transforms by sample type: 9 / 10 bit = h264dsp_hbd.cuh (uint16 samples, int32 coefficients), 8 bit = h264dsp.cuh (uint8, int16; the 4:2:2
+// pictures: 8-bit 4:2:0 has its own kernels in h264_residual.cu)
+template <typename PX> struct Transform;
+template <> struct Transform<uint16_t> {
+    typedef int32_t coef;
+    static __device__ __forceinline__ void idct4(int bits, uint16_t *d, coef *b, int st) { hbd::idct4_add(bits, d, b, st); }
+    static __device__ __forceinline__ void idct8(int bits, uint16_t *d, coef *b, int st) { hbd::idct8_add(bits, d, b, st); }
+    static __device__ __forceinline__ void dc(int bits, uint16_t *d, coef *b, int st, int n) { hbd::dc_add(bits, d, b, st, n); }
+};
+template <> struct Transform<uint8_t> {
+    typedef int16_t coef;
+    static __device__ __forceinline__ void idct4(int, uint8_t *d, coef *b, int st) { h264_idct4_add(d, b, st); }
+    static __device__ __forceinline__ void idct8(int, uint8_t *d, coef *b, int st) { h264_idct8_add(d, b, st); }
+    static __device__ __forceinline__ void dc(int, uint8_t *d, coef *b, int st, int n) { h264_dc_add(d, b, st, n); }
+};
 
 // ---------------------------------------------------------------------------------------------------------------------------------
+template <typename PX>
 __global__ void __launch_bounds__(128)
-h264_residual_hbd_kernel(int bits, int c422, const FFH264ResidualMB *__restrict__ mbs, size_t n, int32_t *__restrict__ coeffs, size_t coeff_stride,
+h264_residual_hbd_kernel(int bits, int c422, const FFH264ResidualMB *__restrict__ mbs, size_t n, typename Transform<PX>::coef *__restrict__ coeffs, size_t coeff_stride,
                          const uint8_t *__restrict__ nnzc, uint8_t *__restrict__ luma, uint8_t *__restrict__ cb, uint8_t *__restrict__ cr, int ls, int uvls)
 {
-    using namespace hbd;
+    typedef Transform<PX> T;
     const int lane = threadIdx.x & 31;
     const size_t mb = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (mb >= n) return;
     const FFH264ResidualMB r = mbs[mb];
-    int32_t *gc = coeffs + mb * coeff_stride;
+    typename T::coef *gc = coeffs + mb * coeff_stride;
     const uint8_t *nz = nnzc + mb * 120;
-    const int lsp = ls >> 1, uvlsp = uvls >> 1;                     // row distance in samples
+    const int lsp = ls / (int)sizeof(PX), uvlsp = uvls / (int)sizeof(PX);                     // row distance in samples
     if (lane < 16) {
         if (r.luma_mode > 2) return;
         const int i = lane;
-        px *d = at_bytes(luma, r.luma_off) + blk_x(i) + (size_t)blk_y(i) * lsp;
-        int32_t *b = gc + 16 * i;
+        PX *d = reinterpret_cast<PX *>(luma + r.luma_off) + blk_x(i) + (size_t)blk_y(i) * lsp;
+        typename T::coef *b = gc + 16 * i;
         const int nnz = nz[scan8_of(i)];
-        if (r.luma_mode == 0)      { if (nnz) { if (nnz == 1 && b[0]) dc_add(bits, d, b, lsp, 4); else idct4_add(bits, d, b, lsp); } }       // :174-183
-        else if (r.luma_mode == 1) { if (nnz) idct4_add(bits, d, b, lsp); else if (b[0]) dc_add(bits, d, b, lsp, 4); }                       // :185-191
-        else if ((i & 3) == 0 && nnz) { if (nnz == 1 && b[0]) dc_add(bits, d, b, lsp, 8); else idct8_add(bits, d, b, lsp); }                 // :193-202
+        if (r.luma_mode == 0)      { if (nnz) { if (nnz == 1 && b[0]) T::dc(bits, d, b, lsp, 4); else T::idct4(bits, d, b, lsp); } }       // :174-183
+        else if (r.luma_mode == 1) { if (nnz) T::idct4(bits, d, b, lsp); else if (b[0]) T::dc(bits, d, b, lsp, 4); }                       // :185-191
+        else if ((i & 3) == 0 && nnz) { if (nnz == 1 && b[0]) T::dc(bits, d, b, lsp, 8); else T::idct8(bits, d, b, lsp); }                 // :193-202
     } else if (r.chroma) {
         // 4:2:0 (:204-214): blocks 16..19 / 32..35.  4:2:2 (:216-236): eight per plane; the lower four keep their coefficients at block i
         // but are addressed through scan8[i + 4] / block_offset[i + 4] (rows 8..15 of the 8 x 16 chroma macroblock)
         const int per = c422 ? 8 : 4, t = lane - 16;
         if (t >= 2 * per) return;
         const int plane = t / per, k = t % per, i = 16 + 16 * plane + k, e = k >= 4 ? i + 4 : i, ke = e & 15;
-        px *d = at_bytes(plane ? cr : cb, r.chroma_off) + blk_x(ke) + (size_t)blk_y(ke) * uvlsp;
-        int32_t *b = gc + 16 * i;
-        if (nz[scan8_of(e)]) idct4_add(bits, d, b, uvlsp); else if (b[0]) dc_add(bits, d, b, uvlsp, 4);
+        PX *d = reinterpret_cast<PX *>((plane ? cr : cb) + r.chroma_off) + blk_x(ke) + (size_t)blk_y(ke) * uvlsp;
+        typename T::coef *b = gc + 16 * i;
+        if (nz[scan8_of(e)]) T::idct4(bits, d, b, uvlsp); else if (b[0]) T::dc(bits, d, b, uvlsp, 4);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // clamped sample fetch = emulated_edge_mc (replicated borders); [y0, y0 + h) are the rows of the record's own picture
-struct EdgeFetch {
-    const px *p; int st, w, h, y0;
+template <typename PX> struct EdgeFetchT {
+    const PX *p; int st, w, h, y0;
     __device__ __forceinline__ int operator()(int x, int y) const { return p[(size_t)min(max(y, y0), y0 + h - 1) * st + min(max(x, 0), w - 1)]; }
 };
 // the (w + 5) x (h + 5) luma patch (or a (w / 2 + 1) x (ch + 1) chroma patch) of a partition staged in shared memory: sample (x, y) of the
 // reference plane sits at p[(y - y0) * pitch + (x - x0)]
-struct PatchFetch {
-    const px *p; int pitch, x0, y0;
+template <typename PX> struct PatchFetchT {
+    const PX *p; int pitch, x0, y0;
     __device__ __forceinline__ int operator()(int x, int y) const { return p[(y - y0) * pitch + (x - x0)]; }
 };
 template <class F> __device__ __forceinline__ int tap6f(const F &S, int x, int y, int dx, int dy)
@@ -115,14 +130,14 @@ template <class F> __device__ __forceinline__ int chroma_at(const F &S, int x, i
 // per output sample), then every lane filters from there.  !STAGED: every tap is a clamped global load -- the same arithmetic with no
 // communication between lanes, which is what tests/hostsim/ compiles.
 constexpr int MCH_LP = 24, MCH_CP = 12;           // patch pitches in samples (21 x 21 luma, 9 x 17 chroma per plane)
-template <bool STAGED>
+template <typename PX, bool STAGED>
 __global__ void __launch_bounds__(128)
 h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, size_t n, const FFH264RefPlanes *__restrict__ refs,
                    uint8_t *__restrict__ dy, uint8_t *__restrict__ dcb, uint8_t *__restrict__ dcr, int ls, int uvls, int pw, int ph, int pass)
 {
 #ifndef AVB_HOSTSIM
-    __shared__ px s_luma[STAGED ? 4 : 1][STAGED ? 21 * MCH_LP : 1];
-    __shared__ px s_chroma[STAGED ? 4 : 1][2][STAGED ? 17 * MCH_CP : 1];
+    __shared__ PX s_luma[STAGED ? 4 : 1][STAGED ? 21 * MCH_LP : 1];
+    __shared__ PX s_chroma[STAGED ? 4 : 1][2][STAGED ? 17 * MCH_CP : 1];
 #endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ri = (size_t)blockIdx.x * 4 + warp;
@@ -130,7 +145,7 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
     const FFH264MCRecord r = recs[ri];
     if ((r.avg != 0) != (pass != 0)) return;
     const FFH264RefPlanes ref = refs[r.ref];
-    const int lsp = ls >> 1, uvlsp = uvls >> 1;
+    const int lsp = ls / (int)sizeof(PX), uvlsp = uvls / (int)sizeof(PX);
     const int ly0 = ((int)r.y / ph) * ph;                                   // first luma row of the record's picture in the stacked planes
     const int mx = (int)r.mvx + 4 * (int)r.x, my = (int)r.mvy + 4 * (int)r.y, w = r.w, h = r.h;
     // chroma: eighth-sample bilinear (h264chroma_template.c:27-173); 4:2:2 keeps the luma's vertical resolution (h264_mb.c:287-316)
@@ -138,32 +153,32 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
     const int sx = mx >> 3, sy = c422 ? my >> 2 : my >> 3, fx = mx & 7, fy = c422 ? (my << 1) & 7 : my & 7;
     const int dx0 = r.x >> 1, dy0 = c422 ? (int)r.y : r.y >> 1;
     const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), Cc = (8 - fx) * fy, D = fx * fy;
-    const EdgeFetch GY = { reinterpret_cast<const px *>(ref.y), lsp, pw, ph, ly0 };
-    px *d0 = reinterpret_cast<px *>(dy) + (size_t)r.y * lsp + r.x;
+    const EdgeFetchT<PX> GY = { reinterpret_cast<const PX *>(ref.y), lsp, pw, ph, ly0 };
+    PX *d0 = reinterpret_cast<PX *>(dy) + (size_t)r.y * lsp + r.x;
     (void)warp;
 #ifndef AVB_HOSTSIM
     if (STAGED) {
         const int lx0 = (mx >> 2) - 2, lyy0 = (my >> 2) - 2;
-        for (int i = lane; i < (w + 5) * (h + 5); i += 32) { const int c = i % (w + 5), rr = i / (w + 5); s_luma[warp][rr * MCH_LP + c] = (px)GY(lx0 + c, lyy0 + rr); }
+        for (int i = lane; i < (w + 5) * (h + 5); i += 32) { const int c = i % (w + 5), rr = i / (w + 5); s_luma[warp][rr * MCH_LP + c] = (PX)GY(lx0 + c, lyy0 + rr); }
         for (int i = lane; i < 2 * (cw + 1) * (ch + 1); i += 32) {
             const int pl = i / ((cw + 1) * (ch + 1)), k = i % ((cw + 1) * (ch + 1)), c = k % (cw + 1), rr = k / (cw + 1);
-            const EdgeFetch GC = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
-            s_chroma[warp][pl][rr * MCH_CP + c] = (px)GC(sx + c, sy + rr);
+            const EdgeFetchT<PX> GC = { reinterpret_cast<const PX *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
+            s_chroma[warp][pl][rr * MCH_CP + c] = (PX)GC(sx + c, sy + rr);
         }
         __syncwarp();
-        const PatchFetch SY = { s_luma[warp], MCH_LP, lx0, lyy0 };
+        const PatchFetchT<PX> SY = { s_luma[warp], MCH_LP, lx0, lyy0 };
         for (int i = lane; i < w * h; i += 32) {
             const int x = i % w, y = i / w;
             const int v = qpel_at(bits, SY, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
-            px *d = d0 + (size_t)y * lsp + x;
-            *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+            PX *d = d0 + (size_t)y * lsp + x;
+            *d = (PX)(r.avg ? (*d + v + 1) >> 1 : v);
         }
         for (int i = lane; i < 2 * cw * ch; i += 32) {
             const int pl = i / (cw * ch), k = i % (cw * ch), x = k % cw, y = k / cw;
-            const PatchFetch SC = { s_chroma[warp][pl], MCH_CP, sx, sy };
+            const PatchFetchT<PX> SC = { s_chroma[warp][pl], MCH_CP, sx, sy };
             const int v = chroma_at(SC, sx + x, sy + y, A, B, Cc, D);
-            px *d = reinterpret_cast<px *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
-            *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+            PX *d = reinterpret_cast<PX *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
+            *d = (PX)(r.avg ? (*d + v + 1) >> 1 : v);
         }
         return;
     }
@@ -171,15 +186,15 @@ h264_mc_hbd_kernel(int bits, int c422, const FFH264MCRecord *__restrict__ recs, 
     for (int i = lane; i < w * h; i += 32) {
         const int x = i % w, y = i / w;
         const int v = qpel_at(bits, GY, (mx >> 2) + x, (my >> 2) + y, mx & 3, my & 3);
-        px *d = d0 + (size_t)y * lsp + x;
-        *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+        PX *d = d0 + (size_t)y * lsp + x;
+        *d = (PX)(r.avg ? (*d + v + 1) >> 1 : v);
     }
     for (int i = lane; i < 2 * cw * ch; i += 32) {
         const int pl = i / (cw * ch), k = i % (cw * ch), x = k % cw, y = k / cw;
-        const EdgeFetch GC = { reinterpret_cast<const px *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
+        const EdgeFetchT<PX> GC = { reinterpret_cast<const PX *>(pl ? ref.cr : ref.cb), uvlsp, pw >> 1, cph, cy0 };
         const int v = chroma_at(GC, sx + x, sy + y, A, B, Cc, D);
-        px *d = reinterpret_cast<px *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
-        *d = (px)(r.avg ? (*d + v + 1) >> 1 : v);
+        PX *d = reinterpret_cast<PX *>(pl ? dcr : dcb) + (size_t)(dy0 + y) * uvlsp + dx0 + x;
+        *d = (PX)(r.avg ? (*d + v + 1) >> 1 : v);
     }
 }
 
@@ -473,6 +488,33 @@ bool hbd_args_ok(const char *where, int bit_depth, int chroma_format_idc, int ls
     return true;
 }
 
+// bit_depth 8 is taken for chroma_format_idc 2 only (8-bit 4:2:0 has the kernels of h264_residual.cu / h264_mc.cu behind the calls without _hbd)
+static bool depth_idc_ok(const char *where, int bit_depth, int chroma_format_idc, int ls, int uvls, const void *a, const void *b, const void *c)
+{
+    if (bit_depth == 8) {
+        if (chroma_format_idc != 2) { set_error_msg(where, "bit_depth 8 is taken with chroma_format_idc 2 only (8-bit 4:2:0: the calls without _hbd)"); return false; }
+        return true;
+    }
+    return hbd_args_ok(where, bit_depth, chroma_format_idc, ls, uvls, a, b, c);
+}
+
+template <typename PX>
+static int launch_mc_generic(int bit_depth, int c422, const FFH264MCRecord *recs, size_t n, const FFH264RefPlanes *refs, uint8_t *dst_y, uint8_t *dst_cb, uint8_t *dst_cr,
+                             int linesize, int uvlinesize, int pic_w, int pic_h, cudaStream_t st)
+{
+    for (int pass = 0; pass < 2; pass++) {
+#ifdef AVB_HOSTSIM
+        AVB_LAUNCH((h264_mc_hbd_kernel<PX, false>), dim3((unsigned)((n + 3) / 4)), dim3(128), 0, st)(bit_depth, c422, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
+#else
+        if (tuning("mc_hbd_staged") == 2)       // (test knob: the clamped-global-load form of the same arithmetic, the one tests/hostsim/ runs)
+            h264_mc_hbd_kernel<PX, false><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(bit_depth, c422, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
+        else
+            h264_mc_hbd_kernel<PX, true><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(bit_depth, c422, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
+#endif
+    }
+    return 0;
+}
+
 }  // namespace
 }  // namespace avb
 
@@ -485,11 +527,15 @@ int ff_h264_idct_add_mb_batch_hbd_cuda(int bit_depth, int chroma_format_idc, con
 {
     avb::enter();
     const char *where = "ff_h264_idct_add_mb_batch_hbd_cuda";
-    if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (!depth_idc_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, luma, cb, cr)) return -1;
     if (n && (!mbs || !coeffs || !nnzc || !luma || !cb || !cr)) { set_error_msg(where, "NULL argument"); return -1; }
     if (!n) return 0;
-    AVB_LAUNCH(h264_residual_hbd_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, mbs, n, coeffs, coeff_stride, nnzc,
-                                                                                                            luma, cb, cr, linesize, uvlinesize);
+    if (bit_depth == 8)         // int16 coefficients behind the pointer
+        AVB_LAUNCH(h264_residual_hbd_kernel<uint8_t>, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(8, 1, mbs, n, (int16_t *)coeffs, coeff_stride, nnzc,
+                                                                                                                         luma, cb, cr, linesize, uvlinesize);
+    else
+        AVB_LAUNCH(h264_residual_hbd_kernel<uint16_t>, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, mbs, n, coeffs, coeff_stride, nnzc,
+                                                                                                                          luma, cb, cr, linesize, uvlinesize);
     return check_launch(where) ? -1 : 0;
 }
 
@@ -498,20 +544,12 @@ int ff_h264_mc_batch_hbd_cuda(int bit_depth, int chroma_format_idc, const FFH264
 {
     avb::enter();
     const char *where = "ff_h264_mc_batch_hbd_cuda";
-    if (!hbd_args_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, dst_y, dst_cb, dst_cr)) return -1;
+    if (!depth_idc_ok(where, bit_depth, chroma_format_idc, linesize, uvlinesize, dst_y, dst_cb, dst_cr)) return -1;
     if (n && (!recs || !refs || !dst_y || !dst_cb || !dst_cr)) { set_error_msg(where, "NULL argument"); return -1; }
     if (pic_w <= 0 || pic_h <= 0 || (pic_w & 1) || (pic_h & 1)) { set_error_msg(where, "picture size must be positive and even"); return -1; }
     if (!n) return 0;
-    for (int pass = 0; pass < 2; pass++)
-#ifdef AVB_HOSTSIM
-        AVB_LAUNCH(h264_mc_hbd_kernel<false>, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, (cudaStream_t)stream)(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr,
-                                                                                                                 linesize, uvlinesize, pic_w, pic_h, pass);
-#else
-        if (tuning("mc_hbd_staged") == 2)       // (test knob: the clamped-global-load form of the same arithmetic, the one tests/hostsim/ runs)
-            h264_mc_hbd_kernel<false><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
-        else
-            h264_mc_hbd_kernel<true><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, pass);
-#endif
+    if (bit_depth == 8) launch_mc_generic<uint8_t>(8, 1, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream);
+    else launch_mc_generic<uint16_t>(bit_depth, chroma_format_idc == 2, recs, n, refs, dst_y, dst_cb, dst_cr, linesize, uvlinesize, pic_w, pic_h, (cudaStream_t)stream);
     return check_launch(where) ? -1 : 0;
 }
 

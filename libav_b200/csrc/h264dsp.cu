@@ -83,7 +83,7 @@ h264_residual_kernel(const FFH264ResidualMB *__restrict__ mbs, size_t n, int16_t
 // (h264_mb.c:714-719 h264_luma_dc_dequant_idct for intra 16x16, h264_mb_template.c:182-189 chroma_dc_dequant_idct).
 // Thread per macroblock; only the 16 + 8 DC positions of its coefficient arena are touched.
 __global__ void __launch_bounds__(128)
-h264_dc_dequant_kernel(const FFH264DCRecord *__restrict__ recs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
+h264_dc_dequant_kernel(int c422, const FFH264DCRecord *__restrict__ recs, size_t n, int16_t *__restrict__ coeffs, size_t coeff_stride,
                        const int16_t *__restrict__ luma_dc)
 {
     const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,8 +96,11 @@ h264_dc_dequant_kernel(const FFH264DCRecord *__restrict__ recs, size_t n, int16_
         for (int i = 0; i < 16; i++) in[i] = luma_dc[16 * m + i];
         h264_luma_dc_dequant(mb, in, (int)r.luma_qmul);
     }
-    if (r.chroma_qmul[0]) h264_chroma_dc_dequant(mb + 256, (int)r.chroma_qmul[0]);
-    if (r.chroma_qmul[1]) h264_chroma_dc_dequant(mb + 512, (int)r.chroma_qmul[1]);
+    for (int pl = 0; pl < 2; pl++) {
+        if (!r.chroma_qmul[pl]) continue;
+        if (c422) h264_chroma422_dc_dequant(mb + 256 * (pl + 1), (int)r.chroma_qmul[pl]);     // 4:2:2: the 2x4 transform (h264idct_template.c:271-306)
+        else h264_chroma_dc_dequant(mb + 256 * (pl + 1), (int)r.chroma_qmul[pl]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -292,8 +295,17 @@ int ff_h264_dc_dequant_batch_cuda(const FFH264DCRecord *recs, size_t n, int16_t 
 {
     avb::enter();
     if (!n) return 0;
-    h264_dc_dequant_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(recs, n, coeffs, coeff_stride, luma_dc);
+    h264_dc_dequant_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(0, recs, n, coeffs, coeff_stride, luma_dc);
     return check_launch("ff_h264_dc_dequant_batch_cuda");
+}
+int ff_h264_dc_dequant_batch_422_cuda(const FFH264DCRecord *recs, size_t n, int16_t *coeffs, size_t coeff_stride, const int16_t *luma_dc,
+                                      void *stream)
+{
+    avb::enter();
+    if (n && (!recs || !coeffs || !luma_dc)) { set_error_msg("ff_h264_dc_dequant_batch_422_cuda", "NULL argument"); return -1; }
+    if (!n) return 0;
+    h264_dc_dequant_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(1, recs, n, coeffs, coeff_stride, luma_dc);
+    return check_launch("ff_h264_dc_dequant_batch_422_cuda");
 }
 int ff_h264_deblock_picture_cuda(const FFH264DeblockMB *mbs, int mb_w, int mb_h, uint8_t *luma, uint8_t *cb, uint8_t *cr,
                                  int linesize, int uvlinesize, uint32_t *progress, void *stream)

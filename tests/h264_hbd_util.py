@@ -14,20 +14,21 @@ def picture(mb_w, mb_h, bits, c422, seed):
     rng = np.random.default_rng(seed)
     w, h = 16 * mb_w, 16 * mb_h
     ch = h if c422 else h // 2
-    return (rng.integers(0, 1 << bits, (h, w)).astype(np.uint16), rng.integers(0, 1 << bits, (ch, w // 2)).astype(np.uint16),
-            rng.integers(0, 1 << bits, (ch, w // 2)).astype(np.uint16))
+    dt = np.uint8 if bits == 8 else np.uint16          # (bits 8: the 8-bit 4:2:2 pictures the generic kernels also take)
+    return (rng.integers(0, 1 << bits, (h, w)).astype(dt), rng.integers(0, 1 << bits, (ch, w // 2)).astype(dt),
+            rng.integers(0, 1 << bits, (ch, w // 2)).astype(dt))
 
 
-def block_offsets(ls, uvls, c422):
-    """block_offset[] in BYTES for 16-bit samples (h264_slice.c:486-493 with pixel_shift 1): luma 0..15, chroma 16.. / 32.. (4:2:2: the entries
-    ff_h264_idct_add8_422 reads, 16..19 and 24..27 per plane)"""
+def block_offsets(ls, uvls, c422, sb=2):
+    """block_offset[] in BYTES (h264_slice.c:486-493; sb = bytes per sample: pixel_shift 1 for 16-bit samples): luma 0..15, chroma 16.. / 32..
+    (4:2:2: the entries ff_h264_idct_add8_422 reads, 16..19 and 24..27 per plane)"""
     bo = np.zeros(48, dtype=np.int32)
     for i in range(16):
-        bo[i] = 2 * 4 * ((i & 1) + 2 * ((i >> 2) & 1)) + 4 * (((i >> 1) & 1) + 2 * (i >> 3)) * ls
+        bo[i] = sb * 4 * ((i & 1) + 2 * ((i >> 2) & 1)) + 4 * (((i >> 1) & 1) + 2 * (i >> 3)) * ls
     for i in range(4):
-        bo[16 + i] = bo[32 + i] = 2 * 4 * (i & 1) + 4 * ((i >> 1) & 1) * uvls
+        bo[16 + i] = bo[32 + i] = sb * 4 * (i & 1) + 4 * ((i >> 1) & 1) * uvls
         if c422:
-            bo[24 + i] = bo[40 + i] = 2 * 4 * (i & 1) + (8 + 4 * ((i >> 1) & 1)) * uvls
+            bo[24 + i] = bo[40 + i] = sb * 4 * (i & 1) + (8 + 4 * ((i >> 1) & 1)) * uvls
     return bo
 
 
@@ -37,11 +38,12 @@ def residual_work(mb_w, mb_h, bits, c422, y, cb, seed):
     n = mb_w * mb_h
     rec = np.zeros(n, dtype=synth.RESIDUAL_DT)
     mbx, mby = np.arange(n) % mb_w, np.arange(n) // mb_w
-    rec["luma_off"] = mby * 16 * y.strides[0] + mbx * 32
-    rec["chroma_off"] = mby * (16 if c422 else 8) * cb.strides[0] + mbx * 16
+    sb = y.itemsize
+    rec["luma_off"] = mby * 16 * y.strides[0] + mbx * 16 * sb
+    rec["chroma_off"] = mby * (16 if c422 else 8) * cb.strides[0] + mbx * 8 * sb
     rec["luma_mode"] = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=n)
     rec["chroma"] = rng.integers(0, 2, size=n)
-    coeffs = np.zeros((n, 768), dtype=np.int32)
+    coeffs = np.zeros((n, 768), dtype=np.int16 if bits == 8 else np.int32)
     nnzc = np.zeros((n, 120), dtype=np.uint8)
     sc = 1 << (bits - 8)
     chroma_blocks = [16, 17, 18, 19, 32, 33, 34, 35] + ([20, 21, 22, 23, 36, 37, 38, 39] if c422 else [])
@@ -65,21 +67,28 @@ def residual_work(mb_w, mb_h, bits, c422, y, cb, seed):
 
 def oracle_residual(o, bits, c422, rec, coeffs, nnzc, y, cb, cr):
     ls, uvls = y.strides[0], cb.strides[0]
-    bo = block_offsets(ls, uvls, c422)
+    bo = block_offsets(ls, uvls, c422, y.itemsize)
+    idct_mb = (lambda which, d, d2, blk, st, nz: o.h264_idct_mb(which, d, d2, ptr(bo), ptr(blk), st, ptr(nz))) if bits == 8 else \
+              (lambda which, d, d2, blk, st, nz: o.h264_hbd_idct_mb(bits, which, d, d2, ptr(bo), ptr(blk), st, ptr(nz)))
     for m in range(rec.shape[0]):
         r = rec[m]
         blk, nz = coeffs[m], nnzc[m]
         if r["luma_mode"] < 3:
-            o.h264_hbd_idct_mb(bits, int(r["luma_mode"]), at(y, r["luma_off"]), None, ptr(bo), ptr(blk), ls, ptr(nz))
+            idct_mb(int(r["luma_mode"]), at(y, r["luma_off"]), None, blk, ls, nz)
         if r["chroma"]:
             d2 = (C.c_void_p * 2)(cb.ctypes.data + int(r["chroma_off"]), cr.ctypes.data + int(r["chroma_off"]))
-            o.h264_hbd_idct_mb(bits, 4 if c422 else 3, None, d2, ptr(bo), ptr(blk), uvls, ptr(nz))
+            idct_mb(4 if c422 else 3, None, d2, blk, uvls, nz)
 
 
 def oracle_mc(o, bits, c422, rec, refs, y, cb, cr, pad=48):
     """refs: list of (y, cb, cr) uint16 planes; emulated_edge_mc = edge-replicated padding of the reference planes"""
     pr = [tuple(np.pad(p, pad, mode="edge") for p in r) for r in refs]
     sizes = {16: 0, 8: 1, 4: 2, 2: 3}
+    sb, dt = y.itemsize, y.dtype
+    qpel = (lambda avg, sidx, mc, dst, src, st: o.h264_qpel(avg, sidx, mc, dst, src, st)) if bits == 8 else \
+           (lambda avg, sidx, mc, dst, src, st: o.h264_hbd_qpel(bits, avg, sidx, mc, dst, src, st))
+    chroma = (lambda avg, widx, dst, src, st, hh_, fx, fy: o.h264_chroma(avg, widx, dst, src, st, hh_, fx, fy)) if bits == 8 else \
+             (lambda avg, widx, dst, src, st, hh_, fx, fy: o.h264_hbd_chroma(bits, avg, widx, dst, src, st, hh_, fx, fy))
     for r in rec:
         ry, rcb, rcr = pr[int(r["ref"])]
         mx, my = int(r["mvx"]) + 4 * int(r["x"]), int(r["mvy"]) + 4 * int(r["y"])
@@ -87,19 +96,19 @@ def oracle_mc(o, bits, c422, rec, refs, y, cb, cr, pad=48):
         mc = (mx & 3) + 4 * (my & 3)
         n = min(w, h)
         for (ox, oy) in [(a, b) for b in range(0, h, n) for a in range(0, w, n)]:     # square calls (h264_mb.c:248-250)
-            dst = at(y, (int(r["y"]) + oy) * y.strides[0] + 2 * (int(r["x"]) + ox))
-            win = np.zeros((n + 5, y.strides[0] // 2), np.uint16)                       # source window at the destination's pitch
+            dst = at(y, (int(r["y"]) + oy) * y.strides[0] + sb * (int(r["x"]) + ox))
+            win = np.zeros((n + 5, y.strides[0] // sb), dt)                             # source window at the destination's pitch
             sy, sx = (my >> 2) + oy - 2 + pad, (mx >> 2) + ox - 2 + pad
             win[:, :n + 5] = ry[sy:sy + n + 5, sx:sx + n + 5]
-            o.h264_hbd_qpel(bits, avg, sizes[n], mc, dst, at(win, 2 * win.strides[0] + 4), y.strides[0])
+            qpel(avg, sizes[n], mc, dst, at(win, 2 * win.strides[0] + 2 * sb), y.strides[0])
         cw, chh = w // 2, (h if c422 else h // 2)
         sy, sx = ((my >> 2) if c422 else (my >> 3)) + pad, (mx >> 3) + pad
         fy = ((my << 1) & 7) if c422 else (my & 7)
         for (pl, rp) in ((cb, rcb), (cr, rcr)):
-            win = np.zeros((chh + 1, pl.strides[0] // 2), np.uint16)
+            win = np.zeros((chh + 1, pl.strides[0] // sb), dt)
             win[:, :cw + 1] = rp[sy:sy + chh + 1, sx:sx + cw + 1]
-            dst = at(pl, (int(r["y"]) if c422 else int(r["y"]) // 2) * pl.strides[0] + 2 * (int(r["x"]) // 2))
-            o.h264_hbd_chroma(bits, avg, {8: 0, 4: 1, 2: 2}[cw], dst, ptr(win), pl.strides[0], chh, mx & 7, fy)
+            dst = at(pl, (int(r["y"]) if c422 else int(r["y"]) // 2) * pl.strides[0] + sb * (int(r["x"]) // 2))
+            chroma(avg, {8: 0, 4: 1, 2: 2}[cw], dst, ptr(win), pl.strides[0], chh, mx & 7, fy)
 
 
 def oracle_deblock(o, bits, rec, mb_w, mb_h, y, cb, cr):

@@ -207,8 +207,7 @@ def test_h264_pred_422(sim, refo, bits):
     assert sim.avb200_last_error().decode() == ""
 
 
-@pytest.mark.parametrize("c422", [0, 1])
-@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("bits,c422", [(9, 0), (9, 1), (10, 0), (10, 1), (8, 1)])
 def test_h264_hbd_batch_residual_and_mc(sim, refo, bits, c422):
     """ff_h264_idct_add_mb_batch_hbd_cuda / ff_h264_mc_batch_hbd_cuda (libav_b200/csrc/h264_hbd_batch.cu, host-compiled) on 9 / 10-bit pictures,
     4:2:0 and 4:2:2, against the compiled reference's BIT_DEPTH > 8 functions applied in the reference's order"""

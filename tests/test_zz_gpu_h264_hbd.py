@@ -16,8 +16,7 @@ def _dev(a):
     return device.DevBuf.from_numpy(a)
 
 
-@pytest.mark.parametrize("c422", [0, 1])
-@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("bits,c422", [(9, 0), (9, 1), (10, 0), (10, 1), (8, 1)])
 @pytest.mark.parametrize("mb_w,mb_h", SIZES)
 def test_residual_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
     from libav_b200 import device
@@ -30,15 +29,14 @@ def test_residual_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422):
     gpu.check(gpu.lib.ff_h264_idct_add_mb_batch_hbd_cuda(bits, 1 + c422, d[0].ptr, rec.shape[0], d[1].ptr, 768, d[2].ptr, d[3].ptr, d[4].ptr, d[5].ptr,
                                                          y.strides[0], cb.strides[0], None))
     device.sync()
-    assert np.array_equal(d[3].download(np.uint16, y.shape), wy)
-    assert np.array_equal(d[4].download(np.uint16, cb.shape), wcb)
-    assert np.array_equal(d[5].download(np.uint16, cr.shape), wcr)
-    assert np.array_equal(d[1].download(np.int32, coeffs.shape), wco)      # consumed coefficients are zeroed identically
+    assert np.array_equal(d[3].download(y.dtype, y.shape), wy)
+    assert np.array_equal(d[4].download(y.dtype, cb.shape), wcb)
+    assert np.array_equal(d[5].download(y.dtype, cr.shape), wcr)
+    assert np.array_equal(d[1].download(coeffs.dtype, coeffs.shape), wco)      # consumed coefficients are zeroed identically
 
 
 @pytest.mark.parametrize("staged", [0, 2])
-@pytest.mark.parametrize("c422", [0, 1])
-@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("bits,c422", [(9, 0), (9, 1), (10, 0), (10, 1), (8, 1)])
 @pytest.mark.parametrize("mb_w,mb_h", SIZES)
 def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422, staged):
     """staged 0: the default kernel (patches staged in shared memory); 2: the clamped-global-load form of the same arithmetic (tests/hostsim/ runs it)"""
@@ -57,9 +55,9 @@ def test_mc_batch_hbd(gpu, checker, mb_w, mb_h, bits, c422, staged):
                                                 16 * mb_w, 16 * mb_h, None))
     device.sync()
     gpu.lib.avb200_set_tuning(b"mc_hbd_staged", 0)
-    assert np.array_equal(dy.download(np.uint16, y.shape), wy)
-    assert np.array_equal(dcb.download(np.uint16, cb.shape), wcb)
-    assert np.array_equal(dcr.download(np.uint16, cr.shape), wcr)
+    assert np.array_equal(dy.download(y.dtype, y.shape), wy)
+    assert np.array_equal(dcb.download(y.dtype, cb.shape), wcb)
+    assert np.array_equal(dcr.download(y.dtype, cr.shape), wcr)
 
 
 @pytest.mark.parametrize("bits", [9, 10])
@@ -257,3 +255,108 @@ def test_flush_hbd_equals_the_chained_checker(gpu, checker, mb_w, mb_h, P, p_int
     assert np.array_equal(gy, wy), np.argwhere(gy != wy)[:5].tolist()
     assert np.array_equal(gcb, np.concatenate([w[1] for w in want])) and np.array_equal(gcr, np.concatenate([w[2] for w in want]))
     assert np.array_equal(d["co"].download(np.int32, (n, 768)), np.concatenate(want_co))
+
+
+def test_dc_dequant_batch_422_8bit(gpu, checker):
+    """ff_h264_dc_dequant_batch_422_cuda: int16 coefficients, the 2 x 4 chroma DC transform of chroma_format_idc 2 (h264idct_template.c:271-306)"""
+    from libav_b200 import device
+    from oracle.loader import ptr
+    rng = np.random.default_rng(422)
+    n = 300
+    recs = np.zeros(n, np.dtype([("luma_qmul", "<u4"), ("chroma_qmul", "<u4", (2,))]))
+    recs["luma_qmul"] = np.where(rng.random(n) < 0.6, rng.integers(16, 1200, n), 0)
+    recs["chroma_qmul"] = np.where(rng.random((n, 2)) < 0.6, rng.integers(16, 1200, (n, 2)), 0)
+    coeffs = rng.integers(-120, 120, size=(n, 768)).astype(np.int16)
+    luma_dc = rng.integers(-500, 500, size=(n, 16)).astype(np.int16)
+    want = coeffs.copy()
+    for m in range(n):
+        if recs["luma_qmul"][m]:
+            checker.h264_luma_dc_dequant_idct(hh.at(want, m * 768 * 2), ptr(luma_dc[m].copy()), int(recs["luma_qmul"][m]))
+        for pl in range(2):
+            if recs["chroma_qmul"][m, pl]:
+                checker.h264_chroma422_dc_dequant_idct(hh.at(want, (m * 768 + 256 * (pl + 1)) * 2), int(recs["chroma_qmul"][m, pl]))
+    d_rec, d_co, d_dc = _dev(recs), _dev(coeffs), _dev(luma_dc)
+    gpu.check(gpu.lib.ff_h264_dc_dequant_batch_422_cuda(d_rec.ptr, n, d_co.ptr, 768, d_dc.ptr, None))
+    device.sync()
+    got = d_co.download(np.int16, coeffs.shape)
+    assert not np.array_equal(want, coeffs) and np.array_equal(got, want), np.argwhere(got != want)[:4].tolist()
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+@pytest.mark.parametrize("mb_w,mb_h,P", [(7, 5, 1), (20, 12, 2)])
+def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
+    """ff_h264_flush_pictures_cuda with chroma_format_idc 2 (8 and 10 bit), inter pictures with caller-filled deblocking records: MC -> weighted
+    prediction -> DC transforms (2 x 4 chroma) -> residual -> 4:2:2 loop filter in one call, against the CPU checker chained in the same order"""
+    import ctypes as C
+    from libav_b200 import device, tables
+    from oracle.loader import ptr
+    sb = 1 if bits == 8 else 2
+    cdt = np.int16 if bits == 8 else np.int32
+    rng = np.random.default_rng(bits * 100 + mb_w)
+    refs = [hh.smooth_picture422(mb_w, mb_h, bits, seed=11), hh.smooth_picture422(mb_w, mb_h, bits, seed=12)]
+    n1 = mb_w * mb_h
+    pics, mcs, ress, cos, nzs, dcs, wrecs, recs, exts, want, want_co = [], [], [], [], [], [], [], [], [], [], []
+    for k in range(P):
+        y, cb, cr = hh.smooth_picture422(mb_w, mb_h, bits, seed=50 + k)
+        ls, uvls = y.strides[0], cb.strides[0]
+        mc = synth.h264_mc_work(mb_w, mb_h, seed=mb_h + k, max_mv=24, avg_second=True)
+        res, co, nz = hh.residual_work(mb_w, mb_h, bits, 1, y, cb, seed=mb_w + k)
+        co = (co // 4).astype(cdt)                                             # small residual: the loop filter still has edges to change
+        dc = np.zeros(n1, np.dtype([("luma_qmul", "<u4"), ("chroma_qmul", "<u4", (2,))]))
+        dc["chroma_qmul"] = np.where(rng.random((n1, 2)) < 0.5, rng.integers(16, 200, (n1, 2)), 0)
+        wr = []
+        for m in range(n1):
+            if rng.random() < 0.4:
+                wr.append(((m // mb_w) * 16 * ls + (m % mb_w) * 16 * sb, 16, 16, int(rng.integers(0, 7)), 0, int(rng.integers(-20, 90)), 0, int(rng.integers(-20, 20)), 0))
+        wr = np.array(wr, dtype=synth.WEIGHT_DT)
+        rec, ext = hh.deblock422_work(mb_w, mb_h, seed=3 + k, slices=2)
+        wy, wcb, wcr, wco = y.copy(), cb.copy(), cr.copy(), co.copy()
+        hh.oracle_mc(checker, bits, 1, mc, refs, wy, wcb, wcr)
+        for r in wr:
+            if bits == 8:
+                checker.h264_weight(0, hh.at(wy, r["off"]), ls, int(r["h"]), int(r["log2_denom"]), int(r["weight"]), int(r["offset"]))
+            else:
+                checker.h264_hbd_weight(bits, 0, hh.at(wy, r["off"]), ls, int(r["h"]), int(r["log2_denom"]), int(r["weight"]), int(r["offset"]))
+        for m in range(n1):
+            for p in range(2):
+                if dc["chroma_qmul"][m, p]:
+                    o_ = (m * 768 + 256 * (p + 1)) * wco.itemsize
+                    if bits == 8:
+                        checker.h264_chroma422_dc_dequant_idct(hh.at(wco, o_), int(dc["chroma_qmul"][m, p]))
+                    else:
+                        checker.h264_hbd_dc_dequant(bits, 2, hh.at(wco, o_), None, int(dc["chroma_qmul"][m, p]))
+        hh.oracle_residual(checker, bits, 1, res, wco, nz, wy, wcb, wcr)
+        pre = wy.copy()
+        hh.oracle_deblock422(checker, bits, rec, ext, mb_w, mb_h, wy, wcb, wcr)
+        assert not np.array_equal(pre, wy)
+        m2 = mc.copy(); m2["y"] += 16 * mb_h * k
+        r2 = res.copy(); r2["luma_off"] += 16 * mb_h * k * ls; r2["chroma_off"] += 16 * mb_h * k * uvls
+        w2 = wr.copy(); w2["off"] += 16 * mb_h * k * ls
+        pics.append((y, cb, cr)); mcs.append(m2); ress.append(r2); cos.append(co); nzs.append(nz); dcs.append(dc); wrecs.append(w2)
+        recs.append(rec); exts.append(ext); want.append((wy, wcb, wcr)); want_co.append(wco)
+    Y, CB, CR = (np.concatenate([p[i] for p in pics]) for i in range(3))
+    mc = np.concatenate(mcs)
+    mc = np.concatenate([mc[mc["avg"] == 0], mc[mc["avg"] != 0]])
+    wrec = np.concatenate(wrecs)
+    dref = [[_dev(np.concatenate([p] * P)) for p in r] for r in refs]
+    d_planes = _dev(np.array([[p.ptr for p in r] for r in dref], dtype=np.uint64))
+    n = n1 * P
+    d = dict(y=_dev(Y), cb=_dev(CB), cr=_dev(CR), mc=_dev(mc), res=_dev(np.concatenate(ress)), w=_dev(wrec), co=_dev(np.concatenate(cos)),
+             nz=_dev(np.concatenate(nzs)), dc=_dev(np.concatenate(dcs)), ldc=_dev(np.zeros((n, 16), cdt)), rec=_dev(np.concatenate(recs)),
+             ext=_dev(np.concatenate(exts)))
+    work = tables.FFH264PictureWork()
+    work.mb_w, work.mb_h, work.n_pictures = mb_w, mb_h, P
+    work.luma, work.cb, work.cr, work.linesize, work.uvlinesize = d["y"].ptr, d["cb"].ptr, d["cr"].ptr, Y.strides[0], CB.strides[0]
+    work.mc, work.n_mc, work.refs = d["mc"].ptr, mc.shape[0], d_planes.ptr
+    work.weight[0], work.n_weight[0] = d["w"].ptr, wrec.shape[0]
+    work.coeffs, work.coeff_stride, work.nnzc = d["co"].ptr, 768, d["nz"].ptr
+    work.dc, work.luma_dc, work.residual = d["dc"].ptr, d["ldc"].ptr, d["res"].ptr
+    work.deblock_records, work.deblock_chroma422 = d["rec"].ptr, d["ext"].ptr
+    work.bit_depth, work.chroma_format_idc = bits, 2
+    gpu.check(gpu.lib.ff_h264_flush_pictures_cuda(C.byref(work), None))
+    device.sync()
+    gy, gcb, gcr = d["y"].download(Y.dtype, Y.shape), d["cb"].download(Y.dtype, CB.shape), d["cr"].download(Y.dtype, CR.shape)
+    wy = np.concatenate([w[0] for w in want])
+    assert np.array_equal(gy, wy), np.argwhere(gy != wy)[:5].tolist()
+    assert np.array_equal(gcb, np.concatenate([w[1] for w in want])) and np.array_equal(gcr, np.concatenate([w[2] for w in want]))
+    assert np.array_equal(d["co"].download(cdt, (n, 768)), np.concatenate(want_co))

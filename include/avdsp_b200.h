@@ -273,6 +273,12 @@ int ff_h264_dc_dequant_batch_hbd_cuda(int chroma_format_idc, const FFH264DCRecor
 int ff_h264_intra_mb_batch_hbd_cuda(int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, int32_t *coeffs,
                                     size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
                                     int uvlinesize, void *stream);
+/* intra reconstruction of 4:2:2 pictures, bit_depth 8 / 9 / 10: the chroma macroblock is 8 x 16 -- pred8x8[] holds the 8 x 16 predictors
+ * (h264pred.c:477-563, h264pred_template.c:502-838) and the chroma residual is h264_idct_add8_422 (h264idct_template.c:216-236: blocks 20..23 /
+ * 36..39 of the arena, counted at scan8[i + 4]).  coeffs: int16 at 8 bit, int32 at 9 / 10 (coeff_stride in elements of that type). */
+int ff_h264_intra_mb_batch_422_cuda(int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, void *coeffs,
+                                    size_t coeff_stride, const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize,
+                                    int uvlinesize, void *stream);
 /* chroma_format_idc 2, bit depth 8 / 9 / 10: the 8 x 16 chroma macroblock has two vertical edges of sixteen lines (the 104-byte record's
  * calpha / cbeta / ctc0 / cintra [plane][0][edge]: h264_h_loop_filter_chroma422, a tc0 entry per four lines) and FOUR horizontal edges, one per
  * luma edge at chroma rows 0, 4, 8, 12 (h264_loopfilter.c:633,693-700: also inside 8x8-transform macroblocks), carried by a second record per
@@ -357,7 +363,7 @@ typedef struct FFH264PictureWork {
     uint32_t *progress;
     int bit_depth, chroma_format_idc;        /* 0 = 8 / 1.  9 / 10-bit pictures (int32 coeffs / luma_dc behind the same pointers) and 4:2:2 chroma at
                                                 8 / 9 / 10 bit run the *_hbd_cuda / *_422_cuda stages in the same order (progress is not used then;
-                                                4:2:2 pictures with intra records are refused) */
+                                                4:2:2 intra macroblocks: ff_h264_intra_mb_batch_422_cuda) */
     const FFH264DeblockChroma422 *deblock_chroma422;   /* 4:2:2 with caller-filled deblock_records: their second record array */
 } FFH264PictureWork;
 int ff_h264_flush_pictures_cuda(const FFH264PictureWork *work /* host struct */, void *stream);

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "ff_h264_mc_batch_hbd_cuda": (i32, [i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ff_h264_deblock_batch_hbd_cuda": (i32, [i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
     "ff_h264_intra_mb_batch_hbd_cuda": (i32, [i32, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, vp]),
+    "ff_h264_intra_mb_batch_422_cuda": (i32, [i32, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp, i32, i32, vp]),
     "ff_h264_weight_batch_hbd_cuda": (i32, [i32, vp, sz, vp, vp, i32, vp]),
     "ff_h264_dc_dequant_batch_hbd_cuda": (i32, [i32, vp, sz, vp, sz, vp, vp]),
     "ff_h264_deblock_batch_422_cuda": (i32, [i32, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),

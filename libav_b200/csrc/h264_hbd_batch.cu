@@ -362,7 +362,8 @@ h264_deblock_generic_kernel(int bits, const FFH264DeblockMB *__restrict__ mbs, c
 // macroblocks behind the row above (prediction reaches left, up-left, up and up-right), progress in shared memory like the deblocking
 // kernel above.  Every lane collects the block's neighbours itself (the table slots' PredJobH) and derives its samples from them;
 // lane 0 (or a lane per 4x4 block) adds the residual; the warp synchronises between a block's prediction, its residual and the next block.
-__device__ __forceinline__ void intra_job_neighbours(PredJobH &j, const px *P, int st, int nt, int nl, bool tr_ok, int ax, int ay, int y0)
+template <typename PX>
+__device__ __forceinline__ void intra_job_neighbours(PredJobH &j, const PX *P, int st, int nt, int nl, bool tr_ok, int ax, int ay, int y0)
 {   // P = the block's first sample at absolute (ax, ay); [y0, ..) = the picture's rows.  nt top samples (4 or 8 more when tr_ok), nl left samples
     const bool top = ay - 1 >= y0, left = ax - 1 >= 0;
     for (int k = 0; k < nt; k++) j.top[k] = top ? P[-st + k] : 0;
@@ -371,18 +372,24 @@ __device__ __forceinline__ void intra_job_neighbours(PredJobH &j, const px *P, i
     j.corner = (top && left) ? P[-st - 1] : 0;
 }
 
+// PX = uint16_t: 9 / 10-bit pictures; uint8_t: the 8-bit 4:2:2 pictures (bits 8: the predictors below are the 8-bit formulas, DC_128 = 128, plane
+// prediction clipped to 255).  C422: the chroma macroblock is 8 x 16 -- pred8x8[] holds the 8 x 16 predictors (h264pred.c:477-563) and the residual
+// is h264_idct_add8_422 (h264idct_template.c:216-236).
+template <typename PX, bool C422>
 __global__ void __launch_bounds__(DB_WARPS * 32)
-h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w, int mb_h, int32_t *__restrict__ coeffs, size_t coeff_stride,
-                      const uint8_t *__restrict__ nnzc_all, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
+h264_intra_generic_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w, int mb_h, typename Transform<PX>::coef *__restrict__ coeffs, size_t coeff_stride,
+                          const uint8_t *__restrict__ nnzc_all, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls)
 {
-    using namespace hbd;
+    typedef Transform<PX> T;
+    typedef typename T::coef coef;
     extern __shared__ int prog_s[];
     volatile int *prog = prog_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pic = blockIdx.x;
     for (int i = threadIdx.x; i < mb_h; i += blockDim.x) prog_s[i] = 0;
     __syncthreads();
-    const int lsp = ls >> 1, uvlsp = uvls >> 1, y0 = pic * mb_h * 16, cy0 = pic * mb_h * 8;
-    px *const Y = reinterpret_cast<px *>(luma), *const C2[2] = { reinterpret_cast<px *>(cb), reinterpret_cast<px *>(cr) };
+    constexpr int CH = C422 ? 16 : 8;                                    // chroma rows per macroblock
+    const int lsp = ls / (int)sizeof(PX), uvlsp = uvls / (int)sizeof(PX), y0 = pic * mb_h * 16, cy0 = pic * mb_h * CH;
+    PX *const Y = reinterpret_cast<PX *>(luma), *const C2[2] = { reinterpret_cast<PX *>(cb), reinterpret_cast<PX *>(cr) };
     for (int row = warp; row < mb_h; row += DB_WARPS) {
         for (int x = 0; x < mb_w; x++) {
             const size_t m = ((size_t)pic * mb_h + row) * mb_w + x;
@@ -394,7 +401,7 @@ h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w,
                     __syncwarp();
                     __threadfence_block();
                 }
-                int32_t *mb = coeffs + m * coeff_stride;
+                coef *mb = coeffs + m * coeff_stride;
                 const uint8_t *nnzc = nnzc_all + m * 120;
                 const int ax0 = x * 16, ay0 = y0 + row * 16;
                 PredJobH j;
@@ -402,7 +409,7 @@ h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w,
                 if (M.kind == 1) {                                      // intra 4x4: 16 blocks in coding order
                     for (int i = 0; i < 16; i++) {
                         const int bx = blk_x(i), by = blk_y(i), mode = M.mode4[i];
-                        px *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
+                        PX *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
                         const bool tr_ok = (M.topright_samples_available << i) & 0x8000;
                         j.tab = 0; j.mode = mode;
                         intra_job_neighbours(j, P, lsp, 4, 4, tr_ok, ax0 + bx, ay0 + by, y0);
@@ -412,16 +419,16 @@ h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w,
                             else { IntraEdges e; hbd_edges(e, j); v = intra_directional(e, 4, mode, lane & 3, lane >> 2); }
                         }
                         __syncwarp();                                   // every lane has read its neighbours
-                        if (lane < 16) P[(size_t)(lane >> 2) * lsp + (lane & 3)] = (px)v;
+                        if (lane < 16) P[(size_t)(lane >> 2) * lsp + (lane & 3)] = (PX)v;
                         __syncwarp();
                         const int nnz = nnzc[scan8_of(i)];
-                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) dc_add(bits, P, mb + 16 * i, lsp, 4); else idct4_add(bits, P, mb + 16 * i, lsp); }
+                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) T::dc(bits, P, mb + 16 * i, lsp, 4); else T::idct4(bits, P, mb + 16 * i, lsp); }
                         __syncwarp();
                     }
                 } else if (M.kind == 2) {                               // intra 8x8 (pred8x8l)
                     for (int k = 0; k < 4; k++) {
                         const int i = 4 * k, bx = 8 * (k & 1), by = 8 * (k >> 1), mode = M.mode4[i];
-                        px *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
+                        PX *P = Y + (size_t)(ay0 + by) * lsp + ax0 + bx;
                         j.tab = 1; j.mode = mode;
                         j.has_tl = ((M.topleft_samples_available << i) & 0x8000) != 0; j.has_tr = ((M.topright_samples_available << i) & 0x4000) != 0;
                         intra_job_neighbours(j, P, lsp, 8, 8, j.has_tr, ax0 + bx, ay0 + by, y0);
@@ -432,43 +439,46 @@ h264_intra_hbd_kernel(int bits, const FFH264IntraMB *__restrict__ mbs, int mb_w,
                             for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; v[q] = mode == 11 ? 1 << (bits - 1) : intra_directional(e, 8, mode, sidx & 7, sidx >> 3); }
                         }
                         __syncwarp();
-                        for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * lsp + (sidx & 7)] = (px)v[q]; }
+                        for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * lsp + (sidx & 7)] = (PX)v[q]; }
                         __syncwarp();
                         const int nnz = nnzc[scan8_of(i)];
-                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) dc_add(bits, P, mb + 16 * i, lsp, 8); else idct8_add(bits, P, mb + 16 * i, lsp); }
+                        if (lane == 0 && nnz) { if (nnz == 1 && mb[16 * i]) T::dc(bits, P, mb + 16 * i, lsp, 8); else T::idct8(bits, P, mb + 16 * i, lsp); }
                         __syncwarp();
                     }
                     j.has_tl = j.has_tr = 0;
                 } else {                                                // intra 16x16, then h264_idct_add16intra
-                    px *P = Y + (size_t)ay0 * lsp + ax0;
+                    PX *P = Y + (size_t)ay0 * lsp + ax0;
                     j.tab = 3; j.mode = M.mode16;
                     intra_job_neighbours(j, P, lsp, 16, 16, false, ax0, ay0, y0);
                     int v[8];
                     for (int q = 0; q < 8; q++) { const int sidx = lane + 32 * q; v[q] = hbd_big_sample(j, 16, sidx & 15, sidx >> 4); }
                     __syncwarp();
-                    for (int q = 0; q < 8; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 4) * lsp + (sidx & 15)] = (px)v[q]; }
+                    for (int q = 0; q < 8; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 4) * lsp + (sidx & 15)] = (PX)v[q]; }
                     __syncwarp();
                     if (lane < 16) {
-                        px *d = P + (size_t)blk_y(lane) * lsp + blk_x(lane);
-                        if (nnzc[scan8_of(lane)]) idct4_add(bits, d, mb + 16 * lane, lsp); else if (mb[16 * lane]) dc_add(bits, d, mb + 16 * lane, lsp, 4);
+                        PX *d = P + (size_t)blk_y(lane) * lsp + blk_x(lane);
+                        if (nnzc[scan8_of(lane)]) T::idct4(bits, d, mb + 16 * lane, lsp); else if (mb[16 * lane]) T::dc(bits, d, mb + 16 * lane, lsp, 4);
                     }
                     __syncwarp();
                 }
-                // chroma: pred8x8 on both planes, then h264_idct_add8
+                // chroma: pred8x8 on both planes, then h264_idct_add8 (4:2:2: the 8 x 16 predictors, then h264_idct_add8_422)
+                const int crow = cy0 + row * CH;
                 for (int pl = 0; pl < 2; pl++) {
-                    px *P = C2[pl] + (size_t)(cy0 + row * 8) * uvlsp + x * 8;
-                    j.tab = 2; j.mode = M.chroma_mode;
-                    intra_job_neighbours(j, P, uvlsp, 8, 8, false, x * 8, cy0 + row * 8, cy0);
-                    int v[2];
-                    for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; v[q] = hbd_big_sample(j, 8, sidx & 7, sidx >> 3); }
+                    PX *P = C2[pl] + (size_t)crow * uvlsp + x * 8;
+                    j.tab = C422 ? 5 : 2; j.mode = M.chroma_mode;
+                    intra_job_neighbours(j, P, uvlsp, 8, CH, false, x * 8, crow, cy0);
+                    int v[CH / 4];
+                    for (int q = 0; q < CH / 4; q++) { const int sidx = lane + 32 * q; v[q] = C422 ? hbd_sample_8x16(j, sidx & 7, sidx >> 3) : hbd_big_sample(j, 8, sidx & 7, sidx >> 3); }
                     __syncwarp();
-                    for (int q = 0; q < 2; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * uvlsp + (sidx & 7)] = (px)v[q]; }
+                    for (int q = 0; q < CH / 4; q++) { const int sidx = lane + 32 * q; P[(size_t)(sidx >> 3) * uvlsp + (sidx & 7)] = (PX)v[q]; }
                 }
                 __syncwarp();
-                if (M.chroma_residual && lane < 8) {
-                    const int pl = lane >> 2, k = lane & 3, i = 16 + 16 * pl + k;
-                    px *d = C2[pl] + (size_t)(cy0 + row * 8 + 4 * (k >> 1)) * uvlsp + x * 8 + 4 * (k & 1);
-                    if (nnzc[scan8_of(i)]) idct4_add(bits, d, mb + 16 * i, uvlsp); else if (mb[16 * i]) dc_add(bits, d, mb + 16 * i, uvlsp, 4);
+                constexpr int PER = C422 ? 8 : 4;                        // 4x4 chroma blocks per plane
+                if (M.chroma_residual && lane < 2 * PER) {
+                    // 4:2:2: the lower four blocks keep their coefficients at block i but are addressed through scan8[i + 4] (rows 8..15)
+                    const int pl = lane / PER, k = lane % PER, i = 16 + 16 * pl + k, e = k >= 4 ? i + 4 : i, ke = e & 15;
+                    PX *d = C2[pl] + (size_t)(crow + blk_y(ke)) * uvlsp + x * 8 + blk_x(ke);
+                    if (nnzc[scan8_of(e)]) T::idct4(bits, d, mb + 16 * i, uvlsp); else if (mb[16 * i]) T::dc(bits, d, mb + 16 * i, uvlsp, 4);
                 }
                 __syncwarp();
                 __threadfence_block();
@@ -514,6 +524,19 @@ static int launch_mc_generic(int bit_depth, int c422, const FFH264MCRecord *recs
     }
     return 0;
 }
+
+#ifndef AVB_HOSTSIM
+template <typename PX, bool C422>
+static int launch_intra_generic(const char *where, int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, void *coeffs, size_t coeff_stride,
+                                const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int ls, int uvls, cudaStream_t st)
+{
+    if (!mbs || !coeffs || !nnzc || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
+    if (!n_pictures) return 0;
+    h264_intra_generic_kernel<PX, C422><<<(unsigned)n_pictures, DB_WARPS * 32, (size_t)mb_h * sizeof(int), st>>>(
+        bit_depth, mbs, mb_w, mb_h, static_cast<typename Transform<PX>::coef *>(coeffs), coeff_stride, nnzc, luma, cb, cr, ls, uvls);
+    return check_launch(where) ? -1 : 0;
+}
+#endif
 
 }  // namespace
 }  // namespace avb
@@ -582,11 +605,18 @@ int ff_h264_intra_mb_batch_hbd_cuda(int bit_depth, const FFH264IntraMB *mbs, int
     avb::enter();
     const char *where = "ff_h264_intra_mb_batch_hbd_cuda";
     if (!hbd_args_ok(where, bit_depth, 1, linesize, uvlinesize, luma, cb, cr)) return -1;
-    if (!mbs || !coeffs || !nnzc || !luma || !cb || !cr || mb_w <= 0 || mb_h <= 0 || n_pictures < 0 || mb_h > 8192) { set_error_msg(where, "bad argument"); return -1; }
-    if (!n_pictures) return 0;
-    h264_intra_hbd_kernel<<<(unsigned)n_pictures, DB_WARPS * 32, (size_t)mb_h * sizeof(int), (cudaStream_t)stream>>>(bit_depth, mbs, mb_w, mb_h, coeffs, coeff_stride, nnzc,
-                                                                                                                  luma, cb, cr, linesize, uvlinesize);
-    return check_launch(where) ? -1 : 0;
+    return launch_intra_generic<uint16_t, false>(where, bit_depth, mbs, mb_w, mb_h, n_pictures, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream);
+}
+
+int ff_h264_intra_mb_batch_422_cuda(int bit_depth, const FFH264IntraMB *mbs, int mb_w, int mb_h, int n_pictures, void *coeffs, size_t coeff_stride,
+                                    const uint8_t *nnzc, uint8_t *luma, uint8_t *cb, uint8_t *cr, int linesize, int uvlinesize, void *stream)
+{
+    avb::enter();
+    const char *where = "ff_h264_intra_mb_batch_422_cuda";
+    if (!depth_idc_ok(where, bit_depth, 2, linesize, uvlinesize, luma, cb, cr)) return -1;
+    if (bit_depth == 8)
+        return launch_intra_generic<uint8_t, true>(where, 8, mbs, mb_w, mb_h, n_pictures, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream);
+    return launch_intra_generic<uint16_t, true>(where, bit_depth, mbs, mb_w, mb_h, n_pictures, coeffs, coeff_stride, nnzc, luma, cb, cr, linesize, uvlinesize, (cudaStream_t)stream);
 }
 #endif
 

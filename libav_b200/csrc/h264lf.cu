@@ -265,7 +265,6 @@ extern "C" int ff_h264_flush_pictures_cuda(const FFH264PictureWork *w, void *str
     if (depth != 8 || idc != 1) {
         // 9 / 10-bit pictures and / or 4:2:2 chroma: the same order through the kernels of h264_hbd_batch.cu (coeffs / luma_dc hold int32 at 9 / 10 bit)
         if ((depth != 8 && depth != 9 && depth != 10) || (idc != 1 && idc != 2)) { set_error_msg("ff_h264_flush_pictures_cuda", "bit_depth 8 / 9 / 10, chroma_format_idc 1 / 2"); return -1; }
-        if (idc == 2 && w->intra) { set_error_msg("ff_h264_flush_pictures_cuda", "4:2:2 intra reconstruction is not batched (table slots)"); return -1; }
         if (w->n_mc && ff_h264_mc_batch_hbd_cuda(depth, idc, w->mc, w->n_mc, w->refs, w->luma, w->cb, w->cr, w->linesize, w->uvlinesize, 16 * w->mb_w, 16 * w->mb_h, stream)) return -1;
         for (int pl = 0; pl < 3; pl++) {
             uint8_t *plane = pl == 0 ? w->luma : pl == 1 ? w->cb : w->cr;
@@ -278,8 +277,10 @@ extern "C" int ff_h264_flush_pictures_cuda(const FFH264PictureWork *w, void *str
                                  : ff_h264_dc_dequant_batch_hbd_cuda(idc, w->dc, n_mb, (int32_t *)w->coeffs, w->coeff_stride, (const int32_t *)w->luma_dc, stream))) return -1;
         if (w->residual && ff_h264_idct_add_mb_batch_hbd_cuda(depth, idc, w->residual, n_mb, (int32_t *)w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
                                                               w->linesize, w->uvlinesize, stream)) return -1;
-        if (w->intra && ff_h264_intra_mb_batch_hbd_cuda(depth, w->intra, w->mb_w, w->mb_h, w->n_pictures, (int32_t *)w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
-                                                        w->linesize, w->uvlinesize, stream)) return -1;
+        if (w->intra && (idc == 2 ? ff_h264_intra_mb_batch_422_cuda(depth, w->intra, w->mb_w, w->mb_h, w->n_pictures, w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
+                                                                    w->linesize, w->uvlinesize, stream)
+                                  : ff_h264_intra_mb_batch_hbd_cuda(depth, w->intra, w->mb_w, w->mb_h, w->n_pictures, (int32_t *)w->coeffs, w->coeff_stride, w->nnzc, w->luma, w->cb, w->cr,
+                                                                    w->linesize, w->uvlinesize, stream))) return -1;
         if (w->deblock_info) {
             if (!w->deblock_records || w->deblock_info->mb_w != w->mb_w || w->deblock_info->mb_h != w->mb_h || w->deblock_info->n_pictures != w->n_pictures ||
                 (idc == 2) != (w->deblock_info->chroma422 != nullptr)) {

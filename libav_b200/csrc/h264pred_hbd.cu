@@ -13,39 +13,6 @@
 
 namespace avb {
 
-// chroma_format_idc 2: sample (x, y) of an 8 x 16 chroma block, modes 0..10 of pred8x8[] (h264pred_template.c:502-838): the DC family per
-// 4 x 4 quadrant (2 across, 4 down), plane prediction with an 8-tap vertical gradient
-__device__ inline int hbd_sample_8x16(const PredJobH &j, int x, int y)
-{
-    const int mode = j.mode, mid = 1 << (j.bits - 1);
-    if (mode == 1) return j.left[y];
-    if (mode == 2) return j.top[x];
-    if (mode == 6) return mid;
-    if (mode == 3) {
-        int H = 0, V = 0;
-        for (int k = 1; k <= 4; k++) H += k * (j.top[3 + k] - (3 - k < 0 ? j.corner : j.top[3 - k]));
-        for (int k = 1; k <= 8; k++) V += k * (j.left[7 + k] - (7 - k < 0 ? j.corner : j.left[7 - k]));
-        H = (17 * H + 16) >> 5; V = (5 * V + 32) >> 6;
-        const int a = 16 * (j.left[15] + j.top[7] + 1) - 7 * V - 3 * H;
-        return min(max((a + x * H + y * V) >> 5, 0), (1 << j.bits) - 1);
-    }
-    int t0 = 0, t1 = 0, l[4] = { 0, 0, 0, 0 };
-    for (int i = 0; i < 4; i++) { t0 += j.top[i]; t1 += j.top[4 + i]; }
-    for (int i = 0; i < 16; i++) l[i >> 2] += j.left[i];
-    const int c = x >> 2, r = y >> 2;
-    const int dc = !c ? (!r ? (t0 + l[0] + 4) >> 3 : (l[r] + 2) >> 2) : (!r ? (t1 + 2) >> 2 : (t1 + l[r] + 4) >> 3);
-    const int ldc = (l[r] + 2) >> 2, tdc = ((c ? t1 : t0) + 2) >> 2;
-    switch (mode) {
-    case 0: return dc;
-    case 4: return ldc;
-    case 5: return tdc;
-    case 7: return (!c && !r) ? (t0 + l[0] + 4) >> 3 : tdc;          // top_dc, then pred4x4_dc on the first block
-    case 8: return (!c && !r) ? (t0 + 2) >> 2 : dc;                  // dc, then pred4x4_top_dc on the first block
-    case 9: return r == 1 ? mid : ldc;                               // left_dc, then 128 on the two blocks of the second row
-    default: return r == 0 ? mid : ldc;                              // left_dc, then 128 on the two blocks of the first row
-    }
-}
-
 // out: n x n samples (pitch n); tab 5: 8 x 16 samples (pitch 8)
 __global__ void __launch_bounds__(256) pred_hbd_kernel(PredJobH j, uint16_t *__restrict__ out)
 {

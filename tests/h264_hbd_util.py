@@ -257,10 +257,20 @@ def weight_dc_cases(run_weight, run_dc, o, bits):
 
 
 # ---- intra reconstruction at 9 / 10 bit ---------------------------------------------------------------------------------------------------
-def oracle_intra(o, bits, rec, coeffs, nnzc, mb_w, mb_h, y, cb, cr):
-    """hl_decode_mb() for intra macroblocks (h264_mb.c:607-731, h264_mb_template.c:158-197) through the oracle's BIT_DEPTH > 8 H264PredContext /
-    H264DSPContext entries, block by block (tests/h264_util.py::oracle_intra for 16-bit samples; strides and offsets in bytes)"""
-    ls, uvls = y.strides[0], cb.strides[0]
+def oracle_intra(o, bits, rec, coeffs, nnzc, mb_w, mb_h, y, cb, cr, c422=0):
+    """hl_decode_mb() for intra macroblocks (h264_mb.c:607-731, h264_mb_template.c:158-197) through the oracle's H264PredContext / H264DSPContext
+    entries of that bit depth, block by block (tests/h264_util.py::oracle_intra generalised: 16-bit samples above 8 bit, strides and offsets in
+    bytes; c422: the 8 x 16 chroma predictors and h264_idct_add8_422)"""
+    ls, uvls, sb = y.strides[0], cb.strides[0], y.itemsize
+    if bits == 8:
+        pred = lambda tab, mode, src, tr, tl, trf, st: o.h264_pred(tab, mode, src, tr, tl, trf, st)
+        idct = lambda which, d, blk, st: o.h264_idct(which, d, blk, st)
+        idct_mb = lambda which, d, d2, bo, blk, st, nz: o.h264_idct_mb(which, d, d2, bo, blk, st, nz)
+    else:
+        pred = lambda tab, mode, src, tr, tl, trf, st: o.h264_hbd_pred(bits, tab, mode, src, tr, tl, trf, st)
+        idct = lambda which, d, blk, st: o.h264_hbd_idct(bits, which, d, blk, st)
+        idct_mb = lambda which, d, d2, bo, blk, st, nz: o.h264_hbd_idct_mb(bits, which, d, d2, bo, blk, st, nz)
+    bo = block_offsets(ls, uvls, c422, sb)
     for m in range(mb_w * mb_h):
         r = rec[m]
         kind = int(r["kind"])
@@ -268,40 +278,58 @@ def oracle_intra(o, bits, rec, coeffs, nnzc, mb_w, mb_h, y, cb, cr):
             continue
         mbx, mby = m % mb_w, m // mb_w
         mb = coeffs[m]
-        org = mby * 16 * ls + mbx * 32
-        corg = mby * 8 * uvls + mbx * 16
+        org = mby * 16 * ls + mbx * 16 * sb
+        corg = mby * (16 if c422 else 8) * uvls + mbx * 8 * sb
         if kind in (1, 2):
             for i in range(0, 16, 1 if kind == 1 else 4):
                 bx, by = (i & 1) + 2 * ((i >> 2) & 1), ((i >> 1) & 1) + 2 * (i >> 3)
-                off = org + 4 * by * ls + 8 * bx
+                off = org + 4 * by * ls + 4 * sb * bx
                 mode = int(r["mode4"][i])
                 nnz = int(nnzc[m, synth.scan8(i)])
                 blk = mb[16 * i:]
                 if kind == 1:
                     tr_ok = (int(r["topright"]) << i) & 0x8000
                     if mode in (3, 7) and not tr_ok:
-                        tr = np.full(4, y[mby * 16 + 4 * by - 1, mbx * 16 + 4 * bx + 3], np.uint16)
-                        o.h264_hbd_pred(bits, 0, mode, at(y, off), ptr(tr), 0, 0, ls)
+                        tr = np.full(4, y[mby * 16 + 4 * by - 1, mbx * 16 + 4 * bx + 3], y.dtype)
+                        pred(0, mode, at(y, off), ptr(tr), 0, 0, ls)
                     else:
-                        o.h264_hbd_pred(bits, 0, mode, at(y, off), at(y, off + 8 - ls), 0, 0, ls)
+                        pred(0, mode, at(y, off), at(y, off + 4 * sb - ls), 0, 0, ls)
                     if nnz:
-                        o.h264_hbd_idct(bits, 2 if (nnz == 1 and blk[0]) else 0, at(y, off), ptr(blk), ls)
+                        idct(2 if (nnz == 1 and blk[0]) else 0, at(y, off), ptr(blk), ls)
                 else:
-                    o.h264_hbd_pred(bits, 1, mode, at(y, off), None, (int(r["topleft"]) << i) & 0x8000, (int(r["topright"]) << i) & 0x4000, ls)
+                    pred(1, mode, at(y, off), None, (int(r["topleft"]) << i) & 0x8000, (int(r["topright"]) << i) & 0x4000, ls)
                     if nnz:
-                        o.h264_hbd_idct(bits, 3 if (nnz == 1 and blk[0]) else 1, at(y, off), ptr(blk), ls)
+                        idct(3 if (nnz == 1 and blk[0]) else 1, at(y, off), ptr(blk), ls)
         else:
-            o.h264_hbd_pred(bits, 3, int(r["mode16"]), at(y, org), None, 0, 0, ls)
-            bo = block_offsets(ls, uvls, 0)
-            o.h264_hbd_idct_mb(bits, 1, at(y, org), None, ptr(bo), ptr(mb), ls, ptr(nnzc[m]))
+            pred(3, int(r["mode16"]), at(y, org), None, 0, 0, ls)
+            idct_mb(1, at(y, org), None, ptr(bo), ptr(mb), ls, ptr(nnzc[m]))
         for pl in (cb, cr):
-            o.h264_hbd_pred(bits, 2, int(r["chroma_mode"]), at(pl, corg), None, 0, 0, uvls)
+            if c422:
+                o.h264_pred422(bits, int(r["chroma_mode"]), at(pl, corg), uvls)
+            else:
+                pred(2, int(r["chroma_mode"]), at(pl, corg), None, 0, 0, uvls)
         if r["chroma_residual"]:
-            bo = block_offsets(ls, uvls, 0)
             dst2 = (C.c_void_p * 2)(cb.ctypes.data + corg, cr.ctypes.data + corg)
-            o.h264_hbd_idct_mb(bits, 3, None, dst2, ptr(bo), ptr(mb), uvls, ptr(nnzc[m]))
+            idct_mb(4 if c422 else 3, None, dst2, ptr(bo), ptr(mb), uvls, ptr(nnzc[m]))
 
 
-def intra_work(mb_w, mb_h, bits, seed, p_intra=1.0):
+def intra_work(mb_w, mb_h, bits, seed, p_intra=1.0, c422=0):
+    """synth.h264_intra_work at this bit depth (int32 coefficients above 8 bit); c422: the lower four chroma blocks of each plane as well
+    (coefficients at block 20..23 / 36..39, their non_zero_count at scan8[i + 4] like h264_idct_add8_422 reads them)"""
     rec, coeffs, nnzc = synth.h264_intra_work(mb_w, mb_h, seed=seed, p_intra=p_intra)
+    if c422:
+        rng = np.random.default_rng(seed + 77)
+        for m in np.nonzero(rec["chroma_residual"])[0]:
+            for i in (20, 21, 22, 23, 36, 37, 38, 39):
+                u = rng.random()
+                if u < 0.3:
+                    continue
+                if u < 0.5:
+                    coeffs[m, 16 * i] = rng.integers(-800, 801) or 64            # DC only: nnz 0
+                else:
+                    coeffs[m, 16 * i:16 * i + 16] = rng.integers(-64, 65, 16) * (rng.random(16) < 0.4) * 4
+                    coeffs[m, 16 * i] = rng.integers(-600, 601)
+                    nnzc[m, scan8(i + 4)] = 16
+    if bits == 8:
+        return rec, coeffs, nnzc
     return rec, coeffs.astype(np.int32) * (1 << (bits - 8)), nnzc

@@ -283,10 +283,11 @@ def test_dc_dequant_batch_422_8bit(gpu, checker):
 
 
 @pytest.mark.parametrize("bits", [8, 10])
-@pytest.mark.parametrize("mb_w,mb_h,P", [(7, 5, 1), (20, 12, 2)])
-def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
-    """ff_h264_flush_pictures_cuda with chroma_format_idc 2 (8 and 10 bit), inter pictures with caller-filled deblocking records: MC -> weighted
-    prediction -> DC transforms (2 x 4 chroma) -> residual -> 4:2:2 loop filter in one call, against the CPU checker chained in the same order"""
+@pytest.mark.parametrize("mb_w,mb_h,P,p_intra", [(7, 5, 1, 0.0), (20, 12, 2, 0.3)])
+def test_flush_422_pictures(gpu, checker, mb_w, mb_h, P, p_intra, bits):
+    """ff_h264_flush_pictures_cuda with chroma_format_idc 2 (8 and 10 bit), caller-filled deblocking records: MC -> weighted prediction -> DC transforms
+    (2 x 4 chroma) -> residual -> intra macroblocks (8 x 16 chroma predictors) -> 4:2:2 loop filter in one call, against the CPU checker chained
+    in the same order"""
     import ctypes as C
     from libav_b200 import device, tables
     from oracle.loader import ptr
@@ -295,18 +296,23 @@ def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
     rng = np.random.default_rng(bits * 100 + mb_w)
     refs = [hh.smooth_picture422(mb_w, mb_h, bits, seed=11), hh.smooth_picture422(mb_w, mb_h, bits, seed=12)]
     n1 = mb_w * mb_h
-    pics, mcs, ress, cos, nzs, dcs, wrecs, recs, exts, want, want_co = [], [], [], [], [], [], [], [], [], [], []
+    pics, mcs, ress, cos, nzs, dcs, wrecs, recs, exts, want, want_co, irecs = [], [], [], [], [], [], [], [], [], [], [], []
     for k in range(P):
         y, cb, cr = hh.smooth_picture422(mb_w, mb_h, bits, seed=50 + k)
         ls, uvls = y.strides[0], cb.strides[0]
         mc = synth.h264_mc_work(mb_w, mb_h, seed=mb_h + k, max_mv=24, avg_second=True)
         res, co, nz = hh.residual_work(mb_w, mb_h, bits, 1, y, cb, seed=mb_w + k)
         co = (co // 4).astype(cdt)                                             # small residual: the loop filter still has edges to change
+        irec, ico, inz = hh.intra_work(mb_w, mb_h, bits, seed=31 + k, p_intra=p_intra, c422=1)
+        intra = irec["kind"] != 0                                              # intra macroblocks: no MC / weight / inter residual, their own coefficients
+        res["luma_mode"][intra] = 3; res["chroma"][intra] = 0
+        co[intra] = ico[intra]; nz[intra] = inz[intra]
+        mc = mc[~intra[(mc["y"] // 16) * mb_w + mc["x"] // 16]]
         dc = np.zeros(n1, np.dtype([("luma_qmul", "<u4"), ("chroma_qmul", "<u4", (2,))]))
         dc["chroma_qmul"] = np.where(rng.random((n1, 2)) < 0.5, rng.integers(16, 200, (n1, 2)), 0)
         wr = []
         for m in range(n1):
-            if rng.random() < 0.4:
+            if rng.random() < 0.4 and not intra[m]:
                 wr.append(((m // mb_w) * 16 * ls + (m % mb_w) * 16 * sb, 16, 16, int(rng.integers(0, 7)), 0, int(rng.integers(-20, 90)), 0, int(rng.integers(-20, 20)), 0))
         wr = np.array(wr, dtype=synth.WEIGHT_DT)
         rec, ext = hh.deblock422_work(mb_w, mb_h, seed=3 + k, slices=2)
@@ -326,13 +332,14 @@ def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
                     else:
                         checker.h264_hbd_dc_dequant(bits, 2, hh.at(wco, o_), None, int(dc["chroma_qmul"][m, p]))
         hh.oracle_residual(checker, bits, 1, res, wco, nz, wy, wcb, wcr)
+        hh.oracle_intra(checker, bits, irec, wco, nz, mb_w, mb_h, wy, wcb, wcr, c422=1)
         pre = wy.copy()
         hh.oracle_deblock422(checker, bits, rec, ext, mb_w, mb_h, wy, wcb, wcr)
         assert not np.array_equal(pre, wy)
         m2 = mc.copy(); m2["y"] += 16 * mb_h * k
         r2 = res.copy(); r2["luma_off"] += 16 * mb_h * k * ls; r2["chroma_off"] += 16 * mb_h * k * uvls
         w2 = wr.copy(); w2["off"] += 16 * mb_h * k * ls
-        pics.append((y, cb, cr)); mcs.append(m2); ress.append(r2); cos.append(co); nzs.append(nz); dcs.append(dc); wrecs.append(w2)
+        pics.append((y, cb, cr)); mcs.append(m2); ress.append(r2); cos.append(co); nzs.append(nz); dcs.append(dc); wrecs.append(w2); irecs.append(irec)
         recs.append(rec); exts.append(ext); want.append((wy, wcb, wcr)); want_co.append(wco)
     Y, CB, CR = (np.concatenate([p[i] for p in pics]) for i in range(3))
     mc = np.concatenate(mcs)
@@ -343,7 +350,7 @@ def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
     n = n1 * P
     d = dict(y=_dev(Y), cb=_dev(CB), cr=_dev(CR), mc=_dev(mc), res=_dev(np.concatenate(ress)), w=_dev(wrec), co=_dev(np.concatenate(cos)),
              nz=_dev(np.concatenate(nzs)), dc=_dev(np.concatenate(dcs)), ldc=_dev(np.zeros((n, 16), cdt)), rec=_dev(np.concatenate(recs)),
-             ext=_dev(np.concatenate(exts)))
+             ext=_dev(np.concatenate(exts)), intra=_dev(np.concatenate(irecs)))
     work = tables.FFH264PictureWork()
     work.mb_w, work.mb_h, work.n_pictures = mb_w, mb_h, P
     work.luma, work.cb, work.cr, work.linesize, work.uvlinesize = d["y"].ptr, d["cb"].ptr, d["cr"].ptr, Y.strides[0], CB.strides[0]
@@ -351,6 +358,8 @@ def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
     work.weight[0], work.n_weight[0] = d["w"].ptr, wrec.shape[0]
     work.coeffs, work.coeff_stride, work.nnzc = d["co"].ptr, 768, d["nz"].ptr
     work.dc, work.luma_dc, work.residual = d["dc"].ptr, d["ldc"].ptr, d["res"].ptr
+    if p_intra:
+        work.intra = d["intra"].ptr
     work.deblock_records, work.deblock_chroma422 = d["rec"].ptr, d["ext"].ptr
     work.bit_depth, work.chroma_format_idc = bits, 2
     gpu.check(gpu.lib.ff_h264_flush_pictures_cuda(C.byref(work), None))
@@ -360,3 +369,30 @@ def test_flush_422_inter_pictures(gpu, checker, mb_w, mb_h, P, bits):
     assert np.array_equal(gy, wy), np.argwhere(gy != wy)[:5].tolist()
     assert np.array_equal(gcb, np.concatenate([w[1] for w in want])) and np.array_equal(gcr, np.concatenate([w[2] for w in want]))
     assert np.array_equal(d["co"].download(cdt, (n, 768)), np.concatenate(want_co))
+
+
+@pytest.mark.parametrize("bits", [8, 9, 10])
+@pytest.mark.parametrize("mb_w,mb_h,P,p_intra", [(3, 2, 1, 1.0), (7, 5, 2, 1.0), (20, 12, 2, 0.6), (40, 30, 3, 1.0)])
+def test_intra_batch_422(gpu, checker, mb_w, mb_h, P, p_intra, bits):
+    """ff_h264_intra_mb_batch_422_cuda: 8 x 16 chroma predictors + h264_idct_add8_422, 8-bit (uint8 / int16) and 9 / 10-bit (uint16 / int32) pictures, stacked"""
+    from libav_b200 import device
+    ys, cbs, crs, recs, cos, nzs, want = [], [], [], [], [], [], []
+    for k in range(P):
+        y, cb, cr = hh.picture(mb_w, mb_h, bits, 1, seed=50 + k)
+        rec, coeffs, nnzc = hh.intra_work(mb_w, mb_h, bits, seed=mb_w + k, p_intra=p_intra, c422=1)
+        wy, wcb, wcr, wco = y.copy(), cb.copy(), cr.copy(), coeffs.copy()
+        hh.oracle_intra(checker, bits, rec, wco, nnzc, mb_w, mb_h, wy, wcb, wcr, c422=1)
+        assert not np.array_equal(wy, y) and not np.array_equal(wcb, cb)
+        ys.append(y); cbs.append(cb); crs.append(cr); recs.append(rec); cos.append(coeffs); nzs.append(nnzc); want.append((wy, wcb, wcr, wco))
+    Y, CB, CR = np.concatenate(ys), np.concatenate(cbs), np.concatenate(crs)
+    R, CO, NZ = np.concatenate(recs), np.concatenate(cos), np.concatenate(nzs)
+    d_rec, d_co, d_nz, dy, dcb, dcr = _dev(R), _dev(CO), _dev(NZ), _dev(Y), _dev(CB), _dev(CR)
+    gpu.check(gpu.lib.ff_h264_intra_mb_batch_422_cuda(bits, d_rec.ptr, mb_w, mb_h, P, d_co.ptr, 768, d_nz.ptr, dy.ptr, dcb.ptr, dcr.ptr, Y.strides[0], CB.strides[0], None))
+    device.sync()
+    gy, gcb, gcr, gco = dy.download(Y.dtype, Y.shape), dcb.download(Y.dtype, CB.shape), dcr.download(Y.dtype, CR.shape), d_co.download(CO.dtype, CO.shape)
+    n, H = mb_w * mb_h, 16 * mb_h
+    for k in range(P):
+        assert np.array_equal(gy[H * k:H * (k + 1)], want[k][0]), (k, np.argwhere(gy[H * k:H * (k + 1)] != want[k][0])[:4].tolist())
+        assert np.array_equal(gcb[H * k:H * (k + 1)], want[k][1]), (k, np.argwhere(gcb[H * k:H * (k + 1)] != want[k][1])[:4].tolist())
+        assert np.array_equal(gcr[H * k:H * (k + 1)], want[k][2]), k
+        assert np.array_equal(gco[n * k:n * (k + 1)], want[k][3]), k

@@ -243,6 +243,8 @@ static __thread int g_dhs = 1, g_dvs = 1, g_dbits = 8, g_dbe = 0;
 static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; } else { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); } }
 #define IS_RGB16(f) (((f) >= 36 && (f) <= 43) || ((f) >= 54 && (f) <= 57))     /* rgb565 / 555 / bgr565 / 555 (36-43), rgb444 / bgr444 (54-57), LE and BE */
 static __thread int g_rgb16;        /* 15 / 16 / 12-bpp destination of the "rgb" entry point: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (output.c:869-902) */
+#define IS_RGB48(f) ((f) == 34 || (f) == 35 || (f) == 59 || (f) == 60)             /* rgb48be 34, rgb48le 35, bgr48be 59, bgr48le 60 */
+static __thread int g_rgb48;        /* 48-bit destination of the "rgb" entry point: 1 rgb48 2 bgr48, + 8 big-endian (yuv2rgb48_X / _2 / _1, output.c:584-760) */
 static __thread int g_pk422;        /* packed 4:2:2 destination of the "rgb" entry point: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576) */
 static __thread int g_nospecial;    /* an nv12 / nv21 destination computed through the planar path: no yuv420p-only special converters */
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
@@ -431,6 +433,65 @@ static void range_lines(int16_t *p, int pitch, int rows, int w, int chroma)
         for (int x = 0; x < w; x++) p[(size_t)y * pitch + x] = range_sample(p[(size_t)y * pitch + x], g_range, chroma);
 }
 
+/* 48-bit rgb destinations behind swscale(): dstBpc 16, so the lines are hScale8To19_c's (swscale.c:728-741; no fast-bilinear line functions at
+ * that depth) and the packed output stage is yuv2rgb48_X / _2 / _1_c_template (output.c:593-760) with swscale()'s X / 2 / 1 selection
+ * (swscale.c:658-683).  int arithmetic wraps like the compiled C does (the X accumulators start at -2^30 for that reason). */
+static uint32_t clip30(uint32_t a) { return (a & 0xC0000000u) ? ((a >> 31) ? 0 : 0x3FFFFFFFu) : a; }
+static void put48(uint8_t *d, int k, uint32_t v30)
+{
+    const unsigned v = clip30(v30) >> 14;
+    if (g_rgb48 & 8) { d[2 * k] = (uint8_t)(v >> 8); d[2 * k + 1] = (uint8_t)v; } else { d[2 * k] = (uint8_t)v; d[2 * k + 1] = (uint8_t)(v >> 8); }
+}
+static int rgb48_scaled(sws_t *c, const uint8_t *const src[3], const int ss[3], int sh, uint8_t *dst, int dstride, int dw, int dh)
+{
+    int lp, cp;
+    int32_t *L = hpass19(src[0], ss[0], sh, &c->hl, &lp), *U = hpass19(src[1], ss[1], c->chrSrcH, &c->hc, &cp), *V = hpass19(src[2], ss[2], c->chrSrcH, &c->hc, &cp);
+    int64_t kcy, koy, kcrv, kcbu, kcgu, kcgv; int kyoffs;
+    cs_coeffs(&kcy, &koy, &kcrv, &kcbu, &kcgu, &kcgv, &kyoffs);
+#define R16(f) ((int16_t)({ int r_ = (int)(((int64_t)(f) + (1 << 15)) >> 16); r_ < -0x7FFF ? -0x8000 : r_ > 0x7FFF ? 0x7FFF : r_; }))
+    const int y_coeff = R16(kcy << 13), y_offset = R16(koy << 9), v2r = R16(kcrv << 13), v2g = R16(kcgv << 13), u2g = R16(kcgu << 13), u2b = R16(kcbu << 13);
+#undef R16
+    const int fl = c->vl.taps, fc = c->vc.taps, bgr = (g_rgb48 & 7) == 2;
+    for (int y = 0; y < dh; y++) {
+        const int firstL = c->vl.pos[y] > 1 - fl ? c->vl.pos[y] : 1 - fl, firstC = c->vc.pos[y] > 1 - fc ? c->vc.pos[y] : 1 - fc;
+        const int16_t *lf = c->vl.coef + (size_t)y * fl, *cf = c->vc.coef + (size_t)y * fc;
+        uint8_t *d = dst + (size_t)y * dstride;
+        for (int i = 0; i < (dw + 1) >> 1; i++) {
+#define L19(j, x) L[(size_t)rowsel(firstL, j, sh) * lp + (x)]
+#define U19(j) U[(size_t)rowsel(firstC, j, c->chrSrcH) * cp + i]
+#define V19(j) V[(size_t)rowsel(firstC, j, c->chrSrcH) * cp + i]
+            int32_t Y1, Y2, Uv, Vv;
+            if (fl == 1 && fc <= 2) {
+                const int ua = fc == 1 ? 0 : cf[1];
+                Y1 = L19(0, 2 * i) >> 2; Y2 = L19(0, 2 * i + 1) >> 2;
+                if (ua < 2048) { Uv = (U19(0) + (-128 * (1 << 11))) >> 2; Vv = (V19(0) + (-128 * (1 << 11))) >> 2; }
+                else { Uv = (U19(0) + U19(1) + (-128 * (1 << 12))) >> 3; Vv = (V19(0) + V19(1) + (-128 * (1 << 12))) >> 3; }
+            } else if (fl == 2 && fc == 2) {
+                const int ya = lf[1], ua = cf[1];
+                Y1 = (int32_t)((uint32_t)L19(0, 2 * i) * (uint32_t)(4096 - ya) + (uint32_t)L19(1, 2 * i) * (uint32_t)ya) >> 14;
+                Y2 = (int32_t)((uint32_t)L19(0, 2 * i + 1) * (uint32_t)(4096 - ya) + (uint32_t)L19(1, 2 * i + 1) * (uint32_t)ya) >> 14;
+                Uv = (int32_t)((uint32_t)U19(0) * (uint32_t)(4096 - ua) + (uint32_t)U19(1) * (uint32_t)ua + (uint32_t)(-128 * (1 << 23))) >> 14;
+                Vv = (int32_t)((uint32_t)V19(0) * (uint32_t)(4096 - ua) + (uint32_t)V19(1) * (uint32_t)ua + (uint32_t)(-128 * (1 << 23))) >> 14;
+            } else {
+                uint32_t a1 = (uint32_t)-0x40000000, a2 = a1, au = (uint32_t)(-128 * (1 << 23)), av = au;
+                for (int j = 0; j < fl; j++) { a1 += (uint32_t)L19(j, 2 * i) * (uint32_t)(int32_t)lf[j]; a2 += (uint32_t)L19(j, 2 * i + 1) * (uint32_t)(int32_t)lf[j]; }
+                for (int j = 0; j < fc; j++) { au += (uint32_t)U19(j) * (uint32_t)(int32_t)cf[j]; av += (uint32_t)V19(j) * (uint32_t)(int32_t)cf[j]; }
+                Y1 = ((int32_t)a1 >> 14) + 0x10000; Y2 = ((int32_t)a2 >> 14) + 0x10000; Uv = (int32_t)au >> 14; Vv = (int32_t)av >> 14;
+            }
+            const uint32_t y1 = (uint32_t)(Y1 - y_offset) * (uint32_t)y_coeff + (1u << 13), y2 = (uint32_t)(Y2 - y_offset) * (uint32_t)y_coeff + (1u << 13);
+            const uint32_t R = (uint32_t)Vv * (uint32_t)v2r, G = (uint32_t)Vv * (uint32_t)v2g + (uint32_t)Uv * (uint32_t)u2g, B = (uint32_t)Uv * (uint32_t)u2b;
+            uint8_t *q = d + 12 * i;
+            put48(q, 0, (bgr ? B : R) + y1); put48(q, 1, G + y1); put48(q, 2, (bgr ? R : B) + y1);
+            if (2 * i + 1 < dw || dstride >= 6 * (dw + 1)) { put48(q, 3, (bgr ? B : R) + y2); put48(q, 4, G + y2); put48(q, 5, (bgr ? R : B) + y2); }
+#undef L19
+#undef U19
+#undef V19
+        }
+    }
+    free(L); free(U); free(V);
+    return dh;
+}
+
 int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int sw, int sh, uint8_t *dst, int dstride,
                              int dw, int dh, int flags)
 {
@@ -441,6 +502,11 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     if (g_rgb16 && sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter() && g_sbits == 8) {
         sws_close(&c);          /* the ordered-dither table converters yuv2rgb_c_16 / _15 / _12_ordered_dither (yuv2rgb.c:377-573): not restated */
         return -1;
+    }
+    if (g_rgb48 && !(sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !uses_filter() && g_sbits == 8)) {
+        int r48 = g_sbits == 8 ? rgb48_scaled(&c, src, ss, sh, dst, dstride, dw, dh) : -1;
+        sws_close(&c);
+        return r48;
     }
     if (sw == dw && sh == dh && !(flags & F_ACCURATE_RND) && !(dh & 1) && g_hs == 1 && g_vs <= 1 && !g_pk422 && !uses_filter() && g_sbits == 8) {
         /* (4:2:0 and 4:2:2 sources only, swscale_unscaled.c:1051; a 4:2:2 source has its chroma pitch doubled, yuv2rgb.c:133-136,
@@ -454,6 +520,14 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
                 const uint8_t *r = ytab + rv[Vv], *g = ytab + gu[Uv] + gv[Vv], *b = ytab + bu[Uv];
                 const uint8_t *py = src[0] + (size_t)y * ss[0] + 2 * i;
                 uint8_t *d = dst + (size_t)y * dstride + 6 * i;
+                if (g_rgb48) {      /* yuv2rgb_c_48 / yuv2rgb_c_bgr48 (yuv2rgb.c:106-124,177-236): the 8-bit table value in both bytes of a component */
+                    const uint8_t *t0 = (g_rgb48 & 7) == 2 ? b : r, *t2 = (g_rgb48 & 7) == 2 ? r : b;
+                    d += 6 * i;
+                    for (int e = 0; e < 2; e++) {
+                        d[6 * e + 0] = d[6 * e + 1] = t0[py[e]]; d[6 * e + 2] = d[6 * e + 3] = g[py[e]]; d[6 * e + 4] = d[6 * e + 5] = t2[py[e]];
+                    }
+                    continue;
+                }
                 d[0] = r[py[0]]; d[1] = g[py[0]]; d[2] = b[py[0]]; d[3] = r[py[1]]; d[4] = g[py[1]]; d[5] = b[py[1]];
             }
         sws_close(&c);
@@ -712,6 +786,13 @@ static int to_rgb_or_bgr(const uint8_t *const src[3], const int ss[3], int sw, i
             g_rgb16 = 0;
             return r16;
         }
+    }
+    if (IS_RGB48(dst_fmt)) {
+        if (uses_filter()) return -1;
+        g_rgb48 = (dst_fmt == 34 || dst_fmt == 35 ? 1 : 2) | (dst_fmt == 34 || dst_fmt == 59 ? 8 : 0);
+        int r48 = orc_sws_yuv420p_to_rgb24(src, ss, sw, sh, dst, dstride, dw, dh, flags & ~F_FULL_CHR_H_INT);
+        g_rgb48 = 0;
+        return r48;
     }
     if (dst_fmt == 1 || dst_fmt == 15) {          /* yuyv422 / uyvy422: the packed output stage without the colour conversion */
         g_pk422 = dst_fmt == 1 ? 1 : 2;
@@ -990,6 +1071,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         }
         if (base >= 0 && g_sbits == 8) {
             int h2, v2, b2 = 8;
+            if (IS_RGB48(dst_fmt)) return -1;          /* (hScale16To19_c lines: not restated) */
             const int rgbd = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || IS_RGB16(dst_fmt), pkd = dst_fmt == 1 || dst_fmt == 15, nvd = g_nospecial;
             const int shs = base == 5 ? 0 : 1, svs = base == 0 ? 1 : 0;
             if (uses_filter()) return -1;
@@ -1011,7 +1093,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     if (src_j || dst_j) {
         const int sf = src_fmt == 12 ? 0 : src_fmt == 13 ? 4 : src_fmt == 14 ? 5 : src_fmt == 32 ? 31 : src_fmt;
         const int df = dst_fmt == 12 ? 0 : dst_fmt == 13 ? 4 : dst_fmt == 14 ? 5 : dst_fmt == 32 ? 31 : dst_fmt;
-        const int dst_rgb = df == 2 || df == 3 || (df >= 25 && df <= 28) || IS_RGB16(df);
+        const int dst_rgb = df == 2 || df == 3 || (df >= 25 && df <= 28) || IS_RGB16(df) || IS_RGB48(df);
         if (dst_rgb) {
             g_cs_jpeg = 1;
             r = sws_any(sf, src, ss, sw, sh, df, dst, dstride, dw, dh, flags);
@@ -1027,7 +1109,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         g_range = 0;
         return r;
     }
-    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk || IS_RGB16(dst_fmt);
+    const int rgb = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28) || pk || IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt);
     for (int wv = 1; wv < 4; wv += 2)                      /* asymmetric vertical vectors (lumV, chrV): the reference's last rows depend on its ring buffer state */
         for (int i = 0; i < g_fv[wv][0].length / 2; i++)
             if (g_fv[wv][0].coeff[i] != g_fv[wv][0].coeff[g_fv[wv][0].length - 1 - i]) return -1;
@@ -1059,8 +1141,9 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
             return sh;
         }
     }
-    if (pk || IS_RGB16(dst_fmt)) flags &= ~F_FULL_CHR_H_INT;
-    if (IS_RGB16(dst_fmt) && uses_filter()) return -1;
+    if (pk || IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) flags &= ~F_FULL_CHR_H_INT;
+    if ((IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) && uses_filter()) return -1;
+    if (IS_RGB48(dst_fmt) && (src_fmt == 23 || src_fmt == 24)) return -1;      /* (48-bit destinations: planar 8-bit yuv sources only) */
     if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT)) return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
@@ -1071,7 +1154,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
     case 1: case 2: case 3: case 15: case 25: case 26: case 27: case 28:
-        if (IS_RGB16(dst_fmt)) return -1;              /* (rgb2rgb converter families and readers in front of the 16-bpp output stage: not restated) */
+        if (IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) return -1;   /* (rgb2rgb converter families and readers in front of the 16 / 48-bpp output stage: not restated) */
         r = packed_source(src_fmt, src[0], ss[0], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;

@@ -463,8 +463,9 @@ int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float 
  * reference's range conversion, planar 8 / 9 / 10-bit only; 9 / 10 / 16-bit 420p = 62 / 64 / 47, 422p = 72 / 66 / 49, 444p = 68 / 70 / 51 little-endian and their big-endian twins), any size, SWS_FULL_CHR_H_INT or not, every scaler
  * algorithm of initFilter (libswscale/utils.c:249-632), results identical to the reference's C path under
  * SWS_ACCURATE_RND | SWS_BITEXACT.  srcFilter / dstFilter: pointers to the reference's SwsFilter (four pointers to { double *coeff; int length; }),
- * taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations, vertical vectors symmetric.  Anything else returns NULL
- * with an error (no fallback).
+ * taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations, vertical vectors symmetric.  48-bit destinations
+ * rgb48be = 34 / rgb48le = 35 / bgr48be = 59 / bgr48le = 60 (yuv2rgb48_X / _2 / _1 on hScale8To19_c lines, libswscale/output.c:593-760; same size without
+ * SWS_ACCURATE_RND: yuv2rgb_c_48, yuv2rgb.c:106-236) from planar 8-bit yuv / yuvj sources.  Anything else returns NULL with an error (no fallback).
  *   sws_scale_cuda         HOST pointers; whole frames (srcSliceY = 0, srcSliceH = srcH) with strides of either sign (bottom-up pictures), or
  *                          slices like sws_scale() takes them (swscale_unscaled.c:1212-1340): srcSlice[] at source row srcSliceY, dst[] at the
  *                          top of the picture, top-down and contiguous, boundaries on whole chroma rows, positive strides; each call returns

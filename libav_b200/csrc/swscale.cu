@@ -41,6 +41,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
     int pk422;                        // packed 4:2:2 destination: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576)
     int rgb16;                        // 15 / 16 / 12-bpp destination: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (yuv2rgb_write, output.c:869-902)
+    int rgb48;                        // 48-bit destination: 1 rgb48 2 bgr48, + 8 big-endian (yuv2rgb48_X / _2 / _1_c_template, output.c:584-760; yuv2rgb_c_48, yuv2rgb.c:106-236)
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
     int srcBits, srcBE;               // 9 / 10 / 16-bit planar sources: 16-bit words (byte-swapped when big-endian), hScale16To15_c; else 8
@@ -281,15 +282,80 @@ sws_unscaled_yuv2rgb24_kernel(SwsDev p, FusedArgs a)
 #pragma unroll
     for (int ry = 0; ry < 2; ry++) {
         const uint8_t *yp = a.y + f * a.yFrame + (size_t)(2 * cyy + ry) * a.yStride + 2 * cx;
-        uint8_t *d = a.dst + f * a.dstFrame + (size_t)(2 * cyy + ry) * a.dstStride + 6 * cx;
+        uint8_t *d = a.dst + f * a.dstFrame + (size_t)(2 * cyy + ry) * a.dstStride + (p.rgb48 ? 12 : 6) * cx;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int Y = yp[e];
-            d[3 * e + 0] = (uint8_t)clip_u8((p.k.cy * Y + tr) >> 16);
-            d[3 * e + 1] = (uint8_t)clip_u8((p.k.cy * Y + t.tg) >> 16);
-            d[3 * e + 2] = (uint8_t)clip_u8((p.k.cy * Y + tb) >> 16);
+            const uint8_t c0 = (uint8_t)clip_u8((p.k.cy * Y + tr) >> 16), c1 = (uint8_t)clip_u8((p.k.cy * Y + t.tg) >> 16), c2 = (uint8_t)clip_u8((p.k.cy * Y + tb) >> 16);
+            if (p.rgb48) {              // yuv2rgb_c_48 / _bgr48 (yuv2rgb.c:106-124): the 8-bit table value in both bytes of a component, whatever the endianness
+                d[6 * e + 0] = d[6 * e + 1] = c0; d[6 * e + 2] = d[6 * e + 3] = c1; d[6 * e + 4] = d[6 * e + 5] = c2;
+            } else { d[3 * e + 0] = c0; d[3 * e + 1] = c1; d[3 * e + 2] = c2; }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 48-bit rgb destinations behind swscale() (dstBpc 16): the lines are hScale8To19_c's (swscale.c:62-80,728-741 -- no fast-bilinear line
+// functions at that depth) and the output stage is yuv2rgb48_X / _2 / _1_c_template (output.c:593-760) under swscale()'s X / 2 / 1 selection
+// (swscale.c:658-683).  One thread = one pixel pair of one output row; it recomputes the horizontal filter for every vertical tap straight
+// from the source planes (no line planes: 19-bit lines would be 4 B per sample), all in the wrapping int arithmetic of the C code.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int h19(const uint8_t *__restrict__ row, const int16_t *__restrict__ f, int pos, int fs)
+{
+    int v = 0;
+    for (int k = 0; k < fs; k++) v += row[pos + k] * f[k];
+    return min(v >> 3, (1 << 19) - 1);
+}
+__device__ __forceinline__ uint32_t clip30(uint32_t a) { return (a & 0xC0000000u) ? ((a >> 31) ? 0u : 0x3FFFFFFFu) : a; }      // av_clip_uintp2(a, 30)
+__device__ __forceinline__ void put48(uint8_t *d, int k, uint32_t v30, int be)
+{
+    const unsigned v = clip30(v30) >> 14;
+    d[2 * k + (be ? 1 : 0)] = (uint8_t)v; d[2 * k + (be ? 0 : 1)] = (uint8_t)(v >> 8);
+}
+
+__global__ void __launch_bounds__(128)
+sws_rgb48_kernel(SwsDev p, FusedArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= ((p.dstW + 1) >> 1) || y >= p.dstH) return;
+    const size_t f = blockIdx.z;
+    const uint8_t *Yp = a.y + f * a.yFrame, *Up = a.u + f * a.uFrame, *Vp = a.v + f * a.vFrame;
+    const int fl = p.vLumSize, fc = p.vChrSize;
+    const int firstL = max(1 - fl, p.vLumP[y]), firstC = max(1 - fc, p.vChrP[y]);
+    const int x0 = 2 * i, x1 = 2 * i + 1;
+    const bool has2 = x1 < p.dstW;            // odd width: the pair's second pixel reads the zeroed tail of the line
+    const int16_t *hf0 = p.hLumF + (size_t)x0 * p.hLumSize, *hf1 = p.hLumF + (size_t)(has2 ? x1 : x0) * p.hLumSize, *hfc = p.hChrF + (size_t)i * p.hChrSize;
+    const int p0 = p.hLumP[x0], p1 = p.hLumP[has2 ? x1 : x0], pc = p.hChrP[i];
+    auto L0 = [&](int j) -> uint32_t { return (uint32_t)h19(Yp + (size_t)clampi(firstL + j, 0, p.srcH - 1) * a.yStride, hf0, p0, p.hLumSize); };
+    auto L1 = [&](int j) -> uint32_t { return has2 ? (uint32_t)h19(Yp + (size_t)clampi(firstL + j, 0, p.srcH - 1) * a.yStride, hf1, p1, p.hLumSize) : 0u; };
+    auto CU = [&](int j) -> uint32_t { return (uint32_t)h19(Up + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.uStride, hfc, pc, p.hChrSize); };
+    auto CV = [&](int j) -> uint32_t { return (uint32_t)h19(Vp + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.vStride, hfc, pc, p.hChrSize); };
+    int Y1, Y2, U, V;
+    if (fl == 1 && fc <= 2) {                                  // yuv2rgb48_1_c_template, output.c:694-760
+        const int uvalpha = fc == 1 ? 0 : p.vChrF[2 * y + 1];
+        Y1 = (int)L0(0) >> 2; Y2 = (int)L1(0) >> 2;
+        if (uvalpha < 2048) { U = ((int)CU(0) - (128 << 11)) >> 2; V = ((int)CV(0) - (128 << 11)) >> 2; }
+        else                { U = ((int)(CU(0) + CU(1)) - (128 << 12)) >> 3; V = ((int)(CV(0) + CV(1)) - (128 << 12)) >> 3; }
+    } else if (fl == 2 && fc == 2) {                           // yuv2rgb48_2_c_template, output.c:652-692
+        const uint32_t ya = (uint32_t)(int)p.vLumF[2 * y + 1], ua = (uint32_t)(int)p.vChrF[2 * y + 1], ya1 = 4096u - ya, ua1 = 4096u - ua, bias = (uint32_t)(-128 * (1 << 23));
+        Y1 = (int)(L0(0) * ya1 + L0(1) * ya) >> 14;
+        Y2 = (int)(L1(0) * ya1 + L1(1) * ya) >> 14;
+        U = (int)(CU(0) * ua1 + CU(1) * ua + bias) >> 14;
+        V = (int)(CV(0) * ua1 + CV(1) * ua + bias) >> 14;
+    } else {                                                   // yuv2rgb48_X_c_template, output.c:593-650
+        const int16_t *lf = p.vLumF + (size_t)y * fl, *cf = p.vChrF + (size_t)y * fc;
+        uint32_t a1 = (uint32_t)-0x40000000, a2 = a1, au = (uint32_t)(-128 * (1 << 23)), av = au;
+        for (int j = 0; j < fl; j++) { a1 += L0(j) * (uint32_t)(int)lf[j]; a2 += L1(j) * (uint32_t)(int)lf[j]; }
+        for (int j = 0; j < fc; j++) { au += CU(j) * (uint32_t)(int)cf[j]; av += CV(j) * (uint32_t)(int)cf[j]; }
+        Y1 = ((int)a1 >> 14) + 0x10000; Y2 = ((int)a2 >> 14) + 0x10000; U = (int)au >> 14; V = (int)av >> 14;
+    }
+    const RgbConstants &k = p.k;
+    const uint32_t y1 = (uint32_t)(Y1 - k.fy_offset) * (uint32_t)k.fy_coeff + (1u << 13), y2 = (uint32_t)(Y2 - k.fy_offset) * (uint32_t)k.fy_coeff + (1u << 13);
+    const uint32_t R = (uint32_t)V * (uint32_t)k.fv2r, G = (uint32_t)V * (uint32_t)k.fv2g + (uint32_t)U * (uint32_t)k.fu2g, B = (uint32_t)U * (uint32_t)k.fu2b;
+    const int bgr = (p.rgb48 & 7) == 2, be = p.rgb48 & 8;
+    uint8_t *d = a.dst + f * a.dstFrame + (size_t)y * a.dstStride + (size_t)i * 12;
+    put48(d, 0, (bgr ? B : R) + y1, be); put48(d, 1, G + y1, be); put48(d, 2, (bgr ? R : B) + y1, be);
+    if (has2 || a.dstStride >= 6 * (p.dstW + 1)) { put48(d, 3, (bgr ? B : R) + y2, be); put48(d, 4, G + y2, be); put48(d, 5, (bgr ? R : B) + y2, be); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1152,6 +1218,7 @@ struct SwsCudaContext {
     int rangeConv = 0;          // yuv destination of the other range: 1 lum / chrRangeFromJpeg_c, 2 lum / chrRangeToJpeg_c on the hscaled lines (two-pass path)
     int pk422 = 0;              // yuyv422 (1) / uyvy422 (2) destination
     int rgb16 = 0;              // rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 destination (SwsDev::rgb16)
+    int rgb48 = 0;              // rgb48 / bgr48 destination, LE or BE (SwsDev::rgb48)
     bool gray = false;          // gray8 destination: the luma plane of the planar conversion (swscale.c:618-630 skips the chroma of a gray destination, the
                                 // unscaled copy takes plane 0 only, swscale_unscaled.c:1155); the chroma planes go to scratch nobody reads
     uint8_t *d_gray[2] = { nullptr, nullptr }; int grayPitch = 0;
@@ -1207,9 +1274,9 @@ static int upload_tables(SwsCudaContext *c)
     d.vLumF = (const int16_t *)(base + off[4]); d.vLumP = (const int32_t *)(base + off[5]);
     d.vChrF = (const int16_t *)(base + off[6]); d.vChrP = (const int32_t *)(base + off[7]);
     d.k = c->k;
-    d.bgr = c->dstFormat == FMT_BGR24;
+    d.bgr = c->dstFormat == FMT_BGR24 || (c->rgb48 & 7) == 2;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422; d.rgb16 = c->rgb16;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422; d.rgb16 = c->rgb16; d.rgb48 = c->rgb48;
     d.srcBits = c->srcBits; d.srcBE = c->srcBE; d.dither = c->srcBits > 8;
     return 0;
 }
@@ -1272,9 +1339,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     case 39: rgb16 = 3; break; case 38: rgb16 = 3 | 8; break; case 43: rgb16 = 4; break; case 42: rgb16 = 4 | 8; break;
     case 54: rgb16 = 5; break; case 55: rgb16 = 5 | 8; break; case 56: rgb16 = 6; break; case 57: rgb16 = 6 | 8; break;
     }
-    if (pk422 || rgb16) flags &= ~SWS_FULL_CHR_H_INT;        // only 24 / 32-bit packed RGB knows the flag (utils.c:998-1014)
-    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422 && !rgb16) {
-        set_error_msg("sws_getContext_cuda", "destinations taken over: gray8, rgb24, bgr24, argb, rgba, abgr, bgra, rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 (LE and BE), yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
+    const int rgb48 = dstFormat == 35 ? 1 : dstFormat == 34 ? 1 | 8 : dstFormat == 60 ? 2 : dstFormat == 59 ? 2 | 8 : 0;      // RGB48BE 34 LE 35, BGR48BE 59 LE 60
+    if (pk422 || rgb16 || rgb48) flags &= ~SWS_FULL_CHR_H_INT;        // only 24 / 32-bit packed RGB knows the flag (utils.c:998-1014)
+    if (!planar && dstFormat != FMT_RGB24 && dstFormat != FMT_BGR24 && !dst32 && !pk422 && !rgb16 && !rgb48) {
+        set_error_msg("sws_getContext_cuda", "destinations taken over: gray8, rgb24, bgr24, argb, rgba, abgr, bgra, rgb48 / bgr48 (LE and BE), rgb565 / bgr565 / rgb555 / bgr555 / rgb444 / bgr444 (LE and BE), yuyv422, uyvy422, nv12, nv21, planar yuv 420p 422p 444p 410p 411p 440p, 9 / 10 / 16-bit 420p 422p 444p (LE and BE)");
         return nullptr;
     }
     if (flags & 0x30000) {                                    // SWS_SRC_V_CHR_DROP_MASK (utils.c:1016-1019, swscale.c:383-384)
@@ -1334,6 +1402,14 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         else if (usesFilter) why = "SwsFilter vectors with a 15 / 16 / 12-bpp destination are not taken over";
         if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
     }
+    if (rgb48) {
+        // 48-bit destinations: the packed output stage on hScale8To19_c lines, and the unscaled table converter; planar 8-bit yuv sources
+        const char *why = nullptr;
+        if (srcRgb || src32 || srcYuy || srcFormat == FMT_NV12 || srcFormat == FMT_NV21) why = "48-bit rgb destinations are taken over for planar 8-bit yuv sources only";
+        else if (srcBits > 8) why = "9 / 10 / 16-bit source to a 48-bit rgb destination (hScale16To19_c lines) is not taken over";
+        else if (usesFilter) why = "SwsFilter vectors with a 48-bit rgb destination are not taken over";
+        if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
+    }
     {   // a shifted / asymmetric vertical vector makes the reference's last output rows depend on stale lines of its ring buffer (measured:
         // port and product, which clamp to the last line, differ from it there and nowhere else): no defined result to match
         auto asym = [](const SwsVec *v) { if (!v) return false; for (int i = 0; i < v->length / 2; i++) if (v->coeff[i] != v->coeff[v->length - 1 - i]) return true; return false; };
@@ -1363,7 +1439,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->pk422 = pk422; c->rgb16 = rgb16; c->gray = gray; c->srcBits = srcBits; c->srcBE = srcBE;
+    c->pk422 = pk422; c->rgb16 = rgb16; c->rgb48 = rgb48; c->gray = gray; c->srcBits = srcBits; c->srcBE = srcBE;
     if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv && srcBits == 8) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
@@ -1404,7 +1480,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
     c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8;
-    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !rgb16 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !rgb16 && !rgb48 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -1488,7 +1564,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
             c->tma_ok = true;
         }
     }
-    if (!c->fused && !c->copy && !c->table_unscaled && !c->to422) {
+    if (!c->fused && !c->copy && !c->table_unscaled && !c->to422 && !rgb48) {          // (rgb48: sws_rgb48_kernel works from the source planes, no line planes)
         int lr = 0, cr = 0, lo, hi;
         std::vector<int2> win;
         for (int y0 = 0; y0 < dstH; y0 += GT_H) {
@@ -1743,6 +1819,14 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         sws_unscaled_yuv2rgb24_kernel<<<dim3(((p.dstW >> 1) + 255) / 256, p.dstH >> 1, nframes), 256, 0, st>>>(p, a);
         return check_launch("sws_scale:unscaled");
     }
+    if (c->rgb48) {
+        FusedArgs a;
+        a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst = dst[0];
+        a.yStride = srcStride[0]; a.uStride = srcStride[1]; a.vStride = srcStride[2]; a.dstStride = dstStride[0];
+        a.yFrame = srcFrame[0]; a.uFrame = srcFrame[1]; a.vFrame = srcFrame[2]; a.dstFrame = dstFrame[0];
+        sws_rgb48_kernel<<<dim3((((p.dstW + 1) >> 1) + 127) / 128, p.dstH, nframes), 128, 0, st>>>(p, a);
+        return check_launch("sws_scale:rgb48");
+    }
     if (c->fused) {
         FusedArgs a;
         a.y = src[0]; a.u = src[1]; a.v = src[2]; a.dst = dst[0];
@@ -1863,7 +1947,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
     if (!c) return false;
     v.rangeConv = c->rangeConv; v.srcBits = c->srcBits;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
-    if (c->rgb16 || c->gray) return false; // (the per-line slots do not cover the 15 / 16 / 12-bpp output stage: the hook leaves the C slots)
+    if (c->rgb16 || c->rgb48 || c->gray) return false; // (the per-line slots do not cover the 15 / 16 / 12 / 48-bpp output stages: the hook leaves the C slots)
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
 }
@@ -1938,7 +2022,7 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
 {
     const SwsGeometry &g = c->g;
     const bool pk = c->srcPacked != 0, nv = c->srcNV != 0, rgb = !c->planar;
-    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
     const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH }, dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
     const size_t sS = c->srcBits > 8 ? 2 : 1;
@@ -2041,7 +2125,7 @@ static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlic
     const int ret = rowMapped ? srcSliceH : dstY1 - dstY0;
     if (dstY1 <= dstY0) return ret;
     // the frame pipeline over the rows so far, into a copy of the caller's picture; the finished rows go back
-    const int sB = c->dstBits > 8 ? 2 : 1, pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
+    const int sB = c->dstBits > 8 ? 2 : 1, pxB = c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     const int dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
     const size_t dstWB[3] = { (size_t)g.dstW * (rgb ? pxB : sB), (size_t)g.chrDstW * (c->dstNV ? 2 : sB), (size_t)g.chrDstW * sB };
     std::vector<uint8_t> dbuf[3];
@@ -2121,7 +2205,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t needS = yB + (nv ? 1 : 2) * cB;
     const int odd = g.dstW & 1;
     const int sB = c->dstBits > 8 ? 2 : 1;                  // bytes per sample of a planar destination
-    const int pxB = (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;        // bytes per packed pixel
+    const int pxB = c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;        // bytes per packed pixel
     const int dP = rgb ? ((g.dstW + odd) * pxB + 15) & ~15 : (g.dstW * sB + 15) & ~15, dcP = (g.chrDstW * sB * (c->dstNV ? 2 : 1) + 15) & ~15;
     const size_t dB = (size_t)dP * g.dstH, dcB = rgb ? 0 : (size_t)dcP * g.chrDstH;
     const size_t needD = dB + 2 * dcB;
@@ -2255,7 +2339,7 @@ int sws_debug_plan_cuda(int srcW, int srcH, int srcFormat, int dstW, int dstH, i
     out[0] = c->to422 ? 6 : c->nvcopy ? 7 : c->special ? 5 : c->copy ? 1 : c->table_unscaled ? 2 : c->fused ? 3 : 4;
     out[1] = c->g.chrSrcW; out[2] = c->g.chrSrcH; out[3] = c->g.chrDstW; out[4] = c->g.chrDstH;
     out[5] = c->srcPacked ? 2 : c->srcNV ? 1 : 0;
-    out[6] = c->planar ? c->dstBits : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
+    out[6] = c->planar ? c->dstBits : c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     out[7] = c->srcRange;
     delete c;
     return 1;

@@ -139,7 +139,7 @@ class SwsContext:
             out = [np.full((self.dst_h, self.dst_w), fill, dt), np.full((ch, cw), fill, dt), np.full((ch, cw), fill, dt)]
         else:
             rgb16 = 36 <= self.dst_fmt <= 43 or 54 <= self.dst_fmt <= 57          # rgb565 / 555 / bgr565 / 555, rgb444 / bgr444 (LE and BE)
-            bpp = 4 if self.dst_fmt in RGB32_FORMATS else 2 if self.dst_fmt in (PIX_FMT_YUYV422, PIX_FMT_UYVY422) or rgb16 else 1 if self.dst_fmt == 8 else 3      # 8 = gray8
+            bpp = 6 if self.dst_fmt in (34, 35, 59, 60) else 4 if self.dst_fmt in RGB32_FORMATS else 2 if self.dst_fmt in (PIX_FMT_YUYV422, PIX_FMT_UYVY422) or rgb16 else 1 if self.dst_fmt == 8 else 3      # 8 = gray8
             out = [np.full((self.dst_h, self.dst_w * bpp + dst_pad), fill, np.uint8)]
         dst = (C.c_void_p * 4)(*([a.ctypes.data for a in out] + [None] * (4 - len(out))))
         dstr = (C.c_int * 4)(*([a.strides[0] for a in out] + [0] * (4 - len(out))))

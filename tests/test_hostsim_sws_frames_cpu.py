@@ -24,7 +24,7 @@ def outputs(df, dw, dh, pad=8, fill=7):
         dt = np.uint8 if bits == 8 else np.dtype(">u2" if df in PLANAR_BE else "<u2")
         cw, ch = -((-dw) >> hs), -((-dh) >> vs)
         return [np.full((dh, dw + pad), fill, dt), np.full((ch, cw + pad), fill, dt), np.full((ch, cw + pad), fill, dt)]
-    bpp = 4 if 25 <= df <= 28 else 2 if df in (1, 15) or 36 <= df <= 43 or 54 <= df <= 57 else 1 if df == 8 else 3
+    bpp = 6 if df in (34, 35, 59, 60) else 4 if 25 <= df <= 28 else 2 if df in (1, 15) or 36 <= df <= 43 or 54 <= df <= 57 else 1 if df == 8 else 3
     return [np.full((dh, dw * bpp + 2 * pad), fill, np.uint8)]
 
 
@@ -109,6 +109,24 @@ def test_rgb16_destinations(sim, refo):
             same(product(sim, sf, pl, 66, 50, df, 100, 80, 4 | ACC), reference(refo, sf, pl, 66, 50, df, 100, 80, 4 | ACC), (sf, df), crop=8)
     # refusals: the ordered-dither table converter's case, packed rgb sources, the per-line slots
     for args in ((64, 48, 0, 64, 48, 37, 4), (64, 48, 2, 128, 96, 37, 4 | ACC), (64, 48, 1, 128, 96, 41, 4 | ACC)):
+        assert not sim.sws_getContext_cuda(*args, None, None, None)
+        sim.avb200_clear_error()
+
+
+def test_rgb48_destinations(sim, refo):
+    """rgb48 / bgr48, LE and BE (tests/test_sws_rgb48_dst.py): the direct 19-bit-line kernel and the byte-doubling table converter"""
+    import test_sws_rgb48_dst as R
+    n = 0
+    for k, df in enumerate(R.DST):
+        for (sf, w, h, dw, dh, flags) in R.combos(thin=2):
+            if (n + k) % 2 and (w, h, dw, dh) not in ((67, 50, 67, 50), (64, 48, 65, 48)):
+                n += 1
+                continue
+            pl = R.source(sf, w, h, 43)
+            same(product(sim, sf, pl, w, h, df, dw, dh, flags), reference(refo, sf, pl, w, h, df, dw, dh, flags), (sf, df, w, h, dw, dh, hex(flags)), crop=8)
+            n += 1
+    assert n > 500
+    for args in ((64, 48, 2, 128, 96, 35, 4 | ACC), (64, 48, 23, 128, 96, 59, 4 | ACC), (64, 48, 64, 128, 96, 34, 4 | ACC)):
         assert not sim.sws_getContext_cuda(*args, None, None, None)
         sim.avb200_clear_error()
 

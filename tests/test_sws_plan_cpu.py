@@ -13,7 +13,7 @@ PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1),
 PACKED_SRC = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
 HBD_SRC = [62, 63, 64, 48, 66, 70]                       # 9 / 10 / 16-bit planar sources (a sample; every one in tests/test_sws_hbd_sources_cpu.py)
 SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24] + HBD_SRC
-DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24, 12, 14, 32, 37, 40, 43, 55, 8]        # 12 14 32: full-range (yuvj) planar
+DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24, 12, 14, 32, 37, 40, 43, 55, 8, 35, 59]        # 12 14 32: full-range (yuvj) planar
 GEOMS = [(64, 48, 64, 48), (66, 50, 66, 50), (64, 48, 96, 80), (96, 80, 64, 48)]
 FLAGS = (4 | ACC, 4, 0x10, 1 | ACC, 2 | ACC | 0x2000, 2)
 
@@ -48,7 +48,7 @@ def dest(fmt, w, h):
         dt = np.uint8 if bits == 8 else np.uint16
         cw, ch = -((-w) >> hs), -((-h) >> vs)
         return [np.zeros((h, w + 8), dt), np.zeros((ch, cw + 8), dt), np.zeros((ch, cw + 8), dt)]
-    return [np.zeros((h + 1, w * 4 + 16), np.uint8)]
+    return [np.zeros((h + 1, w * 6 + 16), np.uint8)]
 
 
 def port_accepts(orc, sf, pl, sw, sh, df, dw, dh, flags):

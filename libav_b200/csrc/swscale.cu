@@ -1303,6 +1303,11 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         return 0;
     };
     srcRange = handle_jpeg(srcFormat); dstRange = handle_jpeg(dstFormat);
+    if (srcFormat == 33) {                // AV_PIX_FMT_YUVA420P: the alpha plane is read only when the destination has alpha too (utils.c:1244, yuv2rgb.c:870);
+        // everywhere else the reference treats the format like yuv420p (swscale_unscaled.c:1041-1153): src[3] is never touched
+        if (dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA) { set_error_msg("sws_getContext_cuda", "yuva420p to a destination with alpha (the alpha plane is scaled too) is not taken over"); return nullptr; }
+        srcFormat = FMT_YUV420P;
+    }
     // 9 / 10 / 16-bit planar sources (LE values of libavutil/pixfmt.h; big-endian twins: 9 / 10-bit LE - 1, 16-bit LE + 1)
     int srcBits = 8, srcBE = 0;
     {

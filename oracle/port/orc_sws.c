@@ -1039,6 +1039,12 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
+    if (src_fmt == 33) {
+        /* yuva420p: the alpha plane is only read when the destination has alpha too (c->alpPixBuf, utils.c:1244; needAlpha, yuv2rgb.c:870); for
+         * every other destination the format is treated like yuv420p wherever the reference tests formats (swscale_unscaled.c:1041-1153) */
+        if (dst_fmt >= 25 && dst_fmt <= 28) return -1;
+        src_fmt = 0;
+    }
     if (dst_fmt == 8) {
         /* gray8: luma only.  swscale() skips the chroma of a gray destination (swscale.c:618-630) and the same-size case is the plane copy for
          * every planar yuv source (isPlanarYUV(src) && isGray(dst), swscale_unscaled.c:1155): the luma plane of the conversion to a planar

@@ -385,8 +385,11 @@ int ref_sws_planar(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     const int nv_dst = dst_fmt == AV_PIX_FMT_NV12 || dst_fmt == AV_PIX_FMT_NV21;
     uint8_t *d[4] = { dst[0], packed_dst ? NULL : dst[1], packed_dst || nv_dst ? NULL : dst[2], NULL };
     int ds[4] = { dstride[0], packed_dst ? 0 : dstride[1], packed_dst || nv_dst ? 0 : dstride[2], 0 };
-    const uint8_t *s[4] = { src[0], packed_src ? NULL : src[1], packed_src ? NULL : src[2], NULL };
-    int sst[4] = { ss[0], packed_src ? 0 : ss[1], packed_src ? 0 : ss[2], 0 };
+    /* a yuva420p source needs a fourth plane to pass sws_scale()'s pointer check (swscale_unscaled.c:1196-1210) even where no alpha is read (every
+     * destination without alpha, utils.c:1244): the luma plane stands in for it */
+    const int alpha_src = src_fmt == AV_PIX_FMT_YUVA420P;
+    const uint8_t *s[4] = { src[0], packed_src ? NULL : src[1], packed_src ? NULL : src[2], alpha_src ? src[0] : NULL };
+    int sst[4] = { ss[0], packed_src ? 0 : ss[1], packed_src ? 0 : ss[2], alpha_src ? ss[0] : 0 };
     int r = sws_scale(c, s, sst, 0, sh, d, ds);
     sws_freeContext(c);
     return r;

@@ -131,6 +131,20 @@ def test_rgb48_destinations(sim, refo):
         sim.avb200_clear_error()
 
 
+def test_yuva420p_sources(sim, refo):
+    """yuva420p (33) to destinations without alpha: the product reads three planes like the reference does (tests/test_sws_yuva_src.py)"""
+    import test_sws_rgb48_dst as R
+    for df in (2, 3, 0, 37, 35):
+        for (w, h, dw, dh) in ((64, 48, 64, 48), (352, 288, 640, 480), (101, 37, 333, 211)):
+            for flags in (4 | ACC, 4):
+                if df == 37 and (w, h) == (dw, dh) and not flags & 0x40000:
+                    continue                     # (the ordered-dither table converter: refused for yuv420p too)
+                pl = R.source(0, w, h, 47)
+                same(product(sim, 33, pl, w, h, df, dw, dh, flags), reference(refo, 33, pl, w, h, df, dw, dh, flags), (df, w, h, dw, dh, hex(flags)), crop=8)
+    assert not sim.sws_getContext_cuda(64, 48, 33, 128, 96, 26, 4 | ACC, None, None, None)
+    sim.avb200_clear_error()
+
+
 def test_gray8_destination(sim, refo):
     """gray8 (tests/test_sws_gray_dst.py): the luma plane of the planar conversion, chroma into the context's scratch"""
     import test_sws_gray_dst as G

@@ -9,7 +9,7 @@ import pytest
 from libav_b200.device import PLANAR_FORMATS
 
 ACC = 0x40000 | 0x80000
-PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0), 32: (0, 1)}
+PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0), 32: (0, 1), 33: (1, 1)}     # 33: yuva420p (alpha never read)
 PACKED_SRC = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
 HBD_SRC = [62, 63, 64, 48, 66, 70]                       # 9 / 10 / 16-bit planar sources (a sample; every one in tests/test_sws_hbd_sources_cpu.py)
 SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24] + HBD_SRC

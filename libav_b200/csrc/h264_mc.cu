@@ -120,13 +120,14 @@ int launch_h264_mc_v2(const FFH264MCRecord *recs, size_t n, const FFH264RefPlane
     if (((uintptr_t)dcb | (uintptr_t)dcr | (uintptr_t)uvls) & 1) return 1;
     if (ph <= 0 || (ph & 1) || (pw & 1)) return 1;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    // compiled for 6 resident CTAs per SM (80 registers, ~40 words of spill): the kernel is latency-bound, 24 warps per SM measured
-    // 18 % faster than the 128-register build with 16 (mc_min_blocks = 4 / 5 select the other builds, profiling)
+    // compiled for 8 resident CTAs per SM (64 registers, ~90 words of spill that stay in L1): the kernel waits on its patch loads (long-scoreboard
+    // stalls, profiles/r2z2_h264_mc_kernel_v2.json), so warps in flight count for more than registers -- measured on the composite: 4 CTAs
+    // (128 registers) 1.00, 6 CTAs 1.18, 8 CTAs 1.25, 10 CTAs 1.16, 12 CTAs 1.06 (profiles/r2z3_mc_occupancy.txt).  mc_min_blocks = 4 / 6: profiling
     const int minb = tuning("mc_min_blocks");
     for (int pass = 0; pass < 2; pass++) {
         if (minb == 4)      h264_mc_kernel_v2<4><<<grid, 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, pass);
-        else if (minb == 5) h264_mc_kernel_v2<5><<<grid, 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, pass);
-        else                h264_mc_kernel_v2<6><<<grid, 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, pass);
+        else if (minb == 6) h264_mc_kernel_v2<6><<<grid, 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, pass);
+        else                h264_mc_kernel_v2<8><<<grid, 128, 0, st>>>(recs, n, refs, dy, dcb, dcr, ls, uvls, pw, ph, pass);
     }
     return check_launch("h264_mc_batch") ? -1 : 0;
 }

@@ -1034,6 +1034,22 @@ sws_rgb24_shuffle_kernel(const uint8_t *__restrict__ src, int srcStride, size_t 
     d[0] = swap ? c : a; d[1] = b; d[2] = swap ? a : c;
 }
 
+// rgbToRgbWrapper's 24 <-> 32 and 32 <-> 32 bit byte converters (rgb2rgb.c:139-175,335-352, rgb2rgb_template.c:31-78,338-350; choice at
+// swscale_unscaled.c:590-660): each is a channel remap -- alpha copied 32 -> 32, 255 for 24 -> 32, dropped 32 -> 24.  map = four nibbles, nibble k =
+// the source byte stored to destination byte k (15: the constant 255).  One thread per pixel.
+__global__ void __launch_bounds__(256)
+sws_rgb_map_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, uint8_t *__restrict__ dst, int dstStride, size_t dstFrame,
+                   int w, int h, int sbpp, int dbpp, unsigned map)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *s = src + blockIdx.z * srcFrame + (size_t)y * srcStride + (size_t)sbpp * x;
+    uint8_t *d = dst + blockIdx.z * dstFrame + (size_t)y * dstStride + (size_t)dbpp * x;
+    uint8_t v[4];
+    for (int k = 0; k < sbpp; k++) v[k] = s[k];
+    for (int k = 0; k < dbpp; k++) { const unsigned m = (map >> (4 * k)) & 15; d[k] = m == 15 ? (uint8_t)255 : v[m]; }
+}
+
 // bgr24ToYv12Wrapper -> rgb24toyv12_c (rgb2rgb_template.c:638-693, 8-bit coefficients rgb2rgb.c:111-120): chroma from the first
 // pixel of each pair of the even rows only; width >> 1 pairs, so an odd last column stays untouched.  One thread per pair and row.
 __global__ void __launch_bounds__(256)
@@ -1207,6 +1223,7 @@ struct SwsCudaContext {
     int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
     int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422, 4 argb / rgba / abgr / bgra: the input readers (input.c) write planes first
     int pkR = 0, pkG = 1, pkB = 2;   //   byte offsets of red, green and blue
+    int srcFormat = 0;          // the source pixel format (after the yuvj / yuva / high-bit-depth twins were folded)
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
     bool planar = false;        // planar yuv destination (else packed rgb)
@@ -1374,9 +1391,12 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "nv12 / nv21 -> nv12 / nv21 of the same size (the reference's plane copy skips the chroma plane there) is not taken over"); return nullptr;
     }
     const bool src32 = srcFormat >= FMT_ARGB && srcFormat <= FMT_BGRA;
-    if (src32 && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar && !pk422))) {
-        // 32 -> 32 bit: the reference scales the alpha plane too; same size -> packed rgb: rgbToRgbWrapper's converters (swscale_unscaled.c:591-710)
-        set_error_msg("sws_getContext_cuda", "32-bit rgb source: only planar yuv destinations and scaled rgb24 / bgr24 are taken over"); return nullptr;
+    // same size, packed rgb on both sides, 32 bits on at least one: rgbToRgbWrapper's byte converters (swscale_unscaled.c:590-705), a channel remap
+    const bool rgb2rgb = unscaled0(srcW, srcH, dstW, dstH) && !usesFilter && (srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24 || src32) &&
+                         (dstFormat == FMT_RGB24 || dstFormat == FMT_BGR24 || dst32) && (src32 || dst32);
+    if (src32 && !rgb2rgb && (dst32 || (unscaled0(srcW, srcH, dstW, dstH) && !planar && !pk422))) {
+        // 32 -> 32 bit at another size: the reference scales the alpha plane too; same size -> 16 / 48-bit rgb: other converter families
+        set_error_msg("sws_getContext_cuda", "32-bit rgb source: planar yuv destinations, scaled rgb24 / bgr24 and same-size 24 / 32-bit rgb are taken over"); return nullptr;
     }
     const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
     const bool unscaled = srcW == dstW && srcH == dstH;
@@ -1384,8 +1404,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "abgr with SWS_FULL_CHR_H_INT: the reference's output function overruns the destination; there is no result to match");
         return nullptr;
     }
-    if (srcRgb && dst32 && unscaled) {                        // rgbToRgbWrapper's 24 <-> 32 bit converters (swscale_unscaled.c:591-710)
-        set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> 32-bit rgb of the same size is the reference's rgb2rgb converter family: not taken over");
+    if (srcRgb && unscaled && (dstFormat == FMT_ARGB || dstFormat == FMT_ABGR)) {
+        // rgbToRgbWrapper moves the 4-byte writer one byte into the row for these two (ALT32_CORR, swscale_unscaled.c:691-692): the first alpha byte is
+        // never written and the last write lands past the row
+        set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> argb / abgr of the same size: the reference's converter writes past the row; there is no result to match");
         return nullptr;
     }
     if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1) && srcRange == dstRange) {
@@ -1456,13 +1478,14 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P && srcBits == 8;
     c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : src32 ? 4 : 0;
-    c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR;
+    c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR; c->srcFormat = srcFormat;
     if (src32) {
         static const int rgbpos[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };       // argb, rgba, abgr, bgra
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
     if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176 (yuv destinations: only with equal ranges, utils.c:1043-1044)
-        if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
+        if (rgb2rgb) c->special = 8;
+        else if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (rangeConv) c->special = 0;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
         else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
@@ -1624,6 +1647,16 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
     if (nframes <= 0) return 0;
     const SwsDev &p = c->dev;
     const int w = p.srcW, h = p.srcH;
+    if (c->special == 8) {
+        // byte of r, g, b, a in rgb24, bgr24, argb, rgba, abgr, bgra
+        static const int chan[6][4] = { { 0, 1, 2, -1 }, { 2, 1, 0, -1 }, { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };
+        const int sf = c->srcPacked == 4 ? 2 + c->srcFormat - FMT_ARGB : c->srcFormat == FMT_BGR24 ? 1 : 0, df = c->dst32 ? 2 + c->dst32 - FMT_ARGB : c->dstFormat == FMT_BGR24 ? 1 : 0;
+        const int sbpp = c->srcPacked == 4 ? 4 : 3, dbpp = c->dst32 ? 4 : 3;
+        unsigned map = 0;
+        for (int ch = 0; ch < 4; ch++) if (chan[df][ch] >= 0) map |= (unsigned)(chan[sf][ch] >= 0 ? chan[sf][ch] : 15) << (4 * chan[df][ch]);
+        sws_rgb_map_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dstStride[0], dstFrame[0], w, h, sbpp, dbpp, map);
+        return check_launch("sws_scale:rgb2rgb");
+    }
     if (c->special == 1 || c->special == 2) {
         sws_rgb24_shuffle_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dstStride[0], dstFrame[0], w, h, c->special == 2);
         return check_launch("sws_scale:rgb24 shuffle");
@@ -1674,7 +1707,7 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
-    if (!c->dst32) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);
+    if (!c->dst32 || c->special == 8) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);      // (special 8: the rgb2rgb remap writes 4-byte pixels itself)
     if (nframes <= 0) return 0;
     const SwsDev &p = c->dev;
     const int pitch = ((p.dstW + 1) * 3 + 15) & ~15;
@@ -2279,7 +2312,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         size_t wbytes = (size_t)g.dstW * pxB;
         if (odd && !c->dev.full && (size_t)dstStride[0] >= wbytes + pxB) wbytes += pxB;      // (full chroma writes single pixels)
         if (c->table_unscaled) wbytes = (size_t)(g.dstW & ~1) * pxB;       // that converter leaves an odd last column untouched
-        if (c->special) wbytes = (size_t)g.dstW * 3;
+        if (c->special) wbytes = (size_t)g.dstW * (c->dst32 ? 4 : 3);
         if (c->to422) {          // (see run_frames_24: an odd pair count is rounded up when the rows have room)
             const int pairs = g.dstW >> 1, pairs_r = (pairs + 1) & ~1;
             const bool extra = pairs_r > pairs && dstStride[0] >= 4 * pairs_r && srcStride[0] >= 2 * pairs_r && srcStride[1] >= pairs_r && srcStride[2] >= pairs_r;

@@ -860,9 +860,28 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     const int rgb_bpp = src32 ? 4 : 3;
     const int real_rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
     const int rgb_dst = real_rgb_dst || dst_fmt == 1 || dst_fmt == 15;       /* packed destinations share the output stage */
-    if (sw == dw && sh == dh && rgb_src && dst_fmt >= 25 && dst_fmt <= 28) return -1;   /* rgb2rgb 24 -> 32 bit converters: not restated */
-    /* 32-bit sources: 32 -> 32 bit scales the alpha plane as well, same size -> packed rgb is the rgb2rgb family: neither is restated */
-    if (src32 && ((dst_fmt >= 25 && dst_fmt <= 28) || (sw == dw && sh == dh && real_rgb_dst))) return -1;
+    const int dst32 = dst_fmt >= 25 && dst_fmt <= 28;
+    if (sw == dw && sh == dh && rgb_src && real_rgb_dst && (src32 || dst32) && !g_nospecial) {
+        /* rgbToRgbWrapper (swscale_unscaled.c:590-705) with the byte converters of rgb2rgb.c:139-175,335-352 / rgb2rgb_template.c:31-78,338-350:
+         * every pair it serves is a channel remap (alpha copied 32 -> 32, 255 for 24 -> 32, dropped 32 -> 24).  A 24-bit source to argb / abgr
+         * runs the 4-byte writer one byte into the row (ALT32_CORR, :691-692): the first alpha byte is never written and the last write lands
+         * past the row -- no defined result, refused.  Only the sw x sh pixels are written here (the reference's one-call variant also converts the
+         * row padding when the pitches are proportional, :694-697). */
+        static const int chan[6][4] = { { 0, 1, 2, -1 }, { 2, 1, 0, -1 }, { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };  /* byte of r, g, b, a: rgb24 bgr24 argb rgba abgr bgra */
+        const int *sc = chan[src32 ? src_fmt - 23 : src_fmt - 2], *dc = chan[dst32 ? dst_fmt - 23 : dst_fmt - 2];
+        const int dbpp = dst32 ? 4 : 3;
+        if (!src32 && (dst_fmt == 25 || dst_fmt == 27)) return -1;
+        for (int y = 0; y < sh; y++)
+            for (int x = 0; x < sw; x++) {
+                const uint8_t *q = src + (size_t)y * stride + (size_t)rgb_bpp * x;
+                uint8_t *d = dst[0] + (size_t)y * ds[0] + (size_t)dbpp * x;
+                for (int k = 0; k < 3; k++) d[dc[k]] = q[sc[k]];
+                if (dst32) d[dc[3]] = src32 ? q[sc[3]] : 255;
+            }
+        return sh;
+    }
+    /* 32 -> 32 bit at another size scales the alpha plane as well: not restated */
+    if (src32 && dst32) return -1;
     if (sw == dw && sh == dh && !g_nospecial && (!g_range || real_rgb_dst)) {
         if (rgb_src && !src32 && real_rgb_dst) {
             for (int y = 0; y < sh; y++)

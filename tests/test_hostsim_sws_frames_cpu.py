@@ -145,6 +145,22 @@ def test_yuva420p_sources(sim, refo):
     sim.avb200_clear_error()
 
 
+def test_rgb2rgb_converters(sim, refo):
+    """same-size 24 <-> 32 and 32 <-> 32 bit packed rgb (tests/test_sws_rgb2rgb.py): the channel-remap kernel against rgbToRgbWrapper"""
+    import test_sws_rgb2rgb as R
+    n = 0
+    for sf, df, refused in R.pairs():
+        for (w, h) in R.GEOMS:
+            if refused:
+                assert not sim.sws_getContext_cuda(w, h, sf, w, h, df, 4, None, None, None)
+                sim.avb200_clear_error()
+                continue
+            src = R.picture(sf, w, h, 21 + w, 6)
+            same(product(sim, sf, [src], w, h, df, w, h, 4), reference(refo, sf, [src], w, h, df, w, h, 4), (sf, df, w, h), crop=8)
+            n += 1
+    assert n > 100
+
+
 def test_gray8_destination(sim, refo):
     """gray8 (tests/test_sws_gray_dst.py): the luma plane of the planar conversion, chroma into the context's scratch"""
     import test_sws_gray_dst as G

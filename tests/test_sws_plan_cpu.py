@@ -112,7 +112,7 @@ def test_refusals_carry_a_reason(built):
     out = (C.c_int32 * 8)()
     cases = [((64, 48, 8, 64, 48, 2, 4), "sources taken over"), ((64, 48, 0, 64, 48, 33, 4), "destinations taken over"),
              ((64, 48, 0, 96, 80, 2, 4 | 0x10000), "CHR_DROP"), ((64, 48, 0, 96, 80, 27, 4 | 0x2000), "abgr"),
-             ((64, 48, 26, 64, 48, 2, 4), "32-bit rgb source"), ((64, 48, 2, 64, 48, 26, 4), "rgb2rgb"), ((64, 49, 3, 64, 49, 0, 4), "even height"),
+             ((64, 48, 26, 96, 80, 28, 4), "32-bit rgb source"), ((64, 48, 2, 64, 48, 25, 4), "writes past the row"), ((64, 49, 3, 64, 49, 0, 4), "even height"),
              ((64, 48, 12, 96, 80, 47, 4), "range conversion"), ((64, 48, 23, 64, 48, 24, 4), "nv12"), ((64, 48, 6, 64, 48, 0, 4), "yvu9ToYv12Wrapper"),
              ((2, 2, 0, 64, 48, 2, 4), ""), ((64, 48, 0, 96, 80, 2, 4 | 2), "")]
     for args, reason in cases:

@@ -210,25 +210,41 @@ bool state_ok(const FFMECmpEncState *s, const char *where)
 }
 
 // ---- device copies of the codec's VLC length tables, keyed by their host addresses (static tables in the reference) ----
+// The per-call slots look the copy up by address alone; the two places a caller announces tables (ff_me_cmp_enc_init_cuda, ff_me_cmp_enc_state_cuda)
+// also compare a checksum of the host bytes with the one taken at upload, so memory that was freed and reused for other tables gets a fresh copy
+// (the old one stays alive for the states that point at it).
 struct VlcKey { const uint8_t *p[5]; bool operator<(const VlcKey &o) const { return memcmp(p, o.p, sizeof(p)) < 0; } };
+struct VlcCopy { uint8_t *d; uint64_t sum; };
 std::mutex g_vlc_mu;
-std::map<VlcKey, uint8_t *> g_vlc;
+std::map<VlcKey, VlcCopy> g_vlc;
 constexpr size_t VLC_BYTES = 4 * 64 * 128 + 512;
 
-const uint8_t *vlc_device(const FFMECmpVlcTables *v, const char *where)
+uint64_t vlc_checksum(const VlcKey &key)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int k = 0; k < 5; k++) {
+        const size_t n = k < 4 ? 8192 : 512;
+        for (size_t i = 0; i < n; i += 8) { uint64_t w; memcpy(&w, key.p[k] + i, 8); h = (h ^ w) * 0x100000001b3ull; h ^= h >> 29; }
+    }
+    return h;
+}
+
+const uint8_t *vlc_device(const FFMECmpVlcTables *v, const char *where, bool verify = false)
 {
     const VlcKey key = { { v->intra_ac_vlc_length, v->intra_ac_vlc_last_length, v->inter_ac_vlc_length, v->inter_ac_vlc_last_length, v->luma_dc_vlc_length } };
     for (int k = 0; k < 5; k++) if (!key.p[k]) { set_error_msg(where, "a VLC length table is NULL"); return nullptr; }
     std::lock_guard<std::mutex> lk(g_vlc_mu);
     auto it = g_vlc.find(key);
-    if (it != g_vlc.end()) return it->second;
+    if (it != g_vlc.end() && !verify) return it->second.d;
+    const uint64_t sum = vlc_checksum(key);
+    if (it != g_vlc.end() && it->second.sum == sum) return it->second.d;
     uint8_t *d = nullptr;
     if (cudaMalloc(&d, VLC_BYTES) != cudaSuccess) { set_error(where, cudaGetLastError()); return nullptr; }
     bool ok = true;
     for (int k = 0; k < 4; k++) ok = ok && cudaMemcpy(d + (size_t)k * 8192, key.p[k], 8192, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(d + 4 * 8192, key.p[4], 512, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) { set_error(where, cudaGetLastError()); cudaFree(d); return nullptr; }
-    g_vlc[key] = d;
+    g_vlc[key] = VlcCopy{ d, sum };
     return d;
 }
 void fill_vlc(EncDev &e, const uint8_t *d) { for (int k = 0; k < 5; k++) e.vlc[k] = d ? d + (size_t)k * 8192 : nullptr; }
@@ -302,7 +318,7 @@ void *ff_me_cmp_enc_state_cuda(const FFMECmpEncState *state, const FFMECmpVlcTab
     memset(&e, 0, sizeof(e));
     e.st = *state;
     if (vlc) {
-        const uint8_t *d = vlc_device(vlc, "ff_me_cmp_enc_state_cuda");
+        const uint8_t *d = vlc_device(vlc, "ff_me_cmp_enc_state_cuda", true);
         if (!d) return nullptr;
         fill_vlc(e, d);
     }
@@ -335,6 +351,12 @@ int ff_me_cmp_enc_init_cuda(MECmpContext *c, struct MpegEncContext *s, const FFM
     if (!view->idct_perm_none || !view->plain_quantiser || (view->fdct != 0 && view->fdct != 2) || view->dequant < 0 || view->dequant > 3) {
         set_error_msg("ff_me_cmp_enc_init_cuda", "not taken over: permuting IDCT, trellis / denoising quantiser or an unknown transform");
         return -1;
+    }
+    {   // (the tables the view points at: uploaded, or checked against their copy, now -- the per-call slots look them up by address)
+        const FFMECmpVlcTables t = { *view->intra_ac_vlc_length, *view->intra_ac_vlc_last_length, *view->inter_ac_vlc_length, *view->inter_ac_vlc_last_length, *view->luma_dc_vlc_length };
+        // (an encoder that has not installed its tables yet is taken as is: bit / rd refuse per call until it has)
+        if (t.intra_ac_vlc_length && t.intra_ac_vlc_last_length && t.inter_ac_vlc_length && t.inter_ac_vlc_last_length && t.luma_dc_vlc_length &&
+            !vlc_device(&t, "ff_me_cmp_enc_init_cuda", true)) return -1;
     }
     { std::lock_guard<std::mutex> lk(g_view_mu); g_views[s] = *view; }
     c->quant_psnr[0] = slot_enc<14, 0>; c->quant_psnr[1] = slot_enc<14, 1>;          // me_cmp.c:926-928 (SET_CMP_FUNC)

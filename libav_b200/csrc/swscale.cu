@@ -634,12 +634,23 @@ static inline void tile_line_window(const int32_t *pos, int fs, int y0, int y1, 
 // one column of a tile: horizontally scaled samples of lines lo + r, r = r0, r0 + rstep, ... < n, into out[r * W]
 // (shared lines hold the 15-bit samples as int32 so the vertical pass multiplies them straight from 16-byte loads)
 // FS > 0: compile-time tap count with the coefficients in registers; FS == 0: run-time tap count; FS < 0: fast bilinear
+// dp2a on (int16 pair) x (unsigned byte pair): .lo takes bytes 0 and 1 of b, .hi bytes 2 and 3; funnel shift right of the pair hi:lo by a multiple of 8
+#ifdef AVB_HOSTSIM
+inline int sws_dp2a_lo(uint32_t k, uint32_t b, int c) { return c + (int)(int16_t)(k & 0xffff) * (int)(b & 255) + (int)(int16_t)(k >> 16) * (int)((b >> 8) & 255); }
+inline int sws_dp2a_hi(uint32_t k, uint32_t b, int c) { return c + (int)(int16_t)(k & 0xffff) * (int)((b >> 16) & 255) + (int)(int16_t)(k >> 16) * (int)(b >> 24); }
+inline uint32_t sws_funnel_r(uint32_t lo, uint32_t hi, int s) { return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+#else
+__device__ __forceinline__ int sws_dp2a_lo(uint32_t k, uint32_t b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(k), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int sws_dp2a_hi(uint32_t k, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(k), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t sws_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, s); }
+#endif
+
 template <int FS>
 __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, int srcStride, int lo, int n, int r0, int rstep,
-                                              int32_t *out, int W, int x, int dstW, const int16_t *__restrict__ filter,
+                                              int32_t *out, int W_, int x, int dstW, const int16_t *__restrict__ filter,
                                               const int32_t *__restrict__ pos, int fs, int srcW, unsigned xInc, int chroma, int sh = 7)
 {   // sh: 7 = hScale8To15_c, 3 = hScale8To19_c (16-bit destinations; swscale.c:62-100)
-    if (x >= dstW) { for (int r = r0; r < n; r += rstep) out[r * W] = 0; return; }     // the reference's zeroed line tail
+    if (x >= dstW) { for (int r = r0; r < n; r += rstep) out[r * W_] = 0; return; }     // the reference's zeroed line tail
     const int step = rstep * srcStride;
     if constexpr (FS < 0) {
         const unsigned xpos = (unsigned)x * xInc, xx = xpos >> 16; const int xa = (xpos & 0xFFFF) >> 9;
@@ -648,7 +659,31 @@ __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, i
 #pragma unroll 2
         for (int r = r0; r < n; r += rstep, sp += step) {
             const int a = sp[xx], b = sp[xx1];
-            out[r * W] = chroma ? a * (xa ^ 127) + b * xa : (a << 7) + (b - a) * xa;
+            out[r * W_] = chroma ? a * (xa ^ 127) + b * xa : (a << 7) + (b - a) * xa;
+        }
+    } else if constexpr (FS == 4) {
+        // four taps: the window's bytes arrive as one or two aligned words, a funnel shift lines them up and two dp2a (int16 pair x byte pair)
+        // do the sum -- 2 LDG + 3 ALU per sample instead of 4 byte loads + 4 byte merges + 2 dp2a.  A window whose second word would reach past
+        // the row's samples (the last columns) and unaligned planes keep the byte loads.
+        const int16_t *f = filter + (size_t)x * 4;
+        const uint32_t k01 = (uint16_t)f[0] | (uint32_t)(uint16_t)f[1] << 16, k23 = (uint16_t)f[2] | (uint32_t)(uint16_t)f[3] << 16;
+        const int ps = pos[x], a0 = ps & ~3, sft = (ps & 3) * 8;
+        const bool vec = !(((uintptr_t)src | (uintptr_t)(unsigned)srcStride) & 3) && (sft == 0 || a0 + 8 <= srcW);
+        const int lim = (1 << (22 - sh)) - 1;
+        if (vec) {
+            const uint8_t *sp = src + a0 + (size_t)(lo + r0) * srcStride;
+#pragma unroll 4
+            for (int r = r0; r < n; r += rstep, sp += step) {
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(sp), w1 = sft ? *reinterpret_cast<const uint32_t *>(sp + 4) : 0u;
+                const uint32_t W = sws_funnel_r(w0, w1, sft);
+                out[r * W_] = min(sws_dp2a_hi(k23, W, sws_dp2a_lo(k01, W, 0)) >> sh, lim);
+            }
+        } else {
+            const uint8_t *sp = src + ps + (size_t)(lo + r0) * srcStride;
+            for (int r = r0; r < n; r += rstep, sp += step) {
+                const uint32_t W = sp[0] | (uint32_t)sp[1] << 8 | (uint32_t)sp[2] << 16 | (uint32_t)sp[3] << 24;
+                out[r * W_] = min(sws_dp2a_hi(k23, W, sws_dp2a_lo(k01, W, 0)) >> sh, lim);
+            }
         }
     } else if constexpr (FS > 0) {
         int cf[FS > 0 ? FS : 1];
@@ -661,7 +696,7 @@ __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, i
             int acc = 0;
 #pragma unroll
             for (int j = 0; j < FS; j++) acc += (int)sp[j] * cf[j];
-            out[r * W] = min(acc >> sh, (1 << (22 - sh)) - 1);
+            out[r * W_] = min(acc >> sh, (1 << (22 - sh)) - 1);
         }
     } else {
         const int16_t *f = filter + (size_t)x * fs;
@@ -669,7 +704,7 @@ __device__ __forceinline__ void hscale_column(const uint8_t *__restrict__ src, i
         for (int r = r0; r < n; r += rstep, sp += step) {
             int acc = 0;
             for (int j = 0; j < fs; j++) acc += (int)sp[j] * f[j];
-            out[r * W] = min(acc >> sh, (1 << (22 - sh)) - 1);
+            out[r * W_] = min(acc >> sh, (1 << (22 - sh)) - 1);
         }
     }
 }
@@ -793,21 +828,43 @@ sws_tile_rgb24_kernel(SwsDev p, TileArgs a)
         for (int k = 0; k < 8; k++) Y[k] = 1 << 18;
 #pragma unroll
         for (int k = 0; k < 4; k++) U[k] = V[k] = 1 << 18;
+        if (fl == 4 && fc == 4) {                              // bicubic's window: straight-line code, no loop control between the taps
+            int lc[4], cc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { lc[j] = lf[j]; cc[j] = cf[j]; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                lds8(LL(j), t8);
+#pragma unroll
+                for (int k = 0; k < 8; k++) Y[k] += t8[k] * lc[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int32_t *cl = CC(j);
+                lds4(cl, t4);
+#pragma unroll
+                for (int k = 0; k < 4; k++) U[k] += t4[k] * cc[j];
+                lds4(cl + chrPlane, t4);
+#pragma unroll
+                for (int k = 0; k < 4; k++) V[k] += t4[k] * cc[j];
+            }
+        } else {
 #pragma unroll 4
-        for (int j = 0; j < fl; j++) {
-            lds8(LL(j), t8); const int c = lf[j];
+            for (int j = 0; j < fl; j++) {
+                lds8(LL(j), t8); const int c = lf[j];
 #pragma unroll
-            for (int k = 0; k < 8; k++) Y[k] += t8[k] * c;
-        }
+                for (int k = 0; k < 8; k++) Y[k] += t8[k] * c;
+            }
 #pragma unroll 4
-        for (int j = 0; j < fc; j++) {
-            const int c = cf[j]; const int32_t *cl = CC(j);
-            lds4(cl, t4);
+            for (int j = 0; j < fc; j++) {
+                const int c = cf[j]; const int32_t *cl = CC(j);
+                lds4(cl, t4);
 #pragma unroll
-            for (int k = 0; k < 4; k++) U[k] += t4[k] * c;
-            lds4(cl + chrPlane, t4);
+                for (int k = 0; k < 4; k++) U[k] += t4[k] * c;
+                lds4(cl + chrPlane, t4);
 #pragma unroll
-            for (int k = 0; k < 4; k++) V[k] += t4[k] * c;
+                for (int k = 0; k < 4; k++) V[k] += t4[k] * c;
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {

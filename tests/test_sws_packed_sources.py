@@ -145,7 +145,7 @@ def test_refusals_are_loud(gpu):
         device.SwsContext(64, 49, 64, 49, device.PIX_FMT_YUV420P, 4, src_fmt=3)      # rgb24toyv12_c with an odd height
     gpu.lib.avb200_clear_error()
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 64, 48, device.PIX_FMT_RGB24, 4, src_fmt=26)      # rgba -> rgb24 of the same size: rgb2rgb family
+        device.SwsContext(64, 48, 64, 48, 25, 4, src_fmt=2)                          # rgb24 -> argb of the same size: the reference's writer runs past the row
     gpu.lib.avb200_clear_error()
     with pytest.raises(Exception):
         device.SwsContext(64, 48, 128, 96, 28, 4, src_fmt=26)                        # rgba -> bgra: the alpha plane would be scaled too

@@ -77,7 +77,7 @@ def test_gpu_device_batch_and_refusal(gpu, checker):
         assert np.array_equal(got[k], want[:, :dw * 4]), k
     ctx.close()
     with pytest.raises(Exception):
-        device.SwsContext(64, 48, 64, 48, 26, 4, src_fmt=2)
+        device.SwsContext(64, 48, 64, 48, 27, 4, src_fmt=2)          # rgb24 -> abgr of the same size (the reference's converter writes past the row)
     gpu.lib.avb200_clear_error()
     with pytest.raises(Exception):
         device.SwsContext(64, 48, 128, 96, 27, 4 | ACC | 0x2000)

@@ -3,6 +3,7 @@ chroma_format_idc 2 entries of H264DSPContext and libswscale's per-line SwsConte
 through the product library on a B200.  (The file name sorts last on purpose: `pytest -x` reaches these after every older test.)"""
 import ctypes as C
 
+import numpy as np
 import pytest
 
 import slot_cases
@@ -380,6 +381,60 @@ def test_me_cmp_quant_metrics_batch(gpu, checker, orc):
     assert enc_cases.batch_cases(lib, run_batch, checker, orc, n=200) > 80000
     assert lib.ff_me_cmp_enc_batch_cuda(13, 0, None, None, None, 0, 8, None, 0, None, None, None) == -1
     lib.avb200_clear_error()
+
+
+def test_me_cmp_enc_tables_at_a_reused_address(gpu, checker, orc):
+    """the device copies of the VLC length tables are found by host address: tables announced again at an address that held others before
+    (freed and reused memory; here rewritten in place) must be uploaded again -- by ff_me_cmp_enc_init_cuda and ff_me_cmp_enc_state_cuda"""
+    import ctypes as C
+    import enc_cases as E
+    from libav_b200 import tables
+    T = E.Tables(4)
+    lib = gpu.lib
+    u8p = C.POINTER(C.c_uint8)
+    for round_ in range(2):
+        if round_:
+            T2 = E.Tables(99)
+            for name in ("intra_len", "intra_last", "inter_len", "inter_last", "luma_dc"):
+                getattr(T, name)[:] = getattr(T2, name)                      # same addresses, other tables
+        enc = E.FakeEncoder(T)
+        table = tables.MECmpContext()
+        key = C.c_void_p(enc.key.ctypes.data)
+        label, st = E.states(T)[5]
+        enc.load(st, checker)
+        assert lib.ff_me_cmp_enc_init_cuda(C.byref(table), key, C.byref(enc.view)) == 0
+        cur, rf = E.block_pairs(6, seed=35)
+        want, wside = E.oracle_scores(checker, 15, 1, st, cur, rf, 6, 8, h263_guard=orc)
+        n = 0
+        for i in range(6):
+            if want[i] is None:
+                continue
+            enc.ints[6], enc.ints[8] = st.mb_intra, -2
+            a = C.cast(cur.ctypes.data + 16 * i * cur.strides[0] + 8, u8p)
+            b = C.cast(rf.ctypes.data + 16 * i * rf.strides[0] + 8, u8p)
+            assert table.bit[1](key, a, b, cur.strides[0], 8) == want[i], (round_, i)
+            n += 1
+        assert n >= 3
+        lib.ff_me_cmp_enc_uninit_cuda(key)
+        # the batch state announces its tables too
+        p, _, _, _ = E.product_state(st, checker)
+        vlc = E.vlc_tables(T)
+        handle = lib.ff_me_cmp_enc_state_cuda(C.byref(p), C.byref(vlc))
+        assert handle
+        recs = np.array([[16 * i * cur.strides[0] + 8, 16 * i * rf.strides[0] + 8] for i in range(6)], np.uint32)
+        got, last = np.zeros(6, np.int32), np.zeros(6, np.int32)
+        bufs = []
+        for a_ in (cur, rf, recs, got, last):
+            d = lib.avb200_malloc(a_.nbytes)
+            assert d and lib.avb200_memcpy_h2d(d, a_.ctypes.data, a_.nbytes, None) == 0
+            bufs.append(d)
+        assert lib.ff_me_cmp_enc_batch_cuda(15, 1, handle, bufs[0], bufs[1], cur.strides[0], 8, bufs[2], 6, bufs[3], bufs[4], None) == 0, gpu.last_error()
+        assert lib.avb200_memcpy_d2h(got.ctypes.data, bufs[3], got.nbytes, None) == 0 and lib.avb200_device_sync() == 0
+        for d in bufs:
+            lib.avb200_free(d)
+        for i in range(6):
+            assert want[i] is None or int(got[i]) == want[i], (round_, "batch", i)
+        lib.ff_me_cmp_enc_state_free_cuda(handle)
 
 
 def test_me_cmp_quant_metrics_slots(gpu, checker, orc):

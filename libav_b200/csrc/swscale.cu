@@ -41,6 +41,7 @@ struct SwsDev {                       // kernel-side view of a context (passed b
     int dstBits;                      // planar destinations: 8, 9 / 10 (16-bit samples, yuv2planeX_10_c) or 16 (yuv2planeX_16_c)
     int pk422;                        // packed 4:2:2 destination: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576)
     int rgb16;                        // 15 / 16 / 12-bpp destination: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (yuv2rgb_write, output.c:869-902)
+    int srcGray;                      // gray8 source: chroma lines are the constant the reference's line buffers hold (bytes of 64)
     int rgb48;                        // 48-bit destination: 1 rgb48 2 bgr48, + 8 big-endian (yuv2rgb48_X / _2 / _1_c_template, output.c:584-760; yuv2rgb_c_48, yuv2rgb.c:106-236)
     int chrStep;                      // 2 for an nv12 / nv21 destination: the chroma planes interleave in one plane (yuv2nv12cX_c, output.c:267-303)
     int dstBE;                        // 16-bit samples are stored big-endian (AV_WB16 in output_pixel, output.c:124-133,176-181)
@@ -328,8 +329,9 @@ sws_rgb48_kernel(SwsDev p, FusedArgs a)
     const int p0 = p.hLumP[x0], p1 = p.hLumP[has2 ? x1 : x0], pc = p.hChrP[i];
     auto L0 = [&](int j) -> uint32_t { return (uint32_t)h19(Yp + (size_t)clampi(firstL + j, 0, p.srcH - 1) * a.yStride, hf0, p0, p.hLumSize); };
     auto L1 = [&](int j) -> uint32_t { return has2 ? (uint32_t)h19(Yp + (size_t)clampi(firstL + j, 0, p.srcH - 1) * a.yStride, hf1, p1, p.hLumSize) : 0u; };
-    auto CU = [&](int j) -> uint32_t { return (uint32_t)h19(Up + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.uStride, hfc, pc, p.hChrSize); };
-    auto CV = [&](int j) -> uint32_t { return (uint32_t)h19(Vp + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.vStride, hfc, pc, p.hChrSize); };
+    // (a gray8 source has no chroma lines: the vertical stage reads the bytes of 64 the reference's line buffers were initialised with, 0x40404040 per 19-bit sample)
+    auto CU = [&](int j) -> uint32_t { return p.srcGray ? 0x40404040u : (uint32_t)h19(Up + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.uStride, hfc, pc, p.hChrSize); };
+    auto CV = [&](int j) -> uint32_t { return p.srcGray ? 0x40404040u : (uint32_t)h19(Vp + (size_t)clampi(firstC + j, 0, p.chrSrcH - 1) * a.vStride, hfc, pc, p.hChrSize); };
     int Y1, Y2, U, V;
     if (fl == 1 && fc <= 2) {                                  // yuv2rgb48_1_c_template, output.c:694-760
         const int uvalpha = fc == 1 ? 0 : p.vChrF[2 * y + 1];
@@ -1280,6 +1282,9 @@ struct SwsCudaContext {
     int srcNV = 0;              // 0 planar yuv420p, 1 nv12, 2 nv21: semi-planar sources are split into planes first (input.c:475-497)
     int srcPacked = 0;          // 1 rgb24 / bgr24, 2 yuyv422, 3 uyvy422, 4 argb / rgba / abgr / bgra: the input readers (input.c) write planes first
     int pkR = 0, pkG = 1, pkB = 2;   //   byte offsets of red, green and blue
+    bool srcGray = false;       // gray8 source: luma only; swscale() never converts chroma lines for it (needs_hcscale, swscale.c:532,768-770) and the vertical stage
+                                // reads what sws_init_context left in the line buffers -- bytes of 64 (utils.c:1273).  Geometry of a format without chroma sub-sampling;
+                                // the entry points hand the kernels the luma plane in place of the two planes the caller does not have (never read)
     int srcFormat = 0;          // the source pixel format (after the yuvj / yuva / high-bit-depth twins were folded)
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
@@ -1350,7 +1355,7 @@ static int upload_tables(SwsCudaContext *c)
     d.k = c->k;
     d.bgr = c->dstFormat == FMT_BGR24 || (c->rgb48 & 7) == 2;
     d.full = (c->g.flags & SWS_FULL_CHR_H_INT) != 0 && !c->planar;
-    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422; d.rgb16 = c->rgb16; d.rgb48 = c->rgb48;
+    d.dstBits = c->dstBits; d.dstBE = c->dstBE; d.chrStep = c->dstNV ? 2 : 1; d.pk422 = c->pk422; d.rgb16 = c->rgb16; d.rgb48 = c->rgb48; d.srcGray = c->srcGray;
     d.srcBits = c->srcBits; d.srcBE = c->srcBE; d.dither = c->srcBits > 8;
     return 0;
 }
@@ -1381,6 +1386,18 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         // everywhere else the reference treats the format like yuv420p (swscale_unscaled.c:1041-1153): src[3] is never touched
         if (dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA) { set_error_msg("sws_getContext_cuda", "yuva420p to a destination with alpha (the alpha plane is scaled too) is not taken over"); return nullptr; }
         srcFormat = FMT_YUV420P;
+    }
+    const bool srcGray = srcFormat == 8;      // AV_PIX_FMT_GRAY8 (pixdesc: one component, log2_chroma_w = log2_chroma_h = 0)
+    bool grayPal = false;
+    if (srcGray) {
+        const bool d32 = dstFormat >= FMT_ARGB && dstFormat <= FMT_BGRA;
+        const char *why = nullptr;
+        if (dstRange) why = "gray8 to a full-range yuvj destination (range conversion) is not taken over";
+        else if (dstFormat == FMT_NV12 || dstFormat == FMT_NV21) why = "gray8 to nv12 / nv21 is not taken over (the reference's plane copy fills half of the interleaved chroma row)";
+        if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
+        // same size to 24 / 32-bit rgb: palToRgbWrapper with the pseudo-palette r = g = b = sample (swscale_unscaled.c:342-384,1114-1121,1257-1259)
+        grayPal = srcW == dstW && srcH == dstH && (dstFormat == FMT_RGB24 || dstFormat == FMT_BGR24 || d32);
+        srcFormat = FMT_YUV444P;
     }
     // 9 / 10 / 16-bit planar sources (LE values of libavutil/pixfmt.h; big-endian twins: 9 / 10-bit LE - 1, 16-bit LE + 1)
     int srcBits = 8, srcBE = 0;
@@ -1442,7 +1459,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         vs = 0;
         break;
     }
-    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p), nv12, nv21, yuyv422, uyvy422, rgb24, bgr24, argb, rgba, abgr, bgra"); return nullptr;
+    default: set_error_msg("sws_getContext_cuda", "sources taken over: planar 8-bit yuv (420p 422p 444p 410p 411p 440p, yuvj, yuva420p), gray8, 9 / 10 / 16-bit planar yuv, nv12, nv21, yuyv422, uyvy422, rgb24, bgr24, argb, rgba, abgr, bgra"); return nullptr;
     }
     if ((srcFormat == FMT_NV12 || srcFormat == FMT_NV21) && (dstFormat == FMT_NV12 || dstFormat == FMT_NV21) && srcW == dstW && srcH == dstH) {
         set_error_msg("sws_getContext_cuda", "nv12 / nv21 -> nv12 / nv21 of the same size (the reference's plane copy skips the chroma plane there) is not taken over"); return nullptr;
@@ -1457,7 +1474,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
     const bool unscaled = srcW == dstW && srcH == dstH;
-    if (dstFormat == FMT_ABGR && (flags & SWS_FULL_CHR_H_INT)) {  // output.c:1231-1237 advances the pointer twice per abgr pixel and runs off the row
+    if (dstFormat == FMT_ABGR && (flags & SWS_FULL_CHR_H_INT) && !grayPal && !rgb2rgb) {      // (the unscaled converters never reach that output function)  // output.c:1231-1237 advances the pointer twice per abgr pixel and runs off the row
         set_error_msg("sws_getContext_cuda", "abgr with SWS_FULL_CHR_H_INT: the reference's output function overruns the destination; there is no result to match");
         return nullptr;
     }
@@ -1484,6 +1501,13 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         else if ((srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && unscaled && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8)
             why = "same-size yuv -> 15 / 16 / 12-bpp rgb without SWS_ACCURATE_RND is the reference's ordered-dither table converter (yuv2rgb.c:377-573): not taken over";
         else if (usesFilter) why = "SwsFilter vectors with a 15 / 16 / 12-bpp destination are not taken over";
+        if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
+    }
+    if (srcGray) {
+        const char *why = nullptr;
+        if (usesFilter) why = "SwsFilter vectors with a gray8 source are not taken over";
+        else if (planar && dbits == 16) why = "gray8 to a 16-bit planar destination is not taken over";
+        else if (planar && dbits != 8 && srcW == dstW && srcH == dstH) why = "gray8 to a 9 / 10-bit planar destination of the same size (planarCopyWrapper's fill_plane9or10) is not taken over";
         if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
     }
     if (rgb48) {
@@ -1523,7 +1547,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (!rgb) flags &= ~SWS_FULL_CHR_H_INT;                 // only packed RGB knows the flag (utils.c:998-1014)
     SwsCudaContext *c = new (std::nothrow) SwsCudaContext();
     if (!c) return nullptr;
-    c->pk422 = pk422; c->rgb16 = rgb16; c->rgb48 = rgb48; c->gray = gray; c->srcBits = srcBits; c->srcBE = srcBE;
+    c->pk422 = pk422; c->rgb16 = rgb16; c->rgb48 = rgb48; c->srcGray = srcGray; c->gray = gray; c->srcBits = srcBits; c->srcBE = srcBE;
     if (pk422 && srcW == dstW && srcH == dstH && !usesFilter && !rangeConv && srcBits == 8) {               // swscale_unscaled.c:1123-1139,1152-1176
         if (srcFormat == FMT_YUV422P) c->to422 = 1;
         else if (srcFormat == FMT_YUV420P && (flags & (SWS_FAST_BILINEAR | SWS_POINT))) c->to422 = 2;
@@ -1541,7 +1565,8 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
     if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176 (yuv destinations: only with equal ranges, utils.c:1043-1044)
-        if (rgb2rgb) c->special = 8;
+        if (grayPal) c->special = 9;
+        else if (rgb2rgb) c->special = 8;
         else if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (rangeConv) c->special = 0;
         else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
@@ -1565,7 +1590,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // swscale_unscaled.c:1051-1055; the table converter only exists for planar sources (an nv12 frame goes through swscale())
     c->table_unscaled = (srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && rgb && !pk422 && srcW == dstW && srcH == dstH && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8;
-    c->fused = srcBits == 8 && !c->table_unscaled && rgb && !pk422 && !rgb16 && !rgb48 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
+    c->fused = srcBits == 8 && !srcGray && !c->table_unscaled && rgb && !pk422 && !rgb16 && !rgb48 && !(flags & SWS_FULL_CHR_H_INT) && !(c->g.flags & SWS_FAST_BILINEAR) && is_identity(c->hLum, 1 << 14) && is_identity(c->hChr, 1 << 14) && is_identity(c->vLum, 1 << 12) &&
                c->vChr.size == 4;
     if (c->fused && !(dstW & 15) && !(dstH & 1)) {
         bool ok = true;
@@ -1582,7 +1607,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     }
     // planarCopyWrapper for planar -> planar of the same size and sub-sampling (swscale_unscaled.c:1152-1176), nv12ToPlanarWrapper for
     // nv12 / nv21 -> yuv420p (:1046-1049); other nv12 destinations go through swscale()
-    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && hs == dhs && vs == dvs && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter && srcBits == 8;
+    c->copy = planar && !c->dstNV && !c->srcPacked && srcW == dstW && srcH == dstH && ((hs == dhs && vs == dvs) || srcGray) && (!c->srcNV || dstFormat == FMT_YUV420P) && !rangeConv && !usesFilter && srcBits == 8;
     c->rangeConv = rangeConv;
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv && srcBits == 8;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
@@ -1664,7 +1689,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         }
         const bool fullc = rgb && (flags & SWS_FULL_CHR_H_INT);
         const size_t need = rgb ? ((size_t)lr * GT_LW + (size_t)cr * (fullc ? 2 * GT_LW : GT_W)) * 4 : (size_t)std::max(lr, cr) * GT_LW * 4;
-        if (need <= 96 * 1024 && !pk422 && !rgb16 && !rangeConv && srcBits == 8) {          // (the packed 4:2:2 / 16-bpp output stages and the range conversion only exist in the two-pass path so far)
+        if (need <= 96 * 1024 && !pk422 && !rgb16 && !rangeConv && srcBits == 8 && !srcGray) {          // (the packed 4:2:2 / 16-bpp output stages and the range conversion only exist in the two-pass path so far)
             c->tileLumRows = lr; c->tileChrRows = cr;
             if (cudaMalloc(&c->d_tile_win, win.size() * sizeof(int2)) != cudaSuccess ||
                 cudaMemcpy(c->d_tile_win, win.data(), win.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1764,7 +1789,7 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
-    if (!c->dst32 || c->special == 8) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);      // (special 8: the rgb2rgb remap writes 4-byte pixels itself)
+    if (!c->dst32 || c->special == 8 || c->special == 9) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);      // (special 8: the rgb2rgb remap writes 4-byte pixels itself)
     if (nframes <= 0) return 0;
     const SwsDev &p = c->dev;
     const int pitch = ((p.dstW + 1) * 3 + 15) & ~15;
@@ -1794,6 +1819,14 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
                          uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st,
                          uint8_t *const *remapped)
 {
+    if (c->special == 9) {             // gray8 -> 24 / 32-bit rgb of the same size: the pseudo-palette lookup is r = g = b = sample, alpha 255
+        if (nframes <= 0) return 0;
+        const SwsDev &q = c->dev;
+        const int dbpp = c->dst32 ? 4 : 3;
+        const unsigned map = !c->dst32 ? 0x000u : (c->dst32 == FMT_ARGB || c->dst32 == FMT_ABGR) ? 0x000Fu : 0xF000u;
+        sws_rgb_map_kernel<<<dim3((q.srcW + 255) / 256, q.srcH, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], dst[0], dstStride[0], dstFrame[0], q.srcW, q.srcH, 1, dbpp, map);
+        return check_launch("sws_scale:gray8 -> rgb");
+    }
     if (c->to422) {
         const SwsDev &q = c->dev;
         if (nframes <= 0) return 0;
@@ -1897,6 +1930,14 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
         }
         return check_launch("sws_scale:copy");
     }
+    if (c->copy && c->srcGray) {       // planarCopyWrapper for a gray source: the luma plane, and 128 in the planes the source does not have (swscale_unscaled.c:812-823)
+        for (int f = 0; f < nframes; f++) {
+            AVB_CUDA(cudaMemcpy2DAsync(dst[0] + f * dstFrame[0], dstStride[0], src[0] + f * srcFrame[0], srcStride[0], p.srcW, p.srcH, cudaMemcpyDeviceToDevice, st), "sws_scale:copy");
+            for (int pl = 1; pl < 3; pl++)
+                AVB_CUDA(cudaMemset2DAsync(dst[pl] + f * dstFrame[pl], dstStride[pl], 128, p.chrDstW, p.chrDstH, st), "sws_scale:copy");
+        }
+        return 0;
+    }
     if (c->copy) {
         for (int f = 0; f < nframes; f++)
             for (int pl = 0; pl < 3; pl++) {
@@ -1996,7 +2037,14 @@ static int run_planar(SwsCudaContext *c, const uint8_t *const src[3], const int 
     for (int f = 0; f < nframes; f++) {      // general path, two passes: frames are serialised on the stream (shared line planes)
         const uint8_t *y = src[0] + f * srcFrame[0], *u = src[1] + f * srcFrame[1], *v = src[2] + f * srcFrame[2];
         dim3 b(256);
-        if (p.srcBits > 8) {                  // no fast-bilinear line functions for these sources (swscale.c:733-743): the designed bank
+        if (c->srcGray) {                     // luma only; the chroma lines keep the bytes of 64 sws_init_context wrote (0x4040 per 15-bit sample)
+            if (c->g.flags & SWS_FAST_BILINEAR)
+                sws_hscale_fast_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.srcW, p.dstW, p.srcH, c->g.lumXInc, 0);
+            else
+                sws_hscale8to15_x4_kernel<<<dim3((p.dstW + 1023) / 1024, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH);
+            AVB_CUDA(cudaMemsetAsync(c->d_chrU, 0x40, (size_t)c->chrStridePx * p.chrSrcH * 2, st), "sws_scale:gray8");
+            AVB_CUDA(cudaMemsetAsync(c->d_chrV, 0x40, (size_t)c->chrStridePx * p.chrSrcH * 2, st), "sws_scale:gray8");
+        } else if (p.srcBits > 8) {                  // no fast-bilinear line functions for these sources (swscale.c:733-743): the designed bank
             sws_hscale16to15_kernel<<<dim3((p.dstW + 255) / 256, p.srcH), b, 0, st>>>(y, srcStride[0], c->d_lum, c->lumStridePx, p.hLumF, p.hLumP, p.hLumSize, p.dstW, p.srcH, p.srcBits, p.srcBE);
             sws_hscale16to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(u, srcStride[1], c->d_chrU, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH, p.srcBits, p.srcBE);
             sws_hscale16to15_kernel<<<dim3((p.chrDstW + 255) / 256, p.chrSrcH), b, 0, st>>>(v, srcStride[2], c->d_chrV, c->chrStridePx, p.hChrF, p.hChrP, p.hChrSize, p.chrDstW, p.chrSrcH, p.srcBits, p.srcBE);
@@ -2042,7 +2090,7 @@ bool sws_slot_view(const void *ctx, SwsSlotView &v)
     if (!c) return false;
     v.rangeConv = c->rangeConv; v.srcBits = c->srcBits;
     v.k = c->k; v.flags = c->g.flags; v.planar = c->planar; v.dstBits = c->dstBits; v.dstBE = c->dstBE; v.dstNV = c->dstNV;
-    if (c->rgb16 || c->rgb48 || c->gray) return false; // (the per-line slots do not cover the 15 / 16 / 12 / 48-bpp output stages: the hook leaves the C slots)
+    if (c->rgb16 || c->rgb48 || c->gray || c->srcGray) return false; // (the per-line slots do not cover the 15 / 16 / 12 / 48-bpp output stages: the hook leaves the C slots)
     v.target = c->planar ? -1 : c->pk422 ? 1 + c->pk422 : c->dst32 ? 4 + (c->dst32 - FMT_ARGB) : c->dstFormat == FMT_BGR24 ? 1 : 0;
     return true;
 }
@@ -2094,6 +2142,12 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c) { set_error_msg("sws_scale_frames_cuda", "NULL context"); return -1; }
     static const size_t zero3[3] = { 0, 0, 0 };
+    if (c->srcGray && src && src[0] && srcStride && (!src[1] || !src[2])) {          // one plane: the luma plane stands in for the two nobody reads
+        const uint8_t *const s3[3] = { src[0], src[0], src[0] };
+        const int ss3[3] = { srcStride[0], srcStride[0], srcStride[0] };
+        const size_t sf3[3] = { srcFrameStride ? srcFrameStride[0] : 0, srcFrameStride ? srcFrameStride[0] : 0, srcFrameStride ? srcFrameStride[0] : 0 };
+        return sws_scale_frames_cuda(ctx, s3, ss3, sf3, dst, dstStride, dstFrameStride, nframes, stream);
+    }
     if (c->gray && dst && dst[0] && dstStride) {      // chroma to scratch (every frame of the batch into the same two planes: nobody reads them)
         uint8_t *const d3[3] = { dst[0], c->d_gray[0], c->d_gray[1] };
         const int ds3[3] = { dstStride[0], c->grayPitch, c->grayPitch };
@@ -2257,6 +2311,12 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     avb::enter();
     SwsCudaContext *c = (SwsCudaContext *)ctx;
     if (!c || srcSliceH == 0) return 0;
+    if (c->srcGray && srcSlice && srcSlice[0] && srcStride && (!srcSlice[1] || !srcSlice[2] || srcStride[1] != srcStride[0] || srcStride[2] != srcStride[0])) {
+        // a gray8 picture has one plane (data[1] of an AVFrame is its pseudo-palette): the luma plane stands in for the two planes nobody reads
+        const uint8_t *const s4[4] = { srcSlice[0], srcSlice[0], srcSlice[0], nullptr };
+        const int ss4[4] = { srcStride[0], srcStride[0], srcStride[0], 0 };
+        return sws_scale_cuda(ctx, s4, ss4, srcSliceY, srcSliceH, dst, dstStride);
+    }
     if (c->gray && dst && dst[0] && dstStride) {        // (a gray8 caller's dst[] has one plane; `gray` is cleared around the inner call)
         // the chroma planes of the planar conversion go to host scratch of the context (they are computed and dropped)
         const size_t bytes = (size_t)c->grayPitch * (c->g.chrDstH + 2);

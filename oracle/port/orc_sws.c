@@ -245,6 +245,10 @@ static void put16(uint8_t *p, int v) { if (g_dbe) { p[0] = (uint8_t)(v >> 8); p[
 static __thread int g_rgb16;        /* 15 / 16 / 12-bpp destination of the "rgb" entry point: 1 rgb565 2 bgr565 3 rgb555 4 bgr555 5 rgb444 6 bgr444, + 8 big-endian (output.c:869-902) */
 #define IS_RGB48(f) ((f) == 34 || (f) == 35 || (f) == 59 || (f) == 60)             /* rgb48be 34, rgb48le 35, bgr48be 59, bgr48le 60 */
 static __thread int g_rgb48;        /* 48-bit destination of the "rgb" entry point: 1 rgb48 2 bgr48, + 8 big-endian (yuv2rgb48_X / _2 / _1, output.c:584-760) */
+static __thread int g_src_gray;     /* gray8 source: swscale() never converts chroma lines for it (needs_hcscale, swscale.c:532,768-770), so the vertical stage reads what
+                                     * sws_init_context left in the line buffers: bytes of 64 (utils.c:1273), i.e. 0x4040 per 15-bit sample, 0x40404040 per 19-bit sample */
+static void gray_lines(int16_t *u, int16_t *v, size_t n) { for (size_t i = 0; g_src_gray && i < n; i++) u[i] = v[i] = 0x4040; }
+static void gray_lines19(int32_t *u, int32_t *v, size_t n) { for (size_t i = 0; g_src_gray && i < n; i++) u[i] = v[i] = 0x40404040; }
 static __thread int g_pk422;        /* packed 4:2:2 destination of the "rgb" entry point: 1 yuyv422, 2 uyvy422 (yuv2422_X / _2 / _1, output.c:448-576) */
 static __thread int g_nospecial;    /* an nv12 / nv21 destination computed through the planar path: no yuv420p-only special converters */
 static __thread int g_nocopy;       /* nv12 / nv21 sources never get planarCopyWrapper (swscale_unscaled.c:1158-1170) */
@@ -446,6 +450,7 @@ static int rgb48_scaled(sws_t *c, const uint8_t *const src[3], const int ss[3], 
 {
     int lp, cp;
     int32_t *L = hpass19(src[0], ss[0], sh, &c->hl, &lp), *U = hpass19(src[1], ss[1], c->chrSrcH, &c->hc, &cp), *V = hpass19(src[2], ss[2], c->chrSrcH, &c->hc, &cp);
+    gray_lines19(U, V, (size_t)cp * c->chrSrcH);
     int64_t kcy, koy, kcrv, kcbu, kcgu, kcgv; int kyoffs;
     cs_coeffs(&kcy, &koy, &kcrv, &kcbu, &kcgu, &kcgv, &kyoffs);
 #define R16(f) ((int16_t)({ int r_ = (int)(((int64_t)(f) + (1 << 15)) >> 16); r_ < -0x7FFF ? -0x8000 : r_ > 0x7FFF ? 0x7FFF : r_; }))
@@ -538,6 +543,7 @@ int orc_sws_yuv420p_to_rgb24(const uint8_t *const src[3], const int ss[3], int s
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    gray_lines(U, V, (size_t)cp * c.chrSrcH);
     if (g_pk422) { range_lines(L, lp, sh, dw, 0); range_lines(U, cp, c.chrSrcH, c.chrDstW, 1); range_lines(V, cp, c.chrSrcH, c.chrDstW, 1); }    /* (a yuv destination: swscale.c:748-765) */
     const int fl = c.vl.taps, fc = c.vc.taps;
     if (flags & F_FULL_CHR_H_INT) {
@@ -691,7 +697,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
 {
     sws_t c;
     if (sws_open(&c, sw, sh, dw, dh, 0, flags)) return -1;
-    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range && !uses_filter() && g_sbits == 8) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
+    if (sw == dw && sh == dh && g_hs == g_dhs && g_vs == g_dvs && !g_nocopy && !g_range && !uses_filter() && g_sbits == 8 && !g_src_gray) {   /* unscaled, same sub-sampling and range: planarCopyWrapper (utils.c:1043-1054,
                                          swscale_unscaled.c:793-1020); 8 -> 9 / 10 bits is a plain shift for limited-range sources (:946-971) */
         for (int p = 0; p < 3; p++) {
             int w = p ? c.chrSrcW : sw, h = p ? c.chrSrcH : sh;
@@ -706,10 +712,21 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
         sws_close(&c);
         return dh;
     }
+    if (g_src_gray && sw == dw && sh == dh && !g_range && !uses_filter()) {
+        /* isPlanarYUV(dst) && isGray(src): planarCopyWrapper whatever the destination's sub-sampling (swscale_unscaled.c:1156) -- the luma plane is
+         * copied, the planes the source does not have are filled with 128 (:812-823).  8-bit destinations (fill_plane9or10 / the 16-bit fill: not restated) */
+        if (g_dbits != 8) { sws_close(&c); return -1; }
+        for (int y = 0; y < sh; y++) memcpy(dst[0] + (size_t)y * ds[0], src[0] + (size_t)y * ss[0], sw);
+        for (int p = 1; p < 3; p++)
+            for (int y = 0; y < c.chrDstH; y++) memset(dst[p] + (size_t)y * ds[p], 128, c.chrDstW);
+        sws_close(&c);
+        return dh;
+    }
     int lp, cp;
     if (g_dbits == 16) {                /* 19-bit lines; no fast-bilinear line functions at this depth (swscale.c:728-741) */
         if (g_range) { sws_close(&c); return -1; }      /* (the *Range*16_c variants are not restated) */
         int32_t *L = hpass19(src[0], ss[0], sh, &c.hl, &lp), *U = hpass19(src[1], ss[1], c.chrSrcH, &c.hc, &cp), *V = hpass19(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+        gray_lines19(U, V, (size_t)cp * c.chrSrcH);
         vplane16(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh);
         vplane16(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH);
         vplane16(V, cp, c.chrSrcH, &c.vc, dst[2], ds[2], c.chrDstW, c.chrDstH);
@@ -721,6 +738,7 @@ int orc_sws_yuv420p_to_yuv420p(const uint8_t *const src[3], const int ss[3], int
     int16_t *L = fast ? hfast(src[0], ss[0], sh, sw, dw, c.lumXInc, 0, &lp) : hpass(src[0], ss[0], sh, &c.hl, &lp);
     int16_t *U = fast ? hfast(src[1], ss[1], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[1], ss[1], c.chrSrcH, &c.hc, &cp);
     int16_t *V = fast ? hfast(src[2], ss[2], c.chrSrcH, c.chrSrcW, c.chrDstW, c.chrXInc, 1, &cp) : hpass(src[2], ss[2], c.chrSrcH, &c.hc, &cp);
+    gray_lines(U, V, (size_t)cp * c.chrSrcH);
     range_lines(L, lp, sh, dw, 0); range_lines(U, cp, c.chrSrcH, c.chrDstW, 1); range_lines(V, cp, c.chrSrcH, c.chrDstW, 1);
     vplane(L, lp, sh, &c.vl, dst[0], ds[0], dw, dh, 0);
     vplane(U, cp, c.chrSrcH, &c.vc, dst[1], ds[1], c.chrDstW, c.chrDstH, 0);
@@ -1058,6 +1076,33 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
                    uint8_t *const dst[3], const int dstride[3], int dw, int dh, int flags)
 {
     int hs, vs, r;
+    if (src_fmt == 8 && !g_src_gray) {
+        /* gray8 source: one plane, chroma geometry of a format without sub-sampling (pixdesc: log2_chroma_w = log2_chroma_h = 0); the chroma lines are
+         * never converted (see g_src_gray).  Not restated: range conversion to a full-range yuvj destination (only the luma function would ever run),
+         * semi-planar destinations (planarCopyWrapper fills half of the interleaved chroma row), SwsFilter vectors. */
+        const int dj = (dst_fmt >= 12 && dst_fmt <= 14) || dst_fmt == 32;
+        if (dj || dst_fmt == 23 || dst_fmt == 24 || uses_filter() || g_nospecial) return -1;
+        { int h2, v2, b2 = 8; if (planar_dst(dst_fmt, &h2, &v2, &b2) && b2 == 16) { g_dbe = 0; return -1; } g_dbe = 0; }      /* (19-bit lines from a gray source: not restated for planar destinations) */
+        if (sw == dw && sh == dh && (dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28))) {
+            /* gray8 is a pseudo-palette format: at the same size a 24 / 32-bit rgb destination gets palToRgbWrapper (swscale_unscaled.c:342-384,
+             * installed at :1114-1121) with the palette sws_scale() builds for it, r = g = b = the sample (:1257-1259), alpha 255 (:1270-1295) */
+            const int bpp = dst_fmt <= 3 ? 3 : 4, a = (dst_fmt == 25 || dst_fmt == 27) ? 0 : 3;
+            for (int y = 0; y < sh; y++)
+                for (int x = 0; x < sw; x++) {
+                    uint8_t *d = dst[0] + (size_t)y * dstride[0] + (size_t)bpp * x;
+                    const uint8_t v = src[0][(size_t)y * ss[0] + x];
+                    if (bpp == 3) { d[0] = d[1] = d[2] = v; }
+                    else { d[0] = d[1] = d[2] = d[3] = v; d[a] = 255; }
+                }
+            return sh;
+        }
+        const uint8_t *const s3[3] = { src[0], src[0], src[0] };
+        const int ss3[3] = { ss[0], ss[0], ss[0] };
+        g_src_gray = 1;
+        r = sws_any(5, s3, ss3, sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+        g_src_gray = 0;
+        return r;
+    }
     if (src_fmt == 33) {
         /* yuva420p: the alpha plane is only read when the destination has alpha too (c->alpPixBuf, utils.c:1244; needAlpha, yuv2rgb.c:870); for
          * every other destination the format is treated like yuv420p wherever the reference tests formats (swscale_unscaled.c:1041-1153) */
@@ -1169,7 +1214,9 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     if (pk || IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) flags &= ~F_FULL_CHR_H_INT;
     if ((IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) && uses_filter()) return -1;
     if (IS_RGB48(dst_fmt) && (src_fmt == 23 || src_fmt == 24)) return -1;      /* (48-bit destinations: planar 8-bit yuv sources only) */
-    if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT)) return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
+    if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT) &&
+        !(sw == dw && sh == dh && (src_fmt == 2 || src_fmt == 3 || (src_fmt >= 25 && src_fmt <= 28)) && !g_nospecial))      /* (rgbToRgbWrapper never reaches that function) */
+        return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
     case 0: hs = 1; vs = 1; break;  case 4: hs = 1; vs = 0; break;  case 5: hs = 0; vs = 0; break;

@@ -76,6 +76,11 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
     return cudaSuccess;
 }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset2DAsync(void *d, size_t dp, int v, size_t w, size_t h, cudaStream_t)
+{
+    for (size_t y = 0; y < h; y++) memset((char *)d + y * dp, v, w);
+    return cudaSuccess;
+}
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 

@@ -161,6 +161,29 @@ def test_rgb2rgb_converters(sim, refo):
     assert n > 100
 
 
+def test_gray8_sources(sim, refo):
+    """gray8 sources (tests/test_sws_gray_src.py): constant chroma lines in the two-pass path, the plane copy with 128 fill, the pseudo-palette converter"""
+    import test_sws_gray_src as G
+    n = 0
+    for df in G.DSTS:
+        for (w, h, dw, dh) in G.GEOMS:
+            for flags in G.FLAGS[::2]:
+                pl = G.picture(w, h, 49)
+                if G.refused(df, w, h, dw, dh, flags):
+                    assert not sim.sws_getContext_cuda(w, h, 8, dw, dh, df, flags, None, None, None), (df, w, h, dw, dh, hex(flags))
+                    sim.avb200_clear_error()
+                    continue
+                rc, want = G.run(refo, pl, w, h, df, dw, dh, flags)
+                assert rc == dh
+                got = product(sim, 8, [pl], w, h, df, dw, dh, flags, outs=G.dest(df, dw, dh))
+                assert all(np.array_equal(x, y) for x, y in zip(G.crop(df, dw, got), G.crop(df, dw, want))), (df, w, h, dw, dh, hex(flags))
+                n += 1
+    assert n > 250
+    for df in (12, 23, 47):
+        assert not sim.sws_getContext_cuda(64, 48, 8, 128, 96, df, 4 | ACC, None, None, None)
+        sim.avb200_clear_error()
+
+
 def test_gray8_destination(sim, refo):
     """gray8 (tests/test_sws_gray_dst.py): the luma plane of the planar conversion, chroma into the context's scratch"""
     import test_sws_gray_dst as G

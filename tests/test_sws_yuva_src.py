@@ -25,7 +25,7 @@ def dest(df, w, h):
         return [np.zeros((h, w + 8), np.uint8 if bits == 8 else np.uint16) for (h, w) in ((h, w), (ch, cw), (ch, cw))]
     if df == 12:
         return [np.zeros((h, w + 8), np.uint8), np.zeros(((h + 1) // 2, (w + 1) // 2 + 8), np.uint8), np.zeros(((h + 1) // 2, (w + 1) // 2 + 8), np.uint8)]
-    return [np.zeros((h, w * {8: 1, 1: 2, 37: 2, 35: 6}.get(df, 3) + 16), np.uint8)]
+    return [np.zeros((h, w * {8: 1, 1: 2, 15: 2, 37: 2, 35: 6}.get(df, 3) + 16), np.uint8)]
 
 
 def run(o, sf, pl, sw, sh, df, dw, dh, flags):
@@ -41,7 +41,7 @@ def crop(df, dw, planes):
     """the pictures only, not the row padding (the reference's plane copies move whole strides when the pitches agree; port and reference differ
     in the room they need to write the pair of an odd last column of packed rgb)"""
     if len(planes) == 1:
-        return [planes[0][:, :dw * {8: 1, 1: 2, 37: 2, 35: 6}.get(df, 3)]]
+        return [planes[0][:, :dw * {8: 1, 1: 2, 15: 2, 37: 2, 35: 6}.get(df, 3)]]
     if df == 23:
         return [planes[0][:, :dw], planes[1][:, :2 * ((dw + 1) // 2)]]
     hs = 1 if df == 12 else PLANAR_FORMATS[df][0]

@@ -227,8 +227,15 @@ def test_sws_filter_frames(sim, refo):
 
 def test_negative_strides(sim):
     for (sf, df, w, h, dw, dh, flags) in [(0, 2, 64, 48, 96, 80, 4), (0, 2, 128, 64, 128, 64, 4 | ACC), (0, 0, 101, 37, 64, 48, 4), (4, 5, 64, 48, 64, 48, 2),
-                                           (1, 2, 64, 48, 96, 80, 4), (0, 28, 64, 48, 33, 25, 4), (0, 23, 64, 48, 96, 80, 4)]:
-        pl = source(sf, w, h, 31)
+                                           (1, 2, 64, 48, 96, 80, 4), (0, 28, 64, 48, 33, 25, 4), (0, 23, 64, 48, 96, 80, 4),
+                                           (0, 35, 64, 48, 96, 80, 4 | ACC), (0, 60, 64, 48, 64, 48, 4), (8, 2, 64, 48, 96, 80, 4), (8, 0, 64, 48, 64, 48, 4),
+                                           (8, 28, 64, 48, 64, 48, 4), (26, 3, 64, 48, 64, 48, 4), (2, 26, 64, 48, 64, 48, 4)]:
+        if sf == 8:
+            pl = [synth.pad_rows(np.random.RandomState(31).randint(0, 256, (h, w)).astype(np.uint8))]
+        elif 25 <= sf <= 28:
+            pl = [np.random.RandomState(31).randint(0, 256, (h, 4 * w + 12)).astype(np.uint8)]
+        else:
+            pl = source(sf, w, h, 31)
         want = product(sim, sf, pl, w, h, df, dw, dh, flags)
         src_up = [np.ascontiguousarray(a[::-1])[::-1] for a in pl]
         store = [np.ascontiguousarray(o[::-1]) for o in outputs(df, dw, dh)]

@@ -30,6 +30,10 @@ def source(sf, w, h, seed):
         return R.planes(sf, w, h, seed)
     if sf == 3:
         return [r.randint(0, 256, (h, 3 * w + 10)).astype(np.uint8)]
+    if sf == 8:                                                       # gray8: one plane
+        return [synth.pad_rows(r.randint(0, 256, (h, w)).astype(np.uint8))]
+    if 25 <= sf <= 28:
+        return [r.randint(0, 256, (h, 4 * w + 12)).astype(np.uint8)]
     if sf == 6:
         cw, ch = -((-w) >> 2), -((-h) >> 2)
         return [synth.pad_rows(r.randint(0, 256, d).astype(np.uint8)) for d in ((h, w), (ch, cw), (ch, cw))]
@@ -124,6 +128,23 @@ def test_unscaled_converter_slices(sim, refo):
                 compare(sim, refo, sf, df, w, h, w, h, flags, plan)
                 n += 1
     assert n >= 80
+
+
+def test_slices_of_the_late_formats(sim, refo):
+    """rgb48 destinations, gray8 sources and the same-size rgb2rgb converters under slices"""
+    n = 0
+    for sf, df in ((0, 35), (5, 60), (8, 2), (8, 0), (8, 37)):
+        for (w, h, dw, dh) in ((64, 48, 96, 80), (66, 50, 33, 25)):
+            for flags in (4 | ACC, 2):
+                for plan in plans(h, 1 << (VSUB.get(sf, 0) if sf != 8 else 0)):
+                    compare(sim, refo, sf, df, w, h, dw, dh, flags, plan)
+                    n += 1
+    for sf, df, flags, align in ((0, 35, 4, 2), (4, 59, 4, 2), (8, 0, 4, 2), (8, 5, 4, 1), (8, 26, 4, 1), (8, 3, 4, 1), (26, 2, 4, 1), (2, 28, 4, 1), (25, 27, 4, 1)):
+        for (w, h) in ((64, 48), (66, 52)):
+            for plan in plans(h, align):
+                compare(sim, refo, sf, df, w, h, w, h, flags, plan)
+                n += 1
+    assert n > 100
 
 
 def test_slice_refusals(sim):

@@ -131,6 +131,31 @@ def test_rgb48_destinations(sim, refo):
         sim.avb200_clear_error()
 
 
+def test_rgb48_colourspace_details(sim, refo):
+    """sws_setColorspaceDetails_cuda reaches the 48-bit output stage (the 16-bit coefficients of yuv2rgb.c:735-740) and its byte-doubling table converter"""
+    import test_sws_colorspace as CS
+    import test_sws_rgb48_dst as R
+    for cs in CS.SETTINGS[:5]:
+        tab = (C.c_int * 4)(*cs[0])
+        for (w, h, dw, dh, flags) in ((64, 48, 64, 48, 4), (101, 37, 333, 211, 4 | ACC), (64, 48, 96, 80, 2 | 0x80000)):
+            for df in (35, 59):
+                pl = R.source(0, w, h, 3)
+                refo.sws_set_colorspace(tab, cs[1], cs[2], cs[3], cs[4])
+                try:
+                    rc, want = R.run(refo, 0, pl, w, h, df, dw, dh, flags)
+                finally:
+                    refo.sws_set_colorspace(None, 0, 0, 0, 0)
+                assert rc == dh
+                ctx = sim.sws_getContext_cuda(w, h, 0, dw, dh, df, flags, None, None, None)
+                assert ctx and sim.sws_setColorspaceDetails_cuda(ctx, tab, cs[1], tab, 0, cs[2], cs[3], cs[4]) == 0, sim.avb200_last_error()
+                out = np.full((dh, dw * 6 + 8), 7, np.uint8)
+                sp, ss = arrays(pl)
+                dp, ds = arrays([out])
+                assert sim.sws_scale_cuda(ctx, sp, ss, 0, h, dp, ds) == dh, sim.avb200_last_error()
+                sim.sws_freeContext_cuda(ctx)
+                assert np.array_equal(out[:, :6 * dw], want[:, :6 * dw]), (cs, w, h, dw, dh, hex(flags), df)
+
+
 def test_yuva420p_sources(sim, refo):
     """yuva420p (33) to destinations without alpha: the product reads three planes like the reference does (tests/test_sws_yuva_src.py)"""
     import test_sws_rgb48_dst as R

@@ -111,3 +111,29 @@ def test_gpu_device_batch_and_refusals(gpu, checker):
         with pytest.raises(Exception):
             device.SwsContext(*args[:6], src_fmt=args[6])
         gpu.lib.avb200_clear_error()
+
+
+def test_colourspace_details(orc, refo, built):
+    """sws_setColorspaceDetails with a 48-bit destination: the 16-bit coefficients of yuv2rgb.c:735-740 (other matrix, full range, brightness /
+    contrast / saturation) -- port vs the compiled reference, and the product's kernels (host-compiled, tests/hostsim/) vs the reference"""
+    import test_sws_colorspace as CS
+    from test_hostsim_slots_cpu import sim as _sim_fixture            # noqa: F401
+    if refo is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+
+    def run_cs(o, pl, w, h, dfmt, dw, dh, flags, cs):
+        o.sws_set_colorspace((C.c_int * 4)(*cs[0]), cs[1], cs[2], cs[3], cs[4])
+        try:
+            return run(o, 0, pl, w, h, dfmt, dw, dh, flags)
+        finally:
+            o.sws_set_colorspace(None, 0, 0, 0, 0)
+    n = 0
+    for cs in CS.SETTINGS:
+        for (w, h, dw, dh) in ((64, 48, 64, 48), (101, 37, 333, 211), (64, 48, 96, 80)):
+            for flags in (4 | ACC, 4, 2 | 0x80000):
+                for dfmt in (35, 59):
+                    pl = source(0, w, h, 3)
+                    a, b = run_cs(refo, pl, w, h, dfmt, dw, dh, flags, cs), run_cs(orc, pl, w, h, dfmt, dw, dh, flags, cs)
+                    assert a[0] == b[0] == dh and np.array_equal(a[1], b[1]), (cs, w, h, dw, dh, hex(flags), dfmt)
+                    n += 1
+    assert n > 100

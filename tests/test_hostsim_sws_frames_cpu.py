@@ -156,6 +156,28 @@ def test_rgb48_colourspace_details(sim, refo):
                 assert np.array_equal(out[:, :6 * dw], want[:, :6 * dw]), (cs, w, h, dw, dh, hex(flags), df)
 
 
+def test_frames_call_with_one_plane_sources(sim, refo):
+    """sws_scale_frames_cuda (the device-pointer batch call; here "device memory" is host memory): a gray8 batch passes one plane, the entry point hands
+    the kernels the luma plane for the two nobody reads; two frames, every path a gray source has"""
+    import test_sws_gray_src as G
+    sim.sws_scale_frames_cuda.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+    for df, (w, h, dw, dh), flags in ((2, (64, 48, 96, 80), 4 | ACC), (0, (64, 48, 64, 48), 4), (26, (64, 48, 64, 48), 4), (35, (66, 50, 33, 25), 2), (0, (64, 48, 96, 80), 4)):
+        frames = [np.ascontiguousarray(G.picture(w, h, 60 + k)[:, :w]) for k in range(2)]
+        src = np.stack(frames)
+        want = [G.run(refo, f, w, h, df, dw, dh, flags)[1] for f in frames]
+        outs = [np.stack([np.zeros_like(p) for _ in range(2)]) for p in G.dest(df, dw, dh)]
+        ctx = sim.sws_getContext_cuda(w, h, 8, dw, dh, df, flags, None, None, None)
+        assert ctx, sim.avb200_last_error()
+        sp, ss, sf = (C.c_void_p * 3)(src.ctypes.data, None, None), (C.c_int * 3)(src.strides[1], 0, 0), (C.c_size_t * 3)(src.strides[0], 0, 0)
+        dp = (C.c_void_p * 3)(*([o.ctypes.data for o in outs] + [None] * (3 - len(outs))))
+        ds = (C.c_int * 3)(*([o.strides[1] for o in outs] + [0] * (3 - len(outs))))
+        dfr = (C.c_size_t * 3)(*([o.strides[0] for o in outs] + [0] * (3 - len(outs))))
+        assert sim.sws_scale_frames_cuda(ctx, sp, ss, sf, dp, ds, dfr, 2, None) == 2 * dh, sim.avb200_last_error()
+        sim.sws_freeContext_cuda(ctx)
+        for k in range(2):
+            assert all(np.array_equal(x, y) for x, y in zip(G.crop(df, dw, [o[k] for o in outs]), G.crop(df, dw, want[k]))), (df, k)
+
+
 def test_yuva420p_sources(sim, refo):
     """yuva420p (33) to destinations without alpha: the product reads three planes like the reference does (tests/test_sws_yuva_src.py)"""
     import test_sws_rgb48_dst as R

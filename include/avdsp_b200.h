@@ -457,7 +457,7 @@ int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float 
 /* ---- libswscale boundary (libswscale/swscale.h:159-207) ------------------------------------------------
  * Same argument lists as sws_getContext / sws_scale / sws_freeContext; pixel formats are the reference's
  * AVPixelFormat values (AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_RGB24 = 2, AV_PIX_FMT_BGR24 = 3), flags the
- * reference's SWS_* bits.  Taken over: planar 8-bit yuv (420p, 422p = 4, 444p = 5, 410p = 6, 411p = 7, 440p = 31; yuva420p = 33 like 420p, src[3] is not read), gray8 = 8 (src[0] only), nv12 = 23,
+ * reference's SWS_* bits.  Taken over: planar 8-bit yuv (420p, 422p = 4, 444p = 5, 410p = 6, 411p = 7, 440p = 31; yuva420p = 33 like 420p, src[3] is not read), gray8 = 8 (src[0] only), pal8 = 11 (src[0] indices, src[1] the 256-entry 0xAARRGGBB palette: 1024 bytes, per frame in the batch call), nv12 = 23,
  * nv21 = 24, planar 9 / 10 / 16-bit yuv 420p 422p 444p (LE and BE; scaled, or to packed destinations / another sub-sampling), and the packed yuyv422 = 1, uyvy422 = 15, rgb24, bgr24, argb / rgba / abgr / bgra (to planar yuv, or scaled to rgb24 / bgr24) sources (src[0] only) -> gray8 = 8 (the luma plane alone) / rgb24 / bgr24 / argb = 25 / rgba = 26 / abgr = 27 / bgra = 28 / rgb565 = 37 / bgr565 = 41 / rgb555 = 39 / bgr555 = 43 / rgb444 = 54 / bgr444 = 56 (and their big-endian twins 36 / 40 / 38 / 42 / 55 / 57; from planar or semi-planar yuv sources through the scaler's dithered 16-bpp output stage, output.c:869-902) / yuyv422 / uyvy422 / nv12 / nv21 (dst[0] luma, dst[1] interleaved chroma) / planar yuv (8-bit 420p
  * 422p 444p 410p 411p 440p and their full-range yuvj twins 12 / 13 / 14 / 32 on either side -- a yuv destination of the other range gets the
  * reference's range conversion, planar 8 / 9 / 10-bit only; 9 / 10 / 16-bit 420p = 62 / 64 / 47, 422p = 72 / 66 / 49, 444p = 68 / 70 / 51 little-endian and their big-endian twins), any size, SWS_FULL_CHR_H_INT or not, every scaler

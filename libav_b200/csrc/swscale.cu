@@ -1078,6 +1078,44 @@ sws_read_packed_kernel(const uint8_t *__restrict__ src, int srcStride, size_t sr
     }
 }
 
+// pal8 sources: src = one index per pixel, pal = 256 native-endian 0xAARRGGBB words (per frame).  sws_scale() converts the palette to limited-range
+// y / u / v for every call (swscale_unscaled.c:1236-1268, constants of swscale_internal.h with RGB2YUV_SHIFT 15, av_clip_uint8 on each) and the readers
+// palToY_c / palToUV_c look the samples up (input.c:321-343) -- chroma at full resolution.  Here a thread converts its own pixel's entry.
+__device__ __forceinline__ void pal8_entry(const uint32_t *__restrict__ pal, int i, int &r, int &g, int &b)
+{
+    const uint32_t p = pal[i];
+    r = (p >> 16) & 255; g = (p >> 8) & 255; b = p & 255;
+}
+__global__ void __launch_bounds__(256)
+sws_read_pal8_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, const uint8_t *__restrict__ pal, size_t palFrame, uint8_t *__restrict__ Y,
+                     uint8_t *__restrict__ U, uint8_t *__restrict__ V, int pitch, size_t plane, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t f = blockIdx.z;
+    using namespace rd;
+    int r, g, b;
+    pal8_entry(reinterpret_cast<const uint32_t *>(pal + f * palFrame), src[f * srcFrame + (size_t)y * srcStride + x], r, g, b);
+    const size_t o = f * plane + (size_t)y * pitch + x;
+    Y[o] = (uint8_t)clip_u8((RY * r + GY * g + BY * b + (33 << (SH - 1))) >> SH);
+    U[o] = (uint8_t)clip_u8((RU * r + GU * g + BU * b + (257 << (SH - 1))) >> SH);
+    V[o] = (uint8_t)clip_u8((RV * r + GV * g + BV * b + (257 << (SH - 1))) >> SH);
+}
+// palToRgbWrapper (swscale_unscaled.c:342-384): same size to 24 / 32-bit rgb is a palette lookup, alpha 255 (the table of :1270-1295); map as in
+// sws_rgb_map_kernel with source "bytes" 0 = r, 1 = g, 2 = b
+__global__ void __launch_bounds__(256)
+sws_pal8_rgb_kernel(const uint8_t *__restrict__ src, int srcStride, size_t srcFrame, const uint8_t *__restrict__ pal, size_t palFrame, uint8_t *__restrict__ dst,
+                    int dstStride, size_t dstFrame, int w, int h, int dbpp, unsigned map)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t f = blockIdx.z;
+    int v[3];
+    pal8_entry(reinterpret_cast<const uint32_t *>(pal + f * palFrame), src[f * srcFrame + (size_t)y * srcStride + x], v[0], v[1], v[2]);
+    uint8_t *d = dst + f * dstFrame + (size_t)y * dstStride + (size_t)dbpp * x;
+    for (int k = 0; k < dbpp; k++) { const unsigned m = (map >> (4 * k)) & 15; d[k] = m == 15 ? (uint8_t)255 : (uint8_t)v[m]; }
+}
+
 // the reference's unscaled special converters for these sources (swscale_unscaled.c:1063-1072,1140-1145):
 // rgb24 <-> bgr24 (rgbToRgbWrapper -> rgb24tobgr24, rgb2rgb_template.c) and the same-format copy (packedCopyWrapper); only the
 // w x h pixels are written (the reference's whole-buffer variants also convert the row padding when the strides match)
@@ -1285,6 +1323,7 @@ struct SwsCudaContext {
     bool srcGray = false;       // gray8 source: luma only; swscale() never converts chroma lines for it (needs_hcscale, swscale.c:532,768-770) and the vertical stage
                                 // reads what sws_init_context left in the line buffers -- bytes of 64 (utils.c:1273).  Geometry of a format without chroma sub-sampling;
                                 // the entry points hand the kernels the luma plane in place of the two planes the caller does not have (never read)
+    uint8_t *d_pal = nullptr;   // pal8 sources through the host-pointer call: the caller's palette (256 x 4 bytes)
     int srcFormat = 0;          // the source pixel format (after the yuvj / yuva / high-bit-depth twins were folded)
     int special = 0;            // the reference's unscaled converters for packed sources: 1 rgb copy, 2 rgb24 <-> bgr24, 3 bgr24 -> yuv420p
                                 // (rgb24toyv12_c), 4 yuyv422 -> yuv420p, 5 uyvy422 -> yuv420p, 6 yuyv422 -> yuv422p, 7 uyvy422 -> yuv422p
@@ -1319,7 +1358,7 @@ static void destroy(SwsCudaContext *c)
 {
     if (!c) return;
     if (c->streams_ok) for (int i = 0; i < 3; i++) cudaStreamDestroy(c->streams[i]);
-    cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_gray[0]); cudaFree(c->d_gray[1]);
+    cudaFree(c->d_pal); cudaFree(c->d_tables); cudaFree(c->d_pair_taps); cudaFree(c->d_pair_taps_t); cudaFree(c->d_nv); cudaFree(c->d_rgb); cudaFree(c->d_tile_win); cudaFree(c->d_lum); cudaFree(c->d_chrU); cudaFree(c->d_chrV); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_gray[0]); cudaFree(c->d_gray[1]);
     delete c;
 }
 
@@ -1453,6 +1492,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     case FMT_YUV411P: hs = 2; vs = 0; break;
     case FMT_YUV440P: hs = 0; break;
     case FMT_YUYV422: case FMT_UYVY422: vs = 0; break;
+    case 11: hs = 0; vs = 0; break;                            // AV_PIX_FMT_PAL8 (pixdesc: one component, no chroma sub-sampling; its readers give chroma per pixel)
     case FMT_RGB24: case FMT_BGR24: case FMT_ARGB: case FMT_RGBA: case FMT_ABGR: case FMT_BGRA: {   // utils.c:1021-1034: every other pixel for chroma unless told / forced otherwise
         const int chrDstHSub = planar ? dhs : (flags & SWS_FULL_CHR_H_INT) ? 0 : 1;
         hs = (!(flags & SWS_FULL_CHR_H_INP) && ((dstW >> chrDstHSub) <= (srcW >> 1) || (flags & SWS_FAST_BILINEAR))) ? 1 : 0;
@@ -1472,9 +1512,9 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         // 32 -> 32 bit at another size: the reference scales the alpha plane too; same size -> 16 / 48-bit rgb: other converter families
         set_error_msg("sws_getContext_cuda", "32-bit rgb source: planar yuv destinations, scaled rgb24 / bgr24 and same-size 24 / 32-bit rgb are taken over"); return nullptr;
     }
-    const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422;
+    const bool srcRgb = srcFormat == FMT_RGB24 || srcFormat == FMT_BGR24, srcYuy = srcFormat == FMT_YUYV422 || srcFormat == FMT_UYVY422, srcPal = srcFormat == 11;
     const bool unscaled = srcW == dstW && srcH == dstH;
-    if (dstFormat == FMT_ABGR && (flags & SWS_FULL_CHR_H_INT) && !grayPal && !rgb2rgb) {      // (the unscaled converters never reach that output function)  // output.c:1231-1237 advances the pointer twice per abgr pixel and runs off the row
+    if (dstFormat == FMT_ABGR && (flags & SWS_FULL_CHR_H_INT) && !grayPal && !rgb2rgb && !(srcPal && unscaled && !usesFilter)) {      // (the unscaled converters never reach that output function)  // output.c:1231-1237 advances the pointer twice per abgr pixel and runs off the row
         set_error_msg("sws_getContext_cuda", "abgr with SWS_FULL_CHR_H_INT: the reference's output function overruns the destination; there is no result to match");
         return nullptr;
     }
@@ -1497,7 +1537,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         // the 15 / 16 / 12-bpp destinations exist where swscale()'s packed output stage runs (yuv2rgb16_X / _2 / _1 ..., output.c:1321-1326);
         // the reference's other routes to them are separate converter families that are not taken over
         const char *why = nullptr;
-        if (srcRgb || src32 || srcYuy) why = "15 / 16 / 12-bpp rgb destinations are taken over for planar / semi-planar yuv sources only";
+        if (srcRgb || src32 || srcYuy || srcPal) why = "15 / 16 / 12-bpp rgb destinations are taken over for planar / semi-planar yuv sources only";
         else if ((srcFormat == FMT_YUV420P || srcFormat == FMT_YUV422P) && unscaled && !(flags & SWS_ACCURATE_RND) && !(dstH & 1) && !usesFilter && srcBits == 8)
             why = "same-size yuv -> 15 / 16 / 12-bpp rgb without SWS_ACCURATE_RND is the reference's ordered-dither table converter (yuv2rgb.c:377-573): not taken over";
         else if (usesFilter) why = "SwsFilter vectors with a 15 / 16 / 12-bpp destination are not taken over";
@@ -1513,7 +1553,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     if (rgb48) {
         // 48-bit destinations: the packed output stage on hScale8To19_c lines, and the unscaled table converter; planar 8-bit yuv sources
         const char *why = nullptr;
-        if (srcRgb || src32 || srcYuy || srcFormat == FMT_NV12 || srcFormat == FMT_NV21) why = "48-bit rgb destinations are taken over for planar 8-bit yuv sources only";
+        if (srcRgb || src32 || srcYuy || srcPal || srcFormat == FMT_NV12 || srcFormat == FMT_NV21) why = "48-bit rgb destinations are taken over for planar 8-bit yuv sources only";
         else if (srcBits > 8) why = "9 / 10 / 16-bit source to a 48-bit rgb destination (hScale16To19_c lines) is not taken over";
         else if (usesFilter) why = "SwsFilter vectors with a 48-bit rgb destination are not taken over";
         if (why) { set_error_msg("sws_getContext_cuda", why); return nullptr; }
@@ -1523,7 +1563,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         auto asym = [](const SwsVec *v) { if (!v) return false; for (int i = 0; i < v->length / 2; i++) if (v->coeff[i] != v->coeff[v->length - 1 - i]) return true; return false; };
         if (asym(sf.lumV) || asym(sf.chrV)) { set_error_msg("sws_getContext_cuda", "asymmetric vertical SwsFilter vectors are not taken over"); return nullptr; }
     }
-    if (usesFilter && (srcRgb || srcYuy || src32 || srcFormat == FMT_NV12 || srcFormat == FMT_NV21 || pk422 || dstFormat == FMT_NV12 || dstFormat == FMT_NV21 || dbits != 8)) {
+    if (usesFilter && (srcRgb || srcYuy || src32 || srcPal || srcFormat == FMT_NV12 || srcFormat == FMT_NV21 || pk422 || dstFormat == FMT_NV12 || dstFormat == FMT_NV21 || dbits != 8)) {
         set_error_msg("sws_getContext_cuda", "SwsFilter vectors are taken over for planar 8-bit yuv sources to packed rgb / planar 8-bit yuv destinations only");
         return nullptr;
     }
@@ -1558,14 +1598,15 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->srcNV = srcFormat == FMT_NV12 ? 1 : srcFormat == FMT_NV21 ? 2 : 0;
     double prm[2] = { param ? param[0] : SWS_PARAM_DEFAULT, param ? param[1] : SWS_PARAM_DEFAULT };
     c->src422 = srcFormat == FMT_YUV422P && srcBits == 8;
-    c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : src32 ? 4 : 0;
+    c->srcPacked = srcRgb ? 1 : srcFormat == FMT_YUYV422 ? 2 : srcFormat == FMT_UYVY422 ? 3 : src32 ? 4 : srcPal ? 5 : 0;
     c->pkR = srcFormat == FMT_BGR24 ? 2 : 0; c->pkB = 2 - c->pkR; c->srcFormat = srcFormat;
     if (src32) {
         static const int rgbpos[4][3] = { { 1, 2, 3 }, { 0, 1, 2 }, { 3, 2, 1 }, { 2, 1, 0 } };       // argb, rgba, abgr, bgra
         c->pkR = rgbpos[srcFormat - FMT_ARGB][0]; c->pkG = rgbpos[srcFormat - FMT_ARGB][1]; c->pkB = rgbpos[srcFormat - FMT_ARGB][2];
     }
     if (unscaled && !usesFilter) {                            // swscale_unscaled.c:1063-1072,1140-1145,1152-1176 (yuv destinations: only with equal ranges, utils.c:1043-1044)
-        if (grayPal) c->special = 9;
+        if (srcPal && (dstFormat == FMT_RGB24 || dstFormat == FMT_BGR24 || dst32)) c->special = 10;      // palToRgbWrapper (swscale_unscaled.c:1114-1121)
+        else if (grayPal) c->special = 9;
         else if (rgb2rgb) c->special = 8;
         else if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (rangeConv) c->special = 0;
@@ -1612,6 +1653,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
     c->nvcopy = c->dstNV && srcFormat == FMT_YUV420P && srcW == dstW && srcH == dstH && !rangeConv && srcBits == 8;           // swscale_unscaled.c:1040-1044
     if (!device_side) return c;
     if (upload_tables(c)) { destroy(c); return nullptr; }
+    if (srcPal && cudaMalloc(&c->d_pal, 1024) != cudaSuccess) { set_error("sws_getContext_cuda", cudaGetLastError()); destroy(c); return nullptr; }
     if (c->gray) {
         c->grayPitch = (c->g.chrDstW + 63) & ~31;
         for (int k = 0; k < 2; k++)
@@ -1768,7 +1810,10 @@ static int run_packed(SwsCudaContext *c, const uint8_t *const src[3], const int 
     uint8_t *Y = c->d_nv, *U = Y + yPlane * nframes, *V = U + cPlane * nframes;
     const dim3 grid(((w + 1) / 2 + 255) / 256, h, nframes);
     const int half = p.chrSrcW != w;
-    if (c->srcPacked == 1)      sws_read_packed_kernel<1><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkG, c->pkB, half);
+    if (c->srcPacked == 5) {
+        if (!src[1]) { set_error_msg("sws_scale", "pal8 source without a palette in plane 1"); return -1; }
+        sws_read_pal8_kernel<<<dim3((w + 255) / 256, h, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], src[1], srcFrame[1], Y, U, V, yPitch, yPlane, w, h);
+    } else if (c->srcPacked == 1)      sws_read_packed_kernel<1><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkG, c->pkB, half);
     else if (c->srcPacked == 4) sws_read_packed_kernel<4><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, c->pkR, c->pkG, c->pkB, half);
     else if (c->srcPacked == 2) sws_read_packed_kernel<2><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 0, 1);
     else                        sws_read_packed_kernel<3><<<grid, 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], Y, U, V, yPitch, cPitch, yPlane, cPlane, w, h, 0, 0, 0, 1);
@@ -1789,7 +1834,7 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
 static int run_frames(SwsCudaContext *c, const uint8_t *const src[3], const int srcStride[3], const size_t srcFrame[3],
                       uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st)
 {
-    if (!c->dst32 || c->special == 8 || c->special == 9) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);      // (special 8: the rgb2rgb remap writes 4-byte pixels itself)
+    if (!c->dst32 || c->special == 8 || c->special == 9 || c->special == 10) return run_frames_24(c, src, srcStride, srcFrame, dst, dstStride, dstFrame, nframes, st);      // (special 8: the rgb2rgb remap writes 4-byte pixels itself)
     if (nframes <= 0) return 0;
     const SwsDev &p = c->dev;
     const int pitch = ((p.dstW + 1) * 3 + 15) & ~15;
@@ -1819,6 +1864,18 @@ static int run_frames_24(SwsCudaContext *c, const uint8_t *const src[3], const i
                          uint8_t *const dst[3], const int dstStride[3], const size_t dstFrame[3], int nframes, cudaStream_t st,
                          uint8_t *const *remapped)
 {
+    if (c->special == 10) {            // pal8 -> 24 / 32-bit rgb of the same size: the palette lookup of palToRgbWrapper
+        if (nframes <= 0) return 0;
+        if (!src[1]) { set_error_msg("sws_scale", "pal8 source without a palette in plane 1"); return -1; }
+        static const int chan[6][4] = { { 0, 1, 2, -1 }, { 2, 1, 0, -1 }, { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };      // byte of r, g, b, a
+        const SwsDev &q = c->dev;
+        const int df = c->dst32 ? 2 + c->dst32 - FMT_ARGB : c->dstFormat == FMT_BGR24 ? 1 : 0, dbpp = c->dst32 ? 4 : 3;
+        unsigned map = 0;
+        for (int ch = 0; ch < 4; ch++) if (chan[df][ch] >= 0) map |= (unsigned)(ch < 3 ? ch : 15) << (4 * chan[df][ch]);
+        sws_pal8_rgb_kernel<<<dim3((q.srcW + 255) / 256, q.srcH, nframes), 256, 0, st>>>(src[0], srcStride[0], srcFrame[0], src[1], srcFrame[1], dst[0], dstStride[0], dstFrame[0],
+                                                                                     q.srcW, q.srcH, dbpp, map);
+        return check_launch("sws_scale:pal8 -> rgb");
+    }
     if (c->special == 9) {             // gray8 -> 24 / 32-bit rgb of the same size: the pseudo-palette lookup is r = g = b = sample, alpha 255
         if (nframes <= 0) return 0;
         const SwsDev &q = c->dev;
@@ -2156,6 +2213,7 @@ int sws_scale_frames_cuda(SwsContextCUDA *ctx, const uint8_t *const src[3], cons
         if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, d3, ds3, df3, nframes, (cudaStream_t)stream)) return -1;
         return c->g.dstH * nframes;
     }
+    if (c->srcPacked == 5 && src && !src[1]) { set_error_msg("sws_scale_frames_cuda", "a pal8 batch needs its palettes in plane 1 (device pointer, 1024 bytes per frame)"); return -1; }
     if (!src || !dst || !src[0] || (!c->srcPacked && (!src[1] || (!c->srcNV && !src[2]))) || !dst[0] || (c->planar && (!dst[1] || (!c->dstNV && !dst[2])))) { set_error_msg("sws_scale_frames_cuda", "bad image pointers"); return -1; }
     if (run_frames(c, src, srcStride, srcFrameStride ? srcFrameStride : zero3, dst, dstStride, dstFrameStride ? dstFrameStride : zero3,
                    nframes, (cudaStream_t)stream)) return -1;
@@ -2171,7 +2229,7 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
 {
     const SwsGeometry &g = c->g;
     const bool pk = c->srcPacked != 0, nv = c->srcNV != 0, rgb = !c->planar;
-    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : c->srcPacked == 5 ? 1 : 2, sB = c->dstBits > 8 ? 2 : 1, pxB = c->rgb48 ? 6 : (c->pk422 || c->rgb16) ? 2 : c->dst32 ? 4 : 3;
     const int nsrc = pk ? 1 : nv ? 2 : 3, ndst = rgb ? 1 : c->dstNV ? 2 : 3;
     const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH }, dstRows[3] = { g.dstH, g.chrDstH, g.chrDstH };
     const size_t sS = c->srcBits > 8 ? 2 : 1;
@@ -2182,6 +2240,7 @@ static int sws_scale_cuda_flipped(SwsCudaContext *c, const uint8_t *const srcSli
     uint8_t *d2[4] = { nullptr, nullptr, nullptr, nullptr };
     int ss[4] = { 0, 0, 0, 0 }, ds[4] = { 0, 0, 0, 0 };
     size_t drow[3] = { 0, 0, 0 };
+    if (c->srcPacked == 5) { s2[1] = srcSlice[1]; ss[1] = srcStride[1]; }       // (pal8: the palette travels as it is)
     for (int p = 0; p < nsrc; p++) {
         s2[p] = srcSlice[p]; ss[p] = srcStride[p];
         if (srcStride[p] >= 0) continue;
@@ -2241,7 +2300,7 @@ static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlic
         if ((srcSliceY & m) || ((srcSliceH & m) && end != g.srcH)) { set_error_msg("sws_scale_cuda", "slice not aligned to the chroma rows"); return 0; }
     }
     // keep the rows
-    const int sS = c->srcBits > 8 ? 2 : 1, pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2;
+    const int sS = c->srcBits > 8 ? 2 : 1, pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : c->srcPacked == 5 ? 1 : 2;
     const int srcRows[3] = { g.srcH, g.chrSrcH, g.chrSrcH };
     const size_t srcWB[3] = { (size_t)g.srcW * (pk ? pkBpp : sS), (size_t)g.chrSrcW * (nv ? 2 : 1) * sS, (size_t)g.chrSrcW * sS };
     const int cY0 = srcSliceY >> g.chrSrcVSub, cY1 = -((-end) >> g.chrSrcVSub);
@@ -2283,6 +2342,7 @@ static int sws_scale_cuda_sliced(SwsCudaContext *c, const uint8_t *const srcSlic
     int ss[4] = { 0, 0, 0, 0 }, ds[4] = { 0, 0, 0, 0 };
     size_t drow[3] = { 0, 0, 0 };
     for (int p = 0; p < nsrc; p++) { s2[p] = c->sliceSrc[p].data(); ss[p] = srcStride[p]; }
+    if (c->srcPacked == 5) { s2[1] = srcSlice[1]; ss[1] = srcStride[1]; }         // (pal8: this slice's palette, like sws_scale() rebuilds its tables per call)
     for (int p = 0; p < ndst; p++) {
         const size_t pitch = (size_t)dstStride[p];
         drow[p] = pitch < dstWB[p] + 16 ? pitch : dstWB[p] + 16;
@@ -2335,6 +2395,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         !dst[0] || !dstStride[0] || (!rgb && (!dst[1] || !dstStride[1] || (!c->dstNV && (!dst[2] || !dstStride[2]))))) {
         set_error_msg("sws_scale_cuda", "bad image pointers"); return 0;
     }
+    if (c->srcPacked == 5 && !srcSlice[1]) { set_error_msg("sws_scale_cuda", "a pal8 picture needs its palette in plane 1"); return 0; }
     if (srcSliceY != 0 || srcSliceH != c->g.srcH) return sws_scale_cuda_sliced(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     c->sliceNextY = 0; c->sliceDstY = 0;
     if (srcStride[0] < 0 || (!pk && (srcStride[1] < 0 || (!nv && srcStride[2] < 0))) || dstStride[0] < 0 ||
@@ -2353,7 +2414,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const SwsGeometry &g = c->g;
     // device staging: tight, aligned pitches
     // (a packed source keeps the caller's pitch: the chroma readers look one pixel past an odd width, into the padding or the next row)
-    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : 2;
+    const int pkBpp = c->srcPacked == 1 ? 3 : c->srcPacked == 4 ? 4 : c->srcPacked == 5 ? 1 : 2;
     const int sS = c->srcBits > 8 ? 2 : 1;                  // bytes per source sample (planar 9 / 10 / 16-bit sources)
     const int yP = pk ? srcStride[0] : (g.srcW * sS + 15) & ~15, cP = ((nv ? 2 : 1) * g.chrSrcW * sS + 15) & ~15;
     const size_t yB = (size_t)yP * g.srcH, cB = pk ? 0 : (size_t)cP * g.chrSrcH;
@@ -2366,7 +2427,7 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     const size_t needD = dB + 2 * dcB;
     if (c->src_bytes < needS) { cudaFree(c->d_src); c->d_src = nullptr; if (cudaMalloc(&c->d_src, needS) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->src_bytes = needS; }
     if (c->dst_bytes < needD) { cudaFree(c->d_dst); c->d_dst = nullptr; if (cudaMalloc(&c->d_dst, needD) != cudaSuccess) { set_error("sws_scale_cuda", cudaGetLastError()); return 0; } c->dst_bytes = needD; }
-    const uint8_t *ds[3] = { c->d_src, c->d_src + yB, c->d_src + yB + cB };
+    const uint8_t *ds[3] = { c->d_src, c->srcPacked == 5 ? c->d_pal : c->d_src + yB, c->d_src + yB + cB };     // (pal8: plane 1 is the palette)
     uint8_t *dd[3] = { c->d_dst, c->d_dst + dB, c->d_dst + dB + dcB };
     const int dsS[3] = { yP, cP, cP }, ddS[3] = { dP, dcP, dcP };
     // Same-size rgb (the dp4a fused kernel): the frame goes through in bands of rows on three streams, so the upload of band
@@ -2413,7 +2474,8 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
     if (pk) {
         size_t rowB = (size_t)g.srcW * pkBpp;
         if ((g.srcW & 1) && rowB + pkBpp <= (size_t)srcStride[0]) rowB += pkBpp;       // the pixel the readers look at past an odd width
-        if (cudaMemcpyAsync((void *)ds[0], srcSlice[0], (size_t)(g.srcH - 1) * srcStride[0] + rowB, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        if (cudaMemcpyAsync((void *)ds[0], srcSlice[0], (size_t)(g.srcH - 1) * srcStride[0] + rowB, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            (c->srcPacked == 5 && cudaMemcpyAsync(c->d_pal, srcSlice[1], 1024, cudaMemcpyHostToDevice, s) != cudaSuccess)) {
             set_error("sws_scale_cuda:h2d", cudaGetLastError()); return 0;
         }
     } else if (cudaMemcpy2DAsync((void *)ds[0], yP, srcSlice[0], srcStride[0], (size_t)(g.srcW + upX) * sS, g.srcH, cudaMemcpyHostToDevice, s) != cudaSuccess ||

@@ -1003,6 +1003,54 @@ static int packed_source(int src_fmt, const uint8_t *src, int stride, int sw, in
     return r;
 }
 
+/* pal8 (AV_PIX_FMT_PAL8 = 11) sources: src[0] = one index per pixel, src[1] = 256 native-endian 0xAARRGGBB entries.  sws_scale() turns the palette into
+ * limited-range y / u / v per entry for every call (swscale_unscaled.c:1236-1268, the rgb -> yuv constants of swscale_internal.h with RGB2YUV_SHIFT 15)
+ * and the readers palToY_c / palToUV_c look the samples up (input.c:321-343): chroma at full resolution (pixdesc: no sub-sampling).  At the same size a
+ * 24 / 32-bit rgb destination is palToRgbWrapper, a lookup of r, g, b with alpha 255 (:342-384,1270-1295); the palette's alpha byte is never used. */
+static int pal8_source(const uint8_t *src, int stride, const uint8_t *pal, int sw, int sh, int dst_fmt, uint8_t *const dst[3], const int ds[3], int dw, int dh, int flags)
+{
+    int R[256], G[256], B[256];
+    for (int i = 0; i < 256; i++) {
+        uint32_t p; memcpy(&p, pal + 4 * i, 4);
+        R[i] = (p >> 16) & 255; G[i] = (p >> 8) & 255; B[i] = p & 255;
+    }
+    const int real_rgb_dst = dst_fmt == 2 || dst_fmt == 3 || (dst_fmt >= 25 && dst_fmt <= 28);
+    const int rgb_dst = real_rgb_dst || dst_fmt == 1 || dst_fmt == 15 || IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt);
+    if (IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) return -1;            /* (like the packed rgb sources: not restated) */
+    if (sw == dw && sh == dh && real_rgb_dst && !uses_filter()) {
+        static const int chan[6][4] = { { 0, 1, 2, -1 }, { 2, 1, 0, -1 }, { 1, 2, 3, 0 }, { 0, 1, 2, 3 }, { 3, 2, 1, 0 }, { 2, 1, 0, 3 } };  /* byte of r, g, b, a */
+        const int *dc = chan[dst_fmt >= 25 ? dst_fmt - 23 : dst_fmt - 2], bpp = dst_fmt >= 25 ? 4 : 3;
+        for (int y = 0; y < sh; y++)
+            for (int x = 0; x < sw; x++) {
+                const int i = src[(size_t)y * stride + x];
+                uint8_t *d = dst[0] + (size_t)y * ds[0] + (size_t)bpp * x;
+                d[dc[0]] = (uint8_t)R[i]; d[dc[1]] = (uint8_t)G[i]; d[dc[2]] = (uint8_t)B[i];
+                if (bpp == 4) d[dc[3]] = 255;
+            }
+        return sh;
+    }
+    if (uses_filter()) return -1;
+    const int yp = sw + 16;
+    uint8_t *Y = calloc((size_t)yp * sh * 3, 1), *U = Y + (size_t)yp * sh, *V = U + (size_t)yp * sh;
+    if (!Y) return -1;
+    for (int y = 0; y < sh; y++)
+        for (int x = 0; x < sw; x++) {
+            const int i = src[(size_t)y * stride + x], r = R[i], g = G[i], b = B[i];
+            Y[(size_t)y * yp + x] = u8clip((C_RY * r + C_GY * g + C_BY * b + (33 << (RSH - 1))) >> RSH);
+            U[(size_t)y * yp + x] = u8clip((C_RU * r + C_GU * g + C_BU * b + (257 << (RSH - 1))) >> RSH);
+            V[(size_t)y * yp + x] = u8clip((C_RV * r + C_GV * g + C_BV * b + (257 << (RSH - 1))) >> RSH);
+        }
+    const uint8_t *pl[3] = { Y, U, V };
+    const int ss[3] = { yp, yp, yp };
+    g_hs = 0; g_vs = 0; g_nocopy = 1;
+    /* (planarCopyWrapper is only installed for planar yuv / gray sources: keep the port off that branch) */
+    int r = rgb_dst ? to_rgb_or_bgr(pl, ss, sw, sh, dst_fmt, dst[0], ds[0], dw, dh, flags)
+                    : orc_sws_yuv420p_to_yuv420p(pl, ss, sw, sh, dst, ds, dw, dh, flags);
+    g_hs = 1; g_vs = 1; g_nocopy = 0;
+    free(Y);
+    return r;
+}
+
 /* planar destinations: AV_PIX_FMT_YUV420P 0, YUV422P 4, YUV444P 5, YUV410P 6, YUV411P 7, YUV440P 31, and the little-endian
  * YUV420P9 62, YUV420P10 64, YUV422P10 66, YUV444P9 68, YUV444P10 70, YUV422P9 72 */
 static int planar_dst(int fmt, int *hs, int *vs, int *bits)
@@ -1215,7 +1263,7 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     if ((IS_RGB16(dst_fmt) || IS_RGB48(dst_fmt)) && uses_filter()) return -1;
     if (IS_RGB48(dst_fmt) && (src_fmt == 23 || src_fmt == 24)) return -1;      /* (48-bit destinations: planar 8-bit yuv sources only) */
     if (dst_fmt == 27 && (flags & F_FULL_CHR_H_INT) &&
-        !(sw == dw && sh == dh && (src_fmt == 2 || src_fmt == 3 || (src_fmt >= 25 && src_fmt <= 28)) && !g_nospecial))      /* (rgbToRgbWrapper never reaches that function) */
+        !(sw == dw && sh == dh && (src_fmt == 2 || src_fmt == 3 || src_fmt == 11 || (src_fmt >= 25 && src_fmt <= 28)) && !g_nospecial))      /* (rgbToRgbWrapper / palToRgbWrapper never reach that function) */
         return -1;    /* yuv2rgb_full_X_c advances twice per abgr pixel (output.c:1231-1237): no defined result */
     if (!rgb && !planar_dst(dst_fmt, &g_dhs, &g_dvs, &g_dbits)) return -1;
     switch (src_fmt) {
@@ -1223,6 +1271,11 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
     case 6: hs = 2; vs = 2; break;  case 7: hs = 2; vs = 0; break;  case 31: hs = 0; vs = 1; break;
     case 23: case 24:                                   /* src[0] luma, src[1] interleaved chroma */
         r = orc_sws_nv12(src_fmt == 24, src[0], ss[0], src[1], ss[1], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
+        g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
+        return r;
+    case 11:                                            /* pal8: src[0] indices, src[1] the palette */
+        if (!src[1] || g_sbits != 8) { g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0; return -1; }
+        r = pal8_source(src[0], ss[0], src[1], sw, sh, dst_fmt, dst, dstride, dw, dh, flags);
         g_dhs = g_dvs = 1; g_dbits = 8; g_dbe = 0;
         return r;
     case 1: case 2: case 3: case 15: case 25: case 26: case 27: case 28:

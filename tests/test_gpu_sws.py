@@ -93,7 +93,7 @@ def test_heavy_downscale_falls_back_to_two_passes(gpu, checker):
 
 def test_unsupported_requests_fail_loudly(gpu):
     L = gpu
-    assert not L.lib.sws_getContext_cuda(640, 480, 11, 640, 480, 2, 4 | ACC, None, None, None)     # pal8: not a source that is taken over
+    assert not L.lib.sws_getContext_cuda(640, 480, 9, 640, 480, 2, 4 | ACC, None, None, None)     # monowhite: not a source that is taken over
     assert "sources taken over" in L.last_error()
     L.lib.avb200_clear_error()
     assert not L.lib.sws_getContext_cuda(2, 2, 0, 640, 480, 2, 4 | ACC, None, None, None)

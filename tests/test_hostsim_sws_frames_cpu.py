@@ -231,6 +231,56 @@ def test_gray8_sources(sim, refo):
         sim.avb200_clear_error()
 
 
+def test_pal8_sources(sim, refo):
+    """pal8 sources (tests/test_sws_pal8_src.py): the palette reader in front of the planar kernels, palToRgbWrapper's lookup; whole frames, a batch through the
+    device-pointer call with one palette per frame, a bottom-up picture"""
+    import test_sws_pal8_src as P
+    import test_sws_gray_src as G
+    n = 0
+    for df in P.DSTS:
+        for (w, h, dw, dh) in P.GEOMS:
+            for flags in P.FLAGS[::2]:
+                if P.skipped(df, w, h, dw, dh, flags):
+                    continue
+                idx, pal = P.picture(w, h, 51)
+                rc, want = P.run(refo, idx, pal, w, h, df, dw, dh, flags)
+                assert rc == dh
+                got = product(sim, 11, [idx, pal.view(np.uint8).reshape(1, 1024)], w, h, df, dw, dh, flags, outs=P.dest(df, dw, dh))
+                assert all(np.array_equal(x, y) for x, y in zip(G.crop(df, dw, got), G.crop(df, dw, want))), (df, w, h, dw, dh, hex(flags))
+                n += 1
+    assert n > 200
+    for df in (37, 35):
+        assert not sim.sws_getContext_cuda(64, 48, 11, 128, 96, df, 4 | ACC, None, None, None)
+        sim.avb200_clear_error()
+    # two frames, two palettes, one call
+    sim.sws_scale_frames_cuda.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+    for df, (w, h, dw, dh), flags in ((2, (64, 48, 96, 80), 4 | ACC), (26, (64, 48, 64, 48), 4), (0, (66, 50, 33, 25), 2)):
+        pics = [P.picture(w, h, 70 + k) for k in range(2)]
+        src = np.stack([np.ascontiguousarray(p[0]) for p in pics])
+        pals = np.stack([p[1] for p in pics])
+        want = [P.run(refo, p[0], p[1], w, h, df, dw, dh, flags)[1] for p in pics]
+        outs = [np.stack([np.zeros_like(q) for _ in range(2)]) for q in P.dest(df, dw, dh)]
+        ctx = sim.sws_getContext_cuda(w, h, 11, dw, dh, df, flags, None, None, None)
+        assert ctx, sim.avb200_last_error()
+        sp, ss, sf = (C.c_void_p * 3)(src.ctypes.data, pals.ctypes.data, None), (C.c_int * 3)(src.strides[1], 1024, 0), (C.c_size_t * 3)(src.strides[0], 1024, 0)
+        dp = (C.c_void_p * 3)(*([o.ctypes.data for o in outs] + [None] * (3 - len(outs))))
+        ds = (C.c_int * 3)(*([o.strides[1] for o in outs] + [0] * (3 - len(outs))))
+        dfr = (C.c_size_t * 3)(*([o.strides[0] for o in outs] + [0] * (3 - len(outs))))
+        assert sim.sws_scale_frames_cuda(ctx, sp, ss, sf, dp, ds, dfr, 2, None) == 2 * dh, sim.avb200_last_error()
+        sim.sws_freeContext_cuda(ctx)
+        for k in range(2):
+            assert all(np.array_equal(x, y) for x, y in zip(G.crop(df, dw, [o[k] for o in outs]), G.crop(df, dw, want[k]))), (df, k)
+    # bottom-up source and destination
+    idx, pal = P.picture(64, 48, 77)
+    want = product(sim, 11, [idx, pal.view(np.uint8).reshape(1, 1024)], 64, 48, 2, 96, 80, 4)
+    up = np.ascontiguousarray(idx[::-1])[::-1]
+    store = np.ascontiguousarray(outputs(2, 96, 80)[0][::-1])
+    got = [store[::-1]]
+    assert up.strides[0] < 0 and got[0].strides[0] < 0
+    product(sim, 11, [up, pal.view(np.uint8).reshape(1, 1024)], 64, 48, 2, 96, 80, 4, outs=got)
+    same(got, want, "pal8 bottom-up")
+
+
 def test_gray8_destination(sim, refo):
     """gray8 (tests/test_sws_gray_dst.py): the luma plane of the planar conversion, chroma into the context's scratch"""
     import test_sws_gray_dst as G

@@ -30,6 +30,9 @@ def source(sf, w, h, seed):
         return R.planes(sf, w, h, seed)
     if sf == 3:
         return [r.randint(0, 256, (h, 3 * w + 10)).astype(np.uint8)]
+    if sf == 11:                                                      # pal8: indices + the palette (which every slice call passes again)
+        idx = r.randint(0, 256, (h, w + 16)).astype(np.uint8)
+        return [idx, r.randint(0, 256, (1, 1024)).astype(np.uint8)]
     if sf == 8:                                                       # gray8: one plane
         return [synth.pad_rows(r.randint(0, 256, (h, w)).astype(np.uint8))]
     if 25 <= sf <= 28:
@@ -41,6 +44,8 @@ def source(sf, w, h, seed):
 
 
 def slice_planes(sf, pl, y0):
+    if sf == 11:
+        return [pl[0][y0:], pl[1]]
     vs = VSUB.get(sf, 0)
     return [pl[0][y0:]] + [p[y0 >> vs:] for p in pl[1:]]
 
@@ -133,13 +138,13 @@ def test_unscaled_converter_slices(sim, refo):
 def test_slices_of_the_late_formats(sim, refo):
     """rgb48 destinations, gray8 sources and the same-size rgb2rgb converters under slices"""
     n = 0
-    for sf, df in ((0, 35), (5, 60), (8, 2), (8, 0), (8, 37)):
+    for sf, df in ((0, 35), (5, 60), (8, 2), (8, 0), (8, 37), (11, 2), (11, 0), (11, 28)):
         for (w, h, dw, dh) in ((64, 48, 96, 80), (66, 50, 33, 25)):
             for flags in (4 | ACC, 2):
-                for plan in plans(h, 1 << (VSUB.get(sf, 0) if sf != 8 else 0)):
+                for plan in plans(h, 1 << (VSUB.get(sf, 0) if sf not in (8, 11) else 0)):
                     compare(sim, refo, sf, df, w, h, dw, dh, flags, plan)
                     n += 1
-    for sf, df, flags, align in ((0, 35, 4, 2), (4, 59, 4, 2), (8, 0, 4, 2), (8, 5, 4, 1), (8, 26, 4, 1), (8, 3, 4, 1), (26, 2, 4, 1), (2, 28, 4, 1), (25, 27, 4, 1)):
+    for sf, df, flags, align in ((0, 35, 4, 2), (4, 59, 4, 2), (8, 0, 4, 2), (8, 5, 4, 1), (8, 26, 4, 1), (8, 3, 4, 1), (26, 2, 4, 1), (2, 28, 4, 1), (25, 27, 4, 1), (11, 3, 4, 1), (11, 25, 4, 1)):
         for (w, h) in ((64, 48), (66, 52)):
             for plan in plans(h, align):
                 compare(sim, refo, sf, df, w, h, w, h, flags, plan)

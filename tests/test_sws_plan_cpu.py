@@ -12,7 +12,7 @@ ACC = 0x40000 | 0x80000
 PLANAR_SRC = {0: (1, 1), 4: (1, 0), 5: (0, 0), 6: (2, 2), 7: (2, 0), 31: (0, 1), 12: (1, 1), 13: (1, 0), 14: (0, 0), 32: (0, 1), 33: (1, 1), 8: (0, 0)}     # 33: yuva420p (alpha never read), 8: gray8 (one plane; the two others are never read)
 PACKED_SRC = {1: 2, 15: 2, 2: 3, 3: 3, 25: 4, 26: 4, 27: 4, 28: 4}
 HBD_SRC = [62, 63, 64, 48, 66, 70]                       # 9 / 10 / 16-bit planar sources (a sample; every one in tests/test_sws_hbd_sources_cpu.py)
-SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24] + HBD_SRC
+SRCS = list(PLANAR_SRC) + list(PACKED_SRC) + [23, 24, 11] + HBD_SRC
 DSTS = [0, 4, 5, 6, 31, 62, 64, 47, 48, 2, 3, 25, 26, 27, 28, 1, 15, 23, 24, 12, 14, 32, 37, 40, 43, 55, 8, 35, 59]        # 12 14 32: full-range (yuvj) planar
 GEOMS = [(64, 48, 64, 48), (66, 50, 66, 50), (64, 48, 96, 80), (96, 80, 64, 48)]
 FLAGS = (4 | ACC, 4, 0x10, 1 | ACC, 2 | ACC | 0x2000, 2)
@@ -31,6 +31,8 @@ def source(fmt, w, h):
         import test_sws_hbd_sources_cpu as H
         return H.planes(fmt, w, h, 3)
     r = np.random.RandomState(fmt * 7 + w)
+    if fmt == 11:                                      # pal8: indices + the palette as plane 1
+        return [r.randint(0, 256, (h + 1, w + 16)).astype(np.uint8), r.randint(0, 256, (1, 1024)).astype(np.uint8)]
     if fmt in PACKED_SRC:
         return [r.randint(0, 256, (h + 1, PACKED_SRC[fmt] * w + 16)).astype(np.uint8)]
     if fmt in (23, 24):
@@ -110,7 +112,7 @@ def test_paths_and_geometry(built):
 def test_refusals_carry_a_reason(built):
     import libav_b200._lib as L
     out = (C.c_int32 * 8)()
-    cases = [((64, 48, 11, 64, 48, 2, 4), "sources taken over"), ((64, 48, 0, 64, 48, 33, 4), "destinations taken over"),
+    cases = [((64, 48, 9, 64, 48, 2, 4), "sources taken over"), ((64, 48, 0, 64, 48, 33, 4), "destinations taken over"),
              ((64, 48, 0, 96, 80, 2, 4 | 0x10000), "CHR_DROP"), ((64, 48, 0, 96, 80, 27, 4 | 0x2000), "abgr"),
              ((64, 48, 26, 96, 80, 28, 4), "32-bit rgb source"), ((64, 48, 2, 64, 48, 25, 4), "writes past the row"), ((64, 49, 3, 64, 49, 0, 4), "even height"),
              ((64, 48, 12, 96, 80, 47, 4), "range conversion"), ((64, 48, 23, 64, 48, 24, 4), "nv12"), ((64, 48, 6, 64, 48, 0, 4), "yvu9ToYv12Wrapper"),

@@ -178,6 +178,41 @@ def test_frames_call_with_one_plane_sources(sim, refo):
             assert all(np.array_equal(x, y) for x, y in zip(G.crop(df, dw, [o[k] for o in outs]), G.crop(df, dw, want[k]))), (df, k)
 
 
+def test_colourspace_details_with_the_late_sources(sim, refo):
+    """sws_setColorspaceDetails_cuda on contexts with gray8 / pal8 / yuva420p sources and rgb destinations (the colour tables change, the constant
+    chroma lines of a gray source and the palette conversion do not)"""
+    import test_sws_colorspace as CS
+    import test_sws_gray_src as G
+    import test_sws_pal8_src as P
+    import test_sws_rgb48_dst as R
+    for cs in CS.SETTINGS[:4]:
+        tab = (C.c_int * 4)(*cs[0])
+        for sf in (8, 11, 33):
+            for df, (w, h, dw, dh), flags in ((2, (64, 48, 96, 80), 4 | ACC), (28, (101, 37, 333, 211), 2), (35, (64, 48, 96, 80), 4 | ACC), (3, (64, 48, 64, 48), 4)):
+                if (sf == 11 and df == 35) or (sf == 33 and df == 28):
+                    continue                     # refused pairs (pal8 -> 48 bit, yuva420p -> a destination with alpha)
+                if sf == 8:
+                    pl = [G.picture(w, h, 9)]
+                elif sf == 11:
+                    idx, pal = P.picture(w, h, 9)
+                    pl = [idx, pal.view(np.uint8).reshape(1, 1024)]
+                else:
+                    pl = R.source(0, w, h, 9)
+                refo.sws_set_colorspace(tab, cs[1], cs[2], cs[3], cs[4])
+                try:
+                    want = reference(refo, sf, pl, w, h, df, dw, dh, flags, outs=outputs(df, dw, dh))
+                finally:
+                    refo.sws_set_colorspace(None, 0, 0, 0, 0)
+                ctx = sim.sws_getContext_cuda(w, h, sf, dw, dh, df, flags, None, None, None)
+                assert ctx and sim.sws_setColorspaceDetails_cuda(ctx, tab, cs[1], tab, 0, cs[2], cs[3], cs[4]) == 0, sim.avb200_last_error()
+                got = outputs(df, dw, dh)
+                sp, ss = arrays(pl)
+                dp, ds = arrays(got)
+                assert sim.sws_scale_cuda(ctx, sp, ss, 0, h, dp, ds) == dh, sim.avb200_last_error()
+                sim.sws_freeContext_cuda(ctx)
+                same(got, want, (cs, sf, df, w, h, dw, dh, hex(flags)), crop=8)
+
+
 def test_yuva420p_sources(sim, refo):
     """yuva420p (33) to destinations without alpha: the product reads three planes like the reference does (tests/test_sws_yuva_src.py)"""
     import test_sws_rgb48_dst as R

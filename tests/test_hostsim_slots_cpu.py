@@ -7,6 +7,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 import slot_cases
@@ -197,6 +198,50 @@ def test_me_cmp_quant_metrics_slots(sim, refo, orc):
     _enc_protos(sim)
     assert enc_cases.slot_cases(sim, refo, orc) > 800
     sim.avb200_clear_error()
+
+
+def test_me_cmp_enc_tables_at_a_reused_address(sim, refo, orc):
+    """the VLC length tables are found by host address: other tables announced at an address that held some before (here rewritten in place) must be
+    taken anew -- by ff_me_cmp_enc_init_cuda and by ff_me_cmp_enc_state_cuda (host-compiled; tests/test_zz_gpu_late_slots.py has the GPU twin)"""
+    import enc_cases as E
+    from libav_b200 import tables
+    _enc_protos(sim)
+    T = E.Tables(4)
+    u8p = C.POINTER(C.c_uint8)
+    for round_ in range(2):
+        if round_:
+            T2 = E.Tables(99)
+            for name in ("intra_len", "intra_last", "inter_len", "inter_last", "luma_dc"):
+                getattr(T, name)[:] = getattr(T2, name)
+        enc = E.FakeEncoder(T)
+        table = tables.MECmpContext()
+        key = C.c_void_p(enc.key.ctypes.data)
+        label, st = E.states(T)[5]
+        enc.load(st, refo)
+        assert sim.ff_me_cmp_enc_init_cuda(C.byref(table), key, C.byref(enc.view)) == 0
+        cur, rf = E.block_pairs(6, seed=35)
+        want, wside = E.oracle_scores(refo, 15, 1, st, cur, rf, 6, 8, h263_guard=orc)
+        n = 0
+        for i in range(6):
+            if want[i] is None:
+                continue
+            enc.ints[6], enc.ints[8] = st.mb_intra, -2
+            a = C.cast(cur.ctypes.data + 16 * i * cur.strides[0] + 8, u8p)
+            b = C.cast(rf.ctypes.data + 16 * i * rf.strides[0] + 8, u8p)
+            assert table.bit[1](key, a, b, cur.strides[0], 8) == want[i], (round_, i)
+            n += 1
+        assert n >= 3
+        sim.ff_me_cmp_enc_uninit_cuda(key)
+        p, _, _, _ = E.product_state(st, refo)
+        vlc = E.vlc_tables(T)
+        handle = sim.ff_me_cmp_enc_state_cuda(C.byref(p), C.byref(vlc))
+        assert handle
+        recs = np.array([[16 * i * cur.strides[0] + 8, 16 * i * rf.strides[0] + 8] for i in range(6)], np.uint32)
+        got, last = np.zeros(6, np.int32), np.zeros(6, np.int32)
+        assert sim.ff_me_cmp_enc_batch_cuda(15, 1, handle, cur.ctypes.data, rf.ctypes.data, cur.strides[0], 8, recs.ctypes.data, 6, got.ctypes.data, last.ctypes.data, None) == 0
+        for i in range(6):
+            assert want[i] is None or int(got[i]) == want[i], (round_, "batch", i)
+        sim.ff_me_cmp_enc_state_free_cuda(handle)
 
 
 @pytest.mark.parametrize("bits", [8, 9, 10])

@@ -467,7 +467,7 @@ int ff_mdct_batch_cuda(int op, int nbits, double scale, float *out, const float 
  * rgb48be = 34 / rgb48le = 35 / bgr48be = 59 / bgr48le = 60 (yuv2rgb48_X / _2 / _1 on hScale8To19_c lines, libswscale/output.c:593-760; same size without
  * SWS_ACCURATE_RND: yuv2rgb_c_48, yuv2rgb.c:106-236) from planar 8-bit yuv / yuvj sources.  Anything else returns NULL with an error (no fallback).
  *   sws_scale_cuda         HOST pointers; whole frames (srcSliceY = 0, srcSliceH = srcH) with strides of either sign (bottom-up pictures), or
- *                          slices like sws_scale() takes them (swscale_unscaled.c:1212-1340): srcSlice[] at source row srcSliceY, dst[] at the
+ *                          slices (not into a gray8 destination) like sws_scale() takes them (swscale_unscaled.c:1212-1340): srcSlice[] at source row srcSliceY, dst[] at the
  *                          top of the picture, top-down and contiguous, boundaries on whole chroma rows, positive strides; each call returns
  *                          (and writes) the rows the reference's loop completes with the same slices (swscale.c:483-485), at the cost of a
  *                          whole-frame pass per slice.  Uploads, runs, downloads, synchronises; returns output lines like sws_scale(),

@@ -2378,6 +2378,11 @@ int sws_scale_cuda(SwsContextCUDA *ctx, const uint8_t *const srcSlice[], const i
         return sws_scale_cuda(ctx, s4, ss4, srcSliceY, srcSliceH, dst, dstStride);
     }
     if (c->gray && dst && dst[0] && dstStride) {        // (a gray8 caller's dst[] has one plane; `gray` is cleared around the inner call)
+        if (srcSliceY != 0 || srcSliceH != c->g.srcH) {
+            // the rows a slice completes follow the destination's chroma geometry; a gray8 destination has none in the reference (chrDstVSubSample 0,
+            // its own vertical chroma filter) while this context carries the planar stand-in's: whole frames only
+            set_error_msg("sws_scale_cuda", "slices into a gray8 destination are not taken over (whole frames are)"); return 0;
+        }
         // the chroma planes of the planar conversion go to host scratch of the context (they are computed and dropped)
         const size_t bytes = (size_t)c->grayPitch * (c->g.chrDstH + 2);
         for (int k = 0; k < 2; k++) if (c->h_gray[k].size() < bytes) c->h_gray[k].resize(bytes);

@@ -6,7 +6,7 @@ down-scaling, every vertical filter size, sub-sampled chroma on either side, and
 Left out, because the reference's sliced result is not a function of the picture there: vertical down-scaling with SWS_POINT or SWS_FAST_BILINEAR
 and slices shorter than the step (its line ring, sized by utils.c:1190-1213 for whole chroma row groups, is over-run while a slice is buffered:
 48x64 -> 48x20 fast-bilinear in 4-row slices differs from its own whole-frame picture in rows 6 and 16, 66x50 -> 33x25 point in 7-row slices
-crashes), and slice boundaries inside a source chroma row (rows before the slice are addressed).  The product returns the whole-frame rows."""
+crashes; a randomised run also met it with SWS_BILINEAR at 48x64 -> 64x25 in 4-row slices, row 10), and slice boundaries inside a source chroma row (rows before the slice are addressed).  The product returns the whole-frame rows."""
 import ctypes as C
 
 import numpy as np
@@ -154,6 +154,15 @@ def test_slices_of_the_late_formats(sim, refo):
 
 def test_slice_refusals(sim):
     pl = source(0, 64, 48, 1)
+    ctx = sim.sws_getContext_cuda(64, 48, 0, 96, 80, 8, 4, None, None, None)             # gray8 destination: whole frames only
+    sp, ss = arrays(slice_planes(0, pl, 0))
+    gray = np.zeros((80, 96), np.uint8)
+    dp, ds = arrays([gray])
+    sim.avb200_clear_error()
+    assert sim.sws_scale_cuda(ctx, sp, ss, 0, 16, dp, ds) == 0 and b"gray8 destination" in sim.avb200_last_error()
+    assert sim.sws_scale_cuda(ctx, sp, ss, 0, 48, dp, ds) == 80
+    sim.sws_freeContext_cuda(ctx)
+    sim.avb200_clear_error()
     ctx = sim.sws_getContext_cuda(64, 48, 0, 96, 80, 2, 4, None, None, None)
     outs = outputs(2, 96, 80)
     dp, ds = arrays(outs)

@@ -1524,7 +1524,7 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         set_error_msg("sws_getContext_cuda", "rgb24 / bgr24 -> argb / abgr of the same size: the reference's converter writes past the row; there is no result to match");
         return nullptr;
     }
-    if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1) && srcRange == dstRange) {
+    if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !gray && unscaled && !(flags & SWS_ACCURATE_RND) && (srcH & 1) && srcRange == dstRange) {
         set_error_msg("sws_getContext_cuda", "bgr24 -> yuv420p of the same size without SWS_ACCURATE_RND is the reference's rgb24toyv12, which needs an even height");
         return nullptr;
     }
@@ -1610,9 +1610,10 @@ static SwsCudaContext *make_context(int srcW, int srcH, int srcFormat, int dstW,
         else if (rgb2rgb) c->special = 8;
         else if (srcRgb && rgb && !pk422) c->special = srcFormat == dstFormat ? 1 : 2;
         else if (rangeConv) c->special = 0;
-        else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !(flags & SWS_ACCURATE_RND)) c->special = 3;
-        else if (srcYuy && dstFormat == FMT_YUV420P) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
-        else if (srcYuy && dstFormat == FMT_YUV422P) c->special = srcFormat == FMT_YUYV422 ? 6 : 7;
+        // (a gray8 destination is served through a planar stand-in: the reference installs these converters for real yuv420p / yuv422p destinations only)
+        else if (srcFormat == FMT_BGR24 && dstFormat == FMT_YUV420P && !gray && !(flags & SWS_ACCURATE_RND)) c->special = 3;
+        else if (srcYuy && dstFormat == FMT_YUV420P && !gray) c->special = srcFormat == FMT_YUYV422 ? 4 : 5;
+        else if (srcYuy && dstFormat == FMT_YUV422P && !gray) c->special = srcFormat == FMT_YUYV422 ? 6 : 7;
     }
     if (derive_geometry(c->g, srcW, srcH, dstW, dstH, rgb, flags, &err, hs, vs, dhs, dvs)) goto fail;
     {

@@ -1173,7 +1173,14 @@ static int sws_any(int src_fmt, const uint8_t *const src[3], const int ss[3], in
         if (!tmp) return -1;
         uint8_t *const d3[3] = { dst[0], tmp, tmp + (size_t)pitch * (dh + 2) };
         const int ds3[3] = { dstride[0], pitch, pitch };
-        r = sws_any(src_fmt, src, ss, sw, sh, df, d3, ds3, dw, dh, flags);
+        {   /* (the unscaled converters of packed sources -- rgb24toyv12, yuyvtoyuv420 ... -- are installed for real yuv420p / yuv422p destinations, swscale_unscaled.c:
+             * 1063-1067,1140-1147: a gray8 destination goes through swscale()) */
+            const int packed = src_fmt == 1 || src_fmt == 2 || src_fmt == 3 || src_fmt == 15 || (src_fmt >= 25 && src_fmt <= 28);
+            const int keep = g_nospecial;
+            if (packed) g_nospecial = 1;
+            r = sws_any(src_fmt, src, ss, sw, sh, df, d3, ds3, dw, dh, flags);
+            g_nospecial = keep;
+        }
         free(tmp);
         return r;
     }

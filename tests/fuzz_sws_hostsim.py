@@ -18,11 +18,14 @@ lib.sws_getContext_cuda.restype = C.c_void_p
 lib.sws_getContext_cuda.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
 lib.sws_freeContext_cuda.argtypes = [C.c_void_p]
 lib.sws_scale_cuda.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-SRCS = [0,4,5,6,7,31,12,13,14,32,33,8,11,23,24,1,15,2,3,25,26,27,28]
-DSTS = [0,4,5,6,7,31,12,13,14,32,2,3,25,26,27,28,1,15,23,24,8,37,36,41,43,54,57,35,34,60,59,62,64,66,68]
+SRCS = [0,4,5,6,7,31,12,13,14,32,33,8,11,23,24,1,15,2,3,25,26,27,28,62,61,64,63,47,48,66,70,72,68,49,51]
+DSTS = [0,4,5,6,7,31,12,13,14,32,2,3,25,26,27,28,1,15,23,24,8,37,36,41,43,54,57,35,34,60,59,62,64,66,68,61,63,72,70]
 SUB = {0:(1,1),4:(1,0),5:(0,0),6:(2,2),7:(2,0),31:(0,1),12:(1,1),13:(1,0),14:(0,0),32:(0,1),33:(1,1)}
 def source(sf,w,h,seed):
     r=np.random.RandomState(seed)
+    if sf>40:
+        import test_sws_hbd_sources_cpu as HB
+        return HB.planes(sf,w,h,seed)
     if sf==8: return [G.picture(w,h,seed)]
     if sf==11:
         i,p=PAL.picture(w,h,seed); return [i,p.view(np.uint8).reshape(1,1024)]

@@ -8,14 +8,16 @@ import pytest
 
 from test_sws_planar_dst import source
 
-SRC = [0, 4, 5, 23, 1, 2, 12]
+SRC = [0, 4, 5, 23, 1, 2, 12, 3, 15, 26]        # 3 = bgr24: at the same size without SWS_ACCURATE_RND a yuv420p destination would get rgb24toyv12 -- a gray8 one does not
 GEOMS = [(64, 48, 64, 48), (352, 288, 640, 480), (640, 480, 352, 288), (101, 37, 333, 211), (67, 51, 67, 51), (66, 50, 33, 25)]
 ACC = 0x40000 | 0x80000
 FLAGS = (4 | ACC, 2 | 0x80000, 4, 0x10 | ACC, 1 | ACC, 0x200 | ACC)
 
 
 def planes(fmt, w, h, seed):
-    return source(0, w, h, seed) if fmt == 12 else source(fmt, w, h, seed)
+    if fmt == 26:
+        return [np.random.RandomState(seed).randint(0, 256, (h, 4 * w + 12)).astype(np.uint8)]
+    return source({12: 0, 3: 2}.get(fmt, fmt), w, h, seed)
 
 
 def run(o, fmt, pl, w, h, dw, dh, flags):
@@ -30,7 +32,7 @@ def combos():
     for fmt in SRC:
         for (w, h, dw, dh) in GEOMS:
             for flags in FLAGS:
-                if flags & 1 and fmt in (23, 1, 2) and dw > w:
+                if flags & 1 and fmt in (23, 1, 2, 3, 15, 26) and dw > w:
                     continue         # undefined right edge, see tests/test_sws_packed_sources.py
                 yield fmt, w, h, dw, dh, flags
 
